@@ -1,0 +1,292 @@
+"""ctypes mirror of include/fargo_b200.h (the C ABI of libfargo_b200.so).
+
+Only plumbing lives here: struct layouts and a thin handle class.  The same handle class is used
+by the tests to drive the CPU oracle (oracle/libfargo_oracle.so, prefix ``fargo_oracle_``), which
+exports the same entry points — so parity tests call both sides through identical code.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+FARGO_ABI_VERSION = 1
+FARGO_MAX_BODIES = 8
+CPUOVERLAP = 7
+
+# enum fargo_field
+(SIGMA, VRAD, VAZI, ENERGY, SIGMA0, VRAD0, VAZI0, ENERGY0, QPLUS, QMINUS, TEMPERATURE, PRESSURE, SOUNDSPEED,
+ SCALE_HEIGHT, VISCOSITY, POTENTIAL) = range(16)
+FIELD_NAMES = {SIGMA: "Sigma", VRAD: "vrad", VAZI: "vazi", ENERGY: "energy", QPLUS: "Qplus", QMINUS: "Qminus"}
+VECTOR_FIELDS = (VRAD, VRAD0)
+
+ARTVISC = {"none": 0, "tw": 1, "sn": 2}
+LIMITER = {"vanleer": 0, "mc": 1}
+SPACING = {"logarithmic": 0, "arithmetic": 1, "exponential": 2, "custom": 3}
+BC = {"none": 0, "zerogradient": 1, "outflow": 2, "reflecting": 3, "keplerian": 4, "reference": 5}
+DAMP = {"none": 0, "initial": 1, "reference": 1, "zero": 2, "mean": 3}
+BETA_REF = {"none": 0, "zero": 0, "reference": 1, "model": 2, "floor": 4}
+
+
+class FargoParams(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int),
+        ("nrad", C.c_int), ("naz", C.c_int), ("radial_spacing", C.c_int),
+        ("rmin", C.c_double), ("rmax", C.c_double),
+        ("adiabatic", C.c_int),
+        ("gamma", C.c_double), ("mu", C.c_double), ("aspectratio_ref", C.c_double), ("flaring_index", C.c_double),
+        ("sigma0", C.c_double), ("sigma_floor", C.c_double), ("sigma_slope", C.c_double),
+        ("minimum_temperature", C.c_double), ("maximum_temperature", C.c_double),
+        ("G", C.c_double), ("Rgas", C.c_double), ("sigma_sb", C.c_double), ("c_light", C.c_double),
+        ("hydro_center_mass", C.c_double),
+        ("cfl", C.c_double), ("cfl_max_var", C.c_double), ("heating_cooling_cfl_limit", C.c_double),
+        ("leapfrog", C.c_int),
+        ("fast_transport", C.c_int), ("flux_limiter", C.c_int),
+        ("artificial_viscosity", C.c_int), ("artificial_viscosity_factor", C.c_double),
+        ("artificial_viscosity_dissipation", C.c_int),
+        ("viscous_alpha", C.c_double), ("constant_viscosity", C.c_double), ("stabilize_viscosity", C.c_int),
+        ("radial_viscosity_factor", C.c_double),
+        ("heating_viscous", C.c_int), ("heating_viscous_factor", C.c_double),
+        ("cooling_beta", C.c_int), ("cooling_beta_value", C.c_double), ("cooling_beta_ramp_up", C.c_double),
+        ("cooling_beta_reference", C.c_int),
+        ("body_force_from_potential", C.c_int), ("thickness_smoothing", C.c_double),
+        ("imposed_disk_drift", C.c_double),
+        ("bc_sigma", C.c_int * 2), ("bc_energy", C.c_int * 2), ("bc_vrad", C.c_int * 2), ("bc_vazi", C.c_int * 2),
+        ("keplerian_azimuthal_factor", C.c_double * 2),
+        ("damping", C.c_int),
+        ("damping_inner_limit", C.c_double), ("damping_outer_limit", C.c_double),
+        ("damping_time_factor", C.c_double), ("damping_time_radius_outer", C.c_double),
+        ("damp_vrad", C.c_int * 2), ("damp_vazi", C.c_int * 2), ("damp_sigma", C.c_int * 2),
+        ("damp_energy", C.c_int * 2),
+    ]
+
+    def as_dict(self):
+        out = {}
+        for name, _ in self._fields_:
+            v = getattr(self, name)
+            out[name] = list(v) if hasattr(v, "__len__") else v
+        return out
+
+    @classmethod
+    def from_dict(cls, d):
+        p = cls()
+        for name, typ in cls._fields_:
+            if name not in d:
+                continue
+            v = d[name]
+            if isinstance(v, (list, tuple)):
+                for k, x in enumerate(v):
+                    getattr(p, name)[k] = x
+            else:
+                setattr(p, name, v)
+        p.abi_version = FARGO_ABI_VERSION
+        return p
+
+
+class FargoBodies(C.Structure):
+    _fields_ = [
+        ("n", C.c_int),
+        ("x", C.c_double * FARGO_MAX_BODIES), ("y", C.c_double * FARGO_MAX_BODIES),
+        ("mass", C.c_double * FARGO_MAX_BODIES), ("cubic_smoothing_radius", C.c_double * FARGO_MAX_BODIES),
+        ("indirect_x", C.c_double), ("indirect_y", C.c_double), ("omega_frame", C.c_double),
+    ]
+
+    @classmethod
+    def make(cls, x, y, mass, rsm=None, indirect=(0.0, 0.0), omega_frame=0.0):
+        b = cls()
+        b.n = len(x)
+        for k in range(b.n):
+            b.x[k], b.y[k], b.mass[k] = x[k], y[k], mass[k]
+            b.cubic_smoothing_radius[k] = 0.0 if rsm is None else rsm[k]
+        b.indirect_x, b.indirect_y = indirect
+        b.omega_frame = omega_frame
+        return b
+
+
+_DP = C.POINTER(C.c_double)
+
+
+def _dptr(a):
+    return a.ctypes.data_as(_DP)
+
+
+def _bind(lib, prefix):
+    """Declare argtypes for every entry point of include/fargo_b200.h on `lib`."""
+    vp = C.c_void_p
+    sig = {
+        "local_nrad": ([vp], C.c_int), "local_imin": ([vp], C.c_int),
+        "upload_field": ([vp, C.c_int, _DP], C.c_int), "download_field": ([vp, C.c_int, _DP], C.c_int),
+        "download_slab": ([vp, C.c_int, _DP], C.c_int),
+        "copy_initial_values": ([vp], C.c_int),
+        "set_bodies": ([vp, C.POINTER(FargoBodies)], C.c_int), "set_time": ([vp, C.c_double], C.c_int),
+        "init_derived": ([vp], C.c_int),
+        "cfl": ([vp, _DP, _DP], C.c_int), "condition_cfl": ([vp, _DP], C.c_int),
+        "step": ([vp, C.c_double], C.c_int),
+        "stage_potential": ([vp], C.c_int), "stage_sources": ([vp, C.c_double], C.c_int),
+        "stage_artvisc": ([vp, C.c_double], C.c_int), "stage_viscosity": ([vp, C.c_double], C.c_int),
+        "stage_substep3": ([vp, C.c_double], C.c_int),
+        "stage_boundary": ([vp, C.c_double, C.c_int], C.c_int),
+        "stage_transport": ([vp, C.c_double], C.c_int), "stage_derived": ([vp], C.c_int),
+        "get_nshift": ([vp, C.POINTER(C.c_int)], C.c_int),
+    }
+    for name, (args, res) in sig.items():
+        fn = getattr(lib, prefix + name)
+        fn.argtypes, fn.restype = args, res
+    return lib
+
+
+class Handle:
+    """One hydro context (== one radial slab == one GPU / one MPI rank of the reference)."""
+
+    def __init__(self, lib, prefix, ptr, params, rank, nranks):
+        self.lib, self.prefix, self.ptr = lib, prefix, C.c_void_p(ptr)
+        self.params, self.rank, self.nranks = params, rank, nranks
+        self.nrad_global, self.naz = params.nrad, params.naz
+        self.nr = self._call("local_nrad")
+        self.imin = self._call("local_imin")
+
+    def _fn(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    def _call(self, name, *args):
+        return self._fn(name)(self.ptr, *args)
+
+    def _check(self, rc, name):
+        if rc != 0:
+            msg = ""
+            if hasattr(self.lib, "fargo_last_error") and self.prefix == "fargo_":
+                self.lib.fargo_last_error.restype = C.c_char_p
+                msg = (self.lib.fargo_last_error() or b"").decode()
+            raise RuntimeError(f"{self.prefix}{name} failed rc={rc}: {msg}")
+
+    def global_shape(self, field):
+        return (self.nrad_global + (1 if field in VECTOR_FIELDS else 0), self.naz)
+
+    def slab_shape(self, field):
+        return (self.nr + (1 if field in VECTOR_FIELDS else 0), self.naz)
+
+    def upload(self, field, arr):
+        a = np.ascontiguousarray(arr, dtype=np.float64)
+        assert a.shape == self.global_shape(field), (a.shape, self.global_shape(field))
+        self._check(self._call("upload_field", field, _dptr(a)), "upload_field")
+
+    def download(self, field, out=None):
+        if out is None:
+            out = np.zeros(self.global_shape(field), dtype=np.float64)
+        self._check(self._call("download_field", field, _dptr(out)), "download_field")
+        return out
+
+    def download_slab(self, field):
+        out = np.zeros(self.slab_shape(field), dtype=np.float64)
+        self._check(self._call("download_slab", field, _dptr(out)), "download_slab")
+        return out
+
+    def copy_initial_values(self):
+        self._check(self._call("copy_initial_values"), "copy_initial_values")
+
+    def set_bodies(self, bodies):
+        self._bodies = bodies
+        self._check(self._call("set_bodies", C.byref(bodies)), "set_bodies")
+
+    def set_time(self, t):
+        self._check(self._call("set_time", float(t)), "set_time")
+
+    def init_derived(self):
+        self._check(self._call("init_derived"), "init_derived")
+
+    def cfl(self, last_dt):
+        l, d = C.c_double(last_dt), C.c_double(0.0)
+        self._check(self._call("cfl", C.byref(l), C.byref(d)), "cfl")
+        return d.value
+
+    def condition_cfl(self):
+        d = C.c_double(0.0)
+        self._check(self._call("condition_cfl", C.byref(d)), "condition_cfl")
+        return d.value
+
+    def step(self, dt):
+        self._check(self._call("step", float(dt)), "step")
+
+    def stage(self, name, *args):
+        self._check(self._call("stage_" + name, *args), "stage_" + name)
+
+    def nshift(self):
+        out = np.zeros(self.nr, dtype=np.int32)
+        self._check(self._call("get_nshift", out.ctypes.data_as(C.POINTER(C.c_int))), "get_nshift")
+        return out
+
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libfargo_b200.so")
+_lib = None
+
+
+def load_library():
+    """Load the CUDA library.  Fails loudly if it was not built — there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        _bind(lib, "fargo_")
+        lib.fargo_ctx_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(FargoParams), _DP, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_int]
+        lib.fargo_ctx_create.restype = C.c_int
+        lib.fargo_ctx_destroy.argtypes = [C.c_void_p]
+        lib.fargo_ctx_destroy.restype = None
+        lib.fargo_last_error.restype = C.c_char_p
+        lib.fargo_get_unique_id.argtypes = [C.c_void_p]
+        lib.fargo_get_unique_id.restype = C.c_int
+        lib.fargo_stage_halo.argtypes = [C.c_void_p]
+        lib.fargo_stage_halo.restype = C.c_int
+        lib.fargo_sync.argtypes = [C.c_void_p]
+        lib.fargo_sync.restype = C.c_int
+        lib.fargo_launch_count.argtypes = [C.c_void_p]
+        lib.fargo_launch_count.restype = C.c_longlong
+        _lib = lib
+    return _lib
+
+
+class HydroContext(Handle):
+    """Device context of libfargo_b200.so (one per GPU)."""
+
+    def __init__(self, params, radii, rank=0, nranks=1, unique_id=None, device=0):
+        lib = load_library()
+        radii = np.ascontiguousarray(radii, dtype=np.float64)
+        assert radii.shape == (params.nrad + 1,)
+        ptr = C.c_void_p()
+        uid = None
+        if unique_id is not None:
+            self._uid = C.create_string_buffer(bytes(unique_id), 128)
+            uid = C.cast(self._uid, C.c_void_p)
+        rc = lib.fargo_ctx_create(C.byref(ptr), C.byref(params), _dptr(radii), rank, nranks, uid, device)
+        if rc != 0:
+            raise RuntimeError("fargo_ctx_create failed: " + (lib.fargo_last_error() or b"").decode())
+        super().__init__(lib, "fargo_", ptr.value, params, rank, nranks)
+
+    def halo(self):
+        self._check(self.lib.fargo_stage_halo(self.ptr), "stage_halo")
+
+    def sync(self):
+        self._check(self.lib.fargo_sync(self.ptr), "sync")
+
+    def launch_count(self):
+        return int(self.lib.fargo_launch_count(self.ptr))
+
+    def close(self):
+        if self.ptr:
+            self.lib.fargo_ctx_destroy(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def get_unique_id():
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    if lib.fargo_get_unique_id(C.cast(buf, C.c_void_p)) != 0:
+        raise RuntimeError("fargo_get_unique_id failed: " + (lib.fargo_last_error() or b"").decode())
+    return bytes(buf.raw)

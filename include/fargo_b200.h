@@ -1,0 +1,215 @@
+/* fargo_b200.h — C ABI of the B200-native FargoCPT hydro step (libfargo_b200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of rometsch/fargocpt: the gas part of
+ * sim::step_Euler (src/simulation.cpp:148-267) plus sim::CalculateTimeStep
+ * (src/simulation.cpp:100-118).  FargoCPT has no plugin registry; the seam is the set of free
+ * functions step_Euler calls with a `t_data&`.  Each entry point below names the reference
+ * function(s) (file:line, relative to the reference's src/) it replaces.  INTEGRATION.md
+ * shows the reference-side binding a maintainer would add.
+ *
+ * Conventions (mirroring the reference):
+ *  - plain C, plain pointers and sizes, no torch / CUDA types in any signature;
+ *  - one opaque context per GPU (== per MPI rank of the reference: one radial slab);
+ *  - the caller is single-threaded per context (reference: MPI_THREAD_FUNNELED);
+ *  - fields are updated in place on the device; host copies only via upload/download;
+ *  - every function returns 0 on success, non-zero on error; fargo_last_error() gives the text.
+ *    (The reference die()s; the host driver above this ABI turns non-zero into exit.)
+ *  - there is NO CPU fallback: without a CUDA device fargo_ctx_create fails.
+ *
+ * Field layout == t_polargrid (src/polargrid.h:111-114): row-major double, azimuth contiguous,
+ * index = naz + nrad*Naz.  "Scalar" grids have nrad rings, v_rad has nrad+1 rings
+ * (ring i = inner interface of cell i), v_azi lives on the azimuthal interface j-1/2.
+ */
+#ifndef FARGO_B200_H
+#define FARGO_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FARGO_ABI_VERSION 1
+#define FARGO_MAX_BODIES 8
+/* src/constants.h:17 (CPUOVERLAP) and :19 (GHOSTCELLS_B) */
+#define FARGO_CPUOVERLAP 7
+#define FARGO_GHOSTCELLS_B 1
+
+/* t_data::t_polargrid_type subset that crosses the boundary (src/data.h:17-86) */
+enum fargo_field {
+    FARGO_SIGMA = 0,      /* Sigma.dat   [nrad][naz]   */
+    FARGO_VRAD = 1,       /* vrad.dat    [nrad+1][naz] */
+    FARGO_VAZI = 2,       /* vazi.dat    [nrad][naz]   */
+    FARGO_ENERGY = 3,     /* energy.dat  [nrad][naz]   */
+    FARGO_SIGMA0 = 4,     /* damping / beta-cooling reference values (data.h:40-43) */
+    FARGO_VRAD0 = 5,
+    FARGO_VAZI0 = 6,
+    FARGO_ENERGY0 = 7,
+    FARGO_QPLUS = 8,      /* stored Q+/alpha_r, read by the next CFL (SourceEuler.cpp:926) */
+    FARGO_QMINUS = 9,
+    FARGO_TEMPERATURE = 10, /* derived, computed on download */
+    FARGO_PRESSURE = 11,
+    FARGO_SOUNDSPEED = 12,
+    FARGO_SCALE_HEIGHT = 13,
+    FARGO_VISCOSITY = 14,
+    FARGO_POTENTIAL = 15,
+    FARGO_NFIELDS = 16
+};
+
+enum fargo_artvisc { FARGO_ARTVISC_NONE = 0, FARGO_ARTVISC_TW = 1, FARGO_ARTVISC_SN = 2 };
+enum fargo_limiter { FARGO_LIMITER_VANLEER = 0, FARGO_LIMITER_MC = 1 };
+enum fargo_spacing { FARGO_SPACING_LOG = 0, FARGO_SPACING_ARITH = 1, FARGO_SPACING_EXP = 2, FARGO_SPACING_CUSTOM = 3 };
+/* per-variable boundary functions (src/boundary_conditions/boundary_conditions.h:13-22) */
+enum fargo_bc {
+    FARGO_BC_NONE = 0,
+    FARGO_BC_ZEROGRADIENT = 1, /* zero_gradient.cpp */
+    FARGO_BC_OUTFLOW = 2,      /* outflow.cpp (v_rad only) */
+    FARGO_BC_REFLECTING = 3,   /* reflecting.cpp (v_rad only) */
+    FARGO_BC_KEPLERIAN = 4,    /* keplerian_azimuthal.cpp (v_azi only, the default) */
+    FARGO_BC_REFERENCE = 5     /* reference.cpp: copy X0 into the ghost rings */
+};
+/* damping.cpp t_damping_type */
+enum fargo_damping { FARGO_DAMP_NONE = 0, FARGO_DAMP_INITIAL = 1, FARGO_DAMP_ZERO = 2, FARGO_DAMP_MEAN = 3 };
+/* beta-cooling reference (SourceEuler.cpp:656-683), bit flags */
+enum fargo_beta_ref { FARGO_BETA_REF_NONE = 0, FARGO_BETA_REF_REFERENCE = 1, FARGO_BETA_REF_MODEL = 2, FARGO_BETA_REF_FLOOR = 4 };
+
+/* POD mirror of the parameters::* globals the hot path reads (src/parameters.h, Interpret.cpp).
+ * All dimensional values are in CODE units (the host converts, like config::cfg.get<T>(key, default, unit)). */
+typedef struct fargo_params {
+    int abi_version;  /* FARGO_ABI_VERSION */
+    /* mesh: global grid (Interpret.cpp:196-231) */
+    int nrad;         /* GlobalNRadial: rings including one ghost ring per side */
+    int naz;          /* NAzimuthal */
+    int radial_spacing; /* enum fargo_spacing: only used for the damping-ring lookup (find_cell_id.cpp) */
+    double rmin, rmax;  /* RMIN, RMAX */
+    /* equation of state */
+    int adiabatic;    /* 1: EquationOfState Ideal (energy equation); 0: locally isothermal */
+    double gamma;     /* ADIABATICINDEX */
+    double mu;        /* MU */
+    double aspectratio_ref; /* AspectRatio */
+    double flaring_index;   /* FlaringIndex */
+    double sigma0;          /* Sigma0 (code units) */
+    double sigma_floor;     /* SigmaFloor (multiples of sigma0) */
+    double sigma_slope;     /* SigmaSlope (imposed disk drift only) */
+    double minimum_temperature, maximum_temperature; /* code units */
+    /* physical constants in code units (constants.cpp) */
+    double G, Rgas, sigma_sb, c_light;
+    double hydro_center_mass; /* global.cpp:146 */
+    /* time step (cfl.cpp, simulation.cpp:100-118) */
+    double cfl;               /* CFL */
+    double cfl_max_var;       /* CFLmaxVar */
+    double heating_cooling_cfl_limit; /* HeatingCoolingCFLlimit */
+    int leapfrog;             /* Integrator: 0 Euler, 1 Leapfrog (affects cfl factor 0.6 and step order) */
+    /* transport */
+    int fast_transport;       /* Transport: FARGO (1) | STANDARD (0) */
+    int flux_limiter;         /* enum fargo_limiter */
+    /* artificial viscosity */
+    int artificial_viscosity;             /* enum fargo_artvisc */
+    double artificial_viscosity_factor;   /* ArtificialViscosityFactor */
+    int artificial_viscosity_dissipation; /* ArtificialViscosityDissipation */
+    /* physical viscosity */
+    double viscous_alpha;        /* ViscousAlpha (>0 selects alpha viscosity, AlphaMode const) */
+    double constant_viscosity;   /* ConstantViscosity (code units) */
+    int stabilize_viscosity;     /* StabilizeViscosity 0|1|2 */
+    double radial_viscosity_factor; /* RadialViscosityFactor */
+    /* energy sources (SubStep3) */
+    int heating_viscous;         /* HeatingViscous */
+    double heating_viscous_factor;
+    int cooling_beta;            /* CoolingBetaLocal */
+    double cooling_beta_value;   /* CoolingBeta */
+    double cooling_beta_ramp_up; /* CoolingBetaRampUp */
+    int cooling_beta_reference;  /* enum fargo_beta_ref flags */
+    /* gravity coupling (Pframeforce.cpp) */
+    int body_force_from_potential; /* BodyForceFromPotential (1: potential, 0: accelerations) */
+    double thickness_smoothing;    /* ThicknessSmoothing */
+    double imposed_disk_drift;     /* ImposedDiskDrift */
+    /* boundaries: [0]=inner, [1]=outer (boundary_conditions/config.cpp) */
+    int bc_sigma[2], bc_energy[2], bc_vrad[2], bc_vazi[2]; /* enum fargo_bc */
+    double keplerian_azimuthal_factor[2];
+    /* damping zones (damping.cpp:185-271) */
+    int damping;
+    double damping_inner_limit, damping_outer_limit, damping_time_factor, damping_time_radius_outer;
+    int damp_vrad[2], damp_vazi[2], damp_sigma[2], damp_energy[2]; /* enum fargo_damping */
+} fargo_params;
+
+/* Star/planets as seen by the gas for ONE step (Pframeforce.cpp:27-36, refframe::IndirectTerm).
+ * The N-body integration stays on the host (planetary_system.cpp); the host refreshes this every step. */
+typedef struct fargo_bodies {
+    int n;
+    double x[FARGO_MAX_BODIES], y[FARGO_MAX_BODIES];
+    double mass[FARGO_MAX_BODIES];                   /* planet.get_rampup_mass(t) */
+    double cubic_smoothing_radius[FARGO_MAX_BODIES]; /* g_cubic_smoothing_radius, 0 = disabled */
+    double indirect_x, indirect_y;                   /* refframe::IndirectTerm */
+    double omega_frame;                              /* refframe::OmegaFrame */
+} fargo_bodies;
+
+typedef struct fargo_ctx fargo_ctx;
+
+/* --- life cycle ---------------------------------------------------------------------------
+ * Replaces SplitDomain (split.cpp:21-87), init_radialarrays (init.cpp:78-249), data.set_size
+ * (data.cpp:308), InitTransport (TransportEuler.cpp:57-96), cfl::init (cfl.cpp:14).
+ * radii: the nrad+1 GLOBAL interface radii (used_rad.dat).  rank/nranks select the radial slab.
+ * nccl_unique_id: 128-byte ncclUniqueId shared by all ranks (NULL when nranks == 1).
+ * device: CUDA ordinal. */
+int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, const double *radii, int rank, int nranks,
+		     const void *nccl_unique_id, int device);
+void fargo_ctx_destroy(fargo_ctx *ctx);
+const char *fargo_last_error(void);
+/* fills a 128-byte buffer with a fresh ncclUniqueId (rank 0 calls this, then broadcasts it) */
+int fargo_get_unique_id(void *out128);
+
+/* slab geometry (split.cpp:38-78): local ring count, global index of local ring 0 */
+int fargo_local_nrad(const fargo_ctx *ctx);
+int fargo_local_imin(const fargo_ctx *ctx);
+
+/* --- field transfer -----------------------------------------------------------------------
+ * Mirrors t_polargrid::read2D / write2D slab semantics (polargrid.cpp:135-180, 301-353):
+ * `host_global` is the GLOBAL array ([nrad(+1)][naz]); upload takes this rank's slab (overlap
+ * rings included); download writes the rings this rank owns (Zero_or_active..Max_or_active),
+ * leaving the rest of host_global untouched, so ranks can fill one global buffer. */
+int fargo_upload_field(fargo_ctx *ctx, int field, const double *host_global);
+int fargo_download_field(fargo_ctx *ctx, int field, double *host_global);
+/* raw slab copy (all local rings, overlap included) — used by tests */
+int fargo_download_slab(fargo_ctx *ctx, int field, double *host_slab);
+
+/* copy_initial_values (damping.cpp:287-296): X0 <- X for the four state fields */
+int fargo_copy_initial_values(fargo_ctx *ctx);
+
+/* --- per-step inputs from the host ---------------------------------------------------------- */
+int fargo_set_bodies(fargo_ctx *ctx, const fargo_bodies *bodies);
+int fargo_set_time(fargo_ctx *ctx, double time); /* sim::time, used by the beta-cooling ramp */
+
+/* --- the hot path ---------------------------------------------------------------------------
+ * init_euler's derived fields (SourceEuler.cpp:251-285): T, c_s, H, P, nu, Q+/- for the first CFL */
+int fargo_init_derived(fargo_ctx *ctx);
+/* sim::CalculateTimeStep (simulation.cpp:100-118) = cfl::condition_cfl (cfl.cpp:185-382) +
+ * MPI_Allreduce(MIN) + min(CFLmaxVar*last_dt, cfl).  `last_dt` is in/out (sim::last_dt). */
+int fargo_cfl(fargo_ctx *ctx, double *last_dt, double *dt_out);
+/* raw cfl::condition_cfl result (global min over ranks) */
+int fargo_condition_cfl(fargo_ctx *ctx, double *cfl_dt_out);
+/* gas part of step_Euler (simulation.cpp:167-175, 187-218, 230-266): potential, source terms,
+ * artificial viscosity, viscosity, SubStep3, boundary, Transport, halo exchange, boundary+damping,
+ * derived quantities.  Uses the bodies/time set before. */
+int fargo_step(fargo_ctx *ctx, double dt);
+
+/* per-stage entry points (same order as fargo_step), exported so parity can be bisected per
+ * reference function */
+int fargo_stage_potential(fargo_ctx *ctx);             /* CalculateNbodyPotential  Pframeforce.cpp:21 */
+int fargo_stage_sources(fargo_ctx *ctx, double dt);    /* update_with_sourceterms  SourceEuler.cpp:435 */
+int fargo_stage_artvisc(fargo_ctx *ctx, double dt);    /* art_visc::update_with_artificial_viscosity artificial_viscosity.cpp:11 */
+int fargo_stage_viscosity(fargo_ctx *ctx, double dt);  /* recalculate_viscosity + compute_viscous_stress_tensor + update_velocities_with_viscosity */
+int fargo_stage_substep3(fargo_ctx *ctx, double dt);   /* SubStep3 SourceEuler.cpp:859 (adiabatic only) */
+int fargo_stage_boundary(fargo_ctx *ctx, double dt, int final_call); /* apply_boundary_condition boundary_conditions.cpp:65 */
+int fargo_stage_transport(fargo_ctx *ctx, double dt);  /* Transport TransportEuler.cpp:112 */
+int fargo_stage_halo(fargo_ctx *ctx);                  /* CommunicateBoundaries commbound.cpp:98 */
+int fargo_stage_derived(fargo_ctx *ctx);               /* recalculate_derived_disk_quantities SourceEuler.cpp:225 */
+
+/* integer FARGO shifts of the last transport (TransportEuler.cpp:49,220), local rings */
+int fargo_get_nshift(fargo_ctx *ctx, int *out_local_nrad);
+
+/* stream sync + launch accounting (for bench.py) */
+int fargo_sync(fargo_ctx *ctx);
+long long fargo_launch_count(const fargo_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FARGO_B200_H */

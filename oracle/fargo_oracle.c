@@ -1,0 +1,1557 @@
+/* fargo_oracle.c — CPU restatement of FargoCPT's per-timestep hydro step.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This file is the parity oracle for the CUDA path in
+ * fargocpt_b200/csrc; it is imported only by tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline leg.  The product path never calls it (there is no CPU fallback).
+ *
+ * It is a plain-C restatement (not a copy) of the reference algorithm, one function per
+ * reference function, each citing the reference file:line it follows (paths relative to the
+ * reference's src/).  Arithmetic is IEEE double with the reference's operation order; build with
+ * -O2 -ffp-contract=off so no FMA contraction happens (the pinned reference build uses the same
+ * flags, see oracle/Makefile.ref).
+ *
+ * PARITY PINNED: tests/test_oracle_vs_golden.py checks this file bit-for-bit against snapshots
+ * produced by the unmodified reference built into oracle/_ref (fixtures in tests/golden/, made by
+ * tests/golden/make_golden.py).
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <float.h>
+
+#include "../include/fargo_b200.h"
+
+#define SEARCH_BUFFER 15 /* init.cpp:43 */
+
+typedef struct fargo_oracle {
+    fargo_params p;
+    int rank, nranks;
+    int nr, ns;	    /* local NRadial, NAzimuthal */
+    int imin, imax; /* split.cpp:50-61 */
+    /* split.cpp:66-78 */
+    int zero_no_ghost, one_no_ghost_vr, max_no_ghost, maxmo_no_ghost_vr;
+    int zero_or_active, max_or_active, first_active, active_size;
+    double dphi, invdphi;
+    /* global 1-D arrays (size nrad_global + SEARCH_BUFFER + 2) and local views (offset imin) */
+    double *g_radii, *g_rmed;
+    double *rinf, *rsup, *rmed, *surf, *invrmed, *invsurf, *invdiffrsup, *invdiffrsuprb, *twodiffrasq,
+	*fourthirdinvrbinvdphisq, *invrinf, *invdiffrmed;
+    double *cosphi, *sinphi;
+    /* state */
+    double *sigma, *vrad, *vazi, *energy;
+    double *sigma0, *vrad0, *vazi0, *energy0;
+    /* derived */
+    double *temperature, *pressure, *soundspeed, *scale_height, *viscosity, *potential;
+    double *qplus, *qminus, *divv, *trr, *tpp, *trp, *qr, *qphi, *nusig, *nusig_rp, *cf_r, *cf_phi, *tau_eff;
+    /* transport scratch (TransportEuler.cpp:32-46) */
+    double *rmp, *rmm, *amp, *amm, *vres, *work, *qrstar, *densstar, *densint, *tempshift, *dq, *vmean;
+    int *nshift;
+    int visc_calculated; /* viscosity.cpp:100 */
+    fargo_bodies bodies;
+    double time;
+    /* multi-rank: halo staging for tests (the exchange itself is done by the caller) */
+} fargo_oracle;
+
+
+/* std::min / std::max semantics (returns the first argument on ties and NaNs), used everywhere the
+ * reference calls them so that signed zeros and NaNs propagate identically */
+static inline double stdmin(double a, double b) { return (b < a) ? b : a; }
+static inline double stdmax(double a, double b) { return (a < b) ? b : a; }
+
+#define IDX(o, i, j) ((size_t)(i) * (size_t)(o)->ns + (size_t)(j))
+
+static double *dalloc(size_t n)
+{
+    double *p = (double *)calloc(n ? n : 1, sizeof(double));
+    if (!p) {
+	fprintf(stderr, "fargo_oracle: out of memory\n");
+	abort();
+    }
+    return p;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * geometry: init_radialarrays, init.cpp:169-225 */
+static void init_geometry(fargo_oracle *o, const double *radii)
+{
+    const int gn = o->p.nrad;
+    const int n1 = gn + SEARCH_BUFFER + 2;
+    o->g_radii = dalloc(n1 + 1);
+    for (int i = 0; i <= gn; ++i)
+	o->g_radii[i] = radii[i];
+    /* rings beyond the grid (search buffer) are never read by the hot path; extend geometrically */
+    for (int i = gn + 1; i <= n1; ++i)
+	o->g_radii[i] = o->g_radii[i - 1] * (o->g_radii[gn] / o->g_radii[gn - 1]);
+    o->dphi = 2.0 * M_PI / (double)o->ns;    /* Interpret.cpp:230 */
+    o->invdphi = (double)o->ns / (2.0 * M_PI); /* Interpret.cpp:231 */
+
+    const int nl = o->nr + 2;
+    o->rinf = dalloc(nl); o->rsup = dalloc(nl); o->rmed = dalloc(nl); o->surf = dalloc(nl);
+    o->invrmed = dalloc(nl); o->invsurf = dalloc(nl); o->invdiffrsup = dalloc(nl);
+    o->invdiffrsuprb = dalloc(nl); o->twodiffrasq = dalloc(nl); o->fourthirdinvrbinvdphisq = dalloc(nl);
+    o->invrinf = dalloc(nl); o->invdiffrmed = dalloc(nl);
+    for (int n = 0; n < nl; ++n) { /* init.cpp:188-216 */
+	const double ri = o->g_radii[n + o->imin], rs = o->g_radii[n + o->imin + 1];
+	o->rinf[n] = ri;
+	o->rsup[n] = rs;
+	double rm = 2.0 / 3.0 * (pow(rs, 3) - pow(ri, 3));
+	rm = rm / (pow(rs, 2) - pow(ri, 2));
+	o->rmed[n] = rm;
+	o->surf[n] = M_PI * (pow(rs, 2) - pow(ri, 2)) / (double)o->ns;
+	o->invrmed[n] = 1.0 / rm;
+	o->invsurf[n] = 1.0 / o->surf[n];
+	o->invdiffrsup[n] = 1.0 / (rs - ri);
+	o->invdiffrsuprb[n] = 1.0 / ((rs - ri) * rm);
+	o->twodiffrasq[n] = 2.0 / (rs * rs - ri * ri);
+	o->fourthirdinvrbinvdphisq[n] = 4.0 / 3.0 / rm * o->invdphi * o->invdphi;
+	o->invrinf[n] = 1.0 / ri;
+    }
+    for (int n = 1; n < nl; ++n) /* init.cpp:221-225 */
+	o->invdiffrmed[n] = 1.0 / (o->rmed[n] - o->rmed[n - 1]);
+    /* cell centres, SideEuler.cpp:56-65: x = Rmed*cos(dphi*j) */
+    o->cosphi = dalloc(o->ns);
+    o->sinphi = dalloc(o->ns);
+    for (int j = 0; j < o->ns; ++j) {
+	o->cosphi[j] = cos(o->dphi * (double)j);
+	o->sinphi[j] = sin(o->dphi * (double)j);
+    }
+}
+
+/* split.cpp:38-87 */
+static int split_domain(fargo_oracle *o)
+{
+    const int N = o->p.nrad, np = o->nranks, r = o->rank;
+    const int size_low = N / np, size_high = size_low + 1, rem = N % np;
+    if (np > 1 && size_low < 2 * FARGO_CPUOVERLAP)
+	return 1;
+    if (r < rem) {
+	o->imin = size_high * r;
+	o->imax = o->imin + size_high - 1;
+    } else {
+	o->imin = size_high * rem + (r - rem) * size_low;
+	o->imax = o->imin + size_low - 1;
+    }
+    if (r > 0)
+	o->imin -= FARGO_CPUOVERLAP;
+    if (r < np - 1)
+	o->imax += FARGO_CPUOVERLAP;
+    o->nr = o->imax - o->imin + 1;
+    const int first = (r == 0), last = (r == np - 1);
+    o->zero_no_ghost = first ? 1 : 0;
+    o->one_no_ghost_vr = first ? 2 : 1;
+    o->max_no_ghost = o->nr - (last ? 1 : 0);
+    o->maxmo_no_ghost_vr = o->nr + 1 - (last ? 2 : 1);
+    o->zero_or_active = first ? 0 : FARGO_CPUOVERLAP;
+    o->first_active = first ? FARGO_GHOSTCELLS_B : FARGO_CPUOVERLAP;
+    o->max_or_active = o->nr - (last ? 0 : FARGO_CPUOVERLAP);
+    o->active_size = o->nr - (last ? FARGO_GHOSTCELLS_B : FARGO_CPUOVERLAP);
+    return 0;
+}
+
+fargo_oracle *fargo_oracle_create(const fargo_params *params, const double *radii, int rank, int nranks)
+{
+    fargo_oracle *o = (fargo_oracle *)calloc(1, sizeof(*o));
+    o->p = *params;
+    o->rank = rank;
+    o->nranks = nranks;
+    o->ns = params->naz;
+    if (split_domain(o)) {
+	free(o);
+	return NULL;
+    }
+    init_geometry(o, radii);
+    const size_t ns = (size_t)(o->nr) * o->ns, nv = (size_t)(o->nr + 1) * o->ns;
+    o->sigma = dalloc(ns); o->vrad = dalloc(nv); o->vazi = dalloc(ns); o->energy = dalloc(ns);
+    o->sigma0 = dalloc(ns); o->vrad0 = dalloc(nv); o->vazi0 = dalloc(ns); o->energy0 = dalloc(ns);
+    o->temperature = dalloc(ns); o->pressure = dalloc(ns); o->soundspeed = dalloc(ns);
+    o->scale_height = dalloc(ns); o->viscosity = dalloc(ns); o->potential = dalloc(ns);
+    o->qplus = dalloc(ns); o->qminus = dalloc(ns); o->divv = dalloc(ns); o->trr = dalloc(ns);
+    o->tpp = dalloc(ns); o->trp = dalloc(nv); o->qr = dalloc(ns); o->qphi = dalloc(ns);
+    o->nusig = dalloc(ns); o->nusig_rp = dalloc(nv + o->ns); o->cf_r = dalloc(ns); o->cf_phi = dalloc(ns);
+    o->tau_eff = dalloc(ns);
+    o->rmp = dalloc(ns); o->rmm = dalloc(ns); o->amp = dalloc(ns); o->amm = dalloc(ns);
+    o->vres = dalloc(ns); o->work = dalloc(ns); o->qrstar = dalloc(nv); o->densstar = dalloc(nv);
+    o->densint = dalloc(ns); o->tempshift = dalloc(ns); o->dq = dalloc(ns); o->vmean = dalloc(o->nr + 1);
+    o->nshift = (int *)calloc(o->nr + 1, sizeof(int));
+    o->bodies.n = 1;
+    o->bodies.mass[0] = params->hydro_center_mass;
+    return o;
+}
+
+void fargo_oracle_destroy(fargo_oracle *o)
+{
+    if (!o)
+	return;
+    double **all[] = {&o->g_radii, &o->rinf, &o->rsup, &o->rmed, &o->surf, &o->invrmed, &o->invsurf, &o->invdiffrsup,
+		      &o->invdiffrsuprb, &o->twodiffrasq, &o->fourthirdinvrbinvdphisq, &o->invrinf, &o->invdiffrmed,
+		      &o->cosphi, &o->sinphi, &o->sigma, &o->vrad, &o->vazi, &o->energy, &o->sigma0, &o->vrad0,
+		      &o->vazi0, &o->energy0, &o->temperature, &o->pressure, &o->soundspeed, &o->scale_height,
+		      &o->viscosity, &o->potential, &o->qplus, &o->qminus, &o->divv, &o->trr, &o->tpp, &o->trp,
+		      &o->qr, &o->qphi, &o->nusig, &o->nusig_rp, &o->cf_r, &o->cf_phi, &o->tau_eff, &o->rmp, &o->rmm,
+		      &o->amp, &o->amm, &o->vres, &o->work, &o->qrstar, &o->densstar, &o->densint, &o->tempshift,
+		      &o->dq, &o->vmean};
+    for (size_t k = 0; k < sizeof(all) / sizeof(all[0]); ++k)
+	free(*all[k]);
+    free(o->nshift);
+    free(o);
+}
+
+int fargo_oracle_local_nrad(const fargo_oracle *o) { return o->nr; }
+int fargo_oracle_local_imin(const fargo_oracle *o) { return o->imin; }
+
+static double *field_ptr(fargo_oracle *o, int f, int *rings)
+{
+    *rings = o->nr;
+    switch (f) {
+    case FARGO_SIGMA: return o->sigma;
+    case FARGO_VRAD: *rings = o->nr + 1; return o->vrad;
+    case FARGO_VAZI: return o->vazi;
+    case FARGO_ENERGY: return o->energy;
+    case FARGO_SIGMA0: return o->sigma0;
+    case FARGO_VRAD0: *rings = o->nr + 1; return o->vrad0;
+    case FARGO_VAZI0: return o->vazi0;
+    case FARGO_ENERGY0: return o->energy0;
+    case FARGO_QPLUS: return o->qplus;
+    case FARGO_QMINUS: return o->qminus;
+    case FARGO_TEMPERATURE: return o->temperature;
+    case FARGO_PRESSURE: return o->pressure;
+    case FARGO_SOUNDSPEED: return o->soundspeed;
+    case FARGO_SCALE_HEIGHT: return o->scale_height;
+    case FARGO_VISCOSITY: return o->viscosity;
+    case FARGO_POTENTIAL: return o->potential;
+    }
+    return NULL;
+}
+
+/* read2D slab semantics, polargrid.cpp:343-349: local ring n <- global ring n+IMIN */
+int fargo_oracle_upload_field(fargo_oracle *o, int f, const double *host_global)
+{
+    int rings;
+    double *d = field_ptr(o, f, &rings);
+    if (!d)
+	return 1;
+    memcpy(d, host_global + (size_t)o->imin * o->ns, (size_t)rings * o->ns * sizeof(double));
+    return 0;
+}
+
+/* write2D slab semantics, polargrid.cpp:150-176 */
+int fargo_oracle_download_field(fargo_oracle *o, int f, double *host_global)
+{
+    int rings;
+    double *d = field_ptr(o, f, &rings);
+    if (!d)
+	return 1;
+    int first = o->zero_or_active, count = o->max_or_active - o->zero_or_active;
+    if (rings == o->nr + 1 && o->rank == o->nranks - 1)
+	count += 1;
+    memcpy(host_global + (size_t)(o->imin + first) * o->ns, d + (size_t)first * o->ns,
+	   (size_t)count * o->ns * sizeof(double));
+    return 0;
+}
+
+int fargo_oracle_download_slab(fargo_oracle *o, int f, double *host_slab)
+{
+    int rings;
+    double *d = field_ptr(o, f, &rings);
+    if (!d)
+	return 1;
+    memcpy(host_slab, d, (size_t)rings * o->ns * sizeof(double));
+    return 0;
+}
+
+/* raw slab overwrite (tests: halo exchange between oracle slabs) */
+int fargo_oracle_upload_slab(fargo_oracle *o, int f, const double *host_slab)
+{
+    int rings;
+    double *d = field_ptr(o, f, &rings);
+    if (!d)
+	return 1;
+    memcpy(d, host_slab, (size_t)rings * o->ns * sizeof(double));
+    return 0;
+}
+
+/* damping.cpp:287-296 */
+int fargo_oracle_copy_initial_values(fargo_oracle *o)
+{
+    const size_t ns = (size_t)o->nr * o->ns, nv = (size_t)(o->nr + 1) * o->ns;
+    memcpy(o->vrad0, o->vrad, nv * sizeof(double));
+    memcpy(o->vazi0, o->vazi, ns * sizeof(double));
+    memcpy(o->sigma0, o->sigma, ns * sizeof(double));
+    memcpy(o->energy0, o->energy, ns * sizeof(double));
+    return 0;
+}
+
+int fargo_oracle_set_bodies(fargo_oracle *o, const fargo_bodies *b)
+{
+    o->bodies = *b;
+    return 0;
+}
+int fargo_oracle_set_time(fargo_oracle *o, double t)
+{
+    o->time = t;
+    return 0;
+}
+
+/* Theo.cpp:246-249 */
+static double omega_kepler(const fargo_oracle *o, double r) { return sqrt(o->p.G * o->p.hydro_center_mass / (r * r * r)); }
+
+/* ------------------------------------------------------------------------------------------
+ * EOS-derived fields */
+
+/* compute_sound_speed_normal, SourceEuler.cpp:957-995 */
+static void compute_sound_speed(fargo_oracle *o)
+{
+    const int Nr = o->nr, Nphi = o->ns;
+#pragma omp parallel for
+    for (int nr = 0; nr < Nr; ++nr) {
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const size_t c = IDX(o, nr, naz);
+	    if (o->p.adiabatic) {
+		const double g = o->p.gamma;
+		o->soundspeed[c] = sqrt(g * (g - 1.0) * o->energy[c] / o->sigma[c]);
+	    } else {
+		const double vK = sqrt(o->p.G * o->p.hydro_center_mass / o->rmed[nr]);
+		const double h = o->p.aspectratio_ref * pow(o->rmed[nr], o->p.flaring_index);
+		o->soundspeed[c] = h * vK;
+	    }
+	}
+    }
+}
+
+/* compute_scale_height_old, SourceEuler.cpp:1121-1154 (ASPECTRATIO grid is output-only: skipped) */
+static void compute_scale_height(fargo_oracle *o)
+{
+    const int Nr = o->nr, Nphi = o->ns;
+#pragma omp parallel for
+    for (int nr = 0; nr < Nr; ++nr) {
+	const double inv_omega_kepler = 1.0 / omega_kepler(o, o->rmed[nr]);
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const size_t c = IDX(o, nr, naz);
+	    if (o->p.adiabatic)
+		o->scale_height[c] = o->soundspeed[c] / (sqrt(o->p.gamma)) * inv_omega_kepler;
+	    else
+		o->scale_height[c] = o->soundspeed[c] * inv_omega_kepler;
+	}
+    }
+}
+
+/* compute_pressure, SourceEuler.cpp:1345-1376 */
+static void compute_pressure(fargo_oracle *o)
+{
+    const size_t n = (size_t)o->nr * o->ns;
+#pragma omp parallel for
+    for (size_t c = 0; c < n; ++c) {
+	if (o->p.adiabatic)
+	    o->pressure[c] = (o->p.gamma - 1.0) * o->energy[c];
+	else
+	    o->pressure[c] = o->sigma[c] * (o->soundspeed[c] * o->soundspeed[c]);
+    }
+}
+
+/* compute_temperature, SourceEuler.cpp:1378-1408 */
+static void compute_temperature(fargo_oracle *o)
+{
+    const size_t n = (size_t)o->nr * o->ns;
+    const double Rgas = o->p.Rgas;
+#pragma omp parallel for
+    for (size_t c = 0; c < n; ++c) {
+	if (o->p.adiabatic) {
+	    const double c_v_inv = o->p.mu / Rgas * (o->p.gamma - 1.0);
+	    o->temperature[c] = c_v_inv * o->energy[c] / o->sigma[c];
+	} else {
+	    o->temperature[c] = o->p.mu / Rgas * o->pressure[c] / o->sigma[c];
+	}
+    }
+}
+
+/* viscosity::update_viscosity, viscosity.cpp:98-137 (AlphaMode CONST_ALPHA) */
+static void update_viscosity(fargo_oracle *o)
+{
+    const size_t n = (size_t)o->nr * o->ns;
+    if (o->p.viscous_alpha > 0) {
+#pragma omp parallel for
+	for (size_t c = 0; c < n; ++c)
+	    o->viscosity[c] = o->p.viscous_alpha * o->scale_height[c] * o->soundspeed[c];
+    } else {
+	if (!o->visc_calculated)
+	    for (size_t c = 0; c < n; ++c)
+		o->viscosity[c] = o->p.constant_viscosity;
+	o->visc_calculated = 1;
+    }
+}
+
+/* assure_temperature_range, SourceEuler.cpp:136-202 */
+static void assure_temperature_range(fargo_oracle *o)
+{
+    const size_t n = (size_t)o->nr * o->ns;
+    const double Tmin = o->p.minimum_temperature, Tmax = o->p.maximum_temperature;
+    const double mu = o->p.mu, g = o->p.gamma, R = o->p.Rgas;
+#pragma omp parallel for
+    for (size_t c = 0; c < n; ++c) {
+	const double minimum_energy = Tmin * o->sigma[c] / mu * R / (g - 1.0);
+	const double maximum_energy = Tmax * o->sigma[c] / mu * R / (g - 1.0);
+	if (!(o->energy[c] > minimum_energy))
+	    o->energy[c] = Tmin * o->sigma[c] / mu * R / (g - 1.0);
+	if (!(o->energy[c] < maximum_energy))
+	    o->energy[c] = Tmax * o->sigma[c] / mu * R / (g - 1.0);
+    }
+}
+
+/* recalculate_viscosity, SourceEuler.cpp:205-223 */
+static void recalculate_viscosity(fargo_oracle *o)
+{
+    if (o->p.adiabatic) {
+	compute_sound_speed(o);
+	compute_scale_height(o);
+    }
+    update_viscosity(o);
+}
+
+/* recalculate_derived_disk_quantities, SourceEuler.cpp:225-249 */
+int fargo_oracle_stage_derived(fargo_oracle *o)
+{
+    if (!o->p.adiabatic) {
+	compute_pressure(o);
+    } else {
+	compute_temperature(o);
+	compute_sound_speed(o);
+	compute_scale_height(o);
+	compute_pressure(o);
+    }
+    update_viscosity(o);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * CalculateNbodyPotential, Pframeforce.cpp:21-86; smoothing: Force.cpp:124-159 */
+int fargo_oracle_stage_potential(fargo_oracle *o)
+{
+    const int Nr = o->nr, Nphi = o->ns;
+    const fargo_bodies *b = &o->bodies;
+#pragma omp parallel for
+    for (int nr = 0; nr < Nr; ++nr) {
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const size_t c = IDX(o, nr, naz);
+	    const double x = o->rmed[nr] * o->cosphi[naz];
+	    const double y = o->rmed[nr] * o->sinphi[naz];
+	    double pot = 0.0;
+	    for (int k = 0; k < b->n; ++k) {
+		const double smooth = o->p.thickness_smoothing * o->scale_height[c];
+		const double dx = x - b->x[k];
+		const double dy = y - b->y[k];
+		const double dist_2 = dx * dx + dy * dy;
+		const double d_smoothed = sqrt(dist_2 + smooth * smooth);
+		double smooth_factor_klahr = 1.0;
+		if (b->cubic_smoothing_radius[k] > 0.0) {
+		    const double r_sm = b->cubic_smoothing_radius[k];
+		    if (d_smoothed < r_sm)
+			smooth_factor_klahr =
+			    (pow(d_smoothed / r_sm, 4.0) - 2.0 * pow(d_smoothed / r_sm, 3.0) + 2.0 * d_smoothed / r_sm);
+		}
+		pot += -o->p.G * b->mass[k] / d_smoothed * smooth_factor_klahr;
+	    }
+	    pot += -b->indirect_x * x - b->indirect_y * y;
+	    o->potential[c] = pot;
+	}
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * update_with_sourceterms, SourceEuler.cpp:325-493 */
+int fargo_oracle_stage_sources(fargo_oracle *o, double dt)
+{
+    const int Nphi = o->ns;
+    const double OmegaF = o->bodies.omega_frame;
+    /* momentum_update_radial :337-370 */
+#pragma omp parallel for
+    for (int nr = o->one_no_ghost_vr; nr < o->maxmo_no_ghost_vr; ++nr) {
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const size_t c = IDX(o, nr, naz), cm = IDX(o, nr - 1, naz);
+	    double gradp = 2.0 / (o->sigma[c] + o->sigma[cm]);
+	    gradp *= (o->pressure[c] - o->pressure[cm]);
+	    gradp *= o->invdiffrmed[nr];
+	    const double gradphi = (o->potential[c] - o->potential[cm]) * o->invdiffrmed[nr];
+	    const int naz_next = (naz == Nphi - 1 ? 0 : naz + 1);
+	    const double vsum = o->vazi[c] + o->vazi[IDX(o, nr, naz_next)] + o->vazi[cm] + o->vazi[IDX(o, nr - 1, naz_next)];
+	    const double vt = 0.25 * vsum + o->rinf[nr] * OmegaF;
+	    const double vt2 = vt * vt;
+	    const double centrifugal_accel = vt2 * o->invrinf[nr];
+	    o->vrad[c] += dt * (-gradp - gradphi + centrifugal_accel);
+	}
+    }
+    /* momentum_update_azimuthal :382-427 */
+#pragma omp parallel for
+    for (int nr = o->zero_no_ghost; nr < o->max_no_ghost; ++nr) {
+	double supp_torque = 0.0;
+	if (o->p.imposed_disk_drift != 0.0)
+	    supp_torque = o->p.imposed_disk_drift * 0.5 * pow(o->rmed[nr], -2.5 + o->p.sigma_slope);
+	const double invdxtheta = 2.0 / (o->dphi * (o->rsup[nr] + o->rinf[nr]));
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const int naz_prev = (naz == 0 ? Nphi - 1 : naz - 1);
+	    const size_t c = IDX(o, nr, naz), cp = IDX(o, nr, naz_prev);
+	    const double gradp = 2.0 / (o->sigma[c] + o->sigma[cp]) * (o->pressure[c] - o->pressure[cp]) * invdxtheta;
+	    const double gradphi = (o->potential[c] - o->potential[cp]) * invdxtheta;
+	    o->vazi[c] = o->vazi[c] + dt * (-gradp - gradphi);
+	    if (o->p.imposed_disk_drift != 0.0)
+		o->vazi[c] += dt * supp_torque;
+	}
+    }
+    /* compression_heating :459-493 */
+    if (o->p.adiabatic) {
+	const int Nr = o->nr - 1;
+#pragma omp parallel for
+	for (int nr = 0; nr < Nr; ++nr) {
+	    for (int naz = 0; naz < Nphi; ++naz) {
+		const int naz_next = (naz == Nphi - 1 ? 0 : naz + 1);
+		const size_t c = IDX(o, nr, naz);
+		const double DIV_V = (o->vrad[IDX(o, nr + 1, naz)] * o->rinf[nr + 1] - o->vrad[c] * o->rinf[nr]) * o->invdiffrsuprb[nr] +
+				     (o->vazi[IDX(o, nr, naz_next)] - o->vazi[c]) * o->invdphi * o->invrmed[nr];
+		const double energy_old = o->energy[c];
+		o->energy[c] = energy_old * exp(-(o->p.gamma - 1.0) * dt * DIV_V);
+	    }
+	}
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * art_visc::update_with_artificial_viscosity, artificial_viscosity.cpp:11-250 */
+static void artvisc_TW(fargo_oracle *o, double dt)
+{
+    const int Nr = o->nr, Nphi = o->ns;
+    const double C = o->p.artificial_viscosity_factor;
+#pragma omp parallel for
+    for (int nr = 0; nr < Nr; ++nr) { /* :49-88 */
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const int naz_next = (naz == Nphi - 1 ? 0 : naz + 1);
+	    const size_t c = IDX(o, nr, naz), cu = IDX(o, nr + 1, naz);
+	    const double eps_rr = (o->vrad[cu] - o->vrad[c]) * o->invdiffrsup[nr];
+	    const double eps_pp =
+		o->invrmed[nr] * ((o->vazi[IDX(o, nr, naz_next)] - o->vazi[c]) * o->invdphi + 0.5 * (o->vrad[cu] + o->vrad[c]));
+	    const double div_V = stdmin(eps_rr + eps_pp, 0.0);
+	    const double Dr = o->rinf[nr + 1] - o->rinf[nr];
+	    const double rDphi = o->rmed[nr] * o->dphi;
+	    double dx_sq;
+	    if (Nphi <= 16) {
+		const double m = stdmin(Dr, rDphi);
+		dx_sq = m * m;
+	    } else {
+		const double m = stdmax(Dr, rDphi);
+		dx_sq = m * m;
+	    }
+	    const double l_sq = (C * C) * dx_sq;
+	    const double q_rr = l_sq * o->sigma[c] * -div_V * (eps_rr - 1.0 / 3.0 * div_V);
+	    const double q_pp = l_sq * o->sigma[c] * -div_V * (eps_pp - 1.0 / 3.0 * div_V);
+	    o->qr[c] = q_rr;
+	    o->qphi[c] = q_pp;
+	    if (o->p.adiabatic && o->p.artificial_viscosity_dissipation) {
+		if (nr > o->zero_no_ghost && nr < o->max_no_ghost) {
+		    const double Qplus = -l_sq * div_V * o->sigma[c] * 1.0 / 3.0 *
+					 (eps_rr * eps_rr + eps_pp * eps_pp + (eps_rr - eps_pp) * (eps_rr - eps_pp));
+		    o->energy[c] += Qplus * dt;
+		}
+	    }
+	}
+    }
+#pragma omp parallel for
+    for (int nr = 1; nr < Nr - 1; ++nr) { /* :90-117 */
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const int naz_prev = (naz == 0 ? Nphi - 1 : naz - 1);
+	    const size_t c = IDX(o, nr, naz), cp = IDX(o, nr, naz_prev);
+	    const double sigma_phi_avg = 0.5 * (o->sigma[c] + o->sigma[cp]);
+	    const double dVp = 2.0 * dt / ((o->rsup[nr] + o->rinf[nr]) * sigma_phi_avg) * (o->qphi[c] - o->qphi[cp]) * o->invdphi;
+	    o->vazi[c] += dVp;
+	}
+    }
+#pragma omp parallel for
+    for (int nr = o->one_no_ghost_vr; nr < o->maxmo_no_ghost_vr; ++nr) { /* :119-139 */
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const size_t c = IDX(o, nr, naz), cm = IDX(o, nr - 1, naz);
+	    const double sigma_r_avg = 0.5 * (o->sigma[c] + o->sigma[cm]);
+	    const double rm = o->rmed[nr], rmm = o->rmed[nr - 1];
+	    const double dVr = o->p.radial_viscosity_factor * dt / sigma_r_avg * 2.0 / (rm * rm - rmm * rmm) *
+			       ((o->qr[c] * rm - o->qr[cm] * rmm) - 0.5 * (o->qphi[c] + o->qphi[cm]) * (rm - rmm));
+	    o->vrad[c] += dVr;
+	}
+    }
+}
+
+static void artvisc_SN(fargo_oracle *o, double dt)
+{
+    if (o->p.artificial_viscosity != FARGO_ARTVISC_SN)
+	return; /* :150-151 */
+    const int Nr = o->nr, Nphi = o->ns;
+    const double C = o->p.artificial_viscosity_factor;
+#pragma omp parallel for
+    for (int nr = 0; nr < Nr; ++nr) { /* :165-189 */
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const int naz_next = (naz == Nphi - 1 ? 0 : naz + 1);
+	    const size_t c = IDX(o, nr, naz);
+	    const double dv_r = o->vrad[IDX(o, nr + 1, naz)] - o->vrad[c];
+	    o->qr[c] = (dv_r < 0.0) ? (C * C) * o->sigma[c] * (dv_r * dv_r) : 0.0;
+	    const double dv_phi = o->vazi[IDX(o, nr, naz_next)] - o->vazi[c];
+	    o->qphi[c] = (dv_phi < 0.0) ? (C * C) * o->sigma[c] * (dv_phi * dv_phi) : 0.0;
+	}
+    }
+    if (o->p.adiabatic && o->p.artificial_viscosity_dissipation) { /* :194-218 */
+#pragma omp parallel for
+	for (int nr = o->zero_no_ghost; nr < o->max_no_ghost; ++nr) {
+	    const double dxtheta = o->dphi * o->rmed[nr];
+	    const double invdxtheta = 1.0 / dxtheta;
+	    for (int naz = 0; naz < Nphi; ++naz) {
+		const int naz_next = (naz == Nphi - 1 ? 0 : naz + 1);
+		const size_t c = IDX(o, nr, naz);
+		const double dv_r = o->vrad[IDX(o, nr + 1, naz)] - o->vrad[c];
+		const double dv_phi = o->vazi[IDX(o, nr, naz_next)] - o->vazi[c];
+		o->energy[c] = o->energy[c] - dt * o->qr[c] * dv_r * o->invdiffrsup[nr] - dt * o->qphi[c] * dv_phi * invdxtheta;
+	    }
+	}
+    }
+#pragma omp parallel for
+    for (int nr = o->one_no_ghost_vr; nr < o->maxmo_no_ghost_vr; ++nr) { /* :221-230 */
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const size_t c = IDX(o, nr, naz), cm = IDX(o, nr - 1, naz);
+	    o->vrad[c] = o->vrad[c] - dt * 2.0 / (o->sigma[c] + o->sigma[cm]) * (o->qr[c] - o->qr[cm]) * o->invdiffrmed[nr];
+	}
+    }
+#pragma omp parallel for
+    for (int nr = o->zero_no_ghost; nr < o->max_no_ghost; ++nr) { /* :233-248 */
+	const double dxtheta = o->dphi * o->rmed[nr];
+	const double invdxtheta = 1.0 / dxtheta;
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const int naz_prev = (naz == 0 ? Nphi - 1 : naz - 1);
+	    const size_t c = IDX(o, nr, naz), cp = IDX(o, nr, naz_prev);
+	    o->vazi[c] = o->vazi[c] - dt * 2.0 / (o->sigma[c] + o->sigma[cp]) * (o->qphi[c] - o->qphi[cp]) * invdxtheta;
+	}
+    }
+}
+
+int fargo_oracle_stage_artvisc(fargo_oracle *o, double dt)
+{
+    if (o->p.artificial_viscosity == FARGO_ARTVISC_TW)
+	artvisc_TW(o, dt);
+    else
+	artvisc_SN(o, dt);
+    if (o->p.adiabatic && o->p.artificial_viscosity_dissipation)
+	assure_temperature_range(o);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * viscosity::compute_viscous_stress_tensor, viscosity.cpp:139-350 */
+static void compute_viscous_stress_tensor(fargo_oracle *o)
+{
+    const int Nr = o->nr, Nphi = o->ns;
+#pragma omp parallel for
+    for (int nr = 0; nr < Nr; ++nr) {
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const int naz_next = (naz == Nphi - 1 ? 0 : naz + 1);
+	    const size_t c = IDX(o, nr, naz), cu = IDX(o, nr + 1, naz);
+	    o->divv[c] = (o->vrad[cu] * o->rinf[nr + 1] - o->vrad[c] * o->rinf[nr]) * o->invdiffrsuprb[nr] +
+			 (o->vazi[IDX(o, nr, naz_next)] - o->vazi[c]) * o->invdphi * o->invrmed[nr];
+	}
+    }
+#pragma omp parallel for
+    for (int nr = 0; nr < Nr; ++nr) {
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const int naz_next = (naz == Nphi - 1 ? 0 : naz + 1);
+	    const size_t c = IDX(o, nr, naz), cu = IDX(o, nr + 1, naz);
+	    const double drr = (o->vrad[cu] - o->vrad[c]) * o->invdiffrsup[nr];
+	    o->trr[c] = 2.0 * o->viscosity[c] * o->sigma[c] * (drr - 1.0 / 3.0 * o->divv[c]);
+	    const double dpp = (o->vazi[IDX(o, nr, naz_next)] - o->vazi[c]) * o->invdphi * o->invrmed[nr] +
+			       0.5 * (o->vrad[cu] + o->vrad[c]) * o->invrmed[nr];
+	    const double nu = o->viscosity[c], sigma = o->sigma[c];
+	    o->tpp[c] = 2.0 * nu * sigma * (dpp - 1.0 / 3.0 * o->divv[c]);
+	    o->nusig[c] = nu * sigma;
+	}
+    }
+#pragma omp parallel for
+    for (int nr = 1; nr < Nr; ++nr) {
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const int naz_prev = (naz == 0 ? Nphi - 1 : naz - 1);
+	    const size_t c = IDX(o, nr, naz), cm = IDX(o, nr - 1, naz), cp = IDX(o, nr, naz_prev), cmp = IDX(o, nr - 1, naz_prev);
+	    const double dvazirdr = (o->vazi[c] * o->invrmed[nr] - o->vazi[cm] * o->invrmed[nr - 1]) * o->invdiffrmed[nr];
+	    const double dvrdphi = (o->vrad[c] - o->vrad[cp]) * o->invdphi;
+	    const double drp = o->rinf[nr] * dvazirdr + dvrdphi * o->invrinf[nr];
+	    const double nu = 0.25 * (o->viscosity[c] + o->viscosity[cm] + o->viscosity[cp] + o->viscosity[cmp]);
+	    const double sigma = 0.25 * (o->sigma[c] + o->sigma[cm] + o->sigma[cp] + o->sigma[cmp]);
+	    o->trp[c] = nu * sigma * drp;
+	    o->nusig_rp[c] = nu * sigma;
+	}
+    }
+    if (o->p.stabilize_viscosity) { /* :256-348 */
+#pragma omp parallel for
+	for (int nr = 1; nr < Nr; ++nr) {
+	    for (int naz = 0; naz < Nphi; ++naz) {
+		const int naz_prev = (naz == 0 ? Nphi - 1 : naz - 1);
+		const int naz_next = (naz == Nphi - 1 ? 0 : naz + 1);
+		const size_t c = IDX(o, nr, naz);
+		const double NuSig_rp = o->nusig_rp[c];
+		const double NuSig_rp_ip = o->nusig_rp[IDX(o, nr + 1, naz)];
+		const double NuSig_rp_jp = o->nusig_rp[IDX(o, nr, naz_next)];
+		const double NuSigma = o->nusig[c];
+		const double NuSigma_jm = o->nusig[IDX(o, nr, naz_prev)];
+		const double NuSigma_im = o->nusig[IDX(o, nr - 1, naz)];
+		const double Ra3a = NuSig_rp * pow(o->rinf[nr], 3) * o->invdiffrmed[nr];
+		const double Ra3b = NuSig_rp_ip * pow(o->rinf[nr + 1], 3) * o->invdiffrmed[nr + 1];
+		const double cphi_rp = -o->invrmed[nr] * o->twodiffrasq[nr] * (Ra3b + Ra3a);
+		const double cphi_pp = -o->fourthirdinvrbinvdphisq[nr] * (NuSigma + NuSigma_jm);
+		const double sigma_avg_phi = 0.5 * (o->sigma[c] + o->sigma[IDX(o, nr, naz_prev)]);
+		o->cf_phi[c] = (cphi_rp + cphi_pp) / (sigma_avg_phi * o->rmed[nr]);
+		const double sigma_avg_r = 0.5 * (o->sigma[c] + o->sigma[IDX(o, nr - 1, naz)]);
+		const double cr_rp = -(NuSig_rp_jp + NuSig_rp) / (o->dphi * o->dphi * o->rinf[nr]);
+		const double cr_pp_1 = 2.0 * NuSigma * (0.5 * o->invrmed[nr] + 1.0 / 3.0 * o->rinf[nr] * o->invdiffrsuprb[nr]);
+		const double cr_pp_2 = 2.0 * NuSigma_im * (0.5 * o->invrmed[nr - 1] - 1.0 / 3.0 * o->rinf[nr] * o->invdiffrsuprb[nr - 1]);
+		const double cr_rr_1 = o->rmed[nr] * 2.0 * NuSigma * (-o->invdiffrsup[nr] + 1.0 / 3.0 * o->rinf[nr] * o->invdiffrsuprb[nr]);
+		const double cr_rr_2 =
+		    -1.0 * o->rmed[nr - 1] * 2.0 * NuSigma_im * (o->invdiffrsup[nr - 1] - 1.0 / 3.0 * o->rinf[nr] * o->invdiffrsuprb[nr - 1]);
+		const double cr_pp = -0.5 * (cr_pp_1 + cr_pp_2);
+		const double cr_rr = o->invdiffrmed[nr] * (cr_rr_1 + cr_rr_2);
+		const double Rmed_mid = 0.5 * (o->rmed[nr] + o->rmed[nr - 1]);
+		o->cf_r[c] = o->p.radial_viscosity_factor * (cr_rr + cr_rp + cr_pp) / (sigma_avg_r * Rmed_mid);
+	    }
+	}
+    }
+}
+
+/* viscosity::update_velocities_with_viscosity, viscosity.cpp:355-426 */
+static void update_velocities_with_viscosity(fargo_oracle *o, double dt)
+{
+    const int Nr = o->nr, Nphi = o->ns;
+#pragma omp parallel for
+    for (int nr = 1; nr < Nr - 1; ++nr) {
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const int naz_prev = (naz == 0 ? Nphi - 1 : naz - 1);
+	    const size_t c = IDX(o, nr, naz), cp = IDX(o, nr, naz_prev);
+	    const double sigma_avg = 0.5 * (o->sigma[c] + o->sigma[cp]);
+	    const double ra2 = o->rinf[nr] * o->rinf[nr], rap2 = o->rinf[nr + 1] * o->rinf[nr + 1];
+	    double dVp = dt * o->invrmed[nr] / (sigma_avg) *
+			 ((2.0 / (rap2 - ra2)) * (rap2 * o->trp[IDX(o, nr + 1, naz)] - ra2 * o->trp[c]) + (o->tpp[c] - o->tpp[cp]) * o->invdphi);
+	    if (o->p.stabilize_viscosity == 1) {
+		const double cphi = o->cf_phi[c];
+		const double corr = 1.0 / (stdmax(1.0 + dt * cphi, 0.0) - dt * cphi);
+		dVp *= corr;
+	    }
+	    o->vazi[c] += dVp;
+	}
+    }
+#pragma omp parallel for
+    for (int nr = o->one_no_ghost_vr; nr < o->maxmo_no_ghost_vr; ++nr) {
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const int naz_next = (naz == Nphi - 1 ? 0 : naz + 1);
+	    const size_t c = IDX(o, nr, naz), cm = IDX(o, nr - 1, naz);
+	    const double sigma_avg = 0.5 * (o->sigma[c] + o->sigma[cm]);
+	    double dVr = dt / (sigma_avg)*o->p.radial_viscosity_factor * 2.0 / (o->rmed[nr] + o->rmed[nr - 1]) *
+			 ((o->rmed[nr] * o->trr[c] - o->rmed[nr - 1] * o->trr[cm]) * o->invdiffrmed[nr] +
+			  (o->trp[IDX(o, nr, naz_next)] - o->trp[c]) * o->invdphi - 0.5 * (o->tpp[c] + o->tpp[cm]));
+	    if (o->p.stabilize_viscosity == 1) {
+		const double cr = o->cf_r[c];
+		const double corr = 1.0 / (stdmax(1.0 + dt * cr, 0.0) - dt * cr);
+		dVr *= corr;
+	    }
+	    o->vrad[c] += dVr;
+	}
+    }
+}
+
+int fargo_oracle_stage_viscosity(fargo_oracle *o, double dt)
+{
+    recalculate_viscosity(o);
+    compute_viscous_stress_tensor(o);
+    update_velocities_with_viscosity(o, dt);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * energy sources: calculate_qminus :834, calculate_qplus :614, SubStep3 :859 (SourceEuler.cpp) */
+static void calculate_qminus(fargo_oracle *o)
+{
+    const int Nr = o->nr - 1, Nphi = o->ns;
+    memset(o->qminus, 0, (size_t)o->nr * o->ns * sizeof(double));
+    if (!o->p.cooling_beta)
+	return;
+    /* thermal_relaxation :632-690 */
+#pragma omp parallel for
+    for (int nr = 1; nr < Nr; ++nr) {
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const size_t c = IDX(o, nr, naz);
+	    const double omega_k = omega_kepler(o, o->rmed[nr]);
+	    const double E = o->energy[c];
+	    const double t_ramp_up = o->p.cooling_beta_ramp_up;
+	    double beta_inv = 1 / o->p.cooling_beta_value;
+	    if (t_ramp_up > 0.0) {
+		const double a = 2 * o->time / t_ramp_up;
+		const double ramp_factor = 1 - exp(-(a * a));
+		beta_inv = beta_inv * ramp_factor;
+	    }
+	    double delta_E = E;
+	    if (o->p.cooling_beta_reference & FARGO_BETA_REF_REFERENCE)
+		delta_E -= o->energy0[c] / o->sigma0[c] * o->sigma[c];
+	    if (o->p.cooling_beta_reference & FARGO_BETA_REF_MODEL) {
+		const double h = o->p.aspectratio_ref;
+		const double E0 = 1.0 / (o->p.gamma - 1.0) * (h * h) * pow(o->rmed[nr], 2.0 * o->p.flaring_index - 1.0) * o->p.G *
+				  o->p.hydro_center_mass * o->sigma[c];
+		delta_E -= E0;
+	    }
+	    if (o->p.cooling_beta_reference & FARGO_BETA_REF_FLOOR) {
+		const double minimum_energy = o->p.minimum_temperature * o->sigma[c] / o->p.mu * o->p.Rgas / (o->p.gamma - 1.0);
+		delta_E -= minimum_energy;
+	    }
+	    o->qminus[c] += delta_E * omega_k * beta_inv;
+	}
+    }
+}
+
+static void calculate_qplus(fargo_oracle *o)
+{
+    const int Nr_m1 = o->nr - 1, Nphi = o->ns;
+    memset(o->qplus, 0, (size_t)o->nr * o->ns * sizeof(double));
+    if (!o->p.heating_viscous)
+	return;
+    /* viscous_heating :496-536 */
+#pragma omp parallel for
+    for (int nr = 1; nr < Nr_m1; ++nr) {
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const size_t c = IDX(o, nr, naz);
+	    if (o->viscosity[c] != 0.0) {
+		const int naz_next = (naz == Nphi - 1 ? 0 : naz + 1);
+		const double tau_r_phi = 0.25 * (o->trp[c] + o->trp[IDX(o, nr + 1, naz)] + o->trp[IDX(o, nr, naz_next)] + o->trp[IDX(o, nr + 1, naz_next)]);
+		double qplus = 1.0 / (2.0 * o->viscosity[c] * o->sigma[c]) * (o->trr[c] * o->trr[c] + 2 * (tau_r_phi * tau_r_phi) + o->tpp[c] * o->tpp[c]);
+		qplus += (2.0 / 9.0) * o->viscosity[c] * o->sigma[c] * (o->divv[c] * o->divv[c]);
+		qplus *= o->p.heating_viscous_factor;
+		o->qplus[c] += qplus;
+	    }
+	}
+    }
+}
+
+/* the alpha_r division shared by SubStep3 :921-927 and compute_heating_cooling_for_CFL :1440-1446 */
+static inline double radiative_alpha(const fargo_oracle *o, double H, double sigma, double energy)
+{
+    const double inv_pow4 = pow(o->p.mu * (o->p.gamma - 1.0) / (o->p.Rgas * sigma), 4);
+    return 1.0 + 2.0 * H * 4.0 * o->p.sigma_sb / o->p.c_light * inv_pow4 * pow(energy, 3);
+}
+
+int fargo_oracle_stage_substep3(fargo_oracle *o, double dt)
+{
+    if (!o->p.adiabatic)
+	return 0;
+    const int Nr = o->nr, Nphi = o->ns;
+    compute_temperature(o);
+    calculate_qminus(o);
+    calculate_qplus(o);
+#pragma omp parallel for
+    for (int nr = 1; nr < Nr - 1; ++nr) {
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const size_t c = IDX(o, nr, naz);
+	    const double sigma = o->sigma[c], energy = o->energy[c];
+	    const double alpha = radiative_alpha(o, o->scale_height[c], sigma, energy);
+	    o->qplus[c] /= alpha;
+	    o->qminus[c] /= alpha;
+	    const double Qplus = o->qplus[c], Qminus = o->qminus[c];
+	    double energy_new = energy + dt * (Qplus - Qminus);
+	    const double SigmaFloor = 10.0 * o->p.sigma0 * o->p.sigma_floor;
+	    if (sigma < SigmaFloor) {
+		const double e4 = Qplus * o->tau_eff[c] / (2.0 * o->p.sigma_sb);
+		const double constant = (o->p.Rgas / o->p.mu * sigma / (o->p.gamma - 1.0));
+		const double eq_energy = pow(e4, 1.0 / 4.0) * constant;
+		o->qminus[c] = Qplus;
+		energy_new = eq_energy;
+	    }
+	    o->energy[c] = energy_new;
+	}
+    }
+    assure_temperature_range(o);
+    return 0;
+}
+
+/* compute_heating_cooling_for_CFL, SourceEuler.cpp:1410-1450 */
+static void compute_heating_cooling_for_CFL(fargo_oracle *o)
+{
+    if (!o->p.adiabatic)
+	return;
+    update_viscosity(o);
+    compute_viscous_stress_tensor(o);
+    calculate_qminus(o);
+    calculate_qplus(o);
+    const int Nr = o->nr - 1, Nphi = o->ns;
+#pragma omp parallel for
+    for (int nr = 1; nr < Nr; ++nr) {
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const size_t c = IDX(o, nr, naz);
+	    const double alpha = radiative_alpha(o, o->scale_height[c], o->sigma[c], o->energy[c]);
+	    o->qplus[c] /= alpha;
+	    o->qminus[c] /= alpha;
+	}
+    }
+}
+
+/* init_euler's derived fields, SourceEuler.cpp:264-284 */
+int fargo_oracle_init_derived(fargo_oracle *o)
+{
+    if (!o->p.adiabatic) {
+	compute_sound_speed(o);
+	compute_pressure(o);
+	compute_temperature(o);
+	compute_scale_height(o);
+    } else {
+	compute_temperature(o);
+	compute_sound_speed(o);
+	compute_scale_height(o);
+	compute_pressure(o);
+    }
+    update_viscosity(o);
+    compute_heating_cooling_for_CFL(o);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * boundary conditions, boundary_conditions.cpp:65-114 and the per-variable functions */
+static int rmed_id(const fargo_oracle *o, double r)
+{ /* find_cell_id.cpp:218-257, 382-412: largest local id with Rmed[id] <= r */
+    if (o->p.radial_spacing == FARGO_SPACING_LOG) {
+	const double gf = pow(o->p.rmax / o->p.rmin, 1.0 / ((double)o->p.nrad - 2.0)); /* init.cpp:94 */
+	const double optimization_const = 3.0 / 2.0 / o->p.rmin * (1 - pow(gf, 2.0)) / (1 - pow(gf, 3.0));
+	const double inv_log_gf = 1.0 / log(gf);
+	const double did = log(r * optimization_const) * inv_log_gf;
+	return (int)floor(did) - o->imin + 1;
+    }
+    int id = 0;
+    while (id < o->nr + 1 && o->rmed[id] < r)
+	id++;
+    return id - 1;
+}
+static int rinf_id(const fargo_oracle *o, double r)
+{ /* find_cell_id.cpp:259-291 */
+    if (o->p.radial_spacing == FARGO_SPACING_LOG) {
+	const double gf = pow(o->p.rmax / o->p.rmin, 1.0 / ((double)o->p.nrad - 2.0));
+	const double inv_log_gf = 1.0 / log(gf);
+	const double did = log(r / o->p.rmin) * inv_log_gf;
+	return (int)floor(did) - o->imin + 1;
+    }
+    int id = 0;
+    while (id < o->nr + 1 && o->rinf[id] < r)
+	id++;
+    return id - 1;
+}
+static int clamp_id(const fargo_oracle *o, int id, int is_vector)
+{ /* find_cell_id.cpp:14-38 */
+    const int mx = o->nr - (is_vector ? 0 : 1);
+    return id < 0 ? 0 : (id > mx ? mx : id);
+}
+
+/* damping_single_{inner,outer}{,_zero,_mean}, damping.cpp:311-752 */
+static void damp_field(fargo_oracle *o, double *x, const double *x0, int is_vector, int is_density, const int type[2], double dt)
+{
+    const int rings = o->nr + (is_vector ? 1 : 0), Nphi = o->ns;
+    const double *radius = is_vector ? o->rinf : o->rmed;
+    const double RMIN = o->p.rmin, RMAX = o->p.rmax;
+    if (type[0] != FARGO_DAMP_NONE && (o->p.damping_inner_limit > 1.0) && (radius[0] < RMIN * o->p.damping_inner_limit)) {
+	const int limit = is_vector ? clamp_id(o, rinf_id(o, RMIN * o->p.damping_inner_limit), 1)
+				    : clamp_id(o, rmed_id(o, RMIN * o->p.damping_inner_limit), 0);
+	const double tau = o->p.damping_time_factor * 2.0 * M_PI / omega_kepler(o, RMIN);
+	for (int nr = 0; nr <= limit; ++nr) {
+	    const double q = (radius[nr] - RMIN * o->p.damping_inner_limit) / (RMIN - RMIN * o->p.damping_inner_limit);
+	    const double factor = q * q;
+	    const double exp_factor = exp(-dt * factor / tau);
+	    double mean = 0.0;
+	    if (type[0] == FARGO_DAMP_MEAN) {
+		for (int j = 0; j < Nphi; ++j)
+		    mean += x[IDX(o, nr, j)];
+		mean /= Nphi;
+	    }
+	    for (int j = 0; j < Nphi; ++j) {
+		const size_t c = IDX(o, nr, j);
+		const double X = x[c];
+		double X0;
+		if (type[0] == FARGO_DAMP_INITIAL)
+		    X0 = x0[c];
+		else if (type[0] == FARGO_DAMP_MEAN)
+		    X0 = mean;
+		else
+		    X0 = is_density ? o->p.sigma_floor * o->p.sigma0 : 0.0;
+		x[c] = (X - X0) * exp_factor + X0;
+	    }
+	}
+    }
+    if (type[1] != FARGO_DAMP_NONE && (o->p.damping_outer_limit < 1.0) && (radius[rings - 1] > RMAX * o->p.damping_outer_limit)) {
+	const int limit = is_vector ? clamp_id(o, rinf_id(o, RMAX * o->p.damping_outer_limit) + 1, 1)
+				    : clamp_id(o, rmed_id(o, RMAX * o->p.damping_outer_limit) + 1, 0);
+	const double tau = o->p.damping_time_factor * 2.0 * M_PI / omega_kepler(o, o->p.damping_time_radius_outer);
+	for (int nr = limit; nr < rings; ++nr) {
+	    const double q = (radius[nr] - RMAX * o->p.damping_outer_limit) / (RMAX - RMAX * o->p.damping_outer_limit);
+	    const double factor = q * q;
+	    const double exp_factor = exp(-dt * factor / tau);
+	    double mean = 0.0;
+	    if (type[1] == FARGO_DAMP_MEAN) {
+		for (int j = 0; j < Nphi; ++j)
+		    mean += x[IDX(o, nr, j)];
+		mean /= Nphi;
+	    }
+	    for (int j = 0; j < Nphi; ++j) {
+		const size_t c = IDX(o, nr, j);
+		const double X = x[c];
+		double X0;
+		if (type[1] == FARGO_DAMP_INITIAL)
+		    X0 = x0[c];
+		else if (type[1] == FARGO_DAMP_MEAN)
+		    X0 = mean;
+		else
+		    X0 = is_density ? o->p.sigma_floor * o->p.sigma0 : 0.0;
+		x[c] = (X - X0) * exp_factor + X0;
+	    }
+	}
+    }
+}
+
+static void bc_scalar(fargo_oracle *o, double *x, const double *x0, const int bc[2])
+{
+    const int Nphi = o->ns, Irad = o->nr - 1;
+    if (o->rank == 0) {
+	if (bc[0] == FARGO_BC_ZEROGRADIENT) /* zero_gradient.cpp:17-27 */
+	    for (int j = 0; j < Nphi; ++j)
+		x[IDX(o, 0, j)] = x[IDX(o, 1, j)];
+	else if (bc[0] == FARGO_BC_REFERENCE) /* reference.cpp:16-25 */
+	    for (int j = 0; j < Nphi; ++j)
+		x[IDX(o, 0, j)] = x0[IDX(o, 0, j)];
+    }
+    if (o->rank == o->nranks - 1) {
+	if (bc[1] == FARGO_BC_ZEROGRADIENT) /* zero_gradient.cpp:56-67 */
+	    for (int j = 0; j < Nphi; ++j)
+		x[IDX(o, Irad, j)] = x[IDX(o, Irad - 1, j)];
+	else if (bc[1] == FARGO_BC_REFERENCE)
+	    for (int j = 0; j < Nphi; ++j)
+		x[IDX(o, Irad, j)] = x0[IDX(o, Irad, j)];
+    }
+}
+
+static void bc_vrad(fargo_oracle *o)
+{
+    const int Nphi = o->ns, Irad = o->nr; /* vector grid: max_radial = Nrad */
+    double *v = o->vrad;
+    const int first = (o->rank == 0), last = (o->rank == o->nranks - 1);
+    switch (o->p.bc_vrad[0]) {
+    case FARGO_BC_ZEROGRADIENT: /* zero_gradient.cpp:29-40 */
+	if (first)
+	    for (int j = 0; j < Nphi; ++j) {
+		v[IDX(o, 0, j)] = v[IDX(o, 2, j)];
+		v[IDX(o, 1, j)] = v[IDX(o, 2, j)];
+	    }
+	break;
+    case FARGO_BC_OUTFLOW: /* outflow.cpp:16-35 */
+	if (first)
+	    for (int j = 0; j < Nphi; ++j) {
+		if (v[IDX(o, 2, j)] > 0.0) {
+		    v[IDX(o, 1, j)] = 0.0;
+		    v[IDX(o, 0, j)] = 0.0;
+		} else {
+		    v[IDX(o, 1, j)] = v[IDX(o, 2, j)];
+		    v[IDX(o, 0, j)] = v[IDX(o, 2, j)];
+		}
+	    }
+	break;
+    case FARGO_BC_REFLECTING: /* reflecting.cpp:15-26 — NO rank guard in the reference */
+	for (int j = 0; j < Nphi; ++j) {
+	    v[IDX(o, 0, j)] = -v[IDX(o, 2, j)];
+	    v[IDX(o, 1, j)] = 0;
+	}
+	break;
+    case FARGO_BC_REFERENCE: /* reference.cpp:27-38 */
+	if (first)
+	    for (int j = 0; j < Nphi; ++j) {
+		v[IDX(o, 0, j)] = o->vrad0[IDX(o, 0, j)];
+		v[IDX(o, 1, j)] = o->vrad0[IDX(o, 1, j)];
+	    }
+	break;
+    default:
+	break;
+    }
+    switch (o->p.bc_vrad[1]) {
+    case FARGO_BC_ZEROGRADIENT: /* zero_gradient.cpp:69-81 */
+	if (last)
+	    for (int j = 0; j < Nphi; ++j) {
+		v[IDX(o, Irad, j)] = v[IDX(o, Irad - 2, j)];
+		v[IDX(o, Irad - 1, j)] = v[IDX(o, Irad - 2, j)];
+	    }
+	break;
+    case FARGO_BC_OUTFLOW: /* outflow.cpp:37-57 */
+	if (last)
+	    for (int j = 0; j < Nphi; ++j) {
+		if (v[IDX(o, Irad - 2, j)] < 0.0) {
+		    v[IDX(o, Irad - 1, j)] = 0.0;
+		    v[IDX(o, Irad, j)] = 0.0;
+		} else {
+		    v[IDX(o, Irad - 1, j)] = v[IDX(o, Irad - 2, j)];
+		    v[IDX(o, Irad, j)] = v[IDX(o, Irad - 2, j)];
+		}
+	    }
+	break;
+    case FARGO_BC_REFLECTING: /* reflecting.cpp:28-40 — NO rank guard */
+	for (int j = 0; j < Nphi; ++j) {
+	    v[IDX(o, Irad, j)] = -v[IDX(o, Irad - 2, j)];
+	    v[IDX(o, Irad - 1, j)] = 0;
+	}
+	break;
+    case FARGO_BC_REFERENCE:
+	if (last)
+	    for (int j = 0; j < Nphi; ++j) {
+		v[IDX(o, Irad, j)] = o->vrad0[IDX(o, Irad, j)];
+		v[IDX(o, Irad - 1, j)] = o->vrad0[IDX(o, Irad - 1, j)];
+	    }
+	break;
+    default:
+	break;
+    }
+}
+
+static void bc_vazi(fargo_oracle *o)
+{
+    const int Nphi = o->ns, Irad = o->nr - 1;
+    const double OmegaF = o->bodies.omega_frame;
+    if (o->rank == 0) {
+	if (o->p.bc_vazi[0] == FARGO_BC_KEPLERIAN) { /* keplerian_azimuthal.cpp:19-39 */
+	    const double vKep = sqrt(o->p.G * o->p.hydro_center_mass / o->rmed[0]);
+	    const double val = o->p.keplerian_azimuthal_factor[0] * vKep - o->rmed[0] * OmegaF;
+	    for (int j = 0; j < Nphi; ++j)
+		o->vazi[IDX(o, 0, j)] = val;
+	} else if (o->p.bc_vazi[0] == FARGO_BC_ZEROGRADIENT) {
+	    for (int j = 0; j < Nphi; ++j)
+		o->vazi[IDX(o, 0, j)] = o->vazi[IDX(o, 1, j)];
+	} else if (o->p.bc_vazi[0] == FARGO_BC_REFERENCE) {
+	    for (int j = 0; j < Nphi; ++j)
+		o->vazi[IDX(o, 0, j)] = o->vazi0[IDX(o, 0, j)];
+	}
+    }
+    if (o->rank == o->nranks - 1) {
+	if (o->p.bc_vazi[1] == FARGO_BC_KEPLERIAN) { /* keplerian_azimuthal.cpp:41-60 */
+	    const double vKep = sqrt(o->p.G * o->p.hydro_center_mass / o->rmed[Irad]);
+	    const double val = o->p.keplerian_azimuthal_factor[1] * vKep - o->rmed[Irad] * OmegaF;
+	    for (int j = 0; j < Nphi; ++j)
+		o->vazi[IDX(o, Irad, j)] = val;
+	} else if (o->p.bc_vazi[1] == FARGO_BC_ZEROGRADIENT) {
+	    for (int j = 0; j < Nphi; ++j)
+		o->vazi[IDX(o, Irad, j)] = o->vazi[IDX(o, Irad - 1, j)];
+	} else if (o->p.bc_vazi[1] == FARGO_BC_REFERENCE) {
+	    for (int j = 0; j < Nphi; ++j)
+		o->vazi[IDX(o, Irad, j)] = o->vazi0[IDX(o, Irad, j)];
+	}
+    }
+}
+
+int fargo_oracle_stage_boundary(fargo_oracle *o, double dt, int final_call)
+{
+    if (final_call && o->p.damping) { /* handle_damping + damping(), order vrad, vazi, sigma, energy (damping.cpp:204-270) */
+	damp_field(o, o->vrad, o->vrad0, 1, 0, o->p.damp_vrad, dt);
+	damp_field(o, o->vazi, o->vazi0, 0, 0, o->p.damp_vazi, dt);
+	damp_field(o, o->sigma, o->sigma0, 0, 1, o->p.damp_sigma, dt);
+	if (o->p.adiabatic) /* Interpret.cpp:559-565 */
+	    damp_field(o, o->energy, o->energy0, 0, 0, o->p.damp_energy, dt);
+    }
+    bc_scalar(o, o->sigma, o->sigma0, o->p.bc_sigma);
+    bc_scalar(o, o->energy, o->energy0, o->p.bc_energy);
+    bc_vrad(o);
+    bc_vazi(o);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Transport, TransportEuler.cpp:112-664 */
+static inline double flux_limiter(const fargo_oracle *o, double a, double b)
+{
+    if (o->p.flux_limiter == FARGO_LIMITER_MC) { /* :314-323 */
+	const double s = 0.5 * (a + b);
+	double mm;
+	if (a * b > 0.0)
+	    mm = fabs(a) < fabs(b) ? a : b;
+	else
+	    mm = 0.0;
+	const double t = 2.0 * mm;
+	if (s * t > 0.0)
+	    return fabs(s) < fabs(t) ? s : t;
+	return 0.0;
+    }
+    if (a * b > 0.0) /* :306-312 */
+	return 2.0 * a * b / (a + b);
+    return 0;
+}
+
+/* compute_momenta_from_velocities :471-493 */
+static void compute_momenta(fargo_oracle *o)
+{
+    const int Nr = o->nr, Nphi = o->ns;
+    const double OmegaF = o->bodies.omega_frame;
+#pragma omp parallel for
+    for (int nr = 0; nr < Nr; ++nr) {
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const size_t c = IDX(o, nr, naz);
+	    o->rmp[c] = o->sigma[c] * o->vrad[IDX(o, nr + 1, naz)];
+	    o->rmm[c] = o->sigma[c] * o->vrad[c];
+	    const int naz_ind = naz == (Nphi - 1) ? 0 : naz + 1;
+	    const double vnext = o->vazi[IDX(o, nr, naz_ind)];
+	    const double r = o->rmed[nr];
+	    o->amp[c] = o->sigma[c] * (vnext + r * OmegaF) * r;
+	    o->amm[c] = o->sigma[c] * (o->vazi[c] + r * OmegaF) * r;
+	}
+    }
+}
+
+/* compute_star_radial :349-406 */
+static void compute_star_radial(fargo_oracle *o, const double *qbase, const double *vr, double *qstar, double dt)
+{
+    const int Nr = o->nr, Nphi = o->ns;
+#pragma omp parallel for
+    for (int nr = 0; nr < Nr; ++nr) {
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const size_t c = IDX(o, nr, naz);
+	    if (nr == 0 || nr == Nr - 1) {
+		o->dq[c] = 0.0;
+	    } else {
+		const double dqm = (qbase[c] - qbase[c - Nphi]) * o->invdiffrmed[nr];
+		const double dqp = (qbase[c + Nphi] - qbase[c]) * o->invdiffrmed[nr + 1];
+		o->dq[c] = flux_limiter(o, dqp, dqm);
+	    }
+	}
+    }
+#pragma omp parallel for
+    for (int nr = 1; nr < Nr; ++nr) {
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const size_t c = IDX(o, nr, naz), cm = c - Nphi;
+	    if (vr[c] > 0.0)
+		qstar[c] = qbase[cm] + (o->rmed[nr] - o->rmed[nr - 1] - vr[c] * dt) * 0.5 * o->dq[cm];
+	    else
+		qstar[c] = qbase[c] - (o->rmed[nr + 1] - o->rmed[nr] + vr[c] * dt) * 0.5 * o->dq[c];
+	}
+    }
+    for (int naz = 0; naz < Nphi; ++naz)
+	qstar[naz] = 0.0;
+}
+
+/* VanLeerRadial :545-620 */
+static void vanleer_radial(fargo_oracle *o, const double *vr, double *qbase, double dt)
+{
+    const int Nr = o->nr, Nphi = o->ns;
+    const size_t n = (size_t)Nr * Nphi;
+#pragma omp parallel for
+    for (size_t c = 0; c < n; ++c) /* divise_polargrid, SideEuler.cpp:27-43 */
+	o->work[c] = qbase[c] / o->densint[c];
+    compute_star_radial(o, o->work, vr, o->qrstar, dt);
+#pragma omp parallel for
+    for (int nr = 0; nr < Nr; ++nr) {
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const size_t c = IDX(o, nr, naz), lip = c + Nphi;
+	    const double varq_inf = dt * o->dphi * o->rinf[nr] * o->qrstar[c] * o->densstar[c] * vr[c];
+	    const double varq_sup = dt * o->dphi * o->rsup[nr] * o->qrstar[lip] * o->densstar[lip] * vr[lip];
+	    qbase[c] += (varq_inf - varq_sup) * o->invsurf[nr];
+	}
+    }
+}
+
+/* ComputeStarTheta :416-466 */
+static void compute_star_theta(fargo_oracle *o, const double *qbase, const double *vazi, double *qstar, double dt)
+{
+    const int Nr = o->nr, Nphi = o->ns;
+#pragma omp parallel for
+    for (int nr = 0; nr < Nr; ++nr) {
+	const double dxtheta = o->dphi * o->rmed[nr];
+	const double invdxtheta = 1.0 / dxtheta;
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const size_t c = IDX(o, nr, naz);
+	    const size_t ljp = (naz == Nphi - 1) ? IDX(o, nr, 0) : c + 1;
+	    const size_t ljm = (naz == 0) ? IDX(o, nr, Nphi - 1) : c - 1;
+	    const double dqm = (qbase[c] - qbase[ljm]);
+	    const double dqp = (qbase[ljp] - qbase[c]);
+	    o->dq[c] = 0.5 * flux_limiter(o, dqp, dqm) * invdxtheta;
+	}
+    }
+#pragma omp parallel for
+    for (int nr = 0; nr < Nr; ++nr) {
+	const double dxtheta = o->dphi * o->rmed[nr];
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const size_t c = IDX(o, nr, naz);
+	    const size_t ljm = (naz == 0) ? IDX(o, nr, Nphi - 1) : c - 1;
+	    const double ksi = vazi[c] * dt;
+	    if (ksi > 0.0)
+		qstar[c] = qbase[ljm] + (dxtheta - ksi) * o->dq[ljm];
+	    else
+		qstar[c] = qbase[c] - (dxtheta + ksi) * o->dq[c];
+	}
+    }
+}
+
+/* VanLeerTheta :630-664 */
+static void vanleer_theta(fargo_oracle *o, const double *vazi, double *qbase, double dt, int uniform)
+{
+    const int Nr = o->nr, Nphi = o->ns;
+    const size_t n = (size_t)Nr * Nphi;
+#pragma omp parallel for
+    for (size_t c = 0; c < n; ++c)
+	o->work[c] = qbase[c] / o->densint[c];
+    compute_star_theta(o, o->work, vazi, o->qrstar, dt);
+    const int nosplit = !o->p.fast_transport; /* NoSplitAdvection[i], :225-234 */
+#pragma omp parallel for
+    for (int nr = 0; nr < Nr; ++nr) {
+	const double dxrad = (o->rsup[nr] - o->rinf[nr]) * dt;
+	const double invsurf = o->invsurf[nr];
+	if (!uniform || !nosplit) {
+	    for (int naz = 0; naz < Nphi; ++naz) {
+		const size_t c = IDX(o, nr, naz);
+		const size_t ljp = (naz == Nphi - 1) ? IDX(o, nr, 0) : c + 1;
+		double varq = dxrad * o->qrstar[c] * o->densstar[c] * vazi[c];
+		varq -= dxrad * o->qrstar[ljp] * o->densstar[ljp] * vazi[ljp];
+		qbase[c] += varq * invsurf;
+	    }
+	}
+    }
+}
+
+/* AdvectSHIFT :238-268 */
+static void advect_shift(fargo_oracle *o, double *val)
+{
+    const int nr = o->nr, ns = o->ns;
+#pragma omp parallel for
+    for (int i = 0; i < nr; i++) {
+	for (int j = 0; j < ns; j++) {
+	    int ji = j - o->nshift[i];
+	    while (ji < 0)
+		ji += ns;
+	    while (ji >= ns)
+		ji -= ns;
+	    o->tempshift[IDX(o, i, j)] = val[IDX(o, i, ji)];
+	}
+    }
+    memcpy(val, o->tempshift, (size_t)nr * ns * sizeof(double));
+}
+
+/* QuantitiesAdvection :292-304 */
+static void quantities_advection(fargo_oracle *o, const double *vazi, double dt, int uniform)
+{
+    const size_t n = (size_t)o->nr * o->ns;
+    compute_star_theta(o, o->sigma, vazi, o->densstar, dt);
+    memcpy(o->densint, o->sigma, n * sizeof(double));
+    vanleer_theta(o, vazi, o->rmp, dt, uniform);
+    vanleer_theta(o, vazi, o->rmm, dt, uniform);
+    vanleer_theta(o, vazi, o->amp, dt, uniform);
+    vanleer_theta(o, vazi, o->amm, dt, uniform);
+    if (o->p.adiabatic)
+	vanleer_theta(o, vazi, o->energy, dt, uniform);
+    vanleer_theta(o, vazi, o->sigma, dt, uniform);
+}
+
+int fargo_oracle_stage_transport(fargo_oracle *o, double dt)
+{
+    const int Nr = o->nr, Nphi = o->ns;
+    const size_t n = (size_t)Nr * Nphi;
+    const double OmegaF = o->bodies.omega_frame;
+    compute_momenta(o);
+    /* OneWindRad :138-167 */
+    memset(o->densstar + n, 0, (size_t)Nphi * sizeof(double)); /* ring Nr of the star grids stays 0 (:82-91) */
+    memset(o->qrstar + n, 0, (size_t)Nphi * sizeof(double));
+    compute_star_radial(o, o->sigma, o->vrad, o->densstar, dt);
+    memcpy(o->densint, o->sigma, n * sizeof(double));
+    vanleer_radial(o, o->vrad, o->rmp, dt);
+    vanleer_radial(o, o->vrad, o->rmm, dt);
+    vanleer_radial(o, o->vrad, o->amp, dt);
+    vanleer_radial(o, o->vrad, o->amm, dt);
+    if (o->p.adiabatic)
+	vanleer_radial(o, o->vrad, o->energy, dt);
+    vanleer_radial(o, o->vrad, o->sigma, dt);
+    /* OneWindTheta :270-288 */
+    for (int nr = 0; nr < Nr; ++nr) { /* compute_average_azimuthal_velocity :174-189 */
+	double s = 0.0;
+	for (int naz = 0; naz < Nphi; ++naz)
+	    s += o->vazi[IDX(o, nr, naz)];
+	o->vmean[nr] = s / (double)Nphi;
+    }
+#pragma omp parallel for
+    for (int nr = 0; nr < Nr; ++nr) /* compute_residual_velocity :194-205 */
+	for (int naz = 0; naz < Nphi; ++naz)
+	    o->vres[IDX(o, nr, naz)] = o->vazi[IDX(o, nr, naz)] - o->vmean[nr];
+    { /* ComputeConstantResidual :207-236 */
+	const double invdt = 1.0 / dt;
+	for (int i = 0; i < Nr; i++) {
+	    const double Ntilde = o->vmean[i] * o->invrmed[i] * dt * o->invdphi;
+	    const double Nround = floor(Ntilde + 0.5);
+	    o->nshift[i] = (int)Nround;
+	    for (int j = 0; j < Nphi; j++)
+		o->vazi[IDX(o, i, j)] = (Ntilde - Nround) * o->rmed[i] * invdt * o->dphi;
+	    if (!o->p.fast_transport) {
+		for (int j = 0; j < Nphi; j++) {
+		    const size_t l = IDX(o, i, j);
+		    o->vres[l] = o->vazi[l] + o->vres[l];
+		    o->vazi[l] = 0.0;
+		}
+	    }
+	}
+    }
+    quantities_advection(o, o->vres, dt, 0);
+    quantities_advection(o, o->vazi, dt, 1);
+    advect_shift(o, o->rmp);
+    advect_shift(o, o->rmm);
+    advect_shift(o, o->amp);
+    advect_shift(o, o->amm);
+    if (o->p.adiabatic)
+	advect_shift(o, o->energy);
+    advect_shift(o, o->sigma);
+    /* compute_velocities_from_momenta :498-535 */
+#pragma omp parallel for
+    for (int nr = 0; nr < Nr; ++nr) {
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const int nm = (naz == 0 ? Nphi - 1 : naz - 1);
+	    const size_t c = IDX(o, nr, naz), cp = IDX(o, nr, nm);
+	    if (nr == 0)
+		o->vrad[c] = 0.0;
+	    else
+		o->vrad[c] = (o->rmp[c - Nphi] + o->rmm[c]) / (o->sigma[c - Nphi] + o->sigma[c]);
+	    o->vazi[c] = (o->amp[cp] + o->amm[c]) / (o->sigma[cp] + o->sigma[c]) * o->invrmed[nr] - o->rmed[nr] * OmegaF;
+	}
+    }
+    /* assure_minimum_value(SIGMA, sigma_floor*sigma0) :124-125, SourceEuler.cpp:102-134 */
+    const double floorv = o->p.sigma_floor * o->p.sigma0;
+#pragma omp parallel for
+    for (size_t c = 0; c < n; ++c)
+	if (o->sigma[c] < floorv)
+	    o->sigma[c] = floorv;
+    if (o->p.adiabatic)
+	assure_temperature_range(o);
+    return 0;
+}
+
+int fargo_oracle_get_nshift(fargo_oracle *o, int *out)
+{
+    memcpy(out, o->nshift, (size_t)o->nr * sizeof(int));
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * cfl::condition_cfl, cfl.cpp:185-382 (local part; the caller does the MIN over ranks) */
+int fargo_oracle_condition_cfl(fargo_oracle *o, double *out)
+{
+    const int Nr = o->nr, Nphi = o->ns;
+    const double CFL = o->p.cfl;
+    const double C = o->p.artificial_viscosity_factor;
+    for (int nr = 0; nr < Nr; ++nr) { /* :196-205 */
+	double s = 0.0;
+	for (int naz = 0; naz < Nphi; ++naz)
+	    s += o->vazi[IDX(o, nr, naz)];
+	o->vmean[nr] = s / (double)Nphi;
+    }
+    const double denom0 = fabs(o->vmean[0] * o->invrmed[0] - o->vmean[1] * o->invrmed[1]) + 1.0e-100;
+    double dt_core = CFL * o->dphi / denom0;
+    const double lf = o->p.leapfrog ? 0.6 : 1.0;
+    for (int nr = o->first_active; nr < o->active_size; ++nr) {
+	const double denom = fabs(o->vmean[nr] * o->invrmed[nr] - o->vmean[nr + 1] * o->invrmed[nr + 1]) + 1.0e-100;
+	const double shear_dt = CFL * o->dphi / denom;
+	if (shear_dt < dt_core)
+	    dt_core = shear_dt;
+	const double dxRadial = o->rsup[nr] - o->rinf[nr];
+	const double dxAzimuthal = o->rmed[nr] * o->dphi;
+	const double cell_size = stdmin(dxRadial, dxAzimuthal);
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const size_t c = IDX(o, nr, naz), cu = IDX(o, nr + 1, naz);
+	    const int naz_next = naz == Nphi - 1 ? 0 : naz + 1;
+	    const double vres = o->p.fast_transport ? o->vazi[c] - o->vmean[nr] : o->vazi[c];
+	    const double invdt1 = o->soundspeed[c] / cell_size;
+	    const double invdt2 = o->vrad[c] / dxRadial;
+	    const double invdt3 = vres / dxAzimuthal;
+	    double invdt4;
+	    if (o->p.artificial_viscosity == FARGO_ARTVISC_SN) {
+		double dvRadial = o->vrad[cu] - o->vrad[c];
+		double dvAzimuthal = o->vazi[IDX(o, nr, naz_next)] - o->vazi[c];
+		dvRadial = (dvRadial > 0.0) ? 0.0 : -dvRadial;
+		dvAzimuthal = (dvAzimuthal > 0.0) ? 0.0 : -dvAzimuthal;
+		invdt4 = 4.0 * (C * C) * stdmax(dvRadial / dxRadial, dvAzimuthal / dxAzimuthal) * lf;
+	    } else {
+		const double eps_rr = (o->vrad[cu] - o->vrad[c]) * o->invdiffrsup[nr];
+		const double eps_pp =
+		    o->invrmed[nr] * ((o->vazi[IDX(o, nr, naz_next)] - o->vazi[c]) * o->invdphi + 0.5 * (o->vrad[cu] + o->vrad[c]));
+		const double mdiv_V = -stdmin(eps_rr + eps_pp, 0.0);
+		invdt4 = 4.0 * (C * C) * mdiv_V * lf;
+	    }
+	    const double invdt5 = 4.0 * o->viscosity[c] / (cell_size * cell_size) * lf;
+	    double invdt6;
+	    if (o->p.adiabatic) {
+		const double inv_limit = 1.0 / o->p.heating_cooling_cfl_limit;
+		invdt6 = inv_limit * fabs((o->qplus[c] - o->qminus[c]) / o->energy[c]) * lf;
+	    } else {
+		invdt6 = 0.0;
+	    }
+	    double dt_cell = CFL / sqrt(invdt1 * invdt1 + invdt2 * invdt2 + invdt3 * invdt3 + invdt4 * invdt4 + invdt5 * invdt5 + invdt6 * invdt6);
+	    if (o->p.stabilize_viscosity == 2) {
+		const double cc = stdmin(o->cf_phi[c], o->cf_r[c]);
+		if (cc != 0.0)
+		    dt_cell = stdmin(dt_cell, -CFL / cc);
+	    }
+	    if (dt_cell < dt_core)
+		dt_core = dt_cell;
+	}
+    }
+    *out = dt_core;
+    return 0;
+}
+
+/* sim::CalculateTimeStep, simulation.cpp:100-118 (single rank; multi-rank callers min-reduce
+ * fargo_oracle_condition_cfl themselves and apply the same min) */
+int fargo_oracle_cfl(fargo_oracle *o, double *last_dt, double *dt_out)
+{
+    double cfl_dt;
+    fargo_oracle_condition_cfl(o, &cfl_dt);
+    const double rv = stdmin(o->p.cfl_max_var * *last_dt, cfl_dt);
+    *last_dt = rv;
+    *dt_out = rv;
+    return 0;
+}
+
+/* CommunicateBoundaries (commbound.cpp:98-182) for oracle slabs living in one process:
+ * copies this slab's send rings into / out of caller-provided buffers of 4*CPUOVERLAP*naz doubles.
+ * side 0 = towards rank-1 (inner), 1 = towards rank+1 (outer). */
+int fargo_oracle_halo_pack(fargo_oracle *o, int side, double *buf)
+{
+    const size_t l = (size_t)FARGO_CPUOVERLAP * o->ns;
+    const size_t off = side == 0 ? l : (size_t)(o->nr - 2 * FARGO_CPUOVERLAP) * o->ns;
+    memcpy(buf, o->sigma + off, l * sizeof(double));
+    memcpy(buf + l, o->vrad + off, l * sizeof(double));
+    memcpy(buf + 2 * l, o->vazi + off, l * sizeof(double));
+    memcpy(buf + 3 * l, o->energy + off, l * sizeof(double));
+    return 0;
+}
+int fargo_oracle_halo_unpack(fargo_oracle *o, int side, const double *buf)
+{
+    const size_t l = (size_t)FARGO_CPUOVERLAP * o->ns;
+    const size_t off = side == 0 ? 0 : (size_t)(o->nr - FARGO_CPUOVERLAP) * o->ns;
+    memcpy(o->sigma + off, buf, l * sizeof(double));
+    memcpy(o->vrad + off, buf + l, l * sizeof(double));
+    memcpy(o->vazi + off, buf + 2 * l, l * sizeof(double));
+    if (o->p.adiabatic)
+	memcpy(o->energy + off, buf + 3 * l, l * sizeof(double));
+    return 0;
+}
+
+/* gas part of step_Euler, simulation.cpp:167-175, 187-218, 230-266.  With nranks > 1 the caller must
+ * split the step at the halo exchange: step_pre, exchange, step_post. */
+int fargo_oracle_step_pre(fargo_oracle *o, double dt)
+{
+    fargo_oracle_stage_potential(o);
+    fargo_oracle_stage_sources(o, dt);
+    fargo_oracle_stage_artvisc(o, dt);
+    fargo_oracle_stage_viscosity(o, dt);
+    if (o->p.adiabatic)
+	fargo_oracle_stage_substep3(o, dt);
+    fargo_oracle_stage_boundary(o, 0.0, 0);
+    fargo_oracle_stage_transport(o, dt);
+    o->time += dt;
+    return 0;
+}
+int fargo_oracle_step_post(fargo_oracle *o, double dt)
+{
+    fargo_oracle_stage_boundary(o, dt, 1);
+    fargo_oracle_stage_derived(o);
+    return 0;
+}
+int fargo_oracle_step(fargo_oracle *o, double dt)
+{
+    fargo_oracle_step_pre(o, dt);
+    fargo_oracle_step_post(o, dt);
+    return 0;
+}

@@ -1,0 +1,162 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in tests/golden/*.npz by RUNNING THE UNMODIFIED REFERENCE
+(oracle/_ref/fargocpt_exe_ieee, built by `make -f oracle/Makefile.ref` from /root/reference).
+
+Runs only in the build container (needs oracle/_ref); the .npz outputs are committed.
+Each case = one small FargoCPT YAML config.  To capture the state after EVERY hydro step the
+configs use Nmonitor: 1 and a MonitorTimestep smaller than the CFL dt, so every hydro step is
+exactly one monitor step and one snapshot (simulation.cpp:528-550).
+
+A fixture holds: the YAML text, the derived FargoParams (as JSON), used_rad.dat, and for every
+snapshot k the raw arrays Sigma/vrad/vazi/energy(/Qplus/Qminus), misc.bin (time, last_dt, N_iter)
+and each body's (mass, x, y, vx, vy).
+"""
+import json
+import os
+import shutil
+import struct
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import yaml
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import reftools  # noqa: E402
+
+EXE = os.path.join(ROOT, "oracle", "_ref", "fargocpt_exe_ieee")
+
+BASE = {
+    "DiskFeedback": "no", "MonitorTimestep": 1.0e-3, "Nmonitor": 1, "Nsnapshots": 6, "FirstDT": 1.0e-1,
+    "CFLmaxVar": 1.1, "ShockTube": 0, "Sigma0": 0.005743125733951172, "SigmaSlope": 1.0, "SigmaFloor": 1e-7,
+    "AspectRatio": 0.05, "FlaringIndex": 0.2857142857142857, "ViscousAlpha": 0.0, "ArtificialViscosity": "TW",
+    "ArtificialViscosityDissipation": "Yes", "ArtificialViscosityFactor": 3.0, "SelfGravity": "No",
+    "EquationOfState": "Ideal", "AdiabaticIndex": 1.4, "CoolingBetaLocal": "No", "CoolingBetaReference": "reference",
+    "CoolingBeta": 100, "RadiativeDiffusion": "No", "HeatingViscous": "no", "MinimumTemperature": "3 K",
+    "MaximumTemperature": "1e100 K", "CFL": 0.5, "HeatingCoolingCFLlimit": 1.0,
+    "l0": "30 au", "m0": "1 solMass", "mu": 2.35, "ThicknessSmoothing": 0.6, "Transport": "FARGO",
+    "Integrator": "Euler", "IndirectTermMode": 0, "InnerBoundary": "Reflecting", "OuterBoundary": "Reflecting",
+    "Damping": "No", "Disk": "yes", "OmegaFrame": 0, "Frame": "F",
+    "Nrad": 24, "Naz": 48, "cps": -1, "Rmin": 0.4, "Rmax": 2.0, "RadialSpacing": "Logarithmic",
+    "DoWrite1DFiles": "No", "WriteAtEveryTimestep": "Yes", "WriteDensity": "Yes", "WriteEnergy": "Yes",
+    "WriteVelocity": "Yes", "WriteQMinus": "Yes", "WriteQPlus": "Yes", "WriteDiskQuantities": "No",
+    "RandomSigma": "No", "IntegrateParticles": "no", "HydroFrameCenter": "primary", "BodyForceFromPotential": "Yes",
+    "LogAfterSteps": 0, "LogAfterRealSeconds": 600,
+    "nbody": [{"name": "Star", "semi-major axis": 0.0, "mass": "1 solMass", "eccentricity": 0,
+               "radius": "1 solRadius", "temperature": 0}],
+}
+DAMP_ALL = {k: "Initial" for k in (
+    "DampingEnergyInner", "DampingVRadialInner", "DampingVAzimuthalInner", "DampingSurfaceDensityInner",
+    "DampingEnergyOuter", "DampingVRadialOuter", "DampingVAzimuthalOuter", "DampingSurfaceDensityOuter")}
+
+CASES = {
+    # adiabatic, TW art-visc + dissipation, alpha viscosity + viscous heating + beta cooling, reflecting + damping
+    "adia_star": dict(ViscousAlpha=1e-3, HeatingViscous="yes", CoolingBetaLocal="yes", CoolingBeta=10,
+                      Damping="Yes", DampingInnerLimit=1.311, DampingOuterLimit=0.763, DampingTimeFactor=0.05,
+                      **DAMP_ALL),
+    # cold_disk-like: adiabatic, no physical viscosity, no heating/cooling (test/cold_disk/setup.yml physics)
+    "adia_cold": dict(Damping="Yes", DampingInnerLimit=1.311, DampingOuterLimit=0.763, DampingTimeFactor=0.05,
+                      **DAMP_ALL),
+    # locally isothermal, alpha viscosity, TW, outflow boundaries, corotating-frame style OmegaFrame != 0
+    "iso_star": dict(EquationOfState="Isothermal", ViscousAlpha=1e-2, ArtificialViscosityFactor=1.41,
+                     InnerBoundary="Outflow", OuterBoundary="Outflow", OmegaFrame=1.0, FlaringIndex=0.0),
+    # locally isothermal, Stone-Norman art-visc, constant viscosity, standard (non-FARGO) transport, MC limiter,
+    # zero-gradient boundaries, arithmetic grid
+    "iso_sn_std": dict(EquationOfState="Isothermal", ArtificialViscosity="SN", ArtificialViscosityFactor=1.41,
+                       ConstantViscosity=1.0e-5, Transport="Standard", FluxLimiter="mc", MonitorTimestep=2.0e-4,
+                       InnerBoundary="ZeroGradient", OuterBoundary="ZeroGradient", RadialSpacing="Arithmetic"),
+    # adiabatic with SN art-visc + dissipation, StabilizeViscosity 1, damping to zero / mean
+    "adia_sn_stab": dict(ArtificialViscosity="SN", ArtificialViscosityFactor=1.41, ViscousAlpha=5e-3,
+                         StabilizeViscosity=1, HeatingViscous="yes", InnerBoundary="Outflow",
+                         OuterBoundary="Reflecting", Damping="Yes", DampingInnerLimit=1.2, DampingOuterLimit=0.8,
+                         DampingTimeFactor=0.1, DampingVRadialInner="Zero", DampingVRadialOuter="Zero",
+                         DampingSurfaceDensityOuter="Mean", DampingEnergyOuter="Mean"),
+    # pressureless viscous ring geometry of test/spreading_ring (Naz = 2): art-visc None, h = 0 disabled here
+    # because the Bessel initial condition is out of scope; same grid/viscosity/boundaries on a power-law disk
+    "ring_like": dict(EquationOfState="Isothermal", AspectRatio=0.01, FlaringIndex=0.0, ArtificialViscosity="None",
+                      ArtificialViscosityFactor=1.41, ConstantViscosity=4.77e-5, InnerBoundary="Outflow",
+                      OuterBoundary="Outflow", Nrad=64, Naz=2, Rmin=0.2, Rmax=1.8, MonitorTimestep=1.0e-4,
+                      ThicknessSmoothing=0.0),
+}
+
+
+def parse_constants(outdir):
+    c = yaml.safe_load(open(os.path.join(outdir, "constants.yml")))
+    u = yaml.safe_load(open(os.path.join(outdir, "units.yml")))
+    consts = {v["symbol"]: float(v["code value"]) for v in c.values()}
+    return consts, float(u["temperature"]["cgs value"])
+
+
+def read_misc(path):
+    raw = open(path, "rb").read()
+    timestep, ntimestep, time, omega_frame, frame_angle, last_dt, n_iter = struct.unpack("<IIddddQ", raw[:48])
+    return dict(time=time, omega_frame=omega_frame, frame_angle=frame_angle, last_dt=last_dt, n_iter=n_iter)
+
+
+def read_body(path):
+    raw = open(path, "rb").read()
+    mass, x, y, vx, vy = struct.unpack("<5d", raw[8:48])  # planet_member_variables (nbody/planet.h:11-17)
+    return [mass, x, y, vx, vy]
+
+
+def run_case(name, overrides, keep=False):
+    cfg = dict(BASE)
+    cfg.update(overrides)
+    tmp = tempfile.mkdtemp(prefix="golden_" + name + "_")
+    cfg["OutputDir"] = os.path.join(tmp, "out")
+    ypath = os.path.join(tmp, "cfg.yml")
+    with open(ypath, "w") as f:
+        yaml.safe_dump(cfg, f, sort_keys=False)
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    res = subprocess.run([EXE, "start", ypath], cwd=tmp, env=env, capture_output=True, text=True)
+    if res.returncode != 0:
+        print(res.stdout[-3000:], res.stderr[-3000:])
+        raise SystemExit(f"reference run failed for {name}")
+    out = cfg["OutputDir"]
+    consts, temp_unit = parse_constants(out)
+    dims = [l for l in open(os.path.join(out, "dimensions.dat")) if not l.startswith("#")][-1].split()
+    nrad, naz = int(dims[4]), int(dims[5])
+    radii = np.loadtxt(os.path.join(out, "used_rad.dat"))
+    assert radii.shape == (nrad + 1,)
+    pdict = reftools.params_from_config(cfg, consts, nrad, naz, temp_unit)
+    nsnap = int(cfg["Nsnapshots"])
+    nb = len(cfg["nbody"])
+    arrays = {"radii": radii}
+    misc = []
+    bodies = []
+    for k in range(nsnap + 1):
+        sd = os.path.join(out, "snapshots", str(k))
+        for fname, rings in (("Sigma", nrad), ("vrad", nrad + 1), ("vazi", nrad), ("energy", nrad),
+                             ("Qplus", nrad), ("Qminus", nrad)):
+            p = os.path.join(sd, fname + ".dat")
+            if os.path.exists(p):
+                arrays[f"{fname}_{k}"] = np.fromfile(p, dtype=np.float64).reshape(rings, naz)
+        misc.append(read_misc(os.path.join(sd, "misc.bin")))
+        bodies.append([read_body(os.path.join(sd, f"nbody{b}.bin")) for b in range(nb)])
+    meta = dict(name=name, config=cfg, params=pdict, consts=consts, temperature_unit_K=temp_unit, nsnap=nsnap,
+                misc=misc, bodies=bodies, first_dt=reftools._num(cfg["FirstDT"]),
+                monitor_timestep=float(cfg["MonitorTimestep"]))
+    arrays["meta"] = np.array(json.dumps(meta))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrays)
+    with open(os.path.join(HERE, name + ".yml"), "w") as f:
+        cfg2 = dict(cfg)
+        cfg2["OutputDir"] = "out/" + name
+        yaml.safe_dump(cfg2, f, sort_keys=False)
+    print(f"{name}: {nrad}x{naz}, {nsnap} snapshots, dt[1]={misc[1]['time'] - misc[0]['time']:.6e}, "
+          f"N_iter={[m['n_iter'] for m in misc]}")
+    if keep:
+        print("  kept", tmp)
+    else:
+        shutil.rmtree(tmp)
+
+
+if __name__ == "__main__":
+    if not os.path.exists(EXE):
+        raise SystemExit("build the reference first: make -f oracle/Makefile.ref -j8")
+    names = [a for a in sys.argv[1:] if not a.startswith("-")] or list(CASES)
+    for n in names:
+        run_case(n, CASES[n], keep="--keep" in sys.argv)

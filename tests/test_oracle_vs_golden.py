@@ -1,0 +1,33 @@
+"""Pins the CPU oracle (oracle/fargo_oracle.c) against the unmodified reference: every fixture in
+tests/golden/ was written by oracle/_ref/fargocpt_exe_ieee (tests/golden/make_golden.py).  Runs on CPU."""
+import numpy as np
+import pytest
+
+import goldenrun
+import reftools
+
+CASES = ["adia_star", "adia_cold", "iso_star", "iso_sn_std", "adia_sn_stab", "ring_like"]
+# Isothermal configs have no per-cell transcendental in the step => demanded bit-exact.
+# Adiabatic configs call exp() per cell (SourceEuler.cpp:487); same libm here => also bit-exact on CPU.
+BIT_EXACT = set(CASES)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference(name):
+    meta, z = reftools.load_golden(name)
+    ctx = reftools.OracleContext(reftools.make_params(meta["params"]), z["radii"])
+    snaps = goldenrun.run_fixture(ctx, meta, z)
+    for k, snap in enumerate(snaps, start=1):
+        m = meta["misc"][k]
+        assert snap["n_iter"] == m["n_iter"]
+        assert snap["time"] == m["time"]
+        assert snap["last_dt"] == m["last_dt"], (snap["last_dt"], m["last_dt"])
+        for fname in ("Sigma", "vrad", "vazi", "energy"):
+            if fname == "energy" and not ctx.params.adiabatic:
+                continue
+            st = reftools.compare_stats(snap[fname], z[f"{fname}_{k}"])
+            if name in BIT_EXACT:
+                assert st["n_diff"] == 0, (name, k, fname, st)
+            else:
+                assert st["max_rel"] < 1e-12, (name, k, fname, st)
+    ctx.close()
