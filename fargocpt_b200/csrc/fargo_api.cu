@@ -1,0 +1,876 @@
+// fargo_api.cu — the C ABI of include/fargo_b200.h on top of the sm_100a kernels.
+//
+// One fargo_ctx == one radial slab == one GPU (the reference's MPI rank).  All device work of a context
+// runs on its own stream; the only per-step host<->device traffic is the CFL scalar (8 bytes back) and the
+// per-ring damping factors / body positions (a few hundred bytes forth), exactly the scalars the reference's
+// host code exchanges with its loop nests.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "fargo_dev.h"
+#include "kernels_ring.cuh"
+#include "kernels_source.cuh"
+#include "kernels_transport.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// error handling: the reference die()s; we return non-zero and keep the message (thread-local)
+static thread_local std::string g_err;
+static int fail(const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+#define CUDA_OK(expr)                                                                                \
+    do {                                                                                             \
+	cudaError_t _e = (expr);                                                                     \
+	if (_e != cudaSuccess)                                                                       \
+	    return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// NCCL through dlopen: libfargo_b200.so must load on a box without NCCL (single GPU) and must share the NCCL
+// already loaded by the host process (torch bundles one) instead of pulling in a second copy.
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclFloat64 = 8, ncclMin = 3 }; // nccl.h: ncclDataType_t / ncclRedOp_t values (stable since NCCL 2.0)
+struct NcclApi {
+    int (*GetUniqueId)(ncclUniqueId *);
+    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    int (*CommDestroy)(ncclComm_t);
+    int (*GroupStart)();
+    int (*GroupEnd)();
+    int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t);
+    int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t);
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
+    const char *(*GetErrorString)(int);
+    bool ok = false;
+};
+static NcclApi g_nccl;
+static int load_nccl()
+{
+    if (g_nccl.ok)
+	return 0;
+    void *h = RTLD_DEFAULT;
+    if (!dlsym(RTLD_DEFAULT, "ncclCommInitRank")) {
+	const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+	h = nullptr;
+	for (int k = 0; names[k] && !h; ++k)
+	    h = dlopen(names[k], RTLD_NOW | RTLD_GLOBAL);
+	if (!h)
+	    return fail("NCCL not found: %s", dlerror());
+    }
+#define SYM(field, name)                                   \
+    *(void **)(&g_nccl.field) = dlsym(h, name);            \
+    if (!g_nccl.field)                                     \
+	return fail("NCCL symbol %s missing", name);
+    SYM(GetUniqueId, "ncclGetUniqueId")
+    SYM(CommInitRank, "ncclCommInitRank")
+    SYM(CommDestroy, "ncclCommDestroy")
+    SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd")
+    SYM(Send, "ncclSend")
+    SYM(Recv, "ncclRecv")
+    SYM(AllReduce, "ncclAllReduce")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    g_nccl.ok = true;
+    return 0;
+}
+#define NCCL_OK(expr)                                                                          \
+    do {                                                                                       \
+	int _r = (expr);                                                                       \
+	if (_r != 0)                                                                           \
+	    return fail("%s failed: %s", #expr, g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?"); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+struct fargo_ctx {
+    DevView v;	   // host copy of what the kernels receive by value
+    int device;
+    cudaStream_t stream;
+    ncclComm_t comm = nullptr;
+    long long launches = 0;
+    // host geometry (local view incl. 2 extra entries) for host-side ring factors
+    std::vector<double> h_radii, h_rinf, h_rsup, h_rmed;
+    std::vector<double *> dev_allocs;
+    // state: A buffers are the "current" state between steps; B buffers hold v during the source stages
+    double *sigma, *energy, *vrA, *vpA, *vrB, *vpB;
+    double *sigma0, *energy0, *vr0, *vp0;
+    double *qplus, *qminus;
+    // stage scratch
+    double *pot, *qr, *qphi, *nu, *divv, *trr, *tpp, *trp, *nusig, *nusig_rp, *cf_r, *cf_phi;
+    double *t_sigma, *t_rmp, *t_rmm, *t_amp, *t_amm, *t_e; // after the radial sweep
+    double *vmean, *vconst, *expf_s, *expf_v, *d_dt, *scratch;
+    int *nshift;
+    double *h_pin; // pinned host staging for the CFL scalar + ring factors
+    bool visc_const_filled = false;
+    bool v_in_B = false; // where the current velocities live (see stage_sources)
+    cudaEvent_t ev_pin = nullptr; // completion of the last H2D copy out of h_pin
+    int az_S, az_R, rad_chunk;
+};
+
+static int dalloc(fargo_ctx *c, double **p, size_t n)
+{
+    CUDA_OK(cudaMalloc((void **)p, (n ? n : 1) * sizeof(double)));
+    CUDA_OK(cudaMemsetAsync(*p, 0, (n ? n : 1) * sizeof(double), c->stream));
+    c->dev_allocs.push_back(*p);
+    return 0;
+}
+static int upload_vec(fargo_ctx *c, const double **dst, const std::vector<double> &h)
+{
+    double *d;
+    if (dalloc(c, &d, h.size()))
+	return 1;
+    CUDA_OK(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    *dst = d;
+    return 0;
+}
+
+static inline unsigned cells_grid(long long n, int block = 256) { return (unsigned)((n + block - 1) / block); }
+
+// split.cpp:38-87
+static int split_domain(DevView &v, int nrad, int rank, int np, int *imax_out)
+{
+    const int size_low = nrad / np, size_high = size_low + 1, rem = nrad % np;
+    if (np > 1 && size_low < 2 * FARGO_CPUOVERLAP)
+	return fail("The number of processes is too large or the mesh is radially too narrow.");
+    int imin, imax;
+    if (rank < rem) {
+	imin = size_high * rank;
+	imax = imin + size_high - 1;
+    } else {
+	imin = size_high * rem + (rank - rem) * size_low;
+	imax = imin + size_low - 1;
+    }
+    if (rank > 0)
+	imin -= FARGO_CPUOVERLAP;
+    if (rank < np - 1)
+	imax += FARGO_CPUOVERLAP;
+    v.imin = imin;
+    v.nr = imax - imin + 1;
+    const bool first = rank == 0, last = rank == np - 1;
+    v.zero_no_ghost = first ? 1 : 0;
+    v.one_no_ghost_vr = first ? 2 : 1;
+    v.max_no_ghost = v.nr - (last ? 1 : 0);
+    v.maxmo_no_ghost_vr = v.nr + 1 - (last ? 2 : 1);
+    v.first_active = first ? FARGO_GHOSTCELLS_B : FARGO_CPUOVERLAP;
+    v.active_size = v.nr - (last ? FARGO_GHOSTCELLS_B : FARGO_CPUOVERLAP);
+    *imax_out = imax;
+    return 0;
+}
+
+static double omega_kepler_host(const fargo_params &p, double r) { return sqrt(p.G * p.hydro_center_mass / (r * r * r)); }
+
+// init_radialarrays (init.cpp:169-225) for the local slab + per-ring constants the kernels use
+static int init_geometry(fargo_ctx *c, const double *radii)
+{
+    DevView &v = c->v;
+    const fargo_params &p = v.p;
+    const int gn = p.nrad, nl = v.nr + 2;
+    c->h_radii.assign(radii, radii + gn + 1);
+    for (int k = 0; k < 4; ++k) // the reference fills a 15-ring search buffer beyond the grid; only entry nr(+1) is read
+	c->h_radii.push_back(c->h_radii.back() * (c->h_radii[gn] / c->h_radii[gn - 1]));
+    v.dphi = 2.0 * M_PI / (double)v.ns;
+    v.invdphi = (double)v.ns / (2.0 * M_PI);
+    v.sqrt_gamma = sqrt(p.gamma);
+    std::vector<double> rinf(nl), rsup(nl), rmed(nl), surf(nl), invrmed(nl), invsurf(nl), invdiffrsup(nl), invdiffrsuprb(nl),
+	twodiffrasq(nl), fourthird(nl), invrinf(nl), invdiffrmed(nl, 0.0), omega_k(nl), inv_omega_k(nl), cs_iso(nl), supp(nl),
+	beta_e0(nl);
+    for (int n = 0; n < nl; ++n) {
+	const double ri = c->h_radii[n + v.imin], rs = c->h_radii[n + v.imin + 1];
+	rinf[n] = ri;
+	rsup[n] = rs;
+	double rm = 2.0 / 3.0 * (pow(rs, 3) - pow(ri, 3));
+	rm = rm / (pow(rs, 2) - pow(ri, 2));
+	rmed[n] = rm;
+	surf[n] = M_PI * (pow(rs, 2) - pow(ri, 2)) / (double)v.ns;
+	invrmed[n] = 1.0 / rm;
+	invsurf[n] = 1.0 / surf[n];
+	invdiffrsup[n] = 1.0 / (rs - ri);
+	invdiffrsuprb[n] = 1.0 / ((rs - ri) * rm);
+	twodiffrasq[n] = 2.0 / (rs * rs - ri * ri);
+	fourthird[n] = 4.0 / 3.0 / rm * v.invdphi * v.invdphi;
+	invrinf[n] = 1.0 / ri;
+	omega_k[n] = omega_kepler_host(p, rm);
+	inv_omega_k[n] = 1.0 / omega_k[n];
+	{ // SourceEuler.cpp:984-991
+	    const double vK = sqrt(p.G * p.hydro_center_mass / rm);
+	    const double h = p.aspectratio_ref * pow(rm, p.flaring_index);
+	    cs_iso[n] = h * vK;
+	}
+	supp[n] = (p.imposed_disk_drift != 0.0) ? p.imposed_disk_drift * 0.5 * pow(rm, -2.5 + p.sigma_slope) : 0.0;
+	// SourceEuler.cpp:668-672: 1/(gamma-1) * h^2 * pow(R, 2 beta - 1) * G * M  (then * sigma per cell)
+	beta_e0[n] = 1.0 / (p.gamma - 1.0) * (p.aspectratio_ref * p.aspectratio_ref) * pow(rm, 2.0 * p.flaring_index - 1.0) * p.G *
+		     p.hydro_center_mass;
+    }
+    for (int n = 1; n < nl; ++n)
+	invdiffrmed[n] = 1.0 / (rmed[n] - rmed[n - 1]);
+    std::vector<double> cosphi(v.ns), sinphi(v.ns);
+    for (int j = 0; j < v.ns; ++j) { // SideEuler.cpp:56-65
+	cosphi[j] = cos(v.dphi * (double)j);
+	sinphi[j] = sin(v.dphi * (double)j);
+    }
+    c->h_rinf = rinf;
+    c->h_rsup = rsup;
+    c->h_rmed = rmed;
+    Geo &g = v.g;
+    if (upload_vec(c, &g.rinf, rinf) || upload_vec(c, &g.rsup, rsup) || upload_vec(c, &g.rmed, rmed) ||
+	upload_vec(c, &g.surf, surf) || upload_vec(c, &g.invrmed, invrmed) || upload_vec(c, &g.invsurf, invsurf) ||
+	upload_vec(c, &g.invdiffrsup, invdiffrsup) || upload_vec(c, &g.invdiffrsuprb, invdiffrsuprb) ||
+	upload_vec(c, &g.twodiffrasq, twodiffrasq) || upload_vec(c, &g.fourthird, fourthird) ||
+	upload_vec(c, &g.invrinf, invrinf) || upload_vec(c, &g.invdiffrmed, invdiffrmed) || upload_vec(c, &g.cosphi, cosphi) ||
+	upload_vec(c, &g.sinphi, sinphi) || upload_vec(c, &g.omega_k, omega_k) || upload_vec(c, &g.inv_omega_k, inv_omega_k) ||
+	upload_vec(c, &g.cs_iso, cs_iso) || upload_vec(c, &g.supp_torque, supp) || upload_vec(c, &g.beta_model_e0, beta_e0))
+	return 1;
+    return 0;
+}
+
+extern "C" const char *fargo_last_error(void) { return g_err.c_str(); }
+
+extern "C" int fargo_get_unique_id(void *out128)
+{
+    if (load_nccl())
+	return 1;
+    ncclUniqueId id;
+    NCCL_OK(g_nccl.GetUniqueId(&id));
+    memcpy(out128, &id, sizeof(id));
+    return 0;
+}
+
+extern "C" void fargo_ctx_destroy(fargo_ctx *c)
+{
+    if (!c)
+	return;
+    cudaSetDevice(c->device);
+    if (c->stream)
+	cudaStreamSynchronize(c->stream);
+    if (c->comm && g_nccl.ok)
+	g_nccl.CommDestroy(c->comm);
+    for (double *p : c->dev_allocs)
+	cudaFree(p);
+    if (c->nshift)
+	cudaFree(c->nshift);
+    if (c->h_pin)
+	cudaFreeHost(c->h_pin);
+    if (c->ev_pin)
+	cudaEventDestroy(c->ev_pin);
+    if (c->stream)
+	cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, const double *radii, int rank, int nranks,
+				 const void *nccl_unique_id, int device)
+{
+    *out = nullptr;
+    if (!params || params->abi_version != FARGO_ABI_VERSION)
+	return fail("fargo_params.abi_version mismatch (got %d, library %d)", params ? params->abi_version : -1, FARGO_ABI_VERSION);
+    if (params->nrad < 5 || params->naz < 1)
+	return fail("grid too small: %d x %d", params->nrad, params->naz);
+    if (nranks < 1 || rank < 0 || rank >= nranks)
+	return fail("bad rank %d / %d", rank, nranks);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+	return fail("no CUDA device available: libfargo_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev)
+	return fail("device %d out of range (%d devices)", device, ndev);
+    CUDA_OK(cudaSetDevice(device));
+    fargo_ctx *c = new fargo_ctx();
+    memset(&c->v, 0, sizeof(c->v));
+    c->device = device;
+    c->h_pin = nullptr;
+    c->ev_pin = nullptr;
+    c->nshift = nullptr;
+    c->stream = nullptr;
+    c->v.p = *params;
+    c->v.ns = params->naz;
+    c->v.rank = rank;
+    c->v.nranks = nranks;
+    int imax;
+    if (split_domain(c->v, params->nrad, rank, nranks, &imax)) {
+	delete c;
+	return 1;
+    }
+    c->v.b.n = 1;
+    c->v.b.mass[0] = params->hydro_center_mass;
+#define TRY(expr)                \
+    if (expr) {                  \
+	fargo_ctx_destroy(c);    \
+	return 1;                \
+    }
+    {
+	cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+	if (e != cudaSuccess) {
+	    fail("cudaStreamCreate: %s", cudaGetErrorString(e));
+	    fargo_ctx_destroy(c);
+	    return 1;
+	}
+    }
+    TRY(init_geometry(c, radii));
+    const size_t ns = (size_t)c->v.nr * c->v.ns, nv = (size_t)(c->v.nr + 1) * c->v.ns;
+    TRY(dalloc(c, &c->sigma, ns) || dalloc(c, &c->energy, ns) || dalloc(c, &c->vrA, nv) || dalloc(c, &c->vpA, ns) ||
+	dalloc(c, &c->vrB, nv) || dalloc(c, &c->vpB, ns));
+    TRY(dalloc(c, &c->sigma0, ns) || dalloc(c, &c->energy0, ns) || dalloc(c, &c->vr0, nv) || dalloc(c, &c->vp0, ns));
+    TRY(dalloc(c, &c->qplus, ns) || dalloc(c, &c->qminus, ns));
+    TRY(dalloc(c, &c->pot, ns) || dalloc(c, &c->qr, ns) || dalloc(c, &c->qphi, ns) || dalloc(c, &c->nu, ns) ||
+	dalloc(c, &c->divv, ns) || dalloc(c, &c->trr, ns) || dalloc(c, &c->tpp, ns) || dalloc(c, &c->trp, nv));
+    if (params->stabilize_viscosity) {
+	TRY(dalloc(c, &c->nusig, ns) || dalloc(c, &c->nusig_rp, nv) || dalloc(c, &c->cf_r, ns) || dalloc(c, &c->cf_phi, ns));
+    } else {
+	c->nusig = c->nusig_rp = c->cf_r = c->cf_phi = nullptr;
+    }
+    TRY(dalloc(c, &c->t_sigma, ns) || dalloc(c, &c->t_rmp, ns) || dalloc(c, &c->t_rmm, ns) || dalloc(c, &c->t_amp, ns) ||
+	dalloc(c, &c->t_amm, ns) || dalloc(c, &c->t_e, params->adiabatic ? ns : 1));
+    TRY(dalloc(c, &c->vmean, c->v.nr + 2) || dalloc(c, &c->vconst, c->v.nr + 2) || dalloc(c, &c->expf_s, 4 * (c->v.nr + 2)) ||
+	dalloc(c, &c->expf_v, 1) || dalloc(c, &c->d_dt, 2) || dalloc(c, &c->scratch, ns));
+    {
+	cudaError_t e = cudaMalloc((void **)&c->nshift, (c->v.nr + 2) * sizeof(int));
+	if (e == cudaSuccess)
+	    e = cudaMemsetAsync(c->nshift, 0, (c->v.nr + 2) * sizeof(int), c->stream);
+	if (e == cudaSuccess)
+	    e = cudaMallocHost((void **)&c->h_pin, (4 * (c->v.nr + 2) + 8) * sizeof(double));
+	if (e == cudaSuccess)
+	    e = cudaEventCreateWithFlags(&c->ev_pin, cudaEventDisableTiming);
+	if (e != cudaSuccess) {
+	    fail("allocation failed: %s", cudaGetErrorString(e));
+	    fargo_ctx_destroy(c);
+	    return 1;
+	}
+    }
+    // launch geometry of the transport kernels
+    c->az_S = 247; // + 9 halo = 256 cells per ring segment
+    c->az_R = 32;
+    c->rad_chunk = 64;
+    {
+	const int L = c->az_S + AZ_HL + AZ_HR;
+	const size_t smem = ((size_t)(3 * AZ_NQ + 1) * L + 2 * c->az_S) * sizeof(double);
+	cudaFuncSetAttribute(k_transport_azimuthal<FARGO_LIMITER_VANLEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	cudaFuncSetAttribute(k_transport_azimuthal<FARGO_LIMITER_MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    if (nranks > 1) {
+	if (!nccl_unique_id) {
+	    fail("nranks > 1 needs an ncclUniqueId");
+	    fargo_ctx_destroy(c);
+	    return 1;
+	}
+	TRY(load_nccl());
+	ncclUniqueId id;
+	memcpy(&id, nccl_unique_id, sizeof(id));
+	int r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
+	if (r != 0) {
+	    fail("ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+	    fargo_ctx_destroy(c);
+	    return 1;
+	}
+    }
+#undef TRY
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
+	fail("context initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
+	fargo_ctx_destroy(c);
+	return 1;
+    }
+    *out = c;
+    return 0;
+}
+
+extern "C" int fargo_local_nrad(const fargo_ctx *c) { return c->v.nr; }
+extern "C" int fargo_local_imin(const fargo_ctx *c) { return c->v.imin; }
+extern "C" long long fargo_launch_count(const fargo_ctx *c) { return c->launches; }
+extern "C" int fargo_sync(fargo_ctx *c)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+#define LAUNCH(c, kernel, grid, block, smem, ...)                        \
+    do {                                                                 \
+	kernel<<<grid, block, smem, (c)->stream>>>(__VA_ARGS__);         \
+	(c)->launches++;                                                 \
+	cudaError_t _e = cudaGetLastError();                             \
+	if (_e != cudaSuccess)                                           \
+	    return fail("launch %s: %s", #kernel, cudaGetErrorString(_e)); \
+    } while (0)
+
+static double *state_ptr(fargo_ctx *c, int f, int *rings)
+{
+    *rings = c->v.nr;
+    switch (f) {
+    case FARGO_SIGMA: return c->sigma;
+    case FARGO_VRAD: *rings = c->v.nr + 1; return c->vrA;
+    case FARGO_VAZI: return c->vpA;
+    case FARGO_ENERGY: return c->energy;
+    case FARGO_SIGMA0: return c->sigma0;
+    case FARGO_VRAD0: *rings = c->v.nr + 1; return c->vr0;
+    case FARGO_VAZI0: return c->vp0;
+    case FARGO_ENERGY0: return c->energy0;
+    case FARGO_QPLUS: return c->qplus;
+    case FARGO_QMINUS: return c->qminus;
+    case FARGO_POTENTIAL: return c->pot;
+    }
+    return nullptr;
+}
+
+// derived fields are never stored; they are evaluated into `scratch` when somebody asks for them
+static int materialize(fargo_ctx *c, int f, double **ptr, int *rings)
+{
+    *ptr = state_ptr(c, f, rings);
+    if (*ptr)
+	return 0;
+    if (f == FARGO_TEMPERATURE || f == FARGO_PRESSURE || f == FARGO_SOUNDSPEED || f == FARGO_SCALE_HEIGHT || f == FARGO_VISCOSITY) {
+	*rings = c->v.nr;
+	LAUNCH(c, k_derived_field, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, c->energy, c->scratch, f);
+	*ptr = c->scratch;
+	return 0;
+    }
+    return fail("unknown field id %d", f);
+}
+
+extern "C" int fargo_upload_field(fargo_ctx *c, int f, const double *host_global)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    int rings;
+    double *d = state_ptr(c, f, &rings);
+    if (!d)
+	return fail("field %d cannot be uploaded", f);
+    CUDA_OK(cudaMemcpyAsync(d, host_global + (size_t)c->v.imin * c->v.ns, (size_t)rings * c->v.ns * sizeof(double),
+			    cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int fargo_download_field(fargo_ctx *c, int f, double *host_global)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    int rings;
+    double *d;
+    if (materialize(c, f, &d, &rings))
+	return 1;
+    // write2D (polargrid.cpp:150-176): rings Zero_or_active .. Max_or_active (+1 for vector grids on the last rank)
+    const bool first = c->v.rank == 0, last = c->v.rank == c->v.nranks - 1;
+    const int lo = first ? 0 : FARGO_CPUOVERLAP;
+    int count = (c->v.nr - (last ? 0 : FARGO_CPUOVERLAP)) - lo;
+    if (rings == c->v.nr + 1 && last)
+	count += 1;
+    CUDA_OK(cudaMemcpyAsync(host_global + (size_t)(c->v.imin + lo) * c->v.ns, d + (size_t)lo * c->v.ns,
+			    (size_t)count * c->v.ns * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int fargo_download_slab(fargo_ctx *c, int f, double *host_slab)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    int rings;
+    double *d;
+    if (materialize(c, f, &d, &rings))
+	return 1;
+    CUDA_OK(cudaMemcpyAsync(host_slab, d, (size_t)rings * c->v.ns * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int fargo_copy_initial_values(fargo_ctx *c)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    const size_t ns = (size_t)c->v.nr * c->v.ns * sizeof(double), nv = (size_t)(c->v.nr + 1) * c->v.ns * sizeof(double);
+    CUDA_OK(cudaMemcpyAsync(c->vr0, c->vrA, nv, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(c->vp0, c->vpA, ns, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(c->sigma0, c->sigma, ns, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(c->energy0, c->energy, ns, cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+
+extern "C" int fargo_set_bodies(fargo_ctx *c, const fargo_bodies *b)
+{
+    if (b->n < 0 || b->n > FARGO_MAX_BODIES)
+	return fail("too many bodies: %d", b->n);
+    c->v.b = *b;
+    return 0;
+}
+extern "C" int fargo_set_time(fargo_ctx *c, double t)
+{
+    c->v.time = t;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stages
+extern "C" int fargo_stage_potential(fargo_ctx *c)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    LAUNCH(c, k_potential, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, c->energy, c->pot);
+    return 0;
+}
+
+// NOTE on buffers: between steps v lives in vrA/vpA.  stage_sources reads A and writes B; artvisc / viscosity
+// update B in place; Transport reads B and writes A.  When stages are called one by one (tests) the same
+// protocol holds because every per-stage entry point leaves the "current" v where the next stage expects it:
+// after sources..substep3 the current v is B, so the boundary stage must know which buffer is current.
+struct VBuf { double *vr, *vp; };
+static inline VBuf cur_v(fargo_ctx *c, bool in_B) { return in_B ? VBuf{c->vrB, c->vpB} : VBuf{c->vrA, c->vpA}; }
+
+extern "C" int fargo_stage_sources(fargo_ctx *c, double dt)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    if (c->v_in_B)
+	return fail("stage_sources called while the velocities are mid-step (call stage_transport first)");
+    LAUNCH(c, k_sources_velocity, cells_grid((long long)(c->v.nr + 1) * c->v.ns), 256, 0, c->v, c->sigma, c->energy, c->pot,
+	   c->vrA, c->vpA, c->vrB, c->vpB, dt);
+    c->v_in_B = true;
+    if (c->v.p.adiabatic)
+	LAUNCH(c, k_compression_heating, cells_grid((long long)(c->v.nr - 1) * c->v.ns), 256, 0, c->v, c->vrB, c->vpB, c->energy, dt);
+    return 0;
+}
+
+// make sure the current velocities are in the B buffers (stages that expect mid-step state, when called
+// stand-alone from a between-steps state)
+static int ensure_v_in_B(fargo_ctx *c)
+{
+    if (!c->v_in_B) {
+	CUDA_OK(cudaMemcpyAsync(c->vrB, c->vrA, (size_t)(c->v.nr + 1) * c->v.ns * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+	CUDA_OK(cudaMemcpyAsync(c->vpB, c->vpA, (size_t)c->v.nr * c->v.ns * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+	c->v_in_B = true;
+    }
+    return 0;
+}
+
+extern "C" int fargo_stage_artvisc(fargo_ctx *c, double dt)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    if (ensure_v_in_B(c))
+	return 1;
+    const fargo_params &p = c->v.p;
+    const bool diss = p.adiabatic && p.artificial_viscosity_dissipation;
+    if (p.artificial_viscosity == FARGO_ARTVISC_NONE && !diss)
+	return 0;
+    const unsigned g = cells_grid((long long)c->v.nr * c->v.ns);
+    LAUNCH(c, k_artvisc_q, g, 256, 0, c->v, c->sigma, c->vrB, c->vpB, c->energy, c->qr, c->qphi, dt);
+    if (p.artificial_viscosity != FARGO_ARTVISC_NONE)
+	LAUNCH(c, k_artvisc_v, g, 256, 0, c->v, c->sigma, c->qr, c->qphi, c->vrB, c->vpB, dt);
+    return 0;
+}
+
+static int launch_stress(fargo_ctx *c)
+{
+    const unsigned g = cells_grid((long long)c->v.nr * c->v.ns);
+    const fargo_params &p = c->v.p;
+    if (p.viscous_alpha > 0 || !c->visc_const_filled) {
+	LAUNCH(c, k_viscosity_nu, g, 256, 0, c->v, c->sigma, c->energy, c->nu);
+	c->visc_const_filled = true;
+    }
+    VBuf v = cur_v(c, c->v_in_B);
+    LAUNCH(c, k_stress, g, 256, 0, c->v, c->sigma, c->nu, v.vr, v.vp, c->divv, c->trr, c->tpp, c->trp, c->nusig, c->nusig_rp);
+    if (p.stabilize_viscosity)
+	LAUNCH(c, k_stress_correction, g, 256, 0, c->v, c->sigma, c->nusig, c->nusig_rp, c->cf_r, c->cf_phi);
+    return 0;
+}
+
+extern "C" int fargo_stage_viscosity(fargo_ctx *c, double dt)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    if (ensure_v_in_B(c))
+	return 1;
+    if (launch_stress(c))
+	return 1;
+    LAUNCH(c, k_viscosity_v, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, c->trr, c->tpp, c->trp, c->cf_r,
+	   c->cf_phi, c->vrB, c->vpB, dt);
+    return 0;
+}
+
+// beta_inv of thermal_relaxation (SourceEuler.cpp:645-653), host side (exp with glibc)
+static double beta_inv_host(const fargo_ctx *c)
+{
+    const fargo_params &p = c->v.p;
+    double beta_inv = 1 / p.cooling_beta_value;
+    if (p.cooling_beta_ramp_up > 0.0) {
+	const double a = 2 * c->v.time / p.cooling_beta_ramp_up;
+	const double ramp_factor = 1 - exp(-(a * a));
+	beta_inv = beta_inv * ramp_factor;
+    }
+    return beta_inv;
+}
+
+extern "C" int fargo_stage_substep3(fargo_ctx *c, double dt)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    if (!c->v.p.adiabatic)
+	return 0;
+    LAUNCH(c, k_substep3, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, c->nu, c->divv, c->trr, c->tpp,
+	   c->trp, c->sigma0, c->energy0, c->energy, c->qplus, c->qminus, dt, beta_inv_host(c), 1);
+    return 0;
+}
+
+// find_cell_id.cpp:218-291 (host, glibc log/pow like the reference)
+static int rmed_id(const fargo_ctx *c, double r)
+{
+    const fargo_params &p = c->v.p;
+    if (p.radial_spacing == FARGO_SPACING_LOG) {
+	const double gf = pow(p.rmax / p.rmin, 1.0 / ((double)p.nrad - 2.0));
+	const double optimization_const = 3.0 / 2.0 / p.rmin * (1 - pow(gf, 2.0)) / (1 - pow(gf, 3.0));
+	const double inv_log_gf = 1.0 / log(gf);
+	const double did = log(r * optimization_const) * inv_log_gf;
+	return (int)floor(did) - c->v.imin + 1;
+    }
+    int id = 0;
+    while (id < c->v.nr + 1 && c->h_rmed[id] < r)
+	id++;
+    return id - 1;
+}
+static int rinf_id(const fargo_ctx *c, double r)
+{
+    const fargo_params &p = c->v.p;
+    if (p.radial_spacing == FARGO_SPACING_LOG) {
+	const double gf = pow(p.rmax / p.rmin, 1.0 / ((double)p.nrad - 2.0));
+	const double inv_log_gf = 1.0 / log(gf);
+	const double did = log(r / p.rmin) * inv_log_gf;
+	return (int)floor(did) - c->v.imin + 1;
+    }
+    int id = 0;
+    while (id < c->v.nr + 1 && c->h_rinf[id] < r)
+	id++;
+    return id - 1;
+}
+static int clamp_id(const fargo_ctx *c, int id, bool is_vector)
+{
+    const int mx = c->v.nr - (is_vector ? 0 : 1);
+    return id < 0 ? 0 : (id > mx ? mx : id);
+}
+
+// damping of one field (damping.cpp:311-752): host computes the ring range and exp factors, device applies
+static int damp_field(fargo_ctx *c, double *x, const double *x0, bool is_vector, bool is_density, const int type[2], double dt,
+		      double *d_expf, double *h_expf)
+{
+    const fargo_params &p = c->v.p;
+    const int rings = c->v.nr + (is_vector ? 1 : 0);
+    const std::vector<double> &radius = is_vector ? c->h_rinf : c->h_rmed;
+    const double RMIN = p.rmin, RMAX = p.rmax;
+    const double x0_const = is_density ? p.sigma_floor * p.sigma0 : 0.0;
+    struct Zone { int lo, hi, type; } zones[2];
+    int nz = 0;
+    for (int n = 0; n < rings; ++n)
+	h_expf[n] = 1.0;
+    if (type[0] != FARGO_DAMP_NONE && (p.damping_inner_limit > 1.0) && (radius[0] < RMIN * p.damping_inner_limit)) {
+	const int limit = is_vector ? clamp_id(c, rinf_id(c, RMIN * p.damping_inner_limit), true)
+				    : clamp_id(c, rmed_id(c, RMIN * p.damping_inner_limit), false);
+	const double tau = p.damping_time_factor * 2.0 * M_PI / omega_kepler_host(p, RMIN);
+	for (int n = 0; n <= limit; ++n) {
+	    const double q = (radius[n] - RMIN * p.damping_inner_limit) / (RMIN - RMIN * p.damping_inner_limit);
+	    const double factor = q * q;
+	    h_expf[n] = exp(-dt * factor / tau);
+	}
+	zones[nz++] = {0, limit + 1, type[0]};
+    }
+    if (type[1] != FARGO_DAMP_NONE && (p.damping_outer_limit < 1.0) && (radius[rings - 1] > RMAX * p.damping_outer_limit)) {
+	const int limit = is_vector ? clamp_id(c, rinf_id(c, RMAX * p.damping_outer_limit) + 1, true)
+				    : clamp_id(c, rmed_id(c, RMAX * p.damping_outer_limit) + 1, false);
+	const double tau = p.damping_time_factor * 2.0 * M_PI / omega_kepler_host(p, p.damping_time_radius_outer);
+	for (int n = limit; n < rings; ++n) {
+	    const double q = (radius[n] - RMAX * p.damping_outer_limit) / (RMAX - RMAX * p.damping_outer_limit);
+	    const double factor = q * q;
+	    h_expf[n] = exp(-dt * factor / tau);
+	}
+	zones[nz++] = {limit, rings, type[1]};
+    }
+    if (nz == 0)
+	return 0;
+    CUDA_OK(cudaMemcpyAsync(d_expf, h_expf, rings * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    for (int z = 0; z < nz; ++z) {
+	const int nrings = zones[z].hi - zones[z].lo;
+	if (nrings <= 0)
+	    continue;
+	const unsigned gx = zones[z].type == FARGO_DAMP_MEAN ? 1u : (unsigned)((c->v.ns + 255) / 256);
+	dim3 grid(gx, (unsigned)nrings);
+	LAUNCH(c, k_damping, grid, 256, 0, c->v, x, x0, d_expf, zones[z].lo, zones[z].hi, zones[z].type, x0_const);
+    }
+    return 0;
+}
+
+extern "C" int fargo_stage_boundary(fargo_ctx *c, double dt, int final_call)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    const fargo_params &p = c->v.p;
+    VBuf v = cur_v(c, c->v_in_B);
+    if (final_call && p.damping) { // order: vrad, vazi, sigma, energy (damping.cpp:204-270)
+	const int st = c->v.nr + 2;
+	double *h = c->h_pin + 8, *d = c->expf_s;
+	CUDA_OK(cudaEventSynchronize(c->ev_pin)); // the previous step's copies out of h_pin are done
+	if (damp_field(c, v.vr, c->vr0, true, false, p.damp_vrad, dt, d, h) ||
+	    damp_field(c, v.vp, c->vp0, false, false, p.damp_vazi, dt, d + st, h + st) ||
+	    damp_field(c, c->sigma, c->sigma0, false, true, p.damp_sigma, dt, d + 2 * st, h + 2 * st))
+	    return 1;
+	if (p.adiabatic && damp_field(c, c->energy, c->energy0, false, false, p.damp_energy, dt, d + 3 * st, h + 3 * st))
+	    return 1;
+	CUDA_OK(cudaEventRecord(c->ev_pin, c->stream));
+    }
+    // keplerian_azimuthal.cpp:29-38, :51-59 (host: sqrt with glibc == IEEE, value is per call)
+    const int Irad = c->v.nr - 1;
+    const double vk_in = p.keplerian_azimuthal_factor[0] * sqrt(p.G * p.hydro_center_mass / c->h_rmed[0]) - c->h_rmed[0] * c->v.b.omega_frame;
+    const double vk_out =
+	p.keplerian_azimuthal_factor[1] * sqrt(p.G * p.hydro_center_mass / c->h_rmed[Irad]) - c->h_rmed[Irad] * c->v.b.omega_frame;
+    LAUNCH(c, k_boundary, (unsigned)((c->v.ns + 255) / 256), 256, 0, c->v, c->sigma, c->energy, v.vr, v.vp, c->sigma0, c->energy0,
+	   c->vr0, c->vp0, vk_in, vk_out);
+    return 0;
+}
+
+template <int LIM> static int launch_transport(fargo_ctx *c, double dt)
+{
+    const DevView &v = c->v;
+    // ring means of the pre-transport v_azi, Nshift, constant residual
+    LAUNCH(c, k_ring_mean, cells_grid((long long)v.nr * 32), 256, 0, v, c->vpB, c->vmean, c->nshift, c->vconst, dt, 1);
+    {
+	dim3 grid((unsigned)((v.ns + 127) / 128), (unsigned)((v.nr + c->rad_chunk - 1) / c->rad_chunk));
+	if (v.p.adiabatic)
+	    LAUNCH(c, (k_transport_radial<LIM, true>), grid, 128, 0, v, c->sigma, c->vrB, c->vpB, c->energy, c->t_sigma, c->t_rmp,
+		   c->t_rmm, c->t_amp, c->t_amm, c->t_e, dt, c->rad_chunk);
+	else
+	    LAUNCH(c, (k_transport_radial<LIM, false>), grid, 128, 0, v, c->sigma, c->vrB, c->vpB, c->energy, c->t_sigma, c->t_rmp,
+		   c->t_rmm, c->t_amp, c->t_amm, c->t_e, dt, c->rad_chunk);
+    }
+    {
+	const int S = c->az_S, L = S + AZ_HL + AZ_HR;
+	const size_t smem = ((size_t)(3 * AZ_NQ + 1) * L + 2 * S) * sizeof(double);
+	dim3 grid((unsigned)((v.ns + S - 1) / S), (unsigned)((v.nr + c->az_R - 1) / c->az_R));
+	LAUNCH(c, k_transport_azimuthal<LIM>, grid, 256, smem, v, c->t_sigma, c->t_rmp, c->t_rmm, c->t_amp, c->t_amm, c->t_e, c->vpB,
+	       c->vrB, c->vmean, c->nshift, c->vconst, c->sigma, c->vrA, c->vpA, c->energy, dt, S, c->az_R);
+    }
+    return 0;
+}
+
+extern "C" int fargo_stage_transport(fargo_ctx *c, double dt)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    if (ensure_v_in_B(c))
+	return 1;
+    int rc = c->v.p.flux_limiter == FARGO_LIMITER_MC ? launch_transport<FARGO_LIMITER_MC>(c, dt)
+						      : launch_transport<FARGO_LIMITER_VANLEER>(c, dt);
+    if (rc)
+	return rc;
+    c->v_in_B = false;
+    return 0;
+}
+
+// CommunicateBoundaries (commbound.cpp:98-182): rings are contiguous, so the CPUOVERLAP rings of each field go
+// straight from / to field memory — no pack / unpack.
+extern "C" int fargo_stage_halo(fargo_ctx *c)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    if (c->v.nranks == 1)
+	return 0;
+    if (c->v_in_B)
+	return fail("stage_halo called mid-step");
+    const size_t l = (size_t)FARGO_CPUOVERLAP * c->v.ns;
+    const size_t oo = (size_t)(c->v.nr - FARGO_CPUOVERLAP) * c->v.ns;
+    const size_t o = (size_t)(c->v.nr - 2 * FARGO_CPUOVERLAP) * c->v.ns;
+    double *fields[4] = {c->sigma, c->vrA, c->vpA, c->energy};
+    const int nf = c->v.p.adiabatic ? 4 : 3;
+    const int prev = c->v.rank - 1, next = c->v.rank + 1;
+    NCCL_OK(g_nccl.GroupStart());
+    for (int f = 0; f < nf; ++f) {
+	if (c->v.rank > 0) {
+	    NCCL_OK(g_nccl.Send(fields[f] + l, l, ncclFloat64, prev, c->comm, c->stream));
+	    NCCL_OK(g_nccl.Recv(fields[f], l, ncclFloat64, prev, c->comm, c->stream));
+	}
+	if (c->v.rank < c->v.nranks - 1) {
+	    NCCL_OK(g_nccl.Send(fields[f] + o, l, ncclFloat64, next, c->comm, c->stream));
+	    NCCL_OK(g_nccl.Recv(fields[f] + oo, l, ncclFloat64, next, c->comm, c->stream));
+	}
+    }
+    NCCL_OK(g_nccl.GroupEnd());
+    c->launches++;
+    return 0;
+}
+
+// recalculate_derived_disk_quantities (SourceEuler.cpp:225-249): T, c_s, H, P, nu are functions of (Sigma, e)
+// that every consumer here re-evaluates in registers, so there is nothing to store.
+extern "C" int fargo_stage_derived(fargo_ctx *c)
+{
+    (void)c;
+    return 0;
+}
+
+// init_euler's compute_heating_cooling_for_CFL (SourceEuler.cpp:1410-1450)
+extern "C" int fargo_init_derived(fargo_ctx *c)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    if (!c->v.p.adiabatic)
+	return 0;
+    if (launch_stress(c))
+	return 1;
+    LAUNCH(c, k_substep3, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, c->nu, c->divv, c->trr, c->tpp,
+	   c->trp, c->sigma0, c->energy0, c->energy, c->qplus, c->qminus, 0.0, beta_inv_host(c), 0);
+    return 0;
+}
+
+extern "C" int fargo_condition_cfl(fargo_ctx *c, double *out)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    const DevView &v = c->v;
+    if (c->v_in_B)
+	return fail("condition_cfl called mid-step");
+    c->h_pin[0] = 1.7976931348623157e308;
+    CUDA_OK(cudaMemcpyAsync(c->d_dt, c->h_pin, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, k_ring_mean, cells_grid((long long)v.nr * 32), 256, 0, v, c->vpA, c->vmean, c->nshift, c->vconst, 0.0, 0);
+    const int nact = v.active_size - v.first_active;
+    if (nact > 0)
+	LAUNCH(c, k_cfl, cells_grid((long long)nact * v.ns), 256, 0, v, c->sigma, c->energy, c->vrA, c->vpA, c->qplus, c->qminus,
+	       c->cf_r, c->cf_phi, c->vmean, c->d_dt);
+    if (v.nranks > 1) { // MPI_Allreduce(MIN), cfl.cpp:379
+	NCCL_OK(g_nccl.AllReduce(c->d_dt, c->d_dt, 1, ncclFloat64, ncclMin, c->comm, c->stream));
+	c->launches++;
+    }
+    CUDA_OK(cudaMemcpyAsync(c->h_pin + 1, c->d_dt, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    *out = c->h_pin[1];
+    return 0;
+}
+
+// sim::CalculateTimeStep (simulation.cpp:100-118)
+extern "C" int fargo_cfl(fargo_ctx *c, double *last_dt, double *dt_out)
+{
+    double cfl_dt;
+    if (fargo_condition_cfl(c, &cfl_dt))
+	return 1;
+    const double lim = c->v.p.cfl_max_var * *last_dt;
+    const double rv = (cfl_dt < lim) ? cfl_dt : lim; // std::min(CFL_max_var * last_dt, cfl_dt)
+    *last_dt = rv;
+    *dt_out = rv;
+    return 0;
+}
+
+// gas part of step_Euler (simulation.cpp:167-175, 187-218, 230-266)
+extern "C" int fargo_step(fargo_ctx *c, double dt)
+{
+    if (fargo_stage_potential(c) || fargo_stage_sources(c, dt) || fargo_stage_artvisc(c, dt) || fargo_stage_viscosity(c, dt))
+	return 1;
+    if (c->v.p.adiabatic && fargo_stage_substep3(c, dt))
+	return 1;
+    if (fargo_stage_boundary(c, 0.0, 0) || fargo_stage_transport(c, dt))
+	return 1;
+    c->v.time += dt;
+    if (fargo_stage_halo(c) || fargo_stage_boundary(c, dt, 1) || fargo_stage_derived(c))
+	return 1;
+    return 0;
+}
+
+extern "C" int fargo_get_nshift(fargo_ctx *c, int *out)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaMemcpyAsync(out, c->nshift, (size_t)c->v.nr * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
