@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py — hydro cell-updates/s (FP64) of the B200-native FargoCPT hydro step.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's own CPU build (oracle/_ref)
+
+A "step" is one iteration of sim::run's loop (simulation.cpp:515-553): CalculateTimeStep (CFL reduction, dt read
+back by the host) followed by the gas part of step_Euler (sources, artificial + physical viscosity, SubStep3,
+boundaries, Transport, halo exchange, damping).  Workload at every N: BASELINE.json configs[4], the
+8192 x 16384 adiabatic planet-disk (strong scaling: the global grid is fixed and split radially over N GPUs).
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import math
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "hydro cell-updates/s (FP64)"
+UNIT = "cell-updates/s"
+# algorithmic bytes per cell-update, SURVEY.md §8d / DESIGN.md: adiabatic 400 B (+96 f in damping zones)
+B_ALG = {"adiabatic_planet": 400.0, "cold_disk_planet": 312.0, "isothermal_planet": 280.0}
+# algorithmic bytes per cell of each kernel (reads + writes of live state arrays only; DESIGN.md "Kernels")
+KERNEL_BYTES = {
+    "k_transport_azimuthal<LIM>": 88.0, "(k_transport_radial<LIM, true>)": 80.0, "(k_transport_radial<LIM, false>)": 64.0,
+    "k_potential": 24.0, "k_sources_velocity": 56.0, "k_compression_heating": 32.0, "k_artvisc_q": 56.0,
+    "k_artvisc_v": 56.0, "k_viscosity_nu": 24.0, "k_stress": 64.0, "k_viscosity_v": 64.0, "k_substep3": 96.0,
+    "k_cfl": 48.0, "k_ring_mean": 8.0,
+}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([x.strip() for x in line.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload_config(args):
+    from fargocpt_b200 import synthetic
+    return synthetic.make_config(args.physics, args.nrad, args.naz)
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """Times the UNMODIFIED reference (oracle/_ref/fargocpt_exe_fast, the reference's own -Ofast flags, OpenMP over
+    all host cores) on a bounded sample of the workload: same physics, same Naz, same dr/r, fewer rings."""
+    import yaml
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    exe = os.path.join(ROOT, "oracle", "_ref", "fargocpt_exe_fast")
+    kind = "reference"
+    cfg = workload_config(args)
+    nrad_s = min(args.ref_nrad, args.nrad)
+    # keep the logarithmic cell aspect ratio: same dr/r, annulus centred on the planet orbit
+    growth = math.pow(float(cfg["Rmax"]) / float(cfg["Rmin"]), 1.0 / (args.nrad - 2.0))
+    half = growth ** ((nrad_s - 2) / 2.0)
+    rmin_s, rmax_s = 1.0 / half, half
+    cores = os.cpu_count() or 1
+    steps, warm = max(args.steps, 1), max(args.warmup, 0)
+    if not os.path.exists(exe):
+        # fall back to the oracle port (the one other place bench.py may execute oracle/)
+        val, sample = time_oracle_port(args, nrad_s, rmin_s, rmax_s, steps + warm)
+        kind = "port"
+    else:
+        ycfg = {
+            "DiskFeedback": "no", "MonitorTimestep": 1.0e9, "Nmonitor": 1, "Nsnapshots": 1, "FirstDT": cfg["FirstDT"],
+            "l0": "30 au", "m0": "1 solMass", "SelfGravity": "No", "RadiativeDiffusion": "No", "Disk": "yes", "Frame": "F",
+            "cps": -1, "DoWrite1DFiles": "No", "WriteAtEveryTimestep": "No", "RandomSigma": "No", "IntegrateParticles": "no",
+            "HydroFrameCenter": "primary", "LogAfterSteps": 0, "LogAfterRealSeconds": 3600, "IndirectTermMode": 0,
+            "ShockTube": 0,
+        }
+        for k, v in cfg.items():
+            if k not in ("planet_mass",):
+                ycfg[k] = v
+        ycfg.update({"Nrad": nrad_s, "Naz": args.naz, "Rmin": rmin_s, "Rmax": rmax_s})
+        nb = [{"name": "Star", "semi-major axis": 0.0, "mass": "1 solMass", "eccentricity": 0, "radius": "1 solRadius",
+               "temperature": 0}]
+        if cfg.get("planet_mass", 0) > 0:
+            nb.append({"name": "planet", "semi-major axis": 1, "mass": float(cfg["planet_mass"]), "accretion efficiency": 0.0,
+                       "eccentricity": 0.0, "radius": "0.01 solRadius", "temperature": "0 K", "ramp-up time": 0})
+        ycfg["nbody"] = nb
+        tmp = tempfile.mkdtemp(prefix="bench_ref_")
+        ycfg["OutputDir"] = os.path.join(tmp, "out")
+        ypath = os.path.join(tmp, "cfg.yml")
+        yaml.safe_dump(ycfg, open(ypath, "w"), sort_keys=False)
+        env = dict(os.environ, OMP_NUM_THREADS=str(cores), OMP_PROC_BIND="close", OMP_PLACES="cores")
+
+        def run(nsteps):
+            t0 = time.time()
+            res = subprocess.run([exe, "-N", str(nsteps), "start", ypath], cwd=tmp, env=env, capture_output=True, text=True)
+            m = re.search(r"Total Hydrosteps (\d+).*?Walltime ([0-9.eE+-]+) seconds", res.stdout)
+            if res.returncode != 0 or not m:
+                raise RuntimeError("reference run failed: " + res.stdout[-800:] + res.stderr[-800:])
+            return int(m.group(1)), float(m.group(2)), time.time() - t0
+        # the binary has no warm-up notion: time W steps and W+K steps and difference them
+        nw, tw, _ = run(warm) if warm > 0 else (0, 0.0, 0.0)
+        nt, tt, _ = run(warm + steps)
+        sec = max(tt - tw, 1e-9)
+        val = nrad_s * args.naz * (nt - nw) / sec
+        sample = (f"unmodified reference -Ofast -march=x86-64-v3, np=1 (no MPI in image) x nt={cores}, {nrad_s}x{args.naz} annulus "
+                  f"r=[{rmin_s:.4f},{rmax_s:.4f}] of the {args.nrad}x{args.naz} grid (same dr/r, same physics), {nt - nw} timed steps")
+        ms = sec / (nt - nw) * 1e3
+    if kind == "port":
+        ms = nrad_s * args.naz / val * 1e3
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.physics} {args.nrad}x{args.naz} (BASELINE configs[4])", "sample_nrad": nrad_s},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def time_oracle_port(args, nrad_s, rmin_s, rmax_s, nsteps):
+    import reftools
+    from fargocpt_b200 import synthetic
+    cfg = synthetic.make_config(args.physics, nrad_s, args.naz, Rmin=rmin_s, Rmax=rmax_s)
+    radii = synthetic.radii_from_config(cfg)
+    params = synthetic.params_from_config(cfg)
+    ctx = reftools.OracleContext(params, radii)
+    t = drive(ctx, cfg, radii, nsteps, timed_from=1)
+    return nrad_s * args.naz * (nsteps - 1) / t["wall"], f"oracle port, {nrad_s}x{args.naz} annulus, {nsteps - 1} steps"
+
+
+def init_state(ctx, cfg, radii, fields=None):
+    from fargocpt_b200 import abi, synthetic
+    if fields is None:
+        fields = synthetic.disk_fields(cfg, radii)
+    ctx.upload(abi.SIGMA, fields["Sigma"])
+    ctx.upload(abi.ENERGY, fields["energy"])
+    ctx.upload(abi.VRAD, fields["vrad"])
+    ctx.upload(abi.VAZI, fields["vazi"])
+    orbit = synthetic.PlanetOrbit(cfg)
+    ctx.set_bodies(orbit.bodies(0.0))
+    ctx.set_time(0.0)
+    ctx.init_derived()
+    ctx.stage("boundary", 0.0, 0)
+    ctx.copy_initial_values()
+    return orbit, fields
+
+
+def drive(ctx, cfg, radii, nsteps, timed_from=0):
+    """Host time loop (sim::run) on an oracle context; returns wall seconds of steps [timed_from, nsteps)."""
+    orbit, _ = init_state(ctx, cfg, radii)
+    last_dt, t = float(cfg["FirstDT"]), 0.0
+    t0 = None
+    for k in range(nsteps):
+        if k == timed_from:
+            t0 = time.time()
+        dt = ctx.cfl(last_dt)
+        last_dt = dt
+        ctx.set_bodies(orbit.bodies(t, dt))
+        ctx.set_time(t)
+        ctx.step(dt)
+        t += dt
+    return {"wall": time.time() - t0}
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from fargocpt_b200 import HydroContext, abi, synthetic
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    uid = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf = torch.frombuffer(bytearray(abi.get_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(buf, 0)
+        uid = bytes(buf.cpu().numpy().tobytes())
+
+    cfg = workload_config(args)
+    radii = synthetic.radii_from_config(cfg)
+    params = synthetic.params_from_config(cfg)
+    ctx = HydroContext(params, radii, rank=rank, nranks=world, unique_id=uid, device=local)
+    ncell = args.nrad * args.naz
+
+    # host copy of the initial state in PINNED memory (e2e leg uploads from it)
+    fields = synthetic.disk_fields(cfg, radii)
+    pinned = {}
+    for k, v in fields.items():
+        t = torch.from_numpy(v).pin_memory()
+        pinned[k] = t.numpy()
+    orbit, _ = init_state(ctx, cfg, radii, pinned)
+    state = {"last_dt": float(cfg["FirstDT"]), "t": 0.0}
+
+    def one_step():
+        dt = ctx.cfl(state["last_dt"])
+        state["last_dt"] = dt
+        ctx.set_bodies(orbit.bodies(state["t"], dt))
+        ctx.set_time(state["t"])
+        ctx.step(dt)
+        state["t"] += dt
+
+    def barrier():
+        ctx.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    # ---- device-resident timed region (value) -------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    l0 = ctx.launch_count()
+    ctx.profile(True)
+    ctx.event_record(0)
+    for _ in range(args.steps):
+        one_step()
+    ctx.event_record(1)
+    ms = ctx.event_elapsed_ms(0, 1)
+    barrier()
+    prof = ctx.profile_report()
+    ctx.profile(False)
+    launches = ctx.launch_count() - l0
+    if world > 1:
+        tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    value = ncell * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end leg: host buffers in, host buffers out -------------------------------------------
+    # One snapshot interval as a user of the C ABI runs it: upload the four state fields from pinned host memory,
+    # K steps (each with its dt read-back), download the four state fields.  Bytes per step = totals / K.
+    out_host = {fid: torch.empty(ctx.global_shape(fid), dtype=torch.float64).pin_memory().numpy()
+                for fid in (abi.SIGMA, abi.VRAD, abi.VAZI, abi.ENERGY)}
+    barrier()
+    ctx.event_record(2)
+    t_e2e0 = time.time()
+    ctx.upload(abi.SIGMA, pinned["Sigma"])
+    ctx.upload(abi.ENERGY, pinned["energy"])
+    ctx.upload(abi.VRAD, pinned["vrad"])
+    ctx.upload(abi.VAZI, pinned["vazi"])
+    state["t"] = 0.0
+    for _ in range(args.steps):
+        one_step()
+    for fid in out_host:
+        ctx.download(fid, out_host[fid])
+    ctx.event_record(3)
+    ms_e2e = ctx.event_elapsed_ms(2, 3)
+    barrier()
+    if world > 1:
+        tms = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms_e2e = float(tms.item())
+    if rank == 0:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    slab_cells = ctx.nr * ctx.naz
+    h2d = (4 * slab_cells + ctx.naz) * 8 / args.steps
+    owned = sum(int(np.prod(ctx.global_shape(f))) for f in out_host) / world
+    d2h = owned * 8 / args.steps + 8  # + the dt scalar every step
+    e2e_val = ncell * args.steps / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel ---------------------------------------------------------------
+    peaks, peak_kind = measured_peaks()
+    top = max(prof.items(), key=lambda kv: kv[1][0]) if prof else (None, (0.0, 0))
+    total_kernel_ms = sum(v[0] for v in prof.values())
+    roof = None
+    if top[0]:
+        kname, (kms, kn) = top
+        bytes_per_cell = KERNEL_BYTES.get(kname, 0.0)
+        per_launch_bytes = bytes_per_cell * slab_cells
+        avg_s = kms / max(kn, 1) * 1e-3
+        achieved = per_launch_bytes / avg_s / 1e9 if avg_s > 0 else 0.0
+        roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
+                "traffic": None, "bytes_per_launch_algorithmic": per_launch_bytes, "avg_launch_ms": avg_s * 1e3,
+                "share_of_step": kms / total_kernel_ms if total_kernel_ms else None}
+    step_roof = B_ALG[args.physics] * value / world / 1e9  # whole-step algorithmic GB/s per GPU
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"{args.physics} {args.nrad}x{args.naz} (BASELINE configs[4]), radial slabs over {world} GPU(s)",
+                   "cells": ncell, "l2": "inputs larger than L2 (1.07 GB per field)" if ncell * 8 > 126e6 else "inputs fit L2",
+                   "b_alg_bytes_per_cell_update": B_ALG[args.physics]},
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "what": f"upload 4 state fields from pinned host memory + {args.steps} steps + download 4 fields, per snapshot interval"},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "step_roofline": {"achieved_gbs_per_gpu": step_roof, "frac_of_measured_peak": step_roof / peaks["hbm_gbs"],
+                          "frac_of_8tbs": step_roof / 8000.0},
+        "kernels_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args)
+    print(json.dumps(line))
+
+
+def cpu_baseline(args):
+    """The reference arm on a bounded sample, run in a subprocess so its threads do not disturb this process."""
+    try:
+        res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "6", "--warmup", "2",
+                              "--physics", args.physics, "--nrad", str(args.nrad), "--naz", str(args.naz),
+                              "--ref-nrad", str(args.ref_nrad)], capture_output=True, text=True, timeout=900)
+        for ln in res.stdout.splitlines()[::-1]:
+            if ln.startswith("{"):
+                return json.loads(ln)["cpu_baseline"]
+        return {"error": (res.stdout + res.stderr)[-400:]}
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--physics", default="adiabatic_planet", choices=list(B_ALG))
+    ap.add_argument("--nrad", type=int, default=8192)
+    ap.add_argument("--naz", type=int, default=16384)
+    ap.add_argument("--ref-nrad", type=int, default=256, help="rings of the CPU sample annulus")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

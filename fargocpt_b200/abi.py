@@ -242,6 +242,14 @@ def load_library():
         lib.fargo_sync.restype = C.c_int
         lib.fargo_launch_count.argtypes = [C.c_void_p]
         lib.fargo_launch_count.restype = C.c_longlong
+        lib.fargo_profile_enable.argtypes = [C.c_void_p, C.c_int]
+        lib.fargo_profile_enable.restype = C.c_int
+        lib.fargo_profile_report.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        lib.fargo_profile_report.restype = C.c_int
+        lib.fargo_event_record.argtypes = [C.c_void_p, C.c_int]
+        lib.fargo_event_record.restype = C.c_int
+        lib.fargo_event_elapsed_ms.argtypes = [C.c_void_p, C.c_int, C.c_int, _DP]
+        lib.fargo_event_elapsed_ms.restype = C.c_int
         _lib = lib
     return _lib
 
@@ -271,6 +279,27 @@ class HydroContext(Handle):
 
     def launch_count(self):
         return int(self.lib.fargo_launch_count(self.ptr))
+
+    def event_record(self, slot):
+        self._check(self.lib.fargo_event_record(self.ptr, slot), "event_record")
+
+    def event_elapsed_ms(self, a, b):
+        ms = C.c_double(0.0)
+        self._check(self.lib.fargo_event_elapsed_ms(self.ptr, a, b, C.byref(ms)), "event_elapsed_ms")
+        return ms.value
+
+    def profile(self, on):
+        self._check(self.lib.fargo_profile_enable(self.ptr, int(on)), "profile_enable")
+
+    def profile_report(self):
+        """{kernel: (total_ms, launches)} since profile(True)."""
+        buf = C.create_string_buffer(1 << 16)
+        self.lib.fargo_profile_report(self.ptr, buf, len(buf))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, ms, n = line.rsplit(" ", 2)
+            out[name] = (float(ms), int(n))
+        return out
 
     def close(self):
         if self.ptr:

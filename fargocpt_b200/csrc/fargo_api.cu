@@ -120,7 +120,51 @@ struct fargo_ctx {
     bool v_in_B = false; // where the current velocities live (see stage_sources)
     cudaEvent_t ev_pin = nullptr; // completion of the last H2D copy out of h_pin
     int az_S, az_R, rad_chunk;
+    cudaEvent_t ev_user[4] = {nullptr, nullptr, nullptr, nullptr}; // fargo_event_record slots
+    // optional per-kernel device timing (bench.py roofline): CUDA events on the launching stream
+    bool profiling = false;
+    struct KStat { std::string name; double ms = 0; long long n = 0; };
+    std::vector<KStat> kstats;
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
 };
+
+static int kstat_id(fargo_ctx *c, const char *name)
+{
+    for (size_t k = 0; k < c->kstats.size(); ++k)
+	if (c->kstats[k].name == name)
+	    return (int)k;
+    fargo_ctx::KStat s;
+    s.name = name;
+    c->kstats.push_back(s);
+    return (int)c->kstats.size() - 1;
+}
+static void prof_begin(fargo_ctx *c, const char *name)
+{
+    std::pair<cudaEvent_t, cudaEvent_t> ev;
+    if (!c->ev_pool.empty()) {
+	ev = c->ev_pool.back();
+	c->ev_pool.pop_back();
+    } else {
+	cudaEventCreate(&ev.first);
+	cudaEventCreate(&ev.second);
+    }
+    cudaEventRecord(ev.first, c->stream);
+    c->pending.push_back({kstat_id(c, name), ev});
+}
+static void prof_end(fargo_ctx *c) { cudaEventRecord(c->pending.back().second.second, c->stream); }
+static void prof_collect(fargo_ctx *c)
+{
+    cudaStreamSynchronize(c->stream);
+    for (auto &p : c->pending) {
+	float ms = 0;
+	cudaEventElapsedTime(&ms, p.second.first, p.second.second);
+	c->kstats[p.first].ms += ms;
+	c->kstats[p.first].n += 1;
+	c->ev_pool.push_back(p.second);
+    }
+    c->pending.clear();
+}
 
 static int dalloc(fargo_ctx *c, double **p, size_t n)
 {
@@ -268,6 +312,9 @@ extern "C" void fargo_ctx_destroy(fargo_ctx *c)
 	cudaFreeHost(c->h_pin);
     if (c->ev_pin)
 	cudaEventDestroy(c->ev_pin);
+    for (int k = 0; k < 4; ++k)
+	if (c->ev_user[k])
+	    cudaEventDestroy(c->ev_user[k]);
     if (c->stream)
 	cudaStreamDestroy(c->stream);
     delete c;
@@ -399,7 +446,11 @@ extern "C" int fargo_sync(fargo_ctx *c)
 
 #define LAUNCH(c, kernel, grid, block, smem, ...)                        \
     do {                                                                 \
+	if ((c)->profiling)                                              \
+	    prof_begin(c, #kernel);                                      \
 	kernel<<<grid, block, smem, (c)->stream>>>(__VA_ARGS__);         \
+	if ((c)->profiling)                                              \
+	    prof_end(c);                                                 \
 	(c)->launches++;                                                 \
 	cudaError_t _e = cudaGetLastError();                             \
 	if (_e != cudaSuccess)                                           \
@@ -872,5 +923,60 @@ extern "C" int fargo_get_nshift(fargo_ctx *c, int *out)
     CUDA_OK(cudaSetDevice(c->device));
     CUDA_OK(cudaMemcpyAsync(out, c->nshift, (size_t)c->v.nr * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-kernel device timing for bench.py (CUDA events on the context's stream)
+extern "C" int fargo_profile_enable(fargo_ctx *c, int on)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    prof_collect(c);
+    c->profiling = on != 0;
+    if (on)
+	for (auto &k : c->kstats) {
+	    k.ms = 0;
+	    k.n = 0;
+	}
+    return 0;
+}
+// writes "name ms count\n" lines into buf; returns the number of bytes needed
+extern "C" int fargo_profile_report(fargo_ctx *c, char *buf, int buflen)
+{
+    cudaSetDevice(c->device);
+    prof_collect(c);
+    std::string out;
+    char line[256];
+    for (auto &k : c->kstats) {
+	snprintf(line, sizeof(line), "%s %.6f %lld\n", k.name.c_str(), k.ms, k.n);
+	out += line;
+    }
+    if (buf && buflen > 0) {
+	strncpy(buf, out.c_str(), buflen - 1);
+	buf[buflen - 1] = 0;
+    }
+    return (int)out.size() + 1;
+}
+
+// device-side wall clock for callers that cannot see the context's stream (bench.py): 4 event slots
+extern "C" int fargo_event_record(fargo_ctx *c, int slot)
+{
+    if (slot < 0 || slot >= 4)
+	return fail("event slot %d out of range", slot);
+    CUDA_OK(cudaSetDevice(c->device));
+    if (!c->ev_user[slot])
+	CUDA_OK(cudaEventCreate(&c->ev_user[slot]));
+    CUDA_OK(cudaEventRecord(c->ev_user[slot], c->stream));
+    return 0;
+}
+extern "C" int fargo_event_elapsed_ms(fargo_ctx *c, int slot_a, int slot_b, double *ms_out)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    if (slot_a < 0 || slot_a >= 4 || slot_b < 0 || slot_b >= 4 || !c->ev_user[slot_a] || !c->ev_user[slot_b])
+	return fail("event slots not recorded");
+    CUDA_OK(cudaEventSynchronize(c->ev_user[slot_b]));
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, c->ev_user[slot_a], c->ev_user[slot_b]));
+    *ms_out = ms;
     return 0;
 }

@@ -209,6 +209,13 @@ int fargo_get_nshift(fargo_ctx *ctx, int *out_local_nrad);
 int fargo_sync(fargo_ctx *ctx);
 long long fargo_launch_count(const fargo_ctx *ctx);
 
+/* per-kernel device timing (CUDA events on the context stream); report = "kernel ms count" lines */
+int fargo_profile_enable(fargo_ctx *ctx, int on);
+int fargo_profile_report(fargo_ctx *ctx, char *buf, int buflen);
+/* device-side wall clock on the context's stream: 4 event slots */
+int fargo_event_record(fargo_ctx *ctx, int slot);
+int fargo_event_elapsed_ms(fargo_ctx *ctx, int slot_a, int slot_b, double *ms_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,108 +79,7 @@ class OracleContext(abi.Handle):
             self.ptr = None
 
 
-# ---------------------------------------------------------------------------------------------
-# config -> params (mirror of the subset of parameters.cpp / Interpret.cpp / boundary_conditions/config.cpp
-# the hot path reads).  `consts` = code-unit constants as the reference printed them (constants.yml).
-
-def _flag(v, default=False):
-    if v is None:
-        return default
-    if isinstance(v, bool):
-        return v
-    return str(v).strip().lower()[0] in ("y", "t", "1")
-
-
-def _num(v, unit_cgs=None):
-    """'3 K' with unit_cgs=<code temperature unit in K> -> 3/unit; plain numbers are code units."""
-    if isinstance(v, (int, float)):
-        return float(v)
-    parts = str(v).split()
-    x = float(parts[0])
-    if len(parts) > 1 and unit_cgs is not None:
-        return x / unit_cgs
-    return x
-
-
-def params_from_config(cfg, consts, nrad, naz, temp_unit_K=1.0):
-    g = {k.lower(): v for k, v in cfg.items()}
-
-    def get(key, default=None):
-        return g.get(key.lower(), default)
-
-    d = {}
-    d["nrad"], d["naz"] = int(nrad), int(naz)
-    spacing = {"l": "logarithmic", "a": "arithmetic", "e": "exponential"}.get(
-        str(get("RadialSpacing", "Arithmetic")).lower()[:1], "custom")
-    d["radial_spacing"] = abi.SPACING[spacing]
-    d["rmin"], d["rmax"] = float(get("Rmin")), float(get("Rmax"))
-    eos = str(get("EquationOfState", "Isothermal")).lower()
-    d["adiabatic"] = 1 if eos in ("ideal", "adiabatic", "perfect") else 0
-    d["gamma"] = float(get("AdiabaticIndex", 1.4))
-    d["mu"] = float(get("mu", 1.0))
-    d["aspectratio_ref"] = float(get("AspectRatio", 0.05))
-    d["flaring_index"] = float(get("FlaringIndex", 0.0))
-    d["sigma0"] = _num(get("Sigma0", 173.0))
-    d["sigma_floor"] = float(get("SigmaFloor", 1e-9))
-    d["sigma_slope"] = float(get("SigmaSlope", 0.0))
-    d["minimum_temperature"] = _num(get("MinimumTemperature", "3 K"), temp_unit_K)
-    d["maximum_temperature"] = _num(get("MaximumTemperature", "1e100 K"), temp_unit_K)
-    d["G"], d["Rgas"], d["sigma_sb"], d["c_light"] = consts["G"], consts["R"], consts["sigma"], consts["c"]
-    d["hydro_center_mass"] = consts.get("hydro_center_mass", 1.0)
-    d["cfl"] = float(get("CFL", 0.5))
-    d["cfl_max_var"] = float(get("CFLmaxVar", 1.1))
-    d["heating_cooling_cfl_limit"] = float(get("HeatingCoolingCFLlimit", 1.0))
-    integ = str(get("Integrator", "Euler")).lower()
-    d["leapfrog"] = 0 if integ.startswith("e") else 1
-    d["fast_transport"] = 1 if str(get("Transport", "FARGO")).lower().startswith("f") else 0
-    # Interpret.cpp:640-664 compares case-sensitively: only the exact strings "mc" / "m" select MC
-    d["flux_limiter"] = 1 if str(get("FluxLimiter", "VanLeer")) in ("mc", "m") else 0
-    d["artificial_viscosity"] = abi.ARTVISC[str(get("ArtificialViscosity", "SN")).lower()]
-    d["artificial_viscosity_factor"] = float(get("ArtificialViscosityFactor", 1.41))
-    d["artificial_viscosity_dissipation"] = int(_flag(get("ArtificialViscosityDissipation"), True))
-    d["viscous_alpha"] = float(get("ViscousAlpha", 0.0))
-    d["constant_viscosity"] = _num(get("ConstantViscosity", 0.0))
-    d["stabilize_viscosity"] = int(get("StabilizeViscosity", 0))
-    d["radial_viscosity_factor"] = float(get("RadialViscosityFactor", 1.0))
-    d["heating_viscous"] = int(_flag(get("HeatingViscous"), False))
-    d["heating_viscous_factor"] = float(get("HeatingViscousFactor", 1.0))
-    d["cooling_beta"] = int(_flag(get("CoolingBetaLocal"), False))
-    d["cooling_beta_value"] = float(get("CoolingBeta", 1.0))
-    d["cooling_beta_ramp_up"] = _num(get("CoolingBetaRampUp", 0.0))
-    d["cooling_beta_reference"] = abi.BETA_REF[str(get("CoolingBetaReference", "zero")).lower()]
-    d["body_force_from_potential"] = int(_flag(get("BodyForceFromPotential"), True))
-    d["thickness_smoothing"] = float(get("ThicknessSmoothing", 0.0))
-    d["imposed_disk_drift"] = float(get("ImposedDiskDrift", 0.0))
-
-    # boundaries: composite names (boundary_conditions/config.cpp:345-436) or individual keys
-    comp = {"zerogradient": ("zerogradient", "zerogradient", "zerogradient"),
-            "outflow": ("zerogradient", "zerogradient", "outflow"),
-            "reflecting": ("zerogradient", "zerogradient", "reflecting"),
-            "reference": ("reference", "reference", "reference")}
-    for side, name in ((0, "Inner"), (1, "Outer")):
-        c = str(get(name + "Boundary", "individual")).lower()
-        if c in comp:
-            s, e, vr = comp[c]
-        else:
-            s = str(get(name + "BoundarySigma", "zerogradient")).lower()
-            e = str(get(name + "BoundaryEnergy", "zerogradient")).lower()
-            vr = str(get(name + "BoundaryVrad", "zerogradient")).lower()
-        va = str(get(name + "BoundaryVazi", "keplerian")).lower()
-        d.setdefault("bc_sigma", [0, 0])[side] = abi.BC[s]
-        d.setdefault("bc_energy", [0, 0])[side] = abi.BC[e]
-        d.setdefault("bc_vrad", [0, 0])[side] = abi.BC[vr]
-        d.setdefault("bc_vazi", [0, 0])[side] = abi.BC[va]
-        d.setdefault("keplerian_azimuthal_factor", [1.0, 1.0])[side] = float(
-            get(name + "BoundaryVaziKeplerianFactor", 1.0))
-    d["damping"] = int(_flag(get("Damping"), False))
-    d["damping_inner_limit"] = float(get("DampingInnerLimit", 1.05))
-    d["damping_outer_limit"] = float(get("DampingOuterLimit", 0.95))
-    d["damping_time_factor"] = float(get("DampingTimeFactor", 1.0))
-    d["damping_time_radius_outer"] = float(get("DampingTimeRadiusOuter", d["rmax"]))
-    for key, name in (("damp_vrad", "VRadial"), ("damp_vazi", "VAzimuthal"), ("damp_sigma", "SurfaceDensity"),
-                      ("damp_energy", "Energy")):
-        d[key] = [abi.DAMP[str(get("Damping" + name + side, "None")).lower()] for side in ("Inner", "Outer")]
-    return d
+from fargocpt_b200.config import params_from_config, _num, _flag  # noqa: E402,F401
 
 
 def make_params(d):
