@@ -33,7 +33,9 @@ UNIT = "cell-updates/s"
 B_ALG = {"adiabatic_planet": 400.0, "cold_disk_planet": 312.0, "isothermal_planet": 280.0}
 # algorithmic bytes per cell of each kernel (reads + writes of live state arrays only; DESIGN.md "Kernels")
 KERNEL_BYTES = {
-    "k_transport_azimuthal<LIM>": 88.0, "(k_transport_radial<LIM, true>)": 80.0, "(k_transport_radial<LIM, false>)": 64.0,
+    "(k_transport_azimuthal<LIM, true>)": 88.0, "(k_transport_azimuthal<LIM, false>)": 72.0,
+    "(k_transport_radial<LIM, true>)": 80.0, "(k_transport_radial<LIM, false>)": 64.0,
+    "k_fused_sources<ADI>": 56.0, "k_fused_artvisc<ADI>": 56.0, "k_fused_viscosity<ADI>": 72.0,
     "k_potential": 24.0, "k_sources_velocity": 56.0, "k_compression_heating": 32.0, "k_artvisc_q": 56.0,
     "k_artvisc_v": 56.0, "k_viscosity_nu": 24.0, "k_stress": 64.0, "k_viscosity_v": 64.0, "k_substep3": 96.0,
     "k_cfl": 48.0, "k_ring_mean": 8.0,

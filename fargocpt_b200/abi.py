@@ -238,6 +238,8 @@ def load_library():
         lib.fargo_get_unique_id.restype = C.c_int
         lib.fargo_stage_halo.argtypes = [C.c_void_p]
         lib.fargo_stage_halo.restype = C.c_int
+        lib.fargo_set_staged.argtypes = [C.c_void_p, C.c_int]
+        lib.fargo_set_staged.restype = C.c_int
         lib.fargo_sync.argtypes = [C.c_void_p]
         lib.fargo_sync.restype = C.c_int
         lib.fargo_launch_count.argtypes = [C.c_void_p]
@@ -276,6 +278,10 @@ class HydroContext(Handle):
 
     def sync(self):
         self._check(self.lib.fargo_sync(self.ptr), "sync")
+
+    def set_staged(self, on):
+        """step() through the per-stage kernels (one per reference loop nest) instead of the fused ones."""
+        self._check(self.lib.fargo_set_staged(self.ptr, int(on)), "set_staged")
 
     def launch_count(self):
         return int(self.lib.fargo_launch_count(self.ptr))

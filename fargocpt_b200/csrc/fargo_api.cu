@@ -19,6 +19,8 @@
 #include "kernels_ring.cuh"
 #include "kernels_source.cuh"
 #include "kernels_transport.cuh"
+#include "kernels_azimuthal.cuh"
+#include "kernels_fused.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // error handling: the reference die()s; we return non-zero and keep the message (thread-local)
@@ -106,8 +108,13 @@ struct fargo_ctx {
     // host geometry (local view incl. 2 extra entries) for host-side ring factors
     std::vector<double> h_radii, h_rinf, h_rsup, h_rmed;
     std::vector<double *> dev_allocs;
-    // state: A buffers are the "current" state between steps; B buffers hold v during the source stages
-    double *sigma, *energy, *vrA, *vpA, *vrB, *vpB;
+    // state.  energy, v_rad and v_azi are double-buffered: the fused kernels read one buffer and write the other
+    // (their column windows overlap on reads), and Transport cannot write v_azi where it still reads the residual
+    // velocity.  ecur / vcur name the buffer holding the state between stages; the staged source kernels keep
+    // their mid-step velocities in the other v buffer (v_mid).
+    double *sigma, *eb[2], *vrb[2], *vpb[2];
+    int ecur = 0, vcur = 0;
+    bool v_mid = false;
     double *sigma0, *energy0, *vr0, *vp0;
     double *qplus, *qminus;
     // stage scratch
@@ -117,9 +124,9 @@ struct fargo_ctx {
     int *nshift;
     double *h_pin; // pinned host staging for the CFL scalar + ring factors
     bool visc_const_filled = false;
-    bool v_in_B = false; // where the current velocities live (see stage_sources)
     cudaEvent_t ev_pin = nullptr; // completion of the last H2D copy out of h_pin
-    int az_S, az_R, rad_chunk;
+    int az_R, rad_chunk, fs_R;
+    bool force_staged = false;
     cudaEvent_t ev_user[4] = {nullptr, nullptr, nullptr, nullptr}; // fargo_event_record slots
     // optional per-kernel device timing (bench.py roofline): CUDA events on the launching stream
     bool profiling = false;
@@ -128,6 +135,13 @@ struct fargo_ctx {
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
 };
+
+// "A" = the buffer holding the velocities between stages, "B" = the other one (mid-step velocities of the staged path)
+#define VRA(c) ((c)->vrb[(c)->vcur])
+#define VPA(c) ((c)->vpb[(c)->vcur])
+#define VRB(c) ((c)->vrb[1 - (c)->vcur])
+#define VPB(c) ((c)->vpb[1 - (c)->vcur])
+#define EN(c) ((c)->eb[(c)->ecur])
 
 static int kstat_id(fargo_ctx *c, const char *name)
 {
@@ -369,8 +383,8 @@ extern "C" int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, con
     }
     TRY(init_geometry(c, radii));
     const size_t ns = (size_t)c->v.nr * c->v.ns, nv = (size_t)(c->v.nr + 1) * c->v.ns;
-    TRY(dalloc(c, &c->sigma, ns) || dalloc(c, &c->energy, ns) || dalloc(c, &c->vrA, nv) || dalloc(c, &c->vpA, ns) ||
-	dalloc(c, &c->vrB, nv) || dalloc(c, &c->vpB, ns));
+    TRY(dalloc(c, &c->sigma, ns) || dalloc(c, &c->eb[0], ns) || dalloc(c, &c->vrb[0], nv) || dalloc(c, &c->vpb[0], ns) ||
+	dalloc(c, &c->vrb[1], nv) || dalloc(c, &c->vpb[1], ns) || dalloc(c, &c->eb[1], params->adiabatic ? ns : 1));
     TRY(dalloc(c, &c->sigma0, ns) || dalloc(c, &c->energy0, ns) || dalloc(c, &c->vr0, nv) || dalloc(c, &c->vp0, ns));
     TRY(dalloc(c, &c->qplus, ns) || dalloc(c, &c->qminus, ns));
     TRY(dalloc(c, &c->pot, ns) || dalloc(c, &c->qr, ns) || dalloc(c, &c->qphi, ns) || dalloc(c, &c->nu, ns) ||
@@ -399,14 +413,16 @@ extern "C" int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, con
 	}
     }
     // launch geometry of the transport kernels
-    c->az_S = 247; // + 9 halo = 256 cells per ring segment
-    c->az_R = 32;
+    { // rings per warp of the azimuthal kernel: long marches amortise the one warm-up ring, short ones fill the GPU
+	const long long nwin = (c->v.ns + AZ_OUT - 1) / AZ_OUT;
+	long long R = ((long long)c->v.nr * nwin) / (148LL * 16);
+	c->az_R = (int)(R < 4 ? 4 : (R > 32 ? 32 : R));
+    }
     c->rad_chunk = 64;
-    {
-	const int L = c->az_S + AZ_HL + AZ_HR;
-	const size_t smem = ((size_t)(3 * AZ_NQ + 1) * L + 2 * c->az_S) * sizeof(double);
-	cudaFuncSetAttribute(k_transport_azimuthal<FARGO_LIMITER_VANLEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	cudaFuncSetAttribute(k_transport_azimuthal<FARGO_LIMITER_MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    { // rings per warp of the fused source kernels (one warm-up ring per march)
+	const long long nwin = (c->v.ns + FS_OUT - 1) / FS_OUT;
+	long long R = ((long long)c->v.nr * nwin) / (148LL * 16);
+	c->fs_R = (int)(R < 4 ? 4 : (R > 64 ? 64 : R));
     }
     if (nranks > 1) {
 	if (!nccl_unique_id) {
@@ -462,9 +478,9 @@ static double *state_ptr(fargo_ctx *c, int f, int *rings)
     *rings = c->v.nr;
     switch (f) {
     case FARGO_SIGMA: return c->sigma;
-    case FARGO_VRAD: *rings = c->v.nr + 1; return c->vrA;
-    case FARGO_VAZI: return c->vpA;
-    case FARGO_ENERGY: return c->energy;
+    case FARGO_VRAD: *rings = c->v.nr + 1; return c->vrb[c->v_mid ? 1 - c->vcur : c->vcur];
+    case FARGO_VAZI: return c->vpb[c->v_mid ? 1 - c->vcur : c->vcur];
+    case FARGO_ENERGY: return c->eb[c->ecur];
     case FARGO_SIGMA0: return c->sigma0;
     case FARGO_VRAD0: *rings = c->v.nr + 1; return c->vr0;
     case FARGO_VAZI0: return c->vp0;
@@ -484,7 +500,7 @@ static int materialize(fargo_ctx *c, int f, double **ptr, int *rings)
 	return 0;
     if (f == FARGO_TEMPERATURE || f == FARGO_PRESSURE || f == FARGO_SOUNDSPEED || f == FARGO_SCALE_HEIGHT || f == FARGO_VISCOSITY) {
 	*rings = c->v.nr;
-	LAUNCH(c, k_derived_field, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, c->energy, c->scratch, f);
+	LAUNCH(c, k_derived_field, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, EN(c), c->scratch, f);
 	*ptr = c->scratch;
 	return 0;
     }
@@ -539,10 +555,10 @@ extern "C" int fargo_copy_initial_values(fargo_ctx *c)
 {
     CUDA_OK(cudaSetDevice(c->device));
     const size_t ns = (size_t)c->v.nr * c->v.ns * sizeof(double), nv = (size_t)(c->v.nr + 1) * c->v.ns * sizeof(double);
-    CUDA_OK(cudaMemcpyAsync(c->vr0, c->vrA, nv, cudaMemcpyDeviceToDevice, c->stream));
-    CUDA_OK(cudaMemcpyAsync(c->vp0, c->vpA, ns, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(c->vr0, VRA(c), nv, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(c->vp0, VPA(c), ns, cudaMemcpyDeviceToDevice, c->stream));
     CUDA_OK(cudaMemcpyAsync(c->sigma0, c->sigma, ns, cudaMemcpyDeviceToDevice, c->stream));
-    CUDA_OK(cudaMemcpyAsync(c->energy0, c->energy, ns, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(c->energy0, EN(c), ns, cudaMemcpyDeviceToDevice, c->stream));
     return 0;
 }
 
@@ -564,38 +580,38 @@ extern "C" int fargo_set_time(fargo_ctx *c, double t)
 extern "C" int fargo_stage_potential(fargo_ctx *c)
 {
     CUDA_OK(cudaSetDevice(c->device));
-    LAUNCH(c, k_potential, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, c->energy, c->pot);
+    LAUNCH(c, k_potential, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, EN(c), c->pot);
     return 0;
 }
 
-// NOTE on buffers: between steps v lives in vrA/vpA.  stage_sources reads A and writes B; artvisc / viscosity
-// update B in place; Transport reads B and writes A.  When stages are called one by one (tests) the same
+// NOTE on buffers (staged path): between steps v lives in buffer A (= vcur).  stage_sources reads A and writes B;
+// artvisc / viscosity update B in place; Transport reads B and writes A.  When stages are called one by one (tests) the same
 // protocol holds because every per-stage entry point leaves the "current" v where the next stage expects it:
 // after sources..substep3 the current v is B, so the boundary stage must know which buffer is current.
 struct VBuf { double *vr, *vp; };
-static inline VBuf cur_v(fargo_ctx *c, bool in_B) { return in_B ? VBuf{c->vrB, c->vpB} : VBuf{c->vrA, c->vpA}; }
+static inline VBuf cur_v(fargo_ctx *c, bool mid) { return mid ? VBuf{VRB(c), VPB(c)} : VBuf{VRA(c), VPA(c)}; }
 
 extern "C" int fargo_stage_sources(fargo_ctx *c, double dt)
 {
     CUDA_OK(cudaSetDevice(c->device));
-    if (c->v_in_B)
+    if (c->v_mid)
 	return fail("stage_sources called while the velocities are mid-step (call stage_transport first)");
-    LAUNCH(c, k_sources_velocity, cells_grid((long long)(c->v.nr + 1) * c->v.ns), 256, 0, c->v, c->sigma, c->energy, c->pot,
-	   c->vrA, c->vpA, c->vrB, c->vpB, dt);
-    c->v_in_B = true;
+    LAUNCH(c, k_sources_velocity, cells_grid((long long)(c->v.nr + 1) * c->v.ns), 256, 0, c->v, c->sigma, EN(c), c->pot,
+	   VRA(c), VPA(c), VRB(c), VPB(c), dt);
+    c->v_mid = true;
     if (c->v.p.adiabatic)
-	LAUNCH(c, k_compression_heating, cells_grid((long long)(c->v.nr - 1) * c->v.ns), 256, 0, c->v, c->vrB, c->vpB, c->energy, dt);
+	LAUNCH(c, k_compression_heating, cells_grid((long long)(c->v.nr - 1) * c->v.ns), 256, 0, c->v, VRB(c), VPB(c), EN(c), dt);
     return 0;
 }
 
 // make sure the current velocities are in the B buffers (stages that expect mid-step state, when called
 // stand-alone from a between-steps state)
-static int ensure_v_in_B(fargo_ctx *c)
+static int ensure_v_mid(fargo_ctx *c)
 {
-    if (!c->v_in_B) {
-	CUDA_OK(cudaMemcpyAsync(c->vrB, c->vrA, (size_t)(c->v.nr + 1) * c->v.ns * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-	CUDA_OK(cudaMemcpyAsync(c->vpB, c->vpA, (size_t)c->v.nr * c->v.ns * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-	c->v_in_B = true;
+    if (!c->v_mid) {
+	CUDA_OK(cudaMemcpyAsync(VRB(c), VRA(c), (size_t)(c->v.nr + 1) * c->v.ns * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+	CUDA_OK(cudaMemcpyAsync(VPB(c), VPA(c), (size_t)c->v.nr * c->v.ns * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+	c->v_mid = true;
     }
     return 0;
 }
@@ -603,16 +619,16 @@ static int ensure_v_in_B(fargo_ctx *c)
 extern "C" int fargo_stage_artvisc(fargo_ctx *c, double dt)
 {
     CUDA_OK(cudaSetDevice(c->device));
-    if (ensure_v_in_B(c))
+    if (ensure_v_mid(c))
 	return 1;
     const fargo_params &p = c->v.p;
     const bool diss = p.adiabatic && p.artificial_viscosity_dissipation;
     if (p.artificial_viscosity == FARGO_ARTVISC_NONE && !diss)
 	return 0;
     const unsigned g = cells_grid((long long)c->v.nr * c->v.ns);
-    LAUNCH(c, k_artvisc_q, g, 256, 0, c->v, c->sigma, c->vrB, c->vpB, c->energy, c->qr, c->qphi, dt);
+    LAUNCH(c, k_artvisc_q, g, 256, 0, c->v, c->sigma, VRB(c), VPB(c), EN(c), c->qr, c->qphi, dt);
     if (p.artificial_viscosity != FARGO_ARTVISC_NONE)
-	LAUNCH(c, k_artvisc_v, g, 256, 0, c->v, c->sigma, c->qr, c->qphi, c->vrB, c->vpB, dt);
+	LAUNCH(c, k_artvisc_v, g, 256, 0, c->v, c->sigma, c->qr, c->qphi, VRB(c), VPB(c), dt);
     return 0;
 }
 
@@ -621,10 +637,10 @@ static int launch_stress(fargo_ctx *c)
     const unsigned g = cells_grid((long long)c->v.nr * c->v.ns);
     const fargo_params &p = c->v.p;
     if (p.viscous_alpha > 0 || !c->visc_const_filled) {
-	LAUNCH(c, k_viscosity_nu, g, 256, 0, c->v, c->sigma, c->energy, c->nu);
+	LAUNCH(c, k_viscosity_nu, g, 256, 0, c->v, c->sigma, EN(c), c->nu);
 	c->visc_const_filled = true;
     }
-    VBuf v = cur_v(c, c->v_in_B);
+    VBuf v = cur_v(c, c->v_mid);
     LAUNCH(c, k_stress, g, 256, 0, c->v, c->sigma, c->nu, v.vr, v.vp, c->divv, c->trr, c->tpp, c->trp, c->nusig, c->nusig_rp);
     if (p.stabilize_viscosity)
 	LAUNCH(c, k_stress_correction, g, 256, 0, c->v, c->sigma, c->nusig, c->nusig_rp, c->cf_r, c->cf_phi);
@@ -634,12 +650,12 @@ static int launch_stress(fargo_ctx *c)
 extern "C" int fargo_stage_viscosity(fargo_ctx *c, double dt)
 {
     CUDA_OK(cudaSetDevice(c->device));
-    if (ensure_v_in_B(c))
+    if (ensure_v_mid(c))
 	return 1;
     if (launch_stress(c))
 	return 1;
     LAUNCH(c, k_viscosity_v, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, c->trr, c->tpp, c->trp, c->cf_r,
-	   c->cf_phi, c->vrB, c->vpB, dt);
+	   c->cf_phi, VRB(c), VPB(c), dt);
     return 0;
 }
 
@@ -662,7 +678,7 @@ extern "C" int fargo_stage_substep3(fargo_ctx *c, double dt)
     if (!c->v.p.adiabatic)
 	return 0;
     LAUNCH(c, k_substep3, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, c->nu, c->divv, c->trr, c->tpp,
-	   c->trp, c->sigma0, c->energy0, c->energy, c->qplus, c->qminus, dt, beta_inv_host(c), 1);
+	   c->trp, c->sigma0, c->energy0, EN(c), c->qplus, c->qminus, dt, beta_inv_host(c), 1);
     return 0;
 }
 
@@ -755,7 +771,7 @@ extern "C" int fargo_stage_boundary(fargo_ctx *c, double dt, int final_call)
 {
     CUDA_OK(cudaSetDevice(c->device));
     const fargo_params &p = c->v.p;
-    VBuf v = cur_v(c, c->v_in_B);
+    VBuf v = cur_v(c, c->v_mid);
     if (final_call && p.damping) { // order: vrad, vazi, sigma, energy (damping.cpp:204-270)
 	const int st = c->v.nr + 2;
 	double *h = c->h_pin + 8, *d = c->expf_s;
@@ -764,7 +780,7 @@ extern "C" int fargo_stage_boundary(fargo_ctx *c, double dt, int final_call)
 	    damp_field(c, v.vp, c->vp0, false, false, p.damp_vazi, dt, d + st, h + st) ||
 	    damp_field(c, c->sigma, c->sigma0, false, true, p.damp_sigma, dt, d + 2 * st, h + 2 * st))
 	    return 1;
-	if (p.adiabatic && damp_field(c, c->energy, c->energy0, false, false, p.damp_energy, dt, d + 3 * st, h + 3 * st))
+	if (p.adiabatic && damp_field(c, EN(c), c->energy0, false, false, p.damp_energy, dt, d + 3 * st, h + 3 * st))
 	    return 1;
 	CUDA_OK(cudaEventRecord(c->ev_pin, c->stream));
     }
@@ -773,31 +789,37 @@ extern "C" int fargo_stage_boundary(fargo_ctx *c, double dt, int final_call)
     const double vk_in = p.keplerian_azimuthal_factor[0] * sqrt(p.G * p.hydro_center_mass / c->h_rmed[0]) - c->h_rmed[0] * c->v.b.omega_frame;
     const double vk_out =
 	p.keplerian_azimuthal_factor[1] * sqrt(p.G * p.hydro_center_mass / c->h_rmed[Irad]) - c->h_rmed[Irad] * c->v.b.omega_frame;
-    LAUNCH(c, k_boundary, (unsigned)((c->v.ns + 255) / 256), 256, 0, c->v, c->sigma, c->energy, v.vr, v.vp, c->sigma0, c->energy0,
+    LAUNCH(c, k_boundary, (unsigned)((c->v.ns + 255) / 256), 256, 0, c->v, c->sigma, EN(c), v.vr, v.vp, c->sigma0, c->energy0,
 	   c->vr0, c->vp0, vk_in, vk_out);
     return 0;
 }
 
-template <int LIM> static int launch_transport(fargo_ctx *c, double dt)
+// Transport: reads (Sigma, e, v) from `in`, writes Sigma and e in place and the new velocities to `out`
+// (out != in: the azimuthal kernel still reads the old v_azi of neighbouring columns while it stores).
+template <int LIM>
+static int launch_transport(fargo_ctx *c, double dt, const double *vr_in, const double *vp_in, double *vr_out, double *vp_out)
 {
     const DevView &v = c->v;
     // ring means of the pre-transport v_azi, Nshift, constant residual
-    LAUNCH(c, k_ring_mean, cells_grid((long long)v.nr * 32), 256, 0, v, c->vpB, c->vmean, c->nshift, c->vconst, dt, 1);
+    LAUNCH(c, k_ring_mean, (unsigned)((v.nr + 31) / 32), 32, 0, v, vp_in, c->vmean, c->nshift, c->vconst, dt, 1);
     {
 	dim3 grid((unsigned)((v.ns + 127) / 128), (unsigned)((v.nr + c->rad_chunk - 1) / c->rad_chunk));
 	if (v.p.adiabatic)
-	    LAUNCH(c, (k_transport_radial<LIM, true>), grid, 128, 0, v, c->sigma, c->vrB, c->vpB, c->energy, c->t_sigma, c->t_rmp,
-		   c->t_rmm, c->t_amp, c->t_amm, c->t_e, dt, c->rad_chunk);
+	    LAUNCH(c, (k_transport_radial<LIM, true>), grid, 128, 0, v, c->sigma, vr_in, vp_in, EN(c), c->t_sigma, c->t_rmp, c->t_rmm,
+		   c->t_amp, c->t_amm, c->t_e, dt, c->rad_chunk);
 	else
-	    LAUNCH(c, (k_transport_radial<LIM, false>), grid, 128, 0, v, c->sigma, c->vrB, c->vpB, c->energy, c->t_sigma, c->t_rmp,
-		   c->t_rmm, c->t_amp, c->t_amm, c->t_e, dt, c->rad_chunk);
+	    LAUNCH(c, (k_transport_radial<LIM, false>), grid, 128, 0, v, c->sigma, vr_in, vp_in, EN(c), c->t_sigma, c->t_rmp, c->t_rmm,
+		   c->t_amp, c->t_amm, c->t_e, dt, c->rad_chunk);
     }
     {
-	const int S = c->az_S, L = S + AZ_HL + AZ_HR;
-	const size_t smem = ((size_t)(3 * AZ_NQ + 1) * L + 2 * S) * sizeof(double);
-	dim3 grid((unsigned)((v.ns + S - 1) / S), (unsigned)((v.nr + c->az_R - 1) / c->az_R));
-	LAUNCH(c, k_transport_azimuthal<LIM>, grid, 256, smem, v, c->t_sigma, c->t_rmp, c->t_rmm, c->t_amp, c->t_amm, c->t_e, c->vpB,
-	       c->vrB, c->vmean, c->nshift, c->vconst, c->sigma, c->vrA, c->vpA, c->energy, dt, S, c->az_R);
+	const int nwin = (v.ns + AZ_OUT - 1) / AZ_OUT;
+	dim3 grid((unsigned)((nwin + 3) / 4), (unsigned)((v.nr + c->az_R - 1) / c->az_R));
+	if (v.p.adiabatic)
+	    LAUNCH(c, (k_transport_azimuthal<LIM, true>), grid, 128, 0, v, c->t_sigma, c->t_rmp, c->t_rmm, c->t_amp, c->t_amm, c->t_e,
+		   vp_in, vr_in, c->vmean, c->nshift, c->vconst, c->sigma, vr_out, vp_out, EN(c), dt, c->az_R);
+	else
+	    LAUNCH(c, (k_transport_azimuthal<LIM, false>), grid, 128, 0, v, c->t_sigma, c->t_rmp, c->t_rmm, c->t_amp, c->t_amm, c->t_e,
+		   vp_in, vr_in, c->vmean, c->nshift, c->vconst, c->sigma, vr_out, vp_out, EN(c), dt, c->az_R);
     }
     return 0;
 }
@@ -805,13 +827,13 @@ template <int LIM> static int launch_transport(fargo_ctx *c, double dt)
 extern "C" int fargo_stage_transport(fargo_ctx *c, double dt)
 {
     CUDA_OK(cudaSetDevice(c->device));
-    if (ensure_v_in_B(c))
+    if (ensure_v_mid(c))
 	return 1;
-    int rc = c->v.p.flux_limiter == FARGO_LIMITER_MC ? launch_transport<FARGO_LIMITER_MC>(c, dt)
-						      : launch_transport<FARGO_LIMITER_VANLEER>(c, dt);
+    int rc = c->v.p.flux_limiter == FARGO_LIMITER_MC ? launch_transport<FARGO_LIMITER_MC>(c, dt, VRB(c), VPB(c), VRA(c), VPA(c))
+						      : launch_transport<FARGO_LIMITER_VANLEER>(c, dt, VRB(c), VPB(c), VRA(c), VPA(c));
     if (rc)
 	return rc;
-    c->v_in_B = false;
+    c->v_mid = false;
     return 0;
 }
 
@@ -822,12 +844,12 @@ extern "C" int fargo_stage_halo(fargo_ctx *c)
     CUDA_OK(cudaSetDevice(c->device));
     if (c->v.nranks == 1)
 	return 0;
-    if (c->v_in_B)
+    if (c->v_mid)
 	return fail("stage_halo called mid-step");
     const size_t l = (size_t)FARGO_CPUOVERLAP * c->v.ns;
     const size_t oo = (size_t)(c->v.nr - FARGO_CPUOVERLAP) * c->v.ns;
     const size_t o = (size_t)(c->v.nr - 2 * FARGO_CPUOVERLAP) * c->v.ns;
-    double *fields[4] = {c->sigma, c->vrA, c->vpA, c->energy};
+    double *fields[4] = {c->sigma, VRA(c), VPA(c), EN(c)};
     const int nf = c->v.p.adiabatic ? 4 : 3;
     const int prev = c->v.rank - 1, next = c->v.rank + 1;
     NCCL_OK(g_nccl.GroupStart());
@@ -863,7 +885,7 @@ extern "C" int fargo_init_derived(fargo_ctx *c)
     if (launch_stress(c))
 	return 1;
     LAUNCH(c, k_substep3, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, c->nu, c->divv, c->trr, c->tpp,
-	   c->trp, c->sigma0, c->energy0, c->energy, c->qplus, c->qminus, 0.0, beta_inv_host(c), 0);
+	   c->trp, c->sigma0, c->energy0, EN(c), c->qplus, c->qminus, 0.0, beta_inv_host(c), 0);
     return 0;
 }
 
@@ -871,15 +893,17 @@ extern "C" int fargo_condition_cfl(fargo_ctx *c, double *out)
 {
     CUDA_OK(cudaSetDevice(c->device));
     const DevView &v = c->v;
-    if (c->v_in_B)
+    if (c->v_mid)
 	return fail("condition_cfl called mid-step");
     c->h_pin[0] = 1.7976931348623157e308;
     CUDA_OK(cudaMemcpyAsync(c->d_dt, c->h_pin, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    LAUNCH(c, k_ring_mean, cells_grid((long long)v.nr * 32), 256, 0, v, c->vpA, c->vmean, c->nshift, c->vconst, 0.0, 0);
+    LAUNCH(c, k_ring_mean, (unsigned)((v.nr + 31) / 32), 32, 0, v, VPA(c), c->vmean, c->nshift, c->vconst, 0.0, 0);
     const int nact = v.active_size - v.first_active;
-    if (nact > 0)
-	LAUNCH(c, k_cfl, cells_grid((long long)nact * v.ns), 256, 0, v, c->sigma, c->energy, c->vrA, c->vpA, c->qplus, c->qminus,
-	       c->cf_r, c->cf_phi, c->vmean, c->d_dt);
+    if (nact > 0) {
+	dim3 grid((unsigned)((v.ns + 511) / 512), (unsigned)nact);
+	LAUNCH(c, k_cfl, grid, 128, 0, v, c->sigma, EN(c), VRA(c), VPA(c), c->qplus, c->qminus, c->cf_r, c->cf_phi, c->vmean,
+	       c->d_dt);
+    }
     if (v.nranks > 1) { // MPI_Allreduce(MIN), cfl.cpp:379
 	NCCL_OK(g_nccl.AllReduce(c->d_dt, c->d_dt, 1, ncclFloat64, ncclMin, c->comm, c->stream));
 	c->launches++;
@@ -903,18 +927,72 @@ extern "C" int fargo_cfl(fargo_ctx *c, double *last_dt, double *dt_out)
     return 0;
 }
 
+// The fused source-term kernels (kernels_fused.cuh): potential + sources + compression | artificial viscosity |
+// viscosity + SubStep3.  Every kernel reads the current (e, v) buffers and writes the other ones.
+template <bool ADI> static int launch_fused_sources(fargo_ctx *c, double dt)
+{
+    const DevView &v = c->v;
+    const fargo_params &p = v.p;
+    const int nwin = (v.ns + FS_OUT - 1) / FS_OUT;
+    dim3 grid((unsigned)((nwin + 3) / 4), (unsigned)((v.nr + c->fs_R - 1) / c->fs_R));
+    const int eo = ADI ? 1 - c->ecur : c->ecur;
+    LAUNCH(c, k_fused_sources<ADI>, grid, 128, 0, v, c->sigma, EN(c), VRA(c), VPA(c), VRB(c), VPB(c), c->eb[eo], dt, c->fs_R);
+    c->vcur = 1 - c->vcur;
+    c->ecur = eo;
+    const bool diss = ADI && p.artificial_viscosity_dissipation;
+    if (p.artificial_viscosity != FARGO_ARTVISC_NONE || diss) {
+	const int eo2 = ADI ? 1 - c->ecur : c->ecur;
+	LAUNCH(c, k_fused_artvisc<ADI>, grid, 128, 0, v, c->sigma, EN(c), VRA(c), VPA(c), VRB(c), VPB(c), c->eb[eo2], dt, c->fs_R);
+	c->vcur = 1 - c->vcur;
+	c->ecur = eo2;
+    }
+    {
+	const int eo3 = ADI ? 1 - c->ecur : c->ecur;
+	LAUNCH(c, k_fused_viscosity<ADI>, grid, 128, 0, v, c->sigma, EN(c), VRA(c), VPA(c), c->sigma0, c->energy0, VRB(c), VPB(c),
+	       c->eb[eo3], c->qplus, c->qminus, dt, ADI ? beta_inv_host(c) : 0.0, c->fs_R);
+	c->vcur = 1 - c->vcur;
+	c->ecur = eo3;
+    }
+    return 0;
+}
+
 // gas part of step_Euler (simulation.cpp:167-175, 187-218, 230-266)
 extern "C" int fargo_step(fargo_ctx *c, double dt)
 {
-    if (fargo_stage_potential(c) || fargo_stage_sources(c, dt) || fargo_stage_artvisc(c, dt) || fargo_stage_viscosity(c, dt))
-	return 1;
-    if (c->v.p.adiabatic && fargo_stage_substep3(c, dt))
-	return 1;
-    if (fargo_stage_boundary(c, 0.0, 0) || fargo_stage_transport(c, dt))
-	return 1;
+    CUDA_OK(cudaSetDevice(c->device));
+    if (c->v_mid)
+	return fail("fargo_step called mid-step (after a per-stage call); finish the step with fargo_stage_transport first");
+    const fargo_params &p = c->v.p;
+    const bool fused = p.stabilize_viscosity == 0 && !c->force_staged;
+    if (fused) {
+	if (p.adiabatic ? launch_fused_sources<true>(c, dt) : launch_fused_sources<false>(c, dt))
+	    return 1;
+	if (fargo_stage_boundary(c, 0.0, 0))
+	    return 1;
+	// Transport out of the current velocity buffer into the other one
+	int rc = p.flux_limiter == FARGO_LIMITER_MC ? launch_transport<FARGO_LIMITER_MC>(c, dt, VRA(c), VPA(c), VRB(c), VPB(c))
+						     : launch_transport<FARGO_LIMITER_VANLEER>(c, dt, VRA(c), VPA(c), VRB(c), VPB(c));
+	if (rc)
+	    return rc;
+	c->vcur = 1 - c->vcur;
+    } else {
+	if (fargo_stage_potential(c) || fargo_stage_sources(c, dt) || fargo_stage_artvisc(c, dt) || fargo_stage_viscosity(c, dt))
+	    return 1;
+	if (p.adiabatic && fargo_stage_substep3(c, dt))
+	    return 1;
+	if (fargo_stage_boundary(c, 0.0, 0) || fargo_stage_transport(c, dt))
+	    return 1;
+    }
     c->v.time += dt;
     if (fargo_stage_halo(c) || fargo_stage_boundary(c, dt, 1) || fargo_stage_derived(c))
 	return 1;
+    return 0;
+}
+
+// test hook: run fargo_step through the staged kernels (one per reference loop nest) instead of the fused ones
+extern "C" int fargo_set_staged(fargo_ctx *c, int on)
+{
+    c->force_staged = on != 0;
     return 0;
 }
 

@@ -1,0 +1,608 @@
+// kernels_fused.cuh — the source-term half of the hydro step as three ring-marching kernels.
+//
+//   k_fused_sources    CalculateNbodyPotential (Pframeforce.cpp:21-86) + momentum_update_radial / _azimuthal
+//                      (SourceEuler.cpp:325-428) + compression_heating (:459-493)
+//   k_fused_artvisc    update_with_artificial_viscosity TW / SN (viscosity/artificial_viscosity.cpp:11-250)
+//   k_fused_viscosity  recalculate_viscosity (SourceEuler.cpp:205-223) + compute_viscous_stress_tensor +
+//                      update_velocities_with_viscosity (viscosity/viscosity.cpp:139-426) + SubStep3
+//                      (SourceEuler.cpp:496-954: viscous heating, beta cooling, energy update, T floor)
+//
+// Same execution shape as the azimuthal transport kernel: a warp owns a window of 128 columns, each lane 4
+// consecutive ones (3 of 4 azimuthal neighbours are the thread's own registers, the 4th is one shuffle away) and
+// marches outward in radius; the rings i-1 / i-2 a stage needs are the registers of the previous iterations, so
+// every state array is read ONCE and every intermediate (Phi, P, Q_rr, Q_phiphi, nu, div v, tau_rr, tau_phiphi,
+// tau_rphi) lives only in registers.  A stage that needs column j+-1 of the previous stage's output makes the
+// outermost columns of the window invalid, so a window of 128 columns yields 120 finished ones ([4, 124)); warps
+// do not communicate.  Outputs go to the OTHER buffer of each double-buffered field (windows overlap on reads).
+//
+// Compared with one kernel per reference loop nest (the staged kernels in kernels_source.cuh, kept for the
+// per-stage entry points) this reads/writes 184 B per cell instead of 472 B and executes ~3x fewer instructions.
+#pragma once
+#include "fargo_dev.h"
+#include "kernels_azimuthal.cuh"
+#include "kernels_source.cuh"
+
+#define FS_WIN 128
+#define FS_HL 4
+#define FS_HR 4
+#define FS_OUT (FS_WIN - FS_HL - FS_HR)
+
+// window bookkeeping shared by the three kernels
+struct FsLane {
+    int jout;	  // unwrapped output column of the thread's first column
+    int col;	  // wrapped column (0 <= col < ns) of the first column
+    bool vec;	  // the 4 columns are contiguous and 32-byte aligned (ns % 4 == 0)
+    bool lane_out; // this lane's columns are inside the valid part of the window and inside the ring
+};
+__device__ __forceinline__ bool fs_setup(const DevView &c, FsLane &L)
+{
+    const int lane = threadIdx.x & 31;
+    const int win = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if ((long long)win * FS_OUT >= c.ns)
+	return false;
+    const int t0 = 4 * lane;
+    L.jout = win * FS_OUT - FS_HL + t0;
+    int col = L.jout % c.ns;
+    if (col < 0)
+	col += c.ns;
+    L.col = col;
+    L.vec = ((c.ns & 3) == 0);
+    L.lane_out = (t0 >= FS_HL) && (t0 < FS_WIN - FS_HR) && (L.jout < c.ns);
+    return true;
+}
+__device__ __forceinline__ void fs_load(const double *__restrict__ arr, const int ring, const DevView &c, const FsLane &L,
+					 double (&x)[4])
+{
+    const double *row = arr + (size_t)ring * c.ns;
+    if (L.vec) {
+	const double2 a = *reinterpret_cast<const double2 *>(row + L.col);
+	const double2 b = *reinterpret_cast<const double2 *>(row + L.col + 2);
+	x[0] = a.x;
+	x[1] = a.y;
+	x[2] = b.x;
+	x[3] = b.y;
+    } else {
+	int cc = L.col;
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+	    x[k] = row[cc];
+	    cc = (cc + 1 == c.ns) ? 0 : cc + 1;
+	}
+    }
+}
+__device__ __forceinline__ void fs_store(double *__restrict__ arr, const int ring, const DevView &c, const FsLane &L,
+					  const double (&x)[4])
+{
+    if (!L.lane_out)
+	return;
+    double *row = arr + (size_t)ring * c.ns;
+    if (L.vec) {
+	*reinterpret_cast<double2 *>(row + L.jout) = make_double2(x[0], x[1]);
+	*reinterpret_cast<double2 *>(row + L.jout + 2) = make_double2(x[2], x[3]);
+    } else {
+#pragma unroll
+	for (int k = 0; k < 4; ++k)
+	    if (L.jout + k < c.ns)
+		row[L.jout + k] = x[k];
+    }
+}
+#define FS_FOR4 _Pragma("unroll") for (int k = 0; k < 4; ++k)
+
+// ---------------------------------------------------------------------------------------------
+// k_fused_sources.  Iteration k loads ring k, forms Phi(k), P(k), v_rad'(k) (needs ring k-1) and v_azi'(k), then
+// finishes ring r = k-1: e'(r) needs v_rad'(r+1).  Output: v_rad', v_azi', e' of ring r.
+template <bool ADI>
+__global__ void __launch_bounds__(128, 3)
+    k_fused_sources(const DevView c, const double *__restrict__ sigma, const double *__restrict__ energy,
+		    const double *__restrict__ vr, const double *__restrict__ vp, double *__restrict__ o_vr,
+		    double *__restrict__ o_vp, double *__restrict__ o_e, const double dt, const int R)
+{
+    FsLane L;
+    if (!fs_setup(c, L))
+	return;
+    const int nr = c.nr;
+    const int i_first = blockIdx.y * R;
+    if (i_first >= nr)
+	return;
+    const int i_last = min(i_first + R, nr);
+    const double OmegaF = c.b.omega_frame;
+    const bool drift = c.p.imposed_disk_drift != 0.0;
+    // azimuth of the thread's columns (SideEuler.cpp:56-65)
+    double cosj[4], sinj[4];
+    {
+	int cc = L.col;
+	FS_FOR4
+	{
+	    cosj[k] = c.g.cosphi[cc];
+	    sinj[k] = c.g.sinphi[cc];
+	    cc = (cc + 1 == c.ns) ? 0 : cc + 1;
+	}
+    }
+    double S1[4], P1[4], F1[4], VP1[4], E1[4], VRn1[4], VPn1[4];
+    FS_FOR4
+    {
+	S1[k] = 1.0;
+	P1[k] = F1[k] = VP1[k] = VRn1[k] = VPn1[k] = 0.0;
+	E1[k] = 1.0;
+    }
+    // ring r = k-1 is finished in iteration k; its v_rad' needs ring r-1, so start one ring early
+    const int kbeg = max(i_first - 1, 0);
+    for (int kr = kbeg; kr <= i_last; ++kr) {
+	const bool has_cells = kr < nr;
+	double S0[4], E0[4], VP0[4], VR0[4], P0[4], F0[4], VRn0[4], VPn0[4];
+	fs_load(vr, kr, c, L, VR0);
+	if (has_cells) {
+	    fs_load(sigma, kr, c, L, S0);
+	    fs_load(vp, kr, c, L, VP0);
+	    if (ADI)
+		fs_load(energy, kr, c, L, E0);
+	    FS_FOR4
+	    {
+		if (!ADI)
+		    E0[k] = 0.0;
+		P0[k] = eos_P(c, kr, S0[k], E0[k]);
+	    }
+	    { // CalculateNbodyPotential (Pframeforce.cpp:44-85)
+		const double rmed = c.g.rmed[kr];
+		FS_FOR4
+		{
+		    const double cs = eos_cs(c, kr, S0[k], E0[k]);
+		    const double H = eos_H(c, kr, cs);
+		    const double x = rmed * cosj[k];
+		    const double y = rmed * sinj[k];
+		    const double smooth = c.p.thickness_smoothing * H;
+		    double pot = 0.0;
+		    for (int b = 0; b < c.b.n; ++b) {
+			const double dx = x - c.b.x[b];
+			const double dy = y - c.b.y[b];
+			const double dist_2 = dx * dx + dy * dy;
+			const double d_smoothed = sqrt(dist_2 + smooth * smooth);
+			double smooth_factor_klahr = 1.0;
+			const double r_sm = c.b.cubic_smoothing_radius[b];
+			if (r_sm > 0.0 && d_smoothed < r_sm) {
+			    const double q = d_smoothed / r_sm;
+			    smooth_factor_klahr = (pow(q, 4.0) - 2.0 * pow(q, 3.0) + 2.0 * d_smoothed / r_sm);
+			}
+			pot += -c.p.G * c.b.mass[b] / d_smoothed * smooth_factor_klahr;
+		    }
+		    pot += -c.b.indirect_x * x - c.b.indirect_y * y;
+		    F0[k] = pot;
+		}
+	    }
+	} else {
+	    FS_FOR4 { S0[k] = 1.0, E0[k] = 1.0, VP0[k] = P0[k] = F0[k] = 0.0; }
+	}
+	// momentum_update_radial (SourceEuler.cpp:325-372): interface k between rings k-1 and k
+	FS_FOR4 VRn0[k] = VR0[k];
+	if (kr >= c.one_no_ghost_vr && kr < c.maxmo_no_ghost_vr) {
+	    const double VP0r = shfl_from_right(VP0[0]), VP1r = shfl_from_right(VP1[0]);
+	    const double idr = c.g.invdiffrmed[kr], rinf = c.g.rinf[kr], invrinf = c.g.invrinf[kr];
+	    FS_FOR4
+	    {
+		double gradp = 2.0 / (S0[k] + S1[k]);
+		gradp *= (P0[k] - P1[k]);
+		gradp *= idr;
+		const double gradphi = (F0[k] - F1[k]) * idr;
+		const double vp0n = (k == 3) ? VP0r : VP0[(k + 1) & 3];
+		const double vp1n = (k == 3) ? VP1r : VP1[(k + 1) & 3];
+		const double vsum = VP0[k] + vp0n + VP1[k] + vp1n;
+		const double vt = 0.25 * vsum + rinf * OmegaF;
+		const double vt2 = vt * vt;
+		const double centrifugal_accel = vt2 * invrinf;
+		VRn0[k] = VR0[k] + dt * (-gradp - gradphi + centrifugal_accel);
+	    }
+	}
+	// momentum_update_azimuthal (:375-428)
+	FS_FOR4 VPn0[k] = VP0[k];
+	if (has_cells && kr >= c.zero_no_ghost && kr < c.max_no_ghost) {
+	    const double invdxtheta = 2.0 / (c.dphi * (c.g.rsup[kr] + c.g.rinf[kr]));
+	    const double Sl = shfl_from_left(S0[3]), Pl = shfl_from_left(P0[3]), Fl = shfl_from_left(F0[3]);
+	    const double supp = drift ? c.g.supp_torque[kr] : 0.0;
+	    FS_FOR4
+	    {
+		const double sp = (k == 0) ? Sl : S0[(k + 3) & 3];
+		const double Pp = (k == 0) ? Pl : P0[(k + 3) & 3];
+		const double Fp = (k == 0) ? Fl : F0[(k + 3) & 3];
+		const double gradp = 2.0 / (S0[k] + sp) * (P0[k] - Pp) * invdxtheta;
+		const double gradphi = (F0[k] - Fp) * invdxtheta;
+		double vpn = VP0[k] + dt * (-gradp - gradphi);
+		if (drift)
+		    vpn += dt * supp;
+		VPn0[k] = vpn;
+	    }
+	}
+	// ring r = k-1: compression_heating (:459-493) with the UPDATED velocities, then store
+	const int r = kr - 1;
+	if (r >= i_first) {
+	    double En[4];
+	    FS_FOR4 En[k] = E1[k];
+	    if (ADI && r < nr - 1) {
+		const double VPn1r = shfl_from_right(VPn1[0]);
+		const double ra1 = c.g.rinf[r + 1], ra0 = c.g.rinf[r], idrb = c.g.invdiffrsuprb[r], irb = c.g.invrmed[r];
+		FS_FOR4
+		{
+		    const double vpn = (k == 3) ? VPn1r : VPn1[(k + 1) & 3];
+		    const double DIV_V = (VRn0[k] * ra1 - VRn1[k] * ra0) * idrb + (vpn - VPn1[k]) * c.invdphi * irb;
+		    En[k] = E1[k] * exp(-(c.p.gamma - 1.0) * dt * DIV_V);
+		}
+	    }
+	    fs_store(o_vr, r, c, L, VRn1);
+	    fs_store(o_vp, r, c, L, VPn1);
+	    if (ADI)
+		fs_store(o_e, r, c, L, En);
+	}
+	FS_FOR4
+	{
+	    S1[k] = S0[k];
+	    P1[k] = P0[k];
+	    F1[k] = F0[k];
+	    VP1[k] = VP0[k];
+	    E1[k] = E0[k];
+	    VRn1[k] = VRn0[k];
+	    VPn1[k] = VPn0[k];
+	}
+    }
+    if (i_last == nr) // v_rad ring nr (outermost interface) is outside every update range
+	fs_store(o_vr, nr, c, L, VRn1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_fused_artvisc.  Iteration k loads ring k; Q(r) of ring r = k-1 needs v_rad(r+1); v_rad''(r) needs Q(r), Q(r-1).
+template <bool ADI>
+__global__ void __launch_bounds__(128, 3)
+    k_fused_artvisc(const DevView c, const double *__restrict__ sigma, const double *__restrict__ energy,
+		    const double *__restrict__ vr, const double *__restrict__ vp, double *__restrict__ o_vr,
+		    double *__restrict__ o_vp, double *__restrict__ o_e, const double dt, const int R)
+{
+    FsLane L;
+    if (!fs_setup(c, L))
+	return;
+    const int nr = c.nr;
+    const int i_first = blockIdx.y * R;
+    if (i_first >= nr)
+	return;
+    const int i_last = min(i_first + R, nr);
+    const int type = c.p.artificial_viscosity;
+    const bool diss = ADI && c.p.artificial_viscosity_dissipation;
+    const double C = c.p.artificial_viscosity_factor;
+    TempClamp tc;
+    if (ADI)
+	tc = make_temp_clamp(c);
+    double S1[4], E1[4], VR1[4], VP1[4], S2[4], QR2[4], QP2[4];
+    FS_FOR4
+    {
+	S1[k] = S2[k] = 1.0;
+	E1[k] = 1.0;
+	VR1[k] = VP1[k] = QR2[k] = QP2[k] = 0.0;
+    }
+    // ring r = k-1 is finished in iteration k and needs Q(r-1), i.e. rings r-1 and r: start at r-1 = i_first-1
+    const int kbeg = max(i_first - 1, 0);
+    for (int kr = kbeg; kr <= i_last; ++kr) {
+	double S0[4], E0[4], VR0[4], VP0[4];
+	fs_load(vr, kr, c, L, VR0);
+	if (kr < nr) {
+	    fs_load(sigma, kr, c, L, S0);
+	    fs_load(vp, kr, c, L, VP0);
+	    if (ADI)
+		fs_load(energy, kr, c, L, E0);
+	    else
+		FS_FOR4 E0[k] = 0.0;
+	} else {
+	    FS_FOR4 { S0[k] = 1.0, E0[k] = 1.0, VP0[k] = 0.0; }
+	}
+	const int r = kr - 1;
+	if (r >= kbeg) { // ring r is complete: S1, E1, VR1 = v_rad(r), VR0 = v_rad(r+1), VP1
+	    double QR1[4], QP1[4], En[4], VRn[4], VPn[4];
+	    const double VP1r = shfl_from_right(VP1[0]);
+	    FS_FOR4
+	    {
+		En[k] = E1[k];
+		VRn[k] = VR1[k];
+		VPn[k] = VP1[k];
+		QR1[k] = QP1[k] = 0.0;
+	    }
+	    if (type == FARGO_ARTVISC_TW) { // artificial_viscosity.cpp:49-88
+		const double ids = c.g.invdiffrsup[r], irb = c.g.invrmed[r];
+		const double Dr = c.g.rinf[r + 1] - c.g.rinf[r];
+		const double rDphi = c.g.rmed[r] * c.dphi;
+		const double m = (c.ns <= 16) ? stdmin(Dr, rDphi) : stdmax(Dr, rDphi);
+		const double dx_sq = m * m;
+		const double l_sq = (C * C) * dx_sq;
+		const bool heat = diss && r > c.zero_no_ghost && r < c.max_no_ghost;
+		FS_FOR4
+		{
+		    const double vpn = (k == 3) ? VP1r : VP1[(k + 1) & 3];
+		    const double eps_rr = (VR0[k] - VR1[k]) * ids;
+		    const double eps_pp = irb * ((vpn - VP1[k]) * c.invdphi + 0.5 * (VR0[k] + VR1[k]));
+		    const double div_V = stdmin(eps_rr + eps_pp, 0.0);
+		    QR1[k] = l_sq * S1[k] * -div_V * (eps_rr - 1.0 / 3.0 * div_V);
+		    QP1[k] = l_sq * S1[k] * -div_V * (eps_pp - 1.0 / 3.0 * div_V);
+		    if (heat) {
+			const double Qplus = -l_sq * div_V * S1[k] * 1.0 / 3.0 *
+					     (eps_rr * eps_rr + eps_pp * eps_pp + (eps_rr - eps_pp) * (eps_rr - eps_pp));
+			En[k] += Qplus * dt;
+		    }
+		}
+	    } else if (type == FARGO_ARTVISC_SN) { // :165-218
+		const bool heat = diss && r >= c.zero_no_ghost && r < c.max_no_ghost;
+		const double dxtheta = c.dphi * c.g.rmed[r];
+		const double invdxtheta = 1.0 / dxtheta;
+		FS_FOR4
+		{
+		    const double vpn = (k == 3) ? VP1r : VP1[(k + 1) & 3];
+		    const double dv_r = VR0[k] - VR1[k];
+		    QR1[k] = (dv_r < 0.0) ? (C * C) * S1[k] * (dv_r * dv_r) : 0.0;
+		    const double dv_phi = vpn - VP1[k];
+		    QP1[k] = (dv_phi < 0.0) ? (C * C) * S1[k] * (dv_phi * dv_phi) : 0.0;
+		    if (heat)
+			En[k] = En[k] - dt * QR1[k] * dv_r * c.g.invdiffrsup[r] - dt * QP1[k] * dv_phi * invdxtheta;
+		}
+	    }
+	    if (diss)
+		FS_FOR4 En[k] = temperature_clamp(tc, S1[k], En[k]); // :19-21
+	    const double QP1l = shfl_from_left(QP1[3]), S1l = shfl_from_left(S1[3]);
+	    if (type == FARGO_ARTVISC_TW) { // :90-139
+		if (r >= 1 && r < nr - 1) {
+		    const double rs = c.g.rsup[r] + c.g.rinf[r];
+		    FS_FOR4
+		    {
+			const double sp = (k == 0) ? S1l : S1[(k + 3) & 3];
+			const double qpp = (k == 0) ? QP1l : QP1[(k + 3) & 3];
+			const double sigma_phi_avg = 0.5 * (S1[k] + sp);
+			const double dVp = 2.0 * dt / (rs * sigma_phi_avg) * (QP1[k] - qpp) * c.invdphi;
+			VPn[k] = VP1[k] + dVp;
+		    }
+		}
+		if (r >= c.one_no_ghost_vr && r < c.maxmo_no_ghost_vr) {
+		    const double rm = c.g.rmed[r], rmm = c.g.rmed[r - 1];
+		    FS_FOR4
+		    {
+			const double sigma_r_avg = 0.5 * (S1[k] + S2[k]);
+			const double dVr = c.p.radial_viscosity_factor * dt / sigma_r_avg * 2.0 / (rm * rm - rmm * rmm) *
+					   ((QR1[k] * rm - QR2[k] * rmm) - 0.5 * (QP1[k] + QP2[k]) * (rm - rmm));
+			VRn[k] = VR1[k] + dVr;
+		    }
+		}
+	    } else if (type == FARGO_ARTVISC_SN) { // :221-248
+		if (r >= c.one_no_ghost_vr && r < c.maxmo_no_ghost_vr) {
+		    const double idr = c.g.invdiffrmed[r];
+		    FS_FOR4 VRn[k] = VR1[k] - dt * 2.0 / (S1[k] + S2[k]) * (QR1[k] - QR2[k]) * idr;
+		}
+		if (r >= c.zero_no_ghost && r < c.max_no_ghost) {
+		    const double dxtheta = c.dphi * c.g.rmed[r];
+		    const double invdxtheta = 1.0 / dxtheta;
+		    FS_FOR4
+		    {
+			const double sp = (k == 0) ? S1l : S1[(k + 3) & 3];
+			const double qpp = (k == 0) ? QP1l : QP1[(k + 3) & 3];
+			VPn[k] = VP1[k] - dt * 2.0 / (S1[k] + sp) * (QP1[k] - qpp) * invdxtheta;
+		    }
+		}
+	    }
+	    if (r >= i_first) {
+		fs_store(o_vr, r, c, L, VRn);
+		fs_store(o_vp, r, c, L, VPn);
+		if (ADI)
+		    fs_store(o_e, r, c, L, En);
+	    }
+	    FS_FOR4
+	    {
+		S2[k] = S1[k];
+		QR2[k] = QR1[k];
+		QP2[k] = QP1[k];
+	    }
+	}
+	FS_FOR4
+	{
+	    S1[k] = S0[k];
+	    E1[k] = E0[k];
+	    VR1[k] = VR0[k];
+	    VP1[k] = VP0[k];
+	}
+    }
+    if (i_last == nr)
+	fs_store(o_vr, nr, c, L, VR1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_fused_viscosity.  Iteration k loads ring k and forms nu(k) and the corner stress tau_rphi(k); ring r = k-1 then
+// has everything: div v, tau_rr, tau_phiphi (need v_rad(r+1)), the velocity updates (need tau_rphi(r+1), the
+// centred stresses of r-1) and, for the energy equation, Q+ / Q- / the new energy.
+// StabilizeViscosity != 0 is not handled here (the host falls back to the staged kernels).
+template <bool ADI>
+__global__ void __launch_bounds__(128, 2)
+    k_fused_viscosity(const DevView c, const double *__restrict__ sigma, const double *__restrict__ energy,
+		      const double *__restrict__ vr, const double *__restrict__ vp, const double *__restrict__ sigma0,
+		      const double *__restrict__ energy0, double *__restrict__ o_vr, double *__restrict__ o_vp,
+		      double *__restrict__ o_e, double *__restrict__ o_qplus, double *__restrict__ o_qminus, const double dt,
+		      const double beta_inv, const int R)
+{
+    FsLane L;
+    if (!fs_setup(c, L))
+	return;
+    const int nr = c.nr;
+    const int i_first = blockIdx.y * R;
+    if (i_first >= nr)
+	return;
+    const int i_last = min(i_first + R, nr);
+    const bool need0 = ADI && c.p.cooling_beta && (c.p.cooling_beta_reference & FARGO_BETA_REF_REFERENCE);
+    TempClamp tc;
+    if (ADI)
+	tc = make_temp_clamp(c);
+    double S1[4], E1[4], VR1[4], VP1[4], N1[4], TRP1[4], S2[4], TRR2[4], TPP2[4];
+    FS_FOR4
+    {
+	S1[k] = S2[k] = 1.0;
+	E1[k] = 1.0;
+	VR1[k] = VP1[k] = N1[k] = TRP1[k] = TRR2[k] = TPP2[k] = 0.0;
+    }
+    // ring r needs the centred stresses of r-1 (rings r-1, r) and tau_rphi(r) (rings r-1, r): start at k = r-1
+    const int kbeg = max(i_first - 1, 0);
+    for (int kr = kbeg; kr <= i_last; ++kr) {
+	double S0[4], E0[4], VR0[4], VP0[4], N0[4], TRP0[4];
+	fs_load(vr, kr, c, L, VR0);
+	if (kr < nr) {
+	    fs_load(sigma, kr, c, L, S0);
+	    fs_load(vp, kr, c, L, VP0);
+	    if (ADI)
+		fs_load(energy, kr, c, L, E0);
+	    else
+		FS_FOR4 E0[k] = 0.0;
+	    FS_FOR4 N0[k] = eos_nu(c, kr, S0[k], E0[k]); // recalculate_viscosity
+	} else {
+	    FS_FOR4 { S0[k] = 1.0, E0[k] = 1.0, VP0[k] = N0[k] = 0.0; }
+	}
+	// tau_rphi at the corner (k, j) (viscosity.cpp:213-253); rings 0 and nr of the grid stay 0
+	{
+	    const double VR0l = shfl_from_left(VR0[3]);
+	    const double N0l = shfl_from_left(N0[3]), N1l = shfl_from_left(N1[3]);
+	    const double S0l = shfl_from_left(S0[3]), S1l = shfl_from_left(S1[3]);
+	    if (kr >= 1 && kr < nr) {
+		const double irb = c.g.invrmed[kr], irbm = c.g.invrmed[kr - 1], idr = c.g.invdiffrmed[kr];
+		const double ra = c.g.rinf[kr], ira = c.g.invrinf[kr];
+		FS_FOR4
+		{
+		    const double vrl = (k == 0) ? VR0l : VR0[(k + 3) & 3];
+		    const double n0l = (k == 0) ? N0l : N0[(k + 3) & 3];
+		    const double n1l = (k == 0) ? N1l : N1[(k + 3) & 3];
+		    const double s0l = (k == 0) ? S0l : S0[(k + 3) & 3];
+		    const double s1l = (k == 0) ? S1l : S1[(k + 3) & 3];
+		    const double dvazirdr = (VP0[k] * irb - VP1[k] * irbm) * idr;
+		    const double dvrdphi = (VR0[k] - vrl) * c.invdphi;
+		    const double drp = ra * dvazirdr + dvrdphi * ira;
+		    const double nua = 0.25 * (N0[k] + N1[k] + n0l + n1l);
+		    const double sa = 0.25 * (S0[k] + S1[k] + s0l + s1l);
+		    TRP0[k] = nua * sa * drp;
+		}
+	    } else {
+		FS_FOR4 TRP0[k] = 0.0;
+	    }
+	}
+	const int r = kr - 1;
+	if (r >= kbeg) {
+	    // centred stresses of ring r (viscosity.cpp:150-211)
+	    double DV1[4], TRR1[4], TPP1[4], VRn[4], VPn[4];
+	    const double VP1r = shfl_from_right(VP1[0]);
+	    {
+		const double ra1 = c.g.rinf[r + 1], ra0 = c.g.rinf[r], idrb = c.g.invdiffrsuprb[r], irb = c.g.invrmed[r];
+		const double ids = c.g.invdiffrsup[r];
+		FS_FOR4
+		{
+		    const double vpn = (k == 3) ? VP1r : VP1[(k + 1) & 3];
+		    const double dv = (VR0[k] * ra1 - VR1[k] * ra0) * idrb + (vpn - VP1[k]) * c.invdphi * irb;
+		    DV1[k] = dv;
+		    const double drr = (VR0[k] - VR1[k]) * ids;
+		    TRR1[k] = 2.0 * N1[k] * S1[k] * (drr - 1.0 / 3.0 * dv);
+		    const double dpp = (vpn - VP1[k]) * c.invdphi * irb + 0.5 * (VR0[k] + VR1[k]) * irb;
+		    TPP1[k] = 2.0 * N1[k] * S1[k] * (dpp - 1.0 / 3.0 * dv);
+		}
+	    }
+	    // update_velocities_with_viscosity (:355-426)
+	    const double TPP1l = shfl_from_left(TPP1[3]), S1l = shfl_from_left(S1[3]);
+	    const double TRP1r = shfl_from_right(TRP1[0]), TRP0r = shfl_from_right(TRP0[0]);
+	    FS_FOR4
+	    {
+		VRn[k] = VR1[k];
+		VPn[k] = VP1[k];
+	    }
+	    if (r >= 1 && r < nr - 1) {
+		const double ra = c.g.rinf[r], rap = c.g.rinf[r + 1];
+		const double ra2 = ra * ra, rap2 = rap * rap;
+		const double irb = c.g.invrmed[r];
+		FS_FOR4
+		{
+		    const double sp = (k == 0) ? S1l : S1[(k + 3) & 3];
+		    const double tppl = (k == 0) ? TPP1l : TPP1[(k + 3) & 3];
+		    const double sigma_avg = 0.5 * (S1[k] + sp);
+		    const double dVp = dt * irb / (sigma_avg) *
+				       ((2.0 / (rap2 - ra2)) * (rap2 * TRP0[k] - ra2 * TRP1[k]) + (TPP1[k] - tppl) * c.invdphi);
+		    VPn[k] = VP1[k] + dVp;
+		}
+	    }
+	    if (r >= c.one_no_ghost_vr && r < c.maxmo_no_ghost_vr) {
+		const double rb = c.g.rmed[r], rbm = c.g.rmed[r - 1], idr = c.g.invdiffrmed[r];
+		FS_FOR4
+		{
+		    const double trpn = (k == 3) ? TRP1r : TRP1[(k + 1) & 3];
+		    const double sigma_avg = 0.5 * (S1[k] + S2[k]);
+		    const double dVr = dt / (sigma_avg)*c.p.radial_viscosity_factor * 2.0 / (rb + rbm) *
+				       ((rb * TRR1[k] - rbm * TRR2[k]) * idr + (trpn - TRP1[k]) * c.invdphi - 0.5 * (TPP1[k] + TPP2[k]));
+		    VRn[k] = VR1[k] + dVr;
+		}
+	    }
+	    if (r >= i_first) {
+		fs_store(o_vr, r, c, L, VRn);
+		fs_store(o_vp, r, c, L, VPn);
+	    }
+	    if (ADI) { // SubStep3 (SourceEuler.cpp:859-954)
+		double Qp[4], Qm[4], En[4], s0[4], e0[4];
+		if (need0 && r >= i_first) {
+		    fs_load(sigma0, r, c, L, s0);
+		    fs_load(energy0, r, c, L, e0);
+		} else {
+		    FS_FOR4 { s0[k] = 1.0, e0[k] = 0.0; }
+		}
+		const bool inner = r >= 1 && r < nr - 1;
+		FS_FOR4
+		{
+		    double q = 0.0;
+		    if (c.p.heating_viscous && inner && N1[k] != 0.0) { // viscous_heating :496-536
+			const double trpn1 = (k == 3) ? TRP1r : TRP1[(k + 1) & 3];
+			const double trpn0 = (k == 3) ? TRP0r : TRP0[(k + 1) & 3];
+			const double tau_r_phi = 0.25 * (TRP1[k] + TRP0[k] + trpn1 + trpn0);
+			double qplus = 1.0 / (2.0 * N1[k] * S1[k]) * (TRR1[k] * TRR1[k] + 2 * (tau_r_phi * tau_r_phi) + TPP1[k] * TPP1[k]);
+			qplus += (2.0 / 9.0) * N1[k] * S1[k] * (DV1[k] * DV1[k]);
+			qplus *= c.p.heating_viscous_factor;
+			q += qplus;
+		    }
+		    Qp[k] = q;
+		    Qm[k] = qminus_cell(c, beta_inv, S1[k], E1[k], s0[k], e0[k], r);
+		    En[k] = E1[k];
+		}
+		if (inner) {
+		    FS_FOR4
+		    {
+			const double alpha = radiative_alpha(c, r, S1[k], E1[k]);
+			const Rcp ra = make_rcp(alpha);
+			Qp[k] = div_by(Qp[k], ra);
+			Qm[k] = div_by(Qm[k], ra);
+			double energy_new = E1[k] + dt * (Qp[k] - Qm[k]);
+			const double SigmaFloor = 10.0 * c.p.sigma0 * c.p.sigma_floor;
+			if (S1[k] < SigmaFloor) {
+			    /* TAU_EFF is only filled by surface cooling (out of scope) => 0 as allocated */
+			    const double e4 = Qp[k] * 0.0 / (2.0 * c.p.sigma_sb);
+			    const double constant = (c.p.Rgas / c.p.mu * S1[k] / (c.p.gamma - 1.0));
+			    const double eq_energy = pow(e4, 1.0 / 4.0) * constant;
+			    Qm[k] = Qp[k];
+			    energy_new = eq_energy;
+			}
+			En[k] = energy_new;
+		    }
+		}
+		FS_FOR4 En[k] = temperature_clamp(tc, S1[k], En[k]);
+		if (r >= i_first) {
+		    fs_store(o_qplus, r, c, L, Qp);
+		    fs_store(o_qminus, r, c, L, Qm);
+		    fs_store(o_e, r, c, L, En);
+		}
+	    }
+	    FS_FOR4
+	    {
+		S2[k] = S1[k];
+		TRR2[k] = TRR1[k];
+		TPP2[k] = TPP1[k];
+	    }
+	}
+	FS_FOR4
+	{
+	    S1[k] = S0[k];
+	    E1[k] = E0[k];
+	    VR1[k] = VR0[k];
+	    VP1[k] = VP0[k];
+	    N1[k] = N0[k];
+	    TRP1[k] = TRP0[k];
+	}
+    }
+    if (i_last == nr)
+	fs_store(o_vr, nr, c, L, VR1);
+}

@@ -154,100 +154,246 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------------------------
-// cfl::condition_cfl (cfl.cpp:185-382).  Per-cell limits are recomputed from the state (c_s, nu are never
-// stored); block min via warp shuffles, then ONE atomicMin per block on the bit pattern of the (positive)
-// double — a single-pass grid reduction.
+// Ring means.  The reference sums v_azi(i, 0..Ns-1) strictly in index order (cfl.cpp:199-204,
+// TransportEuler.cpp:179-187); the result feeds the CFL dt and the integer shifts, which must be bit-exact, so
+// the order is kept: every LANE owns one ring and adds its ring's values one after the other.  A warp therefore
+// works on 32 rings at once; 32x32 tiles are brought in with coalesced 8-byte cp.async copies through a 4-stage
+// shared-memory ring (row stride 33 doubles: the transposed reads are conflict-free), so ~6 MB of loads are in
+// flight chip-wide while the dependent DADD chains run.
+// mode 0: only vmean (CFL).  mode 1: also Nshift[i] and the constant residual velocity (transport).
+#define RM_STAGES 4
+__device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(32)
+    k_ring_mean(const DevView c, const double *__restrict__ vp, double *__restrict__ vmean, int *__restrict__ nshift,
+		double *__restrict__ vconst, const double dt, const int mode)
+{
+    __shared__ double tile[RM_STAGES][32][33];
+    const int lane = threadIdx.x;
+    const int ring0 = blockIdx.x * 32;
+    const int nrows = min(32, c.nr - ring0);
+    const int ns = c.ns;
+    const int ntiles = (ns + 31) >> 5;
+    auto issue = [&](const int t) {
+	if (t < ntiles) {
+	    const int j = (t << 5) + lane;
+	    if (j < ns) {
+		double(*dst)[33] = tile[t % RM_STAGES];
+		const double *src = vp + (size_t)ring0 * ns + j;
+		for (int r = 0; r < nrows; ++r)
+		    cp_async_8(&dst[r][lane], src + (size_t)r * ns);
+	    }
+	}
+	cp_async_commit();
+    };
+#pragma unroll
+    for (int t = 0; t < RM_STAGES - 1; ++t)
+	issue(t);
+    double s = 0.0;
+    for (int t = 0; t < ntiles; ++t) {
+	cp_async_wait<RM_STAGES - 2>();
+	__syncwarp();
+	const double *rowp = tile[t % RM_STAGES][lane];
+	const int kmax = min(32, ns - (t << 5));
+	if (kmax == 32) {
+#pragma unroll
+	    for (int k = 0; k < 32; ++k)
+		s += rowp[k];
+	} else {
+	    for (int k = 0; k < kmax; ++k)
+		s += rowp[k];
+	}
+	__syncwarp();
+	issue(t + RM_STAGES - 1);
+    }
+    if (lane < nrows) {
+	const int i = ring0 + lane;
+	const double mean = s / (double)ns;
+	vmean[i] = mean;
+	if (mode == 1) {
+	    const double invdt = 1.0 / dt;
+	    const double Ntilde = mean * c.g.invrmed[i] * dt * c.invdphi;
+	    const double Nround = floor(Ntilde + 0.5);
+	    nshift[i] = (int)Nround;
+	    vconst[i] = (Ntilde - Nround) * c.g.rmed[i] * invdt * c.dphi;
+	}
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// cfl::condition_cfl (cfl.cpp:185-382).  dt_cell = CFL / sqrt(A) with A the sum of the six squared inverse time
+// scales; sqrt and the division are monotone under round-to-nearest, so min(dt_cell) == CFL / sqrt(max A) and the
+// kernel reduces A exactly as the reference forms it (same operations, same order) and pays for one sqrt + one
+// division per BLOCK.  NaN limits are ignored like the reference's `dt_cell < dt` does.  A thread owns 4
+// consecutive columns of one ring, so the divisions by per-ring constants (cell sizes, sqrt(gamma)) go through
+// shared exact reciprocals; what remains per cell is 2 IEEE divisions (by Sigma and by e) and one sqrt, and the
+// kernel is bound by its 6 array reads.  Block-max via warp shuffles, then ONE atomicMin per block on the bit
+// pattern of the (non-negative) double: a single-pass grid reduction.
 __device__ __forceinline__ void atomic_min_pos_double(double *addr, double v)
 {
     // for non-negative IEEE doubles the unsigned bit pattern is monotone in the value
     atomicMin(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
 }
 
-__global__ void __launch_bounds__(256)
+// grid: x over azimuth (512 columns per block of 128 threads), y over the active rings
+__global__ void __launch_bounds__(128)
     k_cfl(const DevView c, const double *__restrict__ sigma, const double *__restrict__ energy,
 	  const double *__restrict__ vr, const double *__restrict__ vp, const double *__restrict__ qplus,
 	  const double *__restrict__ qminus, const double *__restrict__ cf_r, const double *__restrict__ cf_phi,
 	  const double *__restrict__ vmean, double *__restrict__ dt_out)
 {
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int nact = c.active_size - c.first_active;
+    const int i = c.first_active + blockIdx.y;
+    const int ns = c.ns;
+    const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const double DMAX = 1.7976931348623157e308;
     const double CFL = c.p.cfl;
-    double best = 1.7976931348623157e308;
-    if (gid < (long long)nact * c.ns) {
-	const int i = c.first_active + (int)(gid / c.ns);
-	const int j = (int)(gid - (long long)(i - c.first_active) * c.ns);
-	const int jp = (j == c.ns - 1) ? 0 : j + 1;
+    double best = DMAX; // limits that are not of the CFL / sqrt(A) form
+    double Amax = -1.0;
+    const bool adiabatic = c.p.adiabatic != 0;
+    const double vm = vmean[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) { // FARGO shear criterion (:207-220); the (0,1) pair is the reference's initial dt_core
+	const double denom = fabs(vm * c.g.invrmed[i] - vmean[i + 1] * c.g.invrmed[i + 1]) + 1.0e-100;
+	best = CFL * c.dphi / denom;
+	if (i == c.first_active) {
+	    const double denom0 = fabs(vmean[0] * c.g.invrmed[0] - vmean[1] * c.g.invrmed[1]) + 1.0e-100;
+	    const double d0 = CFL * c.dphi / denom0;
+	    if (d0 < best)
+		best = d0;
+	}
+    }
+    if (j0 < ns) {
 	const double lf = c.p.leapfrog ? 0.6 : 1.0;
 	const double C = c.p.artificial_viscosity_factor;
-	if (j == 0) { // FARGO shear criterion (:207-220); the (0,1) pair is the reference's initial dt_core
-	    const double denom = fabs(vmean[i] * c.g.invrmed[i] - vmean[i + 1] * c.g.invrmed[i + 1]) + 1.0e-100;
-	    best = CFL * c.dphi / denom;
-	    if (i == c.first_active) {
-		const double denom0 = fabs(vmean[0] * c.g.invrmed[0] - vmean[1] * c.g.invrmed[1]) + 1.0e-100;
-		const double d0 = CFL * c.dphi / denom0;
-		if (d0 < best)
-		    best = d0;
-	    }
-	}
 	const double dxRadial = c.g.rsup[i] - c.g.rinf[i];
 	const double dxAzimuthal = c.g.rmed[i] * c.dphi;
 	const double cell_size = stdmin(dxRadial, dxAzimuthal);
-	const double s = AT(sigma, i, j), e = AT(energy, i, j);
-	const double vr0 = AT(vr, i, j), vr1 = AT(vr, i + 1, j), vp0 = AT(vp, i, j), vp1 = AT(vp, i, jp);
-	const double vres = c.p.fast_transport ? vp0 - vmean[i] : vp0;
-	const double invdt1 = eos_cs(c, i, s, e) / cell_size;
-	const double invdt2 = vr0 / dxRadial;
-	const double invdt3 = vres / dxAzimuthal;
-	double invdt4;
-	if (c.p.artificial_viscosity == FARGO_ARTVISC_SN) {
-	    double dvRadial = vr1 - vr0;
-	    double dvAzimuthal = vp1 - vp0;
-	    dvRadial = (dvRadial > 0.0) ? 0.0 : -dvRadial;
-	    dvAzimuthal = (dvAzimuthal > 0.0) ? 0.0 : -dvAzimuthal;
-	    invdt4 = 4.0 * (C * C) * stdmax(dvRadial / dxRadial, dvAzimuthal / dxAzimuthal) * lf;
-	} else { // TW form, also for ArtificialViscosity: None
-	    const double eps_rr = (vr1 - vr0) * c.g.invdiffrsup[i];
-	    const double eps_pp = c.g.invrmed[i] * ((vp1 - vp0) * c.invdphi + 0.5 * (vr1 + vr0));
-	    const double mdiv_V = -stdmin(eps_rr + eps_pp, 0.0);
-	    invdt4 = 4.0 * (C * C) * mdiv_V * lf;
+	const Rcp r_cell = make_rcp(cell_size), r_dxr = make_rcp(dxRadial), r_dxa = make_rcp(dxAzimuthal);
+	const Rcp r_cell2 = make_rcp(cell_size * cell_size), r_sqg = make_rcp(c.sqrt_gamma);
+	const double inv_limit = 1.0 / c.p.heating_cooling_cfl_limit;
+	const double ids = c.g.invdiffrsup[i], irb = c.g.invrmed[i], iok = c.g.inv_omega_k[i];
+	const bool vec = ((ns & 3) == 0);
+	double S[4], E[4], V0[4], V1[4], P[5], QP[4], QM[4];
+	const size_t row = (size_t)i * ns;
+	if (vec) {
+	    auto ld4 = [&](const double *base, double *x) {
+		const double2 a = *reinterpret_cast<const double2 *>(base + j0);
+		const double2 b = *reinterpret_cast<const double2 *>(base + j0 + 2);
+		x[0] = a.x, x[1] = a.y, x[2] = b.x, x[3] = b.y;
+	    };
+	    ld4(sigma + row, S);
+	    ld4(vr + row, V0);
+	    ld4(vr + row + ns, V1);
+	    ld4(vp + row, P);
+	    P[4] = vp[row + ((j0 + 4 == ns) ? 0 : j0 + 4)];
+	    if (adiabatic) {
+		ld4(energy + row, E);
+		ld4(qplus + row, QP);
+		ld4(qminus + row, QM);
+	    }
+	} else {
+#pragma unroll
+	    for (int k = 0; k < 5; ++k) {
+		const int j = j0 + k;
+		const int jj = (j < ns) ? j : j - ns; // only the neighbour column may wrap; surplus columns are masked below
+		P[k] = vp[row + (jj < ns ? jj : 0)];
+		if (k < 4) {
+		    const int js = (j < ns) ? j : 0;
+		    S[k] = sigma[row + js];
+		    V0[k] = vr[row + js];
+		    V1[k] = vr[row + ns + js];
+		    if (adiabatic) {
+			E[k] = energy[row + js];
+			QP[k] = qplus[row + js];
+			QM[k] = qminus[row + js];
+		    }
+		}
+	    }
 	}
-	const double invdt5 = 4.0 * eos_nu(c, i, s, e) / (cell_size * cell_size) * lf;
-	double invdt6 = 0.0;
-	if (c.p.adiabatic) {
-	    const double inv_limit = 1.0 / c.p.heating_cooling_cfl_limit;
-	    invdt6 = inv_limit * fabs((AT(qplus, i, j) - AT(qminus, i, j)) / e) * lf;
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+	    if (!vec && j0 + k >= ns)
+		continue;
+	    const double s = S[k], e = adiabatic ? E[k] : 0.0;
+	    const double vr0 = V0[k], vr1 = V1[k], vp0 = P[k], vp1 = P[k + 1];
+	    const double vres = c.p.fast_transport ? vp0 - vm : vp0;
+	    const double cs = eos_cs(c, i, s, e);
+	    const double invdt1 = div_by(cs, r_cell);
+	    const double invdt2 = div_by(vr0, r_dxr);
+	    const double invdt3 = div_by(vres, r_dxa);
+	    double invdt4;
+	    if (c.p.artificial_viscosity == FARGO_ARTVISC_SN) {
+		double dvRadial = vr1 - vr0;
+		double dvAzimuthal = vp1 - vp0;
+		dvRadial = (dvRadial > 0.0) ? 0.0 : -dvRadial;
+		dvAzimuthal = (dvAzimuthal > 0.0) ? 0.0 : -dvAzimuthal;
+		invdt4 = 4.0 * (C * C) * stdmax(div_by(dvRadial, r_dxr), div_by(dvAzimuthal, r_dxa)) * lf;
+	    } else { // TW form, also for ArtificialViscosity: None
+		const double eps_rr = (vr1 - vr0) * ids;
+		const double eps_pp = irb * ((vp1 - vp0) * c.invdphi + 0.5 * (vr1 + vr0));
+		const double mdiv_V = -stdmin(eps_rr + eps_pp, 0.0);
+		invdt4 = 4.0 * (C * C) * mdiv_V * lf;
+	    }
+	    double nu;
+	    if (c.p.viscous_alpha > 0) { // eos_nu with the division by sqrt(gamma) shared
+		const double H = adiabatic ? div_by(cs, r_sqg) * iok : cs * iok;
+		nu = c.p.viscous_alpha * H * cs;
+	    } else {
+		nu = c.p.constant_viscosity;
+	    }
+	    const double invdt5 = div_by(4.0 * nu, r_cell2) * lf;
+	    double invdt6 = 0.0;
+	    if (adiabatic)
+		invdt6 = inv_limit * fabs((QP[k] - QM[k]) / e) * lf;
+	    const double A = invdt1 * invdt1 + invdt2 * invdt2 + invdt3 * invdt3 + invdt4 * invdt4 + invdt5 * invdt5 + invdt6 * invdt6;
+	    if (c.p.stabilize_viscosity == 2) { // per-cell min(dt_cell, -CFL / min(c_phi, c_r)), cfl.cpp:330-338
+		double dt_cell = CFL / sqrt(A);
+		const double cc = stdmin(cf_phi[row + j0 + k], cf_r[row + j0 + k]);
+		if (cc != 0.0)
+		    dt_cell = stdmin(dt_cell, -CFL / cc);
+		if (dt_cell < best)
+		    best = dt_cell;
+	    } else if (A > Amax) {
+		Amax = A;
+	    }
 	}
-	double dt_cell =
-	    CFL / sqrt(invdt1 * invdt1 + invdt2 * invdt2 + invdt3 * invdt3 + invdt4 * invdt4 + invdt5 * invdt5 + invdt6 * invdt6);
-	if (c.p.stabilize_viscosity == 2) {
-	    const double cc = stdmin(AT(cf_phi, i, j), AT(cf_r, i, j));
-	    if (cc != 0.0)
-		dt_cell = stdmin(dt_cell, -CFL / cc);
-	}
-	if (dt_cell < best)
-	    best = dt_cell;
     }
-    // block reduction
+    // block reduction: max of A, min of the other limits
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-	const double other = __shfl_xor_sync(0xffffffffu, best, o);
-	if (other < best)
-	    best = other;
+	const double oa = __shfl_xor_sync(0xffffffffu, Amax, o);
+	const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+	if (oa > Amax)
+	    Amax = oa;
+	if (ob < best)
+	    best = ob;
     }
-    __shared__ double wmin[8];
+    __shared__ double wa[4], wb[4];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0)
-	wmin[w] = best;
+    if (lane == 0) {
+	wa[w] = Amax;
+	wb[w] = best;
+    }
     __syncthreads();
-    if (w == 0) {
-	best = (lane < (blockDim.x >> 5)) ? wmin[lane] : 1.7976931348623157e308;
+    if (threadIdx.x == 0) {
 #pragma unroll
-	for (int o = 4; o > 0; o >>= 1) {
-	    const double other = __shfl_xor_sync(0xffffffffu, best, o);
-	    if (other < best)
-		best = other;
+	for (int k = 1; k < 4; ++k) {
+	    if (wa[k] > Amax)
+		Amax = wa[k];
+	    if (wb[k] < best)
+		best = wb[k];
 	}
-	if (lane == 0)
+	if (Amax >= 0.0) {
+	    const double dt_cell = CFL / sqrt(Amax);
+	    if (dt_cell < best)
+		best = dt_cell;
+	}
+	if (best < DMAX)
 	    atomic_min_pos_double(dt_out, best);
     }
 }

@@ -202,6 +202,10 @@ int fargo_stage_transport(fargo_ctx *ctx, double dt);  /* Transport TransportEul
 int fargo_stage_halo(fargo_ctx *ctx);                  /* CommunicateBoundaries commbound.cpp:98 */
 int fargo_stage_derived(fargo_ctx *ctx);               /* recalculate_derived_disk_quantities SourceEuler.cpp:225 */
 
+/* fargo_step normally runs the fused source-term kernels; on != 0 makes it go through the per-stage kernels above
+ * instead (same results; used by the parity tests to cross-check both) */
+int fargo_set_staged(fargo_ctx *ctx, int on);
+
 /* integer FARGO shifts of the last transport (TransportEuler.cpp:49,220), local rings */
 int fargo_get_nshift(fargo_ctx *ctx, int *out_local_nrad);
 

@@ -69,10 +69,13 @@ def test_stage_by_stage_vs_oracle(name):
         assert gpu.condition_cfl() == pytest.approx(cpu.condition_cfl(), rel=0 if name in ISOTHERMAL else 1e-12)
 
 
+@pytest.mark.parametrize("staged", [False, True], ids=["fused", "staged"])
 @pytest.mark.parametrize("name", CASES)
-def test_golden_run_vs_reference(name):
-    """Full time loop over the recorded fixture: dt sequence, N_iter, time and fields against the reference."""
+def test_golden_run_vs_reference(name, staged):
+    """Full time loop over the recorded fixture: dt sequence, N_iter, time and fields against the reference.
+    fargo_step's fused source-term kernels and the per-stage kernels must both reproduce it."""
     meta, z, gpu, cpu = _ctx_pair(name)
+    gpu.set_staged(staged)
     snaps = goldenrun.run_fixture(gpu, meta, z)
     for k, snap in enumerate(snaps, start=1):
         m = meta["misc"][k]
