@@ -13,10 +13,11 @@
 // transported Sigma and rm+ (v_rad couples rings i-1 and i at the same output column).
 //
 // Arithmetic is the reference's, operation for operation (-fmad=false); the only algebraic liberties are exact
-// ones: x - c*d == x + (-c)*d, dx + ksi == dx - |ksi| for ksi <= 0, and the shared-reciprocal division of
-// fargo_dev.h.
+// ones: x - c*d == x + (-c)*d, dx + ksi == dx - |ksi| for ksi <= 0, and the branch-free division of fargo_math.h
+// (the compiler's own IEEE sequence, emitted straight-line so the Newton chains of the 4 columns interleave).
 #pragma once
 #include "fargo_dev.h"
+#include "fargo_math.h"
 
 #define AZ_WIN 128 // columns per warp window
 #define AZ_HL 8	   // invalid columns at the left end (5 needed, rounded up for 32-byte aligned stores)
@@ -30,6 +31,25 @@ struct AzRing {
     double dxtheta, invdxtheta, dxrad, invsurf;
 };
 
+// Branch-free flux limiter (TransportEuler.cpp:306-337): the division runs unconditionally (its result is
+// discarded where a*b <= 0, whatever it is) and its validity key is masked by the same predicate.
+template <int LIM> __device__ __forceinline__ double limiter_nb(const double a, const double b, FmAcc &acc)
+{
+    if (LIM == FARGO_LIMITER_MC) {
+	return flux_limiter<LIM>(a, b); // compares and selects only
+    } else {
+	const double p = a * b;
+	const bool pos = p > 0.0;
+	const double den = a + b;
+	const double num = 2.0 * a * b;
+	const double y = fm_rcp_raw(den);
+	const double q = fm_div_raw(num, den, y);
+	fm_acc_num_if(acc, pos, num);
+	fm_acc_rcp_if(acc, pos, y);
+	return pos ? q : 0.0;
+    }
+}
+
 // ComputeStarTheta (:416-466) for one base quantity B on the thread's 4 columns: limited slopes, then the
 // upwinded interface values.  pos[c]: ksi > 0 at interface c (between columns c-1 and c); cf[c] = +-(dxtheta -+ ksi).
 template <int LIM>
@@ -38,11 +58,17 @@ __device__ __forceinline__ void az_star(const double (&B)[4], const AzRing &g, c
 {
     const double Bm = shfl_from_left(B[3]);
     const double Bp = shfl_from_right(B[0]);
+    const double dq[5] = {B[0] - Bm, B[1] - B[0], B[2] - B[1], B[3] - B[2], Bp - B[3]};
     double D[4];
-    D[0] = 0.5 * flux_limiter<LIM>(B[1] - B[0], B[0] - Bm) * g.invdxtheta;
-    D[1] = 0.5 * flux_limiter<LIM>(B[2] - B[1], B[1] - B[0]) * g.invdxtheta;
-    D[2] = 0.5 * flux_limiter<LIM>(B[3] - B[2], B[2] - B[1]) * g.invdxtheta;
-    D[3] = 0.5 * flux_limiter<LIM>(Bp - B[3], B[3] - B[2]) * g.invdxtheta;
+    FmAcc acc;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+	D[c] = 0.5 * limiter_nb<LIM>(dq[c + 1], dq[c], acc) * g.invdxtheta;
+    if (!fm_acc_ok(acc)) { // cold: extreme exponents
+#pragma unroll
+	for (int c = 0; c < 4; ++c)
+	    D[c] = 0.5 * flux_limiter<LIM>(dq[c + 1], dq[c]) * g.invdxtheta;
+    }
     const double Dm = shfl_from_left(D[3]);
     star[0] = (pos[0] ? Bm : B[0]) + cf[0] * (pos[0] ? Dm : D[0]);
     star[1] = (pos[1] ? B[0] : B[1]) + cf[1] * (pos[1] ? D[0] : D[1]);
@@ -85,18 +111,29 @@ __device__ __forceinline__ void az_pass(double (&Q)[6][4], const double (&u)[4],
     }
     double starS[4];
     az_star<LIM>(Q[5], g, pos, cf, starS);
-    Rcp rS[4];
+    double yS[4];
+    FmAcc accS;
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
-	rS[c] = make_rcp(Q[5][c]);
+    for (int c = 0; c < 4; ++c) {
+	yS[c] = fm_rcp_raw(Q[5][c]);
+	fm_acc_rcp(accS, yS[c]);
+    }
 #pragma unroll
     for (int q = 0; q < 5; ++q) {
 	if (q == 4 && !ADI)
 	    continue;
 	double W[4], st[4], G[4];
+	FmAcc acc = accS;
 #pragma unroll
-	for (int c = 0; c < 4; ++c)
-	    W[c] = div_by(Q[q][c], rS[c]); // divise_polargrid (SideEuler.cpp:27-43)
+	for (int c = 0; c < 4; ++c) {
+	    W[c] = fm_div_raw(Q[q][c], Q[5][c], yS[c]); // divise_polargrid (SideEuler.cpp:27-43)
+	    fm_acc_num(acc, Q[q][c]);
+	}
+	if (!fm_acc_ok(acc)) { // cold: zero / tiny momenta
+#pragma unroll
+	    for (int c = 0; c < 4; ++c)
+		W[c] = Q[q][c] / Q[5][c];
+	}
 	az_star<LIM>(W, g, pos, cf, st);
 #pragma unroll
 	for (int c = 0; c < 4; ++c)
@@ -137,9 +174,9 @@ __global__ void __launch_bounds__(128, 3)
     const double OmegaF = c.b.omega_frame;
     const double floorv = c.p.sigma_floor * c.p.sigma0;
     const bool fargo = c.p.fast_transport != 0;
-    TempClamp tc;
+    TempClampNB tc;
     if (ADI)
-	tc = make_temp_clamp(c);
+	tc = make_temp_clamp_nb(c);
 
     double PS[4] = {0.0, 0.0, 0.0, 0.0}, PR[4] = {0.0, 0.0, 0.0, 0.0}; // previous ring: transported Sigma, rm+
 
@@ -173,26 +210,49 @@ __global__ void __launch_bounds__(128, 3)
 	    U[k] = u;
 	    col = (col + 1 == ns) ? 0 : col + 1;
 	}
-	// pass 1: residual velocity; pass 2: constant residual velocity (skipped for standard transport, :646)
-	az_pass<LIM, ADI>(Q, U, g, dt);
-	if (fargo) {
-	    const double UC[4] = {vc, vc, vc, vc};
-	    az_pass<LIM, ADI>(Q, UC, g, dt);
+	// pass 1: residual velocity; pass 2: constant residual velocity (skipped for standard transport, :646).
+	// One copy of the pass code (the loop is deliberately not unrolled: the kernel must stay inside the I-cache).
+	const int npass = fargo ? 2 : 1;
+#pragma unroll 1
+	for (int pass = 0; pass < npass; ++pass) {
+	    az_pass<LIM, ADI>(Q, U, g, dt);
+#pragma unroll
+	    for (int k = 0; k < 4; ++k)
+		U[k] = vc;
 	}
 	// velocities from momenta (:498-535), floors (:123-131)
 	const double am_left = shfl_from_left(Q[2][3]);
 	const double s_left = shfl_from_left(Q[5][3]);
 	if (i >= i_first && lane_out) {
-	    double vrn[4], vpn[4], sf[4], en[4];
+	    double vrn[4], vpn[4], sf[4], en[4], nvr[4], dvr[4], nvp[4], dvp[4];
+	    FmAcc acc;
 #pragma unroll
 	    for (int k = 0; k < 4; ++k) {
 		const double s = Q[5][k];
 		const double sm = (k == 0) ? s_left : Q[5][k - 1];
 		const double amp_m = (k == 0) ? am_left : Q[2][k - 1];
-		vrn[k] = (i == 0) ? 0.0 : (PR[k] + Q[1][k]) / (PS[k] + s);
-		vpn[k] = (amp_m + Q[3][k]) / (sm + s) * invrmed - rmed * OmegaF;
+		nvr[k] = PR[k] + Q[1][k];
+		dvr[k] = PS[k] + s;
+		nvp[k] = amp_m + Q[3][k];
+		dvp[k] = sm + s;
+		const double yr = fm_rcp_raw(dvr[k]), yp = fm_rcp_raw(dvp[k]);
+		fm_acc_num_if(acc, i != 0, nvr[k]);
+		fm_acc_rcp_if(acc, i != 0, yr);
+		fm_acc_num(acc, nvp[k]);
+		fm_acc_rcp(acc, yp);
+		vrn[k] = (i == 0) ? 0.0 : fm_div_raw(nvr[k], dvr[k], yr);
+		vpn[k] = fm_div_raw(nvp[k], dvp[k], yp) * invrmed - rmed * OmegaF;
 		sf[k] = (s < floorv) ? floorv : s;
-		en[k] = ADI ? temperature_clamp(tc, sf[k], Q[4][k]) : 0.0;
+		en[k] = ADI ? temperature_clamp_nb(tc, sf[k], Q[4][k], acc) : 0.0;
+	    }
+	    if (!fm_acc_ok(acc)) { // cold
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+		    vrn[k] = (i == 0) ? 0.0 : nvr[k] / dvr[k];
+		    vpn[k] = nvp[k] / dvp[k] * invrmed - rmed * OmegaF;
+		    if (ADI)
+			en[k] = temperature_clamp(c, sf[k], Q[4][k]);
+		}
 	    }
 	    if (vec_ok) {
 		if (jout < ns) { // jout is a multiple of 4, so all four columns are inside
