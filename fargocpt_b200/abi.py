@@ -240,6 +240,8 @@ def load_library():
         lib.fargo_stage_halo.restype = C.c_int
         lib.fargo_set_staged.argtypes = [C.c_void_p, C.c_int]
         lib.fargo_set_staged.restype = C.c_int
+        lib.fargo_selftest_math.argtypes = [C.c_void_p, C.c_ulonglong, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_ulonglong)]
+        lib.fargo_selftest_math.restype = C.c_int
         lib.fargo_sync.argtypes = [C.c_void_p]
         lib.fargo_sync.restype = C.c_int
         lib.fargo_launch_count.argtypes = [C.c_void_p]
@@ -278,6 +280,12 @@ class HydroContext(Handle):
 
     def sync(self):
         self._check(self.lib.fargo_sync(self.ptr), "sync")
+
+    def selftest_math(self, seed=1, blocks=1024, per_thread=256, wide=False):
+        out = (C.c_ulonglong * 4)()
+        self._check(self.lib.fargo_selftest_math(self.ptr, seed, blocks, per_thread, int(wide), out), "selftest_math")
+        return {"div_mismatch": out[0], "sqrt_mismatch": out[1], "exp_mismatch": out[2], "div_fast": out[3],
+                "pairs": 256 * blocks * per_thread}
 
     def set_staged(self, on):
         """step() through the per-stage kernels (one per reference loop nest) instead of the fused ones."""

@@ -21,6 +21,7 @@
 #include "kernels_transport.cuh"
 #include "kernels_azimuthal.cuh"
 #include "kernels_fused.cuh"
+#include "fargo_selftest.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // error handling: the reference die()s; we return non-zero and keep the message (thread-local)
@@ -1056,5 +1057,23 @@ extern "C" int fargo_event_elapsed_ms(fargo_ctx *c, int slot_a, int slot_b, doub
     float ms = 0;
     CUDA_OK(cudaEventElapsedTime(&ms, c->ev_user[slot_a], c->ev_user[slot_b]));
     *ms_out = ms;
+    return 0;
+}
+
+// device self-test of the branch-free arithmetic (fargo_math.h) against the plain operators; counts[4] =
+// {division mismatches, sqrt mismatches, exp mismatches, divisions that took the fast path}
+extern "C" int fargo_selftest_math(fargo_ctx *c, unsigned long long seed, int blocks, int per_thread, int wide,
+				    unsigned long long *counts4)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    unsigned long long *d = nullptr;
+    CUDA_OK(cudaMalloc((void **)&d, 4 * sizeof(unsigned long long)));
+    CUDA_OK(cudaMemsetAsync(d, 0, 4 * sizeof(unsigned long long), c->stream));
+    k_selftest_math<<<blocks, 256, 0, c->stream>>>(seed, per_thread, wide, d);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(counts4, d, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(cudaFree(d));
     return 0;
 }

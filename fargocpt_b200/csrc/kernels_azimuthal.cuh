@@ -42,10 +42,10 @@ template <int LIM> __device__ __forceinline__ double limiter_nb(const double a, 
 	const bool pos = p > 0.0;
 	const double den = a + b;
 	const double num = 2.0 * a * b;
-	const double y = fm_rcp_raw(den);
-	const double q = fm_div_raw(num, den, y);
+	const double q = fm_div_raw(num, den, fm_rcp_raw(den));
 	fm_acc_num_if(acc, pos, num);
-	fm_acc_rcp_if(acc, pos, y);
+	fm_acc_nrm_if(acc, pos, den);
+	fm_acc_nrm_if(acc, pos, q);
 	return pos ? q : 0.0;
     }
 }
@@ -116,7 +116,7 @@ __device__ __forceinline__ void az_pass(double (&Q)[6][4], const double (&u)[4],
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
 	yS[c] = fm_rcp_raw(Q[5][c]);
-	fm_acc_rcp(accS, yS[c]);
+	fm_acc_nrm(accS, Q[5][c]);
     }
 #pragma unroll
     for (int q = 0; q < 5; ++q) {
@@ -128,6 +128,7 @@ __device__ __forceinline__ void az_pass(double (&Q)[6][4], const double (&u)[4],
 	for (int c = 0; c < 4; ++c) {
 	    W[c] = fm_div_raw(Q[q][c], Q[5][c], yS[c]); // divise_polargrid (SideEuler.cpp:27-43)
 	    fm_acc_num(acc, Q[q][c]);
+	    fm_acc_nrm(acc, W[c]);
 	}
 	if (!fm_acc_ok(acc)) { // cold: zero / tiny momenta
 #pragma unroll
@@ -235,13 +236,16 @@ __global__ void __launch_bounds__(128, 3)
 		dvr[k] = PS[k] + s;
 		nvp[k] = amp_m + Q[3][k];
 		dvp[k] = sm + s;
-		const double yr = fm_rcp_raw(dvr[k]), yp = fm_rcp_raw(dvp[k]);
+		const double qr = fm_div_raw(nvr[k], dvr[k], fm_rcp_raw(dvr[k]));
+		const double qp = fm_div_raw(nvp[k], dvp[k], fm_rcp_raw(dvp[k]));
 		fm_acc_num_if(acc, i != 0, nvr[k]);
-		fm_acc_rcp_if(acc, i != 0, yr);
+		fm_acc_nrm_if(acc, i != 0, dvr[k]);
+		fm_acc_nrm_if(acc, i != 0, qr);
 		fm_acc_num(acc, nvp[k]);
-		fm_acc_rcp(acc, yp);
-		vrn[k] = (i == 0) ? 0.0 : fm_div_raw(nvr[k], dvr[k], yr);
-		vpn[k] = fm_div_raw(nvp[k], dvp[k], yp) * invrmed - rmed * OmegaF;
+		fm_acc_nrm(acc, dvp[k]);
+		fm_acc_nrm(acc, qp);
+		vrn[k] = (i == 0) ? 0.0 : qr;
+		vpn[k] = qp * invrmed - rmed * OmegaF;
 		sf[k] = (s < floorv) ? floorv : s;
 		en[k] = ADI ? temperature_clamp_nb(tc, sf[k], Q[4][k], acc) : 0.0;
 	    }

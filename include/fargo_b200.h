@@ -209,6 +209,12 @@ int fargo_set_staged(fargo_ctx *ctx, int on);
 /* integer FARGO shifts of the last transport (TransportEuler.cpp:49,220), local rings */
 int fargo_get_nshift(fargo_ctx *ctx, int *out_local_nrad);
 
+/* device self-test of the branch-free IEEE arithmetic the kernels use (csrc/fargo_math.h) against the plain
+ * operators on random + adversarial operands: counts4 = {division mismatches, sqrt mismatches, exp mismatches,
+ * divisions that took the fast path}; 256 * blocks * per_thread operand pairs; wide != 0 spans the full exponent range */
+int fargo_selftest_math(fargo_ctx *ctx, unsigned long long seed, int blocks, int per_thread, int wide,
+			unsigned long long *counts4);
+
 /* stream sync + launch accounting (for bench.py) */
 int fargo_sync(fargo_ctx *ctx);
 long long fargo_launch_count(const fargo_ctx *ctx);
