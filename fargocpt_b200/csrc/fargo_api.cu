@@ -248,7 +248,7 @@ static int init_geometry(fargo_ctx *c, const double *radii)
     v.sqrt_gamma = sqrt(p.gamma);
     std::vector<double> rinf(nl), rsup(nl), rmed(nl), surf(nl), invrmed(nl), invsurf(nl), invdiffrsup(nl), invdiffrsuprb(nl),
 	twodiffrasq(nl), fourthird(nl), invrinf(nl), invdiffrmed(nl, 0.0), omega_k(nl), inv_omega_k(nl), cs_iso(nl), supp(nl),
-	beta_e0(nl);
+	beta_e0(nl), idxt_mid(nl), idxt(nl);
     for (int n = 0; n < nl; ++n) {
 	const double ri = c->h_radii[n + v.imin], rs = c->h_radii[n + v.imin + 1];
 	rinf[n] = ri;
@@ -264,6 +264,11 @@ static int init_geometry(fargo_ctx *c, const double *radii)
 	twodiffrasq[n] = 2.0 / (rs * rs - ri * ri);
 	fourthird[n] = 4.0 / 3.0 / rm * v.invdphi * v.invdphi;
 	invrinf[n] = 1.0 / ri;
+	idxt_mid[n] = 2.0 / (v.dphi * (rs + ri));
+	{
+	    const double dxtheta = v.dphi * rm;
+	    idxt[n] = 1.0 / dxtheta;
+	}
 	omega_k[n] = omega_kepler_host(p, rm);
 	inv_omega_k[n] = 1.0 / omega_k[n];
 	{ // SourceEuler.cpp:984-991
@@ -293,7 +298,8 @@ static int init_geometry(fargo_ctx *c, const double *radii)
 	upload_vec(c, &g.twodiffrasq, twodiffrasq) || upload_vec(c, &g.fourthird, fourthird) ||
 	upload_vec(c, &g.invrinf, invrinf) || upload_vec(c, &g.invdiffrmed, invdiffrmed) || upload_vec(c, &g.cosphi, cosphi) ||
 	upload_vec(c, &g.sinphi, sinphi) || upload_vec(c, &g.omega_k, omega_k) || upload_vec(c, &g.inv_omega_k, inv_omega_k) ||
-	upload_vec(c, &g.cs_iso, cs_iso) || upload_vec(c, &g.supp_torque, supp) || upload_vec(c, &g.beta_model_e0, beta_e0))
+	upload_vec(c, &g.cs_iso, cs_iso) || upload_vec(c, &g.supp_torque, supp) || upload_vec(c, &g.beta_model_e0, beta_e0) ||
+	upload_vec(c, &g.invdxtheta_mid, idxt_mid) || upload_vec(c, &g.invdxtheta, idxt))
 	return 1;
     return 0;
 }

@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(128, 3)
 	const double rmed = c.g.rmed[i], invrmed = c.g.invrmed[i];
 	AzRing g;
 	g.dxtheta = c.dphi * rmed;
-	g.invdxtheta = 1.0 / g.dxtheta;
+	g.invdxtheta = c.g.invdxtheta[i]; // 1.0 / dxtheta, formed on the host with the same IEEE division
 	g.dxrad = (c.g.rsup[i] - c.g.rinf[i]) * dt;
 	g.invsurf = c.g.invsurf[i];
 	// pre-shift column of c = 0

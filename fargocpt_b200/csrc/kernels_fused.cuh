@@ -89,14 +89,139 @@ __device__ __forceinline__ void fs_store(double *__restrict__ arr, const int rin
 #define FS_FOR4 _Pragma("unroll") for (int k = 0; k < 4; ++k)
 
 // ---------------------------------------------------------------------------------------------
-// k_fused_sources.  Iteration k loads ring k, forms Phi(k), P(k), v_rad'(k) (needs ring k-1) and v_azi'(k), then
-// finishes ring r = k-1: e'(r) needs v_rad'(r+1).  Output: v_rad', v_azi', e' of ring r.
+// Stage bodies.  Each is written once against the arithmetic policy M (fargo_math.h): MathP<true> emits the
+// divisions / square roots / exponentials as straight-line fast paths and accumulates their validity in A,
+// MathP<false> uses the plain operators.  A kernel runs stage<MathP<true>> and, only if the accumulator failed
+// (exponents far outside anything physical, exact zeros as numerators), redoes the stage with MathP<false> from
+// the same inputs — outputs never alias inputs.  The hot path has no branch inside a stage, so the instruction
+// streams of the 4 columns (and of the bodies / quantities) interleave and hide the 12-cycle DFMA latency.
+#define FS_RUN(stage_call_fast, stage_call_slow) \
+    {                                            \
+	FmAcc A_;                                \
+	{                                        \
+	    FmAcc &A = A_;                       \
+	    stage_call_fast;                     \
+	}                                        \
+	if (!fm_acc_ok(A_)) {                    \
+	    FmAcc &A = A_;                       \
+	    stage_call_slow;                     \
+	}                                        \
+    }
+
+// CalculateNbodyPotential (Pframeforce.cpp:44-85) + pressure, ring kr
+template <class M, bool ADI>
+__device__ __forceinline__ void st_potential(const DevView &c, const EosC &ec, const int kr, const double (&S0)[4],
+					      const double (&E0)[4], const double (&cosj)[4], const double (&sinj)[4],
+					      double (&P0)[4], double (&F0)[4], FmAcc &A)
+{
+    const double rmed = c.g.rmed[kr];
+    double smooth[4], x[4], y[4], pot[4];
+    FS_FOR4
+    {
+	P0[k] = eos_P(c, kr, S0[k], E0[k]);
+	const double cs = eos_cs_m<M>(c, kr, S0[k], E0[k], A);
+	const double H = eos_H_m<M>(c, ec, kr, cs, A);
+	x[k] = rmed * cosj[k];
+	y[k] = rmed * sinj[k];
+	smooth[k] = c.p.thickness_smoothing * H;
+	pot[k] = 0.0;
+    }
+    for (int b = 0; b < c.b.n; ++b) {
+	const double bx = c.b.x[b], by = c.b.y[b], gm = -c.p.G * c.b.mass[b], r_sm = c.b.cubic_smoothing_radius[b];
+	FS_FOR4
+	{
+	    const double dx = x[k] - bx;
+	    const double dy = y[k] - by;
+	    const double dist_2 = dx * dx + dy * dy;
+	    const double d_smoothed = M::sqrt(dist_2 + smooth[k] * smooth[k], A);
+	    double smooth_factor_klahr = 1.0;
+	    if (r_sm > 0.0 && d_smoothed < r_sm) { // rare: inside a planet's cubic smoothing radius
+		const double q = d_smoothed / r_sm;
+		smooth_factor_klahr = (pow(q, 4.0) - 2.0 * pow(q, 3.0) + 2.0 * d_smoothed / r_sm);
+	    }
+	    pot[k] += M::div(gm, d_smoothed, A) * smooth_factor_klahr;
+	}
+    }
+    FS_FOR4
+    {
+	pot[k] += -c.b.indirect_x * x[k] - c.b.indirect_y * y[k];
+	F0[k] = pot[k];
+    }
+}
+
+// momentum_update_radial (SourceEuler.cpp:325-372): interface kr between rings kr-1 and kr
+template <class M>
+__device__ __forceinline__ void st_vrad(const DevView &c, const int kr, const double dt, const double (&S0)[4],
+					 const double (&S1)[4], const double (&P0)[4], const double (&P1)[4],
+					 const double (&F0)[4], const double (&F1)[4], const double (&VP0)[4], const double VP0r,
+					 const double (&VP1)[4], const double VP1r, const double (&VR0)[4], double (&VRn0)[4], FmAcc &A)
+{
+    const double idr = c.g.invdiffrmed[kr], rinf = c.g.rinf[kr], invrinf = c.g.invrinf[kr];
+    const double OmegaF = c.b.omega_frame;
+    FS_FOR4
+    {
+	double gradp = M::div(2.0, S0[k] + S1[k], A);
+	gradp *= (P0[k] - P1[k]);
+	gradp *= idr;
+	const double gradphi = (F0[k] - F1[k]) * idr;
+	const double vp0n = (k == 3) ? VP0r : VP0[(k + 1) & 3];
+	const double vp1n = (k == 3) ? VP1r : VP1[(k + 1) & 3];
+	const double vsum = VP0[k] + vp0n + VP1[k] + vp1n;
+	const double vt = 0.25 * vsum + rinf * OmegaF;
+	const double vt2 = vt * vt;
+	const double centrifugal_accel = vt2 * invrinf;
+	VRn0[k] = VR0[k] + dt * (-gradp - gradphi + centrifugal_accel);
+    }
+}
+
+// momentum_update_azimuthal (:375-428), ring kr
+template <class M>
+__device__ __forceinline__ void st_vazi(const DevView &c, const int kr, const double dt, const bool drift, const double (&S0)[4],
+					 const double Sl, const double (&P0)[4], const double Pl, const double (&F0)[4],
+					 const double Fl, const double (&VP0)[4], double (&VPn0)[4], FmAcc &A)
+{
+    const double invdxtheta = c.g.invdxtheta_mid[kr];
+    const double supp = drift ? c.g.supp_torque[kr] : 0.0;
+    FS_FOR4
+    {
+	const double sp = (k == 0) ? Sl : S0[(k + 3) & 3];
+	const double Pp = (k == 0) ? Pl : P0[(k + 3) & 3];
+	const double Fp = (k == 0) ? Fl : F0[(k + 3) & 3];
+	const double gradp = M::div(2.0, S0[k] + sp, A) * (P0[k] - Pp) * invdxtheta;
+	const double gradphi = (F0[k] - Fp) * invdxtheta;
+	double vpn = VP0[k] + dt * (-gradp - gradphi);
+	if (drift)
+	    vpn += dt * supp;
+	VPn0[k] = vpn;
+    }
+}
+
+// compression_heating (:459-493), ring r, with the UPDATED velocities
+template <class M>
+__device__ __forceinline__ void st_compress(const DevView &c, const int r, const double dt, const double (&E1)[4],
+					     const double (&VRn0)[4], const double (&VRn1)[4], const double (&VPn1)[4],
+					     const double VPn1r, double (&En)[4], FmAcc &A)
+{
+    const double ra1 = c.g.rinf[r + 1], ra0 = c.g.rinf[r], idrb = c.g.invdiffrsuprb[r], irb = c.g.invrmed[r];
+    FS_FOR4
+    {
+	const double vpn = (k == 3) ? VPn1r : VPn1[(k + 1) & 3];
+	const double DIV_V = (VRn0[k] * ra1 - VRn1[k] * ra0) * idrb + (vpn - VPn1[k]) * c.invdphi * irb;
+	En[k] = E1[k] * M::exp(-(c.p.gamma - 1.0) * dt * DIV_V, A);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_fused_sources.  Iteration kr loads ring kr, forms Phi(kr), P(kr), v_rad'(kr) (needs ring kr-1) and v_azi'(kr),
+// then finishes ring r = kr-1: e'(r) needs v_rad'(r+1).  Output: v_rad', v_azi', e' of ring r.
 template <bool ADI>
 __global__ void __launch_bounds__(128, 3)
     k_fused_sources(const DevView c, const double *__restrict__ sigma, const double *__restrict__ energy,
 		    const double *__restrict__ vr, const double *__restrict__ vp, double *__restrict__ o_vr,
 		    double *__restrict__ o_vp, double *__restrict__ o_e, const double dt, const int R)
 {
+    typedef MathP<true> MF;
+    typedef MathP<false> MS;
     FsLane L;
     if (!fs_setup(c, L))
 	return;
@@ -105,8 +230,8 @@ __global__ void __launch_bounds__(128, 3)
     if (i_first >= nr)
 	return;
     const int i_last = min(i_first + R, nr);
-    const double OmegaF = c.b.omega_frame;
     const bool drift = c.p.imposed_disk_drift != 0.0;
+    const EosC ec = make_eos_c(c);
     // azimuth of the thread's columns (SideEuler.cpp:56-65)
     double cosj[4], sinj[4];
     {
@@ -125,7 +250,7 @@ __global__ void __launch_bounds__(128, 3)
 	P1[k] = F1[k] = VP1[k] = VRn1[k] = VPn1[k] = 0.0;
 	E1[k] = 1.0;
     }
-    // ring r = k-1 is finished in iteration k; its v_rad' needs ring r-1, so start one ring early
+    // ring r = kr-1 is finished in iteration kr; its v_rad' needs ring r-1, so start one ring early
     const int kbeg = max(i_first - 1, 0);
     for (int kr = kbeg; kr <= i_last; ++kr) {
 	const bool has_cells = kr < nr;
@@ -136,95 +261,37 @@ __global__ void __launch_bounds__(128, 3)
 	    fs_load(vp, kr, c, L, VP0);
 	    if (ADI)
 		fs_load(energy, kr, c, L, E0);
-	    FS_FOR4
-	    {
-		if (!ADI)
-		    E0[k] = 0.0;
-		P0[k] = eos_P(c, kr, S0[k], E0[k]);
-	    }
-	    { // CalculateNbodyPotential (Pframeforce.cpp:44-85)
-		const double rmed = c.g.rmed[kr];
-		FS_FOR4
-		{
-		    const double cs = eos_cs(c, kr, S0[k], E0[k]);
-		    const double H = eos_H(c, kr, cs);
-		    const double x = rmed * cosj[k];
-		    const double y = rmed * sinj[k];
-		    const double smooth = c.p.thickness_smoothing * H;
-		    double pot = 0.0;
-		    for (int b = 0; b < c.b.n; ++b) {
-			const double dx = x - c.b.x[b];
-			const double dy = y - c.b.y[b];
-			const double dist_2 = dx * dx + dy * dy;
-			const double d_smoothed = sqrt(dist_2 + smooth * smooth);
-			double smooth_factor_klahr = 1.0;
-			const double r_sm = c.b.cubic_smoothing_radius[b];
-			if (r_sm > 0.0 && d_smoothed < r_sm) {
-			    const double q = d_smoothed / r_sm;
-			    smooth_factor_klahr = (pow(q, 4.0) - 2.0 * pow(q, 3.0) + 2.0 * d_smoothed / r_sm);
-			}
-			pot += -c.p.G * c.b.mass[b] / d_smoothed * smooth_factor_klahr;
-		    }
-		    pot += -c.b.indirect_x * x - c.b.indirect_y * y;
-		    F0[k] = pot;
-		}
-	    }
+	    else
+		FS_FOR4 E0[k] = 0.0;
+	    FS_RUN((st_potential<MF, ADI>(c, ec, kr, S0, E0, cosj, sinj, P0, F0, A)),
+		   (st_potential<MS, ADI>(c, ec, kr, S0, E0, cosj, sinj, P0, F0, A)));
 	} else {
 	    FS_FOR4 { S0[k] = 1.0, E0[k] = 1.0, VP0[k] = P0[k] = F0[k] = 0.0; }
 	}
-	// momentum_update_radial (SourceEuler.cpp:325-372): interface k between rings k-1 and k
-	FS_FOR4 VRn0[k] = VR0[k];
+	FS_FOR4
+	{
+	    VRn0[k] = VR0[k];
+	    VPn0[k] = VP0[k];
+	}
 	if (kr >= c.one_no_ghost_vr && kr < c.maxmo_no_ghost_vr) {
 	    const double VP0r = shfl_from_right(VP0[0]), VP1r = shfl_from_right(VP1[0]);
-	    const double idr = c.g.invdiffrmed[kr], rinf = c.g.rinf[kr], invrinf = c.g.invrinf[kr];
-	    FS_FOR4
-	    {
-		double gradp = 2.0 / (S0[k] + S1[k]);
-		gradp *= (P0[k] - P1[k]);
-		gradp *= idr;
-		const double gradphi = (F0[k] - F1[k]) * idr;
-		const double vp0n = (k == 3) ? VP0r : VP0[(k + 1) & 3];
-		const double vp1n = (k == 3) ? VP1r : VP1[(k + 1) & 3];
-		const double vsum = VP0[k] + vp0n + VP1[k] + vp1n;
-		const double vt = 0.25 * vsum + rinf * OmegaF;
-		const double vt2 = vt * vt;
-		const double centrifugal_accel = vt2 * invrinf;
-		VRn0[k] = VR0[k] + dt * (-gradp - gradphi + centrifugal_accel);
-	    }
+	    FS_RUN((st_vrad<MF>(c, kr, dt, S0, S1, P0, P1, F0, F1, VP0, VP0r, VP1, VP1r, VR0, VRn0, A)),
+		   (st_vrad<MS>(c, kr, dt, S0, S1, P0, P1, F0, F1, VP0, VP0r, VP1, VP1r, VR0, VRn0, A)));
 	}
-	// momentum_update_azimuthal (:375-428)
-	FS_FOR4 VPn0[k] = VP0[k];
 	if (has_cells && kr >= c.zero_no_ghost && kr < c.max_no_ghost) {
-	    const double invdxtheta = 2.0 / (c.dphi * (c.g.rsup[kr] + c.g.rinf[kr]));
 	    const double Sl = shfl_from_left(S0[3]), Pl = shfl_from_left(P0[3]), Fl = shfl_from_left(F0[3]);
-	    const double supp = drift ? c.g.supp_torque[kr] : 0.0;
-	    FS_FOR4
-	    {
-		const double sp = (k == 0) ? Sl : S0[(k + 3) & 3];
-		const double Pp = (k == 0) ? Pl : P0[(k + 3) & 3];
-		const double Fp = (k == 0) ? Fl : F0[(k + 3) & 3];
-		const double gradp = 2.0 / (S0[k] + sp) * (P0[k] - Pp) * invdxtheta;
-		const double gradphi = (F0[k] - Fp) * invdxtheta;
-		double vpn = VP0[k] + dt * (-gradp - gradphi);
-		if (drift)
-		    vpn += dt * supp;
-		VPn0[k] = vpn;
-	    }
+	    FS_RUN((st_vazi<MF>(c, kr, dt, drift, S0, Sl, P0, Pl, F0, Fl, VP0, VPn0, A)),
+		   (st_vazi<MS>(c, kr, dt, drift, S0, Sl, P0, Pl, F0, Fl, VP0, VPn0, A)));
 	}
-	// ring r = k-1: compression_heating (:459-493) with the UPDATED velocities, then store
+	// ring r = kr-1: compression heating, then store
 	const int r = kr - 1;
 	if (r >= i_first) {
 	    double En[4];
 	    FS_FOR4 En[k] = E1[k];
 	    if (ADI && r < nr - 1) {
 		const double VPn1r = shfl_from_right(VPn1[0]);
-		const double ra1 = c.g.rinf[r + 1], ra0 = c.g.rinf[r], idrb = c.g.invdiffrsuprb[r], irb = c.g.invrmed[r];
-		FS_FOR4
-		{
-		    const double vpn = (k == 3) ? VPn1r : VPn1[(k + 1) & 3];
-		    const double DIV_V = (VRn0[k] * ra1 - VRn1[k] * ra0) * idrb + (vpn - VPn1[k]) * c.invdphi * irb;
-		    En[k] = E1[k] * exp(-(c.p.gamma - 1.0) * dt * DIV_V);
-		}
+		FS_RUN((st_compress<MF>(c, r, dt, E1, VRn0, VRn1, VPn1, VPn1r, En, A)),
+		       (st_compress<MS>(c, r, dt, E1, VRn0, VRn1, VPn1, VPn1r, En, A)));
 	    }
 	    fs_store(o_vr, r, c, L, VRn1);
 	    fs_store(o_vp, r, c, L, VPn1);
@@ -247,13 +314,121 @@ __global__ void __launch_bounds__(128, 3)
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_fused_artvisc.  Iteration k loads ring k; Q(r) of ring r = k-1 needs v_rad(r+1); v_rad''(r) needs Q(r), Q(r-1).
+// artificial viscosity stage bodies (viscosity/artificial_viscosity.cpp)
+struct AvIn {
+    // ring r: Sigma, e, v_rad(r), v_rad(r+1), v_azi (+ right neighbour), and ring r-1: Sigma, Q
+    double S1[4], E1[4], VR1[4], VR0[4], VP1[4], VP1r, S2[4], QR2[4], QP2[4];
+};
+// Q_rr / Q_phiphi of ring r and the dissipation into e: TW :49-88, SN :165-218 (no division: exact on any input)
+template <bool ADI>
+__device__ __forceinline__ void st_av_q(const DevView &c, const int r, const double dt, const int type, const bool diss,
+					 const AvIn &I, double (&QR1)[4], double (&QP1)[4], double (&En)[4])
+{
+    const double C = c.p.artificial_viscosity_factor;
+    FS_FOR4
+    {
+	En[k] = I.E1[k];
+	QR1[k] = QP1[k] = 0.0;
+    }
+    if (type == FARGO_ARTVISC_TW) {
+	const double ids = c.g.invdiffrsup[r], irb = c.g.invrmed[r];
+	const double Dr = c.g.rinf[r + 1] - c.g.rinf[r];
+	const double rDphi = c.g.rmed[r] * c.dphi;
+	const double m = (c.ns <= 16) ? stdmin(Dr, rDphi) : stdmax(Dr, rDphi);
+	const double dx_sq = m * m;
+	const double l_sq = (C * C) * dx_sq;
+	const bool heat = diss && r > c.zero_no_ghost && r < c.max_no_ghost;
+	FS_FOR4
+	{
+	    const double vpn = (k == 3) ? I.VP1r : I.VP1[(k + 1) & 3];
+	    const double eps_rr = (I.VR0[k] - I.VR1[k]) * ids;
+	    const double eps_pp = irb * ((vpn - I.VP1[k]) * c.invdphi + 0.5 * (I.VR0[k] + I.VR1[k]));
+	    const double div_V = stdmin(eps_rr + eps_pp, 0.0);
+	    QR1[k] = l_sq * I.S1[k] * -div_V * (eps_rr - 1.0 / 3.0 * div_V);
+	    QP1[k] = l_sq * I.S1[k] * -div_V * (eps_pp - 1.0 / 3.0 * div_V);
+	    if (heat) {
+		const double Qplus = -l_sq * div_V * I.S1[k] * 1.0 / 3.0 *
+				     (eps_rr * eps_rr + eps_pp * eps_pp + (eps_rr - eps_pp) * (eps_rr - eps_pp));
+		En[k] += Qplus * dt;
+	    }
+	}
+    } else if (type == FARGO_ARTVISC_SN) {
+	const bool heat = diss && r >= c.zero_no_ghost && r < c.max_no_ghost;
+	const double invdxtheta = c.g.invdxtheta[r];
+	FS_FOR4
+	{
+	    const double vpn = (k == 3) ? I.VP1r : I.VP1[(k + 1) & 3];
+	    const double dv_r = I.VR0[k] - I.VR1[k];
+	    QR1[k] = (dv_r < 0.0) ? (C * C) * I.S1[k] * (dv_r * dv_r) : 0.0;
+	    const double dv_phi = vpn - I.VP1[k];
+	    QP1[k] = (dv_phi < 0.0) ? (C * C) * I.S1[k] * (dv_phi * dv_phi) : 0.0;
+	    if (heat)
+		En[k] = En[k] - dt * QR1[k] * dv_r * c.g.invdiffrsup[r] - dt * QP1[k] * dv_phi * invdxtheta;
+	}
+    }
+}
+// velocity updates of ring r from Q(r), Q(r-1): TW :90-139, SN :221-248
+template <class M>
+__device__ __forceinline__ void st_av_v(const DevView &c, const int r, const double dt, const int type, const AvIn &I,
+					 const double (&QR1)[4], const double (&QP1)[4], const double QP1l, const double S1l,
+					 double (&VRn)[4], double (&VPn)[4], FmAcc &A)
+{
+    const int nr = c.nr;
+    FS_FOR4
+    {
+	VRn[k] = I.VR1[k];
+	VPn[k] = I.VP1[k];
+    }
+    if (type == FARGO_ARTVISC_TW) {
+	if (r >= 1 && r < nr - 1) {
+	    const double rs = c.g.rsup[r] + c.g.rinf[r];
+	    FS_FOR4
+	    {
+		const double sp = (k == 0) ? S1l : I.S1[(k + 3) & 3];
+		const double qpp = (k == 0) ? QP1l : QP1[(k + 3) & 3];
+		const double sigma_phi_avg = 0.5 * (I.S1[k] + sp);
+		const double dVp = M::div(2.0 * dt, rs * sigma_phi_avg, A) * (QP1[k] - qpp) * c.invdphi;
+		VPn[k] = I.VP1[k] + dVp;
+	    }
+	}
+	if (r >= c.one_no_ghost_vr && r < c.maxmo_no_ghost_vr) {
+	    const double rm = c.g.rmed[r], rmm = c.g.rmed[r - 1];
+	    const double dr2 = rm * rm - rmm * rmm;
+	    const double ydr2 = M::rcp(dr2, A);
+	    FS_FOR4
+	    {
+		const double sigma_r_avg = 0.5 * (I.S1[k] + I.S2[k]);
+		const double dVr = M::div_y(M::div(c.p.radial_viscosity_factor * dt, sigma_r_avg, A) * 2.0, dr2, ydr2, A) *
+				   ((QR1[k] * rm - I.QR2[k] * rmm) - 0.5 * (QP1[k] + I.QP2[k]) * (rm - rmm));
+		VRn[k] = I.VR1[k] + dVr;
+	    }
+	}
+    } else if (type == FARGO_ARTVISC_SN) {
+	if (r >= c.one_no_ghost_vr && r < c.maxmo_no_ghost_vr) {
+	    const double idr = c.g.invdiffrmed[r];
+	    FS_FOR4 VRn[k] = I.VR1[k] - M::div(dt * 2.0, I.S1[k] + I.S2[k], A) * (QR1[k] - I.QR2[k]) * idr;
+	}
+	if (r >= c.zero_no_ghost && r < c.max_no_ghost) {
+	    const double invdxtheta = c.g.invdxtheta[r];
+	    FS_FOR4
+	    {
+		const double sp = (k == 0) ? S1l : I.S1[(k + 3) & 3];
+		const double qpp = (k == 0) ? QP1l : QP1[(k + 3) & 3];
+		VPn[k] = I.VP1[k] - M::div(dt * 2.0, I.S1[k] + sp, A) * (QP1[k] - qpp) * invdxtheta;
+	    }
+	}
+    }
+}
+
+// k_fused_artvisc.  Iteration kr loads ring kr; Q(r) of ring r = kr-1 needs v_rad(r+1); v_rad''(r) needs Q(r), Q(r-1).
 template <bool ADI>
 __global__ void __launch_bounds__(128, 3)
     k_fused_artvisc(const DevView c, const double *__restrict__ sigma, const double *__restrict__ energy,
 		    const double *__restrict__ vr, const double *__restrict__ vp, double *__restrict__ o_vr,
 		    double *__restrict__ o_vp, double *__restrict__ o_e, const double dt, const int R)
 {
+    typedef MathP<true> MF;
+    typedef MathP<false> MS;
     FsLane L;
     if (!fs_setup(c, L))
 	return;
@@ -264,22 +439,21 @@ __global__ void __launch_bounds__(128, 3)
     const int i_last = min(i_first + R, nr);
     const int type = c.p.artificial_viscosity;
     const bool diss = ADI && c.p.artificial_viscosity_dissipation;
-    const double C = c.p.artificial_viscosity_factor;
-    TempClamp tc;
+    TempClampNB tc;
     if (ADI)
-	tc = make_temp_clamp(c);
-    double S1[4], E1[4], VR1[4], VP1[4], S2[4], QR2[4], QP2[4];
+	tc = make_temp_clamp_nb(c);
+    AvIn I;
     FS_FOR4
     {
-	S1[k] = S2[k] = 1.0;
-	E1[k] = 1.0;
-	VR1[k] = VP1[k] = QR2[k] = QP2[k] = 0.0;
+	I.S1[k] = I.S2[k] = 1.0;
+	I.E1[k] = 1.0;
+	I.VR1[k] = I.VP1[k] = I.QR2[k] = I.QP2[k] = 0.0;
     }
-    // ring r = k-1 is finished in iteration k and needs Q(r-1), i.e. rings r-1 and r: start at r-1 = i_first-1
+    // ring r = kr-1 is finished in iteration kr and needs Q(r-1), i.e. rings r-1 and r: start at r-1 = i_first-1
     const int kbeg = max(i_first - 1, 0);
     for (int kr = kbeg; kr <= i_last; ++kr) {
-	double S0[4], E0[4], VR0[4], VP0[4];
-	fs_load(vr, kr, c, L, VR0);
+	double S0[4], E0[4], VP0[4];
+	fs_load(vr, kr, c, L, I.VR0);
 	if (kr < nr) {
 	    fs_load(sigma, kr, c, L, S0);
 	    fs_load(vp, kr, c, L, VP0);
@@ -293,92 +467,16 @@ __global__ void __launch_bounds__(128, 3)
 	const int r = kr - 1;
 	if (r >= kbeg) { // ring r is complete: S1, E1, VR1 = v_rad(r), VR0 = v_rad(r+1), VP1
 	    double QR1[4], QP1[4], En[4], VRn[4], VPn[4];
-	    const double VP1r = shfl_from_right(VP1[0]);
-	    FS_FOR4
-	    {
-		En[k] = E1[k];
-		VRn[k] = VR1[k];
-		VPn[k] = VP1[k];
-		QR1[k] = QP1[k] = 0.0;
+	    I.VP1r = shfl_from_right(I.VP1[0]);
+	    st_av_q<ADI>(c, r, dt, type, diss, I, QR1, QP1, En);
+	    if (diss) { // :19-21
+		double Ec[4];
+		FS_RUN(FS_FOR4 Ec[k] = temperature_clamp_nb(tc, I.S1[k], En[k], A), FS_FOR4 Ec[k] = temperature_clamp(c, I.S1[k], En[k]));
+		FS_FOR4 En[k] = Ec[k];
 	    }
-	    if (type == FARGO_ARTVISC_TW) { // artificial_viscosity.cpp:49-88
-		const double ids = c.g.invdiffrsup[r], irb = c.g.invrmed[r];
-		const double Dr = c.g.rinf[r + 1] - c.g.rinf[r];
-		const double rDphi = c.g.rmed[r] * c.dphi;
-		const double m = (c.ns <= 16) ? stdmin(Dr, rDphi) : stdmax(Dr, rDphi);
-		const double dx_sq = m * m;
-		const double l_sq = (C * C) * dx_sq;
-		const bool heat = diss && r > c.zero_no_ghost && r < c.max_no_ghost;
-		FS_FOR4
-		{
-		    const double vpn = (k == 3) ? VP1r : VP1[(k + 1) & 3];
-		    const double eps_rr = (VR0[k] - VR1[k]) * ids;
-		    const double eps_pp = irb * ((vpn - VP1[k]) * c.invdphi + 0.5 * (VR0[k] + VR1[k]));
-		    const double div_V = stdmin(eps_rr + eps_pp, 0.0);
-		    QR1[k] = l_sq * S1[k] * -div_V * (eps_rr - 1.0 / 3.0 * div_V);
-		    QP1[k] = l_sq * S1[k] * -div_V * (eps_pp - 1.0 / 3.0 * div_V);
-		    if (heat) {
-			const double Qplus = -l_sq * div_V * S1[k] * 1.0 / 3.0 *
-					     (eps_rr * eps_rr + eps_pp * eps_pp + (eps_rr - eps_pp) * (eps_rr - eps_pp));
-			En[k] += Qplus * dt;
-		    }
-		}
-	    } else if (type == FARGO_ARTVISC_SN) { // :165-218
-		const bool heat = diss && r >= c.zero_no_ghost && r < c.max_no_ghost;
-		const double dxtheta = c.dphi * c.g.rmed[r];
-		const double invdxtheta = 1.0 / dxtheta;
-		FS_FOR4
-		{
-		    const double vpn = (k == 3) ? VP1r : VP1[(k + 1) & 3];
-		    const double dv_r = VR0[k] - VR1[k];
-		    QR1[k] = (dv_r < 0.0) ? (C * C) * S1[k] * (dv_r * dv_r) : 0.0;
-		    const double dv_phi = vpn - VP1[k];
-		    QP1[k] = (dv_phi < 0.0) ? (C * C) * S1[k] * (dv_phi * dv_phi) : 0.0;
-		    if (heat)
-			En[k] = En[k] - dt * QR1[k] * dv_r * c.g.invdiffrsup[r] - dt * QP1[k] * dv_phi * invdxtheta;
-		}
-	    }
-	    if (diss)
-		FS_FOR4 En[k] = temperature_clamp(tc, S1[k], En[k]); // :19-21
-	    const double QP1l = shfl_from_left(QP1[3]), S1l = shfl_from_left(S1[3]);
-	    if (type == FARGO_ARTVISC_TW) { // :90-139
-		if (r >= 1 && r < nr - 1) {
-		    const double rs = c.g.rsup[r] + c.g.rinf[r];
-		    FS_FOR4
-		    {
-			const double sp = (k == 0) ? S1l : S1[(k + 3) & 3];
-			const double qpp = (k == 0) ? QP1l : QP1[(k + 3) & 3];
-			const double sigma_phi_avg = 0.5 * (S1[k] + sp);
-			const double dVp = 2.0 * dt / (rs * sigma_phi_avg) * (QP1[k] - qpp) * c.invdphi;
-			VPn[k] = VP1[k] + dVp;
-		    }
-		}
-		if (r >= c.one_no_ghost_vr && r < c.maxmo_no_ghost_vr) {
-		    const double rm = c.g.rmed[r], rmm = c.g.rmed[r - 1];
-		    FS_FOR4
-		    {
-			const double sigma_r_avg = 0.5 * (S1[k] + S2[k]);
-			const double dVr = c.p.radial_viscosity_factor * dt / sigma_r_avg * 2.0 / (rm * rm - rmm * rmm) *
-					   ((QR1[k] * rm - QR2[k] * rmm) - 0.5 * (QP1[k] + QP2[k]) * (rm - rmm));
-			VRn[k] = VR1[k] + dVr;
-		    }
-		}
-	    } else if (type == FARGO_ARTVISC_SN) { // :221-248
-		if (r >= c.one_no_ghost_vr && r < c.maxmo_no_ghost_vr) {
-		    const double idr = c.g.invdiffrmed[r];
-		    FS_FOR4 VRn[k] = VR1[k] - dt * 2.0 / (S1[k] + S2[k]) * (QR1[k] - QR2[k]) * idr;
-		}
-		if (r >= c.zero_no_ghost && r < c.max_no_ghost) {
-		    const double dxtheta = c.dphi * c.g.rmed[r];
-		    const double invdxtheta = 1.0 / dxtheta;
-		    FS_FOR4
-		    {
-			const double sp = (k == 0) ? S1l : S1[(k + 3) & 3];
-			const double qpp = (k == 0) ? QP1l : QP1[(k + 3) & 3];
-			VPn[k] = VP1[k] - dt * 2.0 / (S1[k] + sp) * (QP1[k] - qpp) * invdxtheta;
-		    }
-		}
-	    }
+	    const double QP1l = shfl_from_left(QP1[3]), S1l = shfl_from_left(I.S1[3]);
+	    FS_RUN((st_av_v<MF>(c, r, dt, type, I, QR1, QP1, QP1l, S1l, VRn, VPn, A)),
+		   (st_av_v<MS>(c, r, dt, type, I, QR1, QP1, QP1l, S1l, VRn, VPn, A)));
 	    if (r >= i_first) {
 		fs_store(o_vr, r, c, L, VRn);
 		fs_store(o_vp, r, c, L, VPn);
@@ -387,25 +485,147 @@ __global__ void __launch_bounds__(128, 3)
 	    }
 	    FS_FOR4
 	    {
-		S2[k] = S1[k];
-		QR2[k] = QR1[k];
-		QP2[k] = QP1[k];
+		I.S2[k] = I.S1[k];
+		I.QR2[k] = QR1[k];
+		I.QP2[k] = QP1[k];
 	    }
 	}
 	FS_FOR4
 	{
-	    S1[k] = S0[k];
-	    E1[k] = E0[k];
-	    VR1[k] = VR0[k];
-	    VP1[k] = VP0[k];
+	    I.S1[k] = S0[k];
+	    I.E1[k] = E0[k];
+	    I.VR1[k] = I.VR0[k];
+	    I.VP1[k] = VP0[k];
 	}
     }
     if (i_last == nr)
-	fs_store(o_vr, nr, c, L, VR1);
+	fs_store(o_vr, nr, c, L, I.VR1);
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_fused_viscosity.  Iteration k loads ring k and forms nu(k) and the corner stress tau_rphi(k); ring r = k-1 then
+// viscosity + SubStep3 stage bodies
+// recalculate_viscosity (SourceEuler.cpp:205-223): c_s, H, nu of ring kr
+template <class M>
+__device__ __forceinline__ void st_nu(const DevView &c, const EosC &ec, const int kr, const double (&S0)[4], const double (&E0)[4],
+				       double (&N0)[4], double (&H0)[4], FmAcc &A)
+{
+    FS_FOR4
+    {
+	const double cs = eos_cs_m<M>(c, kr, S0[k], E0[k], A);
+	const double H = eos_H_m<M>(c, ec, kr, cs, A);
+	H0[k] = H;
+	N0[k] = (c.p.viscous_alpha > 0) ? c.p.viscous_alpha * H * cs : c.p.constant_viscosity; // viscosity.cpp:98-137
+    }
+}
+struct VsIn {
+    // ring r: Sigma, v_rad(r), v_azi, tau_rphi(r) (+ right neighbour), tau_rphi(r+1) (+ right neighbour); ring r-1
+    double S1[4], VR1[4], VP1[4], TRP1[4], TRP0[4], TRP1r, TRP0r, S2[4], TRR2[4], TPP2[4];
+};
+// update_velocities_with_viscosity (viscosity.cpp:355-426), ring r
+template <class M>
+__device__ __forceinline__ void st_visc_v(const DevView &c, const int r, const double dt, const VsIn &I, const double (&TRR1)[4],
+					   const double (&TPP1)[4], const double TPP1l, const double S1l, double (&VRn)[4],
+					   double (&VPn)[4], FmAcc &A)
+{
+    FS_FOR4
+    {
+	VRn[k] = I.VR1[k];
+	VPn[k] = I.VP1[k];
+    }
+    if (r >= 1 && r < c.nr - 1) {
+	const double ra = c.g.rinf[r], rap = c.g.rinf[r + 1];
+	const double ra2 = ra * ra, rap2 = rap * rap;
+	const double irb = c.g.invrmed[r];
+	const double tdr = c.g.twodiffrasq[r]; // 2.0 / (Ra[r+1]^2 - Ra[r]^2), formed on the host with the same IEEE operations
+	FS_FOR4
+	{
+	    const double sp = (k == 0) ? S1l : I.S1[(k + 3) & 3];
+	    const double tppl = (k == 0) ? TPP1l : TPP1[(k + 3) & 3];
+	    const double sigma_avg = 0.5 * (I.S1[k] + sp);
+	    const double dVp = M::div(dt * irb, sigma_avg, A) * (tdr * (rap2 * I.TRP0[k] - ra2 * I.TRP1[k]) + (TPP1[k] - tppl) * c.invdphi);
+	    VPn[k] = I.VP1[k] + dVp;
+	}
+    }
+    if (r >= c.one_no_ghost_vr && r < c.maxmo_no_ghost_vr) {
+	const double rb = c.g.rmed[r], rbm = c.g.rmed[r - 1], idr = c.g.invdiffrmed[r];
+	const double rsum = rb + rbm;
+	const double yrsum = M::rcp(rsum, A);
+	FS_FOR4
+	{
+	    const double trpn = (k == 3) ? I.TRP1r : I.TRP1[(k + 1) & 3];
+	    const double sigma_avg = 0.5 * (I.S1[k] + I.S2[k]);
+	    const double dVr = M::div_y(M::div(dt, sigma_avg, A) * c.p.radial_viscosity_factor * 2.0, rsum, yrsum, A) *
+			       ((rb * TRR1[k] - rbm * I.TRR2[k]) * idr + (trpn - I.TRP1[k]) * c.invdphi - 0.5 * (TPP1[k] + I.TPP2[k]));
+	    VRn[k] = I.VR1[k] + dVr;
+	}
+    }
+}
+// SubStep3 (SourceEuler.cpp:859-954) for ring r: Q+ (viscous_heating :496-536), Q- (thermal_relaxation :632-690),
+// radiative alpha_r, the energy update and the temperature floor / ceiling
+template <class M>
+__device__ __forceinline__ void st_substep3(const DevView &c, const TempClampNB &tc, const int r, const double dt,
+					     const double beta_inv, const VsIn &I, const double (&E1)[4], const double (&N1)[4],
+					     const double (&H1)[4], const double (&DV1)[4], const double (&TRR1)[4],
+					     const double (&TPP1)[4], const double (&s0)[4], const double (&e0)[4], double (&Qp)[4],
+					     double (&Qm)[4], double (&En)[4], FmAcc &A)
+{
+    const bool inner = r >= 1 && r < c.nr - 1;
+    const fargo_params &p = c.p;
+    FS_FOR4
+    {
+	double qp = 0.0, qm = 0.0;
+	if (p.heating_viscous && inner) {
+	    const double trpn1 = (k == 3) ? I.TRP1r : I.TRP1[(k + 1) & 3];
+	    const double trpn0 = (k == 3) ? I.TRP0r : I.TRP0[(k + 1) & 3];
+	    const double tau_r_phi = 0.25 * (I.TRP1[k] + I.TRP0[k] + trpn1 + trpn0);
+	    // nu == 0 cells are skipped by the reference; evaluate with a harmless denominator and select
+	    const bool on = N1[k] != 0.0;
+	    const double den = on ? 2.0 * N1[k] * I.S1[k] : 1.0;
+	    double qplus = M::div(1.0, den, A) * (TRR1[k] * TRR1[k] + 2 * (tau_r_phi * tau_r_phi) + TPP1[k] * TPP1[k]);
+	    qplus += (2.0 / 9.0) * N1[k] * I.S1[k] * (DV1[k] * DV1[k]);
+	    qplus *= p.heating_viscous_factor;
+	    qp = on ? 0.0 + qplus : 0.0;
+	}
+	if (p.cooling_beta && inner) { // qminus_cell
+	    double delta_E = E1[k];
+	    if (p.cooling_beta_reference & FARGO_BETA_REF_REFERENCE)
+		delta_E -= M::div(e0[k], s0[k], A) * I.S1[k];
+	    if (p.cooling_beta_reference & FARGO_BETA_REF_MODEL)
+		delta_E -= c.g.beta_model_e0[r] * I.S1[k];
+	    if (p.cooling_beta_reference & FARGO_BETA_REF_FLOOR)
+		delta_E -= M::div_y(M::div_y(p.minimum_temperature * I.S1[k], tc.mu, tc.ymu, A) * p.Rgas, tc.gm1, tc.ygm1, A);
+	    qm = 0.0 + delta_E * c.g.omega_k[r] * beta_inv;
+	}
+	double en = E1[k];
+	if (inner) {
+	    // alpha_r = 1 + 2 H 4 sigma_SB / c (mu (gamma-1) / (R Sigma))^4 e^3  (:921-924)
+	    const double inv_pow4 = fm_pow4(M::div(p.mu * (p.gamma - 1.0), p.Rgas * I.S1[k], A));
+	    const double alpha = 1.0 + 2.0 * H1[k] * 4.0 * p.sigma_sb / p.c_light * inv_pow4 * fm_pow3(E1[k]);
+	    const double ya = M::rcp(alpha, A);
+	    qp = M::div_y(qp, alpha, ya, A);
+	    qm = M::div_y(qm, alpha, ya, A);
+	    en = E1[k] + dt * (qp - qm);
+	}
+	Qp[k] = qp;
+	Qm[k] = qm;
+	En[k] = en;
+    }
+    const double SigmaFloor = 10.0 * p.sigma0 * p.sigma_floor;
+    if (inner) {
+	FS_FOR4
+	{
+	    if (I.S1[k] < SigmaFloor) { // rare: cells at the density floor
+		/* TAU_EFF is only filled by surface cooling (out of scope) => 0 as allocated */
+		const double e4 = Qp[k] * 0.0 / (2.0 * p.sigma_sb);
+		const double constant = (p.Rgas / p.mu * I.S1[k] / (p.gamma - 1.0));
+		Qm[k] = Qp[k];
+		En[k] = pow(e4, 1.0 / 4.0) * constant;
+	    }
+	}
+    }
+}
+
+// k_fused_viscosity.  Iteration kr loads ring kr and forms nu(kr) and the corner stress tau_rphi(kr); ring r = kr-1 then
 // has everything: div v, tau_rr, tau_phiphi (need v_rad(r+1)), the velocity updates (need tau_rphi(r+1), the
 // centred stresses of r-1) and, for the energy equation, Q+ / Q- / the new energy.
 // StabilizeViscosity != 0 is not handled here (the host falls back to the staged kernels).
@@ -417,6 +637,8 @@ __global__ void __launch_bounds__(128, 2)
 		      double *__restrict__ o_e, double *__restrict__ o_qplus, double *__restrict__ o_qminus, const double dt,
 		      const double beta_inv, const int R)
 {
+    typedef MathP<true> MF;
+    typedef MathP<false> MS;
     FsLane L;
     if (!fs_setup(c, L))
 	return;
@@ -426,20 +648,22 @@ __global__ void __launch_bounds__(128, 2)
 	return;
     const int i_last = min(i_first + R, nr);
     const bool need0 = ADI && c.p.cooling_beta && (c.p.cooling_beta_reference & FARGO_BETA_REF_REFERENCE);
-    TempClamp tc;
+    const EosC ec = make_eos_c(c);
+    TempClampNB tc;
     if (ADI)
-	tc = make_temp_clamp(c);
-    double S1[4], E1[4], VR1[4], VP1[4], N1[4], TRP1[4], S2[4], TRR2[4], TPP2[4];
+	tc = make_temp_clamp_nb(c);
+    VsIn I;
+    double E1[4], N1[4], H1[4];
     FS_FOR4
     {
-	S1[k] = S2[k] = 1.0;
+	I.S1[k] = I.S2[k] = 1.0;
 	E1[k] = 1.0;
-	VR1[k] = VP1[k] = N1[k] = TRP1[k] = TRR2[k] = TPP2[k] = 0.0;
+	I.VR1[k] = I.VP1[k] = N1[k] = H1[k] = I.TRP1[k] = I.TRR2[k] = I.TPP2[k] = 0.0;
     }
-    // ring r needs the centred stresses of r-1 (rings r-1, r) and tau_rphi(r) (rings r-1, r): start at k = r-1
+    // ring r needs the centred stresses of r-1 (rings r-1, r) and tau_rphi(r) (rings r-1, r): start at kr = r-1
     const int kbeg = max(i_first - 1, 0);
     for (int kr = kbeg; kr <= i_last; ++kr) {
-	double S0[4], E0[4], VR0[4], VP0[4], N0[4], TRP0[4];
+	double S0[4], E0[4], VR0[4], VP0[4], N0[4], H0[4];
 	fs_load(vr, kr, c, L, VR0);
 	if (kr < nr) {
 	    fs_load(sigma, kr, c, L, S0);
@@ -448,15 +672,15 @@ __global__ void __launch_bounds__(128, 2)
 		fs_load(energy, kr, c, L, E0);
 	    else
 		FS_FOR4 E0[k] = 0.0;
-	    FS_FOR4 N0[k] = eos_nu(c, kr, S0[k], E0[k]); // recalculate_viscosity
+	    FS_RUN((st_nu<MF>(c, ec, kr, S0, E0, N0, H0, A)), (st_nu<MS>(c, ec, kr, S0, E0, N0, H0, A)));
 	} else {
-	    FS_FOR4 { S0[k] = 1.0, E0[k] = 1.0, VP0[k] = N0[k] = 0.0; }
+	    FS_FOR4 { S0[k] = 1.0, E0[k] = 1.0, VP0[k] = N0[k] = H0[k] = 0.0; }
 	}
-	// tau_rphi at the corner (k, j) (viscosity.cpp:213-253); rings 0 and nr of the grid stay 0
+	// tau_rphi at the corner (kr, j) (viscosity.cpp:213-253); rings 0 and nr of the grid stay 0
 	{
 	    const double VR0l = shfl_from_left(VR0[3]);
 	    const double N0l = shfl_from_left(N0[3]), N1l = shfl_from_left(N1[3]);
-	    const double S0l = shfl_from_left(S0[3]), S1l = shfl_from_left(S1[3]);
+	    const double S0l = shfl_from_left(S0[3]), S1l = shfl_from_left(I.S1[3]);
 	    if (kr >= 1 && kr < nr) {
 		const double irb = c.g.invrmed[kr], irbm = c.g.invrmed[kr - 1], idr = c.g.invdiffrmed[kr];
 		const double ra = c.g.rinf[kr], ira = c.g.invrinf[kr];
@@ -466,143 +690,81 @@ __global__ void __launch_bounds__(128, 2)
 		    const double n0l = (k == 0) ? N0l : N0[(k + 3) & 3];
 		    const double n1l = (k == 0) ? N1l : N1[(k + 3) & 3];
 		    const double s0l = (k == 0) ? S0l : S0[(k + 3) & 3];
-		    const double s1l = (k == 0) ? S1l : S1[(k + 3) & 3];
-		    const double dvazirdr = (VP0[k] * irb - VP1[k] * irbm) * idr;
+		    const double s1l = (k == 0) ? S1l : I.S1[(k + 3) & 3];
+		    const double dvazirdr = (VP0[k] * irb - I.VP1[k] * irbm) * idr;
 		    const double dvrdphi = (VR0[k] - vrl) * c.invdphi;
 		    const double drp = ra * dvazirdr + dvrdphi * ira;
 		    const double nua = 0.25 * (N0[k] + N1[k] + n0l + n1l);
-		    const double sa = 0.25 * (S0[k] + S1[k] + s0l + s1l);
-		    TRP0[k] = nua * sa * drp;
+		    const double sa = 0.25 * (S0[k] + I.S1[k] + s0l + s1l);
+		    I.TRP0[k] = nua * sa * drp;
 		}
 	    } else {
-		FS_FOR4 TRP0[k] = 0.0;
+		FS_FOR4 I.TRP0[k] = 0.0;
 	    }
 	}
 	const int r = kr - 1;
 	if (r >= kbeg) {
 	    // centred stresses of ring r (viscosity.cpp:150-211)
 	    double DV1[4], TRR1[4], TPP1[4], VRn[4], VPn[4];
-	    const double VP1r = shfl_from_right(VP1[0]);
+	    const double VP1r = shfl_from_right(I.VP1[0]);
 	    {
 		const double ra1 = c.g.rinf[r + 1], ra0 = c.g.rinf[r], idrb = c.g.invdiffrsuprb[r], irb = c.g.invrmed[r];
 		const double ids = c.g.invdiffrsup[r];
 		FS_FOR4
 		{
-		    const double vpn = (k == 3) ? VP1r : VP1[(k + 1) & 3];
-		    const double dv = (VR0[k] * ra1 - VR1[k] * ra0) * idrb + (vpn - VP1[k]) * c.invdphi * irb;
+		    const double vpn = (k == 3) ? VP1r : I.VP1[(k + 1) & 3];
+		    const double dv = (VR0[k] * ra1 - I.VR1[k] * ra0) * idrb + (vpn - I.VP1[k]) * c.invdphi * irb;
 		    DV1[k] = dv;
-		    const double drr = (VR0[k] - VR1[k]) * ids;
-		    TRR1[k] = 2.0 * N1[k] * S1[k] * (drr - 1.0 / 3.0 * dv);
-		    const double dpp = (vpn - VP1[k]) * c.invdphi * irb + 0.5 * (VR0[k] + VR1[k]) * irb;
-		    TPP1[k] = 2.0 * N1[k] * S1[k] * (dpp - 1.0 / 3.0 * dv);
+		    const double drr = (VR0[k] - I.VR1[k]) * ids;
+		    TRR1[k] = 2.0 * N1[k] * I.S1[k] * (drr - 1.0 / 3.0 * dv);
+		    const double dpp = (vpn - I.VP1[k]) * c.invdphi * irb + 0.5 * (VR0[k] + I.VR1[k]) * irb;
+		    TPP1[k] = 2.0 * N1[k] * I.S1[k] * (dpp - 1.0 / 3.0 * dv);
 		}
 	    }
-	    // update_velocities_with_viscosity (:355-426)
-	    const double TPP1l = shfl_from_left(TPP1[3]), S1l = shfl_from_left(S1[3]);
-	    const double TRP1r = shfl_from_right(TRP1[0]), TRP0r = shfl_from_right(TRP0[0]);
-	    FS_FOR4
-	    {
-		VRn[k] = VR1[k];
-		VPn[k] = VP1[k];
-	    }
-	    if (r >= 1 && r < nr - 1) {
-		const double ra = c.g.rinf[r], rap = c.g.rinf[r + 1];
-		const double ra2 = ra * ra, rap2 = rap * rap;
-		const double irb = c.g.invrmed[r];
-		FS_FOR4
-		{
-		    const double sp = (k == 0) ? S1l : S1[(k + 3) & 3];
-		    const double tppl = (k == 0) ? TPP1l : TPP1[(k + 3) & 3];
-		    const double sigma_avg = 0.5 * (S1[k] + sp);
-		    const double dVp = dt * irb / (sigma_avg) *
-				       ((2.0 / (rap2 - ra2)) * (rap2 * TRP0[k] - ra2 * TRP1[k]) + (TPP1[k] - tppl) * c.invdphi);
-		    VPn[k] = VP1[k] + dVp;
-		}
-	    }
-	    if (r >= c.one_no_ghost_vr && r < c.maxmo_no_ghost_vr) {
-		const double rb = c.g.rmed[r], rbm = c.g.rmed[r - 1], idr = c.g.invdiffrmed[r];
-		FS_FOR4
-		{
-		    const double trpn = (k == 3) ? TRP1r : TRP1[(k + 1) & 3];
-		    const double sigma_avg = 0.5 * (S1[k] + S2[k]);
-		    const double dVr = dt / (sigma_avg)*c.p.radial_viscosity_factor * 2.0 / (rb + rbm) *
-				       ((rb * TRR1[k] - rbm * TRR2[k]) * idr + (trpn - TRP1[k]) * c.invdphi - 0.5 * (TPP1[k] + TPP2[k]));
-		    VRn[k] = VR1[k] + dVr;
-		}
-	    }
+	    const double TPP1l = shfl_from_left(TPP1[3]), S1l = shfl_from_left(I.S1[3]);
+	    I.TRP1r = shfl_from_right(I.TRP1[0]);
+	    I.TRP0r = shfl_from_right(I.TRP0[0]);
+	    FS_RUN((st_visc_v<MF>(c, r, dt, I, TRR1, TPP1, TPP1l, S1l, VRn, VPn, A)),
+		   (st_visc_v<MS>(c, r, dt, I, TRR1, TPP1, TPP1l, S1l, VRn, VPn, A)));
 	    if (r >= i_first) {
 		fs_store(o_vr, r, c, L, VRn);
 		fs_store(o_vp, r, c, L, VPn);
 	    }
-	    if (ADI) { // SubStep3 (SourceEuler.cpp:859-954)
-		double Qp[4], Qm[4], En[4], s0[4], e0[4];
+	    if (ADI) {
+		double Qp[4], Qm[4], En[4], Ec[4], s0[4], e0[4];
 		if (need0 && r >= i_first) {
 		    fs_load(sigma0, r, c, L, s0);
 		    fs_load(energy0, r, c, L, e0);
 		} else {
-		    FS_FOR4 { s0[k] = 1.0, e0[k] = 0.0; }
+		    FS_FOR4 { s0[k] = 1.0, e0[k] = 1.0; }
 		}
-		const bool inner = r >= 1 && r < nr - 1;
-		FS_FOR4
-		{
-		    double q = 0.0;
-		    if (c.p.heating_viscous && inner && N1[k] != 0.0) { // viscous_heating :496-536
-			const double trpn1 = (k == 3) ? TRP1r : TRP1[(k + 1) & 3];
-			const double trpn0 = (k == 3) ? TRP0r : TRP0[(k + 1) & 3];
-			const double tau_r_phi = 0.25 * (TRP1[k] + TRP0[k] + trpn1 + trpn0);
-			double qplus = 1.0 / (2.0 * N1[k] * S1[k]) * (TRR1[k] * TRR1[k] + 2 * (tau_r_phi * tau_r_phi) + TPP1[k] * TPP1[k]);
-			qplus += (2.0 / 9.0) * N1[k] * S1[k] * (DV1[k] * DV1[k]);
-			qplus *= c.p.heating_viscous_factor;
-			q += qplus;
-		    }
-		    Qp[k] = q;
-		    Qm[k] = qminus_cell(c, beta_inv, S1[k], E1[k], s0[k], e0[k], r);
-		    En[k] = E1[k];
-		}
-		if (inner) {
-		    FS_FOR4
-		    {
-			const double alpha = radiative_alpha(c, r, S1[k], E1[k]);
-			const Rcp ra = make_rcp(alpha);
-			Qp[k] = div_by(Qp[k], ra);
-			Qm[k] = div_by(Qm[k], ra);
-			double energy_new = E1[k] + dt * (Qp[k] - Qm[k]);
-			const double SigmaFloor = 10.0 * c.p.sigma0 * c.p.sigma_floor;
-			if (S1[k] < SigmaFloor) {
-			    /* TAU_EFF is only filled by surface cooling (out of scope) => 0 as allocated */
-			    const double e4 = Qp[k] * 0.0 / (2.0 * c.p.sigma_sb);
-			    const double constant = (c.p.Rgas / c.p.mu * S1[k] / (c.p.gamma - 1.0));
-			    const double eq_energy = pow(e4, 1.0 / 4.0) * constant;
-			    Qm[k] = Qp[k];
-			    energy_new = eq_energy;
-			}
-			En[k] = energy_new;
-		    }
-		}
-		FS_FOR4 En[k] = temperature_clamp(tc, S1[k], En[k]);
+		FS_RUN((st_substep3<MF>(c, tc, r, dt, beta_inv, I, E1, N1, H1, DV1, TRR1, TPP1, s0, e0, Qp, Qm, En, A)),
+		       (st_substep3<MS>(c, tc, r, dt, beta_inv, I, E1, N1, H1, DV1, TRR1, TPP1, s0, e0, Qp, Qm, En, A)));
+		FS_RUN(FS_FOR4 Ec[k] = temperature_clamp_nb(tc, I.S1[k], En[k], A), FS_FOR4 Ec[k] = temperature_clamp(c, I.S1[k], En[k]));
 		if (r >= i_first) {
 		    fs_store(o_qplus, r, c, L, Qp);
 		    fs_store(o_qminus, r, c, L, Qm);
-		    fs_store(o_e, r, c, L, En);
+		    fs_store(o_e, r, c, L, Ec);
 		}
 	    }
 	    FS_FOR4
 	    {
-		S2[k] = S1[k];
-		TRR2[k] = TRR1[k];
-		TPP2[k] = TPP1[k];
+		I.S2[k] = I.S1[k];
+		I.TRR2[k] = TRR1[k];
+		I.TPP2[k] = TPP1[k];
 	    }
 	}
 	FS_FOR4
 	{
-	    S1[k] = S0[k];
+	    I.S1[k] = S0[k];
 	    E1[k] = E0[k];
-	    VR1[k] = VR0[k];
-	    VP1[k] = VP0[k];
+	    I.VR1[k] = VR0[k];
+	    I.VP1[k] = VP0[k];
 	    N1[k] = N0[k];
-	    TRP1[k] = TRP0[k];
+	    H1[k] = H0[k];
+	    I.TRP1[k] = I.TRP0[k];
 	}
     }
     if (i_last == nr)
-	fs_store(o_vr, nr, c, L, VR1);
+	fs_store(o_vr, nr, c, L, I.VR1);
 }
