@@ -216,7 +216,8 @@ class Handle:
 
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libfargo_b200.so")
+# FARGO_B200_LIB: experiment builds of the SAME CUDA library (kernel tuning variants); never a CPU path
+LIB_PATH = os.environ.get("FARGO_B200_LIB") or os.path.join(_HERE, "csrc", "libfargo_b200.so")
 _lib = None
 
 

@@ -31,25 +31,6 @@ struct AzRing {
     double dxtheta, invdxtheta, dxrad, invsurf;
 };
 
-// Branch-free flux limiter (TransportEuler.cpp:306-337): the division runs unconditionally (its result is
-// discarded where a*b <= 0, whatever it is) and its validity key is masked by the same predicate.
-template <int LIM> __device__ __forceinline__ double limiter_nb(const double a, const double b, FmAcc &acc)
-{
-    if (LIM == FARGO_LIMITER_MC) {
-	return flux_limiter<LIM>(a, b); // compares and selects only
-    } else {
-	const double p = a * b;
-	const bool pos = p > 0.0;
-	const double den = a + b;
-	const double num = 2.0 * a * b;
-	const double q = fm_div_raw(num, den, fm_rcp_raw(den));
-	fm_acc_num_if(acc, pos, num);
-	fm_acc_nrm_if(acc, pos, den);
-	fm_acc_nrm_if(acc, pos, q);
-	return pos ? q : 0.0;
-    }
-}
-
 // ComputeStarTheta (:416-466) for one base quantity B on the thread's 4 columns: limited slopes, then the
 // upwinded interface values.  pos[c]: ksi > 0 at interface c (between columns c-1 and c); cf[c] = +-(dxtheta -+ ksi).
 template <int LIM>
@@ -195,6 +176,21 @@ __global__ void __launch_bounds__(128, 3)
 	if (col < 0)
 	    col += ns;
 	const size_t row = (size_t)i * ns;
+	if (i + 1 < i_last) { // prefetch the next ring's (rotated) segment: first and last of the 4 columns cover its sectors
+	    int cn = (jout - nshift[i + 1]) % ns;
+	    if (cn < 0)
+		cn += ns;
+	    const int cl = (cn + 3 >= ns) ? cn + 3 - ns : cn + 3;
+	    const size_t a0 = row + (size_t)ns + (size_t)cn, a1 = row + (size_t)ns + (size_t)cl;
+	    pf_global(t_rmp + a0), pf_global(t_rmp + a1);
+	    pf_global(t_rmm + a0), pf_global(t_rmm + a1);
+	    pf_global(t_amp + a0), pf_global(t_amp + a1);
+	    pf_global(t_amm + a0), pf_global(t_amm + a1);
+	    pf_global(t_sigma + a0), pf_global(t_sigma + a1);
+	    pf_global(vp_old + a0), pf_global(vp_old + a1);
+	    if (ADI)
+		pf_global(t_e + a0), pf_global(t_e + a1);
+	}
 	double Q[6][4], U[4];
 #pragma unroll
 	for (int k = 0; k < 4; ++k) {

@@ -87,6 +87,21 @@ __device__ __forceinline__ void fs_store(double *__restrict__ arr, const int rin
     }
 }
 #define FS_FOR4 _Pragma("unroll") for (int k = 0; k < 4; ++k)
+// software prefetch of the next ring's row segment (the marching loops touch every row exactly once, so the
+// hardware sees no reuse to exploit; without this the first consumer of each row eats the full DRAM latency)
+__device__ __forceinline__ void fs_prefetch(const double *__restrict__ arr, const int ring, const DevView &c, const FsLane &L)
+{
+    pf_global(arr + (size_t)ring * c.ns + L.col);
+}
+#ifndef FS_MINB_SRC
+#define FS_MINB_SRC 3
+#endif
+#ifndef FS_MINB_AV
+#define FS_MINB_AV 3
+#endif
+#ifndef FS_MINB_VISC
+#define FS_MINB_VISC 3
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Stage bodies.  Each is written once against the arithmetic policy M (fargo_math.h): MathP<true> emits the
@@ -215,7 +230,7 @@ __device__ __forceinline__ void st_compress(const DevView &c, const int r, const
 // k_fused_sources.  Iteration kr loads ring kr, forms Phi(kr), P(kr), v_rad'(kr) (needs ring kr-1) and v_azi'(kr),
 // then finishes ring r = kr-1: e'(r) needs v_rad'(r+1).  Output: v_rad', v_azi', e' of ring r.
 template <bool ADI>
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(128, FS_MINB_SRC)
     k_fused_sources(const DevView c, const double *__restrict__ sigma, const double *__restrict__ energy,
 		    const double *__restrict__ vr, const double *__restrict__ vp, double *__restrict__ o_vr,
 		    double *__restrict__ o_vp, double *__restrict__ o_e, const double dt, const int R)
@@ -256,6 +271,15 @@ __global__ void __launch_bounds__(128, 3)
 	const bool has_cells = kr < nr;
 	double S0[4], E0[4], VP0[4], VR0[4], P0[4], F0[4], VRn0[4], VPn0[4];
 	fs_load(vr, kr, c, L, VR0);
+	if (kr < i_last) {
+	    fs_prefetch(vr, kr + 1, c, L);
+	    if (kr + 1 < nr) {
+		fs_prefetch(sigma, kr + 1, c, L);
+		fs_prefetch(vp, kr + 1, c, L);
+		if (ADI)
+		    fs_prefetch(energy, kr + 1, c, L);
+	    }
+	}
 	if (has_cells) {
 	    fs_load(sigma, kr, c, L, S0);
 	    fs_load(vp, kr, c, L, VP0);
@@ -422,7 +446,7 @@ __device__ __forceinline__ void st_av_v(const DevView &c, const int r, const dou
 
 // k_fused_artvisc.  Iteration kr loads ring kr; Q(r) of ring r = kr-1 needs v_rad(r+1); v_rad''(r) needs Q(r), Q(r-1).
 template <bool ADI>
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(128, FS_MINB_AV)
     k_fused_artvisc(const DevView c, const double *__restrict__ sigma, const double *__restrict__ energy,
 		    const double *__restrict__ vr, const double *__restrict__ vp, double *__restrict__ o_vr,
 		    double *__restrict__ o_vp, double *__restrict__ o_e, const double dt, const int R)
@@ -454,6 +478,15 @@ __global__ void __launch_bounds__(128, 3)
     for (int kr = kbeg; kr <= i_last; ++kr) {
 	double S0[4], E0[4], VP0[4];
 	fs_load(vr, kr, c, L, I.VR0);
+	if (kr < i_last) {
+	    fs_prefetch(vr, kr + 1, c, L);
+	    if (kr + 1 < nr) {
+		fs_prefetch(sigma, kr + 1, c, L);
+		fs_prefetch(vp, kr + 1, c, L);
+		if (ADI)
+		    fs_prefetch(energy, kr + 1, c, L);
+	    }
+	}
 	if (kr < nr) {
 	    fs_load(sigma, kr, c, L, S0);
 	    fs_load(vp, kr, c, L, VP0);
@@ -630,7 +663,7 @@ __device__ __forceinline__ void st_substep3(const DevView &c, const TempClampNB 
 // centred stresses of r-1) and, for the energy equation, Q+ / Q- / the new energy.
 // StabilizeViscosity != 0 is not handled here (the host falls back to the staged kernels).
 template <bool ADI>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(128, FS_MINB_VISC)
     k_fused_viscosity(const DevView c, const double *__restrict__ sigma, const double *__restrict__ energy,
 		      const double *__restrict__ vr, const double *__restrict__ vp, const double *__restrict__ sigma0,
 		      const double *__restrict__ energy0, double *__restrict__ o_vr, double *__restrict__ o_vp,
@@ -665,6 +698,19 @@ __global__ void __launch_bounds__(128, 2)
     for (int kr = kbeg; kr <= i_last; ++kr) {
 	double S0[4], E0[4], VR0[4], VP0[4], N0[4], H0[4];
 	fs_load(vr, kr, c, L, VR0);
+	if (kr < i_last) {
+	    fs_prefetch(vr, kr + 1, c, L);
+	    if (kr + 1 < nr) {
+		fs_prefetch(sigma, kr + 1, c, L);
+		fs_prefetch(vp, kr + 1, c, L);
+		if (ADI)
+		    fs_prefetch(energy, kr + 1, c, L);
+	    }
+	    if (need0 && kr >= i_first) { // ring r + 1 = kr of the reference fields, read one iteration from now
+		fs_prefetch(sigma0, kr, c, L);
+		fs_prefetch(energy0, kr, c, L);
+	    }
+	}
 	if (kr < nr) {
 	    fs_load(sigma, kr, c, L, S0);
 	    fs_load(vp, kr, c, L, VP0);

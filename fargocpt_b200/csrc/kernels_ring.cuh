@@ -241,8 +241,52 @@ __device__ __forceinline__ void atomic_min_pos_double(double *addr, double v)
     atomicMin(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
 }
 
+// per-ring constants of the CFL criterion: cell sizes with the reciprocals the divisions use
+struct CflRing {
+    double cell_size, dxr, dxa, cell2, sqg;	  // denominators
+    double ycell, ydxr, ydxa, ycell2, ysqg;	  // fm_rcp_raw of them
+    double ids, irb, iok, inv_limit, lf, C, vm;
+};
+// the six inverse time scales of one cell (cfl.cpp:240-328) against the arithmetic policy M; returns A = sum of squares
+template <class M>
+__device__ __forceinline__ double cfl_cell(const DevView &c, const CflRing &g, const int i, const bool adiabatic, const double s,
+					    const double e, const double vr0, const double vr1, const double vp0, const double vp1,
+					    const double qp, const double qm, FmAcc &A)
+{
+    const double vres = c.p.fast_transport ? vp0 - g.vm : vp0;
+    const double cs = eos_cs_m<M>(c, i, s, e, A);
+    const double invdt1 = M::div_y(cs, g.cell_size, g.ycell, A);
+    const double invdt2 = M::div_y(vr0, g.dxr, g.ydxr, A);
+    const double invdt3 = M::div_y(vres, g.dxa, g.ydxa, A);
+    double invdt4;
+    if (c.p.artificial_viscosity == FARGO_ARTVISC_SN) {
+	double dvRadial = vr1 - vr0;
+	double dvAzimuthal = vp1 - vp0;
+	dvRadial = (dvRadial > 0.0) ? 0.0 : -dvRadial;
+	dvAzimuthal = (dvAzimuthal > 0.0) ? 0.0 : -dvAzimuthal;
+	invdt4 = 4.0 * (g.C * g.C) * stdmax(dvRadial / g.dxr, dvAzimuthal / g.dxa) * g.lf; // SN is not a throughput config
+    } else { // TW form, also for ArtificialViscosity: None
+	const double eps_rr = (vr1 - vr0) * g.ids;
+	const double eps_pp = g.irb * ((vp1 - vp0) * c.invdphi + 0.5 * (vr1 + vr0));
+	const double mdiv_V = -stdmin(eps_rr + eps_pp, 0.0);
+	invdt4 = 4.0 * (g.C * g.C) * mdiv_V * g.lf;
+    }
+    double nu;
+    if (c.p.viscous_alpha > 0) { // eos_nu with the division by sqrt(gamma) shared
+	const double H = adiabatic ? M::div_y(cs, g.sqg, g.ysqg, A) * g.iok : cs * g.iok;
+	nu = c.p.viscous_alpha * H * cs;
+    } else {
+	nu = c.p.constant_viscosity;
+    }
+    const double invdt5 = M::div_y(4.0 * nu, g.cell2, g.ycell2, A) * g.lf;
+    double invdt6 = 0.0;
+    if (adiabatic)
+	invdt6 = g.inv_limit * fabs(M::div(qp - qm, e, A)) * g.lf;
+    return invdt1 * invdt1 + invdt2 * invdt2 + invdt3 * invdt3 + invdt4 * invdt4 + invdt5 * invdt5 + invdt6 * invdt6;
+}
+
 // grid: x over azimuth (512 columns per block of 128 threads), y over the active rings
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
     k_cfl(const DevView c, const double *__restrict__ sigma, const double *__restrict__ energy,
 	  const double *__restrict__ vr, const double *__restrict__ vp, const double *__restrict__ qplus,
 	  const double *__restrict__ qminus, const double *__restrict__ cf_r, const double *__restrict__ cf_phi,
@@ -268,15 +312,21 @@ __global__ void __launch_bounds__(128)
 	}
     }
     if (j0 < ns) {
-	const double lf = c.p.leapfrog ? 0.6 : 1.0;
-	const double C = c.p.artificial_viscosity_factor;
-	const double dxRadial = c.g.rsup[i] - c.g.rinf[i];
-	const double dxAzimuthal = c.g.rmed[i] * c.dphi;
-	const double cell_size = stdmin(dxRadial, dxAzimuthal);
-	const Rcp r_cell = make_rcp(cell_size), r_dxr = make_rcp(dxRadial), r_dxa = make_rcp(dxAzimuthal);
-	const Rcp r_cell2 = make_rcp(cell_size * cell_size), r_sqg = make_rcp(c.sqrt_gamma);
-	const double inv_limit = 1.0 / c.p.heating_cooling_cfl_limit;
-	const double ids = c.g.invdiffrsup[i], irb = c.g.invrmed[i], iok = c.g.inv_omega_k[i];
+	CflRing g;
+	g.lf = c.p.leapfrog ? 0.6 : 1.0;
+	g.C = c.p.artificial_viscosity_factor;
+	g.dxr = c.g.rsup[i] - c.g.rinf[i];
+	g.dxa = c.g.rmed[i] * c.dphi;
+	g.cell_size = stdmin(g.dxr, g.dxa);
+	g.cell2 = g.cell_size * g.cell_size;
+	g.sqg = c.sqrt_gamma;
+	g.ycell = fm_rcp_raw(g.cell_size), g.ydxr = fm_rcp_raw(g.dxr), g.ydxa = fm_rcp_raw(g.dxa);
+	g.ycell2 = fm_rcp_raw(g.cell2), g.ysqg = fm_rcp_raw(g.sqg);
+	g.inv_limit = 1.0 / c.p.heating_cooling_cfl_limit;
+	g.ids = c.g.invdiffrsup[i], g.irb = c.g.invrmed[i], g.iok = c.g.inv_omega_k[i];
+	g.vm = vm;
+	FmAcc A0; // validity of the five shared denominators
+	fm_acc_nrm(A0, g.cell_size), fm_acc_nrm(A0, g.dxr), fm_acc_nrm(A0, g.dxa), fm_acc_nrm(A0, g.cell2), fm_acc_nrm(A0, g.sqg);
 	const bool vec = ((ns & 3) == 0);
 	double S[4], E[4], V0[4], V1[4], P[5], QP[4], QM[4];
 	const size_t row = (size_t)i * ns;
@@ -315,51 +365,36 @@ __global__ void __launch_bounds__(128)
 		}
 	    }
 	}
+	if (!adiabatic) {
+#pragma unroll
+	    for (int k = 0; k < 4; ++k)
+		E[k] = QP[k] = QM[k] = 0.0;
+	}
+	// the four cells straight-line on the fast arithmetic, one validity test; cold redo with the plain operators
+	double Ac[4];
+	FmAcc A = A0;
+#pragma unroll
+	for (int k = 0; k < 4; ++k)
+	    Ac[k] = cfl_cell<MathP<true>>(c, g, i, adiabatic, S[k], E[k], V0[k], V1[k], P[k], P[k + 1], QP[k], QM[k], A);
+	if (!fm_acc_ok(A)) {
+#pragma unroll
+	    for (int k = 0; k < 4; ++k)
+		Ac[k] = cfl_cell<MathP<false>>(c, g, i, adiabatic, S[k], E[k], V0[k], V1[k], P[k], P[k + 1], QP[k], QM[k], A);
+	}
 #pragma unroll
 	for (int k = 0; k < 4; ++k) {
 	    if (!vec && j0 + k >= ns)
 		continue;
-	    const double s = S[k], e = adiabatic ? E[k] : 0.0;
-	    const double vr0 = V0[k], vr1 = V1[k], vp0 = P[k], vp1 = P[k + 1];
-	    const double vres = c.p.fast_transport ? vp0 - vm : vp0;
-	    const double cs = eos_cs(c, i, s, e);
-	    const double invdt1 = div_by(cs, r_cell);
-	    const double invdt2 = div_by(vr0, r_dxr);
-	    const double invdt3 = div_by(vres, r_dxa);
-	    double invdt4;
-	    if (c.p.artificial_viscosity == FARGO_ARTVISC_SN) {
-		double dvRadial = vr1 - vr0;
-		double dvAzimuthal = vp1 - vp0;
-		dvRadial = (dvRadial > 0.0) ? 0.0 : -dvRadial;
-		dvAzimuthal = (dvAzimuthal > 0.0) ? 0.0 : -dvAzimuthal;
-		invdt4 = 4.0 * (C * C) * stdmax(div_by(dvRadial, r_dxr), div_by(dvAzimuthal, r_dxa)) * lf;
-	    } else { // TW form, also for ArtificialViscosity: None
-		const double eps_rr = (vr1 - vr0) * ids;
-		const double eps_pp = irb * ((vp1 - vp0) * c.invdphi + 0.5 * (vr1 + vr0));
-		const double mdiv_V = -stdmin(eps_rr + eps_pp, 0.0);
-		invdt4 = 4.0 * (C * C) * mdiv_V * lf;
-	    }
-	    double nu;
-	    if (c.p.viscous_alpha > 0) { // eos_nu with the division by sqrt(gamma) shared
-		const double H = adiabatic ? div_by(cs, r_sqg) * iok : cs * iok;
-		nu = c.p.viscous_alpha * H * cs;
-	    } else {
-		nu = c.p.constant_viscosity;
-	    }
-	    const double invdt5 = div_by(4.0 * nu, r_cell2) * lf;
-	    double invdt6 = 0.0;
-	    if (adiabatic)
-		invdt6 = inv_limit * fabs((QP[k] - QM[k]) / e) * lf;
-	    const double A = invdt1 * invdt1 + invdt2 * invdt2 + invdt3 * invdt3 + invdt4 * invdt4 + invdt5 * invdt5 + invdt6 * invdt6;
+	    const double Ak = Ac[k];
 	    if (c.p.stabilize_viscosity == 2) { // per-cell min(dt_cell, -CFL / min(c_phi, c_r)), cfl.cpp:330-338
-		double dt_cell = CFL / sqrt(A);
+		double dt_cell = CFL / sqrt(Ak);
 		const double cc = stdmin(cf_phi[row + j0 + k], cf_r[row + j0 + k]);
 		if (cc != 0.0)
 		    dt_cell = stdmin(dt_cell, -CFL / cc);
 		if (dt_cell < best)
 		    best = dt_cell;
-	    } else if (A > Amax) {
-		Amax = A;
+	    } else if (Ak > Amax) {
+		Amax = Ak;
 	    }
 	}
     }

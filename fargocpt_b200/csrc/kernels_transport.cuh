@@ -13,6 +13,8 @@
 // State per transported base b (w = Q / Sigma_int for the five non-density quantities, Sigma itself for
 // Sigma*): b(k-2), b(k-1), dq(k-2).  When ring k arrives: dq(k-1), star(k-1) -> interface flux F(k-1), then
 // cell k-2 is finished:  Q(k-2) += (F(k-2) - F(k-1)) * InvSurf[k-2].
+// The 5 + 6 divisions of an iteration (Q / Sigma_int, van Leer slopes) run straight-line on the branch-free
+// arithmetic of fargo_math.h with one validity test; upwinding is done by selects.
 template <int LIM, bool ADIABATIC>
 __global__ void __launch_bounds__(128)
     k_transport_radial(const DevView c, const double *__restrict__ sigma, const double *__restrict__ vr,
@@ -43,13 +45,25 @@ __global__ void __launch_bounds__(128)
     }
 
     const int kstart = max(i0 - 2, 0);
+    double vnext = AT(vr, kstart, j); // v_r(k), carried from the previous iteration's v_r(k+1)
+    // (unrolling the march six-fold over the rotation phases of the window removes the register copies at the end of
+    // the loop body but was not faster on B200: 3.36 vs 3.28 ms at 8192x16384)
     for (int k = kstart; k <= i1 + 1; ++k) {
-	double bk[NB], rawk[NB];
-	double vk = 0.0;
+	double bk[NB], rawk[NB], dq1[NB], F1[NB];
+	const double vk = vnext;
+	if (k + 1 < nr && k < i1 + 1) { // prefetch the next ring
+	    pf_global(&AT(sigma, k + 1, j));
+	    pf_global(&AT(vr, k + 2, j));
+	    pf_global(&AT(vp, k + 1, j));
+	    if (ADIABATIC)
+		pf_global(&AT(energy, k + 1, j));
+	}
+	const int m = k - 1;
+	const bool slopes = (m >= 1 && m < nr - 1 && k < nr);
 	if (k < nr) {
 	    const double s = AT(sigma, k, j);
-	    vk = AT(vr, k, j);
 	    const double vk1 = AT(vr, k + 1, j);
+	    vnext = vk1;
 	    const double vpj = AT(vp, k, j), vpn = AT(vp, k, jp);
 	    const double r = c.g.rmed[k];
 	    rawk[0] = s;
@@ -59,49 +73,64 @@ __global__ void __launch_bounds__(128)
 	    rawk[4] = s * (vpj + r * OmegaF) * r; // angular_momentum_minus(:490)
 	    if (ADIABATIC)
 		rawk[5] = AT(energy, k, j);
+	    // divise_polargrid (SideEuler.cpp:27-43; Sigma_int == Sigma before the sweep) and the limited slopes of ring
+	    // k-1 (compute_star_radial :356-371): 5 + 6 divisions, straight-line with one validity test (fargo_math.h)
+	    const double idm = slopes ? c.g.invdiffrmed[m] : 0.0, idp = slopes ? c.g.invdiffrmed[m + 1] : 0.0;
+	    FmAcc acc;
 	    bk[0] = s;
+	    {
+		const double ys = fm_rcp_raw(s);
+		fm_acc_nrm(acc, s);
 #pragma unroll
-	    for (int q = 1; q < NB; ++q)
-		bk[q] = rawk[q] / s; // divise_polargrid (SideEuler.cpp:27-43), Sigma_int == Sigma before the sweep
-	} else {
+		for (int q = 1; q < NB; ++q) {
+		    bk[q] = fm_div_raw(rawk[q], s, ys);
+		    fm_acc_num(acc, rawk[q]);
+		    fm_acc_nrm(acc, bk[q]);
+		}
+	    }
+	    if (slopes) {
 #pragma unroll
-	    for (int q = 0; q < NB; ++q)
-		bk[q] = rawk[q] = 0.0;
-	    if (k == nr)
-		vk = AT(vr, nr, j);
-	}
-	// slopes of ring k-1 (compute_star_radial :356-371)
-	const int m = k - 1;
-	double dq1[NB];
-	if (m >= 1 && m < nr - 1 && k < nr) {
-	    const double idm = c.g.invdiffrmed[m], idp = c.g.invdiffrmed[m + 1];
+		for (int q = 0; q < NB; ++q) {
+		    const double dqm = (b1[q] - b2[q]) * idm;
+		    const double dqp = (bk[q] - b1[q]) * idp;
+		    dq1[q] = limiter_nb<LIM>(dqp, dqm, acc);
+		}
+	    } else {
 #pragma unroll
-	    for (int q = 0; q < NB; ++q) {
-		const double dqm = (b1[q] - b2[q]) * idm;
-		const double dqp = (bk[q] - b1[q]) * idp;
-		dq1[q] = flux_limiter<LIM>(dqp, dqm);
+		for (int q = 0; q < NB; ++q)
+		    dq1[q] = 0.0;
+	    }
+	    if (!fm_acc_ok(acc)) { // cold: exact zeros (v_rad == 0 at the boundaries) or extreme exponents
+#pragma unroll
+		for (int q = 1; q < NB; ++q)
+		    bk[q] = rawk[q] / s;
+		if (slopes) {
+#pragma unroll
+		    for (int q = 0; q < NB; ++q) {
+			const double dqm = (b1[q] - b2[q]) * idm;
+			const double dqp = (bk[q] - b1[q]) * idp;
+			dq1[q] = flux_limiter<LIM>(dqp, dqm);
+		    }
+		}
 	    }
 	} else {
 #pragma unroll
 	    for (int q = 0; q < NB; ++q)
-		dq1[q] = 0.0;
+		bk[q] = rawk[q] = dq1[q] = 0.0;
+	    if (k == nr)
+		vnext = 0.0;
 	}
-	// star values and fluxes through interface m = k-1 (:376-392, :569-575)
-	double F1[NB];
+	// star values and fluxes through interface m = k-1 (:376-392, :569-575); upwinding by selects
 	if (m >= 1 && m < nr && m >= kstart + 1) {
 	    const double geo = dtdphi * c.g.rinf[m];
+	    const bool pos = v1 > 0.0;
+	    const double hp = (c.g.rmed[m] - c.g.rmed[m - 1] - v1 * dt) * 0.5;
+	    const double hm = (c.g.rmed[m + 1] - c.g.rmed[m] + v1 * dt) * 0.5;
+	    const double hh = pos ? hp : -hm; // b1 - hm * dq1 == b1 + (-hm) * dq1 exactly
 	    double star[NB];
-	    if (v1 > 0.0) {
-		const double h = (c.g.rmed[m] - c.g.rmed[m - 1] - v1 * dt) * 0.5;
 #pragma unroll
-		for (int q = 0; q < NB; ++q)
-		    star[q] = b2[q] + h * dq2[q];
-	    } else {
-		const double h = (c.g.rmed[m + 1] - c.g.rmed[m] + v1 * dt) * 0.5;
-#pragma unroll
-		for (int q = 0; q < NB; ++q)
-		    star[q] = b1[q] - h * dq1[q];
-	    }
+	    for (int q = 0; q < NB; ++q)
+		star[q] = (pos ? b2[q] : b1[q]) + hh * (pos ? dq2[q] : dq1[q]);
 	    F1[0] = geo * 1.0 * star[0] * v1; // Sigma: QRStar == 1 (Sigma/Sigma_int), DensityStar = star[0]
 #pragma unroll
 	    for (int q = 1; q < NB; ++q)
@@ -135,4 +164,3 @@ __global__ void __launch_bounds__(128)
 	v1 = vk;
     }
 }
-
