@@ -126,7 +126,11 @@ struct fargo_ctx {
     double *h_pin; // pinned host staging for the CFL scalar + ring factors
     bool visc_const_filled = false;
     cudaEvent_t ev_pin = nullptr; // completion of the last H2D copy out of h_pin
-    int az_R, rad_chunk, fs_R;
+    int az_R, rad_chunk, fs_R, n_sm;
+    int rm_chunk = 0;	       // columns per TMA chunk of k_ring_mean (0: generic kernel)
+    size_t rm_smem = 0;
+    cudaStream_t stream2 = nullptr; // side stream: the transport ring means run beside the radial sweep
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool force_staged = false;
     cudaEvent_t ev_user[4] = {nullptr, nullptr, nullptr, nullptr}; // fargo_event_record slots
     // optional per-kernel device timing (bench.py roofline): CUDA events on the launching stream
@@ -154,7 +158,7 @@ static int kstat_id(fargo_ctx *c, const char *name)
     c->kstats.push_back(s);
     return (int)c->kstats.size() - 1;
 }
-static void prof_begin(fargo_ctx *c, const char *name)
+static void prof_begin(fargo_ctx *c, const char *name, cudaStream_t strm)
 {
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     if (!c->ev_pool.empty()) {
@@ -164,13 +168,15 @@ static void prof_begin(fargo_ctx *c, const char *name)
 	cudaEventCreate(&ev.first);
 	cudaEventCreate(&ev.second);
     }
-    cudaEventRecord(ev.first, c->stream);
+    cudaEventRecord(ev.first, strm);
     c->pending.push_back({kstat_id(c, name), ev});
 }
-static void prof_end(fargo_ctx *c) { cudaEventRecord(c->pending.back().second.second, c->stream); }
+static void prof_end(fargo_ctx *c, cudaStream_t strm) { cudaEventRecord(c->pending.back().second.second, strm); }
 static void prof_collect(fargo_ctx *c)
 {
     cudaStreamSynchronize(c->stream);
+    if (c->stream2)
+	cudaStreamSynchronize(c->stream2);
     for (auto &p : c->pending) {
 	float ms = 0;
 	cudaEventElapsedTime(&ms, p.second.first, p.second.second);
@@ -197,6 +203,27 @@ static int upload_vec(fargo_ctx *c, const double **dst, const std::vector<double
     CUDA_OK(cudaStreamSynchronize(c->stream));
     *dst = d;
     return 0;
+}
+
+// Rings per march of a ring-marching kernel.  A CTA marches R rings after `warm` warm-up rings; the grid has
+// ctas_x * ceil(nr / R) CTAs for `slots` resident CTA slots.  Model: one wave costs (R + warm); several waves are
+// scheduled dynamically, so they cost their fractional count plus half a CTA of tail.
+static int rings_per_march(int nr, int ctas_x, int slots, int warm)
+{
+    int best_R = nr;
+    double best = 1e300;
+    for (int R = (nr < 4 ? nr : 4); R <= nr; ++R) {
+	const int y = (nr + R - 1) / R;
+	if (R > 4 && (nr + R - 2) / (R - 1) == y)
+	    continue; // same number of bands as R-1: the smaller R is the balanced choice
+	const double ctas = (double)ctas_x * y;
+	const double cost = (ctas <= slots) ? (double)(R + warm) : (R + warm) * (ctas / slots + 0.5);
+	if (cost < best * 0.999) {
+	    best = cost;
+	    best_R = R;
+	}
+    }
+    return best_R < 1 ? 1 : best_R;
 }
 
 static inline unsigned cells_grid(long long n, int block = 256) { return (unsigned)((n + block - 1) / block); }
@@ -336,6 +363,12 @@ extern "C" void fargo_ctx_destroy(fargo_ctx *c)
     for (int k = 0; k < 4; ++k)
 	if (c->ev_user[k])
 	    cudaEventDestroy(c->ev_user[k]);
+    if (c->ev_fork)
+	cudaEventDestroy(c->ev_fork);
+    if (c->ev_join)
+	cudaEventDestroy(c->ev_join);
+    if (c->stream2)
+	cudaStreamDestroy(c->stream2);
     if (c->stream)
 	cudaStreamDestroy(c->stream);
     delete c;
@@ -388,6 +421,18 @@ extern "C" int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, con
 	    return 1;
 	}
     }
+    {
+	cudaError_t e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
+	if (e == cudaSuccess)
+	    e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+	if (e == cudaSuccess)
+	    e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+	if (e != cudaSuccess) {
+	    fail("side stream: %s", cudaGetErrorString(e));
+	    fargo_ctx_destroy(c);
+	    return 1;
+	}
+    }
     TRY(init_geometry(c, radii));
     const size_t ns = (size_t)c->v.nr * c->v.ns, nv = (size_t)(c->v.nr + 1) * c->v.ns;
     TRY(dalloc(c, &c->sigma, ns) || dalloc(c, &c->eb[0], ns) || dalloc(c, &c->vrb[0], nv) || dalloc(c, &c->vpb[0], ns) ||
@@ -419,17 +464,37 @@ extern "C" int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, con
 	    return 1;
 	}
     }
-    // launch geometry of the transport kernels
-    { // rings per warp of the azimuthal kernel: long marches amortise the one warm-up ring, short ones fill the GPU
-	const long long nwin = (c->v.ns + AZ_OUT - 1) / AZ_OUT;
-	long long R = ((long long)c->v.nr * nwin) / (148LL * 16);
-	c->az_R = (int)(R < 4 ? 4 : (R > 32 ? 32 : R));
-    }
-    c->rad_chunk = 64;
-    { // rings per warp of the fused source kernels (one warm-up ring per march)
-	const long long nwin = (c->v.ns + FS_OUT - 1) / FS_OUT;
-	long long R = ((long long)c->v.nr * nwin) / (148LL * 16);
-	c->fs_R = (int)(R < 4 ? 4 : (R > 64 ? 64 : R));
+    // launch geometry of the marching kernels: rings per march chosen so that the CTAs fill the GPU evenly
+    {
+	int sms = 148;
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+	c->n_sm = sms;
+	const int nwin_az = (c->v.ns + AZ_OUT - 1) / AZ_OUT, nwin_fs = (c->v.ns + FS_OUT - 1) / FS_OUT;
+	c->az_R = rings_per_march(c->v.nr, (nwin_az + 3) / 4, 3 * sms, 1);
+	c->fs_R = rings_per_march(c->v.nr, (nwin_fs + 3) / 4, 3 * sms, 1);
+	c->rad_chunk = rings_per_march(c->v.nr, (c->v.ns + 127) / 128, 3 * sms, 2);
+	// ring means: one warp per 32 rings; give each resident warp as much of the SM's shared memory as its share allows
+	if ((c->v.ns & 1) == 0) {
+	    const int nblocks = (c->v.nr + 31) / 32;
+	    const int per_sm = (nblocks + sms - 1) / sms;
+	    const size_t budget = (size_t)200 * 1024 / (per_sm > 4 ? 4 : per_sm);
+	    int chunk = (int)(budget / (RM_STAGES * 32 * sizeof(double))) - 2;
+	    chunk &= ~15;
+	    if (chunk > 256)
+		chunk = 256;
+	    if (chunk > ((c->v.ns + 15) & ~15))
+		chunk = (c->v.ns + 15) & ~15;
+	    if (chunk >= 16) {
+		c->rm_chunk = chunk;
+		c->rm_smem = (size_t)RM_STAGES * 32 * (chunk + 2) * sizeof(double) + RM_STAGES * sizeof(unsigned long long);
+		cudaError_t e = cudaFuncSetAttribute(k_ring_mean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->rm_smem);
+		if (e != cudaSuccess) {
+		    fail("k_ring_mean shared memory opt-in: %s", cudaGetErrorString(e));
+		    fargo_ctx_destroy(c);
+		    return 1;
+		}
+	    }
+	}
     }
     if (nranks > 1) {
 	if (!nccl_unique_id) {
@@ -467,13 +532,15 @@ extern "C" int fargo_sync(fargo_ctx *c)
     return 0;
 }
 
-#define LAUNCH(c, kernel, grid, block, smem, ...)                        \
+#define LAUNCH(c, kernel, grid, block, smem, ...) LAUNCH_ON(c, (c)->stream, kernel, grid, block, smem, __VA_ARGS__)
+#define LAUNCH_ON(c, strm, kernel, grid, block, smem, ...) LAUNCH_NAMED(c, strm, #kernel, kernel, grid, block, smem, __VA_ARGS__)
+#define LAUNCH_NAMED(c, strm, label, kernel, grid, block, smem, ...)     \
     do {                                                                 \
 	if ((c)->profiling)                                              \
-	    prof_begin(c, #kernel);                                      \
-	kernel<<<grid, block, smem, (c)->stream>>>(__VA_ARGS__);         \
+	    prof_begin(c, label, strm);                                  \
+	kernel<<<grid, block, smem, strm>>>(__VA_ARGS__);                \
 	if ((c)->profiling)                                              \
-	    prof_end(c);                                                 \
+	    prof_end(c, strm);                                           \
 	(c)->launches++;                                                 \
 	cudaError_t _e = cudaGetLastError();                             \
 	if (_e != cudaSuccess)                                           \
@@ -727,7 +794,7 @@ static int clamp_id(const fargo_ctx *c, int id, bool is_vector)
 
 // damping of one field (damping.cpp:311-752): host computes the ring range and exp factors, device applies
 static int damp_field(fargo_ctx *c, double *x, const double *x0, bool is_vector, bool is_density, const int type[2], double dt,
-		      double *d_expf, double *h_expf)
+		      double *d_expf, double *h_expf, DampJobs &jobs, int &rows)
 {
     const fargo_params &p = c->v.p;
     const int rings = c->v.nr + (is_vector ? 1 : 0);
@@ -760,16 +827,15 @@ static int damp_field(fargo_ctx *c, double *x, const double *x0, bool is_vector,
 	}
 	zones[nz++] = {limit, rings, type[1]};
     }
-    if (nz == 0)
-	return 0;
-    CUDA_OK(cudaMemcpyAsync(d_expf, h_expf, rings * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     for (int z = 0; z < nz; ++z) {
 	const int nrings = zones[z].hi - zones[z].lo;
 	if (nrings <= 0)
 	    continue;
-	const unsigned gx = zones[z].type == FARGO_DAMP_MEAN ? 1u : (unsigned)((c->v.ns + 255) / 256);
-	dim3 grid(gx, (unsigned)nrings);
-	LAUNCH(c, k_damping, grid, 256, 0, c->v, x, x0, d_expf, zones[z].lo, zones[z].hi, zones[z].type, x0_const);
+	DampJob &J = jobs.j[jobs.n++];
+	J.x = x, J.x0 = x0, J.expf = d_expf;
+	J.ring_lo = zones[z].lo, J.ring_hi = zones[z].hi, J.type = zones[z].type, J.row0 = rows;
+	J.x0_const = x0_const;
+	rows += nrings;
     }
     return 0;
 }
@@ -779,17 +845,25 @@ extern "C" int fargo_stage_boundary(fargo_ctx *c, double dt, int final_call)
     CUDA_OK(cudaSetDevice(c->device));
     const fargo_params &p = c->v.p;
     VBuf v = cur_v(c, c->v_mid);
-    if (final_call && p.damping) { // order: vrad, vazi, sigma, energy (damping.cpp:204-270)
+    if (final_call && p.damping) { // order: vrad, vazi, sigma, energy (damping.cpp:204-270); the fields are independent
 	const int st = c->v.nr + 2;
 	double *h = c->h_pin + 8, *d = c->expf_s;
-	CUDA_OK(cudaEventSynchronize(c->ev_pin)); // the previous step's copies out of h_pin are done
-	if (damp_field(c, v.vr, c->vr0, true, false, p.damp_vrad, dt, d, h) ||
-	    damp_field(c, v.vp, c->vp0, false, false, p.damp_vazi, dt, d + st, h + st) ||
-	    damp_field(c, c->sigma, c->sigma0, false, true, p.damp_sigma, dt, d + 2 * st, h + 2 * st))
+	CUDA_OK(cudaEventSynchronize(c->ev_pin)); // the previous step's copy out of h_pin is done
+	DampJobs jobs;
+	jobs.n = 0;
+	int rows = 0;
+	if (damp_field(c, v.vr, c->vr0, true, false, p.damp_vrad, dt, d, h, jobs, rows) ||
+	    damp_field(c, v.vp, c->vp0, false, false, p.damp_vazi, dt, d + st, h + st, jobs, rows) ||
+	    damp_field(c, c->sigma, c->sigma0, false, true, p.damp_sigma, dt, d + 2 * st, h + 2 * st, jobs, rows))
 	    return 1;
-	if (p.adiabatic && damp_field(c, EN(c), c->energy0, false, false, p.damp_energy, dt, d + 3 * st, h + 3 * st))
+	if (p.adiabatic && damp_field(c, EN(c), c->energy0, false, false, p.damp_energy, dt, d + 3 * st, h + 3 * st, jobs, rows))
 	    return 1;
-	CUDA_OK(cudaEventRecord(c->ev_pin, c->stream));
+	if (jobs.n > 0) {
+	    CUDA_OK(cudaMemcpyAsync(d, h, 4 * (size_t)st * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	    CUDA_OK(cudaEventRecord(c->ev_pin, c->stream));
+	    dim3 grid((unsigned)((c->v.ns + 1023) / 1024), (unsigned)rows);
+	    LAUNCH(c, k_damping, grid, 256, 0, c->v, jobs);
+	}
     }
     // keplerian_azimuthal.cpp:29-38, :51-59 (host: sqrt with glibc == IEEE, value is per call)
     const int Irad = c->v.nr - 1;
@@ -801,14 +875,32 @@ extern "C" int fargo_stage_boundary(fargo_ctx *c, double dt, int final_call)
     return 0;
 }
 
+// ring means of v_azi (+ Nshift and the constant residual for the transport) on stream `strm`
+static int launch_ring_mean(fargo_ctx *c, cudaStream_t strm, const double *vp, double dt, int mode)
+{
+    const DevView &v = c->v;
+    const unsigned nb = (unsigned)((v.nr + 31) / 32);
+    const char *label = mode == 1 ? "k_ring_mean[transport,side-stream]" : "k_ring_mean[cfl]";
+    if (c->rm_chunk > 0)
+	LAUNCH_NAMED(c, strm, label, k_ring_mean, nb, 32, c->rm_smem, v, vp, c->vmean, c->nshift, c->vconst, dt, mode, c->rm_chunk);
+    else
+	LAUNCH_NAMED(c, strm, label, k_ring_mean_generic, nb, 32, 0, v, vp, c->vmean, c->nshift, c->vconst, dt, mode);
+    return 0;
+}
+
 // Transport: reads (Sigma, e, v) from `in`, writes Sigma and e in place and the new velocities to `out`
 // (out != in: the azimuthal kernel still reads the old v_azi of neighbouring columns while it stores).
 template <int LIM>
 static int launch_transport(fargo_ctx *c, double dt, const double *vr_in, const double *vp_in, double *vr_out, double *vp_out)
 {
     const DevView &v = c->v;
-    // ring means of the pre-transport v_azi, Nshift, constant residual
-    LAUNCH(c, k_ring_mean, (unsigned)((v.nr + 31) / 32), 32, 0, v, vp_in, c->vmean, c->nshift, c->vconst, dt, 1);
+    // ring means of the pre-transport v_azi, Nshift, constant residual: latency-bound (one dependent add chain per
+    // ring) and not needed by the radial sweep, so they run beside it on the side stream
+    CUDA_OK(cudaEventRecord(c->ev_fork, c->stream));
+    CUDA_OK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+    if (launch_ring_mean(c, c->stream2, vp_in, dt, 1))
+	return 1;
+    CUDA_OK(cudaEventRecord(c->ev_join, c->stream2));
     {
 	dim3 grid((unsigned)((v.ns + 127) / 128), (unsigned)((v.nr + c->rad_chunk - 1) / c->rad_chunk));
 	if (v.p.adiabatic)
@@ -818,6 +910,7 @@ static int launch_transport(fargo_ctx *c, double dt, const double *vr_in, const 
 	    LAUNCH(c, (k_transport_radial<LIM, false>), grid, 128, 0, v, c->sigma, vr_in, vp_in, EN(c), c->t_sigma, c->t_rmp, c->t_rmm,
 		   c->t_amp, c->t_amm, c->t_e, dt, c->rad_chunk);
     }
+    CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     {
 	const int nwin = (v.ns + AZ_OUT - 1) / AZ_OUT;
 	dim3 grid((unsigned)((nwin + 3) / 4), (unsigned)((v.nr + c->az_R - 1) / c->az_R));
@@ -904,7 +997,8 @@ extern "C" int fargo_condition_cfl(fargo_ctx *c, double *out)
 	return fail("condition_cfl called mid-step");
     c->h_pin[0] = 1.7976931348623157e308;
     CUDA_OK(cudaMemcpyAsync(c->d_dt, c->h_pin, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    LAUNCH(c, k_ring_mean, (unsigned)((v.nr + 31) / 32), 32, 0, v, VPA(c), c->vmean, c->nshift, c->vconst, 0.0, 0);
+    if (launch_ring_mean(c, c->stream, VPA(c), 0.0, 0))
+	return 1;
     const int nact = v.active_size - v.first_active;
     if (nact > 0) {
 	dim3 grid((unsigned)((v.ns + 511) / 512), (unsigned)nact);

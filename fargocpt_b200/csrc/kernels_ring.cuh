@@ -125,17 +125,40 @@ __global__ void __launch_bounds__(256)
 // damping zones (damping.cpp:311-752).  The per-ring factors exp(-dt*f/tau) are computed on the host with
 // glibc (bit-identical to the reference) and uploaded; `ring_lo..ring_hi` is the ring range of one zone.
 // type: FARGO_DAMP_INITIAL (X0 = x0 field), _ZERO (X0 = x0_const), _MEAN (X0 = ring mean, index-ordered sum).
-__global__ void __launch_bounds__(256)
-    k_damping(const DevView c, double *__restrict__ x, const double *__restrict__ x0, const double *__restrict__ expf,
-	      const int ring_lo, const int ring_hi, const int type, const double x0_const)
+// All zones of all fields go through ONE launch: blockIdx.y runs over the concatenated ring ranges of the jobs.
+#define FARGO_MAX_DAMP_JOBS 8
+struct DampJob {
+    double *x;
+    const double *x0, *expf;
+    int ring_lo, ring_hi, type, row0; // row0 = first blockIdx.y of this job
+    double x0_const;
+};
+struct DampJobs {
+    int n;
+    DampJob j[FARGO_MAX_DAMP_JOBS];
+};
+__global__ void __launch_bounds__(256) k_damping(const DevView c, const DampJobs jobs)
 {
-    const int ring = ring_lo + blockIdx.y;
-    if (ring >= ring_hi)
+    int q = 0;
+#pragma unroll
+    for (int k = 1; k < FARGO_MAX_DAMP_JOBS; ++k)
+	if (k < jobs.n && (int)blockIdx.y >= jobs.j[k].row0)
+	    q = k;
+    const DampJob &J = jobs.j[q];
+    const int ring = J.ring_lo + ((int)blockIdx.y - J.row0);
+    if (ring >= J.ring_hi)
 	return;
+    double *__restrict__ x = J.x;
+    const double *__restrict__ x0 = J.x0;
+    const int type = J.type;
     __shared__ double mean_sh;
+    int jbeg = blockIdx.x * blockDim.x + threadIdx.x, jstride = gridDim.x * blockDim.x;
     if (type == FARGO_DAMP_MEAN) {
-	// launched with ONE block per ring: thread 0 does the index-ordered sum (damping.cpp:578-585) before
-	// anyone modifies the ring
+	// ONE block handles the whole ring: thread 0 does the index-ordered sum (damping.cpp:578-585) before anyone
+	// modifies the ring
+	if (blockIdx.x != 0)
+	    return;
+	jbeg = threadIdx.x, jstride = blockDim.x;
 	if (threadIdx.x == 0) {
 	    double s = 0.0;
 	    for (int j = 0; j < c.ns; ++j)
@@ -145,10 +168,10 @@ __global__ void __launch_bounds__(256)
 	__syncthreads();
     }
     const double mean = (type == FARGO_DAMP_MEAN) ? mean_sh : 0.0;
-    const double ef = expf[ring];
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < c.ns; j += gridDim.x * blockDim.x) {
+    const double ef = J.expf[ring];
+    for (int j = jbeg; j < c.ns; j += jstride) {
 	const double X = AT(x, ring, j);
-	const double X0 = (type == FARGO_DAMP_INITIAL) ? AT(x0, ring, j) : (type == FARGO_DAMP_MEAN ? mean : x0_const);
+	const double X0 = (type == FARGO_DAMP_INITIAL) ? AT(x0, ring, j) : (type == FARGO_DAMP_MEAN ? mean : J.x0_const);
 	AT(x, ring, j) = (X - X0) * ef + X0;
     }
 }
@@ -161,6 +184,7 @@ __global__ void __launch_bounds__(256)
 // shared-memory ring (row stride 33 doubles: the transposed reads are conflict-free), so ~6 MB of loads are in
 // flight chip-wide while the dependent DADD chains run.
 // mode 0: only vmean (CFL).  mode 1: also Nshift[i] and the constant residual velocity (transport).
+// k_ring_mean_generic: any Ns (8-byte cp.async).  k_ring_mean (below): even Ns, TMA bulk copies.
 #define RM_STAGES 4
 __device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gmem_src)
 {
@@ -171,7 +195,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(32)
-    k_ring_mean(const DevView c, const double *__restrict__ vp, double *__restrict__ vmean, int *__restrict__ nshift,
+    k_ring_mean_generic(const DevView c, const double *__restrict__ vp, double *__restrict__ vmean, int *__restrict__ nshift,
 		double *__restrict__ vconst, const double dt, const int mode)
 {
     __shared__ double tile[RM_STAGES][32][33];
@@ -224,6 +248,107 @@ __global__ void __launch_bounds__(32)
 	    vconst[i] = (Ntilde - Nround) * c.g.rmed[i] * invdt * c.dphi;
 	}
     }
+}
+
+// ring_mean_finish: mean, and for the transport also Nshift and the constant residual (TransportEuler.cpp:215-235)
+__device__ __forceinline__ void ring_mean_finish(const DevView &c, const int i, const double s, double *__restrict__ vmean,
+						  int *__restrict__ nshift, double *__restrict__ vconst, const double dt, const int mode)
+{
+    const double mean = s / (double)c.ns;
+    vmean[i] = mean;
+    if (mode == 1) {
+	const double invdt = 1.0 / dt;
+	const double Ntilde = mean * c.g.invrmed[i] * dt * c.invdphi;
+	const double Nround = floor(Ntilde + 0.5);
+	nshift[i] = (int)Nround;
+	vconst[i] = (Ntilde - Nround) * c.g.rmed[i] * invdt * c.dphi;
+    }
+}
+
+// TMA version: the kernel is bound by the latency of ONE dependent DADD chain per ring (Ns adds, ~10 clk each), so the
+// only job of the memory side is to never let a chain wait.  Every lane fetches ITS ring's next `chunk` columns with
+// one cp.async.bulk (1-D TMA) into its own shared-memory row, RM_STAGES chunks deep, completion through one mbarrier per
+// stage; the row stride (chunk + 2 doubles) keeps the 16-byte LDS of the 32 lanes bank-conflict free.
+// Dynamic shared memory: RM_STAGES * 32 * (chunk + 2) doubles + RM_STAGES mbarriers.  Requires even Ns and chunk.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__global__ void __launch_bounds__(32)
+    k_ring_mean(const DevView c, const double *__restrict__ vp, double *__restrict__ vmean, int *__restrict__ nshift,
+		double *__restrict__ vconst, const double dt, const int mode, const int chunk)
+{
+    extern __shared__ __align__(128) unsigned char rm_smem[];
+    const int lane = threadIdx.x;
+    const int ring0 = blockIdx.x * 32;
+    const int nrows = min(32, c.nr - ring0);
+    const int ns = c.ns;
+    const int stride = chunk + 2;
+    double *tiles = reinterpret_cast<double *>(rm_smem);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(tiles + (size_t)RM_STAGES * 32 * stride);
+    const int nchunks = (ns + chunk - 1) / chunk;
+    if (lane == 0) {
+#pragma unroll
+	for (int st = 0; st < RM_STAGES; ++st)
+	    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[st])), "r"(1));
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const double *src_row = vp + (size_t)(ring0 + (lane < nrows ? lane : 0)) * ns;
+    auto issue = [&](const int t) {
+	if (t >= nchunks)
+	    return;
+	const int st = t % RM_STAGES;
+	const int cols = min(chunk, ns - t * chunk);
+	const unsigned bytes = (unsigned)cols * 8u;
+	if (lane == 0)
+	    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bars[st])), "r"(bytes * (unsigned)nrows)
+			 : "memory");
+	__syncwarp();
+	if (lane < nrows)
+	    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+			     smem_u32(tiles + ((size_t)st * 32 + lane) * stride)),
+			 "l"(src_row + (size_t)t * chunk), "r"(bytes), "r"(smem_u32(&bars[st]))
+			 : "memory");
+    };
+#pragma unroll
+    for (int t = 0; t < RM_STAGES - 1; ++t)
+	issue(t);
+    double s = 0.0;
+    for (int t = 0; t < nchunks; ++t) {
+	__syncwarp(); // every lane is done reading the stage chunk t + RM_STAGES - 1 goes into
+	issue(t + RM_STAGES - 1);
+	const int st = t % RM_STAGES;
+	const unsigned parity = (unsigned)(t / RM_STAGES) & 1u;
+	asm volatile("{\n"
+		     ".reg .pred p;\n"
+		     "RM_WAIT_%=:\n"
+		     "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		     "@p bra RM_DONE_%=;\n"
+		     "bra RM_WAIT_%=;\n"
+		     "RM_DONE_%=:\n"
+		     "}" ::"r"(smem_u32(&bars[st])),
+		     "r"(parity)
+		     : "memory");
+	const double2 *rowp = reinterpret_cast<const double2 *>(tiles + ((size_t)st * 32 + lane) * stride);
+	const int n2 = min(chunk, ns - t * chunk) >> 1;
+	int k = 0;
+	for (; k + 8 <= n2; k += 8) {
+	    double2 v[8];
+#pragma unroll
+	    for (int u = 0; u < 8; ++u)
+		v[u] = rowp[k + u];
+#pragma unroll
+	    for (int u = 0; u < 8; ++u) {
+		s += v[u].x;
+		s += v[u].y;
+	    }
+	}
+	for (; k < n2; ++k) {
+	    const double2 v = rowp[k];
+	    s += v.x;
+	    s += v.y;
+	}
+    }
+    if (lane < nrows)
+	ring_mean_finish(c, ring0 + lane, s, vmean, nshift, vconst, dt, mode);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,111 @@
+#!/usr/bin/env python
+"""N-GPU vs 1-GPU parity of the radial-slab path (split.cpp:21-87 + commbound.cpp:98-182 + the dt all-reduce).
+
+Run under torchrun, one rank per GPU:
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
+        tools/multi_gpu_check.py [--physics isothermal_planet] [--nrad 256] [--naz 512] [--steps 12]
+Every rank runs its slab for K CFL-limited steps; the owned rings are stitched with an all-reduce and rank 0
+compares them with a single-slab run of the same library on its own GPU.  The reference states that its result
+does not depend on the number of ranks (constants.h:17); so: dt sequence bit-equal, fields bit-equal.
+Prints one JSON line; exit code 1 on mismatch.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def run_slab(ctx, cfg, radii, fields, nsteps, synthetic, abi):
+    ctx.upload(abi.SIGMA, fields["Sigma"])
+    ctx.upload(abi.ENERGY, fields["energy"])
+    ctx.upload(abi.VRAD, fields["vrad"])
+    ctx.upload(abi.VAZI, fields["vazi"])
+    orbit = synthetic.PlanetOrbit(cfg)
+    ctx.set_bodies(orbit.bodies(0.0))
+    ctx.set_time(0.0)
+    ctx.init_derived()
+    ctx.stage("boundary", 0.0, 0)
+    ctx.copy_initial_values()
+    last_dt, t, dts = float(cfg["FirstDT"]), 0.0, []
+    for _ in range(nsteps):
+        dt = ctx.cfl(last_dt)
+        last_dt = dt
+        dts.append(dt)
+        ctx.set_bodies(orbit.bodies(t, dt))
+        ctx.set_time(t)
+        ctx.step(dt)
+        t += dt
+    out = {}
+    for fid, name in ((abi.SIGMA, "Sigma"), (abi.VRAD, "vrad"), (abi.VAZI, "vazi"), (abi.ENERGY, "energy")):
+        out[name] = ctx.download(fid)  # only the rings this rank owns are written, the rest stays 0
+    return dts, out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--physics", default="isothermal_planet")
+    ap.add_argument("--nrad", type=int, default=256)
+    ap.add_argument("--naz", type=int, default=512)
+    ap.add_argument("--steps", type=int, default=12)
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    from fargocpt_b200 import HydroContext, abi, synthetic
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        buf = torch.frombuffer(bytearray(abi.get_unique_id()), dtype=torch.uint8).cuda()
+    dist.broadcast(buf, 0)
+    uid = bytes(buf.cpu().numpy().tobytes())
+
+    cfg = synthetic.make_config(args.physics, args.nrad, args.naz)
+    radii = synthetic.radii_from_config(cfg)
+    params = synthetic.params_from_config(cfg)
+    fields = synthetic.disk_fields(cfg, radii, perturb=2e-2)
+    fields["vrad"] = fields["vrad"] + 1e-3 * np.sin(np.arange(args.naz) * 2 * np.pi * 3 / args.naz)[None, :]
+
+    ctx = HydroContext(params, radii, rank=rank, nranks=world, unique_id=uid, device=local)
+    dts, out = run_slab(ctx, cfg, radii, fields, args.steps, synthetic, abi)
+    ctx.close()
+    stitched = {}
+    for name, a in out.items():
+        t = torch.from_numpy(a).cuda()
+        dist.all_reduce(t)  # owned ring sets are disjoint, the rest is exactly 0: the sum stitches bit-exactly
+        stitched[name] = t.cpu().numpy()
+    rc = 0
+    if rank == 0:
+        one = HydroContext(params, radii, rank=0, nranks=1, device=local)
+        dts1, out1 = run_slab(one, cfg, radii, fields, args.steps, synthetic, abi)
+        import reftools
+        res = {"n_gpus": world, "physics": args.physics, "grid": [args.nrad, args.naz], "steps": args.steps,
+               "dt_bit_equal": dts == dts1, "fields": {}}
+        adiabatic = bool(params.adiabatic)
+        for name in stitched:
+            if name == "energy" and not adiabatic:
+                continue
+            st = reftools.compare_stats(stitched[name], out1[name])
+            res["fields"][name] = st
+            if st["n_diff"] != 0:
+                rc = 1
+        if not res["dt_bit_equal"]:
+            rc = 1
+        res["ok"] = rc == 0
+        print(json.dumps(res))
+    flag = torch.tensor([rc], device="cuda")
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(int(flag.item()))
+
+
+if __name__ == "__main__":
+    main()
