@@ -81,6 +81,17 @@ CASES = {
                       ArtificialViscosityFactor=1.41, ConstantViscosity=4.77e-5, InnerBoundary="Outflow",
                       OuterBoundary="Outflow", Nrad=64, Naz=2, Rmin=0.2, Rmax=1.8, MonitorTimestep=1.0e-4,
                       ThicknessSmoothing=0.0),
+    # 100 hydro steps with a Jupiter-mass planet (north_star: fields <= 1e-10 after 100 steps; dt and Nshift bit-exact).
+    # IndirectTermMode 1 (Euler): the indirect term is a closed formula of the recorded body states
+    # (frame_of_reference.cpp:112-132, Pframeforce.cpp:225-251) which tests/goldenrun.py restates.
+    "adia_planet_100": dict(Nrad=48, Naz=160, Rmax=2.5, Nsnapshots=100, MonitorTimestep=4.0e-3, IndirectTermMode=1,
+                            ViscousAlpha=1e-3, HeatingViscous="yes", CoolingBetaLocal="yes", CoolingBeta=10,
+                            Damping="Yes", DampingInnerLimit=1.25, DampingOuterLimit=0.84, DampingTimeFactor=0.1,
+                            _planet=1e-3, _keep=(0, 50, 100), **DAMP_ALL),
+    "iso_planet_100": dict(Nrad=48, Naz=160, Rmax=2.5, Nsnapshots=100, MonitorTimestep=4.0e-3, IndirectTermMode=1,
+                           EquationOfState="Isothermal", ViscousAlpha=1e-3, ArtificialViscosityFactor=1.41, OmegaFrame=1.0,
+                           FlaringIndex=0.0, Damping="Yes", DampingInnerLimit=1.25, DampingOuterLimit=0.84,
+                           DampingTimeFactor=0.1, _planet=1e-3, _keep=(0, 50, 100), **DAMP_ALL),
 }
 
 
@@ -106,6 +117,12 @@ def read_body(path):
 def run_case(name, overrides, keep=False):
     cfg = dict(BASE)
     cfg.update(overrides)
+    planet = cfg.pop("_planet", 0.0)
+    keep_snaps = cfg.pop("_keep", None)
+    if planet > 0:
+        cfg["nbody"] = list(cfg["nbody"]) + [{"name": "planet", "semi-major axis": 1.0, "mass": float(planet),
+                                               "accretion efficiency": 0.0, "eccentricity": 0.0, "radius": "0.01 solRadius",
+                                               "temperature": "0 K", "ramp-up time": 0}]
     tmp = tempfile.mkdtemp(prefix="golden_" + name + "_")
     cfg["OutputDir"] = os.path.join(tmp, "out")
     ypath = os.path.join(tmp, "cfg.yml")
@@ -133,10 +150,14 @@ def run_case(name, overrides, keep=False):
         for fname, rings in (("Sigma", nrad), ("vrad", nrad + 1), ("vazi", nrad), ("energy", nrad),
                              ("Qplus", nrad), ("Qminus", nrad)):
             p = os.path.join(sd, fname + ".dat")
+            if keep_snaps is not None and k not in keep_snaps:
+                continue
             if os.path.exists(p):
                 arrays[f"{fname}_{k}"] = np.fromfile(p, dtype=np.float64).reshape(rings, naz)
         misc.append(read_misc(os.path.join(sd, "misc.bin")))
         bodies.append([read_body(os.path.join(sd, f"nbody{b}.bin")) for b in range(nb)])
+    if keep_snaps is not None:
+        cfg["_keep"] = list(keep_snaps)
     meta = dict(name=name, config=cfg, params=pdict, consts=consts, temperature_unit_K=temp_unit, nsnap=nsnap,
                 misc=misc, bodies=bodies, first_dt=reftools._num(cfg["FirstDT"]),
                 monitor_timestep=float(cfg["MonitorTimestep"]))

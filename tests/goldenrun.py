@@ -8,9 +8,34 @@ from fargocpt_b200 import abi
 STATE = ((abi.SIGMA, "Sigma"), (abi.VRAD, "vrad"), (abi.VAZI, "vazi"), (abi.ENERGY, "energy"))
 
 
+def indirect_term_euler(G, bl):
+    """refframe::ComputeIndirectTermNbodyEuler (frame_of_reference.cpp:112-132) over ComputeNbodyOnNbodyAccel
+    (Pframeforce.cpp:225-251) for a hydro frame centred on body 0, same operation order (IEEE doubles; math.pow is
+    the libm pow the reference's std::pow(dist, 3) resolves to; std::pow(x, 2) is folded to x * x by the compiler)."""
+    import math
+    mass0, x, y = bl[0][0], bl[0][1], bl[0][2]
+    ax = ay = 0.0
+    for b in bl[1:]:
+        mass, xo, yo = b[0], b[1], b[2]
+        dist = math.sqrt((x - xo) * (x - xo) + (y - yo) * (y - yo))
+        ax -= G * mass / math.pow(dist, 3) * (x - xo)
+        ay -= G * mass / math.pow(dist, 3) * (y - yo)
+    ix = iy = 0.0
+    mass_center = 0.0
+    ix -= mass0 * ax
+    iy -= mass0 * ay
+    mass_center += mass0
+    return ix / mass_center, iy / mass_center
+
+
 def bodies_at(meta, k, omega_frame):
     bl = meta["bodies"][k]
-    return abi.FargoBodies.make([b[1] for b in bl], [b[2] for b in bl], [b[0] for b in bl], omega_frame=omega_frame)
+    indirect = (0.0, 0.0)
+    if len(bl) > 1:
+        assert int(meta["config"].get("IndirectTermMode", 0)) == 1, "only the Euler indirect term is restated here"
+        indirect = indirect_term_euler(meta["consts"]["G"], bl)
+    return abi.FargoBodies.make([b[1] for b in bl], [b[2] for b in bl], [b[0] for b in bl], indirect=indirect,
+                                omega_frame=omega_frame)
 
 
 def start_from_snapshot0(ctx, meta, z):
@@ -46,7 +71,8 @@ def run_fixture(ctx, meta, z, nsteps=None, on_snapshot=None):
             assert guard < 1000
             if hit:
                 break
-        snap = {name: ctx.download(fid) for fid, name in STATE}
+        keep = meta["config"].get("_keep")
+        snap = {name: ctx.download(fid) for fid, name in STATE} if (keep is None or k in keep) else {}
         snap["time"], snap["n_iter"], snap["last_dt"] = loop.time, loop.n_iter, loop.last_dt
         out.append(snap)
         if on_snapshot:

@@ -16,8 +16,11 @@ from fargocpt_b200 import abi
 pytestmark = pytest.mark.gpu
 
 CASES = ["adia_star", "adia_cold", "iso_star", "iso_sn_std", "adia_sn_stab", "ring_like"]
-ISOTHERMAL = {"iso_star", "iso_sn_std", "ring_like"}
+# 100 hydro steps with a Jupiter-mass planet (48 x 160: two warp windows per ring), recorded from the reference
+LONG_CASES = ["adia_planet_100", "iso_planet_100"]
+ISOTHERMAL = {"iso_star", "iso_sn_std", "ring_like", "iso_planet_100"}
 ADIABATIC_RTOL = 1e-12
+LONG_RTOL = 1e-10  # north_star: fields <= 1e-10 relative after 100 steps
 
 
 def _ctx_pair(name):
@@ -32,7 +35,7 @@ def _check(name, what, a, b):
     if name in ISOTHERMAL:
         assert st["n_diff"] == 0, (name, what, st)
     else:
-        assert st["max_rel"] <= ADIABATIC_RTOL, (name, what, st)
+        assert st["max_rel"] <= (LONG_RTOL if name in LONG_CASES else ADIABATIC_RTOL), (name, what, st)
     return st
 
 
@@ -70,7 +73,7 @@ def test_stage_by_stage_vs_oracle(name):
 
 
 @pytest.mark.parametrize("staged", [False, True], ids=["fused", "staged"])
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", CASES + LONG_CASES)
 def test_golden_run_vs_reference(name, staged):
     """Full time loop over the recorded fixture: dt sequence, N_iter, time and fields against the reference.
     fargo_step's fused source-term kernels and the per-stage kernels must both reproduce it."""
@@ -84,9 +87,9 @@ def test_golden_run_vs_reference(name, staged):
         if name in ISOTHERMAL:
             assert snap["last_dt"] == m["last_dt"], (snap["last_dt"], m["last_dt"])
         else:
-            assert snap["last_dt"] == pytest.approx(m["last_dt"], rel=1e-12)
+            assert snap["last_dt"] == pytest.approx(m["last_dt"], rel=LONG_RTOL if name in LONG_CASES else 1e-12)
         for fname in ("Sigma", "vrad", "vazi", "energy"):
-            if fname == "energy" and not gpu.params.adiabatic:
+            if (fname == "energy" and not gpu.params.adiabatic) or fname not in snap:
                 continue
             _check(name, (k, fname), snap[fname], z[f"{fname}_{k}"])
 

@@ -1,0 +1,142 @@
+"""world_size-2 CPU test (gloo) of the multi-rank host logic: radial slabs as SplitDomain makes them (split.cpp:21-87),
+the 7-ring ghost exchange of CommunicateBoundaries (commbound.cpp:98-182) and the dt all-reduce (cfl.cpp:379), driven
+exactly like the GPU ranks are (one process per slab, torch.distributed for the plumbing) but with the CPU oracle as
+the slab engine.  The 2-rank result must equal the 1-rank result bit for bit (the reference's np-independence,
+constants.h:17).  This pins the slab / halo semantics the CUDA path implements with ncclSend/ncclRecv."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, name, nsteps, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    import goldenrun
+    import reftools
+    from fargocpt_b200 import abi
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    meta, z = reftools.load_golden(name)
+    params = reftools.make_params(meta["params"])
+    ctx = reftools.OracleContext(params, z["radii"], rank=rank, nranks=world)
+    for fid, fname in goldenrun.STATE:
+        ctx.upload(fid, z[fname + "_0"])
+    omega = float(meta["config"].get("OmegaFrame", 0.0))
+    ctx.set_bodies(goldenrun.bodies_at(meta, 0, omega))
+    ctx.set_time(0.0)
+    ctx.init_derived()
+    ctx.copy_initial_values()
+    ctx.stage("boundary", 0.0, 0)
+    n = abi.CPUOVERLAP * ctx.naz
+
+    def exchange():
+        # even/odd ordered pairwise exchange like commbound.cpp:130-158 (blocking gloo send/recv)
+        for side, peer in ((0, rank - 1), (1, rank + 1)):
+            if peer < 0 or peer >= world:
+                continue
+            out = torch.from_numpy(ctx.halo_pack(side))
+            inc = torch.zeros(4 * n, dtype=torch.float64)
+            if rank % 2 == 0:
+                dist.send(out, peer)
+                dist.recv(inc, peer)
+            else:
+                dist.recv(inc, peer)
+                dist.send(out, peer)
+            ctx.halo_unpack(side, inc.numpy())
+
+    last_dt, t, dts = meta["first_dt"], 0.0, []
+    for k in range(nsteps):
+        loc = torch.tensor([ctx.condition_cfl()], dtype=torch.float64)
+        dist.all_reduce(loc, op=dist.ReduceOp.MIN)  # MPI_Allreduce(MIN), cfl.cpp:379
+        dt = min(params.cfl_max_var * last_dt, float(loc.item()))  # simulation.cpp:100-118
+        last_dt = dt
+        dts.append(dt)
+        ctx.set_bodies(goldenrun.bodies_at(meta, k, omega))
+        ctx.set_time(t)
+        ctx.step_pre(dt)
+        exchange()
+        ctx.step_post(dt)
+        t += dt
+    res = {}
+    for fid, fname in goldenrun.STATE:
+        part = torch.from_numpy(ctx.download(fid))  # owned rings only, zeros elsewhere
+        dist.all_reduce(part)
+        res[fname] = part.numpy()
+    if rank == 0:
+        q.put((dts, res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["iso_planet_100", "adia_planet_100"])
+def test_two_ranks_equal_one_rank(name):
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import goldenrun
+    import reftools
+    nsteps = 8
+    ctx_mp = mp.get_context("spawn")
+    q = ctx_mp.Queue()
+    port = 29700 + os.getpid() % 200
+    procs = [ctx_mp.Process(target=_worker, args=(r, 2, port, name, nsteps, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    dts2, res2 = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single rank, same driver
+    meta, z = reftools.load_golden(name)
+    params = reftools.make_params(meta["params"])
+    one = reftools.OracleContext(params, z["radii"])
+    for fid, fname in goldenrun.STATE:
+        one.upload(fid, z[fname + "_0"])
+    omega = float(meta["config"].get("OmegaFrame", 0.0))
+    one.set_bodies(goldenrun.bodies_at(meta, 0, omega))
+    one.set_time(0.0)
+    one.init_derived()
+    one.copy_initial_values()
+    one.stage("boundary", 0.0, 0)
+    last_dt, t, dts1 = meta["first_dt"], 0.0, []
+    for k in range(nsteps):
+        dt = min(params.cfl_max_var * last_dt, one.condition_cfl())
+        last_dt = dt
+        dts1.append(dt)
+        one.set_bodies(goldenrun.bodies_at(meta, k, omega))
+        one.set_time(t)
+        one.step(dt)
+        t += dt
+    assert dts1 == dts2
+    for fid, fname in goldenrun.STATE:
+        if fname == "energy" and not params.adiabatic:
+            continue
+        st = reftools.compare_stats(res2[fname], one.download(fid))
+        assert st["n_diff"] == 0, (fname, st)
+
+
+def test_slab_partition_matches_split_domain():
+    """split.cpp:38-61: contiguous slabs, +1 ring for the first `remainder` ranks, 7 overlap rings on interior sides."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import reftools
+    meta, z = reftools.load_golden("iso_planet_100")
+    params = reftools.make_params(meta["params"])
+    nrad = params.nrad
+    for world in (2, 3):
+        owned = np.zeros(nrad, dtype=int)
+        for r in range(world):
+            c = reftools.OracleContext(params, z["radii"], rank=r, nranks=world)
+            low, rem = nrad // world, nrad % world
+            size = low + 1 if r < rem else low
+            start = (low + 1) * r if r < rem else (low + 1) * rem + (r - rem) * low
+            imin = start - (7 if r > 0 else 0)
+            assert c.imin == imin and c.nr == size + (7 if r > 0 else 0) + (7 if r < world - 1 else 0)
+            owned[start:start + size] += 1
+            c.close()
+        assert (owned == 1).all()
