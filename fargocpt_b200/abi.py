@@ -243,6 +243,8 @@ def load_library():
         lib.fargo_set_staged.restype = C.c_int
         lib.fargo_selftest_math.argtypes = [C.c_void_p, C.c_ulonglong, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_ulonglong)]
         lib.fargo_selftest_math.restype = C.c_int
+        lib.fargo_selftest_exp.argtypes = [C.c_void_p, C.c_int, _DP, _DP]
+        lib.fargo_selftest_exp.restype = C.c_int
         lib.fargo_sync.argtypes = [C.c_void_p]
         lib.fargo_sync.restype = C.c_int
         lib.fargo_launch_count.argtypes = [C.c_void_p]
@@ -287,6 +289,12 @@ class HydroContext(Handle):
         self._check(self.lib.fargo_selftest_math(self.ptr, seed, blocks, per_thread, int(wide), out), "selftest_math")
         return {"div_mismatch": out[0], "sqrt_mismatch": out[1], "exp_mismatch": out[2], "div_fast": out[3],
                 "pairs": 256 * blocks * per_thread}
+
+    def selftest_exp(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty_like(x)
+        self._check(self.lib.fargo_selftest_exp(self.ptr, x.size, _dptr(x), _dptr(y)), "selftest_exp")
+        return y
 
     def set_staged(self, on):
         """step() through the per-stage kernels (one per reference loop nest) instead of the fused ones."""

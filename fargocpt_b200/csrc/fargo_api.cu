@@ -1177,3 +1177,19 @@ extern "C" int fargo_selftest_math(fargo_ctx *c, unsigned long long seed, int bl
     CUDA_OK(cudaFree(d));
     return 0;
 }
+
+// exp_ref on caller-provided arguments, for the host-side comparison with libm's exp
+extern "C" int fargo_selftest_exp(fargo_ctx *c, int n, const double *x_host, double *y_host)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    double *d = nullptr;
+    CUDA_OK(cudaMalloc((void **)&d, 2 * (size_t)n * sizeof(double)));
+    CUDA_OK(cudaMemcpyAsync(d, x_host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    k_selftest_exp<<<(n + 255) / 256, 256, 0, c->stream>>>(n, d, d + n);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(y_host, d + n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(cudaFree(d));
+    return 0;
+}

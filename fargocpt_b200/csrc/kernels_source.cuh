@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) k_compression_heating(const DevView c, co
     CELL_INDEX(c.nr - 1);
     const double DIV_V = div_v(c, vr, vp, i, j, jp);
     const double e_old = AT(energy, i, j);
-    AT(energy, i, j) = e_old * exp(-(c.p.gamma - 1.0) * dt * DIV_V);
+    AT(energy, i, j) = e_old * exp_ref(-(c.p.gamma - 1.0) * dt * DIV_V); // glibc-exact exp (fargo_math.h)
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -215,6 +215,10 @@ int fargo_get_nshift(fargo_ctx *ctx, int *out_local_nrad);
 int fargo_selftest_math(fargo_ctx *ctx, unsigned long long seed, int blocks, int per_thread, int wide,
 			unsigned long long *counts4);
 
+/* the device exp of the energy equation (csrc/fargo_math.h: glibc's algorithm, operation by operation) on n host-provided
+ * arguments; the caller compares with its libm */
+int fargo_selftest_exp(fargo_ctx *ctx, int n, const double *x_host, double *y_host);
+
 /* stream sync + launch accounting (for bench.py) */
 int fargo_sync(fargo_ctx *ctx);
 long long fargo_launch_count(const fargo_ctx *ctx);
