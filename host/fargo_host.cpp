@@ -1,0 +1,784 @@
+// fargo_host.cpp — C++ host driver above the C ABI of include/fargo_b200.h.
+//
+// Mirrors the part of the reference's host that sits around the hydro hot path (paths relative to the reference's src/):
+//   main.cpp:48-164 + sim::run simulation.cpp:505-558   -> run()            (time loop, monitor / snapshot cadence)
+//   sim::CalculateTimeStep simulation.cpp:100-118        -> fargo_cfl
+//   step_Euler simulation.cpp:148-267                    -> step(): indirect term, N-body kick, fargo_step, N-body drift
+//   config.cpp / parameters.cpp / boundary_conditions/config.cpp / damping.cpp:185-271 -> Config, make_params()
+//   restart.cpp:19-131, polargrid.cpp:301-353            -> load_snapshot()   (raw double[Nrad(+1)][Naz], no header)
+//   output.cpp:249-330, polargrid.cpp:135-180, output.h:16-24 (misc.bin), nbody/planet.h:11-45 (nbodyK.bin)
+//                                                        -> write_snapshot()
+// It is a drop-in for an EXISTING FargoCPT output directory: `restart N <dir>` reads the directory the reference wrote
+// (config.yml of the snapshot, constants.yml / units.yml for the code-unit constants, dimensions.dat, used_rad.dat, the
+// snapshot's fields, misc.bin, nbodyK.bin and snapshots/reference/ for the damping targets) and continues the run on the
+// GPU, writing snapshots in the same binary format, so Tools/compare_binary_output.py can diff the two runs file by file.
+// Out of scope here: initial-condition generators, unit-string parsing beyond "<number> <unit>" with the
+// unit factors taken from units.yml, REBOUND (bodies are advanced with RK4 sub-steps, see nbody_integrate), monitors.
+//
+// The hydro arithmetic all happens behind the C ABI; build with -DFARGO_HOST_ORACLE to bind the same driver to the CPU
+// oracle (TEST INFRASTRUCTURE: lets the host logic be tested without a GPU; never shipped).
+#include <algorithm>
+#include <cctype>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <sys/stat.h>
+#include <vector>
+
+#include "../include/fargo_b200.h"
+
+#ifdef FARGO_HOST_ORACLE
+extern "C" {
+typedef struct fargo_oracle fargo_oracle;
+fargo_oracle *fargo_oracle_create(const fargo_params *, const double *, int, int);
+void fargo_oracle_destroy(fargo_oracle *);
+int fargo_oracle_upload_field(fargo_oracle *, int, const double *);
+int fargo_oracle_download_field(fargo_oracle *, int, double *);
+int fargo_oracle_copy_initial_values(fargo_oracle *);
+int fargo_oracle_set_bodies(fargo_oracle *, const fargo_bodies *);
+int fargo_oracle_set_time(fargo_oracle *, double);
+int fargo_oracle_init_derived(fargo_oracle *);
+int fargo_oracle_cfl(fargo_oracle *, double *, double *);
+int fargo_oracle_step(fargo_oracle *, double);
+int fargo_oracle_stage_boundary(fargo_oracle *, double, int);
+}
+typedef fargo_oracle backend_ctx;
+#define BK(name) fargo_oracle_##name
+static const char *backend_error() { return "oracle call failed"; }
+#else
+typedef fargo_ctx backend_ctx;
+#define BK(name) fargo_##name
+static const char *backend_error() { return fargo_last_error(); }
+#endif
+
+[[noreturn]] static void die(const char *fmt, const std::string &a = "")
+{ // the reference die()s on every error (LowTasks.cpp:67-120)
+    fprintf(stderr, "fargocpt_b200: ");
+    fprintf(stderr, fmt, a.c_str());
+    fprintf(stderr, "\n");
+    exit(1);
+}
+#define CHECK(call)                                         \
+    do {                                                    \
+	if ((call) != 0)                                    \
+	    die("%s", std::string(#call ": ") + backend_error()); \
+    } while (0)
+
+static std::string lower(std::string s)
+{
+    std::transform(s.begin(), s.end(), s.begin(), [](unsigned char c) { return std::tolower(c); });
+    return s;
+}
+static std::string trim(const std::string &s)
+{
+    size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
+    return a == std::string::npos ? "" : s.substr(a, b - a + 1);
+}
+static std::string unquote(std::string v)
+{
+    v = trim(v);
+    if (v.size() >= 2 && ((v.front() == '\'' && v.back() == '\'') || (v.front() == '"' && v.back() == '"')))
+	v = v.substr(1, v.size() - 2);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The YAML subset FargoCPT setups use: top-level `Key: value  # comment` pairs and one `nbody:` list of maps.
+// Keys are case-insensitive like config::Config (config.h:33-72).
+struct Config {
+    std::map<std::string, std::string> kv;
+    std::vector<std::map<std::string, std::string>> nbody;
+
+    static std::string strip_comment(const std::string &line)
+    {
+	bool q1 = false, q2 = false;
+	for (size_t i = 0; i < line.size(); ++i) {
+	    if (line[i] == '\'' && !q2)
+		q1 = !q1;
+	    else if (line[i] == '"' && !q1)
+		q2 = !q2;
+	    else if (line[i] == '#' && !q1 && !q2 && (i == 0 || std::isspace((unsigned char)line[i - 1])))
+		return line.substr(0, i);
+	}
+	return line;
+    }
+    void load(const std::string &path)
+    {
+	std::ifstream f(path);
+	if (!f)
+	    die("cannot open config %s", path);
+	std::string line;
+	bool in_nbody = false;
+	while (std::getline(f, line)) {
+	    line = strip_comment(line);
+	    if (trim(line).empty())
+		continue;
+	    const size_t indent = line.find_first_not_of(" \t");
+	    std::string body = trim(line);
+	    if (indent == 0 && body[0] != '-') {
+		const size_t c = body.find(':');
+		if (c == std::string::npos)
+		    continue;
+		const std::string key = lower(trim(body.substr(0, c)));
+		const std::string val = unquote(body.substr(c + 1));
+		in_nbody = (key == "nbody");
+		if (!in_nbody)
+		    kv[key] = val;
+		continue;
+	    }
+	    if (!in_nbody)
+		continue; // nested maps other than nbody are not part of the hot path's surface
+	    if (body[0] == '-') {
+		nbody.emplace_back();
+		body = trim(body.substr(1));
+		if (body.empty())
+		    continue;
+	    }
+	    const size_t c = body.find(':');
+	    if (c == std::string::npos || nbody.empty())
+		continue;
+	    nbody.back()[lower(trim(body.substr(0, c)))] = unquote(body.substr(c + 1));
+	}
+    }
+    bool has(const std::string &k) const { return kv.count(lower(k)) != 0; }
+    std::string str(const std::string &k, const std::string &def) const
+    {
+	auto it = kv.find(lower(k));
+	return it == kv.end() ? def : it->second;
+    }
+    // "<number> [unit]": with a unit the value is divided by unit_in_cgs (config::cfg.get<T>(key, default, unit))
+    static double number(const std::string &v, double unit_in_cgs = 0.0)
+    {
+	std::istringstream is(v);
+	double x = 0;
+	std::string unit;
+	if (!(is >> x))
+	    die("not a number: %s", v);
+	if ((is >> unit) && unit_in_cgs > 0.0)
+	    return x / unit_in_cgs;
+	return x;
+    }
+    double num(const std::string &k, double def, double unit_in_cgs = 0.0) const
+    {
+	auto it = kv.find(lower(k));
+	return it == kv.end() ? def : number(it->second, unit_in_cgs);
+    }
+    bool flag(const std::string &k, bool def) const
+    { // config.h:55-72: first letter y / t / 1
+	auto it = kv.find(lower(k));
+	if (it == kv.end() || it->second.empty())
+	    return def;
+	const char c = (char)std::tolower((unsigned char)it->second[0]);
+	return c == 'y' || c == 't' || c == '1';
+    }
+};
+
+// constants.yml / units.yml as written by the reference (output.cpp, units.cpp:270-310): blocks of `symbol:` / `code value:`
+struct CodeConstants {
+    double G = 1.0, R = 1.0, sigma_sb = 0.0, c_light = 0.0, temperature_unit_K = 1.0;
+    void load(const std::string &dir)
+    {
+	std::ifstream f(dir + "/constants.yml");
+	if (!f)
+	    die("cannot open %s/constants.yml (needed for the code-unit constants)", dir);
+	std::string line, sym;
+	while (std::getline(f, line)) {
+	    const std::string t = trim(line);
+	    if (t.rfind("symbol:", 0) == 0)
+		sym = trim(t.substr(7));
+	    else if (t.rfind("code value:", 0) == 0) {
+		const double v = atof(t.substr(11).c_str());
+		if (sym == "G")
+		    G = v;
+		else if (sym == "R")
+		    R = v;
+		else if (sym == "sigma")
+		    sigma_sb = v;
+		else if (sym == "c")
+		    c_light = v;
+	    }
+	}
+	std::ifstream u(dir + "/units.yml");
+	bool in_temp = false;
+	while (std::getline(u, line)) {
+	    const std::string t = trim(line);
+	    if (!line.empty() && !std::isspace((unsigned char)line[0]))
+		in_temp = (t == "temperature:");
+	    else if (in_temp && t.rfind("cgs value:", 0) == 0)
+		temperature_unit_K = atof(t.substr(10).c_str());
+	}
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// parameters.cpp / Interpret.cpp / boundary_conditions/config.cpp / damping.cpp -> fargo_params
+static int enum_of(const std::string &v, const std::vector<std::pair<std::string, int>> &table, const char *what)
+{
+    const std::string l = lower(v);
+    for (auto &p : table)
+	if (p.first == l)
+	    return p.second;
+    die((std::string("unknown ") + what + " '%s'").c_str(), v);
+}
+static fargo_params make_params(const Config &c, const CodeConstants &k, int nrad, int naz)
+{
+    fargo_params p;
+    memset(&p, 0, sizeof(p));
+    p.abi_version = FARGO_ABI_VERSION;
+    p.nrad = nrad, p.naz = naz;
+    const char sp = (char)std::tolower((unsigned char)c.str("RadialSpacing", "Arithmetic")[0]);
+    p.radial_spacing = sp == 'l' ? FARGO_SPACING_LOG : sp == 'a' ? FARGO_SPACING_ARITH : sp == 'e' ? FARGO_SPACING_EXP : FARGO_SPACING_CUSTOM;
+    p.rmin = c.num("Rmin", 0.0), p.rmax = c.num("Rmax", 0.0);
+    const std::string eos = lower(c.str("EquationOfState", "Isothermal"));
+    p.adiabatic = (eos == "ideal" || eos == "adiabatic" || eos == "perfect") ? 1 : 0;
+    p.gamma = c.num("AdiabaticIndex", 1.4);
+    p.mu = c.num("mu", 1.0);
+    p.aspectratio_ref = c.num("AspectRatio", 0.05);
+    p.flaring_index = c.num("FlaringIndex", 0.0);
+    p.sigma0 = c.num("Sigma0", 173.0);
+    p.sigma_floor = c.num("SigmaFloor", 1e-9);
+    p.sigma_slope = c.num("SigmaSlope", 0.0);
+    p.minimum_temperature = Config::number(c.str("MinimumTemperature", "3 K"), k.temperature_unit_K);
+    p.maximum_temperature = Config::number(c.str("MaximumTemperature", "1.0e300 K"), k.temperature_unit_K);
+    p.G = k.G, p.Rgas = k.R, p.sigma_sb = k.sigma_sb, p.c_light = k.c_light;
+    p.hydro_center_mass = 1.0; // overwritten from the bodies (global.cpp:146)
+    p.cfl = c.num("CFL", 0.5);
+    p.cfl_max_var = c.num("CFLmaxVar", 1.1);
+    p.heating_cooling_cfl_limit = c.num("HeatingCoolingCFLlimit", 1.0);
+    p.leapfrog = std::tolower((unsigned char)c.str("Integrator", "Euler")[0]) == 'e' ? 0 : 1;
+    p.fast_transport = std::tolower((unsigned char)c.str("Transport", "FARGO")[0]) == 'f' ? 1 : 0;
+    const std::string fl = c.str("FluxLimiter", "VanLeer"); // Interpret.cpp:640-664 compares case-sensitively
+    p.flux_limiter = (fl == "mc" || fl == "m") ? FARGO_LIMITER_MC : FARGO_LIMITER_VANLEER;
+    p.artificial_viscosity = enum_of(c.str("ArtificialViscosity", "SN"), {{"none", 0}, {"tw", 1}, {"sn", 2}}, "ArtificialViscosity");
+    p.artificial_viscosity_factor = c.num("ArtificialViscosityFactor", 1.41);
+    p.artificial_viscosity_dissipation = c.flag("ArtificialViscosityDissipation", true);
+    p.viscous_alpha = c.num("ViscousAlpha", 0.0);
+    p.constant_viscosity = c.num("ConstantViscosity", 0.0);
+    p.stabilize_viscosity = (int)c.num("StabilizeViscosity", 0);
+    p.radial_viscosity_factor = c.num("RadialViscosityFactor", 1.0);
+    p.heating_viscous = c.flag("HeatingViscous", false);
+    p.heating_viscous_factor = c.num("HeatingViscousFactor", 1.0);
+    p.cooling_beta = c.flag("CoolingBetaLocal", false);
+    p.cooling_beta_value = c.num("CoolingBeta", 1.0);
+    p.cooling_beta_ramp_up = c.num("CoolingBetaRampUp", 0.0);
+    p.cooling_beta_reference = enum_of(c.str("CoolingBetaReference", "zero"),
+				       {{"zero", 0}, {"none", 0}, {"reference", 1}, {"model", 2}, {"floor", 4}}, "CoolingBetaReference");
+    p.body_force_from_potential = c.flag("BodyForceFromPotential", true);
+    p.thickness_smoothing = c.num("ThicknessSmoothing", 0.0);
+    p.imposed_disk_drift = c.num("ImposedDiskDrift", 0.0);
+    const std::vector<std::pair<std::string, int>> BC = {{"none", 0}, {"zerogradient", 1}, {"zero_gradient", 1}, {"outflow", 2},
+							  {"reflecting", 3}, {"keplerian", 4}, {"reference", 5}};
+    const char *sides[2] = {"Inner", "Outer"};
+    for (int s = 0; s < 2; ++s) { // composite names boundary_conditions/config.cpp:345-436, else the individual keys
+	const std::string comp = lower(c.str(std::string(sides[s]) + "Boundary", "individual"));
+	std::string bs, be, bvr;
+	if (comp == "zerogradient")
+	    bs = be = bvr = "zerogradient";
+	else if (comp == "outflow")
+	    bs = be = "zerogradient", bvr = "outflow";
+	else if (comp == "reflecting")
+	    bs = be = "zerogradient", bvr = "reflecting";
+	else if (comp == "reference")
+	    bs = be = bvr = "reference";
+	else {
+	    bs = c.str(std::string(sides[s]) + "BoundarySigma", "zerogradient");
+	    be = c.str(std::string(sides[s]) + "BoundaryEnergy", "zerogradient");
+	    bvr = c.str(std::string(sides[s]) + "BoundaryVrad", "zerogradient");
+	}
+	p.bc_sigma[s] = enum_of(bs, BC, "boundary");
+	p.bc_energy[s] = enum_of(be, BC, "boundary");
+	p.bc_vrad[s] = enum_of(bvr, BC, "boundary");
+	p.bc_vazi[s] = enum_of(c.str(std::string(sides[s]) + "BoundaryVazi", "keplerian"), BC, "boundary");
+	p.keplerian_azimuthal_factor[s] = c.num(std::string(sides[s]) + "BoundaryVaziKeplerianFactor", 1.0);
+    }
+    p.damping = c.flag("Damping", false);
+    p.damping_inner_limit = c.num("DampingInnerLimit", 1.05);
+    p.damping_outer_limit = c.num("DampingOuterLimit", 0.95);
+    p.damping_time_factor = c.num("DampingTimeFactor", 1.0);
+    p.damping_time_radius_outer = c.num("DampingTimeRadiusOuter", p.rmax);
+    const std::vector<std::pair<std::string, int>> DAMP = {{"none", 0}, {"initial", 1}, {"zero", 2}, {"mean", 3}};
+    for (int s = 0; s < 2; ++s) {
+	p.damp_vrad[s] = enum_of(c.str(std::string("DampingVRadial") + sides[s], "None"), DAMP, "damping type");
+	p.damp_vazi[s] = enum_of(c.str(std::string("DampingVAzimuthal") + sides[s], "None"), DAMP, "damping type");
+	p.damp_sigma[s] = enum_of(c.str(std::string("DampingSurfaceDensity") + sides[s], "None"), DAMP, "damping type");
+	p.damp_energy[s] = enum_of(c.str(std::string("DampingEnergy") + sides[s], "None"), DAMP, "damping type");
+    }
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// binary records of a snapshot directory
+#pragma pack(push, 1)
+struct MiscEntry { // output.h:16-24 (48 bytes with natural alignment)
+    uint32_t timestep, nTimeStep;
+    double time, OmegaFrame, FrameAngle, last_dt;
+    uint64_t N_iter;
+};
+#pragma pack(pop)
+static_assert(sizeof(MiscEntry) == 48, "misc.bin layout");
+
+struct PlanetRecord { // nbody/planet.h:11-45 planet_member_variables with the compiler's natural alignment (256 bytes)
+    uint32_t timestep;
+    uint32_t pad0;
+    double mass, x, y, vx, vy, cubic_smoothing_factor, acc, accreted_mass;
+    uint32_t planet_number;
+    uint32_t pad1;
+    double temperature, radius;
+    uint8_t irradiate;
+    uint8_t pad2[7];
+    double irradiation_rampuptime, rampuptime;
+    double disk_on_planet_acceleration[2], nbody_on_planet_acceleration[2];
+    double distance_to_primary, dimensionless_roche_radius, circumplanetary_mass;
+    double semi_major_axis, eccentricity, mean_anomaly, true_anomaly, eccentric_anomaly, pericenter_angle;
+    double torque, gas_torque_acc, accretion_torque_acc, indirect_torque_acc;
+};
+static_assert(sizeof(PlanetRecord) == 256, "nbodyK.bin layout");
+
+static std::vector<double> read_doubles(const std::string &path, size_t n, bool required = true)
+{
+    std::vector<double> v;
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) {
+	if (required)
+	    die("cannot open %s", path);
+	return v;
+    }
+    v.resize(n);
+    const size_t got = fread(v.data(), sizeof(double), n, f);
+    fclose(f);
+    if (got != n)
+	die("short read on %s", path);
+    return v;
+}
+static void write_doubles(const std::string &path, const std::vector<double> &v)
+{
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f || fwrite(v.data(), sizeof(double), v.size(), f) != v.size())
+	die("cannot write %s", path);
+    fclose(f);
+}
+static void mkdirs(const std::string &p)
+{
+    std::string cur;
+    for (size_t i = 0; i <= p.size(); ++i) {
+	if (i == p.size() || p[i] == '/') {
+	    if (!cur.empty())
+		mkdir(cur.c_str(), 0755);
+	}
+	if (i < p.size())
+	    cur += p[i];
+    }
+}
+static bool exists(const std::string &p)
+{
+    struct stat st;
+    return stat(p.c_str(), &st) == 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct Body {
+    PlanetRecord rec; // carried through so the records we write keep the fields we do not touch
+    double orbital_period = 0.0;
+};
+
+// planet.get_rampup_mass (nbody/planet.cpp:166-179)
+static double rampup_mass(const Body &b, double t)
+{
+    double ramping = 1.0;
+    if (b.rec.rampuptime > 0 && t < b.rec.rampuptime * b.orbital_period) {
+	const double cs = std::cos(t * M_PI_2 / (b.rec.rampuptime * b.orbital_period));
+	ramping = 1.0 - cs * cs;
+    }
+    return b.rec.mass * ramping;
+}
+
+// ComputeNbodyOnNbodyAccel (Pframeforce.cpp:225-251) + ComputeIndirectTermNbodyEuler (frame_of_reference.cpp:112-132),
+// hydro frame centred on body 0 (HydroFrameCenter: primary)
+static void indirect_term_euler(const std::vector<Body> &b, double G, double &ix, double &iy)
+{
+    ix = iy = 0.0;
+    if (b.size() < 2)
+	return;
+    const double x = b[0].rec.x, y = b[0].rec.y;
+    double ax = 0.0, ay = 0.0;
+    for (size_t o = 1; o < b.size(); ++o) {
+	const double xo = b[o].rec.x, yo = b[o].rec.y, mass = b[o].rec.mass;
+	const double dist = std::sqrt((x - xo) * (x - xo) + (y - yo) * (y - yo));
+	ax -= G * mass / std::pow(dist, 3) * (x - xo);
+	ay -= G * mass / std::pow(dist, 3) * (y - yo);
+    }
+    double mass_center = 0.0;
+    ix -= b[0].rec.mass * ax;
+    iy -= b[0].rec.mass * ay;
+    mass_center += b[0].rec.mass;
+    ix /= mass_center;
+    iy /= mass_center;
+}
+
+// planetary_system.integrate (nbody/planetary_system.cpp:878-889) advances the bodies under their mutual gravity with
+// REBOUND's IAS15 (accurate to rounding).  REBOUND is out of scope; the same system is advanced here with classical RK4
+// over sub-steps h with (orbital frequency * h) <= 2e-3, i.e. a local error below 1e-16 of the orbit per step.
+static void nbody_integrate(std::vector<Body> &b, double G, double dt)
+{
+    const size_t n = b.size();
+    if (n < 2)
+	return; // a single particle that does not move (:880-883)
+    double wmax = 0.0;
+    for (size_t i = 0; i < n; ++i)
+	for (size_t j = i + 1; j < n; ++j) {
+	    const double dx = b[i].rec.x - b[j].rec.x, dy = b[i].rec.y - b[j].rec.y;
+	    const double d = std::sqrt(dx * dx + dy * dy);
+	    wmax = std::max(wmax, std::sqrt(G * (b[i].rec.mass + b[j].rec.mass) / (d * d * d)));
+	}
+    int nsub = (int)std::ceil(wmax * dt / 2e-3);
+    nsub = std::max(1, std::min(nsub, 100000));
+    const double h = dt / nsub;
+    std::vector<double> s(4 * n), k1(4 * n), k2(4 * n), k3(4 * n), k4(4 * n), tmp(4 * n);
+    auto rhs = [&](const std::vector<double> &q, std::vector<double> &dq) {
+	for (size_t i = 0; i < n; ++i) {
+	    double ax = 0, ay = 0;
+	    for (size_t j = 0; j < n; ++j) {
+		if (j == i)
+		    continue;
+		const double dx = q[4 * i] - q[4 * j], dy = q[4 * i + 1] - q[4 * j + 1];
+		const double d2 = dx * dx + dy * dy, d = std::sqrt(d2);
+		const double f = G * b[j].rec.mass / (d2 * d);
+		ax -= f * dx, ay -= f * dy;
+	    }
+	    dq[4 * i] = q[4 * i + 2], dq[4 * i + 1] = q[4 * i + 3], dq[4 * i + 2] = ax, dq[4 * i + 3] = ay;
+	}
+    };
+    for (size_t i = 0; i < n; ++i)
+	s[4 * i] = b[i].rec.x, s[4 * i + 1] = b[i].rec.y, s[4 * i + 2] = b[i].rec.vx, s[4 * i + 3] = b[i].rec.vy;
+    for (int it = 0; it < nsub; ++it) {
+	rhs(s, k1);
+	for (size_t q = 0; q < 4 * n; ++q)
+	    tmp[q] = s[q] + 0.5 * h * k1[q];
+	rhs(tmp, k2);
+	for (size_t q = 0; q < 4 * n; ++q)
+	    tmp[q] = s[q] + 0.5 * h * k2[q];
+	rhs(tmp, k3);
+	for (size_t q = 0; q < 4 * n; ++q)
+	    tmp[q] = s[q] + h * k3[q];
+	rhs(tmp, k4);
+	for (size_t q = 0; q < 4 * n; ++q)
+	    s[q] += h / 6.0 * (k1[q] + 2.0 * k2[q] + 2.0 * k3[q] + k4[q]);
+    }
+    for (size_t i = 0; i < n; ++i)
+	b[i].rec.x = s[4 * i], b[i].rec.y = s[4 * i + 1], b[i].rec.vx = s[4 * i + 2], b[i].rec.vy = s[4 * i + 3];
+}
+
+// ---------------------------------------------------------------------------------------------
+struct Run {
+    Config cfg;
+    CodeConstants consts;
+    fargo_params params;
+    std::vector<double> radii;
+    int nrad = 0, naz = 0;
+    backend_ctx *ctx = nullptr;
+    std::vector<Body> bodies;
+    double omega_frame = 0.0, frame_angle = 0.0;
+    // sim:: state (simulation.cpp:27-41)
+    double time = 0.0, last_dt = 0.0;
+    uint64_t n_iter = 0;
+    unsigned n_snapshot = 0, n_monitor = 0;
+    double monitor_timestep = 0.0;
+    unsigned nmonitor = 1, nsnapshots = 1;
+    int indirect_mode = 1;
+    std::string refdir, outdir;
+
+    size_t cells(bool vector) const { return (size_t)(nrad + (vector ? 1 : 0)) * naz; }
+
+    void set_bodies_on_device()
+    { // CalculateNbodyPotential's planet setup (Pframeforce.cpp:27-36) + refframe::IndirectTerm
+	fargo_bodies fb;
+	memset(&fb, 0, sizeof(fb));
+	fb.n = (int)bodies.size();
+	for (int k = 0; k < fb.n; ++k) {
+	    const Body &b = bodies[k];
+	    fb.x[k] = b.rec.x, fb.y[k] = b.rec.y, fb.mass[k] = rampup_mass(b, time);
+	    fb.cubic_smoothing_radius[k] = b.rec.dimensionless_roche_radius * b.rec.distance_to_primary * b.rec.cubic_smoothing_factor;
+	}
+	indirect_term_euler(bodies, consts.G, fb.indirect_x, fb.indirect_y);
+	fb.omega_frame = omega_frame;
+	CHECK(BK(set_bodies)(ctx, &fb));
+	ind_x = fb.indirect_x, ind_y = fb.indirect_y;
+    }
+    double ind_x = 0.0, ind_y = 0.0;
+
+    void load(const std::string &dir, unsigned nsnap, int device)
+    {
+	refdir = dir;
+	const std::string sd = dir + "/snapshots/" + std::to_string(nsnap);
+	cfg.load(exists(sd + "/config.yml") ? sd + "/config.yml" : dir + "/parameters/cfg.yml");
+	consts.load(dir);
+	{ // dimensions.dat: RMIN RMAX PHIMIN PHIMAX NRAD NAZ NGHRAD NGHAZ Radial_spacing (init.cpp:227-247)
+	    std::ifstream f(dir + "/dimensions.dat");
+	    if (!f)
+		die("cannot open %s/dimensions.dat", dir);
+	    std::string line;
+	    while (std::getline(f, line)) {
+		if (line.empty() || line[0] == '#')
+		    continue;
+		std::istringstream is(line);
+		double a, b, c, d;
+		is >> a >> b >> c >> d >> nrad >> naz;
+	    }
+	}
+	radii = std::vector<double>();
+	{
+	    std::ifstream f(dir + "/used_rad.dat");
+	    double r;
+	    while (f >> r)
+		radii.push_back(r);
+	    if ((int)radii.size() != nrad + 1)
+		die("used_rad.dat does not hold Nrad + 1 radii in %s", dir);
+	}
+	params = make_params(cfg, consts, nrad, naz);
+	// bodies
+	for (size_t k = 0; k < cfg.nbody.size(); ++k) {
+	    Body b;
+	    FILE *f = fopen((sd + "/nbody" + std::to_string(k) + ".bin").c_str(), "rb");
+	    if (!f || fread(&b.rec, sizeof(PlanetRecord), 1, f) != 1)
+		die("cannot read nbody record %s", sd + "/nbody" + std::to_string(k) + ".bin");
+	    fclose(f);
+	    if (b.rec.semi_major_axis > 0.0) // planet.cpp: T = 2 pi sqrt(a^3 / (G (M + m)))
+		b.orbital_period = 2.0 * M_PI * std::sqrt(std::pow(b.rec.semi_major_axis, 3) / (consts.G * (1.0 + b.rec.mass)));
+	    bodies.push_back(b);
+	}
+	if (bodies.empty())
+	    die("config has no nbody entries: %s", sd);
+	if (bodies.size() > FARGO_MAX_BODIES)
+	    die("too many bodies in %s", sd);
+	params.hydro_center_mass = bodies[0].rec.mass; // global.cpp:146 (HydroFrameCenter: primary)
+	indirect_mode = (int)cfg.num("IndirectTermMode", 0);
+	if (indirect_mode != 1 && bodies.size() > 1)
+	    fprintf(stderr, "fargocpt_b200: IndirectTermMode %d needs REBOUND's predictor; using the Euler form (mode 1)\n", indirect_mode);
+	MiscEntry m;
+	{
+	    FILE *f = fopen((sd + "/misc.bin").c_str(), "rb");
+	    if (!f || fread(&m, sizeof(m), 1, f) != 1)
+		die("cannot read %s/misc.bin", sd);
+	    fclose(f);
+	}
+	time = m.time, last_dt = m.last_dt, n_iter = m.N_iter, n_snapshot = m.timestep, n_monitor = m.nTimeStep;
+	omega_frame = m.OmegaFrame, frame_angle = m.FrameAngle;
+	monitor_timestep = cfg.num("MonitorTimestep", 1.0);
+	nmonitor = (unsigned)cfg.num("Nmonitor", 1);
+	nsnapshots = (unsigned)cfg.num("Nsnapshots", 1);
+#ifdef FARGO_HOST_ORACLE
+	(void)device;
+	ctx = fargo_oracle_create(&params, radii.data(), 0, 1);
+	if (!ctx)
+	    die("fargo_oracle_create failed");
+#else
+	if (fargo_ctx_create(&ctx, &params, radii.data(), 0, 1, nullptr, device) != 0)
+	    die("fargo_ctx_create: %s", fargo_last_error());
+#endif
+	// restart_load (restart.cpp:19-131): the four state fields
+	const std::pair<int, const char *> state[4] = {{FARGO_SIGMA, "Sigma"}, {FARGO_VRAD, "vrad"}, {FARGO_VAZI, "vazi"}, {FARGO_ENERGY, "energy"}};
+	for (auto &s : state)
+	    CHECK(BK(upload_field)(ctx, s.first, read_doubles(sd + "/" + s.second + ".dat", cells(s.first == FARGO_VRAD)).data()));
+	set_bodies_on_device();
+	CHECK(BK(set_time)(ctx, time));
+	CHECK(BK(init_derived)(ctx));
+	// Q+/- as the reference stored them (needed by the first CFL; `BitwiseExactRestarting`, output.cpp:258-266)
+	if (params.adiabatic) {
+	    auto qp = read_doubles(sd + "/Qplus.dat", cells(false), false), qm = read_doubles(sd + "/Qminus.dat", cells(false), false);
+	    if (!qp.empty() && !qm.empty()) {
+		CHECK(BK(upload_field)(ctx, FARGO_QPLUS, qp.data()));
+		CHECK(BK(upload_field)(ctx, FARGO_QMINUS, qm.data()));
+	    }
+	}
+	// damping / beta-cooling targets: snapshots/reference (simulation.cpp:43-48), else the loaded state itself
+	const std::string rd = dir + "/snapshots/reference";
+	if (exists(rd + "/Sigma.dat")) {
+	    const std::pair<int, const char *> ref[4] = {{FARGO_SIGMA0, "Sigma"}, {FARGO_VRAD0, "vrad"}, {FARGO_VAZI0, "vazi"}, {FARGO_ENERGY0, "energy"}};
+	    for (auto &s : ref)
+		CHECK(BK(upload_field)(ctx, s.first, read_doubles(rd + "/" + s.second + ".dat", cells(s.first == FARGO_VRAD0)).data()));
+	} else {
+	    CHECK(BK(copy_initial_values)(ctx));
+	}
+    }
+
+    // sim::CalculateTimeStep (simulation.cpp:100-118)
+    double calculate_time_step()
+    {
+	double dt = 0.0;
+	CHECK(BK(cfl)(ctx, &last_dt, &dt));
+	return dt;
+    }
+
+    // step_Euler (simulation.cpp:148-267) around the gas part
+    void step(double dt)
+    {
+	set_bodies_on_device(); // indirect term from the current bodies (:160-162), potential inputs (:170)
+	for (auto &b : bodies) { // apply_indirect_term_on_Nbody (:164)
+	    b.rec.vx = b.rec.vx + dt * ind_x;
+	    b.rec.vy = b.rec.vy + dt * ind_y;
+	}
+	{ // refframe::handle_corotation (frame_of_reference.cpp:30-60) for a frame with fixed OmegaFrame (Frame: F):
+	  // the bodies are rotated into the frame, t_planetary_system::rotate (nbody/planetary_system.cpp:409-432)
+	    const double angle = omega_frame * dt;
+	    for (auto &b : bodies) {
+		const double x = b.rec.x, y = b.rec.y, vx = b.rec.vx, vy = b.rec.vy;
+		b.rec.x = x * std::cos(angle) + y * std::sin(angle);
+		b.rec.y = -x * std::sin(angle) + y * std::cos(angle);
+		b.rec.vx = vx * std::cos(angle) + vy * std::sin(angle);
+		b.rec.vy = -vx * std::sin(angle) + vy * std::cos(angle);
+	    }
+	    frame_angle += omega_frame * dt;
+	}
+	CHECK(BK(set_time)(ctx, time));
+	CHECK(BK(step)(ctx, dt));		  // :187-218, :230-266
+	nbody_integrate(bodies, consts.G, dt); // :222
+	if (bodies.size() > 1) {		  // move_to_hydro_frame_center (:224)
+	    const double cx = bodies[0].rec.x, cy = bodies[0].rec.y, cvx = bodies[0].rec.vx, cvy = bodies[0].rec.vy;
+	    for (auto &b : bodies) {
+		b.rec.x -= cx, b.rec.y -= cy, b.rec.vx -= cvx, b.rec.vy -= cvy;
+	    }
+	}
+	time += dt;
+	n_iter++;
+    }
+
+    // output::write_full_output (output.cpp:249-330) for the files the parity tooling reads
+    void write_snapshot()
+    {
+	const std::string sd = outdir + "/snapshots/" + std::to_string(n_snapshot);
+	mkdirs(sd);
+	const std::pair<int, const char *> state[4] = {{FARGO_SIGMA, "Sigma"}, {FARGO_VRAD, "vrad"}, {FARGO_VAZI, "vazi"}, {FARGO_ENERGY, "energy"}};
+	for (auto &s : state) {
+	    if (s.first == FARGO_ENERGY && !params.adiabatic && !exists(refdir + "/snapshots/0/energy.dat"))
+		continue;
+	    std::vector<double> buf(cells(s.first == FARGO_VRAD), 0.0);
+	    CHECK(BK(download_field)(ctx, s.first, buf.data()));
+	    write_doubles(sd + "/" + s.second + ".dat", buf);
+	}
+	if (params.adiabatic) {
+	    for (auto &s : {std::make_pair((int)FARGO_QPLUS, "Qplus"), std::make_pair((int)FARGO_QMINUS, "Qminus")}) {
+		std::vector<double> buf(cells(false), 0.0);
+		CHECK(BK(download_field)(ctx, s.first, buf.data()));
+		write_doubles(sd + "/" + s.second + ".dat", buf);
+	    }
+	}
+	MiscEntry m;
+	m.timestep = n_snapshot, m.nTimeStep = n_monitor, m.time = time, m.OmegaFrame = omega_frame, m.FrameAngle = frame_angle;
+	m.last_dt = last_dt, m.N_iter = n_iter;
+	FILE *f = fopen((sd + "/misc.bin").c_str(), "wb");
+	if (!f || fwrite(&m, sizeof(m), 1, f) != 1)
+	    die("cannot write %s/misc.bin", sd);
+	fclose(f);
+	for (size_t k = 0; k < bodies.size(); ++k) {
+	    bodies[k].rec.timestep = n_snapshot;
+	    FILE *g = fopen((sd + "/nbody" + std::to_string(k) + ".bin").c_str(), "wb");
+	    if (!g || fwrite(&bodies[k].rec, sizeof(PlanetRecord), 1, g) != 1)
+		die("cannot write nbody record in %s", sd);
+	    fclose(g);
+	}
+	{ // snapshots/list.txt (output.cpp:332-350)
+	    std::ofstream l(outdir + "/snapshots/list.txt", std::ios::app);
+	    l << n_snapshot << "\n";
+	}
+    }
+
+    void write_static_files()
+    { // dimensions.dat / used_rad.dat (init.cpp:227-247) so python_module/fargocpt/data.py can load the directory
+	mkdirs(outdir + "/snapshots");
+	mkdirs(outdir + "/monitor");
+	FILE *f = fopen((outdir + "/dimensions.dat").c_str(), "w");
+	fprintf(f, "#RMIN\tRMAX\tPHIMIN\tPHIMAX          \tNRAD\tNAZ\tNGHRAD\tNGHAZ\tRadial_spacing\n");
+	fprintf(f, "%.16g\t%.16g\t%d\t%.16g\t%d\t%d\t%d\t%d\t%s\n", params.rmin, params.rmax, 0, 2.0 * M_PI, nrad, naz, 1, 1,
+		cfg.str("RadialSpacing", "Arithmetic").c_str());
+	fclose(f);
+	f = fopen((outdir + "/used_rad.dat").c_str(), "w");
+	for (double r : radii)
+	    fprintf(f, "%.18g\n", r);
+	fclose(f);
+	f = fopen((outdir + "/monitor/timestepLogging.dat").c_str(), "w");
+	fprintf(f, "#version: 1.1-b200\n#variable: 0 | snapshot number | 1\n#variable: 1 | monitor number | 1\n#variable: 2 | hydrostep number | 1\n"
+		   "#variable: 3 | time | code\n#variable: 4 | hydro dt | code\n");
+	fclose(f);
+    }
+
+    // sim::run (simulation.cpp:505-558) until `until_snapshot` has been written
+    void run(unsigned until_snapshot, long max_steps)
+    {
+	write_static_files();
+	// main.cpp:117 + sim::init (simulation.cpp:462-470): first CFL, boundaries, CFL again
+	if (n_iter == 0) {
+	    last_dt = cfg.num("FirstDT", 1e-9);
+	    calculate_time_step();
+	}
+	CHECK(BK(stage_boundary)(ctx, 0.0, 0));
+	calculate_time_step(); // sim::init (simulation.cpp:467)
+	long steps = 0;
+	FILE *tl = fopen((outdir + "/monitor/timestepLogging.dat").c_str(), "a");
+	while (n_snapshot < until_snapshot) {
+	    if (max_steps >= 0 && steps >= max_steps)
+		break; // -N: stops WITHOUT writing a snapshot (simulation.cpp:517-519)
+	    const double cfl_dt = calculate_time_step();
+	    const double time_next_monitor = (n_monitor + 1) * monitor_timestep;
+	    const double left = time_next_monitor - time;
+	    const bool overshoot = cfl_dt > left, almost_there = left < cfl_dt * (1 + 0.05);
+	    const double step_dt = (overshoot || almost_there) ? left : cfl_dt; // :528-540
+	    step(step_dt);
+	    ++steps;
+	    fprintf(tl, "%u\t%u\t%llu\t%.17g\t%.17g\n", n_snapshot, n_monitor, (unsigned long long)n_iter, time, step_dt);
+	    if (std::fabs(time_next_monitor - time) < 1e-6 * cfl_dt) { // :544-550
+		n_monitor++;
+		if (n_monitor % nmonitor == 0) {
+		    n_snapshot = n_monitor / nmonitor;
+		    write_snapshot();
+		}
+	    }
+	}
+	fclose(tl);
+    }
+};
+
+int main(int argc, char **argv)
+{
+    // options.cpp:42-189 subset: `restart N <dir>`, -N <steps>, plus --out / --until / --device
+    std::string mode, dir, out;
+    long nrestart = -1, max_steps = -1, until = -1;
+    int device = 0;
+    for (int i = 1; i < argc; ++i) {
+	const std::string a = argv[i];
+	if (a == "restart" && i + 2 < argc) {
+	    mode = a;
+	    nrestart = atol(argv[++i]);
+	    dir = argv[++i];
+	} else if (a == "-N" && i + 1 < argc)
+	    max_steps = atol(argv[++i]);
+	else if (a == "--out" && i + 1 < argc)
+	    out = argv[++i];
+	else if (a == "--until" && i + 1 < argc)
+	    until = atol(argv[++i]);
+	else if (a == "--device" && i + 1 < argc)
+	    device = atoi(argv[++i]);
+	else
+	    die("unknown argument %s", a);
+    }
+    if (mode != "restart" || out.empty()) {
+	fprintf(stderr, "usage: fargocpt_b200 restart <N> <fargocpt output dir> --out <new output dir> [--until <snapshot>] [-N <steps>] [--device <id>]\n");
+	return 2;
+    }
+    Run r;
+    r.outdir = out;
+    r.load(dir, (unsigned)nrestart, device);
+    r.run(until >= 0 ? (unsigned)until : r.nsnapshots, max_steps);
+    printf("-- Final: Total Hydrosteps %llu, time %.17g, last snapshot %u\n", (unsigned long long)r.n_iter, r.time, r.n_snapshot);
+#ifdef FARGO_HOST_ORACLE
+    fargo_oracle_destroy(r.ctx);
+#else
+    fargo_ctx_destroy(r.ctx);
+#endif
+    return 0;
+}

@@ -1,0 +1,117 @@
+"""The C++ host driver (host/fargo_host.cpp) as a drop-in on a FargoCPT output directory.
+
+A directory in the reference's own format (config.yml, constants.yml, units.yml, dimensions.dat, used_rad.dat,
+snapshots/0/{Sigma,vrad,vazi,energy,Qplus,Qminus}.dat, misc.bin, nbodyK.bin, snapshots/reference/) is materialised from a
+golden fixture (recorded from the unmodified reference), the host restarts from snapshot 0 and continues the run, and
+the snapshot files it writes are compared with the ones the reference wrote:
+  * star-only configs: every field file byte-identical, misc.bin (time, last_dt, N_iter) identical;
+  * with a planet the bodies are advanced by the host's RK4 instead of REBOUND's IAS15 (out of scope), which agrees to
+    rounding per step; fields then agree to the north_star tolerance (<= 1e-10) instead of bit for bit.
+CPU leg: the same driver bound to the oracle (host logic without a GPU).  GPU leg: the real binary on libfargo_b200.so.
+"""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+import yaml
+
+import reftools
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def materialise(name, dest):
+    """Write the fixture as a FargoCPT output directory (formats: SURVEY.md §5 'Checkpoint / resume')."""
+    meta, z = reftools.load_golden(name)
+    cfg = {k: v for k, v in meta["config"].items() if not k.startswith("_")}
+    nrad, naz = meta["params"]["nrad"], meta["params"]["naz"]
+    os.makedirs(os.path.join(dest, "snapshots", "0"))
+    os.makedirs(os.path.join(dest, "snapshots", "reference"))
+    c = meta["consts"]
+    with open(os.path.join(dest, "constants.yml"), "w") as f:
+        for sym in ("G", "R", "sigma", "c"):
+            f.write(f"{sym} constant:\n  symbol: {sym}\n  code value: {c[sym]!r}\n\n")
+    with open(os.path.join(dest, "units.yml"), "w") as f:
+        f.write(f"temperature:\n  cgs symbol: K\n  cgs value: {meta['temperature_unit_K']!r}\n")
+    with open(os.path.join(dest, "dimensions.dat"), "w") as f:
+        f.write("#RMIN\tRMAX\tPHIMIN\tPHIMAX\tNRAD\tNAZ\tNGHRAD\tNGHAZ\tRadial_spacing\n")
+        f.write(f"{cfg['Rmin']!r}\t{cfg['Rmax']!r}\t0\t{2 * np.pi!r}\t{nrad}\t{naz}\t1\t1\t{cfg['RadialSpacing']}\n")
+    with open(os.path.join(dest, "used_rad.dat"), "w") as f:
+        for r in z["radii"]:
+            f.write(f"{float(r)!r}\n")
+    for sub in ("0", "reference"):
+        sd = os.path.join(dest, "snapshots", sub)
+        yaml.safe_dump(cfg, open(os.path.join(sd, "config.yml"), "w"), sort_keys=False)
+        for fname in ("Sigma", "vrad", "vazi", "energy", "Qplus", "Qminus"):
+            if f"{fname}_0" in z:
+                z[f"{fname}_0"].astype(np.float64).tofile(os.path.join(sd, fname + ".dat"))
+        m = meta["misc"][0]
+        with open(os.path.join(sd, "misc.bin"), "wb") as f:  # output.h:16-24
+            f.write(struct.pack("<IIddddQ", 0, 0, m["time"], m["omega_frame"], m["frame_angle"], m["last_dt"], m["n_iter"]))
+        for k, b in enumerate(meta["bodies"][0]):  # nbody/planet.h:11-45, 256 bytes
+            rec = bytearray(256)
+            struct.pack_into("<5d", rec, 8, *b)
+            with open(os.path.join(sd, f"nbody{k}.bin"), "wb") as f:
+                f.write(bytes(rec))
+    return meta, z
+
+
+def run_host(exe, name, tmp_path, until):
+    src, out = str(tmp_path / "ref"), str(tmp_path / "out")
+    meta, z = materialise(name, src)
+    res = subprocess.run([exe, "restart", "0", src, "--out", out, "--until", str(until)], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    return meta, z, out
+
+
+def check(meta, z, out, k, exact):
+    nrad, naz = meta["params"]["nrad"], meta["params"]["naz"]
+    raw = open(os.path.join(out, "snapshots", str(k), "misc.bin"), "rb").read()
+    ts, nts, time, omega, angle, last_dt, n_iter = struct.unpack("<IIddddQ", raw)
+    m = meta["misc"][k]
+    assert (ts, n_iter, time) == (k, m["n_iter"], m["time"])
+    assert angle == m["frame_angle"]
+    if exact:
+        assert last_dt == m["last_dt"]
+    else:
+        assert last_dt == pytest.approx(m["last_dt"], rel=1e-10)
+    for fname, rings in (("Sigma", nrad), ("vrad", nrad + 1), ("vazi", nrad), ("energy", nrad)):
+        if f"{fname}_{k}" not in z:
+            continue
+        got = np.fromfile(os.path.join(out, "snapshots", str(k), fname + ".dat")).reshape(rings, naz)
+        ref = z[f"{fname}_{k}"]
+        if exact:
+            assert got.tobytes() == ref.tobytes(), (fname, reftools.compare_stats(got, ref))
+        else:  # Tools/compare_binary_output.py statistics, relative to the field's scale (v_rad crosses zero)
+            st = reftools.compare_stats(got, ref)
+            assert st["max_abs"] <= 1e-10 * float(np.abs(ref).max()), (fname, st)
+
+
+def _oracle_exe():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "host"), "oracle_test"])
+    return os.path.join(ROOT, "host", "fargocpt_b200_oracle_test")
+
+
+@pytest.mark.parametrize("name", ["iso_star", "adia_star", "adia_sn_stab"])
+def test_host_driver_star_only_bytes_identical_cpu(name, tmp_path):
+    meta, z, out = run_host(_oracle_exe(), name, tmp_path, 6)
+    for k in (1, 3, 6):
+        check(meta, z, out, k, exact=True)
+    assert open(os.path.join(out, "snapshots", "list.txt")).read().split() == [str(k) for k in range(1, 7)]
+
+
+def test_host_driver_planet_within_tolerance_cpu(tmp_path):
+    meta, z, out = run_host(_oracle_exe(), "iso_planet_100", tmp_path, 50)
+    check(meta, z, out, 50, exact=False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,until,exact", [("iso_star", 6, True), ("adia_star", 6, True), ("adia_planet_100", 100, False)])
+def test_host_driver_on_gpu(name, until, exact, tmp_path):
+    exe = os.path.join(ROOT, "host", "fargocpt_b200")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "host")])
+    meta, z, out = run_host(exe, name, tmp_path, until)
+    check(meta, z, out, until, exact)
