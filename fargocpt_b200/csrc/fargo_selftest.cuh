@@ -1,5 +1,6 @@
 // fargo_selftest.cuh — device self-test of fargo_math.h: the branch-free fast paths against the plain operators.
 #pragma once
+#include "fargo_dev.h"
 #include "fargo_math.h"
 
 __device__ __forceinline__ unsigned long long st_rng(unsigned long long &s)
@@ -45,6 +46,13 @@ __global__ void k_selftest_math(const unsigned long long seed, const int per_thr
 	    FmAcc A;
 	    const double q2 = MathP<true>::div(a, b, A);
 	    if (fm_acc_ok(A) != ok || (ok && __double_as_longlong(q2) != __double_as_longlong(qr)))
+		++bad_div;
+	}
+	{ // the van Leer limiter's single-key validity (fargo_dev.h:limiter_nb) against the plain operators
+	    FmAcc A;
+	    const double bb = (a < 0.0) == (b < 0.0) ? b : -b; // same sign as a: the branch where the division counts
+	    const double q = limiter_nb<FARGO_LIMITER_VANLEER>(a, bb, A);
+	    if (fm_acc_ok(A) && __double_as_longlong(q) != __double_as_longlong(flux_limiter<FARGO_LIMITER_VANLEER>(a, bb)))
 		++bad_div;
 	}
 	{

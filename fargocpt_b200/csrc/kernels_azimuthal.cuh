@@ -108,7 +108,6 @@ __device__ __forceinline__ void az_pass(double (&Q)[6][4], const double (&u)[4],
 #pragma unroll
 	for (int c = 0; c < 4; ++c) {
 	    W[c] = fm_div_raw(Q[q][c], Q[5][c], yS[c]); // divise_polargrid (SideEuler.cpp:27-43)
-	    fm_acc_num(acc, Q[q][c]);
 	    fm_acc_nrm(acc, W[c]);
 	}
 	if (!fm_acc_ok(acc)) { // cold: zero / tiny momenta
@@ -234,10 +233,8 @@ __global__ void __launch_bounds__(128, 3)
 		dvp[k] = sm + s;
 		const double qr = fm_div_raw(nvr[k], dvr[k], fm_rcp_raw(dvr[k]));
 		const double qp = fm_div_raw(nvp[k], dvp[k], fm_rcp_raw(dvp[k]));
-		fm_acc_num_if(acc, i != 0, nvr[k]);
 		fm_acc_nrm_if(acc, i != 0, dvr[k]);
 		fm_acc_nrm_if(acc, i != 0, qr);
-		fm_acc_num(acc, nvp[k]);
 		fm_acc_nrm(acc, dvp[k]);
 		fm_acc_nrm(acc, qp);
 		vrn[k] = (i == 0) ? 0.0 : qr;

@@ -84,7 +84,6 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
 		for (int q = 1; q < NB; ++q) {
 		    bk[q] = fm_div_raw(rawk[q], s, ys);
-		    fm_acc_num(acc, rawk[q]);
 		    fm_acc_nrm(acc, bk[q]);
 		}
 	    }
