@@ -9,13 +9,13 @@ import os
 
 import numpy as np
 
-FARGO_ABI_VERSION = 1
+FARGO_ABI_VERSION = 2
 FARGO_MAX_BODIES = 8
 CPUOVERLAP = 7
 
 # enum fargo_field
 (SIGMA, VRAD, VAZI, ENERGY, SIGMA0, VRAD0, VAZI0, ENERGY0, QPLUS, QMINUS, TEMPERATURE, PRESSURE, SOUNDSPEED,
- SCALE_HEIGHT, VISCOSITY, POTENTIAL) = range(16)
+ SCALE_HEIGHT, VISCOSITY, POTENTIAL, T_REYNOLDS) = range(17)
 FIELD_NAMES = {SIGMA: "Sigma", VRAD: "vrad", VAZI: "vazi", ENERGY: "energy", QPLUS: "Qplus", QMINUS: "Qminus"}
 VECTOR_FIELDS = (VRAD, VRAD0)
 
@@ -57,6 +57,7 @@ class FargoParams(C.Structure):
         ("damping_time_factor", C.c_double), ("damping_time_radius_outer", C.c_double),
         ("damp_vrad", C.c_int * 2), ("damp_vazi", C.c_int * 2), ("damp_sigma", C.c_int * 2),
         ("damp_energy", C.c_int * 2),
+        ("correct_disk_selfgravity", C.c_int),
     ]
 
     def as_dict(self):
@@ -78,6 +79,8 @@ class FargoParams(C.Structure):
                     getattr(p, name)[k] = x
             else:
                 setattr(p, name, v)
+        if "correct_disk_selfgravity" not in d:
+            p.correct_disk_selfgravity = 1  # parameters.cpp:699 default without self-gravity
         p.abi_version = FARGO_ABI_VERSION
         return p
 
@@ -208,6 +211,15 @@ class Handle:
 
     def stage(self, name, *args):
         self._check(self._call("stage_" + name, *args), "stage_" + name)
+
+    def disk_on_body_accel(self, body, klahr_factor=0.0):
+        """{ax_inner, ay_inner, ax_outer, ay_outer} of ComputeDiskOnPlanetAccel (Force.cpp:23-122)."""
+        out = (C.c_double * 4)()
+        fn = self._fn("disk_on_body_accel")
+        fn.argtypes = [C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_double)]
+        fn.restype = C.c_int
+        self._check(fn(self.ptr, int(body), float(klahr_factor), out), "disk_on_body_accel")
+        return np.array(list(out))
 
     def nshift(self):
         out = np.zeros(self.nr, dtype=np.int32)

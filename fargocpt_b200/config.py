@@ -95,6 +95,7 @@ def params_from_config(cfg, consts, nrad, naz, temp_unit_K=1.0):
         d.setdefault("bc_vazi", [0, 0])[side] = abi.BC[va]
         d.setdefault("keplerian_azimuthal_factor", [1.0, 1.0])[side] = float(
             get(name + "BoundaryVaziKeplerianFactor", 1.0))
+    d["correct_disk_selfgravity"] = int(_flag(get("CorrectDiskSelfgravity"), not _flag(get("SelfGravity"), False)))
     d["damping"] = int(_flag(get("Damping"), False))
     d["damping_inner_limit"] = float(get("DampingInnerLimit", 1.05))
     d["damping_outer_limit"] = float(get("DampingOuterLimit", 0.95))

@@ -21,6 +21,7 @@
 #include "kernels_transport.cuh"
 #include "kernels_azimuthal.cuh"
 #include "kernels_fused.cuh"
+#include "kernels_diag.cuh"
 #include "fargo_selftest.cuh"
 
 // ---------------------------------------------------------------------------------------------
@@ -121,7 +122,7 @@ struct fargo_ctx {
     // stage scratch
     double *pot, *qr, *qphi, *nu, *divv, *trr, *tpp, *trp, *nusig, *nusig_rp, *cf_r, *cf_phi;
     double *t_sigma, *t_rmp, *t_rmm, *t_amp, *t_amm, *t_e; // after the radial sweep
-    double *vmean, *vconst, *expf_s, *expf_v, *d_dt, *scratch;
+    double *vmean, *vconst, *expf_s, *expf_v, *d_dt, *scratch, *force4;
     int *nshift;
     double *h_pin; // pinned host staging for the CFL scalar + ring factors
     bool visc_const_filled = false;
@@ -449,7 +450,7 @@ extern "C" int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, con
     TRY(dalloc(c, &c->t_sigma, ns) || dalloc(c, &c->t_rmp, ns) || dalloc(c, &c->t_rmm, ns) || dalloc(c, &c->t_amp, ns) ||
 	dalloc(c, &c->t_amm, ns) || dalloc(c, &c->t_e, params->adiabatic ? ns : 1));
     TRY(dalloc(c, &c->vmean, c->v.nr + 2) || dalloc(c, &c->vconst, c->v.nr + 2) || dalloc(c, &c->expf_s, 4 * (c->v.nr + 2)) ||
-	dalloc(c, &c->expf_v, 1) || dalloc(c, &c->d_dt, 2) || dalloc(c, &c->scratch, ns));
+	dalloc(c, &c->expf_v, 1) || dalloc(c, &c->d_dt, 2) || dalloc(c, &c->scratch, ns) || dalloc(c, &c->force4, 4));
     {
 	cudaError_t e = cudaMalloc((void **)&c->nshift, (c->v.nr + 2) * sizeof(int));
 	if (e == cudaSuccess)
@@ -566,6 +567,9 @@ static double *state_ptr(fargo_ctx *c, int f, int *rings)
     return nullptr;
 }
 
+struct VBuf { double *vr, *vp; };
+static inline VBuf cur_v(fargo_ctx *c, bool mid) { return mid ? VBuf{VRB(c), VPB(c)} : VBuf{VRA(c), VPA(c)}; }
+
 // derived fields are never stored; they are evaluated into `scratch` when somebody asks for them
 static int materialize(fargo_ctx *c, int f, double **ptr, int *rings)
 {
@@ -575,6 +579,15 @@ static int materialize(fargo_ctx *c, int f, double **ptr, int *rings)
     if (f == FARGO_TEMPERATURE || f == FARGO_PRESSURE || f == FARGO_SOUNDSPEED || f == FARGO_SCALE_HEIGHT || f == FARGO_VISCOSITY) {
 	*rings = c->v.nr;
 	LAUNCH(c, k_derived_field, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, EN(c), c->scratch, f);
+	*ptr = c->scratch;
+	return 0;
+    }
+    if (f == FARGO_T_REYNOLDS) { // stress::calculate_Reynolds_stress, evaluated when an output asks for it
+	*rings = c->v.nr;
+	VBuf vb = cur_v(c, c->v_mid);
+	LAUNCH(c, k_reynolds_means, (unsigned)((c->v.nr + 63) / 64), 64, 0, c->v, vb.vr, vb.vp, c->vconst, c->vmean);
+	LAUNCH(c, k_reynolds_cells, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, vb.vr, vb.vp, c->vconst, c->vmean,
+	       c->scratch);
 	*ptr = c->scratch;
 	return 0;
     }
@@ -662,9 +675,6 @@ extern "C" int fargo_stage_potential(fargo_ctx *c)
 // artvisc / viscosity update B in place; Transport reads B and writes A.  When stages are called one by one (tests) the same
 // protocol holds because every per-stage entry point leaves the "current" v where the next stage expects it:
 // after sources..substep3 the current v is B, so the boundary stage must know which buffer is current.
-struct VBuf { double *vr, *vp; };
-static inline VBuf cur_v(fargo_ctx *c, bool mid) { return mid ? VBuf{VRB(c), VPB(c)} : VBuf{VRA(c), VPA(c)}; }
-
 extern "C" int fargo_stage_sources(fargo_ctx *c, double dt)
 {
     CUDA_OK(cudaSetDevice(c->device));
@@ -1191,5 +1201,42 @@ extern "C" int fargo_selftest_exp(fargo_ctx *c, int n, const double *x_host, dou
     CUDA_OK(cudaMemcpyAsync(y_host, d + n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     CUDA_OK(cudaFree(d));
+    return 0;
+}
+
+// ComputeDiskOnPlanetAccel (Force.cpp:23-122) + MPI_Allreduce(SUM, 4 doubles) (:115)
+extern "C" int fargo_disk_on_body_accel(fargo_ctx *c, int body, double klahr_factor, double out4[4])
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    if (body < 0 || body >= c->v.b.n)
+	return fail("body %d out of range (%d bodies set)", body, c->v.b.n);
+    if (c->v_mid)
+	return fail("fargo_disk_on_body_accel called mid-step");
+    BodyForceIn B;
+    B.x = c->v.b.x[body], B.y = c->v.b.y[body];
+    B.a = sqrt(B.x * B.x + B.y * B.y); // t_planet::get_r
+    B.klahr_factor = klahr_factor;
+    B.r_sm = c->v.b.cubic_smoothing_radius[body];
+    const int nact = c->v.active_size - c->v.first_active;
+    const unsigned gx = (unsigned)((c->v.ns + 4 * DOB_THREADS - 1) / (4 * DOB_THREADS));
+    const int nblocks = (int)gx * (nact > 0 ? nact : 0);
+    if ((size_t)nblocks * 4 > (size_t)c->v.nr * c->v.ns)
+	return fail("scratch too small for the force partials");
+    double *d_out = c->force4;
+    if (nblocks > 0) {
+	dim3 grid(gx, (unsigned)nact);
+	if (c->v.p.correct_disk_selfgravity) // the ring means land in vmean (rewritten by the next CFL / transport before use)
+	    LAUNCH(c, k_sigma_ring_mean, (unsigned)((c->v.nr + 63) / 64), 64, 0, c->v, c->sigma, c->vmean);
+	LAUNCH(c, k_disk_on_body, grid, DOB_THREADS, 0, c->v, c->sigma, EN(c), c->vmean, B, c->scratch);
+	LAUNCH(c, k_disk_on_body_final, 1, 128, 0, c->scratch, nblocks, d_out);
+    } else {
+	CUDA_OK(cudaMemsetAsync(d_out, 0, 4 * sizeof(double), c->stream));
+    }
+    if (c->v.nranks > 1) {
+	NCCL_OK(g_nccl.AllReduce(d_out, d_out, 4, ncclFloat64, 0 /* ncclSum */, c->comm, c->stream));
+	c->launches++;
+    }
+    CUDA_OK(cudaMemcpyAsync(out4, d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
     return 0;
 }

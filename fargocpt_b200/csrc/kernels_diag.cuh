@@ -1,0 +1,120 @@
+// kernels_diag.cuh — full-grid work the reference does outside the gas update proper but on the same fields:
+//   k_reynolds_means / k_reynolds_cells   stress::calculate_Reynolds_stress (stress.cpp:34-70), output diagnostic
+//   k_disk_on_body / k_disk_on_body_final ComputeDiskOnPlanetAccel (Force.cpp:23-122), per step with DiskFeedback
+#pragma once
+#include "fargo_dev.h"
+#include "kernels_source.cuh"
+
+// ring means of the cell-centred velocities, summed strictly in index order like the reference's serial inner loop
+// (stress.cpp:48-58).  One thread per ring: a diagnostic evaluated when an output asks for it, not per step.
+__global__ void __launch_bounds__(64) k_reynolds_means(const DevView c, const double *__restrict__ vr, const double *__restrict__ vp,
+							 double *__restrict__ vr_mean, double *__restrict__ vp_mean)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.nr)
+	return;
+    double a = 0.0, b = 0.0;
+    for (int j = 0; j < c.ns; ++j) {
+	const int jn = (j == c.ns - 1) ? 0 : j + 1;
+	a += 0.5 * (AT(vr, i, j) + AT(vr, i + 1, j));
+	b += 0.5 * (AT(vp, i, j) + AT(vp, i, jn));
+    }
+    vp_mean[i] = b / (double)c.ns;
+    vr_mean[i] = a / (double)c.ns;
+}
+__global__ void __launch_bounds__(256) k_reynolds_cells(const DevView c, const double *__restrict__ sigma, const double *__restrict__ vr,
+							 const double *__restrict__ vp, const double *__restrict__ vr_mean,
+							 const double *__restrict__ vp_mean, double *__restrict__ out)
+{
+    CELL_INDEX(c.nr);
+    AT(out, i, j) = AT(sigma, i, j) * (0.5 * (AT(vr, i, j) + AT(vr, i + 1, j)) - vr_mean[i]) *
+		    (0.5 * (AT(vp, i, j) + AT(vp, i, jp)) - vp_mean[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// ComputeDiskOnPlanetAccel (Force.cpp:23-122): acceleration of body nb by the gas of the active rings, split into
+// the parts from inside / outside the body's orbit {axi, ayi, axo, ayo}.  The reference sums with an OpenMP
+// reduction + MPI_Allreduce, i.e. in no defined order; here the order is FIXED (per-thread serial over a column
+// strip, shuffle tree, one partial per block, partials added in block order by the final kernel), so the result is
+// reproducible from run to run and independent of the launch geometry of other kernels.
+// ComputeAverageDensity (Pframeforce.cpp:174-188): ring mean of Sigma, serial sum in index order
+__global__ void __launch_bounds__(64) k_sigma_ring_mean(const DevView c, const double *__restrict__ sigma, double *__restrict__ sigma1d)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.nr)
+	return;
+    double sum = 0;
+    for (int j = 0; j < c.ns; ++j)
+	sum += AT(sigma, i, j);
+    sigma1d[i] = sum / c.ns;
+}
+struct BodyForceIn {
+    double x, y, a;	     // position, distance to the origin (planet.get_r())
+    double klahr_factor, r_sm; // cubic smoothing factor and l1 * factor (0: off)
+};
+#define DOB_THREADS 256
+__global__ void __launch_bounds__(DOB_THREADS) k_disk_on_body(const DevView c, const double *__restrict__ sigma,
+								const double *__restrict__ energy, const double *__restrict__ sigma1d,
+								const BodyForceIn B, double *__restrict__ partials /* [gridDim.y * gridDim.x][4] */)
+{
+    const int i = c.first_active + blockIdx.y;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    if (i < c.active_size) {
+	const double rmed = c.g.rmed[i], surf = c.g.surf[i];
+	const bool inner = rmed < B.a;
+	const double s1d = c.p.correct_disk_selfgravity ? sigma1d[i] : 0.0;
+	for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < c.ns; j += gridDim.x * blockDim.x) {
+	    const double s = AT(sigma, i, j), e = c.p.adiabatic ? AT(energy, i, j) : 0.0;
+	    const double smooth = c.p.thickness_smoothing * eos_H(c, i, eos_cs(c, i, s, e)); // compute_smoothing, Force.cpp:124-159
+	    const double xc = rmed * c.g.cosphi[j], yc = rmed * c.g.sinphi[j];
+	    double cell_sigma = s;
+	    if (c.p.correct_disk_selfgravity)
+		cell_sigma -= s1d;
+	    const double cellmass = surf * cell_sigma;
+	    const double dx = xc - B.x, dy = yc - B.y;
+	    const double dist_2 = dx * dx + dy * dy;
+	    const double dist_sm_2 = dist_2 + smooth * smooth;
+	    const double dist_sm = sqrt(dist_sm_2);
+	    const double dist_sm_3 = dist_sm_2 * dist_sm;
+	    const double inv_dist_sm_3 = 1.0 / dist_sm_3;
+	    double smooth_factor_klahr = 1.0;
+	    if (B.klahr_factor > 0.0 && dist_sm < B.r_sm)
+		smooth_factor_klahr = -(3.0 * pow(dist_sm / B.r_sm, 4.0) - 4.0 * pow(dist_sm / B.r_sm, 3.0));
+	    const double fx = c.p.G * cellmass * dx * inv_dist_sm_3 * smooth_factor_klahr;
+	    const double fy = c.p.G * cellmass * dy * inv_dist_sm_3 * smooth_factor_klahr;
+	    acc[inner ? 0 : 2] += fx;
+	    acc[inner ? 1 : 3] += fy;
+	}
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+	    acc[q] += __shfl_down_sync(0xffffffffu, acc[q], o);
+    __shared__ double sh[DOB_THREADS / 32][4];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0)
+#pragma unroll
+	for (int q = 0; q < 4; ++q)
+	    sh[w][q] = acc[q];
+    __syncthreads();
+    if (threadIdx.x < 4) {
+	double s = 0.0;
+	for (int k = 0; k < DOB_THREADS / 32; ++k)
+	    s += sh[k][threadIdx.x];
+	partials[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 4 + threadIdx.x] = s;
+    }
+}
+// adds the block partials in block order: 4 warps, one per component, each lane a strided serial sum, then a shuffle tree
+__global__ void __launch_bounds__(128) k_disk_on_body_final(const double *__restrict__ partials, const int nblocks, double *__restrict__ out4)
+{
+    const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double s = 0.0;
+    for (int b = lane; b < nblocks; b += 32)
+	s += partials[(size_t)b * 4 + q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+	s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0)
+	out4[q] = s;
+}

@@ -47,6 +47,7 @@ int fargo_oracle_init_derived(fargo_oracle *);
 int fargo_oracle_cfl(fargo_oracle *, double *, double *);
 int fargo_oracle_step(fargo_oracle *, double);
 int fargo_oracle_stage_boundary(fargo_oracle *, double, int);
+int fargo_oracle_disk_on_body_accel(fargo_oracle *, int, double, double *);
 }
 typedef fargo_oracle backend_ctx;
 #define BK(name) fargo_oracle_##name
@@ -297,6 +298,7 @@ static fargo_params make_params(const Config &c, const CodeConstants &k, int nra
 	p.bc_vazi[s] = enum_of(c.str(std::string(sides[s]) + "BoundaryVazi", "keplerian"), BC, "boundary");
 	p.keplerian_azimuthal_factor[s] = c.num(std::string(sides[s]) + "BoundaryVaziKeplerianFactor", 1.0);
     }
+    p.correct_disk_selfgravity = c.flag("CorrectDiskSelfgravity", !c.flag("SelfGravity", false)); // parameters.cpp:699
     p.damping = c.flag("Damping", false);
     p.damping_inner_limit = c.num("DampingInnerLimit", 1.05);
     p.damping_outer_limit = c.num("DampingOuterLimit", 0.95);
@@ -505,12 +507,46 @@ struct Run {
 	    fb.x[k] = b.rec.x, fb.y[k] = b.rec.y, fb.mass[k] = rampup_mass(b, time);
 	    fb.cubic_smoothing_radius[k] = b.rec.dimensionless_roche_radius * b.rec.distance_to_primary * b.rec.cubic_smoothing_factor;
 	}
-	indirect_term_euler(bodies, consts.G, fb.indirect_x, fb.indirect_y);
+	double px = 0.0, py = 0.0;
+	indirect_term_euler(bodies, consts.G, px, py);
+	// refframe::ComputeIndirectTermFully (frame_of_reference.cpp:166-169)
+	fb.indirect_x = ind_disk_x + px;
+	fb.indirect_y = ind_disk_y + py;
 	fb.omega_frame = omega_frame;
 	CHECK(BK(set_bodies)(ctx, &fb));
 	ind_x = fb.indirect_x, ind_y = fb.indirect_y;
     }
-    double ind_x = 0.0, ind_y = 0.0;
+    double ind_x = 0.0, ind_y = 0.0, ind_disk_x = 0.0, ind_disk_y = 0.0;
+    bool disk_feedback = false;
+
+    // ComputeDiskOnNbodyAccel (Pframeforce.cpp:194-220) + UpdatePlanetVelocitiesWithDiskForce (:257-275) +
+    // refframe::ComputeIndirectTermDisk (frame_of_reference.cpp:69-90); only with DiskFeedback: yes (simulation.cpp:155-160)
+    void disk_feedback_kick(double dt)
+    {
+	ind_disk_x = ind_disk_y = 0.0;
+	if (!disk_feedback)
+	    return;
+	set_bodies_on_device(); // positions for the force integral
+	for (size_t k = 0; k < bodies.size(); ++k) {
+	    double a4[4];
+	    CHECK(BK(disk_on_body_accel)(ctx, (int)k, bodies[k].rec.cubic_smoothing_factor, a4));
+	    Body &b = bodies[k];
+	    b.rec.disk_on_planet_acceleration[0] = a4[0] + a4[2]; // Force.cpp:117-119
+	    b.rec.disk_on_planet_acceleration[1] = a4[1] + a4[3];
+	    b.rec.torque = (b.rec.x * b.rec.disk_on_planet_acceleration[1] - b.rec.y * b.rec.disk_on_planet_acceleration[0]) * b.rec.mass;
+	}
+	for (auto &b : bodies) {
+	    b.rec.vx = b.rec.vx + dt * b.rec.disk_on_planet_acceleration[0];
+	    b.rec.vy = b.rec.vy + dt * b.rec.disk_on_planet_acceleration[1];
+	}
+	// hydro frame centred on body 0
+	double mass_center = 0.0;
+	ind_disk_x -= bodies[0].rec.mass * bodies[0].rec.disk_on_planet_acceleration[0];
+	ind_disk_y -= bodies[0].rec.mass * bodies[0].rec.disk_on_planet_acceleration[1];
+	mass_center += bodies[0].rec.mass;
+	ind_disk_x /= mass_center;
+	ind_disk_y /= mass_center;
+    }
 
     void load(const std::string &dir, unsigned nsnap, int device)
     {
@@ -557,6 +593,7 @@ struct Run {
 	if (bodies.size() > FARGO_MAX_BODIES)
 	    die("too many bodies in %s", sd);
 	params.hydro_center_mass = bodies[0].rec.mass; // global.cpp:146 (HydroFrameCenter: primary)
+	disk_feedback = cfg.flag("DiskFeedback", true); // parameters.cpp:755
 	indirect_mode = (int)cfg.num("IndirectTermMode", 0);
 	if (indirect_mode != 1 && bodies.size() > 1)
 	    fprintf(stderr, "fargocpt_b200: IndirectTermMode %d needs REBOUND's predictor; using the Euler form (mode 1)\n", indirect_mode);
@@ -618,6 +655,7 @@ struct Run {
     // step_Euler (simulation.cpp:148-267) around the gas part
     void step(double dt)
     {
+	disk_feedback_kick(dt);
 	set_bodies_on_device(); // indirect term from the current bodies (:160-162), potential inputs (:170)
 	for (auto &b : bodies) { // apply_indirect_term_on_Nbody (:164)
 	    b.rec.vx = b.rec.vx + dt * ind_x;

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FARGO_ABI_VERSION 1
+#define FARGO_ABI_VERSION 2
 #define FARGO_MAX_BODIES 8
 /* src/constants.h:17 (CPUOVERLAP) and :19 (GHOSTCELLS_B) */
 #define FARGO_CPUOVERLAP 7
@@ -51,7 +51,8 @@ enum fargo_field {
     FARGO_SCALE_HEIGHT = 13,
     FARGO_VISCOSITY = 14,
     FARGO_POTENTIAL = 15,
-    FARGO_NFIELDS = 16
+    FARGO_T_REYNOLDS = 16, /* T_Reynolds.dat: stress::calculate_Reynolds_stress (stress.cpp:34-70), computed on download */
+    FARGO_NFIELDS = 17
 };
 
 enum fargo_artvisc { FARGO_ARTVISC_NONE = 0, FARGO_ARTVISC_TW = 1, FARGO_ARTVISC_SN = 2 };
@@ -128,6 +129,8 @@ typedef struct fargo_params {
     int damping;
     double damping_inner_limit, damping_outer_limit, damping_time_factor, damping_time_radius_outer;
     int damp_vrad[2], damp_vazi[2], damp_sigma[2], damp_energy[2]; /* enum fargo_damping */
+    /* disk -> body force (Force.cpp:64-66): subtract the ring-mean density; CorrectDiskSelfgravity, default yes without self-gravity */
+    int correct_disk_selfgravity;
 } fargo_params;
 
 /* Star/planets as seen by the gas for ONE step (Pframeforce.cpp:27-36, refframe::IndirectTerm).
@@ -205,6 +208,12 @@ int fargo_stage_derived(fargo_ctx *ctx);               /* recalculate_derived_di
 /* fargo_step normally runs the fused source-term kernels; on != 0 makes it go through the per-stage kernels above
  * instead (same results; used by the parity tests to cross-check both) */
 int fargo_set_staged(fargo_ctx *ctx, int on);
+
+/* ComputeDiskOnPlanetAccel (Force.cpp:23-122): acceleration of body `body` (index into the bodies set with
+ * fargo_set_bodies; its cubic smoothing radius is taken from there) by the gas of this rank's active rings, summed over
+ * all ranks: out4 = {ax_inner, ay_inner, ax_outer, ay_outer} (parts from inside / outside the body's orbit; the
+ * reference adds them, Force.cpp:117-119).  klahr_factor = planet.get_cubic_smoothing_factor(). */
+int fargo_disk_on_body_accel(fargo_ctx *ctx, int body, double klahr_factor, double out4[4]);
 
 /* integer FARGO shifts of the last transport (TransportEuler.cpp:49,220), local rings */
 int fargo_get_nshift(fargo_ctx *ctx, int *out_local_nrad);

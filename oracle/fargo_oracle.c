@@ -200,10 +200,36 @@ void fargo_oracle_destroy(fargo_oracle *o)
 int fargo_oracle_local_nrad(const fargo_oracle *o) { return o->nr; }
 int fargo_oracle_local_imin(const fargo_oracle *o) { return o->imin; }
 
+/* stress::calculate_Reynolds_stress (stress.cpp:34-70): ring means of the cell-centred velocities (serial sums in index
+ * order), then Sigma * (v_r - <v_r>) * (v_phi - <v_phi>).  Written into the transport scratch grid `work`. */
+static double *reynolds_stress(fargo_oracle *o)
+{
+    const int ns = o->ns;
+    for (int nr = 0; nr < o->nr; ++nr) {
+	double v_radial_mean = 0.0;
+	double v_azimuthal_mean = 0.0;
+	for (int naz = 0; naz < ns; ++naz) {
+	    const int naz_next = (naz == ns - 1 ? 0 : naz + 1);
+	    v_radial_mean += 0.5 * (o->vrad[IDX(o, nr, naz)] + o->vrad[IDX(o, nr + 1, naz)]);
+	    v_azimuthal_mean += 0.5 * (o->vazi[IDX(o, nr, naz)] + o->vazi[IDX(o, nr, naz_next)]);
+	}
+	v_azimuthal_mean /= (double)ns;
+	v_radial_mean /= (double)ns;
+	for (int naz = 0; naz < ns; ++naz) {
+	    const int naz_next = (naz == ns - 1 ? 0 : naz + 1);
+	    o->work[IDX(o, nr, naz)] = o->sigma[IDX(o, nr, naz)] *
+				       (0.5 * (o->vrad[IDX(o, nr, naz)] + o->vrad[IDX(o, nr + 1, naz)]) - v_radial_mean) *
+				       (0.5 * (o->vazi[IDX(o, nr, naz)] + o->vazi[IDX(o, nr, naz_next)]) - v_azimuthal_mean);
+	}
+    }
+    return o->work;
+}
+
 static double *field_ptr(fargo_oracle *o, int f, int *rings)
 {
     *rings = o->nr;
     switch (f) {
+    case FARGO_T_REYNOLDS: return reynolds_stress(o);
     case FARGO_SIGMA: return o->sigma;
     case FARGO_VRAD: *rings = o->nr + 1; return o->vrad;
     case FARGO_VAZI: return o->vazi;
@@ -1553,5 +1579,54 @@ int fargo_oracle_step(fargo_oracle *o, double dt)
 {
     fargo_oracle_step_pre(o, dt);
     fargo_oracle_step_post(o, dt);
+    return 0;
+}
+
+/* ComputeDiskOnPlanetAccel (Force.cpp:23-122), serial sum in index order (the reference's own order is undefined:
+ * OpenMP reduction).  out4 = {axi, ayi, axo, ayo}. */
+int fargo_oracle_disk_on_body_accel(fargo_oracle *o, int body, double klahr_factor, double out4[4])
+{
+    if (body < 0 || body >= o->bodies.n)
+	return 1;
+    const double x = o->bodies.x[body], y = o->bodies.y[body];
+    const double a = sqrt(x * x + y * y);
+    const double r_sm = o->bodies.cubic_smoothing_radius[body];
+    double axi = 0.0, ayi = 0.0, axo = 0.0, ayo = 0.0;
+    for (int n_rad = o->first_active; n_rad < o->active_size; ++n_rad) {
+	double sigma1d = 0.0; /* ComputeAverageDensity (Pframeforce.cpp:174-188) */
+	if (o->p.correct_disk_selfgravity) {
+	    double sum = 0;
+	    for (int n_az = 0; n_az < o->ns; ++n_az)
+		sum += o->sigma[IDX(o, n_rad, n_az)];
+	    sigma1d = sum / o->ns;
+	}
+	for (int n_az = 0; n_az < o->ns; ++n_az) {
+	    const double smooth = o->p.thickness_smoothing * o->scale_height[IDX(o, n_rad, n_az)];
+	    const double xc = o->rmed[n_rad] * o->cosphi[n_az];
+	    const double yc = o->rmed[n_rad] * o->sinphi[n_az];
+	    double cell_sigma = o->sigma[IDX(o, n_rad, n_az)];
+	    if (o->p.correct_disk_selfgravity)
+		cell_sigma -= sigma1d;
+	    const double cellmass = o->surf[n_rad] * cell_sigma;
+	    const double dx = xc - x;
+	    const double dy = yc - y;
+	    const double dist_2 = dx * dx + dy * dy;
+	    const double dist_sm_2 = dist_2 + smooth * smooth;
+	    const double dist_sm = sqrt(dist_sm_2);
+	    const double dist_sm_3 = dist_sm_2 * dist_sm;
+	    const double inv_dist_sm_3 = 1.0 / dist_sm_3;
+	    double smooth_factor_klahr = 1.0;
+	    if (klahr_factor > 0.0 && dist_sm < r_sm)
+		smooth_factor_klahr = -(3.0 * pow(dist_sm / r_sm, 4.0) - 4.0 * pow(dist_sm / r_sm, 3.0));
+	    if (o->rmed[n_rad] < a) {
+		axi += o->p.G * cellmass * dx * inv_dist_sm_3 * smooth_factor_klahr;
+		ayi += o->p.G * cellmass * dy * inv_dist_sm_3 * smooth_factor_klahr;
+	    } else {
+		axo += o->p.G * cellmass * dx * inv_dist_sm_3 * smooth_factor_klahr;
+		ayo += o->p.G * cellmass * dy * inv_dist_sm_3 * smooth_factor_klahr;
+	    }
+	}
+    }
+    out4[0] = axi, out4[1] = ayi, out4[2] = axo, out4[3] = ayo;
     return 0;
 }

@@ -81,6 +81,14 @@ CASES = {
                       ArtificialViscosityFactor=1.41, ConstantViscosity=4.77e-5, InnerBoundary="Outflow",
                       OuterBoundary="Outflow", Nrad=64, Naz=2, Rmin=0.2, Rmax=1.8, MonitorTimestep=1.0e-4,
                       ThicknessSmoothing=0.0),
+    # stress::calculate_Reynolds_stress (stress.cpp:34-70): T_Reynolds.dat is filled when the alpha-Reynolds output runs
+    "rey_star": dict(ViscousAlpha=1e-3, HeatingViscous="yes", CoolingBetaLocal="yes", CoolingBeta=10, Nsnapshots=2,
+                     WriteAlphaReynolds="yes", WriteTReynolds="yes", _planet=3e-4, IndirectTermMode=1),
+    # DiskFeedback: yes — the disk's pull on star and planet (Force.cpp:23-122) enters the bodies' velocities and the
+    # indirect term every step (simulation.cpp:155-165)
+    "iso_feedback_20": dict(Nrad=48, Naz=160, Rmax=2.5, Nsnapshots=20, MonitorTimestep=4.0e-3, IndirectTermMode=1,
+                            EquationOfState="Isothermal", ViscousAlpha=1e-3, ArtificialViscosityFactor=1.41,
+                            FlaringIndex=0.0, DiskFeedback="yes", _planet=1e-3, _keep=(0, 20)),
     # 100 hydro steps with a Jupiter-mass planet (north_star: fields <= 1e-10 after 100 steps; dt and Nshift bit-exact).
     # IndirectTermMode 1 (Euler): the indirect term is a closed formula of the recorded body states
     # (frame_of_reference.cpp:112-132, Pframeforce.cpp:225-251) which tests/goldenrun.py restates.
@@ -111,7 +119,8 @@ def read_misc(path):
 def read_body(path):
     raw = open(path, "rb").read()
     mass, x, y, vx, vy = struct.unpack("<5d", raw[8:48])  # planet_member_variables (nbody/planet.h:11-17)
-    return [mass, x, y, vx, vy]
+    dax, day = struct.unpack("<2d", raw[120:136])  # m_disk_on_planet_acceleration (:27), refreshed at every monitor output
+    return [mass, x, y, vx, vy, dax, day]
 
 
 def run_case(name, overrides, keep=False):
@@ -148,7 +157,7 @@ def run_case(name, overrides, keep=False):
     for k in range(nsnap + 1):
         sd = os.path.join(out, "snapshots", str(k))
         for fname, rings in (("Sigma", nrad), ("vrad", nrad + 1), ("vazi", nrad), ("energy", nrad),
-                             ("Qplus", nrad), ("Qminus", nrad)):
+                             ("Qplus", nrad), ("Qminus", nrad), ("T_Reynolds", nrad)):
             p = os.path.join(sd, fname + ".dat")
             if keep_snaps is not None and k not in keep_snaps:
                 continue

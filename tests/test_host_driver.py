@@ -52,7 +52,7 @@ def materialise(name, dest):
             f.write(struct.pack("<IIddddQ", 0, 0, m["time"], m["omega_frame"], m["frame_angle"], m["last_dt"], m["n_iter"]))
         for k, b in enumerate(meta["bodies"][0]):  # nbody/planet.h:11-45, 256 bytes
             rec = bytearray(256)
-            struct.pack_into("<5d", rec, 8, *b)
+            struct.pack_into("<5d", rec, 8, *b[:5])
             with open(os.path.join(sd, f"nbody{k}.bin"), "wb") as f:
                 f.write(bytes(rec))
     return meta, z
@@ -107,8 +107,18 @@ def test_host_driver_planet_within_tolerance_cpu(tmp_path):
     check(meta, z, out, 50, exact=False)
 
 
+def test_host_driver_disk_feedback_cpu(tmp_path):
+    """DiskFeedback: yes — ComputeDiskOnNbodyAccel, the velocity kick and the disk part of the indirect term every step."""
+    meta, z, out = run_host(_oracle_exe(), "iso_feedback_20", tmp_path, 20)
+    check(meta, z, out, 20, exact=False)
+    raw = open(os.path.join(out, "snapshots", "20", "nbody1.bin"), "rb").read()
+    got = np.array(struct.unpack("<5d", raw[8:48]))
+    assert np.allclose(got, np.array(meta["bodies"][20][1][:5]), rtol=1e-12, atol=1e-13)
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,until,exact", [("iso_star", 6, True), ("adia_star", 6, True), ("adia_planet_100", 100, False)])
+@pytest.mark.parametrize("name,until,exact", [("iso_star", 6, True), ("adia_star", 6, True), ("adia_planet_100", 100, False),
+                                              ("iso_feedback_20", 20, False)])
 def test_host_driver_on_gpu(name, until, exact, tmp_path):
     exe = os.path.join(ROOT, "host", "fargocpt_b200")
     if not os.path.exists(exe):
