@@ -124,6 +124,7 @@ def _bind(lib, prefix):
         "init_derived": ([vp], C.c_int),
         "cfl": ([vp, _DP, _DP], C.c_int), "condition_cfl": ([vp, _DP], C.c_int),
         "step": ([vp, C.c_double], C.c_int),
+        "kick": ([vp, C.c_double], C.c_int), "drift": ([vp, C.c_double], C.c_int), "finish_step": ([vp, C.c_double], C.c_int),
         "stage_potential": ([vp], C.c_int), "stage_sources": ([vp, C.c_double], C.c_int),
         "stage_artvisc": ([vp, C.c_double], C.c_int), "stage_viscosity": ([vp, C.c_double], C.c_int),
         "stage_substep3": ([vp, C.c_double], C.c_int),
@@ -208,6 +209,27 @@ class Handle:
 
     def step(self, dt):
         self._check(self._call("step", float(dt)), "step")
+
+    def kick(self, dt):
+        self._check(self._call("kick", float(dt)), "kick")
+
+    def drift(self, dt):
+        self._check(self._call("drift", float(dt)), "drift")
+
+    def finish_step(self, dt):
+        self._check(self._call("finish_step", float(dt)), "finish_step")
+
+    def step_leapfrog(self, time, dt, bodies_mid=None):
+        """step_LeapFrog's gas part (simulation.cpp:276-459): kick dt/2, drift dt, (bodies at mid-step), kick dt/2."""
+        frog = dt / 2
+        self.set_time(time)
+        self.kick(frog)
+        self.drift(dt)
+        if bodies_mid is not None:
+            self.set_bodies(bodies_mid)
+        self.set_time(time + frog)
+        self.kick(frog)
+        self.finish_step(dt)
 
     def stage(self, name, *args):
         self._check(self._call("stage_" + name, *args), "stage_" + name)

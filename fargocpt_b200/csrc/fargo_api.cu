@@ -123,6 +123,8 @@ struct fargo_ctx {
     double *pot, *qr, *qphi, *nu, *divv, *trr, *tpp, *trp, *nusig, *nusig_rp, *cf_r, *cf_phi;
     double *t_sigma, *t_rmp, *t_rmm, *t_amp, *t_amm, *t_e; // after the radial sweep
     double *vmean, *vconst, *expf_s, *expf_v, *d_dt, *scratch, *force4;
+    double *hstale = nullptr; // leapfrog: scale height of the first kick's viscosity stage (see fargo_kick)
+    bool h_stale = false;
     int *nshift;
     double *h_pin; // pinned host staging for the CFL scalar + ring factors
     bool visc_const_filled = false;
@@ -451,6 +453,8 @@ extern "C" int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, con
 	dalloc(c, &c->t_amm, ns) || dalloc(c, &c->t_e, params->adiabatic ? ns : 1));
     TRY(dalloc(c, &c->vmean, c->v.nr + 2) || dalloc(c, &c->vconst, c->v.nr + 2) || dalloc(c, &c->expf_s, 4 * (c->v.nr + 2)) ||
 	dalloc(c, &c->expf_v, 1) || dalloc(c, &c->d_dt, 2) || dalloc(c, &c->scratch, ns) || dalloc(c, &c->force4, 4));
+    if (params->leapfrog)
+	TRY(dalloc(c, &c->hstale, ns));
     {
 	cudaError_t e = cudaMalloc((void **)&c->nshift, (c->v.nr + 2) * sizeof(int));
 	if (e == cudaSuccess)
@@ -667,7 +671,8 @@ extern "C" int fargo_set_time(fargo_ctx *c, double t)
 extern "C" int fargo_stage_potential(fargo_ctx *c)
 {
     CUDA_OK(cudaSetDevice(c->device));
-    LAUNCH(c, k_potential, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, EN(c), c->pot);
+    LAUNCH(c, k_potential, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, EN(c), c->pot,
+	   (const double *)(c->h_stale ? c->hstale : nullptr));
     return 0;
 }
 
@@ -720,9 +725,10 @@ static int launch_stress(fargo_ctx *c)
 {
     const unsigned g = cells_grid((long long)c->v.nr * c->v.ns);
     const fargo_params &p = c->v.p;
-    if (p.viscous_alpha > 0 || !c->visc_const_filled) {
-	LAUNCH(c, k_viscosity_nu, g, 256, 0, c->v, c->sigma, EN(c), c->nu);
+    if (p.viscous_alpha > 0 || !c->visc_const_filled || p.leapfrog) {
+	LAUNCH(c, k_viscosity_nu, g, 256, 0, c->v, c->sigma, EN(c), c->nu, (double *)(p.leapfrog ? c->hstale : nullptr));
 	c->visc_const_filled = true;
+	c->h_stale = p.leapfrog != 0;
     }
     VBuf v = cur_v(c, c->v_mid);
     LAUNCH(c, k_stress, g, 256, 0, c->v, c->sigma, c->nu, v.vr, v.vp, c->divv, c->trr, c->tpp, c->trp, c->nusig, c->nusig_rp);
@@ -982,7 +988,7 @@ extern "C" int fargo_stage_halo(fargo_ctx *c)
 // that every consumer here re-evaluates in registers, so there is nothing to store.
 extern "C" int fargo_stage_derived(fargo_ctx *c)
 {
-    (void)c;
+    c->h_stale = false; // the scale height is the current state's again (only a leapfrog mid-step keeps an older one)
     return 0;
 }
 
@@ -996,6 +1002,7 @@ extern "C" int fargo_init_derived(fargo_ctx *c)
 	return 1;
     LAUNCH(c, k_substep3, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, c->nu, c->divv, c->trr, c->tpp,
 	   c->trp, c->sigma0, c->energy0, EN(c), c->qplus, c->qminus, 0.0, beta_inv_host(c), 0);
+    c->h_stale = false;
     return 0;
 }
 
@@ -1047,7 +1054,8 @@ template <bool ADI> static int launch_fused_sources(fargo_ctx *c, double dt)
     const int nwin = (v.ns + FS_OUT - 1) / FS_OUT;
     dim3 grid((unsigned)((nwin + 3) / 4), (unsigned)((v.nr + c->fs_R - 1) / c->fs_R));
     const int eo = ADI ? 1 - c->ecur : c->ecur;
-    LAUNCH(c, k_fused_sources<ADI>, grid, 128, 0, v, c->sigma, EN(c), VRA(c), VPA(c), VRB(c), VPB(c), c->eb[eo], dt, c->fs_R);
+    LAUNCH(c, k_fused_sources<ADI>, grid, 128, 0, v, c->sigma, EN(c), VRA(c), VPA(c), (const double *)(c->h_stale ? c->hstale : nullptr),
+	   VRB(c), VPB(c), c->eb[eo], dt, c->fs_R);
     c->vcur = 1 - c->vcur;
     c->ecur = eo;
     const bool diss = ADI && p.artificial_viscosity_dissipation;
@@ -1060,10 +1068,68 @@ template <bool ADI> static int launch_fused_sources(fargo_ctx *c, double dt)
     {
 	const int eo3 = ADI ? 1 - c->ecur : c->ecur;
 	LAUNCH(c, k_fused_viscosity<ADI>, grid, 128, 0, v, c->sigma, EN(c), VRA(c), VPA(c), c->sigma0, c->energy0, VRB(c), VPB(c),
-	       c->eb[eo3], c->qplus, c->qminus, dt, ADI ? beta_inv_host(c) : 0.0, c->fs_R);
+	       c->eb[eo3], c->qplus, c->qminus, (double *)(p.leapfrog ? c->hstale : nullptr), dt, ADI ? beta_inv_host(c) : 0.0, c->fs_R);
+	c->h_stale = p.leapfrog != 0;
 	c->vcur = 1 - c->vcur;
 	c->ecur = eo3;
     }
+    return 0;
+}
+
+// The gas update in three pieces, so that a host can arrange them like step_Euler (kick dt, drift dt) or like
+// step_LeapFrog (kick dt/2, drift dt, bodies moved to mid-step, kick dt/2): simulation.cpp:148-267 / 276-459.
+//
+// fargo_kick: CalculateNbodyPotential, update_with_sourceterms, artificial viscosity, recalculate_viscosity,
+// viscous stress + velocity update, SubStep3 (simulation.cpp:167-175, 187-203) over a time step `dt`
+extern "C" int fargo_kick(fargo_ctx *c, double dt)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    const fargo_params &p = c->v.p;
+    const bool fused = p.stabilize_viscosity == 0 && !c->force_staged;
+    if (fused) {
+	if (c->v_mid)
+	    return fail("fargo_kick (fused) called mid-step after a per-stage call; finish with fargo_stage_transport first");
+	return p.adiabatic ? launch_fused_sources<true>(c, dt) : launch_fused_sources<false>(c, dt);
+    }
+    if (c->v_mid)
+	return fail("fargo_kick (staged) called mid-step");
+    if (fargo_stage_potential(c) || fargo_stage_sources(c, dt) || fargo_stage_artvisc(c, dt) || fargo_stage_viscosity(c, dt))
+	return 1;
+    if (p.adiabatic && fargo_stage_substep3(c, dt))
+	return 1;
+    return 0;
+}
+
+// fargo_drift: apply_boundary_condition(final = false) + Transport over `dt` (simulation.cpp:213-215)
+extern "C" int fargo_drift(fargo_ctx *c, double dt)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    const fargo_params &p = c->v.p;
+    if (fargo_stage_boundary(c, 0.0, 0))
+	return 1;
+    if (c->v_mid) // staged kernels left the velocities in the B buffers
+	return fargo_stage_transport(c, dt);
+    // Transport out of the current velocity buffer into the other one
+    int rc = p.flux_limiter == FARGO_LIMITER_MC ? launch_transport<FARGO_LIMITER_MC>(c, dt, VRA(c), VPA(c), VRB(c), VPB(c))
+						 : launch_transport<FARGO_LIMITER_VANLEER>(c, dt, VRA(c), VPA(c), VRB(c), VPB(c));
+    if (rc)
+	return rc;
+    c->vcur = 1 - c->vcur;
+    return 0;
+}
+
+// fargo_finish_step: CommunicateBoundaries, apply_boundary_condition(final = true) with the damping zones over the
+// whole step `dt`, derived quantities (simulation.cpp:230-266)
+extern "C" int fargo_finish_step(fargo_ctx *c, double dt)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    if (c->v_mid) { // staged second kick of a leapfrog step: the mid-step buffers hold the final velocities
+	c->vcur = 1 - c->vcur;
+	c->v_mid = false;
+    }
+    if (fargo_stage_halo(c) || fargo_stage_boundary(c, dt, 1) || fargo_stage_derived(c))
+	return 1;
+    c->h_stale = false; // recalculate_derived_disk_quantities: H is the current state's again
     return 0;
 }
 
@@ -1073,31 +1139,10 @@ extern "C" int fargo_step(fargo_ctx *c, double dt)
     CUDA_OK(cudaSetDevice(c->device));
     if (c->v_mid)
 	return fail("fargo_step called mid-step (after a per-stage call); finish the step with fargo_stage_transport first");
-    const fargo_params &p = c->v.p;
-    const bool fused = p.stabilize_viscosity == 0 && !c->force_staged;
-    if (fused) {
-	if (p.adiabatic ? launch_fused_sources<true>(c, dt) : launch_fused_sources<false>(c, dt))
-	    return 1;
-	if (fargo_stage_boundary(c, 0.0, 0))
-	    return 1;
-	// Transport out of the current velocity buffer into the other one
-	int rc = p.flux_limiter == FARGO_LIMITER_MC ? launch_transport<FARGO_LIMITER_MC>(c, dt, VRA(c), VPA(c), VRB(c), VPB(c))
-						     : launch_transport<FARGO_LIMITER_VANLEER>(c, dt, VRA(c), VPA(c), VRB(c), VPB(c));
-	if (rc)
-	    return rc;
-	c->vcur = 1 - c->vcur;
-    } else {
-	if (fargo_stage_potential(c) || fargo_stage_sources(c, dt) || fargo_stage_artvisc(c, dt) || fargo_stage_viscosity(c, dt))
-	    return 1;
-	if (p.adiabatic && fargo_stage_substep3(c, dt))
-	    return 1;
-	if (fargo_stage_boundary(c, 0.0, 0) || fargo_stage_transport(c, dt))
-	    return 1;
-    }
-    c->v.time += dt;
-    if (fargo_stage_halo(c) || fargo_stage_boundary(c, dt, 1) || fargo_stage_derived(c))
+    if (fargo_kick(c, dt) || fargo_drift(c, dt))
 	return 1;
-    return 0;
+    c->v.time += dt;
+    return fargo_finish_step(c, dt);
 }
 
 // test hook: run fargo_step through the staged kernels (one per reference loop nest) instead of the fused ones

@@ -127,15 +127,20 @@ __device__ __forceinline__ void fs_prefetch(const double *__restrict__ arr, cons
 template <class M, bool ADI>
 __device__ __forceinline__ void st_potential(const DevView &c, const EosC &ec, const int kr, const double (&S0)[4],
 					      const double (&E0)[4], const double (&cosj)[4], const double (&sinj)[4],
-					      double (&P0)[4], double (&F0)[4], FmAcc &A)
+					      const bool have_h, const double (&Hin)[4], double (&P0)[4], double (&F0)[4], FmAcc &A)
 {
     const double rmed = c.g.rmed[kr];
     double smooth[4], x[4], y[4], pot[4];
     FS_FOR4
     {
 	P0[k] = eos_P(c, kr, S0[k], E0[k]);
-	const double cs = eos_cs_m<M>(c, kr, S0[k], E0[k], A);
-	const double H = eos_H_m<M>(c, ec, kr, cs, A);
+	double H;
+	if (have_h) { // leapfrog, second kick: the scale height stored by the first kick's viscosity stage
+	    H = Hin[k];
+	} else {
+	    const double cs = eos_cs_m<M>(c, kr, S0[k], E0[k], A);
+	    H = eos_H_m<M>(c, ec, kr, cs, A);
+	}
 	x[k] = rmed * cosj[k];
 	y[k] = rmed * sinj[k];
 	smooth[k] = c.p.thickness_smoothing * H;
@@ -232,8 +237,8 @@ __device__ __forceinline__ void st_compress(const DevView &c, const int r, const
 template <bool ADI>
 __global__ void __launch_bounds__(128, FS_MINB_SRC)
     k_fused_sources(const DevView c, const double *__restrict__ sigma, const double *__restrict__ energy,
-		    const double *__restrict__ vr, const double *__restrict__ vp, double *__restrict__ o_vr,
-		    double *__restrict__ o_vp, double *__restrict__ o_e, const double dt, const int R)
+		    const double *__restrict__ vr, const double *__restrict__ vp, const double *__restrict__ h_in,
+		    double *__restrict__ o_vr, double *__restrict__ o_vp, double *__restrict__ o_e, const double dt, const int R)
 {
     typedef MathP<true> MF;
     typedef MathP<false> MS;
@@ -246,6 +251,7 @@ __global__ void __launch_bounds__(128, FS_MINB_SRC)
 	return;
     const int i_last = min(i_first + R, nr);
     const bool drift = c.p.imposed_disk_drift != 0.0;
+    const bool have_h = h_in != nullptr;
     const EosC ec = make_eos_c(c);
     // azimuth of the thread's columns (SideEuler.cpp:56-65)
     double cosj[4], sinj[4];
@@ -287,8 +293,11 @@ __global__ void __launch_bounds__(128, FS_MINB_SRC)
 		fs_load(energy, kr, c, L, E0);
 	    else
 		FS_FOR4 E0[k] = 0.0;
-	    FS_RUN((st_potential<MF, ADI>(c, ec, kr, S0, E0, cosj, sinj, P0, F0, A)),
-		   (st_potential<MS, ADI>(c, ec, kr, S0, E0, cosj, sinj, P0, F0, A)));
+	    double Hin[4] = {0.0, 0.0, 0.0, 0.0};
+	    if (have_h)
+		fs_load(h_in, kr, c, L, Hin);
+	    FS_RUN((st_potential<MF, ADI>(c, ec, kr, S0, E0, cosj, sinj, have_h, Hin, P0, F0, A)),
+		   (st_potential<MS, ADI>(c, ec, kr, S0, E0, cosj, sinj, have_h, Hin, P0, F0, A)));
 	} else {
 	    FS_FOR4 { S0[k] = 1.0, E0[k] = 1.0, VP0[k] = P0[k] = F0[k] = 0.0; }
 	}
@@ -667,8 +676,8 @@ __global__ void __launch_bounds__(128, FS_MINB_VISC)
     k_fused_viscosity(const DevView c, const double *__restrict__ sigma, const double *__restrict__ energy,
 		      const double *__restrict__ vr, const double *__restrict__ vp, const double *__restrict__ sigma0,
 		      const double *__restrict__ energy0, double *__restrict__ o_vr, double *__restrict__ o_vp,
-		      double *__restrict__ o_e, double *__restrict__ o_qplus, double *__restrict__ o_qminus, const double dt,
-		      const double beta_inv, const int R)
+		      double *__restrict__ o_e, double *__restrict__ o_qplus, double *__restrict__ o_qminus,
+		      double *__restrict__ o_h, const double dt, const double beta_inv, const int R)
 {
     typedef MathP<true> MF;
     typedef MathP<false> MS;
@@ -775,6 +784,8 @@ __global__ void __launch_bounds__(128, FS_MINB_VISC)
 	    if (r >= i_first) {
 		fs_store(o_vr, r, c, L, VRn);
 		fs_store(o_vp, r, c, L, VPn);
+		if (o_h) // leapfrog: H as recalculate_viscosity sees it, for the second kick's potential smoothing
+		    fs_store(o_h, r, c, L, H1);
 	    }
 	    if (ADI) {
 		double Qp[4], Qm[4], En[4], Ec[4], s0[4], e0[4];

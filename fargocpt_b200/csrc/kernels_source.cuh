@@ -28,10 +28,11 @@
 // ---------------------------------------------------------------------------------------------
 // Pframeforce.cpp:44-85.  Smoothing = ThicknessSmoothing * H(cell) (Force.cpp:124-159), H from the
 // current (Sigma, e) exactly as the end-of-step recalculate_derived_disk_quantities left it.
-__device__ __forceinline__ double potential_at(const DevView &c, int i, int j, double sigma, double energy)
+// h_in: the scale height recalculate_viscosity stored during the first kick of a leapfrog step (the reference does not
+// recompute c_s / H before the second kick, simulation.cpp:364-381); nullptr: H of the current state
+__device__ __forceinline__ double potential_at(const DevView &c, int i, int j, double sigma, double energy, const double *h_in = nullptr)
 {
-    const double cs = eos_cs(c, i, sigma, energy);
-    const double H = eos_H(c, i, cs);
+    const double H = h_in ? h_in[(size_t)i * c.ns + j] : eos_H(c, i, eos_cs(c, i, sigma, energy));
     const double x = c.g.rmed[i] * c.g.cosphi[j];
     const double y = c.g.rmed[i] * c.g.sinphi[j];
     const double smooth = c.p.thickness_smoothing * H;
@@ -54,10 +55,11 @@ __device__ __forceinline__ double potential_at(const DevView &c, int i, int j, d
 }
 
 __global__ void __launch_bounds__(256) k_potential(const DevView c, const double *__restrict__ sigma,
-						    const double *__restrict__ energy, double *__restrict__ pot)
+						    const double *__restrict__ energy, double *__restrict__ pot,
+						    const double *__restrict__ h_in)
 {
     CELL_INDEX(c.nr);
-    AT(pot, i, j) = potential_at(c, i, j, AT(sigma, i, j), AT(energy, i, j));
+    AT(pot, i, j) = potential_at(c, i, j, AT(sigma, i, j), AT(energy, i, j), h_in);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -207,10 +209,13 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------------------------------------
 // nu field (viscosity.cpp:98-137) from the current (Sigma, e)
 __global__ void __launch_bounds__(256) k_viscosity_nu(const DevView c, const double *__restrict__ sigma,
-						       const double *__restrict__ energy, double *__restrict__ nu)
+						       const double *__restrict__ energy, double *__restrict__ nu,
+						       double *__restrict__ o_h)
 {
     CELL_INDEX(c.nr);
     AT(nu, i, j) = eos_nu(c, i, AT(sigma, i, j), AT(energy, i, j));
+    if (o_h) // leapfrog: keep the scale height of this moment for the second kick's potential smoothing
+	AT(o_h, i, j) = eos_H(c, i, eos_cs(c, i, AT(sigma, i, j), AT(energy, i, j)));
 }
 
 // compute_viscous_stress_tensor (viscosity.cpp:139-254): div v, tau_rr, tau_phiphi (cell centred), tau_rphi (corner)

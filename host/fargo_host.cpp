@@ -48,6 +48,9 @@ int fargo_oracle_cfl(fargo_oracle *, double *, double *);
 int fargo_oracle_step(fargo_oracle *, double);
 int fargo_oracle_stage_boundary(fargo_oracle *, double, int);
 int fargo_oracle_disk_on_body_accel(fargo_oracle *, int, double, double *);
+int fargo_oracle_kick(fargo_oracle *, double);
+int fargo_oracle_drift(fargo_oracle *, double);
+int fargo_oracle_finish_step(fargo_oracle *, double);
 }
 typedef fargo_oracle backend_ctx;
 #define BK(name) fargo_oracle_##name
@@ -652,38 +655,83 @@ struct Run {
 	return dt;
     }
 
-    // step_Euler (simulation.cpp:148-267) around the gas part
-    void step(double dt)
-    {
-	disk_feedback_kick(dt);
-	set_bodies_on_device(); // indirect term from the current bodies (:160-162), potential inputs (:170)
-	for (auto &b : bodies) { // apply_indirect_term_on_Nbody (:164)
+    void rotate_frame(double dt)
+    { // refframe::handle_corotation (frame_of_reference.cpp:30-60) for a frame with fixed OmegaFrame (Frame: F):
+      // the bodies are rotated into the frame, t_planetary_system::rotate (nbody/planetary_system.cpp:409-432)
+	const double angle = omega_frame * dt;
+	for (auto &b : bodies) {
+	    const double x = b.rec.x, y = b.rec.y, vx = b.rec.vx, vy = b.rec.vy;
+	    b.rec.x = x * std::cos(angle) + y * std::sin(angle);
+	    b.rec.y = -x * std::sin(angle) + y * std::cos(angle);
+	    b.rec.vx = vx * std::cos(angle) + vy * std::sin(angle);
+	    b.rec.vy = -vx * std::sin(angle) + vy * std::cos(angle);
+	}
+	frame_angle += omega_frame * dt;
+    }
+    void apply_indirect_term_on_nbody(double dt)
+    { // nbody/planetary_system.cpp:730-744
+	for (auto &b : bodies) {
 	    b.rec.vx = b.rec.vx + dt * ind_x;
 	    b.rec.vy = b.rec.vy + dt * ind_y;
 	}
-	{ // refframe::handle_corotation (frame_of_reference.cpp:30-60) for a frame with fixed OmegaFrame (Frame: F):
-	  // the bodies are rotated into the frame, t_planetary_system::rotate (nbody/planetary_system.cpp:409-432)
-	    const double angle = omega_frame * dt;
-	    for (auto &b : bodies) {
-		const double x = b.rec.x, y = b.rec.y, vx = b.rec.vx, vy = b.rec.vy;
-		b.rec.x = x * std::cos(angle) + y * std::sin(angle);
-		b.rec.y = -x * std::sin(angle) + y * std::cos(angle);
-		b.rec.vx = vx * std::cos(angle) + vy * std::sin(angle);
-		b.rec.vy = -vx * std::sin(angle) + vy * std::cos(angle);
-	    }
-	    frame_angle += omega_frame * dt;
-	}
-	CHECK(BK(set_time)(ctx, time));
-	CHECK(BK(step)(ctx, dt));		  // :187-218, :230-266
-	nbody_integrate(bodies, consts.G, dt); // :222
-	if (bodies.size() > 1) {		  // move_to_hydro_frame_center (:224)
+    }
+    void integrate_and_recentre(double dt)
+    { // planetary_system.integrate + move_to_hydro_frame_center (simulation.cpp:222-224)
+	nbody_integrate(bodies, consts.G, dt);
+	if (bodies.size() > 1) {
 	    const double cx = bodies[0].rec.x, cy = bodies[0].rec.y, cvx = bodies[0].rec.vx, cvy = bodies[0].rec.vy;
 	    for (auto &b : bodies) {
 		b.rec.x -= cx, b.rec.y -= cy, b.rec.vx -= cvx, b.rec.vy -= cvy;
 	    }
 	}
+    }
+
+    // step_Euler (simulation.cpp:148-267) around the gas part
+    void step_euler(double dt)
+    {
+	disk_feedback_kick(dt);
+	set_bodies_on_device(); // indirect term from the current bodies (:160-162), potential inputs (:170)
+	apply_indirect_term_on_nbody(dt); // :164
+	rotate_frame(dt);		  // :184
+	CHECK(BK(set_time)(ctx, time));
+	CHECK(BK(step)(ctx, dt)); // :187-218, :230-266
+	integrate_and_recentre(dt);
 	time += dt;
 	n_iter++;
+    }
+
+    // step_LeapFrog (simulation.cpp:276-459): the bodies drift dt/2 first, kick dt/2, gas drift dt, kick dt/2 with the
+    // bodies at mid-step, bodies drift dt/2
+    void step_leapfrog(double dt)
+    {
+	const double frog = dt / 2, start_time = time, mid_time = time + frog;
+	integrate_and_recentre(frog);	  // :286-294
+	disk_feedback_kick(frog);	  // :297-313 (ComputeDiskOnNbodyAccel, UpdatePlanetVelocitiesWithDiskForce)
+	set_bodies_on_device();
+	apply_indirect_term_on_nbody(frog); // :315
+	rotate_frame(frog);		  // :322
+	CHECK(BK(set_time)(ctx, start_time));
+	CHECK(BK(kick)(ctx, frog));  // :326-345
+	CHECK(BK(drift)(ctx, dt));   // :347-352
+	time = mid_time;	       // the ramp-up mass and the beta-cooling ramp see the mid-step time (:364-398)
+	disk_feedback_kick(frog);    // :355-361 and :412-414
+	set_bodies_on_device();
+	CHECK(BK(set_time)(ctx, mid_time));
+	CHECK(BK(kick)(ctx, frog));
+	apply_indirect_term_on_nbody(frog); // :416
+	integrate_and_recentre(frog);	  // :419-424
+	rotate_frame(frog);		  // :428
+	time = start_time + dt;
+	n_iter++;
+	CHECK(BK(finish_step)(ctx, dt)); // :437-458
+    }
+
+    void step(double dt)
+    {
+	if (params.leapfrog)
+	    step_leapfrog(dt);
+	else
+	    step_euler(dt);
     }
 
     // output::write_full_output (output.cpp:249-330) for the files the parity tooling reads

@@ -193,6 +193,16 @@ int fargo_condition_cfl(fargo_ctx *ctx, double *cfl_dt_out);
  * derived quantities.  Uses the bodies/time set before. */
 int fargo_step(fargo_ctx *ctx, double dt);
 
+/* The same gas update in three pieces, for hosts that arrange them like step_LeapFrog (simulation.cpp:276-459):
+ *   Euler:    fargo_kick(dt); fargo_drift(dt); fargo_finish_step(dt)                         == fargo_step(dt)
+ *   Leapfrog: fargo_kick(dt/2); fargo_drift(dt); <bodies/time at mid-step>; fargo_kick(dt/2); fargo_finish_step(dt)
+ * kick  = CalculateNbodyPotential, update_with_sourceterms, artificial viscosity, viscosity, SubStep3 (:167-175, :187-203)
+ * drift = apply_boundary_condition(final = false) + Transport (:213-215)
+ * finish_step = CommunicateBoundaries + apply_boundary_condition(final = true, damping over dt) + derived (:230-266) */
+int fargo_kick(fargo_ctx *ctx, double dt);
+int fargo_drift(fargo_ctx *ctx, double dt);
+int fargo_finish_step(fargo_ctx *ctx, double dt);
+
 /* per-stage entry points (same order as fargo_step), exported so parity can be bisected per
  * reference function */
 int fargo_stage_potential(fargo_ctx *ctx);             /* CalculateNbodyPotential  Pframeforce.cpp:21 */

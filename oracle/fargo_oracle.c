@@ -1630,3 +1630,31 @@ int fargo_oracle_disk_on_body_accel(fargo_oracle *o, int body, double klahr_fact
     out4[0] = axi, out4[1] = ayi, out4[2] = axo, out4[3] = ayo;
     return 0;
 }
+
+/* kick / drift / finish_step: the pieces step_Euler and step_LeapFrog (simulation.cpp:148-267, 276-459) arrange */
+int fargo_oracle_kick(fargo_oracle *o, double dt)
+{
+    /* step_LeapFrog recomputes the pressure before its second kick (simulation.cpp:381) but NOT c_s / H: the potential
+     * smoothing of that kick uses the scale height recalculate_viscosity left during the first kick.  For step_Euler
+     * the pressure is already the end-of-step one, so recomputing it changes nothing. */
+    compute_pressure(o);
+    fargo_oracle_stage_potential(o);
+    fargo_oracle_stage_sources(o, dt);
+    fargo_oracle_stage_artvisc(o, dt);
+    fargo_oracle_stage_viscosity(o, dt);
+    if (o->p.adiabatic)
+	fargo_oracle_stage_substep3(o, dt);
+    return 0;
+}
+int fargo_oracle_drift(fargo_oracle *o, double dt)
+{
+    fargo_oracle_stage_boundary(o, 0.0, 0);
+    fargo_oracle_stage_transport(o, dt);
+    return 0;
+}
+int fargo_oracle_finish_step(fargo_oracle *o, double dt)
+{
+    fargo_oracle_stage_boundary(o, dt, 1);
+    fargo_oracle_stage_derived(o);
+    return 0;
+}

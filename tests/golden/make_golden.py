@@ -84,6 +84,9 @@ CASES = {
     # stress::calculate_Reynolds_stress (stress.cpp:34-70): T_Reynolds.dat is filled when the alpha-Reynolds output runs
     "rey_star": dict(ViscousAlpha=1e-3, HeatingViscous="yes", CoolingBetaLocal="yes", CoolingBeta=10, Nsnapshots=2,
                      WriteAlphaReynolds="yes", WriteTReynolds="yes", _planet=3e-4, IndirectTermMode=1),
+    # Integrator: Leapfrog (step_LeapFrog simulation.cpp:276-459: kick dt/2, drift dt, kick dt/2; CFL factor 0.6)
+    "adia_leapfrog": dict(Integrator="Leapfrog", ViscousAlpha=1e-3, HeatingViscous="yes", CoolingBetaLocal="yes", CoolingBeta=10,
+                          Damping="Yes", DampingInnerLimit=1.311, DampingOuterLimit=0.763, DampingTimeFactor=0.05, **DAMP_ALL),
     # DiskFeedback: yes — the disk's pull on star and planet (Force.cpp:23-122) enters the bodies' velocities and the
     # indirect term every step (simulation.cpp:155-165)
     "iso_feedback_20": dict(Nrad=48, Naz=160, Rmax=2.5, Nsnapshots=20, MonitorTimestep=4.0e-3, IndirectTermMode=1,

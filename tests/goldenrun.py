@@ -34,6 +34,18 @@ def bodies_at(meta, k, omega_frame):
     if len(bl) > 1:
         assert int(meta["config"].get("IndirectTermMode", 0)) == 1, "only the Euler indirect term is restated here"
         indirect = indirect_term_euler(meta["consts"]["G"], bl)
+        if str(meta["config"].get("DiskFeedback", "yes")).lower()[0] == "y":
+            # refframe::ComputeIndirectTermDisk (frame_of_reference.cpp:69-90) from the recorded disk-on-body acceleration
+            # of the centre body, + ComputeIndirectTermFully (:166-169)
+            # with DiskFeedback the record written at snapshot k+1 holds the acceleration computed at the START of the
+            # step k -> k+1 (simulation.cpp:155-156; handle_outputs does not refresh it, simulation.cpp:59-61)
+            acc = meta["bodies"][min(k + 1, len(meta["bodies"]) - 1)][0]
+            dx = dy = 0.0
+            dx -= bl[0][0] * acc[5]
+            dy -= bl[0][0] * acc[6]
+            dx /= bl[0][0]
+            dy /= bl[0][0]
+            indirect = (dx + indirect[0], dy + indirect[1])
     return abi.FargoBodies.make([b[1] for b in bl], [b[2] for b in bl], [b[0] for b in bl], indirect=indirect,
                                 omega_frame=omega_frame)
 

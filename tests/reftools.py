@@ -120,7 +120,10 @@ class TimeLoop:
         if bodies_fn is not None:
             self.ctx.set_bodies(bodies_fn(self.time, step_dt))
         self.ctx.set_time(self.time)
-        self.ctx.step(step_dt)
+        if self.ctx.params.leapfrog:
+            self.ctx.step_leapfrog(self.time, step_dt)
+        else:
+            self.ctx.step(step_dt)
         self.time += step_dt
         self.n_iter += 1
         self.dts.append(step_dt)

@@ -16,7 +16,7 @@ from fargocpt_b200 import abi
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["adia_star", "adia_cold", "iso_star", "iso_sn_std", "adia_sn_stab", "ring_like"]
+CASES = ["adia_star", "adia_cold", "iso_star", "iso_sn_std", "adia_sn_stab", "ring_like", "adia_leapfrog", "iso_feedback_20"]
 # 100 hydro steps with a Jupiter-mass planet (48 x 160: two warp windows per ring), recorded from the reference
 LONG_CASES = ["adia_planet_100", "iso_planet_100"]
 ISOTHERMAL = {"iso_star", "iso_sn_std", "ring_like", "iso_planet_100"}

@@ -94,7 +94,7 @@ def _oracle_exe():
     return os.path.join(ROOT, "host", "fargocpt_b200_oracle_test")
 
 
-@pytest.mark.parametrize("name", ["iso_star", "adia_star", "adia_sn_stab"])
+@pytest.mark.parametrize("name", ["iso_star", "adia_star", "adia_sn_stab", "adia_leapfrog"])
 def test_host_driver_star_only_bytes_identical_cpu(name, tmp_path):
     meta, z, out = run_host(_oracle_exe(), name, tmp_path, 6)
     for k in (1, 3, 6):
@@ -117,7 +117,7 @@ def test_host_driver_disk_feedback_cpu(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,until,exact", [("iso_star", 6, True), ("adia_star", 6, True), ("adia_planet_100", 100, False),
+@pytest.mark.parametrize("name,until,exact", [("iso_star", 6, True), ("adia_star", 6, True), ("adia_leapfrog", 6, True), ("adia_planet_100", 100, False),
                                               ("iso_feedback_20", 20, False)])
 def test_host_driver_on_gpu(name, until, exact, tmp_path):
     exe = os.path.join(ROOT, "host", "fargocpt_b200")

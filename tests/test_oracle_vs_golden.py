@@ -6,9 +6,12 @@ import pytest
 import goldenrun
 import reftools
 
-CASES = ["adia_star", "adia_cold", "iso_star", "iso_sn_std", "adia_sn_stab", "ring_like", "adia_planet_100", "iso_planet_100"]
+CASES = ["adia_star", "adia_cold", "iso_star", "iso_sn_std", "adia_sn_stab", "ring_like", "adia_planet_100", "iso_planet_100",
+         "adia_leapfrog", "iso_feedback_20"]
 # Isothermal configs have no per-cell transcendental in the step => demanded bit-exact.
 # Adiabatic configs call exp() per cell (SourceEuler.cpp:487); same libm here => also bit-exact on CPU.
+# DiskFeedback: the reference sums the disk's pull with an OpenMP reduction in no defined order, so the acceleration
+# it used inside a step differs in the last bits from the one it recorded at the previous output: tolerance there.
 BIT_EXACT = set(CASES)
 
 
@@ -21,7 +24,10 @@ def test_oracle_matches_reference(name):
         m = meta["misc"][k]
         assert snap["n_iter"] == m["n_iter"]
         assert snap["time"] == m["time"]
-        assert snap["last_dt"] == m["last_dt"], (snap["last_dt"], m["last_dt"])
+        if name in BIT_EXACT:
+            assert snap["last_dt"] == m["last_dt"], (snap["last_dt"], m["last_dt"])
+        else:
+            assert snap["last_dt"] == pytest.approx(m["last_dt"], rel=1e-12)
         for fname in ("Sigma", "vrad", "vazi", "energy"):
             if (fname == "energy" and not ctx.params.adiabatic) or fname not in snap:
                 continue
@@ -29,5 +35,5 @@ def test_oracle_matches_reference(name):
             if name in BIT_EXACT:
                 assert st["n_diff"] == 0, (name, k, fname, st)
             else:
-                assert st["max_rel"] < 1e-12, (name, k, fname, st)
+                assert st["max_abs"] <= 1e-12 * float(np.abs(z[f"{fname}_{k}"]).max()), (name, k, fname, st)
     ctx.close()
