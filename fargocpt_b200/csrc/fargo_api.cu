@@ -14,6 +14,7 @@
 
 #include <string>
 #include <vector>
+#include <algorithm>
 
 #include "fargo_dev.h"
 #include "kernels_ring.cuh"
@@ -311,8 +312,12 @@ static int init_geometry(fargo_ctx *c, const double *radii)
 	beta_e0[n] = 1.0 / (p.gamma - 1.0) * (p.aspectratio_ref * p.aspectratio_ref) * pow(rm, 2.0 * p.flaring_index - 1.0) * p.G *
 		     p.hydro_center_mass;
     }
-    for (int n = 1; n < nl; ++n)
+    c->v.limiter_geo_ok = 1;
+    for (int n = 1; n < nl; ++n) {
 	invdiffrmed[n] = 1.0 / (rmed[n] - rmed[n - 1]);
+	if (!(fabs(invdiffrmed[n]) >= 0x1p-30 && fabs(invdiffrmed[n]) <= 0x1p30))
+	    c->v.limiter_geo_ok = 0; // fargo_dev.h:limiter_nb
+    }
     std::vector<double> cosphi(v.ns), sinphi(v.ns);
     for (int j = 0; j < v.ns; ++j) { // SideEuler.cpp:56-65
 	cosphi[j] = cos(v.dphi * (double)j);
@@ -475,9 +480,29 @@ extern "C" int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, con
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
 	c->n_sm = sms;
 	const int nwin_az = (c->v.ns + AZ_OUT - 1) / AZ_OUT, nwin_fs = (c->v.ns + FS_OUT - 1) / FS_OUT;
-	c->az_R = rings_per_march(c->v.nr, (nwin_az + 3) / 4, 3 * sms, 1);
-	c->fs_R = rings_per_march(c->v.nr, (nwin_fs + 3) / 4, 3 * sms, 1);
-	c->rad_chunk = rings_per_march(c->v.nr, (c->v.ns + 127) / 128, 3 * sms, 2);
+	// resident CTAs per SM as the driver reports them for the kernels this configuration launches
+	const bool adi = c->v.p.adiabatic != 0, mc = c->v.p.flux_limiter == FARGO_LIMITER_MC;
+	auto occ = [](const void *k) {
+	    int n = 0;
+	    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, 128, 0) != cudaSuccess || n < 1)
+		n = 1;
+	    return n;
+	};
+	const int occ_fs = adi ? std::min(occ((const void *)k_fused_sources<true>),
+					  std::min(occ((const void *)k_fused_artvisc<true>), occ((const void *)k_fused_viscosity<true>)))
+			       : std::min(occ((const void *)k_fused_sources<false>),
+					  std::min(occ((const void *)k_fused_artvisc<false>), occ((const void *)k_fused_viscosity<false>)));
+	const int occ_az = mc ? (adi ? occ((const void *)k_transport_azimuthal<FARGO_LIMITER_MC, true>)
+				     : occ((const void *)k_transport_azimuthal<FARGO_LIMITER_MC, false>))
+			      : (adi ? occ((const void *)k_transport_azimuthal<FARGO_LIMITER_VANLEER, true>)
+				     : occ((const void *)k_transport_azimuthal<FARGO_LIMITER_VANLEER, false>));
+	const int occ_rad = mc ? (adi ? occ((const void *)k_transport_radial<FARGO_LIMITER_MC, true>)
+				      : occ((const void *)k_transport_radial<FARGO_LIMITER_MC, false>))
+			       : (adi ? occ((const void *)k_transport_radial<FARGO_LIMITER_VANLEER, true>)
+				      : occ((const void *)k_transport_radial<FARGO_LIMITER_VANLEER, false>));
+	c->az_R = rings_per_march(c->v.nr, (nwin_az + 3) / 4, occ_az * sms, 1);
+	c->fs_R = rings_per_march(c->v.nr, (nwin_fs + 3) / 4, occ_fs * sms, 1);
+	c->rad_chunk = rings_per_march(c->v.nr, (c->v.ns + 127) / 128, occ_rad * sms, 2);
 	// ring means: one warp per 32 rings; give each resident warp as much of the SM's shared memory as its share allows
 	if ((c->v.ns & 1) == 0) {
 	    const int nblocks = (c->v.nr + 31) / 32;

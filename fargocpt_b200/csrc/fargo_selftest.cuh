@@ -48,12 +48,21 @@ __global__ void k_selftest_math(const unsigned long long seed, const int per_thr
 	    if (fm_acc_ok(A) != ok || (ok && __double_as_longlong(q2) != __double_as_longlong(qr)))
 		++bad_div;
 	}
-	{ // the van Leer limiter's single-key validity (fargo_dev.h:limiter_nb) against the plain operators
-	    FmAcc A;
-	    const double bb = (a < 0.0) == (b < 0.0) ? b : -b; // same sign as a: the branch where the division counts
-	    const double q = limiter_nb<FARGO_LIMITER_VANLEER>(a, bb, A);
-	    if (fm_acc_ok(A) && __double_as_longlong(q) != __double_as_longlong(flux_limiter<FARGO_LIMITER_VANLEER>(a, bb)))
-		++bad_div;
+	{ // the key-free van Leer limiter (fargo_dev.h:limiter_nb) against the plain operators on the operand range its
+	  // callers guarantee — 0 or +-[2^-483, 2^431]: same signs (the branch where the division counts), the operands as
+	  // drawn (half of them of opposite sign, some zero), and the 0.5 * limiter form of the azimuthal sweep
+	    const bool in_range = (a == 0.0 || (fabs(a) >= 0x1p-483 && fabs(a) <= 0x1p431)) && fabs(b) >= 0x1p-483 && fabs(b) <= 0x1p431;
+	    const double bb = (a < 0.0) == (b < 0.0) ? b : -b;
+	    const double bs[2] = {bb, b};
+	    for (int v = 0; v < 2 && in_range; ++v) {
+		const double q = limiter_nb<FARGO_LIMITER_VANLEER>(a, bs[v]);
+		const double qh = limiter_nb<FARGO_LIMITER_VANLEER, true>(a, bs[v]);
+		const double ref = flux_limiter<FARGO_LIMITER_VANLEER>(a, bs[v]);
+		if (__double_as_longlong(q) != __double_as_longlong(ref))
+		    ++bad_div;
+		if (__double_as_longlong(qh) != __double_as_longlong(0.5 * ref))
+		    ++bad_div;
+	    }
 	}
 	{
 	    bool ok;

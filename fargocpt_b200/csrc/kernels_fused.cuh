@@ -7,13 +7,15 @@
 //                      update_velocities_with_viscosity (viscosity/viscosity.cpp:139-426) + SubStep3
 //                      (SourceEuler.cpp:496-954: viscous heating, beta cooling, energy update, T floor)
 //
-// Same execution shape as the azimuthal transport kernel: a warp owns a window of 128 columns, each lane 4
-// consecutive ones (3 of 4 azimuthal neighbours are the thread's own registers, the 4th is one shuffle away) and
-// marches outward in radius; the rings i-1 / i-2 a stage needs are the registers of the previous iterations, so
-// every state array is read ONCE and every intermediate (Phi, P, Q_rr, Q_phiphi, nu, div v, tau_rr, tau_phiphi,
-// tau_rphi) lives only in registers.  A stage that needs column j+-1 of the previous stage's output makes the
-// outermost columns of the window invalid, so a window of 128 columns yields 120 finished ones ([4, 124)); warps
-// do not communicate.  Outputs go to the OTHER buffer of each double-buffered field (windows overlap on reads).
+// Same execution shape as the azimuthal transport kernel: a warp owns a window of 32 * FS_NC columns, each lane FS_NC
+// consecutive ones (azimuthal neighbours are the thread's own registers or one shuffle away) and marches outward in
+// radius; the rings i-1 / i-2 a stage needs are the registers of the previous iterations, so every state array is
+// read ONCE and every intermediate (Phi, P, Q_rr, Q_phiphi, nu, div v, tau_rr, tau_phiphi, tau_rphi) lives only in
+// registers.  A stage that needs column j+-1 of the previous stage's output makes the outermost columns of the window
+// invalid, so a window of 64 columns yields 56 finished ones ([4, 60)); warps do not communicate.  Outputs go to the
+// OTHER buffer of each double-buffered field (windows overlap on reads).
+// FS_NC = 2 at 4 CTAs / SM (128 registers) beats 4 columns per lane at 3 CTAs / SM (168 registers, spills) by 17 % on
+// the viscosity and source kernels: the FP64 chains need warps, not wider threads, to hide their latency.
 //
 // Compared with one kernel per reference loop nest (the staged kernels in kernels_source.cuh, kept for the
 // per-stage entry points) this reads/writes 184 B per cell instead of 472 B and executes ~3x fewer instructions.
@@ -22,7 +24,10 @@
 #include "kernels_azimuthal.cuh"
 #include "kernels_source.cuh"
 
-#define FS_WIN 128
+#ifndef FS_NC
+#define FS_NC 2 // columns per lane
+#endif
+#define FS_WIN (32 * FS_NC)
 #define FS_HL 4
 #define FS_HR 4
 #define FS_OUT (FS_WIN - FS_HL - FS_HR)
@@ -40,67 +45,116 @@ __device__ __forceinline__ bool fs_setup(const DevView &c, FsLane &L)
     const int win = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if ((long long)win * FS_OUT >= c.ns)
 	return false;
-    const int t0 = 4 * lane;
+    const int t0 = FS_NC * lane;
     L.jout = win * FS_OUT - FS_HL + t0;
     int col = L.jout % c.ns;
     if (col < 0)
 	col += c.ns;
     L.col = col;
-    L.vec = ((c.ns & 3) == 0);
+    L.vec = ((c.ns % FS_NC) == 0);
     L.lane_out = (t0 >= FS_HL) && (t0 < FS_WIN - FS_HR) && (L.jout < c.ns);
     return true;
 }
 __device__ __forceinline__ void fs_load(const double *__restrict__ arr, const int ring, const DevView &c, const FsLane &L,
-					 double (&x)[4])
+					 double (&x)[FS_NC])
 {
     const double *row = arr + (size_t)ring * c.ns;
     if (L.vec) {
-	const double2 a = *reinterpret_cast<const double2 *>(row + L.col);
-	const double2 b = *reinterpret_cast<const double2 *>(row + L.col + 2);
-	x[0] = a.x;
-	x[1] = a.y;
-	x[2] = b.x;
-	x[3] = b.y;
+#pragma unroll
+	for (int k = 0; k < FS_NC; k += 2) {
+	    const double2 a = *reinterpret_cast<const double2 *>(row + L.col + k);
+	    x[k] = a.x;
+	    x[k + 1] = a.y;
+	}
     } else {
 	int cc = L.col;
 #pragma unroll
-	for (int k = 0; k < 4; ++k) {
+	for (int k = 0; k < FS_NC; ++k) {
 	    x[k] = row[cc];
 	    cc = (cc + 1 == c.ns) ? 0 : cc + 1;
 	}
     }
 }
 __device__ __forceinline__ void fs_store(double *__restrict__ arr, const int ring, const DevView &c, const FsLane &L,
-					  const double (&x)[4])
+					  const double (&x)[FS_NC])
 {
     if (!L.lane_out)
 	return;
     double *row = arr + (size_t)ring * c.ns;
     if (L.vec) {
-	*reinterpret_cast<double2 *>(row + L.jout) = make_double2(x[0], x[1]);
-	*reinterpret_cast<double2 *>(row + L.jout + 2) = make_double2(x[2], x[3]);
+#pragma unroll
+	for (int k = 0; k < FS_NC; k += 2)
+	    *reinterpret_cast<double2 *>(row + L.jout + k) = make_double2(x[k], x[k + 1]);
     } else {
 #pragma unroll
-	for (int k = 0; k < 4; ++k)
+	for (int k = 0; k < FS_NC; ++k)
 	    if (L.jout + k < c.ns)
 		row[L.jout + k] = x[k];
     }
 }
-#define FS_FOR4 _Pragma("unroll") for (int k = 0; k < 4; ++k)
+#define FS_FOR4 _Pragma("unroll") for (int k = 0; k < FS_NC; ++k)
 // software prefetch of the next ring's row segment (the marching loops touch every row exactly once, so the
 // hardware sees no reuse to exploit; without this the first consumer of each row eats the full DRAM latency)
 __device__ __forceinline__ void fs_prefetch(const double *__restrict__ arr, const int ring, const DevView &c, const FsLane &L)
 {
     pf_global(arr + (size_t)ring * c.ns + L.col);
 }
+// One ring of the four state fields as the fused kernels consume it: v_rad has nr + 1 rings, the cell-centred fields
+// nr (ring nr reads as Sigma = e = 1, v_azi = 0: harmless operands for the stages that run on it).
+// (Fetching ring kr + 1 into registers while ring kr is computed was measured and is slower on B200: the extra live
+// registers cost more than the load latency they hide; 25.6 vs 23.3 ms/step.  The compiler hoists the loads of ring kr
+// to the top of the iteration and the L2 prefetch of ring kr + 1 covers the DRAM latency.)
+struct FsRing {
+    double S[FS_NC], E[FS_NC], VP[FS_NC], VR[FS_NC];
+};
+template <bool ADI>
+__device__ __forceinline__ void fs_fetch_ring(const DevView &c, const FsLane &L, const double *__restrict__ sigma,
+					       const double *__restrict__ energy, const double *__restrict__ vr,
+					       const double *__restrict__ vp, const int kr, FsRing &N)
+{
+    fs_load(vr, kr, c, L, N.VR);
+    if (kr < c.nr) {
+	fs_load(sigma, kr, c, L, N.S);
+	fs_load(vp, kr, c, L, N.VP);
+	if (ADI)
+	    fs_load(energy, kr, c, L, N.E);
+	else
+	    FS_FOR4 N.E[k] = 0.0;
+    } else {
+	FS_FOR4 { N.S[k] = 1.0, N.E[k] = 1.0, N.VP[k] = 0.0; }
+    }
+}
+template <bool ADI>
+__device__ __forceinline__ void fs_prefetch_ring(const DevView &c, const FsLane &L, const double *__restrict__ sigma,
+						  const double *__restrict__ energy, const double *__restrict__ vr,
+						  const double *__restrict__ vp, const int kr)
+{
+    fs_prefetch(vr, kr, c, L);
+    if (kr < c.nr) {
+	fs_prefetch(sigma, kr, c, L);
+	fs_prefetch(vp, kr, c, L);
+	if (ADI)
+	    fs_prefetch(energy, kr, c, L);
+    }
+}
+// top of a marching iteration: ring kr into R, L2 prefetch of ring kr + 1
+template <bool ADI>
+__device__ __forceinline__ void fs_next_ring(const DevView &c, const FsLane &L, const double *__restrict__ sigma,
+					      const double *__restrict__ energy, const double *__restrict__ vr,
+					      const double *__restrict__ vp, const int kr, const int i_last, FsRing &R)
+{
+    fs_fetch_ring<ADI>(c, L, sigma, energy, vr, vp, kr, R);
+    if (kr < i_last)
+	fs_prefetch_ring<ADI>(c, L, sigma, energy, vr, vp, kr + 1);
+}
 #ifndef FS_MINB_SRC
-#define FS_MINB_SRC 3
+#define FS_MINB_SRC 4
 #endif
 #ifndef FS_MINB_AV
-#define FS_MINB_AV 3
+#define FS_MINB_AV 4
 #endif
 #ifndef FS_MINB_VISC
-#define FS_MINB_VISC 3
+#define FS_MINB_VISC 4
 #endif
 
 // ---------------------------------------------------------------------------------------------
@@ -125,12 +179,12 @@ __device__ __forceinline__ void fs_prefetch(const double *__restrict__ arr, cons
 
 // CalculateNbodyPotential (Pframeforce.cpp:44-85) + pressure, ring kr
 template <class M, bool ADI>
-__device__ __forceinline__ void st_potential(const DevView &c, const EosC &ec, const int kr, const double (&S0)[4],
-					      const double (&E0)[4], const double (&cosj)[4], const double (&sinj)[4],
-					      const bool have_h, const double (&Hin)[4], double (&P0)[4], double (&F0)[4], FmAcc &A)
+__device__ __forceinline__ void st_potential(const DevView &c, const EosC &ec, const int kr, const double (&S0)[FS_NC],
+					      const double (&E0)[FS_NC], const double (&cosj)[FS_NC], const double (&sinj)[FS_NC],
+					      const bool have_h, const double (&Hin)[FS_NC], double (&P0)[FS_NC], double (&F0)[FS_NC], FmAcc &A)
 {
     const double rmed = c.g.rmed[kr];
-    double smooth[4], x[4], y[4], pot[4];
+    double smooth[FS_NC], x[FS_NC], y[FS_NC], pot[FS_NC];
     FS_FOR4
     {
 	P0[k] = eos_P(c, kr, S0[k], E0[k]);
@@ -171,10 +225,10 @@ __device__ __forceinline__ void st_potential(const DevView &c, const EosC &ec, c
 
 // momentum_update_radial (SourceEuler.cpp:325-372): interface kr between rings kr-1 and kr
 template <class M>
-__device__ __forceinline__ void st_vrad(const DevView &c, const int kr, const double dt, const double (&S0)[4],
-					 const double (&S1)[4], const double (&P0)[4], const double (&P1)[4],
-					 const double (&F0)[4], const double (&F1)[4], const double (&VP0)[4], const double VP0r,
-					 const double (&VP1)[4], const double VP1r, const double (&VR0)[4], double (&VRn0)[4], FmAcc &A)
+__device__ __forceinline__ void st_vrad(const DevView &c, const int kr, const double dt, const double (&S0)[FS_NC],
+					 const double (&S1)[FS_NC], const double (&P0)[FS_NC], const double (&P1)[FS_NC],
+					 const double (&F0)[FS_NC], const double (&F1)[FS_NC], const double (&VP0)[FS_NC], const double VP0r,
+					 const double (&VP1)[FS_NC], const double VP1r, const double (&VR0)[FS_NC], double (&VRn0)[FS_NC], FmAcc &A)
 {
     const double idr = c.g.invdiffrmed[kr], rinf = c.g.rinf[kr], invrinf = c.g.invrinf[kr];
     const double OmegaF = c.b.omega_frame;
@@ -184,8 +238,8 @@ __device__ __forceinline__ void st_vrad(const DevView &c, const int kr, const do
 	gradp *= (P0[k] - P1[k]);
 	gradp *= idr;
 	const double gradphi = (F0[k] - F1[k]) * idr;
-	const double vp0n = (k == 3) ? VP0r : VP0[(k + 1) & 3];
-	const double vp1n = (k == 3) ? VP1r : VP1[(k + 1) & 3];
+	const double vp0n = (k == FS_NC - 1) ? VP0r : VP0[(k + 1) % FS_NC];
+	const double vp1n = (k == FS_NC - 1) ? VP1r : VP1[(k + 1) % FS_NC];
 	const double vsum = VP0[k] + vp0n + VP1[k] + vp1n;
 	const double vt = 0.25 * vsum + rinf * OmegaF;
 	const double vt2 = vt * vt;
@@ -196,17 +250,17 @@ __device__ __forceinline__ void st_vrad(const DevView &c, const int kr, const do
 
 // momentum_update_azimuthal (:375-428), ring kr
 template <class M>
-__device__ __forceinline__ void st_vazi(const DevView &c, const int kr, const double dt, const bool drift, const double (&S0)[4],
-					 const double Sl, const double (&P0)[4], const double Pl, const double (&F0)[4],
-					 const double Fl, const double (&VP0)[4], double (&VPn0)[4], FmAcc &A)
+__device__ __forceinline__ void st_vazi(const DevView &c, const int kr, const double dt, const bool drift, const double (&S0)[FS_NC],
+					 const double Sl, const double (&P0)[FS_NC], const double Pl, const double (&F0)[FS_NC],
+					 const double Fl, const double (&VP0)[FS_NC], double (&VPn0)[FS_NC], FmAcc &A)
 {
     const double invdxtheta = c.g.invdxtheta_mid[kr];
     const double supp = drift ? c.g.supp_torque[kr] : 0.0;
     FS_FOR4
     {
-	const double sp = (k == 0) ? Sl : S0[(k + 3) & 3];
-	const double Pp = (k == 0) ? Pl : P0[(k + 3) & 3];
-	const double Fp = (k == 0) ? Fl : F0[(k + 3) & 3];
+	const double sp = (k == 0) ? Sl : S0[(k + FS_NC - 1) % FS_NC];
+	const double Pp = (k == 0) ? Pl : P0[(k + FS_NC - 1) % FS_NC];
+	const double Fp = (k == 0) ? Fl : F0[(k + FS_NC - 1) % FS_NC];
 	const double gradp = M::div(2.0, S0[k] + sp, A) * (P0[k] - Pp) * invdxtheta;
 	const double gradphi = (F0[k] - Fp) * invdxtheta;
 	double vpn = VP0[k] + dt * (-gradp - gradphi);
@@ -218,14 +272,14 @@ __device__ __forceinline__ void st_vazi(const DevView &c, const int kr, const do
 
 // compression_heating (:459-493), ring r, with the UPDATED velocities
 template <class M>
-__device__ __forceinline__ void st_compress(const DevView &c, const int r, const double dt, const double (&E1)[4],
-					     const double (&VRn0)[4], const double (&VRn1)[4], const double (&VPn1)[4],
-					     const double VPn1r, double (&En)[4], FmAcc &A)
+__device__ __forceinline__ void st_compress(const DevView &c, const int r, const double dt, const double (&E1)[FS_NC],
+					     const double (&VRn0)[FS_NC], const double (&VRn1)[FS_NC], const double (&VPn1)[FS_NC],
+					     const double VPn1r, double (&En)[FS_NC], FmAcc &A)
 {
     const double ra1 = c.g.rinf[r + 1], ra0 = c.g.rinf[r], idrb = c.g.invdiffrsuprb[r], irb = c.g.invrmed[r];
     FS_FOR4
     {
-	const double vpn = (k == 3) ? VPn1r : VPn1[(k + 1) & 3];
+	const double vpn = (k == FS_NC - 1) ? VPn1r : VPn1[(k + 1) % FS_NC];
 	const double DIV_V = (VRn0[k] * ra1 - VRn1[k] * ra0) * idrb + (vpn - VPn1[k]) * c.invdphi * irb;
 	En[k] = E1[k] * M::exp(-(c.p.gamma - 1.0) * dt * DIV_V, A);
     }
@@ -254,7 +308,7 @@ __global__ void __launch_bounds__(128, FS_MINB_SRC)
     const bool have_h = h_in != nullptr;
     const EosC ec = make_eos_c(c);
     // azimuth of the thread's columns (SideEuler.cpp:56-65)
-    double cosj[4], sinj[4];
+    double cosj[FS_NC], sinj[FS_NC];
     {
 	int cc = L.col;
 	FS_FOR4
@@ -264,7 +318,7 @@ __global__ void __launch_bounds__(128, FS_MINB_SRC)
 	    cc = (cc + 1 == c.ns) ? 0 : cc + 1;
 	}
     }
-    double S1[4], P1[4], F1[4], VP1[4], E1[4], VRn1[4], VPn1[4];
+    double S1[FS_NC], P1[FS_NC], F1[FS_NC], VP1[FS_NC], E1[FS_NC], VRn1[FS_NC], VPn1[FS_NC];
     FS_FOR4
     {
 	S1[k] = 1.0;
@@ -275,31 +329,19 @@ __global__ void __launch_bounds__(128, FS_MINB_SRC)
     const int kbeg = max(i_first - 1, 0);
     for (int kr = kbeg; kr <= i_last; ++kr) {
 	const bool has_cells = kr < nr;
-	double S0[4], E0[4], VP0[4], VR0[4], P0[4], F0[4], VRn0[4], VPn0[4];
-	fs_load(vr, kr, c, L, VR0);
-	if (kr < i_last) {
-	    fs_prefetch(vr, kr + 1, c, L);
-	    if (kr + 1 < nr) {
-		fs_prefetch(sigma, kr + 1, c, L);
-		fs_prefetch(vp, kr + 1, c, L);
-		if (ADI)
-		    fs_prefetch(energy, kr + 1, c, L);
-	    }
-	}
+	double P0[FS_NC], F0[FS_NC], VRn0[FS_NC], VPn0[FS_NC];
+	FsRing R0;
+	fs_next_ring<ADI>(c, L, sigma, energy, vr, vp, kr, i_last, R0);
+	double(&S0)[FS_NC] = R0.S, (&E0)[FS_NC] = R0.E, (&VP0)[FS_NC] = R0.VP, (&VR0)[FS_NC] = R0.VR;
 	if (has_cells) {
-	    fs_load(sigma, kr, c, L, S0);
-	    fs_load(vp, kr, c, L, VP0);
-	    if (ADI)
-		fs_load(energy, kr, c, L, E0);
-	    else
-		FS_FOR4 E0[k] = 0.0;
-	    double Hin[4] = {0.0, 0.0, 0.0, 0.0};
+	    double Hin[FS_NC];
+	    FS_FOR4 Hin[k] = 0.0;
 	    if (have_h)
 		fs_load(h_in, kr, c, L, Hin);
 	    FS_RUN((st_potential<MF, ADI>(c, ec, kr, S0, E0, cosj, sinj, have_h, Hin, P0, F0, A)),
 		   (st_potential<MS, ADI>(c, ec, kr, S0, E0, cosj, sinj, have_h, Hin, P0, F0, A)));
 	} else {
-	    FS_FOR4 { S0[k] = 1.0, E0[k] = 1.0, VP0[k] = P0[k] = F0[k] = 0.0; }
+	    FS_FOR4 { P0[k] = F0[k] = 0.0; }
 	}
 	FS_FOR4
 	{
@@ -312,14 +354,14 @@ __global__ void __launch_bounds__(128, FS_MINB_SRC)
 		   (st_vrad<MS>(c, kr, dt, S0, S1, P0, P1, F0, F1, VP0, VP0r, VP1, VP1r, VR0, VRn0, A)));
 	}
 	if (has_cells && kr >= c.zero_no_ghost && kr < c.max_no_ghost) {
-	    const double Sl = shfl_from_left(S0[3]), Pl = shfl_from_left(P0[3]), Fl = shfl_from_left(F0[3]);
+	    const double Sl = shfl_from_left(S0[FS_NC - 1]), Pl = shfl_from_left(P0[FS_NC - 1]), Fl = shfl_from_left(F0[FS_NC - 1]);
 	    FS_RUN((st_vazi<MF>(c, kr, dt, drift, S0, Sl, P0, Pl, F0, Fl, VP0, VPn0, A)),
 		   (st_vazi<MS>(c, kr, dt, drift, S0, Sl, P0, Pl, F0, Fl, VP0, VPn0, A)));
 	}
 	// ring r = kr-1: compression heating, then store
 	const int r = kr - 1;
 	if (r >= i_first) {
-	    double En[4];
+	    double En[FS_NC];
 	    FS_FOR4 En[k] = E1[k];
 	    if (ADI && r < nr - 1) {
 		const double VPn1r = shfl_from_right(VPn1[0]);
@@ -350,12 +392,12 @@ __global__ void __launch_bounds__(128, FS_MINB_SRC)
 // artificial viscosity stage bodies (viscosity/artificial_viscosity.cpp)
 struct AvIn {
     // ring r: Sigma, e, v_rad(r), v_rad(r+1), v_azi (+ right neighbour), and ring r-1: Sigma, Q
-    double S1[4], E1[4], VR1[4], VR0[4], VP1[4], VP1r, S2[4], QR2[4], QP2[4];
+    double S1[FS_NC], E1[FS_NC], VR1[FS_NC], VR0[FS_NC], VP1[FS_NC], VP1r, S2[FS_NC], QR2[FS_NC], QP2[FS_NC];
 };
 // Q_rr / Q_phiphi of ring r and the dissipation into e: TW :49-88, SN :165-218 (no division: exact on any input)
 template <bool ADI>
 __device__ __forceinline__ void st_av_q(const DevView &c, const int r, const double dt, const int type, const bool diss,
-					 const AvIn &I, double (&QR1)[4], double (&QP1)[4], double (&En)[4])
+					 const AvIn &I, double (&QR1)[FS_NC], double (&QP1)[FS_NC], double (&En)[FS_NC])
 {
     const double C = c.p.artificial_viscosity_factor;
     FS_FOR4
@@ -373,7 +415,7 @@ __device__ __forceinline__ void st_av_q(const DevView &c, const int r, const dou
 	const bool heat = diss && r > c.zero_no_ghost && r < c.max_no_ghost;
 	FS_FOR4
 	{
-	    const double vpn = (k == 3) ? I.VP1r : I.VP1[(k + 1) & 3];
+	    const double vpn = (k == FS_NC - 1) ? I.VP1r : I.VP1[(k + 1) % FS_NC];
 	    const double eps_rr = (I.VR0[k] - I.VR1[k]) * ids;
 	    const double eps_pp = irb * ((vpn - I.VP1[k]) * c.invdphi + 0.5 * (I.VR0[k] + I.VR1[k]));
 	    const double div_V = stdmin(eps_rr + eps_pp, 0.0);
@@ -390,7 +432,7 @@ __device__ __forceinline__ void st_av_q(const DevView &c, const int r, const dou
 	const double invdxtheta = c.g.invdxtheta[r];
 	FS_FOR4
 	{
-	    const double vpn = (k == 3) ? I.VP1r : I.VP1[(k + 1) & 3];
+	    const double vpn = (k == FS_NC - 1) ? I.VP1r : I.VP1[(k + 1) % FS_NC];
 	    const double dv_r = I.VR0[k] - I.VR1[k];
 	    QR1[k] = (dv_r < 0.0) ? (C * C) * I.S1[k] * (dv_r * dv_r) : 0.0;
 	    const double dv_phi = vpn - I.VP1[k];
@@ -403,8 +445,8 @@ __device__ __forceinline__ void st_av_q(const DevView &c, const int r, const dou
 // velocity updates of ring r from Q(r), Q(r-1): TW :90-139, SN :221-248
 template <class M>
 __device__ __forceinline__ void st_av_v(const DevView &c, const int r, const double dt, const int type, const AvIn &I,
-					 const double (&QR1)[4], const double (&QP1)[4], const double QP1l, const double S1l,
-					 double (&VRn)[4], double (&VPn)[4], FmAcc &A)
+					 const double (&QR1)[FS_NC], const double (&QP1)[FS_NC], const double QP1l, const double S1l,
+					 double (&VRn)[FS_NC], double (&VPn)[FS_NC], FmAcc &A)
 {
     const int nr = c.nr;
     FS_FOR4
@@ -417,8 +459,8 @@ __device__ __forceinline__ void st_av_v(const DevView &c, const int r, const dou
 	    const double rs = c.g.rsup[r] + c.g.rinf[r];
 	    FS_FOR4
 	    {
-		const double sp = (k == 0) ? S1l : I.S1[(k + 3) & 3];
-		const double qpp = (k == 0) ? QP1l : QP1[(k + 3) & 3];
+		const double sp = (k == 0) ? S1l : I.S1[(k + FS_NC - 1) % FS_NC];
+		const double qpp = (k == 0) ? QP1l : QP1[(k + FS_NC - 1) % FS_NC];
 		const double sigma_phi_avg = 0.5 * (I.S1[k] + sp);
 		const double dVp = M::div(2.0 * dt, rs * sigma_phi_avg, A) * (QP1[k] - qpp) * c.invdphi;
 		VPn[k] = I.VP1[k] + dVp;
@@ -445,8 +487,8 @@ __device__ __forceinline__ void st_av_v(const DevView &c, const int r, const dou
 	    const double invdxtheta = c.g.invdxtheta[r];
 	    FS_FOR4
 	    {
-		const double sp = (k == 0) ? S1l : I.S1[(k + 3) & 3];
-		const double qpp = (k == 0) ? QP1l : QP1[(k + 3) & 3];
+		const double sp = (k == 0) ? S1l : I.S1[(k + FS_NC - 1) % FS_NC];
+		const double qpp = (k == 0) ? QP1l : QP1[(k + FS_NC - 1) % FS_NC];
 		VPn[k] = I.VP1[k] - M::div(dt * 2.0, I.S1[k] + sp, A) * (QP1[k] - qpp) * invdxtheta;
 	    }
 	}
@@ -485,38 +527,21 @@ __global__ void __launch_bounds__(128, FS_MINB_AV)
     // ring r = kr-1 is finished in iteration kr and needs Q(r-1), i.e. rings r-1 and r: start at r-1 = i_first-1
     const int kbeg = max(i_first - 1, 0);
     for (int kr = kbeg; kr <= i_last; ++kr) {
-	double S0[4], E0[4], VP0[4];
-	fs_load(vr, kr, c, L, I.VR0);
-	if (kr < i_last) {
-	    fs_prefetch(vr, kr + 1, c, L);
-	    if (kr + 1 < nr) {
-		fs_prefetch(sigma, kr + 1, c, L);
-		fs_prefetch(vp, kr + 1, c, L);
-		if (ADI)
-		    fs_prefetch(energy, kr + 1, c, L);
-	    }
-	}
-	if (kr < nr) {
-	    fs_load(sigma, kr, c, L, S0);
-	    fs_load(vp, kr, c, L, VP0);
-	    if (ADI)
-		fs_load(energy, kr, c, L, E0);
-	    else
-		FS_FOR4 E0[k] = 0.0;
-	} else {
-	    FS_FOR4 { S0[k] = 1.0, E0[k] = 1.0, VP0[k] = 0.0; }
-	}
+	FsRing R0;
+	fs_next_ring<ADI>(c, L, sigma, energy, vr, vp, kr, i_last, R0);
+	double(&S0)[FS_NC] = R0.S, (&E0)[FS_NC] = R0.E, (&VP0)[FS_NC] = R0.VP;
+	FS_FOR4 I.VR0[k] = R0.VR[k];
 	const int r = kr - 1;
 	if (r >= kbeg) { // ring r is complete: S1, E1, VR1 = v_rad(r), VR0 = v_rad(r+1), VP1
-	    double QR1[4], QP1[4], En[4], VRn[4], VPn[4];
+	    double QR1[FS_NC], QP1[FS_NC], En[FS_NC], VRn[FS_NC], VPn[FS_NC];
 	    I.VP1r = shfl_from_right(I.VP1[0]);
 	    st_av_q<ADI>(c, r, dt, type, diss, I, QR1, QP1, En);
 	    if (diss) { // :19-21
-		double Ec[4];
+		double Ec[FS_NC];
 		FS_RUN(FS_FOR4 Ec[k] = temperature_clamp_nb(tc, I.S1[k], En[k], A), FS_FOR4 Ec[k] = temperature_clamp(c, I.S1[k], En[k]));
 		FS_FOR4 En[k] = Ec[k];
 	    }
-	    const double QP1l = shfl_from_left(QP1[3]), S1l = shfl_from_left(I.S1[3]);
+	    const double QP1l = shfl_from_left(QP1[FS_NC - 1]), S1l = shfl_from_left(I.S1[FS_NC - 1]);
 	    FS_RUN((st_av_v<MF>(c, r, dt, type, I, QR1, QP1, QP1l, S1l, VRn, VPn, A)),
 		   (st_av_v<MS>(c, r, dt, type, I, QR1, QP1, QP1l, S1l, VRn, VPn, A)));
 	    if (r >= i_first) {
@@ -548,8 +573,8 @@ __global__ void __launch_bounds__(128, FS_MINB_AV)
 // viscosity + SubStep3 stage bodies
 // recalculate_viscosity (SourceEuler.cpp:205-223): c_s, H, nu of ring kr
 template <class M>
-__device__ __forceinline__ void st_nu(const DevView &c, const EosC &ec, const int kr, const double (&S0)[4], const double (&E0)[4],
-				       double (&N0)[4], double (&H0)[4], FmAcc &A)
+__device__ __forceinline__ void st_nu(const DevView &c, const EosC &ec, const int kr, const double (&S0)[FS_NC], const double (&E0)[FS_NC],
+				       double (&N0)[FS_NC], double (&H0)[FS_NC], FmAcc &A)
 {
     FS_FOR4
     {
@@ -561,13 +586,13 @@ __device__ __forceinline__ void st_nu(const DevView &c, const EosC &ec, const in
 }
 struct VsIn {
     // ring r: Sigma, v_rad(r), v_azi, tau_rphi(r) (+ right neighbour), tau_rphi(r+1) (+ right neighbour); ring r-1
-    double S1[4], VR1[4], VP1[4], TRP1[4], TRP0[4], TRP1r, TRP0r, S2[4], TRR2[4], TPP2[4];
+    double S1[FS_NC], VR1[FS_NC], VP1[FS_NC], TRP1[FS_NC], TRP0[FS_NC], TRP1r, TRP0r, S2[FS_NC], TRR2[FS_NC], TPP2[FS_NC];
 };
 // update_velocities_with_viscosity (viscosity.cpp:355-426), ring r
 template <class M>
-__device__ __forceinline__ void st_visc_v(const DevView &c, const int r, const double dt, const VsIn &I, const double (&TRR1)[4],
-					   const double (&TPP1)[4], const double TPP1l, const double S1l, double (&VRn)[4],
-					   double (&VPn)[4], FmAcc &A)
+__device__ __forceinline__ void st_visc_v(const DevView &c, const int r, const double dt, const VsIn &I, const double (&TRR1)[FS_NC],
+					   const double (&TPP1)[FS_NC], const double TPP1l, const double S1l, double (&VRn)[FS_NC],
+					   double (&VPn)[FS_NC], FmAcc &A)
 {
     FS_FOR4
     {
@@ -581,8 +606,8 @@ __device__ __forceinline__ void st_visc_v(const DevView &c, const int r, const d
 	const double tdr = c.g.twodiffrasq[r]; // 2.0 / (Ra[r+1]^2 - Ra[r]^2), formed on the host with the same IEEE operations
 	FS_FOR4
 	{
-	    const double sp = (k == 0) ? S1l : I.S1[(k + 3) & 3];
-	    const double tppl = (k == 0) ? TPP1l : TPP1[(k + 3) & 3];
+	    const double sp = (k == 0) ? S1l : I.S1[(k + FS_NC - 1) % FS_NC];
+	    const double tppl = (k == 0) ? TPP1l : TPP1[(k + FS_NC - 1) % FS_NC];
 	    const double sigma_avg = 0.5 * (I.S1[k] + sp);
 	    const double dVp = M::div(dt * irb, sigma_avg, A) * (tdr * (rap2 * I.TRP0[k] - ra2 * I.TRP1[k]) + (TPP1[k] - tppl) * c.invdphi);
 	    VPn[k] = I.VP1[k] + dVp;
@@ -594,7 +619,7 @@ __device__ __forceinline__ void st_visc_v(const DevView &c, const int r, const d
 	const double yrsum = M::rcp(rsum, A);
 	FS_FOR4
 	{
-	    const double trpn = (k == 3) ? I.TRP1r : I.TRP1[(k + 1) & 3];
+	    const double trpn = (k == FS_NC - 1) ? I.TRP1r : I.TRP1[(k + 1) % FS_NC];
 	    const double sigma_avg = 0.5 * (I.S1[k] + I.S2[k]);
 	    const double dVr = M::div_y(M::div(dt, sigma_avg, A) * c.p.radial_viscosity_factor * 2.0, rsum, yrsum, A) *
 			       ((rb * TRR1[k] - rbm * I.TRR2[k]) * idr + (trpn - I.TRP1[k]) * c.invdphi - 0.5 * (TPP1[k] + I.TPP2[k]));
@@ -606,10 +631,10 @@ __device__ __forceinline__ void st_visc_v(const DevView &c, const int r, const d
 // radiative alpha_r, the energy update and the temperature floor / ceiling
 template <class M>
 __device__ __forceinline__ void st_substep3(const DevView &c, const TempClampNB &tc, const int r, const double dt,
-					     const double beta_inv, const VsIn &I, const double (&E1)[4], const double (&N1)[4],
-					     const double (&H1)[4], const double (&DV1)[4], const double (&TRR1)[4],
-					     const double (&TPP1)[4], const double (&s0)[4], const double (&e0)[4], double (&Qp)[4],
-					     double (&Qm)[4], double (&En)[4], FmAcc &A)
+					     const double beta_inv, const VsIn &I, const double (&E1)[FS_NC], const double (&N1)[FS_NC],
+					     const double (&H1)[FS_NC], const double (&DV1)[FS_NC], const double (&TRR1)[FS_NC],
+					     const double (&TPP1)[FS_NC], const double (&s0)[FS_NC], const double (&e0)[FS_NC], double (&Qp)[FS_NC],
+					     double (&Qm)[FS_NC], double (&En)[FS_NC], FmAcc &A)
 {
     const bool inner = r >= 1 && r < c.nr - 1;
     const fargo_params &p = c.p;
@@ -617,8 +642,8 @@ __device__ __forceinline__ void st_substep3(const DevView &c, const TempClampNB 
     {
 	double qp = 0.0, qm = 0.0;
 	if (p.heating_viscous && inner) {
-	    const double trpn1 = (k == 3) ? I.TRP1r : I.TRP1[(k + 1) & 3];
-	    const double trpn0 = (k == 3) ? I.TRP0r : I.TRP0[(k + 1) & 3];
+	    const double trpn1 = (k == FS_NC - 1) ? I.TRP1r : I.TRP1[(k + 1) % FS_NC];
+	    const double trpn0 = (k == FS_NC - 1) ? I.TRP0r : I.TRP0[(k + 1) % FS_NC];
 	    const double tau_r_phi = 0.25 * (I.TRP1[k] + I.TRP0[k] + trpn1 + trpn0);
 	    // nu == 0 cells are skipped by the reference; evaluate with a harmless denominator and select
 	    const bool on = N1[k] != 0.0;
@@ -695,7 +720,7 @@ __global__ void __launch_bounds__(128, FS_MINB_VISC)
     if (ADI)
 	tc = make_temp_clamp_nb(c);
     VsIn I;
-    double E1[4], N1[4], H1[4];
+    double E1[FS_NC], N1[FS_NC], H1[FS_NC];
     FS_FOR4
     {
 	I.S1[k] = I.S2[k] = 1.0;
@@ -705,47 +730,34 @@ __global__ void __launch_bounds__(128, FS_MINB_VISC)
     // ring r needs the centred stresses of r-1 (rings r-1, r) and tau_rphi(r) (rings r-1, r): start at kr = r-1
     const int kbeg = max(i_first - 1, 0);
     for (int kr = kbeg; kr <= i_last; ++kr) {
-	double S0[4], E0[4], VR0[4], VP0[4], N0[4], H0[4];
-	fs_load(vr, kr, c, L, VR0);
-	if (kr < i_last) {
-	    fs_prefetch(vr, kr + 1, c, L);
-	    if (kr + 1 < nr) {
-		fs_prefetch(sigma, kr + 1, c, L);
-		fs_prefetch(vp, kr + 1, c, L);
-		if (ADI)
-		    fs_prefetch(energy, kr + 1, c, L);
-	    }
-	    if (need0 && kr >= i_first) { // ring r + 1 = kr of the reference fields, read one iteration from now
-		fs_prefetch(sigma0, kr, c, L);
-		fs_prefetch(energy0, kr, c, L);
-	    }
+	double N0[FS_NC], H0[FS_NC];
+	FsRing R0;
+	fs_next_ring<ADI>(c, L, sigma, energy, vr, vp, kr, i_last, R0);
+	double(&S0)[FS_NC] = R0.S, (&E0)[FS_NC] = R0.E, (&VP0)[FS_NC] = R0.VP, (&VR0)[FS_NC] = R0.VR;
+	if (need0 && kr < i_last && kr >= i_first) { // ring r + 1 = kr of the reference fields, read one iteration from now
+	    fs_prefetch(sigma0, kr, c, L);
+	    fs_prefetch(energy0, kr, c, L);
 	}
 	if (kr < nr) {
-	    fs_load(sigma, kr, c, L, S0);
-	    fs_load(vp, kr, c, L, VP0);
-	    if (ADI)
-		fs_load(energy, kr, c, L, E0);
-	    else
-		FS_FOR4 E0[k] = 0.0;
 	    FS_RUN((st_nu<MF>(c, ec, kr, S0, E0, N0, H0, A)), (st_nu<MS>(c, ec, kr, S0, E0, N0, H0, A)));
 	} else {
-	    FS_FOR4 { S0[k] = 1.0, E0[k] = 1.0, VP0[k] = N0[k] = H0[k] = 0.0; }
+	    FS_FOR4 { N0[k] = H0[k] = 0.0; }
 	}
 	// tau_rphi at the corner (kr, j) (viscosity.cpp:213-253); rings 0 and nr of the grid stay 0
 	{
-	    const double VR0l = shfl_from_left(VR0[3]);
-	    const double N0l = shfl_from_left(N0[3]), N1l = shfl_from_left(N1[3]);
-	    const double S0l = shfl_from_left(S0[3]), S1l = shfl_from_left(I.S1[3]);
+	    const double VR0l = shfl_from_left(VR0[FS_NC - 1]);
+	    const double N0l = shfl_from_left(N0[FS_NC - 1]), N1l = shfl_from_left(N1[FS_NC - 1]);
+	    const double S0l = shfl_from_left(S0[FS_NC - 1]), S1l = shfl_from_left(I.S1[FS_NC - 1]);
 	    if (kr >= 1 && kr < nr) {
 		const double irb = c.g.invrmed[kr], irbm = c.g.invrmed[kr - 1], idr = c.g.invdiffrmed[kr];
 		const double ra = c.g.rinf[kr], ira = c.g.invrinf[kr];
 		FS_FOR4
 		{
-		    const double vrl = (k == 0) ? VR0l : VR0[(k + 3) & 3];
-		    const double n0l = (k == 0) ? N0l : N0[(k + 3) & 3];
-		    const double n1l = (k == 0) ? N1l : N1[(k + 3) & 3];
-		    const double s0l = (k == 0) ? S0l : S0[(k + 3) & 3];
-		    const double s1l = (k == 0) ? S1l : I.S1[(k + 3) & 3];
+		    const double vrl = (k == 0) ? VR0l : VR0[(k + FS_NC - 1) % FS_NC];
+		    const double n0l = (k == 0) ? N0l : N0[(k + FS_NC - 1) % FS_NC];
+		    const double n1l = (k == 0) ? N1l : N1[(k + FS_NC - 1) % FS_NC];
+		    const double s0l = (k == 0) ? S0l : S0[(k + FS_NC - 1) % FS_NC];
+		    const double s1l = (k == 0) ? S1l : I.S1[(k + FS_NC - 1) % FS_NC];
 		    const double dvazirdr = (VP0[k] * irb - I.VP1[k] * irbm) * idr;
 		    const double dvrdphi = (VR0[k] - vrl) * c.invdphi;
 		    const double drp = ra * dvazirdr + dvrdphi * ira;
@@ -760,14 +772,14 @@ __global__ void __launch_bounds__(128, FS_MINB_VISC)
 	const int r = kr - 1;
 	if (r >= kbeg) {
 	    // centred stresses of ring r (viscosity.cpp:150-211)
-	    double DV1[4], TRR1[4], TPP1[4], VRn[4], VPn[4];
+	    double DV1[FS_NC], TRR1[FS_NC], TPP1[FS_NC], VRn[FS_NC], VPn[FS_NC];
 	    const double VP1r = shfl_from_right(I.VP1[0]);
 	    {
 		const double ra1 = c.g.rinf[r + 1], ra0 = c.g.rinf[r], idrb = c.g.invdiffrsuprb[r], irb = c.g.invrmed[r];
 		const double ids = c.g.invdiffrsup[r];
 		FS_FOR4
 		{
-		    const double vpn = (k == 3) ? VP1r : I.VP1[(k + 1) & 3];
+		    const double vpn = (k == FS_NC - 1) ? VP1r : I.VP1[(k + 1) % FS_NC];
 		    const double dv = (VR0[k] * ra1 - I.VR1[k] * ra0) * idrb + (vpn - I.VP1[k]) * c.invdphi * irb;
 		    DV1[k] = dv;
 		    const double drr = (VR0[k] - I.VR1[k]) * ids;
@@ -776,7 +788,7 @@ __global__ void __launch_bounds__(128, FS_MINB_VISC)
 		    TPP1[k] = 2.0 * N1[k] * I.S1[k] * (dpp - 1.0 / 3.0 * dv);
 		}
 	    }
-	    const double TPP1l = shfl_from_left(TPP1[3]), S1l = shfl_from_left(I.S1[3]);
+	    const double TPP1l = shfl_from_left(TPP1[FS_NC - 1]), S1l = shfl_from_left(I.S1[FS_NC - 1]);
 	    I.TRP1r = shfl_from_right(I.TRP1[0]);
 	    I.TRP0r = shfl_from_right(I.TRP0[0]);
 	    FS_RUN((st_visc_v<MF>(c, r, dt, I, TRR1, TPP1, TPP1l, S1l, VRn, VPn, A)),
@@ -788,7 +800,7 @@ __global__ void __launch_bounds__(128, FS_MINB_VISC)
 		    fs_store(o_h, r, c, L, H1);
 	    }
 	    if (ADI) {
-		double Qp[4], Qm[4], En[4], Ec[4], s0[4], e0[4];
+		double Qp[FS_NC], Qm[FS_NC], En[FS_NC], Ec[FS_NC], s0[FS_NC], e0[FS_NC];
 		if (need0 && r >= i_first) {
 		    fs_load(sigma0, r, c, L, s0);
 		    fs_load(energy0, r, c, L, e0);

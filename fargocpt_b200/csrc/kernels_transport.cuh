@@ -15,8 +15,13 @@
 // cell k-2 is finished:  Q(k-2) += (F(k-2) - F(k-1)) * InvSurf[k-2].
 // The 5 + 6 divisions of an iteration (Q / Sigma_int, van Leer slopes) run straight-line on the branch-free
 // arithmetic of fargo_math.h with one validity test; upwinding is done by selects.
+#ifdef TR_MINB
+#define TR_BOUNDS __launch_bounds__(128, TR_MINB)
+#else
+#define TR_BOUNDS __launch_bounds__(128)
+#endif
 template <int LIM, bool ADIABATIC>
-__global__ void __launch_bounds__(128)
+__global__ void TR_BOUNDS
     k_transport_radial(const DevView c, const double *__restrict__ sigma, const double *__restrict__ vr,
 		       const double *__restrict__ vp, const double *__restrict__ energy, double *__restrict__ o_sigma,
 		       double *__restrict__ o_rmp, double *__restrict__ o_rmm, double *__restrict__ o_amp,
@@ -39,6 +44,9 @@ __global__ void __launch_bounds__(128)
     double raw1[NB], raw2[NB];	    // raw transported quantities of rings k-1, k-2 (index 0 = Sigma)
     double F2[NB];		    // interface fluxes F(k-2) (index 0 = mass flux)
     double v1 = 0.0;		    // v_r(k-1)
+    // rings k-1, k-2 had all their bases inside the validity window R (fargo_math.h).  The slopes that involve a ring
+    // below kstart (never loaded) only feed warm-up interfaces whose fluxes reach no stored cell, so "true" is safe.
+    bool ok1 = true, ok2 = true;
 #pragma unroll
     for (int q = 0; q < NB; ++q) {
 	b1[q] = b2[q] = dq2[q] = raw1[q] = raw2[q] = F2[q] = 0.0;
@@ -77,6 +85,8 @@ __global__ void __launch_bounds__(128)
 	    // k-1 (compute_star_radial :356-371): 5 + 6 divisions, straight-line with one validity test (fargo_math.h)
 	    const double idm = slopes ? c.g.invdiffrmed[m] : 0.0, idp = slopes ? c.g.invdiffrmed[m + 1] : 0.0;
 	    FmAcc acc;
+	    if (!c.limiter_geo_ok)
+		acc.m = 0xffffffffu; // radial spacing outside [2^-30, 2^30]: plain operators (fargo_dev.h:limiter_nb)
 	    bk[0] = s;
 	    {
 		const double ys = fm_rcp_raw(s);
@@ -92,14 +102,19 @@ __global__ void __launch_bounds__(128)
 		for (int q = 0; q < NB; ++q) {
 		    const double dqm = (b1[q] - b2[q]) * idm;
 		    const double dqp = (bk[q] - b1[q]) * idp;
-		    dq1[q] = limiter_nb<LIM>(dqp, dqm, acc);
+		    dq1[q] = limiter_nb<LIM>(dqp, dqm); // key-free: b1, b2, bk are keyed, the geometry is checked by the host
 		}
 	    } else {
 #pragma unroll
 		for (int q = 0; q < NB; ++q)
 		    dq1[q] = 0.0;
 	    }
-	    if (!fm_acc_ok(acc)) { // cold: exact zeros (v_rad == 0 at the boundaries) or extreme exponents
+	    // the key-free limiter needs the bases of rings k, k-1 and k-2 inside R: remember the last two verdicts
+	    const bool okk = fm_acc_ok(acc);
+	    const bool fast = okk && ok1 && ok2;
+	    ok2 = ok1;
+	    ok1 = okk;
+	    if (!fast) { // cold: exact zeros (v_rad == 0 at the boundaries) or extreme exponents
 #pragma unroll
 		for (int q = 1; q < NB; ++q)
 		    bk[q] = rawk[q] / s;
@@ -116,6 +131,8 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
 	    for (int q = 0; q < NB; ++q)
 		bk[q] = rawk[q] = dq1[q] = 0.0;
+	    ok2 = ok1;
+	    ok1 = false;
 	    if (k == nr)
 		vnext = 0.0;
 	}
