@@ -351,7 +351,9 @@ def run_gpu(args):
         "data": "synthetic",
         "config": {"workload": f"{args.physics} {args.nrad}x{args.naz} (BASELINE configs[4]), radial slabs over {world} GPU(s)",
                    "cells": ncell, "l2": "inputs larger than L2 (1.07 GB per field)" if ncell * 8 > 126e6 else "inputs fit L2",
-                   "b_alg_bytes_per_cell_update": B_ALG[args.physics]},
+                   "b_alg_bytes_per_cell_update": B_ALG[args.physics],
+                   "halo_exchange": {0: "none (1 GPU)", 1: "ncclSend/ncclRecv after Transport",
+                                     2: "NVLink peer-memory stores from the transport kernel's edge launch, overlapped with the interior rings"}[ctx.halo_mode()]},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "what": f"upload 4 state fields from pinned host memory + {args.steps} steps + download 4 fields, per snapshot interval"},

@@ -277,10 +277,14 @@ def load_library():
         lib.fargo_set_staged.restype = C.c_int
         lib.fargo_selftest_math.argtypes = [C.c_void_p, C.c_ulonglong, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_ulonglong)]
         lib.fargo_selftest_math.restype = C.c_int
+        lib.fargo_selftest_ringsum.argtypes = [C.c_void_p, C.c_int, C.c_int, _DP, _DP, _DP]
+        lib.fargo_selftest_ringsum.restype = C.c_int
         lib.fargo_selftest_exp.argtypes = [C.c_void_p, C.c_int, _DP, _DP]
         lib.fargo_selftest_exp.restype = C.c_int
         lib.fargo_sync.argtypes = [C.c_void_p]
         lib.fargo_sync.restype = C.c_int
+        lib.fargo_halo_mode.argtypes = [C.c_void_p]
+        lib.fargo_halo_mode.restype = C.c_int
         lib.fargo_launch_count.argtypes = [C.c_void_p]
         lib.fargo_launch_count.restype = C.c_longlong
         lib.fargo_profile_enable.argtypes = [C.c_void_p, C.c_int]
@@ -330,9 +334,20 @@ class HydroContext(Handle):
         self._check(self.lib.fargo_selftest_exp(self.ptr, x.size, _dptr(x), _dptr(y)), "selftest_exp")
         return y
 
+    def selftest_ringsum(self, rows):
+        """Ring sums of the rows of a 2-D float64 array by the scan kernel and by the plain chain (fargo_selftest_ringsum)."""
+        x = np.ascontiguousarray(rows, dtype=np.float64)
+        a, b = np.empty(x.shape[0]), np.empty(x.shape[0])
+        self._check(self.lib.fargo_selftest_ringsum(self.ptr, x.shape[0], x.shape[1], _dptr(x), _dptr(a), _dptr(b)), "selftest_ringsum")
+        return a, b
+
     def set_staged(self, on):
         """step() through the per-stage kernels (one per reference loop nest) instead of the fused ones."""
         self._check(self.lib.fargo_set_staged(self.ptr, int(on)), "set_staged")
+
+    def halo_mode(self):
+        """0 single rank, 1 NCCL send/recv, 2 peer-memory stores from the transport kernel (fargo_halo_mode)."""
+        return int(self.lib.fargo_halo_mode(self.ptr))
 
     def launch_count(self):
         return int(self.lib.fargo_launch_count(self.ptr))

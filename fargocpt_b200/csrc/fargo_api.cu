@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <string>
 #include <vector>
@@ -18,6 +19,7 @@
 
 #include "fargo_dev.h"
 #include "kernels_ring.cuh"
+#include "kernels_ringsum.cuh"
 #include "kernels_source.cuh"
 #include "kernels_transport.cuh"
 #include "kernels_azimuthal.cuh"
@@ -131,14 +133,31 @@ struct fargo_ctx {
     bool visc_const_filled = false;
     cudaEvent_t ev_pin = nullptr; // completion of the last H2D copy out of h_pin
     int az_R, rad_chunk, fs_R, n_sm;
+    bool ringsum_scan = false;  // ring sums by k_ring_sum_scan (a warp per ring) instead of the one-thread-per-ring chain
     int rm_chunk = 0;	       // columns per TMA chunk of k_ring_mean (0: generic kernel)
     size_t rm_smem = 0;
     cudaStream_t stream2 = nullptr; // side stream: the transport ring means run beside the radial sweep
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // Ghost-ring exchange over peer memory (fargo_stage_halo): every rank owns an inbox its neighbours write into
+    // (double-buffered by step parity) and two arrival counters; the neighbours' inboxes are mapped with CUDA IPC.
+    struct Halo {
+	bool p2p = false;		   // peer path set up on every rank (else: ncclSend / ncclRecv)
+	double *inbox = nullptr;	   // [parity 2][side 2: from prev, from next][field 4][CPUOVERLAP * ns], then 2 counters
+	unsigned long long *flags = nullptr; // inside the inbox allocation: steps received from prev / from next
+	void *peer_base[2] = {nullptr, nullptr}; // prev's / next's inbox allocation as mapped here
+	size_t field_len = 0;		   // CPUOVERLAP * ns doubles
+	unsigned long long seq = 0;	   // halo exchanges started
+	bool pushed = false;		   // this step's edge rings are on their way (launch_transport), not yet received
+	unsigned int *done = nullptr;	   // edge warps of the running transport launch that have finished (device)
+	int az_R_int = 0;		   // rings per march of the interior segment
+    } halo;
     bool force_staged = false;
     cudaEvent_t ev_user[4] = {nullptr, nullptr, nullptr, nullptr}; // fargo_event_record slots
     // optional per-kernel device timing (bench.py roofline): CUDA events on the launching stream
     bool profiling = false;
+    // host time between the CFL result reaching the host and the step's first kernel launch (the GPU idles meanwhile)
+    double t_cfl_done = 0.0, host_turnaround_ms = 0.0;
+    long long host_turnaround_n = 0;
     struct KStat { std::string name; double ms = 0; long long n = 0; };
     std::vector<KStat> kstats;
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
@@ -371,6 +390,13 @@ extern "C" void fargo_ctx_destroy(fargo_ctx *c)
     for (int k = 0; k < 4; ++k)
 	if (c->ev_user[k])
 	    cudaEventDestroy(c->ev_user[k]);
+    for (int k = 0; k < 2; ++k)
+	if (c->halo.peer_base[k])
+	    cudaIpcCloseMemHandle(c->halo.peer_base[k]);
+    if (c->halo.inbox)
+	cudaFree(c->halo.inbox);
+    if (c->halo.done)
+	cudaFree(c->halo.done);
     if (c->ev_fork)
 	cudaEventDestroy(c->ev_fork);
     if (c->ev_join)
@@ -381,6 +407,75 @@ extern "C" void fargo_ctx_destroy(fargo_ctx *c)
 	cudaStreamDestroy(c->stream);
     delete c;
 }
+
+// Peer-memory halo path: allocate the inbox, swap CUDA IPC handles with the two neighbours over NCCL, map theirs.
+// All ranks must agree (one allreduce); FARGO_B200_HALO=nccl forces the ncclSend / ncclRecv path.
+static int halo_setup(fargo_ctx *c)
+{
+    fargo_ctx::Halo &h = c->halo;
+    const DevView &v = c->v;
+    h.field_len = (size_t)FARGO_CPUOVERLAP * v.ns;
+    const char *env = getenv("FARGO_B200_HALO");
+    bool want = !(env && strcmp(env, "nccl") == 0) && v.nr >= 4 * FARGO_CPUOVERLAP;
+    const size_t ndbl = 2 * 2 * 4 * h.field_len;
+    cudaIpcMemHandle_t mine, theirs[2];
+    memset(&mine, 0, sizeof(mine));
+    memset(theirs, 0, sizeof(theirs));
+    if (want) {
+	if (cudaMalloc((void **)&h.inbox, ndbl * sizeof(double) + 2 * sizeof(unsigned long long)) != cudaSuccess ||
+	    cudaMemset(h.inbox, 0, ndbl * sizeof(double) + 2 * sizeof(unsigned long long)) != cudaSuccess ||
+	    cudaIpcGetMemHandle(&mine, h.inbox) != cudaSuccess) {
+	    cudaGetLastError();
+	    want = false;
+	}
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    // handles travel as 8 doubles each through the scratch field (device memory NCCL can address)
+    double *d_mine = c->scratch, *d_prev = c->scratch + 8, *d_next = c->scratch + 16;
+    CUDA_OK(cudaMemcpyAsync(d_mine, &mine, 64, cudaMemcpyHostToDevice, c->stream));
+    NCCL_OK(g_nccl.GroupStart());
+    if (v.rank > 0) {
+	NCCL_OK(g_nccl.Send(d_mine, 8, ncclFloat64, v.rank - 1, c->comm, c->stream));
+	NCCL_OK(g_nccl.Recv(d_prev, 8, ncclFloat64, v.rank - 1, c->comm, c->stream));
+    }
+    if (v.rank < v.nranks - 1) {
+	NCCL_OK(g_nccl.Send(d_mine, 8, ncclFloat64, v.rank + 1, c->comm, c->stream));
+	NCCL_OK(g_nccl.Recv(d_next, 8, ncclFloat64, v.rank + 1, c->comm, c->stream));
+    }
+    NCCL_OK(g_nccl.GroupEnd());
+    CUDA_OK(cudaMemcpyAsync(&theirs[0], d_prev, 64, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(&theirs[1], d_next, 64, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (want) {
+	for (int k = 0; k < 2 && want; ++k) {
+	    const bool have = k == 0 ? v.rank > 0 : v.rank < v.nranks - 1;
+	    if (!have)
+		continue;
+	    cudaIpcMemHandle_t zero;
+	    memset(&zero, 0, sizeof(zero));
+	    if (memcmp(&theirs[k], &zero, sizeof(zero)) == 0 ||
+		cudaIpcOpenMemHandle(&h.peer_base[k], theirs[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+		cudaGetLastError();
+		h.peer_base[k] = nullptr;
+		want = false;
+	    }
+	}
+    }
+    // agreement: min over ranks of "my side is ready"
+    c->h_pin[0] = want ? 1.0 : 0.0;
+    CUDA_OK(cudaMemcpyAsync(c->d_dt, c->h_pin, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    NCCL_OK(g_nccl.AllReduce(c->d_dt, c->d_dt, 1, ncclFloat64, ncclMin, c->comm, c->stream));
+    CUDA_OK(cudaMemcpyAsync(c->h_pin + 1, c->d_dt, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    h.p2p = c->h_pin[1] == 1.0;
+    if (h.p2p) {
+	h.flags = (unsigned long long *)(h.inbox + ndbl);
+	CUDA_OK(cudaMalloc((void **)&h.done, sizeof(unsigned int)));
+	CUDA_OK(cudaMemset(h.done, 0, sizeof(unsigned int)));
+    }
+    return 0;
+}
+extern "C" int fargo_halo_mode(const fargo_ctx *c) { return c->v.nranks == 1 ? 0 : (c->halo.p2p ? 2 : 1); }
 
 extern "C" int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, const double *radii, int rank, int nranks,
 				 const void *nccl_unique_id, int device)
@@ -441,6 +536,17 @@ extern "C" int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, con
 	    return 1;
 	}
     }
+    { // Ring sums: the chain kernel (a thread per ring) has nr / 32 warps and is bound by the latency of one dependent
+      // DADD chain per ring until there are enough rings to fill the GPU's memory pipes; the scan kernel (a warp per ring)
+      // costs ~60x the instructions but spreads them.  Measured at Ns = 16384 (ms, chain / scan): 1038 rings 0.166 / 0.100,
+      // 2048 rings 0.166 / 0.142, 8192 rings 0.258 / 0.447.  FARGO_B200_RINGSUM=chain|scan overrides.
+	const char *env = getenv("FARGO_B200_RINGSUM");
+	c->ringsum_scan = c->v.nr <= 2560;
+	if (env && strcmp(env, "chain") == 0)
+	    c->ringsum_scan = false;
+	if (env && strcmp(env, "scan") == 0)
+	    c->ringsum_scan = true;
+    }
     TRY(init_geometry(c, radii));
     const size_t ns = (size_t)c->v.nr * c->v.ns, nv = (size_t)(c->v.nr + 1) * c->v.ns;
     TRY(dalloc(c, &c->sigma, ns) || dalloc(c, &c->eb[0], ns) || dalloc(c, &c->vrb[0], nv) || dalloc(c, &c->vpb[0], ns) ||
@@ -492,15 +598,19 @@ extern "C" int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, con
 					  std::min(occ((const void *)k_fused_artvisc<true>), occ((const void *)k_fused_viscosity<true>)))
 			       : std::min(occ((const void *)k_fused_sources<false>),
 					  std::min(occ((const void *)k_fused_artvisc<false>), occ((const void *)k_fused_viscosity<false>)));
-	const int occ_az = mc ? (adi ? occ((const void *)k_transport_azimuthal<FARGO_LIMITER_MC, true>)
-				     : occ((const void *)k_transport_azimuthal<FARGO_LIMITER_MC, false>))
-			      : (adi ? occ((const void *)k_transport_azimuthal<FARGO_LIMITER_VANLEER, true>)
-				     : occ((const void *)k_transport_azimuthal<FARGO_LIMITER_VANLEER, false>));
+	const int occ_az = mc ? (adi ? occ((const void *)k_transport_azimuthal<FARGO_LIMITER_MC, true, false>)
+				     : occ((const void *)k_transport_azimuthal<FARGO_LIMITER_MC, false, false>))
+			      : (adi ? occ((const void *)k_transport_azimuthal<FARGO_LIMITER_VANLEER, true, false>)
+				     : occ((const void *)k_transport_azimuthal<FARGO_LIMITER_VANLEER, false, false>));
 	const int occ_rad = mc ? (adi ? occ((const void *)k_transport_radial<FARGO_LIMITER_MC, true>)
 				      : occ((const void *)k_transport_radial<FARGO_LIMITER_MC, false>))
 			       : (adi ? occ((const void *)k_transport_radial<FARGO_LIMITER_VANLEER, true>)
 				      : occ((const void *)k_transport_radial<FARGO_LIMITER_VANLEER, false>));
 	c->az_R = rings_per_march(c->v.nr, (nwin_az + 3) / 4, occ_az * sms, 1);
+	{ // interior launch of the peer-memory halo path: the slab without its 2 x CPUOVERLAP edge rings per interior side
+	    const int nint = c->v.nr - 2 * FARGO_CPUOVERLAP * ((rank > 0 ? 1 : 0) + (rank < nranks - 1 ? 1 : 0));
+	    c->halo.az_R_int = nint > 0 ? rings_per_march(nint, (nwin_az + 3) / 4, occ_az * sms, 1) : 1;
+	}
 	c->fs_R = rings_per_march(c->v.nr, (nwin_fs + 3) / 4, occ_fs * sms, 1);
 	c->rad_chunk = rings_per_march(c->v.nr, (c->v.ns + 127) / 128, occ_rad * sms, 2);
 	// ring means: one warp per 32 rings; give each resident warp as much of the SM's shared memory as its share allows
@@ -541,6 +651,7 @@ extern "C" int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, con
 	    fargo_ctx_destroy(c);
 	    return 1;
 	}
+	TRY(halo_setup(c));
     }
 #undef TRY
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
@@ -564,8 +675,19 @@ extern "C" int fargo_sync(fargo_ctx *c)
 
 #define LAUNCH(c, kernel, grid, block, smem, ...) LAUNCH_ON(c, (c)->stream, kernel, grid, block, smem, __VA_ARGS__)
 #define LAUNCH_ON(c, strm, kernel, grid, block, smem, ...) LAUNCH_NAMED(c, strm, #kernel, kernel, grid, block, smem, __VA_ARGS__)
+static inline double host_now_ms()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
 #define LAUNCH_NAMED(c, strm, label, kernel, grid, block, smem, ...)     \
     do {                                                                 \
+	if ((c)->t_cfl_done != 0.0) {                                    \
+	    (c)->host_turnaround_ms += host_now_ms() - (c)->t_cfl_done;  \
+	    (c)->host_turnaround_n++;                                    \
+	    (c)->t_cfl_done = 0.0;                                       \
+	}                                                                \
 	if ((c)->profiling)                                              \
 	    prof_begin(c, label, strm);                                  \
 	kernel<<<grid, block, smem, strm>>>(__VA_ARGS__);                \
@@ -922,6 +1044,11 @@ static int launch_ring_mean(fargo_ctx *c, cudaStream_t strm, const double *vp, d
     const DevView &v = c->v;
     const unsigned nb = (unsigned)((v.nr + 31) / 32);
     const char *label = mode == 1 ? "k_ring_mean[transport,side-stream]" : "k_ring_mean[cfl]";
+    if (c->ringsum_scan) { // a warp per ring, scans instead of the dependent chain (kernels_ringsum.cuh)
+	LAUNCH_NAMED(c, strm, label, k_ring_sum_scan, (unsigned)((v.nr + 3) / 4), 128, 0, v, vp, c->vmean, c->nshift, c->vconst, dt, mode,
+		     v.nr, v.ns);
+	return 0;
+    }
     if (c->rm_chunk > 0)
 	LAUNCH_NAMED(c, strm, label, k_ring_mean, nb, 32, c->rm_smem, v, vp, c->vmean, c->nshift, c->vconst, dt, mode, c->rm_chunk);
     else
@@ -951,17 +1078,62 @@ static int launch_transport(fargo_ctx *c, double dt, const double *vr_in, const 
 	    LAUNCH(c, (k_transport_radial<LIM, false>), grid, 128, 0, v, c->sigma, vr_in, vp_in, EN(c), c->t_sigma, c->t_rmp, c->t_rmm,
 		   c->t_amp, c->t_amm, c->t_e, dt, c->rad_chunk);
     }
+    const int nwin = (v.ns + AZ_OUT - 1) / AZ_OUT;
+    const unsigned gx = (unsigned)((nwin + 3) / 4);
+    fargo_ctx::Halo &h = c->halo;
+    AzSegs segs;
+    memset(&segs, 0, sizeof(segs));
+#define AZ_LAUNCH(strm, label, PUSH, gy, R)                                                                                     \
+    do {                                                                                                                    \
+	dim3 grid(gx, (unsigned)(gy));                                                                                      \
+	if (v.p.adiabatic)                                                                                                  \
+	    LAUNCH_NAMED(c, strm, label, (k_transport_azimuthal<LIM, true, PUSH>), grid, 128, 0, v, c->t_sigma, c->t_rmp, c->t_rmm, \
+			 c->t_amp, c->t_amm, c->t_e, vp_in, vr_in, c->vmean, c->nshift, c->vconst, c->sigma, vr_out, vp_out, EN(c), \
+			 dt, R, segs);                                                                                      \
+	else                                                                                                                \
+	    LAUNCH_NAMED(c, strm, label, (k_transport_azimuthal<LIM, false, PUSH>), grid, 128, 0, v, c->t_sigma, c->t_rmp, c->t_rmm, \
+			 c->t_amp, c->t_amm, c->t_e, vp_in, vr_in, c->vmean, c->nshift, c->vconst, c->sigma, vr_out, vp_out, EN(c), \
+			 dt, R, segs);                                                                                      \
+    } while (0)
     CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
-    {
-	const int nwin = (v.ns + AZ_OUT - 1) / AZ_OUT;
-	dim3 grid((unsigned)((nwin + 3) / 4), (unsigned)((v.nr + c->az_R - 1) / c->az_R));
-	if (v.p.adiabatic)
-	    LAUNCH(c, (k_transport_azimuthal<LIM, true>), grid, 128, 0, v, c->t_sigma, c->t_rmp, c->t_rmm, c->t_amp, c->t_amm, c->t_e,
-		   vp_in, vr_in, c->vmean, c->nshift, c->vconst, c->sigma, vr_out, vp_out, EN(c), dt, c->az_R);
-	else
-	    LAUNCH(c, (k_transport_azimuthal<LIM, false>), grid, 128, 0, v, c->t_sigma, c->t_rmp, c->t_rmm, c->t_amp, c->t_amm, c->t_e,
-		   vp_in, vr_in, c->vmean, c->nshift, c->vconst, c->sigma, vr_out, vp_out, EN(c), dt, c->az_R);
+    if (!h.p2p) {
+	segs.hi[2] = v.nr;
+	AZ_LAUNCH(c->stream, "k_transport_azimuthal", false, (v.nr + c->az_R - 1) / c->az_R, c->az_R);
+	return 0;
     }
+    // Peer-memory halo path: the 2 x CPUOVERLAP rings at either interior edge of the slab are the first marches of the
+    // launch; their epilogue stores the rings the neighbours need straight into their inboxes (NVLink peer stores) and
+    // the last edge warp bumps the neighbours' arrival counters.  The interior marches follow in the same launch, so the
+    // exchange costs no time of its own (fargo_stage_halo only waits for the counters and unpacks).
+    {
+	const int E = 2 * FARGO_CPUOVERLAP;
+	const bool has_prev = v.rank > 0, has_next = v.rank < v.nranks - 1;
+	const unsigned long long parity = h.seq & 1ull;
+	const size_t ndbl = 2 * 2 * 4 * h.field_len;
+	if (has_prev) { // rings [7, 14) -> prev's inbox, side "from next"
+	    segs.edge_seg[segs.n_edge++] = 0;
+	    segs.lo[0] = 0, segs.hi[0] = E, segs.push_lo[0] = FARGO_CPUOVERLAP;
+	    for (int f = 0; f < 4; ++f)
+		segs.push[0][f] = (double *)h.peer_base[0] + ((parity * 2 + 1) * 4 + f) * h.field_len;
+	    segs.peer_flag[0] = (unsigned long long *)((double *)h.peer_base[0] + ndbl) + 1;
+	}
+	if (has_next) { // rings [nr-14, nr-7) -> next's inbox, side "from prev"
+	    segs.edge_seg[segs.n_edge++] = 1;
+	    segs.lo[1] = v.nr - E, segs.hi[1] = v.nr, segs.push_lo[1] = v.nr - E;
+	    for (int f = 0; f < 4; ++f)
+		segs.push[1][f] = (double *)h.peer_base[1] + ((parity * 2 + 0) * 4 + f) * h.field_len;
+	    segs.peer_flag[1] = (unsigned long long *)((double *)h.peer_base[1] + ndbl) + 0;
+	}
+	segs.lo[2] = has_prev ? E : 0;
+	segs.hi[2] = has_next ? v.nr - E : v.nr;
+	segs.seq = h.seq + 1;
+	segs.done = h.done;
+	segs.expected = (unsigned)(nwin * segs.n_edge);
+	AZ_LAUNCH(c->stream, "k_transport_azimuthal[+halo push]", true,
+		  segs.n_edge + (segs.hi[2] - segs.lo[2] + h.az_R_int - 1) / h.az_R_int, h.az_R_int);
+	h.pushed = true;
+    }
+#undef AZ_LAUNCH
     return 0;
 }
 
@@ -989,6 +1161,33 @@ extern "C" int fargo_stage_halo(fargo_ctx *c)
 	return fail("stage_halo called mid-step");
     const size_t l = (size_t)FARGO_CPUOVERLAP * c->v.ns;
     const size_t oo = (size_t)(c->v.nr - FARGO_CPUOVERLAP) * c->v.ns;
+    if (c->halo.pushed) { // peer path: the transport kernel has already stored our edge rings into the neighbours' inboxes
+	fargo_ctx::Halo &h = c->halo;
+	const bool has_prev = c->v.rank > 0, has_next = c->v.rank < c->v.nranks - 1;
+	const unsigned long long parity = h.seq & 1ull;
+	HaloUnpack u;
+	memset(&u, 0, sizeof(u));
+	double *fld[4] = {c->sigma, VRA(c), VPA(c), EN(c)};
+	const int nfld = c->v.p.adiabatic ? 4 : 3;
+	for (int side = 0; side < 2; ++side) {
+	    if (side == 0 ? !has_prev : !has_next)
+		continue;
+	    for (int f = 0; f < nfld; ++f) {
+		u.src[u.n] = h.inbox + ((parity * 2 + side) * 4 + f) * h.field_len;
+		u.dst[u.n] = fld[f] + (side == 0 ? 0 : oo);
+		++u.n;
+	    }
+	}
+	u.len = l;
+	u.flag[0] = has_prev ? h.flags + 0 : nullptr;
+	u.flag[1] = has_next ? h.flags + 1 : nullptr;
+	u.want = h.seq + 1;
+	dim3 grid((unsigned)((l + 4 * 256 - 1) / (4 * 256)), (unsigned)u.n);
+	LAUNCH(c, k_halo_unpack, grid, 256, 0, u);
+	h.seq++;
+	h.pushed = false;
+	return 0;
+    }
     const size_t o = (size_t)(c->v.nr - 2 * FARGO_CPUOVERLAP) * c->v.ns;
     double *fields[4] = {c->sigma, VRA(c), VPA(c), EN(c)};
     const int nf = c->v.p.adiabatic ? 4 : 3;
@@ -1054,6 +1253,8 @@ extern "C" int fargo_condition_cfl(fargo_ctx *c, double *out)
     CUDA_OK(cudaMemcpyAsync(c->h_pin + 1, c->d_dt, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     *out = c->h_pin[1];
+    if (c->profiling)
+	c->t_cfl_done = host_now_ms();
     return 0;
 }
 
@@ -1192,11 +1393,14 @@ extern "C" int fargo_profile_enable(fargo_ctx *c, int on)
     CUDA_OK(cudaSetDevice(c->device));
     prof_collect(c);
     c->profiling = on != 0;
-    if (on)
+    if (on) {
 	for (auto &k : c->kstats) {
 	    k.ms = 0;
 	    k.n = 0;
 	}
+	c->host_turnaround_ms = 0.0;
+	c->host_turnaround_n = 0;
+    }
     return 0;
 }
 // writes "name ms count\n" lines into buf; returns the number of bytes needed
@@ -1208,6 +1412,10 @@ extern "C" int fargo_profile_report(fargo_ctx *c, char *buf, int buflen)
     char line[256];
     for (auto &k : c->kstats) {
 	snprintf(line, sizeof(line), "%s %.6f %lld\n", k.name.c_str(), k.ms, k.n);
+	out += line;
+    }
+    if (c->host_turnaround_n > 0) {
+	snprintf(line, sizeof(line), "host:cfl-result->first-launch %.6f %lld\n", c->host_turnaround_ms, c->host_turnaround_n);
 	out += line;
     }
     if (buf && buflen > 0) {
@@ -1259,6 +1467,30 @@ extern "C" int fargo_selftest_math(fargo_ctx *c, unsigned long long seed, int bl
 }
 
 // exp_ref on caller-provided arguments, for the host-side comparison with libm's exp
+// the scan ring sums (kernels_ringsum.cuh) and the one-thread-per-ring chain on caller-provided rows: sums_scan[r] and
+// sums_chain[r] must both equal the sequential sum  s = 0; for j: s += x[r][j]  bit for bit
+extern "C" int fargo_selftest_ringsum(fargo_ctx *c, int nrows, int ns, const double *x_host, double *sums_scan, double *sums_chain)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    if (nrows < 1 || ns < 1)
+	return fail("selftest_ringsum: empty input");
+    double *d_x = nullptr, *d_s = nullptr;
+    CUDA_OK(cudaMalloc((void **)&d_x, (size_t)nrows * ns * sizeof(double)));
+    CUDA_OK(cudaMalloc((void **)&d_s, (size_t)2 * nrows * sizeof(double)));
+    CUDA_OK(cudaMemcpyAsync(d_x, x_host, (size_t)nrows * ns * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    DevView v = c->v;
+    v.nr = nrows;
+    v.ns = ns;
+    LAUNCH(c, k_ring_sum_scan, (unsigned)((nrows + 3) / 4), 128, 0, v, d_x, d_s, nullptr, nullptr, 0.0, 2, nrows, ns);
+    LAUNCH(c, k_ring_sum_chain, (unsigned)((nrows + 127) / 128), 128, 0, d_x, d_s + nrows, nrows, ns);
+    CUDA_OK(cudaMemcpyAsync(sums_scan, d_s, (size_t)nrows * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(sums_chain, d_s + nrows, (size_t)nrows * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_x);
+    cudaFree(d_s);
+    return 0;
+}
+
 extern "C" int fargo_selftest_exp(fargo_ctx *c, int n, const double *x_host, double *y_host)
 {
     CUDA_OK(cudaSetDevice(c->device));

@@ -261,24 +261,49 @@ __device__ __forceinline__ void az_ring(const DevView &c, const TempClampNB &tc,
     }
 }
 
-template <int LIM, bool ADI>
+// Which rings a launch covers.  Segment 2 is the bulk of the slab, in marches of R rings.  Segments 0 and 1 exist on the
+// peer-memory halo path (PUSH): the 2 x CPUOVERLAP rings at the slab's inner / outer edge, one march each, scheduled
+// FIRST (lowest blockIdx.y).  Their epilogue stores the finished rings the neighbour needs not only into this GPU's
+// fields but also straight into the neighbouring GPU's halo inbox (peer memory mapped over NVLink), and the last edge
+// warp to finish publishes the step number in the neighbours' arrival counters — so the ghost-ring exchange
+// (CommunicateBoundaries, commbound.cpp:98-182) is part of this kernel and is over long before the interior marches are.
+struct AzSegs {
+    int lo[3], hi[3];
+    int n_edge;	     // edge marches in this launch (0, 1 or 2)
+    int edge_seg[2]; // which segment blockIdx.y = 0, 1 runs
+    int push_lo[2];  // rings [push_lo[s], push_lo[s] + CPUOVERLAP) of segment s are mirrored to push[s][field]
+    double *push[2][4]; // Sigma, v_rad, v_azi, e
+    unsigned long long *peer_flag[2]; // the neighbour's arrival counter for rings coming from this rank
+    unsigned long long seq;	      // value to publish
+    unsigned int *done;		      // edge warps finished (local device memory, returns to 0)
+    unsigned int expected;	      // edge warps in this launch
+};
+
+template <int LIM, bool ADI, bool PUSH>
 __global__ void __launch_bounds__(128, AZ_MINB)
     k_transport_azimuthal(const DevView c, const double *__restrict__ t_sigma, const double *__restrict__ t_rmp,
 			  const double *__restrict__ t_rmm, const double *__restrict__ t_amp,
 			  const double *__restrict__ t_amm, const double *__restrict__ t_e, const double *__restrict__ vp_old,
 			  const double *__restrict__ vr_old, const double *__restrict__ vmean, const int *__restrict__ nshift,
 			  const double *__restrict__ vconst, double *__restrict__ o_sigma, double *__restrict__ o_vr,
-			  double *__restrict__ o_vp, double *__restrict__ o_e, const double dt, const int R)
+			  double *__restrict__ o_vp, double *__restrict__ o_e, const double dt, const int R, const AzSegs segs)
 {
     const int ns = c.ns, nr = c.nr;
     const int lane = threadIdx.x & 31;
     const int win = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if ((long long)win * AZ_OUT >= ns)
 	return; // whole warp; warps never synchronise with each other
-    const int i_first = blockIdx.y * R;
-    if (i_first >= nr)
-	return;
-    const int i_last = min(i_first + R, nr);
+    int seg = 2, i_first, i_last;
+    if (PUSH && (int)blockIdx.y < segs.n_edge) {
+	seg = segs.edge_seg[blockIdx.y];
+	i_first = segs.lo[seg];
+	i_last = segs.hi[seg];
+    } else {
+	i_first = segs.lo[2] + ((int)blockIdx.y - (PUSH ? segs.n_edge : 0)) * R;
+	if (i_first >= segs.hi[2])
+	    return;
+	i_last = min(i_first + R, segs.hi[2]);
+    }
     const int t0 = AZ_NC * lane;		    // local column of c = 0
     const int jout = win * AZ_OUT - AZ_HL + t0;	    // output column of c = 0 (negative / >= ns in the halo)
     const bool lane_out = (t0 >= AZ_HL) && (t0 < AZ_WIN - AZ_HR);
@@ -315,6 +340,22 @@ __global__ void __launch_bounds__(128, AZ_MINB)
 	    AzIn IN;
 	    az_fetch<ADI>(IN, ns, jout, nsh, row, t_rmp, t_rmm, t_amp, t_amm, t_e, t_sigma, vp_old);
 	    az_ring<LIM, ADI, false>(c, tc, IN, g, dt, vm, vc, fargo, i, lane_out, PS, PR, Q, vrn, vpn, sf, en, A);
+	}
+	if (PUSH && seg < 2 && i >= i_first && lane_out) { // edge ring of the slab: mirror it into the neighbour's halo inbox
+	    const int pr = i - segs.push_lo[seg];
+	    if (pr >= 0 && pr < FARGO_CPUOVERLAP) {
+#pragma unroll
+		for (int k = 0; k < AZ_NC; ++k) {
+		    if (jout + k < ns) {
+			const size_t a = (size_t)pr * ns + (size_t)(jout + k);
+			segs.push[seg][0][a] = sf[k];
+			segs.push[seg][1][a] = vrn[k];
+			segs.push[seg][2][a] = vpn[k];
+			if (ADI)
+			    segs.push[seg][3][a] = en[k];
+		    }
+		}
+	    }
 	}
 	if (i >= i_first && lane_out) {
 	    if (vec_ok) {
@@ -355,5 +396,23 @@ __global__ void __launch_bounds__(128, AZ_MINB)
 	for (int k = 0; k < AZ_NC; ++k)
 	    if (jout + k < ns)
 		o_vr[(size_t)nr * ns + jout + k] = vr_old[(size_t)nr * ns + jout + k];
+    }
+    if (PUSH && seg < 2) {
+	// every lane orders its peer stores before what follows, system-wide; the warp's lane 0 then counts the warp in, and
+	// the last edge warp of the launch publishes the step in the neighbours' arrival counters (k_halo_unpack spins on them)
+	__threadfence_system();
+	__syncwarp();
+	if (lane == 0) {
+	    const unsigned int before = atomicAdd(segs.done, 1u);
+	    if (before == segs.expected - 1u) {
+		*segs.done = 0u; // next launch starts from 0 (every other edge warp has already counted itself in)
+		__threadfence_system();
+		if (segs.peer_flag[0])
+		    *(volatile unsigned long long *)segs.peer_flag[0] = segs.seq;
+		if (segs.peer_flag[1])
+		    *(volatile unsigned long long *)segs.peer_flag[1] = segs.seq;
+		__threadfence_system();
+	    }
+	}
     }
 }

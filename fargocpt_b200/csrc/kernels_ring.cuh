@@ -588,3 +588,35 @@ __global__ void __launch_bounds__(256) k_derived_field(const DevView c, const do
     }
     AT(out, i, j) = v;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Ghost-ring exchange over peer memory (CommunicateBoundaries, commbound.cpp:98-182), receiving side.  The transport
+// kernel's edge marches store the rings a neighbour needs into that neighbour's inbox and publish the step number in
+// its arrival counters (kernels_azimuthal.cuh: AzSegs).  k_halo_unpack holds the receiver's stream until both counters
+// have reached the step, then moves the inbox into the ghost rings.
+struct HaloUnpack {
+    const double *src[8];
+    double *dst[8];
+    int n;
+    size_t len;
+    const unsigned long long *flag[2];
+    unsigned long long want;
+};
+__global__ void __launch_bounds__(256) k_halo_unpack(const HaloUnpack u)
+{
+    if (threadIdx.x == 0) {
+	for (int k = 0; k < 2; ++k)
+	    if (u.flag[k])
+		while (*(const volatile unsigned long long *)u.flag[k] < u.want)
+		    __nanosleep(200);
+	__threadfence_system();
+    }
+    __syncthreads();
+    const double *__restrict__ s = u.src[blockIdx.y];
+    double *__restrict__ d = u.dst[blockIdx.y];
+    const size_t i0 = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+	if (i0 + k < u.len)
+	    d[i0 + k] = __ldcv(s + i0 + k); // written by another GPU: never through a stale cache line
+}

@@ -213,6 +213,10 @@ int fargo_stage_substep3(fargo_ctx *ctx, double dt);   /* SubStep3 SourceEuler.c
 int fargo_stage_boundary(fargo_ctx *ctx, double dt, int final_call); /* apply_boundary_condition boundary_conditions.cpp:65 */
 int fargo_stage_transport(fargo_ctx *ctx, double dt);  /* Transport TransportEuler.cpp:112 */
 int fargo_stage_halo(fargo_ctx *ctx);                  /* CommunicateBoundaries commbound.cpp:98 */
+/* how the ghost rings travel: 0 = single rank, 1 = ncclSend / ncclRecv after Transport, 2 = stored into the neighbour's
+ * inbox over NVLink peer memory by the transport kernel's edge launch while the interior rings are still being
+ * transported (default when CUDA IPC maps on every rank; FARGO_B200_HALO=nccl in the environment forces 1) */
+int fargo_halo_mode(const fargo_ctx *ctx);
 int fargo_stage_derived(fargo_ctx *ctx);               /* recalculate_derived_disk_quantities SourceEuler.cpp:225 */
 
 /* fargo_step normally runs the fused source-term kernels; on != 0 makes it go through the per-stage kernels above
@@ -233,6 +237,11 @@ int fargo_get_nshift(fargo_ctx *ctx, int *out_local_nrad);
  * divisions that took the fast path}; 256 * blocks * per_thread operand pairs; wide != 0 spans the full exponent range */
 int fargo_selftest_math(fargo_ctx *ctx, unsigned long long seed, int blocks, int per_thread, int wide,
 			unsigned long long *counts4);
+
+/* the ring sums behind the CFL dt and the FARGO shifts (cfl.cpp:199-204, TransportEuler.cpp:215-219: a strictly sequential
+ * sum per ring) on nrows caller-provided rows of ns doubles: by the scan kernel (csrc/kernels_ringsum.cuh) and by a plain
+ * one-thread-per-row chain; the caller compares both with its own sequential sum, bit for bit */
+int fargo_selftest_ringsum(fargo_ctx *ctx, int nrows, int ns, const double *x_host, double *sums_scan, double *sums_chain);
 
 /* the device exp of the energy equation (csrc/fargo_math.h: glibc's algorithm, operation by operation) on n host-provided
  * arguments; the caller compares with its libm */

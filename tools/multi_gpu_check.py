@@ -75,6 +75,7 @@ def main():
     fields["vrad"] = fields["vrad"] + 1e-3 * np.sin(np.arange(args.naz) * 2 * np.pi * 3 / args.naz)[None, :]
 
     ctx = HydroContext(params, radii, rank=rank, nranks=world, unique_id=uid, device=local)
+    halo_mode = ctx.halo_mode()
     dts, out = run_slab(ctx, cfg, radii, fields, args.steps, synthetic, abi)
     ctx.close()
     stitched = {}
@@ -88,7 +89,8 @@ def main():
         dts1, out1 = run_slab(one, cfg, radii, fields, args.steps, synthetic, abi)
         import reftools
         res = {"n_gpus": world, "physics": args.physics, "grid": [args.nrad, args.naz], "steps": args.steps,
-               "dt_bit_equal": dts == dts1, "fields": {}}
+               "dt_bit_equal": dts == dts1, "fields": {},
+               "halo_mode": {1: "nccl send/recv", 2: "peer-memory stores from the transport kernel"}.get(halo_mode, halo_mode)}
         adiabatic = bool(params.adiabatic)
         for name in stitched:
             if name == "energy" and not adiabatic:
