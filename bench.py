@@ -33,7 +33,7 @@ UNIT = "cell-updates/s"
 B_ALG = {"adiabatic_planet": 400.0, "cold_disk_planet": 312.0, "isothermal_planet": 280.0}
 # algorithmic bytes per cell of each kernel (reads + writes of live state arrays only; DESIGN.md "Kernels")
 KERNEL_BYTES = {
-    "(k_transport_azimuthal<LIM, true>)": 88.0, "(k_transport_azimuthal<LIM, false>)": 72.0,
+    "k_transport_azimuthal<ADI>": 88.0, "k_transport_azimuthal<ISO>": 72.0,
     "(k_transport_radial<LIM, true>)": 80.0, "(k_transport_radial<LIM, false>)": 64.0,
     "k_fused_sources<ADI>": 56.0, "k_fused_artvisc<ADI>": 56.0, "k_fused_viscosity<ADI>": 88.0,  # 72 + Sigma0, e0 (beta cooling)
     "k_potential": 24.0, "k_sources_velocity": 56.0, "k_compression_heating": 32.0, "k_artvisc_q": 56.0,
@@ -43,7 +43,7 @@ KERNEL_BYTES = {
 # measured DRAM traffic per cell of the same kernels: dram__bytes_read.sum + dram__bytes_write.sum of one
 # `ncu --set full` capture (profiles/r01_v4_ncu_full_4096x8192.md, 4096 x 8192 adiabatic_planet) / 33.55e6 cells
 NCU_TRAFFIC_B_PER_CELL = {
-    "(k_transport_azimuthal<LIM, true>)": 88.3, "(k_transport_radial<LIM, true>)": 81.2, "k_fused_sources<ADI>": 57.5,
+    "k_transport_azimuthal<ADI>": 88.3, "(k_transport_radial<LIM, true>)": 81.2, "k_fused_sources<ADI>": 57.5,
     "k_fused_artvisc<ADI>": 56.5, "k_fused_viscosity<ADI>": 90.3, "k_cfl": 48.2,
 }
 
@@ -334,6 +334,7 @@ def run_gpu(args):
     roof = None
     if top[0]:
         kname, (kms, kn) = top
+        kname = kname.replace("[+halo push]", "")  # the multi-GPU launch of the same kernel (edge rings mirrored to the neighbours)
         bytes_per_cell = KERNEL_BYTES.get(kname, 0.0)
         per_launch_bytes = bytes_per_cell * slab_cells
         avg_s = kms / max(kn, 1) * 1e-3

@@ -132,7 +132,7 @@ struct fargo_ctx {
     double *h_pin; // pinned host staging for the CFL scalar + ring factors
     bool visc_const_filled = false;
     cudaEvent_t ev_pin = nullptr; // completion of the last H2D copy out of h_pin
-    int az_R, rad_chunk, fs_R, n_sm;
+    int az_slots, rad_chunk, fs_R, n_sm;
     bool ringsum_scan = false;  // ring sums by k_ring_sum_scan (a warp per ring) instead of the one-thread-per-ring chain
     int rm_chunk = 0;	       // columns per TMA chunk of k_ring_mean (0: generic kernel)
     size_t rm_smem = 0;
@@ -149,7 +149,6 @@ struct fargo_ctx {
 	unsigned long long seq = 0;	   // halo exchanges started
 	bool pushed = false;		   // this step's edge rings are on their way (launch_transport), not yet received
 	unsigned int *done = nullptr;	   // edge warps of the running transport launch that have finished (device)
-	int az_R_int = 0;		   // rings per march of the interior segment
     } halo;
     bool force_staged = false;
     cudaEvent_t ev_user[4] = {nullptr, nullptr, nullptr, nullptr}; // fargo_event_record slots
@@ -240,7 +239,11 @@ static int rings_per_march(int nr, int ctas_x, int slots, int warm)
 	if (R > 4 && (nr + R - 2) / (R - 1) == y)
 	    continue; // same number of bands as R-1: the smaller R is the balanced choice
 	const double ctas = (double)ctas_x * y;
-	const double cost = (ctas <= slots) ? (double)(R + warm) : (R + warm) * (ctas / slots + 0.5);
+	const double waves = ctas / slots;
+	// A few waves of equal CTAs finish in whole waves, and SMs do not all run at the same speed, which whole waves cannot
+	// absorb (measured on the azimuthal kernel: 1 CTA per slot 5-10 % slower than 8 per slot, 4 waves 2 % slower than 26);
+	// with many waves the block scheduler evens the SMs out to about half a CTA of tail.
+	const double cost = (R + warm) * (waves <= 4.0 ? ceil(waves) * (1.0 + 0.10 / sqrt(ceil(waves))) : waves + 0.5);
 	if (cost < best * 0.999) {
 	    best = cost;
 	    best_R = R;
@@ -252,7 +255,13 @@ static int rings_per_march(int nr, int ctas_x, int slots, int warm)
 static inline unsigned cells_grid(long long n, int block = 256) { return (unsigned)((n + block - 1) / block); }
 
 // split.cpp:38-87
-static int split_domain(DevView &v, int nrad, int rank, int np, int *imax_out)
+// SplitDomain (split.cpp:38-87): contiguous rings per rank plus CPUOVERLAP ghost rings per interior side, and the loop
+// bounds of a slab.  The reference gives every rank the same number of rings; here the cut points balance COST: a ring
+// inside a damping zone is also read and written by k_damping (~2.5 % of a ring's step per damped field, measured on
+// B200), and the damping zones sit on the first and last ranks — at 8 GPUs their step was 6 % longer than everyone
+// else's.  Results do not depend on where the cuts are (constants.h:17; tests/test_gpu_multi.py holds N ranks to 1 rank
+// bit for bit).  FARGO_B200_SPLIT=equal restores the reference's cut points.
+static int split_domain(DevView &v, int nrad, int rank, int np, int *imax_out, const double *radii, const fargo_params &p)
 {
     const int size_low = nrad / np, size_high = size_low + 1, rem = nrad % np;
     if (np > 1 && size_low < 2 * FARGO_CPUOVERLAP)
@@ -264,6 +273,37 @@ static int split_domain(DevView &v, int nrad, int rank, int np, int *imax_out)
     } else {
 	imin = size_high * rem + (rank - rem) * size_low;
 	imax = imin + size_low - 1;
+    }
+    const char *env = getenv("FARGO_B200_SPLIT");
+    if (np > 1 && p.damping && radii && !(env && strcmp(env, "equal") == 0)) {
+	int nf = 0;
+	for (int k = 0; k < 2; ++k)
+	    nf += (p.damp_vrad[k] != FARGO_DAMP_NONE) + (p.damp_vazi[k] != FARGO_DAMP_NONE) + (p.damp_sigma[k] != FARGO_DAMP_NONE) +
+		  (p.adiabatic && p.damp_energy[k] != FARGO_DAMP_NONE);
+	const double wd = 0.025 * 0.5 * nf; // both sides configured: nf counts every damped field twice
+	std::vector<double> cum(nrad + 1, 0.0);
+	for (int i = 0; i < nrad; ++i) {
+	    const double r = 0.5 * (radii[i] + radii[i + 1]);
+	    const bool damped = (p.damping_inner_limit > 1.0 && r < p.rmin * p.damping_inner_limit) ||
+				(p.damping_outer_limit < 1.0 && r > p.rmax * p.damping_outer_limit);
+	    cum[i + 1] = cum[i] + 1.0 + (damped ? wd : 0.0);
+	}
+	std::vector<int> cut(np + 1, 0);
+	cut[np] = nrad;
+	bool ok = true;
+	for (int r = 1; r < np; ++r) {
+	    const double target = cum[nrad] * r / np;
+	    int i = cut[r - 1];
+	    while (i < nrad && cum[i] < target)
+		++i;
+	    cut[r] = i;
+	}
+	for (int r = 0; r < np; ++r)
+	    ok = ok && (cut[r + 1] - cut[r] >= 2 * FARGO_CPUOVERLAP);
+	if (ok) {
+	    imin = cut[rank];
+	    imax = cut[rank + 1] - 1;
+	}
     }
     if (rank > 0)
 	imin -= FARGO_CPUOVERLAP;
@@ -505,7 +545,7 @@ extern "C" int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, con
     c->v.rank = rank;
     c->v.nranks = nranks;
     int imax;
-    if (split_domain(c->v, params->nrad, rank, nranks, &imax)) {
+    if (split_domain(c->v, params->nrad, rank, nranks, &imax, radii, *params)) {
 	delete c;
 	return 1;
     }
@@ -606,11 +646,7 @@ extern "C" int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, con
 				      : occ((const void *)k_transport_radial<FARGO_LIMITER_MC, false>))
 			       : (adi ? occ((const void *)k_transport_radial<FARGO_LIMITER_VANLEER, true>)
 				      : occ((const void *)k_transport_radial<FARGO_LIMITER_VANLEER, false>));
-	c->az_R = rings_per_march(c->v.nr, (nwin_az + 3) / 4, occ_az * sms, 1);
-	{ // interior launch of the peer-memory halo path: the slab without its 2 x CPUOVERLAP edge rings per interior side
-	    const int nint = c->v.nr - 2 * FARGO_CPUOVERLAP * ((rank > 0 ? 1 : 0) + (rank < nranks - 1 ? 1 : 0));
-	    c->halo.az_R_int = nint > 0 ? rings_per_march(nint, (nwin_az + 3) / 4, occ_az * sms, 1) : 1;
-	}
+	c->az_slots = occ_az * sms; // resident CTAs of the azimuthal kernel (launch_transport sizes its ring bands with it)
 	c->fs_R = rings_per_march(c->v.nr, (nwin_fs + 3) / 4, occ_fs * sms, 1);
 	c->rad_chunk = rings_per_march(c->v.nr, (c->v.ns + 127) / 128, occ_rad * sms, 2);
 	// ring means: one warp per 32 rings; give each resident warp as much of the SM's shared memory as its share allows
@@ -1079,31 +1115,40 @@ static int launch_transport(fargo_ctx *c, double dt, const double *vr_in, const 
 		   c->t_amp, c->t_amm, c->t_e, dt, c->rad_chunk);
     }
     const int nwin = (v.ns + AZ_OUT - 1) / AZ_OUT;
-    const unsigned gx = (unsigned)((nwin + 3) / 4);
+    const int gx = (nwin + 3) / 4;
     fargo_ctx::Halo &h = c->halo;
     AzSegs segs;
     memset(&segs, 0, sizeof(segs));
-#define AZ_LAUNCH(strm, label, PUSH, gy, R)                                                                                     \
+    segs.nwin = nwin;
+    // segment 2 in bands of rings sized so that its (groups x bands) CTAs fill the GPU in whole waves
+    int nbands = 0;
+    auto cut_bands = [&](void) {
+	const int nb = segs.hi[2] - segs.lo[2];
+	segs.band = nb > 0 ? rings_per_march(nb, gx, c->az_slots, 1) : 1;
+	nbands = nb > 0 ? (nb + segs.band - 1) / segs.band : 0;
+    };
+#define AZ_LAUNCH(strm, label, PUSH)                                                                                        \
     do {                                                                                                                    \
-	dim3 grid(gx, (unsigned)(gy));                                                                                      \
+	const unsigned nblk = (unsigned)((segs.n_edge + nbands) * gx);                                        \
 	if (v.p.adiabatic)                                                                                                  \
-	    LAUNCH_NAMED(c, strm, label, (k_transport_azimuthal<LIM, true, PUSH>), grid, 128, 0, v, c->t_sigma, c->t_rmp, c->t_rmm, \
+	    LAUNCH_NAMED(c, strm, label "<ADI>", (k_transport_azimuthal<LIM, true, PUSH>), nblk, 128, 0, v, c->t_sigma, c->t_rmp, c->t_rmm, \
 			 c->t_amp, c->t_amm, c->t_e, vp_in, vr_in, c->vmean, c->nshift, c->vconst, c->sigma, vr_out, vp_out, EN(c), \
-			 dt, R, segs);                                                                                      \
+			 dt, segs);                                                                                         \
 	else                                                                                                                \
-	    LAUNCH_NAMED(c, strm, label, (k_transport_azimuthal<LIM, false, PUSH>), grid, 128, 0, v, c->t_sigma, c->t_rmp, c->t_rmm, \
+	    LAUNCH_NAMED(c, strm, label "<ISO>", (k_transport_azimuthal<LIM, false, PUSH>), nblk, 128, 0, v, c->t_sigma, c->t_rmp, c->t_rmm, \
 			 c->t_amp, c->t_amm, c->t_e, vp_in, vr_in, c->vmean, c->nshift, c->vconst, c->sigma, vr_out, vp_out, EN(c), \
-			 dt, R, segs);                                                                                      \
+			 dt, segs);                                                                                         \
     } while (0)
     CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     if (!h.p2p) {
 	segs.hi[2] = v.nr;
-	AZ_LAUNCH(c->stream, "k_transport_azimuthal", false, (v.nr + c->az_R - 1) / c->az_R, c->az_R);
+	cut_bands();
+	AZ_LAUNCH(c->stream, "k_transport_azimuthal", false);
 	return 0;
     }
-    // Peer-memory halo path: the 2 x CPUOVERLAP rings at either interior edge of the slab are the first marches of the
+    // Peer-memory halo path: the 2 x CPUOVERLAP rings at either interior edge of the slab are the first CTAs of the
     // launch; their epilogue stores the rings the neighbours need straight into their inboxes (NVLink peer stores) and
-    // the last edge warp bumps the neighbours' arrival counters.  The interior marches follow in the same launch, so the
+    // the last edge warp bumps the neighbours' arrival counters.  The interior pieces follow in the same launch, so the
     // exchange costs no time of its own (fargo_stage_halo only waits for the counters and unpacks).
     {
 	const int E = 2 * FARGO_CPUOVERLAP;
@@ -1126,11 +1171,11 @@ static int launch_transport(fargo_ctx *c, double dt, const double *vr_in, const 
 	}
 	segs.lo[2] = has_prev ? E : 0;
 	segs.hi[2] = has_next ? v.nr - E : v.nr;
+	cut_bands();
 	segs.seq = h.seq + 1;
 	segs.done = h.done;
 	segs.expected = (unsigned)(nwin * segs.n_edge);
-	AZ_LAUNCH(c->stream, "k_transport_azimuthal[+halo push]", true,
-		  segs.n_edge + (segs.hi[2] - segs.lo[2] + h.az_R_int - 1) / h.az_R_int, h.az_R_int);
+	AZ_LAUNCH(c->stream, "k_transport_azimuthal[+halo push]", true);
 	h.pushed = true;
     }
 #undef AZ_LAUNCH

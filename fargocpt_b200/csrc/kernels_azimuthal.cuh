@@ -261,16 +261,25 @@ __device__ __forceinline__ void az_ring(const DevView &c, const TempClampNB &tc,
     }
 }
 
-// Which rings a launch covers.  Segment 2 is the bulk of the slab, in marches of R rings.  Segments 0 and 1 exist on the
-// peer-memory halo path (PUSH): the 2 x CPUOVERLAP rings at the slab's inner / outer edge, one march each, scheduled
-// FIRST (lowest blockIdx.y).  Their epilogue stores the finished rings the neighbour needs not only into this GPU's
-// fields but also straight into the neighbouring GPU's halo inbox (peer memory mapped over NVLink), and the last edge
-// warp to finish publishes the step number in the neighbours' arrival counters — so the ghost-ring exchange
-// (CommunicateBoundaries, commbound.cpp:98-182) is part of this kernel and is over long before the interior marches are.
+// Which (window, ring) work a launch covers.  One CTA = four neighbouring windows (one per warp, so their overlapping
+// columns meet in L1) marched through one band of rings.
+// Segment 2 is the bulk of the slab: ceil(nwin / 4) window groups x bands of `band` rings, band-major in the block index,
+// so the CTAs running at any moment sweep whole ring rows together (DRAM sees long sequential reads) and the block
+// scheduler balances the bands over the SMs (rings_per_march picks `band`).  (Cutting the groups' ring ranges into one
+// equal run per resident CTA instead was measured: 10 % slower at 8192 rings — SMs do not all run at the same speed —
+// and a loop over the two marches such a run can consist of cost the single-march kernel 4.5 %.)
+// Segments 0 and 1 exist on the peer-memory halo path (PUSH): the 2 x CPUOVERLAP rings at the slab's inner / outer edge,
+// one march per window, scheduled FIRST (lowest block indices).  Their epilogue stores the finished rings the neighbour
+// needs not only into this GPU's fields but also straight into the neighbouring GPU's halo inbox (peer memory mapped
+// over NVLink), and the last edge warp to finish publishes the step number in the neighbours' arrival counters — so the
+// ghost-ring exchange (CommunicateBoundaries, commbound.cpp:98-182) is part of this kernel and is over long before the
+// interior bands are.
 struct AzSegs {
     int lo[3], hi[3];
-    int n_edge;	     // edge marches in this launch (0, 1 or 2)
-    int edge_seg[2]; // which segment blockIdx.y = 0, 1 runs
+    int nwin;	     // windows per ring
+    int band;	     // rings per band of segment 2
+    int n_edge;	     // edge segments in this launch (0, 1 or 2); their CTAs come first: n_edge * ceil(nwin / 4)
+    int edge_seg[2]; // which segment the e-th group of edge CTAs runs
     int push_lo[2];  // rings [push_lo[s], push_lo[s] + CPUOVERLAP) of segment s are mirrored to push[s][field]
     double *push[2][4]; // Sigma, v_rad, v_azi, e
     unsigned long long *peer_flag[2]; // the neighbour's arrival counter for rings coming from this rank
@@ -286,27 +295,33 @@ __global__ void __launch_bounds__(128, AZ_MINB)
 			  const double *__restrict__ t_amm, const double *__restrict__ t_e, const double *__restrict__ vp_old,
 			  const double *__restrict__ vr_old, const double *__restrict__ vmean, const int *__restrict__ nshift,
 			  const double *__restrict__ vconst, double *__restrict__ o_sigma, double *__restrict__ o_vr,
-			  double *__restrict__ o_vp, double *__restrict__ o_e, const double dt, const int R, const AzSegs segs)
+			  double *__restrict__ o_vp, double *__restrict__ o_e, const double dt, const AzSegs segs)
 {
     const int ns = c.ns, nr = c.nr;
     const int lane = threadIdx.x & 31;
-    const int win = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if ((long long)win * AZ_OUT >= ns)
-	return; // whole warp; warps never synchronise with each other
-    int seg = 2, i_first, i_last;
-    if (PUSH && (int)blockIdx.y < segs.n_edge) {
-	seg = segs.edge_seg[blockIdx.y];
+    const int wib = threadIdx.x >> 5; // warp in block; warps never synchronise with each other
+    const int gx = (segs.nwin + 3) >> 2;
+    const int t0 = AZ_NC * lane; // local column of c = 0
+    const bool lane_out = (t0 >= AZ_HL) && (t0 < AZ_WIN - AZ_HR);
+    // this block's work: an edge march (PUSH) or one (band, window group) cell of segment 2
+    int seg = 2, grp, i_first, i_last;
+    const int edge_ctas = PUSH ? segs.n_edge * gx : 0;
+    if (PUSH && (int)blockIdx.x < edge_ctas) {
+	seg = segs.edge_seg[blockIdx.x / gx];
+	grp = (int)blockIdx.x % gx;
 	i_first = segs.lo[seg];
 	i_last = segs.hi[seg];
     } else {
-	i_first = segs.lo[2] + ((int)blockIdx.y - (PUSH ? segs.n_edge : 0)) * R;
-	if (i_first >= segs.hi[2])
-	    return;
-	i_last = min(i_first + R, segs.hi[2]);
+	const int cell = (int)blockIdx.x - edge_ctas;
+	const int b = cell / gx;
+	grp = cell - b * gx;
+	i_first = segs.lo[2] + b * segs.band;
+	i_last = min(i_first + segs.band, segs.hi[2]);
     }
-    const int t0 = AZ_NC * lane;		    // local column of c = 0
-    const int jout = win * AZ_OUT - AZ_HL + t0;	    // output column of c = 0 (negative / >= ns in the halo)
-    const bool lane_out = (t0 >= AZ_HL) && (t0 < AZ_WIN - AZ_HR);
+    const int win = grp * 4 + wib;
+    if (win >= segs.nwin || i_first >= i_last)
+	return; // whole warp (the last group of four may be incomplete)
+    const int jout = win * AZ_OUT - AZ_HL + t0; // output column of c = 0 (negative / >= ns in the halo)
     const bool vec_ok = ((ns % AZ_NC) == 0);
     const bool fargo = c.p.fast_transport != 0;
     TempClampNB tc;
