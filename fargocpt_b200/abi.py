@@ -243,6 +243,16 @@ class Handle:
         self._check(fn(self.ptr, int(body), float(klahr_factor), out), "disk_on_body_accel")
         return np.array(list(out))
 
+    def monitor_quantities(self, radius_limit=1e300):
+        """Global sums of monitor/Quantities.dat (fargo_monitor_quantities): dict of mass, angular_momentum, internal_energy,
+        kinetic_energy, radial_kinetic_energy, azimuthal_kinetic_energy, viscous_dissipation, luminosity."""
+        out = (C.c_double * 8)()
+        fn = self._fn("monitor_quantities")
+        fn.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double)]
+        fn.restype = C.c_int
+        self._check(fn(self.ptr, float(radius_limit), out), "monitor_quantities")
+        return dict(zip(MONITOR_QUANTITIES, list(out)))
+
     def nshift(self):
         out = np.zeros(self.nr, dtype=np.int32)
         self._check(self._call("get_nshift", out.ctypes.data_as(C.POINTER(C.c_int))), "get_nshift")
@@ -250,6 +260,8 @@ class Handle:
 
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
+MONITOR_QUANTITIES = ("mass", "angular_momentum", "internal_energy", "kinetic_energy", "radial_kinetic_energy",
+                      "azimuthal_kinetic_energy", "viscous_dissipation", "luminosity")
 # FARGO_B200_LIB: experiment builds of the SAME CUDA library (kernel tuning variants); never a CPU path
 LIB_PATH = os.environ.get("FARGO_B200_LIB") or os.path.join(_HERE, "csrc", "libfargo_b200.so")
 _lib = None
@@ -283,6 +295,8 @@ def load_library():
         lib.fargo_selftest_exp.restype = C.c_int
         lib.fargo_sync.argtypes = [C.c_void_p]
         lib.fargo_sync.restype = C.c_int
+        lib.fargo_monitor_quantities.argtypes = [C.c_void_p, C.c_double, _DP]
+        lib.fargo_monitor_quantities.restype = C.c_int
         lib.fargo_halo_mode.argtypes = [C.c_void_p]
         lib.fargo_halo_mode.restype = C.c_int
         lib.fargo_launch_count.argtypes = [C.c_void_p]

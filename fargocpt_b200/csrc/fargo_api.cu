@@ -1438,6 +1438,35 @@ extern "C" int fargo_get_nshift(fargo_ctx *c, int *out)
     return 0;
 }
 
+// monitor/Quantities.dat sums (quantities.cpp:51-480 through output::write_quantities, output.cpp:326-520)
+extern "C" int fargo_monitor_quantities(fargo_ctx *c, double radius_limit, double out8[8])
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    if (c->v_mid)
+	return fail("fargo_monitor_quantities called mid-step");
+    const int nact = c->v.active_size - c->v.first_active;
+    const unsigned gx = (unsigned)((c->v.ns + 4 * MQ_THREADS - 1) / (4 * MQ_THREADS));
+    const int nblocks = (int)gx * (nact > 0 ? nact : 0);
+    if ((size_t)(nblocks + 1) * MQ_N > (size_t)c->v.nr * c->v.ns)
+	return fail("scratch too small for the monitor partials");
+    double *d_out = c->scratch + (size_t)nblocks * MQ_N; // behind the partials
+    if (nblocks > 0) {
+	dim3 grid(gx, (unsigned)nact);
+	LAUNCH(c, k_monitor_quantities, grid, MQ_THREADS, 0, c->v, c->sigma, EN(c), VRA(c), VPA(c), c->qplus, c->qminus, radius_limit,
+	       c->scratch);
+	LAUNCH(c, k_monitor_final, 1, 32 * MQ_N, 0, c->scratch, nblocks, d_out);
+    } else {
+	CUDA_OK(cudaMemsetAsync(d_out, 0, MQ_N * sizeof(double), c->stream));
+    }
+    if (c->v.nranks > 1) { // MPI_Allreduce / MPI_Reduce(SUM), quantities.cpp:73, 274, ...
+	NCCL_OK(g_nccl.AllReduce(d_out, d_out, MQ_N, ncclFloat64, 0 /* ncclSum */, c->comm, c->stream));
+	c->launches++;
+    }
+    CUDA_OK(cudaMemcpyAsync(out8, d_out, MQ_N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // per-kernel device timing for bench.py (CUDA events on the context's stream)
 extern "C" int fargo_profile_enable(fargo_ctx *c, int on)

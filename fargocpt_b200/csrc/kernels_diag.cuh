@@ -118,3 +118,78 @@ __global__ void __launch_bounds__(128) k_disk_on_body_final(const double *__rest
     if (lane == 0)
 	out4[q] = s;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Global disk quantities of monitor/Quantities.dat (quantities.cpp:51-78 mass, :242-276 angular momentum, :281-304
+// internal energy, :306-355 viscous dissipation and luminosity, :357-480 kinetic energies; written by
+// output::write_quantities, output.cpp:326-520): sums over the active cells with Rmed <= radius_limit.
+// The reference adds them with an OpenMP reduction (no defined order); here: per-block partials by warp shuffles, then one
+// block adding the partials in block order — a fixed order, so the result is reproducible run to run.
+// q: 0 mass, 1 angular momentum, 2 internal energy, 3 kinetic energy, 4 radial kinetic, 5 azimuthal kinetic,
+//    6 viscous dissipation (sum Surf Q+), 7 luminosity (sum Surf Q-)
+#define MQ_N 8
+#define MQ_THREADS 128
+__global__ void __launch_bounds__(MQ_THREADS)
+    k_monitor_quantities(const DevView c, const double *__restrict__ sigma, const double *__restrict__ energy,
+			 const double *__restrict__ vr, const double *__restrict__ vp, const double *__restrict__ qplus,
+			 const double *__restrict__ qminus, const double radius_limit, double *__restrict__ partials)
+{
+    const int i = c.first_active + blockIdx.y;
+    double acc[MQ_N];
+#pragma unroll
+    for (int q = 0; q < MQ_N; ++q)
+	acc[q] = 0.0;
+    if (i < c.active_size && c.g.rmed[i] <= radius_limit) {
+	const double rmed = c.g.rmed[i], surf = c.g.surf[i], rinf = c.g.rinf[i], rsup = c.g.rsup[i];
+	const double OmegaF = c.b.omega_frame;
+	const int ns = c.ns;
+	for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < ns; j += gridDim.x * blockDim.x) {
+	    const int jm = (j == 0) ? ns - 1 : j - 1, jp = (j == ns - 1) ? 0 : j + 1;
+	    const double s = AT(sigma, i, j);
+	    acc[0] += surf * s;
+	    acc[1] += surf * 0.5 * (s + AT(sigma, i, jm)) * rmed * (AT(vp, i, j) + OmegaF * rmed);
+	    if (c.p.adiabatic) {
+		acc[2] += surf * AT(energy, i, j);
+		acc[6] += surf * AT(qplus, i, j);
+		acc[7] += surf * AT(qminus, i, j);
+	    }
+	    double v_radial_center = (rmed - rinf) * AT(vr, i + 1, j) + (rsup - rmed) * AT(vr, i, j);
+	    v_radial_center /= (rsup - rinf);
+	    const double v_azimuthal_center = 0.5 * (AT(vp, i, j) + AT(vp, i, jp)) + rmed * OmegaF;
+	    acc[3] += 0.5 * surf * s * (v_radial_center * v_radial_center + v_azimuthal_center * v_azimuthal_center);
+	    acc[4] += 0.5 * surf * s * (v_radial_center * v_radial_center);
+	    acc[5] += 0.5 * surf * s * (v_azimuthal_center * v_azimuthal_center);
+	}
+    }
+#pragma unroll
+    for (int q = 0; q < MQ_N; ++q)
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+	    acc[q] += __shfl_down_sync(0xffffffffu, acc[q], o);
+    __shared__ double sh[MQ_THREADS / 32][MQ_N];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0)
+#pragma unroll
+	for (int q = 0; q < MQ_N; ++q)
+	    sh[w][q] = acc[q];
+    __syncthreads();
+    if (threadIdx.x < MQ_N) {
+	double t = 0.0;
+	for (int k = 0; k < MQ_THREADS / 32; ++k)
+	    t += sh[k][threadIdx.x];
+	partials[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * MQ_N + threadIdx.x] = t;
+    }
+}
+// adds the block partials in block order: one warp per quantity, each lane a strided serial sum, then a shuffle tree
+__global__ void __launch_bounds__(32 * MQ_N) k_monitor_final(const double *__restrict__ partials, const int nblocks, double *__restrict__ out)
+{
+    const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double s = 0.0;
+    for (int b = lane; b < nblocks; b += 32)
+	s += partials[(size_t)b * MQ_N + q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+	s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0)
+	out[q] = s;
+}

@@ -229,6 +229,14 @@ int fargo_set_staged(fargo_ctx *ctx, int on);
  * reference adds them, Force.cpp:117-119).  klahr_factor = planet.get_cubic_smoothing_factor(). */
 int fargo_disk_on_body_accel(fargo_ctx *ctx, int body, double klahr_factor, double out4[4]);
 
+/* Global disk quantities of monitor/Quantities.dat (output::write_quantities output.cpp:326-520 -> quantities.cpp):
+ * sums over the active cells with Rmed <= radius_limit (QuantitiesRadiusLimit, default 2 Rmax), all ranks.
+ * out8 = { mass (quantities.cpp:51-78), angular momentum (:242-276), internal energy (:281-304), kinetic energy (:357-401),
+ * radial kinetic energy (:406-438), azimuthal kinetic energy (:443-479), viscous dissipation sum(Surf Q+) (:306-328),
+ * luminosity sum(Surf Q-) (:330-352) }.  The reference adds with an OpenMP reduction (order undefined); the device adds in a
+ * fixed order (reproducible run to run; agrees with a serial sum to rounding). */
+int fargo_monitor_quantities(fargo_ctx *ctx, double radius_limit, double out8[8]);
+
 /* integer FARGO shifts of the last transport (TransportEuler.cpp:49,220), local rings */
 int fargo_get_nshift(fargo_ctx *ctx, int *out_local_nrad);
 

@@ -1582,6 +1582,42 @@ int fargo_oracle_step(fargo_oracle *o, double dt)
     return 0;
 }
 
+/* Global disk quantities of monitor/Quantities.dat (output::write_quantities, output.cpp:326-520): serial sums in index
+ * order, which is what the reference computes with OMP_NUM_THREADS=1 (its reductions have no defined order otherwise).
+ * out8 = mass (quantities.cpp:51-78), angular momentum (:242-276), internal energy (:281-304), kinetic energy (:357-401),
+ * radial kinetic (:406-438), azimuthal kinetic (:443-479), viscous dissipation (:306-328), luminosity (:330-352). */
+int fargo_oracle_monitor_quantities(fargo_oracle *o, double radius_limit, double out8[8])
+{
+    const double OmegaF = o->bodies.omega_frame;
+    const int ns = o->ns;
+    double mass = 0.0, angmom = 0.0, eint = 0.0, ekin = 0.0, ekin_r = 0.0, ekin_a = 0.0, qp = 0.0, qm = 0.0;
+    for (int i = o->first_active; i < o->active_size; ++i) {
+	if (!(o->rmed[i] <= radius_limit))
+	    continue;
+	for (int j = 0; j < ns; ++j) {
+	    const int jm = j == 0 ? ns - 1 : j - 1, jp = j == ns - 1 ? 0 : j + 1;
+	    mass += o->surf[i] * o->sigma[IDX(o, i, j)];
+	    angmom += o->surf[i] * 0.5 * (o->sigma[IDX(o, i, j)] + o->sigma[IDX(o, i, jm)]) * o->rmed[i] *
+		      (o->vazi[IDX(o, i, j)] + OmegaF * o->rmed[i]);
+	    if (o->p.adiabatic) {
+		eint += o->surf[i] * o->energy[IDX(o, i, j)];
+		qp += o->surf[i] * o->qplus[IDX(o, i, j)];
+		qm += o->surf[i] * o->qminus[IDX(o, i, j)];
+	    }
+	    double v_radial_center =
+		(o->rmed[i] - o->rinf[i]) * o->vrad[IDX(o, i + 1, j)] + (o->rsup[i] - o->rmed[i]) * o->vrad[IDX(o, i, j)];
+	    v_radial_center /= (o->rsup[i] - o->rinf[i]);
+	    const double v_azimuthal_center = 0.5 * (o->vazi[IDX(o, i, j)] + o->vazi[IDX(o, i, jp)]) + o->rmed[i] * OmegaF;
+	    ekin += 0.5 * o->surf[i] * o->sigma[IDX(o, i, j)] *
+		    (v_radial_center * v_radial_center + v_azimuthal_center * v_azimuthal_center);
+	    ekin_r += 0.5 * o->surf[i] * o->sigma[IDX(o, i, j)] * (v_radial_center * v_radial_center);
+	    ekin_a += 0.5 * o->surf[i] * o->sigma[IDX(o, i, j)] * (v_azimuthal_center * v_azimuthal_center);
+	}
+    }
+    out8[0] = mass, out8[1] = angmom, out8[2] = eint, out8[3] = ekin, out8[4] = ekin_r, out8[5] = ekin_a, out8[6] = qp, out8[7] = qm;
+    return 0;
+}
+
 /* ComputeDiskOnPlanetAccel (Force.cpp:23-122), serial sum in index order (the reference's own order is undefined:
  * OpenMP reduction).  out4 = {axi, ayi, axo, ayo}. */
 int fargo_oracle_disk_on_body_accel(fargo_oracle *o, int body, double klahr_factor, double out4[4])

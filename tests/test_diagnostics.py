@@ -60,3 +60,60 @@ def test_gpu_diagnostics_vs_oracle(name, k):
         assert np.allclose(a, b, rtol=1e-12, atol=1e-13 * np.abs(b).max()), (body, a, b)
     # reproducible: the device sums in a fixed order
     assert np.array_equal(gpu.disk_on_body_accel(1), gpu.disk_on_body_accel(1))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# monitor/Quantities.dat sums (output::write_quantities output.cpp:326-520 -> quantities.cpp:51-480)
+def _quantities_fixture():
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "quantities.json")))["quantities"]
+
+
+def _load_with_q(ctx, meta, z, k):
+    _load(ctx, meta, z, k)
+    if f"Qplus_{k}" in z.files and meta["params"]["adiabatic"]:  # the Q+- of the step that ended at snapshot k, as the reference kept them
+        ctx.upload(abi.QPLUS, z[f"Qplus_{k}"])
+        ctx.upload(abi.QMINUS, z[f"Qminus_{k}"])
+
+
+QUANT_CASES = [("adia_planet_100", 50), ("adia_planet_100", 100), ("iso_planet_100", 50), ("iso_planet_100", 100), ("rey_star", 2),
+               ("adia_star", 3), ("adia_star", 6)]
+
+
+@pytest.mark.parametrize("name,k", QUANT_CASES)
+def test_oracle_monitor_quantities_match_reference(name, k):
+    """The oracle's serial sums against the reference's own Quantities.dat (recorded with OMP_NUM_THREADS=1, i.e. the same
+    summation order): bit for bit for every quantity the fixture carries the inputs of."""
+    meta, z, ctx = _oracle(name)
+    _load_with_q(ctx, meta, z, k)
+    got = ctx.monitor_quantities()
+    ref = _quantities_fixture()[name][str(k)]
+    names = ["mass", "angular_momentum", "kinetic_energy", "radial_kinetic_energy", "azimuthal_kinetic_energy"]
+    if meta["params"]["adiabatic"]:
+        names += ["internal_energy"]
+        if f"Qplus_{k}" in z.files:
+            names += ["viscous_dissipation", "luminosity"]
+    for q in names:
+        assert got[q] == ref[q], (q, got[q], ref[q])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,k", QUANT_CASES)
+def test_gpu_monitor_quantities_vs_oracle(name, k):
+    """The device sums (fixed order, but not the serial one) against the oracle's: 1e-13 relative; and reproducible."""
+    from fargocpt_b200 import HydroContext
+    meta, z, cpu = _oracle(name)
+    gpu = HydroContext(reftools.make_params(meta["params"]), z["radii"])
+    for ctx in (cpu, gpu):
+        _load_with_q(ctx, meta, z, k)
+    a, b, a2 = gpu.monitor_quantities(), cpu.monitor_quantities(), gpu.monitor_quantities()
+    assert a == a2
+    for q in abi.MONITOR_QUANTITIES:
+        assert abs(a[q] - b[q]) <= 1e-13 * max(abs(b[q]), 1e-300), (q, a[q], b[q])
+    # a radius limit inside the grid: both leave out the same rings
+    rl = float(0.5 * (z["radii"][len(z["radii"]) // 2] + z["radii"][len(z["radii"]) // 2 + 1]))
+    a, b = gpu.monitor_quantities(rl), cpu.monitor_quantities(rl)
+    for q in abi.MONITOR_QUANTITIES:
+        assert abs(a[q] - b[q]) <= 1e-13 * max(abs(b[q]), 1e-300), (q, a[q], b[q])
+    assert 0.0 < b["mass"] < cpu.monitor_quantities()["mass"]
