@@ -28,6 +28,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 METRIC = "hydro cell-updates/s (FP64)"
+E2E_INTERVALS = 3  # snapshot intervals in the end-to-end leg
 UNIT = "cell-updates/s"
 # algorithmic bytes per cell-update, SURVEY.md §8d / DESIGN.md: adiabatic 400 B (+96 f in damping zones)
 B_ALG = {"adiabatic_planet": 400.0, "cold_disk_planet": 312.0, "isothermal_planet": 280.0}
@@ -293,10 +294,12 @@ def run_gpu(args):
     value = ncell * args.steps / (ms * 1e-3)
 
     # ---- end-to-end leg: host buffers in, host buffers out -------------------------------------------
-    # One snapshot interval as a user of the C ABI runs it: upload the four state fields from pinned host memory,
-    # K steps (each with its dt read-back), download the four state fields.  Bytes per step = totals / K.
-    out_host = {fid: torch.empty(ctx.global_shape(fid), dtype=torch.float64).pin_memory().numpy()
-                for fid in (abi.SIGMA, abi.VRAD, abi.VAZI, abi.ENERGY)}
+    # A restart + E2E_INTERVALS snapshot intervals as a user of the C ABI runs them: upload the four state fields from
+    # pinned host memory, then per interval K steps (each with its dt read-back) and one snapshot of the four state fields
+    # into pinned host memory (fargo_snapshot_async: the copy overlaps the next interval's steps); the region ends when
+    # the last snapshot is on the host.  Bytes per step = totals / (E2E_INTERVALS * K).
+    out_host = [{fid: torch.empty(ctx.global_shape(fid), dtype=torch.float64).pin_memory().numpy()
+                 for fid in (abi.SIGMA, abi.VRAD, abi.VAZI, abi.ENERGY)} for _ in range(2)]
     barrier()
     ctx.event_record(2)
     t_e2e0 = time.time()
@@ -305,10 +308,12 @@ def run_gpu(args):
     ctx.upload(abi.VRAD, pinned["vrad"])
     ctx.upload(abi.VAZI, pinned["vazi"])
     state["t"] = 0.0
-    for _ in range(args.steps):
-        one_step()
-    for fid in out_host:
-        ctx.download(fid, out_host[fid])
+    for it in range(E2E_INTERVALS):
+        for _ in range(args.steps):
+            one_step()
+        o = out_host[it % 2]
+        ctx.snapshot_async(o[abi.SIGMA], o[abi.VRAD], o[abi.VAZI], o[abi.ENERGY])
+    ctx.snapshot_wait()
     ctx.event_record(3)
     ms_e2e = ctx.event_elapsed_ms(2, 3)
     barrier()
@@ -320,10 +325,11 @@ def run_gpu(args):
         sampler.stop_flag = True
         sampler.join(timeout=2)
     slab_cells = ctx.nr * ctx.naz
-    h2d = (4 * slab_cells + ctx.naz) * 8 / args.steps
-    owned = sum(int(np.prod(ctx.global_shape(f))) for f in out_host) / world
-    d2h = owned * 8 / args.steps + 8  # + the dt scalar every step
-    e2e_val = ncell * args.steps / (ms_e2e * 1e-3)
+    e2e_steps = E2E_INTERVALS * args.steps
+    h2d = (4 * slab_cells + ctx.naz) * 8 / e2e_steps
+    owned = sum(int(np.prod(ctx.global_shape(f))) for f in out_host[0]) / world
+    d2h = owned * 8 / args.steps + 8  # one snapshot per interval + the dt scalar every step
+    e2e_val = ncell * e2e_steps / (ms_e2e * 1e-3)
 
     if rank != 0:
         return
@@ -357,7 +363,8 @@ def run_gpu(args):
                                      2: "NVLink peer-memory stores from the transport kernel's edge launch, overlapped with the interior rings"}[ctx.halo_mode()]},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "what": f"upload 4 state fields from pinned host memory + {args.steps} steps + download 4 fields, per snapshot interval"},
+                "what": f"restart (upload 4 state fields from pinned host memory) + {E2E_INTERVALS} intervals of {args.steps} steps, each ending in an "
+                        "asynchronous snapshot of the 4 state fields into pinned host memory (overlaps the next interval); ends when the last snapshot is on the host"},
         "gpu_launches": int(launches),
         "roofline": roof,
         "step_roofline": {"achieved_gbs_per_gpu": step_roof, "frac_of_measured_peak": step_roof / peaks["hbm_gbs"],

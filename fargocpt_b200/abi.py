@@ -295,6 +295,10 @@ def load_library():
         lib.fargo_selftest_exp.restype = C.c_int
         lib.fargo_sync.argtypes = [C.c_void_p]
         lib.fargo_sync.restype = C.c_int
+        lib.fargo_snapshot_async.argtypes = [C.c_void_p, _DP, _DP, _DP, _DP]
+        lib.fargo_snapshot_async.restype = C.c_int
+        lib.fargo_snapshot_wait.argtypes = [C.c_void_p]
+        lib.fargo_snapshot_wait.restype = C.c_int
         lib.fargo_monitor_quantities.argtypes = [C.c_void_p, C.c_double, _DP]
         lib.fargo_monitor_quantities.restype = C.c_int
         lib.fargo_halo_mode.argtypes = [C.c_void_p]
@@ -358,6 +362,16 @@ class HydroContext(Handle):
     def set_staged(self, on):
         """step() through the per-stage kernels (one per reference loop nest) instead of the fused ones."""
         self._check(self.lib.fargo_set_staged(self.ptr, int(on)), "set_staged")
+
+    def snapshot_async(self, sigma, vrad, vazi, energy=None):
+        """Start an asynchronous snapshot into global-shaped float64 arrays (pinned memory overlaps with later steps)."""
+        for a in (sigma, vrad, vazi, energy):
+            assert a is None or (a.dtype == np.float64 and a.flags["C_CONTIGUOUS"])
+        self._check(self.lib.fargo_snapshot_async(self.ptr, _dptr(sigma), _dptr(vrad), _dptr(vazi),
+                                                  _dptr(energy) if energy is not None else None), "snapshot_async")
+
+    def snapshot_wait(self):
+        self._check(self.lib.fargo_snapshot_wait(self.ptr), "snapshot_wait")
 
     def halo_mode(self):
         """0 single rank, 1 NCCL send/recv, 2 peer-memory stores from the transport kernel (fargo_halo_mode)."""

@@ -150,6 +150,10 @@ struct fargo_ctx {
 	bool pushed = false;		   // this step's edge rings are on their way (launch_transport), not yet received
 	unsigned int *done = nullptr;	   // edge warps of the running transport launch that have finished (device)
     } halo;
+    // asynchronous snapshots (fargo_snapshot_async): device-side copies of the four state fields and a copy stream
+    double *snap[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t stream_snap = nullptr;
+    cudaEvent_t ev_snap_ready = nullptr, ev_snap_done = nullptr;
     bool force_staged = false;
     cudaEvent_t ev_user[4] = {nullptr, nullptr, nullptr, nullptr}; // fargo_event_record slots
     // optional per-kernel device timing (bench.py roofline): CUDA events on the launching stream
@@ -433,6 +437,15 @@ extern "C" void fargo_ctx_destroy(fargo_ctx *c)
     for (int k = 0; k < 2; ++k)
 	if (c->halo.peer_base[k])
 	    cudaIpcCloseMemHandle(c->halo.peer_base[k]);
+    for (int k = 0; k < 4; ++k)
+	if (c->snap[k])
+	    cudaFree(c->snap[k]);
+    if (c->ev_snap_ready)
+	cudaEventDestroy(c->ev_snap_ready);
+    if (c->ev_snap_done)
+	cudaEventDestroy(c->ev_snap_done);
+    if (c->stream_snap)
+	cudaStreamDestroy(c->stream_snap);
     if (c->halo.inbox)
 	cudaFree(c->halo.inbox);
     if (c->halo.done)
@@ -829,6 +842,63 @@ extern "C" int fargo_download_slab(fargo_ctx *c, int f, double *host_slab)
 	return 1;
     CUDA_OK(cudaMemcpyAsync(host_slab, d, (size_t)rings * c->v.ns * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// Asynchronous snapshot (the output half of sim::handle_outputs / write_full_output, simulation.cpp:50-98, output.cpp:249:
+// the reference stops the time loop while it writes).  The four state fields as they are NOW are copied device-to-device
+// on the compute stream (1.4 ms at 8192 x 16384) and from there to the caller's host arrays on a copy stream, so the next
+// steps run while the snapshot crosses PCIe.  Host arrays: global layout as fargo_download_field (only the owned rings are
+// written), page-locked for the copy to be asynchronous; `energy` may be NULL.  fargo_snapshot_wait blocks until the
+// data is on the host; a second fargo_snapshot_async waits for the first one's copies by itself.
+extern "C" int fargo_snapshot_async(fargo_ctx *c, double *sigma, double *vrad, double *vazi, double *energy)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    if (c->v_mid)
+	return fail("fargo_snapshot_async called mid-step");
+    const size_t ns = (size_t)c->v.nr * c->v.ns, nv = (size_t)(c->v.nr + 1) * c->v.ns;
+    if (!c->stream_snap) {
+	CUDA_OK(cudaStreamCreateWithFlags(&c->stream_snap, cudaStreamNonBlocking));
+	CUDA_OK(cudaEventCreateWithFlags(&c->ev_snap_ready, cudaEventDisableTiming));
+	CUDA_OK(cudaEventCreateWithFlags(&c->ev_snap_done, cudaEventDisableTiming));
+	CUDA_OK(cudaEventRecord(c->ev_snap_done, c->stream_snap));
+	const size_t len[4] = {ns, nv, ns, ns};
+	for (int k = 0; k < 4; ++k)
+	    if (k < 3 || c->v.p.adiabatic)
+		CUDA_OK(cudaMalloc((void **)&c->snap[k], len[k] * sizeof(double)));
+    }
+    double *src[4] = {c->sigma, VRA(c), VPA(c), EN(c)};
+    double *host[4] = {sigma, vrad, vazi, energy};
+    const bool first = c->v.rank == 0, last = c->v.rank == c->v.nranks - 1;
+    const int lo = first ? 0 : FARGO_CPUOVERLAP;
+    CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_snap_done, 0)); // the previous snapshot has left the device buffers
+    size_t off[4], cnt[4];
+    for (int k = 0; k < 4; ++k) {
+	int count = (c->v.nr - (last ? 0 : FARGO_CPUOVERLAP)) - lo; // write2D (polargrid.cpp:150-176)
+	if (k == 1 && last)
+	    count += 1;
+	off[k] = (size_t)lo * c->v.ns;
+	cnt[k] = (size_t)count * c->v.ns;
+	if (!host[k] || !c->snap[k])
+	    continue;
+	CUDA_OK(cudaMemcpyAsync(c->snap[k] + off[k], src[k] + off[k], cnt[k] * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    CUDA_OK(cudaEventRecord(c->ev_snap_ready, c->stream));
+    CUDA_OK(cudaStreamWaitEvent(c->stream_snap, c->ev_snap_ready, 0));
+    for (int k = 0; k < 4; ++k) {
+	if (!host[k] || !c->snap[k])
+	    continue;
+	CUDA_OK(cudaMemcpyAsync(host[k] + (size_t)c->v.imin * c->v.ns + off[k], c->snap[k] + off[k], cnt[k] * sizeof(double),
+				cudaMemcpyDeviceToHost, c->stream_snap));
+    }
+    CUDA_OK(cudaEventRecord(c->ev_snap_done, c->stream_snap));
+    return 0;
+}
+extern "C" int fargo_snapshot_wait(fargo_ctx *c)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    if (c->ev_snap_done)
+	CUDA_OK(cudaEventSynchronize(c->ev_snap_done));
     return 0;
 }
 

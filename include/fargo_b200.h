@@ -229,6 +229,14 @@ int fargo_set_staged(fargo_ctx *ctx, int on);
  * reference adds them, Force.cpp:117-119).  klahr_factor = planet.get_cubic_smoothing_factor(). */
 int fargo_disk_on_body_accel(fargo_ctx *ctx, int body, double klahr_factor, double out4[4]);
 
+/* Asynchronous snapshot of the four state fields (the output half of sim::handle_outputs simulation.cpp:50-98 /
+ * output::write_full_output output.cpp:249, during which the reference's time loop stands still): returns at once; the
+ * fields as of the call travel to the host arrays (global layout as fargo_download_field, owned rings only; page-locked
+ * memory for the copy to overlap; energy may be NULL) while later fargo_step calls run.  fargo_snapshot_wait blocks until
+ * they have arrived. */
+int fargo_snapshot_async(fargo_ctx *ctx, double *sigma, double *vrad, double *vazi, double *energy);
+int fargo_snapshot_wait(fargo_ctx *ctx);
+
 /* Global disk quantities of monitor/Quantities.dat (output::write_quantities output.cpp:326-520 -> quantities.cpp):
  * sums over the active cells with Rmed <= radius_limit (QuantitiesRadiusLimit, default 2 Rmax), all ranks.
  * out8 = { mass (quantities.cpp:51-78), angular momentum (:242-276), internal energy (:281-304), kinetic energy (:357-401),

@@ -114,3 +114,29 @@ def test_no_device_fallback_message():
     meta, z = reftools.load_golden("iso_star")
     with pytest.raises(RuntimeError):
         HydroContext(reftools.make_params(meta["params"]), z["radii"], device=99)
+
+
+def test_async_snapshot_is_the_state_at_the_call():
+    """fargo_snapshot_async hands back the four state fields as they were when it was called, although the context goes on
+    stepping while they travel (the reference's output path stops the time loop instead: simulation.cpp:50-98)."""
+    import numpy as np
+    from fargocpt_b200 import HydroContext, abi
+    meta, z = reftools.load_golden("adia_planet_100")
+    ctx = HydroContext(reftools.make_params(meta["params"]), z["radii"])
+    goldenrun.run_fixture(ctx, meta, z, nsteps=3)
+    want = {fid: ctx.download(fid) for fid, _ in goldenrun.STATE}
+    snaps = []
+    for rep in range(2):  # the second snapshot has to wait for the first one's copies by itself
+        got = {fid: np.full_like(want[fid], np.nan) for fid in want}
+        ctx.snapshot_async(got[abi.SIGMA], got[abi.VRAD], got[abi.VAZI], got[abi.ENERGY])
+        snaps.append(got)
+        last_dt = 1e-3
+        for _ in range(2):  # keep stepping while the copies are in flight
+            last_dt = ctx.cfl(last_dt)
+            ctx.step(last_dt)
+        if rep == 0:
+            want_second = {fid: ctx.download(fid) for fid, _ in goldenrun.STATE}
+    ctx.snapshot_wait()
+    for fid in want:
+        assert np.array_equal(snaps[0][fid], want[fid]), fid
+        assert np.array_equal(snaps[1][fid], want_second[fid]), fid
