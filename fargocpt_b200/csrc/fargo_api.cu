@@ -894,6 +894,22 @@ extern "C" int fargo_snapshot_async(fargo_ctx *c, double *sigma, double *vrad, d
     CUDA_OK(cudaEventRecord(c->ev_snap_done, c->stream_snap));
     return 0;
 }
+// page-locked host memory for callers that do not link the CUDA runtime themselves (host/fargo_host.cpp)
+extern "C" void *fargo_pinned_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+	cudaGetLastError();
+	fail("fargo_pinned_alloc(%zu) failed", bytes);
+	return nullptr;
+    }
+    return p;
+}
+extern "C" void fargo_pinned_free(void *p)
+{
+    if (p)
+	cudaFreeHost(p);
+}
 extern "C" int fargo_snapshot_wait(fargo_ctx *c)
 {
     CUDA_OK(cudaSetDevice(c->device));

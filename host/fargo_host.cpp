@@ -29,6 +29,7 @@
 #include <sstream>
 #include <string>
 #include <sys/stat.h>
+#include <thread>
 #include <vector>
 
 #include "../include/fargo_b200.h"
@@ -734,19 +735,64 @@ struct Run {
 	    step_euler(dt);
     }
 
+#ifndef FARGO_HOST_ORACLE
+    // The four state fields of a snapshot leave the device asynchronously (fargo_snapshot_async) into page-locked buffers
+    // and are written to disk by a writer thread while the time loop goes on; the reference's loop stands still during
+    // write_full_output.  One snapshot in flight: the next one joins the writer first.
+    double *snap_host[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::thread snap_writer;
+    void finish_pending_snapshot()
+    {
+	if (snap_writer.joinable())
+	    snap_writer.join();
+    }
+#else
+    void finish_pending_snapshot() {}
+#endif
+
     // output::write_full_output (output.cpp:249-330) for the files the parity tooling reads
     void write_snapshot()
     {
 	const std::string sd = outdir + "/snapshots/" + std::to_string(n_snapshot);
 	mkdirs(sd);
 	const std::pair<int, const char *> state[4] = {{FARGO_SIGMA, "Sigma"}, {FARGO_VRAD, "vrad"}, {FARGO_VAZI, "vazi"}, {FARGO_ENERGY, "energy"}};
+	const bool write_energy = params.adiabatic || exists(refdir + "/snapshots/0/energy.dat");
+#ifndef FARGO_HOST_ORACLE
+	finish_pending_snapshot();
+	for (int k = 0; k < 4; ++k)
+	    if (!snap_host[k]) {
+		snap_host[k] = (double *)fargo_pinned_alloc(cells(k == 1) * sizeof(double));
+		if (!snap_host[k])
+		    die("%s", std::string("fargo_pinned_alloc: ") + backend_error());
+		std::fill(snap_host[k], snap_host[k] + cells(k == 1), 0.0);
+	    }
+	CHECK(fargo_snapshot_async(ctx, snap_host[0], snap_host[1], snap_host[2], write_energy ? snap_host[3] : nullptr));
+	{
+	    backend_ctx *cx = ctx;
+	    std::vector<std::pair<std::string, std::pair<double *, size_t>>> jobs;
+	    for (int k = 0; k < 4; ++k)
+		if (k < 3 || write_energy)
+		    jobs.push_back({sd + "/" + state[k].second + ".dat", {snap_host[k], cells(k == 1)}});
+	    snap_writer = std::thread([cx, jobs]() {
+		if (fargo_snapshot_wait(cx) != 0)
+		    die("%s", std::string("fargo_snapshot_wait: ") + backend_error());
+		for (auto &j : jobs) {
+		    FILE *f = fopen(j.first.c_str(), "wb");
+		    if (!f || fwrite(j.second.first, sizeof(double), j.second.second, f) != j.second.second)
+			die("cannot write %s", j.first);
+		    fclose(f);
+		}
+	    });
+	}
+#else
 	for (auto &s : state) {
-	    if (s.first == FARGO_ENERGY && !params.adiabatic && !exists(refdir + "/snapshots/0/energy.dat"))
+	    if (s.first == FARGO_ENERGY && !write_energy)
 		continue;
 	    std::vector<double> buf(cells(s.first == FARGO_VRAD), 0.0);
 	    CHECK(BK(download_field)(ctx, s.first, buf.data()));
 	    write_doubles(sd + "/" + s.second + ".dat", buf);
 	}
+#endif
 	if (params.adiabatic) {
 	    for (auto &s : {std::make_pair((int)FARGO_QPLUS, "Qplus"), std::make_pair((int)FARGO_QMINUS, "Qminus")}) {
 		std::vector<double> buf(cells(false), 0.0);
@@ -826,6 +872,7 @@ struct Run {
 	    }
 	}
 	fclose(tl);
+	finish_pending_snapshot(); // the last snapshot's files are complete when run() returns
     }
 };
 

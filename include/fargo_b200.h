@@ -23,6 +23,7 @@
 #ifndef FARGO_B200_H
 #define FARGO_B200_H
 
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -236,6 +237,9 @@ int fargo_disk_on_body_accel(fargo_ctx *ctx, int body, double klahr_factor, doub
  * they have arrived. */
 int fargo_snapshot_async(fargo_ctx *ctx, double *sigma, double *vrad, double *vazi, double *energy);
 int fargo_snapshot_wait(fargo_ctx *ctx);
+/* page-locked host memory for those arrays, for hosts that do not link the CUDA runtime themselves (NULL on failure) */
+void *fargo_pinned_alloc(size_t bytes);
+void fargo_pinned_free(void *p);
 
 /* Global disk quantities of monitor/Quantities.dat (output::write_quantities output.cpp:326-520 -> quantities.cpp):
  * sums over the active cells with Rmed <= radius_limit (QuantitiesRadiusLimit, default 2 Rmax), all ranks.
