@@ -11,8 +11,8 @@
 // for vector stores); warps are independent — no shared memory, no block barrier.  The warp then marches outward
 // ring by ring, carrying the previous ring's transported Sigma and rm+ (v_rad couples rings i-1 and i at the same
 // output column).
-// AZ_NC = 2 at 4 CTAs / SM (128 registers, no spills) beats 4 columns per lane at 3 CTAs / SM (168 registers,
-// spills) although it recomputes 16 % instead of 9 % of the columns: 4.97 vs 5.53 ms at 8192x16384.
+// AZ_NC = 2 at 4-5 CTAs / SM (128 / 96 registers) beats 4 columns per lane at 3 CTAs / SM (168 registers, spills)
+// although it recomputes 16 % instead of 9 % of the columns: 4.97 (4.77) vs 5.53 ms at 8192x16384.
 //
 // Arithmetic is the reference's, operation for operation (-fmad=false); the only algebraic liberties are exact
 // ones: x - c*d == x + (-c)*d, dx + ksi == dx - |ksi| for ksi <= 0, 0.5 * (2ab / (a+b)) == ab / (a+b) inside the
@@ -29,7 +29,7 @@
 #define AZ_WIN (32 * AZ_NC) // columns per warp window
 #define AZ_HL (AZ_NC == 2 ? 6 : 8) // invalid columns at the left end (5 needed, rounded up for aligned vector stores)
 #ifndef AZ_MINB
-#define AZ_MINB 4
+#define AZ_MINB 5 // 96 registers (a few spills) at 20 warps / SM: 4.77 vs 4.96 ms with 128 registers at 16 warps / SM
 #endif
 #define AZ_HR 4	   // invalid columns at the right end
 #define AZ_OUT (AZ_WIN - AZ_HL - AZ_HR)
