@@ -42,7 +42,7 @@ KERNEL_BYTES = {
     "k_cfl": 48.0, "k_ring_mean[cfl]": 8.0, "k_ring_mean[transport,side-stream]": 8.0,
 }
 # measured DRAM traffic per cell of the same kernels: dram__bytes_read.sum + dram__bytes_write.sum of one
-# `ncu --set full` capture (profiles/r01_v6_ncu_full_4096x8192.md, 4096 x 8192 adiabatic_planet) / 33.55e6 cells
+# `ncu --set full` capture (profiles/r01_v7_ncu_full_4096x8192.md, 4096 x 8192 adiabatic_planet) / 33.55e6 cells
 NCU_TRAFFIC_B_PER_CELL = {
     "k_transport_azimuthal<ADI>": 88.2, "(k_transport_radial<LIM, true>)": 81.1, "k_fused_sources<ADI>": 56.0,
     "k_fused_artvisc<ADI>": 56.0, "k_fused_viscosity<ADI>": 88.2, "k_cfl": 48.2,
@@ -348,7 +348,7 @@ def run_gpu(args):
         roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
                 "traffic": (NCU_TRAFFIC_B_PER_CELL[kname] * slab_cells if kname in NCU_TRAFFIC_B_PER_CELL else None),
-                "traffic_source": "ncu --set full, profiles/r01_v6_ncu_full_4096x8192.md (bytes per cell x cells of this launch)",
+                "traffic_source": "ncu --set full, profiles/r01_v7_ncu_full_4096x8192.md (bytes per cell x cells of this launch)",
                 "bytes_per_launch_algorithmic": per_launch_bytes, "avg_launch_ms": avg_s * 1e3,
                 "share_of_step": kms / total_kernel_ms if total_kernel_ms else None}
     step_roof = B_ALG[args.physics] * value / world / 1e9  # whole-step algorithmic GB/s per GPU
