@@ -265,19 +265,18 @@ static inline unsigned cells_grid(long long n, int block = 256) { return (unsign
 // B200), and the damping zones sit on the first and last ranks — at 8 GPUs their step was 6 % longer than everyone
 // else's.  Results do not depend on where the cuts are (constants.h:17; tests/test_gpu_multi.py holds N ranks to 1 rank
 // bit for bit).  FARGO_B200_SPLIT=equal restores the reference's cut points.
-static int split_domain(DevView &v, int nrad, int rank, int np, int *imax_out, const double *radii, const fargo_params &p)
+// cut[r] = first ring owned by rank r (cut[np] = nrad); pure host arithmetic, no device needed
+extern "C" int fargo_split_cuts(const fargo_params *params, const double *radii, int np, int *cut /* np + 1 */)
 {
+    const fargo_params &p = *params;
+    const int nrad = p.nrad;
+    if (np < 1)
+	return fail("bad number of ranks %d", np);
     const int size_low = nrad / np, size_high = size_low + 1, rem = nrad % np;
     if (np > 1 && size_low < 2 * FARGO_CPUOVERLAP)
 	return fail("The number of processes is too large or the mesh is radially too narrow.");
-    int imin, imax;
-    if (rank < rem) {
-	imin = size_high * rank;
-	imax = imin + size_high - 1;
-    } else {
-	imin = size_high * rem + (rank - rem) * size_low;
-	imax = imin + size_low - 1;
-    }
+    for (int r = 0; r <= np; ++r) // the reference's equal split (split.cpp:38-55)
+	cut[r] = r < rem ? size_high * r : size_high * rem + (r - rem) * size_low;
     const char *env = getenv("FARGO_B200_SPLIT");
     if (np > 1 && p.damping && radii && !(env && strcmp(env, "equal") == 0)) {
 	int nf = 0;
@@ -292,23 +291,32 @@ static int split_domain(DevView &v, int nrad, int rank, int np, int *imax_out, c
 				(p.damping_outer_limit < 1.0 && r > p.rmax * p.damping_outer_limit);
 	    cum[i + 1] = cum[i] + 1.0 + (damped ? wd : 0.0);
 	}
-	std::vector<int> cut(np + 1, 0);
-	cut[np] = nrad;
+	std::vector<int> w(np + 1, 0);
+	w[np] = nrad;
 	bool ok = true;
 	for (int r = 1; r < np; ++r) {
 	    const double target = cum[nrad] * r / np;
-	    int i = cut[r - 1];
+	    int i = w[r - 1];
 	    while (i < nrad && cum[i] < target)
 		++i;
-	    cut[r] = i;
+	    w[r] = i;
 	}
 	for (int r = 0; r < np; ++r)
-	    ok = ok && (cut[r + 1] - cut[r] >= 2 * FARGO_CPUOVERLAP);
-	if (ok) {
-	    imin = cut[rank];
-	    imax = cut[rank + 1] - 1;
-	}
+	    ok = ok && (w[r + 1] - w[r] >= 2 * FARGO_CPUOVERLAP);
+	if (ok)
+	    for (int r = 0; r <= np; ++r)
+		cut[r] = w[r];
     }
+    return 0;
+}
+
+static int split_domain(DevView &v, int nrad, int rank, int np, int *imax_out, const double *radii, const fargo_params &p)
+{
+    (void)nrad;
+    std::vector<int> cut(np + 1, 0);
+    if (fargo_split_cuts(&p, radii, np, cut.data()))
+	return 1;
+    int imin = cut[rank], imax = cut[rank + 1] - 1;
     if (rank > 0)
 	imin -= FARGO_CPUOVERLAP;
     if (rank < np - 1)

@@ -214,6 +214,12 @@ int fargo_stage_substep3(fargo_ctx *ctx, double dt);   /* SubStep3 SourceEuler.c
 int fargo_stage_boundary(fargo_ctx *ctx, double dt, int final_call); /* apply_boundary_condition boundary_conditions.cpp:65 */
 int fargo_stage_transport(fargo_ctx *ctx, double dt);  /* Transport TransportEuler.cpp:112 */
 int fargo_stage_halo(fargo_ctx *ctx);                  /* CommunicateBoundaries commbound.cpp:98 */
+/* Where the radial slabs are cut (SplitDomain, split.cpp:38-55): cut[r] = first ring owned by rank r, cut[nranks] = nrad.
+ * The reference gives every rank the same number of rings; these cuts balance cost instead (rings inside a damping zone
+ * weigh more), which changes no result (constants.h:17).  FARGO_B200_SPLIT=equal in the environment restores the
+ * reference's cuts.  Pure host arithmetic: needs no device and no context. */
+int fargo_split_cuts(const fargo_params *params, const double *radii, int nranks, int *cut /* nranks + 1 */);
+
 /* how the ghost rings travel: 0 = single rank, 1 = ncclSend / ncclRecv after Transport, 2 = stored into the neighbour's
  * inbox over NVLink peer memory by the transport kernel's edge launch while the interior rings are still being
  * transported (default when CUDA IPC maps on every rank; FARGO_B200_HALO=nccl in the environment forces 1) */
