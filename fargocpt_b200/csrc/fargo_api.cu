@@ -1328,6 +1328,7 @@ extern "C" int fargo_stage_halo(fargo_ctx *c)
 	u.flag[0] = has_prev ? h.flags + 0 : nullptr;
 	u.flag[1] = has_next ? h.flags + 1 : nullptr;
 	u.want = h.seq + 1;
+	u.timed_out = c->d_dt + 1;
 	dim3 grid((unsigned)((l + 4 * 256 - 1) / (4 * 256)), (unsigned)u.n);
 	LAUNCH(c, k_halo_unpack, grid, 256, 0, u);
 	h.seq++;
@@ -1396,9 +1397,11 @@ extern "C" int fargo_condition_cfl(fargo_ctx *c, double *out)
 	NCCL_OK(g_nccl.AllReduce(c->d_dt, c->d_dt, 1, ncclFloat64, ncclMin, c->comm, c->stream));
 	c->launches++;
     }
-    CUDA_OK(cudaMemcpyAsync(c->h_pin + 1, c->d_dt, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(c->h_pin + 1, c->d_dt, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     *out = c->h_pin[1];
+    if (c->h_pin[2] != 0.0) // k_halo_unpack gave up waiting (kernels_ring.cuh)
+	return fail("ghost-ring exchange timed out: a neighbouring rank did not deliver its rings");
     if (c->profiling)
 	c->t_cfl_done = host_now_ms();
     return 0;

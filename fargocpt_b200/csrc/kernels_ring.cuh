@@ -601,14 +601,24 @@ struct HaloUnpack {
     size_t len;
     const unsigned long long *flag[2];
     unsigned long long want;
+    double *timed_out; // set to 1.0 if a neighbour's rings never arrived (read back with the next CFL result)
 };
+#define HALO_SPIN_LIMIT (1u << 26) // x >= 200 ns: gives up after roughly 15-30 s instead of hanging the GPU for ever
 __global__ void __launch_bounds__(256) k_halo_unpack(const HaloUnpack u)
 {
     if (threadIdx.x == 0) {
-	for (int k = 0; k < 2; ++k)
-	    if (u.flag[k])
-		while (*(const volatile unsigned long long *)u.flag[k] < u.want)
-		    __nanosleep(200);
+	for (int k = 0; k < 2; ++k) {
+	    if (!u.flag[k])
+		continue;
+	    unsigned spins = 0;
+	    while (*(const volatile unsigned long long *)u.flag[k] < u.want) {
+		__nanosleep(200);
+		if (++spins == HALO_SPIN_LIMIT) { // a neighbouring rank has died or fallen out of step: do not hang, report
+		    *u.timed_out = 1.0;
+		    break;
+		}
+	    }
+	}
 	__threadfence_system();
     }
     __syncthreads();
