@@ -243,6 +243,15 @@ class Handle:
         self._check(fn(self.ptr, int(body), float(klahr_factor), out), "disk_on_body_accel")
         return np.array(list(out))
 
+    def accrete_kley(self, x, y, r_hill, facc, frac=1.0):
+        """accretion::AccreteOntoSinglePlanet (accretion.cpp:84-221); returns (dM, dPx, dPy) taken from the active cells."""
+        out = (C.c_double * 3)()
+        fn = self._fn("accrete_kley")
+        fn.argtypes = [C.c_void_p] + [C.c_double] * 5 + [C.POINTER(C.c_double)]
+        fn.restype = C.c_int
+        self._check(fn(self.ptr, float(x), float(y), float(r_hill), float(facc), float(frac), out), "accrete_kley")
+        return tuple(out)
+
     def monitor_quantities(self, radius_limit=1e300):
         """Global sums of monitor/Quantities.dat (fargo_monitor_quantities): dict of mass, angular_momentum, internal_energy,
         kinetic_energy, radial_kinetic_energy, azimuthal_kinetic_energy, viscous_dissipation, luminosity."""

@@ -1535,6 +1535,49 @@ extern "C" int fargo_get_nshift(fargo_ctx *c, int *out)
     return 0;
 }
 
+// accretion::AccreteOntoSinglePlanet (accretion.cpp:84-221)
+extern "C" int fargo_accrete_kley(fargo_ctx *c, double x, double y, double r_hill, double facc, double frac, double out3[3])
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    if (c->v_mid)
+	return fail("fargo_accrete_kley called mid-step");
+    const DevView &v = c->v;
+    AccretionIn a;
+    a.x = x, a.y = y, a.r_hill = r_hill;
+    a.facc1 = 1.0 / 3.0 * facc, a.facc2 = 2.0 / 3.0 * facc;
+    a.frac1 = frac, a.frac2 = 0.5 * frac;
+    a.density_floor = v.p.sigma_floor * v.p.sigma0;
+    // rings whose centres can lie within the accretion radius of the planet (with a ring of slack on either side)
+    const double rp = sqrt(x * x + y * y), reach = frac * r_hill;
+    int lo = 0, hi = v.nr;
+    while (lo < v.nr && c->h_rmed[lo] < rp - reach)
+	++lo;
+    while (hi > lo && c->h_rmed[hi - 1] > rp + reach)
+	--hi;
+    a.ring_lo = lo > 0 ? lo - 1 : 0;
+    a.ring_hi = hi < v.nr ? hi + 1 : v.nr;
+    const int nrings = a.ring_hi - a.ring_lo;
+    double *d_out = c->force4;
+    if (nrings > 0) {
+	const unsigned gx = (unsigned)((v.ns + ACC_THREADS - 1) / ACC_THREADS);
+	const int nblocks = (int)gx * nrings;
+	if ((size_t)nblocks * 3 > (size_t)v.nr * v.ns)
+	    return fail("scratch too small for the accretion partials");
+	dim3 grid(gx, (unsigned)nrings);
+	LAUNCH(c, k_accrete_kley, grid, ACC_THREADS, 0, v, c->sigma, EN(c), VRA(c), VPA(c), a, c->scratch);
+	LAUNCH(c, k_accrete_final, 1, 96, 0, c->scratch, nblocks, d_out);
+    } else {
+	CUDA_OK(cudaMemsetAsync(d_out, 0, 3 * sizeof(double), c->stream));
+    }
+    if (v.nranks > 1) { // MPI_Allreduce(SUM), accretion.cpp:199-213
+	NCCL_OK(g_nccl.AllReduce(d_out, d_out, 3, ncclFloat64, 0 /* ncclSum */, c->comm, c->stream));
+	c->launches++;
+    }
+    CUDA_OK(cudaMemcpyAsync(out3, d_out, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 // monitor/Quantities.dat sums (quantities.cpp:51-480 through output::write_quantities, output.cpp:326-520)
 extern "C" int fargo_monitor_quantities(fargo_ctx *c, double radius_limit, double out8[8])
 {

@@ -193,3 +193,94 @@ __global__ void __launch_bounds__(32 * MQ_N) k_monitor_final(const double *__res
     if (lane == 0)
 	out[q] = s;
 }
+
+// ---------------------------------------------------------------------------------------------
+// accretion::AccreteOntoSinglePlanet (accretion.cpp:84-221, "kley" accretion onto a planet): see fargo_b200.h.
+// One thread per cell of the rings [ring_lo, ring_hi) that can reach into the accretion radius; the cells inside it are
+// changed in place exactly as the reference changes them (same operations, same order); mass and momentum taken from active
+// cells are summed per block (shuffles) and then in block order (k_monitor_final's scheme).
+struct AccretionIn {
+    double x, y, r_hill, facc1, facc2, frac1, frac2, density_floor;
+    int ring_lo, ring_hi;
+};
+#define ACC_THREADS 128
+__global__ void __launch_bounds__(ACC_THREADS)
+    k_accrete_kley(const DevView c, double *__restrict__ sigma, double *__restrict__ energy, const double *__restrict__ vr,
+		   const double *__restrict__ vp, const AccretionIn a, double *__restrict__ partials)
+{
+    const int i = a.ring_lo + blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[3] = {0.0, 0.0, 0.0};
+    if (i < a.ring_hi && j < c.ns) {
+	const double rmed = c.g.rmed[i];
+	const double xc = rmed * c.g.cosphi[j], yc = rmed * c.g.sinphi[j];
+	const double dx = a.x - xc, dy = a.y - yc;
+	const double distance = sqrt(dx * dx + dy * dy);
+	if (distance < a.frac1 * a.r_hill) {
+	    const int jp = (j == c.ns - 1) ? 0 : j + 1;
+	    const double vtcell = 0.5 * (AT(vp, i, j) + AT(vp, i, jp)) + rmed * c.b.omega_frame;
+	    const double vrcell = 0.5 * (AT(vr, i, j) + AT(vr, i + 1, j));
+	    const double vxcell = (vrcell * xc - vtcell * yc) / rmed;
+	    const double vycell = (vrcell * yc + vtcell * xc) / rmed;
+	    double s = AT(sigma, i, j);
+	    double e = c.p.adiabatic ? AT(energy, i, j) : 0.0;
+	    const double facc_max = 1 - a.density_floor / s;
+	    const bool active = c.first_active < i && i < c.active_size;
+	    {
+		const double facc_ceil = stdmin(a.facc1, facc_max);
+		const double deltaM = facc_ceil * s * c.g.surf[i];
+		s *= 1.0 - facc_ceil;
+		e *= 1.0 - facc_ceil;
+		if (active) {
+		    acc[1] += deltaM * vxcell;
+		    acc[2] += deltaM * vycell;
+		    acc[0] += deltaM;
+		}
+	    }
+	    if (distance < a.frac2 * a.r_hill) {
+		const double facc_ceil = stdmin(a.facc2, facc_max);
+		const double deltaM = facc_ceil * s * c.g.surf[i];
+		s *= 1.0 - facc_ceil;
+		e *= 1.0 - a.facc2;
+		if (active) {
+		    acc[1] += deltaM * vxcell;
+		    acc[2] += deltaM * vycell;
+		    acc[0] += deltaM;
+		}
+	    }
+	    AT(sigma, i, j) = s;
+	    if (c.p.adiabatic)
+		AT(energy, i, j) = e;
+	}
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+	    acc[q] += __shfl_down_sync(0xffffffffu, acc[q], o);
+    __shared__ double sh[ACC_THREADS / 32][3];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0)
+#pragma unroll
+	for (int q = 0; q < 3; ++q)
+	    sh[w][q] = acc[q];
+    __syncthreads();
+    if (threadIdx.x < 3) {
+	double t = 0.0;
+	for (int k = 0; k < ACC_THREADS / 32; ++k)
+	    t += sh[k][threadIdx.x];
+	partials[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 3 + threadIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(96) k_accrete_final(const double *__restrict__ partials, const int nblocks, double *__restrict__ out3)
+{
+    const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double s = 0.0;
+    for (int b = lane; b < nblocks; b += 32)
+	s += partials[(size_t)b * 3 + q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+	s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0)
+	out3[q] = s;
+}

@@ -52,6 +52,7 @@ int fargo_oracle_disk_on_body_accel(fargo_oracle *, int, double, double *);
 int fargo_oracle_kick(fargo_oracle *, double);
 int fargo_oracle_drift(fargo_oracle *, double);
 int fargo_oracle_finish_step(fargo_oracle *, double);
+int fargo_oracle_accrete_kley(fargo_oracle *, double, double, double, double, double, double *);
 }
 typedef fargo_oracle backend_ctx;
 #define BK(name) fargo_oracle_##name
@@ -687,9 +688,30 @@ struct Run {
 	}
     }
 
+    // accretion::AccreteOntoPlanets (accretion.cpp:419-452), first thing in a step (simulation.cpp:150-153, :302-303, :403-404):
+    // bodies with an accretion efficiency take gas out of their Hill sphere ("accretion method: kley", the default).  The
+    // body itself only changes when it feels the disk (accretion.cpp:203-218), which this driver does not restate: it
+    // refuses that combination instead of running on with the wrong planet mass.
+    void accrete(double dt)
+    {
+	for (size_t k = 1; k < bodies.size(); ++k) {
+	    Body &b = bodies[k];
+	    if (!(b.rec.acc > 0.0) || !(b.orbital_period > 0.0))
+		continue;
+	    if (disk_feedback)
+		die("%s", std::string("accreting bodies that feel the disk (DiskFeedback: yes) are not supported by this driver"));
+	    const double facc = dt * b.rec.acc / b.orbital_period * std::log(2);
+	    const double r_hill = b.rec.dimensionless_roche_radius * b.rec.distance_to_primary;
+	    double taken[3];
+	    CHECK(BK(accrete_kley)(ctx, b.rec.x, b.rec.y, r_hill, facc, cfg.num("MassAccretionRadius", 1.0), taken));
+	    b.rec.accreted_mass += taken[0]; // monitoring only (accretion.cpp:201)
+	}
+    }
+
     // step_Euler (simulation.cpp:148-267) around the gas part
     void step_euler(double dt)
     {
+	accrete(dt);
 	disk_feedback_kick(dt);
 	set_bodies_on_device(); // indirect term from the current bodies (:160-162), potential inputs (:170)
 	apply_indirect_term_on_nbody(dt); // :164
@@ -707,6 +729,7 @@ struct Run {
     {
 	const double frog = dt / 2, start_time = time, mid_time = time + frog;
 	integrate_and_recentre(frog);	  // :286-294
+	accrete(frog);			  // :302-303
 	disk_feedback_kick(frog);	  // :297-313 (ComputeDiskOnNbodyAccel, UpdatePlanetVelocitiesWithDiskForce)
 	set_bodies_on_device();
 	apply_indirect_term_on_nbody(frog); // :315
@@ -719,6 +742,7 @@ struct Run {
 	set_bodies_on_device();
 	CHECK(BK(set_time)(ctx, mid_time));
 	CHECK(BK(kick)(ctx, frog));
+	accrete(frog);			  // :403-404, after the gas's second kick
 	apply_indirect_term_on_nbody(frog); // :416
 	integrate_and_recentre(frog);	  // :419-424
 	rotate_frame(frog);		  // :428

@@ -247,6 +247,14 @@ int fargo_snapshot_wait(fargo_ctx *ctx);
 void *fargo_pinned_alloc(size_t bytes);
 void fargo_pinned_free(void *p);
 
+/* accretion::AccreteOntoSinglePlanet (accretion.cpp:84-221; "accretion method: kley", called first thing in a step,
+ * simulation.cpp:150-153): gas within frac * r_hill of the body at (x, y) loses the fraction facc / 3, within frac / 2 * r_hill
+ * another 2 facc / 3, never below the density floor; Sigma (and the energy of an adiabatic disk) are changed in place.
+ * The N-body side provides r_hill = dimensionless Roche radius * distance to the primary, facc = dt * accretion efficiency /
+ * orbital period * ln 2 and frac = MassAccretionRadius.  out3 = {mass, x-momentum, y-momentum} taken from the active cells of all
+ * ranks (what update_planet, accretion.cpp:60-82, adds to the body when it feels the disk). */
+int fargo_accrete_kley(fargo_ctx *ctx, double x, double y, double r_hill, double facc, double frac, double out3[3]);
+
 /* Global disk quantities of monitor/Quantities.dat (output::write_quantities output.cpp:326-520 -> quantities.cpp):
  * sums over the active cells with Rmed <= radius_limit (QuantitiesRadiusLimit, default 2 Rmax), all ranks.
  * out8 = { mass (quantities.cpp:51-78), angular momentum (:242-276), internal energy (:281-304), kinetic energy (:357-401),

@@ -1582,6 +1582,65 @@ int fargo_oracle_step(fargo_oracle *o, double dt)
     return 0;
 }
 
+/* accretion::AccreteOntoSinglePlanet (accretion.cpp:84-221, "kley" accretion): a fraction facc1 = facc / 3 of the gas within
+ * frac * RHill of the planet and another facc2 = 2 facc / 3 within frac / 2 * RHill leaves the disk (never below the density
+ * floor); the energy of an adiabatic disk is scaled with it (zone 2 by 1 - facc2, as the reference does).  facc = dt *
+ * accretion efficiency / orbital period * ln 2 and RHill = dimensionless Roche radius * distance to the primary are the
+ * N-body side's numbers.  The reference walks a window of cells around the planet that contains every cell inside
+ * frac * RHill; testing every cell's distance gives the same cells.  out3 = mass and momentum taken from ACTIVE cells
+ * (radial_first_active < i < radial_active_size, :171), summed in index order. */
+int fargo_oracle_accrete_kley(fargo_oracle *o, double xp, double yp, double r_hill, double facc, double frac, double out3[3])
+{
+    const double OmegaF = o->bodies.omega_frame;
+    const double density_floor = o->p.sigma_floor * o->p.sigma0;
+    const double facc1 = 1.0 / 3.0 * facc, facc2 = 2.0 / 3.0 * facc;
+    const double frac1 = frac, frac2 = 0.5 * frac;
+    double dM = 0.0, dPx = 0.0, dPy = 0.0;
+    for (int i = 0; i < o->nr; ++i) {
+	for (int j = 0; j < o->ns; ++j) {
+	    const size_t l = IDX(o, i, j);
+	    const int jp = j == o->ns - 1 ? 0 : j + 1;
+	    const double xc = o->rmed[i] * o->cosphi[j], yc = o->rmed[i] * o->sinphi[j];
+	    const double dx = xp - xc, dy = yp - yc;
+	    const double distance = sqrt(dx * dx + dy * dy);
+	    if (!(distance < frac1 * r_hill))
+		continue; /* zone 2 lies inside zone 1 */
+	    const double vtcell = 0.5 * (o->vazi[l] + o->vazi[IDX(o, i, jp)]) + o->rmed[i] * OmegaF;
+	    const double vrcell = 0.5 * (o->vrad[l] + o->vrad[IDX(o, i + 1, j)]);
+	    const double vxcell = (vrcell * xc - vtcell * yc) / o->rmed[i];
+	    const double vycell = (vrcell * yc + vtcell * xc) / o->rmed[i];
+	    const double facc_max = 1 - density_floor / o->sigma[l];
+	    const int active = o->first_active < i && i < o->active_size;
+	    {
+		const double facc_ceil = facc_max < facc1 ? facc_max : facc1; /* std::min(facc1, facc_max) */
+		const double deltaM = facc_ceil * o->sigma[l] * o->surf[i];
+		o->sigma[l] *= 1.0 - facc_ceil;
+		if (o->p.adiabatic)
+		    o->energy[l] *= 1.0 - facc_ceil;
+		if (active) {
+		    dPx += deltaM * vxcell;
+		    dPy += deltaM * vycell;
+		    dM += deltaM;
+		}
+	    }
+	    if (distance < frac2 * r_hill) {
+		const double facc_ceil = facc_max < facc2 ? facc_max : facc2;
+		const double deltaM = facc_ceil * o->sigma[l] * o->surf[i];
+		o->sigma[l] *= 1.0 - facc_ceil;
+		if (o->p.adiabatic)
+		    o->energy[l] *= 1.0 - facc2;
+		if (active) {
+		    dPx += deltaM * vxcell;
+		    dPy += deltaM * vycell;
+		    dM += deltaM;
+		}
+	    }
+	}
+    }
+    out3[0] = dM, out3[1] = dPx, out3[2] = dPy;
+    return 0;
+}
+
 /* Global disk quantities of monitor/Quantities.dat (output::write_quantities, output.cpp:326-520): serial sums in index
  * order, which is what the reference computes with OMP_NUM_THREADS=1 (its reductions have no defined order otherwise).
  * out8 = mass (quantities.cpp:51-78), angular momentum (:242-276), internal energy (:281-304), kinetic energy (:357-401),

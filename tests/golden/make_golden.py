@@ -99,6 +99,14 @@ CASES = {
                             ViscousAlpha=1e-3, HeatingViscous="yes", CoolingBetaLocal="yes", CoolingBeta=10,
                             Damping="Yes", DampingInnerLimit=1.25, DampingOuterLimit=0.84, DampingTimeFactor=0.1,
                             _planet=1e-3, _keep=(0, 50, 100), **DAMP_ALL),
+    # accretion::AccreteOntoSinglePlanet (accretion.cpp:84-221): a planet that accretes ("kley", efficiency 5 per orbit) but
+    # does not feel the disk (DiskFeedback: no), so the only feedback of the accretion is the gas it removes
+    "iso_accrete_20": dict(Nrad=48, Naz=160, Rmax=2.5, Nsnapshots=20, MonitorTimestep=4.0e-3, IndirectTermMode=1,
+                           EquationOfState="Isothermal", ViscousAlpha=1e-3, ArtificialViscosityFactor=1.41, FlaringIndex=0.0,
+                           _planet=3e-3, _accretion=5.0, _keep=(0, 10, 20)),
+    "adia_accrete_20": dict(Nrad=48, Naz=160, Rmax=2.5, Nsnapshots=20, MonitorTimestep=4.0e-3, IndirectTermMode=1,
+                            ViscousAlpha=1e-3, HeatingViscous="yes", CoolingBetaLocal="yes", CoolingBeta=10,
+                            _planet=3e-3, _accretion=5.0, _keep=(0, 10, 20)),
     "iso_planet_100": dict(Nrad=48, Naz=160, Rmax=2.5, Nsnapshots=100, MonitorTimestep=4.0e-3, IndirectTermMode=1,
                            EquationOfState="Isothermal", ViscousAlpha=1e-3, ArtificialViscosityFactor=1.41, OmegaFrame=1.0,
                            FlaringIndex=0.0, Damping="Yes", DampingInnerLimit=1.25, DampingOuterLimit=0.84,
@@ -123,7 +131,12 @@ def read_body(path):
     raw = open(path, "rb").read()
     mass, x, y, vx, vy = struct.unpack("<5d", raw[8:48])  # planet_member_variables (nbody/planet.h:11-17)
     dax, day = struct.unpack("<2d", raw[120:136])  # m_disk_on_planet_acceleration (:27), refreshed at every monitor output
-    return [mass, x, y, vx, vy, dax, day]
+    # what accretion::AccreteOntoSinglePlanet reads off the body (accretion.cpp:104-118): accretion efficiency (:20),
+    # accreted mass so far (:21), distance to the primary and dimensionless Roche radius (:31-32), semi-major axis (:36)
+    acc_eff, accreted = struct.unpack("<2d", raw[56:72])
+    dist_primary, roche = struct.unpack("<2d", raw[152:168])
+    (semi_major,) = struct.unpack("<d", raw[176:184])
+    return [mass, x, y, vx, vy, dax, day, acc_eff, accreted, dist_primary, roche, semi_major]
 
 
 def run_case(name, overrides, keep=False):
@@ -131,10 +144,13 @@ def run_case(name, overrides, keep=False):
     cfg.update(overrides)
     planet = cfg.pop("_planet", 0.0)
     keep_snaps = cfg.pop("_keep", None)
+    accretion = cfg.pop("_accretion", 0.0)
     if planet > 0:
         cfg["nbody"] = list(cfg["nbody"]) + [{"name": "planet", "semi-major axis": 1.0, "mass": float(planet),
-                                               "accretion efficiency": 0.0, "eccentricity": 0.0, "radius": "0.01 solRadius",
+                                               "accretion efficiency": float(accretion), "eccentricity": 0.0, "radius": "0.01 solRadius",
                                                "temperature": "0 K", "ramp-up time": 0}]
+        if accretion > 0:
+            cfg["nbody"][-1]["accretion method"] = "kley"
     tmp = tempfile.mkdtemp(prefix="golden_" + name + "_")
     cfg["OutputDir"] = os.path.join(tmp, "out")
     ypath = os.path.join(tmp, "cfg.yml")

@@ -70,15 +70,41 @@ def start_from_snapshot0(ctx, meta, z):
     return loop, omega
 
 
-def run_fixture(ctx, meta, z, nsteps=None, on_snapshot=None):
-    """Returns list of per-snapshot dicts of downloaded state fields."""
+def accretion_inputs(meta, k, body, dt):
+    """What accretion::AccreteOntoSinglePlanet (accretion.cpp:104-118) reads off body `body` as recorded at snapshot k, for a
+    step of length dt starting there: (x, y, RHill, facc, frac).  The orbital period is t_planet::calculate_orbital_elements'
+    (planet.cpp:516-517) from the recorded semi-major axis; std::pow / std::log are the libm functions Python calls."""
+    import math
+    rec, primary = meta["bodies"][k][body], meta["bodies"][k][0]
+    acc_eff, dist_primary, roche, a = rec[7], rec[9], rec[10], rec[11]
+    G = meta["consts"]["G"]
+    m = primary[0] + rec[0]
+    period = 2.0 * math.pi * math.sqrt(math.pow(a, 3) / (m * G))
+    facc = dt * acc_eff / period * math.log(2)
+    r_hill = roche * dist_primary
+    frac = float(meta["config"].get("MassAccretionRadius", 1.0))
+    return rec[1], rec[2], r_hill, facc, frac
+
+
+def run_fixture(ctx, meta, z, nsteps=None, on_snapshot=None, accreted=None):
+    """Returns list of per-snapshot dicts of downloaded state fields.  Bodies with an accretion efficiency accrete first
+    thing in every step (simulation.cpp:150-153); `accreted` (a list) receives (snapshot, body, dM, dPx, dPy)."""
     loop, omega = start_from_snapshot0(ctx, meta, z)
     nsnap = meta["nsnap"] if nsteps is None else nsteps
     out = []
+    accretors = [b for b, rec in enumerate(meta["bodies"][0]) if len(rec) > 7 and rec[7] > 0.0]
+
+    def before_step(k, dt):
+        for b in accretors:
+            d = ctx.accrete_kley(*accretion_inputs(meta, k - 1, b, dt))
+            if accreted is not None:
+                accreted.append((k, b) + tuple(d))
+        return bodies_at(meta, k - 1, omega)
+
     for k in range(1, nsnap + 1):
         guard = 0
         while True:
-            hit = loop.advance(lambda t, dt: bodies_at(meta, k - 1, omega))
+            hit = loop.advance(lambda t, dt: before_step(k, dt))
             guard += 1
             assert guard < 1000
             if hit:

@@ -117,3 +117,38 @@ def test_gpu_monitor_quantities_vs_oracle(name, k):
     for q in abi.MONITOR_QUANTITIES:
         assert abs(a[q] - b[q]) <= 1e-13 * max(abs(b[q]), 1e-300), (q, a[q], b[q])
     assert 0.0 < b["mass"] < cpu.monitor_quantities()["mass"]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# accretion::AccreteOntoSinglePlanet (accretion.cpp:84-221)
+@pytest.mark.parametrize("name", ["iso_accrete_20", "adia_accrete_20"])
+def test_oracle_accreted_mass_matches_reference(name):
+    """The mass the oracle takes out of the Hill sphere in every step against the planet's recorded m_accreted_mass (the
+    reference sums it with an OpenMP reduction: 1e-12).  The fields of the same runs are held bit for bit in
+    test_oracle_vs_golden.py."""
+    meta, z, ctx = _oracle(name)
+    acc = []
+    goldenrun.run_fixture(ctx, meta, z, accreted=acc)
+    assert len(acc) == meta["nsnap"]
+    for k, body, dm, dpx, dpy in acc:
+        ref = meta["bodies"][k][body][8]
+        assert dm > 0.0 and abs(dm - ref) <= 1e-12 * ref, (k, dm, ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["iso_accrete_20", "adia_accrete_20"])
+def test_gpu_accretion_vs_oracle(name):
+    """One accretion call from identical states: the cells changed bit for bit, the sums within 1e-13."""
+    from fargocpt_b200 import HydroContext
+    meta, z, cpu = _oracle(name)
+    gpu = HydroContext(reftools.make_params(meta["params"]), z["radii"])
+    res = []
+    for ctx in (cpu, gpu):
+        _load(ctx, meta, z, 10)
+        res.append(ctx.accrete_kley(*goldenrun.accretion_inputs(meta, 10, 1, meta["monitor_timestep"])))
+    for fid in (abi.SIGMA, abi.ENERGY) if meta["params"]["adiabatic"] else (abi.SIGMA,):
+        st = reftools.compare_stats(gpu.download(fid), cpu.download(fid))
+        assert st["n_diff"] == 0, (fid, st)
+    assert (gpu.download(abi.SIGMA) != z["Sigma_10"]).sum() > 4  # the Hill sphere covers cells on this grid
+    for a, b in zip(res[1], res[0]):
+        assert abs(a - b) <= 1e-13 * abs(b), (res)

@@ -19,7 +19,9 @@ pytestmark = pytest.mark.gpu
 CASES = ["adia_star", "adia_cold", "iso_star", "iso_sn_std", "adia_sn_stab", "ring_like", "adia_leapfrog", "iso_feedback_20"]
 # 100 hydro steps with a Jupiter-mass planet (48 x 160: two warp windows per ring), recorded from the reference
 LONG_CASES = ["adia_planet_100", "iso_planet_100"]
-ISOTHERMAL = {"iso_star", "iso_sn_std", "ring_like", "iso_planet_100"}
+# a planet that accretes gas out of its Hill sphere first thing in every step (accretion.cpp:84-221)
+LONG_CASES += ["iso_accrete_20", "adia_accrete_20"]
+ISOTHERMAL = {"iso_star", "iso_sn_std", "ring_like", "iso_planet_100", "iso_accrete_20"}
 ADIABATIC_RTOL = 0.0
 LONG_RTOL = 0.0  # north_star allows 1e-10 after 100 steps; the glibc-exact exp makes the adiabatic runs bit-exact too
 
