@@ -128,6 +128,10 @@ struct fargo_ctx {
     double *vmean, *vconst, *expf_s, *expf_v, *d_dt, *scratch, *force4;
     double *hstale = nullptr; // leapfrog: scale height of the first kick's viscosity stage (see fargo_kick)
     bool h_stale = false;
+    // pre-accretion Sigma / e of rings [pre_lo, pre_hi) (fargo_dev.h:PreState): written by fargo_accrete_kley, consumed by
+    // the next source-term stage, dropped when the derived quantities are recalculated (fargo_finish_step)
+    double *sig_pre = nullptr, *e_pre = nullptr;
+    int pre_lo = 0, pre_hi = 0;
     int *nshift;
     double *h_pin; // pinned host staging for the CFL scalar + ring factors
     bool visc_const_filled = false;
@@ -662,9 +666,9 @@ extern "C" int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, con
 		n = 1;
 	    return n;
 	};
-	const int occ_fs = adi ? std::min(occ((const void *)k_fused_sources<true>),
+	const int occ_fs = adi ? std::min(occ((const void *)k_fused_sources<true, false>),
 					  std::min(occ((const void *)k_fused_artvisc<true>), occ((const void *)k_fused_viscosity<true>)))
-			       : std::min(occ((const void *)k_fused_sources<false>),
+			       : std::min(occ((const void *)k_fused_sources<false, false>),
 					  std::min(occ((const void *)k_fused_artvisc<false>), occ((const void *)k_fused_viscosity<false>)));
 	const int occ_az = mc ? (adi ? occ((const void *)k_transport_azimuthal<FARGO_LIMITER_MC, true, false>)
 				     : occ((const void *)k_transport_azimuthal<FARGO_LIMITER_MC, false, false>))
@@ -950,13 +954,21 @@ extern "C" int fargo_set_time(fargo_ctx *c, double t)
     return 0;
 }
 
+// what fargo_accrete_kley kept of the state before the accretion (fargo_dev.h:PreState)
+static PreState pre_state(const fargo_ctx *c)
+{
+    PreState q;
+    q.sigma = c->sig_pre, q.energy = c->e_pre, q.lo = c->pre_lo, q.hi = c->pre_hi;
+    return q;
+}
+
 // ---------------------------------------------------------------------------------------------
 // stages
 extern "C" int fargo_stage_potential(fargo_ctx *c)
 {
     CUDA_OK(cudaSetDevice(c->device));
     LAUNCH(c, k_potential, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, EN(c), c->pot,
-	   (const double *)(c->h_stale ? c->hstale : nullptr));
+	   (const double *)(c->h_stale ? c->hstale : nullptr), pre_state(c));
     return 0;
 }
 
@@ -970,7 +982,8 @@ extern "C" int fargo_stage_sources(fargo_ctx *c, double dt)
     if (c->v_mid)
 	return fail("stage_sources called while the velocities are mid-step (call stage_transport first)");
     LAUNCH(c, k_sources_velocity, cells_grid((long long)(c->v.nr + 1) * c->v.ns), 256, 0, c->v, c->sigma, EN(c), c->pot,
-	   VRA(c), VPA(c), VRB(c), VPB(c), dt);
+	   VRA(c), VPA(c), VRB(c), VPB(c), dt, pre_state(c));
+    c->pre_lo = c->pre_hi = 0; // the stored PRESSURE has had its last reader (SourceEuler.cpp:325-428)
     c->v_mid = true;
     if (c->v.p.adiabatic)
 	LAUNCH(c, k_compression_heating, cells_grid((long long)(c->v.nr - 1) * c->v.ns), 256, 0, c->v, VRB(c), VPB(c), EN(c), dt);
@@ -1429,8 +1442,14 @@ template <bool ADI> static int launch_fused_sources(fargo_ctx *c, double dt)
     const int nwin = (v.ns + FS_OUT - 1) / FS_OUT;
     dim3 grid((unsigned)((nwin + 3) / 4), (unsigned)((v.nr + c->fs_R - 1) / c->fs_R));
     const int eo = ADI ? 1 - c->ecur : c->ecur;
-    LAUNCH(c, k_fused_sources<ADI>, grid, 128, 0, v, c->sigma, EN(c), VRA(c), VPA(c), (const double *)(c->h_stale ? c->hstale : nullptr),
-	   VRB(c), VPB(c), c->eb[eo], dt, c->fs_R);
+    if (c->pre_hi > c->pre_lo) { // the step began with an accretion call: P and H of the touched rings from the state before it
+	LAUNCH(c, (k_fused_sources<ADI, true>), grid, 128, 0, v, c->sigma, EN(c), VRA(c), VPA(c),
+	       (const double *)(c->h_stale ? c->hstale : nullptr), VRB(c), VPB(c), c->eb[eo], dt, c->fs_R, pre_state(c));
+	c->pre_lo = c->pre_hi = 0;
+    } else {
+	LAUNCH(c, (k_fused_sources<ADI, false>), grid, 128, 0, v, c->sigma, EN(c), VRA(c), VPA(c),
+	       (const double *)(c->h_stale ? c->hstale : nullptr), VRB(c), VPB(c), c->eb[eo], dt, c->fs_R, pre_state(c));
+    }
     c->vcur = 1 - c->vcur;
     c->ecur = eo;
     const bool diss = ADI && p.artificial_viscosity_dissipation;
@@ -1505,6 +1524,7 @@ extern "C" int fargo_finish_step(fargo_ctx *c, double dt)
     if (fargo_stage_halo(c) || fargo_stage_boundary(c, dt, 1) || fargo_stage_derived(c))
 	return 1;
     c->h_stale = false; // recalculate_derived_disk_quantities: H is the current state's again
+    c->pre_lo = c->pre_hi = 0; // ... and so is the pressure (an accretion call after the last kick of a leapfrog step)
     return 0;
 }
 
@@ -1559,6 +1579,35 @@ extern "C" int fargo_accrete_kley(fargo_ctx *c, double x, double y, double r_hil
     const int nrings = a.ring_hi - a.ring_lo;
     double *d_out = c->force4;
     if (nrings > 0) {
+	// The reference's stored PRESSURE / SCALE_HEIGHT keep describing the state before the accretion until the end of the
+	// step (fargo_dev.h:PreState): keep the rows about to change.  Several bodies may accrete before one step: the kept
+	// band grows to the union, and rows outside the band kept so far have not been touched yet.
+	const size_t rowb = (size_t)v.ns * sizeof(double);
+	if (!c->sig_pre && dalloc(c, &c->sig_pre, (size_t)v.nr * v.ns))
+	    return 1;
+	if (v.p.adiabatic && !c->e_pre && dalloc(c, &c->e_pre, (size_t)v.nr * v.ns))
+	    return 1;
+	auto keep = [&](int lo_, int hi_) -> cudaError_t {
+	    if (hi_ <= lo_)
+		return cudaSuccess;
+	    const size_t off = (size_t)lo_ * v.ns, len = (size_t)(hi_ - lo_) * rowb;
+	    cudaError_t e = cudaMemcpyAsync(c->sig_pre + off, c->sigma + off, len, cudaMemcpyDeviceToDevice, c->stream);
+	    if (e == cudaSuccess && v.p.adiabatic)
+		e = cudaMemcpyAsync(c->e_pre + off, EN(c) + off, len, cudaMemcpyDeviceToDevice, c->stream);
+	    return e;
+	};
+	if (c->pre_hi <= c->pre_lo) {
+	    CUDA_OK(keep(a.ring_lo, a.ring_hi));
+	    c->pre_lo = a.ring_lo, c->pre_hi = a.ring_hi;
+	} else {
+	    CUDA_OK(keep(a.ring_lo, std::min(a.ring_hi, c->pre_lo)));
+	    CUDA_OK(keep(std::max(a.ring_lo, c->pre_hi), a.ring_hi));
+	    if (a.ring_lo > c->pre_hi) // rows between two disjoint bands: untouched so far
+		CUDA_OK(keep(c->pre_hi, a.ring_lo));
+	    if (a.ring_hi < c->pre_lo)
+		CUDA_OK(keep(a.ring_hi, c->pre_lo));
+	    c->pre_lo = std::min(c->pre_lo, a.ring_lo), c->pre_hi = std::max(c->pre_hi, a.ring_hi);
+	}
 	const unsigned gx = (unsigned)((v.ns + ACC_THREADS - 1) / ACC_THREADS);
 	const int nblocks = (int)gx * nrings;
 	if ((size_t)nblocks * 3 > (size_t)v.nr * v.ns)

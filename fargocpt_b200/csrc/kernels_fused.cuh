@@ -288,11 +288,15 @@ __device__ __forceinline__ void st_compress(const DevView &c, const int r, const
 // ---------------------------------------------------------------------------------------------
 // k_fused_sources.  Iteration kr loads ring kr, forms Phi(kr), P(kr), v_rad'(kr) (needs ring kr-1) and v_azi'(kr),
 // then finishes ring r = kr-1: e'(r) needs v_rad'(r+1).  Output: v_rad', v_azi', e' of ring r.
-template <bool ADI>
+// PRE: the step began with an accretion call (fargo_dev.h:PreState) — P and H of the rings it may have touched are those of
+// the pre-accretion state, like the reference's stored PRESSURE / SCALE_HEIGHT; a separate instantiation, so the kernel
+// of every other step is unchanged.
+template <bool ADI, bool PRE>
 __global__ void __launch_bounds__(128, FS_MINB_SRC)
     k_fused_sources(const DevView c, const double *__restrict__ sigma, const double *__restrict__ energy,
 		    const double *__restrict__ vr, const double *__restrict__ vp, const double *__restrict__ h_in,
-		    double *__restrict__ o_vr, double *__restrict__ o_vp, double *__restrict__ o_e, const double dt, const int R)
+		    double *__restrict__ o_vr, double *__restrict__ o_vp, double *__restrict__ o_e, const double dt, const int R,
+		    const PreState pre)
 {
     typedef MathP<true> MF;
     typedef MathP<false> MS;
@@ -338,8 +342,19 @@ __global__ void __launch_bounds__(128, FS_MINB_SRC)
 	    FS_FOR4 Hin[k] = 0.0;
 	    if (have_h)
 		fs_load(h_in, kr, c, L, Hin);
-	    FS_RUN((st_potential<MF, ADI>(c, ec, kr, S0, E0, cosj, sinj, have_h, Hin, P0, F0, A)),
-		   (st_potential<MS, ADI>(c, ec, kr, S0, E0, cosj, sinj, have_h, Hin, P0, F0, A)));
+	    if (PRE && pre_has(pre, kr)) { // warp-uniform: a warp marches through whole rings
+		double Sp[FS_NC], Ep[FS_NC];
+		fs_load(pre.sigma, kr, c, L, Sp);
+		if (ADI)
+		    fs_load(pre.energy, kr, c, L, Ep);
+		else
+		    FS_FOR4 Ep[k] = 0.0;
+		FS_RUN((st_potential<MF, ADI>(c, ec, kr, Sp, Ep, cosj, sinj, have_h, Hin, P0, F0, A)),
+		       (st_potential<MS, ADI>(c, ec, kr, Sp, Ep, cosj, sinj, have_h, Hin, P0, F0, A)));
+	    } else {
+		FS_RUN((st_potential<MF, ADI>(c, ec, kr, S0, E0, cosj, sinj, have_h, Hin, P0, F0, A)),
+		       (st_potential<MS, ADI>(c, ec, kr, S0, E0, cosj, sinj, have_h, Hin, P0, F0, A)));
+	    }
 	} else {
 	    FS_FOR4 { P0[k] = F0[k] = 0.0; }
 	}

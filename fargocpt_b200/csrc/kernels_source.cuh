@@ -54,12 +54,16 @@ __device__ __forceinline__ double potential_at(const DevView &c, int i, int j, d
     return pot;
 }
 
+// pre: the pre-accretion state the reference's stored SCALE_HEIGHT still describes (fargo_dev.h:PreState)
 __global__ void __launch_bounds__(256) k_potential(const DevView c, const double *__restrict__ sigma,
 						    const double *__restrict__ energy, double *__restrict__ pot,
-						    const double *__restrict__ h_in)
+						    const double *__restrict__ h_in, const PreState pre)
 {
     CELL_INDEX(c.nr);
-    AT(pot, i, j) = potential_at(c, i, j, AT(sigma, i, j), AT(energy, i, j), h_in);
+    const bool old = pre_has(pre, i);
+    const double s = old ? AT(pre.sigma, i, j) : AT(sigma, i, j);
+    const double e = (old && c.p.adiabatic) ? AT(pre.energy, i, j) : AT(energy, i, j);
+    AT(pot, i, j) = potential_at(c, i, j, s, e, h_in);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -68,14 +72,22 @@ __global__ void __launch_bounds__(256) k_potential(const DevView c, const double
 __global__ void __launch_bounds__(256)
     k_sources_velocity(const DevView c, const double *__restrict__ sigma, const double *__restrict__ energy,
 		       const double *__restrict__ pot, const double *__restrict__ vr, const double *__restrict__ vp,
-		       double *__restrict__ vr_out, double *__restrict__ vp_out, const double dt)
+		       double *__restrict__ vr_out, double *__restrict__ vp_out, const double dt, const PreState pre)
 {
     CELL_INDEX(c.nr + 1);
+    // the stored PRESSURE of the reference: of the pre-accretion state where accretion has touched the ring (PreState);
+    // the densities in the denominators are the current ones (SourceEuler.cpp:349-353, :401-405)
+    auto pressure = [&](int ii, int jj) {
+	const bool old = pre_has(pre, ii);
+	const double ps = old ? AT(pre.sigma, ii, jj) : AT(sigma, ii, jj);
+	const double pe = (old && c.p.adiabatic) ? AT(pre.energy, ii, jj) : AT(energy, ii, jj);
+	return eos_P(c, ii, ps, pe);
+    };
     double vr_new = AT(vr, i, j);
     if (i >= c.one_no_ghost_vr && i < c.maxmo_no_ghost_vr) {
 	const double s = AT(sigma, i, j), sm = AT(sigma, i - 1, j);
-	const double P = eos_P(c, i, s, AT(energy, i, j));
-	const double Pm = eos_P(c, i - 1, sm, AT(energy, i - 1, j));
+	const double P = pressure(i, j);
+	const double Pm = pressure(i - 1, j);
 	double gradp = 2.0 / (s + sm);
 	gradp *= (P - Pm);
 	gradp *= c.g.invdiffrmed[i];
@@ -92,8 +104,8 @@ __global__ void __launch_bounds__(256)
 	if (i >= c.zero_no_ghost && i < c.max_no_ghost) {
 	    const double invdxtheta = 2.0 / (c.dphi * (c.g.rsup[i] + c.g.rinf[i]));
 	    const double s = AT(sigma, i, j), sp = AT(sigma, i, jm);
-	    const double P = eos_P(c, i, s, AT(energy, i, j));
-	    const double Pp = eos_P(c, i, sp, AT(energy, i, jm));
+	    const double P = pressure(i, j);
+	    const double Pp = pressure(i, jm);
 	    const double gradp = 2.0 / (s + sp) * (P - Pp) * invdxtheta;
 	    const double gradphi = (AT(pot, i, j) - AT(pot, i, jm)) * invdxtheta;
 	    vp_new = vp_new + dt * (-gradp - gradphi);
