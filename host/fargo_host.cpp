@@ -8,12 +8,15 @@
 //   restart.cpp:19-131, polargrid.cpp:301-353            -> load_snapshot()   (raw double[Nrad(+1)][Naz], no header)
 //   output.cpp:249-330, polargrid.cpp:135-180, output.h:16-24 (misc.bin), nbody/planet.h:11-45 (nbodyK.bin)
 //                                                        -> write_snapshot()
-// It is a drop-in for an EXISTING FargoCPT output directory: `restart N <dir>` reads the directory the reference wrote
+// `start <setup.yml>` begins a run from a FargoCPT setup file like `fargocpt start` (units, constants, radial grid, N-body
+// initial state and the power-law disk of init.cpp: host/fargo_init.hpp) and writes snapshot 0 exactly as the reference does.
+// It is also a drop-in for an EXISTING FargoCPT output directory: `restart N <dir>` reads the directory the reference wrote
 // (config.yml of the snapshot, constants.yml / units.yml for the code-unit constants, dimensions.dat, used_rad.dat, the
 // snapshot's fields, misc.bin, nbodyK.bin and snapshots/reference/ for the damping targets) and continues the run on the
 // GPU, writing snapshots in the same binary format, so Tools/compare_binary_output.py can diff the two runs file by file.
-// Out of scope here: initial-condition generators, unit-string parsing beyond "<number> <unit>" with the
-// unit factors taken from units.yml, REBOUND (bodies are advanced with RK4 sub-steps, see nbody_integrate), monitors.
+// Out of scope here: initial conditions other than the power-law profile (read-in files, N-body-centred
+// disks, test problems), units beyond the table in fargo_init.hpp, REBOUND (bodies are advanced with RK4 sub-steps, see
+// nbody_integrate), monitors other than timestepLogging.dat and Quantities.dat.
 //
 // The hydro arithmetic all happens behind the C ABI; build with -DFARGO_HOST_ORACLE to bind the same driver to the CPU
 // oracle (TEST INFRASTRUCTURE: lets the host logic be tested without a GPU; never shipped).
@@ -33,6 +36,7 @@
 #include <vector>
 
 #include "../include/fargo_b200.h"
+#include "fargo_init.hpp"
 
 #ifdef FARGO_HOST_ORACLE
 extern "C" {
@@ -557,7 +561,8 @@ struct Run {
     {
 	refdir = dir;
 	const std::string sd = dir + "/snapshots/" + std::to_string(nsnap);
-	cfg.load(exists(sd + "/config.yml") ? sd + "/config.yml" : dir + "/parameters/cfg.yml");
+	config_path = exists(sd + "/config.yml") ? sd + "/config.yml" : dir + "/parameters/cfg.yml";
+	cfg.load(config_path);
 	consts.load(dir);
 	{ // dimensions.dat: RMIN RMAX PHIMIN PHIMAX NRAD NAZ NGHRAD NGHAZ Radial_spacing (init.cpp:227-247)
 	    std::ifstream f(dir + "/dimensions.dat");
@@ -614,15 +619,7 @@ struct Run {
 	monitor_timestep = cfg.num("MonitorTimestep", 1.0);
 	nmonitor = (unsigned)cfg.num("Nmonitor", 1);
 	nsnapshots = (unsigned)cfg.num("Nsnapshots", 1);
-#ifdef FARGO_HOST_ORACLE
-	(void)device;
-	ctx = fargo_oracle_create(&params, radii.data(), 0, 1);
-	if (!ctx)
-	    die("fargo_oracle_create failed");
-#else
-	if (fargo_ctx_create(&ctx, &params, radii.data(), 0, 1, nullptr, device) != 0)
-	    die("fargo_ctx_create: %s", fargo_last_error());
-#endif
+	create_context(device);
 	// restart_load (restart.cpp:19-131): the four state fields
 	const std::pair<int, const char *> state[4] = {{FARGO_SIGMA, "Sigma"}, {FARGO_VRAD, "vrad"}, {FARGO_VAZI, "vazi"}, {FARGO_ENERGY, "energy"}};
 	for (auto &s : state)
@@ -646,6 +643,150 @@ struct Run {
 		CHECK(BK(upload_field)(ctx, s.first, read_doubles(rd + "/" + s.second + ".dat", cells(s.first == FARGO_VRAD0)).data()));
 	} else {
 	    CHECK(BK(copy_initial_values)(ctx));
+	}
+    }
+
+    void create_context(int device)
+    {
+#ifdef FARGO_HOST_ORACLE
+	(void)device;
+	ctx = fargo_oracle_create(&params, radii.data(), 0, 1);
+	if (!ctx)
+	    die("fargo_oracle_create failed");
+#else
+	if (fargo_ctx_create(&ctx, &params, radii.data(), 0, 1, nullptr, device) != 0)
+	    die("fargo_ctx_create: %s", fargo_last_error());
+#endif
+    }
+
+    // main.cpp:48-164 up to the first output, for `start`: units and constants, grid, bodies, init_physics (init.cpp:255-345)
+    std::string config_path;
+    bool started_fresh = false;
+    void start(const std::string &cfgfile, int device)
+    {
+	config_path = cfgfile;
+	cfg.load(cfgfile);
+	// what this driver's initial conditions do not cover is refused by name
+	const std::pair<const char *, const char *> off[] = {
+	    {"ShockTube", "0"}, {"SpreadingRing", "no"}, {"RandomSigma", "no"}, {"SetSigma0", "no"}, {"ProfileCutoffOuter", "no"},
+	    {"ProfileCutoffInner", "no"}, {"InitializePureKeplerian", "no"}, {"SelfGravity", "no"}, {"IntegrateParticles", "no"},
+	    {"RadiativeDiffusion", "no"}, {"SecondaryDisk", "no"}, {"CbdRing", "no"}, {"VazimuthalConsidersQuadropoleMoment", "no"}};
+	for (auto &k : off) {
+	    const std::string v = lower(cfg.str(k.first, k.second));
+	    if (!(v.empty() || v[0] == 'n' || v[0] == 'f' || v[0] == '0'))
+		die((std::string(k.first) + ": %s is not supported by `fargocpt_b200 start`").c_str(), v);
+	}
+	for (const char *k : {"SigmaCondition", "EnergyCondition"})
+	    if (std::tolower((unsigned char)cfg.str(k, "Profile")[0]) != 'p')
+		die((std::string(k) + ": only 'Profile' is supported by `fargocpt_b200 start` (got %s)").c_str(), cfg.str(k, ""));
+	if (lower(cfg.str("HydroFrameCenter", "primary")) != "primary")
+	    die("HydroFrameCenter: %s is not supported (primary only)", cfg.str("HydroFrameCenter", ""));
+	if (std::tolower((unsigned char)cfg.str("Frame", "Fixed")[0]) != 'f')
+	    die("Frame: %s is not supported (a frame with fixed OmegaFrame only)", cfg.str("Frame", ""));
+	finit::UnitSystem U;
+	U.set_baseunits(cfg.str("l0", "1.0"), cfg.str("m0", "1.0"));
+	U.calculate();
+	consts.G = U.G.code, consts.R = U.R.code, consts.sigma_sb = U.sigma.code, consts.c_light = U.c.code;
+	consts.temperature_unit_K = U.temperature;
+	// values that may carry units become plain code-unit numbers (config::Config::get<double>(key, unit))
+	const std::pair<const char *, char> dims[] = {{"Rmin", 'L'}, {"Rmax", 'L'}, {"Sigma0", 'S'}, {"MonitorTimestep", 'T'},
+						       {"FirstDT", 'T'}, {"DampingTimeRadiusOuter", 'L'}};
+	for (auto &k : dims)
+	    if (cfg.has(k.first))
+		cfg.kv[lower(k.first)] = finit::UnitSystem::num17(U.in_code_units(cfg.str(k.first, ""), k.second));
+	if (!cfg.has("Rmin") || !cfg.has("Rmax"))
+	    die("%s: Rmin and Rmax are required", cfgfile);
+	nrad = (int)cfg.num("Nrad", 64), naz = (int)cfg.num("Naz", 64);
+	{ // Interpret.cpp:204-227: resolution from cells per scale height
+	    const double cps = cfg.num("cps", -1.0), H = cfg.num("AspectRatio", 0.05), rmin = cfg.num("Rmin", 0), rmax = cfg.num("Rmax", 0);
+	    const char sp = (char)std::tolower((unsigned char)cfg.str("RadialSpacing", "Arithmetic")[0]);
+	    if (cps > 0) {
+		if (sp == 'a') {
+		    nrad = (int)std::round(cps * (rmax - rmin) / H);
+		    naz = (int)std::round(2 * M_PI / (rmax - rmin) * nrad);
+		} else if (sp == 'l') {
+		    nrad = (int)std::round(std::log(rmax / (double)rmin) / std::log(1 + H / cps));
+		    naz = (int)std::round(2 * M_PI / (std::pow(rmax / (double)rmin, 1.0 / (double)nrad) - 1));
+		} else {
+		    die("%s", std::string("Setting resolution is not supported for the selected radial grid spacing."));
+		}
+	    }
+	}
+	params = make_params(cfg, consts, nrad, naz);
+	radii = finit::make_radii(params.radial_spacing, nrad, params.rmin, params.rmax, cfg.num("ExponentialCellSizeFactor", 1.41));
+	// bodies
+	const auto B = finit::init_bodies(cfg.nbody, U, params.rmax);
+	if (B.size() > FARGO_MAX_BODIES)
+	    die("too many bodies in %s", cfgfile);
+	for (size_t k = 0; k < B.size(); ++k) {
+	    Body b;
+	    memset(&b.rec, 0, sizeof(b.rec));
+	    const finit::BodyInit &q = B[k];
+	    b.rec.mass = q.mass, b.rec.x = q.x, b.rec.y = q.y, b.rec.vx = q.vx, b.rec.vy = q.vy;
+	    b.rec.cubic_smoothing_factor = q.cubic_smoothing_factor, b.rec.acc = q.accretion_efficiency;
+	    b.rec.planet_number = (uint32_t)k;
+	    b.rec.temperature = q.temperature, b.rec.radius = q.radius;
+	    b.rec.irradiation_rampuptime = q.irradiation_rampuptime, b.rec.rampuptime = q.rampuptime;
+	    b.rec.distance_to_primary = q.distance_to_primary, b.rec.dimensionless_roche_radius = q.roche;
+	    b.rec.semi_major_axis = q.semi_major_axis, b.rec.eccentricity = q.eccentricity, b.rec.mean_anomaly = q.mean_anomaly;
+	    b.rec.true_anomaly = q.true_anomaly, b.rec.eccentric_anomaly = q.eccentric_anomaly, b.rec.pericenter_angle = q.pericenter_angle;
+	    b.orbital_period = q.orbital_period;
+	    bodies.push_back(b);
+	}
+	if (bodies.size() == 2) { // a binary: both carry the secondary's elements (planetary_system.cpp:797-802)
+	    PlanetRecord &p0 = bodies[0].rec;
+	    const PlanetRecord &p1 = bodies[1].rec;
+	    p0.semi_major_axis = p1.semi_major_axis, p0.eccentricity = p1.eccentricity, p0.mean_anomaly = p1.mean_anomaly;
+	    p0.true_anomaly = p1.true_anomaly, p0.eccentric_anomaly = p1.eccentric_anomaly, p0.pericenter_angle = p1.pericenter_angle;
+	    bodies[0].orbital_period = bodies[1].orbital_period;
+	}
+	params.hydro_center_mass = bodies[0].rec.mass; // global.cpp:146
+	disk_feedback = cfg.flag("DiskFeedback", true);
+	indirect_mode = (int)cfg.num("IndirectTermMode", 0);
+	if (indirect_mode != 1 && bodies.size() > 1)
+	    fprintf(stderr, "fargocpt_b200: IndirectTermMode %d needs REBOUND's predictor; using the Euler form (mode 1)\n", indirect_mode);
+	omega_frame = cfg.num("OmegaFrame", 0.0), frame_angle = 0.0;
+	monitor_timestep = cfg.num("MonitorTimestep", 1.0);
+	nmonitor = (unsigned)cfg.num("Nmonitor", 10); // Interpret.cpp:201
+	nsnapshots = (unsigned)cfg.num("Nsnapshots", 1);
+	create_context(device);
+	// init_physics (init.cpp:255-345)
+	finit::DiskModel d;
+	d.sigma0 = params.sigma0, d.sigma_slope = params.sigma_slope, d.sigma_floor = params.sigma_floor;
+	d.h0 = params.aspectratio_ref, d.flaring = params.flaring_index, d.gamma = params.gamma, d.mu = params.mu;
+	d.Rgas = consts.R, d.G = consts.G, d.viscous_alpha = params.viscous_alpha, d.constant_viscosity = params.constant_viscosity;
+	d.thickness_smoothing = params.thickness_smoothing, d.tmin = params.minimum_temperature, d.tmax = params.maximum_temperature;
+	d.omega_frame = omega_frame, d.imposed_drift = params.imposed_disk_drift;
+	d.adiabatic = params.adiabatic != 0, d.vradial_zero = cfg.flag("InitializeVradialZero", false);
+	const finit::InitialState s0 = finit::init_gas(d, radii, nrad, naz, params.hydro_center_mass);
+	// init_euler (SourceEuler.cpp:250-285) runs BEFORE the velocities exist: Q+/- of the first CFL see a gas at rest
+	CHECK(BK(upload_field)(ctx, FARGO_SIGMA, s0.sigma.data()));
+	if (params.adiabatic)
+	    CHECK(BK(upload_field)(ctx, FARGO_ENERGY, s0.energy.data()));
+	set_bodies_on_device();
+	CHECK(BK(set_time)(ctx, time));
+	CHECK(BK(init_derived)(ctx));
+	CHECK(BK(upload_field)(ctx, FARGO_VRAD, s0.vrad.data()));
+	CHECK(BK(upload_field)(ctx, FARGO_VAZI, s0.vazi.data()));
+	CHECK(BK(copy_initial_values)(ctx));	  // init.cpp:340-344
+	CHECK(BK(stage_boundary)(ctx, 0.0, 0));
+	CHECK(BK(copy_initial_values)(ctx));
+	last_dt = cfg.num("FirstDT", 1e-9);
+	calculate_time_step(); // main.cpp:117
+	started_fresh = true;
+	write_static_files();
+	U.write_files(outdir);
+	write_snapshot(); // sim::handle_outputs before sim::run (main.cpp:150)
+	finish_pending_snapshot();
+	if (params.damping || params.cooling_beta_reference == 1) { // the damping reference (simulation.cpp:42-47)
+	    const std::string from = outdir + "/snapshots/0", to = outdir + "/snapshots/reference";
+	    mkdirs(to);
+	    for (const char *f : {"Sigma.dat", "vrad.dat", "vazi.dat", "energy.dat"})
+		if (exists(from + "/" + f)) {
+		    std::ifstream in(from + "/" + f, std::ios::binary);
+		    std::ofstream o(to + "/" + f, std::ios::binary);
+		    o << in.rdbuf();
+		}
 	}
     }
 
@@ -780,7 +921,8 @@ struct Run {
 	const std::string sd = outdir + "/snapshots/" + std::to_string(n_snapshot);
 	mkdirs(sd);
 	const std::pair<int, const char *> state[4] = {{FARGO_SIGMA, "Sigma"}, {FARGO_VRAD, "vrad"}, {FARGO_VAZI, "vazi"}, {FARGO_ENERGY, "energy"}};
-	const bool write_energy = params.adiabatic || exists(refdir + "/snapshots/0/energy.dat");
+	// isothermal runs of the reference write their (all-zero) energy grid too unless WriteEnergy says no
+	const bool write_energy = params.adiabatic || (started_fresh ? cfg.flag("WriteEnergy", true) : exists(refdir + "/snapshots/0/energy.dat"));
 #ifndef FARGO_HOST_ORACLE
 	finish_pending_snapshot();
 	for (int k = 0; k < 4; ++k)
@@ -838,6 +980,11 @@ struct Run {
 		die("cannot write nbody record in %s", sd);
 	    fclose(g);
 	}
+	if (!config_path.empty()) { // the setup travels with every snapshot (output.cpp:190-200), so `restart` works on our own output
+	    std::ifstream in(config_path, std::ios::binary);
+	    std::ofstream o(sd + "/config.yml", std::ios::binary);
+	    o << in.rdbuf();
+	}
 	{ // snapshots/list.txt (output.cpp:332-350)
 	    std::ofstream l(outdir + "/snapshots/list.txt", std::ios::app);
 	    l << n_snapshot << "\n";
@@ -866,9 +1013,10 @@ struct Run {
     // sim::run (simulation.cpp:505-558) until `until_snapshot` has been written
     void run(unsigned until_snapshot, long max_steps)
     {
-	write_static_files();
+	if (!started_fresh)
+	    write_static_files();
 	// main.cpp:117 + sim::init (simulation.cpp:462-470): first CFL, boundaries, CFL again
-	if (n_iter == 0) {
+	if (n_iter == 0 && !started_fresh) {
 	    last_dt = cfg.num("FirstDT", 1e-9);
 	    calculate_time_step();
 	}
@@ -902,13 +1050,16 @@ struct Run {
 
 int main(int argc, char **argv)
 {
-    // options.cpp:42-189 subset: `restart N <dir>`, -N <steps>, plus --out / --until / --device
+    // options.cpp:42-189 subset: `start <setup.yml>`, `restart N <dir>`, -N <steps>, plus --out / --until / --device
     std::string mode, dir, out;
     long nrestart = -1, max_steps = -1, until = -1;
     int device = 0;
     for (int i = 1; i < argc; ++i) {
 	const std::string a = argv[i];
-	if (a == "restart" && i + 2 < argc) {
+	if (a == "start" && i + 1 < argc) {
+	    mode = a;
+	    dir = argv[++i];
+	} else if (a == "restart" && i + 2 < argc) {
 	    mode = a;
 	    nrestart = atol(argv[++i]);
 	    dir = argv[++i];
@@ -923,13 +1074,17 @@ int main(int argc, char **argv)
 	else
 	    die("unknown argument %s", a);
     }
-    if (mode != "restart" || out.empty()) {
-	fprintf(stderr, "usage: fargocpt_b200 restart <N> <fargocpt output dir> --out <new output dir> [--until <snapshot>] [-N <steps>] [--device <id>]\n");
+    if ((mode != "restart" && mode != "start") || out.empty()) {
+	fprintf(stderr, "usage: fargocpt_b200 start <setup.yml> --out <output dir> [--until <snapshot>] [-N <steps>] [--device <id>]\n"
+			"       fargocpt_b200 restart <N> <fargocpt output dir> --out <new output dir> [--until <snapshot>] [-N <steps>] [--device <id>]\n");
 	return 2;
     }
     Run r;
     r.outdir = out;
-    r.load(dir, (unsigned)nrestart, device);
+    if (mode == "start")
+	r.start(dir, device);
+    else
+	r.load(dir, (unsigned)nrestart, device);
     r.run(until >= 0 ? (unsigned)until : r.nsnapshots, max_steps);
     printf("-- Final: Total Hydrosteps %llu, time %.17g, last snapshot %u\n", (unsigned long long)r.n_iter, r.time, r.n_snapshot);
 #ifdef FARGO_HOST_ORACLE

@@ -1,0 +1,627 @@
+// fargo_init.hpp — what the reference does between reading a setup YAML and the first hydro step, for `fargocpt_b200 start`:
+//   units::set_baseunits / calculate_unit_factors          units.cpp:131-185, 270-377    -> UnitSystem
+//   constants::initialize_constants / ..._in_code_units    constants.cpp:178-262         -> UnitSystem
+//   write_code_units_file / write_code_constants_file      units.cpp:451-501, constants.cpp:332-362
+//   init_radialarrays                                      init.cpp:78-150               -> make_radii
+//   t_planetary_system::init_system / init_planet / initialize_planet_jacobi(_adjust_first_two) / move_to_hydro_frame_center /
+//   calculate_orbital_elements / compute_dist_to_primary / init_roche_radii
+//                                                          nbody/planetary_system.cpp:68-260, 483-578, 750-805, 941-1004
+//   init_gas_density / init_gas_energy / init_gas_velocities (power-law profile branch)
+//                                                          init.cpp:937-960, 1257-1300, 1717-1771, Theo.cpp:86-201,
+//                                                          viscosity/viscous_radial_speed.cpp:19-200
+// The arithmetic follows the reference expression by expression (same libm, -ffp-contract=off), so the initial state and
+// the code-unit constants come out bit-identical to the reference's IEEE build for the setups this driver supports:
+// power-law disks (`SigmaCondition` / `EnergyCondition`: profile), star-only or star + planets, HydroFrameCenter: primary.
+// Anything else is refused by name instead of being silently ignored.
+#pragma once
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <limits>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+namespace finit
+{
+
+[[noreturn]] inline void refuse(const std::string &what)
+{
+    fprintf(stderr, "fargocpt_b200: %s\n", what.c_str());
+    exit(1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The units of measurement FargoCPT setups use, as SI multipliers (units.cpp:111-129 for the astronomical ones; llnl/units
+// for the rest).  dim: 'L' length, 'M' mass, 'T' time, 'K' temperature, 'S' surface density.
+struct UnitDef {
+    double si;
+    char dim;
+};
+inline const std::map<std::string, UnitDef> &unit_table()
+{
+    static const std::map<std::string, UnitDef> t = {
+	{"au", {1.495978707e11, 'L'}},	     {"solRadius", {6.95700e8, 'L'}},	 {"jupiterRadius", {69911000, 'L'}},
+	{"earthRadius", {6371000, 'L'}},     {"m", {1.0, 'L'}},			 {"cm", {0.01, 'L'}},
+	{"km", {1000.0, 'L'}},		     {"solMass", {1.98847e30, 'M'}},	 {"jupiterMass", {1.8982e27, 'M'}},
+	{"earthMass", {5.97217e24, 'M'}},    {"kg", {1.0, 'M'}},		 {"g", {0.001, 'M'}},
+	{"s", {1.0, 'T'}},		     {"K", {1.0, 'K'}},			 {"g/cm2", {0.001 / (0.01 * 0.01), 'S'}},
+	{"g/cm^2", {0.001 / (0.01 * 0.01), 'S'}},
+    };
+    return t;
+}
+// "<number> [unit]" -> (number, unit name or "")
+inline bool split_value(const std::string &v, double &x, std::string &unit)
+{
+    std::istringstream is(v);
+    unit.clear();
+    if (!(is >> x))
+	return false;
+    is >> unit;
+    return true;
+}
+
+struct UnitSystem {
+    // base units as SI multipliers (units::L0, M0, T0, Temp0 are llnl precise_units; only their multipliers matter)
+    double L0 = 0.01, M0 = 0.001, T0 = 1.0, Temp0 = 1.0;
+    // code -> cgs factors (units.cpp:270-377), in the order of write_code_units_file
+    double length, mass, time, temperature, energy, energy_density, density, surface_density, opacity, energy_flux, velocity,
+	angular_momentum, kinematic_viscosity, dynamic_viscosity, acceleration, stress, pressure, power, potential, torque, force,
+	mass_accretion_rate;
+    struct Constant {
+	const char *name, *symbol, *cgs_unit;
+	double code, cgs;
+    };
+    Constant G, k_B, m_u, h, c, R, sigma, m_H, m_e, eV;
+
+    // units::set_baseunits (units.cpp:131-185) with the default t0 / temp0 (derived from G, k_B, m_u)
+    void set_baseunits(const std::string &l0s, const std::string &m0s)
+    {
+	double lv, mv;
+	std::string lu, mu_;
+	if (!split_value(l0s, lv, lu) || !split_value(m0s, mv, mu_))
+	    refuse("l0 / m0 are not numbers: " + l0s + ", " + m0s);
+	if (lu.empty() != mu_.empty())
+	    refuse("l0 and m0 need to either all have a unit or all have no unit");
+	if (lu.empty()) { // "Physical units implicitly applied": au and solMass
+	    lu = "au", mu_ = "solMass";
+	}
+	const auto &t = unit_table();
+	if (!t.count(lu) || t.at(lu).dim != 'L')
+	    refuse("l0: unknown unit of length '" + lu + "'");
+	if (!t.count(mu_) || t.at(mu_).dim != 'M')
+	    refuse("m0: unknown unit of mass '" + mu_ + "'");
+	L0 = lv * t.at(lu).si;	// measurement(value, unit).as_unit(): value * multiplier
+	M0 = mv * t.at(mu_).si;
+	// llnl constants (units/units.hpp:2033-2063), SI
+	const double G_si = 6.67430e-11, k_si = 1.380649e-23, mu_si = 1.66053906660e-27;
+	// T0 = sqrt((1 * L0 * L0 * L0) / (1 * M0 * G)).as_unit(): the measurement's value and the unit's multiplier take their
+	// square roots separately (units/units.cpp:92-107)
+	const double unit_mult = ((L0 * L0) * L0) / (M0 * 1.0);
+	const double value = 1.0 / (1.0 * G_si);
+	T0 = std::sqrt(value) * std::sqrt(unit_mult);
+	// Temp0 = (1 * G * mu / kB * M0 / L0).as_unit()
+	Temp0 = ((1.0 * G_si) * mu_si / k_si) * (M0 / L0);
+    }
+
+    // units::calculate_unit_factors (units.cpp:270-377) + constants::initialize_constants / calculate_constants_in_code_units
+    void calculate()
+    {
+	length = L0 / 0.01;
+	mass = M0 / 0.001;
+	time = T0 / 1.0;
+	energy = length * length * mass / (time * time);
+	energy_density = mass / (time * time);
+	temperature = Temp0 / 1.0;
+	density = mass / (length * length * length);
+	surface_density = mass / (length * length);
+	opacity = length * length / mass;
+	energy_flux = energy / (length * length * time);
+	velocity = length / time;
+	acceleration = length / (time * time);
+	angular_momentum = length * mass * velocity;
+	kinematic_viscosity = length * length / time;
+	dynamic_viscosity = mass / (length * time);
+	stress = mass / (time * time);
+	pressure = mass / (time * time);
+	power = mass * length * length / (time * time * time);
+	potential = length * length / (time * time);
+	torque = length * length * mass / (time * time);
+	force = mass * length / (time * time);
+	mass_accretion_rate = mass / time;
+	// constants.cpp:48-85: value_as(cgs unit) = value * 1 / multiplier(cgs unit), the unit products left to right
+	const double cm = 0.01, g = 0.001, s = 1.0, K = 1.0;
+	const double cgs_G = 6.67430e-11 * 1.0 / (cm * cm * cm / (g * s * s));
+	const double cgs_k_B = 1.380649e-23 * 1.0 / (g * cm * cm / (K * s * s));
+	const double cgs_m_u = 1.66053906660e-27 * 1.0 / g;
+	const double cgs_h = 6.62607015e-34 * 1.0 / (g * cm * cm / s);
+	const double cgs_c = 299792458.0 * 1.0 / (cm / s);
+	const double cgs_m_e = 9.1093837015e-31 * 1.0 / g;
+	const double cgs_eV = 1.0e7 * 1.602176634e-19;
+	const double cgs_m_H = 1.007825 * cgs_m_u;
+	G = {"gravitational constant", "G", "cm^3 g^-1 s^-2", 1.0, cgs_G};
+	k_B = {"Boltzmann constant", "k_B", "erg K^-1", 1.0, cgs_k_B};
+	m_u = {"molecular mass", "m_u", "g", 1.0, cgs_m_u};
+	h = {"Planck constant", "h", "erg s", 1.0, cgs_h};
+	c = {"speed of light", "c", "cm s^-1", 1.0, cgs_c};
+	R = {"specific gas constant", "R", "erg K^-1 g^-1", 1.0, cgs_k_B / cgs_m_u};
+	eV = {"electron volt", "eV", "erg", 1.0, cgs_eV};
+	m_e = {"electron mass", "m_e", "g", 1.0, cgs_m_e};
+	m_H = {"hydrogen atom mass", "m_H", "g", 1.0, cgs_m_H};
+	sigma = {"Stefan-Boltzmann constant", "sigma", "erg cm^-2 s^-1 K^-4", 1.0,
+		 2. * pow(M_PI, 5) * pow(cgs_k_B, 4) / (15. * pow(cgs_h, 3) * pow(cgs_c, 2))};
+	G.code = G.cgs / (length * length * length / (mass * time * time));
+	k_B.code = k_B.cgs / (energy / temperature);
+	m_u.code = m_u.cgs / (mass);
+	h.code = h.cgs / (energy * time);
+	c.code = c.cgs / (length / time);
+	m_e.code = m_e.cgs / (mass);
+	m_H.code = m_H.cgs / (mass);
+	eV.code = eV.cgs / (energy);
+	R.code = R.cgs / (energy / (temperature * mass));
+	sigma.code = sigma.cgs / (energy / (length * length * time * temperature * temperature * temperature * temperature));
+    }
+
+    // config::Config::get<double>(key, default, unit) (config.cpp:333-383): a value with a unit is converted to the code
+    // unit of dimension `dim` (value * multiplier / code multiplier), a bare number is taken as it is
+    double in_code_units(const std::string &v, char dim) const
+    {
+	double x;
+	std::string u;
+	if (!split_value(v, x, u))
+	    refuse("not a number: " + v);
+	if (u.empty())
+	    return x;
+	const auto &t = unit_table();
+	if (!t.count(u))
+	    refuse("unit '" + u + "' is not known to this driver (value '" + v + "')");
+	if (t.at(u).dim != dim)
+	    refuse("unit '" + u + "' has the wrong dimension in '" + v + "'");
+	const double target = dim == 'L' ? L0 : dim == 'M' ? M0 : dim == 'T' ? T0 : dim == 'K' ? Temp0 : M0 / (L0 * L0);
+	return x * t.at(u).si / target;
+    }
+
+    static std::string num17(double x)
+    { // std::ostream with precision(max_digits10)
+	char b[64];
+	snprintf(b, sizeof b, "%.17g", x);
+	return b;
+    }
+    void write_files(const std::string &outdir) const
+    {
+	{
+	    std::ofstream of(outdir + "/units.yml");
+	    of << "# code units file\n# version 0.2\n\n";
+	    const std::pair<const char *, std::pair<double, const char *>> u[] = {
+		{"length", {length, "cm"}},
+		{"mass", {mass, "g"}},
+		{"time", {time, "s"}},
+		{"temperature", {temperature, "K"}},
+		{"energy", {energy, "erg"}},
+		{"energy surface density", {energy_density, "erg cm^-2"}},
+		{"density", {density, "g cm^-3"}},
+		{"mass surface density", {surface_density, "g cm^-2"}},
+		{"opacity", {opacity, "g^-1 cm^2"}},
+		{"energy flux", {energy_flux, "erg cm^-2 s^-1"}},
+		{"velocity", {velocity, "cm s^-1"}},
+		{"angular momentum", {angular_momentum, "cm^2 g s^-1"}},
+		{"kinematic viscosity", {kinematic_viscosity, "cm^2 s^-1"}},
+		{"dynamic viscosity", {dynamic_viscosity, "P"}},
+		{"acceleration", {acceleration, "cm s^-2"}},
+		{"stress", {stress, "g s^-2"}},
+		{"pressure", {pressure, "dyn cm^-1"}},
+		{"power", {power, "erg/s"}},
+		{"potential", {potential, "erg/g"}},
+		{"torque", {torque, "erg"}},
+		{"force", {force, "dyn"}},
+		{"mass accretion rate", {mass_accretion_rate, "g s^-1"}},
+	    };
+	    for (auto &e : u) {
+		of << e.first << ":\n  cgs symbol: " << e.second.second << "\n  cgs value: " << num17(e.second.first)
+		   << "\n  unit: " << num17(e.second.first) << " " << e.second.second << "\n\n";
+	    }
+	}
+	{
+	    std::ofstream of(outdir + "/constants.yml");
+	    of << "# log output of physical constants file\n# version 0.1\n\n";
+	    for (const Constant *k : {&G, &k_B, &m_u, &h, &c, &R, &sigma, &m_H, &m_e, &eV})
+		of << k->name << ":\n  symbol: " << k->symbol << "\n  code value: " << num17(k->code) << "\n  cgs value: " << num17(k->cgs)
+		   << "\n  cgs unit symbol: " << k->cgs_unit << "\n\n";
+	}
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// init_radialarrays (init.cpp:78-150): Radii[0 .. Nrad], one ghost cell on either side of [Rmin, Rmax]
+inline std::vector<double> make_radii(int spacing /* fargo_params::radial_spacing */, int nrad, double rmin, double rmax,
+				      double exp_cell_size_factor)
+{
+    std::vector<double> r((size_t)nrad + 1);
+    if (spacing == 0 /* FARGO_SPACING_LOG */) {
+	const double f = std::pow((rmax / rmin), 1.0 / ((double)nrad - 2.0));
+	for (int n = 0; n <= nrad; ++n)
+	    r[n] = rmin * std::pow(f, (double)n - 1.0);
+    } else if (spacing == 1 /* FARGO_SPACING_ARITH */) {
+	const double interval = (rmax - rmin) / (double)(nrad - 2.0);
+	for (int n = 0; n <= nrad; ++n)
+	    r[n] = rmin + interval * (double)(n - 1.0);
+    } else if (spacing == 2 /* FARGO_SPACING_EXP */) {
+	const double cgf = std::pow((rmax / rmin), 1.0 / ((double)nrad - 2.0));
+	const double first = rmin * (cgf - 1.0) * exp_cell_size_factor;
+	const double f = (rmax - rmin) / first;
+	double egf = 1.02;
+	const double Nr = (double)nrad - 2.0;
+	for (int i = 0; i < 500000; ++i)
+	    egf = egf - ((std::pow(egf, Nr) - egf * f + f - 1)) / (Nr * std::pow(egf, Nr - 1.0) - f);
+	for (int n = 0; n <= nrad; ++n)
+	    r[n] = rmin + first * (std::pow(egf, (double)n - 1.0) - 1.0) / (egf - 1.0);
+    } else {
+	refuse("RadialSpacing: custom grids (radii.dat) are read by `restart`, not by `start`");
+    }
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// N-body initial state.  Only what the hydro step and the snapshot records need.
+struct BodyInit {
+    std::string name;
+    double mass = 0, x = 0, y = 0, vx = 0, vy = 0;
+    double cubic_smoothing_factor = 0, accretion_efficiency = 0, radius = 0, temperature = 0, irradiation_rampuptime = 0,
+	   rampuptime = 0;
+    double distance_to_primary = 0, roche = 0;
+    double semi_major_axis = 0, eccentricity = 0, mean_anomaly = 0, true_anomaly = 0, eccentric_anomaly = 0, pericenter_angle = 0,
+	   orbital_period = 0, omega = 0;
+};
+
+// Theo.cpp:251-279
+inline double init_l1(const double central_star_mass, const double other_star_mass)
+{
+    const double q = central_star_mass / (central_star_mass + other_star_mass);
+    double x = std::pow(other_star_mass / (3.0 * central_star_mass), 1.0 / 3.0);
+    double f, df;
+    int counter = 0;
+    do {
+	counter++;
+	if (counter > 10)
+	    break;
+	f = q / std::pow(1.0 - x, 2) - (1.0 - q) / std::pow(x, 2) - q + x;
+	df = 2.0 * q / std::pow(1.0 - x, 3) + 2.0 * (1.0 - q) / std::pow(x, 3) + 1.0;
+	x = x - f / df;
+    } while (std::fabs(f) > 1e-14);
+    return x;
+}
+
+// t_planet::calculate_orbital_elements (nbody/planet.cpp:488-573)
+inline void orbital_elements(BodyInit &b, double x, double y, double vx, double vy, double com_mass, double G)
+{
+    auto zero = [&]() {
+	b.omega = b.orbital_period = b.semi_major_axis = b.eccentricity = b.mean_anomaly = b.true_anomaly = b.eccentric_anomaly =
+	    b.pericenter_angle = 0.0;
+    };
+    double E, V, PerihelionPA, temp;
+    const double m = com_mass + b.mass;
+    const double h = x * vy - y * vx;
+    const double d = std::sqrt(x * x + y * y);
+    if (d * d < 1e-26 || h == 0.0) { // is_distance_zero (util.cpp:105-110)
+	zero();
+	return;
+    }
+    const double Ax = x * vy * vy - y * vx * vy - G * m * x / d;
+    const double Ay = y * vx * vx - x * vx * vy - G * m * y / d;
+    const double e = std::sqrt(Ax * Ax + Ay * Ay) / G / m;
+    const double a = h * h / G / m / (1.0 - e * e);
+    if (e > 1.0 || e < 0 || a < 0.0) {
+	zero();
+	return;
+    }
+    const double P = 2.0 * M_PI * std::sqrt(std::pow(a, 3) / (m * G));
+    const double omega = std::sqrt((m * G) / std::pow(a, 3));
+    if (e != 0.0) {
+	temp = (1.0 - d / a) / e;
+	E = temp > 1.0 ? 0.0 : temp < -1.0 ? M_PI : std::acos(temp);
+    } else {
+	E = 0.0;
+    }
+    if ((x * y * (vy * vy - vx * vx) + vx * vy * (x * x - y * y)) < 0)
+	E = -E;
+    const double M = E - e * std::sin(E);
+    if (e != 0.0) {
+	temp = (a * (1.0 - e * e) / d - 1.0) / e;
+	V = temp > 1.0 ? 0.0 : temp < -1.0 ? M_PI : std::acos(temp);
+    } else {
+	V = 0.0;
+    }
+    if (E < 0.0)
+	V = -V;
+    PerihelionPA = e != 0.0 ? std::atan2(Ay, Ax) : std::atan2(y, x);
+    b.omega = omega, b.orbital_period = P, b.semi_major_axis = a, b.eccentricity = e, b.mean_anomaly = M, b.true_anomaly = V;
+    b.eccentric_anomaly = V; // sic (planet.cpp:571)
+    b.pericenter_angle = PerihelionPA;
+}
+
+// t_planetary_system::init_system for HydroFrameCenter: primary (nbody/planetary_system.cpp:68-134).
+// `nbody`: the YAML's list of maps, keys lower-cased.
+inline std::vector<BodyInit> init_bodies(const std::vector<std::map<std::string, std::string>> &nbody, const UnitSystem &U, double rmax)
+{
+    std::vector<BodyInit> B;
+    const double G = U.G.code;
+    auto get = [](const std::map<std::string, std::string> &m, const char *k, const char *def) {
+	auto it = m.find(k);
+	return it == m.end() ? std::string(def) : it->second;
+    };
+    for (const auto &cfg : nbody) {
+	if (!cfg.count("semi-major axis") || !cfg.count("mass"))
+	    refuse("One of the planets does not have all of: semi-major axis and mass!");
+	BodyInit p;
+	const double a = U.in_code_units(cfg.at("semi-major axis"), 'L');
+	const double mass = U.in_code_units(cfg.at("mass"), 'M');
+	const double e = atof(get(cfg, "eccentricity", "0.0").c_str());
+	p.cubic_smoothing_factor = atof(get(cfg, "cubic smoothing factor", "0.0").c_str());
+	p.accretion_efficiency = atof(get(cfg, "accretion efficiency", "0.0").c_str());
+	p.radius = U.in_code_units(get(cfg, "radius", "0.009304813 au"), 'L');
+	p.temperature = U.in_code_units(get(cfg, "temperature", "0.0 K"), 'K');
+	p.irradiation_rampuptime = U.in_code_units(get(cfg, "irradiation ramp-up time", "0.0"), 'T');
+	const double nu = atof(get(cfg, "trueanomaly", "0.0").c_str());
+	double omega = atof(get(cfg, "argument of pericenter", "0.0").c_str());
+	p.rampuptime = atof(get(cfg, "ramp-up time", "0.0").c_str());
+	p.name = get(cfg, "name", ("planet" + std::to_string(B.size())).c_str());
+	const std::string method = get(cfg, "accretion method", "kley");
+	if (p.accretion_efficiency > 0.0 && method != "kley")
+	    refuse("accretion method '" + method + "' is not supported by this driver (kley only)");
+	// initialize_planet_jacobi (:539-578) around the centre of mass of the bodies added so far
+	auto jacobi = [&](double om) {
+	    p.mass = mass;
+	    double cx = 0, cy = 0, cm = 0; // get_center_of_mass / get_mass over the previously added bodies (:592-623)
+	    for (auto &q : B) {
+		cx += q.x * q.mass, cy += q.y * q.mass;
+		cm += q.mass;
+	    }
+	    if (cm > 0.0)
+		cx /= cm, cy /= cm;
+	    else
+		cx = cy = 0.0;
+	    const double cos_ota = std::cos(om + nu), sin_ota = std::sin(om + nu);
+	    const double cos_o = std::cos(om), sin_o = std::sin(om), cos_ta = std::cos(nu), sin_ta = std::sin(nu);
+	    const double r = a * (1 - e * e) / (1 + e * cos_ta);
+	    p.x = cx + r * cos_ota;
+	    p.y = cy + r * sin_ota;
+	    double v = 0.0;
+	    if (a > 0.0)
+		v = sqrt(G * (cm + mass) / (a * (1 - e * e)));
+	    p.vx = v * (-cos_o * sin_ta - sin_o * (e + cos_ta));
+	    p.vy = v * (-sin_o * sin_ta + cos_o * (e + cos_ta));
+	};
+	if (B.empty()) { // first body always goes to the origin (:487-494)
+	    p.mass = mass;
+	} else if (B.size() == 1) { // the first two share the barycentre (:495-533)
+	    if (mass > B[0].mass)
+		omega += M_PI;
+	    jacobi(omega);
+	    const double m1 = B[0].mass, m2 = p.mass;
+	    const double x = p.x, y = p.y, vx = p.vx, vy = p.vy;
+	    const double k1 = m2 / (m1 + m2);
+	    B[0].x = -k1 * x, B[0].y = -k1 * y, B[0].vx = -k1 * vx, B[0].vy = -k1 * vy;
+	    const double k2 = m1 / (m1 + m2);
+	    p.x = k2 * x, p.y = k2 * y, p.vx = k2 * vx, p.vy = k2 * vy;
+	} else {
+	    jacobi(omega);
+	}
+	B.push_back(p);
+    }
+    if (B.empty())
+	refuse("config has no nbody entries");
+    { // move_to_hydro_frame_center (:750-768), hydro frame centre = body 0
+	const double cx = B[0].x, cy = B[0].y, cvx = B[0].vx, cvy = B[0].vy;
+	for (auto &b : B) {
+	    const double x = b.x, y = b.y, vx = b.vx, vy = b.vy;
+	    b.x = x - cx, b.y = y - cy, b.vx = vx - cvx, b.vy = vy - cvy;
+	}
+    }
+    // compute_dist_to_primary (:941-964), init_roche_radii (:966-1004)
+    if (B.size() < 2) {
+	B[0].roche = 1.0;
+	B[0].distance_to_primary = rmax;
+    } else {
+	for (size_t i = 1; i < B.size(); ++i) {
+	    const double dx = B[i].x - B[0].x, dy = B[i].y - B[0].y;
+	    const double dist = std::sqrt(std::pow(dx, 2) + std::pow(dy, 2));
+	    B[i].distance_to_primary = dist;
+	    if (i == 1)
+		B[0].distance_to_primary = dist;
+	}
+	const double M = B[0].mass;
+	for (size_t i = 1; i < B.size(); ++i) {
+	    const double m = B[i].mass;
+	    if (m == 0) {
+		B[i].roche = 0.0, B[0].roche = 1.0;
+		break;
+	    }
+	    if (M == 0) {
+		B[0].roche = 0.0, B[i].roche = 1.0;
+		break;
+	    }
+	    B[i].roche = M > m ? init_l1(M, m) : 1.0 - init_l1(m, M);
+	    if (i == 1) // boundary_conditions::rof_planet, default 1 (:1000-1002)
+		B[0].roche = 1.0 - B[i].roche;
+	}
+    }
+    // calculate_orbital_elements (:773-805) about the centre of mass of the bodies inside
+    for (size_t i = 1; i < B.size(); ++i) {
+	double cx = 0, cy = 0, cvx = 0, cvy = 0, cm = 0;
+	for (size_t k = 0; k < i; ++k) {
+	    cx += B[k].x * B[k].mass, cy += B[k].y * B[k].mass;
+	    cvx += B[k].vx * B[k].mass, cvy += B[k].vy * B[k].mass;
+	    cm += B[k].mass;
+	}
+	if (cm > 0.0)
+	    cx /= cm, cy /= cm, cvx /= cm, cvy /= cm;
+	else
+	    cx = cy = cvx = cvy = 0.0;
+	orbital_elements(B[i], B[i].x - cx, B[i].y - cy, B[i].vx - cvx, B[i].vy - cvy, cm, G);
+    }
+    return B;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gas initial conditions, power-law profile (parameters::initialize_condition_profile)
+struct DiskModel {
+    double sigma0, sigma_slope, sigma_floor, h0, flaring, gamma, mu, Rgas, G, viscous_alpha, constant_viscosity, thickness_smoothing,
+	tmin, tmax, omega_frame, imposed_drift;
+    bool adiabatic, vradial_zero;
+};
+
+struct InitialState {
+    std::vector<double> sigma, energy, vrad, vazi; // [nrad][naz], v_rad [nrad + 1][naz]
+};
+
+namespace detail
+{
+// Theo.cpp:122-153
+inline double support_azi_pressure(const DiskModel &d, const double R)
+{
+    const double h = d.h0 * std::pow(R, d.flaring);
+    return (2.0 * d.flaring - 1.0 - d.sigma_slope) * std::pow(h, 2);
+}
+inline double support_azi_smoothing_derivative(const DiskModel &d, const double R)
+{
+    const double h = d.h0 * std::pow(R, d.flaring);
+    const double eps = d.thickness_smoothing;
+    return (1.0 + (d.flaring + 1.0) * std::pow(h * eps, 2)) / std::pow(std::sqrt(1 + std::pow(h * eps, 2)), 3);
+}
+// initial_locally_isothermal_smoothed_v_az (Theo.cpp:166-180)
+inline double v_az(const DiskModel &d, const double R, const double M)
+{
+    const double smoothing_derivative_2 = support_azi_smoothing_derivative(d, R);
+    const double pressure_support_2 = support_azi_pressure(d, R);
+    const double support = smoothing_derivative_2 + pressure_support_2;
+    const double vk_2 = d.G * M / R;
+    return std::sqrt(vk_2 * support);
+}
+// viscosity/viscous_radial_speed.cpp:36-95 (get_nu2) and :97-119 (get_sigma), without profile cutoffs
+inline double get_sigma(const DiskModel &d, const double R)
+{
+    double density = d.sigma0 * std::pow(R, -d.sigma_slope);
+    const double density_floor = d.sigma_floor * d.sigma0;
+    density = std::max(density, density_floor);
+    return density;
+}
+inline double get_nu2(const DiskModel &d, const double R, const double M, const double Sigma)
+{
+    const double v_k = std::sqrt(d.G * M / R);
+    const double h = d.h0 * std::pow(R, d.flaring);
+    double cutoff = 1.0;
+    double cs_adb, H;
+    if (d.adiabatic) {
+	const double gamma = d.gamma;
+	double energy = cutoff * 1.0 / (gamma - 1.0) * Sigma * std::pow(h * v_k, 2);
+	const double energy_floor = d.tmin * Sigma / d.mu * d.Rgas / (gamma - 1.0);
+	const double energy_ceil = d.tmax * Sigma / d.mu * d.Rgas / (gamma - 1.0);
+	energy = std::max(energy, energy_floor);
+	energy = std::min(energy, energy_ceil);
+	cs_adb = std::sqrt(gamma * (gamma - 1.0) * energy / Sigma);
+	const double cs_iso = std::sqrt((gamma - 1.0) * energy / Sigma);
+	const double omega_k = v_k / R;
+	H = cs_iso / omega_k;
+    } else {
+	cs_adb = h * v_k;
+	H = h * R;
+    }
+    return d.viscous_alpha * cs_adb * H;
+}
+typedef double (*fn2)(const DiskModel &, double, double);
+// viscous_speed::derive (:129-143): five-point stencil with h = 8e-4 x
+inline double derive(const DiskModel &d, const double r, const double mass, fn2 f)
+{
+    const double x = r;
+    const double h = 8.0e-4 * x;
+    const double f1 = -1.0 * f(d, x + 2.0 * h, mass);
+    const double f2 = 8.0 * f(d, x + h, mass);
+    const double f3 = -8.0 * f(d, x - h, mass);
+    const double f4 = 1.0 * f(d, x - 2.0 * h, mass);
+    return (f1 + f2 + f3 + f4) / (12.0 * h);
+}
+inline double get_w(const DiskModel &d, const double r, const double mass) { return v_az(d, r, mass) / r; }
+inline double get_r2_w(const DiskModel &d, const double r, const double mass)
+{
+    const double omega = get_w(d, r, mass);
+    return std::pow(r, 2) * omega;
+}
+inline double get_nu_S_r3_dwdr(const DiskModel &d, const double r, const double mass)
+{
+    const double dw_dr = derive(d, r, mass, get_w);
+    const double Sigma = get_sigma(d, r);
+    const double nu = get_nu2(d, r, mass, Sigma);
+    return nu * Sigma * std::pow(r, 3) * dw_dr;
+}
+// get_vr_with_numerical_viscous_speed (:184-197)
+inline double viscous_vr(const DiskModel &d, const double r, const double mass)
+{
+    const double num = 1.0 / r * derive(d, r, mass, get_nu_S_r3_dwdr);
+    const double Sigma = get_sigma(d, r);
+    const double den = Sigma * derive(d, r, mass, get_r2_w);
+    return num / den;
+}
+} // namespace detail
+
+// init_gas_density (init.cpp:937-960), init_gas_energy (:1257-1300), init_gas_velocities (:1717-1771) for a disk around the
+// hydro frame centre of mass M.  v_rad ring nrad stays 0 (the boundary stage fills the ghost interfaces).
+inline InitialState init_gas(const DiskModel &d, const std::vector<double> &radii, int nrad, int naz, double M)
+{
+    InitialState s;
+    const size_t ns = (size_t)nrad * naz;
+    s.sigma.assign(ns, 0.0);
+    s.vazi.assign(ns, 0.0);
+    s.vrad.assign((size_t)(nrad + 1) * naz, 0.0);
+    if (d.adiabatic)
+	s.energy.assign(ns, 0.0);
+    std::vector<double> rmed(nrad), sigmed(nrad), siginf(nrad);
+    for (int i = 0; i < nrad; ++i) { // init.cpp:185-190
+	rmed[i] = 2.0 / 3.0 * (std::pow(radii[i + 1], 3) - std::pow(radii[i], 3));
+	rmed[i] = rmed[i] / (std::pow(radii[i + 1], 2) - std::pow(radii[i], 2));
+    }
+    for (int i = 0; i < nrad; ++i) {
+	const double density = d.sigma0 * std::pow(rmed[i], -d.sigma_slope);
+	const double density_floor = d.sigma_floor * d.sigma0;
+	const double sig = std::max(density, density_floor);
+	for (int j = 0; j < naz; ++j)
+	    s.sigma[(size_t)i * naz + j] = sig;
+	if (d.adiabatic) { // initial_energy (Theo.cpp:86-98)
+	    const double energy = 1.0 / (d.gamma - 1.0) * d.sigma0 * std::pow(d.h0, 2) *
+				  std::pow(rmed[i], -d.sigma_slope - 1.0 + 2.0 * d.flaring) * d.G * M;
+	    const double energy_floor = d.tmin * sig / d.mu * d.Rgas / (d.gamma - 1.0);
+	    const double en = std::max(energy, energy_floor);
+	    for (int j = 0; j < naz; ++j)
+		s.energy[(size_t)i * naz + j] = en;
+	}
+    }
+    // compute_azi_avg_Sigma (Theo.cpp:30-48): SigmaMed = ring mean, SigmaInf = its interpolation to the inner interfaces
+    for (int i = 0; i < nrad; ++i) {
+	double sum = 0.0;
+	for (int j = 0; j < naz; ++j)
+	    sum += s.sigma[(size_t)i * naz + j];
+	sigmed[i] = sum / (double)naz;
+    }
+    siginf[0] = sigmed[0];
+    for (int i = 1; i < nrad; ++i) {
+	const double dr = (rmed[i] - rmed[i - 1]);
+	siginf[i] = (sigmed[i - 1] * (rmed[i] - radii[i]) + sigmed[i] * (radii[i] - rmed[i - 1])) / dr;
+    }
+    for (int i = 0; i < nrad; ++i) {
+	const double r = rmed[i], ri = radii[i];
+	double vazi = detail::v_az(d, r, M);
+	vazi -= d.omega_frame * r;
+	double vrad = d.imposed_drift * d.sigma0 / siginf[i] / ri;
+	if (!d.vradial_zero)
+	    vrad += detail::viscous_vr(d, ri, M);
+	else
+	    vrad = 0.0;
+	for (int j = 0; j < naz; ++j) {
+	    s.vazi[(size_t)i * naz + j] = vazi;
+	    s.vrad[(size_t)i * naz + j] = vrad;
+	}
+    }
+    return s;
+}
+
+} // namespace finit

@@ -146,3 +146,85 @@ def test_host_driver_on_gpu(name, until, exact, tmp_path):
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "host")])
     meta, z, out = run_host(exe, name, tmp_path, until)
     check(meta, z, out, until, exact)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# `fargocpt_b200 start <setup.yml>`: units, constants, radial grid, N-body initial state and the power-law disk (host/fargo_init.hpp)
+def start_host(exe, name, tmp_path, until):
+    out = str(tmp_path / "out")
+    yml = os.path.join(ROOT, "tests", "golden", name + ".yml")  # the very setup file the reference ran to record the fixture
+    res = subprocess.run([exe, "start", yml, "--out", out, "--until", str(until)], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    meta, z = reftools.load_golden(name)
+    return meta, z, out
+
+
+def check_start(meta, z, out, until, exact):
+    """Snapshot 0 — the state the reference builds from the setup file — must be the reference's bit for bit: the code-unit
+    constants, the radii, every field, misc.bin, and what the hydro path reads off the N-body records."""
+    consts = {v["symbol"]: float(v["code value"]) for v in yaml.safe_load(open(os.path.join(out, "constants.yml"))).values()}
+    assert consts == {k: float(v) for k, v in meta["consts"].items()}
+    units = yaml.safe_load(open(os.path.join(out, "units.yml")))
+    assert float(units["temperature"]["cgs value"]) == meta["temperature_unit_K"]
+    assert np.array_equal(np.loadtxt(os.path.join(out, "used_rad.dat")), z["radii"])
+    check(meta, z, out, 0, exact=True)
+    nrad, naz = meta["params"]["nrad"], meta["params"]["naz"]
+    for fname in ("Qplus", "Qminus"):  # the reference's first Q- is NaN where the beta-cooling reference does not exist yet
+        if f"{fname}_0" in z and os.path.exists(os.path.join(out, "snapshots", "0", fname + ".dat")):
+            got = np.fromfile(os.path.join(out, "snapshots", "0", fname + ".dat")).reshape(nrad, naz)
+            assert np.array_equal(got, z[f"{fname}_0"], equal_nan=True), fname
+    for k, b in enumerate(meta["bodies"][0]):
+        raw = open(os.path.join(out, "snapshots", "0", f"nbody{k}.bin"), "rb").read()
+        assert len(raw) == 256
+        assert list(struct.unpack("<5d", raw[8:48])) == b[:5], (k, struct.unpack("<5d", raw[8:48]), b[:5])
+        if len(b) >= 12:  # accretion efficiency, distance to the primary, Roche radius, semi-major axis
+            assert struct.unpack("<d", raw[56:64])[0] == b[7]
+            assert list(struct.unpack("<2d", raw[152:168])) == b[9:11]
+            assert struct.unpack("<d", raw[176:184])[0] == b[11]
+    if os.path.exists(os.path.join(out, "snapshots", "reference")):
+        for fname in ("Sigma", "vrad", "vazi"):
+            a = open(os.path.join(out, "snapshots", "reference", fname + ".dat"), "rb").read()
+            assert a == open(os.path.join(out, "snapshots", "0", fname + ".dat"), "rb").read()
+    check(meta, z, out, until, exact)
+
+
+START_CASES = [("iso_star", 6, True), ("adia_star", 6, True), ("adia_cold", 6, True), ("adia_sn_stab", 6, True), ("iso_sn_std", 6, True),
+               ("ring_like", 6, True), ("adia_leapfrog", 6, True), ("iso_planet_100", 50, False), ("adia_accrete_20", 10, False),
+               ("iso_feedback_20", 20, False)]
+
+
+@pytest.mark.parametrize("name,until,exact", START_CASES)
+def test_host_start_from_setup_file_cpu(name, until, exact, tmp_path):
+    """From the setup YAML alone to the reference's snapshots: star-only runs byte-identical all the way, runs with a planet
+    byte-identical at snapshot 0 and within the planet tolerance (RK4 instead of IAS15) afterwards."""
+    meta, z, out = start_host(_oracle_exe(), name, tmp_path, until)
+    check_start(meta, z, out, until, exact)
+
+
+def test_host_start_output_restarts_cpu(tmp_path):
+    """The directory `start` writes is a FargoCPT output directory: `restart` continues from it to the same bytes."""
+    exe = _oracle_exe()
+    meta, z, out = start_host(exe, "adia_star", tmp_path, 3)
+    out2 = str(tmp_path / "out2")
+    res = subprocess.run([exe, "restart", "3", out, "--out", out2, "--until", "6"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    check(meta, z, out2, 6, exact=True)
+
+
+def test_host_start_refuses_what_it_does_not_cover(tmp_path):
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "tests", "golden", "iso_star.yml")))
+    cfg["SigmaCondition"] = "2D"
+    yml = str(tmp_path / "setup.yml")
+    yaml.safe_dump(cfg, open(yml, "w"), sort_keys=False)
+    res = subprocess.run([_oracle_exe(), "start", yml, "--out", str(tmp_path / "out")], capture_output=True, text=True, timeout=60)
+    assert res.returncode != 0 and "SigmaCondition" in res.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,until,exact", [("adia_star", 6, True), ("iso_star", 6, True), ("iso_planet_100", 50, False)])
+def test_host_start_from_setup_file_gpu(name, until, exact, tmp_path):
+    exe = os.path.join(ROOT, "host", "fargocpt_b200")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "host")])
+    meta, z, out = start_host(exe, name, tmp_path, until)
+    check_start(meta, z, out, until, exact)
