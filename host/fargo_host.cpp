@@ -516,16 +516,39 @@ struct Run {
 	    fb.x[k] = b.rec.x, fb.y[k] = b.rec.y, fb.mass[k] = rampup_mass(b, time);
 	    fb.cubic_smoothing_radius[k] = b.rec.dimensionless_roche_radius * b.rec.distance_to_primary * b.rec.cubic_smoothing_factor;
 	}
-	double px = 0.0, py = 0.0;
-	indirect_term_euler(bodies, consts.G, px, py);
 	// refframe::ComputeIndirectTermFully (frame_of_reference.cpp:166-169)
-	fb.indirect_x = ind_disk_x + px;
-	fb.indirect_y = ind_disk_y + py;
+	fb.indirect_x = ind_disk_x + ind_nbody_x;
+	fb.indirect_y = ind_disk_y + ind_nbody_y;
 	fb.omega_frame = omega_frame;
 	CHECK(BK(set_bodies)(ctx, &fb));
 	ind_x = fb.indirect_x, ind_y = fb.indirect_y;
     }
-    double ind_x = 0.0, ind_y = 0.0, ind_disk_x = 0.0, ind_disk_y = 0.0;
+    double ind_x = 0.0, ind_y = 0.0, ind_disk_x = 0.0, ind_disk_y = 0.0, ind_nbody_x = 0.0, ind_nbody_y = 0.0;
+
+    // refframe::ComputeIndirectTermNbody (frame_of_reference.cpp:134-164): the acceleration of the hydro frame centre (body 0)
+    // by the other bodies over the coming `dt`, forward looking, so it is taken while the bodies are still at the start of it.
+    // IndirectTermMode 1: the instantaneous N-body acceleration (Euler); mode 0 (the default): the velocity change of the
+    // centre over dt from a predictor integration of a copy of the system (:146-157, planetary_system.cpp:671-705) — with
+    // this driver's integrator in place of REBOUND's, like the bodies themselves.
+    void compute_indirect_nbody(double dt)
+    {
+	ind_nbody_x = ind_nbody_y = 0.0;
+	if (bodies.size() < 2)
+	    return; // every body belongs to the frame centre (:137-141)
+	if (indirect_mode == 1) {
+	    indirect_term_euler(bodies, consts.G, ind_nbody_x, ind_nbody_y);
+	} else if (dt != 0.0) {
+	    std::vector<Body> predictor = bodies;
+	    nbody_integrate(predictor, consts.G, dt);
+	    const double m = bodies[0].rec.mass;
+	    if (m > 0) {
+		const double dvx = (predictor[0].rec.vx * m - bodies[0].rec.vx * m) / m;
+		const double dvy = (predictor[0].rec.vy * m - bodies[0].rec.vy * m) / m;
+		ind_nbody_x = -(dvx / dt);
+		ind_nbody_y = -(dvy / dt);
+	    }
+	}
+    }
     bool disk_feedback = false;
 
     // ComputeDiskOnNbodyAccel (Pframeforce.cpp:194-220) + UpdatePlanetVelocitiesWithDiskForce (:257-275) +
@@ -605,8 +628,6 @@ struct Run {
 	params.hydro_center_mass = bodies[0].rec.mass; // global.cpp:146 (HydroFrameCenter: primary)
 	disk_feedback = cfg.flag("DiskFeedback", true); // parameters.cpp:755
 	indirect_mode = (int)cfg.num("IndirectTermMode", 0);
-	if (indirect_mode != 1 && bodies.size() > 1)
-	    fprintf(stderr, "fargocpt_b200: IndirectTermMode %d needs REBOUND's predictor; using the Euler form (mode 1)\n", indirect_mode);
 	MiscEntry m;
 	{
 	    FILE *f = fopen((sd + "/misc.bin").c_str(), "rb");
@@ -743,8 +764,6 @@ struct Run {
 	params.hydro_center_mass = bodies[0].rec.mass; // global.cpp:146
 	disk_feedback = cfg.flag("DiskFeedback", true);
 	indirect_mode = (int)cfg.num("IndirectTermMode", 0);
-	if (indirect_mode != 1 && bodies.size() > 1)
-	    fprintf(stderr, "fargocpt_b200: IndirectTermMode %d needs REBOUND's predictor; using the Euler form (mode 1)\n", indirect_mode);
 	omega_frame = cfg.num("OmegaFrame", 0.0), frame_angle = 0.0;
 	monitor_timestep = cfg.num("MonitorTimestep", 1.0);
 	nmonitor = (unsigned)cfg.num("Nmonitor", 10); // Interpret.cpp:201
@@ -854,7 +873,8 @@ struct Run {
     {
 	accrete(dt);
 	disk_feedback_kick(dt);
-	set_bodies_on_device(); // indirect term from the current bodies (:160-162), potential inputs (:170)
+	compute_indirect_nbody(dt); // :161
+	set_bodies_on_device();	    // indirect term (:160-162), potential inputs (:170)
 	apply_indirect_term_on_nbody(dt); // :164
 	rotate_frame(dt);		  // :184
 	CHECK(BK(set_time)(ctx, time));
@@ -869,7 +889,8 @@ struct Run {
     void step_leapfrog(double dt)
     {
 	const double frog = dt / 2, start_time = time, mid_time = time + frog;
-	integrate_and_recentre(frog);	  // :286-294
+	compute_indirect_nbody(frog);	  // :285-287, while the bodies are still at the start of the step
+	integrate_and_recentre(frog);	  // :288-292
 	accrete(frog);			  // :302-303
 	disk_feedback_kick(frog);	  // :297-313 (ComputeDiskOnNbodyAccel, UpdatePlanetVelocitiesWithDiskForce)
 	set_bodies_on_device();
@@ -880,6 +901,7 @@ struct Run {
 	CHECK(BK(drift)(ctx, dt));   // :347-352
 	time = mid_time;	       // the ramp-up mass and the beta-cooling ramp see the mid-step time (:364-398)
 	disk_feedback_kick(frog);    // :355-361 and :412-414
+	compute_indirect_nbody(frog); // :356, bodies at mid-step
 	set_bodies_on_device();
 	CHECK(BK(set_time)(ctx, mid_time));
 	CHECK(BK(kick)(ctx, frog));

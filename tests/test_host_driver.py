@@ -228,3 +228,33 @@ def test_host_start_from_setup_file_gpu(name, until, exact, tmp_path):
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "host")])
     meta, z, out = start_host(exe, name, tmp_path, until)
     check_start(meta, z, out, until, exact)
+
+
+REFERENCE_SETUPS = ["/root/reference/test/cold_disk_planet/setup.yml", "/root/reference/examples/config.yml"]
+
+
+@pytest.mark.parametrize("setup", REFERENCE_SETUPS)
+def test_host_start_on_the_references_own_setup_files(setup):
+    """BASELINE configs[1] (test/cold_disk_planet/setup.yml: units, cps, ramped planet, damping, IndirectTermMode 0) and the
+    physics of configs[3] (examples/config.yml: DiskFeedback) verbatim through the unmodified reference and through
+    `fargocpt_b200 start`: identical constants / units / radii files, identical snapshot 0, fields within the north_star
+    tolerance afterwards.  Needs the reference tree and oracle/_ref (build container only)."""
+    if not (os.path.exists(setup) and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "fargocpt_exe_ieee"))):
+        pytest.skip("the reference tree / oracle/_ref are not available here")
+    _oracle_exe()
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("cmpstart", os.path.join(ROOT, "tools", "compare_start_with_reference.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    import contextlib
+    import io
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        worst = mod.main([setup, "--snapshots", "2", "--dt", "1e-3"])
+    text = buf.getvalue()
+    for f in ("constants.yml", "units.yml", "used_rad.dat"):
+        assert f + ": identical" in text, text
+    snap0 = [l for l in text.splitlines() if l.startswith("snapshot 0:")][0]
+    assert "ndiff=0" in snap0 and "DIFF" not in snap0 and snap0.count("identical") >= 2, snap0
+    assert all("ndiff=0 " in part or "ndiff" not in part for part in snap0.split("max|d|")), snap0
+    assert worst <= 1e-10, text

@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""Run a FargoCPT setup file through the unmodified reference (oracle/_ref/fargocpt_exe_ieee) AND through
+`fargocpt_b200 start` (bound to the oracle: host/fargocpt_b200_oracle_test, or --gpu for the real binary) and compare the
+output directories file by file (Tools/compare_binary_output.py statistics).  Build container only (needs oracle/_ref).
+
+    python tools/compare_start_with_reference.py /root/reference/test/cold_disk_planet/setup.yml [--snapshots 3] [--dt 1e-3] [key=value ...]
+
+The setup is run with MonitorTimestep = --dt, Nmonitor 1, so every snapshot is one short monitor step."""
+import os
+import shutil
+import struct
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import yaml
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "fargocpt_exe_ieee")
+
+
+def main(argv=None):
+    args = list(sys.argv[1:] if argv is None else argv)
+    gpu = "--gpu" in args
+    nsnap, dt, over = 3, 1e-3, {}
+    setup = None
+    i = 0
+    while i < len(args):
+        a = args[i]
+        if a == "--snapshots":
+            nsnap = int(args[i + 1]); i += 1
+        elif a == "--dt":
+            dt = float(args[i + 1]); i += 1
+        elif a == "--gpu":
+            pass
+        elif "=" in a:
+            k, v = a.split("=", 1)
+            over[k] = yaml.safe_load(v)
+        else:
+            setup = a
+        i += 1
+    cfg = yaml.safe_load(open(setup))
+    cfg.update({"MonitorTimestep": dt, "Nmonitor": 1, "Nsnapshots": nsnap, "WriteAtEveryTimestep": "yes"})
+    cfg.update(over)
+    tmp = tempfile.mkdtemp(prefix="cmpstart_")
+    cfg["OutputDir"] = os.path.join(tmp, "ref")
+    ypath = os.path.join(tmp, "setup.yml")
+    yaml.safe_dump(cfg, open(ypath, "w"), sort_keys=False)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([REF, "start", ypath], cwd=tmp, env=env, capture_output=True, text=True)
+    if r.returncode != 0:
+        print(r.stdout[-2000:], r.stderr[-2000:])
+        raise SystemExit("reference run failed")
+    exe = os.path.join(ROOT, "host", "fargocpt_b200" if gpu else "fargocpt_b200_oracle_test")
+    ours = os.path.join(tmp, "ours")
+    r = subprocess.run([exe, "start", ypath, "--out", ours, "--until", str(nsnap)], capture_output=True, text=True)
+    print(r.stdout[-300:], r.stderr[-600:])
+    if r.returncode != 0:
+        raise SystemExit("fargocpt_b200 start failed")
+    ref = cfg["OutputDir"]
+    worst = 0.0
+    for f in ("constants.yml", "units.yml", "used_rad.dat"):
+        same = open(os.path.join(ref, f)).read() == open(os.path.join(ours, f)).read()
+        print(f"{f}: {'identical' if same else 'DIFFERENT'}")
+    for k in range(nsnap + 1):
+        sd_r, sd_o = os.path.join(ref, "snapshots", str(k)), os.path.join(ours, "snapshots", str(k))
+        line = [f"snapshot {k}:"]
+        for f in ("Sigma", "vrad", "vazi", "energy"):
+            pr, po = os.path.join(sd_r, f + ".dat"), os.path.join(sd_o, f + ".dat")
+            if not (os.path.exists(pr) and os.path.exists(po)):
+                continue
+            a, b = np.fromfile(pr), np.fromfile(po)
+            if a.shape != b.shape:
+                line.append(f"{f} SHAPE {a.shape} vs {b.shape}")
+                continue
+            d = np.abs(a - b)
+            scale = np.abs(a).max() or 1.0
+            worst = max(worst, float(d.max() / scale))
+            line.append(f"{f} ndiff={int((d != 0).sum())} max|d|/scale={d.max() / scale:.2e}")
+        mr = struct.unpack("<IIddddQ", open(os.path.join(sd_r, "misc.bin"), "rb").read()[:48])
+        mo = struct.unpack("<IIddddQ", open(os.path.join(sd_o, "misc.bin"), "rb").read()[:48])
+        line.append(f"misc {'identical' if mr == mo else f'ref={mr} ours={mo}'}")
+        nb = 0
+        while os.path.exists(os.path.join(sd_r, f"nbody{nb}.bin")):
+            br = open(os.path.join(sd_r, f"nbody{nb}.bin"), "rb").read()
+            bo = open(os.path.join(sd_o, f"nbody{nb}.bin"), "rb").read()
+            sr, so = np.array(struct.unpack("<5d", br[8:48])), np.array(struct.unpack("<5d", bo[8:48]))
+            line.append(f"body{nb} {'identical' if np.array_equal(sr, so) else f'max|d|={np.abs(sr - so).max():.1e}'}")
+            nb += 1
+        print(" ".join(line))
+    print(f"worst field deviation relative to the field scale: {worst:.2e}")
+    return worst
+    if "--keep" not in args:
+        shutil.rmtree(tmp)
+    else:
+        print("kept", tmp)
+
+
+if __name__ == "__main__":
+    main()
