@@ -57,6 +57,7 @@ int fargo_oracle_kick(fargo_oracle *, double);
 int fargo_oracle_drift(fargo_oracle *, double);
 int fargo_oracle_finish_step(fargo_oracle *, double);
 int fargo_oracle_accrete_kley(fargo_oracle *, double, double, double, double, double, double *);
+int fargo_oracle_monitor_quantities(fargo_oracle *, double, double *);
 }
 typedef fargo_oracle backend_ctx;
 #define BK(name) fargo_oracle_##name
@@ -192,6 +193,7 @@ struct Config {
 // constants.yml / units.yml as written by the reference (output.cpp, units.cpp:270-310): blocks of `symbol:` / `code value:`
 struct CodeConstants {
     double G = 1.0, R = 1.0, sigma_sb = 0.0, c_light = 0.0, temperature_unit_K = 1.0;
+    double length_cgs = 1.0, mass_cgs = 1.0, time_cgs = 1.0; // units.yml: code -> cgs factors of the base units
     void load(const std::string &dir)
     {
 	std::ifstream f(dir + "/constants.yml");
@@ -215,13 +217,22 @@ struct CodeConstants {
 	    }
 	}
 	std::ifstream u(dir + "/units.yml");
-	bool in_temp = false;
+	std::string block;
 	while (std::getline(u, line)) {
 	    const std::string t = trim(line);
 	    if (!line.empty() && !std::isspace((unsigned char)line[0]))
-		in_temp = (t == "temperature:");
-	    else if (in_temp && t.rfind("cgs value:", 0) == 0)
-		temperature_unit_K = atof(t.substr(10).c_str());
+		block = t;
+	    else if (t.rfind("cgs value:", 0) == 0) {
+		const double v = atof(t.substr(10).c_str());
+		if (block == "temperature:")
+		    temperature_unit_K = v;
+		else if (block == "length:")
+		    length_cgs = v;
+		else if (block == "mass:")
+		    mass_cgs = v;
+		else if (block == "time:")
+		    time_cgs = v;
+	    }
 	}
     }
 };
@@ -709,6 +720,7 @@ struct Run {
 	U.calculate();
 	consts.G = U.G.code, consts.R = U.R.code, consts.sigma_sb = U.sigma.code, consts.c_light = U.c.code;
 	consts.temperature_unit_K = U.temperature;
+	consts.length_cgs = U.length, consts.mass_cgs = U.mass, consts.time_cgs = U.time;
 	// values that may carry units become plain code-unit numbers (config::Config::get<double>(key, unit))
 	const std::pair<const char *, char> dims[] = {{"Rmin", 'L'}, {"Rmax", 'L'}, {"Sigma0", 'S'}, {"MonitorTimestep", 'T'},
 						       {"FirstDT", 'T'}, {"DampingTimeRadiusOuter", 'L'}};
@@ -797,6 +809,7 @@ struct Run {
 	U.write_files(outdir);
 	write_snapshot(); // sim::handle_outputs before sim::run (main.cpp:150)
 	finish_pending_snapshot();
+	write_quantities();
 	if (params.damping || params.cooling_beta_reference == 1) { // the damping reference (simulation.cpp:42-47)
 	    const std::string from = outdir + "/snapshots/0", to = outdir + "/snapshots/reference";
 	    mkdirs(to);
@@ -1013,6 +1026,67 @@ struct Run {
 	}
     }
 
+    // output::write_quantities (output.cpp:326-493): one row of monitor/Quantities.dat per monitor step, file version 2.4 with
+    // the 35 columns of quantities_file_column_v2_5 (output.cpp:39-75).  The global sums come from fargo_monitor_quantities
+    // (device reductions); columns this path does not evaluate (disk radius, potential energy, eccentricity / periastron,
+    // pdivv, boundary and damping mass flows, aspect ratio, torques) are written as nan, never as made-up numbers.
+    bool quantities_header_written = false;
+    void write_quantities()
+    {
+	if (!cfg.flag("WriteDiskQuantities", true))
+	    return;
+	const std::string path = outdir + "/monitor/Quantities.dat";
+	FILE *fd = fopen(path.c_str(), quantities_header_written ? "a" : "w");
+	if (!fd)
+	    die("cannot write %s", path);
+	if (!quantities_header_written) {
+	    const double L = consts.length_cgs, M = consts.mass_cgs, T = consts.time_cgs;
+	    auto desc = [](double v, const char *sym) {
+		char b[96];
+		snprintf(b, sizeof b, "%.16e %s", v, sym);
+		return std::string(b);
+	    };
+	    const std::string mass = desc(M, "g"), time_ = desc(T, "s"), length = desc(L, "cm"), energy = desc(L * L * M / (T * T), "erg"),
+			      angmom = desc(L * M * (L / T), "cm^2 g s^-1"), power = desc(M * L * L / (T * T * T), "erg/s"),
+			      accel = desc(L / (T * T), "cm s^-2"), freq = desc(1.0 / T, "1/s"), torque = desc(L * L * M / (T * T), "erg"),
+			      ppt = desc(M / (T * T) / T, "dyn/cm/s"), one = "1";
+	    const std::pair<const char *, const std::string *> cols[35] = {
+		{"snapshot number", &one}, {"monitor number", &one}, {"time", &time_}, {"mass", &mass}, {"radius", &length},
+		{"angular momentum", &angmom}, {"total energy", &energy}, {"internal energy", &energy}, {"kinematic energy", &energy},
+		{"potential energy", &energy}, {"radial kinetic energy", &energy}, {"azimuthal kinetic energy", &energy},
+		{"eccentricity", &one}, {"periastron", &one}, {"viscous dissipation", &power}, {"luminosity", &power}, {"pdivv", &ppt},
+		{"inner boundary mass inflow", &mass}, {"inner boundary mass outflow", &mass}, {"outer boundary mass inflow", &mass},
+		{"outer boundary mass outflow", &mass}, {"wave damping inner mass creation", &mass},
+		{"wave damping inner mass removal", &mass}, {"wave damping outer mass creation", &mass},
+		{"wave damping outer mass removal", &mass}, {"density floor mass creation", &mass}, {"aspect ratio", &one},
+		{"indirect term nbody x", &accel}, {"indirect term nbody y", &accel}, {"indirect term disk x", &accel},
+		{"indirect term disk y", &accel}, {"frame angle", &freq}, {"advection torque", &torque}, {"viscous torque", &torque},
+		{"gravitational torque", &torque}};
+	    fprintf(fd, "#FargoCPT quantities file\n#version: 2.4\n");
+	    for (int k = 0; k < 35; ++k)
+		fprintf(fd, "#variable: %d | %s | %s\n", k, cols[k].first, cols[k].second->c_str());
+	    quantities_header_written = true;
+	}
+	// parameters::quantities_radius_limit (parameters.cpp:516-522)
+	double limit = cfg.has("QuantitiesRadiusLimit") ? cfg.num("QuantitiesRadiusLimit", 0.0) : 2.0 * params.rmax;
+	if (limit <= params.rmin)
+	    limit = 2.0 * params.rmax;
+	double q[8];
+	CHECK(BK(monitor_quantities)(ctx, limit, q));
+	const double nan = std::nan("");
+	double row[33];
+	for (double &x : row)
+	    x = nan;
+	row[0] = time, row[1] = q[0], row[3] = q[1], row[5] = q[2], row[6] = q[3], row[8] = q[4], row[9] = q[5];
+	row[12] = q[6], row[13] = q[7];
+	row[25] = ind_nbody_x, row[26] = ind_nbody_y, row[27] = ind_disk_x, row[28] = ind_disk_y, row[29] = frame_angle;
+	fprintf(fd, "%u\t%u", n_monitor / nmonitor, n_monitor); // N_snapshot = N_monitor / Nmonitor (simulation.cpp:52)
+	for (double x : row)
+	    fprintf(fd, "\t%#.16e", x);
+	fprintf(fd, "\n");
+	fclose(fd);
+    }
+
     void write_static_files()
     { // dimensions.dat / used_rad.dat (init.cpp:227-247) so python_module/fargocpt/data.py can load the directory
 	mkdirs(outdir + "/snapshots");
@@ -1059,10 +1133,13 @@ struct Run {
 	    fprintf(tl, "%u\t%u\t%llu\t%.17g\t%.17g\n", n_snapshot, n_monitor, (unsigned long long)n_iter, time, step_dt);
 	    if (std::fabs(time_next_monitor - time) < 1e-6 * cfl_dt) { // :544-550
 		n_monitor++;
-		if (n_monitor % nmonitor == 0) {
+		const bool snapshot_now = n_monitor % nmonitor == 0;
+		if (snapshot_now) {
 		    n_snapshot = n_monitor / nmonitor;
 		    write_snapshot();
 		}
+		if (snapshot_now || cfg.flag("WriteAtEveryTimestep", true)) // sim::handle_outputs (simulation.cpp:50-98)
+		    write_quantities();
 	    }
 	}
 	fclose(tl);

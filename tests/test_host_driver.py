@@ -258,3 +258,37 @@ def test_host_start_on_the_references_own_setup_files(setup):
     assert "ndiff=0" in snap0 and "DIFF" not in snap0 and snap0.count("identical") >= 2, snap0
     assert all("ndiff=0 " in part or "ndiff" not in part for part in snap0.split("max|d|")), snap0
     assert worst <= 1e-10, text
+
+
+@pytest.mark.parametrize("name", ["adia_star", "iso_planet_100"])
+def test_host_writes_quantities_dat_cpu(name, tmp_path):
+    """monitor/Quantities.dat (output::write_quantities, output.cpp:326-493) from `start`: the reference's header and 35-column
+    layout; the global sums equal the ones recorded from the reference's own Quantities.dat (tests/golden/quantities.json,
+    bit for bit on the star-only run, to the planet tolerance otherwise); columns this path does not evaluate are nan."""
+    import json
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "tests", "golden", name + ".yml")))
+    cfg["WriteDiskQuantities"] = "Yes"
+    yml = str(tmp_path / "setup.yml")
+    yaml.safe_dump(cfg, open(yml, "w"), sort_keys=False)
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "quantities.json")))["quantities"][name]
+    until = max(int(k) for k in ref)
+    out = str(tmp_path / "out")
+    res = subprocess.run([_oracle_exe(), "start", yml, "--out", out, "--until", str(until)], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    lines = open(os.path.join(out, "monitor", "Quantities.dat")).read().splitlines()
+    assert lines[0] == "#FargoCPT quantities file" and lines[1] == "#version: 2.4"
+    header = [l for l in lines if l.startswith("#variable:")]
+    assert len(header) == 35 and header[3].startswith("#variable: 3 | mass | ") and header[34].startswith("#variable: 34 | gravitational torque | ")
+    rows = [l.split("\t") for l in lines if not l.startswith("#")]
+    assert [int(r[1]) for r in rows] == list(range(until + 1)) and all(len(r) == 35 for r in rows)
+    cols = {"mass": 3, "angular_momentum": 5, "internal_energy": 7, "kinetic_energy": 8, "radial_kinetic_energy": 10,
+            "azimuthal_kinetic_energy": 11, "viscous_dissipation": 14, "luminosity": 15}
+    for snap, want in ref.items():
+        row = rows[int(snap)]
+        assert int(row[0]) == int(snap)
+        for q, c in cols.items():
+            if name == "adia_star":
+                assert float(row[c]) == want[q], (snap, q, row[c], want[q])
+            else:
+                assert float(row[c]) == pytest.approx(want[q], rel=1e-9, abs=1e-300), (snap, q)
+        assert row[4] == "nan" and row[12] == "nan"
