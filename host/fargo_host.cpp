@@ -527,13 +527,14 @@ struct Run {
 	    fb.x[k] = b.rec.x, fb.y[k] = b.rec.y, fb.mass[k] = rampup_mass(b, time);
 	    fb.cubic_smoothing_radius[k] = b.rec.dimensionless_roche_radius * b.rec.distance_to_primary * b.rec.cubic_smoothing_factor;
 	}
-	// refframe::ComputeIndirectTermFully (frame_of_reference.cpp:166-169)
-	fb.indirect_x = ind_disk_x + ind_nbody_x;
-	fb.indirect_y = ind_disk_y + ind_nbody_y;
+	combine_indirect();
+	fb.indirect_x = ind_x;
+	fb.indirect_y = ind_y;
 	fb.omega_frame = omega_frame;
 	CHECK(BK(set_bodies)(ctx, &fb));
-	ind_x = fb.indirect_x, ind_y = fb.indirect_y;
     }
+    // refframe::ComputeIndirectTermFully (frame_of_reference.cpp:166-169)
+    void combine_indirect() { ind_x = ind_disk_x + ind_nbody_x, ind_y = ind_disk_y + ind_nbody_y; }
     double ind_x = 0.0, ind_y = 0.0, ind_disk_x = 0.0, ind_disk_y = 0.0, ind_nbody_x = 0.0, ind_nbody_y = 0.0;
 
     // refframe::ComputeIndirectTermNbody (frame_of_reference.cpp:134-164): the acceleration of the hydro frame centre (body 0)
@@ -906,9 +907,10 @@ struct Run {
 	integrate_and_recentre(frog);	  // :288-292
 	accrete(frog);			  // :302-303
 	disk_feedback_kick(frog);	  // :297-313 (ComputeDiskOnNbodyAccel, UpdatePlanetVelocitiesWithDiskForce)
-	set_bodies_on_device();
-	apply_indirect_term_on_nbody(frog); // :315
-	rotate_frame(frog);		  // :322
+	combine_indirect();		  // :299
+	apply_indirect_term_on_nbody(frog); // :306
+	rotate_frame(frog);		  // :313
+	set_bodies_on_device();		  // unlike step_Euler, the potential of the first kick sees the bodies AFTER the frame rotation (:317-322)
 	CHECK(BK(set_time)(ctx, start_time));
 	CHECK(BK(kick)(ctx, frog));  // :326-345
 	CHECK(BK(drift)(ctx, dt));   // :347-352

@@ -230,11 +230,15 @@ def test_host_start_from_setup_file_gpu(name, until, exact, tmp_path):
     check_start(meta, z, out, until, exact)
 
 
-REFERENCE_SETUPS = ["/root/reference/test/cold_disk_planet/setup.yml", "/root/reference/examples/config.yml"]
+REFERENCE_SETUPS = [("/root/reference/test/cold_disk_planet/setup.yml", []), ("/root/reference/examples/config.yml", []),
+                    # step_LeapFrog with a planet: forward-looking indirect term, potential after the frame rotation, rotating frame
+                    ("/root/reference/test/cold_disk_planet/setup.yml", ["Integrator=Leapfrog"]),
+                    ("/root/reference/examples/config.yml", ["Integrator=Leapfrog"]),
+                    ("/root/reference/examples/config.yml", ["IndirectTermMode=1"])]
 
 
-@pytest.mark.parametrize("setup", REFERENCE_SETUPS)
-def test_host_start_on_the_references_own_setup_files(setup):
+@pytest.mark.parametrize("setup,overrides", REFERENCE_SETUPS)
+def test_host_start_on_the_references_own_setup_files(setup, overrides):
     """BASELINE configs[1] (test/cold_disk_planet/setup.yml: units, cps, ramped planet, damping, IndirectTermMode 0) and the
     physics of configs[3] (examples/config.yml: DiskFeedback) verbatim through the unmodified reference and through
     `fargocpt_b200 start`: identical constants / units / radii files, identical snapshot 0, fields within the north_star
@@ -250,7 +254,7 @@ def test_host_start_on_the_references_own_setup_files(setup):
     import io
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):
-        worst = mod.main([setup, "--snapshots", "2", "--dt", "1e-3"])
+        worst = mod.main([setup, "--snapshots", "2", "--dt", "1e-3"] + overrides)
     text = buf.getvalue()
     for f in ("constants.yml", "units.yml", "used_rad.dat"):
         assert f + ": identical" in text, text
