@@ -276,7 +276,13 @@ static fargo_params make_params(const Config &c, const CodeConstants &k, int nra
     p.fast_transport = std::tolower((unsigned char)c.str("Transport", "FARGO")[0]) == 'f' ? 1 : 0;
     const std::string fl = c.str("FluxLimiter", "VanLeer"); // Interpret.cpp:640-664 compares case-sensitively
     p.flux_limiter = (fl == "mc" || fl == "m") ? FARGO_LIMITER_MC : FARGO_LIMITER_VANLEER;
-    p.artificial_viscosity = enum_of(c.str("ArtificialViscosity", "SN"), {{"none", 0}, {"tw", 1}, {"sn", 2}}, "ArtificialViscosity");
+    { // parameters.cpp:637-650: first letter only ("No" is none)
+	const std::string av = c.str("ArtificialViscosity", "SN");
+	const char l = av.empty() ? 's' : (char)std::tolower((unsigned char)av[0]);
+	if (l != 'n' && l != 't' && l != 's')
+	    die("Invalid setting for ArtificialViscosity: %s", av);
+	p.artificial_viscosity = l == 'n' ? 0 : l == 't' ? 1 : 2;
+    }
     p.artificial_viscosity_factor = c.num("ArtificialViscosityFactor", 1.41);
     p.artificial_viscosity_dissipation = c.flag("ArtificialViscosityDissipation", true);
     p.viscous_alpha = c.num("ViscousAlpha", 0.0);
@@ -701,7 +707,7 @@ struct Run {
 	cfg.load(cfgfile);
 	// what this driver's initial conditions do not cover is refused by name
 	const std::pair<const char *, const char *> off[] = {
-	    {"ShockTube", "0"}, {"SpreadingRing", "no"}, {"RandomSigma", "no"}, {"SetSigma0", "no"}, {"ProfileCutoffOuter", "no"},
+	    {"ShockTube", "0"}, {"SpreadingRing", "no"}, {"RandomSigma", "no"}, {"ProfileCutoffOuter", "no"},
 	    {"ProfileCutoffInner", "no"}, {"InitializePureKeplerian", "no"}, {"SelfGravity", "no"}, {"IntegrateParticles", "no"},
 	    {"RadiativeDiffusion", "no"}, {"SecondaryDisk", "no"}, {"CbdRing", "no"}, {"VazimuthalConsidersQuadropoleMoment", "no"}};
 	for (auto &k : off) {
@@ -709,6 +715,8 @@ struct Run {
 	    if (!(v.empty() || v[0] == 'n' || v[0] == 'f' || v[0] == '0'))
 		die((std::string(k.first) + ": %s is not supported by `fargocpt_b200 start`").c_str(), v);
 	}
+	if (!cfg.flag("Disk", true))
+	    die("%s", std::string("Disk: no (an N-body run without gas) is not what this driver is for"));
 	for (const char *k : {"SigmaCondition", "EnergyCondition"})
 	    if (std::tolower((unsigned char)cfg.str(k, "Profile")[0]) != 'p')
 		die((std::string(k) + ": only 'Profile' is supported by `fargocpt_b200 start` (got %s)").c_str(), cfg.str(k, ""));
@@ -781,7 +789,6 @@ struct Run {
 	monitor_timestep = cfg.num("MonitorTimestep", 1.0);
 	nmonitor = (unsigned)cfg.num("Nmonitor", 10); // Interpret.cpp:201
 	nsnapshots = (unsigned)cfg.num("Nsnapshots", 1);
-	create_context(device);
 	// init_physics (init.cpp:255-345)
 	finit::DiskModel d;
 	d.sigma0 = params.sigma0, d.sigma_slope = params.sigma_slope, d.sigma_floor = params.sigma_floor;
@@ -790,7 +797,11 @@ struct Run {
 	d.thickness_smoothing = params.thickness_smoothing, d.tmin = params.minimum_temperature, d.tmax = params.maximum_temperature;
 	d.omega_frame = omega_frame, d.imposed_drift = params.imposed_disk_drift;
 	d.adiabatic = params.adiabatic != 0, d.vradial_zero = cfg.flag("InitializeVradialZero", false);
+	d.set_sigma0 = cfg.flag("SetSigma0", false);
+	d.diskmass = cfg.has("DiskMass") ? U.in_code_units(cfg.str("DiskMass", "0.01"), 'M') : 0.01;
 	const finit::InitialState s0 = finit::init_gas(d, radii, nrad, naz, params.hydro_center_mass);
+	params.sigma0 = d.sigma0; // SetSigma0 rescales it; the density floor follows (init.cpp:1155)
+	create_context(device);
 	// init_euler (SourceEuler.cpp:250-285) runs BEFORE the velocities exist: Q+/- of the first CFL see a gas at rest
 	CHECK(BK(upload_field)(ctx, FARGO_SIGMA, s0.sigma.data()));
 	if (params.adiabatic)

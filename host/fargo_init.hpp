@@ -469,6 +469,8 @@ struct DiskModel {
     double sigma0, sigma_slope, sigma_floor, h0, flaring, gamma, mu, Rgas, G, viscous_alpha, constant_viscosity, thickness_smoothing,
 	tmin, tmax, omega_frame, imposed_drift;
     bool adiabatic, vradial_zero;
+    bool set_sigma0 = false; // SetSigma0: rescale Sigma0 so that the disk holds DiskMass (renormalize_sigma_and_report, init.cpp:1150-1188)
+    double diskmass = 0.0;
 };
 
 struct InitialState {
@@ -566,7 +568,7 @@ inline double viscous_vr(const DiskModel &d, const double r, const double mass)
 
 // init_gas_density (init.cpp:937-960), init_gas_energy (:1257-1300), init_gas_velocities (:1717-1771) for a disk around the
 // hydro frame centre of mass M.  v_rad ring nrad stays 0 (the boundary stage fills the ghost interfaces).
-inline InitialState init_gas(const DiskModel &d, const std::vector<double> &radii, int nrad, int naz, double M)
+inline InitialState init_gas(DiskModel &d, const std::vector<double> &radii, int nrad, int naz, double M)
 {
     InitialState s;
     const size_t ns = (size_t)nrad * naz;
@@ -593,6 +595,20 @@ inline InitialState init_gas(const DiskModel &d, const std::vector<double> &radi
 	    const double en = std::max(energy, energy_floor);
 	    for (int j = 0; j < naz; ++j)
 		s.energy[(size_t)i * naz + j] = en;
+	}
+    }
+    if (d.set_sigma0) { // quantities::gas_total_mass over the active rings (quantities.cpp:51-75), summed in index order
+	double total_mass = 0.0;
+	for (int i = 1; i < nrad - 1; ++i) {
+	    const double surf = M_PI * (std::pow(radii[i + 1], 2) - std::pow(radii[i], 2)) / (double)naz;
+	    for (int j = 0; j < naz; ++j)
+		total_mass += surf * s.sigma[(size_t)i * naz + j];
+	}
+	d.sigma0 *= d.diskmass / total_mass;
+	for (size_t l = 0; l < ns; ++l) {
+	    s.sigma[l] *= d.diskmass / total_mass;
+	    if (d.adiabatic)
+		s.energy[l] *= d.diskmass / total_mass; // keeps the temperature
 	}
     }
     // compute_azi_avg_Sigma (Theo.cpp:30-48): SigmaMed = ring mean, SigmaInf = its interpolation to the inner interfaces
