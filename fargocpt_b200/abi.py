@@ -243,10 +243,11 @@ class Handle:
         self._check(fn(self.ptr, int(body), float(klahr_factor), out), "disk_on_body_accel")
         return np.array(list(out))
 
-    def accrete_kley(self, x, y, r_hill, facc, frac=1.0):
-        """accretion::AccreteOntoSinglePlanet (accretion.cpp:84-221); returns (dM, dPx, dPy) taken from the active cells."""
+    def accrete_kley(self, x, y, r_hill, facc, frac=1.0, method="kley"):
+        """accretion::AccreteOntoSinglePlanet (accretion.cpp:84-221) or, with method="sinkhole", SinkHoleSinglePlanet
+        (:223-333); returns (dM, dPx, dPy) taken from the active cells."""
         out = (C.c_double * 3)()
-        fn = self._fn("accrete_kley")
+        fn = self._fn("accrete_" + method)
         fn.argtypes = [C.c_void_p] + [C.c_double] * 5 + [C.POINTER(C.c_double)]
         fn.restype = C.c_int
         self._check(fn(self.ptr, float(x), float(y), float(r_hill), float(facc), float(frac), out), "accrete_kley")

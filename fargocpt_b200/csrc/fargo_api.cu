@@ -1555,17 +1555,20 @@ extern "C" int fargo_get_nshift(fargo_ctx *c, int *out)
     return 0;
 }
 
-// accretion::AccreteOntoSinglePlanet (accretion.cpp:84-221)
-extern "C" int fargo_accrete_kley(fargo_ctx *c, double x, double y, double r_hill, double facc, double frac, double out3[3])
+// accretion::AccreteOntoSinglePlanet (accretion.cpp:84-221) and SinkHoleSinglePlanet (:223-333): gas within frac1 * r_hill
+// of the body loses the fraction facc1, within frac2 * r_hill another facc2 (frac2 = 0: no second zone)
+static int accrete_zones(fargo_ctx *c, double x, double y, double r_hill, double facc1, double facc2, double frac1, double frac2,
+			 double out3[3])
 {
     CUDA_OK(cudaSetDevice(c->device));
     if (c->v_mid)
-	return fail("fargo_accrete_kley called mid-step");
+	return fail("accretion called mid-step");
     const DevView &v = c->v;
+    const double frac = frac1;
     AccretionIn a;
     a.x = x, a.y = y, a.r_hill = r_hill;
-    a.facc1 = 1.0 / 3.0 * facc, a.facc2 = 2.0 / 3.0 * facc;
-    a.frac1 = frac, a.frac2 = 0.5 * frac;
+    a.facc1 = facc1, a.facc2 = facc2;
+    a.frac1 = frac1, a.frac2 = frac2;
     a.density_floor = v.p.sigma_floor * v.p.sigma0;
     // rings whose centres can lie within the accretion radius of the planet (with a ring of slack on either side)
     const double rp = sqrt(x * x + y * y), reach = frac * r_hill;
@@ -1625,6 +1628,15 @@ extern "C" int fargo_accrete_kley(fargo_ctx *c, double x, double y, double r_hil
     CUDA_OK(cudaMemcpyAsync(out3, d_out, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     return 0;
+}
+
+extern "C" int fargo_accrete_kley(fargo_ctx *c, double x, double y, double r_hill, double facc, double frac, double out3[3])
+{
+    return accrete_zones(c, x, y, r_hill, 1.0 / 3.0 * facc, 2.0 / 3.0 * facc, frac, 0.5 * frac, out3);
+}
+extern "C" int fargo_accrete_sinkhole(fargo_ctx *c, double x, double y, double r_hill, double facc, double frac, double out3[3])
+{
+    return accrete_zones(c, x, y, r_hill, facc, 0.0, frac, 0.0, out3); // distance < 0 * r_hill never holds: one zone
 }
 
 // monitor/Quantities.dat sums (quantities.cpp:51-480 through output::write_quantities, output.cpp:326-520)

@@ -58,6 +58,7 @@ int fargo_oracle_drift(fargo_oracle *, double);
 int fargo_oracle_finish_step(fargo_oracle *, double);
 int fargo_oracle_accrete_kley(fargo_oracle *, double, double, double, double, double, double *);
 int fargo_oracle_monitor_quantities(fargo_oracle *, double, double *);
+int fargo_oracle_accrete_sinkhole(fargo_oracle *, double, double, double, double, double, double *);
 }
 typedef fargo_oracle backend_ctx;
 #define BK(name) fargo_oracle_##name
@@ -871,26 +872,116 @@ struct Run {
 		b.rec.x -= cx, b.rec.y -= cy, b.rec.vx -= cvx, b.rec.vy -= cvy;
 	    }
 	}
+	refresh_orbital_parameters();
+    }
+
+    // move_to_hydro_center_and_update_orbital_parameters (nbody/planetary_system.cpp:861-872): the distance to the primary
+    // (compute_dist_to_primary :941-964) and the osculating elements (calculate_orbital_elements :773-805) follow the bodies
+    // every step; the accretion rate and the mass ramp-up read the orbital period off them
+    void refresh_orbital_parameters()
+    {
+	if (bodies.size() < 2)
+	    return;
+	for (size_t i = 1; i < bodies.size(); ++i) {
+	    const double dx = bodies[i].rec.x - bodies[0].rec.x, dy = bodies[i].rec.y - bodies[0].rec.y;
+	    const double dist = std::sqrt(std::pow(dx, 2) + std::pow(dy, 2));
+	    bodies[i].rec.distance_to_primary = dist;
+	    if (i == 1)
+		bodies[0].rec.distance_to_primary = dist;
+	}
+	for (size_t i = 1; i < bodies.size(); ++i) {
+	    double cx = 0, cy = 0, cvx = 0, cvy = 0, cm = 0;
+	    for (size_t k = 0; k < i; ++k) {
+		const PlanetRecord &q = bodies[k].rec;
+		cx += q.x * q.mass, cy += q.y * q.mass, cvx += q.vx * q.mass, cvy += q.vy * q.mass;
+		cm += q.mass;
+	    }
+	    if (cm > 0.0)
+		cx /= cm, cy /= cm, cvx /= cm, cvy /= cm;
+	    else
+		cx = cy = cvx = cvy = 0.0;
+	    finit::BodyInit e;
+	    PlanetRecord &r = bodies[i].rec;
+	    e.mass = r.mass;
+	    finit::orbital_elements(e, r.x - cx, r.y - cy, r.vx - cvx, r.vy - cvy, cm, consts.G);
+	    r.semi_major_axis = e.semi_major_axis, r.eccentricity = e.eccentricity, r.mean_anomaly = e.mean_anomaly;
+	    r.true_anomaly = e.true_anomaly, r.eccentric_anomaly = e.eccentric_anomaly, r.pericenter_angle = e.pericenter_angle;
+	    bodies[i].orbital_period = e.orbital_period;
+	}
+	if (bodies.size() == 2) { // a binary: both carry the secondary's elements (:797-802)
+	    PlanetRecord &p0 = bodies[0].rec;
+	    const PlanetRecord &p1 = bodies[1].rec;
+	    p0.semi_major_axis = p1.semi_major_axis, p0.eccentricity = p1.eccentricity, p0.mean_anomaly = p1.mean_anomaly;
+	    p0.true_anomaly = p1.true_anomaly, p0.eccentric_anomaly = p1.eccentric_anomaly, p0.pericenter_angle = p1.pericenter_angle;
+	    bodies[0].orbital_period = bodies[1].orbital_period;
+	}
     }
 
     // accretion::AccreteOntoPlanets (accretion.cpp:419-452), first thing in a step (simulation.cpp:150-153, :302-303, :403-404):
-    // bodies with an accretion efficiency take gas out of their Hill sphere ("accretion method: kley", the default).  The
-    // body itself only changes when it feels the disk (accretion.cpp:203-218), which this driver does not restate: it
-    // refuses that combination instead of running on with the wrong planet mass.
+    // bodies with an accretion efficiency take gas out of their Hill sphere: "accretion method: kley" (the default, two
+    // zones, :84-221) or "sinkhole" (one zone, :223-333); "viscous" is refused.  A body that feels the disk (DiskFeedback,
+    // or AccreteWithoutDiskFeedback) also gains the mass and momentum of that gas: update_planet (:60-82).
     void accrete(double dt)
     {
-	for (size_t k = 1; k < bodies.size(); ++k) {
+	bool masses_changed = false;
+	for (size_t k = 0; k < bodies.size(); ++k) {
 	    Body &b = bodies[k];
 	    if (!(b.rec.acc > 0.0) || !(b.orbital_period > 0.0))
 		continue;
-	    if (disk_feedback)
-		die("%s", std::string("accreting bodies that feel the disk (DiskFeedback: yes) are not supported by this driver"));
+	    std::string method = "kley";
+	    if (k < cfg.nbody.size() && cfg.nbody[k].count("accretion method"))
+		method = lower(cfg.nbody[k].at("accretion method"));
+	    if (method == "no" || method == "none")
+		continue;
+	    if (method != "kley" && method != "sinkhole")
+		die("accretion method '%s' is not supported by this driver (kley, sinkhole)", method);
 	    const double facc = dt * b.rec.acc / b.orbital_period * std::log(2);
 	    const double r_hill = b.rec.dimensionless_roche_radius * b.rec.distance_to_primary;
+	    const double frac = cfg.num("MassAccretionRadius", 1.0);
 	    double taken[3];
-	    CHECK(BK(accrete_kley)(ctx, b.rec.x, b.rec.y, r_hill, facc, cfg.num("MassAccretionRadius", 1.0), taken));
+	    if (method == "kley")
+		CHECK(BK(accrete_kley)(ctx, b.rec.x, b.rec.y, r_hill, facc, frac, taken));
+	    else
+		CHECK(BK(accrete_sinkhole)(ctx, b.rec.x, b.rec.y, r_hill, facc, frac, taken));
 	    b.rec.accreted_mass += taken[0]; // monitoring only (accretion.cpp:201)
+	    if (disk_feedback || cfg.flag("AccreteWithoutDiskFeedback", false)) { // update_planet (accretion.cpp:60-82)
+		double Mplanet = b.rec.mass;
+		double PxPlanet = Mplanet * b.rec.vx, PyPlanet = Mplanet * b.rec.vy;
+		Mplanet += taken[0];
+		PxPlanet += taken[1];
+		PyPlanet += taken[2];
+		b.rec.accretion_torque_acc += (b.rec.x * taken[2] - b.rec.y * taken[1]);
+		b.rec.vx = PxPlanet / Mplanet;
+		b.rec.vy = PyPlanet / Mplanet;
+		b.rec.mass = Mplanet;
+		masses_changed = masses_changed || taken[0] > 0;
+	    }
 	}
+	if (masses_changed && bodies.size() > 1) { // update_global_hydro_frame_center_mass + update_roche_radii (accretion.cpp:510-514)
+	    params_hydro_center_mass_changed();
+	    const double M = bodies[0].rec.mass;
+	    for (size_t i = 1; i < bodies.size(); ++i) {
+		const double m = bodies[i].rec.mass;
+		double x = bodies[i].rec.dimensionless_roche_radius;
+		if (M > m) {
+		    x = finit::update_l1(M, m, x);
+		    bodies[i].rec.dimensionless_roche_radius = x;
+		} else { // sic (planetary_system.cpp:1025-1029): the planet keeps its value
+		    x = 1.0 - x;
+		    x = finit::update_l1(m, M, x);
+		    x = 1.0 - x;
+		}
+		if (i == 1)
+		    bodies[0].rec.dimensionless_roche_radius = 1.0 - x;
+	    }
+	}
+    }
+    // hydro_center_mass is the primary's mass (HydroFrameCenter: primary); only an accreting primary could change it, and the
+    // device holds it as a context constant
+    void params_hydro_center_mass_changed()
+    {
+	if (bodies[0].rec.mass != params.hydro_center_mass)
+	    die("%s", std::string("an accreting primary (a changing hydro-frame-centre mass) is not supported by this driver"));
     }
 
     // step_Euler (simulation.cpp:148-267) around the gas part

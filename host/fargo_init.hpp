@@ -292,6 +292,17 @@ inline double init_l1(const double central_star_mass, const double other_star_ma
     return x;
 }
 
+// Theo.cpp:288-303: one Newton-Raphson iteration from the previous value
+inline double update_l1(const double central_star_mass, const double other_star_mass, double l1)
+{
+    const double q = central_star_mass / (central_star_mass + other_star_mass);
+    double x = l1;
+    double f = q / std::pow(1.0 - x, 2) - (1.0 - q) / std::pow(x, 2) - q + x;
+    double df = 2.0 * q / std::pow(1.0 - x, 3) + 2.0 * (1.0 - q) / std::pow(x, 3) + 1.0;
+    x = x - f / df;
+    return x;
+}
+
 // t_planet::calculate_orbital_elements (nbody/planet.cpp:488-573)
 inline void orbital_elements(BodyInit &b, double x, double y, double vx, double vy, double com_mass, double G)
 {
@@ -367,8 +378,8 @@ inline std::vector<BodyInit> init_bodies(const std::vector<std::map<std::string,
 	p.rampuptime = atof(get(cfg, "ramp-up time", "0.0").c_str());
 	p.name = get(cfg, "name", ("planet" + std::to_string(B.size())).c_str());
 	const std::string method = get(cfg, "accretion method", "kley");
-	if (p.accretion_efficiency > 0.0 && method != "kley")
-	    refuse("accretion method '" + method + "' is not supported by this driver (kley only)");
+	if (p.accretion_efficiency > 0.0 && method != "kley" && method != "sinkhole" && method != "no" && method != "none")
+	    refuse("accretion method '" + method + "' is not supported by this driver (kley, sinkhole)");
 	// initialize_planet_jacobi (:539-578) around the centre of mass of the bodies added so far
 	auto jacobi = [&](double om) {
 	    p.mass = mass;

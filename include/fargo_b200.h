@@ -254,6 +254,9 @@ void fargo_pinned_free(void *p);
  * orbital period * ln 2 and frac = MassAccretionRadius.  out3 = {mass, x-momentum, y-momentum} taken from the active cells of all
  * ranks (what update_planet, accretion.cpp:60-82, adds to the body when it feels the disk). */
 int fargo_accrete_kley(fargo_ctx *ctx, double x, double y, double r_hill, double facc, double frac, double out3[3]);
+/* accretion::SinkHoleSinglePlanet (accretion.cpp:223-333; "accretion method: sinkhole"): one zone — gas within frac * r_hill
+ * loses the fraction facc (never below the density floor).  Same inputs and outputs as fargo_accrete_kley. */
+int fargo_accrete_sinkhole(fargo_ctx *ctx, double x, double y, double r_hill, double facc, double frac, double out3[3]);
 
 /* Global disk quantities of monitor/Quantities.dat (output::write_quantities output.cpp:326-520 -> quantities.cpp):
  * sums over the active cells with Rmed <= radius_limit (QuantitiesRadiusLimit, default 2 Rmax), all ranks.

@@ -1589,6 +1589,7 @@ int fargo_oracle_step(fargo_oracle *o, double dt)
  * N-body side's numbers.  The reference walks a window of cells around the planet that contains every cell inside
  * frac * RHill; testing every cell's distance gives the same cells.  out3 = mass and momentum taken from ACTIVE cells
  * (radial_first_active < i < radial_active_size, :171), summed in index order. */
+int fargo_oracle_accrete_sinkhole(fargo_oracle *o, double xp, double yp, double r_hill, double facc, double frac, double out3[3]);
 int fargo_oracle_accrete_kley(fargo_oracle *o, double xp, double yp, double r_hill, double facc, double frac, double out3[3])
 {
     const double OmegaF = o->bodies.omega_frame;
@@ -1634,6 +1635,42 @@ int fargo_oracle_accrete_kley(fargo_oracle *o, double xp, double yp, double r_hi
 		    dPy += deltaM * vycell;
 		    dM += deltaM;
 		}
+	    }
+	}
+    }
+    out3[0] = dM, out3[1] = dPx, out3[2] = dPy;
+    return 0;
+}
+
+/* accretion::SinkHoleSinglePlanet (accretion.cpp:223-333): one zone of radius frac * RHill losing the fraction facc */
+int fargo_oracle_accrete_sinkhole(fargo_oracle *o, double xp, double yp, double r_hill, double facc, double frac, double out3[3])
+{
+    const double OmegaF = o->bodies.omega_frame;
+    const double density_floor = o->p.sigma_floor * o->p.sigma0;
+    double dM = 0.0, dPx = 0.0, dPy = 0.0;
+    for (int i = 0; i < o->nr; ++i) {
+	for (int j = 0; j < o->ns; ++j) {
+	    const size_t l = IDX(o, i, j);
+	    const int jp = j == o->ns - 1 ? 0 : j + 1;
+	    const double xc = o->rmed[i] * o->cosphi[j], yc = o->rmed[i] * o->sinphi[j];
+	    const double dx = xp - xc, dy = yp - yc;
+	    const double distance = sqrt(dx * dx + dy * dy);
+	    if (!(distance < frac * r_hill))
+		continue;
+	    const double vtcell = 0.5 * (o->vazi[l] + o->vazi[IDX(o, i, jp)]) + o->rmed[i] * OmegaF;
+	    const double vrcell = 0.5 * (o->vrad[l] + o->vrad[IDX(o, i + 1, j)]);
+	    const double vxcell = (vrcell * xc - vtcell * yc) / o->rmed[i];
+	    const double vycell = (vrcell * yc + vtcell * xc) / o->rmed[i];
+	    const double facc_max = 1 - density_floor / o->sigma[l];
+	    const double facc_ceil = facc_max < facc ? facc_max : facc; /* std::min(facc, facc_max) */
+	    const double deltaM = facc_ceil * o->sigma[l] * o->surf[i];
+	    o->sigma[l] *= 1.0 - facc_ceil;
+	    if (o->p.adiabatic)
+		o->energy[l] *= 1.0 - facc_ceil;
+	    if (o->first_active < i && i < o->active_size) {
+		dPx += deltaM * vxcell;
+		dPy += deltaM * vycell;
+		dM += deltaM;
 	    }
 	}
     }

@@ -107,6 +107,14 @@ CASES = {
     "adia_accrete_20": dict(Nrad=48, Naz=160, Rmax=2.5, Nsnapshots=20, MonitorTimestep=4.0e-3, IndirectTermMode=1,
                             ViscousAlpha=1e-3, HeatingViscous="yes", CoolingBetaLocal="yes", CoolingBeta=10,
                             _planet=3e-3, _accretion=5.0, _keep=(0, 10, 20)),
+    # "accretion method: sinkhole" (accretion.cpp:223-333): one zone of radius MassAccretionRadius * R_Hill
+    "iso_sinkhole_20": dict(Nrad=48, Naz=160, Rmax=2.5, Nsnapshots=20, MonitorTimestep=4.0e-3, IndirectTermMode=1,
+                            EquationOfState="Isothermal", ViscousAlpha=1e-3, ArtificialViscosityFactor=1.41, FlaringIndex=0.0,
+                            MassAccretionRadius=0.75, _planet=3e-3, _accretion=5.0, _accretion_method="sinkhole", _keep=(0, 10, 20)),
+    # an accreting planet that feels the disk: update_planet (accretion.cpp:60-82) adds the accreted mass and momentum to it
+    "adia_accfb_20": dict(Nrad=48, Naz=160, Rmax=2.5, Nsnapshots=20, MonitorTimestep=4.0e-3, IndirectTermMode=1,
+                          ViscousAlpha=1e-3, HeatingViscous="yes", CoolingBetaLocal="yes", CoolingBeta=10, DiskFeedback="yes",
+                          _planet=3e-3, _accretion=5.0, _keep=(0, 10, 20)),
     "iso_planet_100": dict(Nrad=48, Naz=160, Rmax=2.5, Nsnapshots=100, MonitorTimestep=4.0e-3, IndirectTermMode=1,
                            EquationOfState="Isothermal", ViscousAlpha=1e-3, ArtificialViscosityFactor=1.41, OmegaFrame=1.0,
                            FlaringIndex=0.0, Damping="Yes", DampingInnerLimit=1.25, DampingOuterLimit=0.84,
@@ -145,12 +153,13 @@ def run_case(name, overrides, keep=False):
     planet = cfg.pop("_planet", 0.0)
     keep_snaps = cfg.pop("_keep", None)
     accretion = cfg.pop("_accretion", 0.0)
+    accretion_method = cfg.pop("_accretion_method", "kley")
     if planet > 0:
         cfg["nbody"] = list(cfg["nbody"]) + [{"name": "planet", "semi-major axis": 1.0, "mass": float(planet),
                                                "accretion efficiency": float(accretion), "eccentricity": 0.0, "radius": "0.01 solRadius",
                                                "temperature": "0 K", "ramp-up time": 0}]
         if accretion > 0:
-            cfg["nbody"][-1]["accretion method"] = "kley"
+            cfg["nbody"][-1]["accretion method"] = accretion_method
     tmp = tempfile.mkdtemp(prefix="golden_" + name + "_")
     cfg["OutputDir"] = os.path.join(tmp, "out")
     ypath = os.path.join(tmp, "cfg.yml")

@@ -46,7 +46,13 @@ def bodies_at(meta, k, omega_frame):
             dx /= bl[0][0]
             dy /= bl[0][0]
             indirect = (dx + indirect[0], dy + indirect[1])
-    return abi.FargoBodies.make([b[1] for b in bl], [b[2] for b in bl], [b[0] for b in bl], indirect=indirect,
+    masses = [b[0] for b in bl]
+    if len(bl) > 1 and str(meta["config"].get("DiskFeedback", "yes")).lower()[0] == "y":
+        # an accreting body that feels the disk has swallowed this step's gas (update_planet, accretion.cpp:60-82) before the
+        # potential is evaluated (simulation.cpp:150-172): its mass is the one recorded at the END of the step
+        nxt = meta["bodies"][min(k + 1, len(meta["bodies"]) - 1)]
+        masses = [nxt[i][0] if (len(b) > 7 and b[7] > 0.0) else b[0] for i, b in enumerate(bl)]
+    return abi.FargoBodies.make([b[1] for b in bl], [b[2] for b in bl], masses, indirect=indirect,
                                 omega_frame=omega_frame)
 
 
@@ -96,7 +102,8 @@ def run_fixture(ctx, meta, z, nsteps=None, on_snapshot=None, accreted=None):
 
     def before_step(k, dt):
         for b in accretors:
-            d = ctx.accrete_kley(*accretion_inputs(meta, k - 1, b, dt))
+            method = meta["config"]["nbody"][b].get("accretion method", "kley")
+            d = ctx.accrete_kley(*accretion_inputs(meta, k - 1, b, dt), method=method)
             if accreted is not None:
                 accreted.append((k, b) + tuple(d))
         return bodies_at(meta, k - 1, omega)

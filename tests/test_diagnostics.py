@@ -121,7 +121,7 @@ def test_gpu_monitor_quantities_vs_oracle(name, k):
 
 # ---------------------------------------------------------------------------------------------------------------------
 # accretion::AccreteOntoSinglePlanet (accretion.cpp:84-221)
-@pytest.mark.parametrize("name", ["iso_accrete_20", "adia_accrete_20"])
+@pytest.mark.parametrize("name", ["iso_accrete_20", "adia_accrete_20", "iso_sinkhole_20"])
 def test_oracle_accreted_mass_matches_reference(name):
     """The mass the oracle takes out of the Hill sphere in every step against the planet's recorded m_accreted_mass (the
     reference sums it with an OpenMP reduction: 1e-12).  The fields of the same runs are held bit for bit in
@@ -136,7 +136,7 @@ def test_oracle_accreted_mass_matches_reference(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["iso_accrete_20", "adia_accrete_20"])
+@pytest.mark.parametrize("name", ["iso_accrete_20", "adia_accrete_20", "iso_sinkhole_20"])
 def test_gpu_accretion_vs_oracle(name):
     """One accretion call from identical states: the cells changed bit for bit, the sums within 1e-13."""
     from fargocpt_b200 import HydroContext
@@ -145,7 +145,8 @@ def test_gpu_accretion_vs_oracle(name):
     res = []
     for ctx in (cpu, gpu):
         _load(ctx, meta, z, 10)
-        res.append(ctx.accrete_kley(*goldenrun.accretion_inputs(meta, 10, 1, meta["monitor_timestep"])))
+        method = meta["config"]["nbody"][1].get("accretion method", "kley")
+        res.append(ctx.accrete_kley(*goldenrun.accretion_inputs(meta, 10, 1, meta["monitor_timestep"]), method=method))
     for fid in (abi.SIGMA, abi.ENERGY) if meta["params"]["adiabatic"] else (abi.SIGMA,):
         st = reftools.compare_stats(gpu.download(fid), cpu.download(fid))
         assert st["n_diff"] == 0, (fid, st)

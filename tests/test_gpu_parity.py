@@ -21,7 +21,9 @@ CASES = ["adia_star", "adia_cold", "iso_star", "iso_sn_std", "adia_sn_stab", "ri
 LONG_CASES = ["adia_planet_100", "iso_planet_100"]
 # a planet that accretes gas out of its Hill sphere first thing in every step (accretion.cpp:84-221)
 LONG_CASES += ["iso_accrete_20", "adia_accrete_20"]
-ISOTHERMAL = {"iso_star", "iso_sn_std", "ring_like", "iso_planet_100", "iso_accrete_20"}
+# "accretion method: sinkhole" (accretion.cpp:223-333)
+LONG_CASES += ["iso_sinkhole_20"]
+ISOTHERMAL = {"iso_star", "iso_sn_std", "ring_like", "iso_planet_100", "iso_accrete_20", "iso_sinkhole_20"}
 ADIABATIC_RTOL = 0.0
 LONG_RTOL = 0.0  # north_star allows 1e-10 after 100 steps; the glibc-exact exp makes the adiabatic runs bit-exact too
 

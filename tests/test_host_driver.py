@@ -190,7 +190,9 @@ def check_start(meta, z, out, until, exact):
 
 START_CASES = [("iso_star", 6, True), ("adia_star", 6, True), ("adia_cold", 6, True), ("adia_sn_stab", 6, True), ("iso_sn_std", 6, True),
                ("ring_like", 6, True), ("adia_leapfrog", 6, True), ("iso_planet_100", 50, False), ("adia_accrete_20", 10, False),
-               ("iso_feedback_20", 20, False)]
+               ("iso_feedback_20", 20, False),
+               # sinkhole accretion; an accreting planet that feels the disk (update_planet, Roche radius and orbital period refreshed)
+               ("iso_sinkhole_20", 20, False), ("adia_accfb_20", 20, False)]
 
 
 @pytest.mark.parametrize("name,until,exact", START_CASES)
@@ -221,7 +223,8 @@ def test_host_start_refuses_what_it_does_not_cover(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,until,exact", [("adia_star", 6, True), ("iso_star", 6, True), ("iso_planet_100", 50, False)])
+@pytest.mark.parametrize("name,until,exact", [("adia_star", 6, True), ("iso_star", 6, True), ("iso_planet_100", 50, False),
+                                              ("iso_sinkhole_20", 20, False), ("adia_accfb_20", 20, False)])
 def test_host_start_from_setup_file_gpu(name, until, exact, tmp_path):
     exe = os.path.join(ROOT, "host", "fargocpt_b200")
     if not os.path.exists(exe):
