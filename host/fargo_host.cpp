@@ -708,7 +708,7 @@ struct Run {
 	cfg.load(cfgfile);
 	// what this driver's initial conditions do not cover is refused by name
 	const std::pair<const char *, const char *> off[] = {
-	    {"ShockTube", "0"}, {"SpreadingRing", "no"}, {"RandomSigma", "no"}, {"ProfileCutoffOuter", "no"},
+	    {"ShockTube", "0"}, {"RandomSigma", "no"}, {"ProfileCutoffOuter", "no"},
 	    {"ProfileCutoffInner", "no"}, {"InitializePureKeplerian", "no"}, {"SelfGravity", "no"}, {"IntegrateParticles", "no"},
 	    {"RadiativeDiffusion", "no"}, {"SecondaryDisk", "no"}, {"CbdRing", "no"}, {"VazimuthalConsidersQuadropoleMoment", "no"}};
 	for (auto &k : off) {
@@ -798,6 +798,7 @@ struct Run {
 	d.thickness_smoothing = params.thickness_smoothing, d.tmin = params.minimum_temperature, d.tmax = params.maximum_temperature;
 	d.omega_frame = omega_frame, d.imposed_drift = params.imposed_disk_drift;
 	d.adiabatic = params.adiabatic != 0, d.vradial_zero = cfg.flag("InitializeVradialZero", false);
+	d.spreading_ring = cfg.flag("SpreadingRing", false);
 	d.set_sigma0 = cfg.flag("SetSigma0", false);
 	d.diskmass = cfg.has("DiskMass") ? U.in_code_units(cfg.str("DiskMass", "0.01"), 'M') : 0.01;
 	const finit::InitialState s0 = finit::init_gas(d, radii, nrad, naz, params.hydro_center_mass);

@@ -480,6 +480,7 @@ struct DiskModel {
     double sigma0, sigma_slope, sigma_floor, h0, flaring, gamma, mu, Rgas, G, viscous_alpha, constant_viscosity, thickness_smoothing,
 	tmin, tmax, omega_frame, imposed_drift;
     bool adiabatic, vradial_zero;
+    bool spreading_ring = false; // SpreadingRing: the Bessel-function ring of init_spreading_ring_test (init.cpp:358-412)
     bool set_sigma0 = false; // SetSigma0: rescale Sigma0 so that the disk holds DiskMass (renormalize_sigma_and_report, init.cpp:1150-1188)
     double diskmass = 0.0;
 };
@@ -606,6 +607,33 @@ inline InitialState init_gas(DiskModel &d, const std::vector<double> &radii, int
 	    const double en = std::max(energy, energy_floor);
 	    for (int j = 0; j < naz; ++j)
 		s.energy[(size_t)i * naz + j] = en;
+	}
+    }
+    if (d.spreading_ring) { // init_spreading_ring_test (init.cpp:358-412; Speith & Kley 2003), replaces the profile
+	const double R0 = 1.0;
+	int R0_id = 0;
+	for (int i = 0; i < nrad; ++i)
+	    if (radii[i + 1] > R0 && R0 > radii[i])
+		R0_id = i;
+	const double Disk_Mass = d.diskmass;
+	const double tau0 = 0.016;
+	double Sigma0;
+	{
+	    const double x = rmed[R0_id] / R0;
+	    const double I = std::cyl_bessel_i(0.25, 2.0 * x / tau0); // gsl_sf_bessel_Inu
+	    Sigma0 = Disk_Mass / (M_PI * R0 * R0) * 1.0 / (tau0 * std::pow(x, 0.25)) * I * std::exp(-(1.0 + x * x) / tau0);
+	}
+	for (int i = 0; i < nrad; ++i) {
+	    const double density_floor = Sigma0 * d.sigma_floor;
+	    const double x = rmed[i] / R0;
+	    const double I = std::cyl_bessel_i(0.25, 2.0 * x / tau0);
+	    double density = Disk_Mass / (M_PI * R0 * R0) * 1.0 / (tau0 * std::pow(x, 0.25)) * I * std::exp(-(1.0 + x * x) / tau0);
+	    density = std::max(density, density_floor);
+	    for (int j = 0; j < naz; ++j) {
+		s.sigma[(size_t)i * naz + j] = density;
+		if (d.adiabatic)
+		    s.energy[(size_t)i * naz + j] = 0.0;
+	    }
 	}
     }
     if (d.set_sigma0) { // quantities::gas_total_mass over the active rings (quantities.cpp:51-75), summed in index order

@@ -299,3 +299,61 @@ def test_host_writes_quantities_dat_cpu(name, tmp_path):
             else:
                 assert float(row[c]) == pytest.approx(want[q], rel=1e-9, abs=1e-300), (snap, q)
         assert row[4] == "nan" and row[12] == "nan"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE configs[0]: test/spreading_ring (pressureless viscous ring, 256 x 2)
+SPREADING_RING = os.path.join(ROOT, "tests", "golden", "spreading_ring_setup.yml")
+
+
+def test_spreading_ring_setup_verbatim_cpu():
+    """The reference's own test/spreading_ring/setup.yml through the unmodified reference and through `fargocpt_b200 start`
+    (Bessel-function ring, SetSigma0, h = 0): every file identical, every field of every snapshot identical."""
+    setup = "/root/reference/test/spreading_ring/setup.yml"
+    if not (os.path.exists(setup) and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "fargocpt_exe_ieee"))):
+        pytest.skip("the reference tree / oracle/_ref are not available here")
+    _oracle_exe()
+    import contextlib
+    import importlib.util
+    import io
+    spec = importlib.util.spec_from_file_location("cmpstart", os.path.join(ROOT, "tools", "compare_start_with_reference.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        worst = mod.main([setup, "--snapshots", "3", "--dt", "0.05"])
+    assert worst == 0.0 and buf.getvalue().count("misc identical") == 4, buf.getvalue()
+
+
+def _run_start(exe, yml, out, until):
+    res = subprocess.run([exe, "start", yml, "--out", out, "--until", str(until)], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def test_spreading_ring_spreads_cpu(tmp_path):
+    """Physics sanity of the ring on the committed minimal setup: mass is conserved to rounding while the peak drops."""
+    out = str(tmp_path / "out")
+    _run_start(_oracle_exe(), SPREADING_RING, out, 4)
+    radii = np.loadtxt(os.path.join(out, "used_rad.dat"))
+    surf = np.pi * (radii[1:] ** 2 - radii[:-1] ** 2) / 2
+    s0 = np.fromfile(os.path.join(out, "snapshots", "0", "Sigma.dat")).reshape(256, 2)
+    s4 = np.fromfile(os.path.join(out, "snapshots", "4", "Sigma.dat")).reshape(256, 2)
+    m0, m4 = (surf[1:-1, None] * s0[1:-1]).sum(), (surf[1:-1, None] * s4[1:-1]).sum()
+    assert m0 == pytest.approx(1.0, rel=1e-12) and m4 == pytest.approx(m0, rel=1e-9)
+    assert s4.max() < s0.max() and np.array_equal(s4[:, 0], s4[:, 1])
+
+
+@pytest.mark.gpu
+def test_spreading_ring_gpu_equals_oracle(tmp_path):
+    """BASELINE configs[0] on the B200: the CUDA path against the oracle-bound driver (the checker), byte for byte."""
+    exe = os.path.join(ROOT, "host", "fargocpt_b200")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "host")])
+    gpu, cpu = str(tmp_path / "gpu"), str(tmp_path / "cpu")
+    _run_start(exe, SPREADING_RING, gpu, 4)
+    _run_start(_oracle_exe(), SPREADING_RING, cpu, 4)
+    for k in range(5):
+        for f in ("Sigma.dat", "vrad.dat", "vazi.dat", "misc.bin"):
+            a = open(os.path.join(gpu, "snapshots", str(k), f), "rb").read()
+            b = open(os.path.join(cpu, "snapshots", str(k), f), "rb").read()
+            assert a == b, (k, f)
