@@ -237,7 +237,10 @@ REFERENCE_SETUPS = [("/root/reference/test/cold_disk_planet/setup.yml", []), ("/
                     # step_LeapFrog with a planet: forward-looking indirect term, potential after the frame rotation, rotating frame
                     ("/root/reference/test/cold_disk_planet/setup.yml", ["Integrator=Leapfrog"]),
                     ("/root/reference/examples/config.yml", ["Integrator=Leapfrog"]),
-                    ("/root/reference/examples/config.yml", ["IndirectTermMode=1"])]
+                    ("/root/reference/examples/config.yml", ["IndirectTermMode=1"]),
+                    # four bodies: eccentric orbits from their elements (Jacobi coordinates), jupiterMass / earthMass units,
+                    # cubic (Klahr) smoothing, ramp-up — this repo's own setup file, run through both codes
+                    (os.path.join(ROOT, "tests", "golden", "multi_body_setup.yml"), ["--dt", "4e-3"])]
 
 
 @pytest.mark.parametrize("setup,overrides", REFERENCE_SETUPS)
