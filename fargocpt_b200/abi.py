@@ -131,6 +131,7 @@ def _bind(lib, prefix):
         "stage_boundary": ([vp, C.c_double, C.c_int], C.c_int),
         "stage_transport": ([vp, C.c_double], C.c_int), "stage_derived": ([vp], C.c_int),
         "get_nshift": ([vp, C.POINTER(C.c_int)], C.c_int),
+        "correct_vazi": ([vp, C.c_double], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(lib, prefix + name)
@@ -262,6 +263,10 @@ class Handle:
         fn.restype = C.c_int
         self._check(fn(self.ptr, float(radius_limit), out), "monitor_quantities")
         return dict(zip(MONITOR_QUANTITIES, list(out)))
+
+    def correct_vazi(self, domega):
+        """correct_v_azimuthal (SideEuler.cpp:79-95): a corotating frame changed its angular velocity by domega."""
+        self._check(self._call("correct_vazi", float(domega)), "correct_vazi")
 
     def nshift(self):
         out = np.zeros(self.nr, dtype=np.int32)

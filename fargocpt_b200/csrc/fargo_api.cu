@@ -1540,6 +1540,16 @@ extern "C" int fargo_step(fargo_ctx *c, double dt)
     return fargo_finish_step(c, dt);
 }
 
+// correct_v_azimuthal (SideEuler.cpp:79-95) for refframe::handle_corotation
+extern "C" int fargo_correct_vazi(fargo_ctx *c, double domega)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    if (c->v_mid)
+	return fail("fargo_correct_vazi called mid-step");
+    LAUNCH(c, k_correct_vazi, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, VPA(c), domega);
+    return 0;
+}
+
 // test hook: run fargo_step through the staged kernels (one per reference loop nest) instead of the fused ones
 extern "C" int fargo_set_staged(fargo_ctx *c, int on)
 {

@@ -116,6 +116,13 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// correct_v_azimuthal (SideEuler.cpp:79-95): the frame's angular velocity changed by dOmega
+__global__ void __launch_bounds__(256) k_correct_vazi(const DevView c, double *__restrict__ vp, const double domega)
+{
+    CELL_INDEX(c.nr);
+    AT(vp, i, j) -= domega * c.g.rmed[i];
+}
+
 // div(v) as used by compression_heating and the viscous stress tensor (SourceEuler.cpp:471-477,
 // viscosity.cpp:154-159)
 __device__ __forceinline__ double div_v(const DevView &c, const double *__restrict__ vr, const double *__restrict__ vp,

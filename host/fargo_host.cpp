@@ -59,6 +59,7 @@ int fargo_oracle_finish_step(fargo_oracle *, double);
 int fargo_oracle_accrete_kley(fargo_oracle *, double, double, double, double, double, double *);
 int fargo_oracle_monitor_quantities(fargo_oracle *, double, double *);
 int fargo_oracle_accrete_sinkhole(fargo_oracle *, double, double, double, double, double, double *);
+int fargo_oracle_correct_vazi(fargo_oracle *, double);
 }
 typedef fargo_oracle backend_ctx;
 #define BK(name) fargo_oracle_##name
@@ -414,6 +415,7 @@ static bool exists(const std::string &p)
 struct Body {
     PlanetRecord rec; // carried through so the records we write keep the fields we do not touch
     double orbital_period = 0.0;
+    double omega = 0.0; // t_planet::m_omega: sqrt(G (M + m) / a^3) of the osculating orbit (planet.cpp:520-521)
 };
 
 // planet.get_rampup_mass (nbody/planet.cpp:166-179)
@@ -539,7 +541,9 @@ struct Run {
 	fb.indirect_y = ind_y;
 	fb.omega_frame = omega_frame;
 	CHECK(BK(set_bodies)(ctx, &fb));
+	last_fb = fb;
     }
+    fargo_bodies last_fb;
     // refframe::ComputeIndirectTermFully (frame_of_reference.cpp:166-169)
     void combine_indirect() { ind_x = ind_disk_x + ind_nbody_x, ind_y = ind_disk_y + ind_nbody_y; }
     double ind_x = 0.0, ind_y = 0.0, ind_disk_x = 0.0, ind_disk_y = 0.0, ind_nbody_x = 0.0, ind_nbody_y = 0.0;
@@ -638,6 +642,8 @@ struct Run {
 	    fclose(f);
 	    if (b.rec.semi_major_axis > 0.0) // planet.cpp: T = 2 pi sqrt(a^3 / (G (M + m)))
 		b.orbital_period = 2.0 * M_PI * std::sqrt(std::pow(b.rec.semi_major_axis, 3) / (consts.G * (1.0 + b.rec.mass)));
+	    if (b.rec.semi_major_axis > 0.0)
+		b.omega = std::sqrt((consts.G * (1.0 + b.rec.mass)) / std::pow(b.rec.semi_major_axis, 3));
 	    bodies.push_back(b);
 	}
 	if (bodies.empty())
@@ -656,6 +662,9 @@ struct Run {
 	}
 	time = m.time, last_dt = m.last_dt, n_iter = m.N_iter, n_snapshot = m.timestep, n_monitor = m.nTimeStep;
 	omega_frame = m.OmegaFrame, frame_angle = m.FrameAngle;
+	read_frame_settings();
+	if (corotating && corotation_body >= bodies.size())
+	    die("%s", std::string("CorotationReferenceBody does not exist"));
 	monitor_timestep = cfg.num("MonitorTimestep", 1.0);
 	nmonitor = (unsigned)cfg.num("Nmonitor", 1);
 	nsnapshots = (unsigned)cfg.num("Nsnapshots", 1);
@@ -684,6 +693,16 @@ struct Run {
 	} else {
 	    CHECK(BK(copy_initial_values)(ctx));
 	}
+    }
+
+    // Interpret.cpp:311-323, parameters.cpp:548-549
+    void read_frame_settings()
+    {
+	const char f = (char)std::tolower((unsigned char)cfg.str("Frame", "Fixed")[0]);
+	if (f != 'f' && f != 'c')
+	    die("Invalid setting for Frame: %s", cfg.str("Frame", ""));
+	corotating = f == 'c';
+	corotation_body = (unsigned)cfg.num("CorotationReferenceBody", 1);
     }
 
     void create_context(int device)
@@ -723,8 +742,7 @@ struct Run {
 		die((std::string(k) + ": only 'Profile' is supported by `fargocpt_b200 start` (got %s)").c_str(), cfg.str(k, ""));
 	if (lower(cfg.str("HydroFrameCenter", "primary")) != "primary")
 	    die("HydroFrameCenter: %s is not supported (primary only)", cfg.str("HydroFrameCenter", ""));
-	if (std::tolower((unsigned char)cfg.str("Frame", "Fixed")[0]) != 'f')
-	    die("Frame: %s is not supported (a frame with fixed OmegaFrame only)", cfg.str("Frame", ""));
+	read_frame_settings();
 	finit::UnitSystem U;
 	U.set_baseunits(cfg.str("l0", "1.0"), cfg.str("m0", "1.0"));
 	U.calculate();
@@ -774,6 +792,7 @@ struct Run {
 	    b.rec.semi_major_axis = q.semi_major_axis, b.rec.eccentricity = q.eccentricity, b.rec.mean_anomaly = q.mean_anomaly;
 	    b.rec.true_anomaly = q.true_anomaly, b.rec.eccentric_anomaly = q.eccentric_anomaly, b.rec.pericenter_angle = q.pericenter_angle;
 	    b.orbital_period = q.orbital_period;
+	    b.omega = q.omega;
 	    bodies.push_back(b);
 	}
 	if (bodies.size() == 2) { // a binary: both carry the secondary's elements (planetary_system.cpp:797-802)
@@ -787,6 +806,11 @@ struct Run {
 	disk_feedback = cfg.flag("DiskFeedback", true);
 	indirect_mode = (int)cfg.num("IndirectTermMode", 0);
 	omega_frame = cfg.num("OmegaFrame", 0.0), frame_angle = 0.0;
+	if (corotating) { // init_physics (init.cpp:259-263)
+	    if (corotation_body >= bodies.size())
+		die("%s", std::string("CorotationReferenceBody does not exist"));
+	    omega_frame = bodies[corotation_body].omega;
+	}
 	monitor_timestep = cfg.num("MonitorTimestep", 1.0);
 	nmonitor = (unsigned)cfg.num("Nmonitor", 10); // Interpret.cpp:201
 	nsnapshots = (unsigned)cfg.num("Nsnapshots", 1);
@@ -844,9 +868,32 @@ struct Run {
 	return dt;
     }
 
+    // refframe::init_corotation (frame_of_reference.cpp:19-28)
+    bool corotating = false;
+    unsigned corotation_body = 1;
+    double corot_old_x = 0.0, corot_old_y = 0.0;
+    void init_corotation()
+    {
+	if (corotating)
+	    corot_old_x = bodies[corotation_body].rec.x, corot_old_y = bodies[corotation_body].rec.y;
+    }
     void rotate_frame(double dt)
-    { // refframe::handle_corotation (frame_of_reference.cpp:30-60) for a frame with fixed OmegaFrame (Frame: F):
-      // the bodies are rotated into the frame, t_planetary_system::rotate (nbody/planetary_system.cpp:409-432)
+    { // refframe::handle_corotation (frame_of_reference.cpp:30-60): a corotating frame (Frame: C) first follows its reference
+      // body — new OmegaFrame from the angle the body has moved, v_azi of the gas corrected by the change — then the
+      // bodies are rotated into the frame, t_planetary_system::rotate (nbody/planetary_system.cpp:409-432)
+	if (corotating) {
+	    const double x = bodies[corotation_body].rec.x, y = bodies[corotation_body].rec.y;
+	    const double distance_new = std::sqrt(std::pow(x, 2) + std::pow(y, 2));
+	    const double distance_old = std::sqrt(std::pow(corot_old_x, 2) + std::pow(corot_old_y, 2));
+	    const double cross = corot_old_x * y - x * corot_old_y;
+	    const double OmegaNew = std::asin(cross / (distance_new * distance_old)) / dt;
+	    const double domega = (OmegaNew - omega_frame);
+	    CHECK(BK(correct_vazi)(ctx, domega));
+	    omega_frame = OmegaNew;
+	    // the gas step that follows reads the new OmegaFrame; the bodies it sees stay the ones of the last set_bodies
+	    last_fb.omega_frame = omega_frame;
+	    CHECK(BK(set_bodies)(ctx, &last_fb));
+	}
 	const double angle = omega_frame * dt;
 	for (auto &b : bodies) {
 	    const double x = b.rec.x, y = b.rec.y, vx = b.rec.vx, vy = b.rec.vy;
@@ -908,6 +955,7 @@ struct Run {
 	    r.semi_major_axis = e.semi_major_axis, r.eccentricity = e.eccentricity, r.mean_anomaly = e.mean_anomaly;
 	    r.true_anomaly = e.true_anomaly, r.eccentric_anomaly = e.eccentric_anomaly, r.pericenter_angle = e.pericenter_angle;
 	    bodies[i].orbital_period = e.orbital_period;
+	    bodies[i].omega = e.omega;
 	}
 	if (bodies.size() == 2) { // a binary: both carry the secondary's elements (:797-802)
 	    PlanetRecord &p0 = bodies[0].rec;
@@ -1007,7 +1055,8 @@ struct Run {
     {
 	const double frog = dt / 2, start_time = time, mid_time = time + frog;
 	compute_indirect_nbody(frog);	  // :285-287, while the bodies are still at the start of the step
-	integrate_and_recentre(frog);	  // :288-292
+	init_corotation();		  // :289
+	integrate_and_recentre(frog);	  // :290-292
 	accrete(frog);			  // :302-303
 	disk_feedback_kick(frog);	  // :297-313 (ComputeDiskOnNbodyAccel, UpdatePlanetVelocitiesWithDiskForce)
 	combine_indirect();		  // :299
@@ -1024,8 +1073,9 @@ struct Run {
 	CHECK(BK(set_time)(ctx, mid_time));
 	CHECK(BK(kick)(ctx, frog));
 	accrete(frog);			  // :403-404, after the gas's second kick
-	apply_indirect_term_on_nbody(frog); // :416
-	integrate_and_recentre(frog);	  // :419-424
+	apply_indirect_term_on_nbody(frog); // :410
+	init_corotation();		  // :413
+	integrate_and_recentre(frog);	  // :414-416
 	rotate_frame(frog);		  // :428
 	time = start_time + dt;
 	n_iter++;
@@ -1222,6 +1272,7 @@ struct Run {
 	    calculate_time_step();
 	}
 	CHECK(BK(stage_boundary)(ctx, 0.0, 0));
+	init_corotation();     // sim::init (simulation.cpp:463-464)
 	calculate_time_step(); // sim::init (simulation.cpp:467)
 	long steps = 0;
 	FILE *tl = fopen((outdir + "/monitor/timestepLogging.dat").c_str(), "a");

@@ -268,6 +268,10 @@ int fargo_monitor_quantities(fargo_ctx *ctx, double radius_limit, double out8[8]
 
 /* integer FARGO shifts of the last transport (TransportEuler.cpp:49,220), local rings */
 int fargo_get_nshift(fargo_ctx *ctx, int *out_local_nrad);
+/* correct_v_azimuthal (SideEuler.cpp:79-95), called by refframe::handle_corotation (frame_of_reference.cpp:30-60) when a
+ * corotating frame (Frame: C) changes its angular velocity by domega: v_azi -= domega * Rmed in every ring, ghost rings
+ * included.  The new OmegaFrame itself reaches the device through fargo_set_bodies. */
+int fargo_correct_vazi(fargo_ctx *ctx, double domega);
 
 /* device self-test of the branch-free IEEE arithmetic the kernels use (csrc/fargo_math.h) against the plain
  * operators on random + adversarial operands: counts4 = {division mismatches, sqrt mismatches, exp mismatches,

@@ -298,6 +298,15 @@ int fargo_oracle_upload_slab(fargo_oracle *o, int f, const double *host_slab)
 }
 
 /* damping.cpp:287-296 */
+/* correct_v_azimuthal, SideEuler.cpp:79-95 */
+int fargo_oracle_correct_vazi(fargo_oracle *o, double domega)
+{
+    for (int i = 0; i < o->nr; ++i)
+	for (int j = 0; j < o->ns; ++j)
+	    o->vazi[IDX(o, i, j)] -= domega * o->rmed[i];
+    return 0;
+}
+
 int fargo_oracle_copy_initial_values(fargo_oracle *o)
 {
     const size_t ns = (size_t)o->nr * o->ns, nv = (size_t)(o->nr + 1) * o->ns;

@@ -153,3 +153,34 @@ def test_gpu_accretion_vs_oracle(name):
     assert (gpu.download(abi.SIGMA) != z["Sigma_10"]).sum() > 4  # the Hill sphere covers cells on this grid
     for a, b in zip(res[1], res[0]):
         assert abs(a - b) <= 1e-13 * abs(b), (res)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# correct_v_azimuthal (SideEuler.cpp:79-95) for corotating frames
+def test_oracle_correct_vazi():
+    meta, z, ctx = _oracle("iso_planet_100")
+    _load(ctx, meta, z, 50)
+    before = ctx.download(abi.VAZI)
+    ctx.correct_vazi(0.125)
+    radii = z["radii"]
+    rmed = 2.0 / 3.0 * (radii[1:] ** 3 - radii[:-1] ** 3) / (radii[1:] ** 2 - radii[:-1] ** 2)
+    assert np.allclose(ctx.download(abi.VAZI), before - 0.125 * rmed[:, None], rtol=1e-15, atol=0.0)
+
+
+@pytest.mark.gpu
+def test_gpu_correct_vazi_vs_oracle():
+    from fargocpt_b200 import HydroContext
+    meta, z, cpu = _oracle("iso_planet_100")
+    gpu = HydroContext(reftools.make_params(meta["params"]), z["radii"])
+    for ctx in (cpu, gpu):
+        _load(ctx, meta, z, 50)
+        ctx.correct_vazi(-3.0e-4)
+    st = reftools.compare_stats(gpu.download(abi.VAZI), cpu.download(abi.VAZI))
+    assert st["n_diff"] == 0, st
+    # and a step on top of it (the marching kernels read the corrected buffer)
+    for ctx in (cpu, gpu):
+        ctx.set_time(0.0)
+        ctx.step(1.0e-3)
+    for fid in (abi.SIGMA, abi.VRAD, abi.VAZI):
+        st = reftools.compare_stats(gpu.download(fid), cpu.download(fid))
+        assert st["n_diff"] == 0, (fid, st)

@@ -240,7 +240,12 @@ REFERENCE_SETUPS = [("/root/reference/test/cold_disk_planet/setup.yml", []), ("/
                     ("/root/reference/examples/config.yml", ["IndirectTermMode=1"]),
                     # four bodies: eccentric orbits from their elements (Jacobi coordinates), jupiterMass / earthMass units,
                     # cubic (Klahr) smoothing, ramp-up — this repo's own setup file, run through both codes
-                    (os.path.join(ROOT, "tests", "golden", "multi_body_setup.yml"), ["--dt", "4e-3"])]
+                    (os.path.join(ROOT, "tests", "golden", "multi_body_setup.yml"), ["--dt", "4e-3"]),
+                    # Frame: C — the frame follows the planet (refframe::handle_corotation: new OmegaFrame every step, v_azi
+                    # corrected through fargo_correct_vazi), Euler / Leapfrog / with DiskFeedback and the predictor indirect term
+                    (os.path.join(ROOT, "tests", "golden", "corotating_setup.yml"), ["--dt", "4e-3"]),
+                    (os.path.join(ROOT, "tests", "golden", "corotating_setup.yml"), ["--dt", "4e-3", "Integrator=Leapfrog"]),
+                    (os.path.join(ROOT, "tests", "golden", "corotating_setup.yml"), ["--dt", "4e-3", "DiskFeedback=yes", "IndirectTermMode=0"])]
 
 
 @pytest.mark.parametrize("setup,overrides", REFERENCE_SETUPS)
