@@ -593,6 +593,7 @@ struct Run {
 	for (auto &b : bodies) {
 	    b.rec.vx = b.rec.vx + dt * b.rec.disk_on_planet_acceleration[0];
 	    b.rec.vy = b.rec.vy + dt * b.rec.disk_on_planet_acceleration[1];
+	    b.rec.gas_torque_acc += b.rec.torque * dt; // t_planet::add_torque (Pframeforce.cpp:272)
 	}
 	// hydro frame centred on body 0
 	double mass_center = 0.0;
@@ -601,6 +602,8 @@ struct Run {
 	mass_center += bodies[0].rec.mass;
 	ind_disk_x /= mass_center;
 	ind_disk_y /= mass_center;
+	for (auto &b : bodies) // the indirect torque monitor (frame_of_reference.cpp:92-107)
+	    b.rec.indirect_torque_acc += (b.rec.x * ind_disk_y - b.rec.y * ind_disk_x) * b.rec.mass * dt;
     }
 
     void load(const std::string &dir, unsigned nsnap, int device)
@@ -847,6 +850,8 @@ struct Run {
 	U.write_files(outdir);
 	write_snapshot(); // sim::handle_outputs before sim::run (main.cpp:150)
 	finish_pending_snapshot();
+	set_bodies_on_device();
+	write_planet_monitor_files();
 	write_quantities();
 	if (params.damping || params.cooling_beta_reference == 1) { // the damping reference (simulation.cpp:42-47)
 	    const std::string from = outdir + "/snapshots/0", to = outdir + "/snapshots/reference";
@@ -1242,6 +1247,67 @@ struct Run {
 	fclose(fd);
     }
 
+    // t_planet::create_planet_file / write_ascii (nbody/planet.cpp:279-372) through t_planetary_system::write_planets(1)
+    // (sim::handle_outputs, simulation.cpp:83-84): monitor/nbodyK.dat, file version 2, 22 columns.  The circumplanetary
+    // mass (column 9, ComputeCircumPlanetaryMasses) is not evaluated on this path: nan.
+    bool planet_files_created = false;
+    void write_planet_monitor_files()
+    {
+	const double L = consts.length_cgs, M = consts.mass_cgs, T = consts.time_cgs;
+	auto desc = [](double v, const char *sym) {
+	    char b[96];
+	    snprintf(b, sizeof b, "%.16e %s", v, sym);
+	    return std::string(b);
+	};
+	const double div = cfg.flag("WriteAtEveryTimestep", true) ? monitor_timestep : monitor_timestep * nmonitor;
+	for (size_t k = 0; k < bodies.size(); ++k) {
+	    const std::string path = outdir + "/monitor/nbody" + std::to_string(k) + ".dat";
+	    FILE *fd = fopen(path.c_str(), planet_files_created ? "a" : "w");
+	    if (!fd)
+		die("cannot write %s", path);
+	    PlanetRecord &r = bodies[k].rec;
+	    if (!planet_files_created) {
+		const std::string one = "1", length = desc(L, "cm"), velocity = desc(L / T, "cm s^-1"), mass = desc(M, "g"), time_ = desc(T, "s"),
+				  freq = desc(1.0 / T, "1/s"), angmom = desc(L * M * (L / T), "cm^2 g s^-1"), torque = desc(L * L * M / (T * T), "erg"),
+				  mdot = desc(M / T, "g s^-1");
+		const std::pair<const char *, const std::string *> cols[22] = {
+		    {"snapshot number", &one}, {"monitor number", &one}, {"x", &length}, {"y", &length}, {"vx", &velocity}, {"vy", &velocity},
+		    {"mass", &mass}, {"time", &time_}, {"omega frame", &freq}, {"mdcp", &mass}, {"eccentricity", &one},
+		    {"angular momentum", &angmom}, {"semi-major axis", &length}, {"omega kepler", &freq}, {"mean anomaly", &one},
+		    {"eccentric anomaly", &one}, {"true anomaly", &one}, {"pericenter angle", &one}, {"gas torque", &torque},
+		    {"accretion torque", &torque}, {"indirect torque", &torque}, {"accretion rate", &mdot}};
+		std::string name = "planet" + std::to_string(k);
+		if (k < cfg.nbody.size() && cfg.nbody[k].count("name"))
+		    name = cfg.nbody[k].at("name");
+		fprintf(fd, "#FargoCPT planet file for planet: %s\n#version: 2\n", name.c_str());
+		for (int c = 0; c < 22; ++c)
+		    fprintf(fd, "#variable: %d | %s | %s\n", c, cols[c].first, cols[c].second->c_str());
+	    }
+	    double torque;
+	    if (disk_feedback) {
+		torque = r.gas_torque_acc / div;
+	    } else { // sim::handle_outputs refreshes the disk's pull for the monitor (simulation.cpp:58-61)
+		double a4[4];
+		CHECK(BK(disk_on_body_accel)(ctx, (int)k, r.cubic_smoothing_factor, a4));
+		r.disk_on_planet_acceleration[0] = a4[0] + a4[2], r.disk_on_planet_acceleration[1] = a4[1] + a4[3];
+		r.torque = (r.x * r.disk_on_planet_acceleration[1] - r.y * r.disk_on_planet_acceleration[0]) * r.mass;
+		torque = r.torque;
+	    }
+	    const double angular_momentum = r.mass * r.x * r.vy - r.mass * r.y * r.vx;
+	    const double row[20] = {r.x, r.y, r.vx, r.vy, r.mass, time, omega_frame, std::nan(""), r.eccentricity, angular_momentum,
+				    r.semi_major_axis, bodies[k].omega, r.mean_anomaly, r.eccentric_anomaly, r.true_anomaly, r.pericenter_angle,
+				    torque, r.accretion_torque_acc / div, r.indirect_torque_acc / div, r.accreted_mass / div};
+	    fprintf(fd, "%u\t%u", n_monitor / nmonitor, n_monitor);
+	    for (double x : row)
+		fprintf(fd, "\t%#.18g", x);
+	    fprintf(fd, "\n");
+	    fclose(fd);
+	    // t_planet::write(1) resets the accumulators (planet.cpp:323-327)
+	    r.accreted_mass = 0.0, r.gas_torque_acc = 0.0, r.accretion_torque_acc = 0.0, r.indirect_torque_acc = 0.0;
+	}
+	planet_files_created = true;
+    }
+
     void write_static_files()
     { // dimensions.dat / used_rad.dat (init.cpp:227-247) so python_module/fargocpt/data.py can load the directory
 	mkdirs(outdir + "/snapshots");
@@ -1294,8 +1360,12 @@ struct Run {
 		    n_snapshot = n_monitor / nmonitor;
 		    write_snapshot();
 		}
-		if (snapshot_now || cfg.flag("WriteAtEveryTimestep", true)) // sim::handle_outputs (simulation.cpp:50-98)
+		if (snapshot_now || cfg.flag("WriteAtEveryTimestep", true)) { // sim::handle_outputs (simulation.cpp:50-98)
+		    if (!disk_feedback)
+			set_bodies_on_device(); // positions for the force integral of the torque monitor
+		    write_planet_monitor_files();
 		    write_quantities();
+		}
 	    }
 	}
 	fclose(tl);

@@ -129,8 +129,12 @@ def test_host_driver_accretion_cpu(name, tmp_path):
     check(meta, z, out, 20, exact=False)
     raw = open(os.path.join(out, "snapshots", "20", "nbody1.bin"), "rb").read()
     (accreted,) = struct.unpack("<d", raw[64:72])
-    total = sum(meta["bodies"][k][1][8] for k in range(1, 21))  # the reference resets its counter at every output
-    assert accreted == pytest.approx(total, rel=1e-9)
+    # like the reference, the counter is reset at every monitor output (t_planet::write, planet.cpp:323-327)
+    assert accreted == pytest.approx(meta["bodies"][20][1][8], rel=1e-9)
+    rows = [l.split("\t") for l in open(os.path.join(out, "monitor", "nbody1.dat")) if not l.startswith("#")]
+    assert len(rows) == 20 and all(len(r) == 22 for r in rows)
+    rate = [float(r[21]) * meta["monitor_timestep"] for r in rows]  # column 21: accretion rate = accreted mass / monitor step
+    assert rate == pytest.approx([meta["bodies"][k][1][8] for k in range(1, 21)], rel=1e-9)
     # and it matters: without the accretion the surface density near the planet is off by far more than the tolerance
     nrad, naz = meta["params"]["nrad"], meta["params"]["naz"]
     got = np.fromfile(os.path.join(out, "snapshots", "20", "Sigma.dat")).reshape(nrad, naz)
@@ -365,3 +369,25 @@ def test_spreading_ring_gpu_equals_oracle(tmp_path):
             a = open(os.path.join(gpu, "snapshots", str(k), f), "rb").read()
             b = open(os.path.join(cpu, "snapshots", str(k), f), "rb").read()
             assert a == b, (k, f)
+
+
+def test_host_planet_monitor_files_cpu(tmp_path):
+    """monitor/nbodyK.dat (t_planet::write_ascii, nbody/planet.cpp:279-372): header of file version 2 with 22 columns, one row per
+    monitor step; positions / velocities / mass equal the snapshot records, the torque column is the disk's torque."""
+    meta, z, out = start_host(_oracle_exe(), "iso_feedback_20", tmp_path, 20)
+    lines = open(os.path.join(out, "monitor", "nbody1.dat")).read().splitlines()
+    assert lines[0] == "#FargoCPT planet file for planet: planet" and lines[1] == "#version: 2"
+    header = [l for l in lines if l.startswith("#variable:")]
+    assert len(header) == 22 and header[12].startswith("#variable: 12 | semi-major axis | ")
+    rows = [l.split("\t") for l in lines if not l.startswith("#")]
+    assert [int(r[1]) for r in rows] == list(range(21))
+    for k in (0, 20):
+        raw = open(os.path.join(out, "snapshots", str(k), "nbody1.bin"), "rb").read()
+        mass, x, y, vx, vy = struct.unpack("<5d", raw[8:48])
+        assert [float(v) for v in rows[k][2:7]] == [x, y, vx, vy, mass]
+    # DiskFeedback: the gas torque column is the accumulated torque per monitor step; it matches the recorded acceleration
+    # (the record of snapshot 20 holds the acceleration computed at the START of step 20, where the planet was at its snapshot-19 position)
+    b, at = meta["bodies"][20][1], meta["bodies"][19][1]
+    torque = (at[1] * b[6] - at[2] * b[5]) * b[0]
+    assert float(rows[20][18]) == pytest.approx(torque, rel=1e-9)
+    assert rows[20][9] == "nan"  # circumplanetary mass: not evaluated on this path

@@ -32,7 +32,7 @@ def main(argv=None):
             nsnap = int(args[i + 1]); i += 1
         elif a == "--dt":
             dt = float(args[i + 1]); i += 1
-        elif a == "--gpu":
+        elif a in ("--gpu", "--keep"):
             pass
         elif "=" in a:
             k, v = a.split("=", 1)
