@@ -730,8 +730,7 @@ struct Run {
 	cfg.load(cfgfile);
 	// what this driver's initial conditions do not cover is refused by name
 	const std::pair<const char *, const char *> off[] = {
-	    {"ShockTube", "0"}, {"RandomSigma", "no"}, {"ProfileCutoffOuter", "no"},
-	    {"ProfileCutoffInner", "no"}, {"InitializePureKeplerian", "no"}, {"SelfGravity", "no"}, {"IntegrateParticles", "no"},
+	    {"ShockTube", "0"}, {"RandomSigma", "no"}, {"InitializePureKeplerian", "no"}, {"SelfGravity", "no"}, {"IntegrateParticles", "no"},
 	    {"RadiativeDiffusion", "no"}, {"SecondaryDisk", "no"}, {"CbdRing", "no"}, {"VazimuthalConsidersQuadropoleMoment", "no"}};
 	for (auto &k : off) {
 	    const std::string v = lower(cfg.str(k.first, k.second));
@@ -825,6 +824,15 @@ struct Run {
 	d.thickness_smoothing = params.thickness_smoothing, d.tmin = params.minimum_temperature, d.tmax = params.maximum_temperature;
 	d.omega_frame = omega_frame, d.imposed_drift = params.imposed_disk_drift;
 	d.adiabatic = params.adiabatic != 0, d.vradial_zero = cfg.flag("InitializeVradialZero", false);
+	d.cutoff_outer = cfg.flag("ProfileCutoffOuter", false), d.cutoff_inner = cfg.flag("ProfileCutoffInner", false);
+	if (cfg.has("ProfileCutoffPointOuter"))
+	    d.cutoff_point_outer = U.in_code_units(cfg.str("ProfileCutoffPointOuter", ""), 'L');
+	if (cfg.has("ProfileCutoffWidthOuter"))
+	    d.cutoff_width_outer = U.in_code_units(cfg.str("ProfileCutoffWidthOuter", ""), 'L');
+	if (cfg.has("ProfileCutoffPointInner"))
+	    d.cutoff_point_inner = U.in_code_units(cfg.str("ProfileCutoffPointInner", ""), 'L');
+	if (cfg.has("ProfileCutoffWidthInner"))
+	    d.cutoff_width_inner = U.in_code_units(cfg.str("ProfileCutoffWidthInner", ""), 'L');
 	d.spreading_ring = cfg.flag("SpreadingRing", false);
 	d.set_sigma0 = cfg.flag("SetSigma0", false);
 	d.diskmass = cfg.has("DiskMass") ? U.in_code_units(cfg.str("DiskMass", "0.01"), 'M') : 0.01;

@@ -480,6 +480,9 @@ struct DiskModel {
     double sigma0, sigma_slope, sigma_floor, h0, flaring, gamma, mu, Rgas, G, viscous_alpha, constant_viscosity, thickness_smoothing,
 	tmin, tmax, omega_frame, imposed_drift;
     bool adiabatic, vradial_zero;
+    // ProfileCutoffOuter / Inner (parameters.cpp:728-742): Fermi-function cut-offs of the initial profiles (util.cpp:69-93)
+    bool cutoff_outer = false, cutoff_inner = false;
+    double cutoff_point_outer = 1.0e300, cutoff_width_outer = 1.0, cutoff_point_inner = 0.0, cutoff_width_inner = 1.0;
     bool spreading_ring = false; // SpreadingRing: the Bessel-function ring of init_spreading_ring_test (init.cpp:358-412)
     bool set_sigma0 = false; // SetSigma0: rescale Sigma0 so that the disk holds DiskMass (renormalize_sigma_and_report, init.cpp:1150-1188)
     double diskmass = 0.0;
@@ -491,6 +494,9 @@ struct InitialState {
 
 namespace detail
 {
+// util.cpp:69-93
+inline double cutoff_outer(double point, double width, double x) { return 1.0 / (1.0 + exp((x - point) / width)); }
+inline double cutoff_inner(double point, double width, double x) { return 1.0 / (1.0 + exp((point - x) / width)); }
 // Theo.cpp:122-153
 inline double support_azi_pressure(const DiskModel &d, const double R)
 {
@@ -517,6 +523,10 @@ inline double get_sigma(const DiskModel &d, const double R)
 {
     double density = d.sigma0 * std::pow(R, -d.sigma_slope);
     const double density_floor = d.sigma_floor * d.sigma0;
+    if (d.cutoff_outer)
+	density *= cutoff_outer(d.cutoff_point_outer, d.cutoff_width_outer, R);
+    if (d.cutoff_inner)
+	density *= cutoff_inner(d.cutoff_point_inner, d.cutoff_width_inner, R);
     density = std::max(density, density_floor);
     return density;
 }
@@ -525,6 +535,10 @@ inline double get_nu2(const DiskModel &d, const double R, const double M, const 
     const double v_k = std::sqrt(d.G * M / R);
     const double h = d.h0 * std::pow(R, d.flaring);
     double cutoff = 1.0;
+    if (d.cutoff_outer)
+	cutoff *= cutoff_outer(d.cutoff_point_outer, d.cutoff_width_outer, R);
+    if (d.cutoff_inner)
+	cutoff *= cutoff_inner(d.cutoff_point_inner, d.cutoff_width_inner, R);
     double cs_adb, H;
     if (d.adiabatic) {
 	const double gamma = d.gamma;
@@ -636,6 +650,33 @@ inline InitialState init_gas(DiskModel &d, const std::vector<double> &radii, int
 	    }
 	}
     }
+    // profile cut-offs (init.cpp:1064-1147 for Sigma, :1361-1464 for the energy): outer first, then inner, each with its floor
+    for (int pass = 0; pass < 2; ++pass) {
+	if (!(pass == 0 ? d.cutoff_outer : d.cutoff_inner))
+	    continue;
+	for (int i = 0; i < nrad; ++i) {
+	    const double f = pass == 0 ? detail::cutoff_outer(d.cutoff_point_outer, d.cutoff_width_outer, rmed[i])
+				       : detail::cutoff_inner(d.cutoff_point_inner, d.cutoff_width_inner, rmed[i]);
+	    for (int j = 0; j < naz; ++j) {
+		const size_t l = (size_t)i * naz + j;
+		s.sigma[l] = std::max(s.sigma[l] * f, d.sigma_floor * d.sigma0);
+	    }
+	}
+    }
+    if (d.adiabatic)
+	for (int pass = 0; pass < 2; ++pass) {
+	    if (!(pass == 0 ? d.cutoff_outer : d.cutoff_inner))
+		continue;
+	    for (int i = 0; i < nrad; ++i) {
+		const double f = pass == 0 ? detail::cutoff_outer(d.cutoff_point_outer, d.cutoff_width_outer, rmed[i])
+					   : detail::cutoff_inner(d.cutoff_point_inner, d.cutoff_width_inner, rmed[i]);
+		for (int j = 0; j < naz; ++j) {
+		    const size_t l = (size_t)i * naz + j;
+		    const double energy_floor = d.tmin * s.sigma[l] / d.mu * d.Rgas / (d.gamma - 1.0);
+		    s.energy[l] = std::max(s.energy[l] * f, energy_floor);
+		}
+	    }
+	}
     if (d.set_sigma0) { // quantities::gas_total_mass over the active rings (quantities.cpp:51-75), summed in index order
 	double total_mass = 0.0;
 	for (int i = 1; i < nrad - 1; ++i) {

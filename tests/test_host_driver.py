@@ -247,6 +247,10 @@ REFERENCE_SETUPS = [("/root/reference/test/cold_disk_planet/setup.yml", []), ("/
                     (os.path.join(ROOT, "tests", "golden", "multi_body_setup.yml"), ["--dt", "4e-3"]),
                     # Frame: C — the frame follows the planet (refframe::handle_corotation: new OmegaFrame every step, v_azi
                     # corrected through fargo_correct_vazi), Euler / Leapfrog / with DiskFeedback and the predictor indirect term
+                    # Fermi-function cut-offs of the initial profiles (also inside the numerically differentiated viscous speed), SetSigma0
+                    (os.path.join(ROOT, "tests", "golden", "adia_planet_100.yml"),
+                     ["--dt", "4e-3", "ProfileCutoffOuter=yes", "ProfileCutoffPointOuter=2.0", "ProfileCutoffWidthOuter=0.1",
+                      "ProfileCutoffInner=yes", "ProfileCutoffPointInner=15 au", "ProfileCutoffWidthInner=0.05", "SetSigma0=yes", "DiskMass=0.02"]),
                     (os.path.join(ROOT, "tests", "golden", "corotating_setup.yml"), ["--dt", "4e-3"]),
                     (os.path.join(ROOT, "tests", "golden", "corotating_setup.yml"), ["--dt", "4e-3", "Integrator=Leapfrog"]),
                     (os.path.join(ROOT, "tests", "golden", "corotating_setup.yml"), ["--dt", "4e-3", "DiskFeedback=yes", "IndirectTermMode=0"])]

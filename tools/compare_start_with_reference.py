@@ -40,7 +40,7 @@ def main(argv=None):
         else:
             setup = a
         i += 1
-    cfg = yaml.safe_load(open(setup))
+    cfg = {k: v for k, v in yaml.safe_load(open(setup)).items() if not k.startswith("_")}  # "_keep" etc.: fixture bookkeeping
     cfg.update({"MonitorTimestep": dt, "Nmonitor": 1, "Nsnapshots": nsnap, "WriteAtEveryTimestep": "yes"})
     cfg.update(over)
     tmp = tempfile.mkdtemp(prefix="cmpstart_")
