@@ -258,13 +258,38 @@ static fargo_params make_params(const Config &c, const CodeConstants &k, int nra
     const char sp = (char)std::tolower((unsigned char)c.str("RadialSpacing", "Arithmetic")[0]);
     p.radial_spacing = sp == 'l' ? FARGO_SPACING_LOG : sp == 'a' ? FARGO_SPACING_ARITH : sp == 'e' ? FARGO_SPACING_EXP : FARGO_SPACING_CUSTOM;
     p.rmin = c.num("Rmin", 0.0), p.rmax = c.num("Rmax", 0.0);
+    // Physics this path does not implement must not be dropped silently: a setup that switches it on is refused by name.
+    {
+	const std::string eos = lower(c.str("EquationOfState", "Isothermal")); // Interpret.cpp:391-470
+	if (eos != "isothermal" && eos != "iso" && eos != "adiabatic" && eos != "ideal")
+	    die("EquationOfState: %s is not supported by this driver (isothermal, ideal)", eos);
+	if (c.has("Adiabatic"))
+	    die("%s", std::string("the deprecated 'Adiabatic' flag is not supported; use EquationOfState"));
+	const bool energy_equation = eos == "adiabatic" || eos == "ideal"; // SubStep3 only runs then (simulation.cpp:203-205)
+	const std::string sc = lower(c.str("SurfaceCooling", "No")); // parameters.cpp:394-406
+	if (energy_equation && !(sc == "no" || sc == "off" || sc == "false"))
+	    die("SurfaceCooling: %s is not supported by this driver (beta cooling only)", sc);
+	const std::pair<const char *, double> zero_only[] = {{"AlphaMode", 0}, {"AspectRatioMode", 0}};
+	for (auto &k : zero_only)
+	    if (c.num(k.first, k.second) != k.second)
+		die((std::string(k.first) + ": %s is not supported by this driver").c_str(), c.str(k.first, ""));
+	for (const char *k : {"SelfGravity", "RadiativeDiffusion", "RocheLobeOverflow", "KeepDiskMassConstant", "PlanetOrbitDiskTest",
+			      "CICPLANET", "CompatibilityNoStarSmoothing", "CompatibilitySmoothingPlanetLoc", "IntegrateParticles",
+			      "ViscAccretMassflowTest"})
+	    if (c.flag(k, false))
+		die((std::string(k) + ": %s is not supported by this driver").c_str(), c.str(k, ""));
+	for (auto &b : c.nbody)
+	    if (energy_equation && b.count("irradiate") && !b.at("irradiate").empty() && std::strchr("yYtT1", b.at("irradiate")[0]))
+		die("%s", std::string("irradiating bodies (nbody: irradiate: yes) are not supported by this driver"));
+    }
     const std::string eos = lower(c.str("EquationOfState", "Isothermal"));
-    p.adiabatic = (eos == "ideal" || eos == "adiabatic" || eos == "perfect") ? 1 : 0;
+    p.adiabatic = (eos == "ideal" || eos == "adiabatic") ? 1 : 0;
     p.gamma = c.num("AdiabaticIndex", 1.4);
     p.mu = c.num("mu", 1.0);
     p.aspectratio_ref = c.num("AspectRatio", 0.05);
     p.flaring_index = c.num("FlaringIndex", 0.0);
-    p.sigma0 = c.num("Sigma0", 173.0);
+    // default "173 g/cm2" (parameters.cpp:625); a value with a unit has been converted by the caller (`start`) already
+    p.sigma0 = c.has("Sigma0") ? c.num("Sigma0", 0.0) : 173.0 / (k.mass_cgs / (k.length_cgs * k.length_cgs));
     p.sigma_floor = c.num("SigmaFloor", 1e-9);
     p.sigma_slope = c.num("SigmaSlope", 0.0);
     p.minimum_temperature = Config::number(c.str("MinimumTemperature", "3 K"), k.temperature_unit_K);
@@ -273,7 +298,7 @@ static fargo_params make_params(const Config &c, const CodeConstants &k, int nra
     p.hydro_center_mass = 1.0; // overwritten from the bodies (global.cpp:146)
     p.cfl = c.num("CFL", 0.5);
     p.cfl_max_var = c.num("CFLmaxVar", 1.1);
-    p.heating_cooling_cfl_limit = c.num("HeatingCoolingCFLlimit", 1.0);
+    p.heating_cooling_cfl_limit = c.num("HeatingCoolingCFLlimit", 10.0); // parameters.cpp:797
     p.leapfrog = std::tolower((unsigned char)c.str("Integrator", "Euler")[0]) == 'e' ? 0 : 1;
     p.fast_transport = std::tolower((unsigned char)c.str("Transport", "FARGO")[0]) == 'f' ? 1 : 0;
     const std::string fl = c.str("FluxLimiter", "VanLeer"); // Interpret.cpp:640-664 compares case-sensitively
@@ -291,7 +316,7 @@ static fargo_params make_params(const Config &c, const CodeConstants &k, int nra
     p.constant_viscosity = c.num("ConstantViscosity", 0.0);
     p.stabilize_viscosity = (int)c.num("StabilizeViscosity", 0);
     p.radial_viscosity_factor = c.num("RadialViscosityFactor", 1.0);
-    p.heating_viscous = c.flag("HeatingViscous", false);
+    p.heating_viscous = c.flag("HeatingViscous", true); // parameters.cpp:561
     p.heating_viscous_factor = c.num("HeatingViscousFactor", 1.0);
     p.cooling_beta = c.flag("CoolingBetaLocal", false);
     p.cooling_beta_value = c.num("CoolingBeta", 1.0);
@@ -299,7 +324,7 @@ static fargo_params make_params(const Config &c, const CodeConstants &k, int nra
     p.cooling_beta_reference = enum_of(c.str("CoolingBetaReference", "zero"),
 				       {{"zero", 0}, {"none", 0}, {"reference", 1}, {"model", 2}, {"floor", 4}}, "CoolingBetaReference");
     p.body_force_from_potential = c.flag("BodyForceFromPotential", true);
-    p.thickness_smoothing = c.num("ThicknessSmoothing", 0.0);
+    p.thickness_smoothing = c.num("ThicknessSmoothing", 0.6);
     p.imposed_disk_drift = c.num("ImposedDiskDrift", 0.0);
     const std::vector<std::pair<std::string, int>> BC = {{"none", 0}, {"zerogradient", 1}, {"zero_gradient", 1}, {"outflow", 2},
 							  {"reflecting", 3}, {"keplerian", 4}, {"reference", 5}};
@@ -316,6 +341,9 @@ static fargo_params make_params(const Config &c, const CodeConstants &k, int nra
 	else if (comp == "reference")
 	    bs = be = bvr = "reference";
 	else {
+	    for (const char *v : {"BoundarySigma", "BoundaryEnergy", "BoundaryVrad"}) // boundary_conditions/config.cpp: no default
+		if (!c.has(std::string(sides[s]) + v))
+		    die((std::string("Can not infer '") + sides[s] + v + "' when '" + sides[s] + "Boundary' is %s").c_str(), comp);
 	    bs = c.str(std::string(sides[s]) + "BoundarySigma", "zerogradient");
 	    be = c.str(std::string(sides[s]) + "BoundaryEnergy", "zerogradient");
 	    bvr = c.str(std::string(sides[s]) + "BoundaryVrad", "zerogradient");
@@ -669,8 +697,8 @@ struct Run {
 	if (corotating && corotation_body >= bodies.size())
 	    die("%s", std::string("CorotationReferenceBody does not exist"));
 	monitor_timestep = cfg.num("MonitorTimestep", 1.0);
-	nmonitor = (unsigned)cfg.num("Nmonitor", 1);
-	nsnapshots = (unsigned)cfg.num("Nsnapshots", 1);
+	nmonitor = (unsigned)cfg.num("Nmonitor", 10); // Interpret.cpp:200-201
+	nsnapshots = (unsigned)cfg.num("Nsnapshots", 1000);
 	create_context(device);
 	// restart_load (restart.cpp:19-131): the four state fields
 	const std::pair<int, const char *> state[4] = {{FARGO_SIGMA, "Sigma"}, {FARGO_VRAD, "vrad"}, {FARGO_VAZI, "vazi"}, {FARGO_ENERGY, "energy"}};
@@ -754,6 +782,8 @@ struct Run {
 	// values that may carry units become plain code-unit numbers (config::Config::get<double>(key, unit))
 	const std::pair<const char *, char> dims[] = {{"Rmin", 'L'}, {"Rmax", 'L'}, {"Sigma0", 'S'}, {"MonitorTimestep", 'T'},
 						       {"FirstDT", 'T'}, {"DampingTimeRadiusOuter", 'L'}};
+	if (!cfg.has("Sigma0"))
+	    cfg.kv["sigma0"] = "173 g/cm2"; // parameters.cpp:625
 	for (auto &k : dims)
 	    if (cfg.has(k.first))
 		cfg.kv[lower(k.first)] = finit::UnitSystem::num17(U.in_code_units(cfg.str(k.first, ""), k.second));
@@ -815,7 +845,7 @@ struct Run {
 	}
 	monitor_timestep = cfg.num("MonitorTimestep", 1.0);
 	nmonitor = (unsigned)cfg.num("Nmonitor", 10); // Interpret.cpp:201
-	nsnapshots = (unsigned)cfg.num("Nsnapshots", 1);
+	nsnapshots = (unsigned)cfg.num("Nsnapshots", 1000);
 	// init_physics (init.cpp:255-345)
 	finit::DiskModel d;
 	d.sigma0 = params.sigma0, d.sigma_slope = params.sigma_slope, d.sigma_floor = params.sigma_floor;

@@ -251,6 +251,9 @@ REFERENCE_SETUPS = [("/root/reference/test/cold_disk_planet/setup.yml", []), ("/
                     (os.path.join(ROOT, "tests", "golden", "adia_planet_100.yml"),
                      ["--dt", "4e-3", "ProfileCutoffOuter=yes", "ProfileCutoffPointOuter=2.0", "ProfileCutoffWidthOuter=0.1",
                       "ProfileCutoffInner=yes", "ProfileCutoffPointInner=15 au", "ProfileCutoffWidthInner=0.05", "SetSigma0=yes", "DiskMass=0.02"]),
+                    # a setup that sets almost nothing: the reference's DEFAULTS (Sigma0 173 g/cm2, l0 / m0, ThicknessSmoothing 0.6,
+                    # HeatingViscous yes, HeatingCoolingCFLlimit 10, IndirectTermMode 0, ArtificialViscosity SN ...)
+                    (os.path.join(ROOT, "tests", "golden", "minimal_defaults_setup.yml"), ["--dt", "5e-3"]),
                     (os.path.join(ROOT, "tests", "golden", "corotating_setup.yml"), ["--dt", "4e-3"]),
                     (os.path.join(ROOT, "tests", "golden", "corotating_setup.yml"), ["--dt", "4e-3", "Integrator=Leapfrog"]),
                     (os.path.join(ROOT, "tests", "golden", "corotating_setup.yml"), ["--dt", "4e-3", "DiskFeedback=yes", "IndirectTermMode=0"])]
