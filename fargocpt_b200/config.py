@@ -52,7 +52,7 @@ def params_from_config(cfg, consts, nrad, naz, temp_unit_K=1.0):
     d["hydro_center_mass"] = consts.get("hydro_center_mass", 1.0)
     d["cfl"] = float(get("CFL", 0.5))
     d["cfl_max_var"] = float(get("CFLmaxVar", 1.1))
-    d["heating_cooling_cfl_limit"] = float(get("HeatingCoolingCFLlimit", 1.0))
+    d["heating_cooling_cfl_limit"] = float(get("HeatingCoolingCFLlimit", 10.0))  # parameters.cpp:797
     integ = str(get("Integrator", "Euler")).lower()
     d["leapfrog"] = 0 if integ.startswith("e") else 1
     d["fast_transport"] = 1 if str(get("Transport", "FARGO")).lower().startswith("f") else 0
@@ -65,14 +65,14 @@ def params_from_config(cfg, consts, nrad, naz, temp_unit_K=1.0):
     d["constant_viscosity"] = _num(get("ConstantViscosity", 0.0))
     d["stabilize_viscosity"] = int(get("StabilizeViscosity", 0))
     d["radial_viscosity_factor"] = float(get("RadialViscosityFactor", 1.0))
-    d["heating_viscous"] = int(_flag(get("HeatingViscous"), False))
+    d["heating_viscous"] = int(_flag(get("HeatingViscous"), True))  # parameters.cpp:561
     d["heating_viscous_factor"] = float(get("HeatingViscousFactor", 1.0))
     d["cooling_beta"] = int(_flag(get("CoolingBetaLocal"), False))
     d["cooling_beta_value"] = float(get("CoolingBeta", 1.0))
     d["cooling_beta_ramp_up"] = _num(get("CoolingBetaRampUp", 0.0))
     d["cooling_beta_reference"] = abi.BETA_REF[str(get("CoolingBetaReference", "zero")).lower()]
     d["body_force_from_potential"] = int(_flag(get("BodyForceFromPotential"), True))
-    d["thickness_smoothing"] = float(get("ThicknessSmoothing", 0.0))
+    d["thickness_smoothing"] = float(get("ThicknessSmoothing", 0.6))
     d["imposed_disk_drift"] = float(get("ImposedDiskDrift", 0.0))
 
     # boundaries: composite names (boundary_conditions/config.cpp:345-436) or individual keys
