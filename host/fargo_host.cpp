@@ -274,7 +274,7 @@ static fargo_params make_params(const Config &c, const CodeConstants &k, int nra
 	    if (c.num(k.first, k.second) != k.second)
 		die((std::string(k.first) + ": %s is not supported by this driver").c_str(), c.str(k.first, ""));
 	for (const char *k : {"SelfGravity", "RadiativeDiffusion", "RocheLobeOverflow", "KeepDiskMassConstant", "PlanetOrbitDiskTest",
-			      "CICPLANET", "CompatibilityNoStarSmoothing", "CompatibilitySmoothingPlanetLoc", "IntegrateParticles",
+			      "CompatibilityNoStarSmoothing", "CompatibilitySmoothingPlanetLoc", "IntegrateParticles",
 			      "ViscAccretMassflowTest"})
 	    if (c.flag(k, false))
 		die((std::string(k) + ": %s is not supported by this driver").c_str(), c.str(k, ""));
@@ -758,7 +758,7 @@ struct Run {
 	cfg.load(cfgfile);
 	// what this driver's initial conditions do not cover is refused by name
 	const std::pair<const char *, const char *> off[] = {
-	    {"ShockTube", "0"}, {"RandomSigma", "no"}, {"InitializePureKeplerian", "no"}, {"SelfGravity", "no"}, {"IntegrateParticles", "no"},
+	    {"ShockTube", "0"}, {"RandomSigma", "no"}, {"SelfGravity", "no"}, {"IntegrateParticles", "no"},
 	    {"RadiativeDiffusion", "no"}, {"SecondaryDisk", "no"}, {"CbdRing", "no"}, {"VazimuthalConsidersQuadropoleMoment", "no"}};
 	for (auto &k : off) {
 	    const std::string v = lower(cfg.str(k.first, k.second));
@@ -808,7 +808,8 @@ struct Run {
 	params = make_params(cfg, consts, nrad, naz);
 	radii = finit::make_radii(params.radial_spacing, nrad, params.rmin, params.rmax, cfg.num("ExponentialCellSizeFactor", 1.41));
 	// bodies
-	const auto B = finit::init_bodies(cfg.nbody, U, params.rmax);
+	const bool cic = cfg.flag("CICPLANET", false);
+	const auto B = finit::init_bodies(cfg.nbody, U, params.rmax, cic ? &radii : nullptr, params.rmin, cfg.num("KlahrSmoothingRadius", 0.0));
 	if (B.size() > FARGO_MAX_BODIES)
 	    die("too many bodies in %s", cfgfile);
 	for (size_t k = 0; k < B.size(); ++k) {
@@ -854,6 +855,7 @@ struct Run {
 	d.thickness_smoothing = params.thickness_smoothing, d.tmin = params.minimum_temperature, d.tmax = params.maximum_temperature;
 	d.omega_frame = omega_frame, d.imposed_drift = params.imposed_disk_drift;
 	d.adiabatic = params.adiabatic != 0, d.vradial_zero = cfg.flag("InitializeVradialZero", false);
+	d.pure_keplerian = cfg.flag("InitializePureKeplerian", false);
 	d.cutoff_outer = cfg.flag("ProfileCutoffOuter", false), d.cutoff_inner = cfg.flag("ProfileCutoffInner", false);
 	if (cfg.has("ProfileCutoffPointOuter"))
 	    d.cutoff_point_outer = U.in_code_units(cfg.str("ProfileCutoffPointOuter", ""), 'L');

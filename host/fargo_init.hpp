@@ -353,7 +353,8 @@ inline void orbital_elements(BodyInit &b, double x, double y, double vx, double 
 
 // t_planetary_system::init_system for HydroFrameCenter: primary (nbody/planetary_system.cpp:68-134).
 // `nbody`: the YAML's list of maps, keys lower-cased.
-inline std::vector<BodyInit> init_bodies(const std::vector<std::map<std::string, std::string>> &nbody, const UnitSystem &U, double rmax)
+inline std::vector<BodyInit> init_bodies(const std::vector<std::map<std::string, std::string>> &nbody, const UnitSystem &U, double rmax,
+					 const std::vector<double> *cic_radii = nullptr, double rmin = 0.0, double klahr_smoothing_radius = 0.0)
 {
     std::vector<BodyInit> B;
     const double G = U.G.code;
@@ -365,7 +366,7 @@ inline std::vector<BodyInit> init_bodies(const std::vector<std::map<std::string,
 	if (!cfg.count("semi-major axis") || !cfg.count("mass"))
 	    refuse("One of the planets does not have all of: semi-major axis and mass!");
 	BodyInit p;
-	const double a = U.in_code_units(cfg.at("semi-major axis"), 'L');
+	double a = U.in_code_units(cfg.at("semi-major axis"), 'L');
 	const double mass = U.in_code_units(cfg.at("mass"), 'M');
 	const double e = atof(get(cfg, "eccentricity", "0.0").c_str());
 	p.cubic_smoothing_factor = atof(get(cfg, "cubic smoothing factor", "0.0").c_str());
@@ -377,6 +378,18 @@ inline std::vector<BodyInit> init_bodies(const std::vector<std::map<std::string,
 	double omega = atof(get(cfg, "argument of pericenter", "0.0").c_str());
 	p.rampuptime = atof(get(cfg, "ramp-up time", "0.0").c_str());
 	p.name = get(cfg, "name", ("planet" + std::to_string(B.size())).c_str());
+	if (cic_radii) { // CICPLANET: the planet starts at a cell centre, find_cell_center_radius (planetary_system.cpp:149-159, :199-205)
+	    if (e > 0)
+		refuse("Centering planet in cell and eccentricity > 0 are not supported at the same time.");
+	    if (a < rmin || a > rmax)
+		refuse("Can not find cell center radius outside the grid");
+	    size_t j = 0;
+	    while ((*cic_radii)[j] < a)
+		j++;
+	    const double r0 = (*cic_radii)[j - 1], r1 = (*cic_radii)[j];
+	    a = 2.0 / 3.0 * (std::pow(r1, 3) - std::pow(r0, 3));
+	    a = a / (std::pow(r1, 2) - std::pow(r0, 2));
+	}
 	const std::string method = get(cfg, "accretion method", "kley");
 	if (p.accretion_efficiency > 0.0 && method != "kley" && method != "sinkhole" && method != "no" && method != "none")
 	    refuse("accretion method '" + method + "' is not supported by this driver (kley, sinkhole)");
@@ -422,6 +435,10 @@ inline std::vector<BodyInit> init_bodies(const std::vector<std::map<std::string,
     }
     if (B.empty())
 	refuse("config has no nbody entries");
+    if (klahr_smoothing_radius > 0.0) // the deprecated global KlahrSmoothingRadius (planetary_system.cpp:95-117), before the recentring
+	for (auto &b : B)
+	    if (std::sqrt(b.x * b.x + b.y * b.y) > 1.0e-10 && b.cubic_smoothing_factor == 0.0)
+		b.cubic_smoothing_factor = klahr_smoothing_radius;
     { // move_to_hydro_frame_center (:750-768), hydro frame centre = body 0
 	const double cx = B[0].x, cy = B[0].y, cvx = B[0].vx, cvy = B[0].vy;
 	for (auto &b : B) {
@@ -480,6 +497,7 @@ struct DiskModel {
     double sigma0, sigma_slope, sigma_floor, h0, flaring, gamma, mu, Rgas, G, viscous_alpha, constant_viscosity, thickness_smoothing,
 	tmin, tmax, omega_frame, imposed_drift;
     bool adiabatic, vradial_zero;
+    bool pure_keplerian = false; // InitializePureKeplerian (init.cpp:1607-1627)
     // ProfileCutoffOuter / Inner (parameters.cpp:728-742): Fermi-function cut-offs of the initial profiles (util.cpp:69-93)
     bool cutoff_outer = false, cutoff_inner = false;
     double cutoff_point_outer = 1.0e300, cutoff_width_outer = 1.0, cutoff_point_inner = 0.0, cutoff_width_inner = 1.0;
@@ -705,13 +723,32 @@ inline InitialState init_gas(DiskModel &d, const std::vector<double> &radii, int
     }
     for (int i = 0; i < nrad; ++i) {
 	const double r = rmed[i], ri = radii[i];
-	double vazi = detail::v_az(d, r, M);
-	vazi -= d.omega_frame * r;
-	double vrad = d.imposed_drift * d.sigma0 / siginf[i] / ri;
-	if (!d.vradial_zero)
-	    vrad += detail::viscous_vr(d, ri, M);
-	else
-	    vrad = 0.0;
+	double vazi, vrad;
+	if (d.pure_keplerian) { // init.cpp:1607-1627 (sic: both at Rmed), Theo.cpp:207-245
+	    double vr;
+	    if (d.viscous_alpha > 0) {
+		const double sqrt_gamma = d.adiabatic ? std::sqrt(d.gamma) : 1.0;
+		const double v_k = std::sqrt(d.G * M / r);
+		const double h = d.h0 * std::pow(r, d.flaring);
+		const double cs = sqrt_gamma * h * v_k;
+		const double H = h * r;
+		const double nu = d.viscous_alpha * cs * H;
+		vr = -3.0 * nu / r * (-d.sigma_slope + 2.0 * d.flaring + 1.0);
+	    } else {
+		const double nu = d.constant_viscosity;
+		vr = -3.0 * nu / r * (-d.sigma_slope + .5);
+	    }
+	    vrad = vr;
+	    vazi = std::sqrt(d.G * M / r) - d.omega_frame * r;
+	} else {
+	    vazi = detail::v_az(d, r, M);
+	    vazi -= d.omega_frame * r;
+	    vrad = d.imposed_drift * d.sigma0 / siginf[i] / ri;
+	    if (!d.vradial_zero)
+		vrad += detail::viscous_vr(d, ri, M);
+	    else
+		vrad = 0.0;
+	}
 	for (int j = 0; j < naz; ++j) {
 	    s.vazi[(size_t)i * naz + j] = vazi;
 	    s.vrad[(size_t)i * naz + j] = vrad;

@@ -254,6 +254,10 @@ REFERENCE_SETUPS = [("/root/reference/test/cold_disk_planet/setup.yml", []), ("/
                     # a setup that sets almost nothing: the reference's DEFAULTS (Sigma0 173 g/cm2, l0 / m0, ThicknessSmoothing 0.6,
                     # HeatingViscous yes, HeatingCoolingCFLlimit 10, IndirectTermMode 0, ArtificialViscosity SN ...)
                     (os.path.join(ROOT, "tests", "golden", "minimal_defaults_setup.yml"), ["--dt", "5e-3"]),
+                    # InitializePureKeplerian with alpha and with constant viscosity; the deprecated global KlahrSmoothingRadius
+                    (os.path.join(ROOT, "tests", "golden", "adia_planet_100.yml"), ["--dt", "4e-3", "InitializePureKeplerian=yes", "KlahrSmoothingRadius=0.4"]),
+                    (os.path.join(ROOT, "tests", "golden", "iso_planet_100.yml"),
+                     ["--dt", "4e-3", "InitializePureKeplerian=yes", "ViscousAlpha=0", "ConstantViscosity=1e-5"]),
                     (os.path.join(ROOT, "tests", "golden", "corotating_setup.yml"), ["--dt", "4e-3"]),
                     (os.path.join(ROOT, "tests", "golden", "corotating_setup.yml"), ["--dt", "4e-3", "Integrator=Leapfrog"]),
                     (os.path.join(ROOT, "tests", "golden", "corotating_setup.yml"), ["--dt", "4e-3", "DiskFeedback=yes", "IndirectTermMode=0"])]
