@@ -458,24 +458,28 @@ static double rampup_mass(const Body &b, double t)
 }
 
 // ComputeNbodyOnNbodyAccel (Pframeforce.cpp:225-251) + ComputeIndirectTermNbodyEuler (frame_of_reference.cpp:112-132),
-// hydro frame centred on body 0 (HydroFrameCenter: primary)
-static void indirect_term_euler(const std::vector<Body> &b, double G, double &ix, double &iy)
+// hydro frame centred on the centre of mass of the first n_center bodies (HydroFrameCenter: primary / binary / ... / all)
+static void indirect_term_euler(const std::vector<Body> &b, double G, unsigned n_center, double &ix, double &iy)
 {
     ix = iy = 0.0;
     if (b.size() < 2)
 	return;
-    const double x = b[0].rec.x, y = b[0].rec.y;
-    double ax = 0.0, ay = 0.0;
-    for (size_t o = 1; o < b.size(); ++o) {
-	const double xo = b[o].rec.x, yo = b[o].rec.y, mass = b[o].rec.mass;
-	const double dist = std::sqrt((x - xo) * (x - xo) + (y - yo) * (y - yo));
-	ax -= G * mass / std::pow(dist, 3) * (x - xo);
-	ay -= G * mass / std::pow(dist, 3) * (y - yo);
-    }
     double mass_center = 0.0;
-    ix -= b[0].rec.mass * ax;
-    iy -= b[0].rec.mass * ay;
-    mass_center += b[0].rec.mass;
+    for (unsigned n = 0; n < n_center; ++n) { // the bodies that make up the hydro frame centre
+	const double x = b[n].rec.x, y = b[n].rec.y;
+	double ax = 0.0, ay = 0.0;
+	for (size_t o = 0; o < b.size(); ++o) {
+	    if (o == n)
+		continue;
+	    const double xo = b[o].rec.x, yo = b[o].rec.y, mass = b[o].rec.mass;
+	    const double dist = std::sqrt(std::pow(x - xo, 2) + std::pow(y - yo, 2));
+	    ax -= G * mass / std::pow(dist, 3) * (x - xo);
+	    ay -= G * mass / std::pow(dist, 3) * (y - yo);
+	}
+	ix -= b[n].rec.mass * ax;
+	iy -= b[n].rec.mass * ay;
+	mass_center += b[n].rec.mass;
+    }
     ix /= mass_center;
     iy /= mass_center;
 }
@@ -575,6 +579,23 @@ struct Run {
     // refframe::ComputeIndirectTermFully (frame_of_reference.cpp:166-169)
     void combine_indirect() { ind_x = ind_disk_x + ind_nbody_x, ind_y = ind_disk_y + ind_nbody_y; }
     double ind_x = 0.0, ind_y = 0.0, ind_disk_x = 0.0, ind_disk_y = 0.0, ind_nbody_x = 0.0, ind_nbody_y = 0.0;
+    unsigned n_center = 1; // parameters::n_bodies_for_hydroframe_center (Interpret.cpp:324-345)
+    void read_hydro_frame_center()
+    {
+	const char c = (char)std::tolower((unsigned char)cfg.str("HydroFrameCenter", "primary")[0]);
+	n_center = c == 'p' ? 1 : c == 'b' ? 2 : c == 't' ? 3 : c == 'q' ? 4 : c == 'a' ? 0 : 99;
+	if (n_center == 99)
+	    die("Invalid setting for HydroFrameCenter: %s", cfg.str("HydroFrameCenter", ""));
+	if (n_center == 0 || n_center > cfg.nbody.size())
+	    n_center = (unsigned)cfg.nbody.size(); // init_hydro_frame_center (planetary_system.cpp:283-292)
+    }
+    double hydro_frame_center_mass() const
+    {
+	double m = 0.0;
+	for (unsigned k = 0; k < n_center && k < bodies.size(); ++k)
+	    m += bodies[k].rec.mass;
+	return m;
+    }
 
     // refframe::ComputeIndirectTermNbody (frame_of_reference.cpp:134-164): the acceleration of the hydro frame centre (body 0)
     // by the other bodies over the coming `dt`, forward looking, so it is taken while the bodies are still at the start of it.
@@ -584,17 +605,22 @@ struct Run {
     void compute_indirect_nbody(double dt)
     {
 	ind_nbody_x = ind_nbody_y = 0.0;
-	if (bodies.size() < 2)
+	if (n_center == bodies.size())
 	    return; // every body belongs to the frame centre (:137-141)
 	if (indirect_mode == 1) {
-	    indirect_term_euler(bodies, consts.G, ind_nbody_x, ind_nbody_y);
+	    indirect_term_euler(bodies, consts.G, n_center, ind_nbody_x, ind_nbody_y);
 	} else if (dt != 0.0) {
 	    std::vector<Body> predictor = bodies;
 	    nbody_integrate(predictor, consts.G, dt);
-	    const double m = bodies[0].rec.mass;
-	    if (m > 0) {
-		const double dvx = (predictor[0].rec.vx * m - bodies[0].rec.vx * m) / m;
-		const double dvy = (predictor[0].rec.vy * m - bodies[0].rec.vy * m) / m;
+	    double vx_old = 0.0, vy_old = 0.0, vx_new = 0.0, vy_new = 0.0, mass = 0.0; // planetary_system.cpp:671-705
+	    for (unsigned i = 0; i < n_center; ++i) {
+		const double m = bodies[i].rec.mass;
+		mass += m;
+		vx_old += bodies[i].rec.vx * m, vy_old += bodies[i].rec.vy * m;
+		vx_new += predictor[i].rec.vx * m, vy_new += predictor[i].rec.vy * m;
+	    }
+	    if (mass > 0) {
+		const double dvx = (vx_new - vx_old) / mass, dvy = (vy_new - vy_old) / mass;
 		ind_nbody_x = -(dvx / dt);
 		ind_nbody_y = -(dvy / dt);
 	    }
@@ -623,11 +649,12 @@ struct Run {
 	    b.rec.vy = b.rec.vy + dt * b.rec.disk_on_planet_acceleration[1];
 	    b.rec.gas_torque_acc += b.rec.torque * dt; // t_planet::add_torque (Pframeforce.cpp:272)
 	}
-	// hydro frame centred on body 0
 	double mass_center = 0.0;
-	ind_disk_x -= bodies[0].rec.mass * bodies[0].rec.disk_on_planet_acceleration[0];
-	ind_disk_y -= bodies[0].rec.mass * bodies[0].rec.disk_on_planet_acceleration[1];
-	mass_center += bodies[0].rec.mass;
+	for (unsigned n = 0; n < n_center; ++n) {
+	    ind_disk_x -= bodies[n].rec.mass * bodies[n].rec.disk_on_planet_acceleration[0];
+	    ind_disk_y -= bodies[n].rec.mass * bodies[n].rec.disk_on_planet_acceleration[1];
+	    mass_center += bodies[n].rec.mass;
+	}
 	ind_disk_x /= mass_center;
 	ind_disk_y /= mass_center;
 	for (auto &b : bodies) // the indirect torque monitor (frame_of_reference.cpp:92-107)
@@ -681,7 +708,8 @@ struct Run {
 	    die("config has no nbody entries: %s", sd);
 	if (bodies.size() > FARGO_MAX_BODIES)
 	    die("too many bodies in %s", sd);
-	params.hydro_center_mass = bodies[0].rec.mass; // global.cpp:146 (HydroFrameCenter: primary)
+	read_hydro_frame_center();
+	params.hydro_center_mass = hydro_frame_center_mass(); // update_global_hydro_frame_center_mass
 	disk_feedback = cfg.flag("DiskFeedback", true); // parameters.cpp:755
 	indirect_mode = (int)cfg.num("IndirectTermMode", 0);
 	MiscEntry m;
@@ -770,8 +798,7 @@ struct Run {
 	for (const char *k : {"SigmaCondition", "EnergyCondition"})
 	    if (std::tolower((unsigned char)cfg.str(k, "Profile")[0]) != 'p')
 		die((std::string(k) + ": only 'Profile' is supported by `fargocpt_b200 start` (got %s)").c_str(), cfg.str(k, ""));
-	if (lower(cfg.str("HydroFrameCenter", "primary")) != "primary")
-	    die("HydroFrameCenter: %s is not supported (primary only)", cfg.str("HydroFrameCenter", ""));
+	read_hydro_frame_center();
 	read_frame_settings();
 	finit::UnitSystem U;
 	U.set_baseunits(cfg.str("l0", "1.0"), cfg.str("m0", "1.0"));
@@ -809,7 +836,7 @@ struct Run {
 	radii = finit::make_radii(params.radial_spacing, nrad, params.rmin, params.rmax, cfg.num("ExponentialCellSizeFactor", 1.41));
 	// bodies
 	const bool cic = cfg.flag("CICPLANET", false);
-	const auto B = finit::init_bodies(cfg.nbody, U, params.rmax, cic ? &radii : nullptr, params.rmin, cfg.num("KlahrSmoothingRadius", 0.0));
+	const auto B = finit::init_bodies(cfg.nbody, U, params.rmax, cic ? &radii : nullptr, params.rmin, cfg.num("KlahrSmoothingRadius", 0.0), n_center);
 	if (B.size() > FARGO_MAX_BODIES)
 	    die("too many bodies in %s", cfgfile);
 	for (size_t k = 0; k < B.size(); ++k) {
@@ -835,7 +862,7 @@ struct Run {
 	    p0.true_anomaly = p1.true_anomaly, p0.eccentric_anomaly = p1.eccentric_anomaly, p0.pericenter_angle = p1.pericenter_angle;
 	    bodies[0].orbital_period = bodies[1].orbital_period;
 	}
-	params.hydro_center_mass = bodies[0].rec.mass; // global.cpp:146
+	params.hydro_center_mass = hydro_frame_center_mass(); // update_global_hydro_frame_center_mass (planetary_system.cpp:724-727)
 	disk_feedback = cfg.flag("DiskFeedback", true);
 	indirect_mode = (int)cfg.num("IndirectTermMode", 0);
 	omega_frame = cfg.num("OmegaFrame", 0.0), frame_angle = 0.0;
@@ -959,8 +986,17 @@ struct Run {
     void integrate_and_recentre(double dt)
     { // planetary_system.integrate + move_to_hydro_frame_center (simulation.cpp:222-224)
 	nbody_integrate(bodies, consts.G, dt);
-	if (bodies.size() > 1) {
-	    const double cx = bodies[0].rec.x, cy = bodies[0].rec.y, cvx = bodies[0].rec.vx, cvy = bodies[0].rec.vy;
+	if (bodies.size() > 1) { // move_to_hydro_frame_center (:750-768)
+	    double cx = 0, cy = 0, cvx = 0, cvy = 0, cm = 0;
+	    for (unsigned k = 0; k < n_center; ++k) {
+		const PlanetRecord &q = bodies[k].rec;
+		cm += q.mass;
+		cx += q.x * q.mass, cy += q.y * q.mass, cvx += q.vx * q.mass, cvy += q.vy * q.mass;
+	    }
+	    if (cm > 0)
+		cx = cx / cm, cy = cy / cm, cvx = cvx / cm, cvy = cvy / cm;
+	    else
+		cx = cy = cvx = cvy = 0.0;
 	    for (auto &b : bodies) {
 		b.rec.x -= cx, b.rec.y -= cy, b.rec.vx -= cvx, b.rec.vy -= cvy;
 	    }
@@ -982,7 +1018,7 @@ struct Run {
 	    if (i == 1)
 		bodies[0].rec.distance_to_primary = dist;
 	}
-	for (size_t i = 1; i < bodies.size(); ++i) {
+	for (size_t i = (n_center == 1 ? 1 : 0); i < bodies.size(); ++i) {
 	    double cx = 0, cy = 0, cvx = 0, cvy = 0, cm = 0;
 	    for (size_t k = 0; k < i; ++k) {
 		const PlanetRecord &q = bodies[k].rec;
@@ -1074,8 +1110,8 @@ struct Run {
     // device holds it as a context constant
     void params_hydro_center_mass_changed()
     {
-	if (bodies[0].rec.mass != params.hydro_center_mass)
-	    die("%s", std::string("an accreting primary (a changing hydro-frame-centre mass) is not supported by this driver"));
+	if (hydro_frame_center_mass() != params.hydro_center_mass)
+	    die("%s", std::string("an accreting frame-centre body (a changing hydro-frame-centre mass) is not supported by this driver"));
     }
 
     // step_Euler (simulation.cpp:148-267) around the gas part

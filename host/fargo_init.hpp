@@ -354,7 +354,8 @@ inline void orbital_elements(BodyInit &b, double x, double y, double vx, double 
 // t_planetary_system::init_system for HydroFrameCenter: primary (nbody/planetary_system.cpp:68-134).
 // `nbody`: the YAML's list of maps, keys lower-cased.
 inline std::vector<BodyInit> init_bodies(const std::vector<std::map<std::string, std::string>> &nbody, const UnitSystem &U, double rmax,
-					 const std::vector<double> *cic_radii = nullptr, double rmin = 0.0, double klahr_smoothing_radius = 0.0)
+					 const std::vector<double> *cic_radii = nullptr, double rmin = 0.0, double klahr_smoothing_radius = 0.0,
+					 unsigned n_center = 1 /* parameters::n_bodies_for_hydroframe_center, 0: all */)
 {
     std::vector<BodyInit> B;
     const double G = U.G.code;
@@ -439,8 +440,19 @@ inline std::vector<BodyInit> init_bodies(const std::vector<std::map<std::string,
 	for (auto &b : B)
 	    if (std::sqrt(b.x * b.x + b.y * b.y) > 1.0e-10 && b.cubic_smoothing_factor == 0.0)
 		b.cubic_smoothing_factor = klahr_smoothing_radius;
-    { // move_to_hydro_frame_center (:750-768), hydro frame centre = body 0
-	const double cx = B[0].x, cy = B[0].y, cvx = B[0].vx, cvy = B[0].vy;
+    if (n_center == 0 || n_center > B.size()) // init_hydro_frame_center (:283-305)
+	n_center = (unsigned)B.size();
+    { // move_to_hydro_frame_center (:750-768): the centre of mass of the first n_center bodies (HydroFrameCenter)
+	double cx = 0, cy = 0, cvx = 0, cvy = 0, cm = 0;
+	for (unsigned k = 0; k < n_center; ++k) {
+	    cm += B[k].mass;
+	    cx += B[k].x * B[k].mass, cy += B[k].y * B[k].mass;
+	    cvx += B[k].vx * B[k].mass, cvy += B[k].vy * B[k].mass;
+	}
+	if (cm > 0)
+	    cx = cx / cm, cy = cy / cm, cvx = cvx / cm, cvy = cvy / cm;
+	else
+	    cx = cy = cvx = cvy = 0.0;
 	for (auto &b : B) {
 	    const double x = b.x, y = b.y, vx = b.vx, vy = b.vy;
 	    b.x = x - cx, b.y = y - cy, b.vx = vx - cvx, b.vy = vy - cvy;
@@ -474,8 +486,9 @@ inline std::vector<BodyInit> init_bodies(const std::vector<std::map<std::string,
 		B[0].roche = 1.0 - B[i].roche;
 	}
     }
-    // calculate_orbital_elements (:773-805) about the centre of mass of the bodies inside
-    for (size_t i = 1; i < B.size(); ++i) {
+    // calculate_orbital_elements (:773-805) about the centre of mass of the bodies inside; body 0 has none when it is the
+    // frame centre on its own
+    for (size_t i = (n_center == 1 ? 1 : 0); i < B.size(); ++i) {
 	double cx = 0, cy = 0, cvx = 0, cvy = 0, cm = 0;
 	for (size_t k = 0; k < i; ++k) {
 	    cx += B[k].x * B[k].mass, cy += B[k].y * B[k].mass;

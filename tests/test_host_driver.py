@@ -258,6 +258,10 @@ REFERENCE_SETUPS = [("/root/reference/test/cold_disk_planet/setup.yml", []), ("/
                     (os.path.join(ROOT, "tests", "golden", "adia_planet_100.yml"), ["--dt", "4e-3", "InitializePureKeplerian=yes", "KlahrSmoothingRadius=0.4"]),
                     (os.path.join(ROOT, "tests", "golden", "iso_planet_100.yml"),
                      ["--dt", "4e-3", "InitializePureKeplerian=yes", "ViscousAlpha=0", "ConstantViscosity=1e-5"]),
+                    # circumbinary disk: HydroFrameCenter binary / all (frame centred on a centre of mass, indirect term over its bodies)
+                    (os.path.join(ROOT, "tests", "golden", "circumbinary_setup.yml"), ["--dt", "2e-3"]),
+                    (os.path.join(ROOT, "tests", "golden", "circumbinary_setup.yml"), ["--dt", "2e-3", "IndirectTermMode=0", "DiskFeedback=yes"]),
+                    (os.path.join(ROOT, "tests", "golden", "circumbinary_setup.yml"), ["--dt", "2e-3", "HydroFrameCenter=all", "Integrator=Leapfrog"]),
                     (os.path.join(ROOT, "tests", "golden", "corotating_setup.yml"), ["--dt", "4e-3"]),
                     (os.path.join(ROOT, "tests", "golden", "corotating_setup.yml"), ["--dt", "4e-3", "Integrator=Leapfrog"]),
                     (os.path.join(ROOT, "tests", "golden", "corotating_setup.yml"), ["--dt", "4e-3", "DiskFeedback=yes", "IndirectTermMode=0"])]
