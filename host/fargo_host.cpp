@@ -787,7 +787,7 @@ struct Run {
 	// what this driver's initial conditions do not cover is refused by name
 	const std::pair<const char *, const char *> off[] = {
 	    {"ShockTube", "0"}, {"RandomSigma", "no"}, {"SelfGravity", "no"}, {"IntegrateParticles", "no"},
-	    {"RadiativeDiffusion", "no"}, {"SecondaryDisk", "no"}, {"CbdRing", "no"}, {"VazimuthalConsidersQuadropoleMoment", "no"}};
+	    {"RadiativeDiffusion", "no"}, {"SecondaryDisk", "no"}, {"CbdRing", "no"}, {"CircumBinaryRing", "no"}};
 	for (auto &k : off) {
 	    const std::string v = lower(cfg.str(k.first, k.second));
 	    if (!(v.empty() || v[0] == 'n' || v[0] == 'f' || v[0] == '0'))
@@ -883,6 +883,16 @@ struct Run {
 	d.omega_frame = omega_frame, d.imposed_drift = params.imposed_disk_drift;
 	d.adiabatic = params.adiabatic != 0, d.vradial_zero = cfg.flag("InitializeVradialZero", false);
 	d.pure_keplerian = cfg.flag("InitializePureKeplerian", false);
+	if (cfg.flag("VazimuthalConsidersQuadropoleMoment", false) && bodies.size() > 1) {
+	    d.quadrupole_support = true;
+	    d.quadrupole_from_radius = 2.0 * bodies[1].rec.distance_to_primary; // init.cpp:1728-1730
+	    if (n_center == 2) { // init_binary_quadropole_moment (Theo.cpp:58-78)
+		const double a_b = bodies[1].rec.semi_major_axis, m1 = bodies[0].rec.mass, m2 = bodies[1].rec.mass;
+		const double q_b = m2 < m1 ? m2 / m1 : m1 / m2;
+		const double e_b = bodies[1].rec.eccentricity;
+		d.quadrupole_moment = std::pow(a_b, 2) / 4.0 * q_b / std::pow((1.0 + q_b), 2) * (1.0 + 3.0 / 2.0 * std::pow(e_b, 2));
+	    }
+	}
 	d.cutoff_outer = cfg.flag("ProfileCutoffOuter", false), d.cutoff_inner = cfg.flag("ProfileCutoffInner", false);
 	if (cfg.has("ProfileCutoffPointOuter"))
 	    d.cutoff_point_outer = U.in_code_units(cfg.str("ProfileCutoffPointOuter", ""), 'L');

@@ -510,6 +510,10 @@ struct DiskModel {
     double sigma0, sigma_slope, sigma_floor, h0, flaring, gamma, mu, Rgas, G, viscous_alpha, constant_viscosity, thickness_smoothing,
 	tmin, tmax, omega_frame, imposed_drift;
     bool adiabatic, vradial_zero;
+    // VazimuthalConsidersQuadropoleMoment: the binary's quadrupole moment (init_binary_quadropole_moment, Theo.cpp:58-78) in the
+    // initial azimuthal velocity outside twice the binary separation and in the viscous-speed model
+    bool quadrupole_support = false;
+    double quadrupole_moment = 0.0, quadrupole_from_radius = 0.0;
     bool pure_keplerian = false; // InitializePureKeplerian (init.cpp:1607-1627)
     // ProfileCutoffOuter / Inner (parameters.cpp:728-742): Fermi-function cut-offs of the initial profiles (util.cpp:69-93)
     bool cutoff_outer = false, cutoff_inner = false;
@@ -600,7 +604,22 @@ inline double derive(const DiskModel &d, const double r, const double mass, fn2 
     const double f4 = 1.0 * f(d, x - 2.0 * h, mass);
     return (f1 + f2 + f3 + f4) / (12.0 * h);
 }
-inline double get_w(const DiskModel &d, const double r, const double mass) { return v_az(d, r, mass) / r; }
+// initial_locally_isothermal_smoothed_v_az_with_quadropole_moment (Theo.cpp:183-199)
+inline double v_az_quadrupole(const DiskModel &d, const double R, const double M)
+{
+    const double pressure_support_2 = support_azi_pressure(d, R);
+    double quadropole_support = 0.0;
+    if (d.quadrupole_moment > 0.0)
+	quadropole_support = 3.0 * d.quadrupole_moment / std::pow(R, 2);
+    const double smoothing_derivative_2 = support_azi_smoothing_derivative(d, R);
+    const double support = quadropole_support + smoothing_derivative_2 + pressure_support_2;
+    const double vk_2 = d.G * M / R;
+    return std::sqrt(vk_2 * support);
+}
+inline double get_w(const DiskModel &d, const double r, const double mass)
+{
+    return (d.quadrupole_support ? v_az_quadrupole(d, r, mass) : v_az(d, r, mass)) / r;
+}
 inline double get_r2_w(const DiskModel &d, const double r, const double mass)
 {
     const double omega = get_w(d, r, mass);
@@ -754,7 +773,7 @@ inline InitialState init_gas(DiskModel &d, const std::vector<double> &radii, int
 	    vrad = vr;
 	    vazi = std::sqrt(d.G * M / r) - d.omega_frame * r;
 	} else {
-	    vazi = detail::v_az(d, r, M);
+	    vazi = (d.quadrupole_support && r > d.quadrupole_from_radius) ? detail::v_az_quadrupole(d, r, M) : detail::v_az(d, r, M);
 	    vazi -= d.omega_frame * r;
 	    vrad = d.imposed_drift * d.sigma0 / siginf[i] / ri;
 	    if (!d.vradial_zero)

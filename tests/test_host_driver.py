@@ -262,6 +262,7 @@ REFERENCE_SETUPS = [("/root/reference/test/cold_disk_planet/setup.yml", []), ("/
                     (os.path.join(ROOT, "tests", "golden", "circumbinary_setup.yml"), ["--dt", "2e-3"]),
                     (os.path.join(ROOT, "tests", "golden", "circumbinary_setup.yml"), ["--dt", "2e-3", "IndirectTermMode=0", "DiskFeedback=yes"]),
                     (os.path.join(ROOT, "tests", "golden", "circumbinary_setup.yml"), ["--dt", "2e-3", "HydroFrameCenter=all", "Integrator=Leapfrog"]),
+                    (os.path.join(ROOT, "tests", "golden", "circumbinary_setup.yml"), ["--dt", "2e-3", "VazimuthalConsidersQuadropoleMoment=yes"]),
                     (os.path.join(ROOT, "tests", "golden", "corotating_setup.yml"), ["--dt", "4e-3"]),
                     (os.path.join(ROOT, "tests", "golden", "corotating_setup.yml"), ["--dt", "4e-3", "Integrator=Leapfrog"]),
                     (os.path.join(ROOT, "tests", "golden", "corotating_setup.yml"), ["--dt", "4e-3", "DiskFeedback=yes", "IndirectTermMode=0"])]
