@@ -795,9 +795,11 @@ struct Run {
 	}
 	if (!cfg.flag("Disk", true))
 	    die("%s", std::string("Disk: no (an N-body run without gas) is not what this driver is for"));
-	for (const char *k : {"SigmaCondition", "EnergyCondition"})
-	    if (std::tolower((unsigned char)cfg.str(k, "Profile")[0]) != 'p')
-		die((std::string(k) + ": only 'Profile' is supported by `fargocpt_b200 start` (got %s)").c_str(), cfg.str(k, ""));
+	for (const char *k : {"SigmaCondition", "EnergyCondition"}) {
+	    const char c0 = (char)std::tolower((unsigned char)cfg.str(k, "Profile")[0]);
+	    if (c0 != 'p' && c0 != '2')
+		die((std::string(k) + ": only 'Profile' and '2D' are supported by `fargocpt_b200 start` (got %s)").c_str(), cfg.str(k, ""));
+	}
 	read_hydro_frame_center();
 	read_frame_settings();
 	finit::UnitSystem U;
@@ -882,6 +884,15 @@ struct Run {
 	d.thickness_smoothing = params.thickness_smoothing, d.tmin = params.minimum_temperature, d.tmax = params.maximum_temperature;
 	d.omega_frame = omega_frame, d.imposed_drift = params.imposed_disk_drift;
 	d.adiabatic = params.adiabatic != 0, d.vradial_zero = cfg.flag("InitializeVradialZero", false);
+	std::vector<double> sigma_in, energy_in; // parameters.cpp:586-611: SigmaFilename / EnergyFilename
+	if (cfg.str("SigmaCondition", "Profile")[0] == '2') {
+	    sigma_in = read_doubles(cfg.str("SigmaFilename", ""), cells(false));
+	    d.sigma_in = &sigma_in;
+	}
+	if (params.adiabatic && cfg.str("EnergyCondition", "Profile")[0] == '2') {
+	    energy_in = read_doubles(cfg.str("EnergyFilename", ""), cells(false));
+	    d.energy_in = &energy_in;
+	}
 	d.pure_keplerian = cfg.flag("InitializePureKeplerian", false);
 	if (cfg.flag("VazimuthalConsidersQuadropoleMoment", false) && bodies.size() > 1) {
 	    d.quadrupole_support = true;

@@ -514,6 +514,8 @@ struct DiskModel {
     // initial azimuthal velocity outside twice the binary separation and in the viscous-speed model
     bool quadrupole_support = false;
     double quadrupole_moment = 0.0, quadrupole_from_radius = 0.0;
+    // SigmaCondition / EnergyCondition: 2D — the profile is read from a raw double[nrad][naz] file (t_polargrid::read2D)
+    const std::vector<double> *sigma_in = nullptr, *energy_in = nullptr;
     bool pure_keplerian = false; // InitializePureKeplerian (init.cpp:1607-1627)
     // ProfileCutoffOuter / Inner (parameters.cpp:728-742): Fermi-function cut-offs of the initial profiles (util.cpp:69-93)
     bool cutoff_outer = false, cutoff_inner = false;
@@ -673,6 +675,10 @@ inline InitialState init_gas(DiskModel &d, const std::vector<double> &radii, int
 		s.energy[(size_t)i * naz + j] = en;
 	}
     }
+    if (d.sigma_in) // initialize_condition_read2D (init.cpp:1013-1017)
+	s.sigma = *d.sigma_in;
+    if (d.adiabatic && d.energy_in) // init.cpp:1355-1358
+	s.energy = *d.energy_in;
     if (d.spreading_ring) { // init_spreading_ring_test (init.cpp:358-412; Speith & Kley 2003), replaces the profile
 	const double R0 = 1.0;
 	int R0_id = 0;

@@ -407,3 +407,32 @@ def test_host_planet_monitor_files_cpu(tmp_path):
     torque = (at[1] * b[6] - at[2] * b[5]) * b[0]
     assert float(rows[20][18]) == pytest.approx(torque, rel=1e-9)
     assert rows[20][9] == "nan"  # circumplanetary mass: not evaluated on this path
+
+
+def test_host_start_reads_2d_profiles_like_the_reference(tmp_path):
+    """SigmaCondition / EnergyCondition: 2D — non-axisymmetric profiles read from raw files (t_polargrid::read2D), through the
+    reference and through `fargocpt_b200 start`."""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "fargocpt_exe_ieee")):
+        pytest.skip("oracle/_ref is not available here")
+    _oracle_exe()
+    meta, z = reftools.load_golden("adia_planet_100")
+    s, e = z["Sigma_0"].copy(), z["energy_0"].copy()
+    i, j = np.meshgrid(np.arange(s.shape[0]), np.arange(s.shape[1]), indexing="ij")
+    s *= 1 + 0.05 * np.sin(3 * j * 2 * np.pi / s.shape[1]) * np.exp(-((i - 24) / 6.0) ** 2)
+    e *= 1 + 0.02 * np.cos(2 * j * 2 * np.pi / s.shape[1])
+    sf, ef = str(tmp_path / "sig2d.dat"), str(tmp_path / "en2d.dat")
+    s.tofile(sf)
+    e.tofile(ef)
+    import contextlib
+    import importlib.util
+    import io
+    spec = importlib.util.spec_from_file_location("cmpstart", os.path.join(ROOT, "tools", "compare_start_with_reference.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        worst = mod.main([os.path.join(ROOT, "tests", "golden", "adia_planet_100.yml"), "--snapshots", "2", "--dt", "4e-3", "SigmaCondition=2D",
+                          f"SigmaFilename={sf}", "EnergyCondition=2D", f"EnergyFilename={ef}"])
+    snap0 = [l for l in buf.getvalue().splitlines() if l.startswith("snapshot 0:")][0]
+    assert snap0.count("ndiff=0 ") == 4 and "misc identical" in snap0, snap0
+    assert worst <= 1e-10
