@@ -797,8 +797,8 @@ struct Run {
 	    die("%s", std::string("Disk: no (an N-body run without gas) is not what this driver is for"));
 	for (const char *k : {"SigmaCondition", "EnergyCondition"}) {
 	    const char c0 = (char)std::tolower((unsigned char)cfg.str(k, "Profile")[0]);
-	    if (c0 != 'p' && c0 != '2')
-		die((std::string(k) + ": only 'Profile' and '2D' are supported by `fargocpt_b200 start` (got %s)").c_str(), cfg.str(k, ""));
+	    if (c0 != 'p' && c0 != '2' && c0 != 'n')
+		die((std::string(k) + ": only 'Profile', 'Nbody' and '2D' are supported by `fargocpt_b200 start` (got %s)").c_str(), cfg.str(k, ""));
 	}
 	read_hydro_frame_center();
 	read_frame_settings();
@@ -894,6 +894,22 @@ struct Run {
 	    d.energy_in = &energy_in;
 	}
 	d.pure_keplerian = cfg.flag("InitializePureKeplerian", false);
+	if (std::tolower((unsigned char)cfg.str("SigmaCondition", "Profile")[0]) == 'n' ||
+	    std::tolower((unsigned char)cfg.str("EnergyCondition", "Profile")[0]) == 'n') { // parameters.cpp:577-581, 600-604: either sets the density's
+	    d.nbody_centered = true;
+	    // parameters.cpp:577-611: 'Nbody' sets the energy condition too, but the EnergyCondition switch that follows (default
+	    // Profile) overrides it again: the energy is N-body-centred only when EnergyCondition says so as well
+	    d.energy_nbody_centered = std::tolower((unsigned char)cfg.str("EnergyCondition", "Profile")[0]) == 'n';
+	    d.density_correction_factor = cfg.num("CenterProfileDensityCorrectionFactor", 1.0);
+	    double m = 0, x = 0, y = 0, vx = 0, vy = 0; // get_center_of_mass / _velocity over all bodies (planetary_system.cpp:600-645)
+	    for (auto &b : bodies) {
+		m += b.rec.mass;
+		x += b.rec.x * b.rec.mass, y += b.rec.y * b.rec.mass, vx += b.rec.vx * b.rec.mass, vy += b.rec.vy * b.rec.mass;
+	    }
+	    d.nbody_mass = m;
+	    if (m > 0)
+		d.cms_x = x / m, d.cms_y = y / m, d.vcms_x = vx / m, d.vcms_y = vy / m;
+	}
 	if (cfg.flag("VazimuthalConsidersQuadropoleMoment", false) && bodies.size() > 1) {
 	    d.quadrupole_support = true;
 	    d.quadrupole_from_radius = 2.0 * bodies[1].rec.distance_to_primary; // init.cpp:1728-1730

@@ -516,6 +516,10 @@ struct DiskModel {
     double quadrupole_moment = 0.0, quadrupole_from_radius = 0.0;
     // SigmaCondition / EnergyCondition: 2D — the profile is read from a raw double[nrad][naz] file (t_polargrid::read2D)
     const std::vector<double> *sigma_in = nullptr, *energy_in = nullptr;
+    // SigmaCondition: Nbody — the profiles are centred on the centre of mass of ALL bodies and the gas orbits it
+    // (initialize_condition_profile_Nbody_centered: init.cpp:962-997, 1302-1346, 1473-1604)
+    bool nbody_centered = false, energy_nbody_centered = false; // SigmaCondition (also the velocities) / EnergyCondition
+    double cms_x = 0, cms_y = 0, vcms_x = 0, vcms_y = 0, nbody_mass = 0, density_correction_factor = 1.0;
     bool pure_keplerian = false; // InitializePureKeplerian (init.cpp:1607-1627)
     // ProfileCutoffOuter / Inner (parameters.cpp:728-742): Fermi-function cut-offs of the initial profiles (util.cpp:69-93)
     bool cutoff_outer = false, cutoff_inner = false;
@@ -675,6 +679,37 @@ inline InitialState init_gas(DiskModel &d, const std::vector<double> &radii, int
 		s.energy[(size_t)i * naz + j] = en;
 	}
     }
+    const double dphi = 2.0 * M_PI / (double)naz;
+    if (d.nbody_centered || (d.adiabatic && d.energy_nbody_centered)) {
+	for (int i = 0; i < nrad; ++i)
+	    for (int j = 0; j < naz; ++j) {
+		const double phi = (double)j * dphi;
+		if (d.nbody_centered) { // density at the cell INTERFACE radius (sic, init.cpp:979-981)
+		    const double rm = radii[i];
+		    const double x = rm * std::cos(phi) - d.cms_x, y = rm * std::sin(phi) - d.cms_y;
+		    const double r = std::sqrt(x * x + y * y);
+		    const double density = d.sigma0 * std::pow(r, -d.sigma_slope) * d.density_correction_factor;
+		    s.sigma[(size_t)i * naz + j] = std::max(density, d.sigma_floor * d.sigma0);
+		}
+		if (d.adiabatic && d.energy_nbody_centered) {
+		    const double rm = rmed[i];
+		    const double x = rm * std::cos(phi) - d.cms_x, y = rm * std::sin(phi) - d.cms_y;
+		    const double r = std::sqrt(x * x + y * y);
+		    const double energy = 1.0 / (d.gamma - 1.0) * d.sigma0 * std::pow(d.h0, 2) *
+					  std::pow(r, -d.sigma_slope - 1.0 + 2.0 * d.flaring) * d.G * d.nbody_mass;
+		    const double energy_floor = d.tmin * s.sigma[(size_t)i * naz + j] / d.mu * d.Rgas / (d.gamma - 1.0);
+		    s.energy[(size_t)i * naz + j] = std::max(energy, energy_floor);
+		}
+	    }
+    }
+    // radius a profile cut-off is evaluated at
+    auto cut_radius = [&](int i, int j, bool centred) {
+	if (!centred)
+	    return rmed[i];
+	const double phi = (double)j * dphi;
+	const double x = rmed[i] * std::cos(phi) - d.cms_x, y = rmed[i] * std::sin(phi) - d.cms_y;
+	return std::sqrt(x * x + y * y);
+    };
     if (d.sigma_in) // initialize_condition_read2D (init.cpp:1013-1017)
 	s.sigma = *d.sigma_in;
     if (d.adiabatic && d.energy_in) // init.cpp:1355-1358
@@ -710,28 +745,28 @@ inline InitialState init_gas(DiskModel &d, const std::vector<double> &radii, int
     for (int pass = 0; pass < 2; ++pass) {
 	if (!(pass == 0 ? d.cutoff_outer : d.cutoff_inner))
 	    continue;
-	for (int i = 0; i < nrad; ++i) {
-	    const double f = pass == 0 ? detail::cutoff_outer(d.cutoff_point_outer, d.cutoff_width_outer, rmed[i])
-				       : detail::cutoff_inner(d.cutoff_point_inner, d.cutoff_width_inner, rmed[i]);
+	for (int i = 0; i < nrad; ++i)
 	    for (int j = 0; j < naz; ++j) {
+		const double r = cut_radius(i, j, d.nbody_centered);
+		const double f = pass == 0 ? detail::cutoff_outer(d.cutoff_point_outer, d.cutoff_width_outer, r)
+					   : detail::cutoff_inner(d.cutoff_point_inner, d.cutoff_width_inner, r);
 		const size_t l = (size_t)i * naz + j;
 		s.sigma[l] = std::max(s.sigma[l] * f, d.sigma_floor * d.sigma0);
 	    }
-	}
     }
     if (d.adiabatic)
 	for (int pass = 0; pass < 2; ++pass) {
 	    if (!(pass == 0 ? d.cutoff_outer : d.cutoff_inner))
 		continue;
-	    for (int i = 0; i < nrad; ++i) {
-		const double f = pass == 0 ? detail::cutoff_outer(d.cutoff_point_outer, d.cutoff_width_outer, rmed[i])
-					   : detail::cutoff_inner(d.cutoff_point_inner, d.cutoff_width_inner, rmed[i]);
+	    for (int i = 0; i < nrad; ++i)
 		for (int j = 0; j < naz; ++j) {
+		    const double r = cut_radius(i, j, d.energy_nbody_centered);
+		    const double f = pass == 0 ? detail::cutoff_outer(d.cutoff_point_outer, d.cutoff_width_outer, r)
+					       : detail::cutoff_inner(d.cutoff_point_inner, d.cutoff_width_inner, r);
 		    const size_t l = (size_t)i * naz + j;
 		    const double energy_floor = d.tmin * s.sigma[l] / d.mu * d.Rgas / (d.gamma - 1.0);
 		    s.energy[l] = std::max(s.energy[l] * f, energy_floor);
 		}
-	    }
 	}
     if (d.set_sigma0) { // quantities::gas_total_mass over the active rings (quantities.cpp:51-75), summed in index order
 	double total_mass = 0.0;
@@ -758,6 +793,59 @@ inline InitialState init_gas(DiskModel &d, const std::vector<double> &radii, int
     for (int i = 1; i < nrad; ++i) {
 	const double dr = (rmed[i] - rmed[i - 1]);
 	siginf[i] = (sigmed[i - 1] * (rmed[i] - radii[i]) + sigmed[i] * (radii[i] - rmed[i - 1])) / dr;
+    }
+    if (d.nbody_centered) { // init_gas_velocities, first branch (init.cpp:1473-1604)
+	const double mass = d.nbody_mass;
+	auto v0 = [&](double r_com, double &vazi0, double &vr0) {
+	    if (d.pure_keplerian) {
+		vazi0 = std::sqrt(d.G * mass / r_com);
+		DiskModel k = d; // initial_viscous_radial_speed (Theo.cpp:220-245)
+		if (d.viscous_alpha > 0) {
+		    const double sqrt_gamma = d.adiabatic ? std::sqrt(d.gamma) : 1.0;
+		    const double v_k = std::sqrt(d.G * mass / r_com);
+		    const double h = d.h0 * std::pow(r_com, d.flaring);
+		    const double nu = d.viscous_alpha * (sqrt_gamma * h * v_k) * (h * r_com);
+		    vr0 = -3.0 * nu / r_com * (-d.sigma_slope + 2.0 * d.flaring + 1.0);
+		} else {
+		    vr0 = -3.0 * d.constant_viscosity / r_com * (-d.sigma_slope + .5);
+		}
+		(void)k;
+	    } else {
+		vazi0 = (d.quadrupole_support && r_com > d.quadrupole_from_radius) ? detail::v_az_quadrupole(d, r_com, mass)
+										    : detail::v_az(d, r_com, mass);
+		vr0 = detail::viscous_vr(d, r_com, mass);
+	    }
+	    if (d.vradial_zero)
+		vr0 = 0.0;
+	};
+	for (int i = 0; i <= nrad; ++i) // v_rad has nrad + 1 rings; the last one sits at Rinf[nrad - 1] (sic, :1491-1495)
+	    for (int j = 0; j < naz; ++j) {
+		const double phi = (double)j * dphi;
+		const double r = i == nrad ? radii[nrad - 1] : radii[i];
+		const double cell_x = r * std::cos(phi), cell_y = r * std::sin(phi);
+		const double x_com = cell_x - d.cms_x, y_com = cell_y - d.cms_y;
+		const double r_com = std::sqrt(x_com * x_com + y_com * y_com);
+		double vazi0, vr0;
+		v0(r_com, vazi0, vr0);
+		const double vx_com = (vr0 * x_com - vazi0 * y_com) / r_com, vy_com = (vr0 * y_com + vazi0 * x_com) / r_com;
+		const double vx = vx_com + d.vcms_x, vy = vy_com + d.vcms_y;
+		s.vrad[(size_t)i * naz + j] = vx * std::cos(phi) + vy * std::sin(phi);
+	    }
+	for (int i = 0; i < nrad; ++i)
+	    for (int j = 0; j < naz; ++j) {
+		const double phi = ((double)j - 0.5) * dphi;
+		const double r = rmed[i];
+		const double cell_x = r * std::cos(phi), cell_y = r * std::sin(phi);
+		const double x_com = cell_x - d.cms_x, y_com = cell_y - d.cms_y;
+		const double r_com = std::sqrt(x_com * x_com + y_com * y_com);
+		double vazi0, vr0;
+		v0(r_com, vazi0, vr0);
+		const double vx_com = (vr0 * x_com - vazi0 * y_com) / r_com, vy_com = (vr0 * y_com + vazi0 * x_com) / r_com;
+		const double vx = vx_com + d.vcms_x, vy = vy_com + d.vcms_y;
+		const double vaz = vy * std::cos(phi) - vx * std::sin(phi);
+		s.vazi[(size_t)i * naz + j] = vaz - d.omega_frame * r;
+	    }
+	return s;
     }
     for (int i = 0; i < nrad; ++i) {
 	const double r = rmed[i], ri = radii[i];

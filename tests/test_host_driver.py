@@ -263,6 +263,13 @@ REFERENCE_SETUPS = [("/root/reference/test/cold_disk_planet/setup.yml", []), ("/
                     (os.path.join(ROOT, "tests", "golden", "circumbinary_setup.yml"), ["--dt", "2e-3", "IndirectTermMode=0", "DiskFeedback=yes"]),
                     (os.path.join(ROOT, "tests", "golden", "circumbinary_setup.yml"), ["--dt", "2e-3", "HydroFrameCenter=all", "Integrator=Leapfrog"]),
                     (os.path.join(ROOT, "tests", "golden", "circumbinary_setup.yml"), ["--dt", "2e-3", "VazimuthalConsidersQuadropoleMoment=yes"]),
+                    # SigmaCondition: Nbody — profiles and gas orbits centred on the centre of mass of all bodies
+                    (os.path.join(ROOT, "tests", "golden", "circumbinary_setup.yml"), ["--dt", "2e-3", "SigmaCondition=Nbody"]),
+                    (os.path.join(ROOT, "tests", "golden", "circumbinary_setup.yml"),
+                     ["--dt", "2e-3", "SigmaCondition=Nbody", "HydroFrameCenter=primary", "ProfileCutoffOuter=yes", "ProfileCutoffPointOuter=2.2",
+                      "ProfileCutoffWidthOuter=0.1"]),
+                    (os.path.join(ROOT, "tests", "golden", "adia_planet_100.yml"), ["--dt", "2e-3", "SigmaCondition=Nbody"]),
+                    (os.path.join(ROOT, "tests", "golden", "adia_planet_100.yml"), ["--dt", "2e-3", "EnergyCondition=Nbody"]),
                     (os.path.join(ROOT, "tests", "golden", "corotating_setup.yml"), ["--dt", "4e-3"]),
                     (os.path.join(ROOT, "tests", "golden", "corotating_setup.yml"), ["--dt", "4e-3", "Integrator=Leapfrog"]),
                     (os.path.join(ROOT, "tests", "golden", "corotating_setup.yml"), ["--dt", "4e-3", "DiskFeedback=yes", "IndirectTermMode=0"])]
