@@ -192,6 +192,60 @@ struct Config {
     }
 };
 
+// The keys the reference's config reader knows (its own default_config.yml, written with `WriteDefaultValues: yes`, plus the
+// ones it only visits later).  config::Config::exit_on_unknown_key (config.cpp) refuses a setup with any other key — a typo
+// must not silently fall back to a default — and so does `start`.  Keys starting with '_' are this repo's fixture bookkeeping.
+static const char *const KNOWN_KEYS =
+	"accretewithoutdiskfeedback adiabatic adiabaticindex alphacold alphahot alphamode artificialviscosity "
+	"artificialviscositydissipation artificialviscosityfactor aspectratio aspectratiomode bitwiseexactrestarting "
+	"bodyforcefrompotential cartesianparticles centerprofiledensitycorrectionfactor cfl cflmaxvar cicplanet "
+	"circumbinarydecayexponent circumbinarydecaywidth circumbinaryring circumbinaryringenhancementfactor "
+	"circumbinaryringposition circumbinaryringwidth compatibilitynostarsmoothing compatibilitysmoothingplanetloc "
+	"constantviscosity coolingbeta coolingbetalocal coolingbetarampup coolingbetareference coolingradiativefactor "
+	"corotationreferencebody correctdiskselfgravity cps cvnr damping dampingenergyinner dampingenergyouter "
+	"dampinginnerlimit dampingouterlimit dampingsurfacedensityinner dampingsurfacedensityouter dampingtimefactor "
+	"dampingtimeradiusouter dampingvazimuthalinner dampingvazimuthalouter dampingvradialinner dampingvradialouter "
+	"densityfactor disk diskfeedback diskmass diskradiusmassfraction dowrite1dfiles energycondition energyfilename "
+	"equationofstate exponentialcellsizefactor featuresize firstdt flaringindex fluxlimiter frame "
+	"heatingcoolingcfllimit heatingviscous heatingviscousfactor hydroframecenter hydrogenmassfraction "
+	"imposeddiskdrift indirecttermmode initializepurekeplerian initializevradialzero innerboundary "
+	"innerboundaryenergy innerboundarysigma innerboundaryvazi innerboundaryvazikeplerianfactor innerboundaryvrad "
+	"innerboundaryvradkeplerianfactor integrateparticles integrator kappaconst kappafactor keepdiskmassconstant "
+	"klahrsmoothingradius l0 logafterrealseconds logaftersteps m0 massaccretionradius maximumtemperature "
+	"minimumtemperature monitortimestep mu naz nbody nmonitor nrad nsnapshots numberofparticles omegaframe opacity "
+	"outerboundary outerboundaryenergy outerboundarysigma outerboundaryvazi outerboundaryvazikeplerianfactor "
+	"outerboundaryvrad outerboundaryvradkeplerianfactor outputdir particledensity particlediskgravityenabled "
+	"particledustdiffusion particleeccentricity particlegasdragenabled particleintegrator "
+	"particlemaximumescaperadius particlemaximumradius particleminimumescaperadius particleminimumradius "
+	"particleradius particleradiusincreasefactor particlespeciesnumber particlesurfacedensityslope "
+	"planetorbitdisktest polytropicconstant profilecutoffinner profilecutoffouter profilecutoffpointinner "
+	"profilecutoffpointouter profilecutoffwidthinner profilecutoffwidthouter quantitiesradiuslimit radialspacing "
+	"radialviscosityfactor radiativediffusion radiativediffusionautoomega radiativediffusionchecksolution "
+	"radiativediffusiondumpdata radiativediffusioninnerboundary radiativediffusionmaxiterations "
+	"radiativediffusionomega radiativediffusionouterboundary radiativediffusiontest1d radiativediffusiontest2d "
+	"radiativediffusiontest2ddensity radiativediffusiontest2dk radiativediffusiontest2dsteps "
+	"radiativediffusiontolerance randomfactor randomseed randomsigma rmax rmin rochelobeoverflow rofaveragingtime "
+	"rofgamma rofplanet roframpingtime roftemperature rofvalue rofvariabletransfer scurvetype secondarydisk "
+	"selfgravity selfgravityaspectratiochangethreshold selfgravitymode selfgravitystepsbetweenkernelupdate "
+	"setsigma0 shocktube sigma0 sigmacondition sigmafilename sigmafloor sigmaslope spreadingring stabilizeviscosity "
+	"surfacecooling t0 taufactor taumin temp0 temperature0 thicknesssmoothing thicknesssmoothingsg transport "
+	"vazimuthalconsidersquadropolemoment viscaccretmassflowtest viscousalpha viscousoutflowspeed writealpha "
+	"writealphagrav writealphagravmean writealphareynolds writealphareynoldsmean writeaspectratio "
+	"writeateverytimestep writedefaultvalues writedensity writediskquantities writedivv writeeccentricity "
+	"writeeccentricitychange writeeffectivegamma writeenergy writefirstadiabaticindex writegastorques writekappa "
+	"writelightcurves writelightcurvesradii writemassflow writemeanmolecularweight writepdv writepotential "
+	"writepressure writeqminus writeqplus writeradialdissipation writeradialluminosity writescaleheight "
+	"writesgaccelazi writesgaccelrad writesoundspeed writetau writetaucool writetemperature writetgravitational "
+	"writetoomre writetorques writetreynolds writevelocity writeverticalopticaldepth writeviscosity writevisibility ";
+static const char *const KNOWN_NBODY_KEYS =
+	"accretion efficiency accretion method argument of pericenter cubic smoothing factor eccentricity irradiate "
+	"irradiation ramp-up time mass name radius ramp-up time semi-major axis temperature trueanomaly ";
+static bool key_is_known(const char *list, const std::string &k)
+{
+    const std::string padded = " " + std::string(list);
+    return padded.find(" " + k + " ") != std::string::npos;
+}
+
 // constants.yml / units.yml as written by the reference (output.cpp, units.cpp:270-310): blocks of `symbol:` / `code value:`
 struct CodeConstants {
     double G = 1.0, R = 1.0, sigma_sb = 0.0, c_light = 0.0, temperature_unit_K = 1.0;
@@ -801,6 +855,13 @@ struct Run {
 		die((std::string(k) + ": only 'Profile', 'Nbody' and '2D' are supported by `fargocpt_b200 start` (got %s)").c_str(), cfg.str(k, ""));
 	}
 	read_hydro_frame_center();
+	for (auto &kv_ : cfg.kv) // config::Config::exit_on_unknown_key
+	    if (kv_.first[0] != '_' && !key_is_known(KNOWN_KEYS, kv_.first))
+		die("Unknown key in the setup file: '%s' (the reference refuses unknown keys too)", kv_.first);
+	for (auto &b : cfg.nbody)
+	    for (auto &kv_ : b)
+		if (!key_is_known(KNOWN_NBODY_KEYS, kv_.first))
+		    die("Unknown key in an nbody entry of the setup file: '%s'", kv_.first);
 	read_frame_settings();
 	finit::UnitSystem U;
 	U.set_baseunits(cfg.str("l0", "1.0"), cfg.str("m0", "1.0"));

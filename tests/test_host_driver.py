@@ -443,3 +443,23 @@ def test_host_start_reads_2d_profiles_like_the_reference(tmp_path):
     snap0 = [l for l in buf.getvalue().splitlines() if l.startswith("snapshot 0:")][0]
     assert snap0.count("ndiff=0 ") == 4 and "misc identical" in snap0, snap0
     assert worst <= 1e-10
+
+
+def test_host_start_refuses_unknown_keys_like_the_reference(tmp_path):
+    """config::Config::exit_on_unknown_key: a misspelt key must not silently fall back to a default."""
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "tests", "golden", "iso_star.yml")))
+    cfg["ViscousAlfa"] = cfg.pop("ViscousAlpha")
+    yml = str(tmp_path / "setup.yml")
+    yaml.safe_dump(cfg, open(yml, "w"), sort_keys=False)
+    res = subprocess.run([_oracle_exe(), "start", yml, "--out", str(tmp_path / "out")], capture_output=True, text=True, timeout=60)
+    assert res.returncode != 0 and "viscousalfa" in res.stderr.lower()
+
+
+def test_host_refuses_physics_it_does_not_implement(tmp_path):
+    for key, value in (("EquationOfState", "PVTE"), ("SurfaceCooling", "thermal"), ("SelfGravity", "yes"), ("AlphaMode", 1)):
+        cfg = yaml.safe_load(open(os.path.join(ROOT, "tests", "golden", "adia_star.yml")))
+        cfg[key] = value
+        yml = str(tmp_path / f"setup_{key}.yml")
+        yaml.safe_dump(cfg, open(yml, "w"), sort_keys=False)
+        res = subprocess.run([_oracle_exe(), "start", yml, "--out", str(tmp_path / ("out_" + key))], capture_output=True, text=True, timeout=60)
+        assert res.returncode != 0 and key in res.stderr, (key, res.stderr)
