@@ -1687,6 +1687,49 @@ int fargo_oracle_accrete_sinkhole(fargo_oracle *o, double xp, double yp, double 
     return 0;
 }
 
+/* accretion::AccreteOntoSinglePlanetViscous (accretion.cpp:335-480; "accretion method: viscous"): the fraction removed from a
+ * cell is facc * nu * f(distance), f = 3 / (pi d_max^2) * (1 - distance / d_max), d_max = frac * RHill, with the VISCOSITY the
+ * previous step stored.  facc = dt * 3 pi * accretion efficiency (the N-body side).  No CUDA counterpart yet: oracle only. */
+int fargo_oracle_accrete_viscous(fargo_oracle *o, double xp, double yp, double r_hill, double facc, double frac, double out3[3])
+{
+    const double OmegaF = o->bodies.omega_frame;
+    const double density_floor = o->p.sigma_floor * o->p.sigma0;
+    const double dist_max = r_hill * frac;
+    const double f_const = 3.0 / M_PI / pow(dist_max, 2);
+    double dM = 0.0, dPx = 0.0, dPy = 0.0;
+    for (int i = 0; i < o->nr; ++i) {
+	for (int j = 0; j < o->ns; ++j) {
+	    const size_t l = IDX(o, i, j);
+	    const int jp = j == o->ns - 1 ? 0 : j + 1;
+	    const double xc = o->rmed[i] * o->cosphi[j], yc = o->rmed[i] * o->sinphi[j];
+	    const double dx = xp - xc, dy = yp - yc;
+	    const double distance = sqrt(dx * dx + dy * dy);
+	    if (!(distance < frac * r_hill))
+		continue;
+	    const double nu = o->viscosity[l];
+	    const double spread = f_const * (1.0 - distance / dist_max);
+	    const double vtcell = 0.5 * (o->vazi[l] + o->vazi[IDX(o, i, jp)]) + o->rmed[i] * OmegaF;
+	    const double vrcell = 0.5 * (o->vrad[l] + o->vrad[IDX(o, i + 1, j)]);
+	    const double vxcell = (vrcell * xc - vtcell * yc) / o->rmed[i];
+	    const double vycell = (vrcell * yc + vtcell * xc) / o->rmed[i];
+	    const double facc_max_dens = 1 - density_floor / o->sigma[l];
+	    const double facc_tmp = facc * nu * spread;
+	    const double facc_ceil = facc_max_dens < facc_tmp ? facc_max_dens : facc_tmp; /* std::min(facc_tmp, facc_max_dens) */
+	    const double deltaM = facc_ceil * o->sigma[l] * o->surf[i];
+	    o->sigma[l] *= 1.0 - facc_ceil;
+	    if (o->p.adiabatic)
+		o->energy[l] *= 1.0 - facc_ceil;
+	    if (o->first_active < i && i < o->active_size) {
+		dPx += deltaM * vxcell;
+		dPy += deltaM * vycell;
+		dM += deltaM;
+	    }
+	}
+    }
+    out3[0] = dM, out3[1] = dPx, out3[2] = dPy;
+    return 0;
+}
+
 /* Global disk quantities of monitor/Quantities.dat (output::write_quantities, output.cpp:326-520): serial sums in index
  * order, which is what the reference computes with OMP_NUM_THREADS=1 (its reductions have no defined order otherwise).
  * out8 = mass (quantities.cpp:51-78), angular momentum (:242-276), internal energy (:281-304), kinetic energy (:357-401),

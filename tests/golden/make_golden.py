@@ -111,6 +111,10 @@ CASES = {
     "iso_sinkhole_20": dict(Nrad=48, Naz=160, Rmax=2.5, Nsnapshots=20, MonitorTimestep=4.0e-3, IndirectTermMode=1,
                             EquationOfState="Isothermal", ViscousAlpha=1e-3, ArtificialViscosityFactor=1.41, FlaringIndex=0.0,
                             MassAccretionRadius=0.75, _planet=3e-3, _accretion=5.0, _accretion_method="sinkhole", _keep=(0, 10, 20)),
+    # "accretion method: viscous" (accretion.cpp:335-480): the removed fraction scales with the local viscosity and a cone profile
+    "adia_viscacc_20": dict(Nrad=48, Naz=160, Rmax=2.5, Nsnapshots=20, MonitorTimestep=4.0e-3, IndirectTermMode=1,
+                            ViscousAlpha=1e-2, HeatingViscous="yes", CoolingBetaLocal="yes", CoolingBeta=10,
+                            _planet=3e-3, _accretion=2.0e3, _accretion_method="viscous", _keep=(0, 10, 20)),
     # an accreting planet that feels the disk: update_planet (accretion.cpp:60-82) adds the accreted mass and momentum to it
     "adia_accfb_20": dict(Nrad=48, Naz=160, Rmax=2.5, Nsnapshots=20, MonitorTimestep=4.0e-3, IndirectTermMode=1,
                           ViscousAlpha=1e-3, HeatingViscous="yes", CoolingBetaLocal="yes", CoolingBeta=10, DiskFeedback="yes",

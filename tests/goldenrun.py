@@ -87,6 +87,8 @@ def accretion_inputs(meta, k, body, dt):
     m = primary[0] + rec[0]
     period = 2.0 * math.pi * math.sqrt(math.pow(a, 3) / (m * G))
     facc = dt * acc_eff / period * math.log(2)
+    if meta["config"]["nbody"][body].get("accretion method", "kley") == "viscous":
+        facc = dt * 3.0 * math.pi * acc_eff  # accretion.cpp:355
     r_hill = roche * dist_primary
     frac = float(meta["config"].get("MassAccretionRadius", 1.0))
     return rec[1], rec[2], r_hill, facc, frac

@@ -121,7 +121,7 @@ def test_gpu_monitor_quantities_vs_oracle(name, k):
 
 # ---------------------------------------------------------------------------------------------------------------------
 # accretion::AccreteOntoSinglePlanet (accretion.cpp:84-221)
-@pytest.mark.parametrize("name", ["iso_accrete_20", "adia_accrete_20", "iso_sinkhole_20"])
+@pytest.mark.parametrize("name", ["iso_accrete_20", "adia_accrete_20", "iso_sinkhole_20", "adia_viscacc_20"])
 def test_oracle_accreted_mass_matches_reference(name):
     """The mass the oracle takes out of the Hill sphere in every step against the planet's recorded m_accreted_mass (the
     reference sums it with an OpenMP reduction: 1e-12).  The fields of the same runs are held bit for bit in
