@@ -841,7 +841,7 @@ struct Run {
 	// what this driver's initial conditions do not cover is refused by name
 	const std::pair<const char *, const char *> off[] = {
 	    {"ShockTube", "0"}, {"RandomSigma", "no"}, {"SelfGravity", "no"}, {"IntegrateParticles", "no"},
-	    {"RadiativeDiffusion", "no"}, {"SecondaryDisk", "no"}, {"CbdRing", "no"}, {"CircumBinaryRing", "no"}};
+	    {"RadiativeDiffusion", "no"}, {"SecondaryDisk", "no"}, {"CbdRing", "no"}};
 	for (auto &k : off) {
 	    const std::string v = lower(cfg.str(k.first, k.second));
 	    if (!(v.empty() || v[0] == 'n' || v[0] == 'f' || v[0] == '0'))
@@ -954,6 +954,14 @@ struct Run {
 	    energy_in = read_doubles(cfg.str("EnergyFilename", ""), cells(false));
 	    d.energy_in = &energy_in;
 	}
+	d.cbd_ring = cfg.flag("CircumBinaryRing", false); // parameters.cpp:712-725
+	if (cfg.has("CircumBinaryRingPosition"))
+	    d.cbd_ring_position = U.in_code_units(cfg.str("CircumBinaryRingPosition", ""), 'L');
+	if (cfg.has("CircumBinaryRingWidth"))
+	    d.cbd_ring_width = U.in_code_units(cfg.str("CircumBinaryRingWidth", ""), 'L');
+	d.cbd_decay_width = cfg.has("CircumBinaryDecayWidth") ? U.in_code_units(cfg.str("CircumBinaryDecayWidth", ""), 'L') : d.cbd_ring_width * 1.4;
+	d.cbd_decay_exponent = cfg.num("CircumBinaryDecayExponent", 0.75);
+	d.cbd_ring_factor = cfg.num("CircumBinaryRingEnhancementFactor", 2.5);
 	d.pure_keplerian = cfg.flag("InitializePureKeplerian", false);
 	if (std::tolower((unsigned char)cfg.str("SigmaCondition", "Profile")[0]) == 'n' ||
 	    std::tolower((unsigned char)cfg.str("EnergyCondition", "Profile")[0]) == 'n') { // parameters.cpp:577-581, 600-604: either sets the density's
@@ -998,7 +1006,7 @@ struct Run {
 	create_context(device);
 	// init_euler (SourceEuler.cpp:250-285) runs BEFORE the velocities exist: Q+/- of the first CFL see a gas at rest
 	CHECK(BK(upload_field)(ctx, FARGO_SIGMA, s0.sigma.data()));
-	if (params.adiabatic)
+	if (!s0.energy.empty()) // adiabatic runs; isothermal ones only carry (and write out) the energy ring of CircumBinaryRing
 	    CHECK(BK(upload_field)(ctx, FARGO_ENERGY, s0.energy.data()));
 	set_bodies_on_device();
 	CHECK(BK(set_time)(ctx, time));

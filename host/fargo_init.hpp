@@ -520,6 +520,9 @@ struct DiskModel {
     // (initialize_condition_profile_Nbody_centered: init.cpp:962-997, 1302-1346, 1473-1604)
     bool nbody_centered = false, energy_nbody_centered = false; // SigmaCondition (also the velocities) / EnergyCondition
     double cms_x = 0, cms_y = 0, vcms_x = 0, vcms_y = 0, nbody_mass = 0, density_correction_factor = 1.0;
+    // CircumBinaryRing: a Gaussian ring on top of the profiles (add_gaussian_density_ring / _energy_ring, init.cpp:889-935, 1208-1255)
+    bool cbd_ring = false;
+    double cbd_ring_position = 4.5, cbd_ring_width = 0.6, cbd_decay_width = 0.6 * 1.4, cbd_decay_exponent = 0.75, cbd_ring_factor = 2.5;
     bool pure_keplerian = false; // InitializePureKeplerian (init.cpp:1607-1627)
     // ProfileCutoffOuter / Inner (parameters.cpp:728-742): Fermi-function cut-offs of the initial profiles (util.cpp:69-93)
     bool cutoff_outer = false, cutoff_inner = false;
@@ -793,6 +796,26 @@ inline InitialState init_gas(DiskModel &d, const std::vector<double> &radii, int
     for (int i = 1; i < nrad; ++i) {
 	const double dr = (rmed[i] - rmed[i - 1]);
 	siginf[i] = (sigmed[i - 1] * (rmed[i] - radii[i]) + sigmed[i] * (radii[i] - rmed[i - 1])) / dr;
+    }
+    if (d.cbd_ring) { // after renormalize_sigma_and_report, i.e. after SigmaMed / SigmaInf were taken (init.cpp:294-297)
+	if (!d.adiabatic)
+	    s.energy.assign(ns, 0.0); // add_gaussian_energy_ring runs whatever the equation of state: an isothermal run writes it out
+	for (int i = 0; i < nrad; ++i)
+	    for (int j = 0; j < naz; ++j) {
+		const size_t l = (size_t)i * naz + j;
+		const double r = cut_radius(i, j, d.nbody_centered);
+		const double mass = d.nbody_centered ? d.nbody_mass : M;
+		const double sigma_ring = d.sigma0 * std::pow(r, -d.sigma_slope);
+		const double energy_ring = 1.0 / (d.gamma - 1.0) * d.sigma0 * std::pow(d.h0, 2) *
+					   std::pow(r, -d.sigma_slope - 1.0 + 2.0 * d.flaring) * d.G * mass;
+		double g;
+		if (r < d.cbd_ring_position)
+		    g = std::exp(-std::pow(d.cbd_ring_position - r, 2) / (2.0 * std::pow(d.cbd_ring_width, 2)));
+		else
+		    g = std::exp(-std::pow(r - d.cbd_ring_position, d.cbd_decay_exponent) / (2.0 * std::pow(d.cbd_decay_width, 2)));
+		s.sigma[l] += sigma_ring * (d.cbd_ring_factor - 1.0) * g;
+		s.energy[l] += energy_ring * (d.cbd_ring_factor - 1.0) * g;
+	    }
     }
     if (d.nbody_centered) { // init_gas_velocities, first branch (init.cpp:1473-1604)
 	const double mass = d.nbody_mass;

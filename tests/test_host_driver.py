@@ -270,6 +270,12 @@ REFERENCE_SETUPS = [("/root/reference/test/cold_disk_planet/setup.yml", []), ("/
                       "ProfileCutoffWidthOuter=0.1"]),
                     (os.path.join(ROOT, "tests", "golden", "adia_planet_100.yml"), ["--dt", "2e-3", "SigmaCondition=Nbody"]),
                     (os.path.join(ROOT, "tests", "golden", "adia_planet_100.yml"), ["--dt", "2e-3", "EnergyCondition=Nbody"]),
+                    # CircumBinaryRing: Gaussian ring on top of the profiles (density and energy; isothermal runs write the energy ring out too)
+                    (os.path.join(ROOT, "tests", "golden", "circumbinary_setup.yml"),
+                     ["--dt", "2e-3", "CircumBinaryRing=yes", "CircumBinaryRingPosition=1.5", "CircumBinaryRingWidth=0.2", "SigmaCondition=Nbody",
+                      "SetSigma0=yes", "DiskMass=0.01"]),
+                    (os.path.join(ROOT, "tests", "golden", "adia_planet_100.yml"),
+                     ["--dt", "2e-3", "CircumBinaryRing=yes", "CircumBinaryRingPosition=1.5", "CircumBinaryRingWidth=0.2"]),
                     (os.path.join(ROOT, "tests", "golden", "corotating_setup.yml"), ["--dt", "4e-3"]),
                     (os.path.join(ROOT, "tests", "golden", "corotating_setup.yml"), ["--dt", "4e-3", "Integrator=Leapfrog"]),
                     (os.path.join(ROOT, "tests", "golden", "corotating_setup.yml"), ["--dt", "4e-3", "DiskFeedback=yes", "IndirectTermMode=0"])]
