@@ -840,7 +840,7 @@ struct Run {
 	cfg.load(cfgfile);
 	// what this driver's initial conditions do not cover is refused by name
 	const std::pair<const char *, const char *> off[] = {
-	    {"ShockTube", "0"}, {"RandomSigma", "no"}, {"SelfGravity", "no"}, {"IntegrateParticles", "no"},
+	    {"RandomSigma", "no"}, {"SelfGravity", "no"}, {"IntegrateParticles", "no"},
 	    {"RadiativeDiffusion", "no"}, {"SecondaryDisk", "no"}, {"CbdRing", "no"}};
 	for (auto &k : off) {
 	    const std::string v = lower(cfg.str(k.first, k.second));
@@ -869,6 +869,9 @@ struct Run {
 	consts.G = U.G.code, consts.R = U.R.code, consts.sigma_sb = U.sigma.code, consts.c_light = U.c.code;
 	consts.temperature_unit_K = U.temperature;
 	consts.length_cgs = U.length, consts.mass_cgs = U.mass, consts.time_cgs = U.time;
+	const int shock_tube = (int)cfg.num("ShockTube", 0);
+	if (shock_tube != 0 && shock_tube != 1)
+	    die("ShockTube: %s is not supported by this driver (1: the ideal-gas tube)", cfg.str("ShockTube", ""));
 	// values that may carry units become plain code-unit numbers (config::Config::get<double>(key, unit))
 	const std::pair<const char *, char> dims[] = {{"Rmin", 'L'}, {"Rmax", 'L'}, {"Sigma0", 'S'}, {"MonitorTimestep", 'T'},
 						       {"FirstDT", 'T'}, {"DampingTimeRadiusOuter", 'L'}};
@@ -896,6 +899,11 @@ struct Run {
 	    }
 	}
 	params = make_params(cfg, consts, nrad, naz);
+	if (shock_tube) { // init_shock_tube_test sets G = R = 1 in memory AFTER the parameters were converted and the unit / constant
+			  // files were written (init.cpp:506-513, main.cpp:85-86): the files keep the l0 / m0 values
+	    consts.G = 1.0, consts.R = 1.0;
+	    params.G = 1.0, params.Rgas = 1.0;
+	}
 	radii = finit::make_radii(params.radial_spacing, nrad, params.rmin, params.rmax, cfg.num("ExponentialCellSizeFactor", 1.41));
 	// bodies
 	const bool cic = cfg.flag("CICPLANET", false);
@@ -1001,6 +1009,11 @@ struct Run {
 	d.spreading_ring = cfg.flag("SpreadingRing", false);
 	d.set_sigma0 = cfg.flag("SetSigma0", false);
 	d.diskmass = cfg.has("DiskMass") ? U.in_code_units(cfg.str("DiskMass", "0.01"), 'M') : 0.01;
+	if (shock_tube) { // the tube replaces every other density / energy initialisation (init.cpp:269-272)
+	    d.shock_tube = true;
+	    d.sigma_in = d.energy_in = nullptr;
+	    d.spreading_ring = d.cutoff_outer = d.cutoff_inner = d.set_sigma0 = d.cbd_ring = d.nbody_centered = d.energy_nbody_centered = false;
+	}
 	const finit::InitialState s0 = finit::init_gas(d, radii, nrad, naz, params.hydro_center_mass);
 	params.sigma0 = d.sigma0; // SetSigma0 rescales it; the density floor follows (init.cpp:1155)
 	create_context(device);

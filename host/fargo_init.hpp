@@ -523,6 +523,7 @@ struct DiskModel {
     // CircumBinaryRing: a Gaussian ring on top of the profiles (add_gaussian_density_ring / _energy_ring, init.cpp:889-935, 1208-1255)
     bool cbd_ring = false;
     double cbd_ring_position = 4.5, cbd_ring_width = 0.6, cbd_decay_width = 0.6 * 1.4, cbd_decay_exponent = 0.75, cbd_ring_factor = 2.5;
+    bool shock_tube = false; // ShockTube: 1 — Sod's shock tube along the radius (init_shock_tube_test, init.cpp:423-522)
     bool pure_keplerian = false; // InitializePureKeplerian (init.cpp:1607-1627)
     // ProfileCutoffOuter / Inner (parameters.cpp:728-742): Fermi-function cut-offs of the initial profiles (util.cpp:69-93)
     bool cutoff_outer = false, cutoff_inner = false;
@@ -683,7 +684,21 @@ inline InitialState init_gas(DiskModel &d, const std::vector<double> &radii, int
 	}
     }
     const double dphi = 2.0 * M_PI / (double)naz;
-    if (d.nbody_centered || (d.adiabatic && d.energy_nbody_centered)) {
+    if (d.shock_tube) { // replaces every other density / energy initialisation, renormalisation included (init.cpp:269-299)
+	for (int i = 0; i < nrad; ++i) {
+	    double density = 1.0, energy = 2.5;
+	    if (rmed[i] - rmed[0] > 0.5) {
+		density = 0.125;
+		energy = 2.0 * 0.125;
+	    }
+	    for (int j = 0; j < naz; ++j) {
+		s.sigma[(size_t)i * naz + j] = density;
+		if (d.adiabatic)
+		    s.energy[(size_t)i * naz + j] = energy;
+	    }
+	}
+    }
+    if (!d.shock_tube && (d.nbody_centered || (d.adiabatic && d.energy_nbody_centered))) {
 	for (int i = 0; i < nrad; ++i)
 	    for (int j = 0; j < naz; ++j) {
 		const double phi = (double)j * dphi;

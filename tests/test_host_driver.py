@@ -469,3 +469,96 @@ def test_host_refuses_physics_it_does_not_implement(tmp_path):
         yaml.safe_dump(cfg, open(yml, "w"), sort_keys=False)
         res = subprocess.run([_oracle_exe(), "start", yml, "--out", str(tmp_path / ("out_" + key))], capture_output=True, text=True, timeout=60)
         assert res.returncode != 0 and key in res.stderr, (key, res.stderr)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Known answer of the reference's test/shockTube (check_results.py: integrated |numerical - analytic| over the tube, thresholds below)
+def _sod_exact(x, t, gamma=1.4, left=(1.0, 1.0), right=(0.125, 0.1), x0=0.5):
+    """Exact solution of Sod's Riemann problem (rho, u, p) at positions x and time t (Toro, ch. 4)."""
+    rl, pl = left
+    rr, pr = right
+    cl, cr = np.sqrt(gamma * pl / rl), np.sqrt(gamma * pr / rr)
+    g1, g2 = (gamma - 1) / (2 * gamma), (gamma + 1) / (2 * gamma)
+
+    def f(p, rk, pk, ck):  # pressure functions and their derivatives
+        if p > pk:
+            a, b = 2 / ((gamma + 1) * rk), (gamma - 1) / (gamma + 1) * pk
+            return (p - pk) * np.sqrt(a / (p + b)), np.sqrt(a / (b + p)) * (1 - (p - pk) / (2 * (b + p)))
+        return 2 * ck / (gamma - 1) * ((p / pk) ** g1 - 1), (p / pk) ** (-g2) / (rk * ck)
+
+    p = 0.5 * (pl + pr)
+    for _ in range(60):
+        fl, dfl = f(p, rl, pl, cl)
+        fr, dfr = f(p, rr, pr, cr)
+        p -= (fl + fr) / (dfl + dfr)
+    u = 0.5 * (f(p, rr, pr, cr)[0] - f(p, rl, pl, cl)[0])
+    rsl = rl * (p / pl) ** (1 / gamma)  # behind the left rarefaction
+    rsr = rr * ((p / pr + (gamma - 1) / (gamma + 1)) / ((gamma - 1) / (gamma + 1) * p / pr + 1))  # behind the right shock
+    csl = cl * (p / pl) ** g1
+    s_shock = cr * np.sqrt(g2 * p / pr + g1)
+    xi = (x - x0) / t
+    rho, vel, prs = np.empty_like(x), np.empty_like(x), np.empty_like(x)
+    for k, s in enumerate(xi):
+        if s < -cl:
+            rho[k], vel[k], prs[k] = rl, 0.0, pl
+        elif s < u - csl:  # inside the fan
+            c = 2 / (gamma + 1) * (cl - (gamma - 1) / 2 * s)
+            vel[k] = 2 / (gamma + 1) * (cl + s)
+            rho[k] = rl * (c / cl) ** (2 / (gamma - 1))
+            prs[k] = pl * (c / cl) ** (2 * gamma / (gamma - 1))
+        elif s < u:
+            rho[k], vel[k], prs[k] = rsl, u, p
+        elif s < s_shock:
+            rho[k], vel[k], prs[k] = rsr, u, p
+        else:
+            rho[k], vel[k], prs[k] = rr, 0.0, pr
+    return rho, vel, prs
+
+
+@pytest.mark.parametrize("integrator,artvisc", [("Euler", "TW"), ("Euler", "SN"), ("Leapfrog", "TW"), ("Leapfrog", "SN")])
+def test_shock_tube_matches_the_exact_riemann_solution_cpu(integrator, artvisc, tmp_path):
+    """The reference's test/shockTube acceptance (check_results.py:15-20, its four setups TW / SN x Euler / Leapfrog):
+    Simpson-integrated absolute deviation from the exact Sod solution at t = 0.228 (membrane at x = 0.5 as in the reference's
+    analytic_shock.dat) below 0.0073 (Sigma), 0.0153 (v_rad), 0.014 (energy), 0.016 (temperature)."""
+    from scipy import integrate
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "tests", "golden", "shock_tube_setup.yml")))
+    cfg["Integrator"], cfg["ArtificialViscosity"] = integrator, artvisc
+    yml, out = str(tmp_path / "setup.yml"), str(tmp_path / "out")
+    yaml.safe_dump(cfg, open(yml, "w"), sort_keys=False)
+    _run_start(_oracle_exe(), yml, out, 1)
+    r12 = np.loadtxt(os.path.join(out, "used_rad.dat"))
+    r1 = 0.5 * (r12[1:] + r12[:-1]) - r12[0]
+    nr = len(r1)
+    sig = np.fromfile(os.path.join(out, "snapshots", "1", "Sigma.dat")).reshape(nr, 2).mean(axis=1)
+    en = np.fromfile(os.path.join(out, "snapshots", "1", "energy.dat")).reshape(nr, 2).mean(axis=1)
+    vr = np.fromfile(os.path.join(out, "snapshots", "1", "vrad.dat")).reshape(nr + 1, 2).mean(axis=1)
+    vr = 0.5 * (vr[1:] + vr[:-1])
+    inside = (r1 >= 0) & (r1 <= 1)
+    x = r1[inside]
+    rho, vel, prs = _sod_exact(x, 0.228)
+    dev = {"Sigma": integrate.simpson(np.abs(sig[inside] - rho), x=x), "vrad": integrate.simpson(np.abs(vr[inside] - vel), x=x),
+           "energy": integrate.simpson(np.abs(en[inside] - prs / 0.4), x=x),
+           "Temperature": integrate.simpson(np.abs(0.4 * en[inside] / sig[inside] - prs / rho), x=x)}
+    limits = {"vrad": 0.0153, "Sigma": 0.0073, "Temperature": 0.016, "energy": 0.014}
+    for q, lim in limits.items():
+        assert dev[q] < lim, (q, dev[q], lim)
+
+
+@pytest.mark.parametrize("setup", ["shocktube_TW.yml", "shocktube_SN.yml", "shocktube_TW_LF.yml", "shocktube_SN_LF.yml"])
+def test_shock_tube_setups_of_the_reference_verbatim_cpu(setup):
+    """test/shockTube/setups/*.yml through the unmodified reference and through `fargocpt_b200 start`: ~150 CFL-limited hydro steps
+    with strong shocks (TW / SN artificial viscosity, Euler / Leapfrog), every double of every snapshot identical."""
+    path = os.path.join("/root/reference/test/shockTube/setups", setup)
+    if not (os.path.exists(path) and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "fargocpt_exe_ieee"))):
+        pytest.skip("the reference tree / oracle/_ref are not available here")
+    _oracle_exe()
+    import contextlib
+    import importlib.util
+    import io
+    spec = importlib.util.spec_from_file_location("cmpstart", os.path.join(ROOT, "tools", "compare_start_with_reference.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        worst = mod.main([path, "--snapshots", "3", "--dt", "0.01"])
+    assert worst == 0.0 and buf.getvalue().count("misc identical") == 4, buf.getvalue()
