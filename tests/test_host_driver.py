@@ -562,3 +562,23 @@ def test_shock_tube_setups_of_the_reference_verbatim_cpu(setup):
     with contextlib.redirect_stdout(buf):
         worst = mod.main([path, "--snapshots", "3", "--dt", "0.01"])
     assert worst == 0.0 and buf.getvalue().count("misc identical") == 4, buf.getvalue()
+
+
+def test_spreading_ring_meets_the_references_acceptance_cpu(tmp_path):
+    """test/spreading_ring/calc_deviation.py:38-66: after t = 314.159 (39 870 hydro steps on the 256 x 2 grid) the ring must
+    follow the analytic viscous-spreading solution (Speith & Kley 2003) with a mean relative deviation below 0.007."""
+    from scipy.special import iv
+    cfg = yaml.safe_load(open(SPREADING_RING))
+    cfg["MonitorTimestep"], cfg["Nsnapshots"] = 314.159265359, 1
+    yml, out = str(tmp_path / "setup.yml"), str(tmp_path / "out")
+    yaml.safe_dump(cfg, open(yml, "w"), sort_keys=False)
+    _run_start(_oracle_exe(), yml, out, 1)
+    ri = np.loadtxt(os.path.join(out, "used_rad.dat"))
+    rinf, rsup = ri[:-1], ri[1:]
+    rc = 2.0 / 3.0 * (rsup ** 3 - rinf ** 3) / (rsup ** 2 - rinf ** 2)
+    sigma = np.fromfile(os.path.join(out, "snapshots", "1", "Sigma.dat")).reshape(256, 2).mean(axis=1)
+    raw = open(os.path.join(out, "snapshots", "1", "misc.bin"), "rb").read()
+    t = struct.unpack("<IIddddQ", raw)[2]
+    tau = 12 * 4.77e-5 * t + 0.016
+    theo = 1.0 / np.pi / tau / rc ** 0.25 * iv(0.25, 2.0 * rc / tau) * np.exp(-(1 + rc ** 2) / tau)
+    assert np.mean(np.abs(sigma / theo - 1)) < 0.007
