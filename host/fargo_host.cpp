@@ -33,6 +33,7 @@
 #include <string>
 #include <sys/stat.h>
 #include <thread>
+#include <tuple>
 #include <vector>
 
 #include "../include/fargo_b200.h"
@@ -1355,6 +1356,19 @@ struct Run {
 		CHECK(BK(download_field)(ctx, s.first, buf.data()));
 		write_doubles(sd + "/" + s.second + ".dat", buf);
 	    }
+	}
+	// optional derived outputs (data.cpp: WriteTemperature, WritePressure, ...): evaluated from the current state on download,
+	// which is what recalculate_derived_disk_quantities left in the reference's grids at the end of the step
+	for (auto &s : {std::make_tuple((int)FARGO_TEMPERATURE, "WriteTemperature", "Temperature"),
+			std::make_tuple((int)FARGO_PRESSURE, "WritePressure", "pressure"),
+			std::make_tuple((int)FARGO_SOUNDSPEED, "WriteSoundSpeed", "soundspeed"),
+			std::make_tuple((int)FARGO_SCALE_HEIGHT, "WriteScaleHeight", "scale_height"),
+			std::make_tuple((int)FARGO_VISCOSITY, "WriteViscosity", "viscosity")}) {
+	    if (!cfg.flag(std::get<1>(s), false))
+		continue;
+	    std::vector<double> buf(cells(false), 0.0);
+	    CHECK(BK(download_field)(ctx, std::get<0>(s), buf.data()));
+	    write_doubles(sd + "/" + std::get<2>(s) + ".dat", buf);
 	}
 	MiscEntry m;
 	m.timestep = n_snapshot, m.nTimeStep = n_monitor, m.time = time, m.OmegaFrame = omega_frame, m.FrameAngle = frame_angle;

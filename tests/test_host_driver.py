@@ -582,3 +582,22 @@ def test_spreading_ring_meets_the_references_acceptance_cpu(tmp_path):
     tau = 12 * 4.77e-5 * t + 0.016
     theo = 1.0 / np.pi / tau / rc ** 0.25 * iv(0.25, 2.0 * rc / tau) * np.exp(-(1 + rc ** 2) / tau)
     assert np.mean(np.abs(sigma / theo - 1)) < 0.007
+
+
+def test_host_writes_derived_fields_on_request_cpu(tmp_path):
+    """WriteTemperature / WritePressure / WriteSoundSpeed: the optional derived outputs of a snapshot (data.cpp), evaluated from the
+    snapshot's own state (identical to the reference's files, tools/compare_start_with_reference.py --keep)."""
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "tests", "golden", "adia_star.yml")))
+    cfg.update({"WriteTemperature": "yes", "WritePressure": "yes", "WriteSoundSpeed": "yes"})
+    yml, out = str(tmp_path / "setup.yml"), str(tmp_path / "out")
+    yaml.safe_dump(cfg, open(yml, "w"), sort_keys=False)
+    _run_start(_oracle_exe(), yml, out, 2)
+    meta, z = reftools.load_golden("adia_star")
+    sd = os.path.join(out, "snapshots", "2")
+    sigma, energy = np.fromfile(os.path.join(sd, "Sigma.dat")), np.fromfile(os.path.join(sd, "energy.dat"))
+    gamma, mu, rgas = meta["params"]["gamma"], meta["params"]["mu"], meta["consts"]["R"]
+    pressure = np.fromfile(os.path.join(sd, "pressure.dat"))
+    assert np.array_equal(pressure, (gamma - 1.0) * energy)
+    assert np.allclose(np.fromfile(os.path.join(sd, "Temperature.dat")), mu / rgas * pressure / sigma, rtol=1e-15, atol=0)
+    assert np.allclose(np.fromfile(os.path.join(sd, "soundspeed.dat")), np.sqrt(gamma * (gamma - 1.0) * energy / sigma), rtol=1e-15, atol=0)
+    assert not os.path.exists(os.path.join(sd, "viscosity.dat"))
