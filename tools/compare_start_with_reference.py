@@ -89,6 +89,27 @@ def main(argv=None):
             line.append(f"body{nb} {'identical' if np.array_equal(sr, so) else f'max|d|={np.abs(sr - so).max():.1e}'}")
             nb += 1
         print(" ".join(line))
+    # monitor files: same header, same columns (nan in ours = a column this path does not evaluate)
+    def table(path):
+        head = [l for l in open(path) if l.startswith("#")]
+        rows = np.array([[float(x) for x in l.split()] for l in open(path) if not l.startswith("#") and l.strip()])
+        return head, rows
+    mon = [f for f in sorted(os.listdir(os.path.join(ours, "monitor"))) if f.startswith(("Quantities", "nbody"))]
+    for f in mon:
+        pr, po = os.path.join(ref, "monitor", f), os.path.join(ours, "monitor", f)
+        if not os.path.exists(pr):
+            continue
+        (hr, a), (ho, b) = table(pr), table(po)
+        n = min(len(a), len(b))
+        if n == 0 or a.shape[1] != b.shape[1]:
+            print(f"monitor/{f}: SHAPE {a.shape} vs {b.shape}")
+            continue
+        with np.errstate(all="ignore"):
+            scale = np.maximum(np.abs(a[:n]).max(axis=0), 1e-300)
+            d = np.abs(a[:n] - b[:n]).max(axis=0) / scale
+        cols = ", ".join(f"{k}:{v:.0e}" for k, v in enumerate(d) if np.isfinite(v) and v > 1e-9)
+        print(f"monitor/{f}: header {'identical' if hr == ho else 'DIFFERENT'}, rows {len(a)} vs {len(b)}, columns not evaluated: "
+              f"{[k for k, v in enumerate(d) if not np.isfinite(v)]}, columns off by more than 1e-9 of their scale: {cols or 'none'}")
     print(f"worst field deviation relative to the field scale: {worst:.2e}")
     return worst
     if "--keep" not in args:
