@@ -3,7 +3,7 @@
 `fargocpt_b200 start` (bound to the oracle: host/fargocpt_b200_oracle_test, or --gpu for the real binary) and compare the
 output directories file by file (Tools/compare_binary_output.py statistics).  Build container only (needs oracle/_ref).
 
-    python tools/compare_start_with_reference.py /root/reference/test/cold_disk_planet/setup.yml [--snapshots 3] [--dt 1e-3] [key=value ...]
+    python tests/checkers/compare_start_with_reference.py /root/reference/test/cold_disk_planet/setup.yml [--snapshots 3] [--dt 1e-3] [key=value ...]
 
 The setup is run with MonitorTimestep = --dt, Nmonitor 1, so every snapshot is one short monitor step."""
 import os
@@ -16,7 +16,7 @@ import tempfile
 import numpy as np
 import yaml
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 REF = os.path.join(ROOT, "oracle", "_ref", "fargocpt_exe_ieee")
 
 

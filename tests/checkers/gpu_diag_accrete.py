@@ -1,13 +1,13 @@
 #!/usr/bin/env python
 """Lock-step GPU-vs-oracle report over a fixture with an accreting planet (diagnostics, not a test).  Run on the GPU box:
-    python tools/gpu_diag_accrete.py [fixture ...]
+    python tests/checkers/gpu_diag_accrete.py [fixture ...]
 Three passes per fixture: (A) fargo_step (fused kernels) with accretion, fields compared after every accretion call and
 after every step; (B) the same without the accretion calls (is it the planet or the accretion?); (C) the per-stage entry
 points with accretion, compared after every stage.  FARGO_DIAG_CPU=1 binds both sides to the oracle (syntax check)."""
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402

@@ -2,8 +2,8 @@
 """The acceptance checks of the reference's own tests, run through `fargocpt_b200 start` on this repo's minimal
 setups of the same physics (tests/golden/*_setup.yml) — no reference tree needed, so it runs on the GPU box too:
 
-    python tools/run_reference_acceptance.py            # oracle-bound driver (CPU; host/fargocpt_b200_oracle_test)
-    python tools/run_reference_acceptance.py --gpu      # the product: host/fargocpt_b200 on libfargo_b200.so
+    python tests/checkers/run_reference_acceptance.py            # oracle-bound driver (CPU; host/fargocpt_b200_oracle_test)
+    python tests/checkers/run_reference_acceptance.py --gpu      # the product: host/fargocpt_b200 on libfargo_b200.so
 
   test/shockTube           check_results.py:15-20     integrated |numerical - exact Sod| at t = 0.228 below 0.0073 / 0.0153 / 0.014 / 0.016
   test/spreading_ring      calc_deviation.py:38-66    mean |Sigma / Sigma_analytic - 1| < 0.007 at t = 314.159 (39 870 hydro steps)
@@ -19,7 +19,7 @@ import time
 import numpy as np
 import yaml
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 GOLDEN = os.path.join(ROOT, "tests", "golden")

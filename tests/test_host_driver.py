@@ -291,7 +291,7 @@ def test_host_start_on_the_references_own_setup_files(setup, overrides):
         pytest.skip("the reference tree / oracle/_ref are not available here")
     _oracle_exe()
     import importlib.util
-    spec = importlib.util.spec_from_file_location("cmpstart", os.path.join(ROOT, "tools", "compare_start_with_reference.py"))
+    spec = importlib.util.spec_from_file_location("cmpstart", os.path.join(ROOT, "tests", "checkers", "compare_start_with_reference.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     import contextlib
@@ -357,7 +357,7 @@ def test_spreading_ring_setup_verbatim_cpu():
     import contextlib
     import importlib.util
     import io
-    spec = importlib.util.spec_from_file_location("cmpstart", os.path.join(ROOT, "tools", "compare_start_with_reference.py"))
+    spec = importlib.util.spec_from_file_location("cmpstart", os.path.join(ROOT, "tests", "checkers", "compare_start_with_reference.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     buf = io.StringIO()
@@ -439,7 +439,7 @@ def test_host_start_reads_2d_profiles_like_the_reference(tmp_path):
     import contextlib
     import importlib.util
     import io
-    spec = importlib.util.spec_from_file_location("cmpstart", os.path.join(ROOT, "tools", "compare_start_with_reference.py"))
+    spec = importlib.util.spec_from_file_location("cmpstart", os.path.join(ROOT, "tests", "checkers", "compare_start_with_reference.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     buf = io.StringIO()
@@ -555,7 +555,7 @@ def test_shock_tube_setups_of_the_reference_verbatim_cpu(setup):
     import contextlib
     import importlib.util
     import io
-    spec = importlib.util.spec_from_file_location("cmpstart", os.path.join(ROOT, "tools", "compare_start_with_reference.py"))
+    spec = importlib.util.spec_from_file_location("cmpstart", os.path.join(ROOT, "tests", "checkers", "compare_start_with_reference.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     buf = io.StringIO()
@@ -586,7 +586,7 @@ def test_spreading_ring_meets_the_references_acceptance_cpu(tmp_path):
 
 def test_host_writes_derived_fields_on_request_cpu(tmp_path):
     """WriteTemperature / WritePressure / WriteSoundSpeed: the optional derived outputs of a snapshot (data.cpp), evaluated from the
-    snapshot's own state (identical to the reference's files, tools/compare_start_with_reference.py --keep)."""
+    snapshot's own state (identical to the reference's files, tests/checkers/compare_start_with_reference.py --keep)."""
     cfg = yaml.safe_load(open(os.path.join(ROOT, "tests", "golden", "adia_star.yml")))
     cfg.update({"WriteTemperature": "yes", "WritePressure": "yes", "WriteSoundSpeed": "yes"})
     yml, out = str(tmp_path / "setup.yml"), str(tmp_path / "out")

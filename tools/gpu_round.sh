@@ -7,7 +7,7 @@ nvidia-smi -L > gpurun_out/${TAG}_smi.txt 2>&1
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest.log
 tail -8 gpurun_out/${TAG}_pytest.log
 # the reference's own acceptance checks (shock tube x4, spreading ring, cold disk + planet) on the product
-timeout 900 python tools/run_reference_acceptance.py --gpu > gpurun_out/${TAG}_acceptance.log 2>&1; echo "acceptance rc=$?" >> gpurun_out/${TAG}_acceptance.log
+timeout 900 python tests/checkers/run_reference_acceptance.py --gpu > gpurun_out/${TAG}_acceptance.log 2>&1; echo "acceptance rc=$?" >> gpurun_out/${TAG}_acceptance.log
 tail -8 gpurun_out/${TAG}_acceptance.log
 timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/${TAG}_bench.log 2>&1; echo "bench rc=$?" >> gpurun_out/${TAG}_bench.log
 tail -3 gpurun_out/${TAG}_bench.log | cut -c1-3500
