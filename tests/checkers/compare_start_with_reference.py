@@ -23,7 +23,7 @@ REF = os.path.join(ROOT, "oracle", "_ref", "fargocpt_exe_ieee")
 def main(argv=None):
     args = list(sys.argv[1:] if argv is None else argv)
     gpu = "--gpu" in args
-    nsnap, dt, over = 3, 1e-3, {}
+    nsnap, dt, over, restart_from = 3, 1e-3, {}, None
     setup = None
     i = 0
     while i < len(args):
@@ -32,6 +32,8 @@ def main(argv=None):
             nsnap = int(args[i + 1]); i += 1
         elif a == "--dt":
             dt = float(args[i + 1]); i += 1
+        elif a == "--restart-from":  # ours does not start from the YAML but restarts from the REFERENCE's snapshot K
+            restart_from = int(args[i + 1]); i += 1
         elif a in ("--gpu", "--keep"):
             pass
         elif "=" in a:
@@ -54,16 +56,21 @@ def main(argv=None):
         raise SystemExit("reference run failed")
     exe = os.path.join(ROOT, "host", "fargocpt_b200" if gpu else "fargocpt_b200_oracle_test")
     ours = os.path.join(tmp, "ours")
-    r = subprocess.run([exe, "start", ypath, "--out", ours, "--until", str(nsnap)], capture_output=True, text=True)
+    if restart_from is None:
+        r = subprocess.run([exe, "start", ypath, "--out", ours, "--until", str(nsnap)], capture_output=True, text=True)
+    else:
+        r = subprocess.run([exe, "restart", str(restart_from), cfg["OutputDir"], "--out", ours, "--until", str(nsnap)], capture_output=True, text=True)
     print(r.stdout[-300:], r.stderr[-600:])
     if r.returncode != 0:
         raise SystemExit("fargocpt_b200 start failed")
     ref = cfg["OutputDir"]
     worst = 0.0
     for f in ("constants.yml", "units.yml", "used_rad.dat"):
+        if restart_from is not None and not os.path.exists(os.path.join(ours, f)):
+            continue
         same = open(os.path.join(ref, f)).read() == open(os.path.join(ours, f)).read()
         print(f"{f}: {'identical' if same else 'DIFFERENT'}")
-    for k in range(nsnap + 1):
+    for k in range(0 if restart_from is None else restart_from + 1, nsnap + 1):
         sd_r, sd_o = os.path.join(ref, "snapshots", str(k)), os.path.join(ours, "snapshots", str(k))
         line = [f"snapshot {k}:"]
         for f in ("Sigma", "vrad", "vazi", "energy"):
@@ -94,7 +101,7 @@ def main(argv=None):
         head = [l for l in open(path) if l.startswith("#")]
         rows = np.array([[float(x) for x in l.split()] for l in open(path) if not l.startswith("#") and l.strip()])
         return head, rows
-    mon = [f for f in sorted(os.listdir(os.path.join(ours, "monitor"))) if f.startswith(("Quantities", "nbody"))]
+    mon = [] if restart_from is not None else [f for f in sorted(os.listdir(os.path.join(ours, "monitor"))) if f.startswith(("Quantities", "nbody"))]
     for f in mon:
         pr, po = os.path.join(ref, "monitor", f), os.path.join(ours, "monitor", f)
         if not os.path.exists(pr):

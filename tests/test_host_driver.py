@@ -601,3 +601,25 @@ def test_host_writes_derived_fields_on_request_cpu(tmp_path):
     assert np.allclose(np.fromfile(os.path.join(sd, "Temperature.dat")), mu / rgas * pressure / sigma, rtol=1e-15, atol=0)
     assert np.allclose(np.fromfile(os.path.join(sd, "soundspeed.dat")), np.sqrt(gamma * (gamma - 1.0) * energy / sigma), rtol=1e-15, atol=0)
     assert not os.path.exists(os.path.join(sd, "viscosity.dat"))
+
+
+@pytest.mark.parametrize("setup,extra", [("/root/reference/test/cold_disk_planet/setup.yml", []),
+                                         ("/root/reference/examples/config.yml", ["Integrator=Leapfrog"]),
+                                         (os.path.join(ROOT, "tests", "golden", "corotating_setup.yml"), ["--dt", "4e-3"])])
+def test_host_restarts_from_a_directory_the_reference_wrote(setup, extra):
+    """`restart 2 <dir>` on an output directory written by the unmodified reference itself (its real constants.yml, units.yml,
+    dimensions.dat, 256-byte nbody records, misc.bin, snapshots/reference): snapshots 3 and 4 against the reference's own."""
+    if not (os.path.exists(setup) and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "fargocpt_exe_ieee"))):
+        pytest.skip("the reference tree / oracle/_ref are not available here")
+    _oracle_exe()
+    import contextlib
+    import importlib.util
+    import io
+    spec = importlib.util.spec_from_file_location("cmpstart", os.path.join(ROOT, "tests", "checkers", "compare_start_with_reference.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        worst = mod.main([setup, "--snapshots", "4", "--dt", "1e-3", "--restart-from", "2"] + extra)
+    text = buf.getvalue()
+    assert worst <= 1e-10 and sum(l.startswith("snapshot ") for l in text.splitlines()) == 2, text
