@@ -34,7 +34,7 @@ def main(argv=None):
             dt = float(args[i + 1]); i += 1
         elif a == "--restart-from":  # ours does not start from the YAML but restarts from the REFERENCE's snapshot K
             restart_from = int(args[i + 1]); i += 1
-        elif a in ("--gpu", "--keep"):
+        elif a in ("--gpu", "--keep", "--vs-reference-restart"):
             pass
         elif "=" in a:
             k, v = a.split("=", 1)
@@ -64,6 +64,21 @@ def main(argv=None):
     if r.returncode != 0:
         raise SystemExit("fargocpt_b200 start failed")
     ref = cfg["OutputDir"]
+    if restart_from is not None and "--vs-reference-restart" in args:
+        # compare with what the REFERENCE does when it restarts from the same snapshot (not with its uninterrupted run: the two
+        # differ where the reference's restart is not seamless, e.g. in a corotating frame, frame_of_reference.cpp:19-28)
+        ref2 = os.path.join(tmp, "ref_restarted")
+        shutil.copytree(ref, ref2)
+        for k in range(restart_from + 1, nsnap + 1):
+            shutil.rmtree(os.path.join(ref2, "snapshots", str(k)))
+        cfg2 = dict(cfg, OutputDir=ref2)
+        ypath2 = os.path.join(tmp, "setup_restart.yml")
+        yaml.safe_dump(cfg2, open(ypath2, "w"), sort_keys=False)
+        r = subprocess.run([REF, "restart", str(restart_from), ypath2], cwd=tmp, env=env, capture_output=True, text=True)
+        if r.returncode != 0:
+            print(r.stdout[-2000:], r.stderr[-2000:])
+            raise SystemExit("reference restart failed")
+        ref = ref2
     worst = 0.0
     for f in ("constants.yml", "units.yml", "used_rad.dat"):
         if restart_from is not None and not os.path.exists(os.path.join(ours, f)):
