@@ -627,3 +627,31 @@ def test_host_restarts_from_a_directory_the_reference_wrote(setup, extra):
         worst = mod.main([setup, "--snapshots", "4", "--dt", "1e-3", "--restart-from", "2"] + extra)
     text = buf.getvalue()
     assert worst <= 1e-10 and sum(l.startswith("snapshot ") for l in text.splitlines()) == 2, text
+
+
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_baseline_config_setups_against_the_reference_at_reduced_resolution(k, tmp_path):
+    """tests/golden/baseline_config{2,3,4}_setup.yml are BASELINE.json's configs[2..4] as setup files for `fargocpt_b200 start`
+    (2048 x 4096, 4096 x 8192, 8192 x 16384).  Here: the same physics at 1/16 of the resolution per direction through the
+    reference and the driver."""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "fargocpt_exe_ieee")):
+        pytest.skip("oracle/_ref is not available here")
+    _oracle_exe()
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "tests", "golden", f"baseline_config{k}_setup.yml")))
+    assert (cfg["Nrad"], cfg["Naz"]) == {2: (2048, 4096), 3: (4096, 8192), 4: (8192, 16384)}[k]
+    shrink = 16 if k < 4 else 64
+    cfg["Nrad"], cfg["Naz"] = cfg["Nrad"] // shrink, cfg["Naz"] // shrink
+    yml = str(tmp_path / "setup.yml")
+    yaml.safe_dump(cfg, open(yml, "w"), sort_keys=False)
+    import contextlib
+    import importlib.util
+    import io
+    spec = importlib.util.spec_from_file_location("cmpstart", os.path.join(ROOT, "tests", "checkers", "compare_start_with_reference.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        worst = mod.main([yml, "--snapshots", "2", "--dt", "1e-3"])
+    snap0 = [l for l in buf.getvalue().splitlines() if l.startswith("snapshot 0:")][0]
+    assert "misc identical" in snap0 and snap0.count("ndiff=0 ") >= 3, snap0
+    assert worst <= 1e-10, buf.getvalue()
