@@ -687,6 +687,13 @@ struct Run {
     // refframe::ComputeIndirectTermDisk (frame_of_reference.cpp:69-90); only with DiskFeedback: yes (simulation.cpp:155-160)
     void disk_feedback_kick(double dt)
     {
+	disk_feedback_compute(dt);
+	disk_feedback_apply(dt);
+    }
+    // step_LeapFrog evaluates the disk's pull BEFORE AccreteOntoPlanets and applies it AFTER (simulation.cpp:294-305, 352-408):
+    // the two halves of disk_feedback_kick
+    void disk_feedback_compute(double dt)
+    {
 	ind_disk_x = ind_disk_y = 0.0;
 	if (!disk_feedback)
 	    return;
@@ -699,11 +706,6 @@ struct Run {
 	    b.rec.disk_on_planet_acceleration[1] = a4[1] + a4[3];
 	    b.rec.torque = (b.rec.x * b.rec.disk_on_planet_acceleration[1] - b.rec.y * b.rec.disk_on_planet_acceleration[0]) * b.rec.mass;
 	}
-	for (auto &b : bodies) {
-	    b.rec.vx = b.rec.vx + dt * b.rec.disk_on_planet_acceleration[0];
-	    b.rec.vy = b.rec.vy + dt * b.rec.disk_on_planet_acceleration[1];
-	    b.rec.gas_torque_acc += b.rec.torque * dt; // t_planet::add_torque (Pframeforce.cpp:272)
-	}
 	double mass_center = 0.0;
 	for (unsigned n = 0; n < n_center; ++n) {
 	    ind_disk_x -= bodies[n].rec.mass * bodies[n].rec.disk_on_planet_acceleration[0];
@@ -714,6 +716,16 @@ struct Run {
 	ind_disk_y /= mass_center;
 	for (auto &b : bodies) // the indirect torque monitor (frame_of_reference.cpp:92-107)
 	    b.rec.indirect_torque_acc += (b.rec.x * ind_disk_y - b.rec.y * ind_disk_x) * b.rec.mass * dt;
+    }
+    void disk_feedback_apply(double dt)
+    { // UpdatePlanetVelocitiesWithDiskForce (Pframeforce.cpp:257-275)
+	if (!disk_feedback)
+	    return;
+	for (auto &b : bodies) {
+	    b.rec.vx = b.rec.vx + dt * b.rec.disk_on_planet_acceleration[0];
+	    b.rec.vy = b.rec.vy + dt * b.rec.disk_on_planet_acceleration[1];
+	    b.rec.gas_torque_acc += b.rec.torque * dt; // t_planet::add_torque (Pframeforce.cpp:272)
+	}
     }
 
     void load(const std::string &dir, unsigned nsnap, int device)
@@ -1258,9 +1270,10 @@ struct Run {
 	compute_indirect_nbody(frog);	  // :285-287, while the bodies are still at the start of the step
 	init_corotation();		  // :289
 	integrate_and_recentre(frog);	  // :290-292
-	accrete(frog);			  // :302-303
-	disk_feedback_kick(frog);	  // :297-313 (ComputeDiskOnNbodyAccel, UpdatePlanetVelocitiesWithDiskForce)
+	disk_feedback_compute(frog);	  // :294-297 ComputeDiskOnNbodyAccel, ComputeIndirectTermDisk — before the accretion
 	combine_indirect();		  // :299
+	accrete(frog);			  // :302-303
+	disk_feedback_apply(frog);	  // :304-305 UpdatePlanetVelocitiesWithDiskForce
 	apply_indirect_term_on_nbody(frog); // :306
 	rotate_frame(frog);		  // :313
 	set_bodies_on_device();		  // unlike step_Euler, the potential of the first kick sees the bodies AFTER the frame rotation (:317-322)
@@ -1268,12 +1281,13 @@ struct Run {
 	CHECK(BK(kick)(ctx, frog));  // :326-345
 	CHECK(BK(drift)(ctx, dt));   // :347-352
 	time = mid_time;	       // the ramp-up mass and the beta-cooling ramp see the mid-step time (:364-398)
-	disk_feedback_kick(frog);    // :355-361 and :412-414
+	disk_feedback_compute(frog); // :352-355
 	compute_indirect_nbody(frog); // :356, bodies at mid-step
 	set_bodies_on_device();
 	CHECK(BK(set_time)(ctx, mid_time));
 	CHECK(BK(kick)(ctx, frog));
 	accrete(frog);			  // :403-404, after the gas's second kick
+	disk_feedback_apply(frog);	  // :406-408
 	apply_indirect_term_on_nbody(frog); // :410
 	init_corotation();		  // :413
 	integrate_and_recentre(frog);	  // :414-416

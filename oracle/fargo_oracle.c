@@ -43,6 +43,7 @@ typedef struct fargo_oracle {
     double *sigma0, *vrad0, *vazi0, *energy0;
     /* derived */
     double *temperature, *pressure, *soundspeed, *scale_height, *viscosity, *potential;
+    int kicks_this_step; /* fargo_oracle_kick calls since the last fargo_oracle_finish_step */
     double *qplus, *qminus, *divv, *trr, *tpp, *trp, *qr, *qphi, *nusig, *nusig_rp, *cf_r, *cf_phi, *tau_eff;
     /* transport scratch (TransportEuler.cpp:32-46) */
     double *rmp, *rmm, *amp, *amm, *vres, *work, *qrstar, *densstar, *densint, *tempshift, *dq, *vmean;
@@ -1818,10 +1819,13 @@ int fargo_oracle_disk_on_body_accel(fargo_oracle *o, int body, double klahr_fact
 /* kick / drift / finish_step: the pieces step_Euler and step_LeapFrog (simulation.cpp:148-267, 276-459) arrange */
 int fargo_oracle_kick(fargo_oracle *o, double dt)
 {
-    /* step_LeapFrog recomputes the pressure before its second kick (simulation.cpp:381) but NOT c_s / H: the potential
-     * smoothing of that kick uses the scale height recalculate_viscosity left during the first kick.  For step_Euler
-     * the pressure is already the end-of-step one, so recomputing it changes nothing. */
-    compute_pressure(o);
+    /* step_LeapFrog recomputes the pressure before its SECOND kick (simulation.cpp:381) but NOT c_s / H: the potential
+     * smoothing of that kick uses the scale height recalculate_viscosity left during the first kick.  The first kick (like
+     * step_Euler's) reads the PRESSURE the previous step stored — which matters when AccreteOntoPlanets has changed Sigma / e in
+     * between (simulation.cpp:302-303): the stored pressure is the pre-accretion one. */
+    if (o->kicks_this_step > 0)
+	compute_pressure(o);
+    o->kicks_this_step++;
     fargo_oracle_stage_potential(o);
     fargo_oracle_stage_sources(o, dt);
     fargo_oracle_stage_artvisc(o, dt);
@@ -1838,6 +1842,7 @@ int fargo_oracle_drift(fargo_oracle *o, double dt)
 }
 int fargo_oracle_finish_step(fargo_oracle *o, double dt)
 {
+    o->kicks_this_step = 0;
     fargo_oracle_stage_boundary(o, dt, 1);
     fargo_oracle_stage_derived(o);
     return 0;

@@ -276,6 +276,10 @@ REFERENCE_SETUPS = [("/root/reference/test/cold_disk_planet/setup.yml", []), ("/
                       "SetSigma0=yes", "DiskMass=0.01"]),
                     (os.path.join(ROOT, "tests", "golden", "adia_planet_100.yml"),
                      ["--dt", "2e-3", "CircumBinaryRing=yes", "CircumBinaryRingPosition=1.5", "CircumBinaryRingWidth=0.2"]),
+                    # step_LeapFrog with an accreting planet: the first kick reads the pressure stored BEFORE the accretion, the disk's
+                    # pull is evaluated before AccreteOntoPlanets and applied after it (simulation.cpp:294-305, 352-408)
+                    (os.path.join(ROOT, "tests", "golden", "iso_accrete_20.yml"), ["--dt", "4e-3", "Integrator=Leapfrog"]),
+                    (os.path.join(ROOT, "tests", "golden", "adia_accfb_20.yml"), ["--dt", "4e-3", "Integrator=Leapfrog", "IndirectTermMode=0"]),
                     (os.path.join(ROOT, "tests", "golden", "corotating_setup.yml"), ["--dt", "4e-3"]),
                     (os.path.join(ROOT, "tests", "golden", "corotating_setup.yml"), ["--dt", "4e-3", "Integrator=Leapfrog"]),
                     (os.path.join(ROOT, "tests", "golden", "corotating_setup.yml"), ["--dt", "4e-3", "DiskFeedback=yes", "IndirectTermMode=0"])]
