@@ -126,6 +126,8 @@ struct fargo_ctx {
     double *pot, *qr, *qphi, *nu, *divv, *trr, *tpp, *trp, *nusig, *nusig_rp, *cf_r, *cf_phi;
     double *t_sigma, *t_rmp, *t_rmm, *t_amp, *t_amm, *t_e; // after the radial sweep
     double *vmean, *vconst, *expf_s, *expf_v, *d_dt, *scratch, *force4;
+    double *partials; // per-block partial sums of the accretion / monitor / disk-on-body reductions (sized from their launch grids)
+    size_t partials_n;
     double *hstale = nullptr; // leapfrog: scale height of the first kick's viscosity stage (see fargo_kick)
     bool h_stale = false;
     // pre-accretion Sigma / e of rings [pre_lo, pre_hi) (fargo_dev.h:PreState): written by fargo_accrete_kley, consumed by
@@ -636,6 +638,14 @@ extern "C" int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, con
 	dalloc(c, &c->t_amm, ns) || dalloc(c, &c->t_e, params->adiabatic ? ns : 1));
     TRY(dalloc(c, &c->vmean, c->v.nr + 2) || dalloc(c, &c->vconst, c->v.nr + 2) || dalloc(c, &c->expf_s, 4 * (c->v.nr + 2)) ||
 	dalloc(c, &c->expf_v, 1) || dalloc(c, &c->d_dt, 2) || dalloc(c, &c->scratch, ns) || dalloc(c, &c->force4, 4));
+    { // the reductions' partials have their own buffer: Nr x Nphi scratch is too small for them on grids with a few sectors
+	const size_t nr_ = (size_t)c->v.nr;
+	const size_t n_acc = (size_t)((c->v.ns + ACC_THREADS - 1) / ACC_THREADS) * nr_ * 3;
+	const size_t n_mq = ((size_t)((c->v.ns + 4 * MQ_THREADS - 1) / (4 * MQ_THREADS)) * nr_ + 1) * MQ_N;
+	const size_t n_dob = (size_t)((c->v.ns + 4 * DOB_THREADS - 1) / (4 * DOB_THREADS)) * nr_ * 4;
+	c->partials_n = std::max(n_acc, std::max(n_mq, n_dob));
+	TRY(dalloc(c, &c->partials, c->partials_n));
+    }
     if (params->leapfrog)
 	TRY(dalloc(c, &c->hstale, ns));
     {
@@ -1623,11 +1633,11 @@ static int accrete_zones(fargo_ctx *c, double x, double y, double r_hill, double
 	}
 	const unsigned gx = (unsigned)((v.ns + ACC_THREADS - 1) / ACC_THREADS);
 	const int nblocks = (int)gx * nrings;
-	if ((size_t)nblocks * 3 > (size_t)v.nr * v.ns)
-	    return fail("scratch too small for the accretion partials");
+	if ((size_t)nblocks * 3 > c->partials_n)
+	    return fail("partials buffer too small for the accretion");
 	dim3 grid(gx, (unsigned)nrings);
-	LAUNCH(c, k_accrete_kley, grid, ACC_THREADS, 0, v, c->sigma, EN(c), VRA(c), VPA(c), a, c->scratch);
-	LAUNCH(c, k_accrete_final, 1, 96, 0, c->scratch, nblocks, d_out);
+	LAUNCH(c, k_accrete_kley, grid, ACC_THREADS, 0, v, c->sigma, EN(c), VRA(c), VPA(c), a, c->partials);
+	LAUNCH(c, k_accrete_final, 1, 96, 0, c->partials, nblocks, d_out);
     } else {
 	CUDA_OK(cudaMemsetAsync(d_out, 0, 3 * sizeof(double), c->stream));
     }
@@ -1658,14 +1668,14 @@ extern "C" int fargo_monitor_quantities(fargo_ctx *c, double radius_limit, doubl
     const int nact = c->v.active_size - c->v.first_active;
     const unsigned gx = (unsigned)((c->v.ns + 4 * MQ_THREADS - 1) / (4 * MQ_THREADS));
     const int nblocks = (int)gx * (nact > 0 ? nact : 0);
-    if ((size_t)(nblocks + 1) * MQ_N > (size_t)c->v.nr * c->v.ns)
-	return fail("scratch too small for the monitor partials");
-    double *d_out = c->scratch + (size_t)nblocks * MQ_N; // behind the partials
+    if ((size_t)(nblocks + 1) * MQ_N > c->partials_n)
+	return fail("partials buffer too small for the monitor sums");
+    double *d_out = c->partials + (size_t)nblocks * MQ_N; // behind the partials
     if (nblocks > 0) {
 	dim3 grid(gx, (unsigned)nact);
 	LAUNCH(c, k_monitor_quantities, grid, MQ_THREADS, 0, c->v, c->sigma, EN(c), VRA(c), VPA(c), c->qplus, c->qminus, radius_limit,
-	       c->scratch);
-	LAUNCH(c, k_monitor_final, 1, 32 * MQ_N, 0, c->scratch, nblocks, d_out);
+	       c->partials);
+	LAUNCH(c, k_monitor_final, 1, 32 * MQ_N, 0, c->partials, nblocks, d_out);
     } else {
 	CUDA_OK(cudaMemsetAsync(d_out, 0, MQ_N * sizeof(double), c->stream));
     }
@@ -1814,15 +1824,15 @@ extern "C" int fargo_disk_on_body_accel(fargo_ctx *c, int body, double klahr_fac
     const int nact = c->v.active_size - c->v.first_active;
     const unsigned gx = (unsigned)((c->v.ns + 4 * DOB_THREADS - 1) / (4 * DOB_THREADS));
     const int nblocks = (int)gx * (nact > 0 ? nact : 0);
-    if ((size_t)nblocks * 4 > (size_t)c->v.nr * c->v.ns)
-	return fail("scratch too small for the force partials");
+    if ((size_t)nblocks * 4 > c->partials_n)
+	return fail("partials buffer too small for the force sums");
     double *d_out = c->force4;
     if (nblocks > 0) {
 	dim3 grid(gx, (unsigned)nact);
 	if (c->v.p.correct_disk_selfgravity) // the ring means land in vmean (rewritten by the next CFL / transport before use)
 	    LAUNCH(c, k_sigma_ring_mean, (unsigned)((c->v.nr + 63) / 64), 64, 0, c->v, c->sigma, c->vmean);
-	LAUNCH(c, k_disk_on_body, grid, DOB_THREADS, 0, c->v, c->sigma, EN(c), c->vmean, B, c->scratch);
-	LAUNCH(c, k_disk_on_body_final, 1, 128, 0, c->scratch, nblocks, d_out);
+	LAUNCH(c, k_disk_on_body, grid, DOB_THREADS, 0, c->v, c->sigma, EN(c), c->vmean, B, c->partials);
+	LAUNCH(c, k_disk_on_body_final, 1, 128, 0, c->partials, nblocks, d_out);
     } else {
 	CUDA_OK(cudaMemsetAsync(d_out, 0, 4 * sizeof(double), c->stream));
     }

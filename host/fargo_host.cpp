@@ -541,7 +541,9 @@ static void indirect_term_euler(const std::vector<Body> &b, double G, unsigned n
 
 // planetary_system.integrate (nbody/planetary_system.cpp:878-889) advances the bodies under their mutual gravity with
 // REBOUND's IAS15 (accurate to rounding).  REBOUND is out of scope; the same system is advanced here with classical RK4
-// over sub-steps h with (orbital frequency * h) <= 2e-3, i.e. a local error below 1e-16 of the orbit per step.
+// over sub-steps h with (orbital frequency * h) <= 5e-4 (truncation error (w h)^5 / 120 = 3e-19 of the orbit per sub-step) and
+// the increments accumulated with compensated (Kahan) summation, so that what is left is one rounding of the state per hydro
+// step — the level IAS15 itself works at.
 static void nbody_integrate(std::vector<Body> &b, double G, double dt)
 {
     const size_t n = b.size();
@@ -554,10 +556,10 @@ static void nbody_integrate(std::vector<Body> &b, double G, double dt)
 	    const double d = std::sqrt(dx * dx + dy * dy);
 	    wmax = std::max(wmax, std::sqrt(G * (b[i].rec.mass + b[j].rec.mass) / (d * d * d)));
 	}
-    int nsub = (int)std::ceil(wmax * dt / 2e-3);
+    int nsub = (int)std::ceil(wmax * dt / 5e-4);
     nsub = std::max(1, std::min(nsub, 100000));
     const double h = dt / nsub;
-    std::vector<double> s(4 * n), k1(4 * n), k2(4 * n), k3(4 * n), k4(4 * n), tmp(4 * n);
+    std::vector<double> s(4 * n), k1(4 * n), k2(4 * n), k3(4 * n), k4(4 * n), tmp(4 * n), comp(4 * n, 0.0);
     auto rhs = [&](const std::vector<double> &q, std::vector<double> &dq) {
 	for (size_t i = 0; i < n; ++i) {
 	    double ax = 0, ay = 0;
@@ -585,8 +587,12 @@ static void nbody_integrate(std::vector<Body> &b, double G, double dt)
 	for (size_t q = 0; q < 4 * n; ++q)
 	    tmp[q] = s[q] + h * k3[q];
 	rhs(tmp, k4);
-	for (size_t q = 0; q < 4 * n; ++q)
-	    s[q] += h / 6.0 * (k1[q] + 2.0 * k2[q] + 2.0 * k3[q] + k4[q]);
+	for (size_t q = 0; q < 4 * n; ++q) { // Kahan: comp carries what the previous additions rounded away
+	    const double inc = h / 6.0 * (k1[q] + 2.0 * k2[q] + 2.0 * k3[q] + k4[q]) - comp[q];
+	    const volatile double t = s[q] + inc;
+	    comp[q] = (t - s[q]) - inc;
+	    s[q] = t;
+	}
     }
     for (size_t i = 0; i < n; ++i)
 	b[i].rec.x = s[4 * i], b[i].rec.y = s[4 * i + 1], b[i].rec.vx = s[4 * i + 2], b[i].rec.vy = s[4 * i + 3];

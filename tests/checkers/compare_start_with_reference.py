@@ -23,7 +23,7 @@ REF = os.path.join(ROOT, "oracle", "_ref", "fargocpt_exe_ieee")
 def main(argv=None):
     args = list(sys.argv[1:] if argv is None else argv)
     gpu = "--gpu" in args
-    nsnap, dt, over, restart_from = 3, 1e-3, {}, None
+    nsnap, dt, over, restart_from, ref_threads = 3, 1e-3, {}, None, 1
     setup = None
     i = 0
     while i < len(args):
@@ -34,6 +34,8 @@ def main(argv=None):
             dt = float(args[i + 1]); i += 1
         elif a == "--restart-from":  # ours does not start from the YAML but restarts from the REFERENCE's snapshot K
             restart_from = int(args[i + 1]); i += 1
+        elif a == "--ref-threads":  # OpenMP threads of the reference run (its fields do not depend on the thread count)
+            ref_threads = int(args[i + 1]); i += 1
         elif a in ("--gpu", "--keep", "--vs-reference-restart"):
             pass
         elif "=" in a:
@@ -49,7 +51,7 @@ def main(argv=None):
     cfg["OutputDir"] = os.path.join(tmp, "ref")
     ypath = os.path.join(tmp, "setup.yml")
     yaml.safe_dump(cfg, open(ypath, "w"), sort_keys=False)
-    env = dict(os.environ, OMP_NUM_THREADS="1")
+    env = dict(os.environ, OMP_NUM_THREADS=str(ref_threads))
     r = subprocess.run([REF, "start", ypath], cwd=tmp, env=env, capture_output=True, text=True)
     if r.returncode != 0:
         print(r.stdout[-2000:], r.stderr[-2000:])
