@@ -1578,7 +1578,7 @@ extern "C" int fargo_get_nshift(fargo_ctx *c, int *out)
 // accretion::AccreteOntoSinglePlanet (accretion.cpp:84-221) and SinkHoleSinglePlanet (:223-333): gas within frac1 * r_hill
 // of the body loses the fraction facc1, within frac2 * r_hill another facc2 (frac2 = 0: no second zone)
 static int accrete_zones(fargo_ctx *c, double x, double y, double r_hill, double facc1, double facc2, double frac1, double frac2,
-			 double out3[3])
+			 double out3[3], bool viscous = false)
 {
     CUDA_OK(cudaSetDevice(c->device));
     if (c->v_mid)
@@ -1636,7 +1636,10 @@ static int accrete_zones(fargo_ctx *c, double x, double y, double r_hill, double
 	if ((size_t)nblocks * 3 > c->partials_n)
 	    return fail("partials buffer too small for the accretion");
 	dim3 grid(gx, (unsigned)nrings);
-	LAUNCH(c, k_accrete_kley, grid, ACC_THREADS, 0, v, c->sigma, EN(c), VRA(c), VPA(c), a, c->partials);
+	if (viscous)
+	    LAUNCH(c, k_accrete_viscous, grid, ACC_THREADS, 0, v, c->sigma, EN(c), VRA(c), VPA(c), a, pre_state(c), c->partials);
+	else
+	    LAUNCH(c, k_accrete_kley, grid, ACC_THREADS, 0, v, c->sigma, EN(c), VRA(c), VPA(c), a, c->partials);
 	LAUNCH(c, k_accrete_final, 1, 96, 0, c->partials, nblocks, d_out);
     } else {
 	CUDA_OK(cudaMemsetAsync(d_out, 0, 3 * sizeof(double), c->stream));
@@ -1657,6 +1660,16 @@ extern "C" int fargo_accrete_kley(fargo_ctx *c, double x, double y, double r_hil
 extern "C" int fargo_accrete_sinkhole(fargo_ctx *c, double x, double y, double r_hill, double facc, double frac, double out3[3])
 {
     return accrete_zones(c, x, y, r_hill, facc, 0.0, frac, 0.0, out3); // distance < 0 * r_hill never holds: one zone
+}
+
+// AccreteOntoSinglePlanetViscous (accretion.cpp:335-417): facc = dt * 3 pi * accretion efficiency; the removed fraction of a cell
+// is facc * nu(cell) * 3 / (pi d_max^2) * (1 - distance / d_max), d_max = frac * r_hill
+extern "C" int fargo_accrete_viscous(fargo_ctx *c, double x, double y, double r_hill, double facc, double frac, double out3[3])
+{
+    const double dist_max = r_hill * frac;		    // accretion.cpp:367
+    const double f_const = 3.0 / M_PI / pow(dist_max, 2); // :368
+    // one zone of radius frac * r_hill; the second pair of slots carries f_const and d_max (k_accrete_viscous)
+    return accrete_zones(c, x, y, r_hill, facc, f_const, frac, dist_max, out3, true);
 }
 
 // monitor/Quantities.dat sums (quantities.cpp:51-480 through output::write_quantities, output.cpp:326-520)

@@ -272,6 +272,69 @@ __global__ void __launch_bounds__(ACC_THREADS)
 	partials[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 3 + threadIdx.x] = t;
     }
 }
+// accretion::AccreteOntoSinglePlanetViscous (accretion.cpp:335-417, "accretion method: viscous"): one zone of radius
+// d_max = frac * RHill; a cell loses the fraction facc * nu * 3 / (pi d_max^2) * (1 - distance / d_max), nu being the VISCOSITY
+// grid the previous step stored — i.e. nu of the state before any accretion of this step.  This path stores no derived fields:
+// nu is evaluated from the kept pre-accretion rows (fargo_dev.h:PreState; accrete_zones keeps this body's band before the
+// launch, so every ring of the launch is inside it).  a.facc1 = dt * 3 pi * efficiency, a.frac1 = frac; a.facc2 = f_const,
+// a.frac2 = d_max (formed on the host with the reference's expressions).
+__global__ void __launch_bounds__(ACC_THREADS)
+    k_accrete_viscous(const DevView c, double *__restrict__ sigma, double *__restrict__ energy, const double *__restrict__ vr,
+		      const double *__restrict__ vp, const AccretionIn a, const PreState pre, double *__restrict__ partials)
+{
+    const int i = a.ring_lo + blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[3] = {0.0, 0.0, 0.0};
+    if (i < a.ring_hi && j < c.ns) {
+	const double rmed = c.g.rmed[i];
+	const double xc = rmed * c.g.cosphi[j], yc = rmed * c.g.sinphi[j];
+	const double dx = a.x - xc, dy = a.y - yc;
+	const double distance = sqrt(dx * dx + dy * dy);
+	if (distance < a.frac1 * a.r_hill) {
+	    const int jp = (j == c.ns - 1) ? 0 : j + 1;
+	    const bool kept = pre_has(pre, i);
+	    const double s_nu = kept ? AT(pre.sigma, i, j) : AT(sigma, i, j);
+	    const double e_nu = c.p.adiabatic ? (kept ? AT(pre.energy, i, j) : AT(energy, i, j)) : 0.0;
+	    const double nu = eos_nu(c, i, s_nu, e_nu);
+	    const double spread = a.facc2 * (1.0 - distance / a.frac2);
+	    const double vtcell = 0.5 * (AT(vp, i, j) + AT(vp, i, jp)) + rmed * c.b.omega_frame;
+	    const double vrcell = 0.5 * (AT(vr, i, j) + AT(vr, i + 1, j));
+	    const double vxcell = (vrcell * xc - vtcell * yc) / rmed;
+	    const double vycell = (vrcell * yc + vtcell * xc) / rmed;
+	    double s = AT(sigma, i, j);
+	    const double facc_max = 1 - a.density_floor / s;
+	    const double facc_tmp = a.facc1 * nu * spread;
+	    const double facc_ceil = stdmin(facc_tmp, facc_max);
+	    const double deltaM = facc_ceil * s * c.g.surf[i];
+	    AT(sigma, i, j) = s * (1.0 - facc_ceil);
+	    if (c.p.adiabatic)
+		AT(energy, i, j) = AT(energy, i, j) * (1.0 - facc_ceil);
+	    if (c.first_active < i && i < c.active_size) {
+		acc[1] += deltaM * vxcell;
+		acc[2] += deltaM * vycell;
+		acc[0] += deltaM;
+	    }
+	}
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+	    acc[q] += __shfl_down_sync(0xffffffffu, acc[q], o);
+    __shared__ double sh[ACC_THREADS / 32][3];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0)
+#pragma unroll
+	for (int q = 0; q < 3; ++q)
+	    sh[w][q] = acc[q];
+    __syncthreads();
+    if (threadIdx.x < 3) {
+	double t = 0.0;
+	for (int k = 0; k < ACC_THREADS / 32; ++k)
+	    t += sh[k][threadIdx.x];
+	partials[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 3 + threadIdx.x] = t;
+    }
+}
 __global__ void __launch_bounds__(96) k_accrete_final(const double *__restrict__ partials, const int nblocks, double *__restrict__ out3)
 {
     const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -60,6 +60,7 @@ int fargo_oracle_finish_step(fargo_oracle *, double);
 int fargo_oracle_accrete_kley(fargo_oracle *, double, double, double, double, double, double *);
 int fargo_oracle_monitor_quantities(fargo_oracle *, double, double *);
 int fargo_oracle_accrete_sinkhole(fargo_oracle *, double, double, double, double, double, double *);
+int fargo_oracle_accrete_viscous(fargo_oracle *, double, double, double, double, double, double *);
 int fargo_oracle_correct_vazi(fargo_oracle *, double);
 }
 typedef fargo_oracle backend_ctx;
@@ -1187,7 +1188,7 @@ struct Run {
 
     // accretion::AccreteOntoPlanets (accretion.cpp:419-452), first thing in a step (simulation.cpp:150-153, :302-303, :403-404):
     // bodies with an accretion efficiency take gas out of their Hill sphere: "accretion method: kley" (the default, two
-    // zones, :84-221) or "sinkhole" (one zone, :223-333); "viscous" is refused.  A body that feels the disk (DiskFeedback,
+    // zones, :84-221), "sinkhole" (one zone, :223-333) or "viscous" (:335-417).  A body that feels the disk (DiskFeedback,
     // or AccreteWithoutDiskFeedback) also gains the mass and momentum of that gas: update_planet (:60-82).
     void accrete(double dt)
     {
@@ -1201,14 +1202,19 @@ struct Run {
 		method = lower(cfg.nbody[k].at("accretion method"));
 	    if (method == "no" || method == "none")
 		continue;
-	    if (method != "kley" && method != "sinkhole")
-		die("accretion method '%s' is not supported by this driver (kley, sinkhole)", method);
-	    const double facc = dt * b.rec.acc / b.orbital_period * std::log(2);
+	    if (method != "kley" && method != "sinkhole" && method != "viscous")
+		die("accretion method '%s' is not supported by this driver (kley, sinkhole, viscous)", method);
+	    if (method == "viscous" && cfg.flag("ViscAccretMassflowTest", false))
+		die("%s", "ViscAccretMassflowTest is not supported by this driver");
+	    const double facc = method == "viscous" ? dt * 3.0 * M_PI * b.rec.acc // accretion.cpp:355
+						    : dt * b.rec.acc / b.orbital_period * std::log(2);
 	    const double r_hill = b.rec.dimensionless_roche_radius * b.rec.distance_to_primary;
 	    const double frac = cfg.num("MassAccretionRadius", 1.0);
 	    double taken[3];
 	    if (method == "kley")
 		CHECK(BK(accrete_kley)(ctx, b.rec.x, b.rec.y, r_hill, facc, frac, taken));
+	    else if (method == "viscous")
+		CHECK(BK(accrete_viscous)(ctx, b.rec.x, b.rec.y, r_hill, facc, frac, taken));
 	    else
 		CHECK(BK(accrete_sinkhole)(ctx, b.rec.x, b.rec.y, r_hill, facc, frac, taken));
 	    b.rec.accreted_mass += taken[0]; // monitoring only (accretion.cpp:201)

@@ -257,6 +257,11 @@ int fargo_accrete_kley(fargo_ctx *ctx, double x, double y, double r_hill, double
 /* accretion::SinkHoleSinglePlanet (accretion.cpp:223-333; "accretion method: sinkhole"): one zone — gas within frac * r_hill
  * loses the fraction facc (never below the density floor).  Same inputs and outputs as fargo_accrete_kley. */
 int fargo_accrete_sinkhole(fargo_ctx *ctx, double x, double y, double r_hill, double facc, double frac, double out3[3]);
+/* accretion::AccreteOntoSinglePlanetViscous (accretion.cpp:335-417; "accretion method: viscous"): one zone of radius
+ * d_max = frac * r_hill; a cell at distance d loses the fraction facc * nu(cell) * 3 / (pi d_max^2) * (1 - d / d_max) (never below
+ * the density floor), nu being the viscosity of the state before this step's accretion (the reference reads the VISCOSITY grid
+ * stored by the previous step).  The N-body side provides facc = dt * 3 pi * accretion efficiency (:355).  Same outputs. */
+int fargo_accrete_viscous(fargo_ctx *ctx, double x, double y, double r_hill, double facc, double frac, double out3[3]);
 
 /* Global disk quantities of monitor/Quantities.dat (output::write_quantities output.cpp:326-520 -> quantities.cpp):
  * sums over the active cells with Rmed <= radius_limit (QuantitiesRadiusLimit, default 2 Rmax), all ranks.

@@ -136,7 +136,7 @@ def test_oracle_accreted_mass_matches_reference(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["iso_accrete_20", "adia_accrete_20", "iso_sinkhole_20"])
+@pytest.mark.parametrize("name", ["iso_accrete_20", "adia_accrete_20", "iso_sinkhole_20", "adia_viscacc_20"])
 def test_gpu_accretion_vs_oracle(name):
     """One accretion call from identical states: the cells changed bit for bit, the sums within 1e-13."""
     from fargocpt_b200 import HydroContext

@@ -23,6 +23,8 @@ LONG_CASES = ["adia_planet_100", "iso_planet_100"]
 LONG_CASES += ["iso_accrete_20", "adia_accrete_20"]
 # "accretion method: sinkhole" (accretion.cpp:223-333)
 LONG_CASES += ["iso_sinkhole_20"]
+# "accretion method: viscous" (accretion.cpp:335-417): the removed fraction scales with the viscosity of the pre-accretion state
+LONG_CASES += ["adia_viscacc_20"]
 ISOTHERMAL = {"iso_star", "iso_sn_std", "ring_like", "iso_planet_100", "iso_accrete_20", "iso_sinkhole_20"}
 ADIABATIC_RTOL = 0.0
 LONG_RTOL = 0.0  # north_star allows 1e-10 after 100 steps; the glibc-exact exp makes the adiabatic runs bit-exact too

@@ -120,7 +120,7 @@ def test_host_driver_disk_feedback_cpu(tmp_path):
     assert np.allclose(got, np.array(meta["bodies"][20][1][:5]), rtol=1e-12, atol=1e-13)
 
 
-@pytest.mark.parametrize("name", ["iso_accrete_20", "adia_accrete_20"])
+@pytest.mark.parametrize("name", ["iso_accrete_20", "adia_accrete_20", "adia_viscacc_20"])
 def test_host_driver_accretion_cpu(name, tmp_path):
     """A planet that accretes (accretion.cpp:84-221) without feeling the disk: the driver takes gas out of its Hill sphere
     first thing in every step.  Its orbital period is the one of the restart record (the reference refreshes it every step),
@@ -142,7 +142,7 @@ def test_host_driver_accretion_cpu(name, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,until,exact", [("iso_accrete_20", 20, False), ("iso_star", 6, True), ("adia_star", 6, True), ("adia_leapfrog", 6, True), ("adia_planet_100", 100, False),
+@pytest.mark.parametrize("name,until,exact", [("iso_accrete_20", 20, False), ("adia_viscacc_20", 20, False), ("iso_star", 6, True), ("adia_star", 6, True), ("adia_leapfrog", 6, True), ("adia_planet_100", 100, False),
                                               ("iso_feedback_20", 20, False)])
 def test_host_driver_on_gpu(name, until, exact, tmp_path):
     exe = os.path.join(ROOT, "host", "fargocpt_b200")
