@@ -190,9 +190,9 @@ def init_state(ctx, cfg, radii, fields=None):
     orbit = synthetic.PlanetOrbit(cfg)
     ctx.set_bodies(orbit.bodies(0.0))
     ctx.set_time(0.0)
-    ctx.init_derived()
     ctx.stage("boundary", 0.0, 0)
-    ctx.copy_initial_values()
+    ctx.copy_initial_values()  # damping / beta-cooling reference state: before init_derived evaluates Q- against it for the first CFL
+    ctx.init_derived()
     return orbit, fields
 
 

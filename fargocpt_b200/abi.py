@@ -24,7 +24,7 @@ LIMITER = {"vanleer": 0, "mc": 1}
 SPACING = {"logarithmic": 0, "arithmetic": 1, "exponential": 2, "custom": 3}
 BC = {"none": 0, "zerogradient": 1, "outflow": 2, "reflecting": 3, "keplerian": 4, "reference": 5}
 DAMP = {"none": 0, "initial": 1, "reference": 1, "zero": 2, "mean": 3}
-BETA_REF = {"none": 0, "zero": 0, "reference": 1, "model": 2, "floor": 4}
+BETA_REF = {"zero": 0, "reference": 1, "diskmodel": 2, "floor": 4}  # parameters.cpp:451-463
 
 
 class FargoParams(C.Structure):

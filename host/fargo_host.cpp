@@ -175,8 +175,12 @@ struct Config {
 	std::string unit;
 	if (!(is >> x))
 	    die("not a number: %s", v);
-	if ((is >> unit) && unit_in_cgs > 0.0)
-	    return x / unit_in_cgs;
+	if (is >> unit) {
+	    if (unit_in_cgs > 0.0)
+		return x / unit_in_cgs;
+	    // a value with a unit on a key this driver has no conversion for must not silently lose the unit
+	    die("value '%s' carries a unit, and this driver converts no units for that key", v);
+	}
 	return x;
     }
     double num(const std::string &k, double def, double unit_in_cgs = 0.0) const
@@ -378,7 +382,7 @@ static fargo_params make_params(const Config &c, const CodeConstants &k, int nra
     p.cooling_beta_value = c.num("CoolingBeta", 1.0);
     p.cooling_beta_ramp_up = c.num("CoolingBetaRampUp", 0.0);
     p.cooling_beta_reference = enum_of(c.str("CoolingBetaReference", "zero"),
-				       {{"zero", 0}, {"none", 0}, {"reference", 1}, {"model", 2}, {"floor", 4}}, "CoolingBetaReference");
+				       {{"zero", 0}, {"reference", 1}, {"diskmodel", 2}, {"floor", 4}}, "CoolingBetaReference"); // parameters.cpp:451-463
     p.body_force_from_potential = c.flag("BodyForceFromPotential", true);
     p.thickness_smoothing = c.num("ThicknessSmoothing", 0.6);
     p.imposed_disk_drift = c.num("ImposedDiskDrift", 0.0);
@@ -742,6 +746,12 @@ struct Run {
 	config_path = exists(sd + "/config.yml") ? sd + "/config.yml" : dir + "/parameters/cfg.yml";
 	cfg.load(config_path);
 	consts.load(dir);
+	{ // the snapshot's config.yml is the setup as the user wrote it: the same unit conversion `start` does
+	    finit::UnitSystem U;
+	    U.set_baseunits(cfg.str("l0", "1.0"), cfg.str("m0", "1.0"));
+	    U.calculate();
+	    convert_units(U);
+	}
 	{ // dimensions.dat: RMIN RMAX PHIMIN PHIMAX NRAD NAZ NGHRAD NGHAZ Radial_spacing (init.cpp:227-247)
 	    std::ifstream f(dir + "/dimensions.dat");
 	    if (!f)
@@ -783,6 +793,7 @@ struct Run {
 	if (bodies.size() > FARGO_MAX_BODIES)
 	    die("too many bodies in %s", sd);
 	read_hydro_frame_center();
+	refresh_orbital_parameters(); // period / omega from the interior centre-of-mass mass, not from a primary of mass 1
 	params.hydro_center_mass = hydro_frame_center_mass(); // update_global_hydro_frame_center_mass
 	disk_feedback = cfg.flag("DiskFeedback", true); // parameters.cpp:755
 	indirect_mode = (int)cfg.num("IndirectTermMode", 0);
@@ -851,6 +862,21 @@ struct Run {
 #endif
     }
 
+    // Values that may carry units become plain code-unit numbers (config::Config::get<double>(key, default, unit): Interpret.cpp,
+    // parameters.cpp).  ONE place, used by `start` and by `restart` (whose config.yml is a verbatim copy of the setup).
+    void convert_units(const finit::UnitSystem &U)
+    {
+	const std::pair<const char *, char> dims[] = {
+	    {"Rmin", 'L'}, {"Rmax", 'L'}, {"Sigma0", 'S'}, {"MonitorTimestep", 'T'}, {"FirstDT", 'T'}, {"DampingTimeRadiusOuter", 'L'},
+	    {"ConstantViscosity", 'V'} /* L0^2/T0, Interpret.cpp:586 */, {"CoolingBetaRampUp", 'T'} /* parameters.cpp:445 */,
+	    {"OmegaFrame", 'F'} /* 1/T0, Interpret.cpp:323 */, {"QuantitiesRadiusLimit", 'L'}};
+	if (!cfg.has("Sigma0"))
+	    cfg.kv["sigma0"] = "173 g/cm2"; // parameters.cpp:625
+	for (auto &k : dims)
+	    if (cfg.has(k.first))
+		cfg.kv[lower(k.first)] = finit::UnitSystem::num17(U.in_code_units(cfg.str(k.first, ""), k.second));
+    }
+
     // main.cpp:48-164 up to the first output, for `start`: units and constants, grid, bodies, init_physics (init.cpp:255-345)
     std::string config_path;
     bool started_fresh = false;
@@ -892,14 +918,7 @@ struct Run {
 	const int shock_tube = (int)cfg.num("ShockTube", 0);
 	if (shock_tube != 0 && shock_tube != 1)
 	    die("ShockTube: %s is not supported by this driver (1: the ideal-gas tube)", cfg.str("ShockTube", ""));
-	// values that may carry units become plain code-unit numbers (config::Config::get<double>(key, unit))
-	const std::pair<const char *, char> dims[] = {{"Rmin", 'L'}, {"Rmax", 'L'}, {"Sigma0", 'S'}, {"MonitorTimestep", 'T'},
-						       {"FirstDT", 'T'}, {"DampingTimeRadiusOuter", 'L'}};
-	if (!cfg.has("Sigma0"))
-	    cfg.kv["sigma0"] = "173 g/cm2"; // parameters.cpp:625
-	for (auto &k : dims)
-	    if (cfg.has(k.first))
-		cfg.kv[lower(k.first)] = finit::UnitSystem::num17(U.in_code_units(cfg.str(k.first, ""), k.second));
+	convert_units(U);
 	if (!cfg.has("Rmin") || !cfg.has("Rmax"))
 	    die("%s: Rmin and Rmax are required", cfgfile);
 	nrad = (int)cfg.num("Nrad", 64), naz = (int)cfg.num("Naz", 64);
@@ -1574,7 +1593,8 @@ struct Run {
 	}
 	CHECK(BK(stage_boundary)(ctx, 0.0, 0));
 	init_corotation();     // sim::init (simulation.cpp:463-464)
-	calculate_time_step(); // sim::init (simulation.cpp:467)
+	if (started_fresh || n_iter == 0) // sim::init (simulation.cpp:465-467): not when restarting — the growth limiter
+	    calculate_time_step();	  // (CFLmaxVar * last_dt) must be applied once per step, not twice before the first one
 	long steps = 0;
 	FILE *tl = fopen((outdir + "/monitor/timestepLogging.dat").c_str(), "a");
 	while (n_snapshot < until_snapshot) {

@@ -48,6 +48,10 @@ inline const std::map<std::string, UnitDef> &unit_table()
 	{"earthMass", {5.97217e24, 'M'}},    {"kg", {1.0, 'M'}},		 {"g", {0.001, 'M'}},
 	{"s", {1.0, 'T'}},		     {"K", {1.0, 'K'}},			 {"g/cm2", {0.001 / (0.01 * 0.01), 'S'}},
 	{"g/cm^2", {0.001 / (0.01 * 0.01), 'S'}},
+	// kinematic viscosity (dim 'V' = L^2 / T) and frequency (dim 'F' = 1 / T)
+	{"cm2/s", {0.01 * 0.01, 'V'}},	     {"cm^2/s", {0.01 * 0.01, 'V'}},	 {"m2/s", {1.0, 'V'}},
+	{"m^2/s", {1.0, 'V'}},		     {"1/s", {1.0, 'F'}},		 {"s^-1", {1.0, 'F'}},
+	{"Hz", {1.0, 'F'}},
     };
     return t;
 }
@@ -178,7 +182,8 @@ struct UnitSystem {
 	    refuse("unit '" + u + "' is not known to this driver (value '" + v + "')");
 	if (t.at(u).dim != dim)
 	    refuse("unit '" + u + "' has the wrong dimension in '" + v + "'");
-	const double target = dim == 'L' ? L0 : dim == 'M' ? M0 : dim == 'T' ? T0 : dim == 'K' ? Temp0 : M0 / (L0 * L0);
+	const double target = dim == 'L' ? L0 : dim == 'M' ? M0 : dim == 'T' ? T0 : dim == 'K' ? Temp0 : dim == 'V' ? L0 * L0 / T0 :
+			      dim == 'F' ? 1.0 / T0 : M0 / (L0 * L0);
 	return x * t.at(u).si / target;
     }
 

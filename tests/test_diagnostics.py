@@ -209,16 +209,22 @@ def test_gpu_reductions_on_grids_with_few_sectors(naz, physics):
             ctx.upload(fid, fields[key])
         ctx.set_bodies(orbit.bodies(0.0))
         ctx.set_time(0.0)
+        ctx.copy_initial_values()  # the beta-cooling reference state Q- is evaluated against
         ctx.init_derived()
         force = [ctx.disk_on_body_accel(b) for b in (0, 1)]
         quant = ctx.monitor_quantities()
         acc = ctx.accrete_kley(1.0, 0.0, 0.3, 0.5)
         res[name] = (force, quant, acc, ctx.download(abi.SIGMA))
     g, c = res["gpu"], res["cpu"]
+    # the pull on the star at the origin is a sum that cancels to rounding: compare on the scale of the terms (the planet's pull)
+    fscale = max(np.abs(c[0][1]).max(), 1e-300)
     for a, b in zip(g[0], c[0]):
-        assert np.allclose(a, b, rtol=1e-12, atol=1e-13 * max(np.abs(b).max(), 1e-300)), (a, b)
+        assert np.allclose(a, b, rtol=1e-12, atol=1e-13 * fscale), (a, b)
     for q in abi.MONITOR_QUANTITIES:
-        assert abs(g[1][q] - c[1][q]) <= 1e-13 * max(abs(c[1][q]), 1e-300), (q, g[1][q], c[1][q])
+        scale = abs(c[1][q])
+        if q == "luminosity":  # sum of surf * Q-, Q- ~ (e - e_ref) = rounding residue at t = 0: judge it on the scale of Q+
+            scale = max(scale, abs(c[1]["viscous_dissipation"]))
+        assert np.isfinite(c[1][q]) and abs(g[1][q] - c[1][q]) <= 1e-13 * max(scale, 1e-300), (q, g[1][q], c[1][q])
     for a, b in zip(g[2], c[2]):
         assert abs(a - b) <= 1e-13 * max(abs(b), 1e-300), (g[2], c[2])
     assert c[2][0] > 0.0  # the zone covers cells: something was accreted

@@ -217,6 +217,16 @@ def test_host_start_output_restarts_cpu(tmp_path):
     check(meta, z, out2, 6, exact=True)
 
 
+def test_host_refuses_a_unit_it_would_have_to_drop(tmp_path):
+    """A value with a unit on a key this driver has no conversion for must not silently lose the unit (Config::number)."""
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "tests", "golden", "minimal_defaults_setup.yml")))
+    cfg["DampingInnerLimit"] = "1.1 au"
+    yml = str(tmp_path / "setup.yml")
+    yaml.safe_dump(cfg, open(yml, "w"), sort_keys=False)
+    res = subprocess.run([_oracle_exe(), "start", yml, "--out", str(tmp_path / "out"), "--until", "0"], capture_output=True, text=True)
+    assert res.returncode != 0 and "carries a unit" in res.stderr, res.stderr
+
+
 def test_host_start_refuses_what_it_does_not_cover(tmp_path):
     cfg = yaml.safe_load(open(os.path.join(ROOT, "tests", "golden", "iso_star.yml")))
     cfg["SigmaCondition"] = "1D"  # needs GSL splines in the reference; not restated
@@ -613,7 +623,15 @@ def test_host_writes_derived_fields_on_request_cpu(tmp_path):
                                          # restart position as the frame's reference position, frame_of_reference.cpp:19-28, so its first
                                          # step after a restart sees OmegaFrame = 0) — the driver reproduces the REFERENCE'S RESTART, quirk included
                                          (os.path.join(ROOT, "tests", "golden", "corotating_setup.yml"), ["--dt", "4e-3", "--vs-reference-restart"]),
-                                         ("/root/reference/test/cold_disk_planet/setup.yml", ["--vs-reference-restart"])])
+                                         ("/root/reference/test/cold_disk_planet/setup.yml", ["--vs-reference-restart"]),
+                                         # values with units in the snapshot's config.yml (a verbatim copy of the setup): `restart` runs the same
+                                         # unit conversion as `start` (l0 = 30 au: Rmin = 0.4, Rmax = 2)
+                                         ("/root/reference/test/cold_disk_planet/setup.yml", ["Rmin=12 au", "Rmax=60 au"]),
+                                         # restarted while dt is still limited by CFLmaxVar * last_dt (default FirstDT 1e-9): the reference skips
+                                         # sim::init's CalculateTimeStep when restarting (simulation.cpp:465), so the limiter acts once per step
+                                         (os.path.join(ROOT, "tests", "golden", "minimal_defaults_setup.yml"), ["FirstDT=1e-9", "--vs-reference-restart"]),
+                                         # a unit on a key whose dimension is L0^2 / T0 (Interpret.cpp:586)
+                                         ("/root/reference/test/cold_disk_planet/setup.yml", ["ConstantViscosity=1e15 cm2/s", "ViscousAlpha=0"])])
 def test_host_restarts_from_a_directory_the_reference_wrote(setup, extra):
     """`restart 2 <dir>` on an output directory written by the unmodified reference itself (its real constants.yml, units.yml,
     dimensions.dat, 256-byte nbody records, misc.bin, snapshots/reference): snapshots 3 and 4 against the reference's own."""
