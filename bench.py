@@ -90,40 +90,64 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def workload_config(args):
+def global_nrad(args, world):
+    """Strong scaling: the global grid is fixed.  Weak scaling: 1024 * g x Naz, a fixed slab per GPU."""
+    return args.nrad if args.scaling == "strong" else args.weak_nrad_per_gpu * world
+
+
+def workload_config(args, nrad=None):
     from fargocpt_b200 import synthetic
-    return synthetic.make_config(args.physics, args.nrad, args.naz)
+    # FirstDT: the reference evaluates Q- for its first CFL before the beta-cooling reference state exists (NaN, SourceEuler.cpp:284),
+    # so its first step is CFLmaxVar^3 * FirstDT whatever the CFL says; a small FirstDT keeps both arms' disks physical
+    return synthetic.make_config(args.physics, nrad or args.nrad, args.naz, FirstDT=1.0e-5)
 
 
 # ------------------------------------------------------------------------------------------------------
 def run_reference(args):
-    """Times the UNMODIFIED reference (oracle/_ref/fargocpt_exe_fast, the reference's own -Ofast flags, OpenMP over
-    all host cores) on a bounded sample of the workload: same physics, same Naz, same dr/r, fewer rings."""
+    """Times the UNMODIFIED reference (oracle/_ref/fargocpt_exe_fast: the reference's own sources and -Ofast flags, OpenMP over
+    all host cores; np = 1 because the image has no MPI) through its stock `start` code path, on the bench workload itself when
+    the host has the memory for it (the reference allocates 76 grids: 82 GB at 8192 x 16384), else on an annulus of the same grid
+    (same dr/r, same physics, fewer rings).  Per-step wall times are the reference's own: `LogAfterSteps: 1` makes
+    logging::print_runtime_info (logging.cpp:204-262) print `timeperstep` after every hydro step; the first W are warm-up."""
     import yaml
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = max(args.gpus, 1)
+    nrad_g = global_nrad(args, world)
     exe = os.path.join(ROOT, "oracle", "_ref", "fargocpt_exe_fast")
     kind = "reference"
-    cfg = workload_config(args)
-    nrad_s = min(args.ref_nrad, args.nrad)
-    # keep the logarithmic cell aspect ratio: same dr/r, annulus centred on the planet orbit
-    growth = math.pow(float(cfg["Rmax"]) / float(cfg["Rmin"]), 1.0 / (args.nrad - 2.0))
-    half = growth ** ((nrad_s - 2) / 2.0)
-    rmin_s, rmax_s = 1.0 / half, half
+    cfg = workload_config(args, nrad_g)
     cores = os.cpu_count() or 1
     steps, warm = max(args.steps, 1), max(args.warmup, 0)
+    nrad_s = args.ref_nrad
+    if nrad_s <= 0:  # auto: the whole grid if it fits in RAM (0.62 kB per cell: 76 grids + slack), else 1/8 of the rings
+        try:
+            avail = int(re.search(r"MemAvailable:\s+(\d+)", open("/proc/meminfo").read()).group(1)) * 1024
+        except Exception:  # noqa: BLE001
+            avail = 0
+        nrad_s = nrad_g if nrad_g * args.naz * 8 * 80 < 0.8 * avail else max(nrad_g // 8, 64)
+    nrad_s = min(nrad_s, nrad_g)
+    # keep the logarithmic cell aspect ratio: same dr/r, annulus centred on the planet orbit
+    if nrad_s == nrad_g:
+        rmin_s, rmax_s = float(cfg["Rmin"]), float(cfg["Rmax"])
+    else:
+        growth = math.pow(float(cfg["Rmax"]) / float(cfg["Rmin"]), 1.0 / (nrad_g - 2.0))
+        half = growth ** ((nrad_s - 2) / 2.0)
+        rmin_s, rmax_s = 1.0 / half, half
     if not os.path.exists(exe):
         # fall back to the oracle port (the one other place bench.py may execute oracle/)
-        val, sample = time_oracle_port(args, nrad_s, rmin_s, rmax_s, steps + warm)
+        val, sample = time_oracle_port(args, min(nrad_s, 256), rmin_s, rmax_s, steps + warm)
+        nrad_s = min(nrad_s, 256)
         kind = "port"
+        ms = nrad_s * args.naz / val * 1e3
     else:
         ycfg = {
-            "DiskFeedback": "no", "MonitorTimestep": 1.0e9, "Nmonitor": 1, "Nsnapshots": 1, "FirstDT": cfg["FirstDT"],
+            "DiskFeedback": "no", "MonitorTimestep": 1.0e9, "Nmonitor": 1, "Nsnapshots": 1,
             "l0": "30 au", "m0": "1 solMass", "SelfGravity": "No", "RadiativeDiffusion": "No", "Disk": "yes", "Frame": "F",
             "cps": -1, "DoWrite1DFiles": "No", "WriteAtEveryTimestep": "No", "RandomSigma": "No", "IntegrateParticles": "no",
-            "HydroFrameCenter": "primary", "LogAfterSteps": 0, "LogAfterRealSeconds": 3600, "IndirectTermMode": 0,
-            "ShockTube": 0,
+            "HydroFrameCenter": "primary", "LogAfterSteps": 1, "LogAfterRealSeconds": 36000, "IndirectTermMode": 0,
+            "ShockTube": 0, "WriteDensity": "no", "WriteVelocity": "no", "WriteEnergy": "no",  # no field output inside the run
         }
         for k, v in cfg.items():
             if k not in ("planet_mass",):
@@ -140,32 +164,35 @@ def run_reference(args):
         ypath = os.path.join(tmp, "cfg.yml")
         yaml.safe_dump(ycfg, open(ypath, "w"), sort_keys=False)
         env = dict(os.environ, OMP_NUM_THREADS=str(cores), OMP_PROC_BIND="close", OMP_PLACES="cores")
-
-        def run(nsteps):
-            t0 = time.time()
-            res = subprocess.run([exe, "-N", str(nsteps), "start", ypath], cwd=tmp, env=env, capture_output=True, text=True)
-            m = re.search(r"Total Hydrosteps (\d+).*?Walltime ([0-9.eE+-]+) seconds", res.stdout)
-            if res.returncode != 0 or not m:
-                raise RuntimeError("reference run failed: " + res.stdout[-800:] + res.stderr[-800:])
-            return int(m.group(1)), float(m.group(2)), time.time() - t0
-        # the binary has no warm-up notion: time W steps and W+K steps and difference them
-        nw, tw, _ = run(warm) if warm > 0 else (0, 0.0, 0.0)
-        nt, tt, _ = run(warm + steps)
-        sec = max(tt - tw, 1e-9)
-        val = nrad_s * args.naz * (nt - nw) / sec
-        sample = (f"unmodified reference -Ofast -march=x86-64-v3, np=1 (no MPI in image) x nt={cores}, {nrad_s}x{args.naz} annulus "
-                  f"r=[{rmin_s:.4f},{rmax_s:.4f}] of the {args.nrad}x{args.naz} grid (same dr/r, same physics), {nt - nw} timed steps")
-        ms = sec / (nt - nw) * 1e3
-    if kind == "port":
-        ms = nrad_s * args.naz / val * 1e3
+        res = subprocess.run([exe, "-N", str(warm + steps), "start", ypath], cwd=tmp, env=env, capture_output=True, text=True)
+        per_step = [float(x) for x in re.findall(r"hydrostep \d+, .*?timeperstep ([0-9.eE+-]+) ms", res.stdout)]
+        if res.returncode != 0 or len(per_step) < warm + steps:
+            raise RuntimeError("reference run failed: " + res.stdout[-800:] + res.stderr[-800:])
+        timed = per_step[warm:warm + steps]
+        ms = sum(timed) / len(timed)
+        val = nrad_s * args.naz / (ms * 1e-3)
+        what = ("the whole grid" if nrad_s == nrad_g else
+                f"annulus r=[{rmin_s:.4f},{rmax_s:.4f}] of the {nrad_g}x{args.naz} grid (same dr/r, same physics)")
+        sample = (f"unmodified reference, -Ofast -march=x86-64-v3 (oracle/Makefile.ref), np=1 (no MPI in image) x nt={cores}, "
+                  f"{nrad_s}x{args.naz}: {what}; {len(timed)} timed hydro steps after {warm} warm-up steps, per-step wall time from the "
+                  f"reference's own log (LogAfterSteps: 1)")
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.physics} {args.nrad}x{args.naz} (BASELINE configs[4])", "sample_nrad": nrad_s},
+        "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args, world), "cells": nrad_g * args.naz, "sample_nrad": nrad_s, "same_grid": nrad_s == nrad_g},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def workload_name(args, world):
+    nrad_g = global_nrad(args, world)
+    which = "BASELINE configs[4]" if (args.physics, nrad_g, args.naz) == ("adiabatic_planet", 8192, 16384) else "BASELINE configs[4] physics"
+    return (f"{args.physics} {nrad_g}x{args.naz} ({which}), " +
+            ("fixed global grid" if args.scaling == "strong" else f"{args.weak_nrad_per_gpu} rings per GPU (weak scaling)"))
 
 
 def time_oracle_port(args, nrad_s, rmin_s, rmax_s, nsteps):
@@ -234,11 +261,12 @@ def run_gpu(args):
         dist.broadcast(buf, 0)
         uid = bytes(buf.cpu().numpy().tobytes())
 
-    cfg = workload_config(args)
+    nrad_g = global_nrad(args, world)
+    cfg = workload_config(args, nrad_g)
     radii = synthetic.radii_from_config(cfg)
     params = synthetic.params_from_config(cfg)
     ctx = HydroContext(params, radii, rank=rank, nranks=world, unique_id=uid, device=local)
-    ncell = args.nrad * args.naz
+    ncell = nrad_g * args.naz
 
     # host copy of the initial state in PINNED memory (e2e leg uploads from it)
     fields = synthetic.disk_fields(cfg, radii)
@@ -292,6 +320,12 @@ def run_gpu(args):
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
     value = ncell * args.steps / (ms * 1e-3)
+    # ---- checksum of the state after the W + K + P device-resident steps -------------------------------
+    # The result of the reference does not depend on the number of ranks (constants.h:17) and neither does ours, bit for bit:
+    # every N of a strong-scaling sweep must print the SAME checksum (same grid, same start, same number of steps) — the
+    # driver-visible proof that the ghost-ring exchange (CommunicateBoundaries, commbound.cpp:98-182) delivers the right rings.
+    checksum = state_checksum(ctx, world, torch, dist if world > 1 else None)
+    steps_done = max(args.warmup, 3) + args.steps + prof_steps
 
     # ---- end-to-end leg: host buffers in, host buffers out -------------------------------------------
     # A restart + E2E_INTERVALS snapshot intervals as a user of the C ABI runs them: upload the four state fields from
@@ -354,9 +388,12 @@ def run_gpu(args):
     step_roof = B_ALG[args.physics] * value / world / 1e9  # whole-step algorithmic GB/s per GPU
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"{args.physics} {args.nrad}x{args.naz} (BASELINE configs[4]), radial slabs over {world} GPU(s)",
+        "checksum": {"sha256": checksum, "after_steps": steps_done,
+                     "of": "Sigma, v_rad, v_azi, e of the whole grid: per-ring 64-bit sums of the bit patterns (plain and column-weighted), "
+                           "owned rings of every rank stitched in ring order; identical for every N of a strong-scaling sweep"},
+        "config": {"workload": workload_name(args, world) + f", radial slabs over {world} GPU(s)",
                    "cells": ncell, "l2": "inputs larger than L2 (1.07 GB per field)" if ncell * 8 > 126e6 else "inputs fit L2",
                    "b_alg_bytes_per_cell_update": B_ALG[args.physics],
                    "halo_exchange": {0: "none (1 GPU)", 1: "ncclSend/ncclRecv after Transport",
@@ -376,12 +413,32 @@ def run_gpu(args):
     print(json.dumps(line))
 
 
+def state_checksum(ctx, world, torch, dist):
+    """SHA-256 over per-ring hashes of the four state fields (partition-independent: a rank contributes the rings it owns)."""
+    import hashlib
+    from fargocpt_b200 import abi
+    parts = []
+    for fid in (abi.SIGMA, abi.VRAD, abi.VAZI, abi.ENERGY):
+        a = ctx.download(fid)  # global shape; only the rings this rank owns are written, the rest stays 0
+        bits = a.view(np.uint64)
+        w = (2 * np.arange(bits.shape[1], dtype=np.uint64) + 1)[None, :]
+        h = np.stack([bits.sum(axis=1, dtype=np.uint64), (bits * w).sum(axis=1, dtype=np.uint64)], axis=1)  # wraps mod 2^64
+        del a, bits
+        if dist is not None:
+            t = torch.from_numpy(h.view(np.int64)).cuda()
+            dist.all_reduce(t)  # owned ring sets are disjoint, the other rows are 0: the (wrapping) sum stitches them
+            h = t.cpu().numpy().view(np.uint64)
+        parts.append(np.ascontiguousarray(h))
+    return hashlib.sha256(b"".join(p.tobytes() for p in parts)).hexdigest()
+
+
 def cpu_baseline(args):
-    """The reference arm on a bounded sample, run in a subprocess so its threads do not disturb this process."""
+    """The reference arm on a bounded sample (256 rings of the same grid: 10-30 s of CPU work), run in a subprocess so its
+    threads do not disturb this process."""
     try:
         res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "6", "--warmup", "2",
                               "--physics", args.physics, "--nrad", str(args.nrad), "--naz", str(args.naz),
-                              "--ref-nrad", str(args.ref_nrad)], capture_output=True, text=True, timeout=900)
+                              "--ref-nrad", str(args.cpu_sample_nrad)], capture_output=True, text=True, timeout=900)
         for ln in res.stdout.splitlines()[::-1]:
             if ln.startswith("{"):
                 return json.loads(ln)["cpu_baseline"]
@@ -399,7 +456,12 @@ def main():
     ap.add_argument("--physics", default="adiabatic_planet", choices=list(B_ALG))
     ap.add_argument("--nrad", type=int, default=8192)
     ap.add_argument("--naz", type=int, default=16384)
-    ap.add_argument("--ref-nrad", type=int, default=256, help="rings of the CPU sample annulus")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: the global grid --nrad x --naz is split over the GPUs; weak: --weak-nrad-per-gpu rings per GPU")
+    ap.add_argument("--weak-nrad-per-gpu", type=int, default=1024)
+    ap.add_argument("--ref-nrad", type=int, default=0,
+                    help="--impl reference: rings of the grid the reference runs (0 = the whole grid if the host has the RAM, else 1/8)")
+    ap.add_argument("--cpu-sample-nrad", type=int, default=256, help="rings of the annulus of the cpu_baseline leg of the GPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

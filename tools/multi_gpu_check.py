@@ -29,9 +29,9 @@ def run_slab(ctx, cfg, radii, fields, nsteps, synthetic, abi):
     orbit = synthetic.PlanetOrbit(cfg)
     ctx.set_bodies(orbit.bodies(0.0))
     ctx.set_time(0.0)
-    ctx.init_derived()
     ctx.stage("boundary", 0.0, 0)
-    ctx.copy_initial_values()
+    ctx.copy_initial_values()  # before init_derived: Q- of the first CFL is evaluated against the beta-cooling reference state
+    ctx.init_derived()
     last_dt, t, dts = float(cfg["FirstDT"]), 0.0, []
     for _ in range(nsteps):
         dt = ctx.cfl(last_dt)
