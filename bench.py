@@ -410,6 +410,8 @@ def run_gpu(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)
+    if world == 1 and not args.no_tolerance_mode and args.scaling == "strong":
+        line["tolerance_mode"] = tolerance_mode(args)
     print(json.dumps(line))
 
 
@@ -430,6 +432,96 @@ def state_checksum(ctx, world, torch, dist):
             h = t.cpu().numpy().view(np.uint64)
         parts.append(np.ascontiguousarray(h))
     return hashlib.sha256(b"".join(p.tobytes() for p in parts)).hexdigest()
+
+
+TOL_LIB = os.path.join(ROOT, "fargocpt_b200", "csrc", "libfargo_b200_tol.so")
+
+
+def run_leg(args):
+    """Helper legs of the tolerance-mode report, each in its own process (a process loads ONE build of the library):
+    --leg time: ms/step of K device-resident steps after W warm-up steps;  --leg dump: N steps from the synthetic start, final
+    fields + dt sequence + Nshift of every step written to --dump."""
+    import torch
+    from fargocpt_b200 import HydroContext, abi, synthetic
+    torch.cuda.set_device(0)
+    cfg = workload_config(args)
+    radii = synthetic.radii_from_config(cfg)
+    params = synthetic.params_from_config(cfg)
+    ctx = HydroContext(params, radii)
+    orbit, _ = init_state(ctx, cfg, radii)
+    state = {"last_dt": float(cfg["FirstDT"]), "t": 0.0}
+    dts, shifts = [], []
+
+    def one_step(record=False):
+        dt = ctx.cfl(state["last_dt"])
+        state["last_dt"] = dt
+        ctx.set_bodies(orbit.bodies(state["t"], dt))
+        ctx.set_time(state["t"])
+        ctx.step(dt)
+        state["t"] += dt
+        if record:
+            dts.append(dt)
+            shifts.append(ctx.nshift().copy())
+    if args.leg == "time":
+        for _ in range(max(args.warmup, 3)):
+            one_step()
+        ctx.sync()
+        ctx.event_record(0)
+        for _ in range(args.steps):
+            one_step()
+        ctx.event_record(1)
+        ms = ctx.event_elapsed_ms(0, 1)
+        print(json.dumps({"leg": "time", "lib": os.path.basename(abi.LIB_PATH), "ms_per_step": ms / args.steps}))
+    else:
+        for _ in range(args.steps):
+            one_step(record=True)
+        np.savez(args.dump, dts=np.array(dts), shifts=np.array(shifts), Sigma=ctx.download(abi.SIGMA), vrad=ctx.download(abi.VRAD),
+                 vazi=ctx.download(abi.VAZI), energy=ctx.download(abi.ENERGY))
+        print(json.dumps({"leg": "dump", "lib": os.path.basename(abi.LIB_PATH), "steps": args.steps}))
+
+
+def tolerance_mode(args):
+    """The tolerance build (fargo_math.h, -DFARGO_TOL: quotients without the final correction step, no validity keys, fused
+    multiply-adds in the transport kernels) timed on the bench workload, and its measured deviation from the exact build (which is
+    bit-identical to the reference) after 100 CFL-limited steps on a 1024 x 2048 grid of the same physics.  A second number,
+    never `value`."""
+    if not os.path.exists(TOL_LIB):
+        return {"error": "libfargo_b200_tol.so not built"}
+    me = [sys.executable, os.path.abspath(__file__), "--physics", args.physics]
+
+    def leg(lib, extra):
+        env = dict(os.environ)
+        if lib:
+            env["FARGO_B200_LIB"] = lib
+        else:
+            env.pop("FARGO_B200_LIB", None)
+        res = subprocess.run(me + extra, env=env, capture_output=True, text=True, timeout=900)
+        for ln in res.stdout.splitlines()[::-1]:
+            if ln.startswith("{"):
+                return json.loads(ln)
+        raise RuntimeError((res.stdout + res.stderr)[-600:])
+    try:
+        t = leg(TOL_LIB, ["--leg", "time", "--nrad", str(args.nrad), "--naz", str(args.naz), "--steps", str(args.steps),
+                          "--warmup", str(args.warmup)])
+        tmp = tempfile.mkdtemp(prefix="bench_tol_")
+        nsteps, nr, na = 100, 1024, 2048
+        for name, lib in (("exact", None), ("tol", TOL_LIB)):
+            leg(lib, ["--leg", "dump", "--nrad", str(nr), "--naz", str(na), "--steps", str(nsteps), "--dump", os.path.join(tmp, name + ".npz")])
+        a, b = np.load(os.path.join(tmp, "exact.npz")), np.load(os.path.join(tmp, "tol.npz"))
+        dev = {f: float(np.abs(a[f] - b[f]).max() / np.abs(a[f]).max()) for f in ("Sigma", "vrad", "vazi", "energy")}
+        dev["vrad_relative_to_sound_speed_scale"] = float(np.abs(a["vrad"] - b["vrad"]).max() / np.sqrt((0.4 * a["energy"][1:-1] / a["Sigma"][1:-1] * 1.4).max()))
+        out = {"ms_per_step": t["ms_per_step"], "value": args.nrad * args.naz / (t["ms_per_step"] * 1e-3), "unit": UNIT,
+               "deviation_from_exact_after_steps": nsteps, "deviation_grid": [nr, na],
+               "max_abs_deviation_over_field_max": dev,
+               "dt_step0_bit_equal": bool(a["dts"][0] == b["dts"][0]),
+               "dt_max_rel_deviation": float(np.abs(a["dts"] / b["dts"] - 1.0).max()),
+               "nshift_steps_equal": int((a["shifts"] == b["shifts"]).all(axis=1).sum()), "nshift_steps": nsteps,
+               "what": "second build of the library (-DFARGO_TOL), see fargocpt_b200/csrc/fargo_math.h; the exact build stays the default and the parity gate"}
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
+        return out
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[-600:]}
 
 
 def cpu_baseline(args):
@@ -463,8 +555,13 @@ def main():
                     help="--impl reference: rings of the grid the reference runs (0 = the whole grid if the host has the RAM, else 1/8)")
     ap.add_argument("--cpu-sample-nrad", type=int, default=256, help="rings of the annulus of the cpu_baseline leg of the GPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tolerance-mode", action="store_true")
+    ap.add_argument("--leg", default=None, choices=["time", "dump"], help="internal: helper legs of the tolerance-mode report")
+    ap.add_argument("--dump", default=None)
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.leg:
+        run_leg(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)

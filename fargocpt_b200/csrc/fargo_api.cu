@@ -126,6 +126,12 @@ struct fargo_ctx {
     double *pot, *qr, *qphi, *nu, *divv, *trr, *tpp, *trp, *nusig, *nusig_rp, *cf_r, *cf_phi;
     double *t_sigma, *t_rmp, *t_rmm, *t_amp, *t_amm, *t_e; // after the radial sweep
     double *vmean, *vconst, *expf_s, *expf_v, *d_dt, *scratch, *force4;
+    // damping zones folded into the azimuthal transport kernel's epilogue (fargo_step of an Euler step; AzSegs::dmask)
+    int *d_dmask = nullptr;	     // per ring: 2 bits per field
+    std::vector<int> h_dmask;	     // what d_dmask holds
+    bool fold_damping = true;	     // FARGO_B200_FOLD_DAMPING=0 keeps k_damping as its own pass
+    bool fold_armed = false;	     // the next launch_transport applies the damping of this step (factors uploaded)
+    bool damp_folded = false;	     // ... and has done so: the final boundary call skips k_damping
     double *partials; // per-block partial sums of the accretion / monitor / disk-on-body reductions (sized from their launch grids)
     size_t partials_n;
     double *hstale = nullptr; // leapfrog: scale height of the first kick's viscosity stage (see fargo_kick)
@@ -441,6 +447,8 @@ extern "C" void fargo_ctx_destroy(fargo_ctx *c)
 	cudaFree(p);
     if (c->nshift)
 	cudaFree(c->nshift);
+    if (c->d_dmask)
+	cudaFree(c->d_dmask);
     if (c->h_pin)
 	cudaFreeHost(c->h_pin);
     if (c->ev_pin)
@@ -614,6 +622,8 @@ extern "C" int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, con
       // DADD chain per ring until there are enough rings to fill the GPU's memory pipes; the scan kernel (a warp per ring)
       // costs ~60x the instructions but spreads them.  Measured at Ns = 16384 (ms, chain / scan): 1038 rings 0.166 / 0.100,
       // 2048 rings 0.166 / 0.142, 8192 rings 0.258 / 0.447.  FARGO_B200_RINGSUM=chain|scan overrides.
+	const char *fold = getenv("FARGO_B200_FOLD_DAMPING");
+	c->fold_damping = !(fold && strcmp(fold, "0") == 0);
 	const char *env = getenv("FARGO_B200_RINGSUM");
 	c->ringsum_scan = c->v.nr <= 2560;
 	if (env && strcmp(env, "chain") == 0)
@@ -1163,27 +1173,78 @@ static int damp_field(fargo_ctx *c, double *x, const double *x0, bool is_vector,
     return 0;
 }
 
+// the damping jobs of one step (order: vrad, vazi, sigma, energy, damping.cpp:204-270; the fields are independent) with this
+// step's factors exp(-dt * f / tau) uploaded into c->expf_s (4 tables of stride nr + 2)
+static int prepare_damping(fargo_ctx *c, const VBuf &v, double dt, DampJobs &jobs, int &rows)
+{
+    const fargo_params &p = c->v.p;
+    const int st = c->v.nr + 2;
+    double *h = c->h_pin + 8, *d = c->expf_s;
+    CUDA_OK(cudaEventSynchronize(c->ev_pin)); // the previous step's copy out of h_pin is done
+    jobs.n = 0;
+    rows = 0;
+    if (damp_field(c, v.vr, c->vr0, true, false, p.damp_vrad, dt, d, h, jobs, rows) ||
+	damp_field(c, v.vp, c->vp0, false, false, p.damp_vazi, dt, d + st, h + st, jobs, rows) ||
+	damp_field(c, c->sigma, c->sigma0, false, true, p.damp_sigma, dt, d + 2 * st, h + 2 * st, jobs, rows))
+	return 1;
+    if (p.adiabatic && damp_field(c, EN(c), c->energy0, false, false, p.damp_energy, dt, d + 3 * st, h + 3 * st, jobs, rows))
+	return 1;
+    if (jobs.n > 0) {
+	CUDA_OK(cudaMemcpyAsync(d, h, 4 * (size_t)st * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	CUDA_OK(cudaEventRecord(c->ev_pin, c->stream));
+    }
+    return 0;
+}
+
+// Arms the fold: this step's damping (over `dt`) will be applied by the next launch_transport in the azimuthal kernel's
+// epilogue instead of by k_damping.  Only for zones that damp towards the initial field or a constant: the ring-mean type needs
+// the finished ring's index-ordered sum first (damping.cpp:578-585) and keeps its own pass.
+static int arm_damping_fold(fargo_ctx *c, double dt)
+{
+    c->fold_armed = false;
+    const fargo_params &p = c->v.p;
+    if (!p.damping || !c->fold_damping)
+	return 0;
+    VBuf v = cur_v(c, c->v_mid);
+    DampJobs jobs;
+    int rows = 0;
+    if (prepare_damping(c, v, dt, jobs, rows))
+	return 1;
+    if (jobs.n == 0)
+	return 0;
+    std::vector<int> mask((size_t)c->v.nr + 1, 0);
+    for (int q = 0; q < jobs.n; ++q) {
+	const DampJob &J = jobs.j[q];
+	if (J.type != FARGO_DAMP_INITIAL && J.type != FARGO_DAMP_ZERO)
+	    return 0; // ring-mean damping somewhere: everything stays with k_damping
+	const int f = J.x == v.vr ? 0 : J.x == v.vp ? 1 : J.x == c->sigma ? 2 : 3;
+	for (int i = J.ring_lo; i < J.ring_hi; ++i)
+	    mask[i] |= (J.type == FARGO_DAMP_INITIAL ? 1 : 2) << (2 * f);
+    }
+    if (mask != c->h_dmask) { // the zones do not move: uploaded once
+	if (!c->d_dmask)
+	    CUDA_OK(cudaMalloc((void **)&c->d_dmask, mask.size() * sizeof(int)));
+	CUDA_OK(cudaMemcpyAsync(c->d_dmask, mask.data(), mask.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+	CUDA_OK(cudaStreamSynchronize(c->stream)); // `mask` is pageable memory of this frame
+	c->h_dmask = mask;
+    }
+    c->fold_armed = true;
+    return 0;
+}
+
 extern "C" int fargo_stage_boundary(fargo_ctx *c, double dt, int final_call)
 {
     CUDA_OK(cudaSetDevice(c->device));
     const fargo_params &p = c->v.p;
     VBuf v = cur_v(c, c->v_mid);
-    if (final_call && p.damping) { // order: vrad, vazi, sigma, energy (damping.cpp:204-270); the fields are independent
-	const int st = c->v.nr + 2;
-	double *h = c->h_pin + 8, *d = c->expf_s;
-	CUDA_OK(cudaEventSynchronize(c->ev_pin)); // the previous step's copy out of h_pin is done
+    if (final_call && p.damping && c->damp_folded) {
+	c->damp_folded = false; // this step's damping was applied in the azimuthal transport kernel's epilogue
+    } else if (final_call && p.damping) {
 	DampJobs jobs;
-	jobs.n = 0;
 	int rows = 0;
-	if (damp_field(c, v.vr, c->vr0, true, false, p.damp_vrad, dt, d, h, jobs, rows) ||
-	    damp_field(c, v.vp, c->vp0, false, false, p.damp_vazi, dt, d + st, h + st, jobs, rows) ||
-	    damp_field(c, c->sigma, c->sigma0, false, true, p.damp_sigma, dt, d + 2 * st, h + 2 * st, jobs, rows))
-	    return 1;
-	if (p.adiabatic && damp_field(c, EN(c), c->energy0, false, false, p.damp_energy, dt, d + 3 * st, h + 3 * st, jobs, rows))
+	if (prepare_damping(c, v, dt, jobs, rows))
 	    return 1;
 	if (jobs.n > 0) {
-	    CUDA_OK(cudaMemcpyAsync(d, h, 4 * (size_t)st * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-	    CUDA_OK(cudaEventRecord(c->ev_pin, c->stream));
 	    dim3 grid((unsigned)((c->v.ns + 1023) / 1024), (unsigned)rows);
 	    LAUNCH(c, k_damping, grid, 256, 0, c->v, jobs);
 	}
@@ -1263,6 +1324,16 @@ static int launch_transport(fargo_ctx *c, double dt, const double *vr_in, const 
 			 c->t_amp, c->t_amm, c->t_e, vp_in, vr_in, c->vmean, c->nshift, c->vconst, c->sigma, vr_out, vp_out, EN(c), \
 			 dt, segs);                                                                                         \
     } while (0)
+    if (c->fold_armed) { // fargo_step armed the fold: the factors of this step are in expf_s (stream order)
+	segs.dmask = c->d_dmask;
+	segs.dexpf = c->expf_s;
+	segs.dstride = v.nr + 2;
+	segs.dx0[0] = c->vr0, segs.dx0[1] = c->vp0, segs.dx0[2] = c->sigma0, segs.dx0[3] = c->energy0;
+	segs.dx0c[0] = segs.dx0c[1] = segs.dx0c[3] = 0.0;
+	segs.dx0c[2] = v.p.sigma_floor * v.p.sigma0; // damping.cpp: the density is damped towards the floor, not towards 0
+	c->fold_armed = false;
+	c->damp_folded = true;
+    }
     CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     if (!h.p2p) {
 	segs.hi[2] = v.nr;
@@ -1544,7 +1615,11 @@ extern "C" int fargo_step(fargo_ctx *c, double dt)
     CUDA_OK(cudaSetDevice(c->device));
     if (c->v_mid)
 	return fail("fargo_step called mid-step (after a per-stage call); finish the step with fargo_stage_transport first");
-    if (fargo_kick(c, dt) || fargo_drift(c, dt))
+    if (fargo_kick(c, dt))
+	return 1;
+    // an Euler step: Transport is the last stage before the final boundary call, so the damping zones of that call
+    // (boundary_conditions.cpp:65-114) are applied to the rings while the transport kernel still holds them
+    if (arm_damping_fold(c, dt) || fargo_drift(c, dt))
 	return 1;
     c->v.time += dt;
     return fargo_finish_step(c, dt);

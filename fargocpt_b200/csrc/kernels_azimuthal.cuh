@@ -65,10 +65,10 @@ __device__ __forceinline__ void az_star(const double (&B)[AZ_NC], const AzRing &
 	    D[c] = 0.5 * flux_limiter<LIM>(dq[c + 1], dq[c]) * g.invdxtheta;
     }
     const double Dm = shfl_from_left(D[AZ_NC - 1]);
-    star[0] = (pos[0] ? Bm : B[0]) + cf[0] * (pos[0] ? Dm : D[0]);
+    star[0] = fm_madd(cf[0], pos[0] ? Dm : D[0], pos[0] ? Bm : B[0]);
 #pragma unroll
     for (int c = 1; c < AZ_NC; ++c)
-	star[c] = (pos[c] ? B[c - 1] : B[c]) + cf[c] * (pos[c] ? D[c - 1] : D[c]);
+	star[c] = fm_madd(cf[c], pos[c] ? D[c - 1] : D[c], pos[c] ? B[c - 1] : B[c]);
 }
 
 // VanLeerTheta (:630-664) conservative update of one quantity from its interface fluxes
@@ -79,7 +79,7 @@ __device__ __forceinline__ void az_update(double (&Q)[AZ_NC], const double (&G)[
     for (int c = 0; c < AZ_NC; ++c) {
 	double varq = G[c];
 	varq -= (c == AZ_NC - 1) ? Gp : G[(c + 1) % AZ_NC];
-	Q[c] += varq * g.invsurf;
+	Q[c] = fm_madd(varq, g.invsurf, Q[c]);
     }
 }
 
@@ -286,7 +286,29 @@ struct AzSegs {
     unsigned long long seq;	      // value to publish
     unsigned int *done;		      // edge warps finished (local device memory, returns to 0)
     unsigned int expected;	      // edge warps in this launch
+    // Damping zones folded into the epilogue (damping.cpp:311-752; boundary_conditions.cpp:65-114 applies them right after
+    // Transport + CommunicateBoundaries in an Euler step): dmask == nullptr: not folded (k_damping runs as its own pass).
+    const int *dmask;	  // per ring (nr + 1 entries): 2 bits per field f = 0 v_rad, 1 v_azi, 2 Sigma, 3 e: 0 none, 1 towards the
+			  // initial field dx0[f], 2 towards the constant dx0c[f]
+    const double *dexpf;  // 4 tables (stride dstride) of this step's exp(-dt * factor / tau) per ring, formed on the host with glibc
+    int dstride;
+    const double *dx0[4];
+    double dx0c[4];
 };
+
+// one field of one ring through the damping formula of damping.cpp (:336-343 and its siblings): X = (X - X0) * e + X0
+__device__ __forceinline__ void az_damp_field(const AzSegs &segs, const int f, const int type, const int i, const size_t a, const bool ld,
+					       const int ncols_in, double (&X)[AZ_NC])
+{
+    const double ef = segs.dexpf[(size_t)f * segs.dstride + i];
+#pragma unroll
+    for (int k = 0; k < AZ_NC; ++k) {
+	double X0 = segs.dx0c[f];
+	if (type == 1 && ld && k < ncols_in)
+	    X0 = segs.dx0[f][a + k];
+	X[k] = (X[k] - X0) * ef + X0;
+    }
+}
 
 template <int LIM, bool ADI, bool PUSH>
 __global__ void __launch_bounds__(128, AZ_MINB)
@@ -356,6 +378,22 @@ __global__ void __launch_bounds__(128, AZ_MINB)
 	    az_fetch<ADI>(IN, ns, jout, nsh, row, t_rmp, t_rmm, t_amp, t_amm, t_e, t_sigma, vp_old);
 	    az_ring<LIM, ADI, false>(c, tc, IN, g, dt, vm, vc, fargo, i, lane_out, PS, PR, Q, vrn, vpn, sf, en, A);
 	}
+	if (segs.dmask != nullptr && i >= i_first) { // warp-uniform: this ring lies in a damping zone of some field
+	    const int dm = segs.dmask[i];
+	    if (dm != 0) {
+		const bool ld = lane_out && jout >= 0 && jout < ns;
+		const int nin = ns - jout; // columns of this lane inside the ring (>= AZ_NC except at a ragged end)
+		const size_t a = row + (size_t)(ld ? jout : 0);
+		if (dm & 3)
+		    az_damp_field(segs, 0, dm & 3, i, a, ld, nin, vrn);
+		if ((dm >> 2) & 3)
+		    az_damp_field(segs, 1, (dm >> 2) & 3, i, a, ld, nin, vpn);
+		if ((dm >> 4) & 3)
+		    az_damp_field(segs, 2, (dm >> 4) & 3, i, a, ld, nin, sf);
+		if (ADI && ((dm >> 6) & 3))
+		    az_damp_field(segs, 3, (dm >> 6) & 3, i, a, ld, nin, en);
+	    }
+	}
 	if (PUSH && seg < 2 && i >= i_first && lane_out) { // edge ring of the slab: mirror it into the neighbour's halo inbox
 	    const int pr = i - segs.push_lo[seg];
 	    if (pr >= 0 && pr < FARGO_CPUOVERLAP) {
@@ -407,10 +445,18 @@ __global__ void __launch_bounds__(128, AZ_MINB)
     }
     // v_rad ring nr is not touched by compute_velocities_from_momenta (:502-507): carry it over
     if (i_last == nr && lane_out) {
+	const int dmv = segs.dmask != nullptr ? (segs.dmask[nr] & 3) : 0; // v_rad's outermost interface is damped like any other
 #pragma unroll
 	for (int k = 0; k < AZ_NC; ++k)
-	    if (jout + k < ns)
-		o_vr[(size_t)nr * ns + jout + k] = vr_old[(size_t)nr * ns + jout + k];
+	    if (jout + k < ns) {
+		const size_t a = (size_t)nr * ns + jout + k;
+		double X = vr_old[a];
+		if (dmv != 0) {
+		    const double X0 = dmv == 1 ? segs.dx0[0][a] : segs.dx0c[0];
+		    X = (X - X0) * segs.dexpf[nr] + X0;
+		}
+		o_vr[a] = X;
+	    }
     }
     if (PUSH && seg < 2) {
 	// every lane orders its peer stores before what follows, system-wide; the warp's lane 0 then counts the warp in, and

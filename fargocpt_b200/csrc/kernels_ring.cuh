@@ -445,13 +445,13 @@ __global__ void __launch_bounds__(128, 4)
 	g.cell_size = stdmin(g.dxr, g.dxa);
 	g.cell2 = g.cell_size * g.cell_size;
 	g.sqg = c.sqrt_gamma;
-	g.ycell = fm_rcp_raw(g.cell_size), g.ydxr = fm_rcp_raw(g.dxr), g.ydxa = fm_rcp_raw(g.dxa);
-	g.ycell2 = fm_rcp_raw(g.cell2), g.ysqg = fm_rcp_raw(g.sqg);
+	g.ycell = fm_rcp_raw_x(g.cell_size), g.ydxr = fm_rcp_raw_x(g.dxr), g.ydxa = fm_rcp_raw_x(g.dxa);
+	g.ycell2 = fm_rcp_raw_x(g.cell2), g.ysqg = fm_rcp_raw_x(g.sqg);
 	g.inv_limit = 1.0 / c.p.heating_cooling_cfl_limit;
 	g.ids = c.g.invdiffrsup[i], g.irb = c.g.invrmed[i], g.iok = c.g.inv_omega_k[i];
 	g.vm = vm;
 	FmAcc A0; // validity of the five shared denominators
-	fm_acc_nrm(A0, g.cell_size), fm_acc_nrm(A0, g.dxr), fm_acc_nrm(A0, g.dxa), fm_acc_nrm(A0, g.cell2), fm_acc_nrm(A0, g.sqg);
+	fm_acc_nrm_x(A0, g.cell_size), fm_acc_nrm_x(A0, g.dxr), fm_acc_nrm_x(A0, g.dxa), fm_acc_nrm_x(A0, g.cell2), fm_acc_nrm_x(A0, g.sqg);
 	const bool vec = ((ns & 3) == 0);
 	double S[4], E[4], V0[4], V1[4], P[5], QP[4], QM[4];
 	const size_t row = (size_t)i * ns;
@@ -500,8 +500,8 @@ __global__ void __launch_bounds__(128, 4)
 	FmAcc A = A0;
 #pragma unroll
 	for (int k = 0; k < 4; ++k)
-	    Ac[k] = cfl_cell<MathP<true>>(c, g, i, adiabatic, S[k], E[k], V0[k], V1[k], P[k], P[k + 1], QP[k], QM[k], A);
-	if (!fm_acc_ok(A)) {
+	    Ac[k] = cfl_cell<MathX>(c, g, i, adiabatic, S[k], E[k], V0[k], V1[k], P[k], P[k + 1], QP[k], QM[k], A);
+	if (!fm_acc_ok_x(A)) {
 #pragma unroll
 	    for (int k = 0; k < 4; ++k)
 		Ac[k] = cfl_cell<MathP<false>>(c, g, i, adiabatic, S[k], E[k], V0[k], V1[k], P[k], P[k + 1], QP[k], QM[k], A);

@@ -146,7 +146,7 @@ __global__ void TR_BOUNDS
 	    double star[NB];
 #pragma unroll
 	    for (int q = 0; q < NB; ++q)
-		star[q] = (pos ? b2[q] : b1[q]) + hh * (pos ? dq2[q] : dq1[q]);
+		star[q] = fm_madd(hh, pos ? dq2[q] : dq1[q], pos ? b2[q] : b1[q]);
 	    F1[0] = geo * 1.0 * star[0] * v1; // Sigma: QRStar == 1 (Sigma/Sigma_int), DensityStar = star[0]
 #pragma unroll
 	    for (int q = 1; q < NB; ++q)
@@ -160,13 +160,13 @@ __global__ void TR_BOUNDS
 	const int n = k - 2;
 	if (n >= i0 && n < i1) {
 	    const double is = c.g.invsurf[n];
-	    AT(o_sigma, n, j) = raw2[0] + (F2[0] - F1[0]) * is;
-	    AT(o_rmp, n, j) = raw2[1] + (F2[1] - F1[1]) * is;
-	    AT(o_rmm, n, j) = raw2[2] + (F2[2] - F1[2]) * is;
-	    AT(o_amp, n, j) = raw2[3] + (F2[3] - F1[3]) * is;
-	    AT(o_amm, n, j) = raw2[4] + (F2[4] - F1[4]) * is;
+	    AT(o_sigma, n, j) = fm_madd(F2[0] - F1[0], is, raw2[0]);
+	    AT(o_rmp, n, j) = fm_madd(F2[1] - F1[1], is, raw2[1]);
+	    AT(o_rmm, n, j) = fm_madd(F2[2] - F1[2], is, raw2[2]);
+	    AT(o_amp, n, j) = fm_madd(F2[3] - F1[3], is, raw2[3]);
+	    AT(o_amm, n, j) = fm_madd(F2[4] - F1[4], is, raw2[4]);
 	    if (ADIABATIC)
-		AT(o_e, n, j) = raw2[5] + (F2[5] - F1[5]) * is;
+		AT(o_e, n, j) = fm_madd(F2[5] - F1[5], is, raw2[5]);
 	}
 #pragma unroll
 	for (int q = 0; q < NB; ++q) {

@@ -36,7 +36,7 @@ def main(argv=None):
             restart_from = int(args[i + 1]); i += 1
         elif a == "--ref-threads":  # OpenMP threads of the reference run (its fields do not depend on the thread count)
             ref_threads = int(args[i + 1]); i += 1
-        elif a in ("--gpu", "--keep", "--vs-reference-restart"):
+        elif a in ("--gpu", "--keep", "--vs-reference-restart", "--ulp-sensitivity"):
             pass
         elif "=" in a:
             k, v = a.split("=", 1)
@@ -134,7 +134,33 @@ def main(argv=None):
         cols = ", ".join(f"{k}:{v:.0e}" for k, v in enumerate(d) if np.isfinite(v) and v > 1e-9)
         print(f"monitor/{f}: header {'identical' if hr == ho else 'DIFFERENT'}, rows {len(a)} vs {len(b)}, columns not evaluated: "
               f"{[k for k, v in enumerate(d) if not np.isfinite(v)]}, columns off by more than 1e-9 of their scale: {cols or 'none'}")
+    if "--ulp-sensitivity" in args and len(cfg.get("nbody", [])) > 1:
+        # How far do two runs of the REFERENCE ITSELF drift apart when the planet starts one ulp further out?  The bodies are advanced
+        # on the host (ours: compensated RK4, the reference: REBOUND IAS15) and agree to ~1e-16; this is the yardstick for what such
+        # a difference does to the gas after the same number of steps.
+        import copy
+        cfg2 = copy.deepcopy(cfg)
+        nb = cfg2["nbody"][1]
+        a0 = float(str(nb.get("semi-major axis", 1.0)).split()[0])
+        unit = " ".join(str(nb.get("semi-major axis", 1.0)).split()[1:])
+        nb["semi-major axis"] = (repr(float(np.nextafter(a0, 2 * a0))) + " " + unit).strip()
+        cfg2["OutputDir"] = os.path.join(tmp, "ref_ulp")
+        y2 = os.path.join(tmp, "setup_ulp.yml")
+        yaml.safe_dump(cfg2, open(y2, "w"), sort_keys=False)
+        r = subprocess.run([REF, "start", y2], cwd=tmp, env=env, capture_output=True, text=True)
+        if r.returncode == 0:
+            line = [f"reference vs reference with the planet one ulp further out, snapshot {nsnap}:"]
+            for f in ("Sigma", "vrad", "vazi", "energy"):
+                pr, po = os.path.join(ref, "snapshots", str(nsnap), f + ".dat"), os.path.join(cfg2["OutputDir"], "snapshots", str(nsnap), f + ".dat")
+                if os.path.exists(pr) and os.path.exists(po):
+                    a, b = np.fromfile(pr), np.fromfile(po)
+                    line.append(f"{f} ulpdev={np.abs(a - b).max() / (np.abs(a).max() or 1.0):.2e}")
+            print(" ".join(line))
     print(f"worst field deviation relative to the field scale: {worst:.2e}")
+    if "--keep" not in args:
+        shutil.rmtree(tmp, ignore_errors=True)
+    else:
+        print("kept", tmp)
     return worst
     if "--keep" not in args:
         shutil.rmtree(tmp)
