@@ -12,7 +12,7 @@
 // radius; the rings i-1 / i-2 a stage needs are the registers of the previous iterations, so every state array is
 // read ONCE and every intermediate (Phi, P, Q_rr, Q_phiphi, nu, div v, tau_rr, tau_phiphi, tau_rphi) lives only in
 // registers.  A stage that needs column j+-1 of the previous stage's output makes the outermost columns of the window
-// invalid, so a window of 64 columns yields 56 finished ones ([4, 60)); warps do not communicate.  Outputs go to the
+// invalid, so a window of 64 columns yields 60 finished ones ([2, 62)); warps do not communicate.  Outputs go to the
 // OTHER buffer of each double-buffered field (windows overlap on reads).
 // FS_NC = 2 at 4 CTAs / SM (128 registers) beats 4 columns per lane at 3 CTAs / SM (168 registers, spills) by 17 % on
 // the viscosity and source kernels: the FP64 chains need warps, not wider threads, to hide their latency.
@@ -28,8 +28,15 @@
 #define FS_NC 2 // columns per lane
 #endif
 #define FS_WIN (32 * FS_NC)
-#define FS_HL 4
-#define FS_HR 4
+// Invalid columns at either end of a window.  Every stage of the three kernels reads column j +- 1 of RAW inputs (valid in
+// every lane) or of the previous stage's output, and no stage chains two such reads, so exactly the first and the last column
+// of a window are wrong (lane 0's "left" and lane 31's "right" shuffle); rounded up to whole lanes (16-byte vector stores).
+#ifndef FS_HL
+#define FS_HL 2
+#endif
+#ifndef FS_HR
+#define FS_HR 2
+#endif
 #define FS_OUT (FS_WIN - FS_HL - FS_HR)
 
 // window bookkeeping shared by the three kernels

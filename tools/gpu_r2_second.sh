@@ -14,3 +14,5 @@ tail -1 gpurun_out/${TAG}_bench_nofold.log | cut -c1-400
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-tolerance-mode > gpurun_out/${TAG}_ncu_bench.log 2>&1
 ls -la gpurun_out/ | tail -12
+# variants: the fused kernels with the old 4 + 4 halo columns against the default 2 + 2
+STEPS=10 BENCH_ARGS="--no-tolerance-mode" bash tools/gpu_variants.sh ${TAG}_var exp/fs44.so
