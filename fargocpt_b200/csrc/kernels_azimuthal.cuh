@@ -187,6 +187,80 @@ __device__ __forceinline__ void az_prefetch(const int ns, const int jout, const 
 	pf_global(t_e + a0), pf_global(t_e + a1);
 }
 
+// The same segment through shared memory (AZ_DEPTH > 0): the copies of ring i + 1 are issued while ring i is computed
+// (fargo_dev.h:cp_async_16), 16 bytes per quantity when the ring's shift keeps the thread's pair of columns aligned, 8 bytes
+// per column otherwise (warp-uniform: every lane starts at an even output column).  Slot layout [quantity][thread][column].
+#ifndef AZ_DEPTH
+#define AZ_DEPTH 1
+#endif
+typedef double AzSlot[7][128][AZ_NC];
+template <bool ADI>
+__device__ __forceinline__ void az_stage(AzSlot &dst, const int ns, const int jout, const int nsh, const size_t row,
+					  const double *__restrict__ t_rmp, const double *__restrict__ t_rmm,
+					  const double *__restrict__ t_amp, const double *__restrict__ t_amm,
+					  const double *__restrict__ t_e, const double *__restrict__ t_sigma,
+					  const double *__restrict__ vp_old)
+{
+    int col = (jout - nsh) % ns; // pre-shift column of c = 0
+    if (col < 0)
+	col += ns;
+    const int t = threadIdx.x;
+    if (AZ_NC == 2 && ((col | ns) & 1) == 0) {
+	const size_t a = row + (size_t)col;
+	cp_async_16(dst[0][t], t_rmp + a);
+	cp_async_16(dst[1][t], t_rmm + a);
+	cp_async_16(dst[2][t], t_amp + a);
+	cp_async_16(dst[3][t], t_amm + a);
+	if (ADI)
+	    cp_async_16(dst[4][t], t_e + a);
+	cp_async_16(dst[5][t], t_sigma + a);
+	cp_async_16(dst[6][t], vp_old + a);
+    } else {
+#pragma unroll
+	for (int k = 0; k < AZ_NC; ++k) {
+	    const size_t a = row + (size_t)col;
+	    cp_async_8(&dst[0][t][k], t_rmp + a);
+	    cp_async_8(&dst[1][t][k], t_rmm + a);
+	    cp_async_8(&dst[2][t][k], t_amp + a);
+	    cp_async_8(&dst[3][t][k], t_amm + a);
+	    if (ADI)
+		cp_async_8(&dst[4][t][k], t_e + a);
+	    cp_async_8(&dst[5][t][k], t_sigma + a);
+	    cp_async_8(&dst[6][t][k], vp_old + a);
+	    col = (col + 1 == ns) ? 0 : col + 1;
+	}
+    }
+}
+template <bool ADI> __device__ __forceinline__ void az_take(const AzSlot &src, AzIn &N)
+{
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+	if (q == 4 && !ADI) {
+#pragma unroll
+	    for (int k = 0; k < AZ_NC; ++k)
+		N.Q[q][k] = 0.0;
+	    continue;
+	}
+	if (AZ_NC == 2) {
+	    const double2 a = *reinterpret_cast<const double2 *>(src[q][t]);
+	    N.Q[q][0] = a.x, N.Q[q][AZ_NC - 1] = a.y;
+	} else {
+#pragma unroll
+	    for (int k = 0; k < AZ_NC; ++k)
+		N.Q[q][k] = src[q][t][k];
+	}
+    }
+    if (AZ_NC == 2) {
+	const double2 a = *reinterpret_cast<const double2 *>(src[6][t]);
+	N.VP[0] = a.x, N.VP[AZ_NC - 1] = a.y;
+    } else {
+#pragma unroll
+	for (int k = 0; k < AZ_NC; ++k)
+	    N.VP[k] = src[6][t][k];
+    }
+}
+
 // Everything the kernel does with one ring segment once it is in registers: the residual-velocity pass, the uniform
 // pass, velocities from momenta (:498-535) and the floors (:123-131).  FAST = true is the hot path: straight-line,
 // branch-free arithmetic whose validity is accumulated in A and tested ONCE per ring by the caller; FAST = false is the
@@ -297,18 +371,40 @@ struct AzSegs {
 };
 
 // one field of one ring through the damping formula of damping.cpp (:336-343 and its siblings): X = (X - X0) * e + X0
+// x0s: the thread's columns of the initial field, staged through shared memory by az_stage_damp (nullptr: plain loads)
 __device__ __forceinline__ void az_damp_field(const AzSegs &segs, const int f, const int type, const int i, const size_t a, const bool ld,
-					       const int ncols_in, double (&X)[AZ_NC])
+					       const int ncols_in, double (&X)[AZ_NC], const double *x0s = nullptr)
 {
     const double ef = segs.dexpf[(size_t)f * segs.dstride + i];
 #pragma unroll
     for (int k = 0; k < AZ_NC; ++k) {
 	double X0 = segs.dx0c[f];
 	if (type == 1 && ld && k < ncols_in)
-	    X0 = segs.dx0[f][a + k];
+	    X0 = x0s ? x0s[k] : segs.dx0[f][a + k];
 	X[k] = (X[k] - X0) * ef + X0;
     }
 }
+#if AZ_DEPTH > 0
+// the initial-field columns the damping of ring i will read, into the slot whose inputs have just been taken (fields 0..3)
+template <bool ADI>
+__device__ __forceinline__ void az_stage_damp(AzSlot &dst, const AzSegs &segs, const int dm, const size_t a, const bool ld, const int ncols_in)
+{
+    if (!ld)
+	return;
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+	if (f == 3 && !ADI)
+	    continue;
+	if (((dm >> (2 * f)) & 3) != 1)
+	    continue;
+#pragma unroll
+	for (int k = 0; k < AZ_NC; ++k)
+	    if (k < ncols_in)
+		cp_async_8(&dst[f][t][k], segs.dx0[f] + a + k);
+    }
+}
+#endif
 
 template <int LIM, bool ADI, bool PUSH>
 __global__ void __launch_bounds__(128, AZ_MINB)
@@ -355,6 +451,19 @@ __global__ void __launch_bounds__(128, AZ_MINB)
     for (int k = 0; k < AZ_NC; ++k)
 	PS[k] = PR[k] = 0.0;
 
+#if AZ_DEPTH > 0
+    __shared__ AzSlot az_stg[AZ_DEPTH + 1];
+    {
+	const int ib = max(i_first - 1, 0);
+#pragma unroll
+	for (int d = 0; d < AZ_DEPTH; ++d) {
+	    if (ib + d < i_last)
+		az_stage<ADI>(az_stg[d], ns, jout, nshift[ib + d], (size_t)(ib + d) * ns, t_rmp, t_rmm, t_amp, t_amm, t_e, t_sigma, vp_old);
+	    cp_async_commit();
+	}
+    }
+    int slot = 0, slot_in = AZ_DEPTH;
+#endif
     for (int i = max(i_first - 1, 0); i < i_last; ++i) {
 	const int nsh = nshift[i];
 	const double vm = vmean[i], vc = vconst[i];
@@ -364,13 +473,36 @@ __global__ void __launch_bounds__(128, AZ_MINB)
 	g.dxrad = (c.g.rsup[i] - c.g.rinf[i]) * dt;
 	g.invsurf = c.g.invsurf[i];
 	const size_t row = (size_t)i * ns;
+#if AZ_DEPTH > 0
+	if (i + AZ_DEPTH < i_last)
+	    az_stage<ADI>(az_stg[slot_in], ns, jout, nshift[i + AZ_DEPTH], row + (size_t)AZ_DEPTH * ns, t_rmp, t_rmm, t_amp, t_amm, t_e,
+			  t_sigma, vp_old);
+	cp_async_commit();
+	slot_in = (slot_in == AZ_DEPTH) ? 0 : slot_in + 1;
+	// damping of this ring (warp-uniform), decided before the inputs are taken so that the initial-field columns it reads
+	// can travel into the just-emptied slot while the ring is computed
+	const int dm = (segs.dmask != nullptr && i >= i_first) ? segs.dmask[i] : 0;
+	const bool dld = lane_out && jout >= 0 && jout < ns;
+	const int dnin = ns - jout; // columns of this lane inside the ring (>= AZ_NC except at a ragged end)
+	const size_t da = row + (size_t)(dld ? jout : 0);
+#else
 	if (i + 1 < i_last)
 	    az_prefetch<ADI>(ns, jout, nshift[i + 1], row + (size_t)ns, t_rmp, t_rmm, t_amp, t_amm, t_e, t_sigma, vp_old);
+#endif
 	double Q[6][AZ_NC], vrn[AZ_NC], vpn[AZ_NC], sf[AZ_NC], en[AZ_NC];
 	FmAcc A;
 	{
 	    AzIn IN;
+#if AZ_DEPTH > 0
+	    cp_async_wait<AZ_DEPTH>(); // ring i has landed
+	    az_take<ADI>(az_stg[slot], IN);
+	    if (dm != 0) {
+		az_stage_damp<ADI>(az_stg[slot], segs, dm, da, dld, dnin);
+		cp_async_commit();
+	    }
+#else
 	    az_fetch<ADI>(IN, ns, jout, nsh, row, t_rmp, t_rmm, t_amp, t_amm, t_e, t_sigma, vp_old);
+#endif
 	    az_ring<LIM, ADI, true>(c, tc, IN, g, dt, vm, vc, fargo, i, lane_out, PS, PR, Q, vrn, vpn, sf, en, A);
 	}
 	if (__any_sync(0xffffffffu, !fm_acc_ok(A))) { // cold, warp-wide (the ring body shuffles): exact zeros, extreme exponents
@@ -378,6 +510,22 @@ __global__ void __launch_bounds__(128, AZ_MINB)
 	    az_fetch<ADI>(IN, ns, jout, nsh, row, t_rmp, t_rmm, t_amp, t_amm, t_e, t_sigma, vp_old);
 	    az_ring<LIM, ADI, false>(c, tc, IN, g, dt, vm, vc, fargo, i, lane_out, PS, PR, Q, vrn, vpn, sf, en, A);
 	}
+#if AZ_DEPTH > 0
+	if (dm != 0) { // warp-uniform: this ring lies in a damping zone of some field
+	    cp_async_wait<0>();
+	    const double(*x0)[128][AZ_NC] = az_stg[slot];
+	    const int t = threadIdx.x;
+	    if (dm & 3)
+		az_damp_field(segs, 0, dm & 3, i, da, dld, dnin, vrn, x0[0][t]);
+	    if ((dm >> 2) & 3)
+		az_damp_field(segs, 1, (dm >> 2) & 3, i, da, dld, dnin, vpn, x0[1][t]);
+	    if ((dm >> 4) & 3)
+		az_damp_field(segs, 2, (dm >> 4) & 3, i, da, dld, dnin, sf, x0[2][t]);
+	    if (ADI && ((dm >> 6) & 3))
+		az_damp_field(segs, 3, (dm >> 6) & 3, i, da, dld, dnin, en, x0[3][t]);
+	}
+	slot = (slot == AZ_DEPTH) ? 0 : slot + 1;
+#else
 	if (segs.dmask != nullptr && i >= i_first) { // warp-uniform: this ring lies in a damping zone of some field
 	    const int dm = segs.dmask[i];
 	    if (dm != 0) {
@@ -394,6 +542,7 @@ __global__ void __launch_bounds__(128, AZ_MINB)
 		    az_damp_field(segs, 3, (dm >> 6) & 3, i, a, ld, nin, en);
 	    }
 	}
+#endif
 	if (PUSH && seg < 2 && i >= i_first && lane_out) { // edge ring of the slab: mirror it into the neighbour's halo inbox
 	    const int pr = i - segs.push_lo[seg];
 	    if (pr >= 0 && pr < FARGO_CPUOVERLAP) {
@@ -443,6 +592,9 @@ __global__ void __launch_bounds__(128, AZ_MINB)
 	    PR[k] = Q[0][k];
 	}
     }
+#if AZ_DEPTH > 0
+    cp_async_wait<0>();
+#endif
     // v_rad ring nr is not touched by compute_velocities_from_momenta (:502-507): carry it over
     if (i_last == nr && lane_out) {
 	const int dmv = segs.dmask != nullptr ? (segs.dmask[nr] & 3) : 0; // v_rad's outermost interface is damped like any other

@@ -186,13 +186,6 @@ __global__ void __launch_bounds__(256) k_damping(const DevView c, const DampJobs
 // mode 0: only vmean (CFL).  mode 1: also Nshift[i] and the constant residual velocity (transport).
 // k_ring_mean_generic: any Ns (8-byte cp.async).  k_ring_mean (below): even Ns, TMA bulk copies.
 #define RM_STAGES 4
-__device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gmem_src)
-{
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(32)
     k_ring_mean_generic(const DevView c, const double *__restrict__ vp, double *__restrict__ vmean, int *__restrict__ nshift,

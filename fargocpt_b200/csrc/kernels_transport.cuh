@@ -15,6 +15,9 @@
 // cell k-2 is finished:  Q(k-2) += (F(k-2) - F(k-1)) * InvSurf[k-2].
 // The 5 + 6 divisions of an iteration (Q / Sigma_int, van Leer slopes) run straight-line on the branch-free
 // arithmetic of fargo_math.h with one validity test; upwinding is done by selects.
+#ifndef TR_DEPTH
+#define TR_DEPTH 2 // rings in flight through shared memory per thread (0: direct loads + L2 prefetch)
+#endif
 #ifdef TR_MINB
 #define TR_BOUNDS __launch_bounds__(128, TR_MINB)
 #else
@@ -54,11 +57,39 @@ __global__ void TR_BOUNDS
 
     const int kstart = max(i0 - 2, 0);
     double vnext = AT(vr, kstart, j); // v_r(k), carried from the previous iteration's v_r(k+1)
+#if TR_DEPTH > 0
+    // The inputs of ring k + TR_DEPTH are on their way into this thread's shared-memory slots while ring k is computed
+    // (fargo_dev.h:cp_async_8).  With only an L2 prefetch the first consumer of every ring (the reciprocal of Sigma) waited
+    // out an L2 hit, 31 % of all stall samples of this kernel (profiles/r02_v1_ncu_full_c5_8192x16384.md).
+    __shared__ double stg[TR_DEPTH + 1][5][128];
+    const int tid = threadIdx.x;
+    const int klast = min(i1 + 1, nr - 1); // last ring this march loads
+    auto stage_ring = [&](const int kk, const int slot) {
+	if (kk <= klast) {
+	    cp_async_8(&stg[slot][0][tid], &AT(sigma, kk, j));
+	    cp_async_8(&stg[slot][1][tid], &AT(vr, kk + 1, j));
+	    cp_async_8(&stg[slot][2][tid], &AT(vp, kk, j));
+	    cp_async_8(&stg[slot][3][tid], &AT(vp, kk, jp));
+	    if (ADIABATIC)
+		cp_async_8(&stg[slot][4][tid], &AT(energy, kk, j));
+	}
+	cp_async_commit(); // (an empty group past the last ring keeps the group count uniform)
+    };
+#pragma unroll
+    for (int d = 0; d < TR_DEPTH; ++d)
+	stage_ring(kstart + d, d);
+    int slot = 0, slot_in = TR_DEPTH; // slot of ring k, slot ring k + TR_DEPTH goes into
+#endif
     // (unrolling the march six-fold over the rotation phases of the window removes the register copies at the end of
     // the loop body but was not faster on B200: 3.36 vs 3.28 ms at 8192x16384)
     for (int k = kstart; k <= i1 + 1; ++k) {
 	double bk[NB], rawk[NB], dq1[NB], F1[NB];
 	const double vk = vnext;
+#if TR_DEPTH > 0
+	stage_ring(k + TR_DEPTH, slot_in);
+	slot_in = (slot_in == TR_DEPTH) ? 0 : slot_in + 1;
+	cp_async_wait<TR_DEPTH>(); // ring k has landed
+#else
 	if (k + 1 < nr && k < i1 + 1) { // prefetch the next ring
 	    pf_global(&AT(sigma, k + 1, j));
 	    pf_global(&AT(vr, k + 2, j));
@@ -66,21 +97,34 @@ __global__ void TR_BOUNDS
 	    if (ADIABATIC)
 		pf_global(&AT(energy, k + 1, j));
 	}
+#endif
 	const int m = k - 1;
 	const bool slopes = (m >= 1 && m < nr - 1 && k < nr);
 	if (k < nr) {
+#if TR_DEPTH > 0
+	    const double s = stg[slot][0][tid];
+	    const double vk1 = stg[slot][1][tid];
+	    vnext = vk1;
+	    const double vpj = stg[slot][2][tid], vpn = stg[slot][3][tid];
+#else
 	    const double s = AT(sigma, k, j);
 	    const double vk1 = AT(vr, k + 1, j);
 	    vnext = vk1;
 	    const double vpj = AT(vp, k, j), vpn = AT(vp, k, jp);
+#endif
 	    const double r = c.g.rmed[k];
 	    rawk[0] = s;
 	    rawk[1] = s * vk1;			 // radial_momentum_plus  (:484)
 	    rawk[2] = s * vk;			 // radial_momentum_minus (:485)
 	    rawk[3] = s * (vpn + r * OmegaF) * r; // angular_momentum_plus (:489)
 	    rawk[4] = s * (vpj + r * OmegaF) * r; // angular_momentum_minus(:490)
-	    if (ADIABATIC)
+	    if (ADIABATIC) {
+#if TR_DEPTH > 0
+		rawk[5] = stg[slot][4][tid];
+#else
 		rawk[5] = AT(energy, k, j);
+#endif
+	    }
 	    // divise_polargrid (SideEuler.cpp:27-43; Sigma_int == Sigma before the sweep) and the limited slopes of ring
 	    // k-1 (compute_star_radial :356-371): 5 + 6 divisions, straight-line with one validity test (fargo_math.h)
 	    const double idm = slopes ? c.g.invdiffrmed[m] : 0.0, idp = slopes ? c.g.invdiffrmed[m + 1] : 0.0;
@@ -178,5 +222,11 @@ __global__ void TR_BOUNDS
 	    F2[q] = F1[q];
 	}
 	v1 = vk;
+#if TR_DEPTH > 0
+	slot = (slot == TR_DEPTH) ? 0 : slot + 1;
+#endif
     }
+#if TR_DEPTH > 0
+    cp_async_wait<0>();
+#endif
 }

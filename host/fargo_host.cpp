@@ -18,6 +18,13 @@
 // disks, test problems), units beyond the table in fargo_init.hpp, REBOUND (bodies are advanced with RK4 sub-steps, see
 // nbody_integrate), monitors other than timestepLogging.dat and Quantities.dat.
 //
+// Multi-GPU (`--ranks N`): one process per GPU like the reference's one process per MPI rank (main.cpp:57,
+// split.cpp:21-87).  The first process forks N - 1 siblings before anything touches CUDA, rank 0 hands the ncclUniqueId over
+// through a file in the output directory, every rank runs this same driver (the bodies are integrated redundantly and
+// identically on every rank, as in the reference; reductions are all-reduced behind the ABI), uploads its radial slab and
+// writes ITS rings of every field file at their offset (pwrite; the reference's stitched MPI-IO writes, polargrid.cpp:135-180);
+// everything else is written by rank 0 only.  `--rank R --ranks N` without forking is for an external launcher.
+//
 // The hydro arithmetic all happens behind the C ABI; build with -DFARGO_HOST_ORACLE to bind the same driver to the CPU
 // oracle (TEST INFRASTRUCTURE: lets the host logic be tested without a GPU; never shipped).
 #include <algorithm>
@@ -31,8 +38,13 @@
 #include <map>
 #include <sstream>
 #include <string>
+#include <fcntl.h>
+#include <signal.h>
+#include <sys/prctl.h>
 #include <sys/stat.h>
+#include <sys/wait.h>
 #include <thread>
+#include <unistd.h>
 #include <tuple>
 #include <vector>
 
@@ -474,13 +486,6 @@ static std::vector<double> read_doubles(const std::string &path, size_t n, bool 
 	die("short read on %s", path);
     return v;
 }
-static void write_doubles(const std::string &path, const std::vector<double> &v)
-{
-    FILE *f = fopen(path.c_str(), "wb");
-    if (!f || fwrite(v.data(), sizeof(double), v.size(), f) != v.size())
-	die("cannot write %s", path);
-    fclose(f);
-}
 static void mkdirs(const std::string &p)
 {
     std::string cur;
@@ -621,6 +626,11 @@ struct Run {
     unsigned nmonitor = 1, nsnapshots = 1;
     int indirect_mode = 1;
     std::string refdir, outdir;
+    // multi-rank (see the file header): `outdir` is where this rank writes the small files (rank 0: the output directory; the
+    // others: a scratch directory nobody reads), `fielddir` the shared output directory the field files live in
+    int rank = 0, nranks = 1;
+    std::string fielddir;
+    int own_lo = 0, own_hi = 0; // global rings [own_lo, own_hi) are written by this rank (write2D, polargrid.cpp:150-176)
 
     size_t cells(bool vector) const { return (size_t)(nrad + (vector ? 1 : 0)) * naz; }
 
@@ -856,10 +866,100 @@ struct Run {
 	ctx = fargo_oracle_create(&params, radii.data(), 0, 1);
 	if (!ctx)
 	    die("fargo_oracle_create failed");
+	own_lo = 0, own_hi = nrad;
 #else
-	if (fargo_ctx_create(&ctx, &params, radii.data(), 0, 1, nullptr, device) != 0)
+	unsigned char uid[128];
+	memset(uid, 0, sizeof(uid));
+	if (nranks > 1) { // rank 0 creates the id, the others wait for the file
+	    mkdirs(fielddir);
+	    const std::string idfile = fielddir + "/.nccl_id";
+	    if (rank == 0) {
+		if (fargo_get_unique_id(uid) != 0)
+		    die("fargo_get_unique_id: %s", fargo_last_error());
+		const std::string tmp = idfile + ".tmp";
+		FILE *f = fopen(tmp.c_str(), "wb");
+		if (!f || fwrite(uid, 1, sizeof(uid), f) != sizeof(uid))
+		    die("cannot write %s", tmp);
+		fclose(f);
+		if (rename(tmp.c_str(), idfile.c_str()) != 0)
+		    die("cannot publish %s", idfile);
+	    } else {
+		bool got = false;
+		for (int tries = 0; tries < 1200 && !got; ++tries) { // two minutes
+		    FILE *f = fopen(idfile.c_str(), "rb");
+		    if (f) {
+			got = fread(uid, 1, sizeof(uid), f) == sizeof(uid);
+			fclose(f);
+		    }
+		    if (!got)
+			usleep(100000);
+		}
+		if (!got)
+		    die("rank 0 did not publish %s", idfile);
+	    }
+	}
+	if (fargo_ctx_create(&ctx, &params, radii.data(), rank, nranks, nranks > 1 ? uid : nullptr, device) != 0)
 	    die("fargo_ctx_create: %s", fargo_last_error());
+	{ // the rings this rank writes: its slab without the ghost rings of interior sides (split.cpp:57-61)
+	    const int imin = fargo_local_imin(ctx), nloc = fargo_local_nrad(ctx);
+	    own_lo = imin + (rank == 0 ? 0 : FARGO_CPUOVERLAP);
+	    own_hi = imin + nloc - (rank == nranks - 1 ? 0 : FARGO_CPUOVERLAP);
+	}
+	rank_barrier(); // everybody has read the id: rank 0 may remove the file
+	if (nranks > 1 && rank == 0)
+	    unlink((fielddir + "/.nccl_id").c_str());
 #endif
+    }
+
+    // All ranks meet here (host side, through the shared output directory: arrival files of a numbered barrier).
+    unsigned barrier_count = 0;
+    void rank_barrier()
+    {
+	if (nranks < 2)
+	    return;
+	const std::string base = fielddir + "/.barrier" + std::to_string(barrier_count++) + ".";
+	{
+	    FILE *f = fopen((base + std::to_string(rank)).c_str(), "w");
+	    if (!f)
+		die("cannot write %s", base + std::to_string(rank));
+	    fclose(f);
+	}
+	for (int r = 0; r < nranks; ++r) {
+	    int tries = 0;
+	    while (!exists(base + std::to_string(r))) {
+		if (++tries > 6000)
+		    die("rank %s did not reach the barrier", std::to_string(r));
+		usleep(20000);
+	    }
+	}
+	// the files of the barrier before this one can go (everybody has left it)
+	if (barrier_count >= 2)
+	    unlink((fielddir + "/.barrier" + std::to_string(barrier_count - 2) + "." + std::to_string(rank)).c_str());
+    }
+
+    // One field file of the shared output directory: this rank's rings at their offset (t_polargrid::write2D,
+    // polargrid.cpp:135-180: MPI_File_write_at of the rank's active rings).  `global` is a whole-grid array of which only
+    // this rank's rings need to be valid.
+    void write_field_file(const std::string &rel, const double *global, bool vector) const
+    {
+	const std::string path = fielddir + "/" + rel;
+	const int hi = own_hi + ((vector && rank == nranks - 1) ? 1 : 0);
+	const size_t off = (size_t)own_lo * naz, cnt = (size_t)(hi - own_lo) * naz;
+	const int fd = open(path.c_str(), O_WRONLY | O_CREAT | (nranks == 1 ? O_TRUNC : 0), 0644);
+	if (fd < 0)
+	    die("cannot write %s", path);
+	if (nranks > 1 && rank == 0 && ftruncate(fd, (off_t)(cells(vector) * sizeof(double))) != 0)
+	    die("cannot size %s", path);
+	const char *src = (const char *)(global + off);
+	size_t left = cnt * sizeof(double);
+	off_t at = (off_t)(off * sizeof(double));
+	while (left > 0) {
+	    const ssize_t w = pwrite(fd, src, left, at);
+	    if (w <= 0)
+		die("cannot write %s", path);
+	    src += w, at += w, left -= (size_t)w;
+	}
+	close(fd);
     }
 
     // Values that may carry units become plain code-unit numbers (config::Config::get<double>(key, default, unit): Interpret.cpp,
@@ -1078,6 +1178,7 @@ struct Run {
 	set_bodies_on_device();
 	write_planet_monitor_files();
 	write_quantities();
+	rank_barrier(); // every rank's rings of snapshot 0 are in the files
 	if (params.damping || params.cooling_beta_reference == 1) { // the damping reference (simulation.cpp:42-47)
 	    const std::string from = outdir + "/snapshots/0", to = outdir + "/snapshots/reference";
 	    mkdirs(to);
@@ -1359,31 +1460,36 @@ struct Run {
 	const std::pair<int, const char *> state[4] = {{FARGO_SIGMA, "Sigma"}, {FARGO_VRAD, "vrad"}, {FARGO_VAZI, "vazi"}, {FARGO_ENERGY, "energy"}};
 	// isothermal runs of the reference write their (all-zero) energy grid too unless WriteEnergy says no
 	const bool write_energy = params.adiabatic || (started_fresh ? cfg.flag("WriteEnergy", true) : exists(refdir + "/snapshots/0/energy.dat"));
+	const std::string rel = "snapshots/" + std::to_string(n_snapshot) + "/";
+	mkdirs(fielddir + "/" + rel);
 #ifndef FARGO_HOST_ORACLE
 	finish_pending_snapshot();
+	// page-locked buffers for the rings this rank writes; the ABI addresses host arrays by GLOBAL ring, so it is handed the
+	// address global ring 0 would have
+	const size_t own_off = (size_t)own_lo * naz;
 	for (int k = 0; k < 4; ++k)
 	    if (!snap_host[k]) {
-		snap_host[k] = (double *)fargo_pinned_alloc(cells(k == 1) * sizeof(double));
+		const size_t n = (size_t)(own_hi - own_lo + (k == 1 ? 1 : 0)) * naz;
+		snap_host[k] = (double *)fargo_pinned_alloc(n * sizeof(double));
 		if (!snap_host[k])
 		    die("%s", std::string("fargo_pinned_alloc: ") + backend_error());
-		std::fill(snap_host[k], snap_host[k] + cells(k == 1), 0.0);
+		std::fill(snap_host[k], snap_host[k] + n, 0.0);
 	    }
-	CHECK(fargo_snapshot_async(ctx, snap_host[0], snap_host[1], snap_host[2], write_energy ? snap_host[3] : nullptr));
+	auto as_global = [own_off](double *own) { return (double *)((uintptr_t)own - own_off * sizeof(double)); };
+	CHECK(fargo_snapshot_async(ctx, as_global(snap_host[0]), as_global(snap_host[1]), as_global(snap_host[2]),
+				   write_energy ? as_global(snap_host[3]) : nullptr));
 	{
 	    backend_ctx *cx = ctx;
-	    std::vector<std::pair<std::string, std::pair<double *, size_t>>> jobs;
+	    std::vector<std::tuple<std::string, const double *, bool>> jobs;
 	    for (int k = 0; k < 4; ++k)
 		if (k < 3 || write_energy)
-		    jobs.push_back({sd + "/" + state[k].second + ".dat", {snap_host[k], cells(k == 1)}});
-	    snap_writer = std::thread([cx, jobs]() {
+		    jobs.push_back(std::make_tuple(rel + state[k].second + ".dat", (const double *)as_global(snap_host[k]), k == 1));
+	    const Run *self = this;
+	    snap_writer = std::thread([cx, jobs, self]() {
 		if (fargo_snapshot_wait(cx) != 0)
 		    die("%s", std::string("fargo_snapshot_wait: ") + backend_error());
-		for (auto &j : jobs) {
-		    FILE *f = fopen(j.first.c_str(), "wb");
-		    if (!f || fwrite(j.second.first, sizeof(double), j.second.second, f) != j.second.second)
-			die("cannot write %s", j.first);
-		    fclose(f);
-		}
+		for (auto &j : jobs)
+		    self->write_field_file(std::get<0>(j), std::get<1>(j), std::get<2>(j));
 	    });
 	}
 #else
@@ -1392,14 +1498,14 @@ struct Run {
 		continue;
 	    std::vector<double> buf(cells(s.first == FARGO_VRAD), 0.0);
 	    CHECK(BK(download_field)(ctx, s.first, buf.data()));
-	    write_doubles(sd + "/" + s.second + ".dat", buf);
+	    write_field_file(rel + s.second + ".dat", buf.data(), s.first == FARGO_VRAD);
 	}
 #endif
 	if (params.adiabatic) {
 	    for (auto &s : {std::make_pair((int)FARGO_QPLUS, "Qplus"), std::make_pair((int)FARGO_QMINUS, "Qminus")}) {
 		std::vector<double> buf(cells(false), 0.0);
 		CHECK(BK(download_field)(ctx, s.first, buf.data()));
-		write_doubles(sd + "/" + s.second + ".dat", buf);
+		write_field_file(rel + s.second + ".dat", buf.data(), false);
 	    }
 	}
 	// optional derived outputs (data.cpp: WriteTemperature, WritePressure, ...): evaluated from the current state on download,
@@ -1413,7 +1519,7 @@ struct Run {
 		continue;
 	    std::vector<double> buf(cells(false), 0.0);
 	    CHECK(BK(download_field)(ctx, std::get<0>(s), buf.data()));
-	    write_doubles(sd + "/" + std::get<2>(s) + ".dat", buf);
+	    write_field_file(rel + std::get<2>(s) + ".dat", buf.data(), false);
 	}
 	MiscEntry m;
 	m.timestep = n_snapshot, m.nTimeStep = n_monitor, m.time = time, m.OmegaFrame = omega_frame, m.FrameAngle = frame_angle;
@@ -1633,7 +1739,7 @@ int main(int argc, char **argv)
     // options.cpp:42-189 subset: `start <setup.yml>`, `restart N <dir>`, -N <steps>, plus --out / --until / --device
     std::string mode, dir, out;
     long nrestart = -1, max_steps = -1, until = -1;
-    int device = 0;
+    int device = 0, nranks = 1, rank = -1;
     for (int i = 1; i < argc; ++i) {
 	const std::string a = argv[i];
 	if (a == "start" && i + 1 < argc) {
@@ -1651,26 +1757,107 @@ int main(int argc, char **argv)
 	    until = atol(argv[++i]);
 	else if (a == "--device" && i + 1 < argc)
 	    device = atoi(argv[++i]);
+	else if (a == "--ranks" && i + 1 < argc)
+	    nranks = atoi(argv[++i]);
+	else if (a == "--rank" && i + 1 < argc)
+	    rank = atoi(argv[++i]);
 	else
 	    die("unknown argument %s", a);
     }
     if ((mode != "restart" && mode != "start") || out.empty()) {
-	fprintf(stderr, "usage: fargocpt_b200 start <setup.yml> --out <output dir> [--until <snapshot>] [-N <steps>] [--device <id>]\n"
+	fprintf(stderr, "usage: fargocpt_b200 start <setup.yml> --out <output dir> [--until <snapshot>] [-N <steps>] [--device <id>] [--ranks <GPUs>]\n"
 			"       fargocpt_b200 restart <N> <fargocpt output dir> --out <new output dir> [--until <snapshot>] [-N <steps>] [--device <id>]\n");
 	return 2;
     }
+#ifdef FARGO_HOST_ORACLE
+    if (nranks != 1)
+	die("%s", std::string("the oracle-bound test driver runs one rank"));
+    rank = 0;
+#else
+    // one process per GPU: rank r computes on device `--device` + r.  Without --rank this process is rank 0 and forks the others
+    // NOW, before anything has touched CUDA; they die with it (PDEATHSIG), and it dies when one of them fails (SIGCHLD).
+    std::vector<pid_t> children;
+    if (nranks < 1 || rank >= nranks)
+	die("bad --ranks / --rank");
+    if (nranks > 1 && rank < 0) {
+	mkdirs(out);
+	unlink((out + "/.nccl_id").c_str());
+	rank = 0;
+	static volatile sig_atomic_t reaping_ok = 0;
+	(void)reaping_ok;
+	struct sigaction sa;
+	memset(&sa, 0, sizeof(sa));
+	sa.sa_handler = [](int) {
+	    int st = 0;
+	    pid_t p;
+	    while ((p = waitpid(-1, &st, WNOHANG)) > 0)
+		if (!(WIFEXITED(st) && WEXITSTATUS(st) == 0)) {
+		    static const char msg[] = "fargocpt_b200: a rank failed, stopping\n";
+		    if (write(2, msg, sizeof(msg) - 1) < 0) {
+		    }
+		    _exit(1);
+		}
+	};
+	sa.sa_flags = SA_NOCLDSTOP | SA_RESTART;
+	sigaction(SIGCHLD, &sa, nullptr);
+	for (int k = 1; k < nranks; ++k) {
+	    const pid_t p = fork();
+	    if (p < 0)
+		die("fork failed");
+	    if (p == 0) {
+		prctl(PR_SET_PDEATHSIG, SIGKILL);
+		signal(SIGCHLD, SIG_DFL);
+		rank = k;
+		children.clear();
+		if (!freopen("/dev/null", "w", stdout)) {
+		}
+		break;
+	    }
+	    children.push_back(p);
+	}
+    }
+    if (rank < 0)
+	rank = 0;
+    device += rank;
+#endif
     Run r;
-    r.outdir = out;
+    r.rank = rank, r.nranks = nranks;
+    r.fielddir = out;
+    r.outdir = rank == 0 ? out : out + "/.rank" + std::to_string(rank);
     if (mode == "start")
 	r.start(dir, device);
     else
 	r.load(dir, (unsigned)nrestart, device);
     r.run(until >= 0 ? (unsigned)until : r.nsnapshots, max_steps);
+    r.rank_barrier(); // all field files are complete
     printf("-- Final: Total Hydrosteps %llu, time %.17g, last snapshot %u\n", (unsigned long long)r.n_iter, r.time, r.n_snapshot);
 #ifdef FARGO_HOST_ORACLE
     fargo_oracle_destroy(r.ctx);
 #else
     fargo_ctx_destroy(r.ctx);
+    if (r.nranks > 1) {
+	// arrival files: everybody has left the barrier before the last one; the last one's files may still be looked at by a
+	// slower rank, so they go when all ranks have exited (below; an external launcher's rank 0 leaves them behind)
+	if (r.barrier_count >= 2)
+	    unlink((out + "/.barrier" + std::to_string(r.barrier_count - 2) + "." + std::to_string(rank)).c_str());
+	if (rank > 0) { // the scratch directory of small files nobody reads
+	    const std::string cmd = "rm -rf '" + r.outdir + "'";
+	    if (system(cmd.c_str()) != 0) {
+	    }
+	}
+    }
+    if (!children.empty()) {
+	signal(SIGCHLD, SIG_DFL);
+	int rc = 0;
+	for (pid_t p : children) {
+	    int st = 0;
+	    if (waitpid(p, &st, 0) == p && !(WIFEXITED(st) && WEXITSTATUS(st) == 0))
+		rc = 1;
+	}
+	for (int k = 0; k < r.nranks; ++k)
+	    unlink((out + "/.barrier" + std::to_string(r.barrier_count - 1) + "." + std::to_string(k)).c_str());
+	return rc;
+    }
 #endif
     return 0;
 }

@@ -47,3 +47,66 @@ def test_nranks_equals_one_rank(physics, halo):
     for name, st in out["fields"].items():
         assert st["n_diff"] == 0, (name, st)
     assert res.returncode == 0
+
+
+def _setup_with(src, dst, **over):
+    """copy of a setup file with top-level keys replaced (the setups are flat `Key: value` files)"""
+    out = []
+    for ln in open(src):
+        key = ln.split(":", 1)[0].strip()
+        if key in over and not ln.startswith((" ", "-", "#")):
+            out.append(f"{key}: {over.pop(key)}\n")
+        else:
+            out.append(ln)
+    out += [f"{k}: {v}\n" for k, v in over.items()]
+    open(dst, "w").write("".join(out))
+
+
+@pytest.mark.parametrize("setup,over,until,tol", [
+    # planet without feedback: nothing of the host arithmetic depends on the number of ranks -> every file identical
+    ("baseline_config2_setup", {"Nrad": 256, "Naz": 512, "cps": -1, "Nsnapshots": 2, "Nmonitor": 2}, 2, 0.0),
+    # adiabatic, accreting planet that feels the disk: the force and mass sums are all-reduced over the ranks (a different
+    # summation order than one rank's), so the bodies, and through them the fields, agree to rounding only
+    ("adia_accfb_20", {"Nrad": 96}, 5, 1e-11),
+])
+def test_host_driver_ranks_equal_one_rank(setup, over, until, tol, tmp_path):
+    """`fargocpt_b200 start <setup> --ranks N` (one process per GPU, each writing its rings of every field file) against the same
+    run on one GPU: the reference's np-independence (constants.h:17) for the C++ host driver."""
+    import numpy as np
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n = 4 if (n >= 4 and over.get("Nrad", 0) >= 256) else 2
+    exe = os.path.join(ROOT, "host", "fargocpt_b200")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "host")])
+    yml = str(tmp_path / "setup.yml")
+    _setup_with(os.path.join(ROOT, "tests", "golden", setup + ".yml"), yml, **dict(over))
+    outs = {}
+    for ranks in (1, n):
+        out = str(tmp_path / f"out{ranks}")
+        cmd = [exe, "start", yml, "--out", out, "--until", str(until)] + (["--ranks", str(ranks)] if ranks > 1 else [])
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+        outs[ranks] = out
+    assert not [f for f in os.listdir(outs[n]) if f.startswith(".")], os.listdir(outs[n])  # rendezvous / barrier / scratch files are gone
+    worst = 0.0
+    for snap in range(until + 1):
+        d1, dn = (os.path.join(outs[r], "snapshots", str(snap)) for r in (1, n))
+        assert sorted(os.listdir(d1)) == sorted(os.listdir(dn)), (snap, os.listdir(d1), os.listdir(dn))
+        for f in sorted(os.listdir(d1)):
+            a, b = open(os.path.join(d1, f), "rb").read(), open(os.path.join(dn, f), "rb").read()
+            if f.startswith("nbody"):
+                continue  # carries torque accumulators of the all-reduced force integral (rounding-level np dependence)
+            if tol == 0.0:
+                assert a == b, (snap, f)
+                continue
+            if not f.endswith(".dat"):
+                continue  # misc.bin / nbodyK.bin carry the bodies, which agree to rounding like the fields
+            x, y = np.frombuffer(a), np.frombuffer(b)
+            assert x.shape == y.shape, (snap, f)
+            scale = max(np.abs(x).max(), 1e-300)
+            dev = float(np.abs(x - y).max() / scale)
+            worst = max(worst, dev)
+            assert dev <= tol, (snap, f, dev)
+    print(setup, f"{n} ranks vs 1: worst deviation / field scale = {worst:.3g}")
