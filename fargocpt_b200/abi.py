@@ -9,7 +9,7 @@ import os
 
 import numpy as np
 
-FARGO_ABI_VERSION = 2
+FARGO_ABI_VERSION = 3
 FARGO_MAX_BODIES = 8
 CPUOVERLAP = 7
 
@@ -24,6 +24,7 @@ LIMITER = {"vanleer": 0, "mc": 1}
 SPACING = {"logarithmic": 0, "arithmetic": 1, "exponential": 2, "custom": 3}
 BC = {"none": 0, "zerogradient": 1, "outflow": 2, "reflecting": 3, "keplerian": 4, "reference": 5}
 DAMP = {"none": 0, "initial": 1, "reference": 1, "zero": 2, "mean": 3}
+OPACITY = {"lin": 0, "bell": 1, "constant": 2, "simple": 3}  # parameters.cpp:414-428
 BETA_REF = {"zero": 0, "reference": 1, "diskmodel": 2, "floor": 4}  # parameters.cpp:451-463
 
 
@@ -58,6 +59,10 @@ class FargoParams(C.Structure):
         ("damp_vrad", C.c_int * 2), ("damp_vazi", C.c_int * 2), ("damp_sigma", C.c_int * 2),
         ("damp_energy", C.c_int * 2),
         ("correct_disk_selfgravity", C.c_int),
+        ("cooling_surface", C.c_int), ("surface_cooling_factor", C.c_double), ("heating_star", C.c_int), ("opacity", C.c_int),
+        ("kappa_const", C.c_double), ("kappa_factor", C.c_double), ("tau_factor", C.c_double), ("tau_min", C.c_double),
+        ("density_factor", C.c_double),
+        ("temperature_cgs", C.c_double), ("density_cgs", C.c_double), ("opacity_code", C.c_double),
     ]
 
     def as_dict(self):
@@ -91,15 +96,20 @@ class FargoBodies(C.Structure):
         ("x", C.c_double * FARGO_MAX_BODIES), ("y", C.c_double * FARGO_MAX_BODIES),
         ("mass", C.c_double * FARGO_MAX_BODIES), ("cubic_smoothing_radius", C.c_double * FARGO_MAX_BODIES),
         ("indirect_x", C.c_double), ("indirect_y", C.c_double), ("omega_frame", C.c_double),
+        ("temperature", C.c_double * FARGO_MAX_BODIES), ("radius", C.c_double * FARGO_MAX_BODIES),
+        ("irradiation_ramp", C.c_double * FARGO_MAX_BODIES),
     ]
 
     @classmethod
-    def make(cls, x, y, mass, rsm=None, indirect=(0.0, 0.0), omega_frame=0.0):
+    def make(cls, x, y, mass, rsm=None, indirect=(0.0, 0.0), omega_frame=0.0, temperature=None, radius=None, ramp=None):
         b = cls()
         b.n = len(x)
         for k in range(b.n):
             b.x[k], b.y[k], b.mass[k] = x[k], y[k], mass[k]
             b.cubic_smoothing_radius[k] = 0.0 if rsm is None else rsm[k]
+            b.temperature[k] = 0.0 if temperature is None else temperature[k]
+            b.radius[k] = 0.0 if radius is None else radius[k]
+            b.irradiation_ramp[k] = 1.0 if ramp is None else ramp[k]
         b.indirect_x, b.indirect_y = indirect
         b.omega_frame = omega_frame
         return b

@@ -25,7 +25,8 @@ def _num(v, unit_cgs=None):
     return x
 
 
-def params_from_config(cfg, consts, nrad, naz, temp_unit_K=1.0):
+def params_from_config(cfg, consts, nrad, naz, temp_unit_K=1.0, units=None):
+    """units: code -> cgs factors of units.yml ({"density": ..., "opacity": ...}); only the radiative terms need them."""
     g = {k.lower(): v for k, v in cfg.items()}
 
     def get(key, default=None):
@@ -71,6 +72,23 @@ def params_from_config(cfg, consts, nrad, naz, temp_unit_K=1.0):
     d["cooling_beta_value"] = float(get("CoolingBeta", 1.0))
     d["cooling_beta_ramp_up"] = _num(get("CoolingBetaRampUp", 0.0))
     d["cooling_beta_reference"] = abi.BETA_REF[str(get("CoolingBetaReference", "zero")).lower()]
+    # radiative surface cooling / stellar irradiation (parameters.cpp:389-435, 628-632; planetary_system.cpp:137-146)
+    sc = str(get("SurfaceCooling", "No")).lower()
+    if sc not in ("no", "off", "false", "thermal"):
+        raise ValueError("SurfaceCooling: %s is outside this path" % sc)
+    d["cooling_surface"] = int(sc == "thermal")
+    d["surface_cooling_factor"] = float(get("CoolingRadiativeFactor", 1.0))
+    d["heating_star"] = int(any(_num(b.get("temperature", 0.0)) > 0 for b in (get("nbody") or [])))
+    d["opacity"] = abi.OPACITY[str(get("Opacity", "Lin")).lower()]
+    units = units or {}
+    d["kappa_const"] = _num(get("KappaConst", 1.0), units.get("opacity"))
+    d["kappa_factor"] = float(get("KappaFactor", 1.0))
+    d["tau_factor"] = float(get("TauFactor", 0.5))
+    d["tau_min"] = float(get("TauMin", 0.01))
+    d["density_factor"] = float(get("DensityFactor", (2.0 * 3.141592653589793) ** 0.5))
+    d["temperature_cgs"] = float(temp_unit_K)
+    d["density_cgs"] = float(units.get("density", 1.0))
+    d["opacity_code"] = 1.0 / float(units.get("opacity", 1.0))
     d["body_force_from_potential"] = int(_flag(get("BodyForceFromPotential"), True))
     d["thickness_smoothing"] = float(get("ThicknessSmoothing", 0.6))
     d["imposed_disk_drift"] = float(get("ImposedDiskDrift", 0.0))

@@ -687,9 +687,9 @@ extern "C" int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, con
 	    return n;
 	};
 	const int occ_fs = adi ? std::min(occ((const void *)k_fused_sources<true, false>),
-					  std::min(occ((const void *)k_fused_artvisc<true>), occ((const void *)k_fused_viscosity<true>)))
+					  std::min(occ((const void *)k_fused_artvisc<true>), occ((const void *)k_fused_viscosity<true, false>)))
 			       : std::min(occ((const void *)k_fused_sources<false, false>),
-					  std::min(occ((const void *)k_fused_artvisc<false>), occ((const void *)k_fused_viscosity<false>)));
+					  std::min(occ((const void *)k_fused_artvisc<false>), occ((const void *)k_fused_viscosity<false, false>)));
 	const int occ_az = mc ? (adi ? occ((const void *)k_transport_azimuthal<FARGO_LIMITER_MC, true, false>)
 				     : occ((const void *)k_transport_azimuthal<FARGO_LIMITER_MC, false, false>))
 			      : (adi ? occ((const void *)k_transport_azimuthal<FARGO_LIMITER_VANLEER, true, false>)
@@ -1542,8 +1542,14 @@ template <bool ADI> static int launch_fused_sources(fargo_ctx *c, double dt)
     }
     {
 	const int eo3 = ADI ? 1 - c->ecur : c->ecur;
-	LAUNCH(c, k_fused_viscosity<ADI>, grid, 128, 0, v, c->sigma, EN(c), VRA(c), VPA(c), c->sigma0, c->energy0, VRB(c), VPB(c),
-	       c->eb[eo3], c->qplus, c->qminus, (double *)(p.leapfrog ? c->hstale : nullptr), dt, ADI ? beta_inv_host(c) : 0.0, c->fs_R);
+	if (ADI && (p.cooling_surface || p.heating_star)) // with thermal_cooling / irradiation (kernels_rad.cuh)
+	    LAUNCH_NAMED(c, c->stream, "k_fused_viscosity<ADI>", (k_fused_viscosity<ADI, ADI>), grid, 128, 0, v, c->sigma, EN(c), VRA(c), VPA(c),
+			 c->sigma0, c->energy0, VRB(c), VPB(c), c->eb[eo3], c->qplus, c->qminus,
+			 (double *)(p.leapfrog ? c->hstale : nullptr), dt, ADI ? beta_inv_host(c) : 0.0, c->fs_R);
+	else
+	    LAUNCH_NAMED(c, c->stream, "k_fused_viscosity<ADI>", (k_fused_viscosity<ADI, false>), grid, 128, 0, v,
+			 c->sigma, EN(c), VRA(c), VPA(c), c->sigma0, c->energy0, VRB(c), VPB(c), c->eb[eo3], c->qplus, c->qminus,
+			 (double *)(p.leapfrog ? c->hstale : nullptr), dt, ADI ? beta_inv_host(c) : 0.0, c->fs_R);
 	c->h_stale = p.leapfrog != 0;
 	c->vcur = 1 - c->vcur;
 	c->ecur = eo3;

@@ -651,15 +651,20 @@ __device__ __forceinline__ void st_visc_v(const DevView &c, const int r, const d
 }
 // SubStep3 (SourceEuler.cpp:859-954) for ring r: Q+ (viscous_heating :496-536), Q- (thermal_relaxation :632-690),
 // radiative alpha_r, the energy update and the temperature floor / ceiling
-template <class M>
+// RAD: also thermal_cooling / irradiation (kernels_rad.cuh; plain operators, a separate instantiation of the kernel);
+// cosj / sinj: azimuth of the thread's columns (only read with RAD)
+template <class M, bool RAD>
 __device__ __forceinline__ void st_substep3(const DevView &c, const TempClampNB &tc, const int r, const double dt,
 					     const double beta_inv, const VsIn &I, const double (&E1)[FS_NC], const double (&N1)[FS_NC],
 					     const double (&H1)[FS_NC], const double (&DV1)[FS_NC], const double (&TRR1)[FS_NC],
-					     const double (&TPP1)[FS_NC], const double (&s0)[FS_NC], const double (&e0)[FS_NC], double (&Qp)[FS_NC],
+					     const double (&TPP1)[FS_NC], const double (&s0)[FS_NC], const double (&e0)[FS_NC],
+					     const double (&cosj)[FS_NC], const double (&sinj)[FS_NC], double (&Qp)[FS_NC],
 					     double (&Qm)[FS_NC], double (&En)[FS_NC], FmAcc &A)
 {
     const bool inner = r >= 1 && r < c.nr - 1;
     const fargo_params &p = c.p;
+    double tau_eff[FS_NC];
+    FS_FOR4 tau_eff[k] = 0.0; // TAU_EFF stays 0 as allocated unless kappa_eff runs
     FS_FOR4
     {
 	double qp = 0.0, qm = 0.0;
@@ -685,6 +690,14 @@ __device__ __forceinline__ void st_substep3(const DevView &c, const TempClampNB 
 		delta_E -= M::div_y(M::div_y(p.minimum_temperature * I.S1[k], tc.mu, tc.ymu, A) * p.Rgas, tc.gm1, tc.ygm1, A);
 	    qm = 0.0 + delta_E * c.g.omega_k[r] * beta_inv;
 	}
+	if (RAD && inner) {
+	    const double T = rad_temperature(c, I.S1[k], E1[k]);
+	    tau_eff[k] = rad_tau_eff(c, I.S1[k], H1[k], T);
+	    if (p.cooling_surface)
+		qm += rad_qminus(c, T, tau_eff[k]);
+	    if (p.heating_star)
+		rad_add_qplus(c, r, cosj[k], sinj[k], H1[k], tau_eff[k], qp);
+	}
 	double en = E1[k];
 	if (inner) {
 	    // alpha_r = 1 + 2 H 4 sigma_SB / c (mu (gamma-1) / (R Sigma))^4 e^3  (:921-924)
@@ -704,8 +717,7 @@ __device__ __forceinline__ void st_substep3(const DevView &c, const TempClampNB 
 	FS_FOR4
 	{
 	    if (I.S1[k] < SigmaFloor) { // rare: cells at the density floor
-		/* TAU_EFF is only filled by surface cooling (out of scope) => 0 as allocated */
-		const double e4 = Qp[k] * 0.0 / (2.0 * p.sigma_sb);
+		const double e4 = Qp[k] * tau_eff[k] / (2.0 * p.sigma_sb);
 		const double constant = (p.Rgas / p.mu * I.S1[k] / (p.gamma - 1.0));
 		Qm[k] = Qp[k];
 		En[k] = pow(e4, 1.0 / 4.0) * constant;
@@ -718,7 +730,7 @@ __device__ __forceinline__ void st_substep3(const DevView &c, const TempClampNB 
 // has everything: div v, tau_rr, tau_phiphi (need v_rad(r+1)), the velocity updates (need tau_rphi(r+1), the
 // centred stresses of r-1) and, for the energy equation, Q+ / Q- / the new energy.
 // StabilizeViscosity != 0 is not handled here (the host falls back to the staged kernels).
-template <bool ADI>
+template <bool ADI, bool RAD>
 __global__ void __launch_bounds__(128, FS_MINB_VISC)
     k_fused_viscosity(const DevView c, const double *__restrict__ sigma, const double *__restrict__ energy,
 		      const double *__restrict__ vr, const double *__restrict__ vp, const double *__restrict__ sigma0,
@@ -741,6 +753,17 @@ __global__ void __launch_bounds__(128, FS_MINB_VISC)
     TempClampNB tc;
     if (ADI)
 	tc = make_temp_clamp_nb(c);
+    double cosj[FS_NC], sinj[FS_NC]; // azimuth of the thread's columns (irradiation only)
+    FS_FOR4 cosj[k] = sinj[k] = 0.0;
+    if (RAD) {
+	int cc = L.col;
+	FS_FOR4
+	{
+	    cosj[k] = c.g.cosphi[cc];
+	    sinj[k] = c.g.sinphi[cc];
+	    cc = (cc + 1 == c.ns) ? 0 : cc + 1;
+	}
+    }
     VsIn I;
     double E1[FS_NC], N1[FS_NC], H1[FS_NC];
     FS_FOR4
@@ -829,8 +852,8 @@ __global__ void __launch_bounds__(128, FS_MINB_VISC)
 		} else {
 		    FS_FOR4 { s0[k] = 1.0, e0[k] = 1.0; }
 		}
-		FS_RUN((st_substep3<MF>(c, tc, r, dt, beta_inv, I, E1, N1, H1, DV1, TRR1, TPP1, s0, e0, Qp, Qm, En, A)),
-		       (st_substep3<MS>(c, tc, r, dt, beta_inv, I, E1, N1, H1, DV1, TRR1, TPP1, s0, e0, Qp, Qm, En, A)));
+		FS_RUN((st_substep3<MF, RAD>(c, tc, r, dt, beta_inv, I, E1, N1, H1, DV1, TRR1, TPP1, s0, e0, cosj, sinj, Qp, Qm, En, A)),
+		       (st_substep3<MS, RAD>(c, tc, r, dt, beta_inv, I, E1, N1, H1, DV1, TRR1, TPP1, s0, e0, cosj, sinj, Qp, Qm, En, A)));
 		FS_RUN(FS_FOR4 Ec[k] = temperature_clamp_nb(tc, I.S1[k], En[k], A), FS_FOR4 Ec[k] = temperature_clamp(c, I.S1[k], En[k]));
 		if (r >= i_first) {
 		    fs_store(o_qplus, r, c, L, Qp);

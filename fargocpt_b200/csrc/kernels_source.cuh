@@ -11,6 +11,7 @@
 // (v_rad / v_azi ping-pong between the A and B buffers), everything else is updated in place.
 #pragma once
 #include "fargo_dev.h"
+#include "kernels_rad.cuh"
 
 #define CELL_INDEX(total_rings)                                              \
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;  \
@@ -400,6 +401,16 @@ __global__ void __launch_bounds__(256)
     const bool need0 = c.p.cooling_beta && (c.p.cooling_beta_reference & FARGO_BETA_REF_REFERENCE);
     double Qp = qplus_cell(c, sigma, nu, divv, trr, tpp, trp, i, j, jp);
     double Qm = qminus_cell(c, beta_inv, s, e, need0 ? AT(sigma0, i, j) : 1.0, need0 ? AT(energy0, i, j) : 0.0, i);
+    double tau_eff = 0.0; // TAU_EFF stays 0 as allocated unless kappa_eff runs
+    if (rad_enabled(c) && i >= 1 && i < c.nr - 1) { // thermal_cooling / irradiation (kernels_rad.cuh)
+	const double H = eos_H(c, i, eos_cs(c, i, s, e));
+	const double T = rad_temperature(c, s, e);
+	tau_eff = rad_tau_eff(c, s, H, T);
+	if (c.p.cooling_surface)
+	    Qm += rad_qminus(c, T, tau_eff);
+	if (c.p.heating_star)
+	    rad_add_qplus(c, i, c.g.cosphi[j], c.g.sinphi[j], H, tau_eff, Qp);
+    }
     if (i >= 1 && i < c.nr - 1) {
 	const double alpha = radiative_alpha(c, i, s, e);
 	Qp /= alpha;
@@ -408,8 +419,7 @@ __global__ void __launch_bounds__(256)
 	    double energy_new = e + dt * (Qp - Qm);
 	    const double SigmaFloor = 10.0 * c.p.sigma0 * c.p.sigma_floor;
 	    if (s < SigmaFloor) {
-		/* TAU_EFF is only filled by surface cooling (out of scope) => 0 as allocated */
-		const double e4 = Qp * 0.0 / (2.0 * c.p.sigma_sb);
+		const double e4 = Qp * tau_eff / (2.0 * c.p.sigma_sb);
 		const double constant = (c.p.Rgas / c.p.mu * s / (c.p.gamma - 1.0));
 		const double eq_energy = pow(e4, 1.0 / 4.0) * constant;
 		Qm = Qp;

@@ -268,6 +268,7 @@ static bool key_is_known(const char *list, const std::string &k)
 struct CodeConstants {
     double G = 1.0, R = 1.0, sigma_sb = 0.0, c_light = 0.0, temperature_unit_K = 1.0;
     double length_cgs = 1.0, mass_cgs = 1.0, time_cgs = 1.0; // units.yml: code -> cgs factors of the base units
+    double density_cgs = 1.0, opacity_cgs = 1.0;	     // ... and of the two the opacity tables need (opacity.cpp:13-14)
     void load(const std::string &dir)
     {
 	std::ifstream f(dir + "/constants.yml");
@@ -306,6 +307,10 @@ struct CodeConstants {
 		    mass_cgs = v;
 		else if (block == "time:")
 		    time_cgs = v;
+		else if (block == "density:")
+		    density_cgs = v;
+		else if (block == "opacity:")
+		    opacity_cgs = v;
 	    }
 	}
     }
@@ -339,8 +344,8 @@ static fargo_params make_params(const Config &c, const CodeConstants &k, int nra
 	    die("%s", std::string("the deprecated 'Adiabatic' flag is not supported; use EquationOfState"));
 	const bool energy_equation = eos == "adiabatic" || eos == "ideal"; // SubStep3 only runs then (simulation.cpp:203-205)
 	const std::string sc = lower(c.str("SurfaceCooling", "No")); // parameters.cpp:394-406
-	if (energy_equation && !(sc == "no" || sc == "off" || sc == "false"))
-	    die("SurfaceCooling: %s is not supported by this driver (beta cooling only)", sc);
+	if (energy_equation && !(sc == "no" || sc == "off" || sc == "false" || sc == "thermal"))
+	    die("SurfaceCooling: %s is not supported by this driver (beta cooling, thermal)", sc);
 	const std::pair<const char *, double> zero_only[] = {{"AlphaMode", 0}, {"AspectRatioMode", 0}};
 	for (auto &k : zero_only)
 	    if (c.num(k.first, k.second) != k.second)
@@ -350,15 +355,17 @@ static fargo_params make_params(const Config &c, const CodeConstants &k, int nra
 			      "ViscAccretMassflowTest"})
 	    if (c.flag(k, false))
 		die((std::string(k) + ": %s is not supported by this driver").c_str(), c.str(k, ""));
-	for (auto &b : c.nbody)
-	    if (energy_equation && b.count("irradiate") && !b.at("irradiate").empty() && std::strchr("yYtT1", b.at("irradiate")[0]))
-		die("%s", std::string("irradiating bodies (nbody: irradiate: yes) are not supported by this driver"));
     }
     const std::string eos = lower(c.str("EquationOfState", "Isothermal"));
     p.adiabatic = (eos == "ideal" || eos == "adiabatic") ? 1 : 0;
     p.gamma = c.num("AdiabaticIndex", 1.4);
     p.mu = c.num("mu", 1.0);
     p.aspectratio_ref = c.num("AspectRatio", 0.05);
+    { // Interpret.cpp:194-197: a reference temperature at r = 1 replaces the aspect ratio
+	const double T0 = c.num("Temperature0", -1.0, k.temperature_unit_K);
+	if (T0 > 0.0)
+	    p.aspectratio_ref = std::sqrt(T0 * k.R / p.mu);
+    }
     p.flaring_index = c.num("FlaringIndex", 0.0);
     // default "173 g/cm2" (parameters.cpp:625); a value with a unit has been converted by the caller (`start`) already
     p.sigma0 = c.has("Sigma0") ? c.num("Sigma0", 0.0) : 173.0 / (k.mass_cgs / (k.length_cgs * k.length_cgs));
@@ -427,6 +434,21 @@ static fargo_params make_params(const Config &c, const CodeConstants &k, int nra
 	p.keplerian_azimuthal_factor[s] = c.num(std::string(sides[s]) + "BoundaryVaziKeplerianFactor", 1.0);
     }
     p.correct_disk_selfgravity = c.flag("CorrectDiskSelfgravity", !c.flag("SelfGravity", false)); // parameters.cpp:699
+    // radiative surface cooling, opacity (parameters.cpp:389-435, 628-632); heating_star is set by the caller from the bodies
+    // (t_planetary_system::derive_config, planetary_system.cpp:137-146)
+    p.cooling_surface = (p.adiabatic && lower(c.str("SurfaceCooling", "No")) == "thermal") ? 1 : 0;
+    p.surface_cooling_factor = c.num("CoolingRadiativeFactor", 1.0);
+    p.heating_star = 0;
+    p.opacity = enum_of(c.str("Opacity", "Lin"), {{"lin", FARGO_OPACITY_LIN}, {"bell", FARGO_OPACITY_BELL}, {"constant", FARGO_OPACITY_CONST},
+						 {"simple", FARGO_OPACITY_SIMPLE}}, "Opacity");
+    p.kappa_const = c.num("KappaConst", 1.0, k.opacity_cgs);
+    p.kappa_factor = c.num("KappaFactor", 1.0);
+    p.tau_factor = c.num("TauFactor", 0.5);
+    p.tau_min = c.num("TauMin", 0.01);
+    p.density_factor = c.num("DensityFactor", std::sqrt(2.0 * M_PI));
+    p.temperature_cgs = k.temperature_unit_K;
+    p.density_cgs = k.density_cgs;
+    p.opacity_code = 1.0 / k.opacity_cgs;
     p.damping = c.flag("Damping", false);
     p.damping_inner_limit = c.num("DampingInnerLimit", 1.05);
     p.damping_outer_limit = c.num("DampingOuterLimit", 0.95);
@@ -643,6 +665,10 @@ struct Run {
 	    const Body &b = bodies[k];
 	    fb.x[k] = b.rec.x, fb.y[k] = b.rec.y, fb.mass[k] = rampup_mass(b, time);
 	    fb.cubic_smoothing_radius[k] = b.rec.dimensionless_roche_radius * b.rec.distance_to_primary * b.rec.cubic_smoothing_factor;
+	    // irradiation_single (SourceEuler.cpp:538-564)
+	    fb.temperature[k] = b.rec.temperature, fb.radius[k] = b.rec.radius;
+	    const double tr = b.rec.irradiation_rampuptime;
+	    fb.irradiation_ramp[k] = time < tr ? 1.0 - std::pow(std::cos(time * M_PI / 2.0 / tr), 2) : 1.0;
 	}
 	combine_indirect();
 	fb.indirect_x = ind_x;
@@ -861,6 +887,11 @@ struct Run {
 
     void create_context(int device)
     {
+	// t_planetary_system::derive_config (planetary_system.cpp:137-146): a body with a temperature irradiates
+	params.heating_star = 0;
+	for (const Body &b : bodies)
+	    if (params.adiabatic && b.rec.temperature > 0)
+		params.heating_star = 1;
 #ifdef FARGO_HOST_ORACLE
 	(void)device;
 	ctx = fargo_oracle_create(&params, radii.data(), 0, 1);
@@ -1015,6 +1046,7 @@ struct Run {
 	consts.G = U.G.code, consts.R = U.R.code, consts.sigma_sb = U.sigma.code, consts.c_light = U.c.code;
 	consts.temperature_unit_K = U.temperature;
 	consts.length_cgs = U.length, consts.mass_cgs = U.mass, consts.time_cgs = U.time;
+	consts.density_cgs = U.density, consts.opacity_cgs = U.opacity;
 	const int shock_tube = (int)cfg.num("ShockTube", 0);
 	if (shock_tube != 0 && shock_tube != 1)
 	    die("ShockTube: %s is not supported by this driver (1: the ideal-gas tube)", cfg.str("ShockTube", ""));

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define FARGO_ABI_VERSION 2
+#define FARGO_ABI_VERSION 3
 #define FARGO_MAX_BODIES 8
 /* src/constants.h:17 (CPUOVERLAP) and :19 (GHOSTCELLS_B) */
 #define FARGO_CPUOVERLAP 7
@@ -132,7 +132,19 @@ typedef struct fargo_params {
     int damp_vrad[2], damp_vazi[2], damp_sigma[2], damp_energy[2]; /* enum fargo_damping */
     /* disk -> body force (Force.cpp:64-66): subtract the ring-mean density; CorrectDiskSelfgravity, default yes without self-gravity */
     int correct_disk_selfgravity;
+    /* radiative surface cooling and stellar irradiation (SubStep3: SourceEuler.cpp:538-612 irradiation_single, :693-723
+     * thermal_cooling; compute.cpp:17-88 midplane_density / kappa_eff; opacity.cpp:11-298).  heating_star is derived by the
+     * host like t_planetary_system::derive_config (a body with temperature > 0 irradiates). */
+    int cooling_surface;           /* SurfaceCooling: thermal */
+    double surface_cooling_factor; /* CoolingRadiativeFactor */
+    int heating_star;
+    int opacity;                   /* enum fargo_opacity */
+    double kappa_const;            /* KappaConst (code units) */
+    double kappa_factor, tau_factor, tau_min, density_factor; /* KappaFactor, TauFactor, TauMin, DensityFactor */
+    double temperature_cgs, density_cgs, opacity_code; /* units::temperature / density code -> cgs, units::opacity cgs -> code */
 } fargo_params;
+/* parameters::t_opacity (parameters.h), Opacity: Lin | Bell | Constant | Simple */
+enum fargo_opacity { FARGO_OPACITY_LIN = 0, FARGO_OPACITY_BELL = 1, FARGO_OPACITY_CONST = 2, FARGO_OPACITY_SIMPLE = 3 };
 
 /* Star/planets as seen by the gas for ONE step (Pframeforce.cpp:27-36, refframe::IndirectTerm).
  * The N-body integration stays on the host (planetary_system.cpp); the host refreshes this every step. */
@@ -143,6 +155,9 @@ typedef struct fargo_bodies {
     double cubic_smoothing_radius[FARGO_MAX_BODIES]; /* g_cubic_smoothing_radius, 0 = disabled */
     double indirect_x, indirect_y;                   /* refframe::IndirectTerm */
     double omega_frame;                              /* refframe::OmegaFrame */
+    /* irradiation_single (SourceEuler.cpp:538-564): temperature > 0 marks an irradiating body; radius = planet_radial_extend;
+     * ramp = 1 - cos^2(t pi / 2 / rampuptime) before the ramp-up time, else 1 (formed on the host) */
+    double temperature[FARGO_MAX_BODIES], radius[FARGO_MAX_BODIES], irradiation_ramp[FARGO_MAX_BODIES];
 } fargo_bodies;
 
 typedef struct fargo_ctx fargo_ctx;

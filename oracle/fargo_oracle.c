@@ -801,16 +801,152 @@ int fargo_oracle_stage_viscosity(fargo_oracle *o, double dt)
 }
 
 /* ------------------------------------------------------------------------------------------
+ * opacities (opacity.cpp:11-298).  The Lin & Papaloizou (1985) and Bell & Lin (1994) tables are eight power laws of
+ * (rho, T) in cgs units joined by smoothing functions; the two differ in their constants and in five expressions, so they
+ * are ONE function over a coefficient set here.  Operation order as in the reference (the results feed pow()). */
+typedef struct {
+    double power1, power2, power3, t234, t456, t678;
+    double ak1, ak2, ak3, bk3, bk4, bk5, bk6, bk7, bk8;
+    int bell;
+} op_law;
+static const op_law OP_LIN = {4.44444444e-2, 2.381e-2, 2.267e-1, 1.6e3, 5.7e3, 2.28e6, 2.e-4, 2.e16, 5.e-3, 50., 2.e-2, 2.e4, 1.e4, 1.5e10, 0.348, 0};
+static const op_law OP_BELL = {2.8369e-2, 1.1464e-2, 2.2667e-1, 1.46e3, 4.51e3, 2.37e6, 2.e-4, 2.e16, 0.1e0, 10., 2.e-15, 1e4, 1e4, 1.5e10, 0.348, 1};
+static double opacity_table(const op_law *L, double density, double temperature)
+{
+    if (L->bell && temperature < 1.0)
+	temperature = 10.0; /* opacity.cpp:204-206 */
+    if (temperature > L->t234 * pow(density, L->power1)) {
+	const double ts4 = 1.e-4 * temperature;
+	const double density13 = pow(density, 1.0 / 3.0);
+	const double density23 = density13 * density13;
+	const double ts42 = ts4 * ts4;
+	const double ts44 = ts42 * ts42;
+	const double ts48 = ts44 * ts44;
+	if (temperature > L->t456 * pow(density, L->power2)) {
+	    const int mid = L->bell ? ((temperature < L->t678 * pow(density, L->power3)) || ((density <= 1e10) && (temperature < 1e4)))
+				    : ((temperature < L->t678 * pow(density, L->power3)) || (density <= 1e-10));
+	    if (mid) { /* laws 5, 6, 7 */
+		const double o5 = L->bk5 * density23 * ts42 * ts4;
+		const double o6 = L->bk6 * density13 * ts48 * ts42;
+		const double o7 = L->bk7 * density / (ts42 * sqrt(ts4));
+		const double o6an = o6 * o6, o7an = o7 * o7;
+		return pow(pow(o6an * o7an / (o6an + o7an), 2) + pow(o5 / (1.0 + pow(ts4 / (1.1 * pow(density, 0.04762)), 10.0)), 4.0), 0.25);
+	    }
+	    { /* laws 7, 8 */
+		const double o7 = L->bk7 * density / (ts42 * sqrt(ts4));
+		const double o8 = L->bk8;
+		const double o7an = o7 * o7, o8an = o8 * o8;
+		return pow(o7an * o7an + o8an * o8an, 0.25);
+	    }
+	}
+	{ /* laws 3, 4, 5 */
+	    const double o3 = L->bell ? L->bk3 * sqrt(ts4) : L->bk3 * ts4;
+	    const double o4 = L->bell ? L->bk4 * density / (ts48 * ts48 * ts48) : L->bk4 * density23 / (ts48 * ts4);
+	    const double o5 = L->bk5 * density23 * ts42 * ts4;
+	    const double o4an = pow(o4, 4), o3an = pow(o3, 4);
+	    const double damp = L->bell ? (1 + 6.561e-5 / ts48 * 1e2 * density23) : (1.0 + 6.561e-5 / ts48);
+	    return pow((o4an * o3an / (o4an + o3an)) + pow(o5 / damp, 4), 0.25);
+	}
+    }
+    { /* laws 1, 2, 3: powers of the temperature itself */
+	const double t2 = temperature * temperature;
+	const double t4 = t2 * t2;
+	const double t8 = t4 * t4;
+	const double t10 = t8 * t2;
+	const double o1 = L->ak1 * t2;
+	const double o2 = L->ak2 * temperature / t8;
+	const double o3 = L->bell ? L->ak3 * sqrt(temperature) : L->ak3 * temperature;
+	const double o1an = o1 * o1, o2an = o2 * o2;
+	return pow(pow(o1an * o2an / (o1an + o2an), 2) + pow(o3 / (1 + 1.e22 / t10), 4), 0.25);
+    }
+}
+/* opacity::opacity (opacity.cpp:11-44), code units in and out */
+static double opacity_code(const fargo_oracle *o, double density, double temperature)
+{
+    const double temperatureCGS = temperature * o->p.temperature_cgs;
+    const double densityCGS = density * o->p.density_cgs;
+    double rv;
+    switch (o->p.opacity) {
+    case FARGO_OPACITY_LIN: rv = opacity_table(&OP_LIN, densityCGS, temperatureCGS) * o->p.opacity_code; break;
+    case FARGO_OPACITY_BELL: rv = opacity_table(&OP_BELL, densityCGS, temperatureCGS) * o->p.opacity_code; break;
+    case FARGO_OPACITY_CONST: rv = o->p.kappa_const; break;
+    default: rv = o->p.kappa_const * pow(temperatureCGS, 2); break; /* Simple */
+    }
+    return o->p.kappa_factor * rv;
+}
+
+/* compute::midplane_density + compute::kappa_eff (compute.cpp:17-88): tau_eff of every cell from the stored temperature and a
+ * freshly recomputed scale height */
+static void compute_tau_eff(fargo_oracle *o)
+{
+    compute_scale_height(o);
+    const size_t n = (size_t)o->nr * o->ns;
+#pragma omp parallel for
+    for (size_t c = 0; c < n; ++c) {
+	const double rho = o->sigma[c] / (o->p.density_factor * o->scale_height[c]);
+	const double kappa = opacity_code(o, rho, o->temperature[c]);
+	const double tau = o->p.tau_factor * (1.0 / o->p.density_factor) * kappa * o->sigma[c];
+	if (o->p.heating_star)
+	    o->tau_eff[c] = 3.0 / 8.0 * tau + 0.5 + 1.0 / (4.0 * tau + o->p.tau_min);
+	else
+	    o->tau_eff[c] = 3.0 / 8.0 * tau + sqrt(3.0) / 4.0 + 1.0 / (4.0 * tau + o->p.tau_min);
+	if (o->p.opacity == FARGO_OPACITY_SIMPLE)
+	    o->tau_eff[c] = 3.0 / 8.0 * tau;
+    }
+}
+
+/* thermal_cooling, SourceEuler.cpp:693-723 */
+static void thermal_cooling(fargo_oracle *o)
+{
+    const int Nr = o->nr - 1, Nphi = o->ns;
+    compute_tau_eff(o);
+#pragma omp parallel for
+    for (int nr = 1; nr < Nr; ++nr) {
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const size_t c = IDX(o, nr, naz);
+	    const double T4 = pow(o->temperature[c], 4);
+	    const double Tmin4 = pow(o->p.minimum_temperature, 4);
+	    o->qminus[c] += o->p.surface_cooling_factor * 2 * o->p.sigma_sb * (T4 - Tmin4) / o->tau_eff[c];
+	}
+    }
+}
+
+/* irradiation_single, SourceEuler.cpp:538-596, for body k */
+static void irradiation_single(fargo_oracle *o, int k)
+{
+    const fargo_bodies *b = &o->bodies;
+    const double ramping = b->irradiation_ramp[k];
+    const double x = b->x[k], y = b->y[k], R_star = b->radius[k], T_star = b->temperature[k];
+    const double min_dist = (x * x + y * y > 1e-10) ? stdmax(R_star, b->cubic_smoothing_radius[k]) : R_star;
+    const int Nrad = o->nr - 1, Naz = o->ns - 1;
+#pragma omp parallel for
+    for (int nrad = 1; nrad < Nrad; ++nrad) {
+	for (int naz = 0; naz <= Naz; ++naz) {
+	    const size_t c = IDX(o, nrad, naz);
+	    const double xc = o->rmed[nrad] * o->cosphi[naz], yc = o->rmed[nrad] * o->sinphi[naz];
+	    const double distance_measured = sqrt(pow(x - xc, 2) + pow(y - yc, 2));
+	    const double distance = stdmax(distance_measured, min_dist);
+	    const double roverd = distance < R_star ? 1.0 : R_star / distance;
+	    const double HoverR = o->scale_height[c] / o->rmed[nrad]; /* ASPECTRATIO of compute_scale_height, SourceEuler.cpp:1148-1151 */
+	    const double eps = 0.5;
+	    const double dlogH_dlogr = 9.0 / 7.0;
+	    const double W_G = 0.4 * roverd + HoverR * (dlogH_dlogr - 1.0);
+	    const double T_irrad_pow4 = (1.0 - eps) * pow(T_star, 4) * pow(roverd, 2) * W_G;
+	    const double qplus = 2.0 * o->p.sigma_sb * T_irrad_pow4 / o->tau_eff[c];
+	    o->qplus[c] += ramping * qplus;
+	}
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
  * energy sources: calculate_qminus :834, calculate_qplus :614, SubStep3 :859 (SourceEuler.cpp) */
 static void calculate_qminus(fargo_oracle *o)
 {
     const int Nr = o->nr - 1, Nphi = o->ns;
     memset(o->qminus, 0, (size_t)o->nr * o->ns * sizeof(double));
-    if (!o->p.cooling_beta)
-	return;
     /* thermal_relaxation :632-690 */
 #pragma omp parallel for
-    for (int nr = 1; nr < Nr; ++nr) {
+    for (int nr = 1; nr < (o->p.cooling_beta ? Nr : 0); ++nr) {
 	for (int naz = 0; naz < Nphi; ++naz) {
 	    const size_t c = IDX(o, nr, naz);
 	    const double omega_k = omega_kepler(o, o->rmed[nr]);
@@ -838,17 +974,17 @@ static void calculate_qminus(fargo_oracle *o)
 	    o->qminus[c] += delta_E * omega_k * beta_inv;
 	}
     }
+    if (o->p.cooling_surface)
+	thermal_cooling(o);
 }
 
 static void calculate_qplus(fargo_oracle *o)
 {
     const int Nr_m1 = o->nr - 1, Nphi = o->ns;
     memset(o->qplus, 0, (size_t)o->nr * o->ns * sizeof(double));
-    if (!o->p.heating_viscous)
-	return;
     /* viscous_heating :496-536 */
 #pragma omp parallel for
-    for (int nr = 1; nr < Nr_m1; ++nr) {
+    for (int nr = 1; nr < (o->p.heating_viscous ? Nr_m1 : 0); ++nr) {
 	for (int naz = 0; naz < Nphi; ++naz) {
 	    const size_t c = IDX(o, nr, naz);
 	    if (o->viscosity[c] != 0.0) {
@@ -860,6 +996,13 @@ static void calculate_qplus(fargo_oracle *o)
 		o->qplus[c] += qplus;
 	    }
 	}
+    }
+    if (o->p.heating_star) { /* calculate_qplus :621-627 */
+	if (!o->p.cooling_surface)
+	    compute_tau_eff(o);
+	for (int k = 0; k < o->bodies.n; ++k)
+	    if (o->bodies.temperature[k] > 0)
+		irradiation_single(o, k);
     }
 }
 

@@ -8,6 +8,7 @@ setups of the same physics (tests/golden/*_setup.yml) — no reference tree need
   test/shockTube           check_results.py:15-20     integrated |numerical - exact Sod| at t = 0.228 below 0.0073 / 0.0153 / 0.014 / 0.016
   test/spreading_ring      calc_deviation.py:38-66    mean |Sigma / Sigma_analytic - 1| < 0.007 at t = 314.159 (39 870 hydro steps)
   test/cold_disk_planet    calc_deviation.py:24-35    max |T(100 orbits) / T(0) - 1| < 0.1 (14 000 hydro steps)
+  test/irradiation         check_results.py:40-120    max |T / T_theory - 1| < 0.03 for 2 < r < 15 au after 62 800 time units (168 596 steps)
 Prints one line per check and exits non-zero if one fails."""
 import os
 import struct
@@ -88,6 +89,25 @@ def main():
     ok &= dev < 0.1
     print(f"cold_disk_planet ({nr} x {naz}): max |T(100 orbits) / T(0) - 1| = {dev:.5f} (< 0.1)  ({steps} steps, {secs:.1f} s)  "
           f"{'PASS' if dev < 0.1 else 'FAIL'}")
+    # --- irradiation: thermal surface cooling against stellar irradiation (D'Angelo & Marzari 2012, eq. 16, as check_results.py
+    # states it: constants and the stellar temperature of the theory curve copied from there)
+    cfg = yaml.safe_load(open(os.path.join(GOLDEN, "irradiation_setup.yml")))
+    out, steps, secs = run(exe, cfg, 10)
+    dims = [l for l in open(os.path.join(out, "dimensions.dat")) if not l.startswith("#")][-1].split()
+    nr, naz = int(dims[4]), int(dims[5])
+    r12 = np.loadtxt(os.path.join(out, "used_rad.dat"))
+    r = 2.0 / 3.0 * (r12[1:] ** 3 - r12[:-1] ** 3) / (r12[1:] ** 2 - r12[:-1] ** 2)  # Rmed (init.cpp:188-195)
+    units = yaml.safe_load(open(os.path.join(out, "units.yml")))
+    T = np.fromfile(os.path.join(out, "snapshots", "10", "Temperature.dat")).reshape(nr, naz).mean(axis=1) * float(units["temperature"]["cgs value"])
+    mu, m_H, k_B, l0, m0, G = 2.35, 1.66054e-24, 1.38065e-16, 14959787070000, 1.98847e+33, 6.6743e-08
+    eta, eps, Rs, Ts = 2 / 7, 0.5, 4.6505e-05 * l0, 100000
+    rc = r * l0
+    htheo = (eta * (1 - eps) * (k_B * Ts / (mu * m_H)) ** 4 * (Rs / (G * m0)) ** 4 * (rc / Rs) ** 2) ** (1 / 7)
+    Ttheo = Ts * np.sqrt(Rs / rc) * ((1 - eps) * (0.4 * (Rs / rc) + htheo * eta)) ** (1 / 4)
+    sel = (r > 2) & (r < 15)
+    dev = float(np.max(np.abs(T - Ttheo)[sel] / Ttheo[sel]))
+    ok &= dev < 0.03
+    print(f"irradiation ({nr} x {naz}): max |T / T_theory - 1| = {dev:.5f} (< 0.03)  ({steps} steps, {secs:.1f} s)  {'PASS' if dev < 0.03 else 'FAIL'}")
     sys.exit(0 if ok else 1)
 
 

@@ -119,6 +119,18 @@ CASES = {
     "adia_accfb_20": dict(Nrad=48, Naz=160, Rmax=2.5, Nsnapshots=20, MonitorTimestep=4.0e-3, IndirectTermMode=1,
                           ViscousAlpha=1e-3, HeatingViscous="yes", CoolingBetaLocal="yes", CoolingBeta=10, DiskFeedback="yes",
                           _planet=3e-3, _accretion=5.0, _keep=(0, 10, 20)),
+    # SurfaceCooling: thermal + an irradiating star (SourceEuler.cpp:538-723, compute.cpp:17-88) with a constant opacity, as
+    # test/irradiation sets them up (there with Naz = 2); viscous heating on, no beta cooling
+    "adia_irrad": dict(ViscousAlpha=1e-3, HeatingViscous="yes", SurfaceCooling="thermal", Opacity="Constant", KappaConst="2.0e-6",
+                       TauFactor=1.0, HeatingCoolingCFLlimit=1000.0, ArtificialViscosity="None", ArtificialViscosityDissipation="No",
+                       _star={"temperature": "10000 K", "irradiation ramp-up time": 5.0e-3}),
+    # the same physics through step_LeapFrog, where SubStep3 runs in both kicks
+    "adia_irrad_lf": dict(Integrator="Leapfrog", ViscousAlpha=1e-3, HeatingViscous="yes", SurfaceCooling="thermal", Opacity="Constant",
+                          KappaConst="2.0e-6", TauFactor=1.0, _star={"temperature": "10000 K"}),
+    # thermal cooling alone (the non-irradiated tau_eff) through the Lin & Papaloizou and the Bell & Lin opacity tables
+    "adia_cool_lin": dict(ViscousAlpha=1e-3, HeatingViscous="yes", SurfaceCooling="thermal", Opacity="Lin"),
+    "adia_cool_bell": dict(ViscousAlpha=1e-3, HeatingViscous="yes", SurfaceCooling="thermal", Opacity="Bell", KappaFactor=2.0,
+                           _planet=3e-4, IndirectTermMode=1),
     "iso_planet_100": dict(Nrad=48, Naz=160, Rmax=2.5, Nsnapshots=100, MonitorTimestep=4.0e-3, IndirectTermMode=1,
                            EquationOfState="Isothermal", ViscousAlpha=1e-3, ArtificialViscosityFactor=1.41, OmegaFrame=1.0,
                            FlaringIndex=0.0, Damping="Yes", DampingInnerLimit=1.25, DampingOuterLimit=0.84,
@@ -130,7 +142,7 @@ def parse_constants(outdir):
     c = yaml.safe_load(open(os.path.join(outdir, "constants.yml")))
     u = yaml.safe_load(open(os.path.join(outdir, "units.yml")))
     consts = {v["symbol"]: float(v["code value"]) for v in c.values()}
-    return consts, float(u["temperature"]["cgs value"])
+    return consts, float(u["temperature"]["cgs value"]), {k: float(u[k]["cgs value"]) for k in ("density", "opacity")}
 
 
 def read_misc(path):
@@ -148,13 +160,21 @@ def read_body(path):
     acc_eff, accreted = struct.unpack("<2d", raw[56:72])
     dist_primary, roche = struct.unpack("<2d", raw[152:168])
     (semi_major,) = struct.unpack("<d", raw[176:184])
-    return [mass, x, y, vx, vy, dax, day, acc_eff, accreted, dist_primary, roche, semi_major]
+    # irradiation_single (SourceEuler.cpp:538-564): temperature and radius (:22-23), irradiation ramp-up time (:25), cubic
+    # smoothing factor (:18)
+    temperature, radius = struct.unpack("<2d", raw[80:96])
+    (irr_rampup,) = struct.unpack("<d", raw[104:112])
+    (cubic,) = struct.unpack("<d", raw[48:56])
+    return [mass, x, y, vx, vy, dax, day, acc_eff, accreted, dist_primary, roche, semi_major, temperature, radius, irr_rampup, cubic]
 
 
 def run_case(name, overrides, keep=False):
     cfg = dict(BASE)
     cfg.update(overrides)
     planet = cfg.pop("_planet", 0.0)
+    star = cfg.pop("_star", None)
+    if star:
+        cfg["nbody"] = [dict(cfg["nbody"][0], **star)]
     keep_snaps = cfg.pop("_keep", None)
     accretion = cfg.pop("_accretion", 0.0)
     accretion_method = cfg.pop("_accretion_method", "kley")
@@ -175,12 +195,12 @@ def run_case(name, overrides, keep=False):
         print(res.stdout[-3000:], res.stderr[-3000:])
         raise SystemExit(f"reference run failed for {name}")
     out = cfg["OutputDir"]
-    consts, temp_unit = parse_constants(out)
+    consts, temp_unit, units = parse_constants(out)
     dims = [l for l in open(os.path.join(out, "dimensions.dat")) if not l.startswith("#")][-1].split()
     nrad, naz = int(dims[4]), int(dims[5])
     radii = np.loadtxt(os.path.join(out, "used_rad.dat"))
     assert radii.shape == (nrad + 1,)
-    pdict = reftools.params_from_config(cfg, consts, nrad, naz, temp_unit)
+    pdict = reftools.params_from_config(cfg, consts, nrad, naz, temp_unit, units)
     nsnap = int(cfg["Nsnapshots"])
     nb = len(cfg["nbody"])
     arrays = {"radii": radii}

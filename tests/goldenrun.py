@@ -52,8 +52,15 @@ def bodies_at(meta, k, omega_frame):
         # potential is evaluated (simulation.cpp:150-172): its mass is the one recorded at the END of the step
         nxt = meta["bodies"][min(k + 1, len(meta["bodies"]) - 1)]
         masses = [nxt[i][0] if (len(b) > 7 and b[7] > 0.0) else b[0] for i, b in enumerate(bl)]
+    rad = {}
+    if len(bl[0]) >= 16:  # fixtures recorded with the irradiation members of the planet records (SourceEuler.cpp:538-564)
+        import math
+        t = meta["misc"][k]["time"]
+        rad = dict(temperature=[b[12] for b in bl], radius=[b[13] for b in bl],
+                   ramp=[1.0 - math.pow(math.cos(t * math.pi / 2.0 / b[14]), 2) if t < b[14] else 1.0 for b in bl],
+                   rsm=[b[10] * b[9] * b[15] for b in bl])  # Pframeforce.cpp:33-35: l1 * cubic smoothing factor
     return abi.FargoBodies.make([b[1] for b in bl], [b[2] for b in bl], masses, indirect=indirect,
-                                omega_frame=omega_frame)
+                                omega_frame=omega_frame, **rad)
 
 
 def start_from_snapshot0(ctx, meta, z):

@@ -17,6 +17,13 @@ from fargocpt_b200 import abi
 pytestmark = pytest.mark.gpu
 
 CASES = ["adia_star", "adia_cold", "iso_star", "iso_sn_std", "adia_sn_stab", "ring_like", "adia_leapfrog", "iso_feedback_20"]
+# SurfaceCooling: thermal + an irradiating star with a constant opacity (SourceEuler.cpp:538-723, compute.cpp:17-88): IEEE
+# operators and x^4 only, so bit-exact like everything else (Euler and Leapfrog)
+CASES += ["adia_irrad", "adia_irrad_lf"]
+# the Lin & Papaloizou / Bell & Lin opacity tables call pow() with fractional exponents (opacity.cpp:49-298): CUDA's pow and
+# glibc's differ in the last bits, so these two runs are held to a tolerance instead (fields, dt)
+POW_CASES = ["adia_cool_lin", "adia_cool_bell"]
+POW_RTOL = 1e-12
 # 100 hydro steps with a Jupiter-mass planet (48 x 160: two warp windows per ring), recorded from the reference
 LONG_CASES = ["adia_planet_100", "iso_planet_100"]
 # a planet that accretes gas out of its Hill sphere first thing in every step (accretion.cpp:84-221)
@@ -93,6 +100,28 @@ def test_golden_run_vs_reference(name, staged):
             if (fname == "energy" and not gpu.params.adiabatic) or fname not in snap:
                 continue
             _check(name, (k, fname), snap[fname], z[f"{fname}_{k}"])
+
+
+@pytest.mark.parametrize("staged", [False, True], ids=["fused", "staged"])
+@pytest.mark.parametrize("name", POW_CASES)
+def test_opacity_table_runs_vs_reference(name, staged):
+    """Thermal cooling through the tabulated opacities: identical step counts and times, dt and fields within POW_RTOL of the
+    reference (of the field's scale), fused and staged kernels."""
+    meta, z, gpu, cpu = _ctx_pair(name)
+    gpu.set_staged(staged)
+    snaps = goldenrun.run_fixture(gpu, meta, z)
+    worst = 0.0
+    for k, snap in enumerate(snaps, start=1):
+        m = meta["misc"][k]
+        assert snap["n_iter"] == m["n_iter"]
+        assert snap["time"] == m["time"]
+        assert snap["last_dt"] == pytest.approx(m["last_dt"], rel=POW_RTOL)
+        for fname in ("Sigma", "vrad", "vazi", "energy"):
+            ref = z[f"{fname}_{k}"]
+            dev = float(np.abs(snap[fname] - ref).max() / np.abs(ref).max())
+            worst = max(worst, dev)
+            assert dev <= POW_RTOL, (name, k, fname, dev)
+    print(name, "worst deviation / field scale:", worst)
 
 
 @pytest.mark.parametrize("name", ["adia_star", "iso_star"])

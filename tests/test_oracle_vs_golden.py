@@ -8,7 +8,10 @@ import reftools
 
 CASES = ["adia_star", "adia_cold", "iso_star", "iso_sn_std", "adia_sn_stab", "ring_like", "adia_planet_100", "iso_planet_100",
          "adia_leapfrog", "iso_feedback_20", "iso_accrete_20", "adia_accrete_20", "iso_sinkhole_20",
-         "adia_viscacc_20"]  # viscous accretion (accretion.cpp:335-417)
+         "adia_viscacc_20",  # viscous accretion (accretion.cpp:335-417)
+         # SurfaceCooling: thermal / irradiating star (SourceEuler.cpp:538-723, compute.cpp:17-88, opacity.cpp): constant
+         # opacity (Euler, Leapfrog), Lin & Papaloizou and Bell & Lin tables
+         "adia_irrad", "adia_irrad_lf", "adia_cool_lin", "adia_cool_bell"]
 # Isothermal configs have no per-cell transcendental in the step => demanded bit-exact.
 # Adiabatic configs call exp() per cell (SourceEuler.cpp:487); same libm here => also bit-exact on CPU.
 # DiskFeedback: the reference sums the disk's pull with an OpenMP reduction in no defined order, so the acceleration
