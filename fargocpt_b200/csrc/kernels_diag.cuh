@@ -3,6 +3,15 @@
 //   k_disk_on_body / k_disk_on_body_final ComputeDiskOnPlanetAccel (Force.cpp:23-122), per step with DiskFeedback
 #pragma once
 #include "fargo_dev.h"
+
+// Which cells credit their accreted gas to the planet: the reference's condition is `radial_first_active < i < radial_active_size`
+// (accretion.cpp:186-187, strictly), which at np = 1 leaves out the first active ring next to the inner boundary — and at np > 1
+// also the first OWNED ring of every further rank, whose gas is then removed from the disk but credited to nobody: the one place
+// where the reference's result depends on np.  Here N GPUs reproduce the np = 1 result: only rank 0 skips its first active ring.
+__device__ __forceinline__ bool accrete_counts(const DevView &c, const int i)
+{
+    return (c.rank == 0 ? c.first_active < i : c.first_active <= i) && i < c.active_size;
+}
 #include "kernels_source.cuh"
 
 // ring means of the cell-centred velocities, summed strictly in index order like the reference's serial inner loop
@@ -225,7 +234,7 @@ __global__ void __launch_bounds__(ACC_THREADS)
 	    double s = AT(sigma, i, j);
 	    double e = c.p.adiabatic ? AT(energy, i, j) : 0.0;
 	    const double facc_max = 1 - a.density_floor / s;
-	    const bool active = c.first_active < i && i < c.active_size;
+	    const bool active = accrete_counts(c, i);
 	    {
 		const double facc_ceil = stdmin(a.facc1, facc_max);
 		const double deltaM = facc_ceil * s * c.g.surf[i];
@@ -309,7 +318,7 @@ __global__ void __launch_bounds__(ACC_THREADS)
 	    AT(sigma, i, j) = s * (1.0 - facc_ceil);
 	    if (c.p.adiabatic)
 		AT(energy, i, j) = AT(energy, i, j) * (1.0 - facc_ceil);
-	    if (c.first_active < i && i < c.active_size) {
+	    if (accrete_counts(c, i)) {
 		acc[1] += deltaM * vxcell;
 		acc[2] += deltaM * vycell;
 		acc[0] += deltaM;

@@ -1741,7 +1741,9 @@ int fargo_oracle_step(fargo_oracle *o, double dt)
  * accretion efficiency / orbital period * ln 2 and RHill = dimensionless Roche radius * distance to the primary are the
  * N-body side's numbers.  The reference walks a window of cells around the planet that contains every cell inside
  * frac * RHill; testing every cell's distance gives the same cells.  out3 = mass and momentum taken from ACTIVE cells
- * (radial_first_active < i < radial_active_size, :171), summed in index order. */
+ * (radial_first_active < i < radial_active_size, :171), summed in index order.  With more than one rank the reference's
+ * condition also drops the first OWNED ring of every rank but the first (its only np-dependent result); slabs here count
+ * that ring, so N slabs reproduce the np = 1 run. */
 int fargo_oracle_accrete_sinkhole(fargo_oracle *o, double xp, double yp, double r_hill, double facc, double frac, double out3[3]);
 int fargo_oracle_accrete_kley(fargo_oracle *o, double xp, double yp, double r_hill, double facc, double frac, double out3[3])
 {
@@ -1764,7 +1766,7 @@ int fargo_oracle_accrete_kley(fargo_oracle *o, double xp, double yp, double r_hi
 	    const double vxcell = (vrcell * xc - vtcell * yc) / o->rmed[i];
 	    const double vycell = (vrcell * yc + vtcell * xc) / o->rmed[i];
 	    const double facc_max = 1 - density_floor / o->sigma[l];
-	    const int active = o->first_active < i && i < o->active_size;
+	    const int active = (o->rank == 0 ? o->first_active < i : o->first_active <= i) && i < o->active_size;
 	    {
 		const double facc_ceil = facc_max < facc1 ? facc_max : facc1; /* std::min(facc1, facc_max) */
 		const double deltaM = facc_ceil * o->sigma[l] * o->surf[i];
@@ -1820,7 +1822,7 @@ int fargo_oracle_accrete_sinkhole(fargo_oracle *o, double xp, double yp, double 
 	    o->sigma[l] *= 1.0 - facc_ceil;
 	    if (o->p.adiabatic)
 		o->energy[l] *= 1.0 - facc_ceil;
-	    if (o->first_active < i && i < o->active_size) {
+	    if ((o->rank == 0 ? o->first_active < i : o->first_active <= i) && i < o->active_size) {
 		dPx += deltaM * vxcell;
 		dPy += deltaM * vycell;
 		dM += deltaM;
@@ -1863,7 +1865,7 @@ int fargo_oracle_accrete_viscous(fargo_oracle *o, double xp, double yp, double r
 	    o->sigma[l] *= 1.0 - facc_ceil;
 	    if (o->p.adiabatic)
 		o->energy[l] *= 1.0 - facc_ceil;
-	    if (o->first_active < i && i < o->active_size) {
+	    if ((o->rank == 0 ? o->first_active < i : o->first_active <= i) && i < o->active_size) {
 		dPx += deltaM * vxcell;
 		dPy += deltaM * vycell;
 		dM += deltaM;
