@@ -36,7 +36,7 @@ B_ALG = {"adiabatic_planet": 400.0, "cold_disk_planet": 312.0, "isothermal_plane
 KERNEL_BYTES = {
     "k_transport_azimuthal<ADI>": 88.0, "k_transport_azimuthal<ISO>": 72.0,
     "(k_transport_radial<LIM, true>)": 80.0, "(k_transport_radial<LIM, false>)": 64.0,
-    "k_fused_sources<ADI>": 56.0, "k_fused_artvisc<ADI>": 56.0, "k_fused_viscosity<ADI>": 88.0,  # 72 + Sigma0, e0 (beta cooling)
+    "(k_fused_sources<ADI, false>)": 56.0, "k_fused_artvisc<ADI>": 56.0, "k_fused_viscosity<ADI>": 88.0,  # 72 + Sigma0, e0 (beta cooling)
     "k_potential": 24.0, "k_sources_velocity": 56.0, "k_compression_heating": 32.0, "k_artvisc_q": 56.0,
     "k_artvisc_v": 56.0, "k_viscosity_nu": 24.0, "k_stress": 64.0, "k_viscosity_v": 64.0, "k_substep3": 96.0,
     "k_cfl": 48.0, "k_ring_mean[cfl]": 8.0, "k_ring_mean[transport,side-stream]": 8.0,
