@@ -403,7 +403,9 @@ def run_gpu(args):
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "what": f"restart (upload 4 state fields from pinned host memory) + {E2E_INTERVALS} intervals of {args.steps} steps, each ending in an "
-                        "asynchronous snapshot of the 4 state fields into pinned host memory (overlaps the next interval); ends when the last snapshot is on the host"},
+                        "asynchronous snapshot of the 4 state fields into pinned host memory (overlaps the next interval); ends when the last snapshot is on the host. "
+                        "A stress cadence: PCIe-bound once a step takes a few ms (N > 2); the reference's own configs write a snapshot every 1e3-1e4 hydro "
+                        "steps, where the end-to-end rate is `value` (every step of `value` already reads its dt back through the ABI)"},
         "gpu_launches": int(launches),
         "roofline": roof,
         "step_roofline": {"achieved_gbs_per_gpu": step_roof, "frac_of_measured_peak": step_roof / peaks["hbm_gbs"],

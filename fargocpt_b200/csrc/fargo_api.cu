@@ -273,7 +273,7 @@ static inline unsigned cells_grid(long long n, int block = 256) { return (unsign
 // split.cpp:38-87
 // SplitDomain (split.cpp:38-87): contiguous rings per rank plus CPUOVERLAP ghost rings per interior side, and the loop
 // bounds of a slab.  The reference gives every rank the same number of rings; here the cut points balance COST: a ring
-// inside a damping zone is also read and written by k_damping (~2.5 % of a ring's step per damped field, measured on
+// inside a damping zone costs more (~1.85 % of a ring's step per damped field in the azimuthal kernel's epilogue, measured on
 // B200), and the damping zones sit on the first and last ranks — at 8 GPUs their step was 6 % longer than everyone
 // else's.  Results do not depend on where the cuts are (constants.h:17; tests/test_gpu_multi.py holds N ranks to 1 rank
 // bit for bit).  FARGO_B200_SPLIT=equal restores the reference's cut points.
@@ -295,7 +295,10 @@ extern "C" int fargo_split_cuts(const fargo_params *params, const double *radii,
 	for (int k = 0; k < 2; ++k)
 	    nf += (p.damp_vrad[k] != FARGO_DAMP_NONE) + (p.damp_vazi[k] != FARGO_DAMP_NONE) + (p.damp_sigma[k] != FARGO_DAMP_NONE) +
 		  (p.adiabatic && p.damp_energy[k] != FARGO_DAMP_NONE);
-	const double wd = 0.025 * 0.5 * nf; // both sides configured: nf counts every damped field twice
+	// (0.025 per field when k_damping was a pass of its own; folded into the azimuthal kernel's epilogue with its initial-field
+	// columns staged through shared memory a damped ring costs 7.4 % more than an undamped one with all four fields damped:
+	// 8-GPU kernel times of the edge rank against the interior ranks, profiles/r02_m8_bench_scaling.jsonl)
+	const double wd = 0.0185 * 0.5 * nf; // both sides configured: nf counts every damped field twice
 	std::vector<double> cum(nrad + 1, 0.0);
 	for (int i = 0; i < nrad; ++i) {
 	    const double r = 0.5 * (radii[i] + radii[i + 1]);
