@@ -897,11 +897,14 @@ extern "C" int fargo_snapshot_async(fargo_ctx *c, double *sigma, double *vrad, d
 	CUDA_OK(cudaEventCreateWithFlags(&c->ev_snap_ready, cudaEventDisableTiming));
 	CUDA_OK(cudaEventCreateWithFlags(&c->ev_snap_done, cudaEventDisableTiming));
 	CUDA_OK(cudaEventRecord(c->ev_snap_done, c->stream_snap));
-	const size_t len[4] = {ns, nv, ns, ns};
-	for (int k = 0; k < 4; ++k)
-	    if (k < 3 || c->v.p.adiabatic)
-		CUDA_OK(cudaMalloc((void **)&c->snap[k], len[k] * sizeof(double)));
+	const size_t len[3] = {ns, nv, ns};
+	for (int k = 0; k < 3; ++k)
+	    CUDA_OK(cudaMalloc((void **)&c->snap[k], len[k] * sizeof(double)));
     }
+    // the energy grid also travels for an isothermal run whose caller asks for it (the reference writes it out too: it holds
+    // the energy ring of CircumBinaryRing, zeros otherwise)
+    if (energy && !c->snap[3])
+	CUDA_OK(cudaMalloc((void **)&c->snap[3], ns * sizeof(double)));
     double *src[4] = {c->sigma, VRA(c), VPA(c), EN(c)};
     double *host[4] = {sigma, vrad, vazi, energy};
     const bool first = c->v.rank == 0, last = c->v.rank == c->v.nranks - 1;

@@ -679,3 +679,65 @@ def test_baseline_config_setups_against_the_reference_at_reduced_resolution(k, t
     snap0 = [l for l in buf.getvalue().splitlines() if l.startswith("snapshot 0:")][0]
     assert "misc identical" in snap0 and snap0.count("ndiff=0 ") >= 3, snap0
     assert worst <= 1e-10, buf.getvalue()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The product driver (GPU) against the oracle-bound driver: the same host code on two backends whose hydro results agree bit for
+# bit, so every file they write must be identical — frames, circumbinary disks, initial-condition variants, monitor files.
+GPU_VS_ORACLE_DRIVER = [
+    ("circumbinary_setup", {}),
+    # an isothermal run that carries an energy grid (the Gaussian ring): it must reach the snapshot through fargo_snapshot_async
+    ("circumbinary_setup", {"CircumBinaryRing": "yes", "CircumBinaryRingPosition": 1.5, "CircumBinaryRingWidth": 0.2, "SigmaCondition": "Nbody",
+                            "SetSigma0": "yes", "DiskMass": 0.01}),
+    ("circumbinary_setup", {"HydroFrameCenter": "all", "Integrator": "Leapfrog", "DiskFeedback": "yes", "IndirectTermMode": 0}),
+    ("corotating_setup", {"DiskFeedback": "yes", "IndirectTermMode": 0}),
+    ("multi_body_setup", {}),
+    ("minimal_defaults_setup", {}),
+    ("adia_irrad_lf", {"WriteTemperature": "yes", "WritePressure": "yes", "WriteSoundSpeed": "yes", "WriteScaleHeight": "yes", "WriteViscosity": "yes"}),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("setup,over", GPU_VS_ORACLE_DRIVER)
+def test_gpu_driver_writes_what_the_oracle_bound_driver_writes(setup, over, tmp_path):
+    cfg = {k: v for k, v in yaml.safe_load(open(os.path.join(ROOT, "tests", "golden", setup + ".yml"))).items() if not k.startswith("_")}
+    cfg.update({"MonitorTimestep": 2e-3, "Nmonitor": 1, "Nsnapshots": 3, "WriteAtEveryTimestep": "yes"})
+    cfg.update(over)
+    yml = str(tmp_path / "setup.yml")
+    yaml.safe_dump(cfg, open(yml, "w"), sort_keys=False)
+    outs = {}
+    for kind, exe in (("gpu", os.path.join(ROOT, "host", "fargocpt_b200")), ("oracle", _oracle_exe())):
+        outs[kind] = str(tmp_path / kind)
+        _run_start(exe, yml, outs[kind], 3)
+    nfiles = 0
+    for dirpath, _, files in os.walk(outs["oracle"]):
+        for f in files:
+            po = os.path.join(dirpath, f)
+            pg = os.path.join(outs["gpu"], os.path.relpath(po, outs["oracle"]))
+            assert os.path.exists(pg), pg
+            if f == "timestepLogging.dat" or f.startswith(("nbody", "Quantities")) and f.endswith(".dat") and "monitor" in dirpath:
+                # monitor sums: device reductions against the oracle's sequential sums agree to rounding, not to the bit
+                a = np.array([[float(x) for x in l.split()] for l in open(po) if not l.startswith("#") and l.strip()])
+                b = np.array([[float(x) for x in l.split()] for l in open(pg) if not l.startswith("#") and l.strip()])
+                assert a.shape == b.shape, f
+                assert np.array_equal(np.isnan(a), np.isnan(b)), f
+                scale = np.maximum(np.nanmax(np.abs(a), axis=0), 1e-300)
+                assert np.nanmax(np.abs(np.nan_to_num(a) - np.nan_to_num(b)) / scale) < 1e-9, f
+                continue
+            rel = os.path.relpath(po, outs["oracle"])
+            a, b = open(po, "rb").read(), open(pg, "rb").read()
+            feedback = str(cfg.get("DiskFeedback", "no")).lower().startswith("y")
+            if f.startswith("nbody") and f.endswith(".bin"):
+                # the record carries the disk's pull on the body (offsets 120-152) and torque sums: device reductions, rounding-level
+                x, y = np.frombuffer(a[8:72]), np.frombuffer(b[8:72])  # mass, x, y, vx, vy, smoothing, accretion efficiency, accreted mass
+                assert np.allclose(x, y, rtol=1e-12 if feedback else 0.0, atol=0.0), (rel, x, y)
+            elif feedback and f.endswith(".dat"):
+                # the reduced pull moves the bodies, so the gas follows to rounding
+                x, y = np.nan_to_num(np.frombuffer(a)), np.nan_to_num(np.frombuffer(b))
+                assert x.shape == y.shape and np.abs(x - y).max() <= 1e-12 * max(np.abs(x).max(), 1e-300), rel
+            elif f == "misc.bin" and feedback:
+                assert np.allclose(np.frombuffer(a[8:40]), np.frombuffer(b[8:40]), rtol=1e-12), rel
+            else:
+                assert a == b, rel
+            nfiles += 1
+    assert nfiles >= 20
