@@ -280,29 +280,29 @@ __global__ void __launch_bounds__(256)
     CELL_INDEX(c.nr);
     if (i < 1)
 	return;
-    const double NuSig_rp = AT(nusig_rp, i, j);
-    const double NuSig_rp_ip = AT(nusig_rp, i + 1, j); /* ring nr of the (vector) grid stays 0 */
-    const double NuSig_rp_jp = AT(nusig_rp, i, jp);
-    const double NuSigma = AT(nusig, i, j);
-    const double NuSigma_jm = AT(nusig, i, jm);
-    const double NuSigma_im = AT(nusig, i - 1, j);
-    const double Ra3a = NuSig_rp * pow(c.g.rinf[i], 3.0) * c.g.invdiffrmed[i];
-    const double Ra3b = NuSig_rp_ip * pow(c.g.rinf[i + 1], 3.0) * c.g.invdiffrmed[i + 1];
-    const double cphi_rp = -c.g.invrmed[i] * c.g.twodiffrasq[i] * (Ra3b + Ra3a);
-    const double cphi_pp = -c.g.fourthird[i] * (NuSigma + NuSigma_jm);
-    const double sigma_avg_phi = 0.5 * (AT(sigma, i, j) + AT(sigma, i, jm));
-    AT(cf_phi, i, j) = (cphi_rp + cphi_pp) / (sigma_avg_phi * c.g.rmed[i]);
-    const double sigma_avg_r = 0.5 * (AT(sigma, i, j) + AT(sigma, i - 1, j));
-    const double cr_rp = -(NuSig_rp_jp + NuSig_rp) / (c.dphi * c.dphi * c.g.rinf[i]);
-    const double cr_pp_1 = 2.0 * NuSigma * (0.5 * c.g.invrmed[i] + 1.0 / 3.0 * c.g.rinf[i] * c.g.invdiffrsuprb[i]);
-    const double cr_pp_2 = 2.0 * NuSigma_im * (0.5 * c.g.invrmed[i - 1] - 1.0 / 3.0 * c.g.rinf[i] * c.g.invdiffrsuprb[i - 1]);
-    const double cr_rr_1 = c.g.rmed[i] * 2.0 * NuSigma * (-c.g.invdiffrsup[i] + 1.0 / 3.0 * c.g.rinf[i] * c.g.invdiffrsuprb[i]);
-    const double cr_rr_2 =
-	-1.0 * c.g.rmed[i - 1] * 2.0 * NuSigma_im * (c.g.invdiffrsup[i - 1] - 1.0 / 3.0 * c.g.rinf[i] * c.g.invdiffrsuprb[i - 1]);
-    const double cr_pp = -0.5 * (cr_pp_1 + cr_pp_2);
-    const double cr_rr = c.g.invdiffrmed[i] * (cr_rr_1 + cr_rr_2);
-    const double Rmed_mid = 0.5 * (c.g.rmed[i] + c.g.rmed[i - 1]);
-    AT(cf_r, i, j) = c.p.radial_viscosity_factor * (cr_rr + cr_rp + cr_pp) / (sigma_avg_r * Rmed_mid);
+    const double ns_corner = AT(nusig_rp, i, j);
+    const double ns_corner_out = AT(nusig_rp, i + 1, j); /* ring nr of the (vector) grid stays 0 */
+    const double ns_corner_next = AT(nusig_rp, i, jp);
+    const double ns_cell = AT(nusig, i, j);
+    const double ns_left = AT(nusig, i, jm);
+    const double ns_inner = AT(nusig, i - 1, j);
+    const double flux_in = ns_corner * pow(c.g.rinf[i], 3.0) * c.g.invdiffrmed[i];
+    const double flux_out = ns_corner_out * pow(c.g.rinf[i + 1], 3.0) * c.g.invdiffrmed[i + 1];
+    const double kphi_shear = -c.g.invrmed[i] * c.g.twodiffrasq[i] * (flux_out + flux_in);
+    const double kphi_normal = -c.g.fourthird[i] * (ns_cell + ns_left);
+    const double s_phi = 0.5 * (AT(sigma, i, j) + AT(sigma, i, jm));
+    AT(cf_phi, i, j) = (kphi_shear + kphi_normal) / (s_phi * c.g.rmed[i]);
+    const double s_rad = 0.5 * (AT(sigma, i, j) + AT(sigma, i - 1, j));
+    const double kr_shear = -(ns_corner_next + ns_corner) / (c.dphi * c.dphi * c.g.rinf[i]);
+    const double kr_hoop_a = 2.0 * ns_cell * (0.5 * c.g.invrmed[i] + 1.0 / 3.0 * c.g.rinf[i] * c.g.invdiffrsuprb[i]);
+    const double kr_hoop_b = 2.0 * ns_inner * (0.5 * c.g.invrmed[i - 1] - 1.0 / 3.0 * c.g.rinf[i] * c.g.invdiffrsuprb[i - 1]);
+    const double kr_norm_a = c.g.rmed[i] * 2.0 * ns_cell * (-c.g.invdiffrsup[i] + 1.0 / 3.0 * c.g.rinf[i] * c.g.invdiffrsuprb[i]);
+    const double kr_norm_b =
+	-1.0 * c.g.rmed[i - 1] * 2.0 * ns_inner * (c.g.invdiffrsup[i - 1] - 1.0 / 3.0 * c.g.rinf[i] * c.g.invdiffrsuprb[i - 1]);
+    const double kr_hoop = -0.5 * (kr_hoop_a + kr_hoop_b);
+    const double kr_norm = c.g.invdiffrmed[i] * (kr_norm_a + kr_norm_b);
+    const double r_iface = 0.5 * (c.g.rmed[i] + c.g.rmed[i - 1]);
+    AT(cf_r, i, j) = c.p.radial_viscosity_factor * (kr_norm + kr_shear + kr_hoop) / (s_rad * r_iface);
 }
 
 // update_velocities_with_viscosity (viscosity.cpp:355-426), in place
