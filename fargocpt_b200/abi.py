@@ -15,7 +15,7 @@ CPUOVERLAP = 7
 
 # enum fargo_field
 (SIGMA, VRAD, VAZI, ENERGY, SIGMA0, VRAD0, VAZI0, ENERGY0, QPLUS, QMINUS, TEMPERATURE, PRESSURE, SOUNDSPEED,
- SCALE_HEIGHT, VISCOSITY, POTENTIAL, T_REYNOLDS) = range(17)
+ SCALE_HEIGHT, VISCOSITY, POTENTIAL, T_REYNOLDS, GAMMAEFF, MU, GAMMA1) = range(20)
 FIELD_NAMES = {SIGMA: "Sigma", VRAD: "vrad", VAZI: "vazi", ENERGY: "energy", QPLUS: "Qplus", QMINUS: "Qminus"}
 VECTOR_FIELDS = (VRAD, VRAD0)
 
@@ -63,6 +63,7 @@ class FargoParams(C.Structure):
         ("kappa_const", C.c_double), ("kappa_factor", C.c_double), ("tau_factor", C.c_double), ("tau_min", C.c_double),
         ("density_factor", C.c_double),
         ("temperature_cgs", C.c_double), ("density_cgs", C.c_double), ("opacity_code", C.c_double),
+        ("pvte", C.c_int), ("energy_density_cgs", C.c_double), ("surface_density_cgs", C.c_double),
     ]
 
     def as_dict(self):
@@ -88,6 +89,26 @@ class FargoParams(C.Structure):
             p.correct_disk_selfgravity = 1  # parameters.cpp:699 default without self-gravity
         p.abi_version = FARGO_ABI_VERSION
         return p
+
+
+class PvteConsts(C.Structure):
+    """fargo_pvte_consts: the cgs constants exactly as constants.cpp:48-85 forms them (same IEEE operations)."""
+    _fields_ = [("xMF", C.c_double), ("m_H", C.c_double), ("m_e", C.c_double), ("eV", C.c_double), ("h", C.c_double),
+                ("k_B", C.c_double), ("mp", C.c_double)]
+
+    @classmethod
+    def make(cls, hydrogen_mass_fraction=0.75):
+        cm, g, s, K = 0.01, 0.001, 1.0, 1.0
+        k = cls()
+        k.xMF = hydrogen_mass_fraction
+        m_u = 1.66053906660e-27 * 1.0 / g
+        k.m_H = 1.007825 * m_u
+        k.m_e = 9.1093837015e-31 * 1.0 / g
+        k.eV = 1.0e7 * 1.602176634e-19
+        k.h = 6.62607015e-34 * 1.0 / (g * cm * cm / s)
+        k.k_B = 1.380649e-23 * 1.0 / (g * cm * cm / (K * s * s))
+        k.mp = 1.67262192369e-27 * 1.0 / g
+        return k
 
 
 class FargoBodies(C.Structure):
@@ -131,7 +152,7 @@ def _bind(lib, prefix):
         "download_slab": ([vp, C.c_int, _DP], C.c_int),
         "copy_initial_values": ([vp], C.c_int),
         "set_bodies": ([vp, C.POINTER(FargoBodies)], C.c_int), "set_time": ([vp, C.c_double], C.c_int),
-        "init_derived": ([vp], C.c_int),
+        "init_derived": ([vp], C.c_int), "set_pvte": ([vp, C.POINTER(PvteConsts)], C.c_int),
         "cfl": ([vp, _DP, _DP], C.c_int), "condition_cfl": ([vp, _DP], C.c_int),
         "step": ([vp, C.c_double], C.c_int),
         "kick": ([vp, C.c_double], C.c_int), "drift": ([vp, C.c_double], C.c_int), "finish_step": ([vp, C.c_double], C.c_int),
@@ -204,6 +225,10 @@ class Handle:
 
     def set_time(self, t):
         self._check(self._call("set_time", float(t)), "set_time")
+
+    def set_pvte(self, hydrogen_mass_fraction=0.75):
+        k = PvteConsts.make(hydrogen_mass_fraction)
+        self._check(self._call("set_pvte", C.byref(k)), "set_pvte")
 
     def init_derived(self):
         self._check(self._call("init_derived"), "init_derived")

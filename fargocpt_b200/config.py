@@ -39,7 +39,8 @@ def params_from_config(cfg, consts, nrad, naz, temp_unit_K=1.0, units=None):
     d["radial_spacing"] = abi.SPACING[spacing]
     d["rmin"], d["rmax"] = float(get("Rmin")), float(get("Rmax"))
     eos = str(get("EquationOfState", "Isothermal")).lower()
-    d["adiabatic"] = 1 if eos in ("ideal", "adiabatic", "perfect") else 0
+    d["adiabatic"] = 1 if eos in ("ideal", "adiabatic", "perfect", "pvte", "pvtelaw") else 0
+    d["pvte"] = 1 if eos in ("pvte", "pvtelaw") else 0  # Interpret.cpp:453-491
     d["gamma"] = float(get("AdiabaticIndex", 1.4))
     d["mu"] = float(get("mu", 1.0))
     d["aspectratio_ref"] = float(get("AspectRatio", 0.05))
@@ -89,6 +90,8 @@ def params_from_config(cfg, consts, nrad, naz, temp_unit_K=1.0, units=None):
     d["temperature_cgs"] = float(temp_unit_K)
     d["density_cgs"] = float(units.get("density", 1.0))
     d["opacity_code"] = 1.0 / float(units.get("opacity", 1.0))
+    d["energy_density_cgs"] = float(units.get("energy surface density", 1.0))
+    d["surface_density_cgs"] = float(units.get("mass surface density", 1.0))
     d["body_force_from_potential"] = int(_flag(get("BodyForceFromPotential"), True))
     d["thickness_smoothing"] = float(get("ThicknessSmoothing", 0.6))
     d["imposed_disk_drift"] = float(get("ImposedDiskDrift", 0.0))

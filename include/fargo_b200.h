@@ -53,7 +53,10 @@ enum fargo_field {
     FARGO_VISCOSITY = 14,
     FARGO_POTENTIAL = 15,
     FARGO_T_REYNOLDS = 16, /* T_Reynolds.dat: stress::calculate_Reynolds_stress (stress.cpp:34-70), computed on download */
-    FARGO_NFIELDS = 17
+    FARGO_GAMMAEFF = 17,   /* gammaeff.dat, mu.dat, gamma1.dat: the PVTE grids (data.cpp:36-47), stored when params.pvte */
+    FARGO_MU = 18,
+    FARGO_GAMMA1 = 19,
+    FARGO_NFIELDS = 20
 };
 
 enum fargo_artvisc { FARGO_ARTVISC_NONE = 0, FARGO_ARTVISC_TW = 1, FARGO_ARTVISC_SN = 2 };
@@ -142,6 +145,10 @@ typedef struct fargo_params {
     double kappa_const;            /* KappaConst (code units) */
     double kappa_factor, tau_factor, tau_min, density_factor; /* KappaFactor, TauFactor, TauMin, DensityFactor */
     double temperature_cgs, density_cgs, opacity_code; /* units::temperature / density code -> cgs, units::opacity cgs -> code */
+    /* EquationOfState: PVTE (pvte_law.cpp:371-568): gamma_eff, mu, Gamma_1 per cell from lookup tables in (rho, e) [cgs]; the
+     * tables come through fargo_set_pvte_tables.  density_factor and density_cgs above are shared with the opacity. */
+    int pvte;
+    double energy_density_cgs, surface_density_cgs; /* units::energy_density / surface_density code -> cgs */
 } fargo_params;
 /* parameters::t_opacity (parameters.h), Opacity: Lin | Bell | Constant | Simple */
 enum fargo_opacity { FARGO_OPACITY_LIN = 0, FARGO_OPACITY_BELL = 1, FARGO_OPACITY_CONST = 2, FARGO_OPACITY_SIMPLE = 3 };
@@ -159,6 +166,14 @@ typedef struct fargo_bodies {
      * ramp = 1 - cos^2(t pi / 2 / rampuptime) before the ramp-up time, else 1 (formed on the host) */
     double temperature[FARGO_MAX_BODIES], radius[FARGO_MAX_BODIES], irradiation_ramp[FARGO_MAX_BODIES];
 } fargo_bodies;
+
+/* What pvte::initializeLookupTables reads besides its own constants (pvte_law.cpp:443-495, 215-241): the hydrogen mass
+ * fraction and physical constants in cgs units exactly as constants.cpp:48-85 forms them. */
+typedef struct fargo_pvte_consts {
+    double xMF;                  /* HydrogenMassFraction */
+    double m_H, m_e, eV, h, k_B; /* constants::*.get_cgs_value() */
+    double mp;                   /* llnl units proton mass in g */
+} fargo_pvte_consts;
 
 typedef struct fargo_ctx fargo_ctx;
 
@@ -195,6 +210,10 @@ int fargo_copy_initial_values(fargo_ctx *ctx);
 /* --- per-step inputs from the host ---------------------------------------------------------- */
 int fargo_set_bodies(fargo_ctx *ctx, const fargo_bodies *bodies);
 int fargo_set_time(fargo_ctx *ctx, double time); /* sim::time, used by the beta-cooling ramp */
+/* init_eos_arrays (init.cpp:1190-1206) for params.pvte: builds the lookup tables of pvte::initializeLookupTables on the host
+ * (host/fargo_pvte.h; a few seconds, cached per process), uploads them and fills the GAMMAEFF / GAMMA1 / MU grids with the
+ * constant gamma / mu.  Call before fargo_init_derived. */
+int fargo_set_pvte(fargo_ctx *ctx, const fargo_pvte_consts *consts);
 
 /* --- the hot path ---------------------------------------------------------------------------
  * init_euler's derived fields (SourceEuler.cpp:251-285): T, c_s, H, P, nu, Q+/- for the first CFL */

@@ -21,6 +21,7 @@
 #include <float.h>
 
 #include "../include/fargo_b200.h"
+#include "../host/fargo_pvte.h" /* the PVTE table builder is product code; the oracle only calls it */
 
 #define SEARCH_BUFFER 15 /* init.cpp:43 */
 
@@ -43,6 +44,9 @@ typedef struct fargo_oracle {
     double *sigma0, *vrad0, *vazi0, *energy0;
     /* derived */
     double *temperature, *pressure, *soundspeed, *scale_height, *viscosity, *potential;
+    /* EquationOfState: PVTE: the GAMMAEFF, MU, GAMMA1 grids (data.h) and the lookup tables */
+    double *gamma_eff, *mu_cell, *gamma1;
+    fargo_pvte_tables *pv;
     int kicks_this_step; /* fargo_oracle_kick calls since the last fargo_oracle_finish_step */
     double *qplus, *qminus, *divv, *trr, *tpp, *trp, *qr, *qphi, *nusig, *nusig_rp, *cf_r, *cf_phi, *tau_eff;
     /* transport scratch (TransportEuler.cpp:32-46) */
@@ -61,6 +65,10 @@ static inline double stdmin(double a, double b) { return (b < a) ? b : a; }
 static inline double stdmax(double a, double b) { return (a < b) ? b : a; }
 
 #define IDX(o, i, j) ((size_t)(i) * (size_t)(o)->ns + (size_t)(j))
+/* pvte::get_gamma_eff / get_mu / get_gamma1 (pvte_law.cpp:543-568) */
+#define GEFF(o, c) ((o)->p.pvte ? (o)->gamma_eff[c] : (o)->p.gamma)
+#define MUC(o, c) ((o)->p.pvte ? (o)->mu_cell[c] : (o)->p.mu)
+#define GAM1(o, c) ((o)->p.pvte ? (o)->gamma1[c] : (o)->p.gamma)
 
 static double *dalloc(size_t n)
 {
@@ -191,9 +199,10 @@ void fargo_oracle_destroy(fargo_oracle *o)
 		      &o->viscosity, &o->potential, &o->qplus, &o->qminus, &o->divv, &o->trr, &o->tpp, &o->trp,
 		      &o->qr, &o->qphi, &o->nusig, &o->nusig_rp, &o->cf_r, &o->cf_phi, &o->tau_eff, &o->rmp, &o->rmm,
 		      &o->amp, &o->amm, &o->vres, &o->work, &o->qrstar, &o->densstar, &o->densint, &o->tempshift,
-		      &o->dq, &o->vmean};
+		      &o->dq, &o->vmean, &o->gamma_eff, &o->mu_cell, &o->gamma1};
     for (size_t k = 0; k < sizeof(all) / sizeof(all[0]); ++k)
 	free(*all[k]);
+    fargo_pvte_free(o->pv);
     free(o->nshift);
     free(o);
 }
@@ -247,6 +256,9 @@ static double *field_ptr(fargo_oracle *o, int f, int *rings)
     case FARGO_SCALE_HEIGHT: return o->scale_height;
     case FARGO_VISCOSITY: return o->viscosity;
     case FARGO_POTENTIAL: return o->potential;
+    case FARGO_GAMMAEFF: return o->gamma_eff;
+    case FARGO_MU: return o->mu_cell;
+    case FARGO_GAMMA1: return o->gamma1;
     }
     return NULL;
 }
@@ -344,8 +356,8 @@ static void compute_sound_speed(fargo_oracle *o)
 	for (int naz = 0; naz < Nphi; ++naz) {
 	    const size_t c = IDX(o, nr, naz);
 	    if (o->p.adiabatic) {
-		const double g = o->p.gamma;
-		o->soundspeed[c] = sqrt(g * (g - 1.0) * o->energy[c] / o->sigma[c]);
+		const double gamma_eff = GEFF(o, c), gamma1 = GAM1(o, c);
+		o->soundspeed[c] = sqrt(gamma1 * (gamma_eff - 1.0) * o->energy[c] / o->sigma[c]);
 	    } else {
 		const double vK = sqrt(o->p.G * o->p.hydro_center_mass / o->rmed[nr]);
 		const double h = o->p.aspectratio_ref * pow(o->rmed[nr], o->p.flaring_index);
@@ -365,7 +377,7 @@ static void compute_scale_height(fargo_oracle *o)
 	for (int naz = 0; naz < Nphi; ++naz) {
 	    const size_t c = IDX(o, nr, naz);
 	    if (o->p.adiabatic)
-		o->scale_height[c] = o->soundspeed[c] / (sqrt(o->p.gamma)) * inv_omega_kepler;
+		o->scale_height[c] = o->soundspeed[c] / (sqrt(GAM1(o, c))) * inv_omega_kepler;
 	    else
 		o->scale_height[c] = o->soundspeed[c] * inv_omega_kepler;
 	}
@@ -379,7 +391,7 @@ static void compute_pressure(fargo_oracle *o)
 #pragma omp parallel for
     for (size_t c = 0; c < n; ++c) {
 	if (o->p.adiabatic)
-	    o->pressure[c] = (o->p.gamma - 1.0) * o->energy[c];
+	    o->pressure[c] = (GEFF(o, c) - 1.0) * o->energy[c];
 	else
 	    o->pressure[c] = o->sigma[c] * (o->soundspeed[c] * o->soundspeed[c]);
     }
@@ -393,7 +405,7 @@ static void compute_temperature(fargo_oracle *o)
 #pragma omp parallel for
     for (size_t c = 0; c < n; ++c) {
 	if (o->p.adiabatic) {
-	    const double c_v_inv = o->p.mu / Rgas * (o->p.gamma - 1.0);
+	    const double c_v_inv = MUC(o, c) / Rgas * (GEFF(o, c) - 1.0);
 	    o->temperature[c] = c_v_inv * o->energy[c] / o->sigma[c];
 	} else {
 	    o->temperature[c] = o->p.mu / Rgas * o->pressure[c] / o->sigma[c];
@@ -422,9 +434,10 @@ static void assure_temperature_range(fargo_oracle *o)
 {
     const size_t n = (size_t)o->nr * o->ns;
     const double Tmin = o->p.minimum_temperature, Tmax = o->p.maximum_temperature;
-    const double mu = o->p.mu, g = o->p.gamma, R = o->p.Rgas;
+    const double R = o->p.Rgas;
 #pragma omp parallel for
     for (size_t c = 0; c < n; ++c) {
+	const double mu = MUC(o, c), g = GEFF(o, c);
 	const double minimum_energy = Tmin * o->sigma[c] / mu * R / (g - 1.0);
 	const double maximum_energy = Tmax * o->sigma[c] / mu * R / (g - 1.0);
 	if (!(o->energy[c] > minimum_energy))
@@ -434,10 +447,26 @@ static void assure_temperature_range(fargo_oracle *o)
     }
 }
 
+/* pvte::compute_gamma_mu (pvte_law.cpp:497-541): gamma_eff, mu, Gamma_1 of every cell from the lookup tables, at the midplane
+ * density the STORED scale height gives and the cell's specific energy */
+static void compute_gamma_mu(fargo_oracle *o)
+{
+    const size_t n = (size_t)o->nr * o->ns;
+#pragma omp parallel for
+    for (size_t c = 0; c < n; ++c) {
+	const double sigma = o->sigma[c], H = o->scale_height[c];
+	const double densityCGS = sigma / (o->p.density_factor * H) * o->p.density_cgs;
+	const double energyCGS = o->energy[c] * o->p.energy_density_cgs / (sigma * o->p.surface_density_cgs);
+	fargo_pvte_lookup(o->pv, densityCGS, energyCGS, &o->gamma_eff[c], &o->mu_cell[c], &o->gamma1[c]);
+    }
+}
+
 /* recalculate_viscosity, SourceEuler.cpp:205-223 */
 static void recalculate_viscosity(fargo_oracle *o)
 {
     if (o->p.adiabatic) {
+	if (o->p.pvte)
+	    compute_gamma_mu(o);
 	compute_sound_speed(o);
 	compute_scale_height(o);
     }
@@ -450,6 +479,8 @@ int fargo_oracle_stage_derived(fargo_oracle *o)
     if (!o->p.adiabatic) {
 	compute_pressure(o);
     } else {
+	if (o->p.pvte)
+	    compute_gamma_mu(o);
 	compute_temperature(o);
 	compute_sound_speed(o);
 	compute_scale_height(o);
@@ -545,7 +576,7 @@ int fargo_oracle_stage_sources(fargo_oracle *o, double dt)
 		const double DIV_V = (o->vrad[IDX(o, nr + 1, naz)] * o->rinf[nr + 1] - o->vrad[c] * o->rinf[nr]) * o->invdiffrsuprb[nr] +
 				     (o->vazi[IDX(o, nr, naz_next)] - o->vazi[c]) * o->invdphi * o->invrmed[nr];
 		const double energy_old = o->energy[c];
-		o->energy[c] = energy_old * exp(-(o->p.gamma - 1.0) * dt * DIV_V);
+		o->energy[c] = energy_old * exp(-(GEFF(o, c) - 1.0) * dt * DIV_V);
 	    }
 	}
     }
@@ -968,7 +999,7 @@ static void calculate_qminus(fargo_oracle *o)
 		delta_E -= E0;
 	    }
 	    if (o->p.cooling_beta_reference & FARGO_BETA_REF_FLOOR) {
-		const double minimum_energy = o->p.minimum_temperature * o->sigma[c] / o->p.mu * o->p.Rgas / (o->p.gamma - 1.0);
+		const double minimum_energy = o->p.minimum_temperature * o->sigma[c] / MUC(o, c) * o->p.Rgas / (GEFF(o, c) - 1.0);
 		delta_E -= minimum_energy;
 	    }
 	    o->qminus[c] += delta_E * omega_k * beta_inv;
@@ -1007,9 +1038,9 @@ static void calculate_qplus(fargo_oracle *o)
 }
 
 /* the alpha_r division shared by SubStep3 :921-927 and compute_heating_cooling_for_CFL :1440-1446 */
-static inline double radiative_alpha(const fargo_oracle *o, double H, double sigma, double energy)
+static inline double radiative_alpha(const fargo_oracle *o, size_t c, double H, double sigma, double energy)
 {
-    const double inv_pow4 = pow(o->p.mu * (o->p.gamma - 1.0) / (o->p.Rgas * sigma), 4);
+    const double inv_pow4 = pow(MUC(o, c) * (GEFF(o, c) - 1.0) / (o->p.Rgas * sigma), 4);
     return 1.0 + 2.0 * H * 4.0 * o->p.sigma_sb / o->p.c_light * inv_pow4 * pow(energy, 3);
 }
 
@@ -1026,7 +1057,7 @@ int fargo_oracle_stage_substep3(fargo_oracle *o, double dt)
 	for (int naz = 0; naz < Nphi; ++naz) {
 	    const size_t c = IDX(o, nr, naz);
 	    const double sigma = o->sigma[c], energy = o->energy[c];
-	    const double alpha = radiative_alpha(o, o->scale_height[c], sigma, energy);
+	    const double alpha = radiative_alpha(o, c, o->scale_height[c], sigma, energy);
 	    o->qplus[c] /= alpha;
 	    o->qminus[c] /= alpha;
 	    const double Qplus = o->qplus[c], Qminus = o->qminus[c];
@@ -1034,7 +1065,7 @@ int fargo_oracle_stage_substep3(fargo_oracle *o, double dt)
 	    const double SigmaFloor = 10.0 * o->p.sigma0 * o->p.sigma_floor;
 	    if (sigma < SigmaFloor) {
 		const double e4 = Qplus * o->tau_eff[c] / (2.0 * o->p.sigma_sb);
-		const double constant = (o->p.Rgas / o->p.mu * sigma / (o->p.gamma - 1.0));
+		const double constant = (o->p.Rgas / MUC(o, c) * sigma / (GEFF(o, c) - 1.0));
 		const double eq_energy = pow(e4, 1.0 / 4.0) * constant;
 		o->qminus[c] = Qplus;
 		energy_new = eq_energy;
@@ -1060,7 +1091,7 @@ static void compute_heating_cooling_for_CFL(fargo_oracle *o)
     for (int nr = 1; nr < Nr; ++nr) {
 	for (int naz = 0; naz < Nphi; ++naz) {
 	    const size_t c = IDX(o, nr, naz);
-	    const double alpha = radiative_alpha(o, o->scale_height[c], o->sigma[c], o->energy[c]);
+	    const double alpha = radiative_alpha(o, c, o->scale_height[c], o->sigma[c], o->energy[c]);
 	    o->qplus[c] /= alpha;
 	    o->qminus[c] /= alpha;
 	}
@@ -1076,6 +1107,11 @@ int fargo_oracle_init_derived(fargo_oracle *o)
 	compute_temperature(o);
 	compute_scale_height(o);
     } else {
+	if (o->p.pvte) { /* init_euler, SourceEuler.cpp:272-276: the arrays still hold the constant gamma / mu of init_eos_arrays */
+	    compute_sound_speed(o);
+	    compute_scale_height(o);
+	    compute_gamma_mu(o);
+	}
 	compute_temperature(o);
 	compute_sound_speed(o);
 	compute_scale_height(o);
@@ -1083,6 +1119,30 @@ int fargo_oracle_init_derived(fargo_oracle *o)
     }
     update_viscosity(o);
     compute_heating_cooling_for_CFL(o);
+    return 0;
+}
+
+/* init_eos_arrays (init.cpp:1190-1206): build the lookup tables, fill GAMMAEFF / GAMMA1 / MU with the constant values.
+ * Must be called before fargo_oracle_init_derived when params.pvte is set. */
+int fargo_oracle_set_pvte(fargo_oracle *o, const fargo_pvte_consts *k)
+{
+    const size_t n = (size_t)o->nr * o->ns;
+    if (!o->p.pvte)
+	return 1;
+    fargo_pvte_free(o->pv);
+    o->pv = fargo_pvte_build(k);
+    if (!o->pv)
+	return 1;
+    if (!o->gamma_eff) {
+	o->gamma_eff = dalloc(n);
+	o->mu_cell = dalloc(n);
+	o->gamma1 = dalloc(n);
+    }
+    for (size_t c = 0; c < n; ++c) {
+	o->gamma_eff[c] = o->p.gamma;
+	o->gamma1[c] = o->p.gamma;
+	o->mu_cell[c] = o->p.mu;
+    }
     return 0;
 }
 
@@ -1725,6 +1785,10 @@ int fargo_oracle_step_pre(fargo_oracle *o, double dt)
 int fargo_oracle_step_post(fargo_oracle *o, double dt)
 {
     fargo_oracle_stage_boundary(o, dt, 1);
+    if (o->p.pvte) { /* simulation.cpp:256-262: the scale height after Transport, for the 3-D density of the lookup */
+	compute_sound_speed(o);
+	compute_scale_height(o);
+    }
     fargo_oracle_stage_derived(o);
     return 0;
 }

@@ -131,6 +131,10 @@ CASES = {
     "adia_cool_lin": dict(ViscousAlpha=1e-3, HeatingViscous="yes", SurfaceCooling="thermal", Opacity="Lin"),
     "adia_cool_bell": dict(ViscousAlpha=1e-3, HeatingViscous="yes", SurfaceCooling="thermal", Opacity="Bell", KappaFactor=2.0,
                            _planet=3e-4, IndirectTermMode=1),
+    # EquationOfState: PVTE (pvte_law.cpp): gamma_eff, mu, Gamma_1 per cell from the lookup tables; the three grids are recorded
+    "adia_pvte": dict(EquationOfState="PVTE", ViscousAlpha=1e-3, HeatingViscous="yes", CoolingBetaLocal="yes", CoolingBeta=10,
+                      WriteEffectiveGamma="yes", WriteFirstAdiabaticIndex="yes", WriteMeanMolecularWeight="yes", WriteScaleHeight="yes",
+                      Damping="Yes", DampingInnerLimit=1.311, DampingOuterLimit=0.763, DampingTimeFactor=0.05, **DAMP_ALL),
     "iso_planet_100": dict(Nrad=48, Naz=160, Rmax=2.5, Nsnapshots=100, MonitorTimestep=4.0e-3, IndirectTermMode=1,
                            EquationOfState="Isothermal", ViscousAlpha=1e-3, ArtificialViscosityFactor=1.41, OmegaFrame=1.0,
                            FlaringIndex=0.0, Damping="Yes", DampingInnerLimit=1.25, DampingOuterLimit=0.84,
@@ -142,7 +146,7 @@ def parse_constants(outdir):
     c = yaml.safe_load(open(os.path.join(outdir, "constants.yml")))
     u = yaml.safe_load(open(os.path.join(outdir, "units.yml")))
     consts = {v["symbol"]: float(v["code value"]) for v in c.values()}
-    return consts, float(u["temperature"]["cgs value"]), {k: float(u[k]["cgs value"]) for k in ("density", "opacity")}
+    return consts, float(u["temperature"]["cgs value"]), {k: float(u[k]["cgs value"]) for k in ("density", "opacity", "energy surface density", "mass surface density")}
 
 
 def read_misc(path):
@@ -209,7 +213,7 @@ def run_case(name, overrides, keep=False):
     for k in range(nsnap + 1):
         sd = os.path.join(out, "snapshots", str(k))
         for fname, rings in (("Sigma", nrad), ("vrad", nrad + 1), ("vazi", nrad), ("energy", nrad),
-                             ("Qplus", nrad), ("Qminus", nrad), ("T_Reynolds", nrad)):
+                             ("Qplus", nrad), ("Qminus", nrad), ("T_Reynolds", nrad), ("gammaeff", nrad), ("mu", nrad), ("gamma1", nrad), ("scale_height", nrad)):
             p = os.path.join(sd, fname + ".dat")
             if keep_snaps is not None and k not in keep_snaps:
                 continue

@@ -69,12 +69,19 @@ def start_from_snapshot0(ctx, meta, z):
     omega = float(meta["config"].get("OmegaFrame", 0.0))
     ctx.set_bodies(bodies_at(meta, 0, omega))
     ctx.set_time(0.0)
+    if ctx.params.pvte:  # init_eos_arrays (init.cpp:290-292) before init_euler
+        ctx.set_pvte(float(meta["config"].get("HydrogenMassFraction", 0.75)))
     ctx.init_derived()
     # the reference evaluates Q+/- for the first CFL before the velocities exist (init.cpp:330-331 ->
     # SourceEuler.cpp:284); take its stored values instead of recomputing them from the full state
     if "Qplus_0" in z and ctx.params.adiabatic:
         ctx.upload(abi.QPLUS, z["Qplus_0"])
         ctx.upload(abi.QMINUS, z["Qminus_0"])
+    if ctx.params.pvte and "gammaeff_0" in z:
+        # the PVTE grids are state of their own: the reference looked them up BEFORE its first boundary conditions changed the
+        # ghost rings of the snapshot-0 energy, and the scale height the next lookup reads was stored then too
+        for fid, name in ((abi.GAMMAEFF, "gammaeff"), (abi.MU, "mu"), (abi.GAMMA1, "gamma1"), (abi.SCALE_HEIGHT, "scale_height")):
+            ctx.upload(fid, z[name + "_0"])
     ctx.copy_initial_values()
     loop = reftools.TimeLoop(ctx, meta["first_dt"], meta["monitor_timestep"])
     loop.calculate_time_step()  # main.cpp:117

@@ -11,7 +11,9 @@ CASES = ["adia_star", "adia_cold", "iso_star", "iso_sn_std", "adia_sn_stab", "ri
          "adia_viscacc_20",  # viscous accretion (accretion.cpp:335-417)
          # SurfaceCooling: thermal / irradiating star (SourceEuler.cpp:538-723, compute.cpp:17-88, opacity.cpp): constant
          # opacity (Euler, Leapfrog), Lin & Papaloizou and Bell & Lin tables
-         "adia_irrad", "adia_irrad_lf", "adia_cool_lin", "adia_cool_bell"]
+         "adia_irrad", "adia_irrad_lf", "adia_cool_lin", "adia_cool_bell",
+         # EquationOfState: PVTE (pvte_law.cpp): lookup tables built by host/fargo_pvte.h, gamma_eff / mu / Gamma_1 / H grids checked too
+         "adia_pvte"]
 # Isothermal configs have no per-cell transcendental in the step => demanded bit-exact.
 # Adiabatic configs call exp() per cell (SourceEuler.cpp:487); same libm here => also bit-exact on CPU.
 # DiskFeedback: the reference sums the disk's pull with an OpenMP reduction in no defined order, so the acceleration
@@ -40,4 +42,9 @@ def test_oracle_matches_reference(name):
                 assert st["n_diff"] == 0, (name, k, fname, st)
             else:
                 assert st["max_abs"] <= 1e-12 * float(np.abs(z[f"{fname}_{k}"]).max()), (name, k, fname, st)
+    if ctx.params.pvte:  # the PVTE grids and the stored scale height after the last step
+        from fargocpt_b200 import abi
+        for fid, fname in ((abi.GAMMAEFF, "gammaeff"), (abi.MU, "mu"), (abi.GAMMA1, "gamma1"), (abi.SCALE_HEIGHT, "scale_height")):
+            st = reftools.compare_stats(ctx.download(fid), z[f"{fname}_{meta['nsnap']}"])
+            assert st["n_diff"] == 0, (name, fname, st)
     ctx.close()
