@@ -18,6 +18,7 @@
 #include <algorithm>
 
 #include "fargo_dev.h"
+#include "../../host/fargo_pvte.h" // the PVTE lookup tables are built on the host (pvte::initializeLookupTables)
 #include "kernels_ring.cuh"
 #include "kernels_ringsum.cuh"
 #include "kernels_source.cuh"
@@ -805,6 +806,10 @@ static double *state_ptr(fargo_ctx *c, int f, int *rings)
     case FARGO_QPLUS: return c->qplus;
     case FARGO_QMINUS: return c->qminus;
     case FARGO_POTENTIAL: return c->pot;
+    case FARGO_GAMMAEFF: return c->v.pv.geff;
+    case FARGO_MU: return c->v.pv.mu;
+    case FARGO_GAMMA1: return c->v.pv.g1;
+    case FARGO_SCALE_HEIGHT: return c->v.pv.H; // PVTE keeps the SCALE_HEIGHT grid (nullptr otherwise: evaluated on download)
     }
     return nullptr;
 }
@@ -974,6 +979,39 @@ extern "C" int fargo_set_bodies(fargo_ctx *c, const fargo_bodies *b)
     c->v.b = *b;
     return 0;
 }
+// init_eos_arrays (init.cpp:1190-1206): lookup tables (built on the host once per process and set of constants), the
+// GAMMAEFF / GAMMA1 / MU grids filled with the constant gamma / mu, the SCALE_HEIGHT grid the lookups read
+extern "C" int fargo_set_pvte(fargo_ctx *c, const fargo_pvte_consts *k)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    if (!c->v.p.pvte || !c->v.p.adiabatic)
+	return fail("fargo_set_pvte: the context was not created with params.pvte");
+    if (c->v.p.leapfrog)
+	return fail("EquationOfState: PVTE is implemented for the Euler integrator only");
+    static fargo_pvte_tables *cached = nullptr;
+    if (!cached || memcmp(&cached->k, k, sizeof(*k)) != 0) {
+	fargo_pvte_free(cached);
+	cached = fargo_pvte_build(k);
+	if (!cached)
+	    return fail("fargo_set_pvte: out of memory building the lookup tables");
+    }
+    DevView::Pvte &pv = c->v.pv;
+    const size_t n = (size_t)c->v.nr * c->v.ns, nt = (size_t)FARGO_PVTE_NI * FARGO_PVTE_NJ;
+    if (!pv.geff) {
+	if (dalloc(c, &pv.geff, n) || dalloc(c, &pv.mu, n) || dalloc(c, &pv.g1, n) || dalloc(c, &pv.H, n))
+	    return 1;
+	auto up = [&](const double **dst, const double *src, size_t cnt) {
+	    return upload_vec(c, dst, std::vector<double>(src, src + cnt));
+	};
+	if (up(&pv.t_rho, cached->rho, FARGO_PVTE_NI) || up(&pv.t_e, cached->e, FARGO_PVTE_NJ) || up(&pv.t_mu, cached->mu, nt) ||
+	    up(&pv.t_geff, cached->geff, nt) || up(&pv.t_g1, cached->g1, nt))
+	    return 1;
+	pv.dlogrho = cached->dlogrho, pv.dloge = cached->dloge;
+    }
+    LAUNCH(c, k_pvte_fill, cells_grid((long long)n), 256, 0, c->v, n);
+    return 0;
+}
+
 extern "C" int fargo_set_time(fargo_ctx *c, double t)
 {
     c->v.time = t;
@@ -1065,6 +1103,8 @@ extern "C" int fargo_stage_viscosity(fargo_ctx *c, double dt)
     CUDA_OK(cudaSetDevice(c->device));
     if (ensure_v_mid(c))
 	return 1;
+    if (c->v.pv.geff) // recalculate_viscosity (SourceEuler.cpp:214-219): gamma_eff, mu, Gamma_1 from the STORED scale height
+	LAUNCH(c, k_pvte_refresh, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, EN(c), 0);
     if (launch_stress(c))
 	return 1;
     LAUNCH(c, k_viscosity_v, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, c->trr, c->tpp, c->trp, c->cf_r,
@@ -1459,6 +1499,10 @@ extern "C" int fargo_stage_halo(fargo_ctx *c)
 // that every consumer here re-evaluates in registers, so there is nothing to store.
 extern "C" int fargo_stage_derived(fargo_ctx *c)
 {
+    if (c->v.pv.geff) { // PVTE: scale height after Transport (simulation.cpp:256-262), then the lookup and the new scale height
+	CUDA_OK(cudaSetDevice(c->device));
+	LAUNCH(c, k_pvte_refresh, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, EN(c), 1);
+    }
     c->h_stale = false; // the scale height is the current state's again (only a leapfrog mid-step keeps an older one)
     return 0;
 }
@@ -1469,6 +1513,12 @@ extern "C" int fargo_init_derived(fargo_ctx *c)
     CUDA_OK(cudaSetDevice(c->device));
     if (!c->v.p.adiabatic)
 	return 0;
+    if (c->v.p.pvte) {
+	if (!c->v.pv.geff)
+	    return fail("EquationOfState: PVTE needs fargo_set_pvte before fargo_init_derived");
+	// init_euler (SourceEuler.cpp:272-276): c_s and H from the constant gamma, the first lookup, c_s and H again
+	LAUNCH(c, k_pvte_refresh, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, EN(c), 1);
+    }
     if (launch_stress(c))
 	return 1;
     LAUNCH(c, k_substep3, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, c->nu, c->divv, c->trr, c->tpp,
@@ -1488,7 +1538,11 @@ extern "C" int fargo_condition_cfl(fargo_ctx *c, double *out)
     if (launch_ring_mean(c, c->stream, VPA(c), 0.0, 0))
 	return 1;
     const int nact = v.active_size - v.first_active;
-    if (nact > 0) {
+    if (nact > 0 && v.pv.geff) { // PVTE: per-cell gamma_eff / Gamma_1
+	dim3 grid((unsigned)((v.ns + 127) / 128), (unsigned)nact);
+	LAUNCH_NAMED(c, c->stream, "k_cfl", k_cfl_cells, grid, 128, 0, v, c->sigma, EN(c), VRA(c), VPA(c), c->qplus, c->qminus, c->cf_r,
+		     c->cf_phi, c->vmean, c->d_dt);
+    } else if (nact > 0) {
 	dim3 grid((unsigned)((v.ns + 511) / 512), (unsigned)nact);
 	LAUNCH(c, k_cfl, grid, 128, 0, v, c->sigma, EN(c), VRA(c), VPA(c), c->qplus, c->qminus, c->cf_r, c->cf_phi, c->vmean,
 	       c->d_dt);
@@ -1572,7 +1626,9 @@ extern "C" int fargo_kick(fargo_ctx *c, double dt)
 {
     CUDA_OK(cudaSetDevice(c->device));
     const fargo_params &p = c->v.p;
-    const bool fused = p.stabilize_viscosity == 0 && !c->force_staged;
+    if (p.pvte && !c->v.pv.geff)
+	return fail("EquationOfState: PVTE needs fargo_set_pvte before the first step");
+    const bool fused = p.stabilize_viscosity == 0 && !c->force_staged && !p.pvte; // PVTE: per-cell gamma lives in the staged kernels
     if (fused) {
 	if (c->v_mid)
 	    return fail("fargo_kick (fused) called mid-step after a per-stage call; finish with fargo_stage_transport first");

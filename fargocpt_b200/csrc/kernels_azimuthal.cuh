@@ -510,6 +510,12 @@ __global__ void __launch_bounds__(128, AZ_MINB)
 	    az_fetch<ADI>(IN, ns, jout, nsh, row, t_rmp, t_rmm, t_amp, t_amm, t_e, t_sigma, vp_old);
 	    az_ring<LIM, ADI, false>(c, tc, IN, g, dt, vm, vc, fargo, i, lane_out, PS, PR, Q, vrn, vpn, sf, en, A);
 	}
+	if (ADI && c.pv.geff != nullptr && lane_out) { // PVTE (uniform): the temperature floor / ceiling with the cell's mu, gamma_eff
+#pragma unroll
+	    for (int k = 0; k < AZ_NC; ++k)
+		if (jout + k >= 0 && jout + k < ns)
+		    en[k] = temperature_clamp_at(c, row + (size_t)(jout + k), sf[k], Q[4][k]);
+	}
 #if AZ_DEPTH > 0
 	if (dm != 0) { // warp-uniform: this ring lies in a damping zone of some field
 	    cp_async_wait<0>();

@@ -74,7 +74,8 @@ __global__ void __launch_bounds__(DOB_THREADS) k_disk_on_body(const DevView c, c
 	const double s1d = c.p.correct_disk_selfgravity ? sigma1d[i] : 0.0;
 	for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < c.ns; j += gridDim.x * blockDim.x) {
 	    const double s = AT(sigma, i, j), e = c.p.adiabatic ? AT(energy, i, j) : 0.0;
-	    const double smooth = c.p.thickness_smoothing * eos_H(c, i, eos_cs(c, i, s, e)); // compute_smoothing, Force.cpp:124-159
+	    const size_t cell_ = (size_t)i * c.ns + j;
+	    const double smooth = c.p.thickness_smoothing * eos_H_at(c, i, cell_, eos_cs_at(c, i, cell_, s, e)); // compute_smoothing, Force.cpp:124-159
 	    const double xc = rmed * c.g.cosphi[j], yc = rmed * c.g.sinphi[j];
 	    double cell_sigma = s;
 	    if (c.p.correct_disk_selfgravity)
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(ACC_THREADS)
 	    const bool kept = pre_has(pre, i);
 	    const double s_nu = kept ? AT(pre.sigma, i, j) : AT(sigma, i, j);
 	    const double e_nu = c.p.adiabatic ? (kept ? AT(pre.energy, i, j) : AT(energy, i, j)) : 0.0;
-	    const double nu = eos_nu(c, i, s_nu, e_nu);
+	    const double nu = eos_nu_at(c, i, (size_t)i * c.ns + j, s_nu, e_nu);
 	    const double spread = a.facc2 * (1.0 - distance / a.frac2);
 	    const double vtcell = 0.5 * (AT(vp, i, j) + AT(vp, i, jp)) + rmed * c.b.omega_frame;
 	    const double vrcell = 0.5 * (AT(vr, i, j) + AT(vr, i + 1, j));

@@ -691,7 +691,7 @@ __device__ __forceinline__ void st_substep3(const DevView &c, const TempClampNB 
 	    qm = 0.0 + delta_E * c.g.omega_k[r] * beta_inv;
 	}
 	if (RAD && inner) {
-	    const double T = rad_temperature(c, I.S1[k], E1[k]);
+	    const double T = rad_temperature(c, I.S1[k], E1[k], p.mu, p.gamma);
 	    tau_eff[k] = rad_tau_eff(c, I.S1[k], H1[k], T);
 	    if (p.cooling_surface)
 		qm += rad_qminus(c, T, tau_eff[k]);

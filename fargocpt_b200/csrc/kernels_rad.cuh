@@ -78,9 +78,10 @@ __device__ __forceinline__ double rad_opacity(const DevView &c, const double rho
     return c.p.kappa_factor * rv;
 }
 // compute_temperature (SourceEuler.cpp:1378-1408), adiabatic
-__device__ __forceinline__ double rad_temperature(const DevView &c, const double sigma, const double energy)
+__device__ __forceinline__ double rad_temperature(const DevView &c, const double sigma, const double energy, const double mu,
+						   const double gamma_eff)
 {
-    const double c_v_inv = c.p.mu / c.p.Rgas * (c.p.gamma - 1.0);
+    const double c_v_inv = mu / c.p.Rgas * (gamma_eff - 1.0);
     return c_v_inv * energy / sigma;
 }
 // kappa_eff (compute.cpp:41-88) of one cell

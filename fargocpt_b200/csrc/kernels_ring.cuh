@@ -551,6 +551,110 @@ __global__ void __launch_bounds__(128, 4)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// EquationOfState: PVTE.  pvte::compute_gamma_mu (pvte_law.cpp:497-541) with the sound speed / scale height refreshes the
+// reference wraps around it, per cell:
+//   mode & 1: first recompute the scale height from the CURRENT grids and state (simulation.cpp:256-262 after Transport;
+//             init_euler SourceEuler.cpp:272-275) — otherwise the lookup reads the STORED one (recalculate_viscosity :214-217,
+//             whose scale height dates from the end of the previous step)
+//   then the lookup at rho = Sigma / (density_factor H) and e / Sigma [cgs], and the scale height of the new grids is stored
+//   (compute_sound_speed + compute_scale_height, :218-219 / :245-246).
+__global__ void __launch_bounds__(256) k_pvte_refresh(const DevView c, const double *__restrict__ sigma,
+						       const double *__restrict__ energy, const int mode)
+{
+    CELL_INDEX(c.nr);
+    const size_t cell = (size_t)i * c.ns + j;
+    const double s = AT(sigma, i, j), e = AT(energy, i, j);
+    double H = c.pv.H[cell];
+    if (mode & 1)
+	H = eos_H_at(c, i, cell, eos_cs_at(c, i, cell, s, e));
+    const double densityCGS = s / (c.p.density_factor * H) * c.p.density_cgs;
+    const double energyCGS = e * c.p.energy_density_cgs / (s * c.p.surface_density_cgs);
+    double geff, mu, g1;
+    pv_lookup(c, densityCGS, energyCGS, geff, mu, g1);
+    c.pv.geff[cell] = geff, c.pv.mu[cell] = mu, c.pv.g1[cell] = g1;
+    const double cs = sqrt(g1 * (geff - 1.0) * e / s);
+    c.pv.H[cell] = cs / (sqrt(g1)) * c.g.inv_omega_k[i];
+}
+__global__ void k_pvte_fill(const DevView c, const size_t n)
+{ // init_eos_arrays (init.cpp:1197-1205)
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n)
+	c.pv.geff[k] = c.p.gamma, c.pv.g1[k] = c.p.gamma, c.pv.mu[k] = c.p.mu, c.pv.H[k] = 0.0;
+}
+// The CFL criterion with per-cell gamma_eff / Gamma_1 (PVTE): one thread per cell on the plain operators (IEEE: the same dt
+// as the keyed fast path would give), cfl.cpp:240-376.
+__global__ void __launch_bounds__(128)
+    k_cfl_cells(const DevView c, const double *__restrict__ sigma, const double *__restrict__ energy,
+		const double *__restrict__ vr, const double *__restrict__ vp, const double *__restrict__ qplus,
+		const double *__restrict__ qminus, const double *__restrict__ cf_r, const double *__restrict__ cf_phi,
+		const double *__restrict__ vmean, double *__restrict__ dt_out)
+{
+    const int i = c.first_active + blockIdx.y;
+    const int ns = c.ns;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const double DMAX = 1.7976931348623157e308;
+    const double CFL = c.p.cfl;
+    double best = DMAX;
+    const double vm = vmean[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) { // FARGO shear criterion (:207-220), as in k_cfl
+	const double denom = fabs(vm * c.g.invrmed[i] - vmean[i + 1] * c.g.invrmed[i + 1]) + 1.0e-100;
+	best = CFL * c.dphi / denom;
+	if (i == c.first_active) {
+	    const double denom0 = fabs(vmean[0] * c.g.invrmed[0] - vmean[1] * c.g.invrmed[1]) + 1.0e-100;
+	    const double d0 = CFL * c.dphi / denom0;
+	    if (d0 < best)
+		best = d0;
+	}
+    }
+    if (j < ns) {
+	const size_t cell = (size_t)i * ns + j;
+	const int jn = (j + 1 == ns) ? 0 : j + 1;
+	const double s = sigma[cell], e = c.p.adiabatic ? energy[cell] : 0.0;
+	const double vr0 = vr[cell], vr1 = vr[cell + ns], vp0 = vp[cell], vp1 = vp[(size_t)i * ns + jn];
+	const double dxr = c.g.rsup[i] - c.g.rinf[i], dxa = c.g.rmed[i] * c.dphi;
+	const double cell_size = stdmin(dxr, dxa);
+	const double lf = c.p.leapfrog ? 0.6 : 1.0, C = c.p.artificial_viscosity_factor;
+	const double vres = c.p.fast_transport ? vp0 - vm : vp0;
+	const double cs = eos_cs_at(c, i, cell, s, e);
+	const double invdt1 = cs / cell_size, invdt2 = vr0 / dxr, invdt3 = vres / dxa;
+	double invdt4;
+	if (c.p.artificial_viscosity == FARGO_ARTVISC_SN) {
+	    double dvR = vr1 - vr0, dvA = vp1 - vp0;
+	    dvR = (dvR > 0.0) ? 0.0 : -dvR;
+	    dvA = (dvA > 0.0) ? 0.0 : -dvA;
+	    invdt4 = 4.0 * (C * C) * stdmax(dvR / dxr, dvA / dxa) * lf;
+	} else {
+	    const double eps_rr = (vr1 - vr0) * c.g.invdiffrsup[i];
+	    const double eps_pp = c.g.invrmed[i] * ((vp1 - vp0) * c.invdphi + 0.5 * (vr1 + vr0));
+	    const double mdiv_V = -stdmin(eps_rr + eps_pp, 0.0);
+	    invdt4 = 4.0 * (C * C) * mdiv_V * lf;
+	}
+	const double nu = eos_nu_at(c, i, cell, s, e);
+	const double invdt5 = 4.0 * nu / (cell_size * cell_size) * lf;
+	double invdt6 = 0.0;
+	if (c.p.adiabatic)
+	    invdt6 = (1.0 / c.p.heating_cooling_cfl_limit) * fabs((qplus[cell] - qminus[cell]) / e) * lf;
+	const double A = invdt1 * invdt1 + invdt2 * invdt2 + invdt3 * invdt3 + invdt4 * invdt4 + invdt5 * invdt5 + invdt6 * invdt6;
+	double dt_cell = CFL / sqrt(A);
+	if (c.p.stabilize_viscosity == 2) {
+	    const double cc = stdmin(cf_phi[cell], cf_r[cell]);
+	    if (cc != 0.0)
+		dt_cell = stdmin(dt_cell, -CFL / cc);
+	}
+	if (dt_cell < best)
+	    best = dt_cell;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+	const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+	if (ob < best)
+	    best = ob;
+    }
+    if ((threadIdx.x & 31) == 0 && best < DMAX)
+	atomic_min_pos_double(dt_out, best);
+}
+
 // derived fields on demand (downloads only): T, P, c_s, H, nu  (SourceEuler.cpp:957-1408, viscosity.cpp:98)
 __global__ void __launch_bounds__(256) k_derived_field(const DevView c, const double *__restrict__ sigma,
 							const double *__restrict__ energy, double *__restrict__ out,
@@ -558,25 +662,26 @@ __global__ void __launch_bounds__(256) k_derived_field(const DevView c, const do
 {
     CELL_INDEX(c.nr);
     const double s = AT(sigma, i, j), e = AT(energy, i, j);
+    const size_t cell = (size_t)i * c.ns + j;
     double v = 0.0;
     switch (which) {
     case FARGO_TEMPERATURE:
 	if (c.p.adiabatic)
-	    v = c.p.mu / c.p.Rgas * (c.p.gamma - 1.0) * e / s;
+	    v = pv_mu(c, cell) / c.p.Rgas * (pv_geff(c, cell) - 1.0) * e / s;
 	else
 	    v = c.p.mu / c.p.Rgas * eos_P(c, i, s, e) / s;
 	break;
     case FARGO_PRESSURE:
-	v = eos_P(c, i, s, e);
+	v = eos_P_at(c, i, cell, s, e);
 	break;
     case FARGO_SOUNDSPEED:
-	v = eos_cs(c, i, s, e);
+	v = eos_cs_at(c, i, cell, s, e);
 	break;
-    case FARGO_SCALE_HEIGHT:
-	v = eos_H(c, i, eos_cs(c, i, s, e));
+    case FARGO_SCALE_HEIGHT: // PVTE: the SCALE_HEIGHT grid as stored
+	v = c.pv.H ? c.pv.H[cell] : eos_H(c, i, eos_cs(c, i, s, e));
 	break;
     case FARGO_VISCOSITY:
-	v = eos_nu(c, i, s, e);
+	v = eos_nu_at(c, i, cell, s, e);
 	break;
     }
     AT(out, i, j) = v;

@@ -33,7 +33,9 @@
 // recompute c_s / H before the second kick, simulation.cpp:364-381); nullptr: H of the current state
 __device__ __forceinline__ double potential_at(const DevView &c, int i, int j, double sigma, double energy, const double *h_in = nullptr)
 {
-    const double H = h_in ? h_in[(size_t)i * c.ns + j] : eos_H(c, i, eos_cs(c, i, sigma, energy));
+    const size_t cell = (size_t)i * c.ns + j;
+    // PVTE: the SCALE_HEIGHT grid as stored (the next lookup's input too); else H of the given state
+    const double H = h_in ? h_in[cell] : (c.pv.H ? c.pv.H[cell] : eos_H(c, i, eos_cs(c, i, sigma, energy)));
     const double x = c.g.rmed[i] * c.g.cosphi[j];
     const double y = c.g.rmed[i] * c.g.sinphi[j];
     const double smooth = c.p.thickness_smoothing * H;
@@ -82,7 +84,7 @@ __global__ void __launch_bounds__(256)
 	const bool old = pre_has(pre, ii);
 	const double ps = old ? AT(pre.sigma, ii, jj) : AT(sigma, ii, jj);
 	const double pe = (old && c.p.adiabatic) ? AT(pre.energy, ii, jj) : AT(energy, ii, jj);
-	return eos_P(c, ii, ps, pe);
+	return eos_P_at(c, ii, (size_t)ii * c.ns + jj, ps, pe);
     };
     double vr_new = AT(vr, i, j);
     if (i >= c.one_no_ghost_vr && i < c.maxmo_no_ghost_vr) {
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(256) k_compression_heating(const DevView c, co
     CELL_INDEX(c.nr - 1);
     const double DIV_V = div_v(c, vr, vp, i, j, jp);
     const double e_old = AT(energy, i, j);
-    AT(energy, i, j) = e_old * exp_ref(-(c.p.gamma - 1.0) * dt * DIV_V); // glibc-exact exp (fargo_math.h)
+    AT(energy, i, j) = e_old * exp_ref(-(pv_geff(c, (size_t)i * c.ns + j) - 1.0) * dt * DIV_V); // glibc-exact exp (fargo_math.h)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(256)
 	}
     }
     if (diss)
-	AT(energy, i, j) = temperature_clamp(c, s, e);
+	AT(energy, i, j) = temperature_clamp_at(c, (size_t)i * c.ns + j, s, e);
 }
 
 // artificial viscosity, pass 2: velocity update from Q (in place: every thread touches only its own v)
@@ -233,9 +235,10 @@ __global__ void __launch_bounds__(256) k_viscosity_nu(const DevView c, const dou
 						       double *__restrict__ o_h)
 {
     CELL_INDEX(c.nr);
-    AT(nu, i, j) = eos_nu(c, i, AT(sigma, i, j), AT(energy, i, j));
+    const size_t cell = (size_t)i * c.ns + j;
+    AT(nu, i, j) = eos_nu_at(c, i, cell, AT(sigma, i, j), AT(energy, i, j));
     if (o_h) // leapfrog: keep the scale height of this moment for the second kick's potential smoothing
-	AT(o_h, i, j) = eos_H(c, i, eos_cs(c, i, AT(sigma, i, j), AT(energy, i, j)));
+	AT(o_h, i, j) = eos_H_at(c, i, cell, eos_cs_at(c, i, cell, AT(sigma, i, j), AT(energy, i, j)));
 }
 
 // compute_viscous_stress_tensor (viscosity.cpp:139-254): div v, tau_rr, tau_phiphi (cell centred), tau_rphi (corner)
@@ -362,7 +365,7 @@ __device__ __forceinline__ double qplus_cell(const DevView &c, const double *__r
 }
 
 __device__ __forceinline__ double qminus_cell(const DevView &c, double beta_inv, double sigma, double energy, double sigma0,
-					       double energy0, int i)
+					       double energy0, int i, size_t cell)
 {
     double q = 0.0;
     if (c.p.cooling_beta && i >= 1 && i < c.nr - 1) {
@@ -372,18 +375,18 @@ __device__ __forceinline__ double qminus_cell(const DevView &c, double beta_inv,
 	if (c.p.cooling_beta_reference & FARGO_BETA_REF_MODEL)
 	    delta_E -= c.g.beta_model_e0[i] * sigma;
 	if (c.p.cooling_beta_reference & FARGO_BETA_REF_FLOOR)
-	    delta_E -= c.p.minimum_temperature * sigma / c.p.mu * c.p.Rgas / (c.p.gamma - 1.0);
+	    delta_E -= c.p.minimum_temperature * sigma / pv_mu(c, cell) * c.p.Rgas / (pv_geff(c, cell) - 1.0);
 	q += delta_E * c.g.omega_k[i] * beta_inv;
     }
     return q;
 }
 
 // alpha_r of SubStep3 (SourceEuler.cpp:921-924); H from recalculate_viscosity, i.e. from the current (Sigma, e)
-__device__ __forceinline__ double radiative_alpha(const DevView &c, int i, double sigma, double energy)
+__device__ __forceinline__ double radiative_alpha(const DevView &c, int i, size_t cell, double sigma, double energy)
 {
-    const double cs = eos_cs(c, i, sigma, energy);
-    const double H = eos_H(c, i, cs);
-    const double inv_pow4 = pow(c.p.mu * (c.p.gamma - 1.0) / (c.p.Rgas * sigma), 4.0);
+    const double cs = eos_cs_at(c, i, cell, sigma, energy);
+    const double H = eos_H_at(c, i, cell, cs);
+    const double inv_pow4 = pow(pv_mu(c, cell) * (pv_geff(c, cell) - 1.0) / (c.p.Rgas * sigma), 4.0);
     return 1.0 + 2.0 * H * 4.0 * c.p.sigma_sb / c.p.c_light * inv_pow4 * pow(energy, 3.0);
 }
 
@@ -400,11 +403,12 @@ __global__ void __launch_bounds__(256)
     double e = AT(energy, i, j);
     const bool need0 = c.p.cooling_beta && (c.p.cooling_beta_reference & FARGO_BETA_REF_REFERENCE);
     double Qp = qplus_cell(c, sigma, nu, divv, trr, tpp, trp, i, j, jp);
-    double Qm = qminus_cell(c, beta_inv, s, e, need0 ? AT(sigma0, i, j) : 1.0, need0 ? AT(energy0, i, j) : 0.0, i);
+    const size_t cell = (size_t)i * c.ns + j;
+    double Qm = qminus_cell(c, beta_inv, s, e, need0 ? AT(sigma0, i, j) : 1.0, need0 ? AT(energy0, i, j) : 0.0, i, cell);
     double tau_eff = 0.0; // TAU_EFF stays 0 as allocated unless kappa_eff runs
     if (rad_enabled(c) && i >= 1 && i < c.nr - 1) { // thermal_cooling / irradiation (kernels_rad.cuh)
-	const double H = eos_H(c, i, eos_cs(c, i, s, e));
-	const double T = rad_temperature(c, s, e);
+	const double H = eos_H_at(c, i, cell, eos_cs_at(c, i, cell, s, e));
+	const double T = rad_temperature(c, s, e, pv_mu(c, cell), pv_geff(c, cell));
 	tau_eff = rad_tau_eff(c, s, H, T);
 	if (c.p.cooling_surface)
 	    Qm += rad_qminus(c, T, tau_eff);
@@ -412,7 +416,7 @@ __global__ void __launch_bounds__(256)
 	    rad_add_qplus(c, i, c.g.cosphi[j], c.g.sinphi[j], H, tau_eff, Qp);
     }
     if (i >= 1 && i < c.nr - 1) {
-	const double alpha = radiative_alpha(c, i, s, e);
+	const double alpha = radiative_alpha(c, i, cell, s, e);
 	Qp /= alpha;
 	Qm /= alpha;
 	if (update_energy) {
@@ -420,7 +424,7 @@ __global__ void __launch_bounds__(256)
 	    const double SigmaFloor = 10.0 * c.p.sigma0 * c.p.sigma_floor;
 	    if (s < SigmaFloor) {
 		const double e4 = Qp * tau_eff / (2.0 * c.p.sigma_sb);
-		const double constant = (c.p.Rgas / c.p.mu * s / (c.p.gamma - 1.0));
+		const double constant = (c.p.Rgas / pv_mu(c, cell) * s / (pv_geff(c, cell) - 1.0));
 		const double eq_energy = pow(e4, 1.0 / 4.0) * constant;
 		Qm = Qp;
 		energy_new = eq_energy;
@@ -431,5 +435,5 @@ __global__ void __launch_bounds__(256)
     AT(qplus, i, j) = Qp;
     AT(qminus, i, j) = Qm;
     if (update_energy)
-	AT(energy, i, j) = temperature_clamp(c, s, e);
+	AT(energy, i, j) = temperature_clamp_at(c, cell, s, e);
 }

@@ -74,6 +74,7 @@ int fargo_oracle_monitor_quantities(fargo_oracle *, double, double *);
 int fargo_oracle_accrete_sinkhole(fargo_oracle *, double, double, double, double, double, double *);
 int fargo_oracle_accrete_viscous(fargo_oracle *, double, double, double, double, double, double *);
 int fargo_oracle_correct_vazi(fargo_oracle *, double);
+int fargo_oracle_set_pvte(fargo_oracle *, const fargo_pvte_consts *);
 }
 typedef fargo_oracle backend_ctx;
 #define BK(name) fargo_oracle_##name
@@ -338,11 +339,13 @@ static fargo_params make_params(const Config &c, const CodeConstants &k, int nra
     // Physics this path does not implement must not be dropped silently: a setup that switches it on is refused by name.
     {
 	const std::string eos = lower(c.str("EquationOfState", "Isothermal")); // Interpret.cpp:391-470
-	if (eos != "isothermal" && eos != "iso" && eos != "adiabatic" && eos != "ideal")
-	    die("EquationOfState: %s is not supported by this driver (isothermal, ideal)", eos);
+	if (eos != "isothermal" && eos != "iso" && eos != "adiabatic" && eos != "ideal" && eos != "pvte" && eos != "pvtelaw")
+	    die("EquationOfState: %s is not supported by this driver (isothermal, ideal, pvte)", eos);
+	if ((eos == "pvte" || eos == "pvtelaw") && lower(c.str("Integrator", "Euler"))[0] != 'e')
+	    die("%s", std::string("EquationOfState: PVTE is implemented for Integrator: Euler only"));
 	if (c.has("Adiabatic"))
 	    die("%s", std::string("the deprecated 'Adiabatic' flag is not supported; use EquationOfState"));
-	const bool energy_equation = eos == "adiabatic" || eos == "ideal"; // SubStep3 only runs then (simulation.cpp:203-205)
+	const bool energy_equation = eos == "adiabatic" || eos == "ideal" || eos == "pvte" || eos == "pvtelaw"; // SubStep3 only runs then (simulation.cpp:203-205)
 	const std::string sc = lower(c.str("SurfaceCooling", "No")); // parameters.cpp:394-406
 	if (energy_equation && !(sc == "no" || sc == "off" || sc == "false" || sc == "thermal"))
 	    die("SurfaceCooling: %s is not supported by this driver (beta cooling, thermal)", sc);
@@ -357,7 +360,10 @@ static fargo_params make_params(const Config &c, const CodeConstants &k, int nra
 		die((std::string(k) + ": %s is not supported by this driver").c_str(), c.str(k, ""));
     }
     const std::string eos = lower(c.str("EquationOfState", "Isothermal"));
-    p.adiabatic = (eos == "ideal" || eos == "adiabatic") ? 1 : 0;
+    p.pvte = (eos == "pvte" || eos == "pvtelaw") ? 1 : 0; // Interpret.cpp:453-491: an ideal gas with a variable adiabatic index
+    p.adiabatic = (eos == "ideal" || eos == "adiabatic" || p.pvte) ? 1 : 0;
+    p.energy_density_cgs = k.mass_cgs / (k.time_cgs * k.time_cgs);	    // units.cpp:270-377 (energy per area of the 2-D disk)
+    p.surface_density_cgs = k.mass_cgs / (k.length_cgs * k.length_cgs);
     p.gamma = c.num("AdiabaticIndex", 1.4);
     p.mu = c.num("mu", 1.0);
     p.aspectratio_ref = c.num("AspectRatio", 0.05);
@@ -811,6 +817,8 @@ struct Run {
 		die("used_rad.dat does not hold Nrad + 1 radii in %s", dir);
 	}
 	params = make_params(cfg, consts, nrad, naz);
+	if (params.pvte)
+	    die("%s", std::string("restart with EquationOfState: PVTE is not supported by this driver (start only)"));
 	// bodies
 	for (size_t k = 0; k < cfg.nbody.size(); ++k) {
 	    Body b;
@@ -1194,6 +1202,13 @@ struct Run {
 	    CHECK(BK(upload_field)(ctx, FARGO_ENERGY, s0.energy.data()));
 	set_bodies_on_device();
 	CHECK(BK(set_time)(ctx, time));
+	if (params.pvte) { // init_eos_arrays (init.cpp:290-292, 1190-1206) with the constants as constants.cpp forms them
+	    fargo_pvte_consts pk;
+	    pk.xMF = cfg.num("HydrogenMassFraction", 0.75); // Interpret.cpp:452
+	    pk.m_H = U.m_H.cgs, pk.m_e = U.m_e.cgs, pk.eV = U.eV.cgs, pk.h = U.h.cgs, pk.k_B = U.k_B.cgs;
+	    pk.mp = 1.67262192369e-27 * 1.0 / 0.001; // llnl constants::mp in g (pvte_law.cpp:232)
+	    CHECK(BK(set_pvte)(ctx, &pk));
+	}
 	CHECK(BK(init_derived)(ctx));
 	CHECK(BK(upload_field)(ctx, FARGO_VRAD, s0.vrad.data()));
 	CHECK(BK(upload_field)(ctx, FARGO_VAZI, s0.vazi.data()));
@@ -1546,7 +1561,10 @@ struct Run {
 			std::make_tuple((int)FARGO_PRESSURE, "WritePressure", "pressure"),
 			std::make_tuple((int)FARGO_SOUNDSPEED, "WriteSoundSpeed", "soundspeed"),
 			std::make_tuple((int)FARGO_SCALE_HEIGHT, "WriteScaleHeight", "scale_height"),
-			std::make_tuple((int)FARGO_VISCOSITY, "WriteViscosity", "viscosity")}) {
+			std::make_tuple((int)FARGO_VISCOSITY, "WriteViscosity", "viscosity"),
+			std::make_tuple((int)FARGO_GAMMAEFF, "WriteEffectiveGamma", "gammaeff"),
+			std::make_tuple((int)FARGO_GAMMA1, "WriteFirstAdiabaticIndex", "gamma1"),
+			std::make_tuple((int)FARGO_MU, "WriteMeanMolecularWeight", "mu")}) {
 	    if (!cfg.flag(std::get<1>(s), false))
 		continue;
 	    std::vector<double> buf(cells(false), 0.0);

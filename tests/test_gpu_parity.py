@@ -124,6 +124,32 @@ def test_opacity_table_runs_vs_reference(name, staged):
     print(name, "worst deviation / field scale:", worst)
 
 
+def test_pvte_run_vs_reference():
+    """EquationOfState: PVTE (pvte_law.cpp:371-568): lookup tables from host/fargo_pvte.h uploaded by fargo_set_pvte, gamma_eff / mu /
+    Gamma_1 / H grids refreshed in the reference's order, per-cell gamma in the staged kernels, the azimuthal kernel's temperature floor
+    and the CFL.  The table index of a cell comes from log10() (CUDA's against glibc's: a cell sitting on a table-cell edge may take
+    the neighbouring cell, where the bilinear interpolation is continuous), everything else is IEEE arithmetic: held to POW_RTOL,
+    with the number of differing doubles reported."""
+    meta, z, gpu, cpu = _ctx_pair("adia_pvte")
+    snaps = goldenrun.run_fixture(gpu, meta, z)
+    worst, ndiff = 0.0, 0
+    for k, snap in enumerate(snaps, start=1):
+        m = meta["misc"][k]
+        assert snap["n_iter"] == m["n_iter"] and snap["time"] == m["time"]
+        assert snap["last_dt"] == pytest.approx(m["last_dt"], rel=POW_RTOL)
+        for fname in ("Sigma", "vrad", "vazi", "energy"):
+            ref = z[f"{fname}_{k}"]
+            worst = max(worst, float(np.abs(snap[fname] - ref).max() / np.abs(ref).max()))
+            ndiff += int((snap[fname] != ref).sum())
+    for fid, fname in ((abi.GAMMAEFF, "gammaeff"), (abi.MU, "mu"), (abi.GAMMA1, "gamma1"), (abi.SCALE_HEIGHT, "scale_height")):
+        ref = z[f"{fname}_{meta['nsnap']}"]
+        got = gpu.download(fid)
+        worst = max(worst, float(np.abs(got - ref).max() / np.abs(ref).max()))
+        ndiff += int((got != ref).sum())
+    print("adia_pvte: worst deviation / field scale", worst, "differing doubles", ndiff)
+    assert worst <= POW_RTOL
+
+
 @pytest.mark.parametrize("name", ["adia_star", "iso_star"])
 def test_first_cfl_dt_bit_exact(name):
     """Step-0 CFL dt from identical inputs must be bit-equal for every config (no transcendental involved)."""

@@ -198,7 +198,9 @@ START_CASES = [("iso_star", 6, True), ("adia_star", 6, True), ("adia_cold", 6, T
                # sinkhole accretion; an accreting planet that feels the disk (update_planet, Roche radius and orbital period refreshed)
                ("iso_sinkhole_20", 20, False), ("adia_accfb_20", 20, False),
                # SurfaceCooling: thermal, irradiating star (ramped), constant opacity and the two opacity tables
-               ("adia_irrad", 6, True), ("adia_irrad_lf", 6, True), ("adia_cool_lin", 6, True), ("adia_cool_bell", 6, False)]
+               ("adia_irrad", 6, True), ("adia_irrad_lf", 6, True), ("adia_cool_lin", 6, True), ("adia_cool_bell", 6, False),
+               # EquationOfState: PVTE: lookup tables built by host/fargo_pvte.h, the reference's refresh order of gamma_eff / mu / Gamma_1
+               ("adia_pvte", 6, True)]
 
 
 @pytest.mark.parametrize("name,until,exact", START_CASES)
@@ -478,7 +480,7 @@ def test_host_start_refuses_unknown_keys_like_the_reference(tmp_path):
 
 
 def test_host_refuses_physics_it_does_not_implement(tmp_path):
-    for key, value in (("EquationOfState", "PVTE"), ("SurfaceCooling", "scurve"), ("SelfGravity", "yes"), ("AlphaMode", 1)):
+    for key, value in (("EquationOfState", "Polytropic"), ("SurfaceCooling", "scurve"), ("SelfGravity", "yes"), ("AlphaMode", 1)):
         cfg = yaml.safe_load(open(os.path.join(ROOT, "tests", "golden", "adia_star.yml")))
         cfg[key] = value
         yml = str(tmp_path / f"setup_{key}.yml")
@@ -694,6 +696,7 @@ GPU_VS_ORACLE_DRIVER = [
     ("multi_body_setup", {}),
     ("minimal_defaults_setup", {}),
     ("adia_irrad_lf", {"WriteTemperature": "yes", "WritePressure": "yes", "WriteSoundSpeed": "yes", "WriteScaleHeight": "yes", "WriteViscosity": "yes"}),
+    ("adia_pvte", {"WriteTemperature": "yes", "WriteScaleHeight": "yes"}),
 ]
 
 
