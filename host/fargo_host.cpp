@@ -1019,6 +1019,7 @@ struct Run {
     // main.cpp:48-164 up to the first output, for `start`: units and constants, grid, bodies, init_physics (init.cpp:255-345)
     std::string config_path;
     bool started_fresh = false;
+    std::map<int, std::vector<double>> derived_at_init; // derived fields of snapshot 0 (see start())
     void start(const std::string &cfgfile, int device)
     {
 	config_path = cfgfile;
@@ -1210,6 +1211,16 @@ struct Run {
 	    CHECK(BK(set_pvte)(ctx, &pk));
 	}
 	CHECK(BK(init_derived)(ctx));
+	// The reference's derived grids of snapshot 0 date from init_euler, i.e. from before the first boundary conditions changed
+	// the ghost rings; this path evaluates derived fields on download, so the ones a setup asks for are taken now.
+	for (auto &s : {std::make_pair((int)FARGO_TEMPERATURE, "WriteTemperature"), std::make_pair((int)FARGO_PRESSURE, "WritePressure"),
+			std::make_pair((int)FARGO_SOUNDSPEED, "WriteSoundSpeed"), std::make_pair((int)FARGO_SCALE_HEIGHT, "WriteScaleHeight"),
+			std::make_pair((int)FARGO_VISCOSITY, "WriteViscosity")})
+	    if (cfg.flag(s.second, false)) {
+		std::vector<double> buf(cells(false), 0.0);
+		CHECK(BK(download_field)(ctx, s.first, buf.data()));
+		derived_at_init[s.first] = buf;
+	    }
 	CHECK(BK(upload_field)(ctx, FARGO_VRAD, s0.vrad.data()));
 	CHECK(BK(upload_field)(ctx, FARGO_VAZI, s0.vazi.data()));
 	CHECK(BK(copy_initial_values)(ctx));	  // init.cpp:340-344
@@ -1568,9 +1579,14 @@ struct Run {
 	    if (!cfg.flag(std::get<1>(s), false))
 		continue;
 	    std::vector<double> buf(cells(false), 0.0);
-	    CHECK(BK(download_field)(ctx, std::get<0>(s), buf.data()));
+	    auto kept = derived_at_init.find(std::get<0>(s));
+	    if (n_snapshot == 0 && started_fresh && kept != derived_at_init.end())
+		buf = kept->second; // snapshot 0: as init_euler left them, before the first boundary conditions touched the ghost rings
+	    else
+		CHECK(BK(download_field)(ctx, std::get<0>(s), buf.data()));
 	    write_field_file(rel + std::get<2>(s) + ".dat", buf.data(), false);
 	}
+	derived_at_init.clear();
 	MiscEntry m;
 	m.timestep = n_snapshot, m.nTimeStep = n_monitor, m.time = time, m.OmegaFrame = omega_frame, m.FrameAngle = frame_angle;
 	m.last_dt = last_dt, m.N_iter = n_iter;

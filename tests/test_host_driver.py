@@ -724,8 +724,8 @@ def test_gpu_driver_writes_what_the_oracle_bound_driver_writes(setup, over, tmp_
                 b = np.array([[float(x) for x in l.split()] for l in open(pg) if not l.startswith("#") and l.strip()])
                 assert a.shape == b.shape, f
                 assert np.array_equal(np.isnan(a), np.isnan(b)), f
-                scale = np.maximum(np.nanmax(np.abs(a), axis=0), 1e-300)
-                assert np.nanmax(np.abs(np.nan_to_num(a) - np.nan_to_num(b)) / scale) < 1e-9, f
+                scale = np.maximum(np.abs(np.nan_to_num(a)).max(axis=0), 1e-300)
+                assert np.max(np.abs(np.nan_to_num(a) - np.nan_to_num(b)) / scale) < 1e-9, f
                 continue
             rel = os.path.relpath(po, outs["oracle"])
             a, b = open(po, "rb").read(), open(pg, "rb").read()
@@ -734,7 +734,7 @@ def test_gpu_driver_writes_what_the_oracle_bound_driver_writes(setup, over, tmp_
                 # the record carries the disk's pull on the body (offsets 120-152) and torque sums: device reductions, rounding-level
                 x, y = np.frombuffer(a[8:72]), np.frombuffer(b[8:72])  # mass, x, y, vx, vy, smoothing, accretion efficiency, accreted mass
                 assert np.allclose(x, y, rtol=1e-12 if feedback else 0.0, atol=0.0), (rel, x, y)
-            elif feedback and f.endswith(".dat"):
+            elif feedback and f.endswith(".dat") and "snapshots" in dirpath:
                 # the reduced pull moves the bodies, so the gas follows to rounding
                 x, y = np.nan_to_num(np.frombuffer(a)), np.nan_to_num(np.frombuffer(b))
                 assert x.shape == y.shape and np.abs(x - y).max() <= 1e-12 * max(np.abs(x).max(), 1e-300), rel
