@@ -64,6 +64,7 @@ class FargoParams(C.Structure):
         ("density_factor", C.c_double),
         ("temperature_cgs", C.c_double), ("density_cgs", C.c_double), ("opacity_code", C.c_double),
         ("pvte", C.c_int), ("energy_density_cgs", C.c_double), ("surface_density_cgs", C.c_double),
+        ("alpha_mode", C.c_int), ("alpha_cold", C.c_double), ("alpha_hot", C.c_double),
     ]
 
     def as_dict(self):

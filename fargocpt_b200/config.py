@@ -65,6 +65,9 @@ def params_from_config(cfg, consts, nrad, naz, temp_unit_K=1.0, units=None):
     d["artificial_viscosity_dissipation"] = int(_flag(get("ArtificialViscosityDissipation"), True))
     d["viscous_alpha"] = float(get("ViscousAlpha", 0.0))
     d["constant_viscosity"] = _num(get("ConstantViscosity", 0.0))
+    d["alpha_mode"] = int(get("AlphaMode", 0))  # parameters.cpp:704-706
+    d["alpha_cold"] = float(get("AlphaCold", 0.01))
+    d["alpha_hot"] = float(get("AlphaHot", 0.1))
     d["stabilize_viscosity"] = int(get("StabilizeViscosity", 0))
     d["radial_viscosity_factor"] = float(get("RadialViscosityFactor", 1.0))
     d["heating_viscous"] = int(_flag(get("HeatingViscous"), True))  # parameters.cpp:561

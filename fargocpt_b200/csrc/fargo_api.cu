@@ -641,6 +641,14 @@ extern "C" int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, con
 	dalloc(c, &c->vrb[1], nv) || dalloc(c, &c->vpb[1], ns) || dalloc(c, &c->eb[1], params->adiabatic ? ns : 1));
     TRY(dalloc(c, &c->sigma0, ns) || dalloc(c, &c->energy0, ns) || dalloc(c, &c->vr0, nv) || dalloc(c, &c->vp0, ns));
     TRY(dalloc(c, &c->qplus, ns) || dalloc(c, &c->qminus, ns));
+    if (params->alpha_mode != 0) { // viscosity::get_alpha (viscosity.cpp:31-49)
+	if (params->alpha_mode != 1 || !params->adiabatic || !(params->viscous_alpha > 0)) {
+	    fail("AlphaMode %d: only the S-curve (1) with the energy equation and ViscousAlpha > 0 is implemented", params->alpha_mode);
+	    fargo_ctx_destroy(c);
+	    return 1;
+	}
+	TRY(dalloc(c, &c->v.t_alpha, ns));
+    }
     TRY(dalloc(c, &c->pot, ns) || dalloc(c, &c->qr, ns) || dalloc(c, &c->qphi, ns) || dalloc(c, &c->nu, ns) ||
 	dalloc(c, &c->divv, ns) || dalloc(c, &c->trr, ns) || dalloc(c, &c->tpp, ns) || dalloc(c, &c->trp, nv));
     if (params->stabilize_viscosity) {
@@ -809,6 +817,7 @@ static double *state_ptr(fargo_ctx *c, int f, int *rings)
     case FARGO_GAMMAEFF: return c->v.pv.geff;
     case FARGO_MU: return c->v.pv.mu;
     case FARGO_GAMMA1: return c->v.pv.g1;
+    case FARGO_TEMPERATURE: return c->v.t_alpha; // AlphaMode 1 keeps the TEMPERATURE grid (nullptr otherwise: evaluated on download)
     case FARGO_SCALE_HEIGHT: return c->v.pv.H; // PVTE keeps the SCALE_HEIGHT grid (nullptr otherwise: evaluated on download)
     }
     return nullptr;
@@ -1497,11 +1506,25 @@ extern "C" int fargo_stage_halo(fargo_ctx *c)
 
 // recalculate_derived_disk_quantities (SourceEuler.cpp:225-249): T, c_s, H, P, nu are functions of (Sigma, e)
 // that every consumer here re-evaluates in registers, so there is nothing to store.
+// AlphaMode 1: the TEMPERATURE grid get_alpha will read during the next recalculate_viscosity (compute_temperature of
+// recalculate_derived_disk_quantities / init_euler)
+static int store_alpha_temperature(fargo_ctx *c)
+{
+    if (c->v.t_alpha)
+	LAUNCH(c, k_derived_field, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, EN(c), c->v.t_alpha, (int)FARGO_TEMPERATURE);
+    return 0;
+}
+
 extern "C" int fargo_stage_derived(fargo_ctx *c)
 {
     if (c->v.pv.geff) { // PVTE: scale height after Transport (simulation.cpp:256-262), then the lookup and the new scale height
 	CUDA_OK(cudaSetDevice(c->device));
 	LAUNCH(c, k_pvte_refresh, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, EN(c), 1);
+    }
+    if (c->v.t_alpha) {
+	CUDA_OK(cudaSetDevice(c->device));
+	if (store_alpha_temperature(c))
+	    return 1;
     }
     c->h_stale = false; // the scale height is the current state's again (only a leapfrog mid-step keeps an older one)
     return 0;
@@ -1519,6 +1542,8 @@ extern "C" int fargo_init_derived(fargo_ctx *c)
 	// init_euler (SourceEuler.cpp:272-276): c_s and H from the constant gamma, the first lookup, c_s and H again
 	LAUNCH(c, k_pvte_refresh, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, EN(c), 1);
     }
+    if (store_alpha_temperature(c))
+	return 1;
     if (launch_stress(c))
 	return 1;
     LAUNCH(c, k_substep3, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, c->nu, c->divv, c->trr, c->tpp,
@@ -1538,7 +1563,7 @@ extern "C" int fargo_condition_cfl(fargo_ctx *c, double *out)
     if (launch_ring_mean(c, c->stream, VPA(c), 0.0, 0))
 	return 1;
     const int nact = v.active_size - v.first_active;
-    if (nact > 0 && v.pv.geff) { // PVTE: per-cell gamma_eff / Gamma_1
+    if (nact > 0 && (v.pv.geff || v.p.alpha_mode != 0)) { // PVTE: per-cell gamma_eff / Gamma_1; AlphaMode: per-cell alpha
 	dim3 grid((unsigned)((v.ns + 127) / 128), (unsigned)nact);
 	LAUNCH_NAMED(c, c->stream, "k_cfl", k_cfl_cells, grid, 128, 0, v, c->sigma, EN(c), VRA(c), VPA(c), c->qplus, c->qminus, c->cf_r,
 		     c->cf_phi, c->vmean, c->d_dt);
@@ -1628,7 +1653,8 @@ extern "C" int fargo_kick(fargo_ctx *c, double dt)
     const fargo_params &p = c->v.p;
     if (p.pvte && !c->v.pv.geff)
 	return fail("EquationOfState: PVTE needs fargo_set_pvte before the first step");
-    const bool fused = p.stabilize_viscosity == 0 && !c->force_staged && !p.pvte; // PVTE: per-cell gamma lives in the staged kernels
+    // PVTE and AlphaMode: per-cell gamma / alpha live in the staged kernels
+    const bool fused = p.stabilize_viscosity == 0 && !c->force_staged && !p.pvte && p.alpha_mode == 0;
     if (fused) {
 	if (c->v_mid)
 	    return fail("fargo_kick (fused) called mid-step after a per-stage call; finish with fargo_stage_transport first");

@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(256) k_viscosity_nu(const DevView c, const dou
 {
     CELL_INDEX(c.nr);
     const size_t cell = (size_t)i * c.ns + j;
-    AT(nu, i, j) = eos_nu_at(c, i, cell, AT(sigma, i, j), AT(energy, i, j));
+    AT(nu, i, j) = eos_nu_at(c, i, cell, AT(sigma, i, j), AT(energy, i, j), /*stored_T=*/true);
     if (o_h) // leapfrog: keep the scale height of this moment for the second kick's potential smoothing
 	AT(o_h, i, j) = eos_H_at(c, i, cell, eos_cs_at(c, i, cell, AT(sigma, i, j), AT(energy, i, j)));
 }
@@ -404,6 +404,8 @@ __global__ void __launch_bounds__(256)
     const bool need0 = c.p.cooling_beta && (c.p.cooling_beta_reference & FARGO_BETA_REF_REFERENCE);
     double Qp = qplus_cell(c, sigma, nu, divv, trr, tpp, trp, i, j, jp);
     const size_t cell = (size_t)i * c.ns + j;
+    if (c.t_alpha && update_energy) // SubStep3 begins with compute_temperature (SourceEuler.cpp:861): the grid a leapfrog's second
+	c.t_alpha[cell] = pv_mu(c, cell) / c.p.Rgas * (pv_geff(c, cell) - 1.0) * e / s; // recalculate_viscosity will read
     double Qm = qminus_cell(c, beta_inv, s, e, need0 ? AT(sigma0, i, j) : 1.0, need0 ? AT(energy0, i, j) : 0.0, i, cell);
     double tau_eff = 0.0; // TAU_EFF stays 0 as allocated unless kappa_eff runs
     if (rad_enabled(c) && i >= 1 && i < c.nr - 1) { // thermal_cooling / irradiation (kernels_rad.cuh)

@@ -349,7 +349,9 @@ static fargo_params make_params(const Config &c, const CodeConstants &k, int nra
 	const std::string sc = lower(c.str("SurfaceCooling", "No")); // parameters.cpp:394-406
 	if (energy_equation && !(sc == "no" || sc == "off" || sc == "false" || sc == "thermal"))
 	    die("SurfaceCooling: %s is not supported by this driver (beta cooling, thermal)", sc);
-	const std::pair<const char *, double> zero_only[] = {{"AlphaMode", 0}, {"AspectRatioMode", 0}};
+	if (c.num("AlphaMode", 0) != 0 && !(c.num("AlphaMode", 0) == 1 && energy_equation && c.num("ViscousAlpha", 0.0) > 0))
+	    die("AlphaMode: %s is not supported by this driver (0; 1 with the energy equation and ViscousAlpha > 0)", c.str("AlphaMode", ""));
+	const std::pair<const char *, double> zero_only[] = {{"AspectRatioMode", 0}};
 	for (auto &k : zero_only)
 	    if (c.num(k.first, k.second) != k.second)
 		die((std::string(k.first) + ": %s is not supported by this driver").c_str(), c.str(k.first, ""));
@@ -398,6 +400,7 @@ static fargo_params make_params(const Config &c, const CodeConstants &k, int nra
     p.artificial_viscosity_factor = c.num("ArtificialViscosityFactor", 1.41);
     p.artificial_viscosity_dissipation = c.flag("ArtificialViscosityDissipation", true);
     p.viscous_alpha = c.num("ViscousAlpha", 0.0);
+    p.alpha_mode = (int)c.num("AlphaMode", 0), p.alpha_cold = c.num("AlphaCold", 0.01), p.alpha_hot = c.num("AlphaHot", 0.1); // parameters.cpp:704-706
     p.constant_viscosity = c.num("ConstantViscosity", 0.0);
     p.stabilize_viscosity = (int)c.num("StabilizeViscosity", 0);
     p.radial_viscosity_factor = c.num("RadialViscosityFactor", 1.0);

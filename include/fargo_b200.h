@@ -149,6 +149,11 @@ typedef struct fargo_params {
      * tables come through fargo_set_pvte_tables.  density_factor and density_cgs above are shared with the opacity. */
     int pvte;
     double energy_density_cgs, surface_density_cgs; /* units::energy_density / surface_density code -> cgs */
+    /* viscosity::get_alpha (viscosity/viscosity.cpp:31-95): AlphaMode 0 constant ViscousAlpha, 1 S-curve in the (stored)
+     * temperature after Ichikawa & Osaki (1992); AlphaCold, AlphaHot.  ViscousAlpha must be > 0 for either
+     * (update_viscosity :102).  Modes 2 and 3 are refused. */
+    int alpha_mode;
+    double alpha_cold, alpha_hot;
 } fargo_params;
 /* parameters::t_opacity (parameters.h), Opacity: Lin | Bell | Constant | Simple */
 enum fargo_opacity { FARGO_OPACITY_LIN = 0, FARGO_OPACITY_BELL = 1, FARGO_OPACITY_CONST = 2, FARGO_OPACITY_SIMPLE = 3 };

@@ -414,13 +414,28 @@ static void compute_temperature(fargo_oracle *o)
 }
 
 /* viscosity::update_viscosity, viscosity.cpp:98-137 (AlphaMode CONST_ALPHA) */
+/* viscosity::get_alpha, viscosity/viscosity.cpp:31-49 (AlphaMode 0 and 1) */
+static double get_alpha(const fargo_oracle *o, int nr, int naz)
+{
+    if (o->p.alpha_mode == 1) { /* SCURVE_ALPHA: reads the TEMPERATURE grid as last computed */
+	const double temperatureCGS = o->temperature[IDX(o, nr, naz)] * o->p.temperature_cgs;
+	const double alpha_cool = o->p.alpha_cold * pow(o->rmed[nr] / 0.4, 0.3);
+	const double alpha_hot = o->p.alpha_hot;
+	return pow(10.0, 0.5 * (log10(alpha_hot) - log10(alpha_cool)) * (1.0 - tanh((4.0 - log10(temperatureCGS)) / 0.4)) + log10(alpha_cool));
+    }
+    return o->p.viscous_alpha;
+}
+
 static void update_viscosity(fargo_oracle *o)
 {
     const size_t n = (size_t)o->nr * o->ns;
     if (o->p.viscous_alpha > 0) {
 #pragma omp parallel for
-	for (size_t c = 0; c < n; ++c)
-	    o->viscosity[c] = o->p.viscous_alpha * o->scale_height[c] * o->soundspeed[c];
+	for (int nr = 0; nr < o->nr; ++nr)
+	    for (int naz = 0; naz < o->ns; ++naz) {
+		const size_t c = IDX(o, nr, naz);
+		o->viscosity[c] = get_alpha(o, nr, naz) * o->scale_height[c] * o->soundspeed[c];
+	    }
     } else {
 	if (!o->visc_calculated)
 	    for (size_t c = 0; c < n; ++c)

@@ -135,6 +135,13 @@ CASES = {
     "adia_pvte": dict(EquationOfState="PVTE", ViscousAlpha=1e-3, HeatingViscous="yes", CoolingBetaLocal="yes", CoolingBeta=10,
                       WriteEffectiveGamma="yes", WriteFirstAdiabaticIndex="yes", WriteMeanMolecularWeight="yes", WriteScaleHeight="yes",
                       Damping="Yes", DampingInnerLimit=1.311, DampingOuterLimit=0.763, DampingTimeFactor=0.05, **DAMP_ALL),
+    # AlphaMode 1: S-curve alpha in the (stored) temperature (viscosity.cpp:36-49); l0 = 0.06 au puts the disk around 1e4 K,
+    # where alpha switches between AlphaCold and AlphaHot
+    "adia_alpha_scurve": dict(AlphaMode=1, ViscousAlpha=1e-3, AlphaCold=0.01, AlphaHot=0.1, HeatingViscous="yes", CoolingBetaLocal="yes",
+                              CoolingBeta=10, l0="0.06 au", Sigma0=0.001, WriteTemperature="yes", WriteViscosity="yes",
+                              Damping="Yes", DampingInnerLimit=1.311, DampingOuterLimit=0.763, DampingTimeFactor=0.05, **DAMP_ALL),
+    "adia_alpha_scurve_lf": dict(Integrator="Leapfrog", AlphaMode=1, ViscousAlpha=1e-3, AlphaCold=0.01, AlphaHot=0.1, HeatingViscous="yes",
+                                 l0="0.06 au", Sigma0=0.001, WriteTemperature="yes"),
     "iso_planet_100": dict(Nrad=48, Naz=160, Rmax=2.5, Nsnapshots=100, MonitorTimestep=4.0e-3, IndirectTermMode=1,
                            EquationOfState="Isothermal", ViscousAlpha=1e-3, ArtificialViscosityFactor=1.41, OmegaFrame=1.0,
                            FlaringIndex=0.0, Damping="Yes", DampingInnerLimit=1.25, DampingOuterLimit=0.84,
@@ -213,7 +220,7 @@ def run_case(name, overrides, keep=False):
     for k in range(nsnap + 1):
         sd = os.path.join(out, "snapshots", str(k))
         for fname, rings in (("Sigma", nrad), ("vrad", nrad + 1), ("vazi", nrad), ("energy", nrad),
-                             ("Qplus", nrad), ("Qminus", nrad), ("T_Reynolds", nrad), ("gammaeff", nrad), ("mu", nrad), ("gamma1", nrad), ("scale_height", nrad)):
+                             ("Qplus", nrad), ("Qminus", nrad), ("T_Reynolds", nrad), ("gammaeff", nrad), ("mu", nrad), ("gamma1", nrad), ("scale_height", nrad), ("Temperature", nrad), ("viscosity", nrad)):
             p = os.path.join(sd, fname + ".dat")
             if keep_snaps is not None and k not in keep_snaps:
                 continue

@@ -82,6 +82,10 @@ def start_from_snapshot0(ctx, meta, z):
         # ghost rings of the snapshot-0 energy, and the scale height the next lookup reads was stored then too
         for fid, name in ((abi.GAMMAEFF, "gammaeff"), (abi.MU, "mu"), (abi.GAMMA1, "gamma1"), (abi.SCALE_HEIGHT, "scale_height")):
             ctx.upload(fid, z[name + "_0"])
+    if ctx.params.alpha_mode and "Temperature_0" in z:
+        # AlphaMode 1 reads the TEMPERATURE grid one refresh late: the reference's dates from init_euler, before the first boundary
+        # conditions changed the ghost rings of the snapshot-0 energy
+        ctx.upload(abi.TEMPERATURE, z["Temperature_0"])
     ctx.copy_initial_values()
     loop = reftools.TimeLoop(ctx, meta["first_dt"], meta["monitor_timestep"])
     loop.calculate_time_step()  # main.cpp:117

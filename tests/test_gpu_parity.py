@@ -150,6 +150,34 @@ def test_pvte_run_vs_reference():
     assert worst <= POW_RTOL
 
 
+@pytest.mark.parametrize("name", ["adia_alpha_scurve", "adia_alpha_scurve_lf"])
+def test_alpha_scurve_run_vs_reference(name):
+    """AlphaMode 1 (viscosity/viscosity.cpp:31-49): alpha of a cell is an S-curve in the TEMPERATURE grid as last stored, formed
+    with pow / log10 / tanh — CUDA's against glibc's differ in the last bits, so fields, dt and the viscosity are held to POW_RTOL
+    (of the field's scale) like the opacity tables; step counts and times are identical.  Euler and Leapfrog (whose second
+    recalculate_viscosity reads the temperature SubStep3 stored)."""
+    meta, z, gpu, cpu = _ctx_pair(name)
+    snaps = goldenrun.run_fixture(gpu, meta, z)
+    worst, ndiff = 0.0, 0
+    for k, snap in enumerate(snaps, start=1):
+        m = meta["misc"][k]
+        assert snap["n_iter"] == m["n_iter"] and snap["time"] == m["time"]
+        assert snap["last_dt"] == pytest.approx(m["last_dt"], rel=POW_RTOL)
+        for fname in ("Sigma", "vrad", "vazi", "energy"):
+            ref = z[f"{fname}_{k}"]
+            worst = max(worst, float(np.abs(snap[fname] - ref).max() / np.abs(ref).max()))
+            ndiff += int((snap[fname] != ref).sum())
+    for fid, fname in ((abi.TEMPERATURE, "Temperature"), (abi.VISCOSITY, "viscosity")):
+        if f"{fname}_{meta['nsnap']}" not in z.files:
+            continue
+        ref = z[f"{fname}_{meta['nsnap']}"]
+        got = gpu.download(fid)
+        worst = max(worst, float(np.abs(got - ref).max() / np.abs(ref).max()))
+        ndiff += int((got != ref).sum())
+    print(name, ": worst deviation / field scale", worst, "differing doubles", ndiff)
+    assert worst <= POW_RTOL
+
+
 @pytest.mark.parametrize("name", ["adia_star", "iso_star"])
 def test_first_cfl_dt_bit_exact(name):
     """Step-0 CFL dt from identical inputs must be bit-equal for every config (no transcendental involved)."""
