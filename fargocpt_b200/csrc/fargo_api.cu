@@ -127,6 +127,9 @@ struct fargo_ctx {
     double *pot, *qr, *qphi, *nu, *divv, *trr, *tpp, *trp, *nusig, *nusig_rp, *cf_r, *cf_phi;
     double *t_sigma, *t_rmp, *t_rmm, *t_amp, *t_amm, *t_e; // after the radial sweep
     double *vmean, *vconst, *expf_s, *expf_v, *d_dt, *scratch, *force4;
+    // two-pass CFL reduction (kernels_ring.cuh:k_cfl_screen / k_cfl_candidates): per-block maxima of the screen, d_cfl_l = their max
+    double *cfl_bmax = nullptr, *d_cfl_l = nullptr;
+    int cfl_mode = 1; // FARGO_B200_CFL=full: 0 (k_cfl over every cell), screen: 1 (default), check: 2 (both, and they must agree)
     // damping zones folded into the azimuthal transport kernel's epilogue (fargo_step of an Euler step; AzSegs::dmask)
     int *d_dmask = nullptr;	     // per ring: 2 bits per field
     std::vector<int> h_dmask;	     // what d_dmask holds
@@ -628,6 +631,8 @@ extern "C" int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, con
       // 2048 rings 0.166 / 0.142, 8192 rings 0.258 / 0.447.  FARGO_B200_RINGSUM=chain|scan overrides.
 	const char *fold = getenv("FARGO_B200_FOLD_DAMPING");
 	c->fold_damping = !(fold && strcmp(fold, "0") == 0);
+	const char *cm = getenv("FARGO_B200_CFL");
+	c->cfl_mode = (cm && strcmp(cm, "full") == 0) ? 0 : (cm && strcmp(cm, "check") == 0) ? 2 : 1;
 	const char *env = getenv("FARGO_B200_RINGSUM");
 	c->ringsum_scan = c->v.nr <= 2560;
 	if (env && strcmp(env, "chain") == 0)
@@ -660,6 +665,7 @@ extern "C" int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, con
 	dalloc(c, &c->t_amm, ns) || dalloc(c, &c->t_e, params->adiabatic ? ns : 1));
     TRY(dalloc(c, &c->vmean, c->v.nr + 2) || dalloc(c, &c->vconst, c->v.nr + 2) || dalloc(c, &c->expf_s, 4 * (c->v.nr + 2)) ||
 	dalloc(c, &c->expf_v, 1) || dalloc(c, &c->d_dt, 2) || dalloc(c, &c->scratch, ns) || dalloc(c, &c->force4, 4));
+    TRY(dalloc(c, &c->cfl_bmax, (size_t)((c->v.ns + 511) / 512) * c->v.nr + 1) || dalloc(c, &c->d_cfl_l, 2));
     { // the reductions' partials have their own buffer: Nr x Nphi scratch is too small for them on grids with a few sectors
 	const size_t nr_ = (size_t)c->v.nr;
 	const size_t n_acc = (size_t)((c->v.ns + ACC_THREADS - 1) / ACC_THREADS) * nr_ * 3;
@@ -1569,8 +1575,31 @@ extern "C" int fargo_condition_cfl(fargo_ctx *c, double *out)
 		     c->cf_phi, c->vmean, c->d_dt);
     } else if (nact > 0) {
 	dim3 grid((unsigned)((v.ns + 511) / 512), (unsigned)nact);
-	LAUNCH(c, k_cfl, grid, 128, 0, v, c->sigma, EN(c), VRA(c), VPA(c), c->qplus, c->qminus, c->cf_r, c->cf_phi, c->vmean,
-	       c->d_dt);
+	const bool screen = c->cfl_mode != 0 && v.p.stabilize_viscosity != 2;
+	if (screen) { // bound A of every cell cheaply, evaluate the criterion exactly only where the maximum can be
+	    const int nrec = (int)(grid.x * grid.y);
+	    CUDA_OK(cudaMemsetAsync(c->d_cfl_l, 0, 2 * sizeof(double), c->stream));
+	    double *dt_dst = c->d_dt;
+	    if (c->cfl_mode == 2) { // check: the screened result goes to d_cfl_l[1], k_cfl's to d_dt
+		CUDA_OK(cudaMemcpyAsync(c->d_cfl_l + 1, c->h_pin, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+		dt_dst = c->d_cfl_l + 1;
+	    }
+	    LAUNCH_NAMED(c, c->stream, "k_cfl", k_cfl_screen, grid, 128, 0, v, c->sigma, EN(c), VRA(c), VPA(c), c->qplus, c->qminus, c->vmean,
+			 dt_dst, c->cfl_bmax, c->d_cfl_l);
+	    LAUNCH_NAMED(c, c->stream, "k_cfl_candidates", k_cfl_candidates, (unsigned)((nrec + 127) / 128), 128, 0, v, c->sigma, EN(c), VRA(c),
+			 VPA(c), c->qplus, c->qminus, c->vmean, c->cfl_bmax, c->d_cfl_l, nrec, (int)grid.x, dt_dst);
+	}
+	if (!screen || c->cfl_mode == 2)
+	    LAUNCH_NAMED(c, c->stream, screen ? "k_cfl[check]" : "k_cfl", k_cfl, grid, 128, 0, v, c->sigma, EN(c), VRA(c), VPA(c), c->qplus,
+			 c->qminus, c->cf_r, c->cf_phi, c->vmean, c->d_dt);
+	if (screen && c->cfl_mode == 2) {
+	    double both[2];
+	    CUDA_OK(cudaMemcpyAsync(&both[0], c->d_dt, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	    CUDA_OK(cudaMemcpyAsync(&both[1], c->d_cfl_l + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	    CUDA_OK(cudaStreamSynchronize(c->stream));
+	    if (memcmp(&both[0], &both[1], sizeof(double)) != 0)
+		return fail("FARGO_B200_CFL=check: screened reduction %.17g != full reduction %.17g", both[1], both[0]);
+	}
     }
     if (v.nranks > 1) { // MPI_Allreduce(MIN), cfl.cpp:379
 	NCCL_OK(g_nccl.AllReduce(c->d_dt, c->d_dt, 1, ncclFloat64, ncclMin, c->comm, c->stream));

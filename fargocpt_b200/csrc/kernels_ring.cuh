@@ -403,6 +403,131 @@ __device__ __forceinline__ double cfl_cell(const DevView &c, const CflRing &g, c
     return invdt1 * invdt1 + invdt2 * invdt2 + invdt3 * invdt3 + invdt4 * invdt4 + invdt5 * invdt5 + invdt6 * invdt6;
 }
 
+// the thread's 4 consecutive columns j0 .. j0 + 3 of ring i (and the right-hand neighbour of v_azi), row-major arrays
+struct CflIn {
+    double S[4], E[4], V0[4], V1[4], P[5], QP[4], QM[4];
+};
+__device__ __forceinline__ void cfl_load4(CflIn &N, const int ns, const int i, const int j0, const bool adiabatic,
+					   const double *__restrict__ sigma, const double *__restrict__ energy, const double *__restrict__ vr,
+					   const double *__restrict__ vp, const double *__restrict__ qplus, const double *__restrict__ qminus)
+{
+    const bool vec = ((ns & 3) == 0);
+    const size_t row = (size_t)i * ns;
+    if (vec) {
+	auto ld4 = [&](const double *base, double *x) {
+	    const double2 a = *reinterpret_cast<const double2 *>(base + j0);
+	    const double2 b = *reinterpret_cast<const double2 *>(base + j0 + 2);
+	    x[0] = a.x, x[1] = a.y, x[2] = b.x, x[3] = b.y;
+	};
+	ld4(sigma + row, N.S);
+	ld4(vr + row, N.V0);
+	ld4(vr + row + ns, N.V1);
+	ld4(vp + row, N.P);
+	N.P[4] = vp[row + ((j0 + 4 == ns) ? 0 : j0 + 4)];
+	if (adiabatic) {
+	    ld4(energy + row, N.E);
+	    ld4(qplus + row, N.QP);
+	    ld4(qminus + row, N.QM);
+	}
+    } else {
+#pragma unroll
+	for (int k = 0; k < 5; ++k) {
+	    const int j = j0 + k;
+	    const int jj = (j < ns) ? j : j - ns; // only the neighbour column may wrap; surplus columns are masked by the caller
+	    N.P[k] = vp[row + (jj < ns ? jj : 0)];
+	    if (k < 4) {
+		const int js = (j < ns) ? j : 0;
+		N.S[k] = sigma[row + js];
+		N.V0[k] = vr[row + js];
+		N.V1[k] = vr[row + ns + js];
+		if (adiabatic) {
+		    N.E[k] = energy[row + js];
+		    N.QP[k] = qplus[row + js];
+		    N.QM[k] = qminus[row + js];
+		}
+	    }
+	}
+    }
+    if (!adiabatic) {
+#pragma unroll
+	for (int k = 0; k < 4; ++k)
+	    N.E[k] = N.QP[k] = N.QM[k] = 0.0;
+    }
+}
+
+// the exact criterion of the thread's 4 columns j0 .. j0 + 3 (j0 < ns) of ring i, folded into Amax (max of A) and `best` (limits
+// that are not of the CFL / sqrt(A) form)
+__device__ __forceinline__ void cfl_exact4(const DevView &c, const int i, const int j0, const double vm,
+					    const double *__restrict__ sigma, const double *__restrict__ energy, const double *__restrict__ vr,
+					    const double *__restrict__ vp, const double *__restrict__ qplus, const double *__restrict__ qminus,
+					    const double *__restrict__ cf_r, const double *__restrict__ cf_phi, double &Amax, double &best)
+{
+    const int ns = c.ns;
+    const double CFL = c.p.cfl;
+    const bool adiabatic = c.p.adiabatic != 0;
+    CflRing g;
+    g.lf = c.p.leapfrog ? 0.6 : 1.0;
+    g.C = c.p.artificial_viscosity_factor;
+    g.dxr = c.g.rsup[i] - c.g.rinf[i];
+    g.dxa = c.g.rmed[i] * c.dphi;
+    g.cell_size = stdmin(g.dxr, g.dxa);
+    g.cell2 = g.cell_size * g.cell_size;
+    g.sqg = c.sqrt_gamma;
+    g.ycell = fm_rcp_raw_x(g.cell_size), g.ydxr = fm_rcp_raw_x(g.dxr), g.ydxa = fm_rcp_raw_x(g.dxa);
+    g.ycell2 = fm_rcp_raw_x(g.cell2), g.ysqg = fm_rcp_raw_x(g.sqg);
+    g.inv_limit = 1.0 / c.p.heating_cooling_cfl_limit;
+    g.ids = c.g.invdiffrsup[i], g.irb = c.g.invrmed[i], g.iok = c.g.inv_omega_k[i];
+    g.vm = vm;
+    FmAcc A0; // validity of the five shared denominators
+    fm_acc_nrm_x(A0, g.cell_size), fm_acc_nrm_x(A0, g.dxr), fm_acc_nrm_x(A0, g.dxa), fm_acc_nrm_x(A0, g.cell2), fm_acc_nrm_x(A0, g.sqg);
+    const bool vec = ((ns & 3) == 0);
+    const size_t row = (size_t)i * ns;
+    CflIn N;
+    cfl_load4(N, ns, i, j0, adiabatic, sigma, energy, vr, vp, qplus, qminus);
+    // the four cells straight-line on the fast arithmetic, one validity test; cold redo with the plain operators
+    double Ac[4];
+    FmAcc A = A0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+	Ac[k] = cfl_cell<MathX>(c, g, i, adiabatic, N.S[k], N.E[k], N.V0[k], N.V1[k], N.P[k], N.P[k + 1], N.QP[k], N.QM[k], A);
+    if (!fm_acc_ok_x(A)) {
+#pragma unroll
+	for (int k = 0; k < 4; ++k)
+	    Ac[k] = cfl_cell<MathP<false>>(c, g, i, adiabatic, N.S[k], N.E[k], N.V0[k], N.V1[k], N.P[k], N.P[k + 1], N.QP[k], N.QM[k], A);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+	if (!vec && j0 + k >= ns)
+	    continue;
+	const double Ak = Ac[k];
+	if (c.p.stabilize_viscosity == 2) { // per-cell min(dt_cell, -CFL / min(c_phi, c_r)), cfl.cpp:330-338
+	    double dt_cell = CFL / sqrt(Ak);
+	    const double cc = stdmin(cf_phi[row + j0 + k], cf_r[row + j0 + k]);
+	    if (cc != 0.0)
+		dt_cell = stdmin(dt_cell, -CFL / cc);
+	    if (dt_cell < best)
+		best = dt_cell;
+	} else if (Ak > Amax) {
+	    Amax = Ak;
+	}
+    }
+}
+
+// FARGO shear criterion of ring i (:207-220); the (0, 1) pair is the reference's initial dt_core
+__device__ __forceinline__ double cfl_shear(const DevView &c, const int i, const double *__restrict__ vmean)
+{
+    const double CFL = c.p.cfl;
+    const double denom = fabs(vmean[i] * c.g.invrmed[i] - vmean[i + 1] * c.g.invrmed[i + 1]) + 1.0e-100;
+    double best = CFL * c.dphi / denom;
+    if (i == c.first_active) {
+	const double denom0 = fabs(vmean[0] * c.g.invrmed[0] - vmean[1] * c.g.invrmed[1]) + 1.0e-100;
+	const double d0 = CFL * c.dphi / denom0;
+	if (d0 < best)
+	    best = d0;
+    }
+    return best;
+}
+
 // grid: x over azimuth (512 columns per block of 128 threads), y over the active rings
 __global__ void __launch_bounds__(128, 4)
     k_cfl(const DevView c, const double *__restrict__ sigma, const double *__restrict__ energy,
@@ -411,111 +536,14 @@ __global__ void __launch_bounds__(128, 4)
 	  const double *__restrict__ vmean, double *__restrict__ dt_out)
 {
     const int i = c.first_active + blockIdx.y;
-    const int ns = c.ns;
     const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const double DMAX = 1.7976931348623157e308;
-    const double CFL = c.p.cfl;
     double best = DMAX; // limits that are not of the CFL / sqrt(A) form
     double Amax = -1.0;
-    const bool adiabatic = c.p.adiabatic != 0;
-    const double vm = vmean[i];
-    if (blockIdx.x == 0 && threadIdx.x == 0) { // FARGO shear criterion (:207-220); the (0,1) pair is the reference's initial dt_core
-	const double denom = fabs(vm * c.g.invrmed[i] - vmean[i + 1] * c.g.invrmed[i + 1]) + 1.0e-100;
-	best = CFL * c.dphi / denom;
-	if (i == c.first_active) {
-	    const double denom0 = fabs(vmean[0] * c.g.invrmed[0] - vmean[1] * c.g.invrmed[1]) + 1.0e-100;
-	    const double d0 = CFL * c.dphi / denom0;
-	    if (d0 < best)
-		best = d0;
-	}
-    }
-    if (j0 < ns) {
-	CflRing g;
-	g.lf = c.p.leapfrog ? 0.6 : 1.0;
-	g.C = c.p.artificial_viscosity_factor;
-	g.dxr = c.g.rsup[i] - c.g.rinf[i];
-	g.dxa = c.g.rmed[i] * c.dphi;
-	g.cell_size = stdmin(g.dxr, g.dxa);
-	g.cell2 = g.cell_size * g.cell_size;
-	g.sqg = c.sqrt_gamma;
-	g.ycell = fm_rcp_raw_x(g.cell_size), g.ydxr = fm_rcp_raw_x(g.dxr), g.ydxa = fm_rcp_raw_x(g.dxa);
-	g.ycell2 = fm_rcp_raw_x(g.cell2), g.ysqg = fm_rcp_raw_x(g.sqg);
-	g.inv_limit = 1.0 / c.p.heating_cooling_cfl_limit;
-	g.ids = c.g.invdiffrsup[i], g.irb = c.g.invrmed[i], g.iok = c.g.inv_omega_k[i];
-	g.vm = vm;
-	FmAcc A0; // validity of the five shared denominators
-	fm_acc_nrm_x(A0, g.cell_size), fm_acc_nrm_x(A0, g.dxr), fm_acc_nrm_x(A0, g.dxa), fm_acc_nrm_x(A0, g.cell2), fm_acc_nrm_x(A0, g.sqg);
-	const bool vec = ((ns & 3) == 0);
-	double S[4], E[4], V0[4], V1[4], P[5], QP[4], QM[4];
-	const size_t row = (size_t)i * ns;
-	if (vec) {
-	    auto ld4 = [&](const double *base, double *x) {
-		const double2 a = *reinterpret_cast<const double2 *>(base + j0);
-		const double2 b = *reinterpret_cast<const double2 *>(base + j0 + 2);
-		x[0] = a.x, x[1] = a.y, x[2] = b.x, x[3] = b.y;
-	    };
-	    ld4(sigma + row, S);
-	    ld4(vr + row, V0);
-	    ld4(vr + row + ns, V1);
-	    ld4(vp + row, P);
-	    P[4] = vp[row + ((j0 + 4 == ns) ? 0 : j0 + 4)];
-	    if (adiabatic) {
-		ld4(energy + row, E);
-		ld4(qplus + row, QP);
-		ld4(qminus + row, QM);
-	    }
-	} else {
-#pragma unroll
-	    for (int k = 0; k < 5; ++k) {
-		const int j = j0 + k;
-		const int jj = (j < ns) ? j : j - ns; // only the neighbour column may wrap; surplus columns are masked below
-		P[k] = vp[row + (jj < ns ? jj : 0)];
-		if (k < 4) {
-		    const int js = (j < ns) ? j : 0;
-		    S[k] = sigma[row + js];
-		    V0[k] = vr[row + js];
-		    V1[k] = vr[row + ns + js];
-		    if (adiabatic) {
-			E[k] = energy[row + js];
-			QP[k] = qplus[row + js];
-			QM[k] = qminus[row + js];
-		    }
-		}
-	    }
-	}
-	if (!adiabatic) {
-#pragma unroll
-	    for (int k = 0; k < 4; ++k)
-		E[k] = QP[k] = QM[k] = 0.0;
-	}
-	// the four cells straight-line on the fast arithmetic, one validity test; cold redo with the plain operators
-	double Ac[4];
-	FmAcc A = A0;
-#pragma unroll
-	for (int k = 0; k < 4; ++k)
-	    Ac[k] = cfl_cell<MathX>(c, g, i, adiabatic, S[k], E[k], V0[k], V1[k], P[k], P[k + 1], QP[k], QM[k], A);
-	if (!fm_acc_ok_x(A)) {
-#pragma unroll
-	    for (int k = 0; k < 4; ++k)
-		Ac[k] = cfl_cell<MathP<false>>(c, g, i, adiabatic, S[k], E[k], V0[k], V1[k], P[k], P[k + 1], QP[k], QM[k], A);
-	}
-#pragma unroll
-	for (int k = 0; k < 4; ++k) {
-	    if (!vec && j0 + k >= ns)
-		continue;
-	    const double Ak = Ac[k];
-	    if (c.p.stabilize_viscosity == 2) { // per-cell min(dt_cell, -CFL / min(c_phi, c_r)), cfl.cpp:330-338
-		double dt_cell = CFL / sqrt(Ak);
-		const double cc = stdmin(cf_phi[row + j0 + k], cf_r[row + j0 + k]);
-		if (cc != 0.0)
-		    dt_cell = stdmin(dt_cell, -CFL / cc);
-		if (dt_cell < best)
-		    best = dt_cell;
-	    } else if (Ak > Amax) {
-		Amax = Ak;
-	    }
-	}
-    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+	best = cfl_shear(c, i, vmean);
+    if (j0 < c.ns)
+	cfl_exact4(c, i, j0, vmean[i], sigma, energy, vr, vp, qplus, qminus, cf_r, cf_phi, Amax, best);
     // block reduction: max of A, min of the other limits
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -542,13 +570,174 @@ __global__ void __launch_bounds__(128, 4)
 		best = wb[k];
 	}
 	if (Amax >= 0.0) {
-	    const double dt_cell = CFL / sqrt(Amax);
+	    const double dt_cell = c.p.cfl / sqrt(Amax);
 	    if (dt_cell < best)
 		best = dt_cell;
 	}
 	if (best < DMAX)
 	    atomic_min_pos_double(dt_out, best);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same reduction in two passes (round 2): a SCREEN that bounds A of every cell without an IEEE division or a square
+// root, and the exact criterion above evaluated only where the maximum can be.
+//
+// k_cfl is bound by its FP64 work (2 IEEE divisions, a square root and five Markstein steps per cell: 84 FP64 instructions
+// for 48 bytes), not by its six array reads.  The screen forms A~ of a cell from the same inputs with reciprocals that are
+// good to 2^-60 (hardware seed + one cubic Newton step) and c_s^2 instead of c_s: every term of A~ is the reference's term to
+// a relative 1e-14 (differences such as v_azi - <v_azi>, Q+ - Q-, the divergence of invdt4 are formed by the reference's own
+// operations, so cancellation cannot amplify the deviation), hence |A~ - A| <= eps A with eps = 1e-10 to spare.  With
+// L = max over all cells of A~, the cell that owns the true maximum of A satisfies A~ >= L (1 - 2 eps), so only blocks whose
+// own maximum of A~ reaches L (1 - 1e-9) can own it: k_cfl_candidates evaluates those (typically one or two of 2.6e5) with
+// cfl_exact4 and the result is the reference's dt bit for bit.  A block with a cell whose A~ is NaN / huge, or whose c_s^2 is
+// negative (the reference's NaN limits are ignored: such a cell must not raise L), is always a candidate and does not count
+// towards L; if L is tiny (< 1e-250: terms may have underflowed) every block is one.
+__device__ __forceinline__ double rcp_screen(const double b)
+{
+    const double y0 = fm_rcp_seed(b);
+    double e = fma(-b, y0, 1.0);
+    e = fma(e, e, e);
+    return fma(y0, e, y0);
+}
+__device__ __forceinline__ void atomic_max_pos_double(double *addr, double v)
+{
+    atomicMax(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+// grid as k_cfl; bmax[blockIdx.y * gridDim.x + blockIdx.x] = the block's max of A~ (+inf: always a candidate), *lmax = L
+__global__ void __launch_bounds__(128, 4)
+    k_cfl_screen(const DevView c, const double *__restrict__ sigma, const double *__restrict__ energy, const double *__restrict__ vr,
+		 const double *__restrict__ vp, const double *__restrict__ qplus, const double *__restrict__ qminus,
+		 const double *__restrict__ vmean, double *__restrict__ dt_out, double *__restrict__ bmax, double *__restrict__ lmax)
+{
+    const int i = c.first_active + blockIdx.y;
+    const int ns = c.ns;
+    const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const bool adiabatic = c.p.adiabatic != 0;
+    double At = -1.0;
+    bool force = false;
+    if (blockIdx.x == 0 && threadIdx.x == 0) // the shear criterion is exact as it is
+	atomic_min_pos_double(dt_out, cfl_shear(c, i, vmean));
+    if (j0 < ns) {
+	const double vm = vmean[i];
+	const double lf = c.p.leapfrog ? 0.6 : 1.0;
+	const double C = c.p.artificial_viscosity_factor;
+	const double dxr = c.g.rsup[i] - c.g.rinf[i];
+	const double dxa = c.g.rmed[i] * c.dphi;
+	const double idxr = fm_rcp_raw_x(dxr), idxa = fm_rcp_raw_x(dxa);
+	const double icell = (dxr < dxa) ? idxr : idxa;
+	const double icell2 = icell * icell;
+	const double ids = c.g.invdiffrsup[i], irb = c.g.invrmed[i], iok = c.g.inv_omega_k[i];
+	const double K4 = 4.0 * (C * C) * lf;
+	const double kcs = c.p.gamma * (c.p.gamma - 1.0);
+	const double cs_iso = c.g.cs_iso[i];
+	double K5 = 0.0, i5c = 0.0; // invdt5 = K5 c_s^2 (alpha viscosity) or a constant of the ring
+	if (c.p.viscous_alpha > 0)
+	    K5 = 4.0 * c.p.viscous_alpha * iok * icell2 * lf * (adiabatic ? fm_rcp_raw_x(c.sqrt_gamma) : 1.0);
+	else
+	    i5c = 4.0 * c.p.constant_viscosity * icell2 * lf;
+	const double K6 = (1.0 / c.p.heating_cooling_cfl_limit) * lf;
+	const bool sn = c.p.artificial_viscosity == FARGO_ARTVISC_SN;
+	const bool vec = ((ns & 3) == 0);
+	CflIn N;
+	cfl_load4(N, ns, i, j0, adiabatic, sigma, energy, vr, vp, qplus, qminus);
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+	    if (!vec && j0 + k >= ns)
+		continue;
+	    const double vr0 = N.V0[k], vr1 = N.V1[k], vp0 = N.P[k], vp1 = N.P[k + 1];
+	    const double cs2 = adiabatic ? kcs * N.E[k] * rcp_screen(N.S[k]) : cs_iso * cs_iso;
+	    const double t2 = vr0 * idxr;
+	    const double vres = c.p.fast_transport ? vp0 - vm : vp0;
+	    const double t3 = vres * idxa;
+	    double t4;
+	    if (sn) {
+		double dvRadial = vr1 - vr0;
+		double dvAzimuthal = vp1 - vp0;
+		dvRadial = (dvRadial > 0.0) ? 0.0 : -dvRadial;
+		dvAzimuthal = (dvAzimuthal > 0.0) ? 0.0 : -dvAzimuthal;
+		t4 = K4 * stdmax(dvRadial * idxr, dvAzimuthal * idxa);
+	    } else {
+		const double eps_rr = (vr1 - vr0) * ids;
+		const double eps_pp = irb * ((vp1 - vp0) * c.invdphi + 0.5 * (vr1 + vr0));
+		t4 = K4 * -stdmin(eps_rr + eps_pp, 0.0);
+	    }
+	    const double t5 = (c.p.viscous_alpha > 0) ? K5 * cs2 : i5c;
+	    double t6 = 0.0;
+	    if (adiabatic)
+		t6 = K6 * fabs((N.QP[k] - N.QM[k]) * rcp_screen(N.E[k]));
+	    const double Ak = cs2 * icell2 + t2 * t2 + t3 * t3 + t4 * t4 + t5 * t5 + t6 * t6;
+	    if (!(Ak < 1.0e300) || cs2 < 0.0)
+		force = true;
+	    else if (Ak > At)
+		At = Ak;
+	}
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+	const double oa = __shfl_xor_sync(0xffffffffu, At, o);
+	if (oa > At)
+	    At = oa;
+    }
+    force = __any_sync(0xffffffffu, force);
+    __shared__ double wa[4];
+    __shared__ int wf[4];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) {
+	wa[w] = At;
+	wf[w] = force ? 1 : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+	for (int k = 1; k < 4; ++k) {
+	    if (wa[k] > At)
+		At = wa[k];
+	    force = force || (wf[k] != 0);
+	}
+	if (At > 0.0)
+	    atomic_max_pos_double(lmax, At);
+	bmax[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = force ? __longlong_as_double(0x7ff0000000000000LL) : At;
+    }
+}
+
+// one thread per record of bmax; a warp evaluates each of its candidate blocks (512 columns of one ring) exactly
+__global__ void __launch_bounds__(128)
+    k_cfl_candidates(const DevView c, const double *__restrict__ sigma, const double *__restrict__ energy, const double *__restrict__ vr,
+		     const double *__restrict__ vp, const double *__restrict__ qplus, const double *__restrict__ qminus,
+		     const double *__restrict__ vmean, const double *__restrict__ bmax, const double *__restrict__ lmax, const int nrec,
+		     const int gx, double *__restrict__ dt_out)
+{
+    const double L = *lmax;
+    const double thr = (L >= 1.0e-250) ? L * (1.0 - 1.0e-9) : -2.0;
+    const int rec = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const double v = (rec < nrec) ? bmax[rec] : -3.0;
+    unsigned mask = __ballot_sync(0xffffffffu, v >= thr);
+    if (mask == 0u)
+	return;
+    double Amax = -1.0, best = 1.7976931348623157e308;
+    while (mask) {
+	const int b = (rec - lane) + (__ffs(mask) - 1);
+	mask &= mask - 1;
+	const int i = c.first_active + b / gx;
+	const int bx = b - (b / gx) * gx;
+	const double vm = vmean[i];
+	for (int pass = 0; pass < 4; ++pass) {
+	    const int j0 = (bx * 128 + pass * 32 + lane) * 4;
+	    if (j0 < c.ns)
+		cfl_exact4(c, i, j0, vm, sigma, energy, vr, vp, qplus, qminus, nullptr, nullptr, Amax, best);
+	}
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+	const double oa = __shfl_xor_sync(0xffffffffu, Amax, o);
+	if (oa > Amax)
+	    Amax = oa;
+    }
+    if (lane == 0 && Amax >= 0.0)
+	atomic_min_pos_double(dt_out, c.p.cfl / sqrt(Amax));
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -146,3 +146,45 @@ def test_damping_folded_into_transport_equals_own_pass_and_oracle(physics, naz, 
     orbit = _start(ctx, cfg2, fields)
     _run(ctx, cfg2, orbit, 5)
     assert reftools.compare_stats(ctx.download(abi.SIGMA), out["oracle"][1][abi.SIGMA])["n_diff"] > 100
+
+
+def test_screened_cfl_equals_full_reduction_on_the_full_grid(monkeypatch):
+    """fargo_condition_cfl bounds A of every cell with a cheap screen and evaluates the exact criterion only where the maximum
+    can be (kernels_ring.cuh:k_cfl_screen / k_cfl_candidates).  FARGO_B200_CFL=check runs the full reduction (k_cfl) next to
+    it on every call and fails the call unless the two dt agree bit for bit: BASELINE configs[4]'s grid (or 2048 x 4096 on a
+    small device), perturbed disk + Jupiter, CFL-limited steps; the dt sequence also equals the full-only run's."""
+    from fargocpt_b200 import HydroContext
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    nrad, naz = (8192, 16384) if free > 90e9 else (2048, 4096)
+    cfg = synthetic.make_config("adiabatic_planet", nrad, naz)
+    radii = synthetic.radii_from_config(cfg)
+    params = synthetic.params_from_config(cfg)
+    fields = synthetic.disk_fields(cfg, radii, perturb=1e-2)
+    seqs = {}
+    for mode in ("check", "full"):
+        monkeypatch.setenv("FARGO_B200_CFL", mode)
+        ctx = HydroContext(params, radii)
+        orbit = _start(ctx, cfg, fields)
+        seqs[mode], _ = _run(ctx, cfg, orbit, 4)
+        ctx.close()
+    assert seqs["check"] == seqs["full"]
+
+
+@pytest.mark.parametrize("physics", ["adiabatic_planet", "isothermal_planet"])
+@pytest.mark.parametrize("nrad,naz", [(96, 131), (64, 2), (128, 1024)])
+def test_screened_cfl_equals_full_reduction_small_grids(physics, nrad, naz, monkeypatch):
+    """The same check on ragged / few-sector grids (no vector path, one partial block per ring) and against the oracle's dt."""
+    from fargocpt_b200 import HydroContext
+    cfg = synthetic.make_config(physics, nrad, naz)
+    radii = synthetic.radii_from_config(cfg)
+    params = synthetic.params_from_config(cfg)
+    fields = synthetic.disk_fields(cfg, radii, perturb=2e-2)
+    monkeypatch.setenv("FARGO_B200_CFL", "check")
+    out = {}
+    for name in ("gpu", "oracle"):
+        ctx = reftools.OracleContext(params, radii) if name == "oracle" else HydroContext(params, radii)
+        orbit = _start(ctx, cfg, fields)
+        out[name], _ = _run(ctx, cfg, orbit, 5)
+        ctx.close()
+    assert out["gpu"] == out["oracle"]
