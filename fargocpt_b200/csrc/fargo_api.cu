@@ -151,6 +151,7 @@ struct fargo_ctx {
     int az_slots, rad_chunk, fs_R, n_sm;
     bool ringsum_scan = false;  // ring sums by k_ring_sum_scan (a warp per ring) instead of the one-thread-per-ring chain
     int rm_chunk = 0;	       // columns per TMA chunk of k_ring_mean (0: generic kernel)
+    int rm_side_chunk = 0;     // ... of the launch that runs beside the radial sweep (0: rm_chunk there too; see fargo_ctx_create)
     size_t rm_smem = 0;
     cudaStream_t stream2 = nullptr; // side stream: the transport ring means run beside the radial sweep
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -614,7 +615,15 @@ extern "C" int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, con
 	// the step is 0.6 % slower than with the default, so there it keeps the default.
 	int prio_lo = 0, prio_hi = 0;
 	cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-	cudaError_t e = cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, c->v.nr <= 2560 ? prio_hi : prio_lo);
+	// Also measured (profiles/r02_v11_*): small chunks for the side-stream launch (FARGO_B200_RM_SIDE_CHUNK=32: 35 KB of shared
+	// memory per warp instead of 100 KB, so that two of its warps fit beside three CTAs of the sweep) at the highest priority.
+	// The sums then do finish in the sweep's shadow (0.9 instead of 3.2 ms after the fork), but the sweep takes 0.28 ms longer —
+	// the 1 GB the sums read costs the same DRAM time wherever it is placed — and the step is unchanged (18.50 vs 18.48 ms).
+	// Not the default.
+	const char *sc = getenv("FARGO_B200_RM_SIDE_CHUNK");
+	c->rm_side_chunk = sc ? atoi(sc) & ~15 : 0;
+	cudaError_t e = cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking,
+						     (c->v.nr <= 2560 || c->rm_side_chunk > 0) ? prio_hi : prio_lo);
 	if (e == cudaSuccess)
 	    e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
 	if (e == cudaSuccess)
@@ -1331,7 +1340,10 @@ static int launch_ring_mean(fargo_ctx *c, cudaStream_t strm, const double *vp, d
 		     v.nr, v.ns);
 	return 0;
     }
-    if (c->rm_chunk > 0)
+    if (c->rm_chunk > 0 && mode == 1 && c->rm_side_chunk > 0 && c->rm_side_chunk < c->rm_chunk) { // beside the radial sweep
+	const size_t smem = (size_t)RM_STAGES * 32 * (c->rm_side_chunk + 2) * sizeof(double) + RM_STAGES * sizeof(unsigned long long);
+	LAUNCH_NAMED(c, strm, label, k_ring_mean, nb, 32, smem, v, vp, c->vmean, c->nshift, c->vconst, dt, mode, c->rm_side_chunk);
+    } else if (c->rm_chunk > 0)
 	LAUNCH_NAMED(c, strm, label, k_ring_mean, nb, 32, c->rm_smem, v, vp, c->vmean, c->nshift, c->vconst, dt, mode, c->rm_chunk);
     else
 	LAUNCH_NAMED(c, strm, label, k_ring_mean_generic, nb, 32, 0, v, vp, c->vmean, c->nshift, c->vconst, dt, mode);
