@@ -129,6 +129,10 @@ struct fargo_ctx {
     double *vmean, *vconst, *expf_s, *expf_v, *d_dt, *scratch, *force4;
     // two-pass CFL reduction (kernels_ring.cuh:k_cfl_screen / k_cfl_candidates): per-block maxima of the screen, d_cfl_l = their max
     double *cfl_bmax = nullptr, *d_cfl_l = nullptr;
+    // FARGO_B200_FUSE_ARTVISC=1: the artificial-viscosity stage runs inside k_fused_sources<.., AV = true> instead of as its own
+    // kernel.  Bit-identical, 56 bytes per cell less traffic — and slower (5.22 against 2.76 + 2.14 ms at 8192 x 16384: 64 bytes
+    // of spills at 128 registers, and these kernels wait on FP64 chains, not on DRAM; profiles/r02_v12_*), so not the default.
+    bool fuse_artvisc = false;
     int cfl_mode = 1; // FARGO_B200_CFL=full: 0 (k_cfl over every cell), screen: 1 (default), check: 2 (both, and they must agree)
     // damping zones folded into the azimuthal transport kernel's epilogue (fargo_step of an Euler step; AzSegs::dmask)
     int *d_dmask = nullptr;	     // per ring: 2 bits per field
@@ -640,6 +644,8 @@ extern "C" int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, con
       // 2048 rings 0.166 / 0.142, 8192 rings 0.258 / 0.447.  FARGO_B200_RINGSUM=chain|scan overrides.
 	const char *fold = getenv("FARGO_B200_FOLD_DAMPING");
 	c->fold_damping = !(fold && strcmp(fold, "0") == 0);
+	const char *fa = getenv("FARGO_B200_FUSE_ARTVISC");
+	c->fuse_artvisc = fa && strcmp(fa, "1") == 0;
 	const char *cm = getenv("FARGO_B200_CFL");
 	c->cfl_mode = (cm && strcmp(cm, "full") == 0) ? 0 : (cm && strcmp(cm, "check") == 0) ? 2 : 1;
 	const char *env = getenv("FARGO_B200_RINGSUM");
@@ -713,9 +719,9 @@ extern "C" int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, con
 		n = 1;
 	    return n;
 	};
-	const int occ_fs = adi ? std::min(occ((const void *)k_fused_sources<true, false>),
+	const int occ_fs = adi ? std::min(occ((const void *)k_fused_sources<true, false, true>),
 					  std::min(occ((const void *)k_fused_artvisc<true>), occ((const void *)k_fused_viscosity<true, false>)))
-			       : std::min(occ((const void *)k_fused_sources<false, false>),
+			       : std::min(occ((const void *)k_fused_sources<false, false, true>),
 					  std::min(occ((const void *)k_fused_artvisc<false>), occ((const void *)k_fused_viscosity<false, false>)));
 	const int occ_az = mc ? (adi ? occ((const void *)k_transport_azimuthal<FARGO_LIMITER_MC, true, false>)
 				     : occ((const void *)k_transport_azimuthal<FARGO_LIMITER_MC, false, false>))
@@ -1649,18 +1655,30 @@ template <bool ADI> static int launch_fused_sources(fargo_ctx *c, double dt)
     const int nwin = (v.ns + FS_OUT - 1) / FS_OUT;
     dim3 grid((unsigned)((nwin + 3) / 4), (unsigned)((v.nr + c->fs_R - 1) / c->fs_R));
     const int eo = ADI ? 1 - c->ecur : c->ecur;
-    if (c->pre_hi > c->pre_lo) { // the step began with an accretion call: P and H of the touched rings from the state before it
-	LAUNCH(c, (k_fused_sources<ADI, true>), grid, 128, 0, v, c->sigma, EN(c), VRA(c), VPA(c),
-	       (const double *)(c->h_stale ? c->hstale : nullptr), VRB(c), VPB(c), c->eb[eo], dt, c->fs_R, pre_state(c));
-	c->pre_lo = c->pre_hi = 0;
+    const bool diss = ADI && p.artificial_viscosity_dissipation;
+    const bool artvisc = p.artificial_viscosity != FARGO_ARTVISC_NONE || diss;
+    const bool av_in_sources = artvisc && c->fuse_artvisc; // the artificial-viscosity stage inside the source-term kernel
+    const bool pre = c->pre_hi > c->pre_lo; // the step began with an accretion call: P and H of the touched rings from the state before it
+#define FS_SRC_LAUNCH(PRE_, AV_, label)                                                                                                  \
+    LAUNCH_NAMED(c, c->stream, label, (k_fused_sources<ADI, PRE_, AV_>), grid, 128, 0, v, c->sigma, EN(c), VRA(c), VPA(c),                  \
+		 (const double *)(c->h_stale ? c->hstale : nullptr), VRB(c), VPB(c), c->eb[eo], dt, c->fs_R, pre_state(c))
+    if (av_in_sources) {
+	if (pre)
+	    FS_SRC_LAUNCH(true, true, "(k_fused_sources+artvisc<ADI, true>)");
+	else
+	    FS_SRC_LAUNCH(false, true, "(k_fused_sources+artvisc<ADI, false>)");
     } else {
-	LAUNCH(c, (k_fused_sources<ADI, false>), grid, 128, 0, v, c->sigma, EN(c), VRA(c), VPA(c),
-	       (const double *)(c->h_stale ? c->hstale : nullptr), VRB(c), VPB(c), c->eb[eo], dt, c->fs_R, pre_state(c));
+	if (pre)
+	    FS_SRC_LAUNCH(true, false, "(k_fused_sources<ADI, true>)");
+	else
+	    FS_SRC_LAUNCH(false, false, "(k_fused_sources<ADI, false>)");
     }
+#undef FS_SRC_LAUNCH
+    if (pre)
+	c->pre_lo = c->pre_hi = 0;
     c->vcur = 1 - c->vcur;
     c->ecur = eo;
-    const bool diss = ADI && p.artificial_viscosity_dissipation;
-    if (p.artificial_viscosity != FARGO_ARTVISC_NONE || diss) {
+    if (artvisc && !av_in_sources) {
 	const int eo2 = ADI ? 1 - c->ecur : c->ecur;
 	LAUNCH(c, k_fused_artvisc<ADI>, grid, 128, 0, v, c->sigma, EN(c), VRA(c), VPA(c), VRB(c), VPB(c), c->eb[eo2], dt, c->fs_R);
 	c->vcur = 1 - c->vcur;

@@ -293,124 +293,6 @@ __device__ __forceinline__ void st_compress(const DevView &c, const int r, const
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_fused_sources.  Iteration kr loads ring kr, forms Phi(kr), P(kr), v_rad'(kr) (needs ring kr-1) and v_azi'(kr),
-// then finishes ring r = kr-1: e'(r) needs v_rad'(r+1).  Output: v_rad', v_azi', e' of ring r.
-// PRE: the step began with an accretion call (fargo_dev.h:PreState) — P and H of the rings it may have touched are those of
-// the pre-accretion state, like the reference's stored PRESSURE / SCALE_HEIGHT; a separate instantiation, so the kernel
-// of every other step is unchanged.
-template <bool ADI, bool PRE>
-__global__ void __launch_bounds__(128, FS_MINB_SRC)
-    k_fused_sources(const DevView c, const double *__restrict__ sigma, const double *__restrict__ energy,
-		    const double *__restrict__ vr, const double *__restrict__ vp, const double *__restrict__ h_in,
-		    double *__restrict__ o_vr, double *__restrict__ o_vp, double *__restrict__ o_e, const double dt, const int R,
-		    const PreState pre)
-{
-    typedef MathP<true> MF;
-    typedef MathP<false> MS;
-    FsLane L;
-    if (!fs_setup(c, L))
-	return;
-    const int nr = c.nr;
-    const int i_first = blockIdx.y * R;
-    if (i_first >= nr)
-	return;
-    const int i_last = min(i_first + R, nr);
-    const bool drift = c.p.imposed_disk_drift != 0.0;
-    const bool have_h = h_in != nullptr;
-    const EosC ec = make_eos_c(c);
-    // azimuth of the thread's columns (SideEuler.cpp:56-65)
-    double cosj[FS_NC], sinj[FS_NC];
-    {
-	int cc = L.col;
-	FS_FOR4
-	{
-	    cosj[k] = c.g.cosphi[cc];
-	    sinj[k] = c.g.sinphi[cc];
-	    cc = (cc + 1 == c.ns) ? 0 : cc + 1;
-	}
-    }
-    double S1[FS_NC], P1[FS_NC], F1[FS_NC], VP1[FS_NC], E1[FS_NC], VRn1[FS_NC], VPn1[FS_NC];
-    FS_FOR4
-    {
-	S1[k] = 1.0;
-	P1[k] = F1[k] = VP1[k] = VRn1[k] = VPn1[k] = 0.0;
-	E1[k] = 1.0;
-    }
-    // ring r = kr-1 is finished in iteration kr; its v_rad' needs ring r-1, so start one ring early
-    const int kbeg = max(i_first - 1, 0);
-    for (int kr = kbeg; kr <= i_last; ++kr) {
-	const bool has_cells = kr < nr;
-	double P0[FS_NC], F0[FS_NC], VRn0[FS_NC], VPn0[FS_NC];
-	FsRing R0;
-	fs_next_ring<ADI>(c, L, sigma, energy, vr, vp, kr, i_last, R0);
-	double(&S0)[FS_NC] = R0.S, (&E0)[FS_NC] = R0.E, (&VP0)[FS_NC] = R0.VP, (&VR0)[FS_NC] = R0.VR;
-	if (has_cells) {
-	    double Hin[FS_NC];
-	    FS_FOR4 Hin[k] = 0.0;
-	    if (have_h)
-		fs_load(h_in, kr, c, L, Hin);
-	    if (PRE && pre_has(pre, kr)) { // warp-uniform: a warp marches through whole rings
-		double Sp[FS_NC], Ep[FS_NC];
-		fs_load(pre.sigma, kr, c, L, Sp);
-		if (ADI)
-		    fs_load(pre.energy, kr, c, L, Ep);
-		else
-		    FS_FOR4 Ep[k] = 0.0;
-		FS_RUN((st_potential<MF, ADI>(c, ec, kr, Sp, Ep, cosj, sinj, have_h, Hin, P0, F0, A)),
-		       (st_potential<MS, ADI>(c, ec, kr, Sp, Ep, cosj, sinj, have_h, Hin, P0, F0, A)));
-	    } else {
-		FS_RUN((st_potential<MF, ADI>(c, ec, kr, S0, E0, cosj, sinj, have_h, Hin, P0, F0, A)),
-		       (st_potential<MS, ADI>(c, ec, kr, S0, E0, cosj, sinj, have_h, Hin, P0, F0, A)));
-	    }
-	} else {
-	    FS_FOR4 { P0[k] = F0[k] = 0.0; }
-	}
-	FS_FOR4
-	{
-	    VRn0[k] = VR0[k];
-	    VPn0[k] = VP0[k];
-	}
-	if (kr >= c.one_no_ghost_vr && kr < c.maxmo_no_ghost_vr) {
-	    const double VP0r = shfl_from_right(VP0[0]), VP1r = shfl_from_right(VP1[0]);
-	    FS_RUN((st_vrad<MF>(c, kr, dt, S0, S1, P0, P1, F0, F1, VP0, VP0r, VP1, VP1r, VR0, VRn0, A)),
-		   (st_vrad<MS>(c, kr, dt, S0, S1, P0, P1, F0, F1, VP0, VP0r, VP1, VP1r, VR0, VRn0, A)));
-	}
-	if (has_cells && kr >= c.zero_no_ghost && kr < c.max_no_ghost) {
-	    const double Sl = shfl_from_left(S0[FS_NC - 1]), Pl = shfl_from_left(P0[FS_NC - 1]), Fl = shfl_from_left(F0[FS_NC - 1]);
-	    FS_RUN((st_vazi<MF>(c, kr, dt, drift, S0, Sl, P0, Pl, F0, Fl, VP0, VPn0, A)),
-		   (st_vazi<MS>(c, kr, dt, drift, S0, Sl, P0, Pl, F0, Fl, VP0, VPn0, A)));
-	}
-	// ring r = kr-1: compression heating, then store
-	const int r = kr - 1;
-	if (r >= i_first) {
-	    double En[FS_NC];
-	    FS_FOR4 En[k] = E1[k];
-	    if (ADI && r < nr - 1) {
-		const double VPn1r = shfl_from_right(VPn1[0]);
-		FS_RUN((st_compress<MF>(c, r, dt, E1, VRn0, VRn1, VPn1, VPn1r, En, A)),
-		       (st_compress<MS>(c, r, dt, E1, VRn0, VRn1, VPn1, VPn1r, En, A)));
-	    }
-	    fs_store(o_vr, r, c, L, VRn1);
-	    fs_store(o_vp, r, c, L, VPn1);
-	    if (ADI)
-		fs_store(o_e, r, c, L, En);
-	}
-	FS_FOR4
-	{
-	    S1[k] = S0[k];
-	    P1[k] = P0[k];
-	    F1[k] = F0[k];
-	    VP1[k] = VP0[k];
-	    E1[k] = E0[k];
-	    VRn1[k] = VRn0[k];
-	    VPn1[k] = VPn0[k];
-	}
-    }
-    if (i_last == nr) // v_rad ring nr (outermost interface) is outside every update range
-	fs_store(o_vr, nr, c, L, VRn1);
-}
-
-// ---------------------------------------------------------------------------------------------
 // artificial viscosity stage bodies (viscosity/artificial_viscosity.cpp)
 struct AvIn {
     // ring r: Sigma, e, v_rad(r), v_rad(r+1), v_azi (+ right neighbour), and ring r-1: Sigma, Q
@@ -517,6 +399,176 @@ __device__ __forceinline__ void st_av_v(const DevView &c, const int r, const dou
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_fused_sources.  Iteration kr loads ring kr, forms Phi(kr), P(kr), v_rad'(kr) (needs ring kr-1) and v_azi'(kr),
+// then finishes ring r = kr-1: e'(r) needs v_rad'(r+1).  Output: v_rad', v_azi', e' of ring r.
+// PRE: the step began with an accretion call (fargo_dev.h:PreState) — P and H of the rings it may have touched are those of
+// the pre-accretion state, like the reference's stored PRESSURE / SCALE_HEIGHT; a separate instantiation, so the kernel
+// of every other step is unchanged.
+// AV: the artificial-viscosity stage (k_fused_artvisc's) runs on ring r in the same iteration, on the registers that hold the
+// source terms' results — v_rad'(r + 1), the one value of the next ring it needs, is already formed — instead of as a second
+// kernel that reads them back: 56 bytes per cell less traffic, one warm-up ring and one set of loads / prefetches / address
+// arithmetic instead of two.  The window yields the same 60 columns (v_azi'' of column j needs v_azi' of columns j - 1 .. j + 1,
+// which needs P of column j - 2: columns [2, 62)); the march starts two rings early instead of one (Q of ring i_first - 1
+// needs v_rad' of that ring, which needs ring i_first - 2).
+template <bool ADI, bool PRE, bool AV>
+__global__ void __launch_bounds__(128, FS_MINB_SRC)
+    k_fused_sources(const DevView c, const double *__restrict__ sigma, const double *__restrict__ energy,
+		    const double *__restrict__ vr, const double *__restrict__ vp, const double *__restrict__ h_in,
+		    double *__restrict__ o_vr, double *__restrict__ o_vp, double *__restrict__ o_e, const double dt, const int R,
+		    const PreState pre)
+{
+    typedef MathP<true> MF;
+    typedef MathP<false> MS;
+    FsLane L;
+    if (!fs_setup(c, L))
+	return;
+    const int nr = c.nr;
+    const int i_first = blockIdx.y * R;
+    if (i_first >= nr)
+	return;
+    const int i_last = min(i_first + R, nr);
+    const bool drift = c.p.imposed_disk_drift != 0.0;
+    const bool have_h = h_in != nullptr;
+    const EosC ec = make_eos_c(c);
+    // azimuth of the thread's columns (SideEuler.cpp:56-65)
+    double cosj[FS_NC], sinj[FS_NC];
+    {
+	int cc = L.col;
+	FS_FOR4
+	{
+	    cosj[k] = c.g.cosphi[cc];
+	    sinj[k] = c.g.sinphi[cc];
+	    cc = (cc + 1 == c.ns) ? 0 : cc + 1;
+	}
+    }
+    double S1[FS_NC], P1[FS_NC], F1[FS_NC], VP1[FS_NC], E1[FS_NC], VRn1[FS_NC], VPn1[FS_NC];
+    FS_FOR4
+    {
+	S1[k] = 1.0;
+	P1[k] = F1[k] = VP1[k] = VRn1[k] = VPn1[k] = 0.0;
+	E1[k] = 1.0;
+    }
+    // AV: ring r - 1 as the artificial-viscosity stage left it (Sigma, Q_rr, Q_phiphi)
+    const int av_type = c.p.artificial_viscosity;
+    const bool av_diss = ADI && c.p.artificial_viscosity_dissipation;
+    TempClampNB tc;
+    if (AV && ADI)
+	tc = make_temp_clamp_nb(c);
+    double S2[FS_NC], QR2[FS_NC], QP2[FS_NC];
+    FS_FOR4
+    {
+	S2[k] = 1.0;
+	QR2[k] = QP2[k] = 0.0;
+    }
+    // ring r = kr-1 is finished in iteration kr; its v_rad' needs ring r-1, so start one ring early (AV: two, see above)
+    const int kbeg = max(i_first - (AV ? 2 : 1), 0);
+    const int rbeg = AV ? max(i_first - 1, 0) : i_first; // first ring whose source terms must be complete
+    for (int kr = kbeg; kr <= i_last; ++kr) {
+	const bool has_cells = kr < nr;
+	double P0[FS_NC], F0[FS_NC], VRn0[FS_NC], VPn0[FS_NC];
+	FsRing R0;
+	fs_next_ring<ADI>(c, L, sigma, energy, vr, vp, kr, i_last, R0);
+	double(&S0)[FS_NC] = R0.S, (&E0)[FS_NC] = R0.E, (&VP0)[FS_NC] = R0.VP, (&VR0)[FS_NC] = R0.VR;
+	if (has_cells) {
+	    double Hin[FS_NC];
+	    FS_FOR4 Hin[k] = 0.0;
+	    if (have_h)
+		fs_load(h_in, kr, c, L, Hin);
+	    if (PRE && pre_has(pre, kr)) { // warp-uniform: a warp marches through whole rings
+		double Sp[FS_NC], Ep[FS_NC];
+		fs_load(pre.sigma, kr, c, L, Sp);
+		if (ADI)
+		    fs_load(pre.energy, kr, c, L, Ep);
+		else
+		    FS_FOR4 Ep[k] = 0.0;
+		FS_RUN((st_potential<MF, ADI>(c, ec, kr, Sp, Ep, cosj, sinj, have_h, Hin, P0, F0, A)),
+		       (st_potential<MS, ADI>(c, ec, kr, Sp, Ep, cosj, sinj, have_h, Hin, P0, F0, A)));
+	    } else {
+		FS_RUN((st_potential<MF, ADI>(c, ec, kr, S0, E0, cosj, sinj, have_h, Hin, P0, F0, A)),
+		       (st_potential<MS, ADI>(c, ec, kr, S0, E0, cosj, sinj, have_h, Hin, P0, F0, A)));
+	    }
+	} else {
+	    FS_FOR4 { P0[k] = F0[k] = 0.0; }
+	}
+	FS_FOR4
+	{
+	    VRn0[k] = VR0[k];
+	    VPn0[k] = VP0[k];
+	}
+	if (kr >= c.one_no_ghost_vr && kr < c.maxmo_no_ghost_vr) {
+	    const double VP0r = shfl_from_right(VP0[0]), VP1r = shfl_from_right(VP1[0]);
+	    FS_RUN((st_vrad<MF>(c, kr, dt, S0, S1, P0, P1, F0, F1, VP0, VP0r, VP1, VP1r, VR0, VRn0, A)),
+		   (st_vrad<MS>(c, kr, dt, S0, S1, P0, P1, F0, F1, VP0, VP0r, VP1, VP1r, VR0, VRn0, A)));
+	}
+	if (has_cells && kr >= c.zero_no_ghost && kr < c.max_no_ghost) {
+	    const double Sl = shfl_from_left(S0[FS_NC - 1]), Pl = shfl_from_left(P0[FS_NC - 1]), Fl = shfl_from_left(F0[FS_NC - 1]);
+	    FS_RUN((st_vazi<MF>(c, kr, dt, drift, S0, Sl, P0, Pl, F0, Fl, VP0, VPn0, A)),
+		   (st_vazi<MS>(c, kr, dt, drift, S0, Sl, P0, Pl, F0, Fl, VP0, VPn0, A)));
+	}
+	// ring r = kr-1: compression heating, then store
+	const int r = kr - 1;
+	if (r >= rbeg) {
+	    double En[FS_NC];
+	    FS_FOR4 En[k] = E1[k];
+	    const double VPn1r = shfl_from_right(VPn1[0]);
+	    if (ADI && r < nr - 1) {
+		FS_RUN((st_compress<MF>(c, r, dt, E1, VRn0, VRn1, VPn1, VPn1r, En, A)),
+		       (st_compress<MS>(c, r, dt, E1, VRn0, VRn1, VPn1, VPn1r, En, A)));
+	    }
+	    if (AV) { // update_with_artificial_viscosity on ring r: Q(r) from v'(r), v_rad'(r + 1); v''(r) from Q(r), Q(r - 1)
+		AvIn I;
+		FS_FOR4
+		{
+		    I.S1[k] = S1[k], I.E1[k] = En[k], I.VR1[k] = VRn1[k], I.VR0[k] = VRn0[k], I.VP1[k] = VPn1[k];
+		    I.S2[k] = S2[k], I.QR2[k] = QR2[k], I.QP2[k] = QP2[k];
+		}
+		I.VP1r = VPn1r;
+		double QR1[FS_NC], QP1[FS_NC], Ea[FS_NC], VRa[FS_NC], VPa[FS_NC];
+		st_av_q<ADI>(c, r, dt, av_type, av_diss, I, QR1, QP1, Ea);
+		if (av_diss) { // :19-21
+		    double Ec[FS_NC];
+		    FS_RUN(FS_FOR4 Ec[k] = temperature_clamp_nb(tc, I.S1[k], Ea[k], A), FS_FOR4 Ec[k] = temperature_clamp(c, I.S1[k], Ea[k]));
+		    FS_FOR4 Ea[k] = Ec[k];
+		}
+		const double QP1l = shfl_from_left(QP1[FS_NC - 1]), S1l = shfl_from_left(S1[FS_NC - 1]);
+		FS_RUN((st_av_v<MF>(c, r, dt, av_type, I, QR1, QP1, QP1l, S1l, VRa, VPa, A)),
+		       (st_av_v<MS>(c, r, dt, av_type, I, QR1, QP1, QP1l, S1l, VRa, VPa, A)));
+		if (r >= i_first) {
+		    fs_store(o_vr, r, c, L, VRa);
+		    fs_store(o_vp, r, c, L, VPa);
+		    if (ADI)
+			fs_store(o_e, r, c, L, Ea);
+		}
+		FS_FOR4
+		{
+		    S2[k] = S1[k];
+		    QR2[k] = QR1[k];
+		    QP2[k] = QP1[k];
+		}
+	    } else {
+		fs_store(o_vr, r, c, L, VRn1);
+		fs_store(o_vp, r, c, L, VPn1);
+		if (ADI)
+		    fs_store(o_e, r, c, L, En);
+	    }
+	}
+	FS_FOR4
+	{
+	    S1[k] = S0[k];
+	    P1[k] = P0[k];
+	    F1[k] = F0[k];
+	    VP1[k] = VP0[k];
+	    E1[k] = E0[k];
+	    VRn1[k] = VRn0[k];
+	    VPn1[k] = VPn0[k];
+	}
+    }
+    if (i_last == nr) // v_rad ring nr (outermost interface) is outside every update range
+	fs_store(o_vr, nr, c, L, VRn1);
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_fused_artvisc.  Iteration kr loads ring kr; Q(r) of ring r = kr-1 needs v_rad(r+1); v_rad''(r) needs Q(r), Q(r-1).
 template <bool ADI>
 __global__ void __launch_bounds__(128, FS_MINB_AV)

@@ -150,6 +150,23 @@ def test_pvte_run_vs_reference():
     assert worst <= POW_RTOL
 
 
+@pytest.mark.parametrize("name", ["adia_star", "iso_sn_std", "adia_planet_100", "adia_accrete_20"])
+def test_artificial_viscosity_inside_the_source_kernel(name, monkeypatch):
+    """FARGO_B200_FUSE_ARTVISC=1: the artificial-viscosity stage on the source-term kernel's registers (k_fused_sources<.., AV>)
+    instead of as its own kernel — measured slower and not the default, but it must stay the reference's result bit for bit
+    (TW and SN forms, with dissipation, with a planet, behind an accretion call)."""
+    monkeypatch.setenv("FARGO_B200_FUSE_ARTVISC", "1")
+    meta, z, gpu, cpu = _ctx_pair(name)
+    snaps = goldenrun.run_fixture(gpu, meta, z)
+    for k, snap in enumerate(snaps, start=1):
+        m = meta["misc"][k]
+        assert snap["n_iter"] == m["n_iter"] and snap["last_dt"] == m["last_dt"]
+        for fname in ("Sigma", "vrad", "vazi", "energy"):
+            if (fname == "energy" and not gpu.params.adiabatic) or fname not in snap:
+                continue
+            _check(name, (k, fname), snap[fname], z[f"{fname}_{k}"])
+
+
 @pytest.mark.parametrize("name", ["adia_alpha_scurve", "adia_alpha_scurve_lf"])
 def test_alpha_scurve_run_vs_reference(name):
     """AlphaMode 1 (viscosity/viscosity.cpp:31-49): alpha of a cell is an S-curve in the TEMPERATURE grid as last stored, formed
