@@ -300,6 +300,19 @@ class Handle:
         self._check(fn(self.ptr, float(radius_limit), out), "monitor_quantities")
         return dict(zip(MONITOR_QUANTITIES, list(out)))
 
+    def monitor_disk(self, radius_limit=1e300, mass_fraction=0.99, frame_angle=0.0):
+        """The mass-weighted columns of monitor/Quantities.dat (fargo_monitor_disk): dict of radius, eccentricity, periastron,
+        aspect_ratio (and the raw ecc_x, ecc_y, mass the first three are formed from, output.cpp:373-423 / quantities.cpp:552-567)."""
+        import math
+        out = (C.c_double * 5)()
+        fn = self._fn("monitor_disk")
+        fn.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double)]
+        fn.restype = C.c_int
+        self._check(fn(self.ptr, float(radius_limit), float(mass_fraction), float(frame_angle), out), "monitor_disk")
+        r, ex, ey, h, m = list(out)
+        return {"radius": r, "eccentricity": math.sqrt(ex ** 2 + ey ** 2), "periastron": math.atan2(ey, ex), "aspect_ratio": h,
+                "ecc_x": ex, "ecc_y": ey, "mass": m}
+
     def correct_vazi(self, domega):
         """correct_v_azimuthal (SideEuler.cpp:79-95): a corotating frame changed its angular velocity by domega."""
         self._check(self._call("correct_vazi", float(domega)), "correct_vazi")
@@ -352,6 +365,8 @@ def load_library():
         lib.fargo_snapshot_wait.restype = C.c_int
         lib.fargo_monitor_quantities.argtypes = [C.c_void_p, C.c_double, _DP]
         lib.fargo_monitor_quantities.restype = C.c_int
+        lib.fargo_monitor_disk.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, _DP]
+        lib.fargo_monitor_disk.restype = C.c_int
         lib.fargo_halo_mode.argtypes = [C.c_void_p]
         lib.fargo_halo_mode.restype = C.c_int
         lib.fargo_launch_count.argtypes = [C.c_void_p]

@@ -129,6 +129,7 @@ struct fargo_ctx {
     double *vmean, *vconst, *expf_s, *expf_v, *d_dt, *scratch, *force4;
     // two-pass CFL reduction (kernels_ring.cuh:k_cfl_screen / k_cfl_candidates): per-block maxima of the screen, d_cfl_l = their max
     double *cfl_bmax = nullptr, *d_cfl_l = nullptr;
+    double *mon_rings = nullptr; // fargo_monitor_disk: MD_N per-ring sums of the whole mesh
     // FARGO_B200_FUSE_ARTVISC=1: the artificial-viscosity stage runs inside k_fused_sources<.., AV = true> instead of as its own
     // kernel.  Bit-identical, 56 bytes per cell less traffic — and slower (5.22 against 2.76 + 2.14 ms at 8192 x 16384: 64 bytes
     // of spills at 128 registers, and these kernels wait on FP64 chains, not on DRAM; profiles/r02_v12_*), so not the default.
@@ -680,6 +681,7 @@ extern "C" int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, con
 	dalloc(c, &c->t_amm, ns) || dalloc(c, &c->t_e, params->adiabatic ? ns : 1));
     TRY(dalloc(c, &c->vmean, c->v.nr + 2) || dalloc(c, &c->vconst, c->v.nr + 2) || dalloc(c, &c->expf_s, 4 * (c->v.nr + 2)) ||
 	dalloc(c, &c->expf_v, 1) || dalloc(c, &c->d_dt, 2) || dalloc(c, &c->scratch, ns) || dalloc(c, &c->force4, 4));
+    TRY(dalloc(c, &c->mon_rings, (size_t)MD_N * params->nrad));
     TRY(dalloc(c, &c->cfl_bmax, (size_t)((c->v.ns + 511) / 512) * c->v.nr + 1) || dalloc(c, &c->d_cfl_l, 2));
     { // the reductions' partials have their own buffer: Nr x Nphi scratch is too small for them on grids with a few sectors
 	const size_t nr_ = (size_t)c->v.nr;
@@ -1926,6 +1928,54 @@ extern "C" int fargo_monitor_quantities(fargo_ctx *c, double radius_limit, doubl
     }
     CUDA_OK(cudaMemcpyAsync(out8, d_out, MQ_N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// The mass-weighted columns of monitor/Quantities.dat (output.cpp:373-423): see k_monitor_disk.  Per-ring sums on the device,
+// summed over the ranks ring by ring (every rank contributes the rings it owns), then walked in ring order on the host like
+// the reference's root (quantities.cpp:213-233).
+extern "C" int fargo_monitor_disk(fargo_ctx *c, double radius_limit, double mass_fraction, double frame_angle, double out5[5])
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    if (c->v_mid)
+	return fail("fargo_monitor_disk called mid-step");
+    const int nrg = c->v.p.nrad;
+    const unsigned gx = (unsigned)((c->v.ns + 4 * MQ_THREADS - 1) / (4 * MQ_THREADS));
+    const size_t npart = (size_t)gx * c->v.nr * MD_N, nrings = (size_t)MD_N * nrg;
+    if (npart > c->partials_n)
+	return fail("partials buffer too small for the per-ring monitor sums");
+    double *d_rings = c->mon_rings;
+    CUDA_OK(cudaMemsetAsync(d_rings, 0, nrings * sizeof(double), c->stream));
+    dim3 grid(gx, (unsigned)c->v.nr);
+    LAUNCH(c, k_monitor_disk, grid, MQ_THREADS, 0, c->v, c->sigma, EN(c), VRA(c), VPA(c), radius_limit, cos(frame_angle), sin(frame_angle),
+	   c->partials);
+    LAUNCH(c, k_monitor_disk_rings, (unsigned)((c->v.nr + 127) / 128), 128, 0, c->v, c->partials, (int)gx, nrg, d_rings);
+    if (c->v.nranks > 1) {
+	NCCL_OK(g_nccl.AllReduce(d_rings, d_rings, nrings, ncclFloat64, 0 /* ncclSum */, c->comm, c->stream));
+	c->launches++;
+    }
+    std::vector<double> h(nrings);
+    CUDA_OK(cudaMemcpyAsync(h.data(), d_rings, nrings * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    double sums[MD_N] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int q = 1; q < MD_N; ++q)
+	for (int i = 0; i < nrg; ++i)
+	    sums[q] += h[(size_t)q * nrg + i];
+    double radius = 0.0, current = 0.0;
+    for (int i = 1; i < nrg - 1; ++i) { // the root walks the active rings of every rank, counter from 1 (split.cpp:339-343)
+	current += h[i];
+	if (current > mass_fraction * sums[1]) {
+	    const double ri = c->h_radii[i], rs = c->h_radii[i + 1];
+	    double rm = 2.0 / 3.0 * (pow(rs, 3) - pow(ri, 3));
+	    radius = rm / (pow(rs, 2) - pow(ri, 2)); // GlobalRmed[i] (init.cpp:178-179)
+	    break;
+	}
+    }
+    out5[0] = radius;
+    out5[1] = sums[1] > 0.0 ? sums[2] / sums[1] : 0.0;
+    out5[2] = sums[1] > 0.0 ? sums[3] / sums[1] : 0.0;
+    out5[3] = sums[1] > 0.0 ? sums[4] / sums[1] : 0.0;
+    out5[4] = sums[1];
     return 0;
 }
 

@@ -205,6 +205,94 @@ __global__ void __launch_bounds__(32 * MQ_N) k_monitor_final(const double *__res
 }
 
 // ---------------------------------------------------------------------------------------------
+// The mass-weighted columns of monitor/Quantities.dat (output.cpp:373-423): disk radius (quantities::gas_disk_radius,
+// quantities.cpp:191-237), disk eccentricity / periastron (calculate_disk_ecc_vector :481-550 + gas_reduce_mass_average
+// :145-182) and the mean aspect ratio (compute_aspectratio mode 0, :784-806).  Per-ring sums, so that the host side of
+// fargo_monitor_disk can walk the rings in order like the reference's root does:
+// q: 0 ring mass sum(Surf Sigma) of every ring, and over the active cells with Rmed <= radius_limit:
+//    1 mass sum(Sigma Surf), 2 sum(e_x m), 3 sum(e_y m) (eccentricity vector rotated by the frame angle), 4 sum(H / Rb m)
+#define MD_N 5
+__global__ void __launch_bounds__(MQ_THREADS)
+    k_monitor_disk(const DevView c, const double *__restrict__ sigma, const double *__restrict__ energy, const double *__restrict__ vr,
+		   const double *__restrict__ vp, const double radius_limit, const double cosF, const double sinF,
+		   double *__restrict__ partials)
+{
+    const int i = blockIdx.y;
+    double acc[MD_N];
+#pragma unroll
+    for (int q = 0; q < MD_N; ++q)
+	acc[q] = 0.0;
+    const double rmed = c.g.rmed[i], surf = c.g.surf[i];
+    const bool in_means = i >= c.first_active && i < c.active_size && rmed <= radius_limit;
+    const double OmegaF = c.b.omega_frame;
+    const int ns = c.ns;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < ns; j += gridDim.x * blockDim.x) {
+	const double s = AT(sigma, i, j);
+	acc[0] += surf * s;
+	if (in_means) {
+	    const int jp = (j == ns - 1) ? 0 : j + 1;
+	    const size_t cell = (size_t)i * ns + j;
+	    const double cell_mass = s * surf;
+	    const double total_mass = c.p.hydro_center_mass + s * surf;
+	    const double cosa = c.g.cosphi[j], sina = c.g.sinphi[j];
+	    const double r_x = rmed * cosa, r_y = rmed * sina;
+	    const double dist = sqrt(r_x * r_x + r_y * r_y);
+	    const double vrc = 0.5 * (AT(vr, i, j) + AT(vr, i + 1, j));
+	    const double vpc = 0.5 * (AT(vp, i, j) + AT(vp, i, jp)) + OmegaF * rmed;
+	    const double v_xmed = cosa * vrc - sina * vpc;
+	    const double v_ymed = sina * vrc + cosa * vpc;
+	    const double jz = r_x * v_ymed - r_y * v_xmed;
+	    const double e_x = jz * v_ymed / (c.p.G * total_mass) - r_x / dist;
+	    const double e_y = -1.0 * jz * v_xmed / (c.p.G * total_mass) - r_y / dist;
+	    const double e = c.p.adiabatic ? AT(energy, i, j) : 0.0;
+	    const double H = c.pv.H ? c.pv.H[cell] : eos_H_at(c, i, cell, eos_cs_at(c, i, cell, s, e));
+	    acc[1] += cell_mass;
+	    acc[2] += (e_x * cosF - e_y * sinF) * cell_mass;
+	    acc[3] += (e_y * cosF + e_x * sinF) * cell_mass;
+	    acc[4] += H / rmed * cell_mass;
+	}
+    }
+#pragma unroll
+    for (int q = 0; q < MD_N; ++q)
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+	    acc[q] += __shfl_down_sync(0xffffffffu, acc[q], o);
+    __shared__ double sh[MQ_THREADS / 32][MD_N];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0)
+#pragma unroll
+	for (int q = 0; q < MD_N; ++q)
+	    sh[w][q] = acc[q];
+    __syncthreads();
+    if (threadIdx.x < MD_N) {
+	double t = 0.0;
+	for (int k = 0; k < MQ_THREADS / 32; ++k)
+	    t += sh[k][threadIdx.x];
+	partials[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * MD_N + threadIdx.x] = t;
+    }
+}
+// block partials of a ring added in block order into rings[q * nrad_global + imin + i] — only the rings this rank owns
+// (write2D's rule), the others stay 0 for the sum over ranks
+__global__ void __launch_bounds__(128) k_monitor_disk_rings(const DevView c, const double *__restrict__ partials, const int gx,
+							     const int nrad_global, double *__restrict__ rings)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.nr)
+	return;
+    const bool first = c.rank == 0, last = c.rank == c.nranks - 1;
+    const bool owned = i >= (first ? 0 : FARGO_CPUOVERLAP) && i < c.nr - (last ? 0 : FARGO_CPUOVERLAP);
+    if (!owned)
+	return;
+#pragma unroll
+    for (int q = 0; q < MD_N; ++q) {
+	double t = 0.0;
+	for (int b = 0; b < gx; ++b)
+	    t += partials[((size_t)i * gx + b) * MD_N + q];
+	rings[(size_t)q * nrad_global + c.imin + i] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // accretion::AccreteOntoSinglePlanet (accretion.cpp:84-221, "kley" accretion onto a planet): see fargo_b200.h.
 // One thread per cell of the rings [ring_lo, ring_hi) that can reach into the accretion radius; the cells inside it are
 // changed in place exactly as the reference changes them (same operations, same order); mass and momentum taken from active

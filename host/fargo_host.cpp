@@ -71,6 +71,7 @@ int fargo_oracle_drift(fargo_oracle *, double);
 int fargo_oracle_finish_step(fargo_oracle *, double);
 int fargo_oracle_accrete_kley(fargo_oracle *, double, double, double, double, double, double *);
 int fargo_oracle_monitor_quantities(fargo_oracle *, double, double *);
+int fargo_oracle_monitor_disk(fargo_oracle *, double, double, double, double *);
 int fargo_oracle_accrete_sinkhole(fargo_oracle *, double, double, double, double, double, double *);
 int fargo_oracle_accrete_viscous(fargo_oracle *, double, double, double, double, double, double *);
 int fargo_oracle_correct_vazi(fargo_oracle *, double);
@@ -1617,8 +1618,8 @@ struct Run {
 
     // output::write_quantities (output.cpp:326-493): one row of monitor/Quantities.dat per monitor step, file version 2.4 with
     // the 35 columns of quantities_file_column_v2_5 (output.cpp:39-75).  The global sums come from fargo_monitor_quantities
-    // (device reductions); columns this path does not evaluate (disk radius, potential energy, eccentricity / periastron,
-    // pdivv, boundary and damping mass flows, aspect ratio, torques) are written as nan, never as made-up numbers.
+    // and fargo_monitor_disk (device reductions); columns this path does not evaluate (potential and total energy, pdivv,
+    // boundary and damping mass flows, torques) are written as nan, never as made-up numbers.
     bool quantities_header_written = false;
     void write_quantities()
     {
@@ -1668,6 +1669,14 @@ struct Run {
 	    x = nan;
 	row[0] = time, row[1] = q[0], row[3] = q[1], row[5] = q[2], row[6] = q[3], row[8] = q[4], row[9] = q[5];
 	row[12] = q[6], row[13] = q[7];
+	{ // disk radius, eccentricity / periastron, aspect ratio (output.cpp:373-423; AspectRatioMode 0 is all make_params lets through)
+	    double d[5];
+	    CHECK(BK(monitor_disk)(ctx, limit, cfg.num("DiskRadiusMassFraction", 0.99), frame_angle, d));
+	    row[2] = d[0];
+	    row[10] = std::sqrt(std::pow(d[1], 2) + std::pow(d[2], 2)); // calculate_disk_ecc_peri (quantities.cpp:552-567)
+	    row[11] = std::atan2(d[2], d[1]);
+	    row[24] = d[3];
+	}
 	row[25] = ind_nbody_x, row[26] = ind_nbody_y, row[27] = ind_disk_x, row[28] = ind_disk_y, row[29] = frame_angle;
 	fprintf(fd, "%u\t%u", n_monitor / nmonitor, n_monitor); // N_snapshot = N_monitor / Nmonitor (simulation.cpp:52)
 	for (double x : row)

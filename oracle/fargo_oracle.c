@@ -1991,6 +1991,75 @@ int fargo_oracle_monitor_quantities(fargo_oracle *o, double radius_limit, double
     return 0;
 }
 
+/* The columns of monitor/Quantities.dat that are mass-weighted means or need the rings in order (output::write_quantities,
+ * output.cpp:373-423): serial sums in index order, like fargo_oracle_monitor_quantities.
+ * out5 = disk radius (quantities::gas_disk_radius, quantities.cpp:191-237: Rmed of the ring at which the running sum of the
+ *        ring masses, ghost rings left out, first exceeds mass_fraction x the mass inside radius_limit),
+ *        mass-weighted means of the cells' eccentricity vector rotated into the non-rotating frame (calculate_disk_ecc_vector
+ *        :481-550, gas_reduce_mass_average :145-182; the caller forms sqrt(ex^2 + ey^2) and atan2(ey, ex), :552-567),
+ *        mass-weighted mean aspect ratio SCALE_HEIGHT / Rb (compute_aspectratio mode 0 :784-806), and the mass of those means.
+ * One rank only (the reference gathers the ring masses on its root). */
+int fargo_oracle_monitor_disk(fargo_oracle *o, double radius_limit, double mass_fraction, double frame_angle, double out5[5])
+{
+    if (o->nranks != 1)
+	return 1;
+    const int ns = o->ns;
+    const double OmegaF = o->bodies.omega_frame;
+    const double cms_mass = o->p.hydro_center_mass;
+    const double sinF = sin(frame_angle), cosF = cos(frame_angle);
+    double mass = 0.0, sum_ex = 0.0, sum_ey = 0.0, sum_h = 0.0, mass_lim = 0.0;
+    for (int i = o->first_active; i < o->active_size; ++i) /* gas_total_mass (:51-78) */
+	for (int j = 0; j < ns; ++j)
+	    if (o->rmed[i] <= radius_limit)
+		mass_lim += o->surf[i] * o->sigma[IDX(o, i, j)];
+    /* the three means are separate loops in the reference, each with its own running mass; the masses are the same number */
+    for (int i = o->first_active; i < o->active_size; ++i) {
+	for (int j = 0; j < ns; ++j) {
+	    if (!(o->rmed[i] <= radius_limit))
+		continue;
+	    const int jp = j == ns - 1 ? 0 : j + 1;
+	    const size_t l = IDX(o, i, j);
+	    const double cell_mass = o->sigma[l] * o->surf[i];
+	    const double total_mass = cms_mass + o->sigma[l] * o->surf[i];
+	    const double angle = (double)j * o->dphi;
+	    const double r_x = o->rmed[i] * cos(angle), r_y = o->rmed[i] * sin(angle);
+	    const double dist = sqrt(r_x * r_x + r_y * r_y);
+	    const double v_xmed = cos(angle) * 0.5 * (o->vrad[l] + o->vrad[IDX(o, i + 1, j)]) -
+				  sin(angle) * (0.5 * (o->vazi[l] + o->vazi[IDX(o, i, jp)]) + OmegaF * o->rmed[i]);
+	    const double v_ymed = sin(angle) * 0.5 * (o->vrad[l] + o->vrad[IDX(o, i + 1, j)]) +
+				  cos(angle) * (0.5 * (o->vazi[l] + o->vazi[IDX(o, i, jp)]) + OmegaF * o->rmed[i]);
+	    const double jz = r_x * v_ymed - r_y * v_xmed;
+	    const double e_x = jz * v_ymed / (o->p.G * total_mass) - r_x / dist;
+	    const double e_y = -1.0 * jz * v_xmed / (o->p.G * total_mass) - r_y / dist;
+	    const double e_x_frame = e_x * cosF - e_y * sinF;
+	    const double e_y_frame = e_y * cosF + e_x * sinF;
+	    mass += cell_mass;
+	    sum_ex += e_x_frame * cell_mass;
+	    sum_ey += e_y_frame * cell_mass;
+	    sum_h += o->scale_height[l] / o->rmed[i] * cell_mass;
+	}
+    }
+    double radius = 0.0, current = 0.0;
+    /* the root walks the rings RootIMIN .. RootIMAX of every rank (split.cpp:339-343: the two ghost rings of the mesh are left
+     * out) with a counter that starts at 1, so the ring that crosses the threshold reports its own GlobalRmed */
+    for (int i = 1; i < o->nr - 1; ++i) {
+	double ring = 0.0;
+	for (int j = 0; j < ns; ++j)
+	    ring += o->surf[i] * o->sigma[IDX(o, i, j)];
+	current += ring;
+	if (current > mass_fraction * mass_lim) {
+	    radius = o->rmed[i];
+	    break;
+	}
+    }
+    out5[0] = radius;
+    out5[1] = mass > 0.0 ? sum_ex / mass : 0.0;
+    out5[2] = mass > 0.0 ? sum_ey / mass : 0.0;
+    out5[3] = mass > 0.0 ? sum_h / mass : 0.0;
+    out5[4] = mass;
+    return 0;
+}
+
 /* ComputeDiskOnPlanetAccel (Force.cpp:23-122), serial sum in index order (the reference's own order is undefined:
  * OpenMP reduction).  out4 = {axi, ayi, axo, ayo}. */
 int fargo_oracle_disk_on_body_accel(fargo_oracle *o, int body, double klahr_factor, double out4[4])

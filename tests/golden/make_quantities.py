@@ -23,7 +23,9 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 EXE = os.path.join(ROOT, "oracle", "_ref", "fargocpt_exe_ieee")
 CASES = {"adia_planet_100": (50, 100), "iso_planet_100": (50, 100), "rey_star": (1, 2), "adia_star": (3, 6)}
 COLUMNS = {"mass": 3, "angular_momentum": 5, "internal_energy": 7, "kinetic_energy": 8, "radial_kinetic_energy": 10,
-           "azimuthal_kinetic_energy": 11, "viscous_dissipation": 14, "luminosity": 15}
+           "azimuthal_kinetic_energy": 11, "viscous_dissipation": 14, "luminosity": 15,
+           # the mass-weighted columns (fargo_monitor_disk)
+           "radius": 4, "eccentricity": 12, "periastron": 13, "aspect_ratio": 26}
 
 
 def main():

@@ -96,6 +96,10 @@ def test_oracle_monitor_quantities_match_reference(name, k):
             names += ["viscous_dissipation", "luminosity"]
     for q in names:
         assert got[q] == ref[q], (q, got[q], ref[q])
+    # the mass-weighted columns (fargo_monitor_disk): disk radius, eccentricity, periastron, aspect ratio — bit for bit too
+    disk = ctx.monitor_disk(frame_angle=meta["misc"][k].get("frame_angle", 0.0))
+    for q in ("radius", "eccentricity", "periastron", "aspect_ratio"):
+        assert disk[q] == ref[q], (q, disk[q], ref[q])
 
 
 @pytest.mark.gpu
@@ -117,6 +121,16 @@ def test_gpu_monitor_quantities_vs_oracle(name, k):
     for q in abi.MONITOR_QUANTITIES:
         assert abs(a[q] - b[q]) <= 1e-13 * max(abs(b[q]), 1e-300), (q, a[q], b[q])
     assert 0.0 < b["mass"] < cpu.monitor_quantities()["mass"]
+    # fargo_monitor_disk: per-ring device sums against the oracle's serial ones; the radius is a ring's Rmed (same ring)
+    fa = meta["misc"][k].get("frame_angle", 0.0)
+    for limit in (1e300, rl):
+        a, b, a2 = gpu.monitor_disk(limit, 0.99, fa), cpu.monitor_disk(limit, 0.99, fa), gpu.monitor_disk(limit, 0.99, fa)
+        assert a == a2
+        assert a["radius"] == b["radius"], (a["radius"], b["radius"])
+        for q in ("aspect_ratio", "mass"):
+            assert abs(a[q] - b[q]) <= 1e-12 * abs(b[q]), (q, a[q], b[q])
+        for q in ("ecc_x", "ecc_y"):  # means of O(h^2) cell values that cancel around the ring: absolute
+            assert abs(a[q] - b[q]) <= 1e-15, (q, a[q], b[q])
 
 
 # ---------------------------------------------------------------------------------------------------------------------

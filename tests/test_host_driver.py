@@ -332,7 +332,8 @@ def test_host_start_on_the_references_own_setup_files(setup, overrides):
 def test_host_writes_quantities_dat_cpu(name, tmp_path):
     """monitor/Quantities.dat (output::write_quantities, output.cpp:326-493) from `start`: the reference's header and 35-column
     layout; the global sums equal the ones recorded from the reference's own Quantities.dat (tests/golden/quantities.json,
-    bit for bit on the star-only run, to the planet tolerance otherwise); columns this path does not evaluate are nan."""
+    bit for bit on the star-only run, to the planet tolerance otherwise), disk radius, eccentricity, periastron and aspect
+    ratio included; columns this path does not evaluate are nan."""
     import json
     cfg = yaml.safe_load(open(os.path.join(ROOT, "tests", "golden", name + ".yml")))
     cfg["WriteDiskQuantities"] = "Yes"
@@ -350,7 +351,9 @@ def test_host_writes_quantities_dat_cpu(name, tmp_path):
     rows = [l.split("\t") for l in lines if not l.startswith("#")]
     assert [int(r[1]) for r in rows] == list(range(until + 1)) and all(len(r) == 35 for r in rows)
     cols = {"mass": 3, "angular_momentum": 5, "internal_energy": 7, "kinetic_energy": 8, "radial_kinetic_energy": 10,
-            "azimuthal_kinetic_energy": 11, "viscous_dissipation": 14, "luminosity": 15}
+            "azimuthal_kinetic_energy": 11, "viscous_dissipation": 14, "luminosity": 15,
+            # the mass-weighted columns (fargo_monitor_disk)
+            "radius": 4, "eccentricity": 12, "periastron": 13, "aspect_ratio": 26}
     for snap, want in ref.items():
         row = rows[int(snap)]
         assert int(row[0]) == int(snap)
@@ -359,7 +362,7 @@ def test_host_writes_quantities_dat_cpu(name, tmp_path):
                 assert float(row[c]) == want[q], (snap, q, row[c], want[q])
             else:
                 assert float(row[c]) == pytest.approx(want[q], rel=1e-9, abs=1e-300), (snap, q)
-        assert row[4] == "nan" and row[12] == "nan"
+        assert row[6] == "nan" and row[9] == "nan" and row[16] == "nan" and row[32] == "nan"  # total / potential energy, pdivv, torques
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -482,7 +485,7 @@ def test_host_start_refuses_unknown_keys_like_the_reference(tmp_path):
 
 
 def test_host_refuses_physics_it_does_not_implement(tmp_path):
-    for key, value in (("EquationOfState", "Polytropic"), ("SurfaceCooling", "scurve"), ("SelfGravity", "yes"), ("AlphaMode", 1)):
+    for key, value in (("EquationOfState", "Polytropic"), ("SurfaceCooling", "scurve"), ("SelfGravity", "yes"), ("AlphaMode", 2)):
         cfg = yaml.safe_load(open(os.path.join(ROOT, "tests", "golden", "adia_star.yml")))
         cfg[key] = value
         yml = str(tmp_path / f"setup_{key}.yml")
