@@ -42,12 +42,12 @@ KERNEL_BYTES = {
     "k_cfl": 48.0, "k_ring_mean[cfl]": 8.0, "k_ring_mean[transport,side-stream]": 8.0,
 }
 # measured DRAM traffic per cell of the same kernels: dram__bytes_read.sum + dram__bytes_write.sum of one
-# `ncu --set full` capture at the bench size (profiles/r02_v4_ncu_full_c5_8192x16384.md, 8192 x 16384 adiabatic_planet) / 134.2e6
+# `ncu --set full` capture at the bench size (profiles/r02_v13_ncu_full_c5_8192x16384.md, 8192 x 16384 adiabatic_planet) / 134.2e6
 # cells.  The azimuthal kernel's 100 B against 88 algorithmic: the 10 overlap columns of neighbouring 64-column windows are staged
 # by different warps at the same moment, so they come from DRAM twice (the kernel is FP64-bound, DRAM at 33 %).
 NCU_TRAFFIC_B_PER_CELL = {
     "k_transport_azimuthal<ADI>": 100.4, "(k_transport_radial<LIM, true>)": 81.3, "(k_fused_sources<ADI, false>)": 57.4,
-    "k_fused_artvisc<ADI>": 57.4, "k_fused_viscosity<ADI>": 89.7, "k_cfl": 48.0,
+    "k_fused_artvisc<ADI>": 57.3, "k_fused_viscosity<ADI>": 89.7, "k_cfl": 48.1,  # k_cfl: the screen pass (k_cfl_screen)
 }
 
 
@@ -406,7 +406,7 @@ def run_gpu(args):
         roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
                 "traffic": (NCU_TRAFFIC_B_PER_CELL[kname] * slab_cells if kname in NCU_TRAFFIC_B_PER_CELL else None),
-                "traffic_source": "ncu --set full, profiles/r02_v4_ncu_full_c5_8192x16384.md (bytes per cell x cells of this launch)",
+                "traffic_source": "ncu --set full, profiles/r02_v13_ncu_full_c5_8192x16384.md (bytes per cell x cells of this launch)",
                 "bytes_per_launch_algorithmic": per_launch_bytes, "avg_launch_ms": avg_s * 1e3,
                 "share_of_step": kms / total_kernel_ms if total_kernel_ms else None}
     step_roof = B_ALG[args.physics] * value / world / 1e9  # whole-step algorithmic GB/s per GPU

@@ -729,8 +729,17 @@ def test_gpu_driver_writes_what_the_oracle_bound_driver_writes(setup, over, tmp_
                 b = np.array([[float(x) for x in l.split()] for l in open(pg) if not l.startswith("#") and l.strip()])
                 assert a.shape == b.shape, f
                 assert np.array_equal(np.isnan(a), np.isnan(b)), f
-                scale = np.maximum(np.abs(np.nan_to_num(a)).max(axis=0), 1e-300)
-                assert np.max(np.abs(np.nan_to_num(a) - np.nan_to_num(b)) / scale) < 1e-9, f
+                a, b = np.nan_to_num(a), np.nan_to_num(b)
+                if f.startswith("Quantities"):
+                    # disk eccentricity (column 12): a mean of O(h^2) cell values that cancel around an axisymmetric disk —
+                    # absolute; its periastron (13) is the angle of that mean: compared only where there is an eccentricity
+                    assert np.max(np.abs(a[:, 12] - b[:, 12])) < 1e-13, f
+                    has_ecc = a[:, 12] > 1e-9
+                    dper = np.abs(np.angle(np.exp(1j * (a[:, 13] - b[:, 13]))))
+                    assert not has_ecc.any() or np.max(dper[has_ecc]) < 1e-6, f
+                    a[:, 12:14] = b[:, 12:14] = 0.0
+                scale = np.maximum(np.abs(a).max(axis=0), 1e-300)
+                assert np.max(np.abs(a - b) / scale) < 1e-9, f
                 continue
             rel = os.path.relpath(po, outs["oracle"])
             a, b = open(po, "rb").read(), open(pg, "rb").read()
