@@ -31,7 +31,7 @@ def test_nranks_equals_one_rank(physics, halo):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tools", "multi_gpu_check.py"), "--physics", physics,
            "--nrad", "256", "--naz", "512", "--steps", "12"]
-    env = dict(os.environ)
+    env = dict(os.environ, FARGO_B200_CFL="check")  # every CFL call also runs the full reduction beside the screened one
     if halo == "nccl":  # the ncclSend / ncclRecv exchange instead of the transport kernel's peer-memory stores
         env["FARGO_B200_HALO"] = "nccl"
     else:
@@ -41,6 +41,7 @@ def test_nranks_equals_one_rank(physics, halo):
     assert lines, res.stdout[-2000:] + res.stderr[-2000:]
     out = json.loads(lines[-1])
     assert out["dt_bit_equal"], out
+    assert out["monitor_disk_equal"] and out["monitor_sums_max_rel_dev"] <= 1e-12, out
     if halo == "nccl":
         assert out["halo_mode"] == "nccl send/recv", out
     print(physics, halo, "->", out["halo_mode"])

@@ -44,7 +44,9 @@ def run_slab(ctx, cfg, radii, fields, nsteps, synthetic, abi):
     out = {}
     for fid, name in ((abi.SIGMA, "Sigma"), (abi.VRAD, "vrad"), (abi.VAZI, "vazi"), (abi.ENERGY, "energy")):
         out[name] = ctx.download(fid)  # only the rings this rank owns are written, the rest stays 0
-    return dts, out
+    # the monitor reductions are collective: global sums (all-reduced) and the per-ring sums behind disk radius / eccentricity
+    mon = dict(ctx.monitor_quantities(), **{"disk_" + k: v for k, v in ctx.monitor_disk(1e300, 0.99, 0.3).items()})
+    return dts, out, mon
 
 
 def main():
@@ -76,7 +78,7 @@ def main():
 
     ctx = HydroContext(params, radii, rank=rank, nranks=world, unique_id=uid, device=local)
     halo_mode = ctx.halo_mode()
-    dts, out = run_slab(ctx, cfg, radii, fields, args.steps, synthetic, abi)
+    dts, out, mon = run_slab(ctx, cfg, radii, fields, args.steps, synthetic, abi)
     ctx.close()
     stitched = {}
     for name, a in out.items():
@@ -86,7 +88,7 @@ def main():
     rc = 0
     if rank == 0:
         one = HydroContext(params, radii, rank=0, nranks=1, device=local)
-        dts1, out1 = run_slab(one, cfg, radii, fields, args.steps, synthetic, abi)
+        dts1, out1, mon1 = run_slab(one, cfg, radii, fields, args.steps, synthetic, abi)
         import reftools
         res = {"n_gpus": world, "physics": args.physics, "grid": [args.nrad, args.naz], "steps": args.steps,
                "dt_bit_equal": dts == dts1, "fields": {},
@@ -101,6 +103,13 @@ def main():
                 rc = 1
         if not res["dt_bit_equal"]:
             rc = 1
+        # per-ring sums are formed by the same kernel in the same order on whichever rank owns the ring and added in ring order:
+        # identical; the global sums of fargo_monitor_quantities are added per rank first: rounding
+        res["monitor_disk_equal"] = all(mon[k] == mon1[k] for k in mon if k.startswith("disk_"))
+        res["monitor_sums_max_rel_dev"] = max(abs(mon[k] - mon1[k]) / max(abs(mon1[k]), 1e-300) for k in mon if not k.startswith("disk_"))
+        if not res["monitor_disk_equal"] or res["monitor_sums_max_rel_dev"] > 1e-12:
+            rc = 1
+            res["monitor"] = {k: (mon[k], mon1[k]) for k in mon}
         res["ok"] = rc == 0
         print(json.dumps(res))
     flag = torch.tensor([rc], device="cuda")
