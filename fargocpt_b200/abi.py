@@ -300,6 +300,15 @@ class Handle:
         self._check(fn(self.ptr, float(radius_limit), out), "monitor_quantities")
         return dict(zip(MONITOR_QUANTITIES, list(out)))
 
+    def circumplanetary_mass(self, x, y, roche_radius):
+        """ComputeCircumPlanetaryMasses (circumplanetary_mass.cpp:11-51): mass inside the Roche radius around (x, y)."""
+        out = C.c_double(0.0)
+        fn = self._fn("circumplanetary_mass")
+        fn.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double)]
+        fn.restype = C.c_int
+        self._check(fn(self.ptr, float(x), float(y), float(roche_radius), C.byref(out)), "circumplanetary_mass")
+        return out.value
+
     def monitor_disk(self, radius_limit=1e300, mass_fraction=0.99, frame_angle=0.0):
         """The mass-weighted columns of monitor/Quantities.dat (fargo_monitor_disk): dict of radius, eccentricity, periastron,
         aspect_ratio (and the raw ecc_x, ecc_y, mass the first three are formed from, output.cpp:373-423 / quantities.cpp:552-567)."""
@@ -365,6 +374,8 @@ def load_library():
         lib.fargo_snapshot_wait.restype = C.c_int
         lib.fargo_monitor_quantities.argtypes = [C.c_void_p, C.c_double, _DP]
         lib.fargo_monitor_quantities.restype = C.c_int
+        lib.fargo_circumplanetary_mass.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, _DP]
+        lib.fargo_circumplanetary_mass.restype = C.c_int
         lib.fargo_monitor_disk.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, _DP]
         lib.fargo_monitor_disk.restype = C.c_int
         lib.fargo_halo_mode.argtypes = [C.c_void_p]

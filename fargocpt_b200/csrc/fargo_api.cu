@@ -1902,6 +1902,39 @@ extern "C" int fargo_accrete_viscous(fargo_ctx *c, double x, double y, double r_
     return accrete_zones(c, x, y, r_hill, facc, f_const, frac, dist_max, out3, true);
 }
 
+// ComputeCircumPlanetaryMasses (circumplanetary_mass.cpp:11-51): the "mdcp" column of monitor/nbodyK.dat
+extern "C" int fargo_circumplanetary_mass(fargo_ctx *c, double x, double y, double roche_radius, double *out)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    const DevView &v = c->v;
+    const double rp = sqrt(x * x + y * y);
+    int lo = v.first_active, hi = v.active_size;
+    while (lo < hi && c->h_rmed[lo] < rp - roche_radius)
+	++lo;
+    while (hi > lo && c->h_rmed[hi - 1] > rp + roche_radius)
+	--hi;
+    double *d_out = c->force4; // 4 doubles of device scratch
+    const int nrings = hi - lo;
+    if (nrings > 0) {
+	const unsigned gx = (unsigned)((v.ns + 127) / 128);
+	const int nblocks = (int)gx * nrings;
+	if ((size_t)nblocks * 3 > c->partials_n)
+	    return fail("partials buffer too small for the circumplanetary mass");
+	dim3 grid(gx, (unsigned)nrings);
+	LAUNCH(c, k_circumplanetary_mass, grid, 128, 0, v, c->sigma, x, y, roche_radius, lo, c->partials);
+	LAUNCH(c, k_accrete_final, 1, 96, 0, c->partials, nblocks, d_out);
+    } else {
+	CUDA_OK(cudaMemsetAsync(d_out, 0, 3 * sizeof(double), c->stream));
+    }
+    if (v.nranks > 1) { // MPI_Allreduce(SUM), circumplanetary_mass.cpp:46
+	NCCL_OK(g_nccl.AllReduce(d_out, d_out, 1, ncclFloat64, 0 /* ncclSum */, c->comm, c->stream));
+	c->launches++;
+    }
+    CUDA_OK(cudaMemcpyAsync(out, d_out, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 // monitor/Quantities.dat sums (quantities.cpp:51-480 through output::write_quantities, output.cpp:326-520)
 extern "C" int fargo_monitor_quantities(fargo_ctx *c, double radius_limit, double out8[8])
 {

@@ -293,6 +293,38 @@ __global__ void __launch_bounds__(128) k_monitor_disk_rings(const DevView c, con
 }
 
 // ---------------------------------------------------------------------------------------------
+// ComputeCircumPlanetaryMasses (circumplanetary_mass.cpp:11-51): sum(Surf Sigma) over the active cells whose centre lies inside
+// the body's Roche radius; rings [ring_lo, ring_hi) can reach it.  Block partials in k_accrete_final's layout (3 per block).
+__global__ void __launch_bounds__(128)
+    k_circumplanetary_mass(const DevView c, const double *__restrict__ sigma, const double x, const double y, const double roche_radius,
+			   const int ring_lo, double *__restrict__ partials)
+{
+    const int i = ring_lo + blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    double m = 0.0;
+    if (j < c.ns && i >= c.first_active && i < c.active_size) {
+	const double rmed = c.g.rmed[i];
+	const double cx = rmed * c.g.cosphi[j], cy = rmed * c.g.sinphi[j];
+	const double dist = sqrt((cx - x) * (cx - x) + (cy - y) * (cy - y));
+	if (dist < roche_radius)
+	    m = c.g.surf[i] * AT(sigma, i, j);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+	m += __shfl_down_sync(0xffffffffu, m, o);
+    __shared__ double sh[4];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0)
+	sh[w] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+	double *p = partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 3;
+	p[0] = (sh[0] + sh[1]) + (sh[2] + sh[3]);
+	p[1] = p[2] = 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // accretion::AccreteOntoSinglePlanet (accretion.cpp:84-221, "kley" accretion onto a planet): see fargo_b200.h.
 // One thread per cell of the rings [ring_lo, ring_hi) that can reach into the accretion radius; the cells inside it are
 // changed in place exactly as the reference changes them (same operations, same order); mass and momentum taken from active

@@ -72,6 +72,7 @@ int fargo_oracle_finish_step(fargo_oracle *, double);
 int fargo_oracle_accrete_kley(fargo_oracle *, double, double, double, double, double, double *);
 int fargo_oracle_monitor_quantities(fargo_oracle *, double, double *);
 int fargo_oracle_monitor_disk(fargo_oracle *, double, double, double, double *);
+int fargo_oracle_circumplanetary_mass(fargo_oracle *, double, double, double, double *);
 int fargo_oracle_accrete_sinkhole(fargo_oracle *, double, double, double, double, double, double *);
 int fargo_oracle_accrete_viscous(fargo_oracle *, double, double, double, double, double, double *);
 int fargo_oracle_correct_vazi(fargo_oracle *, double);
@@ -1686,8 +1687,7 @@ struct Run {
     }
 
     // t_planet::create_planet_file / write_ascii (nbody/planet.cpp:279-372) through t_planetary_system::write_planets(1)
-    // (sim::handle_outputs, simulation.cpp:83-84): monitor/nbodyK.dat, file version 2, 22 columns.  The circumplanetary
-    // mass (column 9, ComputeCircumPlanetaryMasses) is not evaluated on this path: nan.
+    // (sim::handle_outputs, simulation.cpp:83-84): monitor/nbodyK.dat, file version 2, 22 columns.
     bool planet_files_created = false;
     void write_planet_monitor_files()
     {
@@ -1698,6 +1698,12 @@ struct Run {
 	    return std::string(b);
 	};
 	const double div = cfg.flag("WriteAtEveryTimestep", true) ? monitor_timestep : monitor_timestep * nmonitor;
+	// ComputeCircumPlanetaryMasses (circumplanetary_mass.cpp:11-51) right before write_planets (simulation.cpp:83-84): every
+	// body but the first; the value also travels in the NEXT snapshot's binary record, like the reference's
+	for (size_t k = 1; k < bodies.size(); ++k) {
+	    PlanetRecord &r = bodies[k].rec;
+	    CHECK(BK(circumplanetary_mass)(ctx, r.x, r.y, r.distance_to_primary * r.dimensionless_roche_radius, &r.circumplanetary_mass));
+	}
 	for (size_t k = 0; k < bodies.size(); ++k) {
 	    const std::string path = outdir + "/monitor/nbody" + std::to_string(k) + ".dat";
 	    FILE *fd = fopen(path.c_str(), planet_files_created ? "a" : "w");
@@ -1732,7 +1738,7 @@ struct Run {
 		torque = r.torque;
 	    }
 	    const double angular_momentum = r.mass * r.x * r.vy - r.mass * r.y * r.vx;
-	    const double row[20] = {r.x, r.y, r.vx, r.vy, r.mass, time, omega_frame, std::nan(""), r.eccentricity, angular_momentum,
+	    const double row[20] = {r.x, r.y, r.vx, r.vy, r.mass, time, omega_frame, r.circumplanetary_mass, r.eccentricity, angular_momentum,
 				    r.semi_major_axis, bodies[k].omega, r.mean_anomaly, r.eccentric_anomaly, r.true_anomaly, r.pericenter_angle,
 				    torque, r.accretion_torque_acc / div, r.indirect_torque_acc / div, r.accreted_mass / div};
 	    fprintf(fd, "%u\t%u", n_monitor / nmonitor, n_monitor);

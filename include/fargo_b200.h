@@ -302,6 +302,11 @@ int fargo_accrete_sinkhole(fargo_ctx *ctx, double x, double y, double r_hill, do
  * stored by the previous step).  The N-body side provides facc = dt * 3 pi * accretion efficiency (:355).  Same outputs. */
 int fargo_accrete_viscous(fargo_ctx *ctx, double x, double y, double r_hill, double facc, double frac, double out3[3]);
 
+/* ComputeCircumPlanetaryMasses (circumplanetary_mass.cpp:11-51; column "mdcp" of monitor/nbodyK.dat): the mass sum(Surf Sigma)
+ * of the active cells whose centre is closer to (x, y) than roche_radius (= distance to the primary x dimensionless Roche
+ * radius, from the N-body side), all ranks. */
+int fargo_circumplanetary_mass(fargo_ctx *ctx, double x, double y, double roche_radius, double *out);
+
 /* Global disk quantities of monitor/Quantities.dat (output::write_quantities output.cpp:326-520 -> quantities.cpp):
  * sums over the active cells with Rmed <= radius_limit (QuantitiesRadiusLimit, default 2 Rmax), all ranks.
  * out8 = { mass (quantities.cpp:51-78), angular momentum (:242-276), internal energy (:281-304), kinetic energy (:357-401),

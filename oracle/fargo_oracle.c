@@ -2060,6 +2060,22 @@ int fargo_oracle_monitor_disk(fargo_oracle *o, double radius_limit, double mass_
     return 0;
 }
 
+/* ComputeCircumPlanetaryMasses (circumplanetary_mass.cpp:11-51): mass of the active cells whose centre lies inside the body's
+ * Roche radius (column "mdcp" of monitor/nbodyK.dat), serial sum in index order. */
+int fargo_oracle_circumplanetary_mass(fargo_oracle *o, double x, double y, double roche_radius, double *out)
+{
+    double m = 0.0;
+    for (int i = o->first_active; i < o->active_size; ++i)
+	for (int j = 0; j < o->ns; ++j) {
+	    const double cx = o->rmed[i] * o->cosphi[j], cy = o->rmed[i] * o->sinphi[j];
+	    const double dist = sqrt((cx - x) * (cx - x) + (cy - y) * (cy - y));
+	    if (dist < roche_radius)
+		m += o->surf[i] * o->sigma[IDX(o, i, j)];
+	}
+    *out = m;
+    return 0;
+}
+
 /* ComputeDiskOnPlanetAccel (Force.cpp:23-122), serial sum in index order (the reference's own order is undefined:
  * OpenMP reduction).  out4 = {axi, ayi, axo, ayo}. */
 int fargo_oracle_disk_on_body_accel(fargo_oracle *o, int body, double klahr_factor, double out4[4])

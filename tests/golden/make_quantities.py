@@ -52,6 +52,15 @@ def main():
             f = line.split()
             if int(f[0]) in snaps and int(f[0]) == int(f[1]):
                 rows[int(f[0])] = {q: float.fromhex(float(f[c]).hex()) for q, c in COLUMNS.items()}  # %.16e round-trips a double
+        # column 9 of monitor/nbody1.dat: the circumplanetary mass (ComputeCircumPlanetaryMasses, circumplanetary_mass.cpp:11-51)
+        pfile = os.path.join(cfg["OutputDir"], "monitor", "nbody1.dat")
+        if os.path.exists(pfile):
+            for line in open(pfile):
+                if line.startswith("#"):
+                    continue
+                f = line.split()
+                if int(f[0]) in snaps and int(f[0]) == int(f[1]):
+                    rows[int(f[0])]["mdcp"] = float(f[9])  # %.18g round-trips a double
         out[name] = {str(k): rows[k] for k in snaps}
         shutil.rmtree(tmp)
         print(name, {k: rows[k]["mass"] for k in snaps})

@@ -121,6 +121,11 @@ def test_gpu_monitor_quantities_vs_oracle(name, k):
     for q in abi.MONITOR_QUANTITIES:
         assert abs(a[q] - b[q]) <= 1e-13 * max(abs(b[q]), 1e-300), (q, a[q], b[q])
     assert 0.0 < b["mass"] < cpu.monitor_quantities()["mass"]
+    # ComputeCircumPlanetaryMasses: the mass inside a Roche radius around the planet (or a point of the disk)
+    for x, y, roche in ((0.92, 0.39, 0.07), (-1.3, 0.2, 0.25), (0.45, 0.0, 0.1), (5.0, 0.0, 0.1)):
+        a, b = gpu.circumplanetary_mass(x, y, roche), cpu.circumplanetary_mass(x, y, roche)
+        assert abs(a - b) <= 1e-13 * abs(b), (x, y, roche, a, b)
+        assert (b > 0.0) == (x < 3.0)
     # fargo_monitor_disk: per-ring device sums against the oracle's serial ones; the radius is a ring's Rmed (same ring)
     fa = meta["misc"][k].get("frame_angle", 0.0)
     for limit in (1e300, rl):

@@ -442,7 +442,22 @@ def test_host_planet_monitor_files_cpu(tmp_path):
     b, at = meta["bodies"][20][1], meta["bodies"][19][1]
     torque = (at[1] * b[6] - at[2] * b[5]) * b[0]
     assert float(rows[20][18]) == pytest.approx(torque, rel=1e-9)
-    assert rows[20][9] == "nan"  # circumplanetary mass: not evaluated on this path
+    assert 0.0 < float(rows[20][9]) < 1e-3  # circumplanetary mass (ComputeCircumPlanetaryMasses): pinned in tests/test_diagnostics.py
+
+
+@pytest.mark.parametrize("name", ["adia_planet_100", "iso_planet_100"])
+def test_host_circumplanetary_mass_is_the_references(name, tmp_path):
+    """Column 9 (mdcp) of monitor/nbody1.dat — ComputeCircumPlanetaryMasses (circumplanetary_mass.cpp:11-51) with the Roche radius
+    the N-body side keeps (update_roche_radii) — against the value the unmodified reference wrote (tests/golden/quantities.json,
+    recorded with OMP_NUM_THREADS=1); the planet's position differs in its last bits (RK4 / IAS15), the set of cells does not."""
+    import json
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "quantities.json")))["quantities"][name]
+    until = max(int(k) for k in ref)
+    meta, z, out = start_host(_oracle_exe(), name, tmp_path, until)
+    rows = [l.split("\t") for l in open(os.path.join(out, "monitor", "nbody1.dat")).read().splitlines() if not l.startswith("#")]
+    for snap, want in ref.items():
+        assert int(rows[int(snap)][0]) == int(snap)
+        assert float(rows[int(snap)][9]) == pytest.approx(want["mdcp"], rel=1e-10), (snap, rows[int(snap)][9], want["mdcp"])
 
 
 def test_host_start_reads_2d_profiles_like_the_reference(tmp_path):

@@ -46,6 +46,7 @@ def run_slab(ctx, cfg, radii, fields, nsteps, synthetic, abi):
         out[name] = ctx.download(fid)  # only the rings this rank owns are written, the rest stays 0
     # the monitor reductions are collective: global sums (all-reduced) and the per-ring sums behind disk radius / eccentricity
     mon = dict(ctx.monitor_quantities(), **{"disk_" + k: v for k, v in ctx.monitor_disk(1e300, 0.99, 0.3).items()})
+    mon["circumplanetary_mass"] = ctx.circumplanetary_mass(0.9, 0.3, 0.3)
     return dts, out, mon
 
 
