@@ -311,16 +311,16 @@ class Handle:
 
     def monitor_disk(self, radius_limit=1e300, mass_fraction=0.99, frame_angle=0.0):
         """The mass-weighted columns of monitor/Quantities.dat (fargo_monitor_disk): dict of radius, eccentricity, periastron,
-        aspect_ratio (and the raw ecc_x, ecc_y, mass the first three are formed from, output.cpp:373-423 / quantities.cpp:552-567)."""
+        aspect_ratio, advection_torque, viscous_torque (and the raw ecc_x, ecc_y, mass the first three are formed from, output.cpp:373-423 / quantities.cpp:552-567)."""
         import math
-        out = (C.c_double * 5)()
+        out = (C.c_double * 7)()
         fn = self._fn("monitor_disk")
         fn.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double)]
         fn.restype = C.c_int
         self._check(fn(self.ptr, float(radius_limit), float(mass_fraction), float(frame_angle), out), "monitor_disk")
-        r, ex, ey, h, m = list(out)
+        r, ex, ey, h, m, tadv, tvisc = list(out)
         return {"radius": r, "eccentricity": math.sqrt(ex ** 2 + ey ** 2), "periastron": math.atan2(ey, ex), "aspect_ratio": h,
-                "ecc_x": ex, "ecc_y": ey, "mass": m}
+                "ecc_x": ex, "ecc_y": ey, "mass": m, "advection_torque": tadv, "viscous_torque": tvisc}
 
     def correct_vazi(self, domega):
         """correct_v_azimuthal (SideEuler.cpp:79-95): a corotating frame changed its angular velocity by domega."""

@@ -1967,7 +1967,7 @@ extern "C" int fargo_monitor_quantities(fargo_ctx *c, double radius_limit, doubl
 // The mass-weighted columns of monitor/Quantities.dat (output.cpp:373-423): see k_monitor_disk.  Per-ring sums on the device,
 // summed over the ranks ring by ring (every rank contributes the rings it owns), then walked in ring order on the host like
 // the reference's root (quantities.cpp:213-233).
-extern "C" int fargo_monitor_disk(fargo_ctx *c, double radius_limit, double mass_fraction, double frame_angle, double out5[5])
+extern "C" int fargo_monitor_disk(fargo_ctx *c, double radius_limit, double mass_fraction, double frame_angle, double out7[7])
 {
     CUDA_OK(cudaSetDevice(c->device));
     if (c->v_mid)
@@ -1990,7 +1990,7 @@ extern "C" int fargo_monitor_disk(fargo_ctx *c, double radius_limit, double mass
     std::vector<double> h(nrings);
     CUDA_OK(cudaMemcpyAsync(h.data(), d_rings, nrings * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
-    double sums[MD_N] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    double sums[MD_N] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     for (int q = 1; q < MD_N; ++q)
 	for (int i = 0; i < nrg; ++i)
 	    sums[q] += h[(size_t)q * nrg + i];
@@ -2004,11 +2004,13 @@ extern "C" int fargo_monitor_disk(fargo_ctx *c, double radius_limit, double mass
 	    break;
 	}
     }
-    out5[0] = radius;
-    out5[1] = sums[1] > 0.0 ? sums[2] / sums[1] : 0.0;
-    out5[2] = sums[1] > 0.0 ? sums[3] / sums[1] : 0.0;
-    out5[3] = sums[1] > 0.0 ? sums[4] / sums[1] : 0.0;
-    out5[4] = sums[1];
+    out7[0] = radius;
+    out7[1] = sums[1] > 0.0 ? sums[2] / sums[1] : 0.0;
+    out7[2] = sums[1] > 0.0 ? sums[3] / sums[1] : 0.0;
+    out7[3] = sums[1] > 0.0 ? sums[4] / sums[1] : 0.0;
+    out7[4] = sums[1];
+    out7[5] = sums[5];
+    out7[6] = sums[6];
     return 0;
 }
 

@@ -210,8 +210,9 @@ __global__ void __launch_bounds__(32 * MQ_N) k_monitor_final(const double *__res
 // :145-182) and the mean aspect ratio (compute_aspectratio mode 0, :784-806).  Per-ring sums, so that the host side of
 // fargo_monitor_disk can walk the rings in order like the reference's root does:
 // q: 0 ring mass sum(Surf Sigma) of every ring, and over the active cells with Rmed <= radius_limit:
-//    1 mass sum(Sigma Surf), 2 sum(e_x m), 3 sum(e_y m) (eccentricity vector rotated by the frame angle), 4 sum(H / Rb m)
-#define MD_N 5
+//    1 mass sum(Sigma Surf), 2 sum(e_x m), 3 sum(e_y m) (eccentricity vector rotated by the frame angle), 4 sum(H / Rb m),
+//    5 advection torque, 6 viscous torque (gas_torques.cpp:11-115 summed by gas_quantity_reduce, quantities.cpp:80-105, 1000-1018)
+#define MD_N 7
 __global__ void __launch_bounds__(MQ_THREADS)
     k_monitor_disk(const DevView c, const double *__restrict__ sigma, const double *__restrict__ energy, const double *__restrict__ vr,
 		   const double *__restrict__ vp, const double radius_limit, const double cosF, const double sinF,
@@ -250,6 +251,29 @@ __global__ void __launch_bounds__(MQ_THREADS)
 	    acc[2] += (e_x * cosF - e_y * sinF) * cell_mass;
 	    acc[3] += (e_y * cosF + e_x * sinF) * cell_mass;
 	    acc[4] += H / rmed * cell_mass;
+	    { // calculate_advection_torque (gas_torques.cpp:11-43)
+		double vr_cell = (rmed - c.g.rinf[i]) * AT(vr, i + 1, j) + (c.g.rsup[i] - rmed) * AT(vr, i, j);
+		vr_cell *= c.g.invdiffrsup[i];
+		const double vazi_cell = 0.5 * (AT(vp, i, j) + AT(vp, i, jp));
+		acc[5] += -(rmed * rmed) * s * vr_cell * vazi_cell;
+	    }
+	    if (i >= 1 && i < c.nr - 1) { // calculate_viscous_torque (:45-115) fills rings 1 .. max_radial - 1
+		const int jm = (j == 0) ? ns - 1 : j - 1;
+		const double inv_dr = c.g.invdiffrsup[i];
+		const double dvr_dphi_top = (AT(vr, i + 1, jp) - AT(vr, i + 1, jm)) * 0.5 * c.invdphi;
+		const double dvr_dphi_bot = (AT(vr, i, jp) - AT(vr, i, jm)) * 0.5 * c.invdphi;
+		double dvr_dphi = (rmed - c.g.rinf[i]) * dvr_dphi_top + (c.g.rsup[i] - rmed) * dvr_dphi_bot;
+		dvr_dphi *= inv_dr;
+		const double phi_dot_top = 0.5 * (AT(vp, i + 1, jp) + AT(vp, i + 1, j)) / c.g.rmed[i + 1];
+		const double phi_dot = 0.5 * (AT(vp, i, jp) + AT(vp, i, j)) / rmed;
+		const double phi_dot_bot = 0.5 * (AT(vp, i - 1, jp) + AT(vp, i - 1, j)) / c.g.rmed[i - 1];
+		const double dphi_dot_dr_top = (phi_dot_top - phi_dot) * c.g.invdiffrmed[i + 1];
+		const double dphi_dot_dr_bot = (phi_dot - phi_dot_bot) * c.g.invdiffrmed[i];
+		double dphi_dot_dr = (rmed - c.g.rinf[i]) * dphi_dot_dr_top + (c.g.rsup[i] - rmed) * dphi_dot_dr_bot;
+		dphi_dot_dr *= inv_dr;
+		const double nu = eos_nu_at(c, i, cell, s, e);
+		acc[6] += -fm_pow3(rmed) * nu * s * (dphi_dot_dr + 1.0 / (rmed * rmed) * dvr_dphi);
+	    }
 	}
     }
 #pragma unroll

@@ -1620,7 +1620,7 @@ struct Run {
     // output::write_quantities (output.cpp:326-493): one row of monitor/Quantities.dat per monitor step, file version 2.4 with
     // the 35 columns of quantities_file_column_v2_5 (output.cpp:39-75).  The global sums come from fargo_monitor_quantities
     // and fargo_monitor_disk (device reductions); columns this path does not evaluate (potential and total energy, pdivv,
-    // boundary and damping mass flows, torques) are written as nan, never as made-up numbers.
+    // boundary and damping mass flows, the gravitational torque) are written as nan, never as made-up numbers.
     bool quantities_header_written = false;
     void write_quantities()
     {
@@ -1671,8 +1671,9 @@ struct Run {
 	row[0] = time, row[1] = q[0], row[3] = q[1], row[5] = q[2], row[6] = q[3], row[8] = q[4], row[9] = q[5];
 	row[12] = q[6], row[13] = q[7];
 	{ // disk radius, eccentricity / periastron, aspect ratio (output.cpp:373-423; AspectRatioMode 0 is all make_params lets through)
-	    double d[5];
+	    double d[7];
 	    CHECK(BK(monitor_disk)(ctx, limit, cfg.num("DiskRadiusMassFraction", 0.99), frame_angle, d));
+	    row[30] = d[5], row[31] = d[6]; // advection and viscous torque (CalculateMonitorQuantitiesForOutput, quantities.cpp:1000-1018)
 	    row[2] = d[0];
 	    row[10] = std::sqrt(std::pow(d[1], 2) + std::pow(d[2], 2)); // calculate_disk_ecc_peri (quantities.cpp:552-567)
 	    row[11] = std::atan2(d[2], d[1]);

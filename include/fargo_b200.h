@@ -316,16 +316,18 @@ int fargo_circumplanetary_mass(fargo_ctx *ctx, double x, double y, double roche_
 int fargo_monitor_quantities(fargo_ctx *ctx, double radius_limit, double out8[8]);
 
 /* The mass-weighted columns of monitor/Quantities.dat (output.cpp:373-423), all ranks:
- * out5 = { disk radius (quantities::gas_disk_radius quantities.cpp:191-237: Rmed of the ring at which the running sum of the ring
+ * out7 = { disk radius (quantities::gas_disk_radius quantities.cpp:191-237: Rmed of the ring at which the running sum of the ring
  *          masses, the mesh's two ghost rings left out, first exceeds mass_fraction (DiskRadiusMassFraction, default 0.99) x the
  *          mass inside radius_limit),
  *          mass-weighted mean of the cells' eccentricity vector, x and y, rotated by frame_angle into the non-rotating frame
  *          (calculate_disk_ecc_vector :481-550, gas_reduce_mass_average :145-182; the caller forms the columns "eccentricity" =
  *          sqrt(x^2 + y^2) and "periastron" = atan2(y, x), :552-567),
  *          mass-weighted mean aspect ratio H / Rb (compute_aspectratio, AspectRatioMode 0, :784-806),
- *          the mass these means are weighted with }.
+ *          the mass these means are weighted with,
+ *          advection torque and viscous torque of the disk (gas_torques::calculate_advection_torque / calculate_viscous_torque,
+ *          gas_torques.cpp:11-115, summed over the active cells inside radius_limit: quantities.cpp:80-105, 1000-1018) }.
  * Per-ring sums on the device in a fixed order, rings added in order on the host. */
-int fargo_monitor_disk(fargo_ctx *ctx, double radius_limit, double mass_fraction, double frame_angle, double out5[5]);
+int fargo_monitor_disk(fargo_ctx *ctx, double radius_limit, double mass_fraction, double frame_angle, double out7[7]);
 
 /* integer FARGO shifts of the last transport (TransportEuler.cpp:49,220), local rings */
 int fargo_get_nshift(fargo_ctx *ctx, int *out_local_nrad);

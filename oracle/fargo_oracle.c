@@ -1997,9 +1997,11 @@ int fargo_oracle_monitor_quantities(fargo_oracle *o, double radius_limit, double
  *        ring masses, ghost rings left out, first exceeds mass_fraction x the mass inside radius_limit),
  *        mass-weighted means of the cells' eccentricity vector rotated into the non-rotating frame (calculate_disk_ecc_vector
  *        :481-550, gas_reduce_mass_average :145-182; the caller forms sqrt(ex^2 + ey^2) and atan2(ey, ex), :552-567),
- *        mass-weighted mean aspect ratio SCALE_HEIGHT / Rb (compute_aspectratio mode 0 :784-806), and the mass of those means.
+ *        mass-weighted mean aspect ratio SCALE_HEIGHT / Rb (compute_aspectratio mode 0 :784-806), the mass of those means,
+ *        and the advection and viscous torques of the disk (gas_torques::calculate_advection_torque / calculate_viscous_torque,
+ *        gas_torques.cpp:11-115, summed by gas_quantity_reduce quantities.cpp:80-105 in CalculateMonitorQuantitiesForOutput :1000-1018).
  * One rank only (the reference gathers the ring masses on its root). */
-int fargo_oracle_monitor_disk(fargo_oracle *o, double radius_limit, double mass_fraction, double frame_angle, double out5[5])
+int fargo_oracle_monitor_disk(fargo_oracle *o, double radius_limit, double mass_fraction, double frame_angle, double out7[7])
 {
     if (o->nranks != 1)
 	return 1;
@@ -2052,11 +2054,49 @@ int fargo_oracle_monitor_disk(fargo_oracle *o, double radius_limit, double mass_
 	    break;
 	}
     }
-    out5[0] = radius;
-    out5[1] = mass > 0.0 ? sum_ex / mass : 0.0;
-    out5[2] = mass > 0.0 ? sum_ey / mass : 0.0;
-    out5[3] = mass > 0.0 ? sum_h / mass : 0.0;
-    out5[4] = mass;
+    double tadv = 0.0, tvisc = 0.0;
+    for (int i = o->first_active; i < o->active_size; ++i) {
+	if (!(o->rmed[i] <= radius_limit))
+	    continue;
+	const double r = o->rmed[i], inv_dr = o->invdiffrsup[i];
+	for (int j = 0; j < ns; ++j) {
+	    const int jp = j == ns - 1 ? 0 : j + 1;
+	    const double sigma_cell = o->sigma[IDX(o, i, j)];
+	    double vr_cell = (o->rmed[i] - o->rinf[i]) * o->vrad[IDX(o, i + 1, j)] + (o->rsup[i] - o->rmed[i]) * o->vrad[IDX(o, i, j)];
+	    vr_cell *= inv_dr;
+	    const double vazi_cell = 0.5 * (o->vazi[IDX(o, i, j)] + o->vazi[IDX(o, i, jp)]);
+	    tadv += 0.0 + -pow(r, 2.0) * sigma_cell * vr_cell * vazi_cell * 1.0; /* worker array cleared, then += ... * dt (= 1) */
+	}
+    }
+    for (int i = o->first_active; i < o->active_size; ++i) {
+	if (!(o->rmed[i] <= radius_limit) || i < 1 || i >= o->nr - 1) /* calculate_viscous_torque fills rings 1 .. max_radial - 1 */
+	    continue;
+	const double r = o->rmed[i], inv_dr = o->invdiffrsup[i];
+	const double inv_dr_med_top = o->invdiffrmed[i + 1], inv_dr_med_bot = o->invdiffrmed[i];
+	for (int j = 0; j < ns; ++j) {
+	    const int jp = j == ns - 1 ? 0 : j + 1, jm = j == 0 ? ns - 1 : j - 1;
+	    const double sigma_cell = o->sigma[IDX(o, i, j)], viscosity_cell = o->viscosity[IDX(o, i, j)];
+	    const double dvr_dphi_top = (o->vrad[IDX(o, i + 1, jp)] - o->vrad[IDX(o, i + 1, jm)]) * 0.5 * o->invdphi;
+	    const double dvr_dphi_bot = (o->vrad[IDX(o, i, jp)] - o->vrad[IDX(o, i, jm)]) * 0.5 * o->invdphi;
+	    double dvr_dphi = (o->rmed[i] - o->rinf[i]) * dvr_dphi_top + (o->rsup[i] - o->rmed[i]) * dvr_dphi_bot;
+	    dvr_dphi *= inv_dr;
+	    const double phi_dot_top = 0.5 * (o->vazi[IDX(o, i + 1, jp)] + o->vazi[IDX(o, i + 1, j)]) / o->rmed[i + 1];
+	    const double phi_dot = 0.5 * (o->vazi[IDX(o, i, jp)] + o->vazi[IDX(o, i, j)]) / o->rmed[i];
+	    const double phi_dot_bot = 0.5 * (o->vazi[IDX(o, i - 1, jp)] + o->vazi[IDX(o, i - 1, j)]) / o->rmed[i - 1];
+	    const double dphi_dot_dr_top = (phi_dot_top - phi_dot) * inv_dr_med_top;
+	    const double dphi_dot_dr_bot = (phi_dot - phi_dot_bot) * inv_dr_med_bot;
+	    double dphi_dot_dr = (o->rmed[i] - o->rinf[i]) * dphi_dot_dr_top + (o->rsup[i] - o->rmed[i]) * dphi_dot_dr_bot;
+	    dphi_dot_dr *= inv_dr;
+	    tvisc += 0.0 + -pow(r, 3.0) * viscosity_cell * sigma_cell * (dphi_dot_dr + 1.0 / (pow(r, 2.0)) * dvr_dphi) * 1.0;
+	}
+    }
+    out7[0] = radius;
+    out7[1] = mass > 0.0 ? sum_ex / mass : 0.0;
+    out7[2] = mass > 0.0 ? sum_ey / mass : 0.0;
+    out7[3] = mass > 0.0 ? sum_h / mass : 0.0;
+    out7[4] = mass;
+    out7[5] = tadv;
+    out7[6] = tvisc;
     return 0;
 }
 

@@ -25,7 +25,8 @@ CASES = {"adia_planet_100": (50, 100), "iso_planet_100": (50, 100), "rey_star": 
 COLUMNS = {"mass": 3, "angular_momentum": 5, "internal_energy": 7, "kinetic_energy": 8, "radial_kinetic_energy": 10,
            "azimuthal_kinetic_energy": 11, "viscous_dissipation": 14, "luminosity": 15,
            # the mass-weighted columns (fargo_monitor_disk)
-           "radius": 4, "eccentricity": 12, "periastron": 13, "aspect_ratio": 26}
+           "radius": 4, "eccentricity": 12, "periastron": 13, "aspect_ratio": 26,
+           "advection_torque": 32, "viscous_torque": 33}
 
 
 def main():

@@ -98,7 +98,7 @@ def test_oracle_monitor_quantities_match_reference(name, k):
         assert got[q] == ref[q], (q, got[q], ref[q])
     # the mass-weighted columns (fargo_monitor_disk): disk radius, eccentricity, periastron, aspect ratio — bit for bit too
     disk = ctx.monitor_disk(frame_angle=meta["misc"][k].get("frame_angle", 0.0))
-    for q in ("radius", "eccentricity", "periastron", "aspect_ratio"):
+    for q in ("radius", "eccentricity", "periastron", "aspect_ratio", "advection_torque", "viscous_torque"):
         assert disk[q] == ref[q], (q, disk[q], ref[q])
 
 
@@ -132,8 +132,10 @@ def test_gpu_monitor_quantities_vs_oracle(name, k):
         a, b, a2 = gpu.monitor_disk(limit, 0.99, fa), cpu.monitor_disk(limit, 0.99, fa), gpu.monitor_disk(limit, 0.99, fa)
         assert a == a2
         assert a["radius"] == b["radius"], (a["radius"], b["radius"])
-        for q in ("aspect_ratio", "mass"):
+        for q in ("aspect_ratio", "mass", "viscous_torque"):
             assert abs(a[q] - b[q]) <= 1e-12 * abs(b[q]), (q, a[q], b[q])
+        # the advection torque is a sum of cell values of both signs: relative to the sum of their magnitudes (~ mass x r v_r v_phi)
+        assert abs(a["advection_torque"] - b["advection_torque"]) <= 1e-12 * max(abs(b["advection_torque"]), 1e-3 * b["mass"]), (a, b)
         for q in ("ecc_x", "ecc_y"):  # means of O(h^2) cell values that cancel around the ring: absolute
             assert abs(a[q] - b[q]) <= 1e-15, (q, a[q], b[q])
 

@@ -353,7 +353,7 @@ def test_host_writes_quantities_dat_cpu(name, tmp_path):
     cols = {"mass": 3, "angular_momentum": 5, "internal_energy": 7, "kinetic_energy": 8, "radial_kinetic_energy": 10,
             "azimuthal_kinetic_energy": 11, "viscous_dissipation": 14, "luminosity": 15,
             # the mass-weighted columns (fargo_monitor_disk)
-            "radius": 4, "eccentricity": 12, "periastron": 13, "aspect_ratio": 26}
+            "radius": 4, "eccentricity": 12, "periastron": 13, "aspect_ratio": 26, "advection_torque": 32, "viscous_torque": 33}
     for snap, want in ref.items():
         row = rows[int(snap)]
         assert int(row[0]) == int(snap)
@@ -362,7 +362,7 @@ def test_host_writes_quantities_dat_cpu(name, tmp_path):
                 assert float(row[c]) == want[q], (snap, q, row[c], want[q])
             else:
                 assert float(row[c]) == pytest.approx(want[q], rel=1e-9, abs=1e-300), (snap, q)
-        assert row[6] == "nan" and row[9] == "nan" and row[16] == "nan" and row[32] == "nan"  # total / potential energy, pdivv, torques
+        assert row[6] == "nan" and row[9] == "nan" and row[16] == "nan" and row[34] == "nan"  # total / potential energy, pdivv, gravitational torque
 
 
 # ---------------------------------------------------------------------------------------------------------------------
