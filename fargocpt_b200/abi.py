@@ -9,7 +9,7 @@ import os
 
 import numpy as np
 
-FARGO_ABI_VERSION = 3
+FARGO_ABI_VERSION = 4
 FARGO_MAX_BODIES = 8
 CPUOVERLAP = 7
 
@@ -65,6 +65,8 @@ class FargoParams(C.Structure):
         ("temperature_cgs", C.c_double), ("density_cgs", C.c_double), ("opacity_code", C.c_double),
         ("pvte", C.c_int), ("energy_density_cgs", C.c_double), ("surface_density_cgs", C.c_double),
         ("alpha_mode", C.c_int), ("alpha_cold", C.c_double), ("alpha_hot", C.c_double),
+        ("cooling_scurve", C.c_int), ("length_cgs", C.c_double), ("mass_cgs", C.c_double), ("energy_flux_cgs", C.c_double),
+        ("sigma_sb_cgs", C.c_double), ("G_cgs", C.c_double),
     ]
 
     def as_dict(self):

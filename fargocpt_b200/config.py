@@ -78,9 +78,11 @@ def params_from_config(cfg, consts, nrad, naz, temp_unit_K=1.0, units=None):
     d["cooling_beta_reference"] = abi.BETA_REF[str(get("CoolingBetaReference", "zero")).lower()]
     # radiative surface cooling / stellar irradiation (parameters.cpp:389-435, 628-632; planetary_system.cpp:137-146)
     sc = str(get("SurfaceCooling", "No")).lower()
-    if sc not in ("no", "off", "false", "thermal"):
+    if sc not in ("no", "off", "false", "thermal", "scurve"):
         raise ValueError("SurfaceCooling: %s is outside this path" % sc)
     d["cooling_surface"] = int(sc == "thermal")
+    # parameters.cpp:374-403: ScurveType Kimura (default) | Ichikawa
+    d["cooling_scurve"] = 0 if sc != "scurve" else {"ichikawa": 1, "kimura": 2}[str(get("ScurveType", "Kimura")).lower()]
     d["surface_cooling_factor"] = float(get("CoolingRadiativeFactor", 1.0))
     d["heating_star"] = int(any(_num(b.get("temperature", 0.0)) > 0 for b in (get("nbody") or [])))
     d["opacity"] = abi.OPACITY[str(get("Opacity", "Lin")).lower()]
@@ -95,6 +97,11 @@ def params_from_config(cfg, consts, nrad, naz, temp_unit_K=1.0, units=None):
     d["opacity_code"] = 1.0 / float(units.get("opacity", 1.0))
     d["energy_density_cgs"] = float(units.get("energy surface density", 1.0))
     d["surface_density_cgs"] = float(units.get("mass surface density", 1.0))
+    d["length_cgs"] = float(units.get("length", 1.0))
+    d["mass_cgs"] = float(units.get("mass", 1.0))
+    d["energy_flux_cgs"] = float(units.get("energy flux", 1.0))
+    d["sigma_sb_cgs"] = float(consts.get("sigma_cgs", 0.0))
+    d["G_cgs"] = float(consts.get("G_cgs", 0.0))
     d["body_force_from_potential"] = int(_flag(get("BodyForceFromPotential"), True))
     d["thickness_smoothing"] = float(get("ThicknessSmoothing", 0.6))
     d["imposed_disk_drift"] = float(get("ImposedDiskDrift", 0.0))

@@ -662,6 +662,13 @@ extern "C" int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, con
 	dalloc(c, &c->vrb[1], nv) || dalloc(c, &c->vpb[1], ns) || dalloc(c, &c->eb[1], params->adiabatic ? ns : 1));
     TRY(dalloc(c, &c->sigma0, ns) || dalloc(c, &c->energy0, ns) || dalloc(c, &c->vr0, nv) || dalloc(c, &c->vp0, ns));
     TRY(dalloc(c, &c->qplus, ns) || dalloc(c, &c->qminus, ns));
+    if (params->cooling_scurve != 0 &&
+	(!params->adiabatic || params->heating_star || params->cooling_scurve < 0 || params->cooling_scurve > 2 || !(params->energy_flux_cgs > 0))) {
+	// with an irradiating body the reference's irradiation would read the TAU_EFF scurve_cooling stored one call earlier
+	fail("SurfaceCooling: scurve needs the energy equation, no irradiating body, ScurveType 1 | 2 and the cgs unit factors");
+	fargo_ctx_destroy(c);
+	return 1;
+    }
     if (params->alpha_mode != 0) { // viscosity::get_alpha (viscosity.cpp:31-49)
 	if (params->alpha_mode != 1 || !params->adiabatic || !(params->viscous_alpha > 0)) {
 	    fail("AlphaMode %d: only the S-curve (1) with the energy equation and ViscousAlpha > 0 is implemented", params->alpha_mode);
@@ -1714,8 +1721,8 @@ extern "C" int fargo_kick(fargo_ctx *c, double dt)
     const fargo_params &p = c->v.p;
     if (p.pvte && !c->v.pv.geff)
 	return fail("EquationOfState: PVTE needs fargo_set_pvte before the first step");
-    // PVTE and AlphaMode: per-cell gamma / alpha live in the staged kernels
-    const bool fused = p.stabilize_viscosity == 0 && !c->force_staged && !p.pvte && p.alpha_mode == 0;
+    // PVTE, AlphaMode and the S-curve cooling: per-cell gamma / alpha / the cgs fit live in the staged kernels
+    const bool fused = p.stabilize_viscosity == 0 && !c->force_staged && !p.pvte && p.alpha_mode == 0 && p.cooling_scurve == 0;
     if (fused) {
 	if (c->v_mid)
 	    return fail("fargo_kick (fused) called mid-step after a per-stage call; finish with fargo_stage_transport first");

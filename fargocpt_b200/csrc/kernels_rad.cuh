@@ -124,3 +124,50 @@ __device__ __forceinline__ void rad_add_qplus(const DevView &c, const int i, con
 	qplus += c.b.irradiation_ramp[k] * q;
     }
 }
+
+// scurve_cooling (SourceEuler.cpp:726-831; SurfaceCooling: scurve): the cooling S-curve of a dwarf-nova disk after Ichikawa &
+// Osaki (1992) / Kimura et al. (2020), a fit written in cgs with log10 / pow — CUDA's against glibc's differ in the last bits,
+// so Q- agrees with the reference's to ~1e-15 relative, not to the bit.  Returns what the function adds to Q- of a cell of
+// ring 1 .. nr - 2 and the TAU_EFF it stores (read by SubStep3's density-floor branch).  T: the cell's temperature, code units.
+__device__ __forceinline__ double rad_scurve_qminus(const DevView &c, const int i, const double sigma, const double T, const double mu,
+						     double &tau_eff)
+{
+    const double SigmaCGS_threshold = 2.0, temperatureCGS_threshold = 1200.0;
+    const bool kimura = c.p.cooling_scurve == 2;
+    const double F_hot_const = kimura ? 23.405 : 25.49, muExponent = kimura ? 0.31 : -0.31;
+    const double SigmaCGS = sigma * c.p.surface_density_cgs;
+    const double SigmaCGS_tmp = stdmax(SigmaCGS, SigmaCGS_threshold);
+    const double temperatureCGS = T * c.p.temperature_cgs;
+    const double temperatureCGS_tmp = stdmax(temperatureCGS, temperatureCGS_threshold);
+    const double rCGS = c.g.rmed[i] * c.p.length_cgs;
+    const double M = c.p.hydro_center_mass * c.p.mass_cgs;
+    const double omega_keplerCGS = sqrt(c.p.G_cgs * M / (rCGS * rCGS * rCGS));
+    const double sigma_sb_cgs = c.p.sigma_sb_cgs;
+    const double logTA = -1.0 / 5.49 * (0.62 * log10(omega_keplerCGS) + 1.62 * log10(SigmaCGS_tmp) + muExponent * log10(mu) - 25.48 -
+				      log10(sigma_sb_cgs));
+    const double TA = pow(10.0, logTA);
+    const double FA = sigma_sb_cgs * fm_pow4(TA);
+    const double logFA = log10(FA);
+    const double KCGS = 11.0 + 0.4 * log10(2.0e10 / rCGS);
+    const double logFB = stdmax(KCGS, logFA);
+    const double logTB_aux = log10(omega_keplerCGS) + 2.0 * log10(SigmaCGS_tmp) + 0.5 * log10(mu) + F_hot_const;
+    const double logTB = (logFB + logTB_aux) / 8.0;
+    const double TB = pow(10.0, logTB);
+    double logFtot;
+    if (temperatureCGS_tmp < TA)
+	logFtot = 9.49 * log10(temperatureCGS_tmp) + 0.62 * log10(omega_keplerCGS) + 1.62 * log10(SigmaCGS_tmp) + muExponent * log10(mu) - 25.48;
+    else if (temperatureCGS_tmp > TB)
+	logFtot = 8.0 * log10(temperatureCGS_tmp) - log10(omega_keplerCGS) - 2.0 * log10(SigmaCGS_tmp) - 0.5 * log10(mu) - F_hot_const;
+    else
+	logFtot = (logFA - logFB) * log10(temperatureCGS_tmp / TB) / log10(TA / TB) + logFB;
+    const double T4 = fm_pow4(T);
+    const double factor = c.p.surface_cooling_factor;
+    double F_tot = pow(10.0, logFtot) * (1.0 / c.p.energy_flux_cgs);
+    F_tot *= sqrt(SigmaCGS / SigmaCGS_tmp); // pow(x, 0.5): correctly rounded in glibc, like sqrt
+    const double tr = temperatureCGS / temperatureCGS_tmp;
+    F_tot *= tr * tr;
+    const double F_Blackbody = c.p.sigma_sb * T4;
+    const double qminus_scurve = 2.0 * factor * stdmin(F_tot, F_Blackbody);
+    tau_eff = factor * 2 * c.p.sigma_sb * T4 / qminus_scurve;
+    return qminus_scurve;
+}

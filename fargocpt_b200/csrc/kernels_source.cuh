@@ -417,6 +417,8 @@ __global__ void __launch_bounds__(256)
 	if (c.p.heating_star)
 	    rad_add_qplus(c, i, c.g.cosphi[j], c.g.sinphi[j], H, tau_eff, Qp);
     }
+    if (c.p.cooling_scurve && i >= 1 && i < c.nr - 1) // scurve_cooling (SourceEuler.cpp:726-831), after thermal_cooling in calculate_qminus
+	Qm += rad_scurve_qminus(c, i, s, rad_temperature(c, s, e, pv_mu(c, cell), pv_geff(c, cell)), pv_mu(c, cell), tau_eff);
     if (i >= 1 && i < c.nr - 1) {
 	const double alpha = radiative_alpha(c, i, cell, s, e);
 	Qp /= alpha;

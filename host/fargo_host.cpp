@@ -272,6 +272,7 @@ struct CodeConstants {
     double G = 1.0, R = 1.0, sigma_sb = 0.0, c_light = 0.0, temperature_unit_K = 1.0;
     double length_cgs = 1.0, mass_cgs = 1.0, time_cgs = 1.0; // units.yml: code -> cgs factors of the base units
     double density_cgs = 1.0, opacity_cgs = 1.0;	     // ... and of the two the opacity tables need (opacity.cpp:13-14)
+    double energy_flux_cgs = 1.0, sigma_cgs = 0.0, G_cgs = 0.0; // what the S-curve cooling fit needs (SourceEuler.cpp:726-831)
     void load(const std::string &dir)
     {
 	std::ifstream f(dir + "/constants.yml");
@@ -292,6 +293,12 @@ struct CodeConstants {
 		    sigma_sb = v;
 		else if (sym == "c")
 		    c_light = v;
+	    } else if (t.rfind("cgs value:", 0) == 0) {
+		const double v = atof(t.substr(10).c_str());
+		if (sym == "G")
+		    G_cgs = v;
+		else if (sym == "sigma")
+		    sigma_cgs = v;
 	    }
 	}
 	std::ifstream u(dir + "/units.yml");
@@ -314,6 +321,8 @@ struct CodeConstants {
 		    density_cgs = v;
 		else if (block == "opacity:")
 		    opacity_cgs = v;
+		else if (block == "energy flux:")
+		    energy_flux_cgs = v;
 	    }
 	}
     }
@@ -349,8 +358,8 @@ static fargo_params make_params(const Config &c, const CodeConstants &k, int nra
 	    die("%s", std::string("the deprecated 'Adiabatic' flag is not supported; use EquationOfState"));
 	const bool energy_equation = eos == "adiabatic" || eos == "ideal" || eos == "pvte" || eos == "pvtelaw"; // SubStep3 only runs then (simulation.cpp:203-205)
 	const std::string sc = lower(c.str("SurfaceCooling", "No")); // parameters.cpp:394-406
-	if (energy_equation && !(sc == "no" || sc == "off" || sc == "false" || sc == "thermal"))
-	    die("SurfaceCooling: %s is not supported by this driver (beta cooling, thermal)", sc);
+	if (energy_equation && !(sc == "no" || sc == "off" || sc == "false" || sc == "thermal" || sc == "scurve"))
+	    die("SurfaceCooling: %s is not supported by this driver (no, thermal, scurve)", sc);
 	if (c.num("AlphaMode", 0) != 0 && !(c.num("AlphaMode", 0) == 1 && energy_equation && c.num("ViscousAlpha", 0.0) > 0))
 	    die("AlphaMode: %s is not supported by this driver (0; 1 with the energy equation and ViscousAlpha > 0)", c.str("AlphaMode", ""));
 	const std::pair<const char *, double> zero_only[] = {{"AspectRatioMode", 0}};
@@ -448,6 +457,9 @@ static fargo_params make_params(const Config &c, const CodeConstants &k, int nra
     // radiative surface cooling, opacity (parameters.cpp:389-435, 628-632); heating_star is set by the caller from the bodies
     // (t_planetary_system::derive_config, planetary_system.cpp:137-146)
     p.cooling_surface = (p.adiabatic && lower(c.str("SurfaceCooling", "No")) == "thermal") ? 1 : 0;
+    if (p.adiabatic && lower(c.str("SurfaceCooling", "No")) == "scurve") // parameters.cpp:374-403: ScurveType Kimura (default) | Ichikawa
+	p.cooling_scurve = enum_of(c.str("ScurveType", "Kimura"), {{"ichikawa", 1}, {"kimura", 2}}, "ScurveType");
+    p.length_cgs = k.length_cgs, p.mass_cgs = k.mass_cgs, p.energy_flux_cgs = k.energy_flux_cgs, p.sigma_sb_cgs = k.sigma_cgs, p.G_cgs = k.G_cgs;
     p.surface_cooling_factor = c.num("CoolingRadiativeFactor", 1.0);
     p.heating_star = 0;
     p.opacity = enum_of(c.str("Opacity", "Lin"), {{"lin", FARGO_OPACITY_LIN}, {"bell", FARGO_OPACITY_BELL}, {"constant", FARGO_OPACITY_CONST},
@@ -905,6 +917,8 @@ struct Run {
 	for (const Body &b : bodies)
 	    if (params.adiabatic && b.rec.temperature > 0)
 		params.heating_star = 1;
+	if (params.cooling_scurve && params.heating_star) // the reference's irradiation would read the TAU_EFF of the previous scurve_cooling call
+	    die("%s", std::string("SurfaceCooling: scurve with an irradiating body is not supported by this driver"));
 #ifdef FARGO_HOST_ORACLE
 	(void)device;
 	ctx = fargo_oracle_create(&params, radii.data(), 0, 1);
@@ -1061,6 +1075,7 @@ struct Run {
 	consts.temperature_unit_K = U.temperature;
 	consts.length_cgs = U.length, consts.mass_cgs = U.mass, consts.time_cgs = U.time;
 	consts.density_cgs = U.density, consts.opacity_cgs = U.opacity;
+	consts.energy_flux_cgs = U.energy_flux, consts.sigma_cgs = U.sigma.cgs, consts.G_cgs = U.G.cgs;
 	const int shock_tube = (int)cfg.num("ShockTube", 0);
 	if (shock_tube != 0 && shock_tube != 1)
 	    die("ShockTube: %s is not supported by this driver (1: the ideal-gas tube)", cfg.str("ShockTube", ""));

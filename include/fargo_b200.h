@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define FARGO_ABI_VERSION 3
+#define FARGO_ABI_VERSION 4
 #define FARGO_MAX_BODIES 8
 /* src/constants.h:17 (CPUOVERLAP) and :19 (GHOSTCELLS_B) */
 #define FARGO_CPUOVERLAP 7
@@ -154,6 +154,11 @@ typedef struct fargo_params {
      * (update_viscosity :102).  Modes 2 and 3 are refused. */
     int alpha_mode;
     double alpha_cold, alpha_hot;
+    /* SurfaceCooling: scurve (scurve_cooling, SourceEuler.cpp:726-831; parameters.cpp:374-403): 0 off, 1 ScurveType Ichikawa
+     * (Ichikawa & Osaki 1992), 2 Kimura (Kimura et al. 2020, the default).  The fit is written in cgs: code -> cgs factors of
+     * length, mass and energy flux (units.cpp), the Stefan-Boltzmann and gravitational constants in cgs (constants.cpp). */
+    int cooling_scurve;
+    double length_cgs, mass_cgs, energy_flux_cgs, sigma_sb_cgs, G_cgs;
 } fargo_params;
 /* parameters::t_opacity (parameters.h), Opacity: Lin | Bell | Constant | Simple */
 enum fargo_opacity { FARGO_OPACITY_LIN = 0, FARGO_OPACITY_BELL = 1, FARGO_OPACITY_CONST = 2, FARGO_OPACITY_SIMPLE = 3 };

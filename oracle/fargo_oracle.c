@@ -957,6 +957,69 @@ static void thermal_cooling(fargo_oracle *o)
     }
 }
 
+/* scurve_cooling, SourceEuler.cpp:726-831 */
+static void scurve_cooling(fargo_oracle *o)
+{
+    const double SigmaCGS_threshold = 2.0;
+    const double temperatureCGS_threshold = 1200.0;
+    double muExponent, F_hot_const;
+    if (o->p.cooling_scurve == 2) { /* Kimura et al. 2020 */
+	F_hot_const = 23.405;
+	muExponent = 0.31;
+    } else { /* Ichikawa & Osaki 1992 */
+	F_hot_const = 25.49;
+	muExponent = -0.31;
+    }
+    const int Nr = o->nr - 1, Nphi = o->ns;
+    const double energy_flux_cgs_to_code = 1.0 / o->p.energy_flux_cgs; /* t_unit::m_inverse_cgs_factor (units.cpp:213) */
+#pragma omp parallel for
+    for (int nr = 1; nr < Nr; ++nr) {
+	for (int naz = 0; naz < Nphi; ++naz) {
+	    const size_t c = IDX(o, nr, naz);
+	    const double Sigma = o->sigma[c];
+	    const double SigmaCGS = Sigma * o->p.surface_density_cgs;
+	    const double SigmaCGS_tmp = stdmax(SigmaCGS, SigmaCGS_threshold);
+	    const double temperatureCGS = o->temperature[c] * o->p.temperature_cgs;
+	    const double temperatureCGS_tmp = stdmax(temperatureCGS, temperatureCGS_threshold);
+	    const double rCGS = o->rmed[nr] * o->p.length_cgs;
+	    const double mu = MUC(o, c);
+	    const double M = o->p.hydro_center_mass * o->p.mass_cgs;
+	    const double cgs_G = o->p.G_cgs;
+	    const double omega_keplerCGS = sqrt(cgs_G * M / (rCGS * rCGS * rCGS));
+	    const double sigma_sb_cgs = o->p.sigma_sb_cgs;
+	    const double logTA = -1.0 / 5.49 * (0.62 * log10(omega_keplerCGS) + 1.62 * log10(SigmaCGS_tmp) + muExponent * log10(mu) - 25.48 -
+					      log10(sigma_sb_cgs));
+	    const double TA = pow(10.0, logTA);
+	    const double FA = sigma_sb_cgs * pow(TA, 4);
+	    const double logFA = log10(FA);
+	    const double KCGS = 11.0 + 0.4 * log10(2.0e10 / rCGS);
+	    const double logFB = stdmax(KCGS, logFA);
+	    const double logTB_aux = log10(omega_keplerCGS) + 2.0 * log10(SigmaCGS_tmp) + 0.5 * log10(mu) + F_hot_const;
+	    const double logTB = (logFB + logTB_aux) / 8.0;
+	    const double TB = pow(10.0, logTB);
+	    double logFtot;
+	    if (temperatureCGS_tmp < TA) {
+		logFtot = 9.49 * log10(temperatureCGS_tmp) + 0.62 * log10(omega_keplerCGS) + 1.62 * log10(SigmaCGS_tmp) +
+			  muExponent * log10(mu) - 25.48;
+	    } else if (temperatureCGS_tmp > TB) {
+		logFtot = 8.0 * log10(temperatureCGS_tmp) - log10(omega_keplerCGS) - 2.0 * log10(SigmaCGS_tmp) - 0.5 * log10(mu) - F_hot_const;
+	    } else {
+		logFtot = (logFA - logFB) * log10(temperatureCGS_tmp / TB) / log10(TA / TB) + logFB;
+	    }
+	    const double T4 = pow(o->temperature[c], 4);
+	    const double sigma_sb = o->p.sigma_sb;
+	    const double factor = o->p.surface_cooling_factor;
+	    double F_tot = pow(10.0, logFtot) * energy_flux_cgs_to_code;
+	    F_tot *= pow((SigmaCGS / SigmaCGS_tmp), 0.5);
+	    F_tot *= pow(temperatureCGS / temperatureCGS_tmp, 2);
+	    const double F_Blackbody = sigma_sb * T4;
+	    const double qminus_scurve = 2.0 * factor * stdmin(F_tot, F_Blackbody);
+	    o->qminus[c] += qminus_scurve;
+	    o->tau_eff[c] = factor * 2 * sigma_sb * T4 / qminus_scurve;
+	}
+    }
+}
+
 /* irradiation_single, SourceEuler.cpp:538-596, for body k */
 static void irradiation_single(fargo_oracle *o, int k)
 {
@@ -1022,6 +1085,8 @@ static void calculate_qminus(fargo_oracle *o)
     }
     if (o->p.cooling_surface)
 	thermal_cooling(o);
+    if (o->p.cooling_scurve)
+	scurve_cooling(o);
 }
 
 static void calculate_qplus(fargo_oracle *o)
@@ -1044,7 +1109,7 @@ static void calculate_qplus(fargo_oracle *o)
 	}
     }
     if (o->p.heating_star) { /* calculate_qplus :621-627 */
-	if (!o->p.cooling_surface)
+	if (!(o->p.cooling_surface || o->p.cooling_scurve))
 	    compute_tau_eff(o);
 	for (int k = 0; k < o->bodies.n; ++k)
 	    if (o->bodies.temperature[k] > 0)

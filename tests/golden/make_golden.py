@@ -142,6 +142,11 @@ CASES = {
                               Damping="Yes", DampingInnerLimit=1.311, DampingOuterLimit=0.763, DampingTimeFactor=0.05, **DAMP_ALL),
     "adia_alpha_scurve_lf": dict(Integrator="Leapfrog", AlphaMode=1, ViscousAlpha=1e-3, AlphaCold=0.01, AlphaHot=0.1, HeatingViscous="yes",
                                  l0="0.06 au", Sigma0=0.001, WriteTemperature="yes"),
+    # SurfaceCooling: scurve (scurve_cooling, SourceEuler.cpp:726-831) together with the S-curve alpha: a dwarf-nova disk
+    "adia_scurve": dict(SurfaceCooling="scurve", ScurveType="Kimura", AlphaMode=1, ViscousAlpha=1e-3, AlphaCold=0.01, AlphaHot=0.1,
+                        HeatingViscous="yes", l0="0.06 au", Sigma0=0.001, WriteTemperature="yes", WriteQminus="yes", WriteQplus="yes"),
+    "adia_scurve_ichikawa_lf": dict(SurfaceCooling="scurve", ScurveType="Ichikawa", Integrator="Leapfrog", ViscousAlpha=1e-3,
+                                    HeatingViscous="yes", l0="0.06 au", Sigma0=0.001, WriteTemperature="yes"),
     "iso_planet_100": dict(Nrad=48, Naz=160, Rmax=2.5, Nsnapshots=100, MonitorTimestep=4.0e-3, IndirectTermMode=1,
                            EquationOfState="Isothermal", ViscousAlpha=1e-3, ArtificialViscosityFactor=1.41, OmegaFrame=1.0,
                            FlaringIndex=0.0, Damping="Yes", DampingInnerLimit=1.25, DampingOuterLimit=0.84,
@@ -153,7 +158,10 @@ def parse_constants(outdir):
     c = yaml.safe_load(open(os.path.join(outdir, "constants.yml")))
     u = yaml.safe_load(open(os.path.join(outdir, "units.yml")))
     consts = {v["symbol"]: float(v["code value"]) for v in c.values()}
-    return consts, float(u["temperature"]["cgs value"]), {k: float(u[k]["cgs value"]) for k in ("density", "opacity", "energy surface density", "mass surface density")}
+    for sym in ("sigma", "G"):  # the S-curve cooling fit is written in cgs (SourceEuler.cpp:726-831)
+        consts[sym + "_cgs"] = [float(v["cgs value"]) for v in c.values() if v["symbol"] == sym][0]
+    return consts, float(u["temperature"]["cgs value"]), {k: float(u[k]["cgs value"]) for k in ("density", "opacity", "energy surface density", "mass surface density",
+                                                                                                "length", "mass", "energy flux")}
 
 
 def read_misc(path):

@@ -167,12 +167,13 @@ def test_artificial_viscosity_inside_the_source_kernel(name, monkeypatch):
             _check(name, (k, fname), snap[fname], z[f"{fname}_{k}"])
 
 
-@pytest.mark.parametrize("name", ["adia_alpha_scurve", "adia_alpha_scurve_lf"])
+@pytest.mark.parametrize("name", ["adia_alpha_scurve", "adia_alpha_scurve_lf", "adia_scurve", "adia_scurve_ichikawa_lf"])
 def test_alpha_scurve_run_vs_reference(name):
     """AlphaMode 1 (viscosity/viscosity.cpp:31-49): alpha of a cell is an S-curve in the TEMPERATURE grid as last stored, formed
     with pow / log10 / tanh — CUDA's against glibc's differ in the last bits, so fields, dt and the viscosity are held to POW_RTOL
     (of the field's scale) like the opacity tables; step counts and times are identical.  Euler and Leapfrog (whose second
-    recalculate_viscosity reads the temperature SubStep3 stored)."""
+    recalculate_viscosity reads the temperature SubStep3 stored).  adia_scurve*: SurfaceCooling: scurve (scurve_cooling,
+    SourceEuler.cpp:726-831: Kimura with the S-curve alpha, Ichikawa with Leapfrog), a cgs fit in log10 / pow: same tolerance."""
     meta, z, gpu, cpu = _ctx_pair(name)
     snaps = goldenrun.run_fixture(gpu, meta, z)
     worst, ndiff = 0.0, 0
@@ -184,7 +185,7 @@ def test_alpha_scurve_run_vs_reference(name):
             ref = z[f"{fname}_{k}"]
             worst = max(worst, float(np.abs(snap[fname] - ref).max() / np.abs(ref).max()))
             ndiff += int((snap[fname] != ref).sum())
-    for fid, fname in ((abi.TEMPERATURE, "Temperature"), (abi.VISCOSITY, "viscosity")):
+    for fid, fname in ((abi.TEMPERATURE, "Temperature"), (abi.VISCOSITY, "viscosity"), (abi.QMINUS, "Qminus")):
         if f"{fname}_{meta['nsnap']}" not in z.files:
             continue
         ref = z[f"{fname}_{meta['nsnap']}"]

@@ -166,8 +166,12 @@ def start_host(exe, name, tmp_path, until):
 def check_start(meta, z, out, until, exact):
     """Snapshot 0 — the state the reference builds from the setup file — must be the reference's bit for bit: the code-unit
     constants, the radii, every field, misc.bin, and what the hydro path reads off the N-body records."""
-    consts = {v["symbol"]: float(v["code value"]) for v in yaml.safe_load(open(os.path.join(out, "constants.yml"))).values()}
-    assert consts == {k: float(v) for k, v in meta["consts"].items()}
+    cyml = yaml.safe_load(open(os.path.join(out, "constants.yml")))
+    consts = {v["symbol"]: float(v["code value"]) for v in cyml.values()}
+    assert consts == {k: float(v) for k, v in meta["consts"].items() if not k.endswith("_cgs")}
+    for k, v in meta["consts"].items():  # newer fixtures also carry the cgs values the S-curve cooling fit reads
+        if k.endswith("_cgs"):
+            assert [float(c["cgs value"]) for c in cyml.values() if c["symbol"] == k[:-4]] == [float(v)], k
     units = yaml.safe_load(open(os.path.join(out, "units.yml")))
     assert float(units["temperature"]["cgs value"]) == meta["temperature_unit_K"]
     assert np.array_equal(np.loadtxt(os.path.join(out, "used_rad.dat")), z["radii"])
@@ -202,7 +206,9 @@ START_CASES = [("iso_star", 6, True), ("adia_star", 6, True), ("adia_cold", 6, T
                # EquationOfState: PVTE: lookup tables built by host/fargo_pvte.h, the reference's refresh order of gamma_eff / mu / Gamma_1
                ("adia_pvte", 6, True),
                # AlphaMode 1: S-curve alpha in the stored temperature (viscosity/viscosity.cpp:31-49), Euler and Leapfrog
-               ("adia_alpha_scurve", 6, True), ("adia_alpha_scurve_lf", 6, True)]
+               ("adia_alpha_scurve", 6, True), ("adia_alpha_scurve_lf", 6, True),
+               # SurfaceCooling: scurve (scurve_cooling, SourceEuler.cpp:726-831): ScurveType Kimura / Ichikawa
+               ("adia_scurve", 6, True), ("adia_scurve_ichikawa_lf", 6, True)]
 
 
 @pytest.mark.parametrize("name,until,exact", START_CASES)
@@ -500,7 +506,7 @@ def test_host_start_refuses_unknown_keys_like_the_reference(tmp_path):
 
 
 def test_host_refuses_physics_it_does_not_implement(tmp_path):
-    for key, value in (("EquationOfState", "Polytropic"), ("SurfaceCooling", "scurve"), ("SelfGravity", "yes"), ("AlphaMode", 2)):
+    for key, value in (("EquationOfState", "Polytropic"), ("SurfaceCooling", "fld"), ("SelfGravity", "yes"), ("AlphaMode", 2)):
         cfg = yaml.safe_load(open(os.path.join(ROOT, "tests", "golden", "adia_star.yml")))
         cfg[key] = value
         yml = str(tmp_path / f"setup_{key}.yml")

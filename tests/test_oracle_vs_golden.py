@@ -15,7 +15,9 @@ CASES = ["adia_star", "adia_cold", "iso_star", "iso_sn_std", "adia_sn_stab", "ri
          # EquationOfState: PVTE (pvte_law.cpp): lookup tables built by host/fargo_pvte.h, gamma_eff / mu / Gamma_1 / H grids checked too
          "adia_pvte",
          # AlphaMode 1: S-curve alpha in the stored TEMPERATURE grid (viscosity/viscosity.cpp:31-49), Euler and Leapfrog
-         "adia_alpha_scurve", "adia_alpha_scurve_lf"]
+         "adia_alpha_scurve", "adia_alpha_scurve_lf",
+         # SurfaceCooling: scurve (scurve_cooling, SourceEuler.cpp:726-831): Kimura with the S-curve alpha, Ichikawa with Leapfrog
+         "adia_scurve", "adia_scurve_ichikawa_lf"]
 # Isothermal configs have no per-cell transcendental in the step => demanded bit-exact.
 # Adiabatic configs call exp() per cell (SourceEuler.cpp:487); same libm here => also bit-exact on CPU.
 # DiskFeedback: the reference sums the disk's pull with an OpenMP reduction in no defined order, so the acceleration
@@ -49,9 +51,9 @@ def test_oracle_matches_reference(name):
         for fid, fname in ((abi.GAMMAEFF, "gammaeff"), (abi.MU, "mu"), (abi.GAMMA1, "gamma1"), (abi.SCALE_HEIGHT, "scale_height")):
             st = reftools.compare_stats(ctx.download(fid), z[f"{fname}_{meta['nsnap']}"])
             assert st["n_diff"] == 0, (name, fname, st)
-    if ctx.params.alpha_mode:  # the grids get_alpha works with, as written by the reference at the last snapshot
+    if ctx.params.alpha_mode or ctx.params.cooling_scurve:  # the grids get_alpha / scurve_cooling work with, as written by the reference at the last snapshot
         from fargocpt_b200 import abi
-        for fid, fname in ((abi.TEMPERATURE, "Temperature"), (abi.VISCOSITY, "viscosity")):
+        for fid, fname in ((abi.TEMPERATURE, "Temperature"), (abi.VISCOSITY, "viscosity"), (abi.QMINUS, "Qminus"), (abi.QPLUS, "Qplus")):
             if f"{fname}_{meta['nsnap']}" in z.files:
                 st = reftools.compare_stats(ctx.download(fid), z[f"{fname}_{meta['nsnap']}"])
                 assert st["n_diff"] == 0, (name, fname, st)
