@@ -1392,14 +1392,27 @@ struct Run {
     {
 	bool masses_changed = false;
 	for (size_t k = 0; k < bodies.size(); ++k) {
+	    masses_changed = accrete_onto(k, dt) || masses_changed;
+	    // AccreteOntoPlanets refreshes the Roche radii INSIDE its loop over the bodies (accretion.cpp:486-515): once one body
+	    // has gained mass, after that body and after every later one — so a later body's Hill radius, and every cubic
+	    // smoothing radius, sees one Newton step of update_l1 per remaining body, not one per step
+	    if (masses_changed && bodies.size() > 1)
+		update_roche_radii();
+	}
+    }
+    // one body of AccreteOntoPlanets; true if it gained mass
+    bool accrete_onto(size_t k, double dt)
+    {
+	bool masses_changed = false;
+	{
 	    Body &b = bodies[k];
 	    if (!(b.rec.acc > 0.0) || !(b.orbital_period > 0.0))
-		continue;
+		return false;
 	    std::string method = "kley";
 	    if (k < cfg.nbody.size() && cfg.nbody[k].count("accretion method"))
 		method = lower(cfg.nbody[k].at("accretion method"));
 	    if (method == "no" || method == "none")
-		continue;
+		return false;
 	    if (method != "kley" && method != "sinkhole" && method != "viscous")
 		die("accretion method '%s' is not supported by this driver (kley, sinkhole, viscous)", method);
 	    if (method == "viscous" && cfg.flag("ViscAccretMassflowTest", false))
@@ -1429,7 +1442,12 @@ struct Run {
 		masses_changed = masses_changed || taken[0] > 0;
 	    }
 	}
-	if (masses_changed && bodies.size() > 1) { // update_global_hydro_frame_center_mass + update_roche_radii (accretion.cpp:510-514)
+	return masses_changed;
+    }
+    // update_global_hydro_frame_center_mass + update_roche_radii (accretion.cpp:510-514, planetary_system.cpp:1006-1033)
+    void update_roche_radii()
+    {
+	{
 	    params_hydro_center_mass_changed();
 	    const double M = bodies[0].rec.mass;
 	    for (size_t i = 1; i < bodies.size(); ++i) {

@@ -267,6 +267,10 @@ REFERENCE_SETUPS = [("/root/reference/test/cold_disk_planet/setup.yml", []), ("/
                     # four bodies: eccentric orbits from their elements (Jacobi coordinates), jupiterMass / earthMass units,
                     # cubic (Klahr) smoothing, ramp-up — this repo's own setup file, run through both codes
                     (os.path.join(ROOT, "tests", "golden", "multi_body_setup.yml"), ["--dt", "4e-3"]),
+                    # ... two of them accreting (kley with a cubic smoothing radius, sinkhole) while they feel the disk: the Roche radii
+                    # are refreshed inside AccreteOntoPlanets' loop over the bodies, after every body once one has gained mass
+                    # (accretion.cpp:486-515) — one update per step instead left 2e-10 in the fields after 5 steps
+                    (os.path.join(ROOT, "tests", "golden", "multi_body_accrete_setup.yml"), ["--dt", "4e-3", "--snapshots", "5"]),
                     # Frame: C — the frame follows the planet (refframe::handle_corotation: new OmegaFrame every step, v_azi
                     # corrected through fargo_correct_vazi), Euler / Leapfrog / with DiskFeedback and the predictor indirect term
                     # Fermi-function cut-offs of the initial profiles (also inside the numerically differentiated viscous speed), SetSigma0
