@@ -702,7 +702,8 @@ __global__ void __launch_bounds__(128, 4)
     }
 }
 
-// one thread per record of bmax; a warp evaluates each of its candidate blocks (512 columns of one ring) exactly
+// one thread per record of bmax; the CTA evaluates each of its candidate blocks (512 columns of one ring) exactly, a warp per
+// 128 columns, like a block of k_cfl (the candidates are few: what counts is the latency of one of them)
 __global__ void __launch_bounds__(128)
     k_cfl_candidates(const DevView c, const double *__restrict__ sigma, const double *__restrict__ energy, const double *__restrict__ vr,
 		     const double *__restrict__ vp, const double *__restrict__ qplus, const double *__restrict__ qminus,
@@ -712,22 +713,26 @@ __global__ void __launch_bounds__(128)
     const double L = *lmax;
     const double thr = (L >= 1.0e-250) ? L * (1.0 - 1.0e-9) : -2.0;
     const int rec = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const double v = (rec < nrec) ? bmax[rec] : -3.0;
-    unsigned mask = __ballot_sync(0xffffffffu, v >= thr);
-    if (mask == 0u)
-	return;
+    __shared__ unsigned cand[4];
+    const unsigned mine = __ballot_sync(0xffffffffu, v >= thr);
+    if (lane == 0)
+	cand[w] = mine;
+    __syncthreads();
+    if ((cand[0] | cand[1] | cand[2] | cand[3]) == 0u)
+	return; // whole CTA
     double Amax = -1.0, best = 1.7976931348623157e308;
-    while (mask) {
-	const int b = (rec - lane) + (__ffs(mask) - 1);
-	mask &= mask - 1;
-	const int i = c.first_active + b / gx;
-	const int bx = b - (b / gx) * gx;
-	const double vm = vmean[i];
-	for (int pass = 0; pass < 4; ++pass) {
-	    const int j0 = (bx * 128 + pass * 32 + lane) * 4;
+    for (int q = 0; q < 4; ++q) {
+	unsigned mask = cand[q];
+	while (mask) {
+	    const int b = blockIdx.x * blockDim.x + q * 32 + (__ffs(mask) - 1);
+	    mask &= mask - 1;
+	    const int i = c.first_active + b / gx;
+	    const int bx = b - (b / gx) * gx;
+	    const int j0 = (bx * 128 + w * 32 + lane) * 4;
 	    if (j0 < c.ns)
-		cfl_exact4(c, i, j0, vm, sigma, energy, vr, vp, qplus, qminus, nullptr, nullptr, Amax, best);
+		cfl_exact4(c, i, j0, vmean[i], sigma, energy, vr, vp, qplus, qminus, nullptr, nullptr, Amax, best);
 	}
     }
 #pragma unroll
