@@ -188,3 +188,71 @@ def test_screened_cfl_equals_full_reduction_small_grids(physics, nrad, naz, monk
         out[name], _ = _run(ctx, cfg, orbit, 5)
         ctx.close()
     assert out["gpu"] == out["oracle"]
+
+
+@pytest.mark.parametrize("case", ["nan_cell", "zero_sigma", "negative_energy", "huge_velocity", "tiny_everything", "inf_q", "zero_energy",
+                                  "uniform_state"])
+def test_screened_cfl_on_adversarial_states(case, monkeypatch):
+    """The screen of the two-pass CFL reduction must never hide the cell that owns the maximum, whatever the state: cells whose
+    criterion is NaN (the reference ignores them: `dt_cell < dt` is false), zero / denormal densities (reciprocal seeds overflow),
+    negative energies (c_s = sqrt(negative) is NaN in the reference, c_s^2 < 0 in the screen), velocities near overflow, values
+    so small that every term underflows, and a perfectly uniform state (every block a candidate).  FARGO_B200_CFL=check compares
+    with the full reduction inside the call; the oracle's condition_cfl must give the same double."""
+    from fargocpt_b200 import HydroContext
+    nrad, naz = 40, 1024
+    cfg = synthetic.make_config("adiabatic_planet", nrad, naz)
+    radii = synthetic.radii_from_config(cfg)
+    params = synthetic.params_from_config(cfg)
+    fields = {k: v.copy() for k, v in synthetic.disk_fields(cfg, radii, perturb=1e-2).items()}
+    rng = np.random.default_rng(7)
+    qp = 1e-7 * rng.random((nrad, naz))
+    qm = 1e-7 * rng.random((nrad, naz))
+    S, E, VR, VP = fields["Sigma"], fields["energy"], fields["vrad"], fields["vazi"]
+    if case == "nan_cell":
+        VR[7, 13] = np.nan
+        E[9, 100] = np.nan
+        qp[11, 5] = np.nan
+    elif case == "zero_sigma":
+        S[5, 17] = 0.0
+        S[6, 18] = 5e-324
+        S[20, 700] = 1e-300
+    elif case == "negative_energy":
+        E[8, 8] = -E[8, 8]
+        E[30, 999] = -1e-30
+    elif case == "huge_velocity":
+        VR[12, 50] = 1e160
+        VP[13, 51] = -3e153
+        VR[14, 52] = 1e-160
+    elif case == "tiny_everything":
+        for a in (E, VR, VP):
+            a *= 1e-170
+        S *= 1e-20
+        qp *= 1e-300
+        qm *= 1e-300
+    elif case == "inf_q":
+        qp[15, 3] = np.inf
+        qm[16, 4] = -np.inf
+        qm[17, 5] = 1e300
+    elif case == "zero_energy":
+        E[18, 6] = 0.0
+        qp[18, 6] = qm[18, 6] = 0.0  # 0 / 0 in invdt6
+        E[19, 7] = 0.0
+    elif case == "uniform_state":
+        S[:] = S[:, :1]
+        E[:] = E[:, :1]
+        VR[:] = 0.0
+        VP[:] = VP[:, :1]
+        qp[:] = 0.0
+        qm[:] = 0.0
+    monkeypatch.setenv("FARGO_B200_CFL", "check")
+    out = {}
+    with np.errstate(all="ignore"):
+        for name in ("gpu", "oracle"):
+            ctx = reftools.OracleContext(params, radii) if name == "oracle" else HydroContext(params, radii)
+            _start(ctx, cfg, fields)
+            ctx.upload(abi.QPLUS, qp)
+            ctx.upload(abi.QMINUS, qm)
+            out[name] = ctx.condition_cfl()
+            ctx.close()
+    a, b = out["gpu"], out["oracle"]
+    assert (a == b) or (np.isnan(a) and np.isnan(b)), (case, a, b)
