@@ -315,14 +315,19 @@ class Handle:
         """The mass-weighted columns of monitor/Quantities.dat (fargo_monitor_disk): dict of radius, eccentricity, periastron,
         aspect_ratio, advection_torque, viscous_torque (and the raw ecc_x, ecc_y, mass the first three are formed from, output.cpp:373-423 / quantities.cpp:552-567)."""
         import math
-        out = (C.c_double * 7)()
+        out = (C.c_double * 9)()
         fn = self._fn("monitor_disk")
         fn.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double)]
         fn.restype = C.c_int
         self._check(fn(self.ptr, float(radius_limit), float(mass_fraction), float(frame_angle), out), "monitor_disk")
-        r, ex, ey, h, m, tadv, tvisc = list(out)
+        r, ex, ey, h, m, tadv, tvisc, epot, tgrav = list(out)
         return {"radius": r, "eccentricity": math.sqrt(ex ** 2 + ey ** 2), "periastron": math.atan2(ey, ex), "aspect_ratio": h,
-                "ecc_x": ex, "ecc_y": ey, "mass": m, "advection_torque": tadv, "viscous_torque": tvisc}
+                "ecc_x": ex, "ecc_y": ey, "mass": m, "advection_torque": tadv, "viscous_torque": tvisc,
+                "potential_energy": epot, "gravitational_torque": tgrav}
+
+    def keep_potential(self, on=True):
+        """fargo_keep_potential: the following kicks also store the POTENTIAL grid (for monitor_disk's potential columns)."""
+        self._check(self._call("keep_potential", int(bool(on))), "keep_potential")
 
     def correct_vazi(self, domega):
         """correct_v_azimuthal (SideEuler.cpp:79-95): a corotating frame changed its angular velocity by domega."""
@@ -378,6 +383,8 @@ def load_library():
         lib.fargo_monitor_quantities.restype = C.c_int
         lib.fargo_circumplanetary_mass.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, _DP]
         lib.fargo_circumplanetary_mass.restype = C.c_int
+        lib.fargo_keep_potential.argtypes = [C.c_void_p, C.c_int]
+        lib.fargo_keep_potential.restype = C.c_int
         lib.fargo_monitor_disk.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, _DP]
         lib.fargo_monitor_disk.restype = C.c_int
         lib.fargo_halo_mode.argtypes = [C.c_void_p]

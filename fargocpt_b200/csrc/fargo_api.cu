@@ -130,6 +130,8 @@ struct fargo_ctx {
     // two-pass CFL reduction (kernels_ring.cuh:k_cfl_screen / k_cfl_candidates): per-block maxima of the screen, d_cfl_l = their max
     double *cfl_bmax = nullptr, *d_cfl_l = nullptr;
     double *mon_rings = nullptr; // fargo_monitor_disk: MD_N per-ring sums of the whole mesh
+    bool keep_pot = false;	 // fargo_keep_potential: fused kicks also store the POTENTIAL grid
+    int pot_state = 0;		 // the POTENTIAL grid: 0 zeros (no kick yet, like the reference's), 1 of the last kick, 2 older
     // FARGO_B200_FUSE_ARTVISC=1: the artificial-viscosity stage runs inside k_fused_sources<.., AV = true> instead of as its own
     // kernel.  Bit-identical, 56 bytes per cell less traffic — and slower (5.22 against 2.76 + 2.14 ms at 8192 x 16384: 64 bytes
     // of spills at 128 registers, and these kernels wait on FP64 chains, not on DRAM; profiles/r02_v12_*), so not the default.
@@ -1072,6 +1074,7 @@ extern "C" int fargo_stage_potential(fargo_ctx *c)
     CUDA_OK(cudaSetDevice(c->device));
     LAUNCH(c, k_potential, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, EN(c), c->pot,
 	   (const double *)(c->h_stale ? c->hstale : nullptr), pre_state(c));
+    c->pot_state = 1;
     return 0;
 }
 
@@ -1726,6 +1729,12 @@ extern "C" int fargo_kick(fargo_ctx *c, double dt)
     if (fused) {
 	if (c->v_mid)
 	    return fail("fargo_kick (fused) called mid-step after a per-stage call; finish with fargo_stage_transport first");
+	if (c->keep_pot) { // before the fused kernels consume the pre-accretion state (fargo_dev.h:PreState)
+	    if (fargo_stage_potential(c))
+		return 1;
+	} else if (c->pot_state == 1) {
+	    c->pot_state = 2;
+	}
 	return p.adiabatic ? launch_fused_sources<true>(c, dt) : launch_fused_sources<false>(c, dt);
     }
     if (c->v_mid)
@@ -1971,10 +1980,21 @@ extern "C" int fargo_monitor_quantities(fargo_ctx *c, double radius_limit, doubl
     return 0;
 }
 
+// The fused source-term kernel evaluates the potential of a cell in registers and stores nothing.  With `on`, every following
+// fargo_kick also runs k_potential into the POTENTIAL grid (the staged kernels always do), so that fargo_monitor_disk can form the
+// reference's "potential energy" and "gravitational torque" columns, which read the grid of the LAST kick's start (output.cpp:413,
+// gas_torques.cpp:122-153).  A host switches it on for the step that ends on a monitor time (one extra pass, 0.3 ms at
+// 8192 x 16384) and off again.
+extern "C" int fargo_keep_potential(fargo_ctx *c, int on)
+{
+    c->keep_pot = on != 0;
+    return 0;
+}
+
 // The mass-weighted columns of monitor/Quantities.dat (output.cpp:373-423): see k_monitor_disk.  Per-ring sums on the device,
 // summed over the ranks ring by ring (every rank contributes the rings it owns), then walked in ring order on the host like
 // the reference's root (quantities.cpp:213-233).
-extern "C" int fargo_monitor_disk(fargo_ctx *c, double radius_limit, double mass_fraction, double frame_angle, double out7[7])
+extern "C" int fargo_monitor_disk(fargo_ctx *c, double radius_limit, double mass_fraction, double frame_angle, double out9[9])
 {
     CUDA_OK(cudaSetDevice(c->device));
     if (c->v_mid)
@@ -1987,8 +2007,8 @@ extern "C" int fargo_monitor_disk(fargo_ctx *c, double radius_limit, double mass
     double *d_rings = c->mon_rings;
     CUDA_OK(cudaMemsetAsync(d_rings, 0, nrings * sizeof(double), c->stream));
     dim3 grid(gx, (unsigned)c->v.nr);
-    LAUNCH(c, k_monitor_disk, grid, MQ_THREADS, 0, c->v, c->sigma, EN(c), VRA(c), VPA(c), radius_limit, cos(frame_angle), sin(frame_angle),
-	   c->partials);
+    LAUNCH(c, k_monitor_disk, grid, MQ_THREADS, 0, c->v, c->sigma, EN(c), VRA(c), VPA(c), c->pot, radius_limit, cos(frame_angle),
+	   sin(frame_angle), c->partials);
     LAUNCH(c, k_monitor_disk_rings, (unsigned)((c->v.nr + 127) / 128), 128, 0, c->v, c->partials, (int)gx, nrg, d_rings);
     if (c->v.nranks > 1) {
 	NCCL_OK(g_nccl.AllReduce(d_rings, d_rings, nrings, ncclFloat64, 0 /* ncclSum */, c->comm, c->stream));
@@ -1997,7 +2017,7 @@ extern "C" int fargo_monitor_disk(fargo_ctx *c, double radius_limit, double mass
     std::vector<double> h(nrings);
     CUDA_OK(cudaMemcpyAsync(h.data(), d_rings, nrings * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
-    double sums[MD_N] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    double sums[MD_N] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     for (int q = 1; q < MD_N; ++q)
 	for (int i = 0; i < nrg; ++i)
 	    sums[q] += h[(size_t)q * nrg + i];
@@ -2011,13 +2031,18 @@ extern "C" int fargo_monitor_disk(fargo_ctx *c, double radius_limit, double mass
 	    break;
 	}
     }
-    out7[0] = radius;
-    out7[1] = sums[1] > 0.0 ? sums[2] / sums[1] : 0.0;
-    out7[2] = sums[1] > 0.0 ? sums[3] / sums[1] : 0.0;
-    out7[3] = sums[1] > 0.0 ? sums[4] / sums[1] : 0.0;
-    out7[4] = sums[1];
-    out7[5] = sums[5];
-    out7[6] = sums[6];
+    out9[0] = radius;
+    out9[1] = sums[1] > 0.0 ? sums[2] / sums[1] : 0.0;
+    out9[2] = sums[1] > 0.0 ? sums[3] / sums[1] : 0.0;
+    out9[3] = sums[1] > 0.0 ? sums[4] / sums[1] : 0.0;
+    out9[4] = sums[1];
+    out9[5] = sums[5];
+    out9[6] = sums[6];
+    // the reference reads its POTENTIAL grid as the last kick left it (zeros before the first step).  The fused kernels keep the
+    // potential in registers: the grid is only that of the last kick if the kick was told to store it (fargo_keep_potential)
+    const bool pot_ok = c->v.p.body_force_from_potential && c->pot_state != 2;
+    out9[7] = pot_ok ? -(sums[1] > 0.0 ? sums[7] / sums[1] : 0.0) : std::nan("");
+    out9[8] = pot_ok ? sums[8] : std::nan("");
     return 0;
 }
 

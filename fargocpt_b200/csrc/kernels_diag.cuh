@@ -211,12 +211,13 @@ __global__ void __launch_bounds__(32 * MQ_N) k_monitor_final(const double *__res
 // fargo_monitor_disk can walk the rings in order like the reference's root does:
 // q: 0 ring mass sum(Surf Sigma) of every ring, and over the active cells with Rmed <= radius_limit:
 //    1 mass sum(Sigma Surf), 2 sum(e_x m), 3 sum(e_y m) (eccentricity vector rotated by the frame angle), 4 sum(H / Rb m),
-//    5 advection torque, 6 viscous torque (gas_torques.cpp:11-115 summed by gas_quantity_reduce, quantities.cpp:80-105, 1000-1018)
-#define MD_N 7
+//    5 advection torque, 6 viscous torque (gas_torques.cpp:11-115 summed by gas_quantity_reduce, quantities.cpp:80-105, 1000-1018),
+//    7 sum(Phi m) of the POTENTIAL grid as stored (output.cpp:413-414), 8 gravitational torque (gas_torques.cpp:122-153)
+#define MD_N 9
 __global__ void __launch_bounds__(MQ_THREADS)
     k_monitor_disk(const DevView c, const double *__restrict__ sigma, const double *__restrict__ energy, const double *__restrict__ vr,
-		   const double *__restrict__ vp, const double radius_limit, const double cosF, const double sinF,
-		   double *__restrict__ partials)
+		   const double *__restrict__ vp, const double *__restrict__ pot, const double radius_limit, const double cosF,
+		   const double sinF, double *__restrict__ partials)
 {
     const int i = blockIdx.y;
     double acc[MD_N];
@@ -256,6 +257,12 @@ __global__ void __launch_bounds__(MQ_THREADS)
 		vr_cell *= c.g.invdiffrsup[i];
 		const double vazi_cell = 0.5 * (AT(vp, i, j) + AT(vp, i, jp));
 		acc[5] += -(rmed * rmed) * s * vr_cell * vazi_cell;
+	    }
+	    { // the stored potential: mass-weighted sum and calculate_gravitational_torque (:122-153, BodyForceFromPotential)
+		const int jm = (j == 0) ? ns - 1 : j - 1;
+		acc[7] += AT(pot, i, j) * cell_mass;
+		const double gradphi = (AT(pot, i, jp) - AT(pot, i, jm)) * c.invdphi * 0.5;
+		acc[8] += -s * gradphi * surf;
 	    }
 	    if (i >= 1 && i < c.nr - 1) { // calculate_viscous_torque (:45-115) fills rings 1 .. max_radial - 1
 		const int jm = (j == 0) ? ns - 1 : j - 1;

@@ -73,6 +73,7 @@ int fargo_oracle_accrete_kley(fargo_oracle *, double, double, double, double, do
 int fargo_oracle_monitor_quantities(fargo_oracle *, double, double *);
 int fargo_oracle_monitor_disk(fargo_oracle *, double, double, double, double *);
 int fargo_oracle_circumplanetary_mass(fargo_oracle *, double, double, double, double *);
+int fargo_oracle_keep_potential(fargo_oracle *, int);
 int fargo_oracle_accrete_sinkhole(fargo_oracle *, double, double, double, double, double, double *);
 int fargo_oracle_accrete_viscous(fargo_oracle *, double, double, double, double, double, double *);
 int fargo_oracle_correct_vazi(fargo_oracle *, double);
@@ -1652,8 +1653,8 @@ struct Run {
 
     // output::write_quantities (output.cpp:326-493): one row of monitor/Quantities.dat per monitor step, file version 2.4 with
     // the 35 columns of quantities_file_column_v2_5 (output.cpp:39-75).  The global sums come from fargo_monitor_quantities
-    // and fargo_monitor_disk (device reductions); columns this path does not evaluate (potential and total energy, pdivv,
-    // boundary and damping mass flows, the gravitational torque) are written as nan, never as made-up numbers.
+    // and fargo_monitor_disk (device reductions); columns this path does not evaluate (pdivv, boundary and damping
+    // mass flows) are written as nan, never as made-up numbers.
     bool quantities_header_written = false;
     void write_quantities()
     {
@@ -1704,9 +1705,11 @@ struct Run {
 	row[0] = time, row[1] = q[0], row[3] = q[1], row[5] = q[2], row[6] = q[3], row[8] = q[4], row[9] = q[5];
 	row[12] = q[6], row[13] = q[7];
 	{ // disk radius, eccentricity / periastron, aspect ratio (output.cpp:373-423; AspectRatioMode 0 is all make_params lets through)
-	    double d[7];
+	    double d[9];
 	    CHECK(BK(monitor_disk)(ctx, limit, cfg.num("DiskRadiusMassFraction", 0.99), frame_angle, d));
-	    row[30] = d[5], row[31] = d[6]; // advection and viscous torque (CalculateMonitorQuantitiesForOutput, quantities.cpp:1000-1018)
+	    row[30] = d[5], row[31] = d[6], row[32] = d[8]; // advection, viscous, gravitational torque (quantities.cpp:1000-1018)
+	    row[7] = d[7];			     // gravitationalEnergy (output.cpp:413-414)
+	    row[4] = q[2] + q[3] + d[7];	     // totalEnergy = internalEnergy + kinematicEnergy + gravitationalEnergy (:416-417)
 	    row[2] = d[0];
 	    row[10] = std::sqrt(std::pow(d[1], 2) + std::pow(d[2], 2)); // calculate_disk_ecc_peri (quantities.cpp:552-567)
 	    row[11] = std::atan2(d[2], d[1]);
@@ -1829,6 +1832,10 @@ struct Run {
 	    const double left = time_next_monitor - time;
 	    const bool overshoot = cfl_dt > left, almost_there = left < cfl_dt * (1 + 0.05);
 	    const double step_dt = (overshoot || almost_there) ? left : cfl_dt; // :528-540
+	    // the "potential energy" / "gravitational torque" columns of Quantities.dat read the POTENTIAL grid of the last step's
+	    // start: a step that ends on a monitor time keeps it (the fused kernels otherwise hold the potential in registers)
+	    if (cfg.flag("WriteDiskQuantities", true))
+		CHECK(BK(keep_potential)(ctx, (overshoot || almost_there) ? 1 : 0));
 	    step(step_dt);
 	    ++steps;
 	    fprintf(tl, "%u\t%u\t%llu\t%.17g\t%.17g\n", n_snapshot, n_monitor, (unsigned long long)n_iter, time, step_dt);

@@ -321,7 +321,7 @@ int fargo_circumplanetary_mass(fargo_ctx *ctx, double x, double y, double roche_
 int fargo_monitor_quantities(fargo_ctx *ctx, double radius_limit, double out8[8]);
 
 /* The mass-weighted columns of monitor/Quantities.dat (output.cpp:373-423), all ranks:
- * out7 = { disk radius (quantities::gas_disk_radius quantities.cpp:191-237: Rmed of the ring at which the running sum of the ring
+ * out9 = { disk radius (quantities::gas_disk_radius quantities.cpp:191-237: Rmed of the ring at which the running sum of the ring
  *          masses, the mesh's two ghost rings left out, first exceeds mass_fraction (DiskRadiusMassFraction, default 0.99) x the
  *          mass inside radius_limit),
  *          mass-weighted mean of the cells' eccentricity vector, x and y, rotated by frame_angle into the non-rotating frame
@@ -330,9 +330,18 @@ int fargo_monitor_quantities(fargo_ctx *ctx, double radius_limit, double out8[8]
  *          mass-weighted mean aspect ratio H / Rb (compute_aspectratio, AspectRatioMode 0, :784-806),
  *          the mass these means are weighted with,
  *          advection torque and viscous torque of the disk (gas_torques::calculate_advection_torque / calculate_viscous_torque,
- *          gas_torques.cpp:11-115, summed over the active cells inside radius_limit: quantities.cpp:80-105, 1000-1018) }.
+ *          gas_torques.cpp:11-115, summed over the active cells inside radius_limit: quantities.cpp:80-105, 1000-1018),
+ *          "potential energy" = -(mass-weighted mean of the POTENTIAL grid) (output.cpp:413-414) and the gravitational torque
+ *          (gas_torques::calculate_gravitational_torque, gas_torques.cpp:122-153) — both read the POTENTIAL grid as the last
+ *          kick stored it, like the reference (zeros before the first step); NaN without BodyForceFromPotential, and NaN when
+ *          the last kick did not store the grid (see fargo_keep_potential) }.
  * Per-ring sums on the device in a fixed order, rings added in order on the host. */
-int fargo_monitor_disk(fargo_ctx *ctx, double radius_limit, double mass_fraction, double frame_angle, double out7[7]);
+int fargo_monitor_disk(fargo_ctx *ctx, double radius_limit, double mass_fraction, double frame_angle, double out9[9]);
+
+/* CalculateNbodyPotential stores the POTENTIAL grid (Pframeforce.cpp:21-86); the fused source-term kernel keeps the potential in
+ * registers.  on != 0: every following fargo_kick also stores the grid (one extra pass) for fargo_monitor_disk's potential
+ * columns; a host switches it on for the step that ends on a monitor time.  The staged kernels always store it. */
+int fargo_keep_potential(fargo_ctx *ctx, int on);
 
 /* integer FARGO shifts of the last transport (TransportEuler.cpp:49,220), local rings */
 int fargo_get_nshift(fargo_ctx *ctx, int *out_local_nrad);

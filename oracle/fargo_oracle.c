@@ -2064,9 +2064,12 @@ int fargo_oracle_monitor_quantities(fargo_oracle *o, double radius_limit, double
  *        :481-550, gas_reduce_mass_average :145-182; the caller forms sqrt(ex^2 + ey^2) and atan2(ey, ex), :552-567),
  *        mass-weighted mean aspect ratio SCALE_HEIGHT / Rb (compute_aspectratio mode 0 :784-806), the mass of those means,
  *        and the advection and viscous torques of the disk (gas_torques::calculate_advection_torque / calculate_viscous_torque,
- *        gas_torques.cpp:11-115, summed by gas_quantity_reduce quantities.cpp:80-105 in CalculateMonitorQuantitiesForOutput :1000-1018).
+ *        gas_torques.cpp:11-115, summed by gas_quantity_reduce quantities.cpp:80-105 in CalculateMonitorQuantitiesForOutput :1000-1018),
+ *        the "potential energy" column -(mass-weighted mean of the POTENTIAL grid) (output.cpp:413-414) and the gravitational
+ *        torque (gas_torques.cpp:122-153) — both from the POTENTIAL grid AS STORED, i.e. of the last kick's start (zeros before
+ *        the first step); BodyForceFromPotential only.
  * One rank only (the reference gathers the ring masses on its root). */
-int fargo_oracle_monitor_disk(fargo_oracle *o, double radius_limit, double mass_fraction, double frame_angle, double out7[7])
+int fargo_oracle_monitor_disk(fargo_oracle *o, double radius_limit, double mass_fraction, double frame_angle, double out9[9])
 {
     if (o->nranks != 1)
 	return 1;
@@ -2155,13 +2158,37 @@ int fargo_oracle_monitor_disk(fargo_oracle *o, double radius_limit, double mass_
 	    tvisc += 0.0 + -pow(r, 3.0) * viscosity_cell * sigma_cell * (dphi_dot_dr + 1.0 / (pow(r, 2.0)) * dvr_dphi) * 1.0;
 	}
     }
-    out7[0] = radius;
-    out7[1] = mass > 0.0 ? sum_ex / mass : 0.0;
-    out7[2] = mass > 0.0 ? sum_ey / mass : 0.0;
-    out7[3] = mass > 0.0 ? sum_h / mass : 0.0;
-    out7[4] = mass;
-    out7[5] = tadv;
-    out7[6] = tvisc;
+    double sum_pot = 0.0, mass_pot = 0.0, tgrav = 0.0;
+    for (int i = o->first_active; i < o->active_size; ++i) {
+	if (!(o->rmed[i] <= radius_limit))
+	    continue;
+	for (int j = 0; j < ns; ++j) {
+	    const int jp = j == ns - 1 ? 0 : j + 1, jm = j == 0 ? ns - 1 : j - 1;
+	    const size_t l = IDX(o, i, j);
+	    const double cell_mass = o->sigma[l] * o->surf[i];
+	    mass_pot += cell_mass;
+	    sum_pot += o->potential[l] * cell_mass;
+	    const double gradphi = (o->potential[IDX(o, i, jp)] - o->potential[IDX(o, i, jm)]) * o->invdphi * 0.5;
+	    tgrav += 0.0 + -o->sigma[l] * gradphi * o->surf[i] * 1.0;
+	}
+    }
+    out9[0] = radius;
+    out9[1] = mass > 0.0 ? sum_ex / mass : 0.0;
+    out9[2] = mass > 0.0 ? sum_ey / mass : 0.0;
+    out9[3] = mass > 0.0 ? sum_h / mass : 0.0;
+    out9[4] = mass;
+    out9[5] = tadv;
+    out9[6] = tvisc;
+    const double nan = 0.0 / 0.0;
+    out9[7] = o->p.body_force_from_potential ? -(mass_pot > 0.0 ? sum_pot / mass_pot : 0.0) : nan;
+    out9[8] = o->p.body_force_from_potential ? tgrav : nan;
+    return 0;
+}
+
+/* the oracle keeps the POTENTIAL grid of every kick like the reference: nothing to arm */
+int fargo_oracle_keep_potential(fargo_oracle *o, int on)
+{
+    (void)o, (void)on;
     return 0;
 }
 

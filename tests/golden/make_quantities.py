@@ -26,7 +26,9 @@ COLUMNS = {"mass": 3, "angular_momentum": 5, "internal_energy": 7, "kinetic_ener
            "azimuthal_kinetic_energy": 11, "viscous_dissipation": 14, "luminosity": 15,
            # the mass-weighted columns (fargo_monitor_disk)
            "radius": 4, "eccentricity": 12, "periastron": 13, "aspect_ratio": 26,
-           "advection_torque": 32, "viscous_torque": 33}
+           "advection_torque": 32, "viscous_torque": 33,
+           # ... and the ones that read the POTENTIAL grid of the last step's start
+           "total_energy": 6, "potential_energy": 9, "gravitational_torque": 34}
 
 
 def main():

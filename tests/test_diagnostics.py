@@ -134,6 +134,9 @@ def test_gpu_monitor_quantities_vs_oracle(name, k):
         assert a["radius"] == b["radius"], (a["radius"], b["radius"])
         for q in ("aspect_ratio", "mass", "viscous_torque"):
             assert abs(a[q] - b[q]) <= 1e-12 * abs(b[q]), (q, a[q], b[q])
+        # no kick since the state was loaded: the POTENTIAL grid is the one init_derived / the oracle's derived stage left
+        for q in ("potential_energy", "gravitational_torque"):
+            assert np.isfinite(a[q]) == np.isfinite(b[q]), (q, a[q], b[q])
         # the advection torque is a sum of cell values of both signs: relative to the sum of their magnitudes (~ mass x r v_r v_phi)
         assert abs(a["advection_torque"] - b["advection_torque"]) <= 1e-12 * max(abs(b["advection_torque"]), 1e-3 * b["mass"]), (a, b)
         for q in ("ecc_x", "ecc_y"):  # means of O(h^2) cell values that cancel around the ring: absolute
@@ -250,3 +253,36 @@ def test_gpu_reductions_on_grids_with_few_sectors(naz, physics):
         assert abs(a - b) <= 1e-13 * max(abs(b), 1e-300), (g[2], c[2])
     assert c[2][0] > 0.0  # the zone covers cells: something was accreted
     assert reftools.compare_stats(g[3], c[3])["n_diff"] == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("physics", ["adiabatic_planet", "isothermal_planet"])
+def test_gpu_potential_columns_need_the_kept_grid(physics):
+    """The "potential energy" / "gravitational torque" columns read the POTENTIAL grid of the last kick's start.  The fused kernels
+    hold the potential in registers: after a step without fargo_keep_potential the columns are NaN (never a stale number), with
+    it they equal the oracle's (which stores the grid in every kick like the reference); before the first step the grid is
+    zeros on both sides."""
+    from fargocpt_b200 import HydroContext, synthetic
+    import test_gpu_fullsize as F
+    nrad, naz = 64, 256
+    cfg = synthetic.make_config(physics, nrad, naz)
+    radii = synthetic.radii_from_config(cfg)
+    params = synthetic.params_from_config(cfg)
+    fields = synthetic.disk_fields(cfg, radii, perturb=1e-2)
+    gpu, cpu = HydroContext(params, radii), reftools.OracleContext(params, radii)
+    orbits = [F._start(c, cfg, fields) for c in (gpu, cpu)]
+    a, b = gpu.monitor_disk(), cpu.monitor_disk()
+    assert a["potential_energy"] == b["potential_energy"] == 0.0 and a["gravitational_torque"] == b["gravitational_torque"] == 0.0
+    for c, o in zip((gpu, cpu), orbits):
+        F._run(c, cfg, o, 2)
+    a, b = gpu.monitor_disk(), cpu.monitor_disk()
+    assert np.isnan(a["potential_energy"]) and np.isnan(a["gravitational_torque"]) and np.isfinite(b["potential_energy"])
+    gpu.keep_potential(True)
+    for c, o in zip((gpu, cpu), orbits):
+        F._run(c, cfg, o, 1)
+    a, b = gpu.monitor_disk(), cpu.monitor_disk()
+    assert abs(a["potential_energy"] - b["potential_energy"]) <= 1e-13 * abs(b["potential_energy"]), (a, b)
+    assert abs(a["gravitational_torque"] - b["gravitational_torque"]) <= 1e-12 * max(abs(b["gravitational_torque"]), 1e-6 * b["mass"]), (a, b)
+    gpu.keep_potential(False)
+    F._run(gpu, cfg, orbits[0], 1)
+    assert np.isnan(gpu.monitor_disk()["potential_energy"])

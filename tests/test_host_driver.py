@@ -363,7 +363,9 @@ def test_host_writes_quantities_dat_cpu(name, tmp_path):
     cols = {"mass": 3, "angular_momentum": 5, "internal_energy": 7, "kinetic_energy": 8, "radial_kinetic_energy": 10,
             "azimuthal_kinetic_energy": 11, "viscous_dissipation": 14, "luminosity": 15,
             # the mass-weighted columns (fargo_monitor_disk)
-            "radius": 4, "eccentricity": 12, "periastron": 13, "aspect_ratio": 26, "advection_torque": 32, "viscous_torque": 33}
+            "radius": 4, "eccentricity": 12, "periastron": 13, "aspect_ratio": 26, "advection_torque": 32, "viscous_torque": 33,
+            # from the POTENTIAL grid of the last step's start (fargo_keep_potential)
+            "total_energy": 6, "potential_energy": 9, "gravitational_torque": 34}
     for snap, want in ref.items():
         row = rows[int(snap)]
         assert int(row[0]) == int(snap)
@@ -372,7 +374,7 @@ def test_host_writes_quantities_dat_cpu(name, tmp_path):
                 assert float(row[c]) == want[q], (snap, q, row[c], want[q])
             else:
                 assert float(row[c]) == pytest.approx(want[q], rel=1e-9, abs=1e-300), (snap, q)
-        assert row[6] == "nan" and row[9] == "nan" and row[16] == "nan" and row[34] == "nan"  # total / potential energy, pdivv, gravitational torque
+        assert row[16] == "nan" and row[17] == "nan" and row[25] == "nan"  # pdivv, mass flows
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -764,6 +766,9 @@ def test_gpu_driver_writes_what_the_oracle_bound_driver_writes(setup, over, tmp_
                     assert not has_ecc.any() or np.max(dper[has_ecc]) < 1e-6, f
                     a[:, 12:14] = b[:, 12:14] = 0.0
                 scale = np.maximum(np.abs(a).max(axis=0), 1e-300)
+                if f.startswith("Quantities"):
+                    # torques of an axisymmetric disk are sums that cancel to rounding noise: measured against the disk's mass
+                    scale[32:35] = np.maximum(scale[32:35], 1e-6 * np.abs(a[:, 3]).max())
                 assert np.max(np.abs(a - b) / scale) < 1e-9, f
                 continue
             rel = os.path.relpath(po, outs["oracle"])
