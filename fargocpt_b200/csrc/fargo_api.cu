@@ -697,7 +697,8 @@ extern "C" int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, con
 	const size_t n_acc = (size_t)((c->v.ns + ACC_THREADS - 1) / ACC_THREADS) * nr_ * 3;
 	const size_t n_mq = ((size_t)((c->v.ns + 4 * MQ_THREADS - 1) / (4 * MQ_THREADS)) * nr_ + 1) * MQ_N;
 	const size_t n_dob = (size_t)((c->v.ns + 4 * DOB_THREADS - 1) / (4 * DOB_THREADS)) * nr_ * 4;
-	c->partials_n = std::max(n_acc, std::max(n_mq, n_dob));
+	const size_t n_md = (size_t)((c->v.ns + 4 * MQ_THREADS - 1) / (4 * MQ_THREADS)) * nr_ * MD_N; // fargo_monitor_disk
+	c->partials_n = std::max(std::max(n_acc, n_md), std::max(n_mq, n_dob));
 	TRY(dalloc(c, &c->partials, c->partials_n));
     }
     if (params->leapfrog)
@@ -1732,8 +1733,8 @@ extern "C" int fargo_kick(fargo_ctx *c, double dt)
 	if (c->keep_pot) { // before the fused kernels consume the pre-accretion state (fargo_dev.h:PreState)
 	    if (fargo_stage_potential(c))
 		return 1;
-	} else if (c->pot_state == 1) {
-	    c->pot_state = 2;
+	} else {
+	    c->pot_state = 2; // whatever the grid holds, it is not this kick's
 	}
 	return p.adiabatic ? launch_fused_sources<true>(c, dt) : launch_fused_sources<false>(c, dt);
     }
