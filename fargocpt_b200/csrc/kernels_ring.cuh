@@ -606,7 +606,10 @@ __device__ __forceinline__ void atomic_max_pos_double(double *addr, double v)
 }
 
 // grid as k_cfl; bmax[blockIdx.y * gridDim.x + blockIdx.x] = the block's max of A~ (+inf: always a candidate), *lmax = L
-__global__ void __launch_bounds__(128, 4)
+#ifndef CFL_SCREEN_MINB
+#define CFL_SCREEN_MINB 4
+#endif
+__global__ void __launch_bounds__(128, CFL_SCREEN_MINB)
     k_cfl_screen(const DevView c, const double *__restrict__ sigma, const double *__restrict__ energy, const double *__restrict__ vr,
 		 const double *__restrict__ vp, const double *__restrict__ qplus, const double *__restrict__ qminus,
 		 const double *__restrict__ vmean, double *__restrict__ dt_out, double *__restrict__ bmax, double *__restrict__ lmax)
