@@ -15,7 +15,7 @@ CPUOVERLAP = 7
 
 # enum fargo_field
 (SIGMA, VRAD, VAZI, ENERGY, SIGMA0, VRAD0, VAZI0, ENERGY0, QPLUS, QMINUS, TEMPERATURE, PRESSURE, SOUNDSPEED,
- SCALE_HEIGHT, VISCOSITY, POTENTIAL, T_REYNOLDS, GAMMAEFF, MU, GAMMA1) = range(20)
+ SCALE_HEIGHT, VISCOSITY, POTENTIAL, T_REYNOLDS, GAMMAEFF, MU, GAMMA1, MASSFLOW) = range(21)
 FIELD_NAMES = {SIGMA: "Sigma", VRAD: "vrad", VAZI: "vazi", ENERGY: "energy", QPLUS: "Qplus", QMINUS: "Qminus"}
 VECTOR_FIELDS = (VRAD, VRAD0)
 
@@ -325,6 +325,13 @@ class Handle:
                 "ecc_x": ex, "ecc_y": ey, "mass": m, "advection_torque": tadv, "viscous_torque": tvisc,
                 "potential_energy": epot, "gravitational_torque": tgrav}
 
+    def track_massflow(self, on=True):
+        """fargo_track_massflow: the radial sweep accumulates the MASSFLOW grid (download(abi.MASSFLOW), clear_massflow())."""
+        self._check(self._call("track_massflow", int(bool(on))), "track_massflow")
+
+    def clear_massflow(self):
+        self._check(self._call("clear_massflow"), "clear_massflow")
+
     def keep_potential(self, on=True):
         """fargo_keep_potential: the following kicks also store the POTENTIAL grid (for monitor_disk's potential columns)."""
         self._check(self._call("keep_potential", int(bool(on))), "keep_potential")
@@ -383,6 +390,10 @@ def load_library():
         lib.fargo_monitor_quantities.restype = C.c_int
         lib.fargo_circumplanetary_mass.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, _DP]
         lib.fargo_circumplanetary_mass.restype = C.c_int
+        lib.fargo_track_massflow.argtypes = [C.c_void_p, C.c_int]
+        lib.fargo_track_massflow.restype = C.c_int
+        lib.fargo_clear_massflow.argtypes = [C.c_void_p]
+        lib.fargo_clear_massflow.restype = C.c_int
         lib.fargo_keep_potential.argtypes = [C.c_void_p, C.c_int]
         lib.fargo_keep_potential.restype = C.c_int
         lib.fargo_monitor_disk.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, _DP]

@@ -130,6 +130,8 @@ struct fargo_ctx {
     // two-pass CFL reduction (kernels_ring.cuh:k_cfl_screen / k_cfl_candidates): per-block maxima of the screen, d_cfl_l = their max
     double *cfl_bmax = nullptr, *d_cfl_l = nullptr;
     double *mon_rings = nullptr; // fargo_monitor_disk: MD_N per-ring sums of the whole mesh
+    double *massflow = nullptr;	 // fargo_track_massflow: MASSFLOW grid [nr + 1][ns]
+    bool track_massflow = false;
     bool keep_pot = false;	 // fargo_keep_potential: fused kicks also store the POTENTIAL grid
     int pot_state = 0;		 // the POTENTIAL grid: 0 zeros (no kick yet, like the reference's), 1 of the last kick, 2 older
     // FARGO_B200_FUSE_ARTVISC=1: the artificial-viscosity stage runs inside k_fused_sources<.., AV = true> instead of as its own
@@ -851,6 +853,7 @@ static double *state_ptr(fargo_ctx *c, int f, int *rings)
     case FARGO_MU: return c->v.pv.mu;
     case FARGO_GAMMA1: return c->v.pv.g1;
     case FARGO_TEMPERATURE: return c->v.t_alpha; // AlphaMode 1 keeps the TEMPERATURE grid (nullptr otherwise: evaluated on download)
+    case FARGO_MASSFLOW: *rings = c->v.nr + 1; return c->massflow; // nullptr unless fargo_track_massflow
     case FARGO_SCALE_HEIGHT: return c->v.pv.H; // PVTE keeps the SCALE_HEIGHT grid (nullptr otherwise: evaluated on download)
     }
     return nullptr;
@@ -1384,7 +1387,14 @@ static int launch_transport(fargo_ctx *c, double dt, const double *vr_in, const 
     CUDA_OK(cudaEventRecord(c->ev_join, c->stream2));
     {
 	dim3 grid((unsigned)((v.ns + 127) / 128), (unsigned)((v.nr + c->rad_chunk - 1) / c->rad_chunk));
-	if (v.p.adiabatic)
+	if (c->track_massflow) { // WriteMassFlow: the same sweep also accumulates the MASSFLOW grid
+	    if (v.p.adiabatic)
+		LAUNCH_NAMED(c, c->stream, "(k_transport_radial<LIM, true>)[+massflow]", (k_transport_radial<LIM, true, true>), grid, 128, 0, v,
+			     c->sigma, vr_in, vp_in, EN(c), c->t_sigma, c->t_rmp, c->t_rmm, c->t_amp, c->t_amm, c->t_e, dt, c->rad_chunk, c->massflow);
+	    else
+		LAUNCH_NAMED(c, c->stream, "(k_transport_radial<LIM, false>)[+massflow]", (k_transport_radial<LIM, false, true>), grid, 128, 0, v,
+			     c->sigma, vr_in, vp_in, EN(c), c->t_sigma, c->t_rmp, c->t_rmm, c->t_amp, c->t_amm, c->t_e, dt, c->rad_chunk, c->massflow);
+	} else if (v.p.adiabatic)
 	    LAUNCH(c, (k_transport_radial<LIM, true>), grid, 128, 0, v, c->sigma, vr_in, vp_in, EN(c), c->t_sigma, c->t_rmp, c->t_rmm,
 		   c->t_amp, c->t_amm, c->t_e, dt, c->rad_chunk);
 	else
@@ -1978,6 +1988,23 @@ extern "C" int fargo_monitor_quantities(fargo_ctx *c, double radius_limit, doubl
     }
     CUDA_OK(cudaMemcpyAsync(out8, d_out, MQ_N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// WriteMassFlow (parameters.cpp:334-335, TransportEuler.cpp:610-616): see fargo_b200.h
+extern "C" int fargo_track_massflow(fargo_ctx *c, int on)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    if (on && !c->massflow && dalloc(c, &c->massflow, (size_t)(c->v.nr + 1) * c->v.ns)) // zeroed
+	return 1;
+    c->track_massflow = on != 0;
+    return 0;
+}
+extern "C" int fargo_clear_massflow(fargo_ctx *c)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    if (c->massflow)
+	CUDA_OK(cudaMemsetAsync(c->massflow, 0, (size_t)(c->v.nr + 1) * c->v.ns * sizeof(double), c->stream));
     return 0;
 }
 

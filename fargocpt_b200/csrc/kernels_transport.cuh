@@ -23,12 +23,15 @@
 #else
 #define TR_BOUNDS __launch_bounds__(128)
 #endif
-template <int LIM, bool ADIABATIC>
+// MF (WriteMassFlow, TransportEuler.cpp:610-616): the mass through the inner interface of cell n in this step, F2[0], is also
+// added to massflow[n] — a separate instantiation, the kernel of every other run is unchanged.
+template <int LIM, bool ADIABATIC, bool MF = false>
 __global__ void TR_BOUNDS
     k_transport_radial(const DevView c, const double *__restrict__ sigma, const double *__restrict__ vr,
 		       const double *__restrict__ vp, const double *__restrict__ energy, double *__restrict__ o_sigma,
 		       double *__restrict__ o_rmp, double *__restrict__ o_rmm, double *__restrict__ o_amp,
-		       double *__restrict__ o_amm, double *__restrict__ o_e, const double dt, const int chunk)
+		       double *__restrict__ o_amm, double *__restrict__ o_e, const double dt, const int chunk,
+		       double *__restrict__ massflow = nullptr)
 {
     constexpr int NB = ADIABATIC ? 6 : 5; // bases: Sigma, w_rm+, w_rm-, w_am+, w_am-, (w_e)
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -211,6 +214,8 @@ __global__ void TR_BOUNDS
 	    AT(o_amm, n, j) = fm_madd(F2[4] - F1[4], is, raw2[4]);
 	    if (ADIABATIC)
 		AT(o_e, n, j) = fm_madd(F2[5] - F1[5], is, raw2[5]);
+	    if (MF) // (+ varq_sup of the mesh's last ring, :613-615: the flux through interface nr, which is 0)
+		AT(massflow, n, j) += F2[0];
 	}
 #pragma unroll
 	for (int q = 0; q < NB; ++q) {

@@ -74,6 +74,8 @@ int fargo_oracle_monitor_quantities(fargo_oracle *, double, double *);
 int fargo_oracle_monitor_disk(fargo_oracle *, double, double, double, double *);
 int fargo_oracle_circumplanetary_mass(fargo_oracle *, double, double, double, double *);
 int fargo_oracle_keep_potential(fargo_oracle *, int);
+int fargo_oracle_track_massflow(fargo_oracle *, int);
+int fargo_oracle_clear_massflow(fargo_oracle *);
 int fargo_oracle_accrete_sinkhole(fargo_oracle *, double, double, double, double, double, double *);
 int fargo_oracle_accrete_viscous(fargo_oracle *, double, double, double, double, double, double *);
 int fargo_oracle_correct_vazi(fargo_oracle *, double);
@@ -968,6 +970,8 @@ struct Run {
 	if (nranks > 1 && rank == 0)
 	    unlink((fielddir + "/.nccl_id").c_str());
 #endif
+	if (cfg.flag("WriteMassFlow", false)) // parameters.cpp:334-335
+	    CHECK(BK(track_massflow)(ctx, 1));
     }
 
     // All ranks meet here (host side, through the shared output directory: arrival files of a numbered barrier).
@@ -1626,6 +1630,37 @@ struct Run {
 	    write_field_file(rel + std::get<2>(s) + ".dat", buf.data(), false);
 	}
 	derived_at_init.clear();
+	if (cfg.flag("WriteMassFlow", false)) {
+	    // MASSFLOW (data.cpp:273-278): mass through the inner interface of every cell since the last snapshot, divided by the
+	    // time between snapshots before it is written (quantities::calculate_massflow, quantities.cpp:771-781), as the 2-D file
+	    // and as the azimuthally integrated 1-D file (t_polargrid::write1D, polargrid.cpp:187-282: radius, sum, min, max per
+	    // interface ring), then cleared
+	    std::vector<double> buf(cells(true), 0.0);
+	    CHECK(BK(download_field)(ctx, FARGO_MASSFLOW, buf.data()));
+	    const double denom = nmonitor * monitor_timestep;
+	    const double inv_c = 1.0 / denom; // t_polargrid::operator/= multiplies by the reciprocal (polargrid.cpp:510-521)
+	    const int hi = own_hi + ((rank == nranks - 1) ? 1 : 0);
+	    for (size_t k = (size_t)own_lo * naz; k < (size_t)hi * naz; ++k)
+		buf[k] *= inv_c;
+	    write_field_file(rel + "MassFlow.dat", buf.data(), true);
+	    std::vector<double> one((size_t)(hi - own_lo) * 4);
+	    for (int i = own_lo; i < hi; ++i) {
+		double sum = 0.0, mn = std::numeric_limits<double>::max(), mx = std::numeric_limits<double>::lowest();
+		for (int j = 0; j < naz; ++j) {
+		    const double v = buf[(size_t)i * naz + j];
+		    sum += v;
+		    mn = std::min(mn, v), mx = std::max(mx, v);
+		}
+		double *o = &one[(size_t)(i - own_lo) * 4];
+		o[0] = radii[i], o[1] = sum, o[2] = mn, o[3] = mx; // vector grid: the interface radius Ra
+	    }
+	    const std::string path = fielddir + "/" + rel + "MassFlow1D.dat";
+	    const int fd = open(path.c_str(), O_WRONLY | O_CREAT | (nranks == 1 ? O_TRUNC : 0), 0644);
+	    if (fd < 0 || pwrite(fd, one.data(), one.size() * sizeof(double), (off_t)own_lo * 4 * sizeof(double)) != (ssize_t)(one.size() * sizeof(double)))
+		die("cannot write %s", path);
+	    close(fd);
+	    CHECK(BK(clear_massflow)(ctx));
+	}
 	MiscEntry m;
 	m.timestep = n_snapshot, m.nTimeStep = n_monitor, m.time = time, m.OmegaFrame = omega_frame, m.FrameAngle = frame_angle;
 	m.last_dt = last_dt, m.N_iter = n_iter;

@@ -56,7 +56,9 @@ enum fargo_field {
     FARGO_GAMMAEFF = 17,   /* gammaeff.dat, mu.dat, gamma1.dat: the PVTE grids (data.cpp:36-47), stored when params.pvte */
     FARGO_MU = 18,
     FARGO_GAMMA1 = 19,
-    FARGO_NFIELDS = 20
+    FARGO_MASSFLOW = 20,   /* MassFlow.dat [nrad+1][naz]: mass through the inner interface of every cell, summed over the steps
+			    * since the last fargo_clear_massflow (VanLeerRadial, TransportEuler.cpp:610-616); fargo_track_massflow */
+    FARGO_NFIELDS = 21
 };
 
 enum fargo_artvisc { FARGO_ARTVISC_NONE = 0, FARGO_ARTVISC_TW = 1, FARGO_ARTVISC_SN = 2 };
@@ -337,6 +339,14 @@ int fargo_monitor_quantities(fargo_ctx *ctx, double radius_limit, double out8[8]
  *          the last kick did not store the grid (see fargo_keep_potential) }.
  * Per-ring sums on the device in a fixed order, rings added in order on the host. */
 int fargo_monitor_disk(fargo_ctx *ctx, double radius_limit, double mass_fraction, double frame_angle, double out9[9]);
+
+/* WriteMassFlow (parameters.cpp:334-335): VanLeerRadial adds the mass that crosses the inner interface of every cell in a step to
+ * the MASSFLOW grid (TransportEuler.cpp:610-616); the output divides it by the time between snapshots and clears it
+ * (quantities::calculate_massflow quantities.cpp:771-781, data.cpp:273-278).  on != 0: the radial transport sweep accumulates the
+ * grid (a separate instantiation of the kernel; 16 bytes per cell more traffic), readable as FARGO_MASSFLOW;
+ * fargo_clear_massflow zeroes it. */
+int fargo_track_massflow(fargo_ctx *ctx, int on);
+int fargo_clear_massflow(fargo_ctx *ctx);
 
 /* CalculateNbodyPotential stores the POTENTIAL grid (Pframeforce.cpp:21-86); the fused source-term kernel keeps the potential in
  * registers.  on != 0: every following fargo_kick also stores the grid (one extra pass) for fargo_monitor_disk's potential

@@ -49,6 +49,7 @@ typedef struct fargo_oracle {
     fargo_pvte_tables *pv;
     int kicks_this_step; /* fargo_oracle_kick calls since the last fargo_oracle_finish_step */
     double *qplus, *qminus, *divv, *trr, *tpp, *trp, *qr, *qphi, *nusig, *nusig_rp, *cf_r, *cf_phi, *tau_eff;
+    double *massflow; /* MASSFLOW grid [nr + 1][ns], NULL unless fargo_oracle_track_massflow */
     /* transport scratch (TransportEuler.cpp:32-46) */
     double *rmp, *rmm, *amp, *amm, *vres, *work, *qrstar, *densstar, *densint, *tempshift, *dq, *vmean;
     int *nshift;
@@ -259,6 +260,7 @@ static double *field_ptr(fargo_oracle *o, int f, int *rings)
     case FARGO_GAMMAEFF: return o->gamma_eff;
     case FARGO_MU: return o->mu_cell;
     case FARGO_GAMMA1: return o->gamma1;
+    case FARGO_MASSFLOW: *rings = o->nr + 1; return o->massflow;
     }
     return NULL;
 }
@@ -1548,7 +1550,7 @@ static void compute_star_radial(fargo_oracle *o, const double *qbase, const doub
 }
 
 /* VanLeerRadial :545-620 */
-static void vanleer_radial(fargo_oracle *o, const double *vr, double *qbase, double dt)
+static void vanleer_radial(fargo_oracle *o, const double *vr, double *qbase, double dt, int is_density)
 {
     const int Nr = o->nr, Nphi = o->ns;
     const size_t n = (size_t)Nr * Nphi;
@@ -1563,6 +1565,11 @@ static void vanleer_radial(fargo_oracle *o, const double *vr, double *qbase, dou
 	    const double varq_inf = dt * o->dphi * o->rinf[nr] * o->qrstar[c] * o->densstar[c] * vr[c];
 	    const double varq_sup = dt * o->dphi * o->rsup[nr] * o->qrstar[lip] * o->densstar[lip] * vr[lip];
 	    qbase[c] += (varq_inf - varq_sup) * o->invsurf[nr];
+	    if (is_density && o->massflow) { /* parameters::write_massflow, :610-616 */
+		o->massflow[c] += varq_inf;
+		if (o->rank == o->nranks - 1 && nr == Nr - 1)
+		    o->massflow[c] += varq_sup;
+	    }
 	}
     }
 }
@@ -1669,13 +1676,13 @@ int fargo_oracle_stage_transport(fargo_oracle *o, double dt)
     memset(o->qrstar + n, 0, (size_t)Nphi * sizeof(double));
     compute_star_radial(o, o->sigma, o->vrad, o->densstar, dt);
     memcpy(o->densint, o->sigma, n * sizeof(double));
-    vanleer_radial(o, o->vrad, o->rmp, dt);
-    vanleer_radial(o, o->vrad, o->rmm, dt);
-    vanleer_radial(o, o->vrad, o->amp, dt);
-    vanleer_radial(o, o->vrad, o->amm, dt);
+    vanleer_radial(o, o->vrad, o->rmp, dt, 0);
+    vanleer_radial(o, o->vrad, o->rmm, dt, 0);
+    vanleer_radial(o, o->vrad, o->amp, dt, 0);
+    vanleer_radial(o, o->vrad, o->amm, dt, 0);
     if (o->p.adiabatic)
-	vanleer_radial(o, o->vrad, o->energy, dt);
-    vanleer_radial(o, o->vrad, o->sigma, dt);
+	vanleer_radial(o, o->vrad, o->energy, dt, 0);
+    vanleer_radial(o, o->vrad, o->sigma, dt, 1);
     /* OneWindTheta :270-288 */
     for (int nr = 0; nr < Nr; ++nr) { /* compute_average_azimuthal_velocity :174-189 */
 	double s = 0.0;
@@ -2182,6 +2189,24 @@ int fargo_oracle_monitor_disk(fargo_oracle *o, double radius_limit, double mass_
     const double nan = 0.0 / 0.0;
     out9[7] = o->p.body_force_from_potential ? -(mass_pot > 0.0 ? sum_pot / mass_pot : 0.0) : nan;
     out9[8] = o->p.body_force_from_potential ? tgrav : nan;
+    return 0;
+}
+
+/* WriteMassFlow: the MASSFLOW grid VanLeerRadial accumulates (TransportEuler.cpp:610-616) */
+int fargo_oracle_track_massflow(fargo_oracle *o, int on)
+{
+    if (on && !o->massflow)
+	o->massflow = (double *)calloc((size_t)(o->nr + 1) * o->ns, sizeof(double));
+    if (!on && o->massflow) {
+	free(o->massflow);
+	o->massflow = NULL;
+    }
+    return 0;
+}
+int fargo_oracle_clear_massflow(fargo_oracle *o)
+{
+    if (o->massflow)
+	memset(o->massflow, 0, (size_t)(o->nr + 1) * o->ns * sizeof(double));
     return 0;
 }
 

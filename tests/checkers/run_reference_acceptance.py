@@ -9,6 +9,8 @@ setups of the same physics (tests/golden/*_setup.yml) — no reference tree need
   test/spreading_ring      calc_deviation.py:38-66    mean |Sigma / Sigma_analytic - 1| < 0.007 at t = 314.159 (39 870 hydro steps)
   test/cold_disk_planet    calc_deviation.py:24-35    max |T(100 orbits) / T(0) - 1| < 0.1 (14 000 hydro steps)
   test/irradiation         check_results.py:40-120    max |T / T_theory - 1| < 0.03 for 2 < r < 15 au after 62 800 time units (168 596 steps)
+  test/steady_state_accretion  check_results.py:69-116  max | |MassFlow| / (1e-8 solMass / yr) - 1 | < 2.2e-4 for 20 < r < 60 au after
+                                                        3 141 526 time units (110 240 steps; the time-averaged mass flow of WriteMassFlow)
 Prints one line per check and exits non-zero if one fails."""
 import os
 import struct
@@ -108,6 +110,21 @@ def main():
     dev = float(np.max(np.abs(T - Ttheo)[sel] / Ttheo[sel]))
     ok &= dev < 0.03
     print(f"irradiation ({nr} x {naz}): max |T / T_theory - 1| = {dev:.5f} (< 0.03)  ({steps} steps, {secs:.1f} s)  {'PASS' if dev < 0.03 else 'FAIL'}")
+    # --- steady-state accretion: the mass flow through every interface, averaged over the last snapshot interval (WriteMassFlow:
+    # MassFlow1D.dat = radius, azimuthal sum, min, max per interface), against the accretion rate of the initial profile
+    cfg = yaml.safe_load(open(os.path.join(GOLDEN, "steady_state_accretion_setup.yml")))
+    out, steps, secs = run(exe, cfg, int(cfg["Nsnapshots"]))
+    units = yaml.safe_load(open(os.path.join(out, "units.yml")))
+    to_msun_yr = float(units["mass"]["cgs value"]) / float(units["time"]["cgs value"]) / (1.98847e33 / 3.15576e7)
+    ri = np.loadtxt(os.path.join(out, "used_rad.dat"))
+    rc = 2.0 / 3.0 * (ri[1:] ** 3 - ri[:-1] ** 3) / (ri[1:] ** 2 - ri[:-1] ** 2)
+    mf = np.fromfile(os.path.join(out, "snapshots", str(cfg["Nsnapshots"]), "MassFlow1D.dat")).reshape(-1, 4)
+    assert np.array_equal(mf[:, 0], ri)
+    diffval = np.abs(mf[1:-1, 1] * to_msun_yr) / 1e-8 - 1  # data[1:-1] of check_results.py
+    inds = (rc[1:] > 20) & (rc[:-1] < 60)		   # x_[1:] > xmin and x_[:-1] < xmax, x_ the cell centres
+    dev = float(np.max(np.abs(diffval[inds])))
+    ok &= dev < 2.2e-4
+    print(f"steady_state_accretion: max | |Mdot| / 1e-8 Msun/yr - 1 | = {dev:.3e} (< 2.2e-4)  ({steps} steps, {secs:.1f} s)  {'PASS' if dev < 2.2e-4 else 'FAIL'}")
     sys.exit(0 if ok else 1)
 
 

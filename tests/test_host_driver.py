@@ -472,6 +472,32 @@ def test_host_circumplanetary_mass_is_the_references(name, tmp_path):
         assert float(rows[int(snap)][9]) == pytest.approx(want["mdcp"], rel=1e-10), (snap, rows[int(snap)][9], want["mdcp"])
 
 
+def _massflow_check(exe, tmp_path):
+    """WriteMassFlow (TransportEuler.cpp:610-616, quantities.cpp:771-781, polargrid.cpp:187-282): MassFlow.dat and MassFlow1D.dat of
+    the steady-state accretion setup (198 x 1), shortened to two snapshots of three monitor steps, against the files the
+    unmodified reference wrote for the same setup (tests/golden/steady_state_massflow.npz)."""
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "tests", "golden", "steady_state_accretion_setup.yml")))
+    cfg["Nsnapshots"], cfg["Nmonitor"] = 2, 3
+    yml, out = str(tmp_path / "setup.yml"), str(tmp_path / "out")
+    yaml.safe_dump(cfg, open(yml, "w"), sort_keys=False)
+    _run_start(exe, yml, out, 2)
+    ref = np.load(os.path.join(ROOT, "tests", "golden", "steady_state_massflow.npz"))
+    for k in (1, 2):
+        for f in ("MassFlow", "MassFlow1D", "Sigma"):
+            got = np.fromfile(os.path.join(out, "snapshots", str(k), f + ".dat"))
+            assert np.array_equal(got, ref[f"{f}_{k}"]), (k, f, float(np.abs(got - ref[f"{f}_{k}"]).max()))
+    assert np.abs(ref["MassFlow_2"]).max() > 0
+
+
+def test_host_writes_the_references_massflow_files_cpu(tmp_path):
+    _massflow_check(_oracle_exe(), tmp_path)
+
+
+@pytest.mark.gpu
+def test_host_writes_the_references_massflow_files_gpu(tmp_path):
+    _massflow_check(os.path.join(ROOT, "host", "fargocpt_b200"), tmp_path)
+
+
 def test_host_start_reads_2d_profiles_like_the_reference(tmp_path):
     """SigmaCondition / EnergyCondition: 2D — non-axisymmetric profiles read from raw files (t_polargrid::read2D), through the
     reference and through `fargocpt_b200 start`."""
