@@ -17,7 +17,7 @@ CPUOVERLAP = 7
 (SIGMA, VRAD, VAZI, ENERGY, SIGMA0, VRAD0, VAZI0, ENERGY0, QPLUS, QMINUS, TEMPERATURE, PRESSURE, SOUNDSPEED,
  SCALE_HEIGHT, VISCOSITY, POTENTIAL, T_REYNOLDS, GAMMAEFF, MU, GAMMA1, MASSFLOW) = range(21)
 FIELD_NAMES = {SIGMA: "Sigma", VRAD: "vrad", VAZI: "vazi", ENERGY: "energy", QPLUS: "Qplus", QMINUS: "Qminus"}
-VECTOR_FIELDS = (VRAD, VRAD0)
+VECTOR_FIELDS = (VRAD, VRAD0, MASSFLOW)  # grids on the radial interfaces: nrad + 1 rings
 
 ARTVISC = {"none": 0, "tw": 1, "sn": 2}
 LIMITER = {"vanleer": 0, "mc": 1}

@@ -286,3 +286,30 @@ def test_gpu_potential_columns_need_the_kept_grid(physics):
     gpu.keep_potential(False)
     F._run(gpu, cfg, orbits[0], 1)
     assert np.isnan(gpu.monitor_disk()["potential_energy"])
+
+
+@pytest.mark.gpu
+def test_gpu_massflow_grid_vs_oracle():
+    """fargo_track_massflow: the MASSFLOW grid the radial sweep accumulates (TransportEuler.cpp:610-616) against the oracle's, bit
+    for bit, over several steps; fargo_clear_massflow zeroes it; an interface grid ([nrad + 1][naz])."""
+    from fargocpt_b200 import HydroContext, synthetic
+    import test_gpu_fullsize as F
+    nrad, naz = 48, 131
+    cfg = synthetic.make_config("adiabatic_planet", nrad, naz)
+    radii = synthetic.radii_from_config(cfg)
+    params = synthetic.params_from_config(cfg)
+    fields = synthetic.disk_fields(cfg, radii, perturb=2e-2)
+    fields["vrad"] = fields["vrad"] + 1e-3 * np.cos(np.arange(naz) * 2 * np.pi * 3 / naz)[None, :]
+    out = {}
+    for name, ctx in (("gpu", HydroContext(params, radii)), ("cpu", reftools.OracleContext(params, radii))):
+        orbit = F._start(ctx, cfg, fields)
+        ctx.track_massflow(True)
+        F._run(ctx, cfg, orbit, 4)
+        mf = ctx.download(abi.MASSFLOW)
+        assert mf.shape == (nrad + 1, naz)
+        ctx.clear_massflow()
+        out[name] = (mf, ctx.download(abi.MASSFLOW))
+        ctx.close()
+    st = reftools.compare_stats(out["gpu"][0], out["cpu"][0])
+    assert st["n_diff"] == 0, st
+    assert np.abs(out["cpu"][0]).max() > 0 and not out["gpu"][1].any() and not out["cpu"][1].any()
