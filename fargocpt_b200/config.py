@@ -126,6 +126,7 @@ def params_from_config(cfg, consts, nrad, naz, temp_unit_K=1.0, units=None):
         d.setdefault("bc_vazi", [0, 0])[side] = abi.BC[va]
         d.setdefault("keplerian_azimuthal_factor", [1.0, 1.0])[side] = float(
             get(name + "BoundaryVaziKeplerianFactor", 1.0))
+    d["balanced_vazi_sq"] = [0.0, 0.0]  # filled by balanced_vazi_sq() once the radii are known
     d["correct_disk_selfgravity"] = int(_flag(get("CorrectDiskSelfgravity"), not _flag(get("SelfGravity"), False)))
     d["damping"] = int(_flag(get("Damping"), False))
     d["damping_inner_limit"] = float(get("DampingInnerLimit", 1.05))
@@ -138,3 +139,22 @@ def params_from_config(cfg, consts, nrad, naz, temp_unit_K=1.0, units=None):
     return d
 
 
+
+
+def balanced_vazi_sq(d, cfg, radii):
+    """v_sq of boundary_conditions::balanced_boundary (balanced.cpp:23-52) for the two ghost rings: pow(v_K, 2) x (pressure support
+    + smoothing-derivative support), Theo.cpp:122-148; no profile cut-off, no quadrupole term, no self-gravity."""
+    import math
+    out = []
+    for i in (0, len(radii) - 2):
+        ri, rs = float(radii[i]), float(radii[i + 1])
+        R = 2.0 / 3.0 * (math.pow(rs, 3) - math.pow(ri, 3))
+        R = R / (math.pow(rs, 2) - math.pow(ri, 2))
+        vk_2 = math.pow(math.sqrt(d["G"] * d["hydro_center_mass"] / R), 2)
+        h = d["aspectratio_ref"] * math.pow(R, d["flaring_index"])
+        eps = d["thickness_smoothing"]
+        support = 0.0
+        support += (2.0 * d["flaring_index"] - 1.0 - d["sigma_slope"]) * math.pow(h, 2)
+        support += (1.0 + (d["flaring_index"] + 1.0) * math.pow(h * eps, 2)) / math.pow(math.sqrt(1 + math.pow(h * eps, 2)), 3)
+        out.append(vk_2 * support)
+    return out

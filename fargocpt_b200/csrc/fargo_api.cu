@@ -1343,9 +1343,17 @@ extern "C" int fargo_stage_boundary(fargo_ctx *c, double dt, int final_call)
     }
     // keplerian_azimuthal.cpp:29-38, :51-59 (host: sqrt with glibc == IEEE, value is per call)
     const int Irad = c->v.nr - 1;
-    const double vk_in = p.keplerian_azimuthal_factor[0] * sqrt(p.G * p.hydro_center_mass / c->h_rmed[0]) - c->h_rmed[0] * c->v.b.omega_frame;
-    const double vk_out =
+    double vk_in = p.keplerian_azimuthal_factor[0] * sqrt(p.G * p.hydro_center_mass / c->h_rmed[0]) - c->h_rmed[0] * c->v.b.omega_frame;
+    double vk_out =
 	p.keplerian_azimuthal_factor[1] * sqrt(p.G * p.hydro_center_mass / c->h_rmed[Irad]) - c->h_rmed[Irad] * c->v.b.omega_frame;
+    if (p.bc_vazi[0] == FARGO_BC_BALANCED) { // balanced.cpp:62-65: sqrt(v_sq), then the frame rotation
+	vk_in = sqrt(p.balanced_vazi_sq[0]);
+	vk_in -= c->h_rmed[0] * c->v.b.omega_frame;
+    }
+    if (p.bc_vazi[1] == FARGO_BC_BALANCED) {
+	vk_out = sqrt(p.balanced_vazi_sq[1]);
+	vk_out -= c->h_rmed[Irad] * c->v.b.omega_frame;
+    }
     LAUNCH(c, k_boundary, (unsigned)((c->v.ns + 255) / 256), 256, 0, c->v, c->sigma, EN(c), v.vr, v.vp, c->sigma0, c->energy0,
 	   c->vr0, c->vp0, vk_in, vk_out);
     return 0;

@@ -109,6 +109,12 @@ __global__ void __launch_bounds__(256)
 		AT(vp, 0, j) = AT(vp, 1, j);
 	    else if (c.p.bc_vazi[0] == FARGO_BC_REFERENCE)
 		AT(vp, 0, j) = AT(vp0, 0, j);
+	    else if (c.p.bc_vazi[0] == FARGO_BC_BALANCED) // balanced.cpp:23-75 (value computed on the host)
+		AT(vp, 0, j) = vkep_inner;
+	    else if (c.p.bc_vazi[0] == FARGO_BC_ZEROSHEAR) { // zero_shear.cpp:20-36
+		const double Omega_active = AT(vp, 1, j) / c.g.rmed[1];
+		AT(vp, 0, j) = c.g.rmed[0] * Omega_active;
+	    }
 	}
 	if (last) {
 	    if (c.p.bc_vazi[1] == FARGO_BC_KEPLERIAN) // keplerian_azimuthal.cpp:41-60
@@ -117,6 +123,12 @@ __global__ void __launch_bounds__(256)
 		AT(vp, Irad, j) = AT(vp, Irad - 1, j);
 	    else if (c.p.bc_vazi[1] == FARGO_BC_REFERENCE)
 		AT(vp, Irad, j) = AT(vp0, Irad, j);
+	    else if (c.p.bc_vazi[1] == FARGO_BC_BALANCED)
+		AT(vp, Irad, j) = vkep_outer;
+	    else if (c.p.bc_vazi[1] == FARGO_BC_ZEROSHEAR) { // zero_shear.cpp:38-54
+		const double Omega_active = AT(vp, Irad - 1, j) / c.g.rmed[Irad - 1];
+		AT(vp, Irad, j) = c.g.rmed[Irad] * Omega_active;
+	    }
 	}
     }
 }

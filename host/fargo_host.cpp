@@ -430,6 +430,8 @@ static fargo_params make_params(const Config &c, const CodeConstants &k, int nra
     p.imposed_disk_drift = c.num("ImposedDiskDrift", 0.0);
     const std::vector<std::pair<std::string, int>> BC = {{"none", 0}, {"zerogradient", 1}, {"zero_gradient", 1}, {"outflow", 2},
 							  {"reflecting", 3}, {"keplerian", 4}, {"reference", 5}};
+    const std::vector<std::pair<std::string, int>> BC_VAZI = {{"none", 0}, {"zerogradient", 1}, {"zero_gradient", 1}, {"keplerian", 4},
+							       {"reference", 5}, {"zeroshear", 6}, {"balanced", 7}};
     const char *sides[2] = {"Inner", "Outer"};
     for (int s = 0; s < 2; ++s) { // composite names boundary_conditions/config.cpp:345-436, else the individual keys
 	const std::string comp = lower(c.str(std::string(sides[s]) + "Boundary", "individual"));
@@ -453,7 +455,7 @@ static fargo_params make_params(const Config &c, const CodeConstants &k, int nra
 	p.bc_sigma[s] = enum_of(bs, BC, "boundary");
 	p.bc_energy[s] = enum_of(be, BC, "boundary");
 	p.bc_vrad[s] = enum_of(bvr, BC, "boundary");
-	p.bc_vazi[s] = enum_of(c.str(std::string(sides[s]) + "BoundaryVazi", "keplerian"), BC, "boundary");
+	p.bc_vazi[s] = enum_of(c.str(std::string(sides[s]) + "BoundaryVazi", "keplerian"), BC_VAZI, "v_azi boundary");
 	p.keplerian_azimuthal_factor[s] = c.num(std::string(sides[s]) + "BoundaryVaziKeplerianFactor", 1.0);
     }
     p.correct_disk_selfgravity = c.flag("CorrectDiskSelfgravity", !c.flag("SelfGravity", false)); // parameters.cpp:699
@@ -837,6 +839,8 @@ struct Run {
 		die("used_rad.dat does not hold Nrad + 1 radii in %s", dir);
 	}
 	params = make_params(cfg, consts, nrad, naz);
+	if (params.bc_vazi[0] == FARGO_BC_BALANCED || params.bc_vazi[1] == FARGO_BC_BALANCED)
+	    die("%s", std::string("a Balanced v_azi boundary needs the disk model of `start`: not supported on restart by this driver"));
 	if (params.pvte)
 	    die("%s", std::string("restart with EquationOfState: PVTE is not supported by this driver (start only)"));
 	// bodies
@@ -1221,6 +1225,22 @@ struct Run {
 	}
 	const finit::InitialState s0 = finit::init_gas(d, radii, nrad, naz, params.hydro_center_mass);
 	params.sigma0 = d.sigma0; // SetSigma0 rescales it; the density floor follows (init.cpp:1155)
+	// FARGO_BC_BALANCED: v_sq of balanced_boundary (boundary_conditions/balanced.cpp:23-52) for the two ghost rings
+	for (int side = 0; side < 2; ++side) {
+	    const int i = side == 0 ? 0 : nrad - 1;
+	    const double ri = radii[i], rs = radii[i + 1];
+	    double R = 2.0 / 3.0 * (std::pow(rs, 3) - std::pow(ri, 3)); // Rb (init.cpp:178-179)
+	    R = R / (std::pow(rs, 2) - std::pow(ri, 2));
+	    const double vk_2 = std::pow(std::sqrt(consts.G * params.hydro_center_mass / R), 2); // pow(compute_v_kepler(R, M), 2)
+	    double support = 0.0;
+	    if (!d.cutoff_outer) {
+		support += finit::detail::support_azi_pressure(d, R);
+		support += finit::detail::support_azi_smoothing_derivative(d, R);
+	    }
+	    if (d.quadrupole_support && d.quadrupole_moment > 0.0) // support_azi_quadrupole (Theo.cpp:150-157)
+		support += 3.0 * d.quadrupole_moment / std::pow(R, 2);
+	    params.balanced_vazi_sq[side] = vk_2 * support;
+	}
 	create_context(device);
 	// init_euler (SourceEuler.cpp:250-285) runs BEFORE the velocities exist: Q+/- of the first CFL see a gas at rest
 	CHECK(BK(upload_field)(ctx, FARGO_SIGMA, s0.sigma.data()));

@@ -71,7 +71,9 @@ enum fargo_bc {
     FARGO_BC_OUTFLOW = 2,      /* outflow.cpp (v_rad only) */
     FARGO_BC_REFLECTING = 3,   /* reflecting.cpp (v_rad only) */
     FARGO_BC_KEPLERIAN = 4,    /* keplerian_azimuthal.cpp (v_azi only, the default) */
-    FARGO_BC_REFERENCE = 5     /* reference.cpp: copy X0 into the ghost rings */
+    FARGO_BC_REFERENCE = 5,    /* reference.cpp: copy X0 into the ghost rings */
+    FARGO_BC_ZEROSHEAR = 6,    /* zero_shear.cpp (v_azi only): the ghost ring rotates at the angular velocity of the first active ring */
+    FARGO_BC_BALANCED = 7      /* balanced.cpp (v_azi only): the equilibrium rotation sqrt(balanced_vazi_sq) - Rb OmegaFrame */
 };
 /* damping.cpp t_damping_type */
 enum fargo_damping { FARGO_DAMP_NONE = 0, FARGO_DAMP_INITIAL = 1, FARGO_DAMP_ZERO = 2, FARGO_DAMP_MEAN = 3 };
@@ -161,6 +163,9 @@ typedef struct fargo_params {
      * length, mass and energy flux (units.cpp), the Stefan-Boltzmann and gravitational constants in cgs (constants.cpp). */
     int cooling_scurve;
     double length_cgs, mass_cgs, energy_flux_cgs, sigma_sb_cgs, G_cgs;
+    /* FARGO_BC_BALANCED (boundary_conditions/balanced.cpp:23-75): v_K^2 x (pressure + smoothing (+ quadrupole) support) of the
+     * inner / outer ghost ring, formed by the host from the disk model (Theo.cpp:122-160); the frame rotation is subtracted per call */
+    double balanced_vazi_sq[2];
 } fargo_params;
 /* parameters::t_opacity (parameters.h), Opacity: Lin | Bell | Constant | Simple */
 enum fargo_opacity { FARGO_OPACITY_LIN = 0, FARGO_OPACITY_BELL = 1, FARGO_OPACITY_CONST = 2, FARGO_OPACITY_SIMPLE = 3 };

@@ -1443,6 +1443,16 @@ static void bc_vazi(fargo_oracle *o)
 	} else if (o->p.bc_vazi[0] == FARGO_BC_REFERENCE) {
 	    for (int j = 0; j < Nphi; ++j)
 		o->vazi[IDX(o, 0, j)] = o->vazi0[IDX(o, 0, j)];
+	} else if (o->p.bc_vazi[0] == FARGO_BC_BALANCED) { /* balanced.cpp:23-75 */
+	    double vaz_balanced = sqrt(o->p.balanced_vazi_sq[0]);
+	    vaz_balanced -= o->rmed[0] * OmegaF;
+	    for (int j = 0; j < Nphi; ++j)
+		o->vazi[IDX(o, 0, j)] = vaz_balanced;
+	} else if (o->p.bc_vazi[0] == FARGO_BC_ZEROSHEAR) { /* zero_shear.cpp:20-36 */
+	    for (int j = 0; j < Nphi; ++j) {
+		const double Omega_active = o->vazi[IDX(o, 1, j)] / o->rmed[1];
+		o->vazi[IDX(o, 0, j)] = o->rmed[0] * Omega_active;
+	    }
 	}
     }
     if (o->rank == o->nranks - 1) {
@@ -1457,6 +1467,16 @@ static void bc_vazi(fargo_oracle *o)
 	} else if (o->p.bc_vazi[1] == FARGO_BC_REFERENCE) {
 	    for (int j = 0; j < Nphi; ++j)
 		o->vazi[IDX(o, Irad, j)] = o->vazi0[IDX(o, Irad, j)];
+	} else if (o->p.bc_vazi[1] == FARGO_BC_BALANCED) {
+	    double vaz_balanced = sqrt(o->p.balanced_vazi_sq[1]);
+	    vaz_balanced -= o->rmed[Irad] * OmegaF;
+	    for (int j = 0; j < Nphi; ++j)
+		o->vazi[IDX(o, Irad, j)] = vaz_balanced;
+	} else if (o->p.bc_vazi[1] == FARGO_BC_ZEROSHEAR) { /* zero_shear.cpp:38-54 */
+	    for (int j = 0; j < Nphi; ++j) {
+		const double Omega_active = o->vazi[IDX(o, Irad - 1, j)] / o->rmed[Irad - 1];
+		o->vazi[IDX(o, Irad, j)] = o->rmed[Irad] * Omega_active;
+	    }
 	}
     }
 }

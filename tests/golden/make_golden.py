@@ -142,6 +142,11 @@ CASES = {
                               Damping="Yes", DampingInnerLimit=1.311, DampingOuterLimit=0.763, DampingTimeFactor=0.05, **DAMP_ALL),
     "adia_alpha_scurve_lf": dict(Integrator="Leapfrog", AlphaMode=1, ViscousAlpha=1e-3, AlphaCold=0.01, AlphaHot=0.1, HeatingViscous="yes",
                                  l0="0.06 au", Sigma0=0.001, WriteTemperature="yes"),
+    # v_azi boundaries: Balanced (balanced.cpp: equilibrium rotation in the ghost rings) and ZeroShear (zero_shear.cpp), also in a
+    # rotating frame
+    "iso_bc_balanced": dict(EquationOfState="Isothermal", InnerBoundaryVazi="Balanced", OuterBoundaryVazi="Balanced", ViscousAlpha=1e-3,
+                            ThicknessSmoothing=0.4, OmegaFrame=0.3),
+    "adia_bc_zeroshear": dict(InnerBoundaryVazi="ZeroShear", OuterBoundaryVazi="ZeroShear", ViscousAlpha=1e-3, HeatingViscous="yes"),
     # SurfaceCooling: scurve (scurve_cooling, SourceEuler.cpp:726-831) together with the S-curve alpha: a dwarf-nova disk
     "adia_scurve": dict(SurfaceCooling="scurve", ScurveType="Kimura", AlphaMode=1, ViscousAlpha=1e-3, AlphaCold=0.01, AlphaHot=0.1,
                         HeatingViscous="yes", l0="0.06 au", Sigma0=0.001, WriteTemperature="yes", WriteQminus="yes", WriteQplus="yes"),
@@ -220,6 +225,8 @@ def run_case(name, overrides, keep=False):
     radii = np.loadtxt(os.path.join(out, "used_rad.dat"))
     assert radii.shape == (nrad + 1,)
     pdict = reftools.params_from_config(cfg, consts, nrad, naz, temp_unit, units)
+    from fargocpt_b200.config import balanced_vazi_sq
+    pdict["balanced_vazi_sq"] = balanced_vazi_sq(pdict, cfg, radii)  # boundary_conditions/balanced.cpp:23-52
     nsnap = int(cfg["Nsnapshots"])
     nb = len(cfg["nbody"])
     arrays = {"radii": radii}

@@ -208,7 +208,9 @@ START_CASES = [("iso_star", 6, True), ("adia_star", 6, True), ("adia_cold", 6, T
                # AlphaMode 1: S-curve alpha in the stored temperature (viscosity/viscosity.cpp:31-49), Euler and Leapfrog
                ("adia_alpha_scurve", 6, True), ("adia_alpha_scurve_lf", 6, True),
                # SurfaceCooling: scurve (scurve_cooling, SourceEuler.cpp:726-831): ScurveType Kimura / Ichikawa
-               ("adia_scurve", 6, True), ("adia_scurve_ichikawa_lf", 6, True)]
+               ("adia_scurve", 6, True), ("adia_scurve_ichikawa_lf", 6, True),
+               # v_azi boundaries Balanced (v_sq of the disk model formed by the host like balanced.cpp:23-52) and ZeroShear
+               ("iso_bc_balanced", 6, True), ("adia_bc_zeroshear", 6, True)]
 
 
 @pytest.mark.parametrize("name,until,exact", START_CASES)

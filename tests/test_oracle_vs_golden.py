@@ -17,7 +17,9 @@ CASES = ["adia_star", "adia_cold", "iso_star", "iso_sn_std", "adia_sn_stab", "ri
          # AlphaMode 1: S-curve alpha in the stored TEMPERATURE grid (viscosity/viscosity.cpp:31-49), Euler and Leapfrog
          "adia_alpha_scurve", "adia_alpha_scurve_lf",
          # SurfaceCooling: scurve (scurve_cooling, SourceEuler.cpp:726-831): Kimura with the S-curve alpha, Ichikawa with Leapfrog
-         "adia_scurve", "adia_scurve_ichikawa_lf"]
+         "adia_scurve", "adia_scurve_ichikawa_lf",
+         # v_azi boundaries Balanced (balanced.cpp, rotating frame) and ZeroShear (zero_shear.cpp)
+         "iso_bc_balanced", "adia_bc_zeroshear"]
 # Isothermal configs have no per-cell transcendental in the step => demanded bit-exact.
 # Adiabatic configs call exp() per cell (SourceEuler.cpp:487); same libm here => also bit-exact on CPU.
 # DiskFeedback: the reference sums the disk's pull with an OpenMP reduction in no defined order, so the acceleration
