@@ -22,7 +22,7 @@ VECTOR_FIELDS = (VRAD, VRAD0, MASSFLOW)  # grids on the radial interfaces: nrad 
 ARTVISC = {"none": 0, "tw": 1, "sn": 2}
 LIMITER = {"vanleer": 0, "mc": 1}
 SPACING = {"logarithmic": 0, "arithmetic": 1, "exponential": 2, "custom": 3}
-BC = {"none": 0, "zerogradient": 1, "outflow": 2, "reflecting": 3, "keplerian": 4, "reference": 5, "zeroshear": 6, "balanced": 7}
+BC = {"none": 0, "zerogradient": 1, "outflow": 2, "reflecting": 3, "keplerian": 4, "reference": 5, "zeroshear": 6, "balanced": 7, "viscous": 8}
 DAMP = {"none": 0, "initial": 1, "reference": 1, "zero": 2, "mean": 3}
 OPACITY = {"lin": 0, "bell": 1, "constant": 2, "simple": 3}  # parameters.cpp:414-428
 BETA_REF = {"zero": 0, "reference": 1, "diskmodel": 2, "floor": 4}  # parameters.cpp:451-463
@@ -68,6 +68,7 @@ class FargoParams(C.Structure):
         ("cooling_scurve", C.c_int), ("length_cgs", C.c_double), ("mass_cgs", C.c_double), ("energy_flux_cgs", C.c_double),
         ("sigma_sb_cgs", C.c_double), ("G_cgs", C.c_double),
         ("balanced_vazi_sq", C.c_double * 2),
+        ("keplerian_radial_factor", C.c_double * 2), ("viscous_outflow_speed", C.c_double),
     ]
 
     def as_dict(self):

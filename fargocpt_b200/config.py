@@ -127,6 +127,8 @@ def params_from_config(cfg, consts, nrad, naz, temp_unit_K=1.0, units=None):
         d.setdefault("keplerian_azimuthal_factor", [1.0, 1.0])[side] = float(
             get(name + "BoundaryVaziKeplerianFactor", 1.0))
     d["balanced_vazi_sq"] = [0.0, 0.0]  # filled by balanced_vazi_sq() once the radii are known
+    d["keplerian_radial_factor"] = [float(get("InnerBoundaryVradKeplerianFactor", 0.1)), float(get("OuterBoundaryVradKeplerianFactor", 0.1))]
+    d["viscous_outflow_speed"] = float(get("ViscousOutflowSpeed", 1.0))
     d["correct_disk_selfgravity"] = int(_flag(get("CorrectDiskSelfgravity"), not _flag(get("SelfGravity"), False)))
     d["damping"] = int(_flag(get("Damping"), False))
     d["damping_inner_limit"] = float(get("DampingInnerLimit", 1.05))

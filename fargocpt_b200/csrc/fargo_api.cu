@@ -112,7 +112,7 @@ struct fargo_ctx {
     ncclComm_t comm = nullptr;
     long long launches = 0;
     // host geometry (local view incl. 2 extra entries) for host-side ring factors
-    std::vector<double> h_radii, h_rinf, h_rsup, h_rmed;
+    std::vector<double> h_radii, h_rinf, h_rsup, h_rmed, h_cs_iso, h_inv_omega_k;
     std::vector<double *> dev_allocs;
     // state.  energy, v_rad and v_azi are double-buffered: the fused kernels read one buffer and write the other
     // (their column windows overlap on reads), and Transport cannot write v_azi where it still reads the residual
@@ -426,6 +426,8 @@ static int init_geometry(fargo_ctx *c, const double *radii)
     c->h_rinf = rinf;
     c->h_rsup = rsup;
     c->h_rmed = rmed;
+    c->h_cs_iso = cs_iso;
+    c->h_inv_omega_k = inv_omega_k;
     Geo &g = v.g;
     if (upload_vec(c, &g.rinf, rinf) || upload_vec(c, &g.rsup, rsup) || upload_vec(c, &g.rmed, rmed) ||
 	upload_vec(c, &g.surf, surf) || upload_vec(c, &g.invrmed, invrmed) || upload_vec(c, &g.invsurf, invsurf) ||
@@ -666,6 +668,14 @@ extern "C" int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, con
 	dalloc(c, &c->vrb[1], nv) || dalloc(c, &c->vpb[1], ns) || dalloc(c, &c->eb[1], params->adiabatic ? ns : 1));
     TRY(dalloc(c, &c->sigma0, ns) || dalloc(c, &c->energy0, ns) || dalloc(c, &c->vr0, nv) || dalloc(c, &c->vp0, ns));
     TRY(dalloc(c, &c->qplus, ns) || dalloc(c, &c->qminus, ns));
+    if (params->bc_vrad[1] == FARGO_BC_KEPLERIAN || params->bc_vrad[1] == FARGO_BC_VISCOUS ||
+	(params->bc_vrad[0] == FARGO_BC_VISCOUS && params->adiabatic && params->viscous_alpha > 0)) {
+	// the outer variants address rings past their grids in the reference; the inner viscous outflow reads the VISCOSITY grid as
+	// last stored, which the fused kernels do not keep
+	fail("v_rad boundary: 'keplerian' / 'viscous' are offered on the inner side only, 'viscous' with a viscosity that does not depend on the state");
+	fargo_ctx_destroy(c);
+	return 1;
+    }
     if (params->cooling_scurve != 0 &&
 	(!params->adiabatic || params->heating_star || params->cooling_scurve < 0 || params->cooling_scurve > 2 || !(params->energy_flux_cgs > 0))) {
 	// with an irradiating body the reference's irradiation would read the TAU_EFF scurve_cooling stored one call earlier
@@ -1354,8 +1364,26 @@ extern "C" int fargo_stage_boundary(fargo_ctx *c, double dt, int final_call)
 	vk_out = sqrt(p.balanced_vazi_sq[1]);
 	vk_out -= c->h_rmed[Irad] * c->v.b.omega_frame;
     }
+    BcVrad bv = {{0.0, 0.0}};
+    if (p.bc_vrad[0] == FARGO_BC_KEPLERIAN) { // keplerian_radial.cpp:29-38
+	for (int k = 0; k <= 1; ++k)
+	    bv.in[k] = p.keplerian_radial_factor[0] * sqrt(p.G * p.hydro_center_mass / c->h_rmed[k]);
+    } else if (p.bc_vrad[0] == FARGO_BC_VISCOUS) { // viscous.cpp:29-45, nu of rings 0 and 1 from the geometry alone
+	double nu01[2];
+	for (int k = 0; k <= 1; ++k) {
+	    if (p.viscous_alpha > 0) { // update_viscosity (viscosity.cpp:98-137) of a locally isothermal disk: alpha H c_s
+		const double cs = c->h_cs_iso[k];
+		nu01[k] = p.viscous_alpha * (cs * c->h_inv_omega_k[k]) * cs;
+	    } else {
+		nu01[k] = p.constant_viscosity;
+	    }
+	}
+	const double Nu = 0.5 * (nu01[0] + nu01[1]);
+	bv.in[1] = -1.5 * p.viscous_outflow_speed / c->h_rinf[1] * Nu;
+	bv.in[0] = -1.5 * p.viscous_outflow_speed / c->h_rinf[0] * Nu;
+    }
     LAUNCH(c, k_boundary, (unsigned)((c->v.ns + 255) / 256), 256, 0, c->v, c->sigma, EN(c), v.vr, v.vp, c->sigma0, c->energy0,
-	   c->vr0, c->vp0, vk_in, vk_out);
+	   c->vr0, c->vp0, vk_in, vk_out, bv);
     return 0;
 }
 

@@ -23,11 +23,16 @@ __device__ __forceinline__ void bc_scalar_col(const DevView &c, double *x, const
     }
 }
 
+// host-formed ghost values of the inner v_rad boundaries that do not depend on the state: keplerian_radial.cpp:18-39 and the
+// viscous outflow of viscous.cpp:18-46 for a state-independent viscosity (interfaces 0 and 1)
+struct BcVrad {
+    double in[2];
+};
 __global__ void __launch_bounds__(256)
     k_boundary(const DevView c, double *__restrict__ sigma, double *__restrict__ energy, double *__restrict__ vr,
 	       double *__restrict__ vp, const double *__restrict__ sigma0, const double *__restrict__ energy0,
 	       const double *__restrict__ vr0, const double *__restrict__ vp0, const double vkep_inner,
-	       const double vkep_outer)
+	       const double vkep_outer, const BcVrad bv)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= c.ns)
@@ -65,6 +70,13 @@ __global__ void __launch_bounds__(256)
 		AT(vr, 1, j) = AT(vr0, 1, j);
 	    }
 	    break;
+	case FARGO_BC_KEPLERIAN: // keplerian_radial.cpp:18-39
+	case FARGO_BC_VISCOUS:	 // viscous.cpp:18-46
+	    if (first) {
+		AT(vr, 0, j) = bv.in[0];
+		AT(vr, 1, j) = bv.in[1];
+	    }
+	    break;
 	default:
 	    break;
 	}
@@ -96,6 +108,7 @@ __global__ void __launch_bounds__(256)
 		AT(vr, Irad - 1, j) = AT(vr0, Irad - 1, j);
 	    }
 	    break;
+
 	default:
 	    break;
 	}

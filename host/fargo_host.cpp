@@ -430,6 +430,8 @@ static fargo_params make_params(const Config &c, const CodeConstants &k, int nra
     p.imposed_disk_drift = c.num("ImposedDiskDrift", 0.0);
     const std::vector<std::pair<std::string, int>> BC = {{"none", 0}, {"zerogradient", 1}, {"zero_gradient", 1}, {"outflow", 2},
 							  {"reflecting", 3}, {"keplerian", 4}, {"reference", 5}};
+    const std::vector<std::pair<std::string, int>> BC_VRAD_INNER = {{"none", 0}, {"zerogradient", 1}, {"zero_gradient", 1}, {"outflow", 2},
+								     {"reflecting", 3}, {"keplerian", 4}, {"reference", 5}, {"viscous", 8}};
     const std::vector<std::pair<std::string, int>> BC_VAZI = {{"none", 0}, {"zerogradient", 1}, {"zero_gradient", 1}, {"keplerian", 4},
 							       {"reference", 5}, {"zeroshear", 6}, {"balanced", 7}};
     const char *sides[2] = {"Inner", "Outer"};
@@ -454,10 +456,12 @@ static fargo_params make_params(const Config &c, const CodeConstants &k, int nra
 	}
 	p.bc_sigma[s] = enum_of(bs, BC, "boundary");
 	p.bc_energy[s] = enum_of(be, BC, "boundary");
-	p.bc_vrad[s] = enum_of(bvr, BC, "boundary");
+	p.bc_vrad[s] = enum_of(bvr, s == 0 ? BC_VRAD_INNER : BC, "v_rad boundary");
+	p.keplerian_radial_factor[s] = c.num(std::string(sides[s]) + "BoundaryVradKeplerianFactor", 0.1); // config.cpp:220-255
 	p.bc_vazi[s] = enum_of(c.str(std::string(sides[s]) + "BoundaryVazi", "keplerian"), BC_VAZI, "v_azi boundary");
 	p.keplerian_azimuthal_factor[s] = c.num(std::string(sides[s]) + "BoundaryVaziKeplerianFactor", 1.0);
     }
+    p.viscous_outflow_speed = c.num("ViscousOutflowSpeed", 1.0); // config.cpp:498
     p.correct_disk_selfgravity = c.flag("CorrectDiskSelfgravity", !c.flag("SelfGravity", false)); // parameters.cpp:699
     // radiative surface cooling, opacity (parameters.cpp:389-435, 628-632); heating_star is set by the caller from the bodies
     // (t_planetary_system::derive_config, planetary_system.cpp:137-146)

@@ -73,7 +73,12 @@ enum fargo_bc {
     FARGO_BC_KEPLERIAN = 4,    /* keplerian_azimuthal.cpp (v_azi only, the default) */
     FARGO_BC_REFERENCE = 5,    /* reference.cpp: copy X0 into the ghost rings */
     FARGO_BC_ZEROSHEAR = 6,    /* zero_shear.cpp (v_azi only): the ghost ring rotates at the angular velocity of the first active ring */
-    FARGO_BC_BALANCED = 7      /* balanced.cpp (v_azi only): the equilibrium rotation sqrt(balanced_vazi_sq) - Rb OmegaFrame */
+    FARGO_BC_BALANCED = 7,     /* balanced.cpp (v_azi only): the equilibrium rotation sqrt(balanced_vazi_sq) - Rb OmegaFrame */
+    FARGO_BC_VISCOUS = 8       /* viscous.cpp:18-46 (v_rad, inner side only): v_rad = -1.5 ViscousOutflowSpeed / Ra x the mean viscosity of
+				* rings 0 and 1 (Kley, Papaloizou & Ogilvie 2008).  Device: viscosities that do not depend on the state
+				* (constant, or alpha in a locally isothermal disk); the outer variant reads past its grid in the
+				* reference and is not offered.  FARGO_BC_KEPLERIAN on the INNER v_rad is keplerian_radial.cpp:18-39:
+				* the two ghost interfaces move at keplerian_radial_factor x v_K(Rmed) */
 };
 /* damping.cpp t_damping_type */
 enum fargo_damping { FARGO_DAMP_NONE = 0, FARGO_DAMP_INITIAL = 1, FARGO_DAMP_ZERO = 2, FARGO_DAMP_MEAN = 3 };
@@ -166,6 +171,8 @@ typedef struct fargo_params {
     /* FARGO_BC_BALANCED (boundary_conditions/balanced.cpp:23-75): v_K^2 x (pressure + smoothing (+ quadrupole) support) of the
      * inner / outer ghost ring, formed by the host from the disk model (Theo.cpp:122-160); the frame rotation is subtracted per call */
     double balanced_vazi_sq[2];
+    double keplerian_radial_factor[2]; /* Inner / OuterBoundaryVradKeplerianFactor (config.cpp:220-255), default 0.1; [0] is used */
+    double viscous_outflow_speed;      /* ViscousOutflowSpeed (config.cpp:498), default 1 */
 } fargo_params;
 /* parameters::t_opacity (parameters.h), Opacity: Lin | Bell | Constant | Simple */
 enum fargo_opacity { FARGO_OPACITY_LIN = 0, FARGO_OPACITY_BELL = 1, FARGO_OPACITY_CONST = 2, FARGO_OPACITY_SIMPLE = 3 };

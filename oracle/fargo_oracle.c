@@ -1386,6 +1386,24 @@ static void bc_vrad(fargo_oracle *o)
 		v[IDX(o, 1, j)] = o->vrad0[IDX(o, 1, j)];
 	    }
 	break;
+    case FARGO_BC_KEPLERIAN: /* keplerian_radial.cpp:18-39 */
+	if (first)
+	    for (int j = 0; j < Nphi; ++j)
+		for (int k = 0; k <= 1; k++) {
+		    const double vKep = sqrt(o->p.G * o->p.hydro_center_mass / o->rmed[k]);
+		    v[IDX(o, k, j)] = o->p.keplerian_radial_factor[0] * vKep;
+		}
+	break;
+    case FARGO_BC_VISCOUS: /* viscous.cpp:18-46: the VISCOSITY grid as last stored */
+	if (first)
+	    for (int j = 0; j < Nphi; ++j) {
+		const double s = o->p.viscous_outflow_speed;
+		const double Nu0 = o->viscosity[IDX(o, 0, j)], Nu1 = o->viscosity[IDX(o, 1, j)];
+		const double Nu = 0.5 * (Nu0 + Nu1);
+		v[IDX(o, 1, j)] = -1.5 * s / o->rinf[1] * Nu;
+		v[IDX(o, 0, j)] = -1.5 * s / o->rinf[0] * Nu;
+	    }
+	break;
     default:
 	break;
     }

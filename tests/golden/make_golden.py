@@ -147,6 +147,11 @@ CASES = {
     "iso_bc_balanced": dict(EquationOfState="Isothermal", InnerBoundaryVazi="Balanced", OuterBoundaryVazi="Balanced", ViscousAlpha=1e-3,
                             ThicknessSmoothing=0.4, OmegaFrame=0.3),
     "adia_bc_zeroshear": dict(InnerBoundaryVazi="ZeroShear", OuterBoundaryVazi="ZeroShear", ViscousAlpha=1e-3, HeatingViscous="yes"),
+    # inner v_rad boundaries Viscous (viscous.cpp: outflow at 1.5 s nu / r) and Keplerian (keplerian_radial.cpp)
+    "iso_bc_viscous": dict(EquationOfState="Isothermal", InnerBoundary="individual", InnerBoundarySigma="zerogradient",
+                           InnerBoundaryEnergy="zerogradient", InnerBoundaryVrad="viscous", ViscousOutflowSpeed=5.0, ViscousAlpha=1e-2),
+    "adia_bc_keplerian_vrad": dict(InnerBoundary="individual", InnerBoundarySigma="zerogradient", InnerBoundaryEnergy="zerogradient",
+                                   InnerBoundaryVrad="keplerian", InnerBoundaryVradKeplerianFactor=-0.01, ViscousAlpha=0.0, ConstantViscosity=1e-5),
     # SurfaceCooling: scurve (scurve_cooling, SourceEuler.cpp:726-831) together with the S-curve alpha: a dwarf-nova disk
     "adia_scurve": dict(SurfaceCooling="scurve", ScurveType="Kimura", AlphaMode=1, ViscousAlpha=1e-3, AlphaCold=0.01, AlphaHot=0.1,
                         HeatingViscous="yes", l0="0.06 au", Sigma0=0.001, WriteTemperature="yes", WriteQminus="yes", WriteQplus="yes"),

@@ -22,6 +22,8 @@ CASES = ["adia_star", "adia_cold", "iso_star", "iso_sn_std", "adia_sn_stab", "ri
 CASES += ["adia_irrad", "adia_irrad_lf"]
 # v_azi boundaries Balanced (balanced.cpp: equilibrium rotation of the disk model in the ghost rings, rotating frame) and ZeroShear
 CASES += ["iso_bc_balanced", "adia_bc_zeroshear"]
+# inner v_rad boundaries Viscous (viscous.cpp: the mean viscosity of rings 0 and 1, state-independent here) and Keplerian
+CASES += ["iso_bc_viscous", "adia_bc_keplerian_vrad"]
 # the Lin & Papaloizou / Bell & Lin opacity tables call pow() with fractional exponents (opacity.cpp:49-298): CUDA's pow and
 # glibc's differ in the last bits, so these two runs are held to a tolerance instead (fields, dt)
 POW_CASES = ["adia_cool_lin", "adia_cool_bell"]
@@ -34,7 +36,7 @@ LONG_CASES += ["iso_accrete_20", "adia_accrete_20"]
 LONG_CASES += ["iso_sinkhole_20"]
 # "accretion method: viscous" (accretion.cpp:335-417): the removed fraction scales with the viscosity of the pre-accretion state
 LONG_CASES += ["adia_viscacc_20"]
-ISOTHERMAL = {"iso_star", "iso_sn_std", "ring_like", "iso_planet_100", "iso_accrete_20", "iso_sinkhole_20", "iso_bc_balanced"}
+ISOTHERMAL = {"iso_star", "iso_sn_std", "ring_like", "iso_planet_100", "iso_accrete_20", "iso_sinkhole_20", "iso_bc_balanced", "iso_bc_viscous"}
 ADIABATIC_RTOL = 0.0
 LONG_RTOL = 0.0  # north_star allows 1e-10 after 100 steps; the glibc-exact exp makes the adiabatic runs bit-exact too
 

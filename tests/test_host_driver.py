@@ -210,7 +210,9 @@ START_CASES = [("iso_star", 6, True), ("adia_star", 6, True), ("adia_cold", 6, T
                # SurfaceCooling: scurve (scurve_cooling, SourceEuler.cpp:726-831): ScurveType Kimura / Ichikawa
                ("adia_scurve", 6, True), ("adia_scurve_ichikawa_lf", 6, True),
                # v_azi boundaries Balanced (v_sq of the disk model formed by the host like balanced.cpp:23-52) and ZeroShear
-               ("iso_bc_balanced", 6, True), ("adia_bc_zeroshear", 6, True)]
+               ("iso_bc_balanced", 6, True), ("adia_bc_zeroshear", 6, True),
+               # inner v_rad boundaries Viscous (ViscousOutflowSpeed) and Keplerian (InnerBoundaryVradKeplerianFactor)
+               ("iso_bc_viscous", 6, True), ("adia_bc_keplerian_vrad", 6, True)]
 
 
 @pytest.mark.parametrize("name,until,exact", START_CASES)

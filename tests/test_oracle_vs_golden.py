@@ -19,7 +19,9 @@ CASES = ["adia_star", "adia_cold", "iso_star", "iso_sn_std", "adia_sn_stab", "ri
          # SurfaceCooling: scurve (scurve_cooling, SourceEuler.cpp:726-831): Kimura with the S-curve alpha, Ichikawa with Leapfrog
          "adia_scurve", "adia_scurve_ichikawa_lf",
          # v_azi boundaries Balanced (balanced.cpp, rotating frame) and ZeroShear (zero_shear.cpp)
-         "iso_bc_balanced", "adia_bc_zeroshear"]
+         "iso_bc_balanced", "adia_bc_zeroshear",
+         # inner v_rad boundaries Viscous (viscous.cpp) and Keplerian (keplerian_radial.cpp)
+         "iso_bc_viscous", "adia_bc_keplerian_vrad"]
 # Isothermal configs have no per-cell transcendental in the step => demanded bit-exact.
 # Adiabatic configs call exp() per cell (SourceEuler.cpp:487); same libm here => also bit-exact on CPU.
 # DiskFeedback: the reference sums the disk's pull with an OpenMP reduction in no defined order, so the acceleration
