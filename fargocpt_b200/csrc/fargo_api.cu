@@ -1786,7 +1786,12 @@ extern "C" int fargo_kick(fargo_ctx *c, double dt)
     }
     if (c->v_mid)
 	return fail("fargo_kick (staged) called mid-step");
-    if (fargo_stage_potential(c) || fargo_stage_sources(c, dt) || fargo_stage_artvisc(c, dt) || fargo_stage_viscosity(c, dt))
+    const bool second_kick = c->h_stale; // a leapfrog step's second kick: the first one left its scale height behind
+    if (fargo_stage_potential(c))
+	return 1;
+    if (second_kick && c->v.pv.geff) // PVTE (simulation.cpp:368-376): after the potential, which still read the stored scale height —
+	LAUNCH(c, k_pvte_refresh, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, EN(c), 1); // c_s, H, lookup, c_s, H
+    if (fargo_stage_sources(c, dt) || fargo_stage_artvisc(c, dt) || fargo_stage_viscosity(c, dt))
 	return 1;
     if (p.adiabatic && fargo_stage_substep3(c, dt))
 	return 1;

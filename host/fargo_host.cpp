@@ -355,8 +355,6 @@ static fargo_params make_params(const Config &c, const CodeConstants &k, int nra
 	const std::string eos = lower(c.str("EquationOfState", "Isothermal")); // Interpret.cpp:391-470
 	if (eos != "isothermal" && eos != "iso" && eos != "adiabatic" && eos != "ideal" && eos != "pvte" && eos != "pvtelaw")
 	    die("EquationOfState: %s is not supported by this driver (isothermal, ideal, pvte)", eos);
-	if ((eos == "pvte" || eos == "pvtelaw") && lower(c.str("Integrator", "Euler"))[0] != 'e')
-	    die("%s", std::string("EquationOfState: PVTE is implemented for Integrator: Euler only"));
 	if (c.has("Adiabatic"))
 	    die("%s", std::string("the deprecated 'Adiabatic' flag is not supported; use EquationOfState"));
 	const bool energy_equation = eos == "adiabatic" || eos == "ideal" || eos == "pvte" || eos == "pvtelaw"; // SubStep3 only runs then (simulation.cpp:203-205)

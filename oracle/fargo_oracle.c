@@ -2327,10 +2327,20 @@ int fargo_oracle_kick(fargo_oracle *o, double dt)
      * smoothing of that kick uses the scale height recalculate_viscosity left during the first kick.  The first kick (like
      * step_Euler's) reads the PRESSURE the previous step stored — which matters when AccreteOntoPlanets has changed Sigma / e in
      * between (simulation.cpp:302-303): the stored pressure is the pre-accretion one. */
-    if (o->kicks_this_step > 0)
-	compute_pressure(o);
+    const int second = o->kicks_this_step > 0;
     o->kicks_this_step++;
     fargo_oracle_stage_potential(o);
+    if (second) {
+	if (o->p.pvte) { /* simulation.cpp:368-376: after the potential (which still read the stored scale height), c_s and H, the
+			  * lookup, and c_s and H again */
+	    compute_sound_speed(o);
+	    compute_scale_height(o);
+	    compute_gamma_mu(o);
+	    compute_sound_speed(o);
+	    compute_scale_height(o);
+	}
+	compute_pressure(o); /* :381 */
+    }
     fargo_oracle_stage_sources(o, dt);
     fargo_oracle_stage_artvisc(o, dt);
     fargo_oracle_stage_viscosity(o, dt);

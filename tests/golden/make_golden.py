@@ -135,6 +135,9 @@ CASES = {
     "adia_pvte": dict(EquationOfState="PVTE", ViscousAlpha=1e-3, HeatingViscous="yes", CoolingBetaLocal="yes", CoolingBeta=10,
                       WriteEffectiveGamma="yes", WriteFirstAdiabaticIndex="yes", WriteMeanMolecularWeight="yes", WriteScaleHeight="yes",
                       Damping="Yes", DampingInnerLimit=1.311, DampingOuterLimit=0.763, DampingTimeFactor=0.05, **DAMP_ALL),
+    # PVTE with Leapfrog: the second kick refreshes c_s, H and the lookup after its potential (simulation.cpp:368-376)
+    "adia_pvte_lf": dict(EquationOfState="PVTE", Integrator="Leapfrog", ViscousAlpha=1e-3, HeatingViscous="yes", CoolingBetaLocal="yes", CoolingBeta=10,
+                         WriteEffectiveGamma="yes", WriteFirstAdiabaticIndex="yes", WriteMeanMolecularWeight="yes", WriteScaleHeight="yes"),
     # AlphaMode 1: S-curve alpha in the (stored) temperature (viscosity.cpp:36-49); l0 = 0.06 au puts the disk around 1e4 K,
     # where alpha switches between AlphaCold and AlphaHot
     "adia_alpha_scurve": dict(AlphaMode=1, ViscousAlpha=1e-3, AlphaCold=0.01, AlphaHot=0.1, HeatingViscous="yes", CoolingBetaLocal="yes",

@@ -128,13 +128,14 @@ def test_opacity_table_runs_vs_reference(name, staged):
     print(name, "worst deviation / field scale:", worst)
 
 
-def test_pvte_run_vs_reference():
+@pytest.mark.parametrize("name", ["adia_pvte", "adia_pvte_lf"])
+def test_pvte_run_vs_reference(name):
     """EquationOfState: PVTE (pvte_law.cpp:371-568): lookup tables from host/fargo_pvte.h uploaded by fargo_set_pvte, gamma_eff / mu /
     Gamma_1 / H grids refreshed in the reference's order, per-cell gamma in the staged kernels, the azimuthal kernel's temperature floor
     and the CFL.  The table index of a cell comes from log10() (CUDA's against glibc's: a cell sitting on a table-cell edge may take
     the neighbouring cell, where the bilinear interpolation is continuous), everything else is IEEE arithmetic: held to POW_RTOL,
     with the number of differing doubles reported."""
-    meta, z, gpu, cpu = _ctx_pair("adia_pvte")
+    meta, z, gpu, cpu = _ctx_pair(name)
     snaps = goldenrun.run_fixture(gpu, meta, z)
     worst, ndiff = 0.0, 0
     for k, snap in enumerate(snaps, start=1):
@@ -150,7 +151,7 @@ def test_pvte_run_vs_reference():
         got = gpu.download(fid)
         worst = max(worst, float(np.abs(got - ref).max() / np.abs(ref).max()))
         ndiff += int((got != ref).sum())
-    print("adia_pvte: worst deviation / field scale", worst, "differing doubles", ndiff)
+    print(name, ": worst deviation / field scale", worst, "differing doubles", ndiff)
     assert worst <= POW_RTOL
 
 

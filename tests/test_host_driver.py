@@ -204,7 +204,7 @@ START_CASES = [("iso_star", 6, True), ("adia_star", 6, True), ("adia_cold", 6, T
                # SurfaceCooling: thermal, irradiating star (ramped), constant opacity and the two opacity tables
                ("adia_irrad", 6, True), ("adia_irrad_lf", 6, True), ("adia_cool_lin", 6, True), ("adia_cool_bell", 6, False),
                # EquationOfState: PVTE: lookup tables built by host/fargo_pvte.h, the reference's refresh order of gamma_eff / mu / Gamma_1
-               ("adia_pvte", 6, True),
+               ("adia_pvte", 6, True), ("adia_pvte_lf", 6, True),
                # AlphaMode 1: S-curve alpha in the stored temperature (viscosity/viscosity.cpp:31-49), Euler and Leapfrog
                ("adia_alpha_scurve", 6, True), ("adia_alpha_scurve_lf", 6, True),
                # SurfaceCooling: scurve (scurve_cooling, SourceEuler.cpp:726-831): ScurveType Kimura / Ichikawa

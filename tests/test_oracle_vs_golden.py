@@ -13,7 +13,7 @@ CASES = ["adia_star", "adia_cold", "iso_star", "iso_sn_std", "adia_sn_stab", "ri
          # opacity (Euler, Leapfrog), Lin & Papaloizou and Bell & Lin tables
          "adia_irrad", "adia_irrad_lf", "adia_cool_lin", "adia_cool_bell",
          # EquationOfState: PVTE (pvte_law.cpp): lookup tables built by host/fargo_pvte.h, gamma_eff / mu / Gamma_1 / H grids checked too
-         "adia_pvte",
+         "adia_pvte", "adia_pvte_lf",  # _lf: the second kick of a leapfrog step refreshes the grids after its potential (simulation.cpp:368-376)
          # AlphaMode 1: S-curve alpha in the stored TEMPERATURE grid (viscosity/viscosity.cpp:31-49), Euler and Leapfrog
          "adia_alpha_scurve", "adia_alpha_scurve_lf",
          # SurfaceCooling: scurve (scurve_cooling, SourceEuler.cpp:726-831): Kimura with the S-curve alpha, Ichikawa with Leapfrog
