@@ -1041,8 +1041,6 @@ extern "C" int fargo_set_pvte(fargo_ctx *c, const fargo_pvte_consts *k)
     CUDA_OK(cudaSetDevice(c->device));
     if (!c->v.p.pvte || !c->v.p.adiabatic)
 	return fail("fargo_set_pvte: the context was not created with params.pvte");
-    if (c->v.p.leapfrog)
-	return fail("EquationOfState: PVTE is implemented for the Euler integrator only");
     static fargo_pvte_tables *cached = nullptr;
     if (!cached || memcmp(&cached->k, k, sizeof(*k)) != 0) {
 	fargo_pvte_free(cached);
@@ -1600,9 +1598,11 @@ static int store_alpha_temperature(fargo_ctx *c)
 
 extern "C" int fargo_stage_derived(fargo_ctx *c)
 {
-    if (c->v.pv.geff) { // PVTE: scale height after Transport (simulation.cpp:256-262), then the lookup and the new scale height
+    if (c->v.pv.geff) { // PVTE: scale height after Transport (step_Euler only: simulation.cpp:256-262), then the lookup and the new
+			// scale height; step_LeapFrog goes straight to recalculate_derived_disk_quantities (:455), whose lookup
+			// reads the scale height its second kick stored
 	CUDA_OK(cudaSetDevice(c->device));
-	LAUNCH(c, k_pvte_refresh, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, EN(c), 1);
+	LAUNCH(c, k_pvte_refresh, cells_grid((long long)c->v.nr * c->v.ns), 256, 0, c->v, c->sigma, EN(c), c->v.p.leapfrog ? 0 : 1);
     }
     if (c->v.t_alpha) {
 	CUDA_OK(cudaSetDevice(c->device));
