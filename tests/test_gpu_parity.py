@@ -28,6 +28,10 @@ CASES += ["iso_bc_viscous", "adia_bc_keplerian_vrad"]
 # glibc's differ in the last bits, so these two runs are held to a tolerance instead (fields, dt)
 POW_CASES = ["adia_cool_lin", "adia_cool_bell"]
 POW_RTOL = 1e-12
+# what the last-bit differences of log10 / pow / tanh can explain in the S-curve fits and the PVTE lookup (measured: 8e-16 for the
+# S-curve alpha, 4e-15 for the S-curve cooling, whose flux is pow(10, x) with |x| ~ 10-25, 0 for PVTE and the opacity tables);
+# an operation out of the reference's order showed up as 3.5e-14 once — hence tighter than POW_RTOL
+LIBM_RTOL = 2e-14
 # 100 hydro steps with a Jupiter-mass planet (48 x 160: two warp windows per ring), recorded from the reference
 LONG_CASES = ["adia_planet_100", "iso_planet_100"]
 # a planet that accretes gas out of its Hill sphere first thing in every step (accretion.cpp:84-221)
@@ -152,7 +156,7 @@ def test_pvte_run_vs_reference(name):
         worst = max(worst, float(np.abs(got - ref).max() / np.abs(ref).max()))
         ndiff += int((got != ref).sum())
     print(name, ": worst deviation / field scale", worst, "differing doubles", ndiff)
-    assert worst <= POW_RTOL
+    assert worst <= LIBM_RTOL
 
 
 @pytest.mark.parametrize("name", ["adia_star", "iso_sn_std", "adia_planet_100", "adia_accrete_20"])
@@ -198,7 +202,7 @@ def test_alpha_scurve_run_vs_reference(name):
         worst = max(worst, float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-300)))  # an all-zero Q- (no cooling) must be 0
         ndiff += int((got != ref).sum())
     print(name, ": worst deviation / field scale", worst, "differing doubles", ndiff)
-    assert worst <= POW_RTOL
+    assert worst <= LIBM_RTOL
 
 
 @pytest.mark.parametrize("name", ["adia_star", "iso_star"])
