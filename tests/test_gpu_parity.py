@@ -128,7 +128,7 @@ def test_opacity_table_runs_vs_reference(name, staged):
             ref = z[f"{fname}_{k}"]
             dev = float(np.abs(snap[fname] - ref).max() / np.abs(ref).max())
             worst = max(worst, dev)
-            assert dev <= POW_RTOL, (name, k, fname, dev)
+            assert dev <= LIBM_RTOL, (name, k, fname, dev)  # measured: 0 (CUDA's pow agrees with glibc's on these arguments)
     print(name, "worst deviation / field scale:", worst)
 
 
