@@ -334,6 +334,18 @@ class Handle:
     def clear_massflow(self):
         self._check(self._call("clear_massflow"), "clear_massflow")
 
+    def track_boundary_flow(self, on=True):
+        self._check(self._call("track_boundary_flow", int(bool(on))), "track_boundary_flow")
+
+    def boundary_flow(self, reset=True):
+        """fargo_boundary_flow: (inner inflow, inner outflow, outer inflow, outer outflow) since the last reset."""
+        out = (C.c_double * 4)()
+        fn = self._fn("boundary_flow")
+        fn.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
+        fn.restype = C.c_int
+        self._check(fn(self.ptr, out, int(bool(reset))), "boundary_flow")
+        return tuple(out)
+
     def keep_potential(self, on=True):
         """fargo_keep_potential: the following kicks also store the POTENTIAL grid (for monitor_disk's potential columns)."""
         self._check(self._call("keep_potential", int(bool(on))), "keep_potential")
@@ -396,6 +408,10 @@ def load_library():
         lib.fargo_track_massflow.restype = C.c_int
         lib.fargo_clear_massflow.argtypes = [C.c_void_p]
         lib.fargo_clear_massflow.restype = C.c_int
+        lib.fargo_track_boundary_flow.argtypes = [C.c_void_p, C.c_int]
+        lib.fargo_track_boundary_flow.restype = C.c_int
+        lib.fargo_boundary_flow.argtypes = [C.c_void_p, _DP, C.c_int]
+        lib.fargo_boundary_flow.restype = C.c_int
         lib.fargo_keep_potential.argtypes = [C.c_void_p, C.c_int]
         lib.fargo_keep_potential.restype = C.c_int
         lib.fargo_monitor_disk.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, _DP]

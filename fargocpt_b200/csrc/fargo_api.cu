@@ -131,6 +131,7 @@ struct fargo_ctx {
     double *cfl_bmax = nullptr, *d_cfl_l = nullptr;
     double *mon_rings = nullptr; // fargo_monitor_disk: MD_N per-ring sums of the whole mesh
     double *massflow = nullptr;	 // fargo_track_massflow: MASSFLOW grid [nr + 1][ns]
+    double *bflow = nullptr;	 // fargo_track_boundary_flow: [4][ns] inner inflow / outflow, outer inflow / outflow, per column
     bool track_massflow = false;
     bool keep_pot = false;	 // fargo_keep_potential: fused kicks also store the POTENTIAL grid
     int pot_state = 0;		 // the POTENTIAL grid: 0 zeros (no kick yet, like the reference's), 1 of the last kick, 2 older
@@ -1421,13 +1422,24 @@ static int launch_transport(fargo_ctx *c, double dt, const double *vr_in, const 
     CUDA_OK(cudaEventRecord(c->ev_join, c->stream2));
     {
 	dim3 grid((unsigned)((v.ns + 127) / 128), (unsigned)((v.nr + c->rad_chunk - 1) / c->rad_chunk));
-	if (c->track_massflow) { // WriteMassFlow: the same sweep also accumulates the MASSFLOW grid
-	    if (v.p.adiabatic)
-		LAUNCH_NAMED(c, c->stream, "(k_transport_radial<LIM, true>)[+massflow]", (k_transport_radial<LIM, true, true>), grid, 128, 0, v,
-			     c->sigma, vr_in, vp_in, EN(c), c->t_sigma, c->t_rmp, c->t_rmm, c->t_amp, c->t_amm, c->t_e, dt, c->rad_chunk, c->massflow);
-	    else
-		LAUNCH_NAMED(c, c->stream, "(k_transport_radial<LIM, false>)[+massflow]", (k_transport_radial<LIM, false, true>), grid, 128, 0, v,
-			     c->sigma, vr_in, vp_in, EN(c), c->t_sigma, c->t_rmp, c->t_rmm, c->t_amp, c->t_amm, c->t_e, dt, c->rad_chunk, c->massflow);
+	if (c->track_massflow || c->bflow) { // WriteMassFlow / the boundary mass flows of Quantities.dat: the same sweep also accumulates them
+#define RADIAL_MF(ADI_, MODE_, label)                                                                                                       \
+    LAUNCH_NAMED(c, c->stream, label, (k_transport_radial<LIM, ADI_, MODE_>), grid, 128, 0, v, c->sigma, vr_in, vp_in, EN(c), c->t_sigma,     \
+		 c->t_rmp, c->t_rmm, c->t_amp, c->t_amm, c->t_e, dt, c->rad_chunk, c->massflow, c->bflow)
+	    if (c->track_massflow && !c->bflow && fargo_track_boundary_flow(c, 1)) // MF == 2 writes both
+		return 1;
+	    if (c->track_massflow) {
+		if (v.p.adiabatic)
+		    RADIAL_MF(true, 2, "(k_transport_radial<LIM, true>)[+massflow]");
+		else
+		    RADIAL_MF(false, 2, "(k_transport_radial<LIM, false>)[+massflow]");
+	    } else {
+		if (v.p.adiabatic)
+		    RADIAL_MF(true, 1, "(k_transport_radial<LIM, true>)[+boundary flow]");
+		else
+		    RADIAL_MF(false, 1, "(k_transport_radial<LIM, false>)[+boundary flow]");
+	    }
+#undef RADIAL_MF
 	} else if (v.p.adiabatic)
 	    LAUNCH(c, (k_transport_radial<LIM, true>), grid, 128, 0, v, c->sigma, vr_in, vp_in, EN(c), c->t_sigma, c->t_rmp, c->t_rmm,
 		   c->t_amp, c->t_amm, c->t_e, dt, c->rad_chunk);
@@ -2046,6 +2058,47 @@ extern "C" int fargo_clear_massflow(fargo_ctx *c)
     CUDA_OK(cudaSetDevice(c->device));
     if (c->massflow)
 	CUDA_OK(cudaMemsetAsync(c->massflow, 0, (size_t)(c->v.nr + 1) * c->v.ns * sizeof(double), c->stream));
+    return 0;
+}
+
+// MassDelta.Inner / OuterBoundaryInflow / Outflow (TransportEuler.cpp:578-608; columns 17-20 of monitor/Quantities.dat, reset after
+// every row: output.cpp:493)
+extern "C" int fargo_track_boundary_flow(fargo_ctx *c, int on)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    if (on && !c->bflow && dalloc(c, &c->bflow, (size_t)4 * c->v.ns)) // zeroed
+	return 1;
+    if (!on && c->bflow) {
+	if (c->track_massflow)
+	    return fail("fargo_track_boundary_flow(0) while the mass-flow grid is tracked");
+	c->bflow = nullptr; // stays allocated until the context goes (dev_allocs)
+    }
+    return 0;
+}
+extern "C" int fargo_boundary_flow(fargo_ctx *c, double out4[4], int reset)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    if (!c->bflow)
+	return fail("fargo_boundary_flow: not tracked (fargo_track_boundary_flow)");
+    const int ns = c->v.ns;
+    std::vector<double> h((size_t)4 * ns);
+    CUDA_OK(cudaMemcpyAsync(h.data(), c->bflow, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    double sums[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int q = 0; q < 4; ++q)
+	for (int j = 0; j < ns; ++j)
+	    sums[q] += h[(size_t)q * ns + j];
+    if (c->v.nranks > 1) { // MPI_Reduce(SUM), output.cpp:438-445: only the first and the last rank hold something
+	CUDA_OK(cudaMemcpyAsync(c->force4, sums, 4 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	NCCL_OK(g_nccl.AllReduce(c->force4, c->force4, 4, ncclFloat64, 0 /* ncclSum */, c->comm, c->stream));
+	c->launches++;
+	CUDA_OK(cudaMemcpyAsync(sums, c->force4, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_OK(cudaStreamSynchronize(c->stream));
+    }
+    for (int q = 0; q < 4; ++q)
+	out4[q] = sums[q];
+    if (reset)
+	CUDA_OK(cudaMemsetAsync(c->bflow, 0, h.size() * sizeof(double), c->stream));
     return 0;
 }
 

@@ -23,15 +23,17 @@
 #else
 #define TR_BOUNDS __launch_bounds__(128)
 #endif
-// MF (WriteMassFlow, TransportEuler.cpp:610-616): the mass through the inner interface of cell n in this step, F2[0], is also
-// added to massflow[n] — a separate instantiation, the kernel of every other run is unchanged.
-template <int LIM, bool ADIABATIC, bool MF = false>
+// MF >= 1 (write_disk_quantities, TransportEuler.cpp:578-608): the mass that crosses the mesh's inner boundary (interface 1) and
+// outer boundary (interface nr - 1) in this step is added, column by column, to bflow[4][ns] = inner inflow, inner outflow, outer
+// inflow, outer outflow.  MF == 2 (WriteMassFlow, :610-616): the mass through the inner interface of every cell n, F2[0], is also
+// added to massflow[n].  Separate instantiations: the kernel of a run that asks for neither is unchanged.
+template <int LIM, bool ADIABATIC, int MF = 0>
 __global__ void TR_BOUNDS
     k_transport_radial(const DevView c, const double *__restrict__ sigma, const double *__restrict__ vr,
 		       const double *__restrict__ vp, const double *__restrict__ energy, double *__restrict__ o_sigma,
 		       double *__restrict__ o_rmp, double *__restrict__ o_rmm, double *__restrict__ o_amp,
 		       double *__restrict__ o_amm, double *__restrict__ o_e, const double dt, const int chunk,
-		       double *__restrict__ massflow = nullptr)
+		       double *__restrict__ massflow = nullptr, double *__restrict__ bflow = nullptr)
 {
     constexpr int NB = ADIABATIC ? 6 : 5; // bases: Sigma, w_rm+, w_rm-, w_am+, w_am-, (w_e)
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -214,8 +216,21 @@ __global__ void TR_BOUNDS
 	    AT(o_amm, n, j) = fm_madd(F2[4] - F1[4], is, raw2[4]);
 	    if (ADIABATIC)
 		AT(o_e, n, j) = fm_madd(F2[5] - F1[5], is, raw2[5]);
-	    if (MF) // (+ varq_sup of the mesh's last ring, :613-615: the flux through interface nr, which is 0)
+	    if (MF == 2) // (+ varq_sup of the mesh's last ring, :613-615: the flux through interface nr, which is 0)
 		AT(massflow, n, j) += F2[0];
+	    if (MF >= 1) {
+		if (n == 1 && c.rank == 0) { // varq_inf of ring 1 (:586-595)
+		    if (F2[0] > 0)
+			bflow[j] += F2[0];
+		    else
+			bflow[c.ns + j] += -F2[0];
+		} else if (n == nr - 2 && c.rank == c.nranks - 1) { // varq_sup of ring nr - 2 (:596-606)
+		    if (F1[0] > 0)
+			bflow[3 * c.ns + j] += F1[0];
+		    else
+			bflow[2 * c.ns + j] += -F1[0];
+		}
+	    }
 	}
 #pragma unroll
 	for (int q = 0; q < NB; ++q) {

@@ -360,6 +360,14 @@ int fargo_monitor_disk(fargo_ctx *ctx, double radius_limit, double mass_fraction
 int fargo_track_massflow(fargo_ctx *ctx, int on);
 int fargo_clear_massflow(fargo_ctx *ctx);
 
+/* MassDelta.InnerBoundaryInflow / InnerBoundaryOutflow / OuterBoundaryInflow / OuterBoundaryOutflow (TransportEuler.cpp:578-608:
+ * the mass VanLeerRadial moves through the inner interface of ring 1 and the outer interface of ring nrad - 2, split by direction;
+ * columns 17-20 of monitor/Quantities.dat, which resets them after every row, output.cpp:493).  on != 0: the radial sweep
+ * accumulates them per column (a separate instantiation of the kernel); fargo_boundary_flow returns the four sums over the
+ * columns and over the ranks — out4 = { inner inflow, inner outflow, outer inflow, outer outflow } — and zeroes them if `reset`. */
+int fargo_track_boundary_flow(fargo_ctx *ctx, int on);
+int fargo_boundary_flow(fargo_ctx *ctx, double out4[4], int reset);
+
 /* CalculateNbodyPotential stores the POTENTIAL grid (Pframeforce.cpp:21-86); the fused source-term kernel keeps the potential in
  * registers.  on != 0: every following fargo_kick also stores the grid (one extra pass) for fargo_monitor_disk's potential
  * columns; a host switches it on for the step that ends on a monitor time.  The staged kernels always store it. */

@@ -50,6 +50,8 @@ typedef struct fargo_oracle {
     int kicks_this_step; /* fargo_oracle_kick calls since the last fargo_oracle_finish_step */
     double *qplus, *qminus, *divv, *trr, *tpp, *trp, *qr, *qphi, *nusig, *nusig_rp, *cf_r, *cf_phi, *tau_eff;
     double *massflow; /* MASSFLOW grid [nr + 1][ns], NULL unless fargo_oracle_track_massflow */
+    int track_bflow;
+    double bflow[4]; /* MassDelta: inner inflow / outflow, outer inflow / outflow */
     /* transport scratch (TransportEuler.cpp:32-46) */
     double *rmp, *rmm, *amp, *amm, *vres, *work, *qrstar, *densstar, *densint, *tempshift, *dq, *vmean;
     int *nshift;
@@ -1603,6 +1605,19 @@ static void vanleer_radial(fargo_oracle *o, const double *vr, double *qbase, dou
 	    const double varq_inf = dt * o->dphi * o->rinf[nr] * o->qrstar[c] * o->densstar[c] * vr[c];
 	    const double varq_sup = dt * o->dphi * o->rsup[nr] * o->qrstar[lip] * o->densstar[lip] * vr[lip];
 	    qbase[c] += (varq_inf - varq_sup) * o->invsurf[nr];
+	    if (is_density && o->track_bflow) { /* parameters::write_disk_quantities, :578-608 */
+		if (o->rank == 0 && nr == 1) {
+		    if (varq_inf > 0)
+			o->bflow[0] += varq_inf;
+		    else
+			o->bflow[1] += -varq_inf;
+		} else if (o->rank == o->nranks - 1 && nr == Nr - 2) {
+		    if (varq_sup > 0)
+			o->bflow[3] += varq_sup;
+		    else
+			o->bflow[2] += -varq_sup;
+		}
+	    }
 	    if (is_density && o->massflow) { /* parameters::write_massflow, :610-616 */
 		o->massflow[c] += varq_inf;
 		if (o->rank == o->nranks - 1 && nr == Nr - 1)
@@ -2245,6 +2260,22 @@ int fargo_oracle_clear_massflow(fargo_oracle *o)
 {
     if (o->massflow)
 	memset(o->massflow, 0, (size_t)(o->nr + 1) * o->ns * sizeof(double));
+    return 0;
+}
+
+/* MassDelta's boundary flows (TransportEuler.cpp:578-608), summed in the reference's order */
+int fargo_oracle_track_boundary_flow(fargo_oracle *o, int on)
+{
+    o->track_bflow = on != 0;
+    return 0;
+}
+int fargo_oracle_boundary_flow(fargo_oracle *o, double out4[4], int reset)
+{
+    for (int q = 0; q < 4; ++q) {
+	out4[q] = o->bflow[q];
+	if (reset)
+	    o->bflow[q] = 0.0;
+    }
     return 0;
 }
 

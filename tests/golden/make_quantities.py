@@ -28,7 +28,9 @@ COLUMNS = {"mass": 3, "angular_momentum": 5, "internal_energy": 7, "kinetic_ener
            "radius": 4, "eccentricity": 12, "periastron": 13, "aspect_ratio": 26,
            "advection_torque": 32, "viscous_torque": 33,
            # ... and the ones that read the POTENTIAL grid of the last step's start
-           "total_energy": 6, "potential_energy": 9, "gravitational_torque": 34}
+           "total_energy": 6, "potential_energy": 9, "gravitational_torque": 34,
+           # MassDelta's boundary flows since the previous row (TransportEuler.cpp:578-608)
+           "inner_boundary_inflow": 17, "inner_boundary_outflow": 18, "outer_boundary_inflow": 19, "outer_boundary_outflow": 20}
 
 
 def main():

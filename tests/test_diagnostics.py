@@ -295,21 +295,28 @@ def test_gpu_massflow_grid_vs_oracle():
     from fargocpt_b200 import HydroContext, synthetic
     import test_gpu_fullsize as F
     nrad, naz = 48, 131
-    cfg = synthetic.make_config("adiabatic_planet", nrad, naz)
+    cfg = synthetic.make_config("adiabatic_planet", nrad, naz, InnerBoundary="outflow", OuterBoundary="outflow", Damping="No")
     radii = synthetic.radii_from_config(cfg)
     params = synthetic.params_from_config(cfg)
     fields = synthetic.disk_fields(cfg, radii, perturb=2e-2)
     fields["vrad"] = fields["vrad"] + 1e-3 * np.cos(np.arange(naz) * 2 * np.pi * 3 / naz)[None, :]
-    out = {}
+    out, flows = {}, {}
     for name, ctx in (("gpu", HydroContext(params, radii)), ("cpu", reftools.OracleContext(params, radii))):
         orbit = F._start(ctx, cfg, fields)
         ctx.track_massflow(True)
+        ctx.track_boundary_flow(True)
         F._run(ctx, cfg, orbit, 4)
         mf = ctx.download(abi.MASSFLOW)
         assert mf.shape == (nrad + 1, naz)
         ctx.clear_massflow()
         out[name] = (mf, ctx.download(abi.MASSFLOW))
+        flows[name] = (ctx.boundary_flow(reset=True), ctx.boundary_flow(reset=False))
         ctx.close()
+    # MassDelta's boundary flows (TransportEuler.cpp:578-608): both directions occur with the perturbed v_rad; per-column sums on
+    # the device against the oracle's per-step sums: rounding
+    a, b = flows["gpu"], flows["cpu"]
+    assert min(b[0]) > 0.0 and a[1] == b[1] == (0.0, 0.0, 0.0, 0.0)
+    assert np.allclose(a[0], b[0], rtol=1e-13, atol=0.0), (a[0], b[0])
     st = reftools.compare_stats(out["gpu"][0], out["cpu"][0])
     assert st["n_diff"] == 0, st
     assert np.abs(out["cpu"][0]).max() > 0 and not out["gpu"][1].any() and not out["cpu"][1].any()

@@ -369,7 +369,9 @@ def test_host_writes_quantities_dat_cpu(name, tmp_path):
             # the mass-weighted columns (fargo_monitor_disk)
             "radius": 4, "eccentricity": 12, "periastron": 13, "aspect_ratio": 26, "advection_torque": 32, "viscous_torque": 33,
             # from the POTENTIAL grid of the last step's start (fargo_keep_potential)
-            "total_energy": 6, "potential_energy": 9, "gravitational_torque": 34}
+            "total_energy": 6, "potential_energy": 9, "gravitational_torque": 34,
+            # MassDelta's boundary flows since the previous row (fargo_boundary_flow)
+            "inner_boundary_inflow": 17, "inner_boundary_outflow": 18, "outer_boundary_inflow": 19, "outer_boundary_outflow": 20}
     for snap, want in ref.items():
         row = rows[int(snap)]
         assert int(row[0]) == int(snap)
@@ -378,7 +380,7 @@ def test_host_writes_quantities_dat_cpu(name, tmp_path):
                 assert float(row[c]) == want[q], (snap, q, row[c], want[q])
             else:
                 assert float(row[c]) == pytest.approx(want[q], rel=1e-9, abs=1e-300), (snap, q)
-        assert row[16] == "nan" and row[17] == "nan" and row[25] == "nan"  # pdivv, mass flows
+        assert row[16] == "nan" and row[21] == "nan" and row[25] == "nan"  # pdivv, damping and floor mass changes
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -491,6 +493,38 @@ def _massflow_check(exe, tmp_path):
             got = np.fromfile(os.path.join(out, "snapshots", str(k), f + ".dat"))
             assert np.array_equal(got, ref[f"{f}_{k}"]), (k, f, float(np.abs(got - ref[f"{f}_{k}"]).max()))
     assert np.abs(ref["MassFlow_2"]).max() > 0
+
+
+def _steady_state_quantities_check(exe, tmp_path, rtol):
+    """monitor/Quantities.dat of the shortened steady-state accretion run against the rows the unmodified reference wrote
+    (tests/golden/steady_state_quantities.npz): every column this path evaluates — the inner-boundary outflow of the accreting
+    disk (MassDelta, TransportEuler.cpp:578-608) among them — and nan in the ones it does not (pdivv, damping / floor mass)."""
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "tests", "golden", "steady_state_accretion_setup.yml")))
+    cfg["Nsnapshots"], cfg["Nmonitor"] = 2, 3
+    yml, out = str(tmp_path / "setup.yml"), str(tmp_path / "out")
+    yaml.safe_dump(cfg, open(yml, "w"), sort_keys=False)
+    _run_start(exe, yml, out, 2)
+    ref = np.load(os.path.join(ROOT, "tests", "golden", "steady_state_quantities.npz"))["rows"]
+    got = np.array([[float(x) for x in l.split()] for l in open(os.path.join(out, "monitor", "Quantities.dat")) if not l.startswith("#")])
+    assert got.shape == ref.shape == (7, 35)
+    nan_cols = [16, 21, 22, 23, 24, 25]
+    assert np.isnan(got[:, nan_cols]).all()
+    cols = [c for c in range(35) if c not in nan_cols]
+    assert ref[-1, 18] > 0  # the disk accretes through the inner boundary
+    if rtol == 0.0:
+        assert np.array_equal(got[:, cols], ref[:, cols]), [c for c in cols if not np.array_equal(got[:, c], ref[:, c])]
+    else:
+        scale = np.maximum(np.abs(ref[:, cols]).max(axis=0), 1e-6 * np.abs(ref[:, 3]).max())
+        assert (np.abs(got[:, cols] - ref[:, cols]) / scale).max() <= rtol
+
+
+def test_host_quantities_of_an_accreting_disk_are_the_references_cpu(tmp_path):
+    _steady_state_quantities_check(_oracle_exe(), tmp_path, 0.0)
+
+
+@pytest.mark.gpu
+def test_host_quantities_of_an_accreting_disk_are_the_references_gpu(tmp_path):
+    _steady_state_quantities_check(os.path.join(ROOT, "host", "fargocpt_b200"), tmp_path, 1e-12)
 
 
 def test_host_writes_the_references_massflow_files_cpu(tmp_path):
