@@ -1714,8 +1714,8 @@ struct Run {
 
     // output::write_quantities (output.cpp:326-493): one row of monitor/Quantities.dat per monitor step, file version 2.4 with
     // the 35 columns of quantities_file_column_v2_5 (output.cpp:39-75).  The global sums come from fargo_monitor_quantities
-    // and fargo_monitor_disk (device reductions); columns this path does not evaluate (pdivv, damping and floor
-    // mass changes) are written as nan, never as made-up numbers.
+    // and fargo_monitor_disk (device reductions); columns this path does not evaluate (damping and floor mass
+    // changes) are written as nan, never as made-up numbers.
     bool quantities_header_written = false;
     void write_quantities()
     {
@@ -1769,6 +1769,11 @@ struct Run {
 	    double d[9];
 	    CHECK(BK(monitor_disk)(ctx, limit, cfg.num("DiskRadiusMassFraction", 0.99), frame_angle, d));
 	    row[30] = d[5], row[31] = d[6], row[32] = d[8]; // advection, viscous, gravitational torque (quantities.cpp:1000-1018)
+	    // pdivv_total is only formed when the P_DIVV grid is written (SourceEuler.cpp:881-899); without WritepDV the reference
+	    // prints the 0 it was initialised with (data.cpp:302)
+	    if (cfg.flag("WritepDV", false))
+		die("%s", std::string("WritepDV is not supported by this driver"));
+	    row[14] = 0.0;
 	    double bf[4]; // MassDelta.Inner / OuterBoundaryInflow / Outflow since the last row (output.cpp:438-445, reset :493)
 	    CHECK(BK(boundary_flow)(ctx, bf, 1));
 	    row[15] = bf[0], row[16] = bf[1], row[17] = bf[2], row[18] = bf[3];
