@@ -346,6 +346,18 @@ class Handle:
         self._check(fn(self.ptr, out, int(bool(reset))), "boundary_flow")
         return tuple(out)
 
+    def track_damping_mass(self, on=True):
+        self._check(self._call("track_damping_mass", int(bool(on))), "track_damping_mass")
+
+    def damping_mass(self, reset=True):
+        """fargo_damping_mass: (inner creation, inner removal, outer creation, outer removal) since the last reset."""
+        out = (C.c_double * 4)()
+        fn = self._fn("damping_mass")
+        fn.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
+        fn.restype = C.c_int
+        self._check(fn(self.ptr, out, int(bool(reset))), "damping_mass")
+        return tuple(out)
+
     def keep_potential(self, on=True):
         """fargo_keep_potential: the following kicks also store the POTENTIAL grid (for monitor_disk's potential columns)."""
         self._check(self._call("keep_potential", int(bool(on))), "keep_potential")
@@ -412,6 +424,10 @@ def load_library():
         lib.fargo_track_boundary_flow.restype = C.c_int
         lib.fargo_boundary_flow.argtypes = [C.c_void_p, _DP, C.c_int]
         lib.fargo_boundary_flow.restype = C.c_int
+        lib.fargo_track_damping_mass.argtypes = [C.c_void_p, C.c_int]
+        lib.fargo_track_damping_mass.restype = C.c_int
+        lib.fargo_damping_mass.argtypes = [C.c_void_p, _DP, C.c_int]
+        lib.fargo_damping_mass.restype = C.c_int
         lib.fargo_keep_potential.argtypes = [C.c_void_p, C.c_int]
         lib.fargo_keep_potential.restype = C.c_int
         lib.fargo_monitor_disk.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, _DP]

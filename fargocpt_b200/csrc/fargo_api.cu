@@ -131,6 +131,7 @@ struct fargo_ctx {
     double *cfl_bmax = nullptr, *d_cfl_l = nullptr;
     double *mon_rings = nullptr; // fargo_monitor_disk: MD_N per-ring sums of the whole mesh
     double *massflow = nullptr;	 // fargo_track_massflow: MASSFLOW grid [nr + 1][ns]
+    double *dmass = nullptr;	 // fargo_track_damping_mass: [4][ns] inner creation / removal, outer creation / removal, per column
     double *bflow = nullptr;	 // fargo_track_boundary_flow: [4][ns] inner inflow / outflow, outer inflow / outflow, per column
     bool track_massflow = false;
     bool keep_pot = false;	 // fargo_keep_potential: fused kicks also store the POTENTIAL grid
@@ -1235,7 +1236,7 @@ static int damp_field(fargo_ctx *c, double *x, const double *x0, bool is_vector,
     const std::vector<double> &radius = is_vector ? c->h_rinf : c->h_rmed;
     const double RMIN = p.rmin, RMAX = p.rmax;
     const double x0_const = is_density ? p.sigma_floor * p.sigma0 : 0.0;
-    struct Zone { int lo, hi, type; } zones[2];
+    struct Zone { int lo, hi, type, outer; } zones[2];
     int nz = 0;
     for (int n = 0; n < rings; ++n)
 	h_expf[n] = 1.0;
@@ -1248,7 +1249,7 @@ static int damp_field(fargo_ctx *c, double *x, const double *x0, bool is_vector,
 	    const double factor = q * q;
 	    h_expf[n] = exp(-dt * factor / tau);
 	}
-	zones[nz++] = {0, limit + 1, type[0]};
+	zones[nz++] = {0, limit + 1, type[0], 0};
     }
     if (type[1] != FARGO_DAMP_NONE && (p.damping_outer_limit < 1.0) && (radius[rings - 1] > RMAX * p.damping_outer_limit)) {
 	const int limit = is_vector ? clamp_id(c, rinf_id(c, RMAX * p.damping_outer_limit) + 1, true)
@@ -1259,7 +1260,7 @@ static int damp_field(fargo_ctx *c, double *x, const double *x0, bool is_vector,
 	    const double factor = q * q;
 	    h_expf[n] = exp(-dt * factor / tau);
 	}
-	zones[nz++] = {limit, rings, type[1]};
+	zones[nz++] = {limit, rings, type[1], 1};
     }
     for (int z = 0; z < nz; ++z) {
 	const int nrings = zones[z].hi - zones[z].lo;
@@ -1267,8 +1268,9 @@ static int damp_field(fargo_ctx *c, double *x, const double *x0, bool is_vector,
 	    continue;
 	DampJob &J = jobs.j[jobs.n++];
 	J.x = x, J.x0 = x0, J.expf = d_expf;
-	J.ring_lo = zones[z].lo, J.ring_hi = zones[z].hi, J.type = zones[z].type, J.row0 = rows;
+	J.ring_lo = zones[z].lo, J.ring_hi = zones[z].hi, J.type = zones[z].type, J.row0 = rows, J.outer = zones[z].outer;
 	J.x0_const = x0_const;
+	J.dmass = (is_density && c->dmass) ? c->scratch : nullptr; // the scratch grid is free between Transport and the CFL
 	rows += nrings;
     }
     return 0;
@@ -1319,6 +1321,8 @@ static int arm_damping_fold(fargo_ctx *c, double dt)
 	if (J.type != FARGO_DAMP_INITIAL && J.type != FARGO_DAMP_ZERO)
 	    return 0; // ring-mean damping somewhere: everything stays with k_damping
 	const int f = J.x == v.vr ? 0 : J.x == v.vp ? 1 : J.x == c->sigma ? 2 : 3;
+	if (f == 2 && c->dmass)
+	    continue; // MassDelta's wave-damping terms need Sigma before and after: its zones keep their own pass (fargo_stage_boundary)
 	for (int i = J.ring_lo; i < J.ring_hi; ++i)
 	    mask[i] |= (J.type == FARGO_DAMP_INITIAL ? 1 : 2) << (2 * f);
     }
@@ -1338,16 +1342,34 @@ extern "C" int fargo_stage_boundary(fargo_ctx *c, double dt, int final_call)
     CUDA_OK(cudaSetDevice(c->device));
     const fargo_params &p = c->v.p;
     VBuf v = cur_v(c, c->v_mid);
-    if (final_call && p.damping && c->damp_folded) {
+    if (final_call && p.damping && c->damp_folded && !c->dmass) {
 	c->damp_folded = false; // this step's damping was applied in the azimuthal transport kernel's epilogue
     } else if (final_call && p.damping) {
 	DampJobs jobs;
 	int rows = 0;
 	if (prepare_damping(c, v, dt, jobs, rows))
 	    return 1;
+	if (c->damp_folded) { // only Sigma's zones were left out of the fold (mass tracking): keep those jobs
+	    DampJobs only;
+	    only.n = 0;
+	    rows = 0;
+	    for (int q = 0; q < jobs.n; ++q)
+		if (jobs.j[q].x == c->sigma) {
+		    only.j[only.n] = jobs.j[q];
+		    only.j[only.n].row0 = rows;
+		    rows += jobs.j[q].ring_hi - jobs.j[q].ring_lo;
+		    only.n++;
+		}
+	    jobs = only;
+	    c->damp_folded = false;
+	}
 	if (jobs.n > 0) {
 	    dim3 grid((unsigned)((c->v.ns + 1023) / 1024), (unsigned)rows);
 	    LAUNCH(c, k_damping, grid, 256, 0, c->v, jobs);
+	    for (int q = 0; q < jobs.n; ++q) // MassDelta: inner and outer zone apart (damping.cpp:311-357 / 359-420)
+		if (jobs.j[q].dmass)
+		    LAUNCH(c, k_dmass_accumulate, (unsigned)((c->v.ns + 127) / 128), 128, 0, c->v, (const double *)jobs.j[q].dmass,
+			   jobs.j[q].ring_lo, jobs.j[q].ring_hi, c->dmass + (jobs.j[q].outer ? 2 : 0) * (size_t)c->v.ns);
 	}
     }
     // keplerian_azimuthal.cpp:29-38, :51-59 (host: sqrt with glibc == IEEE, value is per call)
@@ -2058,6 +2080,45 @@ extern "C" int fargo_clear_massflow(fargo_ctx *c)
     CUDA_OK(cudaSetDevice(c->device));
     if (c->massflow)
 	CUDA_OK(cudaMemsetAsync(c->massflow, 0, (size_t)(c->v.nr + 1) * c->v.ns * sizeof(double), c->stream));
+    return 0;
+}
+
+// MassDelta.Inner / OuterWaveDampingMassCreation / Removal (damping.cpp:335-357, 394-420 and the _zero / _mean siblings; columns
+// 21-24 of monitor/Quantities.dat).  While tracked, the zones of Sigma are damped by k_damping in its own pass (the other fields stay
+// folded into the transport kernel): the mass change of a cell needs Sigma before and after.
+extern "C" int fargo_track_damping_mass(fargo_ctx *c, int on)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    if (on && !c->dmass && dalloc(c, &c->dmass, (size_t)4 * c->v.ns)) // zeroed
+	return 1;
+    if (!on)
+	c->dmass = nullptr; // stays allocated until the context goes (dev_allocs)
+    return 0;
+}
+extern "C" int fargo_damping_mass(fargo_ctx *c, double out4[4], int reset)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    if (!c->dmass)
+	return fail("fargo_damping_mass: not tracked (fargo_track_damping_mass)");
+    const int ns = c->v.ns;
+    std::vector<double> h((size_t)4 * ns);
+    CUDA_OK(cudaMemcpyAsync(h.data(), c->dmass, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    double sums[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int q = 0; q < 4; ++q)
+	for (int j = 0; j < ns; ++j)
+	    sums[q] += h[(size_t)q * ns + j];
+    if (c->v.nranks > 1) { // MPI_Reduce(SUM), output.cpp:446-453
+	CUDA_OK(cudaMemcpyAsync(c->force4, sums, 4 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	NCCL_OK(g_nccl.AllReduce(c->force4, c->force4, 4, ncclFloat64, 0 /* ncclSum */, c->comm, c->stream));
+	c->launches++;
+	CUDA_OK(cudaMemcpyAsync(sums, c->force4, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_OK(cudaStreamSynchronize(c->stream));
+    }
+    for (int q = 0; q < 4; ++q)
+	out4[q] = sums[q];
+    if (reset)
+	CUDA_OK(cudaMemsetAsync(c->dmass, 0, h.size() * sizeof(double), c->stream));
     return 0;
 }
 

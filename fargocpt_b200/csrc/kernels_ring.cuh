@@ -156,7 +156,10 @@ struct DampJob {
     double *x;
     const double *x0, *expf;
     int ring_lo, ring_hi, type, row0; // row0 = first blockIdx.y of this job
+    int outer;			       // 0: the inner damping zone, 1: the outer one
     double x0_const;
+    double *dmass; // Sigma jobs of a run that tracks MassDelta's wave-damping terms (damping.cpp:335-357 and its siblings): the mass
+		   // (Xnew - X) Surf a cell gained, stored at the cell's place in this scratch grid; nullptr otherwise
 };
 struct DampJobs {
     int n;
@@ -197,7 +200,12 @@ __global__ void __launch_bounds__(256) k_damping(const DevView c, const DampJobs
     for (int j = jbeg; j < c.ns; j += jstride) {
 	const double X = AT(x, ring, j);
 	const double X0 = (type == FARGO_DAMP_INITIAL) ? AT(x0, ring, j) : (type == FARGO_DAMP_MEAN ? mean : J.x0_const);
-	AT(x, ring, j) = (X - X0) * ef + X0;
+	const double Xnew = (X - X0) * ef + X0;
+	AT(x, ring, j) = Xnew;
+	if (J.dmass) {
+	    const double delta = Xnew - X;
+	    AT(J.dmass, ring, j) = delta * c.g.surf[ring];
+	}
     }
 }
 
@@ -367,6 +375,27 @@ __global__ void __launch_bounds__(32)
     }
     if (lane < nrows)
 	ring_mean_finish(c, ring0 + lane, s, vmean, nshift, vconst, dt, mode);
+}
+
+// MassDelta.Inner / OuterWaveDampingMassCreation / Removal: the per-cell mass changes k_damping left in `cellmass`, added per
+// column in ring order over the ACTIVE rings of a zone (sum_without_ghost_cells) to acc[2][ns] = creation, removal
+__global__ void __launch_bounds__(128)
+    k_dmass_accumulate(const DevView c, const double *__restrict__ cellmass, const int ring_lo, const int ring_hi, double *__restrict__ acc)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= c.ns)
+	return;
+    double created = acc[j], removed = acc[c.ns + j];
+    const int lo = max(ring_lo, c.first_active), hi = min(ring_hi, c.active_size);
+    for (int i = lo; i < hi; ++i) {
+	const double m = AT(cellmass, i, j);
+	if (m > 0)
+	    created += m;
+	else
+	    removed += -m;
+    }
+    acc[j] = created;
+    acc[c.ns + j] = removed;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -78,6 +78,8 @@ int fargo_oracle_track_massflow(fargo_oracle *, int);
 int fargo_oracle_clear_massflow(fargo_oracle *);
 int fargo_oracle_track_boundary_flow(fargo_oracle *, int);
 int fargo_oracle_boundary_flow(fargo_oracle *, double *, int);
+int fargo_oracle_track_damping_mass(fargo_oracle *, int);
+int fargo_oracle_damping_mass(fargo_oracle *, double *, int);
 int fargo_oracle_accrete_sinkhole(fargo_oracle *, double, double, double, double, double, double *);
 int fargo_oracle_accrete_viscous(fargo_oracle *, double, double, double, double, double, double *);
 int fargo_oracle_correct_vazi(fargo_oracle *, double);
@@ -980,8 +982,11 @@ struct Run {
 #endif
 	if (cfg.flag("WriteMassFlow", false)) // parameters.cpp:334-335
 	    CHECK(BK(track_massflow)(ctx, 1));
-	if (cfg.flag("WriteDiskQuantities", true)) // MassDelta's boundary flows (TransportEuler.cpp:578-608)
+	if (cfg.flag("WriteDiskQuantities", true)) { // MassDelta's boundary flows (TransportEuler.cpp:578-608) and wave-damping terms
 	    CHECK(BK(track_boundary_flow)(ctx, 1));
+	    if (params.damping)
+		CHECK(BK(track_damping_mass)(ctx, 1));
+	}
     }
 
     // All ranks meet here (host side, through the shared output directory: arrival files of a numbered barrier).
@@ -1714,8 +1719,8 @@ struct Run {
 
     // output::write_quantities (output.cpp:326-493): one row of monitor/Quantities.dat per monitor step, file version 2.4 with
     // the 35 columns of quantities_file_column_v2_5 (output.cpp:39-75).  The global sums come from fargo_monitor_quantities
-    // and fargo_monitor_disk (device reductions); columns this path does not evaluate (damping and floor mass
-    // changes) are written as nan, never as made-up numbers.
+    // and fargo_monitor_disk (device reductions); the one column this path does not evaluate (the density-floor
+    // mass creation) are written as nan, never as made-up numbers.
     bool quantities_header_written = false;
     void write_quantities()
     {
@@ -1777,6 +1782,10 @@ struct Run {
 	    double bf[4]; // MassDelta.Inner / OuterBoundaryInflow / Outflow since the last row (output.cpp:438-445, reset :493)
 	    CHECK(BK(boundary_flow)(ctx, bf, 1));
 	    row[15] = bf[0], row[16] = bf[1], row[17] = bf[2], row[18] = bf[3];
+	    double dm[4] = {0.0, 0.0, 0.0, 0.0}; // Inner / OuterWaveDampingMassCreation / Removal (output.cpp:446-453): 0 without damping
+	    if (params.damping)
+		CHECK(BK(damping_mass)(ctx, dm, 1));
+	    row[19] = dm[0], row[20] = dm[1], row[21] = dm[2], row[22] = dm[3];
 	    row[7] = d[7];			     // gravitationalEnergy (output.cpp:413-414)
 	    row[4] = q[2] + q[3] + d[7];	     // totalEnergy = internalEnergy + kinematicEnergy + gravitationalEnergy (:416-417)
 	    row[2] = d[0];

@@ -368,6 +368,13 @@ int fargo_clear_massflow(fargo_ctx *ctx);
 int fargo_track_boundary_flow(fargo_ctx *ctx, int on);
 int fargo_boundary_flow(fargo_ctx *ctx, double out4[4], int reset);
 
+/* MassDelta.InnerWaveDampingMassCreation / Removal, OuterWaveDampingMassCreation / Removal (damping.cpp:335-357 and its inner /
+ * outer, initial / zero / mean siblings: the mass (Xnew - X) Surf the damping of Sigma adds to or takes from the active cells of a
+ * zone; columns 21-24 of monitor/Quantities.dat, reset after every row).  While tracked the zones of Sigma are damped in their own
+ * pass.  fargo_damping_mass: out4 = { inner creation, inner removal, outer creation, outer removal }, all ranks; zeroes if `reset`. */
+int fargo_track_damping_mass(fargo_ctx *ctx, int on);
+int fargo_damping_mass(fargo_ctx *ctx, double out4[4], int reset);
+
 /* CalculateNbodyPotential stores the POTENTIAL grid (Pframeforce.cpp:21-86); the fused source-term kernel keeps the potential in
  * registers.  on != 0: every following fargo_kick also stores the grid (one extra pass) for fargo_monitor_disk's potential
  * columns; a host switches it on for the step that ends on a monitor time.  The staged kernels always store it. */

@@ -52,6 +52,7 @@ typedef struct fargo_oracle {
     double *massflow; /* MASSFLOW grid [nr + 1][ns], NULL unless fargo_oracle_track_massflow */
     int track_bflow;
     double bflow[4]; /* MassDelta: inner inflow / outflow, outer inflow / outflow */
+    double dmass[4]; /* MassDelta: inner wave-damping mass creation / removal, outer creation / removal */
     /* transport scratch (TransportEuler.cpp:32-46) */
     double *rmp, *rmm, *amp, *amm, *vres, *work, *qrstar, *densstar, *densint, *tempshift, *dq, *vmean;
     int *nshift;
@@ -1275,6 +1276,7 @@ static void damp_field(fargo_oracle *o, double *x, const double *x0, int is_vect
 	const int limit = is_vector ? clamp_id(o, rinf_id(o, RMIN * o->p.damping_inner_limit), 1)
 				    : clamp_id(o, rmed_id(o, RMIN * o->p.damping_inner_limit), 0);
 	const double tau = o->p.damping_time_factor * 2.0 * M_PI / omega_kepler(o, RMIN);
+	double created = 0.0, removed = 0.0; /* the privates of `reduction(+ : ...)` (damping.cpp:338), added to MassDelta at the end */
 	for (int nr = 0; nr <= limit; ++nr) {
 	    const double q = (radius[nr] - RMIN * o->p.damping_inner_limit) / (RMIN - RMIN * o->p.damping_inner_limit);
 	    const double factor = q * q;
@@ -1295,14 +1297,25 @@ static void damp_field(fargo_oracle *o, double *x, const double *x0, int is_vect
 		    X0 = mean;
 		else
 		    X0 = is_density ? o->p.sigma_floor * o->p.sigma0 : 0.0;
-		x[c] = (X - X0) * exp_factor + X0;
+		const double Xnew = (X - X0) * exp_factor + X0;
+		x[c] = Xnew;
+		const double delta = Xnew - X;
+		if (is_density && o->first_active <= nr && nr < o->active_size) { /* sum_without_ghost_cells, damping.cpp:345-357 */
+		    if (delta > 0)
+			created += delta * o->surf[nr];
+		    else
+			removed += -delta * o->surf[nr];
+		}
 	    }
 	}
+	o->dmass[0] += created;
+	o->dmass[1] += removed;
     }
     if (type[1] != FARGO_DAMP_NONE && (o->p.damping_outer_limit < 1.0) && (radius[rings - 1] > RMAX * o->p.damping_outer_limit)) {
 	const int limit = is_vector ? clamp_id(o, rinf_id(o, RMAX * o->p.damping_outer_limit) + 1, 1)
 				    : clamp_id(o, rmed_id(o, RMAX * o->p.damping_outer_limit) + 1, 0);
 	const double tau = o->p.damping_time_factor * 2.0 * M_PI / omega_kepler(o, o->p.damping_time_radius_outer);
+	double created = 0.0, removed = 0.0;
 	for (int nr = limit; nr < rings; ++nr) {
 	    const double q = (radius[nr] - RMAX * o->p.damping_outer_limit) / (RMAX - RMAX * o->p.damping_outer_limit);
 	    const double factor = q * q;
@@ -1323,9 +1336,19 @@ static void damp_field(fargo_oracle *o, double *x, const double *x0, int is_vect
 		    X0 = mean;
 		else
 		    X0 = is_density ? o->p.sigma_floor * o->p.sigma0 : 0.0;
-		x[c] = (X - X0) * exp_factor + X0;
+		const double Xnew = (X - X0) * exp_factor + X0;
+		x[c] = Xnew;
+		const double delta = Xnew - X;
+		if (is_density && o->first_active <= nr && nr < o->active_size) { /* sum_without_ghost_cells, damping.cpp:345-357 */
+		    if (delta > 0)
+			created += delta * o->surf[nr];
+		    else
+			removed += -delta * o->surf[nr];
+		}
 	    }
 	}
+	o->dmass[2] += created;
+	o->dmass[3] += removed;
     }
 }
 
@@ -2275,6 +2298,22 @@ int fargo_oracle_boundary_flow(fargo_oracle *o, double out4[4], int reset)
 	out4[q] = o->bflow[q];
 	if (reset)
 	    o->bflow[q] = 0.0;
+    }
+    return 0;
+}
+
+/* MassDelta's wave-damping terms (damping.cpp:335-357 and siblings), always kept */
+int fargo_oracle_track_damping_mass(fargo_oracle *o, int on)
+{
+    (void)o, (void)on;
+    return 0;
+}
+int fargo_oracle_damping_mass(fargo_oracle *o, double out4[4], int reset)
+{
+    for (int q = 0; q < 4; ++q) {
+	out4[q] = o->dmass[q];
+	if (reset)
+	    o->dmass[q] = 0.0;
     }
     return 0;
 }

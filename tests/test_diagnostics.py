@@ -320,3 +320,31 @@ def test_gpu_massflow_grid_vs_oracle():
     st = reftools.compare_stats(out["gpu"][0], out["cpu"][0])
     assert st["n_diff"] == 0, st
     assert np.abs(out["cpu"][0]).max() > 0 and not out["gpu"][1].any() and not out["cpu"][1].any()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("naz", [160, 131])
+def test_gpu_damping_mass_vs_oracle(naz):
+    """fargo_track_damping_mass: MassDelta's wave-damping mass creation / removal of both zones (damping.cpp:335-357 and siblings).
+    While tracked, Sigma's zones are damped in their own pass (the other fields stay folded into the transport kernel): the fields
+    must stay the oracle's bit for bit, the four sums agree to rounding (per-column sums on the device)."""
+    from fargocpt_b200 import HydroContext, synthetic
+    import test_gpu_fullsize as F
+    nrad = 96
+    cfg = synthetic.make_config("adiabatic_planet", nrad, naz, DampingInnerLimit=1.4, DampingOuterLimit=0.7, DampingSurfaceDensityOuter="Zero")
+    radii = synthetic.radii_from_config(cfg)
+    params = synthetic.params_from_config(cfg)
+    fields = synthetic.disk_fields(cfg, radii, perturb=2e-2)
+    out = {}
+    for name, ctx in (("gpu", HydroContext(params, radii)), ("cpu", reftools.OracleContext(params, radii))):
+        orbit = F._start(ctx, cfg, fields)
+        ctx.track_damping_mass(True)
+        dts, _ = F._run(ctx, cfg, orbit, 4)
+        out[name] = (dts, {f: ctx.download(f) for f in (abi.SIGMA, abi.VRAD, abi.VAZI, abi.ENERGY)}, ctx.damping_mass(reset=True), ctx.damping_mass(reset=False))
+        ctx.close()
+    assert out["gpu"][0] == out["cpu"][0]
+    for f in (abi.SIGMA, abi.VRAD, abi.VAZI, abi.ENERGY):
+        assert reftools.compare_stats(out["gpu"][1][f], out["cpu"][1][f])["n_diff"] == 0, f
+    a, b = out["gpu"][2], out["cpu"][2]
+    assert max(b) > 0.0 and out["gpu"][3] == out["cpu"][3] == (0.0, 0.0, 0.0, 0.0)
+    assert np.allclose(a, b, rtol=1e-12, atol=1e-20), (a, b)

@@ -380,7 +380,7 @@ def test_host_writes_quantities_dat_cpu(name, tmp_path):
                 assert float(row[c]) == want[q], (snap, q, row[c], want[q])
             else:
                 assert float(row[c]) == pytest.approx(want[q], rel=1e-9, abs=1e-300), (snap, q)
-        assert float(row[16]) == 0.0 and row[21] == "nan" and row[25] == "nan"  # pdivv without WritepDV; damping and floor mass changes
+        assert float(row[16]) == 0.0 and row[25] == "nan"  # pdivv without WritepDV; density-floor mass creation
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -498,7 +498,7 @@ def _massflow_check(exe, tmp_path):
 def _steady_state_quantities_check(exe, tmp_path, rtol):
     """monitor/Quantities.dat of the shortened steady-state accretion run against the rows the unmodified reference wrote
     (tests/golden/steady_state_quantities.npz): every column this path evaluates — the inner-boundary outflow of the accreting
-    disk (MassDelta, TransportEuler.cpp:578-608) among them — and nan in the ones it does not (damping / floor mass changes)."""
+    disk (MassDelta, TransportEuler.cpp:578-608) among them — the wave-damping mass creation / removal of both zones too — and nan in the one it does not (density-floor mass creation)."""
     cfg = yaml.safe_load(open(os.path.join(ROOT, "tests", "golden", "steady_state_accretion_setup.yml")))
     cfg["Nsnapshots"], cfg["Nmonitor"] = 2, 3
     yml, out = str(tmp_path / "setup.yml"), str(tmp_path / "out")
@@ -507,7 +507,7 @@ def _steady_state_quantities_check(exe, tmp_path, rtol):
     ref = np.load(os.path.join(ROOT, "tests", "golden", "steady_state_quantities.npz"))["rows"]
     got = np.array([[float(x) for x in l.split()] for l in open(os.path.join(out, "monitor", "Quantities.dat")) if not l.startswith("#")])
     assert got.shape == ref.shape == (7, 35)
-    nan_cols = [21, 22, 23, 24, 25]
+    nan_cols = [25]
     assert np.isnan(got[:, nan_cols]).all()
     cols = [c for c in range(35) if c not in nan_cols]
     assert ref[-1, 18] > 0  # the disk accretes through the inner boundary
