@@ -32,6 +32,8 @@ def run_slab(ctx, cfg, radii, fields, nsteps, synthetic, abi):
     ctx.stage("boundary", 0.0, 0)
     ctx.copy_initial_values()  # before init_derived: Q- of the first CFL is evaluated against the beta-cooling reference state
     ctx.init_derived()
+    ctx.track_massflow(True)      # the tracking instantiations of the radial sweep and Sigma's own damping pass, slab by slab
+    ctx.track_damping_mass(True)
     last_dt, t, dts = float(cfg["FirstDT"]), 0.0, []
     for _ in range(nsteps):
         dt = ctx.cfl(last_dt)
@@ -47,6 +49,11 @@ def run_slab(ctx, cfg, radii, fields, nsteps, synthetic, abi):
     # the monitor reductions are collective: global sums (all-reduced) and the per-ring sums behind disk radius / eccentricity
     mon = dict(ctx.monitor_quantities(), **{"disk_" + k: v for k, v in ctx.monitor_disk(1e300, 0.99, 0.3).items()})
     mon["circumplanetary_mass"] = ctx.circumplanetary_mass(0.9, 0.3, 0.3)
+    for k, v in zip(("inner_creation", "inner_removal", "outer_creation", "outer_removal"), ctx.damping_mass()):
+        mon["damping_" + k] = v  # per-column sums over the rings of a rank, then over the ranks: rounding
+    for k, v in zip(("inner_in", "inner_out", "outer_in", "outer_out"), ctx.boundary_flow()):
+        mon["boundary_" + k] = v
+    out["MassFlow"] = ctx.download(abi.MASSFLOW)
     return dts, out, mon
 
 
