@@ -52,6 +52,9 @@ def _worker(rank, world, port, name, nsteps, q):
             ctx.halo_unpack(side, inc.numpy())
 
     accretors = [b for b, rec in enumerate(meta["bodies"][0]) if len(rec) > 7 and rec[7] > 0.0]
+    ctx.track_massflow(True)  # MASSFLOW grid, MassDelta's boundary flows and wave-damping terms: every slab keeps its own share
+    ctx.track_boundary_flow(True)
+    ctx.track_damping_mass(True)
     last_dt, t, dts, accreted = meta["first_dt"], 0.0, [], []
     for k in range(nsteps):
         loc = torch.tensor([ctx.condition_cfl()], dtype=torch.float64)
@@ -76,6 +79,12 @@ def _worker(rank, world, port, name, nsteps, q):
         part = torch.from_numpy(ctx.download(fid))  # owned rings only, zeros elsewhere
         dist.all_reduce(part)
         res[fname] = part.numpy()
+    part = torch.from_numpy(ctx.download(abi.MASSFLOW))
+    dist.all_reduce(part)
+    res["MassFlow"] = part.numpy()
+    sums = torch.tensor(list(ctx.damping_mass()) + list(ctx.boundary_flow()), dtype=torch.float64)  # MPI_Reduce(SUM), output.cpp:438-453
+    dist.all_reduce(sums)
+    res["mass_delta"] = sums.numpy()
     if rank == 0:
         q.put((dts, res, accreted))
     dist.barrier()
@@ -112,6 +121,9 @@ def test_two_ranks_equal_one_rank(name):
     one.copy_initial_values()
     one.stage("boundary", 0.0, 0)
     accretors = [b for b, rec in enumerate(meta["bodies"][0]) if len(rec) > 7 and rec[7] > 0.0]
+    one.track_massflow(True)
+    one.track_boundary_flow(True)
+    one.track_damping_mass(True)
     last_dt, t, dts1, acc1 = meta["first_dt"], 0.0, [], []
     for k in range(nsteps):
         dt = min(params.cfl_max_var * last_dt, one.condition_cfl())
@@ -137,6 +149,14 @@ def test_two_ranks_equal_one_rank(name):
             continue
         st = reftools.compare_stats(res2[fname], one.download(fid))
         assert st["n_diff"] == 0, (fname, st)
+    # the mass-flow grid is np-independent ring by ring; MassDelta's sums only count active cells (sum_without_ghost_cells), so the
+    # slabs' shares add up to the one-slab value up to the order of the additions
+    from fargocpt_b200 import abi
+    assert reftools.compare_stats(res2["MassFlow"], one.download(abi.MASSFLOW))["n_diff"] == 0
+    want = np.array(list(one.damping_mass()) + list(one.boundary_flow()))
+    if params.damping:
+        assert np.abs(want[:4]).max() > 0
+    assert np.allclose(res2["mass_delta"], want, rtol=1e-12, atol=0.0), (res2["mass_delta"], want)
 
 
 def test_slab_partition_matches_split_domain():
