@@ -103,26 +103,43 @@ def params_from_config(cfg, consts, nrad, naz, temp_unit_K=1.0, units=None):
     d["sigma_sb_cgs"] = float(consts.get("sigma_cgs", 0.0))
     d["G_cgs"] = float(consts.get("G_cgs", 0.0))
     d["body_force_from_potential"] = int(_flag(get("BodyForceFromPotential"), True))
+    if not d["body_force_from_potential"]:  # SourceEuler.cpp:348-353, 406-413: the kicks would read the acceleration grids
+        raise ValueError("BodyForceFromPotential: no is outside this path")
     d["thickness_smoothing"] = float(get("ThicknessSmoothing", 0.6))
     d["imposed_disk_drift"] = float(get("ImposedDiskDrift", 0.0))
 
-    # boundaries: composite names (boundary_conditions/config.cpp:345-436) or individual keys
+    # boundaries: composite names first (boundary_conditions/config.cpp:345-436), then the individual keys, which overwrite what the
+    # composite set (get_type, config.cpp:75-94).  The reference infers the INNER energy type from the OUTER side's name, and an explicit
+    # InnerBoundaryEnergy overwrites that name too (config.cpp:147): reproduced.
     comp = {"zerogradient": ("zerogradient", "zerogradient", "zerogradient"),
             "outflow": ("zerogradient", "zerogradient", "outflow"),
             "reflecting": ("zerogradient", "zerogradient", "reflecting"),
-            "reference": ("reference", "reference", "reference")}
+            "reference": ("reference", "reference", "reference"),
+            "viscous": ("zerogradient", "zerogradient", "viscous"),
+            "individual": ("", "", "")}
+    names = {}
+    for side in ("Inner", "Outer"):
+        c = str(get(side + "Boundary", "individual")).lower()
+        if c not in comp or (c == "viscous" and side == "Outer"):
+            raise ValueError("%sBoundary: %s is outside this path" % (side, c))
+        names[side + "Sigma"], names[side + "Energy"], names[side + "Vrad"] = comp[c]
+
+    def get_type(key, name):
+        v = get(key)
+        if v is not None:
+            names[name] = str(v).lower()
+        elif not names[name]:
+            raise ValueError("Can not infer '%s' when 'InnerBoundary/OuterBoundary' is set to 'individual'" % key)
+        return names[name]
+
+    s = [get_type("InnerBoundarySigma", "InnerSigma"), get_type("OuterBoundarySigma", "OuterSigma")]
+    e = [get_type("InnerBoundaryEnergy", "OuterEnergy"), get_type("OuterBoundaryEnergy", "OuterEnergy")]  # sic, in this order
+    vr = [get_type("InnerBoundaryVrad", "InnerVrad"), get_type("OuterBoundaryVrad", "OuterVrad")]
     for side, name in ((0, "Inner"), (1, "Outer")):
-        c = str(get(name + "Boundary", "individual")).lower()
-        if c in comp:
-            s, e, vr = comp[c]
-        else:
-            s = str(get(name + "BoundarySigma", "zerogradient")).lower()
-            e = str(get(name + "BoundaryEnergy", "zerogradient")).lower()
-            vr = str(get(name + "BoundaryVrad", "zerogradient")).lower()
         va = str(get(name + "BoundaryVazi", "keplerian")).lower()
-        d.setdefault("bc_sigma", [0, 0])[side] = abi.BC[s]
-        d.setdefault("bc_energy", [0, 0])[side] = abi.BC[e]
-        d.setdefault("bc_vrad", [0, 0])[side] = abi.BC[vr]
+        d.setdefault("bc_sigma", [0, 0])[side] = abi.BC[s[side]]
+        d.setdefault("bc_energy", [0, 0])[side] = abi.BC[e[side]]
+        d.setdefault("bc_vrad", [0, 0])[side] = abi.BC[vr[side]]
         d.setdefault("bc_vazi", [0, 0])[side] = abi.BC[va]
         d.setdefault("keplerian_azimuthal_factor", [1.0, 1.0])[side] = float(
             get(name + "BoundaryVaziKeplerianFactor", 1.0))

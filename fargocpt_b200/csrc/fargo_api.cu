@@ -685,6 +685,11 @@ extern "C" int fargo_ctx_create(fargo_ctx **out, const fargo_params *params, con
 	fargo_ctx_destroy(c);
 	return 1;
     }
+    if (!params->body_force_from_potential) { // SourceEuler.cpp:348-353, 406-413: the kicks would read ACCEL_RADIAL / ACCEL_AZIMUTHAL
+	fail("BodyForceFromPotential: no (body forces from the acceleration grids) is not implemented");
+	fargo_ctx_destroy(c);
+	return 1;
+    }
     if (params->alpha_mode != 0) { // viscosity::get_alpha (viscosity.cpp:31-49)
 	if (params->alpha_mode != 1 || !params->adiabatic || !(params->viscous_alpha > 0)) {
 	    fail("AlphaMode %d: only the S-curve (1) with the energy equation and ViscousAlpha > 0 is implemented", params->alpha_mode);

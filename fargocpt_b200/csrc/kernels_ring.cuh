@@ -192,6 +192,9 @@ __global__ void __launch_bounds__(256) k_damping(const DevView c, const DampJobs
 	    for (int j = 0; j < c.ns; ++j)
 		s += AT(x, ring, j);
 	    mean_sh = s / c.ns;
+	    // the reference keeps the mean IN quantity0(n_radial, 0) (damping.cpp:578-585, 706-713): the zone's initial-value grid
+	    // carries it from then on (reference boundaries, beta cooling towards the reference state).  Nobody reads x0 in this job.
+	    const_cast<double *>(J.x0)[(size_t)ring * c.ns] = mean_sh;
 	}
 	__syncthreads();
     }

@@ -428,6 +428,8 @@ static fargo_params make_params(const Config &c, const CodeConstants &k, int nra
     p.cooling_beta_reference = enum_of(c.str("CoolingBetaReference", "zero"),
 				       {{"zero", 0}, {"reference", 1}, {"diskmodel", 2}, {"floor", 4}}, "CoolingBetaReference"); // parameters.cpp:451-463
     p.body_force_from_potential = c.flag("BodyForceFromPotential", true);
+    if (!p.body_force_from_potential) // SourceEuler.cpp:348-353, 406-413: the kicks would read the ACCEL_RADIAL / ACCEL_AZIMUTHAL grids
+	die("BodyForceFromPotential: no (body forces from the acceleration grids) is outside this path");
     p.thickness_smoothing = c.num("ThicknessSmoothing", 0.6);
     p.imposed_disk_drift = c.num("ImposedDiskDrift", 0.0);
     const std::vector<std::pair<std::string, int>> BC = {{"none", 0}, {"zerogradient", 1}, {"zero_gradient", 1}, {"outflow", 2},
@@ -437,25 +439,38 @@ static fargo_params make_params(const Config &c, const CodeConstants &k, int nra
     const std::vector<std::pair<std::string, int>> BC_VAZI = {{"none", 0}, {"zerogradient", 1}, {"zero_gradient", 1}, {"keplerian", 4},
 							       {"reference", 5}, {"zeroshear", 6}, {"balanced", 7}};
     const char *sides[2] = {"Inner", "Outer"};
-    for (int s = 0; s < 2; ++s) { // composite names boundary_conditions/config.cpp:345-436, else the individual keys
+    // Composite names first (boundary_conditions/config.cpp:345-436), then the individual keys, which overwrite what the composite set
+    // (get_type, config.cpp:75-94).  The reference infers the INNER energy type from the OUTER side's name and an explicit
+    // InnerBoundaryEnergy overwrites that name too (config.cpp:147); reproduced, since a setup means what the reference makes of it.
+    std::string name_sigma[2], name_energy[2], name_vrad[2];
+    for (int s = 0; s < 2; ++s) {
 	const std::string comp = lower(c.str(std::string(sides[s]) + "Boundary", "individual"));
-	std::string bs, be, bvr;
 	if (comp == "zerogradient")
-	    bs = be = bvr = "zerogradient";
+	    name_sigma[s] = name_energy[s] = name_vrad[s] = "zerogradient";
 	else if (comp == "outflow")
-	    bs = be = "zerogradient", bvr = "outflow";
+	    name_sigma[s] = name_energy[s] = "zerogradient", name_vrad[s] = "outflow";
 	else if (comp == "reflecting")
-	    bs = be = "zerogradient", bvr = "reflecting";
+	    name_sigma[s] = name_energy[s] = "zerogradient", name_vrad[s] = "reflecting";
 	else if (comp == "reference")
-	    bs = be = bvr = "reference";
-	else {
-	    for (const char *v : {"BoundarySigma", "BoundaryEnergy", "BoundaryVrad"}) // boundary_conditions/config.cpp: no default
-		if (!c.has(std::string(sides[s]) + v))
-		    die((std::string("Can not infer '") + sides[s] + v + "' when '" + sides[s] + "Boundary' is %s").c_str(), comp);
-	    bs = c.str(std::string(sides[s]) + "BoundarySigma", "zerogradient");
-	    be = c.str(std::string(sides[s]) + "BoundaryEnergy", "zerogradient");
-	    bvr = c.str(std::string(sides[s]) + "BoundaryVrad", "zerogradient");
-	}
+	    name_sigma[s] = name_energy[s] = name_vrad[s] = "reference";
+	else if (comp == "viscous" && s == 0)
+	    name_sigma[s] = name_energy[s] = "zerogradient", name_vrad[s] = "viscous";
+	else if (comp != "individual")
+	    die((std::string(sides[s]) + "Boundary: %s is outside this path").c_str(), comp);
+    }
+    auto get_type = [&](const std::string &key, std::string &name) {
+	if (c.has(key))
+	    name = lower(c.str(key, ""));
+	else if (name.empty())
+	    die("Can not infer '%s' when 'InnerBoundary/OuterBoundary' is set to 'individual'", key);
+	return name;
+    };
+    const std::string type_sigma[2] = {get_type("InnerBoundarySigma", name_sigma[0]), get_type("OuterBoundarySigma", name_sigma[1])};
+    const std::string type_energy_inner = get_type("InnerBoundaryEnergy", name_energy[1]); // sic: the outer name, and in this order
+    const std::string type_energy[2] = {type_energy_inner, get_type("OuterBoundaryEnergy", name_energy[1])};
+    const std::string type_vrad[2] = {get_type("InnerBoundaryVrad", name_vrad[0]), get_type("OuterBoundaryVrad", name_vrad[1])};
+    for (int s = 0; s < 2; ++s) {
+	const std::string &bs = type_sigma[s], &be = type_energy[s], &bvr = type_vrad[s];
 	p.bc_sigma[s] = enum_of(bs, BC, "boundary");
 	p.bc_energy[s] = enum_of(be, BC, "boundary");
 	p.bc_vrad[s] = enum_of(bvr, s == 0 ? BC_VRAD_INNER : BC, "v_rad boundary");

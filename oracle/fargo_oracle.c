@@ -1267,7 +1267,7 @@ static int clamp_id(const fargo_oracle *o, int id, int is_vector)
 }
 
 /* damping_single_{inner,outer}{,_zero,_mean}, damping.cpp:311-752 */
-static void damp_field(fargo_oracle *o, double *x, const double *x0, int is_vector, int is_density, const int type[2], double dt)
+static void damp_field(fargo_oracle *o, double *x, double *x0, int is_vector, int is_density, const int type[2], double dt)
 {
     const int rings = o->nr + (is_vector ? 1 : 0), Nphi = o->ns;
     const double *radius = is_vector ? o->rinf : o->rmed;
@@ -1286,6 +1286,8 @@ static void damp_field(fargo_oracle *o, double *x, const double *x0, int is_vect
 		for (int j = 0; j < Nphi; ++j)
 		    mean += x[IDX(o, nr, j)];
 		mean /= Nphi;
+		x0[IDX(o, nr, 0)] = mean; /* the reference keeps the mean IN quantity0(n_radial, 0), damping.cpp:578-585 / 706-713: the
+					     initial-value grid of this zone carries it from then on (reference boundaries, beta cooling) */
 	    }
 	    for (int j = 0; j < Nphi; ++j) {
 		const size_t c = IDX(o, nr, j);
@@ -1325,6 +1327,8 @@ static void damp_field(fargo_oracle *o, double *x, const double *x0, int is_vect
 		for (int j = 0; j < Nphi; ++j)
 		    mean += x[IDX(o, nr, j)];
 		mean /= Nphi;
+		x0[IDX(o, nr, 0)] = mean; /* the reference keeps the mean IN quantity0(n_radial, 0), damping.cpp:578-585 / 706-713: the
+					     initial-value grid of this zone carries it from then on (reference boundaries, beta cooling) */
 	    }
 	    for (int j = 0; j < Nphi; ++j) {
 		const size_t c = IDX(o, nr, j);

@@ -160,6 +160,12 @@ CASES = {
                         HeatingViscous="yes", l0="0.06 au", Sigma0=0.001, WriteTemperature="yes", WriteQminus="yes", WriteQplus="yes"),
     "adia_scurve_ichikawa_lf": dict(SurfaceCooling="scurve", ScurveType="Ichikawa", Integrator="Leapfrog", ViscousAlpha=1e-3,
                                     HeatingViscous="yes", l0="0.06 au", Sigma0=0.001, WriteTemperature="yes"),
+    # damping towards the ring mean leaves the mean in column 0 of the initial-value grid (damping.cpp:578-585, 706-713), which the
+    # Reference boundaries and the beta cooling towards the reference state read afterwards: all of it in one run, with a planet
+    "adia_damp_mean_ref": dict(InnerBoundary="Reference", OuterBoundary="Reference", InnerBoundaryVazi="Reference", OuterBoundaryVazi="Reference",
+                               ViscousAlpha=1e-2, HeatingViscous="yes", CoolingBetaLocal="yes", CoolingBeta=1, CoolingBetaReference="reference",
+                               Damping="Yes", DampingInnerLimit=1.6, DampingOuterLimit=0.6, DampingTimeFactor=0.01, IndirectTermMode=1,
+                               Nsnapshots=12, _planet=1e-3, **{k: "Mean" for k in DAMP_ALL}),
     "iso_planet_100": dict(Nrad=48, Naz=160, Rmax=2.5, Nsnapshots=100, MonitorTimestep=4.0e-3, IndirectTermMode=1,
                            EquationOfState="Isothermal", ViscousAlpha=1e-3, ArtificialViscosityFactor=1.41, OmegaFrame=1.0,
                            FlaringIndex=0.0, Damping="Yes", DampingInnerLimit=1.25, DampingOuterLimit=0.84,

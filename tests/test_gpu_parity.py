@@ -24,6 +24,9 @@ CASES += ["adia_irrad", "adia_irrad_lf"]
 CASES += ["iso_bc_balanced", "adia_bc_zeroshear"]
 # inner v_rad boundaries Viscous (viscous.cpp: the mean viscosity of rings 0 and 1, state-independent here) and Keplerian
 CASES += ["iso_bc_viscous", "adia_bc_keplerian_vrad"]
+# damping towards the ring mean keeps the mean in column 0 of the initial-value grid (damping.cpp:578-585, 706-713); Reference
+# boundaries and the beta cooling towards the reference state read it afterwards
+CASES += ["adia_damp_mean_ref"]
 # the Lin & Papaloizou / Bell & Lin opacity tables call pow() with fractional exponents (opacity.cpp:49-298): CUDA's pow and
 # glibc's differ in the last bits, so these two runs are held to a tolerance instead (fields, dt)
 POW_CASES = ["adia_cool_lin", "adia_cool_bell"]

@@ -212,7 +212,9 @@ START_CASES = [("iso_star", 6, True), ("adia_star", 6, True), ("adia_cold", 6, T
                # v_azi boundaries Balanced (v_sq of the disk model formed by the host like balanced.cpp:23-52) and ZeroShear
                ("iso_bc_balanced", 6, True), ("adia_bc_zeroshear", 6, True),
                # inner v_rad boundaries Viscous (ViscousOutflowSpeed) and Keplerian (InnerBoundaryVradKeplerianFactor)
-               ("iso_bc_viscous", 6, True), ("adia_bc_keplerian_vrad", 6, True)]
+               ("iso_bc_viscous", 6, True), ("adia_bc_keplerian_vrad", 6, True),
+               # ring-mean damping (the mean stays in column 0 of the initial-value grid) + Reference boundaries + beta cooling towards them
+               ("adia_damp_mean_ref", 12, False)]
 
 
 @pytest.mark.parametrize("name,until,exact", START_CASES)
@@ -576,13 +578,51 @@ def test_host_start_refuses_unknown_keys_like_the_reference(tmp_path):
 
 
 def test_host_refuses_physics_it_does_not_implement(tmp_path):
-    for key, value in (("EquationOfState", "Polytropic"), ("SurfaceCooling", "fld"), ("SelfGravity", "yes"), ("AlphaMode", 2)):
+    for key, value in (("EquationOfState", "Polytropic"), ("SurfaceCooling", "fld"), ("SelfGravity", "yes"), ("AlphaMode", 2),
+                       ("BodyForceFromPotential", "no")):
         cfg = yaml.safe_load(open(os.path.join(ROOT, "tests", "golden", "adia_star.yml")))
         cfg[key] = value
         yml = str(tmp_path / f"setup_{key}.yml")
         yaml.safe_dump(cfg, open(yml, "w"), sort_keys=False)
         res = subprocess.run([_oracle_exe(), "start", yml, "--out", str(tmp_path / ("out_" + key))], capture_output=True, text=True, timeout=60)
         assert res.returncode != 0 and key in res.stderr, (key, res.stderr)
+
+
+def test_boundary_types_are_inferred_like_the_reference(tmp_path):
+    """boundary_conditions/config.cpp:75-94, 145-147: individual keys overwrite what a composite set; the inner energy type is inferred
+    from the OUTER side's name, and an explicit InnerBoundaryEnergy also becomes the outer default.  Checked on the Python mirror of
+    the host's parser; the side-by-side runs of tests/checkers/fuzz_against_reference.py cover the host against the reference."""
+    import sys
+    sys.path.insert(0, ROOT)
+    from fargocpt_b200 import abi, config
+    base = {k: v for k, v in yaml.safe_load(open(os.path.join(ROOT, "tests", "golden", "adia_star.yml"))).items()}
+    consts = {"G": 1.0, "R": 1.0, "sigma": 1.0, "c": 1.0}
+
+    def bc(**over):
+        cfg = dict(base)
+        for k in ("InnerBoundary", "OuterBoundary"):
+            cfg.pop(k, None)
+        cfg.update(over)
+        d = config.params_from_config(cfg, consts, 24, 48)
+        return d["bc_sigma"], d["bc_energy"], d["bc_vrad"]
+
+    ZG, REF, RFL, OUT = abi.BC["zerogradient"], abi.BC["reference"], abi.BC["reflecting"], abi.BC["outflow"]
+    # inner composite Reference, outer Reflecting: the inner ENERGY follows the outer composite (zerogradient)
+    assert bc(InnerBoundary="Reference", OuterBoundary="Reflecting") == ([REF, ZG], [ZG, ZG], [REF, RFL])
+    # an individual key overwrites the composite's choice
+    assert bc(InnerBoundary="Reflecting", OuterBoundary="Reflecting", InnerBoundaryVrad="outflow")[2] == [OUT, RFL]
+    # an explicit InnerBoundaryEnergy also becomes the outer side's type unless that is given too
+    assert bc(InnerBoundary="Reflecting", OuterBoundary="Reflecting", InnerBoundaryEnergy="reference")[1] == [REF, REF]
+    # inner composite + outer individual: the inner energy cannot be inferred (the reference throws)
+    with pytest.raises(ValueError, match="InnerBoundaryEnergy"):
+        bc(InnerBoundary="Reflecting", OuterBoundarySigma="zerogradient", OuterBoundaryEnergy="zerogradient", OuterBoundaryVrad="outflow")
+    cfg = dict(base, InnerBoundary="Reflecting")
+    cfg.pop("OuterBoundary", None)
+    cfg.update(OuterBoundarySigma="zerogradient", OuterBoundaryEnergy="zerogradient", OuterBoundaryVrad="outflow")
+    yml = str(tmp_path / "setup.yml")
+    yaml.safe_dump(cfg, open(yml, "w"), sort_keys=False)
+    res = subprocess.run([_oracle_exe(), "start", yml, "--out", str(tmp_path / "out")], capture_output=True, text=True, timeout=60)
+    assert res.returncode != 0 and "InnerBoundaryEnergy" in res.stderr, res.stderr
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -21,7 +21,10 @@ CASES = ["adia_star", "adia_cold", "iso_star", "iso_sn_std", "adia_sn_stab", "ri
          # v_azi boundaries Balanced (balanced.cpp, rotating frame) and ZeroShear (zero_shear.cpp)
          "iso_bc_balanced", "adia_bc_zeroshear",
          # inner v_rad boundaries Viscous (viscous.cpp) and Keplerian (keplerian_radial.cpp)
-         "iso_bc_viscous", "adia_bc_keplerian_vrad"]
+         "iso_bc_viscous", "adia_bc_keplerian_vrad",
+         # damping towards the ring mean keeps the mean in column 0 of the initial-value grid (damping.cpp:578-585), which Reference
+         # boundaries and the beta cooling towards the reference state then read
+         "adia_damp_mean_ref"]
 # Isothermal configs have no per-cell transcendental in the step => demanded bit-exact.
 # Adiabatic configs call exp() per cell (SourceEuler.cpp:487); same libm here => also bit-exact on CPU.
 # DiskFeedback: the reference sums the disk's pull with an OpenMP reduction in no defined order, so the acceleration
