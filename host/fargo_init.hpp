@@ -397,8 +397,8 @@ inline std::vector<BodyInit> init_bodies(const std::vector<std::map<std::string,
 	    a = a / (std::pow(r1, 2) - std::pow(r0, 2));
 	}
 	const std::string method = get(cfg, "accretion method", "kley");
-	if (p.accretion_efficiency > 0.0 && method != "kley" && method != "sinkhole" && method != "no" && method != "none")
-	    refuse("accretion method '" + method + "' is not supported by this driver (kley, sinkhole)");
+	if (p.accretion_efficiency > 0.0 && method != "kley" && method != "sinkhole" && method != "viscous" && method != "no" && method != "none")
+	    refuse("accretion method '" + method + "' is not supported by this driver (kley, sinkhole, viscous)");
 	// initialize_planet_jacobi (:539-578) around the centre of mass of the bodies added so far
 	auto jacobi = [&](double om) {
 	    p.mass = mass;

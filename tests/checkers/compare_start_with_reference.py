@@ -52,7 +52,10 @@ def main(argv=None):
     ypath = os.path.join(tmp, "setup.yml")
     yaml.safe_dump(cfg, open(ypath, "w"), sort_keys=False)
     env = dict(os.environ, OMP_NUM_THREADS=str(ref_threads))
-    r = subprocess.run([REF, "start", ypath], cwd=tmp, env=env, capture_output=True, text=True)
+    try:
+        r = subprocess.run([REF, "start", ypath], cwd=tmp, env=env, capture_output=True, text=True, timeout=float(os.environ.get("CMPSTART_TIMEOUT", 3600)))
+    except subprocess.TimeoutExpired:
+        raise SystemExit("reference run timed out")
     if r.returncode != 0:
         print(r.stdout[-2000:], r.stderr[-2000:])
         raise SystemExit("reference run failed")
