@@ -118,6 +118,8 @@ def params_from_config(cfg, consts, nrad, naz, temp_unit_K=1.0, units=None):
             "viscous": ("zerogradient", "zerogradient", "viscous"),
             "individual": ("", "", "")}
     names = {}
+    if get("OuterBoundary") is None:  # Interpret.cpp:290-293
+        raise ValueError("OuterBoundary doesn't exist. Old parameter file?")
     for side in ("Inner", "Outer"):
         c = str(get(side + "Boundary", "individual")).lower()
         if c not in comp or (c == "viscous" and side == "Outer"):

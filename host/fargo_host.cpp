@@ -443,6 +443,8 @@ static fargo_params make_params(const Config &c, const CodeConstants &k, int nra
     // (get_type, config.cpp:75-94).  The reference infers the INNER energy type from the OUTER side's name and an explicit
     // InnerBoundaryEnergy overwrites that name too (config.cpp:147); reproduced, since a setup means what the reference makes of it.
     std::string name_sigma[2], name_energy[2], name_vrad[2];
+    if (!c.has("OuterBoundary")) // Interpret.cpp:290-293
+	die("OuterBoundary doesn't exist. Old parameter file?");
     for (int s = 0; s < 2; ++s) {
 	const std::string comp = lower(c.str(std::string(sides[s]) + "Boundary", "individual"));
 	if (comp == "zerogradient")

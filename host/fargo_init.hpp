@@ -259,6 +259,11 @@ inline std::vector<double> make_radii(int spacing /* fargo_params::radial_spacin
 	const double Nr = (double)nrad - 2.0;
 	for (int i = 0; i < 500000; ++i)
 	    egf = egf - ((std::pow(egf, Nr) - egf * f + f - 1)) / (Nr * std::pow(egf, Nr - 1.0) - f);
+	// On coarse grids (about Nrad < 40 with the default ExponentialCellSizeFactor) the reference's Newton iteration falls into the
+	// trivial root 1: its grid then stops short of Rmax (or is 0 / 0) and its ring lookups (find_cell_id.cpp:236-246, 1 / log(g)) return
+	// clamped garbage.  Nothing to be faithful to: refused.
+	if (!(egf > 1.0 + 1.0e-9))
+	    refuse("RadialSpacing: Exponential: the growth factor iteration of init.cpp:112-128 degenerates to 1 on this grid (too few rings)");
 	for (int n = 0; n <= nrad; ++n)
 	    r[n] = rmin + first * (std::pow(egf, (double)n - 1.0) - 1.0) / (egf - 1.0);
     } else {

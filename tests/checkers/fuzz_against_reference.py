@@ -30,6 +30,8 @@ def draw(seed):
     cfg.pop("cps", None)
     cfg["Nrad"], cfg["Naz"] = pick([24, 33, 48]), pick([32, 48, 96])
     cfg["RadialSpacing"] = pick(["Logarithmic", "Arithmetic", "Exponential"])
+    if cfg["RadialSpacing"] == "Exponential":  # coarser grids send the reference's growth-factor iteration into its trivial root (init.cpp:112-128)
+        cfg["Nrad"] = 48
     cfg["Rmin"], cfg["Rmax"] = pick([0.3, 0.4, 0.5]), pick([2.0, 2.5, 3.1])
     eos = pick(["Isothermal", "Ideal", "Ideal", "PVTE"])
     cfg["EquationOfState"] = eos
@@ -74,7 +76,7 @@ def draw(seed):
     for side in ("Inner", "Outer"):
         comp = "individual" if individual else pick(["Reflecting", "Outflow", "Zerogradient", "Reference"])
         if comp == "individual":
-            cfg.pop(side + "Boundary", None)
+            cfg[side + "Boundary"] = "individual"  # the key itself must exist (Interpret.cpp:286-293)
             cfg[side + "BoundarySigma"] = pick(["zerogradient", "reference"])
             cfg[side + "BoundaryEnergy"] = pick(["zerogradient", "reference"])
             vr = ["zerogradient", "reflecting", "outflow", "reference"] + (["viscous", "keplerian"] if side == "Inner" else [])

@@ -599,9 +599,7 @@ def test_boundary_types_are_inferred_like_the_reference(tmp_path):
     consts = {"G": 1.0, "R": 1.0, "sigma": 1.0, "c": 1.0}
 
     def bc(**over):
-        cfg = dict(base)
-        for k in ("InnerBoundary", "OuterBoundary"):
-            cfg.pop(k, None)
+        cfg = dict(base, InnerBoundary="individual", OuterBoundary="individual")
         cfg.update(over)
         d = config.params_from_config(cfg, consts, 24, 48)
         return d["bc_sigma"], d["bc_energy"], d["bc_vrad"]
@@ -616,8 +614,7 @@ def test_boundary_types_are_inferred_like_the_reference(tmp_path):
     # inner composite + outer individual: the inner energy cannot be inferred (the reference throws)
     with pytest.raises(ValueError, match="InnerBoundaryEnergy"):
         bc(InnerBoundary="Reflecting", OuterBoundarySigma="zerogradient", OuterBoundaryEnergy="zerogradient", OuterBoundaryVrad="outflow")
-    cfg = dict(base, InnerBoundary="Reflecting")
-    cfg.pop("OuterBoundary", None)
+    cfg = dict(base, InnerBoundary="Reflecting", OuterBoundary="individual")
     cfg.update(OuterBoundarySigma="zerogradient", OuterBoundaryEnergy="zerogradient", OuterBoundaryVrad="outflow")
     yml = str(tmp_path / "setup.yml")
     yaml.safe_dump(cfg, open(yml, "w"), sort_keys=False)
