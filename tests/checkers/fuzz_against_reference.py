@@ -3,7 +3,7 @@
 (oracle/_ref/fargocpt_exe_ieee) and through `fargocpt_b200 start` (oracle-bound test binary, or --gpu for the product), and report
 the worst field deviation per draw (compare_start_with_reference.py does the comparison).  Build container only.
 
-    python tests/checkers/fuzz_against_reference.py [--seeds 0:40] [--gpu] [--snapshots 3]
+    python tests/checkers/fuzz_against_reference.py [--seeds 0:40] [--wide] [--gpu] [--snapshots 3]
 
 A draw that the host refuses by name is reported as "refused" (that is the contract for physics outside the path); a draw the
 reference itself rejects is skipped."""
@@ -23,7 +23,7 @@ import compare_start_with_reference as cmp  # noqa: E402
 BASE = os.path.join(ROOT, "tests", "golden", "cold_disk_planet_setup.yml")
 
 
-def draw(seed):
+def draw(seed, wide=False):
     rng = random.Random(seed)
     pick = rng.choice
     cfg = {k: v for k, v in yaml.safe_load(open(BASE)).items() if not k.startswith("_")}
@@ -103,6 +103,49 @@ def draw(seed):
             cfg["Frame"] = "F"
     cfg["WriteDiskQuantities"] = pick(["Yes", "No"])
     cfg["WriteMassFlow"] = pick(["yes", "no"])
+    if wide:  # a second round of switches: disk model, frame centre, several bodies, irradiation, profile cut-offs, limits
+        cfg["CFLmaxVar"] = pick([1.1, 1.5])
+        cfg["SigmaFloor"] = pick([1e-9, 1e-7])
+        cfg["RadialViscosityFactor"] = pick([1.0, 1.0, 0.5])
+        cfg["HeatingViscousFactor"] = pick([1.0, 0.5])
+        cfg["ImposedDiskDrift"] = pick([0.0, 0.0, 1e-3])
+        cfg["InitializePureKeplerian"] = pick(["no", "no", "yes"])
+        cfg["InitializeVradialZero"] = pick(["no", "yes"])
+        cfg["HeatingCoolingCFLlimit"] = pick([1.0, 10.0, 1000.0])
+        cfg["MinimumTemperature"] = pick(["3 K", "10 K"])
+        cfg["MaximumTemperature"] = pick(["1e100 K", "5000 K"])
+        cfg["InnerBoundaryVaziKeplerianFactor"] = pick([1.0, 0.98])
+        cfg["DampingTimeFactor"] = pick([0.05, 1.0])
+        cfg["DampingInnerLimit"], cfg["DampingOuterLimit"] = pick([1.1, 1.311]), pick([0.763, 0.9])
+        if rng.random() < 0.3:
+            cfg["ProfileCutoffOuter"], cfg["ProfileCutoffPointOuter"], cfg["ProfileCutoffWidthOuter"] = "yes", 0.8 * cfg["Rmax"], 0.1
+        if rng.random() < 0.3:
+            cfg["ProfileCutoffInner"], cfg["ProfileCutoffPointInner"], cfg["ProfileCutoffWidthInner"] = "yes", 1.5 * cfg["Rmin"], 0.05
+        if cfg.get("CoolingBetaLocal") == "Yes":
+            cfg["CoolingBetaRampUp"] = pick([0.0, 0.3])
+        if cfg.get("SurfaceCooling") == "thermal":
+            cfg["KappaFactor"], cfg["TauFactor"], cfg["TauMin"] = pick([1.0, 2.0]), pick([0.5, 1.0]), pick([0.01, 0.1])
+            cfg["CoolingRadiativeFactor"] = pick([1.0, 0.5])
+            if rng.random() < 0.5:
+                cfg["nbody"][0]["temperature"] = "5000 K"
+                cfg["nbody"][0]["irradiation ramp-up time"] = pick([0.0, 0.2])
+        if eos == "PVTE":
+            cfg["HydrogenMassFraction"] = pick([0.75, 0.7])
+        if len(cfg["nbody"]) > 1:
+            planet = cfg["nbody"][1]
+            planet["semi-major axis"] = pick([1, 1.3])
+            planet["cubic smoothing factor"] = pick([0.0, 0.5])
+            planet["argument of pericenter"] = pick([0.0, 1.0])
+            planet["trueanomaly"] = pick([0.0, 2.0])
+            if rng.random() < 0.4:
+                second = dict(planet, name="second", mass=pick([1e-4, 5e-4]))
+                second["semi-major axis"] = 1.7
+                second["accretion efficiency"] = 0.0
+                second.pop("accretion method", None)
+                cfg["nbody"].append(second)
+            cfg["HydroFrameCenter"] = pick(["primary", "primary", "binary", "all"]) if planet["mass"] >= 1e-3 else "primary"
+            if cfg["HydroFrameCenter"] != "primary":
+                cfg["Frame"] = "F"
     return cfg
 
 
@@ -118,7 +161,7 @@ def main():
     tmp = tempfile.mkdtemp(prefix="fuzz_")
     worst_all = 0.0
     for seed in range(lo, hi):
-        cfg = draw(seed)
+        cfg = draw(seed, wide="--wide" in args)
         path = os.path.join(tmp, f"draw_{seed}.yml")
         yaml.safe_dump(cfg, open(path, "w"), sort_keys=False)
         out = io.StringIO()
