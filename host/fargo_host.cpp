@@ -917,6 +917,11 @@ struct Run {
 	    if (!qp.empty() && !qm.empty()) {
 		CHECK(BK(upload_field)(ctx, FARGO_QPLUS, qp.data()));
 		CHECK(BK(upload_field)(ctx, FARGO_QMINUS, qm.data()));
+	    } else {
+		// restart.cpp:73-88: the reference then estimates them (compute_heating_cooling_for_CFL) and says so; here the first
+		// CFL after the restart simply has no heating / cooling limit.  Write them with BitwiseExactRestarting: yes.
+		fprintf(stderr, "fargocpt_b200: cannot read Qplus / Qminus in %s, no bitwise identical restarting possible "
+				"(BitwiseExactRestarting: yes writes them)\n", sd.c_str());
 	    }
 	}
 	// damping / beta-cooling targets: snapshots/reference (simulation.cpp:43-48), else the loaded state itself

@@ -3,7 +3,7 @@
 (oracle/_ref/fargocpt_exe_ieee) and through `fargocpt_b200 start` (oracle-bound test binary, or --gpu for the product), and report
 the worst field deviation per draw (compare_start_with_reference.py does the comparison).  Build container only.
 
-    python tests/checkers/fuzz_against_reference.py [--seeds 0:40] [--wide] [--gpu] [--snapshots 3]
+    python tests/checkers/fuzz_against_reference.py [--seeds 0:40] [--wide] [--gpu] [--snapshots 3] [--dt 0.05] [-- <arguments of compare_start_with_reference.py>]
 
 A draw that the host refuses by name is reported as "refused" (that is the contract for physics outside the path); a draw the
 reference itself rejects is skipped."""
@@ -155,6 +155,9 @@ def main():
     if "--seeds" in args:
         lo, hi = (int(x) for x in args[args.index("--seeds") + 1].split(":"))
     extra = [a for a in ("--gpu",) if a in args]
+    if "--" in args:  # everything after "--" goes to compare_start_with_reference.py (e.g. -- --restart-from 1 --vs-reference-restart)
+        extra += args[args.index("--") + 1:]
+    dt = args[args.index("--dt") + 1] if "--dt" in args else "0.05"
     nsnap = args[args.index("--snapshots") + 1] if "--snapshots" in args else "3"
     import tempfile
     os.environ.setdefault("CMPSTART_TIMEOUT", "120")  # a draw whose time step collapses in the reference is skipped
@@ -169,7 +172,7 @@ def main():
         worst = float("nan")
         try:
             with contextlib.redirect_stdout(out):
-                worst = cmp.main([path, "--snapshots", nsnap, "--dt", "0.05"] + extra)
+                worst = cmp.main([path, "--snapshots", nsnap, "--dt", dt] + extra)
         except SystemExit as e:
             status = str(e)
         text = out.getvalue()
